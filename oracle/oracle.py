@@ -1,0 +1,210 @@
+"""TEST INFRASTRUCTURE -- NOT PRODUCT CODE.
+
+ctypes/numpy front end of the CPU oracle (oracle/liboracle.so, built from solid_oracle.cpp) and,
+when present, of oracle/_ref/libref_solid.so (built on the reference's own headers).  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+HEX8, HEX27, TET10 = 0, 1, 2
+MAT_COUP_NEOHOOKE, MAT_ISO_VOL, MAT_SVK = 0, 1, 2
+ACTION_FORCE, ACTION_FORCE_STIFF = 0, 1
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_lp = C.POINTER(C.c_int64)
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip) if a is not None else None
+
+
+def _l(a):
+    return a.ctypes.data_as(_lp) if a is not None else None
+
+
+def build(force=False):
+    """Compile liboracle.so (always) and _ref/libref_solid.so (only where /root/reference exists)."""
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "solid_oracle.cpp")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "oracle"], stdout=subprocess.DEVNULL)
+    ref = os.path.join(_HERE, "_ref", "libref_solid.so")
+    if os.path.isdir("/root/reference/src"):
+        rsrc = os.path.join(_HERE, "ref_driver.cpp")
+        if force or not os.path.exists(ref) or os.path.getmtime(ref) < os.path.getmtime(rsrc):
+            subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(os.path.join(_HERE, "liboracle.so"))
+        L.orc_svk_strain_energy.restype = C.c_double
+        L.orc_evaluate_assemble.restype = C.c_int64
+        L.orc_evaluate_assemble.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int64, _ip,
+                                            C.c_int64, _dp, _dp, _ip, _ip, C.c_int64, _lp, _ip, _dp,
+                                            _dp, C.c_int]
+        L.orc_build_graph.argtypes = [C.c_int, C.c_int64, _ip, C.c_int64, _ip, _ip, C.c_int64, _lp,
+                                      _ip]
+        L.orc_element.argtypes = [C.c_int, C.c_int, _dp, C.c_int, _dp, _dp, _dp, _dp]
+        for fn in (L.orc_stiffness_bfree, L.orc_stiffness_bop):
+            fn.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_double, _dp]
+        _lib = L
+    return _lib
+
+
+def ref_lib():
+    """oracle/_ref (reference headers) or None when it was never built (e.g. no /root/reference)."""
+    global _ref
+    if _ref is None:
+        p = os.path.join(_HERE, "_ref", "libref_solid.so")
+        if not os.path.exists(p):
+            try:
+                build()
+            except Exception:
+                pass
+        if not os.path.exists(p):
+            return None
+        R = C.CDLL(p)
+        R.ref_element.argtypes = [C.c_int, C.c_int, _dp, C.c_int, _dp, _dp, _dp, _dp, C.c_int, _dp,
+                                  _dp]
+        R.ref_stiffness_bfree.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_double, _dp]
+        _ref = R
+    return _ref
+
+
+def num_nodes(ct):
+    return lib().orc_num_nodes(ct)
+
+
+def num_gp(ct):
+    return lib().orc_num_gp(ct)
+
+
+def shape(ct, xi):
+    n = num_nodes(ct)
+    xi = np.ascontiguousarray(xi, dtype=np.float64)
+    N = np.zeros(n)
+    dN = np.zeros(3 * n)
+    lib().orc_shape(ct, _d(xi), _d(N), _d(dN))
+    return N, dN.reshape(n, 3).T.copy()  # dN[a,k]
+
+
+def gauss(ct):
+    g = num_gp(ct)
+    xi = np.zeros(3 * g)
+    w = np.zeros(g)
+    lib().orc_gauss(ct, _d(xi), _d(w))
+    return xi.reshape(g, 3), w
+
+
+def node_param_coords(ct):
+    n = num_nodes(ct)
+    xi = np.zeros(3 * n)
+    lib().orc_node_param_coords(ct, _d(xi))
+    return xi.reshape(n, 3)
+
+
+def material(kind, params, E, F=None):
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    E = np.ascontiguousarray(E, dtype=np.float64)
+    F = np.eye(3).T.copy().ravel() if F is None else np.ascontiguousarray(F, dtype=np.float64)
+    S = np.zeros(6)
+    Cm = np.zeros(36)
+    lib().orc_material(kind, _d(params), _d(F), _d(E), _d(S), _d(Cm))
+    return S, Cm.reshape(6, 6).T.copy()  # Cm[I,J]
+
+
+def element(ct, matkind, params, X, u, action=ACTION_FORCE_STIFF):
+    """X,u: (n,3). Returns (Ke (nd,nd) with Ke[row,col], fe, err)."""
+    n = num_nodes(ct)
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    X = np.ascontiguousarray(X, dtype=np.float64).reshape(n, 3)
+    u = np.ascontiguousarray(u, dtype=np.float64).reshape(n, 3)
+    Ke = np.zeros((3 * n) ** 2)
+    fe = np.zeros(3 * n)
+    err = lib().orc_element(ct, matkind, _d(params), action, _d(X), _d(u), _d(Ke), _d(fe))
+    return Ke.reshape(3 * n, 3 * n).T.copy(), fe, err
+
+
+def ref_element(ct, matkind, params, X, u, action=ACTION_FORCE_STIFF):
+    R = ref_lib()
+    n = num_nodes(ct)
+    gxi, gw = gauss(ct)
+    gxi = np.ascontiguousarray(gxi)
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    X = np.ascontiguousarray(X, dtype=np.float64).reshape(n, 3)
+    u = np.ascontiguousarray(u, dtype=np.float64).reshape(n, 3)
+    Ke = np.zeros((3 * n) ** 2)
+    fe = np.zeros(3 * n)
+    err = R.ref_element(ct, matkind, _d(params), action, _d(X), _d(u), _d(gxi), _d(gw), len(gw),
+                        _d(Ke), _d(fe))
+    return Ke.reshape(3 * n, 3 * n).T.copy(), fe, err
+
+
+def stiffness_point(ct, X, u, xi, S, Cm, fac=1.0, which="bfree"):
+    n = num_nodes(ct)
+    X = np.ascontiguousarray(X, dtype=np.float64).reshape(n, 3)
+    u = np.ascontiguousarray(u, dtype=np.float64).reshape(n, 3)
+    xi = np.ascontiguousarray(xi, dtype=np.float64)
+    S = np.ascontiguousarray(S, dtype=np.float64)
+    Cc = np.ascontiguousarray(np.asarray(Cm, dtype=np.float64).T).ravel()  # -> column-major
+    Ke = np.zeros((3 * n) ** 2)
+    if which == "ref":
+        ref_lib().ref_stiffness_bfree(ct, _d(X), _d(u), _d(xi), _d(S), _d(Cc), fac, _d(Ke))
+    else:
+        fn = lib().orc_stiffness_bfree if which == "bfree" else lib().orc_stiffness_bop
+        fn(ct, _d(X), _d(u), _d(xi), _d(S), _d(Cc), fac, _d(Ke))
+    return Ke.reshape(3 * n, 3 * n).T.copy()
+
+
+def build_graph(ct, conn, node_row_lid, node_col_lid, n_row_nodes):
+    n = num_nodes(ct)
+    conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, n)
+    node_row_lid = np.ascontiguousarray(node_row_lid, dtype=np.int32)
+    node_col_lid = np.ascontiguousarray(node_col_lid, dtype=np.int32)
+    rowptr = np.zeros(3 * n_row_nodes + 1, dtype=np.int64)
+    lib().orc_build_graph(ct, conn.shape[0], _i(conn), len(node_row_lid), _i(node_row_lid),
+                          _i(node_col_lid), n_row_nodes, _l(rowptr), None)
+    colind = np.zeros(rowptr[-1], dtype=np.int32)
+    lib().orc_build_graph(ct, conn.shape[0], _i(conn), len(node_row_lid), _i(node_row_lid),
+                          _i(node_col_lid), n_row_nodes, _l(rowptr), _i(colind))
+    return rowptr, colind
+
+
+def evaluate_assemble(ct, matkind, params, conn, X, u_col, node_row_lid, node_col_lid, n_row_nodes,
+                      rowptr, colind, action=ACTION_FORCE_STIFF, mue_per_ele=None, nthreads=1):
+    n = num_nodes(ct)
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, n)
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    u_col = np.ascontiguousarray(u_col, dtype=np.float64)
+    node_row_lid = np.ascontiguousarray(node_row_lid, dtype=np.int32)
+    node_col_lid = np.ascontiguousarray(node_col_lid, dtype=np.int32)
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+    colind = np.ascontiguousarray(colind, dtype=np.int32)
+    if mue_per_ele is not None:
+        mue_per_ele = np.ascontiguousarray(mue_per_ele, dtype=np.float64)
+    values = np.zeros(rowptr[-1]) if action == ACTION_FORCE_STIFF else None
+    f = np.zeros(3 * n_row_nodes)
+    nbad = lib().orc_evaluate_assemble(ct, matkind, _d(params), _d(mue_per_ele), action,
+                                       conn.shape[0], _i(conn), len(node_row_lid), _d(X), _d(u_col),
+                                       _i(node_row_lid), _i(node_col_lid), n_row_nodes, _l(rowptr),
+                                       _i(colind), _d(values), _d(f), nthreads)
+    return values, f, int(nbad)

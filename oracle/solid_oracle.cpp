@@ -1,0 +1,729 @@
+/*
+ * TEST INFRASTRUCTURE -- NOT PRODUCT CODE.  See solid_oracle.h for the contract.
+ *
+ * Plain C++ restatement of the 4C solid element evaluate + assemble path.  Citations are
+ * relative to /root/reference (4C @ 96b9fa91).  Nothing here includes reference sources; the
+ * numerical constants of the quadrature tables are data taken verbatim (incl. the truncated
+ * hex27 decimals) because parity at 1e-12 depends on them.
+ */
+#include "solid_oracle.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <set>
+#include <thread>
+#include <vector>
+
+namespace
+{
+  constexpr int MAXN = 27;
+
+  // ---- node coordinates in parameter space
+  // (src/core/fem/src/general/utils/4C_fem_general_utils_local_connectivity_matrices.hpp:291,314)
+  const double hex27_ref[27][3] = {{-1, -1, -1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1}, {-1, -1, 1},
+      {1, -1, 1}, {1, 1, 1}, {-1, 1, 1}, {0, -1, -1}, {1, 0, -1}, {0, 1, -1}, {-1, 0, -1},
+      {-1, -1, 0}, {1, -1, 0}, {1, 1, 0}, {-1, 1, 0}, {0, -1, 1}, {1, 0, 1}, {0, 1, 1}, {-1, 0, 1},
+      {0, 0, -1}, {0, -1, 0}, {1, 0, 0}, {0, 1, 0}, {-1, 0, 0}, {0, 0, 1}, {0, 0, 0}};
+  const double tet10_ref[10][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0.5, 0, 0},
+      {0.5, 0.5, 0}, {0, 0.5, 0}, {0, 0, 0.5}, {0.5, 0, 0.5}, {0, 0.5, 0.5}};
+
+  int nnodes(int ct) { return ct == ORC_HEX8 ? 8 : (ct == ORC_HEX27 ? 27 : 10); }
+  int ngauss(int ct) { return ct == ORC_HEX8 ? 8 : (ct == ORC_HEX27 ? 27 : 4); }
+
+  void node_ref(int ct, int k, double* xi)
+  {
+    const double* p = (ct == ORC_TET10) ? tet10_ref[k] : hex27_ref[k];  // hex8 = first 8 of hex27
+    xi[0] = p[0], xi[1] = p[1], xi[2] = p[2];
+  }
+
+  // ---- shape functions and first derivatives
+  // (src/core/fem/src/general/utils/4C_fem_general_utils_fem_shapefunctions.hpp
+  //  hex8 :61-79,409-450; hex27 :198-238,706-830; tet10 :252-267,831-875)
+  void shape(int ct, const double* xi, double* N, double* dN)
+  {
+    const double r = xi[0], s = xi[1], t = xi[2];
+    if (ct == ORC_HEX8)
+    {
+      for (int k = 0; k < 8; ++k)
+      {
+        const double rk = hex27_ref[k][0], sk = hex27_ref[k][1], tk = hex27_ref[k][2];
+        const double fr = 1.0 + rk * r, fs = 1.0 + sk * s, ft = 1.0 + tk * t;
+        N[k] = 0.125 * fr * fs * ft;
+        dN[0 + 3 * k] = rk * 0.125 * fs * ft;
+        dN[1 + 3 * k] = sk * 0.125 * ft * fr;
+        dN[2 + 3 * k] = tk * 0.125 * fr * fs;
+      }
+    }
+    else if (ct == ORC_HEX27)
+    {
+      // 1-D quadratic Lagrange functions indexed by node coordinate -1,0,+1 -> slot 0,1,2
+      auto lag = [](double x, double* L, double* dL)
+      {
+        L[0] = 0.5 * x * (x - 1.0), L[1] = 1.0 - x * x, L[2] = 0.5 * x * (x + 1.0);
+        dL[0] = x - 0.5, dL[1] = -2.0 * x, dL[2] = x + 0.5;
+      };
+      double Lr[3], Ls[3], Lt[3], dLr[3], dLs[3], dLt[3];
+      lag(r, Lr, dLr), lag(s, Ls, dLs), lag(t, Lt, dLt);
+      for (int k = 0; k < 27; ++k)
+      {
+        const int a = (int)hex27_ref[k][0] + 1, b = (int)hex27_ref[k][1] + 1,
+                  c = (int)hex27_ref[k][2] + 1;
+        N[k] = Lr[a] * Ls[b] * Lt[c];
+        dN[0 + 3 * k] = Ls[b] * Lt[c] * dLr[a];
+        dN[1 + 3 * k] = Lr[a] * Lt[c] * dLs[b];
+        dN[2 + 3 * k] = Lr[a] * Ls[b] * dLt[c];
+      }
+    }
+    else
+    {
+      const double u = 1.0 - r - s - t;
+      N[0] = u * (2.0 * u - 1.0), N[1] = r * (2.0 * r - 1.0), N[2] = s * (2.0 * s - 1.0),
+      N[3] = t * (2.0 * t - 1.0);
+      N[4] = 4.0 * r * u, N[5] = 4.0 * r * s, N[6] = 4.0 * s * u, N[7] = 4.0 * t * u,
+      N[8] = 4.0 * r * t, N[9] = 4.0 * s * t;
+      const double d0 = -4.0 * u + 1.0;
+      const double D[10][3] = {{d0, d0, d0}, {4.0 * r - 1.0, 0, 0}, {0, 4.0 * s - 1.0, 0},
+          {0, 0, 4.0 * t - 1.0}, {4.0 * (u - r), -4.0 * r, -4.0 * r}, {4.0 * s, 4.0 * r, 0},
+          {-4.0 * s, 4.0 * (u - s), -4.0 * s}, {-4.0 * t, -4.0 * t, 4.0 * (u - t)},
+          {4.0 * t, 0, 4.0 * r}, {0, 4.0 * t, 4.0 * s}};
+      for (int k = 0; k < 10; ++k)
+        for (int a = 0; a < 3; ++a) dN[a + 3 * k] = D[k][a];
+    }
+  }
+
+  // ---- Gauss rules for force/stiffness
+  // (rule selection src/solid_ele/4C_solid_ele_calc_lib_integration.hpp:43-64; tables
+  //  src/core/fem/src/general/utils/4C_fem_general_utils_integration.cpp hex_8point :74-104,
+  //  hex_27point :130-245 (truncated decimals!), tet_4point :331-352)
+  void gauss(int ct, double* xi, double* w)
+  {
+    if (ct == ORC_HEX8)
+    {
+      const double g = 1.0 / std::sqrt(3.0);
+      for (int q = 0; q < 8; ++q)
+      {
+        for (int d = 0; d < 3; ++d) xi[3 * q + d] = hex27_ref[q][d] * g;
+        w[q] = 1.0;
+      }
+    }
+    else if (ct == ORC_HEX27)
+    {
+      const double xi3 = 0.7745966692415;
+      const double w1 = 0.5555555555556, w2 = 0.8888888888889;
+      for (int q = 0; q < 27; ++q)
+      {
+        for (int d = 0; d < 3; ++d) xi[3 * q + d] = hex27_ref[q][d] * xi3;
+        const double wx = hex27_ref[q][0] == 0.0 ? w2 : w1, wy = hex27_ref[q][1] == 0.0 ? w2 : w1,
+                     wz = hex27_ref[q][2] == 0.0 ? w2 : w1;
+        w[q] = wx * wy * wz;
+      }
+    }
+    else
+    {
+      const double pa = (5.0 + 3.0 * std::sqrt(5.0)) / 20.0, pb = (5.0 - std::sqrt(5.0)) / 20.0;
+      const double P[4][3] = {{pb, pb, pb}, {pa, pb, pb}, {pb, pa, pb}, {pb, pb, pa}};
+      for (int q = 0; q < 4; ++q)
+      {
+        for (int d = 0; d < 3; ++d) xi[3 * q + d] = P[q][d];
+        w[q] = 1.0 / 6.0 / 4.0;
+      }
+    }
+  }
+
+  // ---- 3x3 helpers, column-major m[a + 3b]
+  // (src/core/linalg/src/dense/4C_linalg_fixedsizematrix.hpp invert3x3 :1306-1335, determinant :1443-1457)
+  double det3(const double* m)
+  {
+    return m[0] * (m[4] * m[8] - m[5] * m[7]) + m[3] * (m[2] * m[7] - m[1] * m[8]) +
+           m[6] * (m[1] * m[5] - m[2] * m[4]);
+  }
+  double inv3(double* o, const double* m)
+  {
+    o[0] = m[4] * m[8] - m[5] * m[7];
+    o[1] = m[2] * m[7] - m[1] * m[8];
+    o[2] = m[1] * m[5] - m[2] * m[4];
+    const double det = m[0] * o[0] + m[3] * o[1] + m[6] * o[2];
+    const double id = 1.0 / det;
+    o[0] *= id, o[1] *= id, o[2] *= id;
+    o[3] = id * (m[5] * m[6] - m[3] * m[8]);
+    o[4] = id * (m[0] * m[8] - m[2] * m[6]);
+    o[5] = id * (m[2] * m[3] - m[0] * m[5]);
+    o[6] = id * (m[3] * m[7] - m[4] * m[6]);
+    o[7] = id * (m[1] * m[6] - m[0] * m[7]);
+    o[8] = id * (m[0] * m[4] - m[1] * m[3]);
+    return det;
+  }
+
+  // Voigt slot of (a,b): [00,11,22,01,12,02]
+  const int VG[3][3] = {{0, 3, 5}, {3, 1, 4}, {5, 4, 2}};
+  const int VA[6] = {0, 1, 2, 0, 1, 0}, VB[6] = {0, 1, 2, 1, 2, 2};
+
+  // ---- Jacobian mapping at one parameter point (src/solid_ele/4C_solid_ele_calc_lib.hpp:499-516)
+  struct JacMap
+  {
+    double J[9], iJ[9], det;
+    double G[MAXN][3];  // N_XYZ
+  };
+  void jacobian_mapping(int n, const double* dN, const double* X, JacMap& jm)
+  {
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b)
+      {
+        double v = 0.0;
+        for (int k = 0; k < n; ++k) v += dN[a + 3 * k] * X[3 * k + b];
+        jm.J[a + 3 * b] = v;
+      }
+    inv3(jm.iJ, jm.J);
+    jm.det = det3(jm.J);
+    for (int k = 0; k < n; ++k)
+      for (int a = 0; a < 3; ++a)
+      {
+        double v = 0.0;
+        for (int b = 0; b < 3; ++b) v += jm.iJ[a + 3 * b] * dN[b + 3 * k];
+        jm.G[k][a] = v;
+      }
+  }
+
+  // F = I + u N_XYZ^T  (src/solid_ele/4C_solid_ele_calc_lib.hpp:646-660)
+  void deformation_gradient(int n, const double* u, const JacMap& jm, double* F)
+  {
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b)
+      {
+        double v = (a == b) ? 1.0 : 0.0;
+        for (int k = 0; k < n; ++k) v += u[3 * k + a] * jm.G[k][b];
+        F[a + 3 * b] = v;
+      }
+  }
+
+  // ---- materials ------------------------------------------------------------------------------
+  // calculate_gamma_delta (src/mat/4C_mat_elasthyper_service.cpp:417-435)
+  void gamma_delta(const double* I, const double* dPI, const double* ddPII, double* g, double* d)
+  {
+    g[0] = 2. * (dPI[0] + I[0] * dPI[1]);
+    g[1] = -2. * dPI[1];
+    g[2] = 2. * I[2] * dPI[2];
+    d[0] = 4. * (ddPII[0] + 2. * I[0] * ddPII[5] + dPI[1] + I[0] * I[0] * ddPII[1]);
+    d[1] = -4. * (ddPII[5] + I[0] * ddPII[1]);
+    d[2] = 4. * (I[2] * ddPII[4] + I[0] * I[2] * ddPII[3]);
+    d[3] = 4. * ddPII[1];
+    d[4] = -4. * I[2] * ddPII[3];
+    d[5] = 4. * (I[2] * dPI[2] + I[2] * I[2] * ddPII[2]);
+    d[6] = -4. * I[2] * dPI[2];
+    d[7] = -4. * dPI[1];
+  }
+
+  // elast_hyper_evaluate_invariant_derivatives for the supported summand sets
+  // (src/mat/4C_mat_elasthyper_service.cpp:84-154; summands
+  //  src/mat/elast/4C_mat_elast_coupneohooke.cpp:17-25,50-68, ..._isoneohooke.cpp:34-40,
+  //  ..._volsussmanbathe.cpp:36-43; invariants_modified src/mat/4C_mat_service.cpp:125-134)
+  void invariant_derivatives(int kind, const double* par, const double* I, double* dPI, double* ddPII)
+  {
+    for (int i = 0; i < 3; ++i) dPI[i] = 0.0;
+    for (int i = 0; i < 6; ++i) ddPII[i] = 0.0;
+    if (kind == ORC_MAT_COUP_NEOHOOKE)
+    {
+      const double youngs = par[0], nue = par[1];
+      const double c = youngs / (4.0 * (1.0 + nue));
+      const double beta = nue / (1.0 - 2.0 * nue);
+      dPI[0] += c;
+      if (I[2] > 0)
+      {
+        const double p = std::exp(std::log(I[2]) * (-beta - 1.));
+        dPI[2] -= c * p;
+        ddPII[2] += c * (beta + 1.) * p / I[2];
+      }
+      else
+        dPI[2] = ddPII[2] = std::numeric_limits<double>::quiet_NaN();
+    }
+    else if (kind == ORC_MAT_ISO_VOL)
+    {
+      const double mue = par[0], kappa = par[1];
+      double modinv[3], dPm[3] = {0, 0, 0}, ddPm[6] = {0, 0, 0, 0, 0, 0};
+      modinv[0] = I[0] * std::pow(I[2], -1. / 3.);
+      modinv[1] = I[1] * std::pow(I[2], -2. / 3.);
+      modinv[2] = std::pow(I[2], 1. / 2.);
+      dPm[0] += 0.5 * mue;                  // IsoNeoHooke
+      dPm[2] += kappa * (modinv[2] - 1.);   // VolSussmanBathe
+      ddPm[2] += kappa;
+      // convert_mod_to_princ (:122-154)
+      dPI[0] += std::pow(I[2], -1. / 3.) * dPm[0];
+      dPI[1] += std::pow(I[2], -2. / 3.) * dPm[1];
+      dPI[2] += 0.5 * std::pow(I[2], -0.5) * dPm[2] -
+                1. / 3. * I[0] * std::pow(I[2], -4. / 3.) * dPm[0] -
+                2. / 3. * I[1] * std::pow(I[2], -5. / 3.) * dPm[1];
+      ddPII[0] += std::pow(I[2], -2. / 3.) * ddPm[0];
+      ddPII[1] += std::pow(I[2], -4. / 3.) * ddPm[1];
+      ddPII[2] += (1. / 9.) * std::pow(I[2], -8. / 3.) * I[0] * I[0] * ddPm[0] +
+                  (4. / 9.) * I[0] * I[1] * std::pow(I[2], -3.) * ddPm[5] -
+                  (1. / 3.) * std::pow(I[2], -11. / 6.) * I[0] * ddPm[4] +
+                  (4. / 9.) * std::pow(I[2], -7. / 3.) * I[0] * dPm[0] +
+                  (4. / 9.) * std::pow(I[2], -10. / 3.) * I[1] * I[1] * ddPm[1] -
+                  (2. / 3.) * std::pow(I[2], -13. / 6.) * I[1] * ddPm[3] +
+                  (10. / 9.) * std::pow(I[2], -8. / 3.) * I[1] * dPm[1] +
+                  0.25 * std::pow(I[2], -1.) * ddPm[2] - 0.25 * std::pow(I[2], -1.5) * dPm[2];
+      ddPII[3] += -(1. / 3.) * std::pow(I[2], -2.) * I[0] * ddPm[5] -
+                  (2. / 3.) * std::pow(I[2], -7. / 3.) * I[1] * ddPm[1] +
+                  0.5 * std::pow(I[2], -7. / 6.) * ddPm[3] -
+                  (2. / 3.) * std::pow(I[2], -5. / 3.) * dPm[1];
+      ddPII[4] += -(1. / 3.) * std::pow(I[2], -5. / 3.) * I[0] * ddPm[0] -
+                  (2. / 3.) * std::pow(I[2], -2.) * I[1] * ddPm[5] +
+                  0.5 * std::pow(I[2], -5. / 6.) * ddPm[4] -
+                  (1. / 3.) * std::pow(I[2], -4. / 3.) * dPm[0];
+      ddPII[5] += std::pow(I[2], -1.) * ddPm[5];
+    }
+  }
+
+  // Mat::ElastHyper::evaluate -> elast_hyper_evaluate (src/mat/4C_mat_elasthyper.cpp:314-325,
+  // src/mat/4C_mat_elasthyper_service.cpp:23-75,156-206)
+  void elasthyper(int kind, const double* par, const double* E, double* S, double* Cm)
+  {
+    double C[6], Cfull[9], iCfull[9], iC[6];
+    for (int i = 0; i < 6; ++i) C[i] = 2.0 * E[i] + (i < 3 ? 1.0 : 0.0);
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) Cfull[a + 3 * b] = C[VG[a][b]];
+    inv3(iCfull, Cfull);
+    for (int i = 0; i < 6; ++i) iC[i] = iCfull[VA[i] + 3 * VB[i]];
+    // invariants_principal (src/core/linalg/src/dense/4C_linalg_fixedsizematrix_voigt_notation.hpp:78-103)
+    double I[3];
+    I[0] = C[0] + C[1] + C[2];
+    I[1] = 0.5 * (I[0] * I[0] - C[0] * C[0] - C[1] * C[1] - C[2] * C[2]) - C[3] * C[3] -
+           C[4] * C[4] - C[5] * C[5];
+    I[2] = C[0] * C[1] * C[2] + 2 * (C[3] * C[4] * C[5]) - C[1] * C[5] * C[5] -
+           C[2] * C[3] * C[3] - C[0] * C[4] * C[4];
+    double dPI[3], ddPII[6], g[3], d[8];
+    invariant_derivatives(kind, par, I, dPI, ddPII);
+    gamma_delta(I, dPI, ddPII, g, d);
+    const double Id[6] = {1, 1, 1, 0, 0, 0};
+    for (int i = 0; i < 6; ++i) S[i] = g[0] * Id[i] + g[1] * C[i] + g[2] * iC[i];
+    for (int Iv = 0; Iv < 6; ++Iv)
+      for (int Jv = 0; Jv < 6; ++Jv)
+      {
+        const int a = VA[Iv], b = VB[Iv], c = VA[Jv], e = VB[Jv];
+        double v = 0.0;
+        v += d[0] * Id[Iv] * Id[Jv];
+        v += d[1] * (Id[Iv] * C[Jv] + C[Iv] * Id[Jv]);
+        v += d[2] * (Id[Iv] * iC[Jv] + iC[Iv] * Id[Jv]);
+        v += d[3] * C[Iv] * C[Jv];
+        v += d[4] * (C[Iv] * iC[Jv] + iC[Iv] * C[Jv]);
+        v += d[5] * iC[Iv] * iC[Jv];
+        // Holzapfel product 1/2 (A_ac A_be + A_ae A_bc)
+        // (src/core/linalg/src/dense/4C_linalg_fixedsizematrix_tensor_products.cpp:207-214)
+        v += d[6] * 0.5 * (iC[VG[a][c]] * iC[VG[b][e]] + iC[VG[a][e]] * iC[VG[b][c]]);
+        // symmetric identity 1/2 (d_ac d_be + d_ae d_bc)
+        v += d[7] * 0.5 * ((a == c && b == e ? 1.0 : 0.0) + (a == e && b == c ? 1.0 : 0.0));
+        Cm[Iv + 6 * Jv] = v;
+      }
+  }
+
+  // Mat::StVenantKirchhoff::evaluate (src/mat/4C_mat_stvenantkirchhoff.cpp:105-113,
+  // src/mat/4C_mat_stvenantkirchhoff.hpp:136-170)
+  void svk(const double* par, const double* E, double* S, double* Cm)
+  {
+    const double Ey = par[0], nu = par[1];
+    const double mue = Ey / (2 * (1 + nu));
+    const double lambda = Ey * nu / ((1 + nu) * (1 - 2 * nu));
+    const double tr = E[0] + E[1] + E[2];
+    for (int i = 0; i < 6; ++i) S[i] = lambda * tr * (i < 3 ? 1.0 : 0.0) + 2 * mue * E[i];
+    for (int i = 0; i < 36; ++i) Cm[i] = 0.0;
+    const double mfac = Ey / ((1.0 + nu) * (1.0 - 2.0 * nu));
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) Cm[i + 6 * j] = (i == j) ? mfac * (1.0 - nu) : mfac * nu;
+    for (int i = 3; i < 6; ++i) Cm[i + 6 * i] = mfac * 0.5 * (1.0 - 2.0 * nu);
+  }
+
+  void material(int kind, const double* par, const double* /*F*/, const double* E, double* S,
+      double* Cm)
+  {
+    if (kind == ORC_MAT_SVK)
+      svk(par, E, S, Cm);
+    else
+      elasthyper(kind, par, E, S, Cm);
+  }
+
+  // ---- B-free stiffness and force at one point (src/solid_ele/4C_solid_ele_calc_lib.hpp:1107-1151)
+  void add_force(int n, const JacMap& jm, const double* F, const double* S, double fac, double* fe)
+  {
+    double P[9];
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b)
+      {
+        double v = 0.0;
+        for (int c = 0; c < 3; ++c) v += F[a + 3 * c] * S[VG[c][b]];
+        P[a + 3 * b] = v;
+      }
+    for (int k = 0; k < n; ++k)
+      for (int a = 0; a < 3; ++a)
+      {
+        double v = 0.0;
+        for (int b = 0; b < 3; ++b) v += P[a + 3 * b] * jm.G[k][b];
+        fe[3 * k + a] += v * fac;
+      }
+  }
+
+  void add_stiffness_bfree(int n, const JacMap& jm, const double* F, const double* S,
+      const double* Cm, double fac, double* Ke)
+  {
+    const int nd = 3 * n;
+    // FCFTw(a,b,c,d) = sum_ij F(b,i) C(a,i,j,d) F(c,j) w   (einsum<"bi","aijd","cj">, free
+    // indices sorted by letter: 4C_linalg_tensor_einstein.hpp:222)
+    double A[3][3][3][3];
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b)
+        for (int c = 0; c < 3; ++c)
+          for (int d = 0; d < 3; ++d)
+          {
+            double v = 0.0;
+            for (int i = 0; i < 3; ++i)
+              for (int j = 0; j < 3; ++j)
+                v += F[b + 3 * i] * Cm[VG[a][i] + 6 * VG[j][d]] * (F[c + 3 * j] * fac);
+            A[a][b][c][d] = v;
+          }
+    for (int i = 0; i < n; ++i)
+    {
+      double Ai[3][3][3], gi[3];
+      for (int b = 0; b < 3; ++b)
+        for (int c = 0; c < 3; ++c)
+          for (int d = 0; d < 3; ++d)
+          {
+            double v = 0.0;
+            for (int a = 0; a < 3; ++a) v += jm.G[i][a] * A[a][b][c][d];
+            Ai[b][c][d] = v;
+          }
+      for (int d = 0; d < 3; ++d)
+      {
+        double v = 0.0;
+        for (int a = 0; a < 3; ++a) v += jm.G[i][a] * S[VG[a][d]];
+        gi[d] = v * fac;
+      }
+      for (int j = 0; j < n; ++j)
+      {
+        for (int b = 0; b < 3; ++b)
+          for (int c = 0; c < 3; ++c)
+          {
+            double v = 0.0;
+            for (int d = 0; d < 3; ++d) v += Ai[b][c][d] * jm.G[j][d];
+            Ke[(3 * i + b) + nd * (3 * j + c)] += v;
+          }
+        double sg = 0.0;
+        for (int d = 0; d < 3; ++d) sg += gi[d] * jm.G[j][d];
+        for (int b = 0; b < 3; ++b) Ke[(3 * i + b) + nd * (3 * j + b)] += sg;
+      }
+    }
+  }
+
+  // B-operator variant (evaluate_strain_gradient :777-826, add_elastic_stiffness_matrix
+  // :1163-1176, add_geometric_stiffness_matrix :1188-1207)
+  void add_stiffness_bop(int n, const JacMap& jm, const double* F, const double* S,
+      const double* Cm, double fac, double* Ke)
+  {
+    const int nd = 3 * n;
+    std::vector<double> B(6 * nd), CB(6 * nd);
+    for (int i = 0; i < n; ++i)
+    {
+      const double* g = jm.G[i];
+      for (int d = 0; d < 3; ++d)
+        for (int e = 0; e < 3; ++e) B[d + 6 * (3 * i + e)] = F[e + 3 * d] * g[d];
+      for (int e = 0; e < 3; ++e)
+      {
+        B[3 + 6 * (3 * i + e)] = F[e + 3 * 0] * g[1] + F[e + 3 * 1] * g[0];
+        B[4 + 6 * (3 * i + e)] = F[e + 3 * 1] * g[2] + F[e + 3 * 2] * g[1];
+        B[5 + 6 * (3 * i + e)] = F[e + 3 * 2] * g[0] + F[e + 3 * 0] * g[2];
+      }
+    }
+    for (int c = 0; c < nd; ++c)
+      for (int I = 0; I < 6; ++I)
+      {
+        double v = 0.0;
+        for (int J = 0; J < 6; ++J) v += Cm[I + 6 * J] * B[J + 6 * c];
+        CB[I + 6 * c] = v;
+      }
+    for (int r = 0; r < nd; ++r)
+      for (int c = 0; c < nd; ++c)
+      {
+        double v = 0.0;
+        for (int I = 0; I < 6; ++I) v += B[I + 6 * r] * CB[I + 6 * c];
+        Ke[r + nd * c] += fac * v;
+      }
+    for (int i = 0; i < n; ++i)
+    {
+      double gi[3];
+      for (int d = 0; d < 3; ++d)
+      {
+        double v = 0.0;
+        for (int a = 0; a < 3; ++a) v += jm.G[i][a] * S[VG[a][d]];
+        gi[d] = v * fac;
+      }
+      for (int j = 0; j < n; ++j)
+      {
+        double sg = 0.0;
+        for (int d = 0; d < 3; ++d) sg += gi[d] * jm.G[j][d];
+        for (int b = 0; b < 3; ++b) Ke[(3 * i + b) + nd * (3 * j + b)] += sg;
+      }
+    }
+  }
+
+  // ---- SolidEleCalc<celltype, DisplacementBased>::evaluate_nonlinear_force_stiffness_mass
+  // (src/solid_ele/4C_solid_ele_calc.cpp:137-281 with the formulation of
+  //  src/solid_ele/4C_solid_ele_calc_displacement_based.hpp:44-63,214-236)
+  int element(int ct, int matkind, const double* par, int action, const double* X, const double* u,
+      double* Ke, double* fe)
+  {
+    const int n = nnodes(ct), nd = 3 * n, ng = ngauss(ct);
+    double N[MAXN], dN[3 * MAXN];
+    JacMap jm;
+    if (Ke) std::memset(Ke, 0, sizeof(double) * nd * nd);  // clear_element_storage
+    std::memset(fe, 0, sizeof(double) * nd);
+
+    // ensure_positive_jacobian_determinant_at_element_nodes (calc_lib.hpp:543-562)
+    int err = 0;
+    for (int k = 0; k < n; ++k)
+    {
+      double xi[3];
+      node_ref(ct, k, xi);
+      shape(ct, xi, N, dN);
+      jacobian_mapping(n, dN, X, jm);
+      if (!(jm.det > 0)) err = 1;
+    }
+    if (err) return 1;
+
+    double gxi[3 * MAXN], gw[MAXN];
+    gauss(ct, gxi, gw);
+    // for_each_gauss_point (calc_lib.hpp:1254-1286)
+    for (int gp = 0; gp < ng; ++gp)
+    {
+      shape(ct, gxi + 3 * gp, N, dN);
+      jacobian_mapping(n, dN, X, jm);
+      const double fac = jm.det * gw[gp];
+      double F[9], C[6], E[6], S[6], Cm[36];
+      deformation_gradient(n, u, jm, F);
+      // evaluate_cauchy_green / evaluate_green_lagrange_strain (calc_lib.hpp:697-722)
+      for (int v = 0; v < 6; ++v)
+      {
+        double s = 0.0;
+        for (int c = 0; c < 3; ++c) s += F[c + 3 * VA[v]] * F[c + 3 * VB[v]];
+        C[v] = s;
+        E[v] = 0.5 * (s - (v < 3 ? 1.0 : 0.0));
+      }
+      material(matkind, par, F, E, S, Cm);
+      add_force(n, jm, F, S, fac, fe);
+      if (action == ORC_ACTION_FORCE_STIFF && Ke) add_stiffness_bfree(n, jm, F, S, Cm, fac, Ke);
+    }
+    return 0;
+  }
+}  // namespace
+
+extern "C"
+{
+  int orc_num_nodes(int ct) { return nnodes(ct); }
+  int orc_num_gp(int ct) { return ngauss(ct); }
+  void orc_shape(int ct, const double* xi, double* N, double* dN) { shape(ct, xi, N, dN); }
+  void orc_gauss(int ct, double* xi, double* w) { gauss(ct, xi, w); }
+  void orc_node_param_coords(int ct, double* xi)
+  {
+    for (int k = 0; k < nnodes(ct); ++k) node_ref(ct, k, xi + 3 * k);
+  }
+  void orc_material(
+      int kind, const double* par, const double* F, const double* E, double* S, double* C)
+  {
+    material(kind, par, F, E, S, C);
+  }
+  void orc_calculate_gamma_delta(
+      const double* prinv, const double* dPI, const double* ddPII, double* gamma, double* delta)
+  {
+    gamma_delta(prinv, dPI, ddPII, gamma, delta);
+  }
+  void orc_invariant_derivatives(
+      int kind, const double* par, const double* prinv, double* dPI, double* ddPII)
+  {
+    invariant_derivatives(kind, par, prinv, dPI, ddPII);
+  }
+  // Mat::StVenantKirchhoff::strain_energy = 1/2 E:C:E (src/mat/4C_mat_stvenantkirchhoff.cpp:119-135)
+  double orc_svk_strain_energy(const double* par, const double* E)
+  {
+    double S[6], Cm[36];
+    svk(par, E, S, Cm);
+    double psi = 0.0;
+    for (int i = 0; i < 6; ++i) psi += 0.5 * S[i] * E[i] * (i < 3 ? 1.0 : 2.0);
+    return psi;
+  }
+  int orc_element(int ct, int matkind, const double* par, int action, const double* X,
+      const double* u, double* Ke, double* fe)
+  {
+    return element(ct, matkind, par, action, X, u, Ke, fe);
+  }
+
+  static void point_setup(
+      int ct, const double* X, const double* u, const double* xi, JacMap& jm, double* F)
+  {
+    double N[MAXN], dN[3 * MAXN];
+    shape(ct, xi, N, dN);
+    jacobian_mapping(nnodes(ct), dN, X, jm);
+    deformation_gradient(nnodes(ct), u, jm, F);
+  }
+  void orc_stiffness_bfree(int ct, const double* X, const double* u, const double* xi,
+      const double* S, const double* C, double fac, double* Ke)
+  {
+    JacMap jm;
+    double F[9];
+    point_setup(ct, X, u, xi, jm, F);
+    add_stiffness_bfree(nnodes(ct), jm, F, S, C, fac, Ke);
+  }
+  void orc_stiffness_bop(int ct, const double* X, const double* u, const double* xi,
+      const double* S, const double* C, double fac, double* Ke)
+  {
+    JacMap jm;
+    double F[9];
+    point_setup(ct, X, u, xi, jm, F);
+    add_stiffness_bop(nnodes(ct), jm, F, S, C, fac, Ke);
+  }
+
+  // First assembly inserts every (owned row, element column) pair in global ids, zeros included
+  // (src/core/linalg/src/sparse/4C_linalg_sparsematrix.cpp:469-494), complete() then sorts each
+  // row by local column id (:700-721).  All three dofs of a node share the node's pattern.
+  int orc_build_graph(int ct, int64_t n_ele, const int32_t* conn, int64_t n_col_nodes,
+      const int32_t* node_row_lid, const int32_t* node_col_lid, int64_t n_row_nodes,
+      int64_t* rowptr, int32_t* colind)
+  {
+    const int n = nnodes(ct);
+    (void)n_col_nodes;
+    std::vector<std::vector<int32_t>> adj(n_row_nodes);
+    for (int64_t e = 0; e < n_ele; ++e)
+      for (int i = 0; i < n; ++i)
+      {
+        const int32_t r = node_row_lid[conn[e * n + i]];
+        if (r < 0) continue;
+        for (int j = 0; j < n; ++j) adj[r].push_back(node_col_lid[conn[e * n + j]]);
+      }
+    int64_t nnz = 0;
+    rowptr[0] = 0;
+    for (int64_t r = 0; r < n_row_nodes; ++r)
+    {
+      auto& a = adj[r];
+      std::sort(a.begin(), a.end());
+      a.erase(std::unique(a.begin(), a.end()), a.end());
+      for (int b = 0; b < 3; ++b)
+      {
+        if (colind)
+          for (size_t q = 0; q < a.size(); ++q)
+            for (int c = 0; c < 3; ++c) colind[nnz + 3 * q + c] = 3 * a[q] + c;
+        nnz += 3 * (int64_t)a.size();
+        rowptr[3 * r + b + 1] = nnz;
+      }
+    }
+    return 0;
+  }
+
+  int64_t orc_evaluate_assemble(int ct, int matkind, const double* matparams,
+      const double* mue_per_ele, int action, int64_t n_ele, const int32_t* conn,
+      int64_t n_col_nodes, const double* X, const double* u_col, const int32_t* node_row_lid,
+      const int32_t* node_col_lid, int64_t n_row_nodes, const int64_t* rowptr,
+      const int32_t* colind, double* values, double* f, int nthreads)
+  {
+    (void)n_col_nodes;
+    const int n = nnodes(ct), nd = 3 * n;
+    if (nthreads < 1) nthreads = 1;
+    std::vector<int64_t> bad(nthreads, 0);
+    auto worker = [&](int tid)
+    {
+      // "rank" tid owns row nodes [r0,r1)
+      const int64_t r0 = n_row_nodes * tid / nthreads, r1 = n_row_nodes * (tid + 1) / nthreads;
+      // SparseMatrix::zero / Vector::put_scalar(0) on the owned rows
+      if (values && action == ORC_ACTION_FORCE_STIFF)
+        std::fill(values + rowptr[3 * r0], values + rowptr[3 * r1], 0.0);
+      std::fill(f + 3 * r0, f + 3 * r1, 0.0);
+      std::vector<double> Ke(nd * nd), fe(nd), Xe(nd), ue(nd);
+      std::vector<int32_t> localcol(nd);
+      double par[4] = {matparams[0], matparams[1], 0, 0};
+      // Discretization::evaluate loop over column elements
+      // (src/core/fem/src/discretization/4C_fem_discretization_evaluate.cpp:85-117)
+      for (int64_t e = 0; e < n_ele; ++e)
+      {
+        const int32_t* ce = conn + e * n;
+        bool mine = false;
+        for (int i = 0; i < n; ++i)
+        {
+          const int32_t r = node_row_lid[ce[i]];
+          if (r >= r0 && r < r1) mine = true;
+        }
+        if (!mine) continue;
+        for (int i = 0; i < n; ++i)
+          for (int d = 0; d < 3; ++d)
+          {
+            Xe[3 * i + d] = X[3 * (int64_t)ce[i] + d];
+            ue[3 * i + d] = u_col[3 * (int64_t)ce[i] + d];  // extract_values via lm
+          }
+        if (mue_per_ele) par[0] = mue_per_ele[e];  // InputField MUE looked up by element id
+        const bool stiff = (action == ORC_ACTION_FORCE_STIFF) && values;
+        if (element(ct, matkind, par, action, Xe.data(), ue.data(), stiff ? Ke.data() : nullptr,
+                fe.data()))
+        {
+          bad[tid]++;
+          continue;
+        }
+        // SparseMatrix::assemble, filled() branch (4C_linalg_sparsematrix.cpp:356-467)
+        for (int j = 0; j < n; ++j)
+          for (int c = 0; c < 3; ++c) localcol[3 * j + c] = 3 * node_col_lid[ce[j]] + c;
+        for (int i = 0; i < n; ++i)
+        {
+          const int32_t r = node_row_lid[ce[i]];
+          if (r < r0 || r >= r1) continue;  // lmrowowner != myrank
+          for (int b = 0; b < 3; ++b)
+          {
+            const int lrow = 3 * i + b;
+            const int64_t rlid = 3 * (int64_t)r + b;
+            // LinAlg::assemble for the vector (4C_linalg_utils_sparse_algebra_assemble.cpp:60-82)
+            f[rlid] += fe[lrow];
+            if (!stiff) continue;
+            const int length = (int)(rowptr[rlid + 1] - rowptr[rlid]);
+            double* valview = values + rowptr[rlid];
+            const int32_t* indices = colind + rowptr[rlid];
+            int dofcount = 0, pos = 0;
+            for (int node = 0; node < n; ++node)
+            {
+              if (pos >= length || indices[pos] != localcol[dofcount])
+              {
+                const int32_t* loc = std::lower_bound(indices, indices + length, localcol[dofcount]);
+                pos = (int)(loc - indices);
+              }
+              const int stride = 3;
+              bool continuous = true;
+              if (stride + pos > length)
+                continuous = false;
+              else
+                for (int j = 1; j < stride; ++j)
+                  if (indices[pos + j] != localcol[dofcount + j])
+                  {
+                    continuous = false;
+                    break;
+                  }
+              if (continuous)
+                for (int j = 0; j < stride; ++j) valview[pos++] += Ke[lrow + nd * (dofcount++)];
+              else
+                for (int j = 0; j < stride; ++j)
+                {  // sum_into_my_values fallback
+                  const int32_t* loc =
+                      std::lower_bound(indices, indices + length, localcol[dofcount]);
+                  valview[loc - indices] += Ke[lrow + nd * dofcount];
+                  dofcount++;
+                }
+            }
+          }
+        }
+      }
+    };
+    if (nthreads == 1)
+      worker(0);
+    else
+    {
+      std::vector<std::thread> th;
+      for (int t = 0; t < nthreads; ++t) th.emplace_back(worker, t);
+      for (auto& t : th) t.join();
+    }
+    int64_t nb = 0;
+    for (auto b : bad) nb += b;
+    return nb;
+  }
+}

@@ -1,0 +1,178 @@
+#!/usr/bin/env python
+"""Regenerates the committed golden fixtures in tests/golden/ from the reference tree.
+
+Run in the build container only (needs /root/reference and oracle/_ref):
+    python tests/golden/make_golden.py
+
+What it writes
+  integration_<cell>.json : inputs + expected nodal displacements (RESULT DESCRIPTION, tol 1e-12)
+        of the reference's own ctest input files
+          tests/input_files/solid_ele_hex8_Standard_eas_none_stressout.4C.yaml
+          tests/input_files/solid_ele_hex27_Standard_stressout.4C.yaml
+          tests/input_files/solid_ele_tet10_Standard_stressout.4C.yaml
+  unit_known_answers.json : known answers of unittests/mat/4C_elasthyper_service_test.cpp:36-155,
+        unittests/mat/4C_stvenantkirchhoff_test.cpp:44-118 and the glibc srand(0)/rand() input
+        sequence of unittests/solid_ele/4C_solid_ele_calc_lib_test.cpp:243-343
+  ref_elements.npz : element matrices / force vectors and material tangents computed HERE by
+        oracle/_ref (the reference's own tensor, einsum and shape-function headers) on seeded
+        random inputs, for all cell types x materials.
+"""
+import ctypes
+import json
+import os
+import re
+import sys
+
+import numpy as np
+import yaml
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+
+CASES = {
+    "hex8": "tests/input_files/solid_ele_hex8_Standard_eas_none_stressout.4C.yaml",
+    "hex27": "tests/input_files/solid_ele_hex27_Standard_stressout.4C.yaml",
+    "tet10": "tests/input_files/solid_ele_tet10_Standard_stressout.4C.yaml",
+}
+
+
+def integration_case(cell, rel):
+    with open(os.path.join(REF, rel)) as fh:
+        y = yaml.safe_load(fh)
+    nodes = {}
+    for line in y["NODE COORDS"]:
+        m = re.match(r"NODE\s+(\d+)\s+COORD\s+(\S+)\s+(\S+)\s+(\S+)", line)
+        nodes[int(m.group(1))] = [float(m.group(i)) for i in (2, 3, 4)]
+    nn = max(nodes)
+    coords = [nodes[i + 1] for i in range(nn)]
+    eles = []
+    for line in y["STRUCTURE ELEMENTS"]:
+        tok = line.split()
+        assert tok[1] == "SOLID" and tok[2].lower() == cell
+        k = 3
+        conn = []
+        while tok[k] != "MAT":
+            conn.append(int(tok[k]) - 1)
+            k += 1
+        assert "nonlinear" in line
+        eles.append(conn)
+    surf = {1: [], 2: []}
+    for line in y["DSURF-NODE TOPOLOGY"]:
+        m = re.match(r"NODE\s+(\d+)\s+DSURFACE\s+(\d+)", line)
+        surf[int(m.group(2))].append(int(m.group(1)) - 1)
+    mats = {m["MAT"]: m for m in y["MATERIALS"]}
+    eh = mats[1]["MAT_ElastHyper"]
+    assert eh["NUMMAT"] == 1
+    nh = mats[eh["MATIDS"][0]]["ELAST_CoupNeoHooke"]
+    dbc = y["DESIGN SURF DIRICH CONDITIONS"][0]
+    neu = y["DESIGN SURF NEUMANN CONDITIONS"][0]
+    assert dbc["E"] == 1 and neu["E"] == 2
+    sd = y["STRUCTURAL DYNAMIC"]
+    expected = []
+    for r in y["RESULT DESCRIPTION"]:
+        s = r["STRUCTURE"]
+        if s["QUANTITY"] in ("dispx", "dispy", "dispz"):
+            expected.append({"node": s["NODE"] - 1, "dof": "xyz".index(s["QUANTITY"][-1]),
+                             "value": float(s["VALUE"]), "tol": float(s["TOLERANCE"])})
+    return {
+        "source": rel,
+        "celltype": cell,
+        "coords": coords,
+        "elements": eles,
+        "material": {"kind": "ELAST_CoupNeoHooke", "YOUNG": float(nh["YOUNG"]),
+                     "NUE": float(nh["NUE"])},
+        "dirichlet_nodes": sorted(surf[1]),
+        "neumann_nodes": sorted(surf[2]),
+        "neumann": {"ONOFF": neu["ONOFF"], "VAL": neu["VAL"], "FUNCT": neu["FUNCT"],
+                    "FUNCT1": y["FUNCT1"][0]["SYMBOLIC_FUNCTION_OF_SPACE_TIME"],
+                    "FUNCT2": y["FUNCT2"][0]["SYMBOLIC_FUNCTION_OF_SPACE_TIME"]},
+        "timestep": float(sd["TIMESTEP"]), "numstep": int(sd["NUMSTEP"]),
+        "tolres": float(sd["TOLRES"]), "toldisp": float(sd["TOLDISP"]),
+        "expected_disp": expected,
+    }
+
+
+def unit_known_answers():
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(0)
+    RAND_MAX = 2147483647
+    seq = [libc.rand() / RAND_MAX for _ in range(2 * 3 * 27)]
+    return {
+        "gamma_delta": {
+            "source": "unittests/mat/4C_elasthyper_service_test.cpp:36-81",
+            "prinv": [3.1, 3.2, 1.05], "dPI": [0.536, 0.681, 3.981],
+            "ddPII": [0.153, 0.861, 2.964, 1.549, 0.682, 3.584],
+            "gamma_ref": [5.294200000000001, -1.362, 8.360099999999999],
+            "delta_ref": [125.31604, -25.0124, 23.03238, 3.444, -6.5058, 29.79144, -16.7202, -2.724],
+            "tol": 1e-10},
+        "right_cauchy_green": {
+            "source": "unittests/mat/4C_elasthyper_service_test.cpp:83-106",
+            "E": [0.1, 0.2, 0.3, 0.01, 0.02, 0.03], "C_ref": [1.2, 1.4, 1.6, 0.02, 0.04, 0.06],
+            "tol": 1e-10},
+        "isoneohooke_invariant_derivatives": {
+            "source": "unittests/mat/4C_elasthyper_service_test.cpp:108-155",
+            "MUE": 1.3, "prinv": [3.1, 3.2, 1.05], "dPI_ref": [0.639514, 0.0, -0.629363],
+            "ddPII_ref": [0.0, 0.0, 0.799191, 0.0, -0.20302, 0.0], "tol": 1e-4},
+        "stvenantkirchhoff": {
+            "source": "unittests/mat/4C_stvenantkirchhoff_test.cpp:44-118",
+            "YOUNG": 210.0, "NUE": 0.3, "E": [1.0, 1.0, 1.0, 0.5, 0.5, 0.5],
+            "strain_energy_ref": 908.6538, "tol": 1e-4},
+        "bfree_stiffness": {
+            "source": "unittests/solid_ele/4C_solid_ele_calc_lib_test.cpp:243-343",
+            "glibc_srand0_rand_over_RAND_MAX": seq,
+            "xi": [0.1, 0.2, 0.3], "pk2_full": [[1.1, 1.2, 1.3], [1.2, 2.2, 2.3], [1.3, 2.3, 3.3]],
+            "tol": 1e-13},
+    }
+
+
+def ref_elements():
+    from oracle import oracle as orc
+    assert orc.ref_lib() is not None, "oracle/_ref not built"
+    rng = np.random.default_rng(20261017)
+    out = {}
+    mats = {orc.MAT_COUP_NEOHOOKE: [200.0, 0.25], orc.MAT_ISO_VOL: [1.0, 1000.0],
+            orc.MAT_SVK: [1000.0, 0.3]}
+    for ct, name in ((orc.HEX8, "hex8"), (orc.HEX27, "hex27"), (orc.TET10, "tet10")):
+        n = orc.num_nodes(ct)
+        X = orc.node_param_coords(ct) * np.array([1.0, 1.1, 1.2]) + 0.05 * rng.uniform(-1, 1, (n, 3))
+        u = 0.04 * rng.uniform(-1, 1, (n, 3))
+        out[f"{name}_X"] = X
+        out[f"{name}_u"] = u
+        for mk, par in mats.items():
+            Ke, fe, err = orc.ref_element(ct, mk, par, X, u)
+            assert err == 0
+            out[f"{name}_m{mk}_K"] = Ke
+            out[f"{name}_m{mk}_f"] = fe
+            out[f"m{mk}_par"] = np.array(par)
+    # material tangents
+    E = np.array([0.11, -0.07, 0.05, 0.02, -0.03, 0.04])
+    out["mat_E"] = E
+    import ctypes as C
+    dp = C.POINTER(C.c_double)
+    for mk, par in mats.items():
+        S = np.zeros(6)
+        Cm = np.zeros(36)
+        p = np.array(par)
+        orc.ref_lib().ref_material(mk, p.ctypes.data_as(dp), E.ctypes.data_as(dp),
+                                   S.ctypes.data_as(dp), Cm.ctypes.data_as(dp))
+        out[f"mat{mk}_S"] = S
+        out[f"mat{mk}_C"] = Cm.reshape(6, 6).T.copy()
+    # the unit-test cmat built by the reference's einsum_sym
+    S = np.array([1.1, 2.2, 3.3, 1.2, 2.3, 1.3])
+    Cm = np.zeros(36)
+    orc.ref_lib().ref_test_cmat_from_pk2(S.ctypes.data_as(dp), Cm.ctypes.data_as(dp))
+    out["unit_pk2"] = S
+    out["unit_cmat"] = Cm.reshape(6, 6).T.copy()
+    return out
+
+
+if __name__ == "__main__":
+    for cell, rel in CASES.items():
+        with open(os.path.join(HERE, f"integration_{cell}.json"), "w") as fh:
+            json.dump(integration_case(cell, rel), fh, indent=1)
+    with open(os.path.join(HERE, "unit_known_answers.json"), "w") as fh:
+        json.dump(unit_known_answers(), fh, indent=1)
+    np.savez_compressed(os.path.join(HERE, "ref_elements.npz"), **ref_elements())
+    print("golden fixtures written to", HERE)

@@ -1,0 +1,97 @@
+"""Test-side restatement of the reference's 'Live' surface Neumann load, needed only to reproduce
+the RESULT DESCRIPTION known answers of the reference's integration tests with the oracle.
+
+Follows src/solid_ele/4C_solid_ele_surface_evaluate.cpp:43-306 (TYPE Live: dead load on the
+material configuration) with the surface Gauss rules of
+src/core/fem/src/general/utils/4C_fem_general_utils_integration.cpp (quad_4point :6151-6183,
+quad_9point :6185-6233, tri_6point :6374-6397; truncated decimals taken verbatim) and the face
+numbering of 4C_fem_general_utils_local_connectivity_matrices.hpp:51-63.
+"""
+import numpy as np
+
+HEX8_FACES = [[0, 3, 2, 1], [0, 1, 5, 4], [1, 2, 6, 5], [2, 3, 7, 6], [0, 4, 7, 3], [4, 5, 6, 7]]
+HEX27_FACES = [[0, 3, 2, 1, 11, 10, 9, 8, 20], [0, 1, 5, 4, 8, 13, 16, 12, 21],
+               [1, 2, 6, 5, 9, 14, 17, 13, 22], [2, 3, 7, 6, 10, 15, 18, 14, 23],
+               [0, 4, 7, 3, 12, 19, 15, 11, 24], [4, 5, 6, 7, 16, 17, 18, 19, 25]]
+TET10_FACES = [[0, 1, 3, 4, 8, 7], [1, 2, 3, 5, 9, 8], [0, 3, 2, 7, 9, 6], [0, 2, 1, 6, 5, 4]]
+FACES = {"hex8": HEX8_FACES, "hex27": HEX27_FACES, "tet10": TET10_FACES}
+
+
+def _quad4(r, s):
+    sg = np.array([[-1, -1], [1, -1], [1, 1], [-1, 1]], float)
+    N = 0.25 * (1 + sg[:, 0] * r) * (1 + sg[:, 1] * s)
+    dN = np.stack([0.25 * sg[:, 0] * (1 + sg[:, 1] * s), 0.25 * sg[:, 1] * (1 + sg[:, 0] * r)])
+    return N, dN
+
+
+def _quad9(r, s):
+    def lag(x):
+        return (np.array([0.5 * x * (x - 1), 1 - x * x, 0.5 * x * (x + 1)]),
+                np.array([x - 0.5, -2 * x, x + 0.5]))
+    Lr, dLr = lag(r)
+    Ls, dLs = lag(s)
+    pos = [(-1, -1), (1, -1), (1, 1), (-1, 1), (0, -1), (1, 0), (0, 1), (-1, 0), (0, 0)]
+    N = np.array([Lr[a + 1] * Ls[b + 1] for a, b in pos])
+    dN = np.array([[dLr[a + 1] * Ls[b + 1] for a, b in pos], [Lr[a + 1] * dLs[b + 1] for a, b in pos]])
+    return N, dN
+
+
+def _tri6(r, s):
+    t1, t2, t3 = 1 - r - s, r, s
+    N = np.array([t1 * (2 * t1 - 1), t2 * (2 * t2 - 1), t3 * (2 * t3 - 1), 4 * t2 * t1, 4 * t2 * t3,
+                  4 * t3 * t1])
+    dN = np.array([[-(4 * t1 - 1), 4 * t2 - 1, 0, 4 * (t1 - t2), 4 * t3, -4 * t3],
+                   [-(4 * t1 - 1), 0, 4 * t3 - 1, -4 * t2, 4 * t2, 4 * (t1 - t3)]])
+    return N, dN
+
+
+def _rule(kind):
+    if kind == "quad4":
+        g = 0.5773502691896
+        return np.array([[-g, -g], [g, -g], [g, g], [-g, g]]), np.ones(4)
+    if kind == "quad9":
+        g, w1, w2 = 0.7745966692415, 0.5555555555556, 0.8888888888889
+        x = np.array([[-g, -g], [g, -g], [g, g], [-g, g], [0, -g], [g, 0], [0, g], [-g, 0], [0, 0]])
+        w = np.array([w1 * w1] * 4 + [w2 * w1, w1 * w2, w2 * w1, w1 * w2, w2 * w2])
+        return x, w
+    a, b, c, d = 0.0915762135098, 0.8168475729805, 0.4459484909160, 0.1081030181681
+    x = np.array([[a, a], [b, a], [a, b], [c, d], [c, c], [d, c]])
+    w = np.array([0.0549758718277] * 3 + [0.1116907948390] * 3)
+    return x, w
+
+
+def neumann_load(case, time):
+    """External force vector (3*nnode) of the golden case at total time `time`."""
+    cell = case["celltype"]
+    X = np.asarray(case["coords"], float)
+    nset = set(case["neumann_nodes"])
+    kind, fn = {"hex8": ("quad4", _quad4), "hex27": ("quad9", _quad9), "tet10": ("tri6", _tri6)}[cell]
+    gx, gw = _rule(kind)
+    val, onoff, funct = case["neumann"]["VAL"], case["neumann"]["ONOFF"], case["neumann"]["FUNCT"]
+    assert case["neumann"]["FUNCT1"] == "t" and case["neumann"]["FUNCT2"] == "(x+1)*(y+2)*(z+3)"
+    f = np.zeros(3 * len(X))
+    for conn in case["elements"]:
+        for face in FACES[cell]:
+            ids = [conn[k] for k in face]
+            if not all(i in nset for i in ids):
+                continue
+            x = X[ids]
+            for (r, s), w in zip(gx, gw):
+                N, dN = fn(r, s)
+                dx = dN @ x  # (2,3)
+                m = dx @ dx.T
+                detA = np.sqrt(m[0, 0] * m[1, 1] - m[0, 1] * m[1, 0])
+                gp = N @ x
+                for dof in range(3):
+                    if not onoff[dof]:
+                        continue
+                    if funct[dof] == 1:
+                        ff = time
+                    elif funct[dof] == 2:
+                        ff = (gp[0] + 1) * (gp[1] + 2) * (gp[2] + 3)
+                    else:
+                        ff = 1.0
+                    fac = w * detA * val[dof] * ff
+                    for a, nid in enumerate(ids):
+                        f[3 * nid + dof] += N[a] * fac
+    return f

@@ -1,0 +1,39 @@
+"""Tiny load-stepping Newton driver (dense solve) used to reproduce the reference's integration-test
+known answers with any evaluate+assemble backend (oracle on CPU, CUDA path on GPU).
+
+Mirrors what the reference's time integrator does around the hot path for DYNAMICTYPE Statics
+(src/structure_new/src/implicit/4C_structure_new_impl_statics.cpp:93-98): residual
+f_int(u) - f_ext(t), Jacobian K_T, Dirichlet rows eliminated, converge on TOLRES and TOLDISP.
+"""
+import numpy as np
+
+from .meshes import csr_to_dense
+from .neumann import neumann_load
+
+
+def solve_case(case, evaluate, max_iter=30):
+    """evaluate(u_flat) -> (rowptr, colind, values, fint). Returns converged displacement (nn,3)."""
+    nn = len(case["coords"])
+    fixed = np.zeros(3 * nn, bool)
+    for n in case["dirichlet_nodes"]:
+        fixed[3 * n:3 * n + 3] = True
+    free = ~fixed
+    u = np.zeros(3 * nn)
+    t = 0.0
+    for _ in range(case["numstep"]):
+        t += case["timestep"]
+        fext = neumann_load(case, t)
+        for it in range(max_iter):
+            rowptr, colind, values, fint = evaluate(u)
+            res = fint - fext
+            K = csr_to_dense(rowptr, colind, values, 3 * nn)
+            du = np.zeros(3 * nn)
+            du[free] = np.linalg.solve(K[np.ix_(free, free)], -res[free])
+            u += du
+            rowptr, colind, values, fint = evaluate(u)
+            rnorm = np.linalg.norm((fint - fext)[free])
+            if rnorm < case["tolres"] and np.linalg.norm(du) < case["toldisp"]:
+                break
+        else:
+            raise RuntimeError(f"Newton did not converge at t={t}: |r|={rnorm}")
+    return u.reshape(nn, 3)
