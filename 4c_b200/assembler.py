@@ -1,0 +1,82 @@
+"""Host-side mirror of the reference call sequence around the hot path, for one rank.
+
+    Solid::ModelEvaluator::Structure::apply_force_stiff_internal   (model_evaluator_structure.cpp:442-472)
+      discret().set_state("displacement", u)                       -> DeviceAssembler.set_state
+      discret().evaluate(p{action}, stiff, nullptr, fint, ...)     -> DeviceAssembler.evaluate
+        AssembleStrategy::zero / assemble_matrix1 / assemble_vector1 (4C_fem_general_assemblestrategy.cpp)
+
+Everything numeric happens in lib4c_b200_solid.so; this class only owns the context and keeps the
+names and argument meaning of the reference interface so that tests read like the reference's.
+"""
+import numpy as np
+
+from . import capi
+
+ACTIONS = {"struct_calc_nlnstiff": capi.ACTION_NLNSTIFF,
+           "struct_calc_internalforce": capi.ACTION_INTERNALFORCE}
+
+
+class DeviceAssembler:
+    def __init__(self, rank_mesh, matkind, matparams, device=0, per_ele_param=None, graph=None):
+        """rank_mesh: partition.RankMesh.  graph: (rowptr, colind) from the reference's matrix, or
+        None to build the FillComplete-equivalent graph on the device."""
+        rm = self.rm = rank_mesh
+        self.ctx = capi.Context(device, rm.rank, rm.nranks)
+        self.ctx.set_mesh(rm.celltype, rm.X, rm.conn)
+        self.ctx.set_material(matkind, matparams, per_ele_param)
+        if graph is None:
+            self.nnz = self.ctx.build_graph(rm.n_row_nodes, rm.node_row_lid, rm.node_col_lid)
+        else:
+            rowptr, colind = graph
+            d = np.arange(3, dtype=np.int32)
+            row = np.where(rm.node_row_lid[:, None] >= 0, 3 * rm.node_row_lid[:, None] + d, -1)
+            col = 3 * rm.node_col_lid[:, None] + d
+            self.ctx.set_graph(rowptr, colind, row.astype(np.int32).ravel(), col.astype(np.int32).ravel())
+            self.nnz = self.ctx.nnz
+        self.n_rows = 3 * rm.n_row_nodes
+        if rm.nranks > 1:
+            self.ctx.set_halo(rm.peers, rm.send_row_nodes, rm.recv_col_nodes)
+        self._u = None
+
+    def graph(self):
+        """(rowptr, colind) of the installed device graph (host copies)."""
+        rm = self.rm
+        _, rowptr, colind = self.ctx.build_graph(rm.n_row_nodes, rm.node_row_lid, rm.node_col_lid,
+                                                 fetch=True)
+        return rowptr, colind
+
+    def set_state(self, name, u_row):
+        assert name == "displacement"
+        self._u = np.ascontiguousarray(u_row, np.float64).ravel()
+        assert self._u.size == self.n_rows
+
+    def evaluate(self, action="struct_calc_nlnstiff", check=True):
+        """Returns (K_values or None, f, error_info) as host arrays."""
+        act = ACTIONS[action]
+        K = np.empty(self.nnz) if act == capi.ACTION_NLNSTIFF else None
+        f = np.empty(self.n_rows)
+        rc, err = self.ctx.evaluate(act, self._u, K, f, check=check)
+        return K, f, err
+
+    def close(self):
+        self.ctx.close()
+
+
+def parity_report(rowptr, values, ref_values, f, ref_f, rtol=1e-12):
+    """Parity norm of SURVEY.md 8(d): per entry |a-b| <= rtol * max(|a|,|b|,s) with s the max-abs of
+    the entry's node block row (3 dof rows of one node) for K, of the whole vector for f.
+    Returns (ok, worst_ratio_K, worst_ratio_f) where ratio = |a-b| / (rtol * scale)."""
+    rowptr = np.asarray(rowptr)
+    n_rows = len(rowptr) - 1
+    rowmax = np.maximum.reduceat(np.maximum(np.abs(values), np.abs(ref_values)),
+                                 rowptr[:-1].clip(max=len(values) - 1))
+    rowmax[np.diff(rowptr) == 0] = 0.0
+    blk = np.repeat(rowmax.reshape(-1, 3).max(axis=1), 3)
+    scale = np.repeat(blk, np.diff(rowptr))
+    assert len(scale) == len(values) and n_rows % 3 == 0
+    dK = np.abs(values - ref_values)
+    rK = float((dK / (rtol * np.maximum(scale, 1e-300))).max()) if len(values) else 0.0
+    sf = max(np.abs(f).max(), np.abs(ref_f).max(), 1e-300)
+    rf = float((np.abs(f - ref_f) / (rtol * sf)).max())
+    finite = np.isfinite(values).all() and np.isfinite(f).all()
+    return bool(finite and rK <= 1.0 and rf <= 1.0), rK, rf

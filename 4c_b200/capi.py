@@ -1,0 +1,254 @@
+"""ctypes binding of lib4c_b200_solid.so (include/b200_solid.h).
+
+The hot path lives entirely in the CUDA library; this module only marshals pointers.  Loading
+fails loudly when the library has not been built -- there is no CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib4c_b200_solid.so")
+
+OK = 0
+ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NEG_JACOBIAN, ERR_NONFINITE, ERR_COMM = -1, -2, -3, -4, -5, -6
+HEX8, HEX27, TET10 = 0, 1, 2
+MAT_COUP_NEOHOOKE, MAT_ISO_VOL, MAT_SVK = 0, 1, 2
+ACTION_INTERNALFORCE, ACTION_NLNSTIFF = 0, 1
+
+# every symbol include/b200_solid.h declares (checked by the CPU test-suite)
+SYMBOLS = [
+    "b200s_create", "b200s_destroy", "b200s_last_error", "b200s_set_option", "b200s_set_mesh",
+    "b200s_set_material", "b200s_set_graph", "b200s_set_halo", "b200s_nccl_unique_id",
+    "b200s_comm_init_nccl", "b200s_evaluate", "b200s_evaluate_async", "b200s_synchronize",
+    "b200s_device_values", "b200s_device_f", "b200s_device_u_row", "b200s_device_u_col",
+    "b200s_stream", "b200s_nnz", "b200s_n_rows", "b200s_get_timers", "b200s_launch_count",
+    "b200s_build_graph", "b200s_measure_fp64_peak", "b200s_microbench", "b200s_host_alloc", "b200s_host_free",
+    "b200s_version",
+]
+
+
+class ErrorInfo(C.Structure):
+    _fields_ = [("code", C.c_int32), ("n_neg_jacobian", C.c_int32), ("first_bad_element", C.c_int64),
+                ("min_detJ", C.c_double), ("min_detF", C.c_double), ("n_nonfinite", C.c_int64)]
+
+
+class B200SolidError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"b200s error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                          "g.build()'` (nvcc, sm_100a). The device path has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
+    L.b200s_create.argtypes = [i32, i32, i32, C.POINTER(vp)]
+    L.b200s_destroy.argtypes = [vp]
+    L.b200s_destroy.restype = None
+    L.b200s_last_error.argtypes = [vp]
+    L.b200s_last_error.restype = C.c_char_p
+    L.b200s_set_option.argtypes = [vp, C.c_char_p, dbl]
+    L.b200s_set_mesh.argtypes = [vp, i32, i64, vp, i64, vp]
+    L.b200s_set_material.argtypes = [vp, i32, vp, i32, vp]
+    L.b200s_set_graph.argtypes = [vp, i64, vp, vp, vp, vp]
+    L.b200s_set_halo.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    L.b200s_nccl_unique_id.argtypes = [vp, vp]
+    L.b200s_comm_init_nccl.argtypes = [vp, vp]
+    L.b200s_evaluate.argtypes = [vp, i32, vp, vp, vp, C.POINTER(ErrorInfo)]
+    L.b200s_evaluate_async.argtypes = [vp, i32]
+    L.b200s_synchronize.argtypes = [vp, C.POINTER(ErrorInfo)]
+    for fn in ("b200s_device_values", "b200s_device_f", "b200s_device_u_row", "b200s_device_u_col",
+               "b200s_stream"):
+        getattr(L, fn).argtypes = [vp]
+        getattr(L, fn).restype = vp
+    L.b200s_nnz.argtypes = [vp]
+    L.b200s_nnz.restype = i64
+    L.b200s_n_rows.argtypes = [vp]
+    L.b200s_n_rows.restype = i64
+    L.b200s_get_timers.argtypes = [vp, vp]
+    L.b200s_launch_count.argtypes = [vp]
+    L.b200s_launch_count.restype = i64
+    L.b200s_build_graph.argtypes = [vp, i64, vp, vp, vp, vp, C.POINTER(i64)]
+    L.b200s_measure_fp64_peak.argtypes = [i32, C.POINTER(dbl), C.POINTER(dbl)]
+    L.b200s_microbench.argtypes = [i32, i32, i64, C.POINTER(dbl)]
+    L.b200s_host_alloc.argtypes = [i64]
+    L.b200s_host_alloc.restype = vp
+    L.b200s_host_free.argtypes = [vp]
+    L.b200s_host_free.restype = None
+    L.b200s_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    """Raw address of a numpy array, torch tensor, int address or None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):  # torch tensor (host or device)
+        assert a.is_contiguous()
+        return a.data_ptr()
+    raise TypeError(type(a))
+
+
+class Context:
+    """One rank's device context (b200s_ctx)."""
+
+    def __init__(self, device=0, rank=0, nranks=1):
+        self.L = load()
+        h = C.c_void_p()
+        rc = self.L.b200s_create(device, rank, nranks, C.byref(h))
+        if rc != OK:
+            raise B200SolidError(rc, "b200s_create failed (no CUDA device?)")
+        self.h = h
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.b200s_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != OK:
+            raise B200SolidError(rc, self.L.b200s_last_error(self.h).decode())
+        return rc
+
+    def set_option(self, key, value):
+        self._ck(self.L.b200s_set_option(self.h, key.encode(), float(value)))
+
+    def set_mesh(self, celltype, X, conn):
+        X = np.ascontiguousarray(X, np.float64)
+        conn = np.ascontiguousarray(conn, np.int32)
+        self.celltype, self.nn = celltype, conn.shape[1]
+        self.n_col_nodes, self.n_col_eles = X.shape[0], conn.shape[0]
+        self._ck(self.L.b200s_set_mesh(self.h, celltype, X.shape[0], _ptr(X), conn.shape[0], _ptr(conn)))
+
+    def set_material(self, kind, params, per_ele_param=None):
+        params = np.ascontiguousarray(params, np.float64)
+        if per_ele_param is not None:
+            per_ele_param = np.ascontiguousarray(per_ele_param, np.float64)
+        self._ck(self.L.b200s_set_material(self.h, kind, _ptr(params), len(params), _ptr(per_ele_param)))
+
+    def set_graph(self, rowptr, colind, dof_row_lid, dof_col_lid):
+        rowptr = rowptr if not isinstance(rowptr, np.ndarray) else np.ascontiguousarray(rowptr, np.int64)
+        colind = colind if not isinstance(colind, np.ndarray) else np.ascontiguousarray(colind, np.int32)
+        dof_row_lid = np.ascontiguousarray(dof_row_lid, np.int32)
+        dof_col_lid = np.ascontiguousarray(dof_col_lid, np.int32)
+        n_rows = (rowptr.shape[0] if hasattr(rowptr, "shape") else len(rowptr)) - 1
+        self._ck(self.L.b200s_set_graph(self.h, n_rows, _ptr(rowptr), _ptr(colind), _ptr(dof_row_lid),
+                                        _ptr(dof_col_lid)))
+
+    def build_graph(self, n_row_nodes, node_row_lid, node_col_lid, fetch=False):
+        """Device-side graph construction + installation; returns nnz (and rowptr, colind if fetch)."""
+        node_row_lid = np.ascontiguousarray(node_row_lid, np.int32)
+        node_col_lid = np.ascontiguousarray(node_col_lid, np.int32)
+        nnz = C.c_int64(0)
+        self._ck(self.L.b200s_build_graph(self.h, n_row_nodes, _ptr(node_row_lid), _ptr(node_col_lid),
+                                          None, None, C.byref(nnz)))
+        if not fetch:
+            return nnz.value
+        rowptr = np.zeros(3 * n_row_nodes + 1, np.int64)
+        colind = np.zeros(nnz.value, np.int32)
+        self._ck(self.L.b200s_build_graph(self.h, n_row_nodes, _ptr(node_row_lid), _ptr(node_col_lid),
+                                          _ptr(rowptr), _ptr(colind), C.byref(nnz)))
+        return nnz.value, rowptr, colind
+
+    def set_halo(self, peers, send_row_nodes, recv_col_nodes):
+        """send_row_nodes: per peer row-NODE indices (row lid of dof 0 = 3*index)."""
+        n = len(peers)
+        peer = np.ascontiguousarray(peers, np.int32)
+        so = np.zeros(n + 1, np.int64)
+        ro = np.zeros(n + 1, np.int64)
+        for i in range(n):
+            so[i + 1] = so[i] + len(send_row_nodes[i])
+            ro[i + 1] = ro[i] + len(recv_col_nodes[i])
+        s = (3 * np.concatenate(send_row_nodes).astype(np.int64)).astype(np.int32) if n and so[-1] else np.zeros(1, np.int32)
+        r = np.concatenate(recv_col_nodes).astype(np.int32) if n and ro[-1] else np.zeros(1, np.int32)
+        self._ck(self.L.b200s_set_halo(self.h, n, _ptr(peer), _ptr(so), _ptr(np.ascontiguousarray(s)),
+                                       _ptr(ro), _ptr(np.ascontiguousarray(r))))
+
+    def nccl_unique_id(self):
+        buf = (C.c_char * 128)()
+        self._ck(self.L.b200s_nccl_unique_id(self.h, C.addressof(buf)))
+        return bytes(buf)
+
+    def comm_init_nccl(self, uid):
+        buf = (C.c_char * 128).from_buffer_copy(uid)
+        self._ck(self.L.b200s_comm_init_nccl(self.h, C.addressof(buf)))
+
+    def evaluate(self, action, u_row=None, K_values=None, f_row=None, check=True):
+        """Synchronous evaluate.  Pointers may be numpy arrays, torch tensors or None."""
+        err = ErrorInfo()
+        rc = self.L.b200s_evaluate(self.h, action, _ptr(u_row), _ptr(K_values), _ptr(f_row), C.byref(err))
+        if check:
+            self._ck(rc)
+        return rc, err
+
+    def evaluate_async(self, action):
+        self._ck(self.L.b200s_evaluate_async(self.h, action))
+
+    def synchronize(self, check=True):
+        err = ErrorInfo()
+        rc = self.L.b200s_synchronize(self.h, C.byref(err))
+        if check:
+            self._ck(rc)
+        return rc, err
+
+    @property
+    def nnz(self):
+        return self.L.b200s_nnz(self.h)
+
+    @property
+    def n_rows(self):
+        return self.L.b200s_n_rows(self.h)
+
+    def device_ptrs(self):
+        return dict(values=self.L.b200s_device_values(self.h), f=self.L.b200s_device_f(self.h),
+                    u_row=self.L.b200s_device_u_row(self.h), u_col=self.L.b200s_device_u_col(self.h),
+                    stream=self.L.b200s_stream(self.h))
+
+    def timers(self):
+        t = np.zeros(6)
+        self.L.b200s_get_timers(self.h, _ptr(t))
+        return dict(halo=t[0], zero=t[1], kernel=t[2], device=t[3], h2d=t[4], d2h=t[5])
+
+    def launch_count(self):
+        return self.L.b200s_launch_count(self.h)
+
+
+def microbench(which, size=0, device=0):
+    L = load()
+    r = C.c_double(0)
+    rc = L.b200s_microbench(device, which, size, C.byref(r))
+    if rc != OK:
+        raise B200SolidError(rc, f"microbench {which} failed")
+    return r.value
+
+
+def measure_fp64_peak(device=0):
+    L = load()
+    tf, mhz = C.c_double(0), C.c_double(0)
+    rc = L.b200s_measure_fp64_peak(device, C.byref(tf), C.byref(mhz))
+    if rc != OK:
+        raise B200SolidError(rc, "fp64 peak measurement failed")
+    return tf.value, mhz.value

@@ -1,0 +1,1094 @@
+// b200_solid.cu -- lib4c_b200_solid.so: context, set-up kernels, evaluate drivers and the C ABI
+// declared in include/b200_solid.h.  sm_100a only; FP64 throughout; no CPU fallback.
+#include <cub/cub.cuh>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200_solid.h"
+#include "hex8_kernel.cuh"
+#include "shape_tables.hpp"
+
+namespace b200s
+{
+  // ------------------------------------------------------------------------------------------------
+  // constant tables (per cell type; filled at set_mesh)
+  // ------------------------------------------------------------------------------------------------
+  struct Hex8Const
+  {
+    double dN_gp[8 * 24];
+    double dN_node[8 * 24];
+    double w[8];
+  };
+  __constant__ Hex8Const c_hex8;
+
+  // ------------------------------------------------------------------------------------------------
+  // hex8 evaluate + assemble kernel (see hex8_kernel.cuh for the phase structure)
+  // ------------------------------------------------------------------------------------------------
+  constexpr int HEX8_WARPS = 4;  // warps per CTA; 2 CTAs/SM = 8 warps = 32 elements in flight / SM
+  constexpr size_t hex8_warp_bytes = (size_t)hex8::WARP_DOUBLES * 8 + 32 * (8 + 4 + 4);
+  constexpr size_t hex8_table_bytes = (size_t)(2 * hex8::TAB_SIZE + 8) * 8;
+  constexpr size_t hex8_smem_bytes = hex8_table_bytes + HEX8_WARPS * hex8_warp_bytes;
+
+  __device__ __forceinline__ void atomic_min_double(double* addr, double v)
+  {
+    unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+    unsigned long long old = *a;
+    while (__longlong_as_double((long long)old) > v)
+    {
+      const unsigned long long assumed = old;
+      old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+      if (old == assumed) break;
+    }
+  }
+
+  template <int MAT, bool STIFF>
+  __global__ void __launch_bounds__(HEX8_WARPS * 32, 2) k_hex8_eval_assemble(const EvalArgs A)
+  {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* tab_gp = reinterpret_cast<double*>(smem_raw);
+    double* tab_node = tab_gp + hex8::TAB_SIZE;
+    double* wgt = tab_node + hex8::TAB_SIZE;
+    for (int t = threadIdx.x; t < 8 * 24; t += blockDim.x)
+    {
+      tab_gp[(t / 24) * hex8::TAB_STRIDE + (t % 24)] = c_hex8.dN_gp[t];
+      tab_node[(t / 24) * hex8::TAB_STRIDE + (t % 24)] = c_hex8.dN_node[t];
+    }
+    if (threadIdx.x < 8) wgt[threadIdx.x] = c_hex8.w[threadIdx.x];
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* wbase = smem_raw + hex8_table_bytes + warp * hex8_warp_bytes;
+    hex8::WarpSmem S;
+    S.mp = reinterpret_cast<double*>(wbase);
+    S.g = S.mp + hex8::MP_SIZE;
+    S.rowstart = reinterpret_cast<int64_t*>(S.g + hex8::G_SIZE);
+    S.rowlen = reinterpret_cast<int32_t*>(S.rowstart + 32);
+    S.frow = S.rowlen + 32;
+
+    const int64_t n_tiles = (A.n_ele + hex8::EPW - 1) / hex8::EPW;
+    const int64_t wstride = (int64_t)gridDim.x * HEX8_WARPS;
+    double detJ_min = 1e300, detF_min = 1e300;
+    long long bad = LLONG_MAX;
+    unsigned int nbad = 0;
+
+    for (int64_t tile = (int64_t)blockIdx.x * HEX8_WARPS + warp; tile < n_tiles; tile += wstride)
+    {
+      const int64_t e0 = tile * hex8::EPW;
+      hex8::phase0(A, S, lane, e0);
+      __syncwarp();
+      double out54[54];
+      double dJ, dF;
+      bool neg;
+      hex8::phase1<MAT, STIFF>(A, S, tab_gp, tab_node, wgt, lane, e0, out54, dJ, dF, neg);
+      if (e0 + (lane >> 3) < A.n_ele)
+      {
+        detJ_min = fmin(detJ_min, dJ);
+        detF_min = fmin(detF_min, dF);
+      }
+      const unsigned negmask = __ballot_sync(0xffffffffu, neg);
+      if (negmask)  // FOUR_C_ASSERT_ALWAYS(det > 0) of the reference: count elements, keep the first
+        for (int el = 0; el < hex8::EPW; ++el)
+          if ((negmask >> (8 * el)) & 0xffu)
+          {
+            ++nbad;
+            bad = min(bad, (long long)(e0 + el));
+          }
+      __syncwarp();  // every lane is done with the staged X/u before M/Pw overwrite them
+      hex8::phase1_store<STIFF>(S, lane, out54);
+      __syncwarp();
+      double Kacc[5][9], facc[3];
+      hex8::phase2<STIFF>(S, lane, Kacc, facc);
+      hex8::phase3<STIFF>(A, S, lane, e0, Kacc, facc);
+      __syncwarp();
+    }
+
+    // error word: warp reduce, one atomic per warp and quantity
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      detJ_min = fmin(detJ_min, __shfl_xor_sync(0xffffffffu, detJ_min, o));
+      detF_min = fmin(detF_min, __shfl_xor_sync(0xffffffffu, detF_min, o));
+    }
+    if (lane == 0)
+    {
+      atomic_min_double(&A.err->min_detJ, detJ_min);
+      atomic_min_double(&A.err->min_detF, detF_min);
+      if (nbad)
+      {
+        atomicMin(&A.err->first_bad, bad);
+        atomicAdd(&A.err->n_neg_jac, (unsigned long long)nbad);
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------------
+  // set-up kernels
+  // ------------------------------------------------------------------------------------------------
+  // per column node: CSR row info derived from the reference's dof maps; validates the node-blocked
+  // layout the fast path of SparseMatrix::assemble relies on (4C_linalg_sparsematrix.cpp:404-441)
+  __global__ void k_node_rows(int64_t n_col_nodes, const int32_t* dof_row_lid,
+      const int32_t* dof_col_lid, const int64_t* rowptr, int64_t n_rows, int64_t* node_rowstart,
+      int32_t* node_rowlen, int32_t* node_frow, int32_t* node_colbase, int* flag)
+  {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_col_nodes) return;
+    const int32_t r0 = dof_row_lid[3 * k], r1 = dof_row_lid[3 * k + 1], r2 = dof_row_lid[3 * k + 2];
+    const int32_t c0 = dof_col_lid[3 * k], c1 = dof_col_lid[3 * k + 1], c2 = dof_col_lid[3 * k + 2];
+    if (c0 < 0 || c1 != c0 + 1 || c2 != c0 + 2) atomicOr(flag, 1);
+    node_colbase[k] = c0;
+    if (r0 < 0)
+    {
+      if (r1 >= 0 || r2 >= 0) atomicOr(flag, 2);
+      node_rowstart[k] = -1;
+      node_rowlen[k] = 0;
+      node_frow[k] = -1;
+      return;
+    }
+    if (r1 != r0 + 1 || r2 != r0 + 2 || r2 >= n_rows)
+    {
+      atomicOr(flag, 2);
+      node_rowstart[k] = -1, node_rowlen[k] = 0, node_frow[k] = -1;
+      return;
+    }
+    const int64_t s0 = rowptr[r0], s1 = rowptr[r1], s2 = rowptr[r2], s3 = rowptr[r2 + 1];
+    if (s1 - s0 != s2 - s1 || s2 - s1 != s3 - s2) atomicOr(flag, 4);
+    node_rowstart[k] = s0;
+    node_rowlen[k] = (int32_t)(s1 - s0);
+    node_frow[k] = r0;
+  }
+
+  // element -> CSR slot map: pos[e][i][j] = offset of the 3 columns of node j inside each row of
+  // node i (same lower_bound + stride-3 contiguity rule as SparseMatrix::assemble :404-441)
+  __global__ void k_build_scatter_map(int nn, int64_t n_ele, const int32_t* conn,
+      const int32_t* colind, const int64_t* node_rowstart, const int32_t* node_rowlen,
+      const int32_t* node_colbase, int32_t* pos, int* flag)
+  {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_ele * nn) return;
+    const int64_t e = t / nn;
+    const int i = (int)(t % nn);
+    const int32_t* ce = conn + e * nn;
+    const int64_t rs = node_rowstart[ce[i]];
+    int32_t* out = pos + (e * nn + i) * nn;
+    if (rs < 0)
+    {
+      for (int j = 0; j < nn; ++j) out[j] = -1;
+      return;
+    }
+    const int32_t len = node_rowlen[ce[i]];
+    const int32_t* idx = colind + rs;
+    for (int j = 0; j < nn; ++j)
+    {
+      const int32_t col = node_colbase[ce[j]];
+      int lo = 0, hi = len;  // lower_bound
+      while (lo < hi)
+      {
+        const int mid = (lo + hi) >> 1;
+        if (idx[mid] < col)
+          lo = mid + 1;
+        else
+          hi = mid;
+      }
+      bool ok = (lo + 3 <= len);
+      if (ok)
+        for (int b = 0; b < 3; ++b)
+          for (int c = 0; c < 3; ++c) ok = ok && (idx[(int64_t)b * len + lo + c] == col + c);
+      if (!ok) atomicOr(flag, 8);
+      out[j] = lo;
+    }
+  }
+
+  // Discretization::set_state: owned part of the column vector (4C_fem_discretization.cpp:640-661)
+  __global__ void k_row_to_col(int64_t n_col_nodes, const int32_t* node_frow, const double* u_row,
+      double* u_col)
+  {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3 * n_col_nodes) return;
+    const int32_t fr = node_frow[t / 3];
+    if (fr >= 0) u_col[t] = u_row[fr + (int)(t % 3)];
+  }
+  __global__ void k_pack_halo(int64_t n, const int32_t* send_row_lid, const double* u_row, double* buf)
+  {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3 * n) return;
+    buf[t] = u_row[send_row_lid[t / 3] + (int)(t % 3)];
+  }
+  __global__ void k_unpack_halo(int64_t n, const int32_t* recv_col_lid, const double* buf, double* u_col)
+  {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3 * n) return;
+    u_col[3 * (int64_t)recv_col_lid[t / 3] + (t % 3)] = buf[t];
+  }
+
+  __global__ void k_count_nonfinite(int64_t n, const double* v, unsigned long long* out)
+  {
+    unsigned long long c = 0;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n;
+         t += (int64_t)gridDim.x * blockDim.x)
+      c += !isfinite(v[t]);
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+  }
+
+  // ---- graph construction (stand-in for the first assembly + FillComplete) -------------------
+  __global__ void k_graph_keys(int nn, int64_t n_ele, const int32_t* conn,
+      const int32_t* node_row_lid, const int32_t* node_col_lid, unsigned long long* keys)
+  {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_ele * nn * nn) return;
+    const int64_t e = t / (nn * nn);
+    const int ij = (int)(t % (nn * nn));
+    const int32_t r = node_row_lid[conn[e * nn + ij / nn]];
+    const int32_t c = node_col_lid[conn[e * nn + ij % nn]];
+    keys[t] = r < 0 ? ~0ull : (((unsigned long long)(uint32_t)r) << 32) | (uint32_t)c;
+  }
+  __global__ void k_graph_count(int64_t n_keys, const unsigned long long* keys, int* cnt)
+  {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_keys || keys[t] == ~0ull) return;
+    atomicAdd(&cnt[keys[t] >> 32], 1);
+  }
+  __global__ void k_graph_rowptr(int64_t n_row_nodes, const int64_t* nodeptr, int64_t* rowptr)
+  {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_row_nodes) return;
+    if (r == n_row_nodes)
+    {
+      rowptr[3 * r] = 9 * nodeptr[r];
+      return;
+    }
+    const int64_t c = nodeptr[r + 1] - nodeptr[r];
+    for (int b = 0; b < 3; ++b) rowptr[3 * r + b] = 9 * nodeptr[r] + 3 * b * c;
+  }
+  __global__ void k_graph_colind(int64_t n_keys, const unsigned long long* keys,
+      const int64_t* nodeptr, int32_t* colind)
+  {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_keys || keys[t] == ~0ull) return;
+    const int64_t r = (int64_t)(keys[t] >> 32);
+    const int32_t c = (int32_t)(keys[t] & 0xffffffffu);
+    const int64_t cnt = nodeptr[r + 1] - nodeptr[r], q = t - nodeptr[r];
+    for (int b = 0; b < 3; ++b)
+      for (int cc = 0; cc < 3; ++cc) colind[9 * nodeptr[r] + 3 * b * cnt + 3 * q + cc] = 3 * c + cc;
+  }
+
+  // ---- FP64 FMA peak ------------------------------------------------------------------------------
+  __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double a, double b)
+  {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
+           x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i)
+    {
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+      {
+        x0 = fma(x0, a, b), x1 = fma(x1, a, b), x2 = fma(x2, a, b), x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b), x5 = fma(x5, a, b), x6 = fma(x6, a, b), x7 = fma(x7, a, b);
+      }
+    }
+    const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 123.456) out[0] = s;
+  }
+
+  // ---- diagnostics: FP64 tensor-core MMA (DMMA m8n8k4) rate, alone and interleaved with DFMA ----
+  template <int MODE>  // 1: DMMA only, 2: DMMA + DFMA interleaved
+  __global__ void __launch_bounds__(256) k_dmma_peak(double* out, int iters, double a, double b)
+  {
+    double c0[2] = {0, 0}, c1[2] = {0, 0}, c2[2] = {0, 0}, c3[2] = {0, 0};
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3;
+    const double av = a + threadIdx.x * 1e-9, bv = b + threadIdx.x * 1e-9;
+    for (int i = 0; i < iters; ++i)
+    {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+      {
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c0[0]), "+d"(c0[1]) : "d"(av), "d"(bv));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c1[0]), "+d"(c1[1]) : "d"(av), "d"(bv));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c2[0]), "+d"(c2[1]) : "d"(av), "d"(bv));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c3[0]), "+d"(c3[1]) : "d"(av), "d"(bv));
+        if (MODE == 2)
+        {
+          x0 = fma(x0, a, b), x1 = fma(x1, a, b), x2 = fma(x2, a, b), x3 = fma(x3, a, b);
+          x0 = fma(x0, a, b), x1 = fma(x1, a, b), x2 = fma(x2, a, b), x3 = fma(x3, a, b);
+        }
+      }
+    }
+    const double s = c0[0] + c0[1] + c1[0] + c1[1] + c2[0] + c2[1] + c3[0] + c3[1] + x0 + x1 + x2 + x3;
+    if (s == 123.456) out[0] = s;
+  }
+
+  // ---- diagnostics: red.global.add.f64 throughput for three address patterns -------------------
+  // pattern 0: warp-contiguous doubles; 1: 24-byte (3 double) runs at pseudo-random row offsets inside
+  // a sliding window (what the CSR scatter does); 2: fully random 8-byte
+  __global__ void k_red_pattern(double* buf, int64_t n, int pattern, int per_thread)
+  {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int r = 0; r < per_thread; ++r)
+    {
+      const int64_t k = tid + (int64_t)r * nthreads;
+      int64_t idx;
+      if (pattern == 0)
+        idx = k % n;
+      else if (pattern == 1)
+      {
+        const int64_t run = k / 3;
+        unsigned long long h = (unsigned long long)run * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 29;
+        const int64_t window = 1 << 22;  // 32 MB of doubles: stays L2 resident
+        const int64_t base = ((k / (3 * 4096)) * 1024) % (n - window - 4);
+        idx = base + (int64_t)(h % (unsigned long long)window) / 3 * 3 + (k % 3);
+      }
+      else
+      {
+        unsigned long long h = (unsigned long long)k * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 31;
+        idx = (int64_t)(h % (unsigned long long)n);
+      }
+      atomicAdd(buf + idx, 1.0);
+    }
+  }
+}  // namespace b200s
+
+using namespace b200s;
+
+// --------------------------------------------------------------------------------------------------
+// context
+// --------------------------------------------------------------------------------------------------
+struct Uid
+{
+  char internal[128];
+};
+struct NcclApi
+{
+  void* handle = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, /*ncclUniqueId by value (128 bytes)*/ Uid, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+
+struct b200s_ctx
+{
+  int device = 0, rank = 0, nranks = 1, n_sm = 148;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  // mesh
+  int celltype = -1, nn = 0;
+  int64_t n_col_nodes = 0, n_col_eles = 0;
+  double* dX = nullptr;
+  int32_t* dconn = nullptr;
+  // material
+  int matkind = -1;
+  MatParams mp{};
+  double* d_per_ele = nullptr;
+  // graph
+  int64_t n_rows = 0, nnz = 0;
+  int64_t* d_rowptr = nullptr;  // only when built/owned here
+  int32_t* d_colind = nullptr;
+  int32_t* d_pos = nullptr;
+  int64_t* d_node_rowstart = nullptr;
+  int32_t *d_node_rowlen = nullptr, *d_node_frow = nullptr, *d_node_colbase = nullptr;
+  double *d_vals = nullptr, *d_f = nullptr, *d_u_row = nullptr, *d_u_col = nullptr;
+  // halo
+  int n_nbr = 0;
+  std::vector<int32_t> peer;
+  std::vector<int64_t> send_off, recv_off;
+  int32_t *d_send_lid = nullptr, *d_recv_lid = nullptr;
+  double *d_sendbuf = nullptr, *d_recvbuf = nullptr;
+  NcclApi nccl;
+  void* comm = nullptr;
+  // errors / timers
+  ErrWord* d_err = nullptr;
+  ErrWord* h_err = nullptr;  // pinned
+  cudaEvent_t ev[7] = {};
+  double timers[6] = {0, 0, 0, 0, 0, 0};
+  int64_t launches = 0;
+  int last_action = 0;
+  bool timed_h2d = false, timed_d2h = false;
+  // options
+  int check_finite = 0, ctas_per_sm = 2, scatter_mode = 0;
+};
+
+namespace
+{
+  int fail(b200s_ctx* c, int code, const char* fmt, ...)
+  {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+  }
+#define CK(call)                                                                            \
+  do                                                                                        \
+  {                                                                                         \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess)                                                                  \
+      return fail(ctx, B200S_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+          __FILE__, __LINE__);                                                              \
+  } while (0)
+
+  template <class T>
+  int to_device(b200s_ctx* ctx, T** dst, const T* src, int64_t n)
+  {
+    if (*dst) cudaFree(*dst);
+    *dst = nullptr;
+    CK(cudaMalloc((void**)dst, sizeof(T) * (size_t)(n > 0 ? n : 1)));
+    if (n > 0 && src)
+      CK(cudaMemcpyAsync(*dst, src, sizeof(T) * (size_t)n, cudaMemcpyDefault, ctx->stream));
+    return 0;
+  }
+  template <class T>
+  void dfree(T*& p)
+  {
+    if (p) cudaFree(p);
+    p = nullptr;
+  }
+  inline unsigned nblk(int64_t n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
+
+  template <class K>
+  int set_smem_attr(K kernel, size_t bytes)
+  {
+    return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  }
+}  // namespace
+
+namespace
+{
+  template <int MAT, bool STIFF>
+  static int launch_hex8(b200s_ctx* ctx, const EvalArgs& A)
+  {
+    auto kern = k_hex8_eval_assemble<MAT, STIFF>;
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+      if (set_smem_attr(kern, hex8_smem_bytes))
+        return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", hex8_smem_bytes);
+      attr_set = true;
+    }
+    const int64_t n_tiles = (A.n_ele + hex8::EPW - 1) / hex8::EPW;
+    int64_t grid = (n_tiles + HEX8_WARPS - 1) / HEX8_WARPS;
+    const int64_t cap = (int64_t)ctx->n_sm * ctx->ctas_per_sm;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, HEX8_WARPS * 32, hex8_smem_bytes, ctx->stream>>>(A);
+    ctx->launches += 1;
+    return 0;
+  }
+
+  template <bool STIFF>
+  static int launch_eval(b200s_ctx* ctx, const EvalArgs& A)
+  {
+    switch (ctx->matkind)
+    {
+      case B200S_MAT_COUP_NEOHOOKE:
+        return launch_hex8<MAT_COUP_NEOHOOKE, STIFF>(ctx, A);
+      case B200S_MAT_ISO_VOL:
+        return launch_hex8<MAT_ISO_VOL, STIFF>(ctx, A);
+      case B200S_MAT_SVK:
+        return launch_hex8<MAT_SVK, STIFF>(ctx, A);
+    }
+    return fail(ctx, B200S_ERR_INVALID, "material not set");
+  }
+
+}  // namespace
+
+extern "C"
+{
+  const char* b200s_version(void) { return "4c_b200 solid 0.1 (sm_100a, fp64)"; }
+
+  int b200s_create(int device, int rank, int nranks, b200s_ctx** out)
+  {
+    if (!out) return B200S_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device >= ndev)
+      return B200S_ERR_CUDA;  // no CUDA device: the product has no CPU fallback
+    b200s_ctx* ctx = new b200s_ctx;
+    ctx->device = device, ctx->rank = rank, ctx->nranks = nranks;
+    cudaSetDevice(device);
+    cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->d_err, sizeof(ErrWord)) != cudaSuccess ||
+        cudaMallocHost((void**)&ctx->h_err, sizeof(ErrWord)) != cudaSuccess)
+    {
+      delete ctx;
+      return B200S_ERR_CUDA;
+    }
+    for (auto& e : ctx->ev) cudaEventCreate(&e);
+    *out = ctx;
+    return B200S_OK;
+  }
+
+  void b200s_destroy(b200s_ctx* ctx)
+  {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
+    dfree(ctx->dX), dfree(ctx->dconn), dfree(ctx->d_per_ele), dfree(ctx->d_rowptr);
+    dfree(ctx->d_colind), dfree(ctx->d_pos), dfree(ctx->d_node_rowstart), dfree(ctx->d_node_rowlen);
+    dfree(ctx->d_node_frow), dfree(ctx->d_node_colbase), dfree(ctx->d_vals), dfree(ctx->d_f);
+    dfree(ctx->d_u_row), dfree(ctx->d_u_col), dfree(ctx->d_send_lid), dfree(ctx->d_recv_lid);
+    dfree(ctx->d_sendbuf), dfree(ctx->d_recvbuf), dfree(ctx->d_err);
+    if (ctx->h_err) cudaFreeHost(ctx->h_err);
+    for (auto& e : ctx->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+  }
+
+  const char* b200s_last_error(const b200s_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+  int b200s_set_option(b200s_ctx* ctx, const char* key, double value)
+  {
+    if (!ctx || !key) return B200S_ERR_INVALID;
+    if (!strcmp(key, "check_finite"))
+      ctx->check_finite = value != 0;
+    else if (!strcmp(key, "ctas_per_sm"))
+      ctx->ctas_per_sm = (int)value;
+    else if (!strcmp(key, "scatter_mode"))
+      ctx->scatter_mode = (int)value;
+    else
+      return fail(ctx, B200S_ERR_INVALID, "unknown option %s", key);
+    return B200S_OK;
+  }
+
+  int b200s_set_mesh(b200s_ctx* ctx, int celltype, int64_t n_col_nodes, const double* X,
+      int64_t n_col_eles, const int32_t* conn)
+  {
+    if (!ctx || !X || !conn || n_col_nodes <= 0 || n_col_eles < 0) return B200S_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    if (celltype != B200S_HEX8)
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "cell type %d is not on the device path yet", celltype);
+    if (n_col_nodes > INT32_MAX / 3) return fail(ctx, B200S_ERR_INVALID, "too many column nodes");
+    const CellTables T = make_cell_tables(celltype);
+    ctx->celltype = celltype, ctx->nn = T.nn;
+    ctx->n_col_nodes = n_col_nodes, ctx->n_col_eles = n_col_eles;
+    if (to_device(ctx, &ctx->dX, X, 3 * n_col_nodes)) return B200S_ERR_CUDA;
+    if (to_device(ctx, &ctx->dconn, conn, n_col_eles * T.nn)) return B200S_ERR_CUDA;
+    if (to_device(ctx, &ctx->d_u_col, (const double*)nullptr, 3 * n_col_nodes)) return B200S_ERR_CUDA;
+    CK(cudaMemsetAsync(ctx->d_u_col, 0, sizeof(double) * 3 * n_col_nodes, ctx->stream));
+    if (celltype == B200S_HEX8)
+    {
+      Hex8Const h;
+      memcpy(h.dN_gp, T.dN_gp.data(), sizeof h.dN_gp);
+      memcpy(h.dN_node, T.dN_node.data(), sizeof h.dN_node);
+      memcpy(h.w, T.w.data(), sizeof h.w);
+      CK(cudaMemcpyToSymbolAsync(c_hex8, &h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    // graph-dependent data is stale now
+    dfree(ctx->d_pos);
+    ctx->nnz = 0, ctx->n_rows = 0;
+    return B200S_OK;
+  }
+
+  int b200s_set_material(b200s_ctx* ctx, int kind, const double* params, int nparams,
+      const double* per_ele_param)
+  {
+    if (!ctx || !params || nparams < 2) return B200S_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    MatParams mp{};
+    if (!make_mat_params(kind, params, mp))
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "material kind %d is not on the device path", kind);
+    if (per_ele_param && kind != B200S_MAT_ISO_VOL)
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "per-element parameter only for ISO_VOL (MUE)");
+    ctx->matkind = kind, ctx->mp = mp;
+    dfree(ctx->d_per_ele);
+    if (per_ele_param)
+    {
+      if (ctx->n_col_eles <= 0) return fail(ctx, B200S_ERR_INVALID, "set_mesh before per-element parameters");
+      if (to_device(ctx, &ctx->d_per_ele, per_ele_param, ctx->n_col_eles)) return B200S_ERR_CUDA;
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return B200S_OK;
+  }
+
+  static int install_graph(b200s_ctx* ctx, int64_t n_rows, const int64_t* d_rowptr,
+      const int32_t* d_colind, const int32_t* d_dof_row_lid, const int32_t* d_dof_col_lid)
+  {
+    const int64_t ncn = ctx->n_col_nodes;
+    int64_t nnz = 0;
+    CK(cudaMemcpyAsync(&nnz, d_rowptr + n_rows, sizeof(int64_t), cudaMemcpyDefault, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_rows = n_rows, ctx->nnz = nnz;
+    if (to_device(ctx, &ctx->d_node_rowstart, (const int64_t*)nullptr, ncn)) return B200S_ERR_CUDA;
+    if (to_device(ctx, &ctx->d_node_rowlen, (const int32_t*)nullptr, ncn)) return B200S_ERR_CUDA;
+    if (to_device(ctx, &ctx->d_node_frow, (const int32_t*)nullptr, ncn)) return B200S_ERR_CUDA;
+    if (to_device(ctx, &ctx->d_node_colbase, (const int32_t*)nullptr, ncn)) return B200S_ERR_CUDA;
+    if (to_device(ctx, &ctx->d_pos, (const int32_t*)nullptr, ctx->n_col_eles * ctx->nn * ctx->nn))
+      return B200S_ERR_CUDA;
+    if (to_device(ctx, &ctx->d_vals, (const double*)nullptr, nnz)) return B200S_ERR_CUDA;
+    if (to_device(ctx, &ctx->d_f, (const double*)nullptr, n_rows)) return B200S_ERR_CUDA;
+    if (to_device(ctx, &ctx->d_u_row, (const double*)nullptr, n_rows)) return B200S_ERR_CUDA;
+    CK(cudaMemsetAsync(ctx->d_u_row, 0, sizeof(double) * n_rows, ctx->stream));
+    int* d_flag = nullptr;
+    CK(cudaMalloc((void**)&d_flag, sizeof(int)));
+    CK(cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
+    k_node_rows<<<nblk(ncn), 256, 0, ctx->stream>>>(ncn, d_dof_row_lid, d_dof_col_lid, d_rowptr,
+        n_rows, ctx->d_node_rowstart, ctx->d_node_rowlen, ctx->d_node_frow, ctx->d_node_colbase,
+        d_flag);
+    k_build_scatter_map<<<nblk(ctx->n_col_eles * ctx->nn), 256, 0, ctx->stream>>>(ctx->nn,
+        ctx->n_col_eles, ctx->dconn, d_colind, ctx->d_node_rowstart, ctx->d_node_rowlen,
+        ctx->d_node_colbase, ctx->d_pos, d_flag);
+    ctx->launches += 2;
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_flag);
+    CK(cudaGetLastError());
+    if (flag)
+    {
+      dfree(ctx->d_pos);
+      ctx->nnz = 0;
+      return fail(ctx, B200S_ERR_UNSUPPORTED,
+          "graph layout outside the fast assembly path (flags 0x%x: 1 col dofs of a node not "
+          "contiguous, 2 row dofs not contiguous, 4 unequal row lengths of a node, 8 element column "
+          "missing / not contiguous in an owned row)",
+          flag);
+    }
+    return B200S_OK;
+  }
+
+  int b200s_set_graph(b200s_ctx* ctx, int64_t n_rows, const int64_t* rowptr, const int32_t* colind,
+      const int32_t* dof_row_lid, const int32_t* dof_col_lid)
+  {
+    if (!ctx || !rowptr || !colind || !dof_row_lid || !dof_col_lid || n_rows <= 0)
+      return B200S_ERR_INVALID;
+    if (ctx->celltype < 0) return fail(ctx, B200S_ERR_INVALID, "set_mesh must precede set_graph");
+    cudaSetDevice(ctx->device);
+    // stage the caller's (host or device) arrays on the device; they are only needed to build the map
+    int64_t* d_rowptr = nullptr;
+    int32_t *d_colind = nullptr, *d_r = nullptr, *d_c = nullptr;
+    int64_t nnz = 0;
+    CK(cudaMemcpy(&nnz, rowptr + n_rows, sizeof(int64_t), cudaMemcpyDefault));
+    int rc = 0;
+    rc |= to_device(ctx, &d_rowptr, rowptr, n_rows + 1);
+    rc |= to_device(ctx, &d_colind, colind, nnz);
+    rc |= to_device(ctx, &d_r, dof_row_lid, 3 * ctx->n_col_nodes);
+    rc |= to_device(ctx, &d_c, dof_col_lid, 3 * ctx->n_col_nodes);
+    if (!rc) rc = install_graph(ctx, n_rows, d_rowptr, d_colind, d_r, d_c);
+    cudaFree(d_rowptr), cudaFree(d_colind), cudaFree(d_r), cudaFree(d_c);
+    return rc ? (rc < 0 ? rc : B200S_ERR_CUDA) : B200S_OK;
+  }
+
+  int b200s_build_graph(b200s_ctx* ctx, int64_t n_row_nodes, const int32_t* node_row_lid,
+      const int32_t* node_col_lid, int64_t* rowptr_out, int32_t* colind_out, int64_t* nnz_out)
+  {
+    if (!ctx || !node_row_lid || !node_col_lid || n_row_nodes <= 0) return B200S_ERR_INVALID;
+    if (ctx->celltype < 0) return fail(ctx, B200S_ERR_INVALID, "set_mesh must precede build_graph");
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    const int nn = ctx->nn;
+    const int64_t ncn = ctx->n_col_nodes, n_keys = ctx->n_col_eles * nn * nn;
+    if (colind_out == nullptr || ctx->d_rowptr == nullptr)
+    {
+      int32_t *d_r = nullptr, *d_c = nullptr;
+      if (to_device(ctx, &d_r, node_row_lid, ncn) || to_device(ctx, &d_c, node_col_lid, ncn))
+        return B200S_ERR_CUDA;
+      unsigned long long *k0 = nullptr, *k1 = nullptr;
+      int64_t* d_nsel = nullptr;
+      CK(cudaMalloc((void**)&k0, sizeof(unsigned long long) * n_keys));
+      CK(cudaMalloc((void**)&k1, sizeof(unsigned long long) * n_keys));
+      CK(cudaMalloc((void**)&d_nsel, sizeof(int64_t)));
+      k_graph_keys<<<nblk(n_keys), 256, 0, st>>>(nn, ctx->n_col_eles, ctx->dconn, d_r, d_c, k0);
+      size_t tmp_bytes = 0, tb2 = 0;
+      cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, k0, k1, n_keys, 0, 64, st);
+      cub::DeviceSelect::Unique(nullptr, tb2, k1, k0, d_nsel, n_keys, st);
+      if (tb2 > tmp_bytes) tmp_bytes = tb2;
+      void* tmp = nullptr;
+      CK(cudaMalloc(&tmp, tmp_bytes));
+      cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, k0, k1, n_keys, 0, 64, st);
+      cub::DeviceSelect::Unique(tmp, tmp_bytes, k1, k0, d_nsel, n_keys, st);
+      int64_t nsel = 0;
+      CK(cudaMemcpyAsync(&nsel, d_nsel, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      // per row node neighbour counts -> nodeptr
+      int* d_cnt = nullptr;
+      int64_t* d_nodeptr = nullptr;
+      CK(cudaMalloc((void**)&d_cnt, sizeof(int) * (n_row_nodes + 1)));
+      CK(cudaMalloc((void**)&d_nodeptr, sizeof(int64_t) * (n_row_nodes + 1)));
+      CK(cudaMemsetAsync(d_cnt, 0, sizeof(int) * (n_row_nodes + 1), st));
+      k_graph_count<<<nblk(nsel), 256, 0, st>>>(nsel, k0, d_cnt);
+      size_t tb3 = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, tb3, d_cnt, d_nodeptr, n_row_nodes + 1, st);
+      void* tmp3 = nullptr;
+      CK(cudaMalloc(&tmp3, tb3));
+      cub::DeviceScan::ExclusiveSum(tmp3, tb3, d_cnt, d_nodeptr, n_row_nodes + 1, st);
+      dfree(ctx->d_rowptr), dfree(ctx->d_colind);
+      CK(cudaMalloc((void**)&ctx->d_rowptr, sizeof(int64_t) * (3 * n_row_nodes + 1)));
+      k_graph_rowptr<<<nblk(n_row_nodes + 1), 256, 0, st>>>(n_row_nodes, d_nodeptr, ctx->d_rowptr);
+      int64_t nnz = 0;
+      CK(cudaMemcpyAsync(&nnz, ctx->d_rowptr + 3 * n_row_nodes, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      CK(cudaMalloc((void**)&ctx->d_colind, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1)));
+      k_graph_colind<<<nblk(nsel), 256, 0, st>>>(nsel, k0, d_nodeptr, ctx->d_colind);
+      ctx->launches += 4;
+      CK(cudaStreamSynchronize(st));
+      CK(cudaGetLastError());
+      cudaFree(k0), cudaFree(k1), cudaFree(d_nsel), cudaFree(tmp), cudaFree(tmp3), cudaFree(d_cnt);
+      cudaFree(d_nodeptr);
+      // install: dof lids are 3*node lid + d
+      std::vector<int32_t> hr(3 * ncn), hc(3 * ncn), nr(ncn), nc(ncn);
+      CK(cudaMemcpy(nr.data(), d_r, sizeof(int32_t) * ncn, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(nc.data(), d_c, sizeof(int32_t) * ncn, cudaMemcpyDeviceToHost));
+      for (int64_t k = 0; k < ncn; ++k)
+        for (int d = 0; d < 3; ++d)
+        {
+          hr[3 * k + d] = nr[k] < 0 ? -1 : 3 * nr[k] + d;
+          hc[3 * k + d] = 3 * nc[k] + d;
+        }
+      int32_t *d_dr = nullptr, *d_dc = nullptr;
+      int rc = to_device(ctx, &d_dr, hr.data(), 3 * ncn) | to_device(ctx, &d_dc, hc.data(), 3 * ncn);
+      if (!rc) rc = install_graph(ctx, 3 * n_row_nodes, ctx->d_rowptr, ctx->d_colind, d_dr, d_dc);
+      cudaFree(d_dr), cudaFree(d_dc), cudaFree(d_r), cudaFree(d_c);
+      if (rc) return rc < 0 ? rc : B200S_ERR_CUDA;
+    }
+    if (nnz_out) *nnz_out = ctx->nnz;
+    if (rowptr_out)
+      CK(cudaMemcpy(rowptr_out, ctx->d_rowptr, sizeof(int64_t) * (ctx->n_rows + 1), cudaMemcpyDefault));
+    if (colind_out)
+      CK(cudaMemcpy(colind_out, ctx->d_colind, sizeof(int32_t) * ctx->nnz, cudaMemcpyDefault));
+    return B200S_OK;
+  }
+
+  // ---- halo ----------------------------------------------------------------------------------------
+  static int load_nccl(b200s_ctx* ctx)
+  {
+    NcclApi& n = ctx->nccl;
+    if (n.handle) return 0;
+    n.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!n.handle) return fail(ctx, B200S_ERR_COMM, "dlopen(libnccl.so.2): %s", dlerror());
+#define SYM(field, name)                                             \
+  *(void**)(&n.field) = dlsym(n.handle, name);                       \
+  if (!n.field) return fail(ctx, B200S_ERR_COMM, "missing %s", name)
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(Send, "ncclSend");
+    SYM(Recv, "ncclRecv");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    return 0;
+  }
+
+  int b200s_nccl_unique_id(b200s_ctx* ctx, char* out128)
+  {
+    if (!ctx || !out128) return B200S_ERR_INVALID;
+    if (load_nccl(ctx)) return B200S_ERR_COMM;
+    Uid id;
+    const int rc = ctx->nccl.GetUniqueId(&id);
+    if (rc) return fail(ctx, B200S_ERR_COMM, "ncclGetUniqueId: %s", ctx->nccl.GetErrorString(rc));
+    memcpy(out128, id.internal, 128);
+    return B200S_OK;
+  }
+
+  int b200s_comm_init_nccl(b200s_ctx* ctx, const char* id128)
+  {
+    if (!ctx || !id128) return B200S_ERR_INVALID;
+    if (load_nccl(ctx)) return B200S_ERR_COMM;
+    cudaSetDevice(ctx->device);
+    Uid id;
+    memcpy(id.internal, id128, 128);
+    const int rc = ctx->nccl.CommInitRank(&ctx->comm, ctx->nranks, id, ctx->rank);
+    if (rc) return fail(ctx, B200S_ERR_COMM, "ncclCommInitRank: %s", ctx->nccl.GetErrorString(rc));
+    return B200S_OK;
+  }
+
+  int b200s_set_halo(b200s_ctx* ctx, int n_nbr, const int32_t* peer, const int64_t* send_offsets,
+      const int32_t* send_row_lids, const int64_t* recv_offsets, const int32_t* recv_col_lids)
+  {
+    if (!ctx || n_nbr < 0) return B200S_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    ctx->n_nbr = n_nbr;
+    ctx->peer.assign(peer, peer + n_nbr);
+    ctx->send_off.assign(send_offsets, send_offsets + n_nbr + 1);
+    ctx->recv_off.assign(recv_offsets, recv_offsets + n_nbr + 1);
+    const int64_t ns = ctx->send_off[n_nbr], nr = ctx->recv_off[n_nbr];
+    if (to_device(ctx, &ctx->d_send_lid, send_row_lids, ns)) return B200S_ERR_CUDA;
+    if (to_device(ctx, &ctx->d_recv_lid, recv_col_lids, nr)) return B200S_ERR_CUDA;
+    if (to_device(ctx, &ctx->d_sendbuf, (const double*)nullptr, 3 * ns)) return B200S_ERR_CUDA;
+    if (to_device(ctx, &ctx->d_recvbuf, (const double*)nullptr, 3 * nr)) return B200S_ERR_CUDA;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B200S_OK;
+  }
+
+  // ---- evaluate -----------------------------------------------------------------------------------
+  int b200s_evaluate_async(b200s_ctx* ctx, int action)
+  {
+    if (!ctx) return B200S_ERR_INVALID;
+    if (!ctx->d_pos || ctx->matkind < 0)
+      return fail(ctx, B200S_ERR_INVALID, "set_mesh, set_material and set_graph must precede evaluate");
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    const bool stiff = action == B200S_ACTION_NLNSTIFF;
+    ctx->last_action = action;
+    CK(cudaEventRecord(ctx->ev[1], st));
+    // set_state("displacement"): ghost import, then owned part
+    if (ctx->n_nbr > 0)
+    {
+      if (!ctx->comm) return fail(ctx, B200S_ERR_COMM, "halo set but no communicator");
+      const int64_t ns = ctx->send_off[ctx->n_nbr], nr = ctx->recv_off[ctx->n_nbr];
+      if (ns) k_pack_halo<<<nblk(3 * ns), 256, 0, st>>>(ns, ctx->d_send_lid, ctx->d_u_row, ctx->d_sendbuf);
+      ctx->nccl.GroupStart();
+      for (int n = 0; n < ctx->n_nbr; ++n)
+      {
+        const int64_t s0 = ctx->send_off[n], s1 = ctx->send_off[n + 1];
+        const int64_t r0 = ctx->recv_off[n], r1 = ctx->recv_off[n + 1];
+        if (s1 > s0)
+          ctx->nccl.Send(ctx->d_sendbuf + 3 * s0, (size_t)(3 * (s1 - s0)), /*ncclDouble*/ 8,
+              ctx->peer[n], ctx->comm, st);
+        if (r1 > r0)
+          ctx->nccl.Recv(ctx->d_recvbuf + 3 * r0, (size_t)(3 * (r1 - r0)), 8, ctx->peer[n],
+              ctx->comm, st);
+      }
+      const int rc = ctx->nccl.GroupEnd();
+      if (rc) return fail(ctx, B200S_ERR_COMM, "halo exchange: %s", ctx->nccl.GetErrorString(rc));
+      if (nr) k_unpack_halo<<<nblk(3 * nr), 256, 0, st>>>(nr, ctx->d_recv_lid, ctx->d_recvbuf, ctx->d_u_col);
+      ctx->launches += (ns > 0) + (nr > 0);
+    }
+    k_row_to_col<<<nblk(3 * ctx->n_col_nodes), 256, 0, st>>>(
+        ctx->n_col_nodes, ctx->d_node_frow, ctx->d_u_row, ctx->d_u_col);
+    ctx->launches += 1;
+    CK(cudaEventRecord(ctx->ev[2], st));
+    // stiff.zero(); fint.put_scalar(0)
+    if (stiff) CK(cudaMemsetAsync(ctx->d_vals, 0, sizeof(double) * (size_t)ctx->nnz, st));
+    CK(cudaMemsetAsync(ctx->d_f, 0, sizeof(double) * (size_t)ctx->n_rows, st));
+    ctx->h_err->n_neg_jac = 0, ctx->h_err->first_bad = LLONG_MAX;
+    ctx->h_err->min_detJ = 1e300, ctx->h_err->min_detF = 1e300, ctx->h_err->n_nonfinite = 0;
+    CK(cudaMemcpyAsync(ctx->d_err, ctx->h_err, sizeof(ErrWord), cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->ev[3], st));
+    EvalArgs A;
+    A.X = ctx->dX, A.u = ctx->d_u_col, A.conn = ctx->dconn, A.pos = ctx->d_pos;
+    A.node_rowstart = ctx->d_node_rowstart, A.node_rowlen = ctx->d_node_rowlen;
+    A.node_frow = ctx->d_node_frow, A.per_ele_param = ctx->d_per_ele;
+    A.vals = ctx->d_vals, A.f = ctx->d_f, A.err = ctx->d_err, A.mp = ctx->mp;
+    A.n_ele = ctx->n_col_eles;
+    A.scatter_mode = ctx->scatter_mode;
+    const int rc = stiff ? launch_eval<true>(ctx, A) : launch_eval<false>(ctx, A);
+    if (rc) return rc;
+    if (ctx->check_finite)
+    {
+      if (stiff)
+        k_count_nonfinite<<<ctx->n_sm * 8, 256, 0, st>>>(ctx->nnz, ctx->d_vals, &ctx->d_err->n_nonfinite);
+      k_count_nonfinite<<<ctx->n_sm, 256, 0, st>>>(ctx->n_rows, ctx->d_f, &ctx->d_err->n_nonfinite);
+      ctx->launches += 1 + stiff;
+    }
+    CK(cudaEventRecord(ctx->ev[4], st));
+    CK(cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(ErrWord), cudaMemcpyDeviceToHost, st));
+    CK(cudaGetLastError());
+    return B200S_OK;
+  }
+
+  int b200s_synchronize(b200s_ctx* ctx, b200s_error_info* err)
+  {
+    if (!ctx) return B200S_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    auto el = [&](int a, int b)
+    {
+      ms = 0;
+      cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]);
+      return (double)ms;
+    };
+    ctx->timers[0] = el(1, 2), ctx->timers[1] = el(2, 3), ctx->timers[2] = el(3, 4);
+    ctx->timers[3] = el(1, 4);
+    ctx->timers[4] = ctx->timed_h2d ? el(0, 1) : 0.0;
+    ctx->timers[5] = ctx->timed_d2h ? el(4, 5) : 0.0;
+    int code = B200S_OK;
+    const ErrWord& w = *ctx->h_err;
+    if (w.n_neg_jac > 0)
+      code = fail(ctx, B200S_ERR_NEG_JACOBIAN,
+          "determinant of jacobian is <= 0 at one node of the element (column element %lld, %llu "
+          "elements affected, min det J %g)",
+          w.first_bad, w.n_neg_jac, w.min_detJ);
+    else if (ctx->check_finite && w.n_nonfinite > 0)
+      code = fail(ctx, B200S_ERR_NONFINITE, "%llu non-finite entries in f/K (min det F %g)",
+          w.n_nonfinite, w.min_detF);
+    if (err)
+    {
+      err->code = code;
+      err->n_neg_jacobian = (int32_t)(w.n_neg_jac > INT32_MAX ? INT32_MAX : w.n_neg_jac);
+      err->first_bad_element = w.n_neg_jac ? w.first_bad : -1;
+      err->min_detJ = w.min_detJ, err->min_detF = w.min_detF;
+      err->n_nonfinite = (int64_t)w.n_nonfinite;
+    }
+    return code;
+  }
+
+  int b200s_evaluate(b200s_ctx* ctx, int action, const double* u_row, double* K_values,
+      double* f_row, b200s_error_info* err)
+  {
+    if (!ctx) return B200S_ERR_INVALID;
+    if (!ctx->d_pos) return fail(ctx, B200S_ERR_INVALID, "set_graph must precede evaluate");
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    ctx->timed_h2d = u_row != nullptr, ctx->timed_d2h = (K_values || f_row);
+    CK(cudaEventRecord(ctx->ev[0], st));
+    if (u_row && u_row != ctx->d_u_row)
+      CK(cudaMemcpyAsync(ctx->d_u_row, u_row, sizeof(double) * (size_t)ctx->n_rows, cudaMemcpyDefault, st));
+    int rc = b200s_evaluate_async(ctx, action);
+    if (rc) return rc;
+    if (K_values && action == B200S_ACTION_NLNSTIFF && K_values != ctx->d_vals)
+      CK(cudaMemcpyAsync(K_values, ctx->d_vals, sizeof(double) * (size_t)ctx->nnz, cudaMemcpyDefault, st));
+    if (f_row && f_row != ctx->d_f)
+      CK(cudaMemcpyAsync(f_row, ctx->d_f, sizeof(double) * (size_t)ctx->n_rows, cudaMemcpyDefault, st));
+    CK(cudaEventRecord(ctx->ev[5], st));
+    return b200s_synchronize(ctx, err);
+  }
+
+  double* b200s_device_values(b200s_ctx* ctx) { return ctx ? ctx->d_vals : nullptr; }
+  double* b200s_device_f(b200s_ctx* ctx) { return ctx ? ctx->d_f : nullptr; }
+  double* b200s_device_u_row(b200s_ctx* ctx) { return ctx ? ctx->d_u_row : nullptr; }
+  double* b200s_device_u_col(b200s_ctx* ctx) { return ctx ? ctx->d_u_col : nullptr; }
+  void* b200s_stream(b200s_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+  int64_t b200s_nnz(const b200s_ctx* ctx) { return ctx ? ctx->nnz : 0; }
+  int64_t b200s_n_rows(const b200s_ctx* ctx) { return ctx ? ctx->n_rows : 0; }
+
+  int b200s_get_timers(b200s_ctx* ctx, double* out6)
+  {
+    if (!ctx || !out6) return B200S_ERR_INVALID;
+    for (int i = 0; i < 6; ++i) out6[i] = ctx->timers[i];
+    return B200S_OK;
+  }
+  int64_t b200s_launch_count(const b200s_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+  int b200s_measure_fp64_peak(int device, double* tflops, double* sm_mhz)
+  {
+    if (cudaSetDevice(device) != cudaSuccess) return B200S_ERR_CUDA;
+    int n_sm = 0;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+    double* d = nullptr;
+    if (cudaMalloc((void**)&d, 8) != cudaSuccess) return B200S_ERR_CUDA;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a), cudaEventCreate(&b);
+    const int iters = 4096, blocks = n_sm * 8, threads = 256;
+    double best = 0;
+    for (int rep = 0; rep < 6; ++rep)
+    {
+      cudaEventRecord(a);
+      k_fp64_peak<<<blocks, threads>>>(d, iters, 0.999999, 1e-7);
+      cudaEventRecord(b);
+      cudaEventSynchronize(b);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, a, b);
+      const double fl = 2.0 * 64.0 * iters * (double)blocks * threads;
+      const double tf = fl / (ms * 1e-3) / 1e12;
+      if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(a), cudaEventDestroy(b), cudaFree(d);
+    if (cudaGetLastError() != cudaSuccess) return B200S_ERR_CUDA;
+    if (tflops) *tflops = best;
+    if (sm_mhz) *sm_mhz = best * 1e12 / (2.0 * 64.0 * n_sm) / 1e6;  // clock implied by 64 DFMA/clk/SM
+    return B200S_OK;
+  }
+
+  // Diagnostics used by tools/ and DESIGN.md measurements (not part of the hot path).
+  //   which 0: DFMA TFLOP/s, 1: DMMA m8n8k4 TFLOP/s, 2: DMMA+DFMA interleaved TFLOP/s,
+  //   3: cudaMemset GB/s over `size` bytes, 4/5/6: red.add.f64 G atomics/s for pattern 0/1/2
+  int b200s_microbench(int device, int which, int64_t size, double* result)
+  {
+    if (!result || cudaSetDevice(device) != cudaSuccess) return B200S_ERR_CUDA;
+    int n_sm = 0;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a), cudaEventCreate(&b);
+    double best = 0;
+    float ms = 0;
+    if (which == 0) return b200s_measure_fp64_peak(device, result, nullptr);
+    if (which == 1 || which == 2)
+    {
+      double* d = nullptr;
+      cudaMalloc((void**)&d, 8);
+      const int iters = 2048, blocks = n_sm * 8, threads = 256;
+      for (int rep = 0; rep < 5; ++rep)
+      {
+        cudaEventRecord(a);
+        if (which == 1)
+          k_dmma_peak<1><<<blocks, threads>>>(d, iters, 0.999999, 1e-7);
+        else
+          k_dmma_peak<2><<<blocks, threads>>>(d, iters, 0.999999, 1e-7);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        cudaEventElapsedTime(&ms, a, b);
+        // per warp and inner step: 4 DMMA x 256 FMA (+ 8 DFMA x 32 lanes)
+        const double fma_per_warp = iters * 4.0 * (4 * 256.0 + (which == 2 ? 8 * 32.0 : 0.0));
+        const double tf = 2.0 * fma_per_warp * blocks * (threads / 32) / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+      }
+      cudaFree(d);
+    }
+    else if (which == 3)
+    {
+      void* d = nullptr;
+      if (cudaMalloc(&d, (size_t)size) != cudaSuccess) return B200S_ERR_CUDA;
+      for (int rep = 0; rep < 5; ++rep)
+      {
+        cudaEventRecord(a);
+        cudaMemsetAsync(d, 0, (size_t)size);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        cudaEventElapsedTime(&ms, a, b);
+        const double gbs = size / (ms * 1e-3) / 1e9;
+        if (rep > 0 && gbs > best) best = gbs;
+      }
+      cudaFree(d);
+    }
+    else if (which >= 4 && which <= 6)
+    {
+      double* d = nullptr;
+      const int64_t n = size / 8;
+      if (cudaMalloc((void**)&d, (size_t)size) != cudaSuccess) return B200S_ERR_CUDA;
+      cudaMemset(d, 0, (size_t)size);
+      const int blocks = n_sm * 16, threads = 256, per_thread = 96;
+      for (int rep = 0; rep < 4; ++rep)
+      {
+        cudaEventRecord(a);
+        k_red_pattern<<<blocks, threads>>>(d, n, which - 4, per_thread);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        cudaEventElapsedTime(&ms, a, b);
+        const double g = (double)blocks * threads * per_thread / (ms * 1e-3) / 1e9;
+        if (rep > 0 && g > best) best = g;
+      }
+      cudaFree(d);
+    }
+    else
+      return B200S_ERR_INVALID;
+    cudaEventDestroy(a), cudaEventDestroy(b);
+    if (cudaGetLastError() != cudaSuccess) return B200S_ERR_CUDA;
+    *result = best;
+    return B200S_OK;
+  }
+
+  void* b200s_host_alloc(int64_t bytes)
+  {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) return nullptr;
+    return p;
+  }
+  void b200s_host_free(void* p)
+  {
+    if (p) cudaFreeHost(p);
+  }
+}

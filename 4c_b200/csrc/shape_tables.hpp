@@ -1,0 +1,141 @@
+// shape_tables.hpp -- host-side generation of the constant per-cell-type tables the kernels use:
+// parametric shape-function derivatives at the Gauss points and at the element nodes, and the
+// Gauss weights.  For Lagrange cells these are compile-time constants of the reference
+// (recomputed there per element and Gauss point); here they are built once
+// per context and kept in constant/shared memory.
+//
+// Reference definitions:
+//   shape functions  src/core/fem/src/general/utils/4C_fem_general_utils_fem_shapefunctions.hpp
+//                    hex8 :409-450, hex27 :706-830, tet10 :831-875
+//   Gauss rules      src/core/fem/src/general/utils/4C_fem_general_utils_integration.cpp
+//                    hex_8point :74-104, hex_27point :130-245, tet_4point :331-352
+//                    (selection src/solid_ele/4C_solid_ele_calc_lib_integration.hpp:43-64)
+//   node parameter coordinates  4C_fem_general_utils_local_connectivity_matrices.hpp:291,314
+#pragma once
+
+#include <cmath>
+#include <vector>
+
+namespace b200s
+{
+  struct CellTables
+  {
+    int nn = 0;   // nodes per element
+    int ngp = 0;  // Gauss points (force/stiffness rule)
+    std::vector<double> dN_gp;    // [ngp][nn][3]  dN_k/dxi_a at Gauss point g
+    std::vector<double> dN_node;  // [nn][nn][3]   same at the element nodes (Jacobian check)
+    std::vector<double> w;        // [ngp]
+  };
+
+  namespace detail
+  {
+    // hex27 node order; the first 8 are the hex8 corners
+    inline const double (*hex_nodes())[3]
+    {
+      static const double c[27][3] = {{-1, -1, -1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1},
+          {-1, -1, 1}, {1, -1, 1}, {1, 1, 1}, {-1, 1, 1}, {0, -1, -1}, {1, 0, -1}, {0, 1, -1},
+          {-1, 0, -1}, {-1, -1, 0}, {1, -1, 0}, {1, 1, 0}, {-1, 1, 0}, {0, -1, 1}, {1, 0, 1},
+          {0, 1, 1}, {-1, 0, 1}, {0, 0, -1}, {0, -1, 0}, {1, 0, 0}, {0, 1, 0}, {-1, 0, 0},
+          {0, 0, 1}, {0, 0, 0}};
+      return c;
+    }
+    inline const double (*tet_nodes())[3]
+    {
+      static const double c[10][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0.5, 0, 0},
+          {0.5, 0.5, 0}, {0, 0.5, 0}, {0, 0, 0.5}, {0.5, 0, 0.5}, {0, 0.5, 0.5}};
+      return c;
+    }
+
+    // dN[k][a] at xi for celltype 0 hex8, 1 hex27, 2 tet10
+    inline void deriv1(int celltype, const double* xi, double* dN)
+    {
+      const double r = xi[0], s = xi[1], t = xi[2];
+      if (celltype == 0)
+      {
+        const double(*c)[3] = hex_nodes();
+        for (int k = 0; k < 8; ++k)
+        {
+          const double fr = 1.0 + c[k][0] * r, fs = 1.0 + c[k][1] * s, ft = 1.0 + c[k][2] * t;
+          dN[3 * k + 0] = c[k][0] * 0.125 * fs * ft;
+          dN[3 * k + 1] = c[k][1] * 0.125 * ft * fr;
+          dN[3 * k + 2] = c[k][2] * 0.125 * fr * fs;
+        }
+      }
+      else if (celltype == 1)
+      {
+        const double(*c)[3] = hex_nodes();
+        double L[3][3], dL[3][3];
+        for (int d = 0; d < 3; ++d)
+        {
+          const double x = xi[d];
+          L[d][0] = 0.5 * x * (x - 1.0), L[d][1] = 1.0 - x * x, L[d][2] = 0.5 * x * (x + 1.0);
+          dL[d][0] = x - 0.5, dL[d][1] = -2.0 * x, dL[d][2] = x + 0.5;
+        }
+        for (int k = 0; k < 27; ++k)
+        {
+          const int a = (int)c[k][0] + 1, b = (int)c[k][1] + 1, e = (int)c[k][2] + 1;
+          dN[3 * k + 0] = L[1][b] * L[2][e] * dL[0][a];
+          dN[3 * k + 1] = L[0][a] * L[2][e] * dL[1][b];
+          dN[3 * k + 2] = L[0][a] * L[1][b] * dL[2][e];
+        }
+      }
+      else
+      {
+        const double u = 1.0 - r - s - t;
+        const double d0 = -4.0 * u + 1.0;
+        const double D[10][3] = {{d0, d0, d0}, {4.0 * r - 1.0, 0, 0}, {0, 4.0 * s - 1.0, 0},
+            {0, 0, 4.0 * t - 1.0}, {4.0 * (u - r), -4.0 * r, -4.0 * r}, {4.0 * s, 4.0 * r, 0},
+            {-4.0 * s, 4.0 * (u - s), -4.0 * s}, {-4.0 * t, -4.0 * t, 4.0 * (u - t)},
+            {4.0 * t, 0, 4.0 * r}, {0, 4.0 * t, 4.0 * s}};
+        for (int k = 0; k < 10; ++k)
+          for (int a = 0; a < 3; ++a) dN[3 * k + a] = D[k][a];
+      }
+    }
+  }  // namespace detail
+
+  inline CellTables make_cell_tables(int celltype)
+  {
+    CellTables T;
+    T.nn = celltype == 0 ? 8 : (celltype == 1 ? 27 : 10);
+    T.ngp = celltype == 0 ? 8 : (celltype == 1 ? 27 : 4);
+    std::vector<double> gxi(3 * T.ngp);
+    T.w.resize(T.ngp);
+    const double(*hc)[3] = detail::hex_nodes();
+    if (celltype == 0)
+    {
+      const double g = 1.0 / std::sqrt(3.0);
+      for (int q = 0; q < 8; ++q)
+      {
+        for (int d = 0; d < 3; ++d) gxi[3 * q + d] = hc[q][d] * g;
+        T.w[q] = 1.0;
+      }
+    }
+    else if (celltype == 1)
+    {
+      // truncated decimals exactly as the reference has them
+      const double xi3 = 0.7745966692415, w1 = 0.5555555555556, w2 = 0.8888888888889;
+      for (int q = 0; q < 27; ++q)
+      {
+        for (int d = 0; d < 3; ++d) gxi[3 * q + d] = hc[q][d] * xi3;
+        T.w[q] = (hc[q][0] == 0.0 ? w2 : w1) * (hc[q][1] == 0.0 ? w2 : w1) *
+                 (hc[q][2] == 0.0 ? w2 : w1);
+      }
+    }
+    else
+    {
+      const double pa = (5.0 + 3.0 * std::sqrt(5.0)) / 20.0, pb = (5.0 - std::sqrt(5.0)) / 20.0;
+      const double P[4][3] = {{pb, pb, pb}, {pa, pb, pb}, {pb, pa, pb}, {pb, pb, pa}};
+      for (int q = 0; q < 4; ++q)
+      {
+        for (int d = 0; d < 3; ++d) gxi[3 * q + d] = P[q][d];
+        T.w[q] = 1.0 / 6.0 / 4.0;
+      }
+    }
+    T.dN_gp.resize((size_t)T.ngp * T.nn * 3);
+    for (int q = 0; q < T.ngp; ++q) detail::deriv1(celltype, &gxi[3 * q], &T.dN_gp[(size_t)q * T.nn * 3]);
+    T.dN_node.resize((size_t)T.nn * T.nn * 3);
+    const double(*nc)[3] = celltype == 2 ? detail::tet_nodes() : hc;
+    for (int k = 0; k < T.nn; ++k) detail::deriv1(celltype, nc[k], &T.dN_node[(size_t)k * T.nn * 3]);
+    return T;
+  }
+}  // namespace b200s

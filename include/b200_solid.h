@@ -1,0 +1,203 @@
+/*
+ * b200_solid.h -- C ABI of lib4c_b200_solid.so
+ *
+ * B200-native (sm_100a, FP64) replacement for ONE hot path of 4C: the per-Newton-iteration
+ * evaluation of solid element internal force + tangent stiffness and its owner-computes
+ * scatter-add into the CSR values of Core::LinAlg::SparseMatrix and the residual vector.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the 4C tree,
+ * commit 96b9fa91).  Plain pointers and sizes only; no exceptions cross the boundary: every call
+ * returns B200S_OK (0) or a negative b200s_status and b200s_last_error() holds the text.  One
+ * context <-> one rank <-> one GPU; calls on a context are made from one host thread (the
+ * reference element loop is single threaded per rank, 4C_mat_elasthyper_service.cpp:31-36).
+ *
+ * Pointers marked [host|dev] may live in host or device memory (resolved by UVA).
+ */
+#ifndef B200_SOLID_H
+#define B200_SOLID_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+  typedef struct b200s_ctx b200s_ctx;
+
+  typedef enum
+  {
+    B200S_OK = 0,
+    B200S_ERR_INVALID = -1,        /* bad argument / call order */
+    B200S_ERR_CUDA = -2,           /* CUDA runtime failure (text in b200s_last_error) */
+    B200S_ERR_UNSUPPORTED = -3,    /* cell/material/graph layout outside the device path:
+                                      the adapter must fall back to the CPU element loop */
+    B200S_ERR_NEG_JACOBIAN = -4,   /* FOUR_C_ASSERT_ALWAYS(det > 0), 4C_solid_ele_calc_lib.hpp:558 */
+    B200S_ERR_NONFINITE = -5,      /* NaN/Inf in f or K (FE trapping, model_evaluator_generic.cpp:229) */
+    B200S_ERR_COMM = -6            /* halo exchange failure */
+  } b200s_status;
+
+  /* Core::FE::CellType values on the device path (4C_fem_general_cell_type.hpp) */
+  typedef enum
+  {
+    B200S_HEX8 = 0,
+    B200S_HEX27 = 1,
+    B200S_TET10 = 2
+  } b200s_celltype;
+
+  /* Mat::So3Material implementations on the device path (Core::Materials::MaterialType):
+   *   COUP_NEOHOOKE : MAT_ElastHyper{ELAST_CoupNeoHooke YOUNG NUE}     params = {YOUNG, NUE}
+   *   ISO_VOL       : MAT_ElastHyper{ELAST_IsoNeoHooke MUE, ELAST_VolSussmanBathe KAPPA}
+   *                   params = {MUE, KAPPA}; MUE may be overridden per element (InputField)
+   *   SVK           : MAT_Struct_StVenantKirchhoff YOUNG NUE           params = {YOUNG, NUE} */
+  typedef enum
+  {
+    B200S_MAT_COUP_NEOHOOKE = 0,
+    B200S_MAT_ISO_VOL = 1,
+    B200S_MAT_SVK = 2
+  } b200s_material;
+
+  /* Core::Elements::ActionType values handled (legacy_enum_definitions):
+   * struct_calc_internalforce, struct_calc_nlnstiff (4C_solid_ele_evaluate.cpp:64-115) */
+  typedef enum
+  {
+    B200S_ACTION_INTERNALFORCE = 0,
+    B200S_ACTION_NLNSTIFF = 1
+  } b200s_action;
+
+  /* Mirror of the element error interface (4C_structure_new_elements_paramsinterface.hpp:46-55). */
+  typedef struct
+  {
+    int32_t code;              /* b200s_status of the evaluate */
+    int32_t n_neg_jacobian;    /* elements with det J <= 0 at an element node or Gauss point */
+    int64_t first_bad_element; /* column-element index of one such element, -1 if none */
+    double min_detJ;           /* over all nodes / Gauss points evaluated */
+    double min_detF;
+    int64_t n_nonfinite;       /* only filled when b200s_set_option(ctx,"check_finite",1) */
+  } b200s_error_info;
+
+  /* ---- life cycle -------------------------------------------------------------------------- */
+  /* One context per rank/GPU.  rank/nranks describe the partition (owner-computes); with
+   * nranks==1 no halo is needed. */
+  int b200s_create(int device, int rank, int nranks, b200s_ctx** out);
+  void b200s_destroy(b200s_ctx* ctx);
+  const char* b200s_last_error(const b200s_ctx* ctx);
+  /* options: "check_finite" (0/1), "ctas_per_sm" (tuning), "scatter" (0 atomic) */
+  int b200s_set_option(b200s_ctx* ctx, const char* key, double value);
+
+  /* ---- set-up (once per discretization) ------------------------------------------------------ */
+  /* Device mesh = what Discretization::evaluate walks: the rank's COLUMN elements and COLUMN nodes
+   * (4C_fem_discretization_evaluate.cpp:85, my_col_element_range).
+   *   X    [host|dev] 3*n_col_nodes, node-major xyz       (Node::x(), calc_lib.hpp:161-190)
+   *   conn [host|dev] n_col_eles*nodes_per_ele, column-node local ids in element node order
+   * All elements of one context share cell type, formulation (displacement based, nonlinear TL)
+   * and material; other element blocks use further contexts or stay on the CPU path. */
+  int b200s_set_mesh(b200s_ctx* ctx, int celltype, int64_t n_col_nodes, const double* X,
+      int64_t n_col_eles, const int32_t* conn);
+
+  /* Replaces the Mat::So3Material object(s) the elements hold (Mat::factory; So3Material::evaluate,
+   * 4C_mat_so3_material.hpp:69-73).  per_ele_param: NULL or n_col_eles doubles overriding params[0]
+   * element-wise (IsoNeoHooke MUE is an InputField looked up by element id,
+   * 4C_mat_elast_isoneohooke.cpp:15-18,38). */
+  int b200s_set_material(b200s_ctx* ctx, int kind, const double* params, int nparams,
+      const double* per_ele_param);
+
+  /* The reference's own sparsity graph after SparseMatrix::complete() (4C_linalg_sparsematrix.cpp:
+   * 700-721): local CSR of the Epetra_CrsMatrix as returned by ExtractCrsDataPointers.
+   *   rowptr      [host|dev] n_rows+1 (64-bit: > 2^31 nnz per rank is supported here)
+   *   colind      [host|dev] nnz, matrix-local column ids, ascending inside each row
+   *   dof_row_lid [host|dev] 3*n_col_nodes: rowmap.lid(gid) of each column-node dof, -1 if the
+   *               dof is not owned by this rank (lmrowowner != myrank, :386)
+   *   dof_col_lid [host|dev] 3*n_col_nodes: colmap.lid(gid) of each column-node dof (:374)
+   * Builds the element -> CSR slot scatter map on the device with the same lower_bound + stride-3
+   * contiguity rule as SparseMatrix::assemble (:404-466).  Returns B200S_ERR_UNSUPPORTED when a
+   * node's three dofs are not contiguous rows/columns (the reference's slow path) or an element
+   * column is missing from an owned row. */
+  int b200s_set_graph(b200s_ctx* ctx, int64_t n_rows, const int64_t* rowptr, const int32_t* colind,
+      const int32_t* dof_row_lid, const int32_t* dof_col_lid);
+
+  /* Ghost-displacement halo = the Epetra_Import of Discretization::set_state
+   * (4C_fem_discretization.cpp:653-661), rank-local view (Epetra_Import::ExportLIDs / RemoteLIDs /
+   * ExportPIDs).  For each neighbour n in [0,n_nbr): peer rank peer[n],
+   *   send_row_lids[send_offsets[n]..send_offsets[n+1]) : ROW lid of dof 0 of each owned node whose
+   *       three displacements go to that peer, in the order the peer expects them
+   *   recv_col_lids[recv_offsets[n]..recv_offsets[n+1]) : COLUMN-node lids filled from that peer
+   * [host] arrays.  The exchange itself is ncclSend/ncclRecv in one group on the context stream
+   * between a pack and an unpack kernel; the communicator comes from b200s_comm_init_nccl. */
+  int b200s_set_halo(b200s_ctx* ctx, int n_nbr, const int32_t* peer, const int64_t* send_offsets,
+      const int32_t* send_row_lids, const int64_t* recv_offsets, const int32_t* recv_col_lids);
+  /* NCCL bootstrap without MPI: rank 0 creates the 128-byte ncclUniqueId, the caller distributes
+   * it (the harness uses torch.distributed; 4C would MPI_Bcast it), every rank initialises.
+   * libnccl.so.2 is resolved at run time (dlopen), the library has no link-time NCCL dependency. */
+  int b200s_nccl_unique_id(b200s_ctx* ctx, char* out128);
+  int b200s_comm_init_nccl(b200s_ctx* ctx, const char* id128);
+
+  /* ---- the hot path ---------------------------------------------------------------------------- */
+  /* One Newton-iteration evaluate = Solid::ModelEvaluator::Structure::apply_force_stiff_internal
+   * (model_evaluator_structure.cpp:442-472) restricted to the device element block:
+   *   set_state("displacement") incl. ghost import      (4C_fem_discretization.cpp:612-665)
+   *   stiff.zero(); fint.put_scalar(0)                  (:167-190; 4C_linalg_sparsematrix.cpp:268-291)
+   *   for every column element: Solid<3>::evaluate(struct_calc_nlnstiff|internalforce) and
+   *   AssembleStrategy::assemble_matrix1 / assemble_vector1 on owned rows
+   *                                                     (4C_fem_discretization_evaluate.cpp:85-117)
+   *   u_row    [host|dev] 3*n_row_nodes displacement on the dof ROW map
+   *   K_values [host|dev] nnz doubles, OVERWRITTEN (zero + assemble); may be NULL for INTERNALFORCE
+   *            or to leave K in the context's device buffer (b200s_device_values)
+   *   f_row    [host|dev] n_rows doubles, OVERWRITTEN; may be NULL (stays on device)
+   *   err      [host] optional
+   * Returns B200S_OK, B200S_ERR_NEG_JACOBIAN (adapter rethrows the reference's message) ... */
+  int b200s_evaluate(b200s_ctx* ctx, int action, const double* u_row, double* K_values,
+      double* f_row, b200s_error_info* err);
+
+  /* Asynchronous flavour used when the caller keeps everything on the device: enqueues on the
+   * context stream, does not synchronise, u already in the context's device row vector. */
+  int b200s_evaluate_async(b200s_ctx* ctx, int action);
+  int b200s_synchronize(b200s_ctx* ctx, b200s_error_info* err);
+
+  /* Device-resident buffers owned by the context (valid until destroy / next set_graph). */
+  double* b200s_device_values(b200s_ctx* ctx);  /* nnz  */
+  double* b200s_device_f(b200s_ctx* ctx);       /* n_rows */
+  double* b200s_device_u_row(b200s_ctx* ctx);   /* 3*n_row_nodes */
+  double* b200s_device_u_col(b200s_ctx* ctx);   /* 3*n_col_nodes */
+  void* b200s_stream(b200s_ctx* ctx);           /* cudaStream_t */
+  int64_t b200s_nnz(const b200s_ctx* ctx);
+  int64_t b200s_n_rows(const b200s_ctx* ctx);
+
+  /* Timers (Teuchos::TimeMonitor stand-in, 4C_fem_discretization_evaluate.cpp:74): milliseconds of
+   * the last evaluate measured with CUDA events on the context stream.
+   * out[0]=halo, [1]=zero, [2]=element kernel(s), [3]=total device, [4]=h2d, [5]=d2h */
+  int b200s_get_timers(b200s_ctx* ctx, double* out6);
+  /* Number of kernels this library launched since create (bench's gpu_launches). */
+  int64_t b200s_launch_count(const b200s_ctx* ctx);
+
+  /* ---- standalone helpers (what 4C/Epetra provide in a real run) ------------------------------ */
+  /* Builds AND installs the CSR graph a first assembly + FillComplete would produce for the mesh
+   * in ctx (4C_linalg_sparsematrix.cpp:469-494,700-721) on the device (radix sort + unique of the
+   * (row node, column node) pairs of all elements).  node_row_lid / node_col_lid [host|dev] are per
+   * COLUMN NODE (row-node index or -1; matrix-local column-node index); dof lids are 3*lid+d.
+   * rowptr_out (3*n_row_nodes+1) / colind_out (nnz) [host|dev] may be NULL; call once with
+   * colind_out==NULL to learn *nnz_out, again to fetch colind.  A 4C run hands Epetra's graph to
+   * b200s_set_graph instead; this helper is what the harness, tests and bench use. */
+  int b200s_build_graph(b200s_ctx* ctx, int64_t n_row_nodes, const int32_t* node_row_lid,
+      const int32_t* node_col_lid, int64_t* rowptr_out, int32_t* colind_out, int64_t* nnz_out);
+
+  /* Roofline denominators measured on this device: FP64 FMA peak (TFLOP/s) of a register-resident
+   * DFMA loop over the whole chip, and achieved clock. */
+  int b200s_measure_fp64_peak(int device, double* tflops, double* sm_mhz);
+
+  /* Diagnostics behind DESIGN.md's measurements (not on the hot path): which 0 DFMA TFLOP/s,
+   * 1 DMMA m8n8k4 TFLOP/s, 2 DMMA+DFMA interleaved TFLOP/s, 3 cudaMemset GB/s over `size` bytes,
+   * 4/5/6 red.global.add.f64 G atomics/s (warp-contiguous / 24-byte runs in an L2 window / random)
+   * over a `size`-byte buffer. */
+  int b200s_microbench(int device, int which, int64_t size, double* result);
+
+  /* Pinned host memory for the adapter's staging of u / values / f. */
+  void* b200s_host_alloc(int64_t bytes);
+  void b200s_host_free(void* p);
+
+  const char* b200s_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -85,6 +85,10 @@ def ref_lib():
         R.ref_element.argtypes = [C.c_int, C.c_int, _dp, C.c_int, _dp, _dp, _dp, _dp, C.c_int, _dp,
                                   _dp]
         R.ref_stiffness_bfree.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_double, _dp]
+        R.ref_evaluate_assemble.restype = C.c_int64
+        R.ref_evaluate_assemble.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int64, _ip, _dp,
+                                            _dp, _ip, _ip, C.c_int64, _lp, _ip, _dp, _dp, C.c_int,
+                                            _dp, _dp, C.c_int]
         _ref = R
     return _ref
 
@@ -189,7 +193,9 @@ def build_graph(ct, conn, node_row_lid, node_col_lid, n_row_nodes):
 
 
 def evaluate_assemble(ct, matkind, params, conn, X, u_col, node_row_lid, node_col_lid, n_row_nodes,
-                      rowptr, colind, action=ACTION_FORCE_STIFF, mue_per_ele=None, nthreads=1):
+                      rowptr, colind, action=ACTION_FORCE_STIFF, mue_per_ele=None, nthreads=1,
+                      impl="oracle"):
+    """impl="oracle": plain restatement; impl="ref": element arithmetic by the reference's headers."""
     n = num_nodes(ct)
     params = np.ascontiguousarray(params, dtype=np.float64)
     conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, n)
@@ -203,6 +209,15 @@ def evaluate_assemble(ct, matkind, params, conn, X, u_col, node_row_lid, node_co
         mue_per_ele = np.ascontiguousarray(mue_per_ele, dtype=np.float64)
     values = np.zeros(rowptr[-1]) if action == ACTION_FORCE_STIFF else None
     f = np.zeros(3 * n_row_nodes)
+    if impl == "ref":
+        gxi, gw = gauss(ct)
+        gxi = np.ascontiguousarray(gxi)
+        nbad = ref_lib().ref_evaluate_assemble(ct, matkind, _d(params), _d(mue_per_ele), action,
+                                               conn.shape[0], _i(conn), _d(X), _d(u_col),
+                                               _i(node_row_lid), _i(node_col_lid), n_row_nodes,
+                                               _l(rowptr), _i(colind), _d(gxi), _d(gw), len(gw),
+                                               _d(values), _d(f), nthreads)
+        return values, f, int(nbad)
     nbad = lib().orc_evaluate_assemble(ct, matkind, _d(params), _d(mue_per_ele), action,
                                        conn.shape[0], _i(conn), len(node_row_lid), _d(X), _d(u_col),
                                        _i(node_row_lid), _i(node_col_lid), n_row_nodes, _l(rowptr),

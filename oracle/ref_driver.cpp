@@ -35,6 +35,9 @@
 #include <source_location>
 #include <stdexcept>
 #include <string>
+#include <algorithm>
+#include <thread>
+#include <vector>
 
 // The real one lives in 4C_utils_exceptions.cpp (needs boost + MPI).
 namespace FourC::Core::Internal
@@ -363,6 +366,90 @@ extern "C"
     if (ct == 0) return element<CT::hex8>(matkind, par, action, X, u, gxi, gw, ngp, Ke, fe);
     if (ct == 1) return element<CT::hex27>(matkind, par, action, X, u, gxi, gw, ngp, Ke, fe);
     return element<CT::tet10>(matkind, par, action, X, u, gxi, gw, ngp, Ke, fe);
+  }
+
+  // Whole-mesh evaluate + owner-computes assembly with the element arithmetic done by the
+  // reference's headers (same contract as orc_evaluate_assemble in solid_oracle.h; the loop and the
+  // assembly restate 4C_fem_discretization_evaluate.cpp:85-117 and 4C_linalg_sparsematrix.cpp:356-467).
+  // This is the "reference" CPU arm of bench.py: one thread per emulated MPI rank.
+  int64_t ref_evaluate_assemble(int ct, int matkind, const double* matparams,
+      const double* mue_per_ele, int action, int64_t n_ele, const int32_t* conn,
+      const double* X, const double* u_col, const int32_t* node_row_lid, const int32_t* node_col_lid,
+      int64_t n_row_nodes, const int64_t* rowptr, const int32_t* colind, const double* gxi,
+      const double* gw, int ngp, double* values, double* f, int nthreads)
+  {
+    const int n = ct == 0 ? 8 : (ct == 1 ? 27 : 10), nd = 3 * n;
+    if (nthreads < 1) nthreads = 1;
+    std::vector<int64_t> bad(nthreads, 0);
+    auto worker = [&](int tid)
+    {
+      const int64_t r0 = n_row_nodes * tid / nthreads, r1 = n_row_nodes * (tid + 1) / nthreads;
+      const bool stiff = action == 1 && values;
+      if (stiff) std::fill(values + rowptr[3 * r0], values + rowptr[3 * r1], 0.0);
+      std::fill(f + 3 * r0, f + 3 * r1, 0.0);
+      std::vector<double> Ke(nd * nd), fe(nd), Xe(nd), ue(nd);
+      std::vector<int32_t> localcol(nd);
+      double par[2] = {matparams[0], matparams[1]};
+      for (int64_t e = 0; e < n_ele; ++e)
+      {
+        const int32_t* ce = conn + e * n;
+        bool mine = false;
+        for (int i = 0; i < n; ++i)
+        {
+          const int32_t r = node_row_lid[ce[i]];
+          if (r >= r0 && r < r1) mine = true;
+        }
+        if (!mine) continue;
+        for (int i = 0; i < n; ++i)
+          for (int d = 0; d < 3; ++d)
+          {
+            Xe[3 * i + d] = X[3 * (int64_t)ce[i] + d];
+            ue[3 * i + d] = u_col[3 * (int64_t)ce[i] + d];
+          }
+        if (mue_per_ele) par[0] = mue_per_ele[e];
+        if (ref_element(ct, matkind, par, action, Xe.data(), ue.data(), gxi, gw, ngp,
+                stiff ? Ke.data() : nullptr, fe.data()))
+        {
+          bad[tid]++;
+          continue;
+        }
+        for (int j = 0; j < n; ++j)
+          for (int c = 0; c < 3; ++c) localcol[3 * j + c] = 3 * node_col_lid[ce[j]] + c;
+        for (int i = 0; i < n; ++i)
+        {
+          const int32_t r = node_row_lid[ce[i]];
+          if (r < r0 || r >= r1) continue;
+          for (int b = 0; b < 3; ++b)
+          {
+            const int lrow = 3 * i + b;
+            const int64_t rlid = 3 * (int64_t)r + b;
+            f[rlid] += fe[lrow];
+            if (!stiff) continue;
+            const int length = (int)(rowptr[rlid + 1] - rowptr[rlid]);
+            double* valview = values + rowptr[rlid];
+            const int32_t* indices = colind + rowptr[rlid];
+            int dofcount = 0, pos = 0;
+            for (int node = 0; node < n; ++node)
+            {
+              if (pos >= length || indices[pos] != localcol[dofcount])
+                pos = (int)(std::lower_bound(indices, indices + length, localcol[dofcount]) - indices);
+              for (int j = 0; j < 3; ++j) valview[pos++] += Ke[lrow + nd * (dofcount++)];
+            }
+          }
+        }
+      }
+    };
+    if (nthreads == 1)
+      worker(0);
+    else
+    {
+      std::vector<std::thread> th;
+      for (int t = 0; t < nthreads; ++t) th.emplace_back(worker, t);
+      for (auto& t : th) t.join();
+    }
+    int64_t nb = 0;
+    for (auto b : bad) nb += b;
+    return nb;
   }
 
   void ref_stiffness_bfree(int ct, const double* X, const double* u, const double* xi_,

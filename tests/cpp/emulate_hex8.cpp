@@ -1,0 +1,90 @@
+// TEST INFRASTRUCTURE: runs the PRODUCT's hex8 device functions (4c_b200/csrc/hex8_kernel.cuh,
+// solid_math.cuh, shape_tables.hpp) on the CPU by stepping the 32 lanes of a warp through the
+// kernel's phases sequentially.  Lets the CPU test-suite check the kernel arithmetic, the shared
+// memory indexing and the scatter addressing against the oracle without a GPU.  Not shipped, not
+// a fallback: the library itself has no host execution path.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../4c_b200/csrc/hex8_kernel.cuh"
+#include "../../4c_b200/csrc/shape_tables.hpp"
+
+using namespace b200s;
+
+template <int MAT, bool STIFF>
+static void run(const EvalArgs& A, double* min_detJ, double* min_detF, int64_t* n_bad)
+{
+  const CellTables T = make_cell_tables(0);
+  std::vector<double> tab_gp(hex8::TAB_SIZE, 0.0), tab_node(hex8::TAB_SIZE, 0.0);
+  for (int t = 0; t < 8 * 24; ++t)
+  {
+    tab_gp[(t / 24) * hex8::TAB_STRIDE + (t % 24)] = T.dN_gp[t];
+    tab_node[(t / 24) * hex8::TAB_STRIDE + (t % 24)] = T.dN_node[t];
+  }
+  std::vector<double> sm(hex8::WARP_DOUBLES + 2, 0.0);
+  std::vector<int64_t> rowstart(32);
+  std::vector<int32_t> rowlen(32), frow(32);
+  hex8::WarpSmem S;
+  // 16-byte align the double2 region
+  S.mp = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sm.data()) + 15) & ~uintptr_t(15));
+  S.g = S.mp + hex8::MP_SIZE;
+  S.rowstart = rowstart.data(), S.rowlen = rowlen.data(), S.frow = frow.data();
+  *min_detJ = 1e300, *min_detF = 1e300, *n_bad = 0;
+  const int64_t n_tiles = (A.n_ele + hex8::EPW - 1) / hex8::EPW;
+  static double out54[32][54];
+  static double Kacc[32][5][9], facc[32][3];
+  for (int64_t tile = 0; tile < n_tiles; ++tile)
+  {
+    const int64_t e0 = tile * hex8::EPW;
+    for (int lane = 0; lane < 32; ++lane) hex8::phase0(A, S, lane, e0);
+    bool negel[4] = {false, false, false, false};
+    for (int lane = 0; lane < 32; ++lane)
+    {
+      double dJ, dF;
+      bool neg;
+      hex8::phase1<MAT, STIFF>(A, S, tab_gp.data(), tab_node.data(), T.w.data(), lane, e0,
+          out54[lane], dJ, dF, neg);
+      if (e0 + (lane >> 3) < A.n_ele)
+      {
+        if (dJ < *min_detJ) *min_detJ = dJ;
+        if (dF < *min_detF) *min_detF = dF;
+      }
+      if (neg) negel[lane >> 3] = true;
+    }
+    for (bool b : negel) *n_bad += b;
+    for (int lane = 0; lane < 32; ++lane) hex8::phase1_store<STIFF>(S, lane, out54[lane]);
+    for (int lane = 0; lane < 32; ++lane) hex8::phase2<STIFF>(S, lane, Kacc[lane], facc[lane]);
+    for (int lane = 0; lane < 32; ++lane) hex8::phase3<STIFF>(A, S, lane, e0, Kacc[lane], facc[lane]);
+  }
+}
+
+extern "C" int emu_hex8(int matkind, const double* params, const double* per_ele, int stiff,
+    int64_t n_ele, const int32_t* conn, const double* X, const double* u_col, const int32_t* pos,
+    const int64_t* node_rowstart, const int32_t* node_rowlen, const int32_t* node_frow, double* vals,
+    double* f, double* min_detJ, double* min_detF, int64_t* n_bad)
+{
+  EvalArgs A;
+  A.X = X, A.u = u_col, A.conn = conn, A.pos = pos, A.node_rowstart = node_rowstart;
+  A.node_rowlen = node_rowlen, A.node_frow = node_frow, A.per_ele_param = per_ele;
+  A.vals = vals, A.f = f, A.err = nullptr, A.n_ele = n_ele, A.scatter_mode = 0;
+  if (!make_mat_params(matkind, params, A.mp)) return -3;
+#define RUN(M)                                                  \
+  if (stiff)                                                    \
+    run<M, true>(A, min_detJ, min_detF, n_bad);                 \
+  else                                                          \
+    run<M, false>(A, min_detJ, min_detF, n_bad)
+  if (matkind == 0)
+  {
+    RUN(MAT_COUP_NEOHOOKE);
+  }
+  else if (matkind == 1)
+  {
+    RUN(MAT_ISO_VOL);
+  }
+  else
+  {
+    RUN(MAT_SVK);
+  }
+  return 0;
+}

@@ -1,0 +1,73 @@
+"""ctypes front end of tests/cpp/emulate_hex8.cpp: the PRODUCT's hex8 device functions stepped on the
+CPU (test infrastructure; see the header of that file)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CPP = os.path.join(os.path.dirname(_HERE), "cpp")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        so = os.path.join(_CPP, "libemu_hex8.so")
+        srcs = [os.path.join(_CPP, "emulate_hex8.cpp")] + [
+            os.path.join(_CPP, "..", "..", "4c_b200", "csrc", f)
+            for f in ("hex8_kernel.cuh", "solid_math.cuh", "shape_tables.hpp")]
+        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", so, srcs[0]])
+        _lib = C.CDLL(so)
+    return _lib
+
+
+def scatter_map(conn, rowptr, colind, node_row_lid, node_col_lid):
+    """numpy version of k_node_rows + k_build_scatter_map (host check of the device set-up)."""
+    conn = np.asarray(conn)
+    ncn = len(node_row_lid)
+    rowstart = np.full(ncn, -1, np.int64)
+    rowlen = np.zeros(ncn, np.int32)
+    frow = np.full(ncn, -1, np.int32)
+    own = node_row_lid >= 0
+    r0 = 3 * node_row_lid[own].astype(np.int64)
+    rowstart[own] = rowptr[r0]
+    rowlen[own] = (rowptr[r0 + 1] - rowptr[r0]).astype(np.int32)
+    frow[own] = r0
+    ne, nn = conn.shape
+    pos = np.full((ne, nn, nn), -1, np.int32)
+    for e in range(ne):
+        for i in range(nn):
+            ni = conn[e, i]
+            if rowstart[ni] < 0:
+                continue
+            idx = colind[rowstart[ni]:rowstart[ni] + rowlen[ni]]
+            for j in range(nn):
+                col = 3 * node_col_lid[conn[e, j]]
+                p = np.searchsorted(idx, col)
+                assert idx[p] == col and idx[p + 2] == col + 2
+                pos[e, i, j] = p
+    return pos, rowstart, rowlen, frow
+
+
+def evaluate(matkind, params, conn, X, u_col, rowptr, colind, node_row_lid, node_col_lid, n_row_nodes,
+             stiff=True, per_ele=None):
+    conn = np.ascontiguousarray(conn, np.int32)
+    X = np.ascontiguousarray(X, np.float64)
+    u_col = np.ascontiguousarray(u_col, np.float64)
+    params = np.ascontiguousarray(params, np.float64)
+    pos, rowstart, rowlen, frow = scatter_map(conn, rowptr, colind, node_row_lid, node_col_lid)
+    vals = np.zeros(rowptr[-1])
+    f = np.zeros(3 * n_row_nodes)
+    dJ, dF, nb = C.c_double(0), C.c_double(0), C.c_int64(0)
+    vp = C.c_void_p
+    p = lambda a: None if a is None else a.ctypes.data_as(vp)
+    if per_ele is not None:
+        per_ele = np.ascontiguousarray(per_ele, np.float64)
+    rc = lib().emu_hex8(C.c_int(matkind), p(params), p(per_ele), C.c_int(int(stiff)),
+                        C.c_int64(conn.shape[0]), p(conn), p(X), p(u_col), p(pos), p(rowstart),
+                        p(rowlen), p(frow), p(vals), p(f), C.byref(dJ), C.byref(dF), C.byref(nb))
+    assert rc == 0
+    return vals, f, dict(min_detJ=dJ.value, min_detF=dF.value, n_bad=nb.value)

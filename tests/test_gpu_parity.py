@@ -1,0 +1,204 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle on the same
+seeded inputs, against the committed golden fixtures, and through size-independent properties at
+BASELINE.json's full size.  Tolerance: 1e-12 relative per entry in the block-row norm of
+SURVEY.md 8(d) (north_star); CSR pattern bit-exact."""
+import importlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests.helpers.newton import solve_case
+
+pytestmark = pytest.mark.gpu
+b200 = importlib.import_module("4c_b200")
+capi = b200.capi
+G = os.path.join(os.path.dirname(__file__), "golden")
+MATS = {capi.MAT_COUP_NEOHOOKE: [200.0, 0.25], capi.MAT_ISO_VOL: [1.0, 1000.0], capi.MAT_SVK: [1000.0, 0.3]}
+RTOL = 1e-12
+
+
+def _oracle(rm, mk, par, u, rowptr, colind, action=orc.ACTION_FORCE_STIFF, per_ele=None):
+    return orc.evaluate_assemble(orc.HEX8, mk, par, rm.conn, rm.X.ravel(), u.ravel(), rm.node_row_lid,
+                                 rm.node_col_lid, rm.n_row_nodes, rowptr, colind, action=action,
+                                 mue_per_ele=per_ele, nthreads=4)
+
+
+@pytest.mark.parametrize("mk", list(MATS))
+@pytest.mark.parametrize("n", [(1, 1, 1), (2, 1, 1), (7, 5, 3), (16, 12, 9)])
+def test_hex8_matches_oracle(mk, n):
+    rm = b200.partition.box_partition(b200.mesh.HEX8, n, 0, 1)
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 1.0 / max(n))
+    per_ele = None
+    if mk == capi.MAT_ISO_VOL:
+        per_ele = 1.0 + 0.1 * np.arange(rm.n_col_eles) / rm.n_col_eles
+    asm = b200.DeviceAssembler(rm, mk, MATS[mk], per_ele_param=per_ele)
+    rowptr, colind = asm.graph()
+    o_rowptr, o_colind = orc.build_graph(orc.HEX8, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    assert rowptr.tobytes() == o_rowptr.tobytes() and colind.tobytes() == o_colind.tobytes()
+    asm.set_state("displacement", u.ravel())
+    K, f, err = asm.evaluate("struct_calc_nlnstiff")
+    rK, rf, nbad = _oracle(rm, mk, MATS[mk], u, rowptr, colind, per_ele=per_ele)
+    ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
+    assert ok and nbad == 0, (wK, wf)
+    assert err.n_neg_jacobian == 0 and err.min_detJ > 0 and 0.5 < err.min_detF < 1.5
+    # struct_calc_internalforce: force only, K untouched
+    _, f2, _ = asm.evaluate("struct_calc_internalforce")
+    assert np.abs(f2 - rf).max() <= RTOL * np.abs(rf).max()
+    asm.close()
+
+
+def test_hex8_reference_graph_through_set_graph():
+    """The drop-in route: CSR graph handed over by the caller (here: the oracle's FillComplete
+    restatement standing in for Epetra) instead of the device graph builder."""
+    n = (5, 4, 3)
+    rm = b200.partition.box_partition(b200.mesh.HEX8, n, 0, 1)
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 0.2)
+    rowptr, colind = orc.build_graph(orc.HEX8, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    asm = b200.DeviceAssembler(rm, capi.MAT_SVK, MATS[capi.MAT_SVK], graph=(rowptr, colind))
+    asm.set_state("displacement", u.ravel())
+    K, f, _ = asm.evaluate()
+    rK, rf, _ = _oracle(rm, capi.MAT_SVK, MATS[capi.MAT_SVK], u, rowptr, colind)
+    ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
+    assert ok, (wK, wf)
+    asm.close()
+
+
+def test_set_graph_rejects_non_blocked_layout():
+    n = (2, 2, 2)
+    rm = b200.partition.box_partition(b200.mesh.HEX8, n, 0, 1)
+    rowptr, colind = orc.build_graph(orc.HEX8, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    ctx = capi.Context(0)
+    ctx.set_mesh(capi.HEX8, rm.X, rm.conn)
+    d = np.arange(3, dtype=np.int32)
+    row = (3 * rm.node_row_lid[:, None] + d).ravel().astype(np.int32)
+    col = (3 * rm.node_col_lid[:, None] + d).ravel().astype(np.int32)
+    bad_col = col.copy()
+    bad_col[1] = col[2]
+    bad_col[2] = col[1]
+    with pytest.raises(capi.B200SolidError) as ei:
+        ctx.set_graph(rowptr, colind, row, bad_col)
+    assert ei.value.code == capi.ERR_UNSUPPORTED
+    ctx.close()
+
+
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+def test_hex8_partitioned_rows_match_oracle(nranks):
+    """Every rank's view on ONE GPU (no halo exchange: the column state is supplied whole):
+    owner-computes rows equal the serial oracle rows."""
+    n = (8, 6, 4)
+    mk = capi.MAT_COUP_NEOHOOKE
+    for rank in range(nranks):
+        rm = b200.partition.box_partition(b200.mesh.HEX8, n, rank, nranks)
+        u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 1.0 / 8)
+        rm1 = b200.partition.RankMesh(**{**rm.__dict__, "nranks": 1, "rank": 0})
+        asm = b200.DeviceAssembler(rm1, mk, MATS[mk])
+        rowptr, colind = asm.graph()
+        o = orc.build_graph(orc.HEX8, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+        assert rowptr.tobytes() == o[0].tobytes() and colind.tobytes() == o[1].tobytes()
+        # ghost displacements go straight into the device column vector
+        import torch
+        ptrs = asm.ctx.device_ptrs()
+        ucol = torch.from_numpy(u.ravel().copy()).cuda()
+        import ctypes
+        cudart = ctypes.CDLL("libcudart.so")
+        cudart.cudaMemcpy(ctypes.c_void_p(ptrs["u_col"]), ctypes.c_void_p(ucol.data_ptr()),
+                          ctypes.c_size_t(ucol.numel() * 8), 3)
+        asm.set_state("displacement", u[:rm.n_row_nodes].ravel())
+        K, f, _ = asm.evaluate()
+        rK, rf, _ = _oracle(rm, mk, MATS[mk], u, rowptr, colind)
+        ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
+        assert ok, (rank, wK, wf)
+        asm.close()
+
+
+def test_golden_hex8_integration_through_cuda_path():
+    """RESULT DESCRIPTION displacements (1e-12) of the reference's hex8 ctest, with the CUDA path as
+    the evaluate+assemble inside the Newton loop."""
+    case = json.load(open(os.path.join(G, "integration_hex8.json")))
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    rm = b200.partition.serial_mesh(b200.mesh.HEX8, X, conn)
+    par = [case["material"]["YOUNG"], case["material"]["NUE"]]
+    asm = b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, par)
+    rowptr, colind = asm.graph()
+
+    def evaluate(u):
+        asm.set_state("displacement", u)
+        K, f, _ = asm.evaluate()
+        return rowptr, colind, K, f
+
+    u = solve_case(case, evaluate)
+    for e in case["expected_disp"]:
+        assert abs(u[e["node"], e["dof"]] - e["value"]) < e["tol"], e
+    asm.close()
+
+
+def test_negative_jacobian_error_code():
+    n = (2, 2, 1)
+    rm = b200.partition.box_partition(b200.mesh.HEX8, n, 0, 1)
+    X = rm.X.copy()
+    X[rm.conn[1, 6]] = X[rm.conn[1, 0]] - 0.2
+    rm.X = X
+    asm = b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, [200.0, 0.25])
+    asm.set_state("displacement", np.zeros(asm.n_rows))
+    rc, err = asm.ctx.evaluate(capi.ACTION_NLNSTIFF, asm._u, None, None, check=False)
+    assert rc == capi.ERR_NEG_JACOBIAN and err.n_neg_jacobian >= 1 and err.min_detJ <= 0
+    assert 0 <= err.first_bad_element < rm.n_col_eles
+    asm.close()
+
+
+def test_full_size_properties_1M_hex8():
+    """BASELINE config 2 (100^3 hex8 Neo-Hooke): size-independent properties of f and K.
+       * sum of internal forces vanishes per direction (self-equilibrated)
+       * K * (rigid translation) = 0 row-wise
+       * K symmetric: x^T K y = y^T K x for random x, y
+       * a sub-block of rows equals the oracle evaluated on the elements touching those rows."""
+    import torch
+    n = (100, 100, 100)
+    rm = b200.partition.box_partition(b200.mesh.HEX8, n, 0, 1)
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 0.01)
+    asm = b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, [200.0, 0.25])
+    assert asm.nnz == 9 * 301 ** 3
+    rowptr, colind = asm.graph()
+    asm.set_state("displacement", u.ravel())
+    K, f, err = asm.evaluate()
+    assert err.n_neg_jacobian == 0 and 0.7 < err.min_detF < 1.3
+    fs = np.abs(f).max()
+    assert np.abs(f.reshape(-1, 3).sum(axis=0)).max() < 1e-9 * fs * np.sqrt(len(f))
+    rows = np.repeat(np.arange(asm.n_rows), np.diff(rowptr))
+    Kt = torch.sparse_csr_tensor(torch.from_numpy(rowptr), torch.from_numpy(colind.astype(np.int64)),
+                                 torch.from_numpy(K), size=(asm.n_rows, asm.n_rows))
+    scale = np.abs(K).max()
+    for d in range(3):
+        t = np.zeros(asm.n_rows)
+        t[d::3] = 1.0
+        r = (Kt @ torch.from_numpy(t)).numpy()
+        assert np.abs(r).max() < 1e-10 * scale
+    rng = np.random.default_rng(0)
+    x, y = rng.standard_normal(asm.n_rows), rng.standard_normal(asm.n_rows)
+    a = float(torch.from_numpy(x) @ (Kt @ torch.from_numpy(y)))
+    bb = float(torch.from_numpy(y) @ (Kt @ torch.from_numpy(x)))
+    assert abs(a - bb) < 1e-10 * max(abs(a), abs(bb), scale)
+    del rows
+    # oracle on a slab: elements with ez in [40,43) -> rows of nodes on planes 41 and 42 are complete
+    ez = rm.ele_gid // (100 * 100)
+    sel = (ez >= 40) & (ez < 43)
+    conn_s = rm.conn[sel]
+    iz = rm.node_gid // (101 * 101)
+    keep = (iz == 41) | (iz == 42)
+    sub_row = np.where(keep, np.cumsum(keep) - 1, -1).astype(np.int32)
+    nsub = int(keep.sum())
+    # sub-graph rows in the same column numbering
+    o_rowptr, o_colind = orc.build_graph(orc.HEX8, conn_s, sub_row, rm.node_col_lid, nsub)
+    rK, rf, nbad = orc.evaluate_assemble(orc.HEX8, orc.MAT_COUP_NEOHOOKE, [200.0, 0.25], conn_s,
+                                         rm.X.ravel(), u.ravel(), sub_row, rm.node_col_lid, nsub, o_rowptr,
+                                         o_colind, nthreads=8)
+    full_rows = (3 * np.nonzero(keep)[0][:, None] + np.arange(3)).ravel()
+    lo, hi = rowptr[full_rows[0]], rowptr[full_rows[-1] + 1]
+    assert np.array_equal(colind[lo:hi], o_colind) and hi - lo == len(rK)
+    ok, wK, wf = b200.parity_report(o_rowptr, K[lo:hi], rK, f[full_rows], rf, RTOL)
+    assert ok and nbad == 0, (wK, wf)
+    asm.close()
