@@ -24,6 +24,7 @@ SYMBOLS = [
     "b200s_comm_init_nccl", "b200s_evaluate", "b200s_evaluate_async", "b200s_synchronize",
     "b200s_device_values", "b200s_device_f", "b200s_device_u_row", "b200s_device_u_col",
     "b200s_stream", "b200s_nnz", "b200s_n_rows", "b200s_get_timers", "b200s_launch_count",
+    "b200s_kernel_time",
     "b200s_build_graph", "b200s_measure_fp64_peak", "b200s_microbench", "b200s_host_alloc", "b200s_host_free",
     "b200s_version",
 ]
@@ -78,6 +79,7 @@ def load():
     L.b200s_get_timers.argtypes = [vp, vp]
     L.b200s_launch_count.argtypes = [vp]
     L.b200s_launch_count.restype = i64
+    L.b200s_kernel_time.argtypes = [vp, C.POINTER(dbl), C.POINTER(i64), i32]
     L.b200s_build_graph.argtypes = [vp, i64, vp, vp, vp, vp, C.POINTER(i64)]
     L.b200s_measure_fp64_peak.argtypes = [i32, C.POINTER(dbl), C.POINTER(dbl)]
     L.b200s_microbench.argtypes = [i32, i32, i64, C.POINTER(dbl)]
@@ -234,6 +236,12 @@ class Context:
 
     def launch_count(self):
         return self.L.b200s_launch_count(self.h)
+
+    def kernel_time(self, reset=False):
+        """(sum_ms, count) of the element kernel launches harvested so far."""
+        s, n = C.c_double(0), C.c_int64(0)
+        self._ck(self.L.b200s_kernel_time(self.h, C.byref(s), C.byref(n), int(reset)))
+        return s.value, n.value
 
 
 def microbench(which, size=0, device=0):

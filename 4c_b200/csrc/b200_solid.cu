@@ -358,6 +358,28 @@ namespace b200s
       atomicAdd(buf + idx, 1.0);
     }
   }
+  // red.global.add.f64 vs coalescing: runs of R contiguous doubles (R consecutive lanes each) at
+  // pseudo-random 8-byte aligned offsets inside a sliding 32 MB (L2 resident) window; 32-bit index
+  // arithmetic with compile-time R so that the ALU work stays far below the atomic rate
+  template <int R>
+  __global__ void k_red_runs(double* buf, unsigned n_pow2, int per_thread)
+  {
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned nthreads = gridDim.x * blockDim.x;
+    const unsigned window = 1u << 22;
+    for (int r = 0; r < per_thread; ++r)
+    {
+      const unsigned k = tid + (unsigned)r * nthreads;
+      const unsigned run = k / R;
+      unsigned h = run * 0x9E3779B9u;
+      h ^= h >> 15;
+      h *= 0x85EBCA6Bu;
+      h ^= h >> 13;
+      const unsigned base = ((k >> 12) * 64u) & (n_pow2 - 1);
+      const unsigned idx = base + (h & (window - 1)) + (k % R);
+      atomicAdd(buf + idx, 1.0);
+    }
+  }
 }  // namespace b200s
 
 using namespace b200s;
@@ -416,6 +438,11 @@ struct b200s_ctx
   ErrWord* d_err = nullptr;
   ErrWord* h_err = nullptr;  // pinned
   cudaEvent_t ev[7] = {};
+  static constexpr int RING = 64;       // element-kernel event pairs not yet harvested
+  cudaEvent_t kev[2 * RING] = {};
+  int kev_pending = 0;
+  double ktime_sum_ms = 0.0;
+  int64_t ktime_count = 0;
   double timers[6] = {0, 0, 0, 0, 0, 0};
   int64_t launches = 0;
   int last_action = 0;
@@ -472,6 +499,23 @@ namespace
 
 namespace
 {
+  // element-kernel durations: one CUDA event pair per evaluate on the context stream, harvested at
+  // the next synchronize (or when the ring is full) so that a timed loop needs no per-step sync
+  void harvest_kernel_times(b200s_ctx* ctx)
+  {
+    for (int i = 0; i < ctx->kev_pending; ++i)
+    {
+      float ms = 0;
+      cudaEventSynchronize(ctx->kev[2 * i + 1]);
+      if (cudaEventElapsedTime(&ms, ctx->kev[2 * i], ctx->kev[2 * i + 1]) == cudaSuccess)
+      {
+        ctx->ktime_sum_ms += ms, ctx->ktime_count += 1;
+        ctx->timers[2] = ms;
+      }
+    }
+    ctx->kev_pending = 0;
+  }
+
   template <int MAT, bool STIFF>
   static int launch_hex8(b200s_ctx* ctx, const EvalArgs& A)
   {
@@ -533,6 +577,7 @@ extern "C"
       return B200S_ERR_CUDA;
     }
     for (auto& e : ctx->ev) cudaEventCreate(&e);
+    for (auto& e : ctx->kev) cudaEventCreate(&e);
     *out = ctx;
     return B200S_OK;
   }
@@ -550,6 +595,7 @@ extern "C"
     dfree(ctx->d_sendbuf), dfree(ctx->d_recvbuf), dfree(ctx->d_err);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
     for (auto& e : ctx->ev) cudaEventDestroy(e);
+    for (auto& e : ctx->kev) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
   }
@@ -884,8 +930,12 @@ extern "C"
     A.vals = ctx->d_vals, A.f = ctx->d_f, A.err = ctx->d_err, A.mp = ctx->mp;
     A.n_ele = ctx->n_col_eles;
     A.scatter_mode = ctx->scatter_mode;
+    if (ctx->kev_pending == b200s_ctx::RING) harvest_kernel_times(ctx);
+    CK(cudaEventRecord(ctx->kev[2 * ctx->kev_pending], st));
     const int rc = stiff ? launch_eval<true>(ctx, A) : launch_eval<false>(ctx, A);
     if (rc) return rc;
+    CK(cudaEventRecord(ctx->kev[2 * ctx->kev_pending + 1], st));
+    ctx->kev_pending += 1;
     if (ctx->check_finite)
     {
       if (stiff)
@@ -911,7 +961,8 @@ extern "C"
       cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]);
       return (double)ms;
     };
-    ctx->timers[0] = el(1, 2), ctx->timers[1] = el(2, 3), ctx->timers[2] = el(3, 4);
+    harvest_kernel_times(ctx);  // sets timers[2] = element kernel of the last evaluate
+    ctx->timers[0] = el(1, 2), ctx->timers[1] = el(2, 3);
     ctx->timers[3] = el(1, 4);
     ctx->timers[4] = ctx->timed_h2d ? el(0, 1) : 0.0;
     ctx->timers[5] = ctx->timed_d2h ? el(4, 5) : 0.0;
@@ -972,6 +1023,15 @@ extern "C"
     return B200S_OK;
   }
   int64_t b200s_launch_count(const b200s_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+  int b200s_kernel_time(b200s_ctx* ctx, double* sum_ms, int64_t* count, int reset)
+  {
+    if (!ctx) return B200S_ERR_INVALID;
+    if (sum_ms) *sum_ms = ctx->ktime_sum_ms;
+    if (count) *count = ctx->ktime_count;
+    if (reset) ctx->ktime_sum_ms = 0.0, ctx->ktime_count = 0;
+    return B200S_OK;
+  }
 
   int b200s_measure_fp64_peak(int device, double* tflops, double* sm_mhz)
   {
@@ -1054,7 +1114,7 @@ extern "C"
       }
       cudaFree(d);
     }
-    else if (which >= 4 && which <= 6)
+    else if ((which >= 4 && which <= 6) || which >= 100)
     {
       double* d = nullptr;
       const int64_t n = size / 8;
@@ -1064,7 +1124,21 @@ extern "C"
       for (int rep = 0; rep < 4; ++rep)
       {
         cudaEventRecord(a);
-        k_red_pattern<<<blocks, threads>>>(d, n, which - 4, per_thread);
+        if (which >= 100)
+        {
+          unsigned np2 = 1;
+          while ((int64_t)np2 * 2 <= n - (1 << 22) - 64) np2 *= 2;
+          switch (which - 100)
+          {
+#define RUNCASE(R) case R: k_red_runs<R><<<blocks, threads>>>(d, np2, per_thread); break
+            RUNCASE(1); RUNCASE(2); RUNCASE(3); RUNCASE(4); RUNCASE(6); RUNCASE(8); RUNCASE(12);
+            RUNCASE(16); RUNCASE(24); RUNCASE(32);
+#undef RUNCASE
+            default: cudaFree(d); return B200S_ERR_INVALID;
+          }
+        }
+        else
+          k_red_pattern<<<blocks, threads>>>(d, n, which - 4, per_thread);
         cudaEventRecord(b);
         cudaEventSynchronize(b);
         cudaEventElapsedTime(&ms, a, b);

@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- solid element evaluate+assemble throughput (FP64) on B200, one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one struct_calc_nlnstiff evaluate of the hot path over the rank's element block
+(BASELINE.json config 2 at N=1: synthetic structured hex8 Neo-Hooke cube, 100^3 = 1M elements):
+ghost import (N>1), zero K/f, element kernel with scatter-add into the CSR values and residual.
+
+  value : whole-job elements/s (row elements of all ranks / max-over-ranks device time); inputs
+          (u on the dof row map) resident in HBM, outputs (K values, f) left in HBM.
+  e2e   : the same metric through the blocking C-ABI call b200s_evaluate with HOST (pinned)
+          buffers -- u copied host->device, K values and f copied device->host every step.
+  roofline / cpu_baseline : see DESIGN.md "Measurement".
+
+--impl reference times the reference's own CPU arithmetic (oracle/_ref, built on the reference's
+header-only tensor/shape-function code; falls back to the oracle port) on all host threads.
+Nothing here reads /root/reference.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "hex8 Neo-Hooke element evaluate+assemble (force + tangent stiffness into CSR), FP64"
+UNIT = "elements/s"
+MAT_PAR = [200.0, 0.25]           # CoupNeoHooke YOUNG, NUE (tests/performance_tests/solid_hex8.4C.yaml:44-53)
+# SURVEY.md 8(d) / Appendix B algorithmic model, per hex8 element
+FLOPS_PER_ELE = 63.8e3            # (62 n^2 + 228 n + 1183 + 1000) * 8 Gauss points, n = 8
+BYTES_PER_ELE = 2304.0            # conn 32 + X,u 48 + scatter map 256 + K 1944 + f 24
+L2_BYTES = 126e6
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        return time.perf_counter()
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.12] or [r for _, r in self.rows]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])), mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def global_box(per_gpu_n, nranks):
+    """Weak scaling: every rank holds a per_gpu_n^3 element box (grid generator partition)."""
+    b200 = importlib.import_module("4c_b200")
+    mult = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(nranks)
+    if mult is None:
+        raise SystemExit("--gpus must be 1, 2, 4 or 8")
+    n = tuple(per_gpu_n * m for m in mult)
+    sub, _ = b200.partition.box_subdivisions(n, nranks)
+    assert tuple(sub) == mult, (sub, mult)
+    return n, tuple(m * per_gpu_n / 100.0 for m in mult)  # h = 0.01 as in config 2
+
+
+def build_rank(per_gpu_n, rank, nranks):
+    b200 = importlib.import_module("4c_b200")
+    n, box = global_box(per_gpu_n, nranks)
+    rm = b200.partition.box_partition(b200.mesh.HEX8, n, rank, nranks, box=box)
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 0.01)
+    return rm, u, n
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arms (the only place outside tests/ and smoke() that executes oracle/)
+# ------------------------------------------------------------------------------------------------
+class CpuArm:
+    def __init__(self, n_sample):
+        b200 = importlib.import_module("4c_b200")
+        from oracle import oracle as orc
+        self.orc = orc
+        self.kind = "reference" if orc.ref_lib() is not None else "port"
+        self.impl = "ref" if self.kind == "reference" else "oracle"
+        n = (n_sample,) * 3
+        self.rm = b200.partition.box_partition(b200.mesh.HEX8, n, 0, 1, box=tuple(x / 100.0 for x in n))
+        self.u = b200.mesh.displacement_field(self.rm.X, self.rm.node_gid, 1.0, 0.01)
+        self.graph = orc.build_graph(orc.HEX8, self.rm.conn, self.rm.node_row_lid, self.rm.node_col_lid,
+                                     self.rm.n_row_nodes)
+        self.n_sample = n_sample
+
+    def step(self, threads):
+        rm, orc = self.rm, self.orc
+        t = time.perf_counter()
+        orc.evaluate_assemble(orc.HEX8, orc.MAT_COUP_NEOHOOKE, MAT_PAR, rm.conn, rm.X.ravel(), self.u.ravel(),
+                              rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, self.graph[0], self.graph[1],
+                              nthreads=threads, impl=self.impl)
+        return time.perf_counter() - t
+
+    def describe(self):
+        return (f"{self.n_sample}^3 = {self.rm.n_col_eles} hex8 Neo-Hooke elements of the same mesh family "
+                f"(h=0.01, same displacement recipe), zero + evaluate + owner-computes assembly")
+
+
+def cpu_sample_size(threads, target_s):
+    """Sub-cube edge so that one CPU step takes about target_s (33k elements/s/thread measured)."""
+    ne = 30e3 * max(threads, 1) * 0.7 * target_s
+    return int(max(8, min(100, round(ne ** (1.0 / 3.0)))))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = host_threads()
+    arm = CpuArm(cpu_sample_size(threads, 1.0))
+    for _ in range(args.warmup):
+        arm.step(threads)
+    ts = [arm.step(threads) for _ in range(args.steps)]
+    tot = sum(ts)
+    val = arm.rm.n_col_eles * args.steps / tot
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "BASELINE config 2 (structured hex8 CoupNeoHooke E=200 nu=0.25 cube, 1M elements); "
+                               "each step is a bounded sample: " + arm.describe(),
+                   "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": arm.kind, "sample": arm.describe()},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    b200 = importlib.import_module("4c_b200")
+    capi = b200.capi
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N "
+                             "--master-addr 127.0.0.1 --master-port P bench.py --gpus N ...")
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    rm, u, n_global = build_rank(args.per_gpu_n, rank, world)
+    asm = b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, MAT_PAR, device=local)
+    ctx = asm.ctx
+    if world > 1:
+        uid = [ctx.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init_nccl(uid[0])
+    n_rows, nnz = asm.n_rows, asm.nnz
+    ptr = ctx.device_ptrs()
+    stream = torch.cuda.ExternalStream(ptr["stream"], device=torch.device("cuda", local))
+    u_row = np.ascontiguousarray(u[:rm.n_row_nodes].ravel())
+
+    # pinned host staging of the reference-facing call (u in; K values, f out)
+    hb = {k: capi.load().b200s_host_alloc(8 * sz) for k, sz in (("u", n_rows), ("K", nnz), ("f", n_rows))}
+    if not all(hb.values()):
+        raise SystemExit("pinned host allocation failed")
+    h_u = np.ctypeslib.as_array((capi.C.c_double * n_rows).from_address(hb["u"]))
+    h_u[:] = u_row
+    # resident input for the device-timed arm
+    ctx.evaluate(capi.ACTION_NLNSTIFF, h_u, None, None)
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        e1.synchronize()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step_dev():
+        ctx.evaluate_async(capi.ACTION_NLNSTIFF)
+
+    def step_e2e():
+        ctx.evaluate(capi.ACTION_NLNSTIFF, hb["u"], hb["K"], hb["f"])
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    # ---- device-resident arm ----------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_dev()
+    ctx.synchronize()
+    ctx.kernel_time(reset=True)
+    l0 = ctx.launch_count()
+    t0 = sampler.mark() if sampler else 0
+    ms_dev = timed(step_dev, args.steps)
+    t1 = sampler.mark() if sampler else 0
+    _, err = ctx.synchronize()
+    launches = ctx.launch_count() - l0
+    ksum, kcnt = ctx.kernel_time(reset=True)
+    tim = ctx.timers()
+    # ---- end-to-end arm (host buffers through the blocking C-ABI call) -------------------
+    e2e_steps = max(3, min(args.steps, args.e2e_steps))
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, e2e_steps)
+    clocks = sampler.stop(t0, t1) if sampler else None
+
+    tot_eles = torch.tensor([rm.n_row_eles, rm.n_col_eles], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tot_eles)
+    row_eles, col_eles = float(tot_eles[0]), float(tot_eles[1])
+    value = row_eles * args.steps / (ms_dev * 1e-3)
+    e2e = row_eles * e2e_steps / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        fp64_tf, fp64_mhz = capi.measure_fp64_peak(local)
+        k_ms = ksum / max(kcnt, 1)
+        eps_kernel = rm.n_col_eles / (k_ms * 1e-3)      # elements this rank's kernel evaluates per second
+        ach_tf = FLOPS_PER_ELE * eps_kernel / 1e12
+        ach_gbs = BYTES_PER_ELE * eps_kernel / 1e9
+        roof = {
+            "bound": "fp64", "kernel": "k_hex8_eval_assemble<COUP_NEOHOOKE,STIFF>",
+            "achieved": ach_tf, "peak": fp64_tf, "unit": "TFLOP/s", "frac": ach_tf / fp64_tf,
+            "peak_source": "DFMA microbenchmark run in this process (b200s_measure_fp64_peak, implied "
+                           f"{fp64_mhz:.0f} MHz); MEASURED_PEAKS.json holds no FP64 figure",
+            "model": "SURVEY 8(d): 63.8 kflop and 2304 B per hex8 element (algorithmic, full non-symmetric K_e)",
+            "kernel_ms": k_ms, "kernel_launches_timed": kcnt,
+            "traffic": args.traffic_bytes,
+            "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach_gbs / peaks["hbm_gbs"], "peak_source": peak_src},
+        }
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            threads = host_threads()
+            arm = CpuArm(cpu_sample_size(threads, 3.0))
+            arm.step(threads)
+            ts = [arm.step(threads) for _ in range(3)]
+            cpu = {"value": arm.rm.n_col_eles / float(np.median(ts)), "unit": UNIT, "cores": threads,
+                   "kind": arm.kind, "sample": arm.describe() + ", median of 3 after 1 warm-up"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"BASELINE config {'2' if world == 1 and args.per_gpu_n == 100 else '5-style weak'}: "
+                            f"structured hex8 CoupNeoHooke (E=200, nu=0.25) cube {n_global[0]}x{n_global[1]}x"
+                            f"{n_global[2]} = {int(row_eles)} elements, {args.per_gpu_n}^3 per GPU, "
+                            f"struct_calc_nlnstiff, nnz/rank={nnz}",
+                "partition": f"{world} box(es), owner-computes rows, {int(col_eles - row_eles)} ghost elements evaluated redundantly",
+                "l2": f"working set per step {8 * nnz / 1e6:.0f} MB of CSR values + {rm.n_col_eles * 256 / 1e6:.0f} MB "
+                      f"scatter map > L2 ({L2_BYTES / 1e6:.0f} MB): inputs larger than L2, no explicit flush",
+                "timers_last_step_ms": {k: round(float(v), 4) for k, v in tim.items()},
+            },
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * n_rows * world,
+                    "d2h_bytes_per_step": 8 * (nnz + n_rows) * world, "ms_per_step": ms_e2e / e2e_steps,
+                    "steps": e2e_steps, "api": "b200s_evaluate(ctx, NLNSTIFF, u_host, K_values_host, f_host) with pinned host buffers"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "error_info": {"n_neg_jacobian": err.n_neg_jacobian, "min_detJ": err.min_detJ, "min_detF": err.min_detF},
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    for p in hb.values():
+        capi.load().b200s_host_free(p)
+    asm.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--per-gpu-n", type=int, default=100, help="edge of each rank's element box (100 -> 1M elements)")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--traffic-bytes", type=float, default=None,
+                    help="dram bytes per launch of the element kernel from the committed ncu capture (profiles/)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    return run_reference(args) if args.impl == "reference" else run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -169,6 +169,10 @@ extern "C"
   int b200s_get_timers(b200s_ctx* ctx, double* out6);
   /* Number of kernels this library launched since create (bench's gpu_launches). */
   int64_t b200s_launch_count(const b200s_ctx* ctx);
+  /* Accumulated device time (CUDA events on the context stream) and count of the element
+   * evaluate+assemble kernel launches harvested so far (at b200s_synchronize); reset!=0 clears the
+   * accumulators after reading.  bench.py's roofline figure is sum_ms/count over its timed region. */
+  int b200s_kernel_time(b200s_ctx* ctx, double* sum_ms, int64_t* count, int reset);
 
   /* ---- standalone helpers (what 4C/Epetra provide in a real run) ------------------------------ */
   /* Builds AND installs the CSR graph a first assembly + FillComplete would produce for the mesh
