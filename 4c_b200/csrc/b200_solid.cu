@@ -32,9 +32,10 @@ namespace b200s
   // hex8 evaluate + assemble kernel (see hex8_kernel.cuh for the phase structure)
   // ------------------------------------------------------------------------------------------------
   constexpr int HEX8_WARPS = 4;  // warps per CTA; 2 CTAs/SM = 8 warps = 32 elements in flight / SM
-  constexpr size_t hex8_warp_bytes = (size_t)hex8::WARP_DOUBLES * 8 + 32 * (8 + 4 + 4);
+  constexpr size_t hex8_warp_bytes = (size_t)hex8::WARP_BYTES;
   constexpr size_t hex8_table_bytes = (size_t)(2 * hex8::TAB_SIZE + 8) * 8;
   constexpr size_t hex8_smem_bytes = hex8_table_bytes + HEX8_WARPS * hex8_warp_bytes;
+  static_assert(hex8_warp_bytes % 16 == 0 && hex8_table_bytes % 16 == 0, "16-byte aligned carve-up");
 
   __device__ __forceinline__ void atomic_min_double(double* addr, double v)
   {
@@ -47,6 +48,71 @@ namespace b200s
       if (old == assumed) break;
     }
   }
+
+  // cp.async (LDGSTS): global -> shared without a register round trip; completion per thread via
+  // wait_group, visibility to the other lanes through the following __syncwarp()
+  __device__ __forceinline__ void cp_async8(void* smem, const void* gmem)
+  {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem)),
+                 "l"(gmem)
+                 : "memory");
+  }
+  __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+  {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem)),
+                 "l"(gmem)
+                 : "memory");
+  }
+  __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+  __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+  namespace hex8
+  {
+    // node id handled by this lane (element e0 + lane/8, local node lane%8) or -1 beyond the mesh
+    __device__ __forceinline__ int load_node(const EvalArgs& A, int lane, int64_t tile, int64_t n_tiles)
+    {
+      if (tile >= n_tiles) return -1;
+      const int64_t e = tile * EPW + (lane >> 3);
+      return e < A.n_ele ? __ldg(A.conn + e * NN + (lane & 7)) : -1;
+    }
+    // X and u of this lane's node -> S.xu (6 x 8 bytes)
+    __device__ __forceinline__ void issue_xu(const EvalArgs& A, const WarpSmem& S, int lane, int node)
+    {
+      if (node < 0)
+      {
+        gather_pad(S, lane);
+        return;
+      }
+      double* xu = S.xu + (lane >> 3) * XU_ESTRIDE + 3 * (lane & 7);
+      const double* gx = A.X + 3 * (int64_t)node;
+      const double* gu = A.u + 3 * (int64_t)node;
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+      {
+        cp_async8(xu + d, gx + d);
+        cp_async8(xu + 24 + d, gu + d);
+      }
+    }
+    // CSR row info of this lane's node and the tile's 4 x 64 scatter-map entries (2 x 16 bytes/lane)
+    __device__ __forceinline__ void issue_rowpos(
+        const EvalArgs& A, const WarpSmem& S, int lane, int node, int64_t tile)
+    {
+      if (node >= 0)
+        cp_async16(S.nrow + lane, A.node_row + node);
+      else
+        S.nrow[lane].rowstart = -1, S.nrow[lane].rowlen = 0, S.nrow[lane].frow = -1;
+      const int64_t e0 = tile * EPW;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+      {
+        const int chunk = lane + 32 * h;  // 16-byte chunk of the tile's 1 KB map; 16 chunks / element
+        if (e0 + (chunk >> 4) < A.n_ele)
+          cp_async16(S.pos + 4 * chunk, A.pos + e0 * (NN * NN) + 4 * chunk);
+      }
+    }
+  }  // namespace hex8
 
   template <int MAT, bool STIFF>
   __global__ void __launch_bounds__(HEX8_WARPS * 32, 2) k_hex8_eval_assemble(const EvalArgs A)
@@ -68,9 +134,9 @@ namespace b200s
     hex8::WarpSmem S;
     S.mp = reinterpret_cast<double*>(wbase);
     S.g = S.mp + hex8::MP_SIZE;
-    S.rowstart = reinterpret_cast<int64_t*>(S.g + hex8::G_SIZE);
-    S.rowlen = reinterpret_cast<int32_t*>(S.rowstart + 32);
-    S.frow = S.rowlen + 32;
+    S.xu = S.g + hex8::G_SIZE;
+    S.nrow = reinterpret_cast<NodeRow*>(S.xu + hex8::XU_SIZE);
+    S.pos = reinterpret_cast<int32_t*>(S.nrow + hex8::EPW * hex8::NN);
 
     const int64_t n_tiles = (A.n_ele + hex8::EPW - 1) / hex8::EPW;
     const int64_t wstride = (int64_t)gridDim.x * HEX8_WARPS;
@@ -78,11 +144,24 @@ namespace b200s
     long long bad = LLONG_MAX;
     unsigned int nbad = 0;
 
-    for (int64_t tile = (int64_t)blockIdx.x * HEX8_WARPS + warp; tile < n_tiles; tile += wstride)
+    // prologue of the gather pipeline: tile 0 in flight, node ids of tile 1 in registers
+    int64_t tile = (int64_t)blockIdx.x * HEX8_WARPS + warp;
+    int node_next = hex8::load_node(A, lane, tile, n_tiles);
+    if (tile < n_tiles)
+    {
+      hex8::issue_xu(A, S, lane, node_next);
+      hex8::issue_rowpos(A, S, lane, node_next, tile);
+      cp_async_commit();
+    }
+    node_next = hex8::load_node(A, lane, tile + wstride, n_tiles);
+
+    for (; tile < n_tiles; tile += wstride)
     {
       const int64_t e0 = tile * hex8::EPW;
-      hex8::phase0(A, S, lane, e0);
+      cp_async_wait_all();
       __syncwarp();
+      // node ids two tiles ahead: consumed at the bottom of the next iteration
+      const int node_next2 = hex8::load_node(A, lane, tile + 2 * wstride, n_tiles);
       double out54[54];
       double dJ, dF;
       bool neg;
@@ -98,15 +177,26 @@ namespace b200s
           if ((negmask >> (8 * el)) & 0xffu)
           {
             ++nbad;
-            bad = min(bad, (long long)(e0 + el));
+            const long long id = A.ele_id ? (long long)A.ele_id[e0 + el] : (long long)(e0 + el);
+            bad = min(bad, id);
           }
-      __syncwarp();  // every lane is done with the staged X/u before M/Pw overwrite them
+      __syncwarp();  // every lane is done with the gathered X/u: refill it for the next tile
+      if (tile + wstride < n_tiles) hex8::issue_xu(A, S, lane, node_next);
       hex8::phase1_store<STIFF>(S, lane, out54);
       __syncwarp();
       double Kacc[5][9], facc[3];
       hex8::phase2<STIFF>(S, lane, Kacc, facc);
-      hex8::phase3<STIFF>(A, S, lane, e0, Kacc, facc);
+      __syncwarp();  // M/Pw/G are dead: K_e / f_e staging overwrites them
+      hex8::stage_ke<STIFF>(S, lane, Kacc, facc);
       __syncwarp();
+      if (A.scatter_mode == 0) hex8::scatter<STIFF>(A, S, lane, e0);
+      __syncwarp();  // row info / scatter map consumed: refill for the next tile
+      if (tile + wstride < n_tiles)
+      {
+        hex8::issue_rowpos(A, S, lane, node_next, tile + wstride);
+        cp_async_commit();
+      }
+      node_next = node_next2;
     }
 
     // error word: warp reduce, one atomic per warp and quantity
@@ -130,11 +220,94 @@ namespace b200s
   // ------------------------------------------------------------------------------------------------
   // set-up kernels
   // ------------------------------------------------------------------------------------------------
+  // ---- locality ordering of the elements (set_mesh) ----------------------------------------------
+  // The assembly result does not depend on the order in which elements are visited (up to rounding
+  // of the sums); the device visits them along a Morton curve of their centroids so that the CSR
+  // rows a neighbourhood of elements adds to stay L2 resident until they are complete, whatever
+  // numbering the caller's mesh has (structured lexicographic, or randomly renumbered tets).
+  __device__ __forceinline__ void atomic_max_double(double* addr, double v)
+  {
+    unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+    unsigned long long old = *a;
+    while (__longlong_as_double((long long)old) < v)
+    {
+      const unsigned long long assumed = old;
+      old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+      if (old == assumed) break;
+    }
+  }
+  __global__ void k_bbox(int64_t n_nodes, const double* X, double* box /*min xyz, max xyz*/)
+  {
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_nodes;
+         k += (int64_t)gridDim.x * blockDim.x)
+      for (int d = 0; d < 3; ++d)
+      {
+        const double x = X[3 * k + d];
+        mn[d] = fmin(mn[d], x), mx[d] = fmax(mx[d], x);
+      }
+    for (int d = 0; d < 3; ++d)
+    {
+      for (int o = 16; o > 0; o >>= 1)
+      {
+        mn[d] = fmin(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+        mx[d] = fmax(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+      }
+      if ((threadIdx.x & 31) == 0)
+      {
+        atomic_min_double(box + d, mn[d]);
+        atomic_max_double(box + 3 + d, mx[d]);
+      }
+    }
+  }
+  __device__ __forceinline__ unsigned long long spread21(unsigned long long v)
+  {
+    v &= 0x1fffffull;
+    v = (v | (v << 32)) & 0x1f00000000ffffull;
+    v = (v | (v << 16)) & 0x1f0000ff0000ffull;
+    v = (v | (v << 8)) & 0x100f00f00f00f00full;
+    v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+    v = (v | (v << 2)) & 0x1249249249249249ull;
+    return v;
+  }
+  __global__ void k_morton_keys(int nn, int64_t n_ele, const int32_t* conn, const double* X,
+      const double* box, unsigned long long* keys, int32_t* idx)
+  {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_ele) return;
+    double c[3] = {0, 0, 0};
+    const int nc = nn < 8 ? nn : 8;  // corner / first nodes are enough for a locality key
+    for (int k = 0; k < nc; ++k)
+      for (int d = 0; d < 3; ++d) c[d] += X[3 * (int64_t)conn[e * nn + k] + d];
+    unsigned long long key = 0;
+    for (int d = 0; d < 3; ++d)
+    {
+      const double ext = box[3 + d] - box[d];
+      double t = ext > 0 ? (c[d] / nc - box[d]) / ext : 0.0;
+      t = fmin(fmax(t, 0.0), 1.0);
+      key |= spread21((unsigned long long)(t * 2097151.0)) << d;
+    }
+    keys[e] = key;
+    idx[e] = (int32_t)e;
+  }
+  __global__ void k_permute_conn(int nn, int64_t n_ele, const int32_t* conn_in, const int32_t* idx,
+      int32_t* conn_out)
+  {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_ele * nn) return;
+    conn_out[t] = conn_in[(int64_t)idx[t / nn] * nn + (t % nn)];
+  }
+  __global__ void k_gather_double(int64_t n, const double* src, const int32_t* idx, double* dst)
+  {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) dst[t] = src[idx[t]];
+  }
+
   // per column node: CSR row info derived from the reference's dof maps; validates the node-blocked
   // layout the fast path of SparseMatrix::assemble relies on (4C_linalg_sparsematrix.cpp:404-441)
   __global__ void k_node_rows(int64_t n_col_nodes, const int32_t* dof_row_lid,
-      const int32_t* dof_col_lid, const int64_t* rowptr, int64_t n_rows, int64_t* node_rowstart,
-      int32_t* node_rowlen, int32_t* node_frow, int32_t* node_colbase, int* flag)
+      const int32_t* dof_col_lid, const int64_t* rowptr, int64_t n_rows, NodeRow* node_row,
+      int32_t* node_colbase, int* flag)
   {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_col_nodes) return;
@@ -142,46 +315,46 @@ namespace b200s
     const int32_t c0 = dof_col_lid[3 * k], c1 = dof_col_lid[3 * k + 1], c2 = dof_col_lid[3 * k + 2];
     if (c0 < 0 || c1 != c0 + 1 || c2 != c0 + 2) atomicOr(flag, 1);
     node_colbase[k] = c0;
+    NodeRow nr;
+    nr.rowstart = -1, nr.rowlen = 0, nr.frow = -1;
     if (r0 < 0)
     {
       if (r1 >= 0 || r2 >= 0) atomicOr(flag, 2);
-      node_rowstart[k] = -1;
-      node_rowlen[k] = 0;
-      node_frow[k] = -1;
+      node_row[k] = nr;
       return;
     }
     if (r1 != r0 + 1 || r2 != r0 + 2 || r2 >= n_rows)
     {
       atomicOr(flag, 2);
-      node_rowstart[k] = -1, node_rowlen[k] = 0, node_frow[k] = -1;
+      node_row[k] = nr;
       return;
     }
     const int64_t s0 = rowptr[r0], s1 = rowptr[r1], s2 = rowptr[r2], s3 = rowptr[r2 + 1];
     if (s1 - s0 != s2 - s1 || s2 - s1 != s3 - s2) atomicOr(flag, 4);
-    node_rowstart[k] = s0;
-    node_rowlen[k] = (int32_t)(s1 - s0);
-    node_frow[k] = r0;
+    nr.rowstart = s0, nr.rowlen = (int32_t)(s1 - s0), nr.frow = r0;
+    node_row[k] = nr;
   }
 
   // element -> CSR slot map: pos[e][i][j] = offset of the 3 columns of node j inside each row of
   // node i (same lower_bound + stride-3 contiguity rule as SparseMatrix::assemble :404-441)
   __global__ void k_build_scatter_map(int nn, int64_t n_ele, const int32_t* conn,
-      const int32_t* colind, const int64_t* node_rowstart, const int32_t* node_rowlen,
-      const int32_t* node_colbase, int32_t* pos, int* flag)
+      const int32_t* colind, const NodeRow* node_row, const int32_t* node_colbase, int32_t* pos,
+      int* flag)
   {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_ele * nn) return;
     const int64_t e = t / nn;
     const int i = (int)(t % nn);
     const int32_t* ce = conn + e * nn;
-    const int64_t rs = node_rowstart[ce[i]];
+    const NodeRow nr = node_row[ce[i]];
+    const int64_t rs = nr.rowstart;
     int32_t* out = pos + (e * nn + i) * nn;
     if (rs < 0)
     {
       for (int j = 0; j < nn; ++j) out[j] = -1;
       return;
     }
-    const int32_t len = node_rowlen[ce[i]];
+    const int32_t len = nr.rowlen;
     const int32_t* idx = colind + rs;
     for (int j = 0; j < nn; ++j)
     {
@@ -205,12 +378,12 @@ namespace b200s
   }
 
   // Discretization::set_state: owned part of the column vector (4C_fem_discretization.cpp:640-661)
-  __global__ void k_row_to_col(int64_t n_col_nodes, const int32_t* node_frow, const double* u_row,
+  __global__ void k_row_to_col(int64_t n_col_nodes, const NodeRow* node_row, const double* u_row,
       double* u_col)
   {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 3 * n_col_nodes) return;
-    const int32_t fr = node_frow[t / 3];
+    const int32_t fr = node_row[t / 3].frow;
     if (fr >= 0) u_col[t] = u_row[fr + (int)(t % 3)];
   }
   __global__ void k_pack_halo(int64_t n, const int32_t* send_row_lid, const double* u_row, double* buf)
@@ -423,8 +596,9 @@ struct b200s_ctx
   int64_t* d_rowptr = nullptr;  // only when built/owned here
   int32_t* d_colind = nullptr;
   int32_t* d_pos = nullptr;
-  int64_t* d_node_rowstart = nullptr;
-  int32_t *d_node_rowlen = nullptr, *d_node_frow = nullptr, *d_node_colbase = nullptr;
+  NodeRow* d_node_row = nullptr;
+  int32_t* d_node_colbase = nullptr;
+  int32_t* d_ele_id = nullptr;  // device element -> caller's column-element index (locality order)
   double *d_vals = nullptr, *d_f = nullptr, *d_u_row = nullptr, *d_u_col = nullptr;
   // halo
   int n_nbr = 0;
@@ -448,7 +622,7 @@ struct b200s_ctx
   int last_action = 0;
   bool timed_h2d = false, timed_d2h = false;
   // options
-  int check_finite = 0, ctas_per_sm = 2, scatter_mode = 0;
+  int check_finite = 0, ctas_per_sm = 2, scatter_mode = 0, reorder = 1;
 };
 
 namespace
@@ -589,8 +763,8 @@ extern "C"
     cudaStreamSynchronize(ctx->stream);
     if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
     dfree(ctx->dX), dfree(ctx->dconn), dfree(ctx->d_per_ele), dfree(ctx->d_rowptr);
-    dfree(ctx->d_colind), dfree(ctx->d_pos), dfree(ctx->d_node_rowstart), dfree(ctx->d_node_rowlen);
-    dfree(ctx->d_node_frow), dfree(ctx->d_node_colbase), dfree(ctx->d_vals), dfree(ctx->d_f);
+    dfree(ctx->d_colind), dfree(ctx->d_pos), dfree(ctx->d_node_row), dfree(ctx->d_ele_id);
+    dfree(ctx->d_node_colbase), dfree(ctx->d_vals), dfree(ctx->d_f);
     dfree(ctx->d_u_row), dfree(ctx->d_u_col), dfree(ctx->d_send_lid), dfree(ctx->d_recv_lid);
     dfree(ctx->d_sendbuf), dfree(ctx->d_recvbuf), dfree(ctx->d_err);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
@@ -611,6 +785,8 @@ extern "C"
       ctx->ctas_per_sm = (int)value;
     else if (!strcmp(key, "scatter_mode"))
       ctx->scatter_mode = (int)value;
+    else if (!strcmp(key, "reorder"))  // takes effect at the next set_mesh
+      ctx->reorder = value != 0;
     else
       return fail(ctx, B200S_ERR_INVALID, "unknown option %s", key);
     return B200S_OK;
@@ -639,6 +815,37 @@ extern "C"
       memcpy(h.w, T.w.data(), sizeof h.w);
       CK(cudaMemcpyToSymbolAsync(c_hex8, &h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
     }
+    dfree(ctx->d_ele_id);
+    if (ctx->reorder && n_col_eles > 1)
+    {
+      if (n_col_eles > INT32_MAX) return fail(ctx, B200S_ERR_INVALID, "too many column elements");
+      cudaStream_t st = ctx->stream;
+      double hbox[6] = {1e300, 1e300, 1e300, -1e300, -1e300, -1e300};
+      double* d_box = nullptr;
+      unsigned long long *k0 = nullptr, *k1 = nullptr;
+      int32_t *i0 = nullptr, *conn2 = nullptr;
+      void* tmp = nullptr;
+      CK(cudaMalloc((void**)&d_box, sizeof hbox));
+      CK(cudaMemcpyAsync(d_box, hbox, sizeof hbox, cudaMemcpyHostToDevice, st));
+      CK(cudaMalloc((void**)&k0, 8 * (size_t)n_col_eles));
+      CK(cudaMalloc((void**)&k1, 8 * (size_t)n_col_eles));
+      CK(cudaMalloc((void**)&i0, 4 * (size_t)n_col_eles));
+      CK(cudaMalloc((void**)&ctx->d_ele_id, 4 * (size_t)n_col_eles));
+      CK(cudaMalloc((void**)&conn2, 4 * (size_t)n_col_eles * T.nn));
+      k_bbox<<<ctx->n_sm * 4, 256, 0, st>>>(n_col_nodes, ctx->dX, d_box);
+      k_morton_keys<<<nblk(n_col_eles), 256, 0, st>>>(T.nn, n_col_eles, ctx->dconn, ctx->dX, d_box, k0, i0);
+      size_t tb = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, tb, k0, k1, i0, ctx->d_ele_id, n_col_eles, 0, 63, st);
+      CK(cudaMalloc(&tmp, tb));
+      cub::DeviceRadixSort::SortPairs(tmp, tb, k0, k1, i0, ctx->d_ele_id, n_col_eles, 0, 63, st);
+      k_permute_conn<<<nblk(n_col_eles * T.nn), 256, 0, st>>>(T.nn, n_col_eles, ctx->dconn, ctx->d_ele_id, conn2);
+      ctx->launches += 3;
+      CK(cudaStreamSynchronize(st));
+      CK(cudaGetLastError());
+      cudaFree(ctx->dconn);
+      ctx->dconn = conn2;
+      cudaFree(d_box), cudaFree(k0), cudaFree(k1), cudaFree(i0), cudaFree(tmp);
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     // graph-dependent data is stale now
     dfree(ctx->d_pos);
@@ -662,6 +869,17 @@ extern "C"
     {
       if (ctx->n_col_eles <= 0) return fail(ctx, B200S_ERR_INVALID, "set_mesh before per-element parameters");
       if (to_device(ctx, &ctx->d_per_ele, per_ele_param, ctx->n_col_eles)) return B200S_ERR_CUDA;
+      if (ctx->d_ele_id)  // caller's element order -> device (locality) order
+      {
+        double* sorted = nullptr;
+        CK(cudaMalloc((void**)&sorted, 8 * (size_t)ctx->n_col_eles));
+        k_gather_double<<<nblk(ctx->n_col_eles), 256, 0, ctx->stream>>>(
+            ctx->n_col_eles, ctx->d_per_ele, ctx->d_ele_id, sorted);
+        ctx->launches += 1;
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_per_ele);
+        ctx->d_per_ele = sorted;
+      }
       CK(cudaStreamSynchronize(ctx->stream));
     }
     return B200S_OK;
@@ -675,9 +893,7 @@ extern "C"
     CK(cudaMemcpyAsync(&nnz, d_rowptr + n_rows, sizeof(int64_t), cudaMemcpyDefault, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->n_rows = n_rows, ctx->nnz = nnz;
-    if (to_device(ctx, &ctx->d_node_rowstart, (const int64_t*)nullptr, ncn)) return B200S_ERR_CUDA;
-    if (to_device(ctx, &ctx->d_node_rowlen, (const int32_t*)nullptr, ncn)) return B200S_ERR_CUDA;
-    if (to_device(ctx, &ctx->d_node_frow, (const int32_t*)nullptr, ncn)) return B200S_ERR_CUDA;
+    if (to_device(ctx, &ctx->d_node_row, (const NodeRow*)nullptr, ncn)) return B200S_ERR_CUDA;
     if (to_device(ctx, &ctx->d_node_colbase, (const int32_t*)nullptr, ncn)) return B200S_ERR_CUDA;
     if (to_device(ctx, &ctx->d_pos, (const int32_t*)nullptr, ctx->n_col_eles * ctx->nn * ctx->nn))
       return B200S_ERR_CUDA;
@@ -689,11 +905,10 @@ extern "C"
     CK(cudaMalloc((void**)&d_flag, sizeof(int)));
     CK(cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
     k_node_rows<<<nblk(ncn), 256, 0, ctx->stream>>>(ncn, d_dof_row_lid, d_dof_col_lid, d_rowptr,
-        n_rows, ctx->d_node_rowstart, ctx->d_node_rowlen, ctx->d_node_frow, ctx->d_node_colbase,
-        d_flag);
+        n_rows, ctx->d_node_row, ctx->d_node_colbase, d_flag);
     k_build_scatter_map<<<nblk(ctx->n_col_eles * ctx->nn), 256, 0, ctx->stream>>>(ctx->nn,
-        ctx->n_col_eles, ctx->dconn, d_colind, ctx->d_node_rowstart, ctx->d_node_rowlen,
-        ctx->d_node_colbase, ctx->d_pos, d_flag);
+        ctx->n_col_eles, ctx->dconn, d_colind, ctx->d_node_row, ctx->d_node_colbase, ctx->d_pos,
+        d_flag);
     ctx->launches += 2;
     int flag = 0;
     CK(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -913,7 +1128,7 @@ extern "C"
       ctx->launches += (ns > 0) + (nr > 0);
     }
     k_row_to_col<<<nblk(3 * ctx->n_col_nodes), 256, 0, st>>>(
-        ctx->n_col_nodes, ctx->d_node_frow, ctx->d_u_row, ctx->d_u_col);
+        ctx->n_col_nodes, ctx->d_node_row, ctx->d_u_row, ctx->d_u_col);
     ctx->launches += 1;
     CK(cudaEventRecord(ctx->ev[2], st));
     // stiff.zero(); fint.put_scalar(0)
@@ -925,8 +1140,7 @@ extern "C"
     CK(cudaEventRecord(ctx->ev[3], st));
     EvalArgs A;
     A.X = ctx->dX, A.u = ctx->d_u_col, A.conn = ctx->dconn, A.pos = ctx->d_pos;
-    A.node_rowstart = ctx->d_node_rowstart, A.node_rowlen = ctx->d_node_rowlen;
-    A.node_frow = ctx->d_node_frow, A.per_ele_param = ctx->d_per_ele;
+    A.node_row = ctx->d_node_row, A.per_ele_param = ctx->d_per_ele, A.ele_id = ctx->d_ele_id;
     A.vals = ctx->d_vals, A.f = ctx->d_f, A.err = ctx->d_err, A.mp = ctx->mp;
     A.n_ele = ctx->n_col_eles;
     A.scatter_mode = ctx->scatter_mode;

@@ -82,7 +82,10 @@ extern "C"
   int b200s_create(int device, int rank, int nranks, b200s_ctx** out);
   void b200s_destroy(b200s_ctx* ctx);
   const char* b200s_last_error(const b200s_ctx* ctx);
-  /* options: "check_finite" (0/1), "ctas_per_sm" (tuning), "scatter" (0 atomic) */
+  /* options: "check_finite" (0/1: count NaN/Inf in f and K after each evaluate),
+   * "reorder" (default 1: the device visits the elements in a locality (Morton) order chosen at the
+   * next b200s_set_mesh; results, element indices in b200s_error_info and per-element parameters
+   * stay in the caller's numbering), "ctas_per_sm" and "scatter_mode" (tuning / profiling only). */
   int b200s_set_option(b200s_ctx* ctx, const char* key, double value);
 
   /* ---- set-up (once per discretization) ------------------------------------------------------ */

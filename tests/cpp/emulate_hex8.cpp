@@ -23,13 +23,14 @@ static void run(const EvalArgs& A, double* min_detJ, double* min_detF, int64_t* 
     tab_node[(t / 24) * hex8::TAB_STRIDE + (t % 24)] = T.dN_node[t];
   }
   std::vector<double> sm(hex8::WARP_DOUBLES + 2, 0.0);
-  std::vector<int64_t> rowstart(32);
-  std::vector<int32_t> rowlen(32), frow(32);
+  std::vector<NodeRow> nrow(hex8::EPW * hex8::NN);
+  std::vector<int32_t> posbuf(hex8::EPW * hex8::NN * hex8::NN);
   hex8::WarpSmem S;
-  // 16-byte align the double2 region
+  // 16-byte align the double2 region; same carve-up as the kernel
   S.mp = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sm.data()) + 15) & ~uintptr_t(15));
   S.g = S.mp + hex8::MP_SIZE;
-  S.rowstart = rowstart.data(), S.rowlen = rowlen.data(), S.frow = frow.data();
+  S.xu = S.g + hex8::G_SIZE;
+  S.nrow = nrow.data(), S.pos = posbuf.data();
   *min_detJ = 1e300, *min_detF = 1e300, *n_bad = 0;
   const int64_t n_tiles = (A.n_ele + hex8::EPW - 1) / hex8::EPW;
   static double out54[32][54];
@@ -37,7 +38,7 @@ static void run(const EvalArgs& A, double* min_detJ, double* min_detF, int64_t* 
   for (int64_t tile = 0; tile < n_tiles; ++tile)
   {
     const int64_t e0 = tile * hex8::EPW;
-    for (int lane = 0; lane < 32; ++lane) hex8::phase0(A, S, lane, e0);
+    for (int lane = 0; lane < 32; ++lane) hex8::gather(A, S, lane, e0);
     bool negel[4] = {false, false, false, false};
     for (int lane = 0; lane < 32; ++lane)
     {
@@ -55,18 +56,23 @@ static void run(const EvalArgs& A, double* min_detJ, double* min_detF, int64_t* 
     for (bool b : negel) *n_bad += b;
     for (int lane = 0; lane < 32; ++lane) hex8::phase1_store<STIFF>(S, lane, out54[lane]);
     for (int lane = 0; lane < 32; ++lane) hex8::phase2<STIFF>(S, lane, Kacc[lane], facc[lane]);
-    for (int lane = 0; lane < 32; ++lane) hex8::phase3<STIFF>(A, S, lane, e0, Kacc[lane], facc[lane]);
+    for (int lane = 0; lane < 32; ++lane) hex8::stage_ke<STIFF>(S, lane, Kacc[lane], facc[lane]);
+    for (int lane = 0; lane < 32; ++lane) hex8::scatter<STIFF>(A, S, lane, e0);
   }
 }
 
 extern "C" int emu_hex8(int matkind, const double* params, const double* per_ele, int stiff,
     int64_t n_ele, const int32_t* conn, const double* X, const double* u_col, const int32_t* pos,
-    const int64_t* node_rowstart, const int32_t* node_rowlen, const int32_t* node_frow, double* vals,
-    double* f, double* min_detJ, double* min_detF, int64_t* n_bad)
+    const int64_t* node_rowstart, const int32_t* node_rowlen, const int32_t* node_frow,
+    int64_t n_col_nodes, double* vals, double* f, double* min_detJ, double* min_detF, int64_t* n_bad)
 {
+  std::vector<NodeRow> node_row(n_col_nodes);
+  for (int64_t k = 0; k < n_col_nodes; ++k)
+    node_row[k].rowstart = node_rowstart[k], node_row[k].rowlen = node_rowlen[k],
+    node_row[k].frow = node_frow[k];
   EvalArgs A;
-  A.X = X, A.u = u_col, A.conn = conn, A.pos = pos, A.node_rowstart = node_rowstart;
-  A.node_rowlen = node_rowlen, A.node_frow = node_frow, A.per_ele_param = per_ele;
+  A.X = X, A.u = u_col, A.conn = conn, A.pos = pos, A.node_row = node_row.data();
+  A.per_ele_param = per_ele, A.ele_id = nullptr;
   A.vals = vals, A.f = f, A.err = nullptr, A.n_ele = n_ele, A.scatter_mode = 0;
   if (!make_mat_params(matkind, params, A.mp)) return -3;
 #define RUN(M)                                                  \

@@ -68,6 +68,6 @@ def evaluate(matkind, params, conn, X, u_col, rowptr, colind, node_row_lid, node
         per_ele = np.ascontiguousarray(per_ele, np.float64)
     rc = lib().emu_hex8(C.c_int(matkind), p(params), p(per_ele), C.c_int(int(stiff)),
                         C.c_int64(conn.shape[0]), p(conn), p(X), p(u_col), p(pos), p(rowstart),
-                        p(rowlen), p(frow), p(vals), p(f), C.byref(dJ), C.byref(dF), C.byref(nb))
+                        p(rowlen), p(frow), C.c_int64(len(rowstart)), p(vals), p(f), C.byref(dJ), C.byref(dF), C.byref(nb))
     assert rc == 0
     return vals, f, dict(min_detJ=dJ.value, min_detF=dF.value, n_bad=nb.value)
