@@ -66,7 +66,8 @@ namespace b200s
                  : "memory");
   }
   __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-  __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+  // all but the most recently committed group are complete
+  __device__ __forceinline__ void cp_async_wait_but_last() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
   namespace hex8
   {
@@ -147,18 +148,18 @@ namespace b200s
     // prologue of the gather pipeline: tile 0 in flight, node ids of tile 1 in registers
     int64_t tile = (int64_t)blockIdx.x * HEX8_WARPS + warp;
     int node_next = hex8::load_node(A, lane, tile, n_tiles);
-    if (tile < n_tiles)
-    {
-      hex8::issue_xu(A, S, lane, node_next);
-      hex8::issue_rowpos(A, S, lane, node_next, tile);
-      cp_async_commit();
-    }
+    // Two commit groups per tile, always in the order [X,u] then [row info, scatter map]; a group
+    // may be empty (no next tile), which keeps the wait_group arithmetic uniform.
+    if (tile < n_tiles) hex8::issue_xu(A, S, lane, node_next);
+    cp_async_commit();
+    if (tile < n_tiles) hex8::issue_rowpos(A, S, lane, node_next, tile);
+    cp_async_commit();
     node_next = hex8::load_node(A, lane, tile + wstride, n_tiles);
 
     for (; tile < n_tiles; tile += wstride)
     {
       const int64_t e0 = tile * hex8::EPW;
-      cp_async_wait_all();
+      cp_async_wait_but_last();  // X,u of this tile landed (its row info / map may still fly)
       __syncwarp();
       // node ids two tiles ahead: consumed at the bottom of the next iteration
       const int node_next2 = hex8::load_node(A, lane, tile + 2 * wstride, n_tiles);
@@ -182,20 +183,19 @@ namespace b200s
           }
       __syncwarp();  // every lane is done with the gathered X/u: refill it for the next tile
       if (tile + wstride < n_tiles) hex8::issue_xu(A, S, lane, node_next);
+      cp_async_commit();
       hex8::phase1_store<STIFF>(S, lane, out54);
       __syncwarp();
       double Kacc[5][9], facc[3];
       hex8::phase2<STIFF>(S, lane, Kacc, facc);
       __syncwarp();  // M/Pw/G are dead: K_e / f_e staging overwrites them
       hex8::stage_ke<STIFF>(S, lane, Kacc, facc);
+      cp_async_wait_but_last();  // row info / scatter map of this tile landed
       __syncwarp();
       if (A.scatter_mode == 0) hex8::scatter<STIFF>(A, S, lane, e0);
       __syncwarp();  // row info / scatter map consumed: refill for the next tile
-      if (tile + wstride < n_tiles)
-      {
-        hex8::issue_rowpos(A, S, lane, node_next, tile + wstride);
-        cp_async_commit();
-      }
+      if (tile + wstride < n_tiles) hex8::issue_rowpos(A, S, lane, node_next, tile + wstride);
+      cp_async_commit();
       node_next = node_next2;
     }
 

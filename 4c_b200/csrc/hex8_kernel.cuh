@@ -168,15 +168,30 @@ namespace b200s
       const double* xu = S.xu + el * XU_ESTRIDE;
       double J[9], iJ[9];
 
-      // ensure_positive_jacobian_determinant_at_element_nodes (calc_lib.hpp:543-562): node g
-      jacobian(tab_node + g * TAB_STRIDE, xu, J);
+      // ensure_positive_jacobian_determinant_at_element_nodes (calc_lib.hpp:543-562): node g.
+      // At a hex8 corner only the node itself and its three edge neighbours have non-zero
+      // parametric derivatives (+-1/2), so the reference's sum over 8 nodes reduces exactly to
+      // J(a,:) = xi_a/2 (X_g - X_nbr_a); tab_node (the full table) documents and tests that.
+      (void)tab_node;
+      {
+        const double sr = ((g ^ (g >> 1)) & 1) ? 0.5 : -0.5, ss = (g & 2) ? 0.5 : -0.5,
+                     st = (g & 4) ? 0.5 : -0.5;
+        const double *xq = xu + 3 * g, *xr = xu + 3 * (g ^ 1), *xs = xu + 3 * (g ^ 3),
+                     *xt = xu + 3 * (g ^ 4);
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+        {
+          J[0 + 3 * b] = sr * (xq[b] - xr[b]);
+          J[1 + 3 * b] = ss * (xq[b] - xs[b]);
+          J[2 + 3 * b] = st * (xq[b] - xt[b]);
+        }
+      }
       const double detJ_node = det3(J);
 
       // evaluate_jacobian_mapping at Gauss point g (calc_lib.hpp:499-516)
       const double* dN = tab_gp + g * TAB_STRIDE;
       jacobian(dN, xu, J);
-      inv3(iJ, J);
-      const double detJ = det3(J);
+      const double detJ = inv3(iJ, J);  // same expression as det3(J)
       neg_jac = !(detJ_node > 0.0) && (e < A.n_ele);
       detJ_min = fmin(detJ_node, detJ);
 
@@ -208,9 +223,17 @@ namespace b200s
       if (A.per_ele_param != nullptr && e < A.n_ele) mp.p[0] = A.per_ele_param[e];
       material_evaluate<MAT>(mp, C, Sv, Cm);
 
-      const double w = detJ * wgt[g];  // integration factor (calc_lib.hpp:1270-1280)
-      if (STIFF) material_geometric_operator(F, Sv, Cm, w, out54);
-      first_piola_w(F, Sv, w, out54 + 45);
+      // integration factor (calc_lib.hpp:1270-1280), folded into S and Cm once
+      const double w = detJ * wgt[g];
+#pragma unroll
+      for (int v = 0; v < 6; ++v) Sv[v] *= w;
+      if (STIFF)
+      {
+#pragma unroll
+        for (int v = 0; v < 21; ++v) Cm[v] *= w;
+        material_geometric_operator(F, Sv, Cm, out54);
+      }
+      first_piola(F, Sv, out54 + 45);
     }
 
     template <bool STIFF>
@@ -257,7 +280,7 @@ namespace b200s
         for (int r = 0; r < 9; ++r) Pw[r] = mp_value(S, el, g, 45 + r);
 #pragma unroll
         for (int a = 0; a < 3; ++a)
-          facc[a] += Pw[a] * Gi[0] + Pw[a + 3] * Gi[1] + Pw[a + 6] * Gi[2];
+          facc[a] = fma(Pw[a + 6], Gi[2], fma(Pw[a + 3], Gi[1], fma(Pw[a], Gi[0], facc[a])));
         if (STIFF)
         {
           // out[b][q] = sum_a Gi(a) M[(a,b)][q]: stream the packed upper triangle once, every
@@ -273,8 +296,8 @@ namespace b200s
             for (int q = p; q < 9; ++q)
             {
               const double m = mp_value(S, el, g, m45(p, q));
-              out[p % 3][q] += Gi[p / 3] * m;
-              if (p != q) out[q % 3][p] += Gi[q / 3] * m;
+              out[p % 3][q] = fma(Gi[p / 3], m, out[p % 3][q]);
+              if (p != q) out[q % 3][p] = fma(Gi[q / 3], m, out[q % 3][p]);
             }
           // K_ij(b,c) += sum_d out[b][3d+c] G_j(d)   (calc_lib.hpp:1135-1149)
 #pragma unroll
@@ -286,8 +309,8 @@ namespace b200s
             for (int b = 0; b < 3; ++b)
 #pragma unroll
               for (int c = 0; c < 3; ++c)
-                Kacc[k][b + 3 * c] +=
-                    out[b][c] * Gj[0] + out[b][3 + c] * Gj[1] + out[b][6 + c] * Gj[2];
+                Kacc[k][b + 3 * c] = fma(out[b][6 + c], Gj[2],
+                    fma(out[b][3 + c], Gj[1], fma(out[b][c], Gj[0], Kacc[k][b + 3 * c])));
           }
         }
       }

@@ -236,25 +236,26 @@ namespace b200s
     }
   }
 
-  // Pw = F S w  (first Piola-Kirchhoff times integration factor, calc_lib.hpp:1116)
-  B2_HD void first_piola_w(const double* F, const double* S, double w, double* Pw)
+  // P = F S  (first Piola-Kirchhoff, calc_lib.hpp:1116; callers pass S already multiplied by the
+  // integration factor)
+  B2_HD void first_piola(const double* F, const double* S, double* P)
   {
 #pragma unroll
     for (int a = 0; a < 3; ++a)
 #pragma unroll
       for (int b = 0; b < 3; ++b)
-        Pw[a + 3 * b] =
-            w * (F[a] * S[vg(0, b)] + F[a + 3] * S[vg(1, b)] + F[a + 6] * S[vg(2, b)]);
+        P[a + 3 * b] = fma(F[a + 6], S[vg(2, b)], fma(F[a + 3], S[vg(1, b)], F[a] * S[vg(0, b)]));
   }
 
-  // The 45 unique entries of the symmetric 9x9 matrix
-  //   M[(a,b)][(d,c)] = w * sum_ij F(b,i) Cm(a,i,j,d) F(c,j) + delta_bc * w * S(a,d)
+  // The 45 unique entries of the symmetric 9x9 matrix (S and Cm already carry the integration
+  // factor w)
+  //   M[(a,b)][(d,c)] = sum_ij F(b,i) Cm(a,i,j,d) F(c,j) + delta_bc * S(a,d)
   // i.e. the reference's FCFTw (einsum<"bi","aijd","cj">, calc_lib.hpp:1131-1133) with the
   // geometric term (:1138,1147-1148) folded in, so that
   //   K_ij(b,c) = sum_ad dN_i(a) M[(a,b)][(d,c)] dN_j(d).
   // p = 3a+b, q = 3d+c; symmetric because of the major symmetry of Cm.
   B2_HD void material_geometric_operator(
-      const double* F, const double* S, const double* Cm, double w, double* M)
+      const double* F, const double* S, const double* Cm, double* M)
   {
 #pragma unroll
     for (int c = 0; c < 3; ++c)
@@ -265,8 +266,8 @@ namespace b200s
       for (int V = 0; V < 6; ++V)
 #pragma unroll
         for (int d = 0; d < 3; ++d)
-          T[V][d] = Cm[c21(V, vg(0, d))] * F[c] + Cm[c21(V, vg(1, d))] * F[c + 3] +
-                    Cm[c21(V, vg(2, d))] * F[c + 6];
+          T[V][d] = fma(Cm[c21(V, vg(2, d))], F[c + 6],
+              fma(Cm[c21(V, vg(1, d))], F[c + 3], Cm[c21(V, vg(0, d))] * F[c]));
 #pragma unroll
       for (int a = 0; a < 3; ++a)
 #pragma unroll
@@ -277,10 +278,8 @@ namespace b200s
             const int p = 3 * a + b, q = 3 * d + c;
             if (p <= q)
             {
-              double v = F[b] * T[vg(a, 0)][d] + F[b + 3] * T[vg(a, 1)][d] +
-                         F[b + 6] * T[vg(a, 2)][d];
-              if (b == c) v += S[vg(a, d)];
-              M[m45(p, q)] = w * v;
+              const double v0 = (b == c) ? fma(F[b], T[vg(a, 0)][d], S[vg(a, d)]) : F[b] * T[vg(a, 0)][d];
+              M[m45(p, q)] = fma(F[b + 6], T[vg(a, 2)][d], fma(F[b + 3], T[vg(a, 1)][d], v0));
             }
           }
     }

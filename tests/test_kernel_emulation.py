@@ -71,3 +71,20 @@ def test_emulated_negative_jacobian_is_reported():
     _, _, info = emu.evaluate(0, [200.0, 0.25], rm.conn, X.ravel(), 0 * u.ravel(), rowptr, colind,
                               rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
     assert nbad > 0 and info["n_bad"] == nbad and info["min_detJ"] <= 0
+
+
+def test_hex8_corner_jacobian_shortcut_is_exact():
+    """The kernel evaluates the reference's nodal Jacobian check (calc_lib.hpp:543-562) from the three
+    edge vectors of the corner; it must equal the full sum over the 8 shape-function derivatives."""
+    rng = np.random.default_rng(7)
+    xi_nodes = orc.node_param_coords(orc.HEX8)
+    for _ in range(20):
+        X = xi_nodes * 0.5 + 0.2 * rng.standard_normal((8, 3))
+        for g in range(8):
+            _, dN = orc.shape(orc.HEX8, xi_nodes[g])        # dN[a, k]
+            J_full = dN @ X                                  # J(a,b) = sum_k dN(a,k) X(k,b)
+            sr = 0.5 if ((g ^ (g >> 1)) & 1) else -0.5
+            ss = 0.5 if (g & 2) else -0.5
+            st = 0.5 if (g & 4) else -0.5
+            J_short = np.stack([sr * (X[g] - X[g ^ 1]), ss * (X[g] - X[g ^ 3]), st * (X[g] - X[g ^ 4])])
+            assert np.array_equal(J_full, J_short)
