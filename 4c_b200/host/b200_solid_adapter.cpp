@@ -1,0 +1,91 @@
+// b200_solid_adapter.cpp -- see b200_solid_adapter.hpp.  Host C++ only; every numeric step is a call
+// into lib4c_b200_solid.so through the C ABI.
+#include "b200_solid_adapter.hpp"
+
+#include <cstring>
+
+namespace B200Solid
+{
+  DeviceElementBlock::DeviceElementBlock(int device, int rank, int nranks)
+  {
+    const int rc = b200s_create(device, rank, nranks, &ctx_);
+    if (rc != B200S_OK)
+      throw Exception(rc, "b200s_create failed: no CUDA device (the device path has no CPU fallback)");
+  }
+
+  DeviceElementBlock::~DeviceElementBlock() { b200s_destroy(ctx_); }
+
+  void DeviceElementBlock::check(int rc) const
+  {
+    if (rc == B200S_OK) return;
+    const std::string msg = b200s_last_error(ctx_);
+    if (rc == B200S_ERR_NEG_JACOBIAN)
+      // message of FOUR_C_ASSERT_ALWAYS in 4C_solid_ele_calc_lib.hpp:558
+      throw Exception(rc, "Determinant of jacobian is smaller or equal to zero at one node of the element: " + msg);
+    throw Exception(rc, msg);
+  }
+
+  bool DeviceElementBlock::supported(int celltype, int material_kind)
+  {
+    const bool cell = celltype == B200S_HEX8 || celltype == B200S_HEX27 || celltype == B200S_TET10;
+    const bool mat = material_kind == B200S_MAT_COUP_NEOHOOKE || material_kind == B200S_MAT_ISO_VOL ||
+                     material_kind == B200S_MAT_SVK;
+    return cell && mat;
+  }
+
+  void DeviceElementBlock::set_block(const ElementBlockView& b)
+  {
+    check(b200s_set_mesh(ctx_, b.celltype, b.n_col_nodes, b.X, b.n_col_eles, b.conn));
+  }
+
+  void DeviceElementBlock::set_material(int kind, const std::vector<double>& params, const double* per_element)
+  {
+    check(b200s_set_material(ctx_, kind, params.data(), (int)params.size(), per_element));
+  }
+
+  void DeviceElementBlock::set_graph(const ElementBlockView& b, const CrsView& crs)
+  {
+    // Epetra's local CRS uses int offsets; the ABI takes 64-bit offsets (configs beyond 2^31 nnz)
+    std::vector<std::int64_t> rowptr(crs.n_rows + 1);
+    for (std::int64_t r = 0; r <= crs.n_rows; ++r) rowptr[r] = crs.index_offset[r];
+    static_assert(sizeof(int) == sizeof(std::int32_t), "Epetra local ids are 32 bit");
+    check(b200s_set_graph(ctx_, crs.n_rows, rowptr.data(), reinterpret_cast<const std::int32_t*>(crs.indices),
+        b.dof_row_lid, b.dof_col_lid));
+  }
+
+  void DeviceElementBlock::set_import(const ImportView& imp)
+  {
+    const int n = (int)imp.peers.size();
+    std::vector<std::int32_t> peer(imp.peers.begin(), imp.peers.end()), s, r;
+    std::vector<std::int64_t> so(n + 1, 0), ro(n + 1, 0);
+    for (int i = 0; i < n; ++i)
+    {
+      s.insert(s.end(), imp.send_row_lids[i].begin(), imp.send_row_lids[i].end());
+      r.insert(r.end(), imp.recv_col_nodes[i].begin(), imp.recv_col_nodes[i].end());
+      so[i + 1] = (std::int64_t)s.size(), ro[i + 1] = (std::int64_t)r.size();
+    }
+    if (s.empty()) s.push_back(0);
+    if (r.empty()) r.push_back(0);
+    check(b200s_set_halo(ctx_, n, peer.data(), so.data(), s.data(), ro.data(), r.data()));
+  }
+
+  std::string DeviceElementBlock::nccl_unique_id()
+  {
+    std::string id(128, '\0');
+    check(b200s_nccl_unique_id(ctx_, id.data()));
+    return id;
+  }
+
+  void DeviceElementBlock::init_communicator(const char* id) { check(b200s_comm_init_nccl(ctx_, id)); }
+
+  void DeviceElementBlock::evaluate(Action action, double* crs_values, double* f_row)
+  {
+    if (!u_row_) throw Exception(B200S_ERR_INVALID, "set_state(\"displacement\") must precede evaluate");
+    b200s_error_info info;
+    std::memset(&info, 0, sizeof info);
+    check(b200s_evaluate(ctx_, (int)action, u_row_, crs_values, f_row, &info));
+  }
+
+  std::int64_t DeviceElementBlock::nnz() const { return b200s_nnz(ctx_); }
+  std::int64_t DeviceElementBlock::n_rows() const { return b200s_n_rows(ctx_); }
+}  // namespace B200Solid

@@ -1,0 +1,114 @@
+// b200_solid_adapter.hpp -- host-side C++ layer above the C ABI (include/b200_solid.h).
+//
+// This is the piece a 4C maintainer links into the structure model evaluator: it owns one device
+// context per (discretization, element block), translates 4C's maps / graph / vectors into the plain
+// arrays the ABI takes and rethrows ABI status codes with the reference's own messages.  It is written
+// against a small set of *views* (plain structs of pointers) instead of Epetra / 4C headers so that it
+// compiles here without Trilinos; INTEGRATION.md shows the few lines that fill the views from
+// Core::FE::Discretization, Core::LinAlg::SparseMatrix and Core::LinAlg::Vector<double>.
+//
+// Interface names follow the reference:
+//   set_state / evaluate        Core::FE::Discretization (4C_fem_discretization.cpp:612-665,
+//                                4C_fem_discretization_evaluate.cpp:67-117)
+//   Action                      Core::Elements::ActionType struct_calc_nlnstiff / _internalforce
+//   assemble semantics          Core::FE::AssembleStrategy::assemble_matrix1 / assemble_vector1
+//                                (4C_fem_general_assemblestrategy.cpp:116-150): owned rows only,
+//                                values ADDED into a zeroed matrix
+#pragma once
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/b200_solid.h"
+
+namespace B200Solid
+{
+  enum class Action
+  {
+    struct_calc_internalforce = B200S_ACTION_INTERNALFORCE,
+    struct_calc_nlnstiff = B200S_ACTION_NLNSTIFF
+  };
+
+  /// What 4C throws: Core::Exception (FOUR_C_THROW).  Stand-in so that unit tests can
+  /// EXPECT_THROW on the same conditions as the reference (unittests/README.md).
+  class Exception : public std::runtime_error
+  {
+   public:
+    Exception(int code, const std::string& what) : std::runtime_error(what), code_(code) {}
+    int code() const { return code_; }
+
+   private:
+    int code_;
+  };
+
+  /// Column-map view of one element block of a discretization (all elements share cell type,
+  /// SolidElementProperties and material type) -- Discretization::my_col_element_range().
+  struct ElementBlockView
+  {
+    int celltype = B200S_HEX8;        // Core::FE::CellType of the block
+    std::int64_t n_col_nodes = 0;
+    const double* X = nullptr;        // 3*n_col_nodes, Node::x() in node column-map order
+    std::int64_t n_col_eles = 0;
+    const std::int32_t* conn = nullptr;  // n_col_eles*nn, node column-map lids (Element::node_ids -> lid)
+    const std::int32_t* dof_row_lid = nullptr;  // 3*n_col_nodes, dof_row_map()->lid(gid) or -1
+    const std::int32_t* dof_col_lid = nullptr;  // 3*n_col_nodes, matrix col_map().lid(gid)
+  };
+
+  /// Epetra_CrsMatrix::ExtractCrsDataPointers of the completed stiffness matrix.  `values` changes
+  /// every Newton iteration (SparseMatrix::zero() re-allocates, 4C_linalg_sparsematrix.cpp:268-291),
+  /// the structure does not.
+  struct CrsView
+  {
+    std::int64_t n_rows = 0;
+    const int* index_offset = nullptr;  // n_rows+1 (Epetra: int)
+    const int* indices = nullptr;       // nnz, local column ids, ascending per row
+    double* values = nullptr;           // nnz
+  };
+
+  /// Epetra_Import of the dof column map (Discretization::set_state), per neighbour.
+  struct ImportView
+  {
+    std::vector<int> peers;
+    std::vector<std::vector<std::int32_t>> send_row_lids;  // row lid of dof 0 of each exported node
+    std::vector<std::vector<std::int32_t>> recv_col_nodes; // column-node lids filled from the peer
+  };
+
+  class DeviceElementBlock
+  {
+   public:
+    DeviceElementBlock(int device, int rank, int nranks);
+    ~DeviceElementBlock();
+    DeviceElementBlock(const DeviceElementBlock&) = delete;
+    DeviceElementBlock& operator=(const DeviceElementBlock&) = delete;
+
+    /// true if (cell type, material) are on the device path; otherwise the caller keeps the CPU loop
+    static bool supported(int celltype, int material_kind);
+
+    void set_block(const ElementBlockView& block);
+    /// Mat::So3Material of the block: kind + parameters (+ optional per-element field, see
+    /// 4C_mat_elast_isoneohooke.cpp:15-18)
+    void set_material(int kind, const std::vector<double>& params, const double* per_element = nullptr);
+    void set_graph(const ElementBlockView& block, const CrsView& crs);
+    void set_import(const ImportView& imp);
+    void init_communicator(const char* nccl_id128);  // id from rank 0's nccl_unique_id(), MPI_Bcast by 4C
+    std::string nccl_unique_id();
+
+    /// discret().set_state("displacement", u): u on the dof ROW map (host pointer)
+    void set_state(const double* u_row) { u_row_ = u_row; }
+    /// discret().evaluate(p{action}, stiff, nullptr, fint, ...): adds nothing on the host; overwrites
+    /// crs.values (zero + assemble) and f_row with the device result.  Throws Exception with the
+    /// reference's message text on det J <= 0.
+    void evaluate(Action action, double* crs_values, double* f_row);
+
+    std::int64_t nnz() const;
+    std::int64_t n_rows() const;
+    b200s_ctx* context() { return ctx_; }
+
+   private:
+    void check(int rc) const;
+    b200s_ctx* ctx_ = nullptr;
+    const double* u_row_ = nullptr;
+  };
+}  // namespace B200Solid
