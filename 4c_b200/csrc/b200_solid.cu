@@ -13,6 +13,7 @@
 
 #include "../../include/b200_solid.h"
 #include "hex8_kernel.cuh"
+#include "tet10_kernel.cuh"
 #include "shape_tables.hpp"
 
 namespace b200s
@@ -27,6 +28,13 @@ namespace b200s
     double w[8];
   };
   __constant__ Hex8Const c_hex8;
+  struct Tet10Const
+  {
+    double dN_gp[4 * 30];
+    double dN_node[10 * 30];
+    double w[4];
+  };
+  __constant__ Tet10Const c_tet10;
 
   // ------------------------------------------------------------------------------------------------
   // hex8 evaluate + assemble kernel (see hex8_kernel.cuh for the phase structure)
@@ -200,6 +208,161 @@ namespace b200s
     }
 
     // error word: warp reduce, one atomic per warp and quantity
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      detJ_min = fmin(detJ_min, __shfl_xor_sync(0xffffffffu, detJ_min, o));
+      detF_min = fmin(detF_min, __shfl_xor_sync(0xffffffffu, detF_min, o));
+    }
+    if (lane == 0)
+    {
+      atomic_min_double(&A.err->min_detJ, detJ_min);
+      atomic_min_double(&A.err->min_detF, detF_min);
+      if (nbad)
+      {
+        atomicMin(&A.err->first_bad, bad);
+        atomicAdd(&A.err->n_neg_jac, (unsigned long long)nbad);
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------------
+  // tet10 evaluate + assemble kernel (see tet10_kernel.cuh; same gather pipeline as hex8)
+  // ------------------------------------------------------------------------------------------------
+  constexpr int TET10_WARPS = 4;
+  constexpr size_t tet10_warp_bytes = (size_t)tet10::WARP_BYTES;
+  constexpr size_t tet10_table_bytes = (size_t)(tet10::TAB_GP_SIZE + tet10::TAB_NODE_SIZE + 4) * 8;
+  constexpr size_t tet10_smem_bytes = tet10_table_bytes + TET10_WARPS * tet10_warp_bytes;
+  static_assert(tet10_warp_bytes % 16 == 0 && tet10_table_bytes % 16 == 0, "16-byte aligned carve-up");
+
+  namespace tet10
+  {
+    __device__ __forceinline__ int load_node(const EvalArgs& A, int lane, int64_t tile, int64_t n_tiles)
+    {
+      const int el = lane / NN;
+      if (tile >= n_tiles || el >= EPW) return -1;
+      const int64_t e = tile * EPW + el;
+      return e < A.n_ele ? __ldg(A.conn + e * NN + (lane - el * NN)) : -1;
+    }
+    __device__ __forceinline__ void issue_xu(const EvalArgs& A, const WarpSmem& S, int lane, int node)
+    {
+      if (node < 0)
+      {
+        gather_pad(S, lane);
+        return;
+      }
+      const int el = lane / NN, q = lane - el * NN;
+      double* xu = S.xu + el * XU_ESTRIDE + 3 * q;
+      const double* gx = A.X + 3 * (int64_t)node;
+      const double* gu = A.u + 3 * (int64_t)node;
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+      {
+        cp_async8(xu + d, gx + d);
+        cp_async8(xu + NDOF + d, gu + d);
+      }
+    }
+    __device__ __forceinline__ void issue_rowpos(
+        const EvalArgs& A, const WarpSmem& S, int lane, int node, int64_t tile)
+    {
+      if (node >= 0)
+        cp_async16(S.nrow + lane, A.node_row + node);
+      else
+        S.nrow[lane].rowstart = -1, S.nrow[lane].rowlen = 0, S.nrow[lane].frow = -1;
+      const int64_t e0 = tile * EPW;
+#pragma unroll
+      for (int h = 0; h < 3; ++h)
+      {
+        const int chunk = lane + 32 * h;  // 16-byte chunk of the tile's 1200-byte map; 25 chunks / element
+        if (chunk < POS_INTS / 4 && e0 + chunk / 25 < A.n_ele)
+          cp_async16(S.pos + 4 * chunk, A.pos + e0 * (NN * NN) + 4 * chunk);
+      }
+    }
+  }  // namespace tet10
+
+  template <int MAT, bool STIFF>
+  __global__ void __launch_bounds__(TET10_WARPS * 32, 2) k_tet10_eval_assemble(const EvalArgs A)
+  {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* tab_gp = reinterpret_cast<double*>(smem_raw);
+    double* tab_node = tab_gp + tet10::TAB_GP_SIZE;
+    double* wgt = tab_node + tet10::TAB_NODE_SIZE;
+    for (int t = threadIdx.x; t < 10 * 30; t += blockDim.x)
+    {
+      if (t < 4 * 30) tab_gp[(t / 30) * tet10::TAB_STRIDE + (t % 30)] = c_tet10.dN_gp[t];
+      tab_node[(t / 30) * tet10::TAB_STRIDE + (t % 30)] = c_tet10.dN_node[t];
+    }
+    if (threadIdx.x < 4) wgt[threadIdx.x] = c_tet10.w[threadIdx.x];
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* wbase = smem_raw + tet10_table_bytes + warp * tet10_warp_bytes;
+    tet10::WarpSmem S;
+    S.mp = reinterpret_cast<double*>(wbase);
+    S.g = S.mp + tet10::MP_SIZE;
+    S.xu = S.mp + tet10::STAGE_SIZE;
+    S.nrow = reinterpret_cast<NodeRow*>(S.xu + tet10::XU_SIZE);
+    S.pos = reinterpret_cast<int32_t*>(S.nrow + 32);
+
+    const int64_t n_tiles = (A.n_ele + tet10::EPW - 1) / tet10::EPW;
+    const int64_t wstride = (int64_t)gridDim.x * TET10_WARPS;
+    const int my_el = lane / tet10::NN;
+    double detJ_min = 1e300, detF_min = 1e300;
+    long long bad = LLONG_MAX;
+    unsigned int nbad = 0;
+
+    int64_t tile = (int64_t)blockIdx.x * TET10_WARPS + warp;
+    int node_next = tet10::load_node(A, lane, tile, n_tiles);
+    if (tile < n_tiles) tet10::issue_xu(A, S, lane, node_next);
+    cp_async_commit();
+    if (tile < n_tiles) tet10::issue_rowpos(A, S, lane, node_next, tile);
+    cp_async_commit();
+    node_next = tet10::load_node(A, lane, tile + wstride, n_tiles);
+
+    for (; tile < n_tiles; tile += wstride)
+    {
+      const int64_t e0 = tile * tet10::EPW;
+      cp_async_wait_but_last();
+      __syncwarp();
+      const int node_next2 = tet10::load_node(A, lane, tile + 2 * wstride, n_tiles);
+      const bool live = my_el < tet10::EPW && e0 + my_el < A.n_ele;
+      // nodal Jacobian check: lane = (element, node)
+      const double dJn = tet10::node_jacobian_det(S, tab_node, lane);
+      const bool neg = live && !(dJn > 0.0);
+      double out54[54];
+      double dJ, dF;
+      tet10::phase1<MAT, STIFF>(A, S, tab_gp, wgt, lane, e0, out54, dJ, dF);
+      if (live)
+      {
+        detJ_min = fmin(detJ_min, fmin(dJn, dJ));
+        detF_min = fmin(detF_min, dF);
+      }
+      const unsigned negmask = __ballot_sync(0xffffffffu, neg);
+      if (negmask)
+        for (int el = 0; el < tet10::EPW; ++el)
+          if ((negmask >> (tet10::NN * el)) & 0x3ffu)
+          {
+            ++nbad;
+            const long long id = A.ele_id ? (long long)A.ele_id[e0 + el] : (long long)(e0 + el);
+            bad = min(bad, id);
+          }
+      __syncwarp();
+      if (tile + wstride < n_tiles) tet10::issue_xu(A, S, lane, node_next);
+      cp_async_commit();
+      tet10::phase1_store<STIFF>(S, lane, out54);
+      __syncwarp();
+      double Kacc[tet10::NBLK][9], facc[3];
+      tet10::phase2<STIFF>(S, lane, Kacc, facc);
+      __syncwarp();
+      tet10::stage_ke<STIFF>(S, lane, Kacc, facc);
+      cp_async_wait_but_last();
+      __syncwarp();
+      if (A.scatter_mode == 0) tet10::scatter<STIFF>(A, S, lane, e0);
+      __syncwarp();
+      if (tile + wstride < n_tiles) tet10::issue_rowpos(A, S, lane, node_next, tile + wstride);
+      cp_async_commit();
+      node_next = node_next2;
+    }
+
     for (int o = 16; o > 0; o >>= 1)
     {
       detJ_min = fmin(detJ_min, __shfl_xor_sync(0xffffffffu, detJ_min, o));
@@ -711,17 +874,51 @@ namespace
     return 0;
   }
 
+  template <int MAT, bool STIFF>
+  static int launch_tet10(b200s_ctx* ctx, const EvalArgs& A)
+  {
+    auto kern = k_tet10_eval_assemble<MAT, STIFF>;
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+      if (set_smem_attr(kern, tet10_smem_bytes))
+        return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", tet10_smem_bytes);
+      attr_set = true;
+    }
+    const int64_t n_tiles = (A.n_ele + tet10::EPW - 1) / tet10::EPW;
+    int64_t grid = (n_tiles + TET10_WARPS - 1) / TET10_WARPS;
+    const int64_t cap = (int64_t)ctx->n_sm * ctx->ctas_per_sm;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, TET10_WARPS * 32, tet10_smem_bytes, ctx->stream>>>(A);
+    ctx->launches += 1;
+    return 0;
+  }
+
+  template <int MAT, bool STIFF>
+  static int launch_cell(b200s_ctx* ctx, const EvalArgs& A)
+  {
+    switch (ctx->celltype)
+    {
+      case B200S_HEX8:
+        return launch_hex8<MAT, STIFF>(ctx, A);
+      case B200S_TET10:
+        return launch_tet10<MAT, STIFF>(ctx, A);
+    }
+    return fail(ctx, B200S_ERR_UNSUPPORTED, "cell type %d has no device kernel", ctx->celltype);
+  }
+
   template <bool STIFF>
   static int launch_eval(b200s_ctx* ctx, const EvalArgs& A)
   {
     switch (ctx->matkind)
     {
       case B200S_MAT_COUP_NEOHOOKE:
-        return launch_hex8<MAT_COUP_NEOHOOKE, STIFF>(ctx, A);
+        return launch_cell<MAT_COUP_NEOHOOKE, STIFF>(ctx, A);
       case B200S_MAT_ISO_VOL:
-        return launch_hex8<MAT_ISO_VOL, STIFF>(ctx, A);
+        return launch_cell<MAT_ISO_VOL, STIFF>(ctx, A);
       case B200S_MAT_SVK:
-        return launch_hex8<MAT_SVK, STIFF>(ctx, A);
+        return launch_cell<MAT_SVK, STIFF>(ctx, A);
     }
     return fail(ctx, B200S_ERR_INVALID, "material not set");
   }
@@ -797,7 +994,7 @@ extern "C"
   {
     if (!ctx || !X || !conn || n_col_nodes <= 0 || n_col_eles < 0) return B200S_ERR_INVALID;
     cudaSetDevice(ctx->device);
-    if (celltype != B200S_HEX8)
+    if (celltype != B200S_HEX8 && celltype != B200S_TET10)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "cell type %d is not on the device path yet", celltype);
     if (n_col_nodes > INT32_MAX / 3) return fail(ctx, B200S_ERR_INVALID, "too many column nodes");
     const CellTables T = make_cell_tables(celltype);
@@ -814,6 +1011,16 @@ extern "C"
       memcpy(h.dN_node, T.dN_node.data(), sizeof h.dN_node);
       memcpy(h.w, T.w.data(), sizeof h.w);
       CK(cudaMemcpyToSymbolAsync(c_hex8, &h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
+    else if (celltype == B200S_TET10)
+    {
+      Tet10Const h;
+      memcpy(h.dN_gp, T.dN_gp.data(), sizeof h.dN_gp);
+      memcpy(h.dN_node, T.dN_node.data(), sizeof h.dN_node);
+      memcpy(h.w, T.w.data(), sizeof h.w);
+      CK(cudaMemcpyToSymbolAsync(c_tet10, &h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
     }
     dfree(ctx->d_ele_id);
     if (ctx->reorder && n_col_eles > 1)

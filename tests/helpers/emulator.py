@@ -8,20 +8,19 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CPP = os.path.join(os.path.dirname(_HERE), "cpp")
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        so = os.path.join(_CPP, "libemu_hex8.so")
-        srcs = [os.path.join(_CPP, "emulate_hex8.cpp")] + [
+def lib(cell="hex8"):
+    if cell not in _libs:
+        so = os.path.join(_CPP, f"libemu_{cell}.so")
+        srcs = [os.path.join(_CPP, f"emulate_{cell}.cpp")] + [
             os.path.join(_CPP, "..", "..", "4c_b200", "csrc", f)
-            for f in ("hex8_kernel.cuh", "solid_math.cuh", "shape_tables.hpp")]
+            for f in ("hex8_kernel.cuh", "tet10_kernel.cuh", "solid_math.cuh", "shape_tables.hpp")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", so, srcs[0]])
-        _lib = C.CDLL(so)
-    return _lib
+        _libs[cell] = C.CDLL(so)
+    return _libs[cell]
 
 
 def scatter_map(conn, rowptr, colind, node_row_lid, node_col_lid):
@@ -53,7 +52,7 @@ def scatter_map(conn, rowptr, colind, node_row_lid, node_col_lid):
 
 
 def evaluate(matkind, params, conn, X, u_col, rowptr, colind, node_row_lid, node_col_lid, n_row_nodes,
-             stiff=True, per_ele=None):
+             stiff=True, per_ele=None, cell="hex8"):
     conn = np.ascontiguousarray(conn, np.int32)
     X = np.ascontiguousarray(X, np.float64)
     u_col = np.ascontiguousarray(u_col, np.float64)
@@ -66,7 +65,7 @@ def evaluate(matkind, params, conn, X, u_col, rowptr, colind, node_row_lid, node
     p = lambda a: None if a is None else a.ctypes.data_as(vp)
     if per_ele is not None:
         per_ele = np.ascontiguousarray(per_ele, np.float64)
-    rc = lib().emu_hex8(C.c_int(matkind), p(params), p(per_ele), C.c_int(int(stiff)),
+    rc = getattr(lib(cell), f"emu_{cell}")(C.c_int(matkind), p(params), p(per_ele), C.c_int(int(stiff)),
                         C.c_int64(conn.shape[0]), p(conn), p(X), p(u_col), p(pos), p(rowstart),
                         p(rowlen), p(frow), C.c_int64(len(rowstart)), p(vals), p(f), C.byref(dJ), C.byref(dF), C.byref(nb))
     assert rc == 0

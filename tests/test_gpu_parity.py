@@ -202,3 +202,83 @@ def test_full_size_properties_1M_hex8():
     ok, wK, wf = b200.parity_report(o_rowptr, K[lo:hi], rK, f[full_rows], rf, RTOL)
     assert ok and nbad == 0, (wK, wf)
     asm.close()
+
+
+# ---- tet10 (BASELINE config 4: unstructured, jittered, randomly renumbered; iso/vol Neo-Hooke) ----
+@pytest.mark.parametrize("mk", list(MATS))
+@pytest.mark.parametrize("n", [1, 3, 6])
+def test_tet10_matches_oracle(mk, n):
+    X, conn = b200.mesh.unstructured_tet10(n)
+    rm = b200.partition.serial_mesh(b200.mesh.TET10, X, conn)
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 1.0 / n)
+    per_ele = None
+    if mk == capi.MAT_ISO_VOL:
+        per_ele = 1.0 + 0.1 * np.arange(rm.n_col_eles) / rm.n_col_eles
+    asm = b200.DeviceAssembler(rm, mk, MATS[mk], per_ele_param=per_ele)
+    rowptr, colind = asm.graph()
+    o_rowptr, o_colind = orc.build_graph(orc.TET10, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    assert rowptr.tobytes() == o_rowptr.tobytes() and colind.tobytes() == o_colind.tobytes()
+    asm.set_state("displacement", u.ravel())
+    K, f, err = asm.evaluate("struct_calc_nlnstiff")
+    rK, rf, nbad = orc.evaluate_assemble(orc.TET10, mk, MATS[mk], rm.conn, rm.X.ravel(), u.ravel(),
+                                         rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, rowptr, colind,
+                                         mue_per_ele=per_ele, nthreads=4)
+    ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
+    assert ok and nbad == 0, (wK, wf)
+    assert err.n_neg_jacobian == 0 and err.min_detJ > 0 and 0.5 < err.min_detF < 1.5
+    _, f2, _ = asm.evaluate("struct_calc_internalforce")
+    assert np.abs(f2 - rf).max() <= RTOL * np.abs(rf).max()
+    asm.close()
+
+
+def test_tet10_partitioned_rows_match_oracle():
+    """3-way node partition of the unstructured tet10 mesh: each rank's owned rows (ghost state supplied
+    whole) equal the oracle's owner-computes rows."""
+    X, conn = b200.mesh.unstructured_tet10(4)
+    rng = np.random.default_rng(5)
+    owner = (X[:, 0] * 2.999).astype(int).clip(0, 2)          # slabs in x
+    flip = rng.random(len(X)) < 0.05                           # ragged interfaces
+    owner[flip] = rng.integers(0, 3, flip.sum())
+    import ctypes
+    import torch
+    cudart = ctypes.CDLL("libcudart.so")
+    for rank in range(3):
+        rm = b200.partition.generic_partition(b200.mesh.TET10, X, conn, owner, rank, 3)
+        u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 0.25)
+        rm1 = b200.partition.RankMesh(**{**rm.__dict__, "nranks": 1, "rank": 0})
+        asm = b200.DeviceAssembler(rm1, capi.MAT_ISO_VOL, MATS[capi.MAT_ISO_VOL])
+        rowptr, colind = asm.graph()
+        o = orc.build_graph(orc.TET10, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+        assert rowptr.tobytes() == o[0].tobytes() and colind.tobytes() == o[1].tobytes()
+        ucol = torch.from_numpy(u.ravel().copy()).cuda()
+        cudart.cudaMemcpy(ctypes.c_void_p(asm.ctx.device_ptrs()["u_col"]), ctypes.c_void_p(ucol.data_ptr()),
+                          ctypes.c_size_t(ucol.numel() * 8), 3)
+        asm.set_state("displacement", u[:rm.n_row_nodes].ravel())
+        K, f, _ = asm.evaluate()
+        rK, rf, _ = orc.evaluate_assemble(orc.TET10, orc.MAT_ISO_VOL, MATS[capi.MAT_ISO_VOL], rm.conn,
+                                          rm.X.ravel(), u.ravel(), rm.node_row_lid, rm.node_col_lid,
+                                          rm.n_row_nodes, rowptr, colind, nthreads=4)
+        ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
+        assert ok, (rank, wK, wf)
+        asm.close()
+
+
+def test_golden_tet10_integration_through_cuda_path():
+    case = json.load(open(os.path.join(G, "integration_tet10.json")))
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    rm = b200.partition.serial_mesh(b200.mesh.TET10, X, conn)
+    mat = case["material"]
+    assert mat["kind"] == "ELAST_CoupNeoHooke"
+    asm = b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, [mat["YOUNG"], mat["NUE"]])
+    rowptr, colind = asm.graph()
+
+    def evaluate(u):
+        asm.set_state("displacement", u)
+        K, f, _ = asm.evaluate()
+        return rowptr, colind, K, f
+
+    u = solve_case(case, evaluate)
+    for e in case["expected_disp"]:
+        assert abs(u[e["node"], e["dof"]] - e["value"]) < e["tol"], e
+    asm.close()

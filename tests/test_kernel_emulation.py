@@ -88,3 +88,34 @@ def test_hex8_corner_jacobian_shortcut_is_exact():
             st = 0.5 if (g & 4) else -0.5
             J_short = np.stack([sr * (X[g] - X[g ^ 1]), ss * (X[g] - X[g ^ 3]), st * (X[g] - X[g ^ 4])])
             assert np.array_equal(J_full, J_short)
+
+
+def _tet_case(n, renumber=True):
+    X, conn = b200.mesh.unstructured_tet10(n, renumber=renumber)
+    rm = b200.partition.serial_mesh(b200.mesh.TET10, X, conn)
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 1.0 / n)
+    rowptr, colind = orc.build_graph(orc.TET10, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    return rm, u, rowptr, colind
+
+
+@pytest.mark.parametrize("mk", list(MATS))
+@pytest.mark.parametrize("n", [1, 2])
+def test_emulated_tet10_kernel_matches_oracle(mk, n):
+    rm, u, rowptr, colind = _tet_case(n)
+    per_ele = None
+    if mk == orc.MAT_ISO_VOL:
+        per_ele = 1.0 + 0.1 * np.arange(rm.n_col_eles) / rm.n_col_eles
+    ref_K, ref_f, nbad = orc.evaluate_assemble(orc.TET10, mk, MATS[mk], rm.conn, rm.X.ravel(), u.ravel(),
+                                               rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, rowptr,
+                                               colind, mue_per_ele=per_ele)
+    assert nbad == 0
+    K, f, info = emu.evaluate(mk, MATS[mk], rm.conn, rm.X.ravel(), u.ravel(), rowptr, colind,
+                              rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, per_ele=per_ele, cell="tet10")
+    ok, rK, rf = b200.parity_report(rowptr, K, ref_K, f, ref_f, 1e-12)
+    assert ok, (rK, rf)
+    assert info["n_bad"] == 0 and info["min_detJ"] > 0 and 0.5 < info["min_detF"] < 1.5
+    # force only
+    _, f2, _ = emu.evaluate(mk, MATS[mk], rm.conn, rm.X.ravel(), u.ravel(), rowptr, colind,
+                            rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, stiff=False, per_ele=per_ele,
+                            cell="tet10")
+    assert np.abs(f2 - ref_f).max() <= 1e-12 * np.abs(ref_f).max()
