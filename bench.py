@@ -32,13 +32,22 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "hex8 Neo-Hooke element evaluate+assemble (force + tangent stiffness into CSR), FP64"
 UNIT = "elements/s"
-MAT_PAR = [200.0, 0.25]           # CoupNeoHooke YOUNG, NUE (tests/performance_tests/solid_hex8.4C.yaml:44-53)
-# SURVEY.md 8(d) / Appendix B algorithmic model, per hex8 element
-FLOPS_PER_ELE = 63.8e3            # (62 n^2 + 228 n + 1183 + 1000) * 8 Gauss points, n = 8
-BYTES_PER_ELE = 2304.0            # conn 32 + X,u 48 + scatter map 256 + K 1944 + f 24
 L2_BYTES = 126e6
+# Workloads = BASELINE.json configs 2 (default, the one the metric is quoted on), 3 and 4.  flops / bytes per
+# element: SURVEY.md 8(d) / Appendix B algorithmic model (62 n^2 + 228 n + 1183 + M per Gauss point).
+WORKLOADS = {
+    "hex8": dict(config="2", cell="HEX8", mat="MAT_COUP_NEOHOOKE", par=[200.0, 0.25], matname="CoupNeoHooke (E=200, nu=0.25)",
+                 flops=63.8e3, bytes=2304.0, kernel="k_hex8_eval_assemble<COUP_NEOHOOKE,STIFF>", default_n=100,
+                 metric="hex8 Neo-Hooke element evaluate+assemble (force + tangent stiffness into CSR), FP64"),
+    "tet10": dict(config="4", cell="TET10", mat="MAT_ISO_VOL", par=[1.0, 1000.0],
+                  matname="IsoNeoHooke mu=1 + VolSussmanBathe kappa=1000", flops=43.3e3, bytes=3300.0,
+                  kernel="k_tet10_eval_assemble<ISO_VOL,STIFF>", default_n=87,
+                  metric="tet10 iso/vol Neo-Hooke element evaluate+assemble (force + tangent stiffness into CSR), FP64"),
+    "hex27": dict(config="3", cell="HEX27", mat="MAT_SVK", par=[1000.0, 0.3], matname="St.Venant-Kirchhoff (E=1000, nu=0.3)",
+                  flops=1.419e6, bytes=40e3, kernel="k_hex27_eval_assemble<SVK,STIFF>", default_n=80,
+                  metric="hex27 St.Venant-Kirchhoff element evaluate+assemble (force + tangent stiffness into CSR), FP64"),
+}
 
 
 def host_threads():
@@ -114,48 +123,69 @@ def global_box(per_gpu_n, nranks):
     return n, tuple(m * per_gpu_n / 100.0 for m in mult)  # h = 0.01 as in config 2
 
 
-def build_rank(per_gpu_n, rank, nranks):
+def build_rank(wl, per_gpu_n, rank, nranks):
+    """Rank-local mesh + displacement state of the workload; returns (rank mesh, u on column nodes, label)."""
     b200 = importlib.import_module("4c_b200")
+    cell = getattr(b200.mesh, wl["cell"])
+    if wl["cell"] == "TET10":
+        if nranks != 1:
+            raise SystemExit("the tet10 workload (config 4) is a single-GPU configuration")
+        X, conn = b200.mesh.unstructured_tet10(per_gpu_n)
+        rm = b200.partition.serial_mesh(cell, X, conn)
+        u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 1.0 / per_gpu_n)
+        return rm, u, f"unstructured tet10 ({per_gpu_n}^3 hex cells x 6, jittered, randomly renumbered)"
     n, box = global_box(per_gpu_n, nranks)
-    rm = b200.partition.box_partition(b200.mesh.HEX8, n, rank, nranks, box=box)
+    rm = b200.partition.box_partition(cell, n, rank, nranks, box=box)
     u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 0.01)
-    return rm, u, n
+    return rm, u, f"structured {wl['cell'].lower()} cube {n[0]}x{n[1]}x{n[2]}"
 
 
 # ------------------------------------------------------------------------------------------------
 # CPU arms (the only place outside tests/ and smoke() that executes oracle/)
 # ------------------------------------------------------------------------------------------------
 class CpuArm:
-    def __init__(self, n_sample):
+    def __init__(self, wl, n_sample):
         b200 = importlib.import_module("4c_b200")
         from oracle import oracle as orc
-        self.orc = orc
+        self.orc, self.wl = orc, wl
         self.kind = "reference" if orc.ref_lib() is not None else "port"
         self.impl = "ref" if self.kind == "reference" else "oracle"
-        n = (n_sample,) * 3
-        self.rm = b200.partition.box_partition(b200.mesh.HEX8, n, 0, 1, box=tuple(x / 100.0 for x in n))
-        self.u = b200.mesh.displacement_field(self.rm.X, self.rm.node_gid, 1.0, 0.01)
-        self.graph = orc.build_graph(orc.HEX8, self.rm.conn, self.rm.node_row_lid, self.rm.node_col_lid,
+        self.ct, self.mk = getattr(orc, wl["cell"]), getattr(orc, wl["mat"])
+        if wl["cell"] == "TET10":
+            X, conn = b200.mesh.unstructured_tet10(n_sample)
+            self.rm = b200.partition.serial_mesh(b200.mesh.TET10, X, conn)
+            self.u = b200.mesh.displacement_field(self.rm.X, self.rm.node_gid, 1.0, 1.0 / n_sample)
+        else:
+            n = (n_sample,) * 3
+            self.rm = b200.partition.box_partition(getattr(b200.mesh, wl["cell"]), n, 0, 1,
+                                                   box=tuple(x / 100.0 for x in n))
+            self.u = b200.mesh.displacement_field(self.rm.X, self.rm.node_gid, 1.0, 0.01)
+        self.graph = orc.build_graph(self.ct, self.rm.conn, self.rm.node_row_lid, self.rm.node_col_lid,
                                      self.rm.n_row_nodes)
         self.n_sample = n_sample
 
     def step(self, threads):
         rm, orc = self.rm, self.orc
         t = time.perf_counter()
-        orc.evaluate_assemble(orc.HEX8, orc.MAT_COUP_NEOHOOKE, MAT_PAR, rm.conn, rm.X.ravel(), self.u.ravel(),
+        orc.evaluate_assemble(self.ct, self.mk, self.wl["par"], rm.conn, rm.X.ravel(), self.u.ravel(),
                               rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, self.graph[0], self.graph[1],
                               nthreads=threads, impl=self.impl)
         return time.perf_counter() - t
 
     def describe(self):
-        return (f"{self.n_sample}^3 = {self.rm.n_col_eles} hex8 Neo-Hooke elements of the same mesh family "
-                f"(h=0.01, same displacement recipe), zero + evaluate + owner-computes assembly")
+        return (f"{self.rm.n_col_eles} {self.wl['cell'].lower()} {self.wl['matname']} elements of the same mesh "
+                f"family (edge parameter {self.n_sample}, same displacement recipe), zero + evaluate + "
+                f"owner-computes assembly")
 
 
-def cpu_sample_size(threads, target_s):
-    """Sub-cube edge so that one CPU step takes about target_s (33k elements/s/thread measured)."""
-    ne = 30e3 * max(threads, 1) * 0.7 * target_s
-    return int(max(8, min(100, round(ne ** (1.0 / 3.0)))))
+def cpu_sample_size(wl, threads, target_s):
+    """Mesh edge parameter so that one CPU step takes about target_s (hex8: 33k elements/s/thread with
+    oracle/_ref measured; scaled by the flop model for the other cells)."""
+    rate = {"HEX8": 30e3, "TET10": 7e3, "HEX27": 1.3e3}[wl["cell"]]  # elements/s/thread, measured
+    ne = rate * max(threads, 1) * 0.7 * target_s
+    if wl["cell"] == "TET10":
+        ne /= 6.0
+    return int(max(4, min(wl["default_n"], round(ne ** (1.0 / 3.0)))))
 
 
 def run_reference(args):
@@ -163,7 +193,9 @@ def run_reference(args):
     if rank != 0:
         return 0
     threads = host_threads()
-    arm = CpuArm(cpu_sample_size(threads, 1.0))
+    wl = WORKLOADS[args.workload]
+    METRIC = wl["metric"]
+    arm = CpuArm(wl, cpu_sample_size(wl, threads, 1.0))
     for _ in range(args.warmup):
         arm.step(threads)
     ts = [arm.step(threads) for _ in range(args.steps)]
@@ -173,7 +205,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "BASELINE config 2 (structured hex8 CoupNeoHooke E=200 nu=0.25 cube, 1M elements); "
+        "config": {"workload": f"BASELINE config {wl['config']} ({wl['cell'].lower()}, {wl['matname']}); "
                                "each step is a bounded sample: " + arm.describe(),
                    "l2": "n/a (CPU)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": arm.kind, "sample": arm.describe()},
@@ -212,8 +244,12 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    rm, u, n_global = build_rank(args.per_gpu_n, rank, world)
-    asm = b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, MAT_PAR, device=local)
+    wl = WORKLOADS[args.workload]
+    METRIC = wl["metric"]
+    FLOPS_PER_ELE, BYTES_PER_ELE = wl["flops"], wl["bytes"]
+    per_gpu_n = args.per_gpu_n or wl["default_n"]
+    rm, u, mesh_label = build_rank(wl, per_gpu_n, rank, world)
+    asm = b200.DeviceAssembler(rm, getattr(capi, wl["mat"]), wl["par"], device=local)
     ctx = asm.ctx
     if world > 1:
         uid = [ctx.nccl_unique_id() if rank == 0 else None]
@@ -253,7 +289,7 @@ def run_b200(args):
     def step_e2e():
         ctx.evaluate(capi.ACTION_NLNSTIFF, hb["u"], hb["K"], hb["f"])
 
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if rank == 0 else None  # covers the device arm AND the e2e arm
     # ---- device-resident arm ----------------------------------------------------------------
     for _ in range(args.warmup):
         step_dev()
@@ -262,7 +298,6 @@ def run_b200(args):
     l0 = ctx.launch_count()
     t0 = sampler.mark() if sampler else 0
     ms_dev = timed(step_dev, args.steps)
-    t1 = sampler.mark() if sampler else 0
     _, err = ctx.synchronize()
     launches = ctx.launch_count() - l0
     ksum, kcnt = ctx.kernel_time(reset=True)
@@ -272,6 +307,7 @@ def run_b200(args):
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, e2e_steps)
+    t1 = sampler.mark() if sampler else 0
     clocks = sampler.stop(t0, t1) if sampler else None
 
     tot_eles = torch.tensor([rm.n_row_eles, rm.n_col_eles], dtype=torch.float64, device="cuda")
@@ -289,11 +325,12 @@ def run_b200(args):
         ach_tf = FLOPS_PER_ELE * eps_kernel / 1e12
         ach_gbs = BYTES_PER_ELE * eps_kernel / 1e9
         roof = {
-            "bound": "fp64", "kernel": "k_hex8_eval_assemble<COUP_NEOHOOKE,STIFF>",
+            "bound": "fp64", "kernel": wl["kernel"],
             "achieved": ach_tf, "peak": fp64_tf, "unit": "TFLOP/s", "frac": ach_tf / fp64_tf,
             "peak_source": "DFMA microbenchmark run in this process (b200s_measure_fp64_peak, implied "
                            f"{fp64_mhz:.0f} MHz); MEASURED_PEAKS.json holds no FP64 figure",
-            "model": "SURVEY 8(d): 63.8 kflop and 2304 B per hex8 element (algorithmic, full non-symmetric K_e)",
+            "model": f"SURVEY 8(d): {FLOPS_PER_ELE / 1e3:.1f} kflop and {BYTES_PER_ELE:.0f} B per {wl['cell'].lower()} "
+                     "element (algorithmic, full non-symmetric K_e)",
             "kernel_ms": k_ms, "kernel_launches_timed": kcnt,
             "traffic": args.traffic_bytes,
             "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -302,7 +339,7 @@ def run_b200(args):
         cpu = None
         if world == 1 and not args.no_cpu:
             threads = host_threads()
-            arm = CpuArm(cpu_sample_size(threads, 3.0))
+            arm = CpuArm(wl, cpu_sample_size(wl, threads, 3.0))
             arm.step(threads)
             ts = [arm.step(threads) for _ in range(3)]
             cpu = {"value": arm.rm.n_col_eles / float(np.median(ts)), "unit": UNIT, "cores": threads,
@@ -312,12 +349,11 @@ def run_b200(args):
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": f"BASELINE config {'2' if world == 1 and args.per_gpu_n == 100 else '5-style weak'}: "
-                            f"structured hex8 CoupNeoHooke (E=200, nu=0.25) cube {n_global[0]}x{n_global[1]}x"
-                            f"{n_global[2]} = {int(row_eles)} elements, {args.per_gpu_n}^3 per GPU, "
+                "workload": f"BASELINE config {wl['config'] if world == 1 else '5-style weak'}: {mesh_label}, "
+                            f"{wl['matname']}, {int(row_eles)} elements ({rm.n_row_eles} on rank 0), "
                             f"struct_calc_nlnstiff, nnz/rank={nnz}",
                 "partition": f"{world} box(es), owner-computes rows, {int(col_eles - row_eles)} ghost elements evaluated redundantly",
-                "l2": f"working set per step {8 * nnz / 1e6:.0f} MB of CSR values + {rm.n_col_eles * 256 / 1e6:.0f} MB "
+                "l2": f"working set per step {8 * nnz / 1e6:.0f} MB of CSR values + {rm.n_col_eles * rm.conn.shape[1] ** 2 * 4 / 1e6:.0f} MB "
                       f"scatter map > L2 ({L2_BYTES / 1e6:.0f} MB): inputs larger than L2, no explicit flush",
                 "timers_last_step_ms": {k: round(float(v), 4) for k, v in tim.items()},
             },
@@ -346,7 +382,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--per-gpu-n", type=int, default=100, help="edge of each rank's element box (100 -> 1M elements)")
+    ap.add_argument("--workload", default="hex8", choices=sorted(WORKLOADS),
+                    help="hex8 = BASELINE config 2 (default, the headline), tet10 = config 4, hex27 = config 3")
+    ap.add_argument("--per-gpu-n", type=int, default=0,
+                    help="edge parameter of each rank's mesh (default: the config's size; hex8 100 -> 1M elements)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--traffic-bytes", type=float, default=None,
