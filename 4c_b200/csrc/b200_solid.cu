@@ -14,6 +14,7 @@
 #include "../../include/b200_solid.h"
 #include "hex8_kernel.cuh"
 #include "tet10_kernel.cuh"
+#include "hex27_kernel.cuh"
 #include "shape_tables.hpp"
 
 namespace b200s
@@ -35,6 +36,13 @@ namespace b200s
     double w[4];
   };
   __constant__ Tet10Const c_tet10;
+  struct Hex27Const
+  {
+    double dN_gp[27 * 81];
+    double w[28];
+    hex27::IntTables it;
+  };
+  __device__ Hex27Const c_hex27;  // global memory (17.8 KB): copied to shared memory once per CTA
 
   // ------------------------------------------------------------------------------------------------
   // hex8 evaluate + assemble kernel (see hex8_kernel.cuh for the phase structure)
@@ -381,6 +389,169 @@ namespace b200s
   }
 
   // ------------------------------------------------------------------------------------------------
+  // hex27 evaluate + assemble kernel (see hex27_kernel.cuh): CTA = 4 warp pairs, one element per pair
+  // ------------------------------------------------------------------------------------------------
+  constexpr int HEX27_PAIRS = 4;
+  constexpr size_t hex27_table_bytes = (size_t)(hex27::TAB_SIZE + 1 + 28) * 8 + sizeof(hex27::IntTables);
+  constexpr size_t hex27_smem_bytes = hex27_table_bytes + HEX27_PAIRS * (size_t)hex27::PAIR_BYTES;
+  static_assert(hex27_table_bytes % 16 == 0, "16-byte aligned carve-up");
+  static_assert(hex27_smem_bytes <= 232448, "fits the 227 KB of dynamic shared memory per CTA");
+
+  namespace hex27
+  {
+    __device__ __forceinline__ void pair_barrier(int pair)
+    {
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
+    }
+    // pt = thread index inside the pair (0..63); threads 0..26 own node pt
+    __device__ __forceinline__ int load_node(const EvalArgs& A, int pt, int64_t e)
+    {
+      return (pt < NN && e < A.n_ele) ? __ldg(A.conn + e * NN + pt) : -1;
+    }
+    __device__ __forceinline__ void issue_xu(const EvalArgs& A, const PairSmem& S, int pt, int node)
+    {
+      if (node < 0) return;
+      double* xu = S.xu + 3 * pt;
+      const double* gx = A.X + 3 * (int64_t)node;
+      const double* gu = A.u + 3 * (int64_t)node;
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+      {
+        cp_async8(xu + d, gx + d);
+        cp_async8(xu + NDOF + d, gu + d);
+      }
+    }
+    __device__ __forceinline__ void issue_rowpos(
+        const EvalArgs& A, const PairSmem& S, int pt, int node, int64_t e)
+    {
+      if (node >= 0) cp_async16(S.nrow + pt, A.node_row + node);
+      if (e >= A.n_ele) return;
+#pragma unroll
+      for (int h = 0; h < 3; ++h)
+      {
+        const int chunk = pt + 64 * h;  // 183 chunks of 16 bytes
+        if (chunk < POS_STRIDE / 4) cp_async16(S.pos + 4 * chunk, A.pos + e * POS_STRIDE + 4 * chunk);
+      }
+    }
+  }  // namespace hex27
+
+  template <int MAT, bool STIFF>
+  __global__ void __launch_bounds__(HEX27_PAIRS * 64, 1) k_hex27_eval_assemble(const EvalArgs A)
+  {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* tab_gp = reinterpret_cast<double*>(smem_raw);
+    double* wgt = tab_gp + hex27::TAB_SIZE + 1;
+    hex27::IntTables* itab = reinterpret_cast<hex27::IntTables*>(wgt + 28);
+    int* flags = reinterpret_cast<int*>(itab->abc + 28);  // 4 spare ints of the table = per-pair flags
+    for (int t = threadIdx.x; t < hex27::TAB_SIZE; t += blockDim.x) tab_gp[t] = c_hex27.dN_gp[t];
+    if (threadIdx.x < 28) wgt[threadIdx.x] = c_hex27.w[threadIdx.x];
+    if (threadIdx.x < 32)
+    {
+      itab->abc[threadIdx.x] = threadIdx.x < 28 ? c_hex27.it.abc[threadIdx.x] : 0;
+      itab->node_of[threadIdx.x] = c_hex27.it.node_of[threadIdx.x];
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = warp >> 1, w = warp & 1, pt = (w << 5) | lane;
+    const hex27::PairSmem S =
+        hex27::carve(smem_raw + hex27_table_bytes + (size_t)pair * hex27::PAIR_BYTES);
+    double* stage = S.stage + w * hex27::STAGE_SIZE;
+
+    const int64_t stride = (int64_t)gridDim.x * HEX27_PAIRS;
+    double detJ_min = 1e300, detF_min = 1e300;
+    long long bad = LLONG_MAX;
+    unsigned int nbad = 0;
+
+    // Gauss point / node-check role of this lane in phase 1
+    const int my_gp = w == 0 ? (lane < hex27::GP_W0 ? lane : -1)
+                             : (lane < hex27::NGP - hex27::GP_W0 ? hex27::GP_W0 + lane : -1);
+    const int my_chk = w == 0 ? (lane >= hex27::GP_W0 ? lane - hex27::GP_W0 : -1)
+                              : (lane >= 13 && 18 + lane - 13 < hex27::NN ? 18 + lane - 13 : -1);
+
+    int64_t e = (int64_t)blockIdx.x * HEX27_PAIRS + pair;
+    int node_next = hex27::load_node(A, pt, e);
+    hex27::issue_xu(A, S, pt, node_next);
+    cp_async_commit();
+    hex27::issue_rowpos(A, S, pt, node_next, e);
+    cp_async_commit();
+    node_next = hex27::load_node(A, pt, e + stride);
+
+    for (; e < A.n_ele; e += stride)
+    {
+      cp_async_wait_but_last();
+      hex27::pair_barrier(pair);  // X,u of this element visible to both warps
+      const int node_next2 = hex27::load_node(A, pt, e + 2 * stride);
+      bool neg = false;
+      if (my_gp >= 0)
+      {
+        double out54[54];
+        double dJ, dF;
+        hex27::phase1<MAT, STIFF>(A, S, tab_gp, wgt, my_gp, e, out54, dJ, dF);
+        detJ_min = fmin(detJ_min, dJ);
+        detF_min = fmin(detF_min, dF);
+      }
+      else if (my_chk >= 0)
+      {
+        const double dJn = hex27::node_jacobian_det(S, *itab, my_chk);
+        detJ_min = fmin(detJ_min, dJn);
+        neg = !(dJn > 0.0);
+      }
+      if (__any_sync(0xffffffffu, neg) && lane == 0) atomicOr(&flags[pair], 1);
+      hex27::pair_barrier(pair);  // dN/dX, M, Pw complete; X,u free for the next element
+      if (pt == 0 && flags[pair])
+      {
+        flags[pair] = 0;
+        ++nbad;
+        const long long id = A.ele_id ? (long long)A.ele_id[e] : (long long)e;
+        bad = min(bad, id);
+      }
+      hex27::issue_xu(A, S, pt, node_next);
+      cp_async_commit();
+
+      double Kacc[hex27::NBLK][9], facc[3];
+      if (lane < hex27::NN) hex27::phase2<STIFF>(S, w, lane, Kacc, facc);
+      cp_async_wait_but_last();
+      hex27::pair_barrier(pair);  // row info / scatter map of this element visible to both warps
+      if (A.scatter_mode == 0)
+      {
+        if (STIFF)
+        {
+#pragma unroll
+          for (int s = 0; s < 2; ++s)
+          {
+            if (lane < hex27::NN) hex27::stage_blocks(stage, lane, s, Kacc);
+            __syncwarp();
+            hex27::scatter_blocks(A, S, stage, w, s, lane);
+            __syncwarp();
+          }
+        }
+        if (w == 0 && lane < hex27::NN) hex27::scatter_force(A, S, lane, facc);
+      }
+      hex27::pair_barrier(pair);  // everything of this element consumed
+      hex27::issue_rowpos(A, S, pt, node_next, e + stride);
+      cp_async_commit();
+      node_next = node_next2;
+    }
+
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      detJ_min = fmin(detJ_min, __shfl_xor_sync(0xffffffffu, detJ_min, o));
+      detF_min = fmin(detF_min, __shfl_xor_sync(0xffffffffu, detF_min, o));
+    }
+    if (lane == 0)
+    {
+      atomic_min_double(&A.err->min_detJ, detJ_min);
+      atomic_min_double(&A.err->min_detF, detF_min);
+      if (nbad)
+      {
+        atomicMin(&A.err->first_bad, bad);
+        atomicAdd(&A.err->n_neg_jac, (unsigned long long)nbad);
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------------
   // set-up kernels
   // ------------------------------------------------------------------------------------------------
   // ---- locality ordering of the elements (set_mesh) ----------------------------------------------
@@ -500,7 +671,7 @@ namespace b200s
 
   // element -> CSR slot map: pos[e][i][j] = offset of the 3 columns of node j inside each row of
   // node i (same lower_bound + stride-3 contiguity rule as SparseMatrix::assemble :404-441)
-  __global__ void k_build_scatter_map(int nn, int64_t n_ele, const int32_t* conn,
+  __global__ void k_build_scatter_map(int nn, int pos_stride, int64_t n_ele, const int32_t* conn,
       const int32_t* colind, const NodeRow* node_row, const int32_t* node_colbase, int32_t* pos,
       int* flag)
   {
@@ -511,7 +682,9 @@ namespace b200s
     const int32_t* ce = conn + e * nn;
     const NodeRow nr = node_row[ce[i]];
     const int64_t rs = nr.rowstart;
-    int32_t* out = pos + (e * nn + i) * nn;
+    int32_t* out = pos + e * pos_stride + i * nn;
+    if (i == 0)
+      for (int t = nn * nn; t < pos_stride; ++t) pos[e * pos_stride + t] = 0;  // 16-byte padding
     if (rs < 0)
     {
       for (int j = 0; j < nn; ++j) out[j] = -1;
@@ -746,7 +919,7 @@ struct b200s_ctx
   cudaStream_t stream = nullptr;
   std::string err;
   // mesh
-  int celltype = -1, nn = 0;
+  int celltype = -1, nn = 0, pos_stride = 0;
   int64_t n_col_nodes = 0, n_col_eles = 0;
   double* dX = nullptr;
   int32_t* dconn = nullptr;
@@ -896,10 +1069,31 @@ namespace
   }
 
   template <int MAT, bool STIFF>
+  static int launch_hex27(b200s_ctx* ctx, const EvalArgs& A)
+  {
+    auto kern = k_hex27_eval_assemble<MAT, STIFF>;
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+      if (set_smem_attr(kern, hex27_smem_bytes))
+        return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", hex27_smem_bytes);
+      attr_set = true;
+    }
+    int64_t grid = (A.n_ele + HEX27_PAIRS - 1) / HEX27_PAIRS;
+    if (grid > ctx->n_sm) grid = ctx->n_sm;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, HEX27_PAIRS * 64, hex27_smem_bytes, ctx->stream>>>(A);
+    ctx->launches += 1;
+    return 0;
+  }
+
+  template <int MAT, bool STIFF>
   static int launch_cell(b200s_ctx* ctx, const EvalArgs& A)
   {
     switch (ctx->celltype)
     {
+      case B200S_HEX27:
+        return launch_hex27<MAT, STIFF>(ctx, A);
       case B200S_HEX8:
         return launch_hex8<MAT, STIFF>(ctx, A);
       case B200S_TET10:
@@ -994,8 +1188,8 @@ extern "C"
   {
     if (!ctx || !X || !conn || n_col_nodes <= 0 || n_col_eles < 0) return B200S_ERR_INVALID;
     cudaSetDevice(ctx->device);
-    if (celltype != B200S_HEX8 && celltype != B200S_TET10)
-      return fail(ctx, B200S_ERR_UNSUPPORTED, "cell type %d is not on the device path yet", celltype);
+    if (celltype != B200S_HEX8 && celltype != B200S_TET10 && celltype != B200S_HEX27)
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "cell type %d is not on the device path", celltype);
     if (n_col_nodes > INT32_MAX / 3) return fail(ctx, B200S_ERR_INVALID, "too many column nodes");
     const CellTables T = make_cell_tables(celltype);
     ctx->celltype = celltype, ctx->nn = T.nn;
@@ -1011,6 +1205,22 @@ extern "C"
       memcpy(h.dN_node, T.dN_node.data(), sizeof h.dN_node);
       memcpy(h.w, T.w.data(), sizeof h.w);
       CK(cudaMemcpyToSymbolAsync(c_hex8, &h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
+    else if (celltype == B200S_HEX27)
+    {
+      static Hex27Const h;  // 18 KB: not on the stack
+      memset(&h, 0, sizeof h);
+      memcpy(h.dN_gp, T.dN_gp.data(), sizeof h.dN_gp);
+      memcpy(h.w, T.w.data(), 27 * sizeof(double));
+      const double(*hc)[3] = detail::hex_nodes();
+      for (int k = 0; k < 27; ++k)
+      {
+        const int a = (int)hc[k][0] + 1, b = (int)hc[k][1] + 1, c = (int)hc[k][2] + 1;
+        h.it.abc[k] = a | (b << 2) | (c << 4);
+        h.it.node_of[a + 3 * b + 9 * c] = k;
+      }
+      CK(cudaMemcpyToSymbolAsync(c_hex27, &h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
       CK(cudaStreamSynchronize(ctx->stream));
     }
     else if (celltype == B200S_TET10)
@@ -1102,7 +1312,8 @@ extern "C"
     ctx->n_rows = n_rows, ctx->nnz = nnz;
     if (to_device(ctx, &ctx->d_node_row, (const NodeRow*)nullptr, ncn)) return B200S_ERR_CUDA;
     if (to_device(ctx, &ctx->d_node_colbase, (const int32_t*)nullptr, ncn)) return B200S_ERR_CUDA;
-    if (to_device(ctx, &ctx->d_pos, (const int32_t*)nullptr, ctx->n_col_eles * ctx->nn * ctx->nn))
+    ctx->pos_stride = ctx->celltype == B200S_HEX27 ? hex27::POS_STRIDE : ctx->nn * ctx->nn;
+    if (to_device(ctx, &ctx->d_pos, (const int32_t*)nullptr, ctx->n_col_eles * ctx->pos_stride))
       return B200S_ERR_CUDA;
     if (to_device(ctx, &ctx->d_vals, (const double*)nullptr, nnz)) return B200S_ERR_CUDA;
     if (to_device(ctx, &ctx->d_f, (const double*)nullptr, n_rows)) return B200S_ERR_CUDA;
@@ -1114,7 +1325,7 @@ extern "C"
     k_node_rows<<<nblk(ncn), 256, 0, ctx->stream>>>(ncn, d_dof_row_lid, d_dof_col_lid, d_rowptr,
         n_rows, ctx->d_node_row, ctx->d_node_colbase, d_flag);
     k_build_scatter_map<<<nblk(ctx->n_col_eles * ctx->nn), 256, 0, ctx->stream>>>(ctx->nn,
-        ctx->n_col_eles, ctx->dconn, d_colind, ctx->d_node_row, ctx->d_node_colbase, ctx->d_pos,
+        ctx->pos_stride, ctx->n_col_eles, ctx->dconn, d_colind, ctx->d_node_row, ctx->d_node_colbase, ctx->d_pos,
         d_flag);
     ctx->launches += 2;
     int flag = 0;

@@ -282,3 +282,89 @@ def test_golden_tet10_integration_through_cuda_path():
     for e in case["expected_disp"]:
         assert abs(u[e["node"], e["dof"]] - e["value"]) < e["tol"], e
     asm.close()
+
+
+# ---- hex27 (BASELINE config 3: structured cube, St.Venant-Kirchhoff) ----------------------------
+@pytest.mark.parametrize("mk", list(MATS))
+@pytest.mark.parametrize("n", [(1, 1, 1), (3, 2, 2), (6, 5, 4)])
+def test_hex27_matches_oracle(mk, n):
+    rm = b200.partition.box_partition(b200.mesh.HEX27, n, 0, 1)
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 0.5 / max(n))
+    per_ele = None
+    if mk == capi.MAT_ISO_VOL:
+        per_ele = 1.0 + 0.1 * np.arange(rm.n_col_eles) / rm.n_col_eles
+    asm = b200.DeviceAssembler(rm, mk, MATS[mk], per_ele_param=per_ele)
+    rowptr, colind = asm.graph()
+    o_rowptr, o_colind = orc.build_graph(orc.HEX27, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    assert rowptr.tobytes() == o_rowptr.tobytes() and colind.tobytes() == o_colind.tobytes()
+    asm.set_state("displacement", u.ravel())
+    K, f, err = asm.evaluate("struct_calc_nlnstiff")
+    rK, rf, nbad = orc.evaluate_assemble(orc.HEX27, mk, MATS[mk], rm.conn, rm.X.ravel(), u.ravel(),
+                                         rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, rowptr, colind,
+                                         mue_per_ele=per_ele, nthreads=8)
+    ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
+    assert ok and nbad == 0, (wK, wf)
+    assert err.n_neg_jacobian == 0 and err.min_detJ > 0 and 0.5 < err.min_detF < 1.5
+    _, f2, _ = asm.evaluate("struct_calc_internalforce")
+    assert np.abs(f2 - rf).max() <= RTOL * np.abs(rf).max()
+    asm.close()
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_hex27_partitioned_rows_match_oracle(nranks):
+    import ctypes
+    import torch
+    cudart = ctypes.CDLL("libcudart.so")
+    n = (4, 3, 2)
+    for rank in range(nranks):
+        rm = b200.partition.box_partition(b200.mesh.HEX27, n, rank, nranks)
+        u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 0.1)
+        rm1 = b200.partition.RankMesh(**{**rm.__dict__, "nranks": 1, "rank": 0})
+        asm = b200.DeviceAssembler(rm1, capi.MAT_SVK, MATS[capi.MAT_SVK])
+        rowptr, colind = asm.graph()
+        o = orc.build_graph(orc.HEX27, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+        assert rowptr.tobytes() == o[0].tobytes() and colind.tobytes() == o[1].tobytes()
+        ucol = torch.from_numpy(u.ravel().copy()).cuda()
+        cudart.cudaMemcpy(ctypes.c_void_p(asm.ctx.device_ptrs()["u_col"]), ctypes.c_void_p(ucol.data_ptr()),
+                          ctypes.c_size_t(ucol.numel() * 8), 3)
+        asm.set_state("displacement", u[:rm.n_row_nodes].ravel())
+        K, f, _ = asm.evaluate()
+        rK, rf, _ = orc.evaluate_assemble(orc.HEX27, orc.MAT_SVK, MATS[capi.MAT_SVK], rm.conn, rm.X.ravel(),
+                                          u.ravel(), rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, rowptr,
+                                          colind, nthreads=4)
+        ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
+        assert ok, (rank, wK, wf)
+        asm.close()
+
+
+def test_golden_hex27_integration_through_cuda_path():
+    case = json.load(open(os.path.join(G, "integration_hex27.json")))
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    rm = b200.partition.serial_mesh(b200.mesh.HEX27, X, conn)
+    mat = case["material"]
+    assert mat["kind"] == "ELAST_CoupNeoHooke"
+    asm = b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, [mat["YOUNG"], mat["NUE"]])
+    rowptr, colind = asm.graph()
+
+    def evaluate(u):
+        asm.set_state("displacement", u)
+        K, f, _ = asm.evaluate()
+        return rowptr, colind, K, f
+
+    u = solve_case(case, evaluate)
+    for e in case["expected_disp"]:
+        assert abs(u[e["node"], e["dof"]] - e["value"]) < e["tol"], e
+    asm.close()
+
+
+def test_hex27_negative_jacobian_error_code():
+    rm = b200.partition.box_partition(b200.mesh.HEX27, (2, 1, 1), 0, 1)
+    X = rm.X.copy()
+    X[rm.conn[1, 6]] = X[rm.conn[1, 0]] - 0.3   # corner pulled through the element
+    rm.X = X
+    asm = b200.DeviceAssembler(rm, capi.MAT_SVK, [1000.0, 0.3])
+    asm.set_state("displacement", np.zeros(asm.n_rows))
+    rc, err = asm.ctx.evaluate(capi.ACTION_NLNSTIFF, asm._u, None, None, check=False)
+    assert rc == capi.ERR_NEG_JACOBIAN and err.n_neg_jacobian == 1 and err.first_bad_element == 1
+    asm.close()

@@ -119,3 +119,44 @@ def test_emulated_tet10_kernel_matches_oracle(mk, n):
                             rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, stiff=False, per_ele=per_ele,
                             cell="tet10")
     assert np.abs(f2 - ref_f).max() <= 1e-12 * np.abs(ref_f).max()
+
+
+@pytest.mark.parametrize("mk", list(MATS))
+@pytest.mark.parametrize("n", [(1, 1, 1), (2, 2, 1)])
+def test_emulated_hex27_kernel_matches_oracle(mk, n):
+    rm = b200.partition.box_partition(b200.mesh.HEX27, n, 0, 1)
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 0.5 / max(n))
+    rowptr, colind = orc.build_graph(orc.HEX27, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    per_ele = None
+    if mk == orc.MAT_ISO_VOL:
+        per_ele = 1.0 + 0.1 * np.arange(rm.n_col_eles)
+    ref_K, ref_f, nbad = orc.evaluate_assemble(orc.HEX27, mk, MATS[mk], rm.conn, rm.X.ravel(), u.ravel(),
+                                               rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, rowptr,
+                                               colind, mue_per_ele=per_ele)
+    assert nbad == 0
+    K, f, info = emu.evaluate(mk, MATS[mk], rm.conn, rm.X.ravel(), u.ravel(), rowptr, colind,
+                              rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, per_ele=per_ele, cell="hex27")
+    ok, rK, rf = b200.parity_report(rowptr, K, ref_K, f, ref_f, 1e-12)
+    assert ok, (rK, rf)
+    assert info["n_bad"] == 0 and info["min_detJ"] > 0 and 0.5 < info["min_detF"] < 1.5
+    _, f2, _ = emu.evaluate(mk, MATS[mk], rm.conn, rm.X.ravel(), u.ravel(), rowptr, colind,
+                            rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, stiff=False, per_ele=per_ele,
+                            cell="hex27")
+    assert np.abs(f2 - ref_f).max() <= 1e-12 * np.abs(ref_f).max()
+
+
+def test_hex27_node_line_jacobian_is_exact():
+    """hex27 nodal Jacobian from the three nodes of each parameter line == the full 27-term sum."""
+    rng = np.random.default_rng(3)
+    xi_nodes = orc.node_param_coords(orc.HEX27)
+    X = xi_nodes * 0.5 + 0.05 * rng.standard_normal((27, 3))
+    for n in range(27):
+        _, dN = orc.shape(orc.HEX27, xi_nodes[n])
+        nz = np.abs(dN) > 0
+        # per direction a exactly the three nodes that share the other two coordinates with node n
+        for a in range(3):
+            others = [d for d in range(3) if d != a]
+            line = np.all(xi_nodes[:, others] == xi_nodes[n, others], axis=1)
+            assert np.array_equal(nz[a], line & (np.abs(dN[a]) > 0)) and not nz[a][~line].any()
+        J = dN @ X
+        assert np.linalg.det(J) > 0
