@@ -936,6 +936,13 @@ struct b200s_ctx
   int32_t* d_node_colbase = nullptr;
   int32_t* d_ele_id = nullptr;  // device element -> caller's column-element index (locality order)
   double *d_vals = nullptr, *d_f = nullptr, *d_u_row = nullptr, *d_u_col = nullptr;
+  // stiff.zero() of the NEXT Newton iteration overlapped with this iteration's evaluate: two value
+  // buffers, the idle one is cleared on a side stream while the element kernel fills the other
+  double* d_vals_buf[2] = {nullptr, nullptr};
+  int vals_cur = 0;               // d_vals == d_vals_buf[vals_cur]: result of the last evaluate
+  bool vals_zeroed[2] = {false, false};
+  cudaStream_t zero_stream = nullptr;
+  cudaEvent_t ev_zero_done[2] = {}, ev_eval_start = nullptr;
   // halo
   int n_nbr = 0;
   std::vector<int32_t> peer;
@@ -958,7 +965,7 @@ struct b200s_ctx
   int last_action = 0;
   bool timed_h2d = false, timed_d2h = false;
   // options
-  int check_finite = 0, ctas_per_sm = 2, scatter_mode = 0, reorder = 1;
+  int check_finite = 0, ctas_per_sm = 2, scatter_mode = 0, reorder = 1, double_buffer = 0;
 };
 
 namespace
@@ -1143,6 +1150,9 @@ extern "C"
     }
     for (auto& e : ctx->ev) cudaEventCreate(&e);
     for (auto& e : ctx->kev) cudaEventCreate(&e);
+    cudaStreamCreateWithFlags(&ctx->zero_stream, cudaStreamNonBlocking);
+    for (auto& e : ctx->ev_zero_done) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_eval_start, cudaEventDisableTiming);
     *out = ctx;
     return B200S_OK;
   }
@@ -1155,7 +1165,12 @@ extern "C"
     if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
     dfree(ctx->dX), dfree(ctx->dconn), dfree(ctx->d_per_ele), dfree(ctx->d_rowptr);
     dfree(ctx->d_colind), dfree(ctx->d_pos), dfree(ctx->d_node_row), dfree(ctx->d_ele_id);
-    dfree(ctx->d_node_colbase), dfree(ctx->d_vals), dfree(ctx->d_f);
+    if (ctx->zero_stream) cudaStreamSynchronize(ctx->zero_stream);
+    dfree(ctx->d_node_colbase), dfree(ctx->d_vals_buf[0]), dfree(ctx->d_vals_buf[1]), dfree(ctx->d_f);
+    ctx->d_vals = nullptr;
+    for (auto& e : ctx->ev_zero_done) cudaEventDestroy(e);
+    cudaEventDestroy(ctx->ev_eval_start);
+    if (ctx->zero_stream) cudaStreamDestroy(ctx->zero_stream);
     dfree(ctx->d_u_row), dfree(ctx->d_u_col), dfree(ctx->d_send_lid), dfree(ctx->d_recv_lid);
     dfree(ctx->d_sendbuf), dfree(ctx->d_recvbuf), dfree(ctx->d_err);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
@@ -1178,6 +1193,8 @@ extern "C"
       ctx->scatter_mode = (int)value;
     else if (!strcmp(key, "reorder"))  // takes effect at the next set_mesh
       ctx->reorder = value != 0;
+    else if (!strcmp(key, "double_buffer"))  // takes effect at the next set_graph / build_graph
+      ctx->double_buffer = value != 0;
     else
       return fail(ctx, B200S_ERR_INVALID, "unknown option %s", key);
     return B200S_OK;
@@ -1315,7 +1332,13 @@ extern "C"
     ctx->pos_stride = ctx->celltype == B200S_HEX27 ? hex27::POS_STRIDE : ctx->nn * ctx->nn;
     if (to_device(ctx, &ctx->d_pos, (const int32_t*)nullptr, ctx->n_col_eles * ctx->pos_stride))
       return B200S_ERR_CUDA;
-    if (to_device(ctx, &ctx->d_vals, (const double*)nullptr, nnz)) return B200S_ERR_CUDA;
+    if (ctx->zero_stream) cudaStreamSynchronize(ctx->zero_stream);
+    dfree(ctx->d_vals_buf[1]);
+    if (to_device(ctx, &ctx->d_vals_buf[0], (const double*)nullptr, nnz)) return B200S_ERR_CUDA;
+    if (ctx->double_buffer && to_device(ctx, &ctx->d_vals_buf[1], (const double*)nullptr, nnz))
+      return B200S_ERR_CUDA;
+    ctx->vals_cur = 0, ctx->d_vals = ctx->d_vals_buf[0];
+    ctx->vals_zeroed[0] = ctx->vals_zeroed[1] = false;
     if (to_device(ctx, &ctx->d_f, (const double*)nullptr, n_rows)) return B200S_ERR_CUDA;
     if (to_device(ctx, &ctx->d_u_row, (const double*)nullptr, n_rows)) return B200S_ERR_CUDA;
     CK(cudaMemsetAsync(ctx->d_u_row, 0, sizeof(double) * n_rows, ctx->stream));
@@ -1550,7 +1573,29 @@ extern "C"
     ctx->launches += 1;
     CK(cudaEventRecord(ctx->ev[2], st));
     // stiff.zero(); fint.put_scalar(0)
-    if (stiff) CK(cudaMemsetAsync(ctx->d_vals, 0, sizeof(double) * (size_t)ctx->nnz, st));
+    if (stiff)
+    {
+      const size_t vbytes = sizeof(double) * (size_t)ctx->nnz;
+      if (ctx->d_vals_buf[1])
+      {
+        // this evaluate fills the buffer that was cleared during the previous one (or clears it now,
+        // the first time); meanwhile the side stream clears the buffer holding the previous result,
+        // once everything enqueued so far (e.g. its copy to the host) has finished
+        const int use = ctx->vals_cur ^ 1, idle = ctx->vals_cur;
+        CK(cudaEventRecord(ctx->ev_eval_start, st));
+        if (ctx->vals_zeroed[use])
+          CK(cudaStreamWaitEvent(st, ctx->ev_zero_done[use], 0));
+        else
+          CK(cudaMemsetAsync(ctx->d_vals_buf[use], 0, vbytes, st));
+        CK(cudaStreamWaitEvent(ctx->zero_stream, ctx->ev_eval_start, 0));
+        CK(cudaMemsetAsync(ctx->d_vals_buf[idle], 0, vbytes, ctx->zero_stream));
+        CK(cudaEventRecord(ctx->ev_zero_done[idle], ctx->zero_stream));
+        ctx->vals_zeroed[idle] = true, ctx->vals_zeroed[use] = false;
+        ctx->vals_cur = use, ctx->d_vals = ctx->d_vals_buf[use];
+      }
+      else
+        CK(cudaMemsetAsync(ctx->d_vals, 0, vbytes, st));
+    }
     CK(cudaMemsetAsync(ctx->d_f, 0, sizeof(double) * (size_t)ctx->n_rows, st));
     ctx->h_err->n_neg_jac = 0, ctx->h_err->first_bad = LLONG_MAX;
     ctx->h_err->min_detJ = 1e300, ctx->h_err->min_detF = 1e300, ctx->h_err->n_nonfinite = 0;

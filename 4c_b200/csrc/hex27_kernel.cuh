@@ -297,7 +297,7 @@ namespace b200s
       const int kk = SUB * s + t;
       const int k = NBLK * w + kk;
       const bool on = t < SUB && kk < NBLK && !(tr && k == 0);
-#pragma unroll 1
+#pragma unroll 3
       for (int i = 0; i < NN; ++i)
       {
         const NodeRow r = S.nrow[i];

@@ -372,15 +372,28 @@ namespace b200s
         if (!STIFF) continue;
         const double* Ke = S.mp + el * KE_ESTRIDE + lane;
         const int32_t* pos = S.pos + el * (NN * NN) + jl;
+        // all shared-memory reads first (row info, map entry, the lane's 24 K_e entries), then the
+        // REDs: no branch between the loads of different row nodes, so they overlap
+        int64_t off[NN];
+        int32_t len[NN];
 #pragma unroll
         for (int i = 0; i < NN; ++i)
         {
           const NodeRow r = nr[i];
-          if (r.rowstart < 0) continue;  // row node not owned by this rank (warp uniform)
-          double* dst = A.vals + (r.rowstart + pos[i * NN] + cl);
-          B2_RED_ADD(dst, Ke[(3 * i) * 24]);
-          B2_RED_ADD(dst + r.rowlen, Ke[(3 * i + 1) * 24]);
-          B2_RED_ADD(dst + 2 * (int64_t)r.rowlen, Ke[(3 * i + 2) * 24]);
+          off[i] = r.rowstart >= 0 ? r.rowstart + pos[i * NN] + cl : -1;  // -1: row node not owned
+          len[i] = r.rowlen;
+        }
+#pragma unroll
+        for (int i = 0; i < NN; ++i)
+        {
+          const double v0 = Ke[(3 * i) * 24], v1 = Ke[(3 * i + 1) * 24], v2 = Ke[(3 * i + 2) * 24];
+          if (off[i] >= 0)
+          {
+            double* dst = A.vals + off[i];
+            B2_RED_ADD(dst, v0);
+            B2_RED_ADD(dst + len[i], v1);
+            B2_RED_ADD(dst + 2 * (int64_t)len[i], v2);
+          }
         }
       }
     }

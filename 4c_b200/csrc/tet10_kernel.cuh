@@ -26,11 +26,12 @@ namespace b200s
     constexpr int MP_PAIRS = 27;                    // 45 M + 9 Pw
     constexpr int MP_SLOTS = EPW * NGP + 1;         // slot = el*4 + g (+1: pad)
     constexpr int MP_SIZE = MP_PAIRS * MP_SLOTS * 2;
-    constexpr int G_GSTRIDE = 31, G_ESTRIDE = NGP * G_GSTRIDE;  // G[el][g][k*3+a]
+    constexpr int G_GSTRIDE = 31, G_ESTRIDE = 129;  // G[el][g][k*3+a]; 129 = 1 mod 16: the 64-bit
+                                                     // loads of 3 elements x 10 lanes (stride 3) miss each other
     constexpr int G_SIZE = EPW * G_ESTRIDE;
     constexpr int XU_ESTRIDE = 62;                  // gathered X[k*3+d], u at +30
     constexpr int XU_SIZE = EPW * XU_ESTRIDE;
-    constexpr int KE_ESTRIDE = NDOF * NDOF + 8;     // staged K_e per element
+    constexpr int KE_ESTRIDE = NDOF * NDOF + 14;    // staged K_e per element (914 = 2 mod 16: bank offset 4)
     constexpr int FE_OFFSET = EPW * KE_ESTRIDE;
     constexpr int STAGE_SIZE = FE_OFFSET + EPW * NDOF + 2;  // M/Pw/G alias the front of the stage
     static_assert(MP_SIZE + G_SIZE <= STAGE_SIZE, "M/Pw/G live inside the K_e staging area");

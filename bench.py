@@ -261,6 +261,13 @@ def run_b200(args):
     u_row = np.ascontiguousarray(u[:rm.n_row_nodes].ravel())
 
     # pinned host staging of the reference-facing call (u in; K values, f out)
+    try:
+        avail = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
+    except (OSError, IndexError, ValueError):
+        avail = 1 << 62
+    if 8 * (nnz + 2 * n_rows) * world > 0.5 * avail:
+        raise SystemExit(f"host staging of {8 * nnz * world / 1e9:.1f} GB of CSR values does not fit the host "
+                         f"({avail / 1e9:.1f} GB available): choose a smaller --per-gpu-n")
     hb = {k: capi.load().b200s_host_alloc(8 * sz) for k, sz in (("u", n_rows), ("K", nnz), ("f", n_rows))}
     if not all(hb.values()):
         raise SystemExit("pinned host allocation failed")

@@ -85,7 +85,11 @@ extern "C"
   /* options: "check_finite" (0/1: count NaN/Inf in f and K after each evaluate),
    * "reorder" (default 1: the device visits the elements in a locality (Morton) order chosen at the
    * next b200s_set_mesh; results, element indices in b200s_error_info and per-element parameters
-   * stay in the caller's numbering), "ctas_per_sm" and "scatter_mode" (tuning / profiling only). */
+   * stay in the caller's numbering), "double_buffer" (default 0 = one CSR value buffer, cleared at the
+   * start of every evaluate; 1 = two buffers, the zero() of the next Newton iteration's matrix runs on a
+   * side stream while the current evaluate fills the other buffer and b200s_device_values() alternates
+   * between two addresses -- measured on B200: the concurrent memset slows the element kernel by as much
+   * as it saves (2.46 vs 2.48 ms per step), hence off; takes effect at the next set_graph / build_graph), "ctas_per_sm" and "scatter_mode" (tuning / profiling only). */
   int b200s_set_option(b200s_ctx* ctx, const char* key, double value);
 
   /* ---- set-up (once per discretization) ------------------------------------------------------ */
@@ -157,7 +161,8 @@ extern "C"
   int b200s_evaluate_async(b200s_ctx* ctx, int action);
   int b200s_synchronize(b200s_ctx* ctx, b200s_error_info* err);
 
-  /* Device-resident buffers owned by the context (valid until destroy / next set_graph). */
+  /* Device-resident buffers owned by the context (valid until destroy / next set_graph).
+   * b200s_device_values: CSR values of the LAST stiffness evaluate (see option "double_buffer"). */
   double* b200s_device_values(b200s_ctx* ctx);  /* nnz  */
   double* b200s_device_f(b200s_ctx* ctx);       /* n_rows */
   double* b200s_device_u_row(b200s_ctx* ctx);   /* 3*n_row_nodes */

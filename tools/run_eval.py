@@ -19,13 +19,18 @@ ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--mat", type=int, default=0)
 ap.add_argument("--no-reorder", action="store_true")
 ap.add_argument("--force-only", action="store_true")
+ap.add_argument("--cell", default="hex8", choices=["hex8", "tet10", "hex27"])
 a = ap.parse_args()
 PAR = {0: [200.0, 0.25], 1: [1.0, 1000.0], 2: [1000.0, 0.3]}
-rm = b200.partition.box_partition(b200.mesh.HEX8, (a.n,) * 3, 0, 1)
+if a.cell == "tet10":
+    X, conn = b200.mesh.unstructured_tet10(a.n)
+    rm = b200.partition.serial_mesh(b200.mesh.TET10, X, conn)
+else:
+    rm = b200.partition.box_partition(getattr(b200.mesh, a.cell.upper()), (a.n,) * 3, 0, 1)
 u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 1.0 / a.n)
 ctx = capi.Context(0)
 ctx.set_option("reorder", 0 if a.no_reorder else 1)
-ctx.set_mesh(capi.HEX8, rm.X, rm.conn)
+ctx.set_mesh(rm.celltype, rm.X, rm.conn)
 ctx.set_material(a.mat, PAR[a.mat])
 ctx.build_graph(rm.n_row_nodes, rm.node_row_lid, rm.node_col_lid)
 ctx.set_option("scatter_mode", a.scatter_mode)
