@@ -50,6 +50,12 @@ WORKLOADS = {
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the element kernel at the workload's default
+# size, from the committed ncu captures profiles/r01e_ncu_metrics_<workload>.csv (same bench.py command)
+NCU_TRAFFIC_BYTES = {"hex8": 2695288832 + 2235513856, "tet10": 20888573696 + 17315611904,
+                     "hex27": 25082223616 + 24644916992}
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -339,7 +345,9 @@ def run_b200(args):
             "model": f"SURVEY 8(d): {FLOPS_PER_ELE / 1e3:.1f} kflop and {BYTES_PER_ELE:.0f} B per {wl['cell'].lower()} "
                      "element (algorithmic, full non-symmetric K_e)",
             "kernel_ms": k_ms, "kernel_launches_timed": kcnt,
-            "traffic": args.traffic_bytes,
+            "traffic": args.traffic_bytes if args.traffic_bytes is not None else (
+                NCU_TRAFFIC_BYTES[args.workload] if per_gpu_n == wl["default_n"] else None),
+            "traffic_source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01e_ncu_metrics_{args.workload}.csv",
             "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": ach_gbs / peaks["hbm_gbs"], "peak_source": peak_src},
         }
