@@ -368,3 +368,59 @@ def test_hex27_negative_jacobian_error_code():
     rc, err = asm.ctx.evaluate(capi.ACTION_NLNSTIFF, asm._u, None, None, check=False)
     assert rc == capi.ERR_NEG_JACOBIAN and err.n_neg_jacobian == 1 and err.first_bad_element == 1
     asm.close()
+
+
+# ---- options of the C ABI ---------------------------------------------------------------------------
+@pytest.mark.parametrize("opts", [{"reorder": 0}, {"double_buffer": 1}, {"reorder": 0, "double_buffer": 1}])
+def test_options_do_not_change_results(opts):
+    """Caller element order instead of the Morton order, and the two-buffer zero() overlap: same K, f
+    (to rounding of the atomic sums), error element index reported in the caller's numbering."""
+    n = (9, 7, 5)
+    rm = b200.partition.box_partition(b200.mesh.HEX8, n, 0, 1)
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 1.0 / 9)
+    ctx = capi.Context(0)
+    for k, v in opts.items():
+        ctx.set_option(k, v)
+    ctx.set_mesh(capi.HEX8, rm.X, rm.conn)
+    ctx.set_material(capi.MAT_COUP_NEOHOOKE, MATS[capi.MAT_COUP_NEOHOOKE])
+    nnz, rowptr, colind = ctx.build_graph(rm.n_row_nodes, rm.node_row_lid, rm.node_col_lid, fetch=True)
+    rK, rf, _ = _oracle(rm, capi.MAT_COUP_NEOHOOKE, MATS[capi.MAT_COUP_NEOHOOKE], u, rowptr, colind)
+    K, f = np.empty(nnz), np.empty(3 * rm.n_row_nodes)
+    for it in range(3):   # repeated evaluates exercise the buffer alternation
+        ctx.evaluate(capi.ACTION_NLNSTIFF, np.ascontiguousarray(u.ravel()), K, f)
+        ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
+        assert ok, (opts, it, wK, wf)
+    ctx.close()
+
+
+def test_first_bad_element_is_in_caller_numbering_with_reordering():
+    n = (6, 5, 4)
+    rm = b200.partition.box_partition(b200.mesh.HEX8, n, 0, 1)
+    bad_e = 77
+    X = rm.X.copy()
+    X[rm.conn[bad_e, 6]] = X[rm.conn[bad_e, 0]] - 0.05
+    # the moved node belongs to up to 8 elements; the smallest caller index among the inverted ones is reported
+    rm.X = X
+    asm = b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, [200.0, 0.25])
+    asm.set_state("displacement", np.zeros(asm.n_rows))
+    rc, err = asm.ctx.evaluate(capi.ACTION_NLNSTIFF, asm._u, None, None, check=False)
+    nbad_ref = 0
+    first = None
+    for e in range(rm.n_col_eles):
+        _, _, bad = orc.element(orc.HEX8, orc.MAT_SVK, [1.0, 0.1], rm.X[rm.conn[e]], np.zeros((8, 3)))
+        if bad:
+            nbad_ref += 1
+            first = e if first is None else first
+    assert rc == capi.ERR_NEG_JACOBIAN and err.n_neg_jacobian == nbad_ref and err.first_bad_element == first
+    asm.close()
+
+
+def test_check_finite_reports_nan():
+    rm = b200.partition.box_partition(b200.mesh.HEX8, (3, 3, 3), 0, 1)
+    asm = b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, [200.0, 0.25])
+    asm.ctx.set_option("check_finite", 1)
+    u = np.zeros(asm.n_rows)
+    u[5] = np.nan
+    rc, err = asm.ctx.evaluate(capi.ACTION_NLNSTIFF, u, None, None, check=False)
+    assert rc == capi.ERR_NONFINITE and err.n_nonfinite > 0
+    asm.close()
