@@ -1037,13 +1037,9 @@ namespace
   static int launch_hex8(b200s_ctx* ctx, const EvalArgs& A)
   {
     auto kern = k_hex8_eval_assemble<MAT, STIFF>;
-    static bool attr_set = false;
-    if (!attr_set)
-    {
-      if (set_smem_attr(kern, hex8_smem_bytes))
-        return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", hex8_smem_bytes);
-      attr_set = true;
-    }
+    // per device and cheap: set on every launch (a process may hold contexts on several GPUs)
+    if (set_smem_attr(kern, hex8_smem_bytes))
+      return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", hex8_smem_bytes);
     const int64_t n_tiles = (A.n_ele + hex8::EPW - 1) / hex8::EPW;
     int64_t grid = (n_tiles + HEX8_WARPS - 1) / HEX8_WARPS;
     const int64_t cap = (int64_t)ctx->n_sm * ctx->ctas_per_sm;
@@ -1058,13 +1054,9 @@ namespace
   static int launch_tet10(b200s_ctx* ctx, const EvalArgs& A)
   {
     auto kern = k_tet10_eval_assemble<MAT, STIFF>;
-    static bool attr_set = false;
-    if (!attr_set)
-    {
-      if (set_smem_attr(kern, tet10_smem_bytes))
-        return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", tet10_smem_bytes);
-      attr_set = true;
-    }
+    // per device and cheap: set on every launch (a process may hold contexts on several GPUs)
+    if (set_smem_attr(kern, tet10_smem_bytes))
+      return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", tet10_smem_bytes);
     const int64_t n_tiles = (A.n_ele + tet10::EPW - 1) / tet10::EPW;
     int64_t grid = (n_tiles + TET10_WARPS - 1) / TET10_WARPS;
     const int64_t cap = (int64_t)ctx->n_sm * ctx->ctas_per_sm;
@@ -1079,13 +1071,9 @@ namespace
   static int launch_hex27(b200s_ctx* ctx, const EvalArgs& A)
   {
     auto kern = k_hex27_eval_assemble<MAT, STIFF>;
-    static bool attr_set = false;
-    if (!attr_set)
-    {
-      if (set_smem_attr(kern, hex27_smem_bytes))
-        return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", hex27_smem_bytes);
-      attr_set = true;
-    }
+    // per device and cheap: set on every launch (a process may hold contexts on several GPUs)
+    if (set_smem_attr(kern, hex27_smem_bytes))
+      return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", hex27_smem_bytes);
     int64_t grid = (A.n_ele + HEX27_PAIRS - 1) / HEX27_PAIRS;
     if (grid > ctx->n_sm) grid = ctx->n_sm;
     if (grid < 1) grid = 1;
@@ -1226,7 +1214,8 @@ extern "C"
     }
     else if (celltype == B200S_HEX27)
     {
-      static Hex27Const h;  // 18 KB: not on the stack
+      std::vector<Hex27Const> hbuf(1);  // 18 KB: not on the stack
+      Hex27Const& h = hbuf[0];
       memset(&h, 0, sizeof h);
       memcpy(h.dN_gp, T.dN_gp.data(), sizeof h.dN_gp);
       memcpy(h.w, T.w.data(), 27 * sizeof(double));

@@ -424,3 +424,81 @@ def test_check_finite_reports_nan():
     rc, err = asm.ctx.evaluate(capi.ACTION_NLNSTIFF, u, None, None, check=False)
     assert rc == capi.ERR_NONFINITE and err.n_nonfinite > 0
     asm.close()
+
+
+# ---- size-independent properties at larger tet10 / hex27 sizes ---------------------------------------
+def _properties(asm, rowptr, colind, K, f, tol=1e-9):
+    import torch
+    n = asm.n_rows
+    Kt = torch.sparse_csr_tensor(torch.from_numpy(rowptr), torch.from_numpy(colind.astype(np.int64)),
+                                 torch.from_numpy(K), size=(n, n))
+    scale = np.abs(K).max()
+    assert np.abs(f.reshape(-1, 3).sum(axis=0)).max() < tol * np.abs(f).max() * np.sqrt(n)   # sum f = 0
+    for d in range(3):                                                                      # K t = 0
+        t = np.zeros(n)
+        t[d::3] = 1.0
+        assert np.abs((Kt @ torch.from_numpy(t)).numpy()).max() < 1e-10 * scale
+    rng = np.random.default_rng(0)                                                          # K = K^T
+    x, y = rng.standard_normal(n), rng.standard_normal(n)
+    a = float(torch.from_numpy(x) @ (Kt @ torch.from_numpy(y)))
+    b = float(torch.from_numpy(y) @ (Kt @ torch.from_numpy(x)))
+    assert abs(a - b) < 1e-10 * max(abs(a), abs(b), scale)
+
+
+def test_tet10_properties_and_sampled_rows_at_scale():
+    """384k unstructured tet10 elements (config 4 family): properties + the rows of 200 random nodes
+    against the oracle evaluated on the elements touching them."""
+    X, conn = b200.mesh.unstructured_tet10(40)
+    rm = b200.partition.serial_mesh(b200.mesh.TET10, X, conn)
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 1.0 / 40)
+    par = MATS[capi.MAT_ISO_VOL]
+    asm = b200.DeviceAssembler(rm, capi.MAT_ISO_VOL, par)
+    rowptr, colind = asm.graph()
+    asm.set_state("displacement", u.ravel())
+    K, f, err = asm.evaluate()
+    assert err.n_neg_jacobian == 0 and 0.7 < err.min_detF < 1.3
+    _properties(asm, rowptr, colind, K, f)
+    rng = np.random.default_rng(11)
+    nodes = np.sort(rng.choice(rm.n_row_nodes, 200, replace=False))
+    keep = np.zeros(rm.n_col_nodes, bool)
+    keep[nodes] = True
+    sel = keep[rm.conn].any(axis=1)
+    sub_row = np.where(keep, np.cumsum(keep) - 1, -1).astype(np.int32)
+    o_rowptr, o_colind = orc.build_graph(orc.TET10, rm.conn[sel], sub_row, rm.node_col_lid, len(nodes))
+    rK, rf, nbad = orc.evaluate_assemble(orc.TET10, orc.MAT_ISO_VOL, par, rm.conn[sel], rm.X.ravel(), u.ravel(),
+                                         sub_row, rm.node_col_lid, len(nodes), o_rowptr, o_colind, nthreads=8)
+    rows = (3 * nodes[:, None] + np.arange(3)).ravel()
+    sl = np.concatenate([np.arange(rowptr[r], rowptr[r + 1]) for r in rows])
+    assert np.array_equal(colind[sl], o_colind)
+    ok, wK, wf = b200.parity_report(o_rowptr, K[sl], rK, f[rows], rf, RTOL)
+    assert ok and nbad == 0, (wK, wf)
+    asm.close()
+
+
+def test_hex27_properties_and_slab_at_scale():
+    """24^3 = 13.8k hex27 elements (config 3 family, nnz 6e7): properties + a slab of rows vs the oracle."""
+    n = (24, 24, 24)
+    rm = b200.partition.box_partition(b200.mesh.HEX27, n, 0, 1, box=(0.24, 0.24, 0.24))
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 0.01)
+    par = MATS[capi.MAT_SVK]
+    asm = b200.DeviceAssembler(rm, capi.MAT_SVK, par)
+    rowptr, colind = asm.graph()
+    asm.set_state("displacement", u.ravel())
+    K, f, err = asm.evaluate()
+    assert err.n_neg_jacobian == 0
+    _properties(asm, rowptr, colind, K, f)
+    ez = rm.ele_gid // (24 * 24)
+    sel = (ez >= 10) & (ez < 12)
+    iz = rm.node_gid // (49 * 49)
+    keep = (iz >= 21) & (iz <= 23)          # node planes strictly inside the two element layers
+    sub_row = np.where(keep, np.cumsum(keep) - 1, -1).astype(np.int32)
+    nsub = int(keep.sum())
+    o_rowptr, o_colind = orc.build_graph(orc.HEX27, rm.conn[sel], sub_row, rm.node_col_lid, nsub)
+    rK, rf, nbad = orc.evaluate_assemble(orc.HEX27, orc.MAT_SVK, par, rm.conn[sel], rm.X.ravel(), u.ravel(), sub_row,
+                                         rm.node_col_lid, nsub, o_rowptr, o_colind, nthreads=8)
+    full_rows = (3 * np.nonzero(keep)[0][:, None] + np.arange(3)).ravel()
+    lo, hi = rowptr[full_rows[0]], rowptr[full_rows[-1] + 1]
+    assert np.array_equal(colind[lo:hi], o_colind)
+    ok, wK, wf = b200.parity_report(o_rowptr, K[lo:hi], rK, f[full_rows], rf, RTOL)
+    assert ok and nbad == 0, (wK, wf)
+    asm.close()
