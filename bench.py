@@ -117,19 +117,23 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # workload
 # ------------------------------------------------------------------------------------------------
-def global_box(per_gpu_n, nranks):
-    """Weak scaling: every rank holds a per_gpu_n^3 element box (grid generator partition)."""
+def global_box(per_gpu_n, nranks, strong=False):
+    """Weak scaling: every rank holds a per_gpu_n^3 element box (grid generator partition); strong scaling:
+    the per_gpu_n^3 box is the whole mesh and is cut into nranks boxes."""
     b200 = importlib.import_module("4c_b200")
     mult = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(nranks)
     if mult is None:
         raise SystemExit("--gpus must be 1, 2, 4 or 8")
+    if strong:
+        n = (per_gpu_n,) * 3
+        return n, tuple(per_gpu_n / 100.0 for _ in range(3))
     n = tuple(per_gpu_n * m for m in mult)
     sub, _ = b200.partition.box_subdivisions(n, nranks)
     assert tuple(sub) == mult, (sub, mult)
     return n, tuple(m * per_gpu_n / 100.0 for m in mult)  # h = 0.01 as in config 2
 
 
-def build_rank(wl, per_gpu_n, rank, nranks):
+def build_rank(wl, per_gpu_n, rank, nranks, strong=False):
     """Rank-local mesh + displacement state of the workload; returns (rank mesh, u on column nodes, label)."""
     b200 = importlib.import_module("4c_b200")
     cell = getattr(b200.mesh, wl["cell"])
@@ -140,7 +144,7 @@ def build_rank(wl, per_gpu_n, rank, nranks):
         rm = b200.partition.serial_mesh(cell, X, conn)
         u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 1.0 / per_gpu_n)
         return rm, u, f"unstructured tet10 ({per_gpu_n}^3 hex cells x 6, jittered, randomly renumbered)"
-    n, box = global_box(per_gpu_n, nranks)
+    n, box = global_box(per_gpu_n, nranks, strong)
     rm = b200.partition.box_partition(cell, n, rank, nranks, box=box)
     u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 0.01)
     return rm, u, f"structured {wl['cell'].lower()} cube {n[0]}x{n[1]}x{n[2]}"
@@ -254,7 +258,7 @@ def run_b200(args):
     METRIC = wl["metric"]
     FLOPS_PER_ELE, BYTES_PER_ELE = wl["flops"], wl["bytes"]
     per_gpu_n = args.per_gpu_n or wl["default_n"]
-    rm, u, mesh_label = build_rank(wl, per_gpu_n, rank, world)
+    rm, u, mesh_label = build_rank(wl, per_gpu_n, rank, world, args.strong)
     asm = b200.DeviceAssembler(rm, getattr(capi, wl["mat"]), wl["par"], device=local)
     ctx = asm.ctx
     if world > 1:
@@ -359,10 +363,13 @@ def run_b200(args):
             ts = [arm.step(threads) for _ in range(3)]
             cpu = {"value": arm.rm.n_col_eles / float(np.median(ts)), "unit": UNIT, "cores": threads,
                    "kind": arm.kind, "sample": arm.describe() + ", median of 3 after 1 warm-up"}
+            arm1 = CpuArm(wl, cpu_sample_size(wl, 1, 2.0))      # also P = 1
+            arm1.step(1)
+            cpu["value_1_core"] = arm1.rm.n_col_eles / min(arm1.step(1) for _ in range(2))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": f"BASELINE config {wl['config'] if world == 1 else '5-style weak'}: {mesh_label}, "
                             f"{wl['matname']}, {int(row_eles)} elements ({rm.n_row_eles} on rank 0), "
@@ -402,6 +409,8 @@ def main():
     ap.add_argument("--per-gpu-n", type=int, default=0,
                     help="edge parameter of each rank's mesh (default: the config's size; hex8 100 -> 1M elements)")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: --per-gpu-n is the edge of the WHOLE mesh, cut into N boxes")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram bytes per launch of the element kernel from the committed ncu capture (profiles/)")
