@@ -17,12 +17,16 @@ ACTIONS = {"struct_calc_nlnstiff": capi.ACTION_NLNSTIFF,
 
 
 class DeviceAssembler:
-    def __init__(self, rank_mesh, matkind, matparams, device=0, per_ele_param=None, graph=None):
+    def __init__(self, rank_mesh, matkind, matparams, device=0, per_ele_param=None, graph=None,
+                 tech=capi.TECH_NONE):
         """rank_mesh: partition.RankMesh.  graph: (rowptr, colind) from the reference's matrix, or
-        None to build the FillComplete-equivalent graph on the device."""
+        None to build the FillComplete-equivalent graph on the device.  tech: element technology of
+        the block (TECH key of the SOLID element line)."""
         rm = self.rm = rank_mesh
         self.ctx = capi.Context(device, rm.rank, rm.nranks)
         self.ctx.set_mesh(rm.celltype, rm.X, rm.conn)
+        if tech != capi.TECH_NONE:
+            self.ctx.set_element_properties(tech=tech)
         self.ctx.set_material(matkind, matparams, per_ele_param)
         if graph is None:
             self.nnz = self.ctx.build_graph(rm.n_row_nodes, rm.node_row_lid, rm.node_col_lid)

@@ -16,11 +16,14 @@ ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NEG_JACOBIAN, ERR_NONFINITE, ERR_COM
 HEX8, HEX27, TET10 = 0, 1, 2
 MAT_COUP_NEOHOOKE, MAT_ISO_VOL, MAT_SVK = 0, 1, 2
 ACTION_INTERNALFORCE, ACTION_NLNSTIFF = 0, 1
+KINEM_NONLINEAR_TOTLAG, KINEM_LINEAR = 0, 1
+TECH_NONE, TECH_FBAR, TECH_EAS_MILD, TECH_EAS_FULL = 0, 1, 2, 3
+PRESTRESS_NONE, PRESTRESS_MULF = 0, 1
 
 # every symbol include/b200_solid.h declares (checked by the CPU test-suite)
 SYMBOLS = [
     "b200s_create", "b200s_destroy", "b200s_last_error", "b200s_set_option", "b200s_set_mesh",
-    "b200s_set_material", "b200s_set_graph", "b200s_set_halo", "b200s_nccl_unique_id",
+    "b200s_set_element_properties", "b200s_set_material", "b200s_set_graph", "b200s_set_halo", "b200s_nccl_unique_id",
     "b200s_comm_init_nccl", "b200s_evaluate", "b200s_evaluate_async", "b200s_synchronize",
     "b200s_device_values", "b200s_device_f", "b200s_device_u_row", "b200s_device_u_col",
     "b200s_stream", "b200s_nnz", "b200s_n_rows", "b200s_get_timers", "b200s_launch_count",
@@ -60,6 +63,7 @@ def load():
     L.b200s_last_error.restype = C.c_char_p
     L.b200s_set_option.argtypes = [vp, C.c_char_p, dbl]
     L.b200s_set_mesh.argtypes = [vp, i32, i64, vp, i64, vp]
+    L.b200s_set_element_properties.argtypes = [vp, i32, i32, i32]
     L.b200s_set_material.argtypes = [vp, i32, vp, i32, vp]
     L.b200s_set_graph.argtypes = [vp, i64, vp, vp, vp, vp]
     L.b200s_set_halo.argtypes = [vp, i32, vp, vp, vp, vp, vp]
@@ -144,6 +148,10 @@ class Context:
         self.celltype, self.nn = celltype, conn.shape[1]
         self.n_col_nodes, self.n_col_eles = X.shape[0], conn.shape[0]
         self._ck(self.L.b200s_set_mesh(self.h, celltype, X.shape[0], _ptr(X), conn.shape[0], _ptr(conn)))
+
+    def set_element_properties(self, kinem=KINEM_NONLINEAR_TOTLAG, tech=TECH_NONE,
+                               prestress=PRESTRESS_NONE):
+        self._ck(self.L.b200s_set_element_properties(self.h, kinem, tech, prestress))
 
     def set_material(self, kind, params, per_ele_param=None):
         params = np.ascontiguousarray(params, np.float64)

@@ -13,6 +13,7 @@
 
 #include "../../include/b200_solid.h"
 #include "hex8_kernel.cuh"
+#include "hex8_fbar_kernel.cuh"
 #include "tet10_kernel.cuh"
 #include "hex27_kernel.cuh"
 #include "shape_tables.hpp"
@@ -48,9 +49,14 @@ namespace b200s
   // hex8 evaluate + assemble kernel (see hex8_kernel.cuh for the phase structure)
   // ------------------------------------------------------------------------------------------------
   constexpr int HEX8_WARPS = 4;  // warps per CTA; 2 CTAs/SM = 8 warps = 32 elements in flight / SM
+  constexpr int HEX8_FBAR_WARPS = 7;  // F-bar variant: one CTA of 7 warps per SM (shared memory bound)
   constexpr size_t hex8_warp_bytes = (size_t)hex8::WARP_BYTES;
+  constexpr size_t hex8_fbar_warp_bytes = (size_t)hex8fbar::WARP_BYTES;
+  static_assert(hex8_fbar_warp_bytes % 16 == 0, "16-byte aligned carve-up");
   constexpr size_t hex8_table_bytes = (size_t)(2 * hex8::TAB_SIZE + 8) * 8;
   constexpr size_t hex8_smem_bytes = hex8_table_bytes + HEX8_WARPS * hex8_warp_bytes;
+  constexpr size_t hex8_fbar_smem_bytes = hex8_table_bytes + HEX8_FBAR_WARPS * hex8_fbar_warp_bytes;
+  static_assert(hex8_fbar_smem_bytes <= 232448, "fits the 227 KB of dynamic shared memory per CTA");
   static_assert(hex8_warp_bytes % 16 == 0 && hex8_table_bytes % 16 == 0, "16-byte aligned carve-up");
 
   __device__ __forceinline__ void atomic_min_double(double* addr, double v)
@@ -131,9 +137,15 @@ namespace b200s
     }
   }  // namespace hex8
 
-  template <int MAT, bool STIFF>
-  __global__ void __launch_bounds__(HEX8_WARPS * 32, 2) k_hex8_eval_assemble(const EvalArgs A)
+  // TECH 0: displacement based (4 warps, 2 CTAs/SM); TECH 1: F-bar (7 warps, 1 CTA/SM, more shared
+  // memory per warp and the full non-symmetric block row per lane, hex8_fbar_kernel.cuh)
+  template <int MAT, bool STIFF, int TECH>
+  __global__ void __launch_bounds__((TECH ? HEX8_FBAR_WARPS : HEX8_WARPS) * 32, TECH ? 1 : 2)
+      k_hex8_eval_assemble(const EvalArgs A)
   {
+    constexpr int WARPS = TECH ? HEX8_FBAR_WARPS : HEX8_WARPS;
+    constexpr size_t warp_bytes = TECH ? hex8_fbar_warp_bytes : hex8_warp_bytes;
+    constexpr int MP_SIZE = TECH ? hex8fbar::MP_SIZE : hex8::MP_SIZE;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* tab_gp = reinterpret_cast<double*>(smem_raw);
     double* tab_node = tab_gp + hex8::TAB_SIZE;
@@ -147,22 +159,23 @@ namespace b200s
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char* wbase = smem_raw + hex8_table_bytes + warp * hex8_warp_bytes;
+    unsigned char* wbase = smem_raw + hex8_table_bytes + warp * warp_bytes;
     hex8::WarpSmem S;
     S.mp = reinterpret_cast<double*>(wbase);
-    S.g = S.mp + hex8::MP_SIZE;
+    S.g = S.mp + MP_SIZE;
     S.xu = S.g + hex8::G_SIZE;
-    S.nrow = reinterpret_cast<NodeRow*>(S.xu + hex8::XU_SIZE);
+    if (TECH) S.h0 = S.xu + hex8::XU_SIZE;
+    S.nrow = reinterpret_cast<NodeRow*>(S.xu + hex8::XU_SIZE + (TECH ? hex8fbar::H0_SIZE : 0));
     S.pos = reinterpret_cast<int32_t*>(S.nrow + hex8::EPW * hex8::NN);
 
     const int64_t n_tiles = (A.n_ele + hex8::EPW - 1) / hex8::EPW;
-    const int64_t wstride = (int64_t)gridDim.x * HEX8_WARPS;
+    const int64_t wstride = (int64_t)gridDim.x * WARPS;
     double detJ_min = 1e300, detF_min = 1e300;
     long long bad = LLONG_MAX;
     unsigned int nbad = 0;
 
     // prologue of the gather pipeline: tile 0 in flight, node ids of tile 1 in registers
-    int64_t tile = (int64_t)blockIdx.x * HEX8_WARPS + warp;
+    int64_t tile = (int64_t)blockIdx.x * WARPS + warp;
     int node_next = hex8::load_node(A, lane, tile, n_tiles);
     // Two commit groups per tile, always in the order [X,u] then [row info, scatter map]; a group
     // may be empty (no next tile), which keeps the wait_group arithmetic uniform.
@@ -182,7 +195,10 @@ namespace b200s
       double out54[54];
       double dJ, dF;
       bool neg;
-      hex8::phase1<MAT, STIFF>(A, S, tab_gp, tab_node, wgt, lane, e0, out54, dJ, dF, neg);
+      if (TECH)
+        hex8fbar::phase1<MAT, STIFF>(A, S, tab_gp, wgt, lane, e0, out54, dJ, dF, neg);
+      else
+        hex8::phase1<MAT, STIFF>(A, S, tab_gp, tab_node, wgt, lane, e0, out54, dJ, dF, neg);
       if (e0 + (lane >> 3) < A.n_ele)
       {
         detJ_min = fmin(detJ_min, dJ);
@@ -202,10 +218,16 @@ namespace b200s
       cp_async_commit();
       hex8::phase1_store<STIFF>(S, lane, out54);
       __syncwarp();
-      double Kacc[5][9], facc[3];
-      hex8::phase2<STIFF>(S, lane, Kacc, facc);
+      double Kacc[TECH ? 8 : 5][9], facc[3];
+      if (TECH)
+        hex8fbar::phase2<STIFF>(S, lane, Kacc, facc);
+      else
+        hex8::phase2<STIFF>(S, lane, Kacc, facc);
       __syncwarp();  // M/Pw/G are dead: K_e / f_e staging overwrites them
-      hex8::stage_ke<STIFF>(S, lane, Kacc, facc);
+      if (TECH)
+        hex8fbar::stage_ke<STIFF>(S, lane, Kacc, facc);
+      else
+        hex8::stage_ke<STIFF>(S, lane, Kacc, facc);
       cp_async_wait_but_last();  // row info / scatter map of this tile landed
       __syncwarp();
       if (A.scatter_mode == 0) hex8::scatter<STIFF>(A, S, lane, e0);
@@ -923,6 +945,8 @@ struct b200s_ctx
   int64_t n_col_nodes = 0, n_col_eles = 0;
   double* dX = nullptr;
   int32_t* dconn = nullptr;
+  // SolidElementProperties of the block (4C_solid_ele_properties.hpp:55-65)
+  int tech = B200S_TECH_NONE;
   // material
   int matkind = -1;
   MatParams mp{};
@@ -1036,7 +1060,20 @@ namespace
   template <int MAT, bool STIFF>
   static int launch_hex8(b200s_ctx* ctx, const EvalArgs& A)
   {
-    auto kern = k_hex8_eval_assemble<MAT, STIFF>;
+    if (ctx->tech == B200S_TECH_FBAR)
+    {
+      auto kern = k_hex8_eval_assemble<MAT, STIFF, 1>;
+      if (set_smem_attr(kern, hex8_fbar_smem_bytes))
+        return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", hex8_fbar_smem_bytes);
+      const int64_t n_tiles = (A.n_ele + hex8::EPW - 1) / hex8::EPW;
+      int64_t grid = (n_tiles + HEX8_FBAR_WARPS - 1) / HEX8_FBAR_WARPS;
+      if (grid > ctx->n_sm) grid = ctx->n_sm;
+      if (grid < 1) grid = 1;
+      kern<<<(unsigned)grid, HEX8_FBAR_WARPS * 32, hex8_fbar_smem_bytes, ctx->stream>>>(A);
+      ctx->launches += 1;
+      return 0;
+    }
+    auto kern = k_hex8_eval_assemble<MAT, STIFF, 0>;
     // per device and cheap: set on every launch (a process may hold contexts on several GPUs)
     if (set_smem_attr(kern, hex8_smem_bytes))
       return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", hex8_smem_bytes);
@@ -1085,6 +1122,8 @@ namespace
   template <int MAT, bool STIFF>
   static int launch_cell(b200s_ctx* ctx, const EvalArgs& A)
   {
+    if (ctx->tech != B200S_TECH_NONE && ctx->celltype != B200S_HEX8)
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "element technology %d needs hex8", ctx->tech);
     switch (ctx->celltype)
     {
       case B200S_HEX27:
@@ -1273,6 +1312,25 @@ extern "C"
     // graph-dependent data is stale now
     dfree(ctx->d_pos);
     ctx->nnz = 0, ctx->n_rows = 0;
+    return B200S_OK;
+  }
+
+  int b200s_set_element_properties(b200s_ctx* ctx, int kinem_type, int element_technology,
+      int prestress_technology)
+  {
+    if (!ctx) return B200S_ERR_INVALID;
+    if (kinem_type != B200S_KINEM_NONLINEAR_TOTLAG)
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "kinematic type %d has no device kernel", kinem_type);
+    if (prestress_technology != B200S_PRESTRESS_NONE)
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "prestress technology %d has no device kernel",
+          prestress_technology);
+    if (element_technology != B200S_TECH_NONE && element_technology != B200S_TECH_FBAR)
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "element technology %d has no device kernel",
+          element_technology);
+    // the reference offers F-bar for hex8 (and pyramid5) only (4C_solid_ele_factory_lib.hpp)
+    if (element_technology == B200S_TECH_FBAR && ctx->celltype >= 0 && ctx->celltype != B200S_HEX8)
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "F-bar is a hex8 technology");
+    ctx->tech = element_technology;
     return B200S_OK;
   }
 

@@ -96,6 +96,7 @@ namespace b200s
       double* xu;    // XU_SIZE
       NodeRow* nrow; // EPW*NN
       int32_t* pos;  // EPW*NN*NN
+      double* h0 = nullptr;  // F-bar only (hex8_fbar_kernel.cuh): EPW*24
     };
 
     B2_HD int mp_index(int pair, int el, int g) { return (pair * MP_SLOTS + el * 9 + g) * 2; }

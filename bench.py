@@ -40,6 +40,14 @@ WORKLOADS = {
     "hex8": dict(config="2", cell="HEX8", mat="MAT_COUP_NEOHOOKE", par=[200.0, 0.25], matname="CoupNeoHooke (E=200, nu=0.25)",
                  flops=63.8e3, bytes=2304.0, kernel="k_hex8_eval_assemble<COUP_NEOHOOKE,STIFF>", default_n=100,
                  metric="hex8 Neo-Hooke element evaluate+assemble (force + tangent stiffness into CSR), FP64"),
+    # Section 8(f) row 1: F-bar hex8 on the config-2 mesh.  Model = hex8 model + the F-bar terms of the
+    # reference per Gauss point: rank-1 update of the 24x24 matrix (2*24^2), Bop^T ccg / Bop^T S (2*2*6*24),
+    # H-operator (2*2*3*24), cmat:C (72), pow (~40), + per element the centroid mapping (~600).
+    "hex8_fbar": dict(config="2 mesh, TECH fbar (SURVEY 8f.1)", cell="HEX8", mat="MAT_COUP_NEOHOOKE", par=[200.0, 0.25],
+                      matname="CoupNeoHooke (E=200, nu=0.25), F-bar", tech="TECH_FBAR",
+                      flops=63.8e3 + 8 * (1152 + 576 + 288 + 72 + 40) + 600, bytes=2304.0,
+                      kernel="k_hex8_eval_assemble<COUP_NEOHOOKE,STIFF,FBAR>", default_n=100,
+                      metric="hex8 F-bar Neo-Hooke element evaluate+assemble (force + tangent stiffness into CSR), FP64"),
     "tet10": dict(config="4", cell="TET10", mat="MAT_ISO_VOL", par=[1.0, 1000.0],
                   matname="IsoNeoHooke mu=1 + VolSussmanBathe kappa=1000", flops=43.3e3, bytes=3300.0,
                   kernel="k_tet10_eval_assemble<ISO_VOL,STIFF>", default_n=87,
@@ -161,6 +169,9 @@ class CpuArm:
         self.kind = "reference" if orc.ref_lib() is not None else "port"
         self.impl = "ref" if self.kind == "reference" else "oracle"
         self.ct, self.mk = getattr(orc, wl["cell"]), getattr(orc, wl["mat"])
+        self.tech = getattr(orc, wl.get("tech", "TECH_NONE"))
+        if self.tech != orc.TECH_NONE:  # oracle/_ref covers the displacement-based formulation only
+            self.kind, self.impl = "port", "oracle"
         if wl["cell"] == "TET10":
             X, conn = b200.mesh.unstructured_tet10(n_sample)
             self.rm = b200.partition.serial_mesh(b200.mesh.TET10, X, conn)
@@ -179,7 +190,7 @@ class CpuArm:
         t = time.perf_counter()
         orc.evaluate_assemble(self.ct, self.mk, self.wl["par"], rm.conn, rm.X.ravel(), self.u.ravel(),
                               rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, self.graph[0], self.graph[1],
-                              nthreads=threads, impl=self.impl)
+                              nthreads=threads, impl=self.impl, tech=self.tech)
         return time.perf_counter() - t
 
     def describe(self):
@@ -259,7 +270,8 @@ def run_b200(args):
     FLOPS_PER_ELE, BYTES_PER_ELE = wl["flops"], wl["bytes"]
     per_gpu_n = args.per_gpu_n or wl["default_n"]
     rm, u, mesh_label = build_rank(wl, per_gpu_n, rank, world, args.strong)
-    asm = b200.DeviceAssembler(rm, getattr(capi, wl["mat"]), wl["par"], device=local)
+    asm = b200.DeviceAssembler(rm, getattr(capi, wl["mat"]), wl["par"], device=local,
+                               tech=getattr(capi, wl.get("tech", "TECH_NONE")))
     ctx = asm.ctx
     if world > 1:
         uid = [ctx.nccl_unique_id() if rank == 0 else None]
@@ -350,7 +362,7 @@ def run_b200(args):
                      "element (algorithmic, full non-symmetric K_e)",
             "kernel_ms": k_ms, "kernel_launches_timed": kcnt,
             "traffic": args.traffic_bytes if args.traffic_bytes is not None else (
-                NCU_TRAFFIC_BYTES[args.workload] if per_gpu_n == wl["default_n"] else None),
+                NCU_TRAFFIC_BYTES.get(args.workload) if per_gpu_n == wl["default_n"] else None),
             "traffic_source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01e_ncu_metrics_{args.workload}.csv",
             "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": ach_gbs / peaks["hbm_gbs"], "peak_source": peak_src},

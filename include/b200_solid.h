@@ -57,6 +57,26 @@ extern "C"
     B200S_MAT_SVK = 2
   } b200s_material;
 
+  /* Discret::Elements::SolidElementProperties of an element block (4C_solid_ele_properties.hpp:30-65;
+   * input keys KINEM / TECH / PRESTRESS_TECH of the SOLID element line) */
+  typedef enum
+  {
+    B200S_KINEM_NONLINEAR_TOTLAG = 0, /* KINEM nonlinear */
+    B200S_KINEM_LINEAR = 1            /* KINEM linear: CPU path */
+  } b200s_kinem_type;
+  typedef enum
+  {
+    B200S_TECH_NONE = 0,
+    B200S_TECH_FBAR = 1,     /* hex8: 4C_solid_ele_calc_fbar.hpp */
+    B200S_TECH_EAS_MILD = 2, /* CPU path */
+    B200S_TECH_EAS_FULL = 3  /* CPU path */
+  } b200s_element_technology;
+  typedef enum
+  {
+    B200S_PRESTRESS_NONE = 0,
+    B200S_PRESTRESS_MULF = 1 /* CPU path */
+  } b200s_prestress_technology;
+
   /* Core::Elements::ActionType values handled (legacy_enum_definitions):
    * struct_calc_internalforce, struct_calc_nlnstiff (4C_solid_ele_evaluate.cpp:64-115) */
   typedef enum
@@ -101,6 +121,13 @@ extern "C"
    * and material; other element blocks use further contexts or stay on the CPU path. */
   int b200s_set_mesh(b200s_ctx* ctx, int celltype, int64_t n_col_nodes, const double* X,
       int64_t n_col_eles, const int32_t* conn);
+
+  /* Formulation of the element block = the SolidCalcVariant the reference's factory would create
+   * (create_solid_calculation_interface, 4C_solid_ele_factory.cpp:53-55,252-305).  Default: nonlinear
+   * total Lagrangean, no element technology, no prestress.  Returns B200S_ERR_UNSUPPORTED for a
+   * combination without device kernel (the adapter keeps such blocks on the CPU element loop). */
+  int b200s_set_element_properties(b200s_ctx* ctx, int kinem_type, int element_technology,
+      int prestress_technology);
 
   /* Replaces the Mat::So3Material object(s) the elements hold (Mat::factory; So3Material::evaluate,
    * 4C_mat_so3_material.hpp:69-73).  per_ele_param: NULL or n_col_eles doubles overriding params[0]

@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 HEX8, HEX27, TET10 = 0, 1, 2
 MAT_COUP_NEOHOOKE, MAT_ISO_VOL, MAT_SVK = 0, 1, 2
 ACTION_FORCE, ACTION_FORCE_STIFF = 0, 1
+TECH_NONE, TECH_FBAR = 0, 1
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -60,6 +61,11 @@ def lib():
         L.orc_evaluate_assemble.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int64, _ip,
                                             C.c_int64, _dp, _dp, _ip, _ip, C.c_int64, _lp, _ip, _dp,
                                             _dp, C.c_int]
+        L.orc_evaluate_assemble_tech.restype = C.c_int64
+        L.orc_evaluate_assemble_tech.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int,
+                                                 C.c_int64, _ip, C.c_int64, _dp, _dp, _ip, _ip,
+                                                 C.c_int64, _lp, _ip, _dp, _dp, C.c_int]
+        L.orc_element_tech.argtypes = [C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp, _dp, _dp]
         L.orc_build_graph.argtypes = [C.c_int, C.c_int64, _ip, C.c_int64, _ip, _ip, C.c_int64, _lp,
                                       _ip]
         L.orc_element.argtypes = [C.c_int, C.c_int, _dp, C.c_int, _dp, _dp, _dp, _dp]
@@ -135,7 +141,7 @@ def material(kind, params, E, F=None):
     return S, Cm.reshape(6, 6).T.copy()  # Cm[I,J]
 
 
-def element(ct, matkind, params, X, u, action=ACTION_FORCE_STIFF):
+def element(ct, matkind, params, X, u, action=ACTION_FORCE_STIFF, tech=TECH_NONE):
     """X,u: (n,3). Returns (Ke (nd,nd) with Ke[row,col], fe, err)."""
     n = num_nodes(ct)
     params = np.ascontiguousarray(params, dtype=np.float64)
@@ -143,7 +149,7 @@ def element(ct, matkind, params, X, u, action=ACTION_FORCE_STIFF):
     u = np.ascontiguousarray(u, dtype=np.float64).reshape(n, 3)
     Ke = np.zeros((3 * n) ** 2)
     fe = np.zeros(3 * n)
-    err = lib().orc_element(ct, matkind, _d(params), action, _d(X), _d(u), _d(Ke), _d(fe))
+    err = lib().orc_element_tech(ct, tech, matkind, _d(params), action, _d(X), _d(u), _d(Ke), _d(fe))
     return Ke.reshape(3 * n, 3 * n).T.copy(), fe, err
 
 
@@ -194,7 +200,7 @@ def build_graph(ct, conn, node_row_lid, node_col_lid, n_row_nodes):
 
 def evaluate_assemble(ct, matkind, params, conn, X, u_col, node_row_lid, node_col_lid, n_row_nodes,
                       rowptr, colind, action=ACTION_FORCE_STIFF, mue_per_ele=None, nthreads=1,
-                      impl="oracle"):
+                      impl="oracle", tech=TECH_NONE):
     """impl="oracle": plain restatement; impl="ref": element arithmetic by the reference's headers."""
     n = num_nodes(ct)
     params = np.ascontiguousarray(params, dtype=np.float64)
@@ -210,6 +216,7 @@ def evaluate_assemble(ct, matkind, params, conn, X, u_col, node_row_lid, node_co
     values = np.zeros(rowptr[-1]) if action == ACTION_FORCE_STIFF else None
     f = np.zeros(3 * n_row_nodes)
     if impl == "ref":
+        assert tech == TECH_NONE, "oracle/_ref covers the displacement-based formulation only"
         gxi, gw = gauss(ct)
         gxi = np.ascontiguousarray(gxi)
         nbad = ref_lib().ref_evaluate_assemble(ct, matkind, _d(params), _d(mue_per_ele), action,
@@ -218,7 +225,7 @@ def evaluate_assemble(ct, matkind, params, conn, X, u_col, node_row_lid, node_co
                                                _l(rowptr), _i(colind), _d(gxi), _d(gw), len(gw),
                                                _d(values), _d(f), nthreads)
         return values, f, int(nbad)
-    nbad = lib().orc_evaluate_assemble(ct, matkind, _d(params), _d(mue_per_ele), action,
+    nbad = lib().orc_evaluate_assemble_tech(ct, tech, matkind, _d(params), _d(mue_per_ele), action,
                                        conn.shape[0], _i(conn), len(node_row_lid), _d(X), _d(u_col),
                                        _i(node_row_lid), _i(node_col_lid), n_row_nodes, _l(rowptr),
                                        _i(colind), _d(values), _d(f), nthreads)

@@ -513,6 +513,175 @@ namespace
     }
     return 0;
   }
+
+  // evaluate_strain_gradient (src/solid_ele/4C_solid_ele_calc_lib.hpp:777-826): B-operator, 6 x 3n
+  // column-major, rows in the order [00,11,22,01,12,02] (strain-like: shear rows hold both terms)
+  void strain_gradient(int n, const JacMap& jm, const double* F, double* B)
+  {
+    for (int i = 0; i < n; ++i)
+    {
+      const double* g = jm.G[i];
+      for (int d = 0; d < 3; ++d)
+        for (int e = 0; e < 3; ++e) B[d + 6 * (3 * i + e)] = F[e + 3 * d] * g[d];
+      for (int e = 0; e < 3; ++e)
+      {
+        B[3 + 6 * (3 * i + e)] = F[e + 3 * 0] * g[1] + F[e + 3 * 1] * g[0];
+        B[4 + 6 * (3 * i + e)] = F[e + 3 * 1] * g[2] + F[e + 3 * 2] * g[1];
+        B[5 + 6 * (3 * i + e)] = F[e + 3 * 2] * g[0] + F[e + 3 * 0] * g[2];
+      }
+    }
+  }
+
+  // add_geometric_stiffness_matrix (calc_lib.hpp:1188-1207)
+  void add_geometric_stiffness(int n, const JacMap& jm, const double* S, double fac, double* Ke)
+  {
+    const int nd = 3 * n;
+    for (int i = 0; i < n; ++i)
+    {
+      double gi[3];
+      for (int d = 0; d < 3; ++d)
+      {
+        double v = 0.0;
+        for (int a = 0; a < 3; ++a) v += jm.G[i][a] * S[VG[a][d]];
+        gi[d] = v * fac;
+      }
+      for (int j = 0; j < n; ++j)
+      {
+        double sg = 0.0;
+        for (int d = 0; d < 3; ++d) sg += gi[d] * jm.G[j][d];
+        for (int b = 0; b < 3; ++b) Ke[(3 * i + b) + nd * (3 * j + b)] += sg;
+      }
+    }
+  }
+
+  // Green-Lagrange strain and right Cauchy-Green tensor of F (calc_lib.hpp:697-722)
+  void cauchy_green(const double* F, double* C, double* E)
+  {
+    for (int v = 0; v < 6; ++v)
+    {
+      double s = 0.0;
+      for (int c = 0; c < 3; ++c) s += F[c + 3 * VA[v]] * F[c + 3 * VB[v]];
+      C[v] = s;
+      if (E) E[v] = 0.5 * (s - (v < 3 ? 1.0 : 0.0));
+    }
+  }
+
+  // ---- SolidEleCalc<hex8, FBarFormulation>  (src/solid_ele/4C_solid_ele_calc_fbar.hpp:58-180,
+  //      src/solid_ele/4C_solid_ele_calc_lib_fbar.hpp:47-160)
+  int element_fbar(int ct, int matkind, const double* par, int action, const double* X,
+      const double* u, double* Ke, double* fe)
+  {
+    const int n = nnodes(ct), nd = 3 * n, ng = ngauss(ct);
+    double N[MAXN], dN[3 * MAXN];
+    JacMap jm, jm0;
+    if (Ke) std::memset(Ke, 0, sizeof(double) * nd * nd);
+    std::memset(fe, 0, sizeof(double) * nd);
+
+    // prepare(): Jacobian mapping and deformation gradient at the element centroid (:58-66)
+    const double xi0[3] = {0.0, 0.0, 0.0};
+    shape(ct, xi0, N, dN);
+    jacobian_mapping(n, dN, X, jm0);
+    double F0[9], iF0[9];
+    deformation_gradient(n, u, jm0, F0);
+    const double detF0 = det3(F0);
+    inv3(iF0, F0);
+
+    int err = 0;
+    for (int k = 0; k < n; ++k)
+    {
+      double xi[3];
+      node_ref(ct, k, xi);
+      shape(ct, xi, N, dN);
+      jacobian_mapping(n, dN, X, jm);
+      if (!(jm.det > 0)) err = 1;
+    }
+    if (err) return 1;
+
+    double gxi[3 * MAXN], gw[MAXN];
+    gauss(ct, gxi, gw);
+    std::vector<double> B(6 * nd), CB(6 * nd), Hop(nd), bops(nd), bopccg(nd);
+    for (int gp = 0; gp < ng; ++gp)
+    {
+      shape(ct, gxi + 3 * gp, N, dN);
+      jacobian_mapping(n, dN, X, jm);
+      const double fac = jm.det * gw[gp];
+      double F[9], iF[9], C[6], Fbar[9], Cbar[6], Ebar[6], S[6], Cm[36];
+      deformation_gradient(n, u, jm, F);
+      const double detF = det3(F);
+      inv3(iF, F);
+      // evaluate_fbar_factor (lib_fbar.hpp:47-51)
+      const double fbar = std::pow(detF0 / detF, 1.0 / 3.0);
+      strain_gradient(n, jm, F, B.data());
+      // evaluate_fbar_h_operator (lib_fbar.hpp:71-104)
+      for (int idof = 0; idof < nd; ++idof)
+      {
+        const int node = idof / 3, c = idof % 3;
+        double h = 0.0;
+        for (int d = 0; d < 3; ++d)
+        {
+          h += iF0[d + 3 * c] * jm0.G[node][d];
+          h -= iF[d + 3 * c] * jm.G[node][d];
+        }
+        Hop[idof] = h;
+      }
+      cauchy_green(F, C, nullptr);
+      // F_bar = (detF_0/detF)^1/3 F and its strains (fbar.hpp:103-112)
+      for (int i = 0; i < 9; ++i) Fbar[i] = fbar * F[i];
+      cauchy_green(Fbar, Cbar, Ebar);
+      material(matkind, par, Fbar, Ebar, S, Cm);
+
+      // add_internal_force_vector(Bop, stress, fac / fbar) (fbar.hpp:152-162)
+      for (int r = 0; r < nd; ++r)
+      {
+        double v = 0.0;
+        for (int I = 0; I < 6; ++I) v += B[I + 6 * r] * S[I];
+        fe[r] += (fac / fbar) * v;
+      }
+      if (!(action == ORC_ACTION_FORCE_STIFF && Ke)) continue;
+      // add_elastic_stiffness_matrix(Bop, stress, fac * fbar) (fbar.hpp:173-174)
+      for (int c = 0; c < nd; ++c)
+        for (int I = 0; I < 6; ++I)
+        {
+          double v = 0.0;
+          for (int J = 0; J < 6; ++J) v += Cm[I + 6 * J] * B[J + 6 * c];
+          CB[I + 6 * c] = v;
+        }
+      for (int r = 0; r < nd; ++r)
+        for (int c = 0; c < nd; ++c)
+        {
+          double v = 0.0;
+          for (int I = 0; I < 6; ++I) v += B[I + 6 * r] * CB[I + 6 * c];
+          Ke[r + nd * c] += (fac * fbar) * v;
+        }
+      // add_geometric_stiffness_matrix(jacobian_mapping, pk2, fac / fbar) (fbar.hpp:175-176)
+      add_geometric_stiffness(n, jm, S, fac / fbar, Ke);
+      // add_fbar_stiffness_matrix (lib_fbar.hpp:121-160): ccg = cmat : C (C of the unscaled F)
+      double ccg[6];
+      for (int I = 0; I < 6; ++I)
+      {
+        double v = 0.0;
+        for (int J = 0; J < 6; ++J) v += Cm[I + 6 * J] * C[J] * (J < 3 ? 1.0 : 2.0);
+        ccg[I] = v;
+      }
+      for (int r = 0; r < nd; ++r)
+      {
+        double a = 0.0, b = 0.0;
+        for (int I = 0; I < 6; ++I) a += B[I + 6 * r] * ccg[I], b += B[I + 6 * r] * S[I];
+        bopccg[r] = (fac * fbar / 3.0) * a;
+        bops[r] = (-fac / fbar / 3.0) * b;
+      }
+      for (int r = 0; r < nd; ++r)
+        for (int c = 0; c < nd; ++c) Ke[r + nd * c] += Hop[c] * (bops[r] + bopccg[r]);
+    }
+    return 0;
+  }
+
+  int element_tech(int ct, int tech, int matkind, const double* par, int action, const double* X,
+      const double* u, double* Ke, double* fe)
+  {
+    if (tech == ORC_TECH_FBAR) return element_fbar(ct, matkind, par, action, X, u, Ke, fe);
+    return element(ct, matkind, par, action, X, u, Ke, fe);
+  }
 }  // namespace
 
 extern "C"
@@ -553,6 +722,11 @@ extern "C"
       const double* u, double* Ke, double* fe)
   {
     return element(ct, matkind, par, action, X, u, Ke, fe);
+  }
+  int orc_element_tech(int ct, int tech, int matkind, const double* par, int action,
+      const double* X, const double* u, double* Ke, double* fe)
+  {
+    return element_tech(ct, tech, matkind, par, action, X, u, Ke, fe);
   }
 
   static void point_setup(
@@ -622,6 +796,17 @@ extern "C"
       const int32_t* node_col_lid, int64_t n_row_nodes, const int64_t* rowptr,
       const int32_t* colind, double* values, double* f, int nthreads)
   {
+    return orc_evaluate_assemble_tech(ct, ORC_TECH_NONE, matkind, matparams, mue_per_ele, action,
+        n_ele, conn, n_col_nodes, X, u_col, node_row_lid, node_col_lid, n_row_nodes, rowptr, colind,
+        values, f, nthreads);
+  }
+
+  int64_t orc_evaluate_assemble_tech(int ct, int tech, int matkind, const double* matparams,
+      const double* mue_per_ele, int action, int64_t n_ele, const int32_t* conn,
+      int64_t n_col_nodes, const double* X, const double* u_col, const int32_t* node_row_lid,
+      const int32_t* node_col_lid, int64_t n_row_nodes, const int64_t* rowptr,
+      const int32_t* colind, double* values, double* f, int nthreads)
+  {
     (void)n_col_nodes;
     const int n = nnodes(ct), nd = 3 * n;
     if (nthreads < 1) nthreads = 1;
@@ -657,8 +842,8 @@ extern "C"
           }
         if (mue_per_ele) par[0] = mue_per_ele[e];  // InputField MUE looked up by element id
         const bool stiff = (action == ORC_ACTION_FORCE_STIFF) && values;
-        if (element(ct, matkind, par, action, Xe.data(), ue.data(), stiff ? Ke.data() : nullptr,
-                fe.data()))
+        if (element_tech(ct, tech, matkind, par, action, Xe.data(), ue.data(),
+                stiff ? Ke.data() : nullptr, fe.data()))
         {
           bad[tid]++;
           continue;

@@ -8,13 +8,15 @@
 #include <vector>
 
 #include "../../4c_b200/csrc/hex8_kernel.cuh"
+#include "../../4c_b200/csrc/hex8_fbar_kernel.cuh"
 #include "../../4c_b200/csrc/shape_tables.hpp"
 
 using namespace b200s;
 
-template <int MAT, bool STIFF>
+template <int MAT, bool STIFF, int TECH>
 static void run(const EvalArgs& A, double* min_detJ, double* min_detF, int64_t* n_bad)
 {
+  constexpr int MP_SIZE = TECH ? hex8fbar::MP_SIZE : hex8::MP_SIZE;
   const CellTables T = make_cell_tables(0);
   std::vector<double> tab_gp(hex8::TAB_SIZE, 0.0), tab_node(hex8::TAB_SIZE, 0.0);
   for (int t = 0; t < 8 * 24; ++t)
@@ -22,19 +24,20 @@ static void run(const EvalArgs& A, double* min_detJ, double* min_detF, int64_t* 
     tab_gp[(t / 24) * hex8::TAB_STRIDE + (t % 24)] = T.dN_gp[t];
     tab_node[(t / 24) * hex8::TAB_STRIDE + (t % 24)] = T.dN_node[t];
   }
-  std::vector<double> sm(hex8::WARP_DOUBLES + 2, 0.0);
+  std::vector<double> sm((TECH ? hex8fbar::WARP_DOUBLES : hex8::WARP_DOUBLES) + 2, 0.0);
   std::vector<NodeRow> nrow(hex8::EPW * hex8::NN);
   std::vector<int32_t> posbuf(hex8::EPW * hex8::NN * hex8::NN);
   hex8::WarpSmem S;
   // 16-byte align the double2 region; same carve-up as the kernel
   S.mp = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sm.data()) + 15) & ~uintptr_t(15));
-  S.g = S.mp + hex8::MP_SIZE;
+  S.g = S.mp + MP_SIZE;
   S.xu = S.g + hex8::G_SIZE;
+  if (TECH) S.h0 = S.xu + hex8::XU_SIZE;
   S.nrow = nrow.data(), S.pos = posbuf.data();
   *min_detJ = 1e300, *min_detF = 1e300, *n_bad = 0;
   const int64_t n_tiles = (A.n_ele + hex8::EPW - 1) / hex8::EPW;
   static double out54[32][54];
-  static double Kacc[32][5][9], facc[32][3];
+  static double Kacc[32][TECH ? 8 : 5][9], facc[32][3];
   for (int64_t tile = 0; tile < n_tiles; ++tile)
   {
     const int64_t e0 = tile * hex8::EPW;
@@ -44,8 +47,12 @@ static void run(const EvalArgs& A, double* min_detJ, double* min_detF, int64_t* 
     {
       double dJ, dF;
       bool neg;
-      hex8::phase1<MAT, STIFF>(A, S, tab_gp.data(), tab_node.data(), T.w.data(), lane, e0,
-          out54[lane], dJ, dF, neg);
+      if (TECH)
+        hex8fbar::phase1<MAT, STIFF>(
+            A, S, tab_gp.data(), T.w.data(), lane, e0, out54[lane], dJ, dF, neg);
+      else
+        hex8::phase1<MAT, STIFF>(A, S, tab_gp.data(), tab_node.data(), T.w.data(), lane, e0,
+            out54[lane], dJ, dF, neg);
       if (e0 + (lane >> 3) < A.n_ele)
       {
         if (dJ < *min_detJ) *min_detJ = dJ;
@@ -55,13 +62,21 @@ static void run(const EvalArgs& A, double* min_detJ, double* min_detF, int64_t* 
     }
     for (bool b : negel) *n_bad += b;
     for (int lane = 0; lane < 32; ++lane) hex8::phase1_store<STIFF>(S, lane, out54[lane]);
-    for (int lane = 0; lane < 32; ++lane) hex8::phase2<STIFF>(S, lane, Kacc[lane], facc[lane]);
-    for (int lane = 0; lane < 32; ++lane) hex8::stage_ke<STIFF>(S, lane, Kacc[lane], facc[lane]);
+    if constexpr (TECH != 0)
+    {
+      for (int lane = 0; lane < 32; ++lane) hex8fbar::phase2<STIFF>(S, lane, Kacc[lane], facc[lane]);
+      for (int lane = 0; lane < 32; ++lane) hex8fbar::stage_ke<STIFF>(S, lane, Kacc[lane], facc[lane]);
+    }
+    else
+    {
+      for (int lane = 0; lane < 32; ++lane) hex8::phase2<STIFF>(S, lane, Kacc[lane], facc[lane]);
+      for (int lane = 0; lane < 32; ++lane) hex8::stage_ke<STIFF>(S, lane, Kacc[lane], facc[lane]);
+    }
     for (int lane = 0; lane < 32; ++lane) hex8::scatter<STIFF>(A, S, lane, e0);
   }
 }
 
-extern "C" int emu_hex8(int matkind, const double* params, const double* per_ele, int stiff,
+static int emu_hex8_tech(int tech, int matkind, const double* params, const double* per_ele, int stiff,
     int64_t n_ele, const int32_t* conn, const double* X, const double* u_col, const int32_t* pos,
     const int64_t* node_rowstart, const int32_t* node_rowlen, const int32_t* node_frow,
     int64_t n_col_nodes, double* vals, double* f, double* min_detJ, double* min_detF, int64_t* n_bad)
@@ -76,10 +91,14 @@ extern "C" int emu_hex8(int matkind, const double* params, const double* per_ele
   A.vals = vals, A.f = f, A.err = nullptr, A.n_ele = n_ele, A.scatter_mode = 0;
   if (!make_mat_params(matkind, params, A.mp)) return -3;
 #define RUN(M)                                                  \
-  if (stiff)                                                    \
-    run<M, true>(A, min_detJ, min_detF, n_bad);                 \
+  if (tech && stiff)                                            \
+    run<M, true, 1>(A, min_detJ, min_detF, n_bad);              \
+  else if (tech)                                                \
+    run<M, false, 1>(A, min_detJ, min_detF, n_bad);             \
+  else if (stiff)                                               \
+    run<M, true, 0>(A, min_detJ, min_detF, n_bad);              \
   else                                                          \
-    run<M, false>(A, min_detJ, min_detF, n_bad)
+    run<M, false, 0>(A, min_detJ, min_detF, n_bad)
   if (matkind == 0)
   {
     RUN(MAT_COUP_NEOHOOKE);
@@ -93,4 +112,22 @@ extern "C" int emu_hex8(int matkind, const double* params, const double* per_ele
     RUN(MAT_SVK);
   }
   return 0;
+}
+
+extern "C" int emu_hex8(int matkind, const double* params, const double* per_ele, int stiff,
+    int64_t n_ele, const int32_t* conn, const double* X, const double* u_col, const int32_t* pos,
+    const int64_t* node_rowstart, const int32_t* node_rowlen, const int32_t* node_frow,
+    int64_t n_col_nodes, double* vals, double* f, double* min_detJ, double* min_detF, int64_t* n_bad)
+{
+  return emu_hex8_tech(0, matkind, params, per_ele, stiff, n_ele, conn, X, u_col, pos, node_rowstart,
+      node_rowlen, node_frow, n_col_nodes, vals, f, min_detJ, min_detF, n_bad);
+}
+// F-bar variant (hex8_fbar_kernel.cuh)
+extern "C" int emu_hex8fbar(int matkind, const double* params, const double* per_ele, int stiff,
+    int64_t n_ele, const int32_t* conn, const double* X, const double* u_col, const int32_t* pos,
+    const int64_t* node_rowstart, const int32_t* node_rowlen, const int32_t* node_frow,
+    int64_t n_col_nodes, double* vals, double* f, double* min_detJ, double* min_detF, int64_t* n_bad)
+{
+  return emu_hex8_tech(1, matkind, params, per_ele, stiff, n_ele, conn, X, u_col, pos, node_rowstart,
+      node_rowlen, node_frow, n_col_nodes, vals, f, min_detJ, min_detF, n_bad);
 }

@@ -10,6 +10,8 @@ What it writes
           tests/input_files/solid_ele_hex8_Standard_eas_none_stressout.4C.yaml
           tests/input_files/solid_ele_hex27_Standard_stressout.4C.yaml
           tests/input_files/solid_ele_tet10_Standard_stressout.4C.yaml
+  integration_cooks_fbar.json : Cook's membrane with 64 F-bar hex8 elements
+          tests/input_files/sohex8fbar_cooks_nl_new_struc.4C.yaml (dispy of node 162, 1e-8)
   unit_known_answers.json : known answers of unittests/mat/4C_elasthyper_service_test.cpp:36-155,
         unittests/mat/4C_stvenantkirchhoff_test.cpp:44-118 and the glibc srand(0)/rand() input
         sequence of unittests/solid_ele/4C_solid_ele_calc_lib_test.cpp:243-343
@@ -94,6 +96,61 @@ def integration_case(cell, rel):
     }
 
 
+def cooks_case(rel, tech):
+    """Cook's membrane inputs (64 hex8, CoupNeoHooke nu=0.4999): several Dirichlet conditions with
+    per-dof ONOFF, one dead surface load, known answer = dispy of node 162 (and internal energy)."""
+    with open(os.path.join(REF, rel)) as fh:
+        y = yaml.safe_load(fh)
+    nodes = {}
+    for line in y["NODE COORDS"]:
+        m = re.match(r"NODE\s+(\d+)\s+COORD\s+(\S+)\s+(\S+)\s+(\S+)", line)
+        nodes[int(m.group(1))] = [float(m.group(i)) for i in (2, 3, 4)]
+    coords = [nodes[i + 1] for i in range(max(nodes))]
+    eles = []
+    for line in y["STRUCTURE ELEMENTS"]:
+        tok = line.split()
+        assert tok[1] == "SOLID" and tok[2] == "HEX8" and f"TECH {tech}" in line and "nonlinear" in line
+        eles.append([int(t) - 1 for t in tok[3:11]])
+    surf = {}
+    for line in y["DSURF-NODE TOPOLOGY"]:
+        m = re.match(r"NODE\s+(\d+)\s+DSURFACE\s+(\d+)", line)
+        surf.setdefault(int(m.group(2)), []).append(int(m.group(1)) - 1)
+    mats = {m["MAT"]: m for m in y["MATERIALS"]}
+    eh = mats[1]["MAT_ElastHyper"]
+    assert eh["NUMMAT"] == 1
+    nh = mats[eh["MATIDS"][0]]["ELAST_CoupNeoHooke"]
+    fixed = set()
+    for dbc in y["DESIGN SURF DIRICH CONDITIONS"]:
+        assert all(v == 0 for v in dbc["VAL"])
+        for n in surf[dbc["E"]]:
+            for d in range(3):
+                if dbc["ONOFF"][d]:
+                    fixed.add(3 * n + d)
+    (neu,) = y["DESIGN SURF NEUMANN CONDITIONS"]
+    sd = y["STRUCTURAL DYNAMIC"]
+    expected, energy = [], None
+    for r in y["RESULT DESCRIPTION"]:
+        s = r["STRUCTURE"]
+        if s["QUANTITY"] in ("dispx", "dispy", "dispz"):
+            expected.append({"node": s["NODE"] - 1, "dof": "xyz".index(s["QUANTITY"][-1]),
+                             "value": float(s["VALUE"]), "tol": float(s["TOLERANCE"])})
+        if s["QUANTITY"] == "internal_energy":
+            energy = {"value": float(s["VALUE"]), "tol": float(s["TOLERANCE"])}
+    return {
+        "source": rel, "celltype": "hex8", "tech": tech, "coords": coords, "elements": eles,
+        "material": {"kind": "ELAST_CoupNeoHooke", "YOUNG": float(nh["YOUNG"]), "NUE": float(nh["NUE"])},
+        "dirichlet_dofs": sorted(fixed), "dirichlet_nodes": [],
+        "neumann_nodes": sorted(surf[neu["E"]]),
+        "neumann": {"ONOFF": neu["ONOFF"] + [0] * 3, "VAL": neu["VAL"] + [0] * 3,
+                    "FUNCT": neu["FUNCT"] + [0] * 3,
+                    "FUNCT1": y["FUNCT1"][0]["SYMBOLIC_FUNCTION_OF_SPACE_TIME"], "FUNCT2": None},
+        "timestep": float(sd["TIMESTEP"]), "numstep": int(sd["NUMSTEP"]),
+        "tolres": float(sd["TOLRES"]), "toldisp": float(sd["TOLDISP"]),
+        "normcombi": sd.get("NORMCOMBI_RESFDISP", "And"),
+        "expected_disp": expected, "expected_internal_energy": energy,
+    }
+
+
 def unit_known_answers():
     libc = ctypes.CDLL("libc.so.6")
     libc.srand(0)
@@ -172,6 +229,10 @@ if __name__ == "__main__":
     for cell, rel in CASES.items():
         with open(os.path.join(HERE, f"integration_{cell}.json"), "w") as fh:
             json.dump(integration_case(cell, rel), fh, indent=1)
+    for name, rel, tech in (
+            ("cooks_fbar", "tests/input_files/sohex8fbar_cooks_nl_new_struc.4C.yaml", "fbar"),):
+        with open(os.path.join(HERE, f"integration_{name}.json"), "w") as fh:
+            json.dump(cooks_case(rel, tech), fh)
     with open(os.path.join(HERE, "unit_known_answers.json"), "w") as fh:
         json.dump(unit_known_answers(), fh, indent=1)
     np.savez_compressed(os.path.join(HERE, "ref_elements.npz"), **ref_elements())

@@ -12,11 +12,12 @@ _libs = {}
 
 
 def lib(cell="hex8"):
+    cell = {"hex8fbar": "hex8"}.get(cell, cell)
     if cell not in _libs:
         so = os.path.join(_CPP, f"libemu_{cell}.so")
         srcs = [os.path.join(_CPP, f"emulate_{cell}.cpp")] + [
             os.path.join(_CPP, "..", "..", "4c_b200", "csrc", f)
-            for f in ("hex8_kernel.cuh", "tet10_kernel.cuh", "hex27_kernel.cuh", "solid_math.cuh", "shape_tables.hpp")]
+            for f in ("hex8_kernel.cuh", "hex8_fbar_kernel.cuh", "tet10_kernel.cuh", "hex27_kernel.cuh", "solid_math.cuh", "shape_tables.hpp")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", so, srcs[0]])
         _libs[cell] = C.CDLL(so)

@@ -68,7 +68,8 @@ def neumann_load(case, time):
     kind, fn = {"hex8": ("quad4", _quad4), "hex27": ("quad9", _quad9), "tet10": ("tri6", _tri6)}[cell]
     gx, gw = _rule(kind)
     val, onoff, funct = case["neumann"]["VAL"], case["neumann"]["ONOFF"], case["neumann"]["FUNCT"]
-    assert case["neumann"]["FUNCT1"] == "t" and case["neumann"]["FUNCT2"] == "(x+1)*(y+2)*(z+3)"
+    assert case["neumann"]["FUNCT1"] == "t"
+    assert case["neumann"]["FUNCT2"] in ("(x+1)*(y+2)*(z+3)", None)
     f = np.zeros(3 * len(X))
     for conn in case["elements"]:
         for face in FACES[cell]:

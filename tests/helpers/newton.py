@@ -17,6 +17,8 @@ def solve_case(case, evaluate, max_iter=30):
     fixed = np.zeros(3 * nn, bool)
     for n in case["dirichlet_nodes"]:
         fixed[3 * n:3 * n + 3] = True
+    fixed[case.get("dirichlet_dofs", [])] = True
+    combine_or = case.get("normcombi", "And") == "Or"  # NORMCOMBI_RESFDISP
     free = ~fixed
     u = np.zeros(3 * nn)
     t = 0.0
@@ -32,7 +34,8 @@ def solve_case(case, evaluate, max_iter=30):
             u += du
             rowptr, colind, values, fint = evaluate(u)
             rnorm = np.linalg.norm((fint - fext)[free])
-            if rnorm < case["tolres"] and np.linalg.norm(du) < case["toldisp"]:
+            ok_r, ok_d = rnorm < case["tolres"], np.linalg.norm(du) < case["toldisp"]
+            if (ok_r or ok_d) if combine_or else (ok_r and ok_d):
                 break
         else:
             raise RuntimeError(f"Newton did not converge at t={t}: |r|={rnorm}")

@@ -502,3 +502,58 @@ def test_hex27_properties_and_slab_at_scale():
     ok, wK, wf = b200.parity_report(o_rowptr, K[lo:hi], rK, f[full_rows], rf, RTOL)
     assert ok and nbad == 0, (wK, wf)
     asm.close()
+
+
+# ---- F-bar hex8 (TECH fbar) -----------------------------------------------------------------------
+@pytest.mark.parametrize("mk", list(MATS))
+@pytest.mark.parametrize("n", [(1, 1, 1), (7, 5, 3), (16, 12, 9)])
+def test_hex8_fbar_matches_oracle(mk, n):
+    rm = b200.partition.box_partition(b200.mesh.HEX8, n, 0, 1)
+    u = 3.0 * b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 1.0 / max(n))
+    per_ele = None
+    if mk == capi.MAT_ISO_VOL:
+        per_ele = 1.0 + 0.1 * np.arange(rm.n_col_eles) / rm.n_col_eles
+    asm = b200.DeviceAssembler(rm, mk, MATS[mk], per_ele_param=per_ele, tech=capi.TECH_FBAR)
+    rowptr, colind = asm.graph()
+    asm.set_state("displacement", u.ravel())
+    K, f, err = asm.evaluate("struct_calc_nlnstiff")
+    rK, rf, nbad = orc.evaluate_assemble(orc.HEX8, mk, MATS[mk], rm.conn, rm.X.ravel(), u.ravel(),
+                                         rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, rowptr, colind,
+                                         mue_per_ele=per_ele, nthreads=4, tech=orc.TECH_FBAR)
+    ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
+    assert ok and nbad == 0, (wK, wf)
+    assert err.n_neg_jacobian == 0 and err.min_detJ > 0
+    _, f2, _ = asm.evaluate("struct_calc_internalforce")
+    assert np.abs(f2 - rf).max() <= RTOL * np.abs(rf).max()
+    asm.close()
+
+
+def test_golden_cooks_membrane_fbar_through_cuda_path():
+    """tests/input_files/sohex8fbar_cooks_nl_new_struc.4C.yaml: 64 F-bar hex8, nu = 0.4999, 20 load
+    steps; dispy of node 162 to the reference's 1e-8 with the CUDA path inside the Newton loop."""
+    case = json.load(open(os.path.join(G, "integration_cooks_fbar.json")))
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    rm = b200.partition.serial_mesh(b200.mesh.HEX8, X, conn)
+    par = [case["material"]["YOUNG"], case["material"]["NUE"]]
+    asm = b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, par, tech=capi.TECH_FBAR)
+    rowptr, colind = asm.graph()
+
+    def evaluate(u):
+        asm.set_state("displacement", u)
+        K, f, _ = asm.evaluate()
+        return rowptr, colind, K, f
+
+    u = solve_case(case, evaluate)
+    for e in case["expected_disp"]:
+        assert abs(u[e["node"], e["dof"]] - e["value"]) < e["tol"], e
+    asm.close()
+
+
+def test_unsupported_element_properties_are_rejected():
+    ctx = capi.Context(0)
+    for kw in (dict(tech=capi.TECH_EAS_FULL), dict(prestress=capi.PRESTRESS_MULF), dict(kinem=capi.KINEM_LINEAR)):
+        with pytest.raises(capi.B200SolidError) as ei:
+            ctx.set_element_properties(**kw)
+        assert ei.value.code == capi.ERR_UNSUPPORTED
+    ctx.close()

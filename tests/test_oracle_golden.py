@@ -177,6 +177,45 @@ def test_integration_known_answers(cell):
         assert abs(u[e["node"], e["dof"]] - e["value"]) < e["tol"], (e, u[e["node"], e["dof"]])
 
 
+def test_cooks_membrane_fbar_known_answer():
+    """tests/input_files/sohex8fbar_cooks_nl_new_struc.4C.yaml (64 F-bar hex8, CoupNeoHooke nu=0.4999,
+    20 load steps): dispy of node 162 to the reference's 1e-8 -- pins the F-bar restatement."""
+    case = json.load(open(os.path.join(G, "integration_cooks_fbar.json")))
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    nn = len(X)
+    row, col = serial_maps(nn)
+    rowptr, colind = orc.build_graph(orc.HEX8, conn, row, col, nn)
+    par = [case["material"]["YOUNG"], case["material"]["NUE"]]
+
+    def evaluate(u):
+        vals, f, nbad = orc.evaluate_assemble(orc.HEX8, orc.MAT_COUP_NEOHOOKE, par, conn, X.ravel(), u,
+                                              row, col, nn, rowptr, colind, tech=orc.TECH_FBAR)
+        assert nbad == 0
+        return rowptr, colind, vals, f
+
+    u = solve_case(case, evaluate)
+    assert case["expected_disp"]
+    for e in case["expected_disp"]:
+        assert abs(u[e["node"], e["dof"]] - e["value"]) < e["tol"], (e, u[e["node"], e["dof"]])
+
+
+def test_fbar_tangent_is_derivative_of_force():
+    rng = np.random.default_rng(11)
+    X, u = REFEL["hex8_X"], 2.0 * REFEL["hex8_u"]
+    for mk in (orc.MAT_COUP_NEOHOOKE, orc.MAT_ISO_VOL, orc.MAT_SVK):
+        par = REFEL[f"m{mk}_par"]
+        Ke, fe, _ = orc.element(orc.HEX8, mk, par, X, u, tech=orc.TECH_FBAR)
+        h = 1e-6
+        for col in rng.choice(24, 6, replace=False):
+            du = np.zeros(24)
+            du[col] = h
+            fp = orc.element(orc.HEX8, mk, par, X, u + du.reshape(8, 3), orc.ACTION_FORCE, tech=orc.TECH_FBAR)[1]
+            fm = orc.element(orc.HEX8, mk, par, X, u - du.reshape(8, 3), orc.ACTION_FORCE, tech=orc.TECH_FBAR)[1]
+            assert np.abs((fp - fm) / (2 * h) - Ke[:, col]).max() < 2e-6 * np.abs(Ke).max()
+        assert np.abs(Ke - Ke.T).max() > 1e-6 * np.abs(Ke).max()  # the F-bar tangent is not symmetric
+
+
 def test_assembly_threads_equal_serial():
     """Owner-computes with emulated ranks (threads) gives bitwise the same rows as one rank."""
     from tests.helpers.meshes import serial_maps
