@@ -13,21 +13,34 @@ import numpy as np
 from . import capi
 
 ACTIONS = {"struct_calc_nlnstiff": capi.ACTION_NLNSTIFF,
-           "struct_calc_internalforce": capi.ACTION_INTERNALFORCE}
+           "struct_calc_internalforce": capi.ACTION_INTERNALFORCE,
+           "struct_calc_nlnstiffmass": capi.ACTION_NLNSTIFFMASS,
+           "struct_calc_nlnstifflmass": capi.ACTION_NLNSTIFFLMASS,
+           "struct_calc_internalinertiaforce": capi.ACTION_INTERNALINERTIAFORCE}
+STIFF_ACTIONS = (capi.ACTION_NLNSTIFF, capi.ACTION_NLNSTIFFMASS, capi.ACTION_NLNSTIFFLMASS)
+NUM_GP = {capi.HEX8: 8, capi.HEX27: 27, capi.TET10: 4}
 
 
 class DeviceAssembler:
     def __init__(self, rank_mesh, matkind, matparams, device=0, per_ele_param=None, graph=None,
-                 tech=capi.TECH_NONE):
+                 tech=capi.TECH_NONE, density=None):
         """rank_mesh: partition.RankMesh.  graph: (rowptr, colind) from the reference's matrix, or
         None to build the FillComplete-equivalent graph on the device.  tech: element technology of
-        the block (TECH key of the SOLID element line)."""
+        the block (TECH key of the SOLID element line).  matkind MAT_ELASTHYPER: matparams is the
+        summand list [(name, [params]), ...].  density: DENS of the material (mass actions)."""
         rm = self.rm = rank_mesh
         self.ctx = capi.Context(device, rm.rank, rm.nranks)
         self.ctx.set_mesh(rm.celltype, rm.X, rm.conn)
         if tech != capi.TECH_NONE:
             self.ctx.set_element_properties(tech=tech)
-        self.ctx.set_material(matkind, matparams, per_ele_param)
+        if matkind == capi.MAT_ELASTHYPER:
+            self.ctx.set_material_elasthyper(matparams)
+        else:
+            self.ctx.set_material(matkind, matparams, per_ele_param)
+        if density is not None:
+            self.ctx.set_density(density)
+        if getattr(rm, "ele_is_row", None) is not None:
+            self.ctx.set_row_elements(rm.ele_is_row)
         if graph is None:
             self.nnz = self.ctx.build_graph(rm.n_row_nodes, rm.node_row_lid, rm.node_col_lid)
         else:
@@ -50,17 +63,33 @@ class DeviceAssembler:
         return rowptr, colind
 
     def set_state(self, name, u_row):
-        assert name == "displacement"
-        self._u = np.ascontiguousarray(u_row, np.float64).ravel()
-        assert self._u.size == self.n_rows
+        v = np.ascontiguousarray(u_row, np.float64).ravel()
+        assert v.size == self.n_rows
+        if name == "displacement":
+            self._u = v
+        self.ctx.set_state(name, v)
 
     def evaluate(self, action="struct_calc_nlnstiff", check=True):
         """Returns (K_values or None, f, error_info) as host arrays."""
         act = ACTIONS[action]
-        K = np.empty(self.nnz) if act == capi.ACTION_NLNSTIFF else None
+        K = np.empty(self.nnz) if act in STIFF_ACTIONS else None
         f = np.empty(self.n_rows)
         rc, err = self.ctx.evaluate(act, self._u, K, f, check=check)
         return K, f, err
+
+    def mass(self, want_matrix=True):
+        """(M_values, f_inertia) of the last mass action."""
+        return self.ctx.get_mass(want_matrix=want_matrix)
+
+    def calc_stress(self, iostress="2pk", iostrain="gl"):
+        """struct_calc_stress: (stress, strain) arrays [n_col_eles, num_gp, 6]."""
+        st = {"none": capi.STRESS_NONE, "2pk": capi.STRESS_2PK, "cauchy": capi.STRESS_CAUCHY}[iostress]
+        en = {"none": capi.STRAIN_NONE, "gl": capi.STRAIN_GL, "ea": capi.STRAIN_EA}[iostrain]
+        return self.ctx.calc_stress(NUM_GP[self.rm.celltype], st, en)
+
+    def calc_energy(self):
+        """struct_calc_energy: internal energy of this rank's row elements."""
+        return self.ctx.calc_energy()
 
     def close(self):
         self.ctx.close()

@@ -14,8 +14,17 @@ LIB_PATH = os.path.join(_HERE, "lib4c_b200_solid.so")
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NEG_JACOBIAN, ERR_NONFINITE, ERR_COMM = -1, -2, -3, -4, -5, -6
 HEX8, HEX27, TET10 = 0, 1, 2
-MAT_COUP_NEOHOOKE, MAT_ISO_VOL, MAT_SVK = 0, 1, 2
-ACTION_INTERNALFORCE, ACTION_NLNSTIFF = 0, 1
+MAT_COUP_NEOHOOKE, MAT_ISO_VOL, MAT_SVK, MAT_ELASTHYPER = 0, 1, 2, 3
+ACTION_INTERNALFORCE, ACTION_NLNSTIFF, ACTION_NLNSTIFFMASS, ACTION_NLNSTIFFLMASS, ACTION_INTERNALINERTIAFORCE = 0, 1, 2, 3, 4
+STRESS_NONE, STRESS_2PK, STRESS_CAUCHY = 0, 1, 2
+STRAIN_NONE, STRAIN_GL, STRAIN_EA = 0, 1, 2
+MATRIX_STIFFNESS, MATRIX_MASS = 0, 1
+# b200s_summand ids (include/b200_solid.h), by name
+SUMMANDS = ["COUP_NEOHOOKE", "COUP_MOONEYRIVLIN", "COUP_LOGNEOHOOKE", "COUP_LOGMIXNEOHOOKE", "COUP_SVK",
+            "COUP_SIMOPISTER", "COUP_BLATZKO", "COUP_EXPPOL", "COUP_1POW", "COUP_2POW", "COUP_3POW",
+            "COUP_13APOW", "ISO_NEOHOOKE", "ISO_MOONEYRIVLIN", "ISO_YEOH", "ISO_1POW", "ISO_2POW",
+            "ISO_EXPOPOW", "VOL_SUSSMANBATHE", "VOL_PENALTY", "VOL_OGDEN", "VOL_POW"]
+SUM = {name: i for i, name in enumerate(SUMMANDS)}
 KINEM_NONLINEAR_TOTLAG, KINEM_LINEAR = 0, 1
 TECH_NONE, TECH_FBAR, TECH_EAS_MILD, TECH_EAS_FULL = 0, 1, 2, 3
 PRESTRESS_NONE, PRESTRESS_MULF = 0, 1
@@ -30,6 +39,10 @@ SYMBOLS = [
     "b200s_kernel_time",
     "b200s_build_graph", "b200s_measure_fp64_peak", "b200s_microbench", "b200s_host_alloc", "b200s_host_free",
     "b200s_version",
+    "b200s_set_material_elasthyper", "b200s_set_density", "b200s_set_row_elements", "b200s_set_state",
+    "b200s_get_mass", "b200s_device_mass_values", "b200s_device_f_inertia", "b200s_calc_stress",
+    "b200s_calc_energy", "b200s_apply_dirichlet", "b200s_apply_dirichlet_to_system", "b200s_multiply",
+    "b200s_last_multiply_ms", "b200s_solve_cg",
 ]
 
 
@@ -92,6 +105,22 @@ def load():
     L.b200s_host_free.argtypes = [vp]
     L.b200s_host_free.restype = None
     L.b200s_version.restype = C.c_char_p
+    L.b200s_set_material_elasthyper.argtypes = [vp, i32, vp, vp, vp]
+    L.b200s_set_density.argtypes = [vp, dbl]
+    L.b200s_set_row_elements.argtypes = [vp, vp]
+    L.b200s_set_state.argtypes = [vp, C.c_char_p, vp]
+    L.b200s_get_mass.argtypes = [vp, vp, vp]
+    for fn in ("b200s_device_mass_values", "b200s_device_f_inertia"):
+        getattr(L, fn).argtypes = [vp]
+        getattr(L, fn).restype = vp
+    L.b200s_calc_stress.argtypes = [vp, i32, i32, vp, vp]
+    L.b200s_calc_energy.argtypes = [vp, C.POINTER(dbl)]
+    L.b200s_apply_dirichlet.argtypes = [vp, i32, vp, i32]
+    L.b200s_apply_dirichlet_to_system.argtypes = [vp, vp, vp, vp, vp]
+    L.b200s_multiply.argtypes = [vp, i32, vp, vp]
+    L.b200s_last_multiply_ms.argtypes = [vp]
+    L.b200s_last_multiply_ms.restype = dbl
+    L.b200s_solve_cg.argtypes = [vp, vp, vp, dbl, i32, C.POINTER(i32), C.POINTER(dbl)]
     _lib = L
     return L
 
@@ -158,6 +187,69 @@ class Context:
         if per_ele_param is not None:
             per_ele_param = np.ascontiguousarray(per_ele_param, np.float64)
         self._ck(self.L.b200s_set_material(self.h, kind, _ptr(params), len(params), _ptr(per_ele_param)))
+
+    def set_material_elasthyper(self, summands):
+        """summands: list of (name or id, [input-file parameters]) or (name, params, mode)."""
+        kinds = np.asarray([SUM[s[0]] if isinstance(s[0], str) else int(s[0]) for s in summands], np.int32)
+        modes = np.asarray([s[2] if len(s) > 2 else 0 for s in summands], np.int32)
+        par = np.zeros((len(summands), 4))
+        for k, s in enumerate(summands):
+            par[k, :len(s[1])] = s[1]
+        self._ck(self.L.b200s_set_material_elasthyper(self.h, len(summands), _ptr(kinds), _ptr(modes), _ptr(par)))
+
+    def set_density(self, density):
+        self._ck(self.L.b200s_set_density(self.h, float(density)))
+
+    def set_row_elements(self, is_row):
+        is_row = None if is_row is None else np.ascontiguousarray(is_row, np.uint8)
+        self._ck(self.L.b200s_set_row_elements(self.h, _ptr(is_row)))
+
+    def set_state(self, name, v_row):
+        v_row = np.ascontiguousarray(v_row, np.float64)
+        self._ck(self.L.b200s_set_state(self.h, name.encode(), _ptr(v_row)))
+
+    def get_mass(self, want_matrix=True, want_inertia=True):
+        M = np.empty(self.nnz) if want_matrix else None
+        fi = np.empty(self.n_rows) if want_inertia else None
+        self._ck(self.L.b200s_get_mass(self.h, _ptr(M), _ptr(fi)))
+        return M, fi
+
+    def calc_stress(self, num_gp, stress_type=STRESS_2PK, strain_type=STRAIN_GL):
+        st = np.empty((self.n_col_eles, num_gp, 6)) if stress_type != STRESS_NONE else None
+        en = np.empty((self.n_col_eles, num_gp, 6)) if strain_type != STRAIN_NONE else None
+        self._ck(self.L.b200s_calc_stress(self.h, stress_type, strain_type, _ptr(st), _ptr(en)))
+        return st, en
+
+    def calc_energy(self):
+        e = C.c_double(0)
+        self._ck(self.L.b200s_calc_energy(self.h, C.byref(e)))
+        return e.value
+
+    def apply_dirichlet(self, dbctoggle_row, diagonalblock=True, which=MATRIX_STIFFNESS):
+        t = np.ascontiguousarray(dbctoggle_row, np.float64)
+        self._ck(self.L.b200s_apply_dirichlet(self.h, which, _ptr(t), int(diagonalblock)))
+
+    def apply_dirichlet_to_system(self, x_row, b_row, dbcval_row, dbctoggle_row):
+        """In place on the numpy arrays x_row / b_row (either may be None)."""
+        v = np.ascontiguousarray(dbcval_row, np.float64)
+        t = np.ascontiguousarray(dbctoggle_row, np.float64)
+        self._ck(self.L.b200s_apply_dirichlet_to_system(self.h, _ptr(x_row), _ptr(b_row), _ptr(v), _ptr(t)))
+
+    def multiply(self, x_row, which=MATRIX_STIFFNESS):
+        x = np.ascontiguousarray(x_row, np.float64)
+        y = np.empty_like(x)
+        self._ck(self.L.b200s_multiply(self.h, which, _ptr(x), _ptr(y)))
+        return y
+
+    def last_multiply_ms(self):
+        return self.L.b200s_last_multiply_ms(self.h)
+
+    def solve_cg(self, b_row, x0=None, rtol=1e-10, maxit=1000):
+        b = np.ascontiguousarray(b_row, np.float64)
+        x = np.zeros_like(b) if x0 is None else np.array(x0, np.float64)
+        it, rel = C.c_int(0), C.c_double(0)
+        self._ck(self.L.b200s_solve_cg(self.h, _ptr(b), _ptr(x), float(rtol), int(maxit), C.byref(it), C.byref(rel)))
+        return x, it.value, rel.value
 
     def set_graph(self, rowptr, colind, dof_row_lid, dof_col_lid):
         rowptr = rowptr if not isinstance(rowptr, np.ndarray) else np.ascontiguousarray(rowptr, np.int64)

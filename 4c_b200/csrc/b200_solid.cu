@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 
 #include <climits>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -16,6 +17,8 @@
 #include "hex8_fbar_kernel.cuh"
 #include "tet10_kernel.cuh"
 #include "hex27_kernel.cuh"
+#include "post_kernels.cuh"
+#include "linalg_kernels.cuh"
 #include "shape_tables.hpp"
 
 namespace b200s
@@ -932,6 +935,7 @@ struct NcclApi
   int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
 
@@ -951,6 +955,27 @@ struct b200s_ctx
   int matkind = -1;
   MatParams mp{};
   double* d_per_ele = nullptr;
+  HyperMat hm{};                // generic MAT_ElastHyper summand list (host copy)
+  HyperMat* d_hyper = nullptr;  // ... and on the device (MatParams::hyper)
+  double density = 0.0;         // Mat::So3Material::density()
+  // cell tables in global memory for the post / mass kernels (post_kernels.cuh)
+  int ngp = 0, ngp_mass = 0;
+  double *d_dN_gp = nullptr, *d_w = nullptr, *d_dN_cen = nullptr;
+  double *d_N_mass = nullptr, *d_dN_mass = nullptr, *d_w_mass = nullptr;
+  uint8_t* d_ele_is_row = nullptr;  // caller numbering; nullptr = every column element is a row element
+  // mass matrix / inertia force (struct_calc_nlnstiffmass & co.)
+  double *d_mass = nullptr, *d_f_inertia = nullptr, *d_acc_row = nullptr, *d_acc_col = nullptr;
+  // post-processing outputs
+  double* d_energy = nullptr;
+  // linear algebra on the assembled matrix (linalg_kernels.cuh)
+  int64_t n_mat_cols = 0;
+  bool node3_ok = false;
+  double *d_xmat = nullptr, *d_la_x = nullptr, *d_la_y = nullptr, *d_toggle = nullptr;
+  double *d_cg[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // r z p Ap dinv(3x)
+  double *d_cg_s = nullptr, *d_cg_hist = nullptr;
+  int cg_hist_len = 0;
+  cudaEvent_t ev_la[2] = {};
+  double last_spmv_ms = 0.0;
   // graph
   int64_t n_rows = 0, nnz = 0;
   int64_t* d_rowptr = nullptr;  // only when built/owned here
@@ -1147,6 +1172,8 @@ namespace
         return launch_cell<MAT_ISO_VOL, STIFF>(ctx, A);
       case B200S_MAT_SVK:
         return launch_cell<MAT_SVK, STIFF>(ctx, A);
+      case B200S_MAT_ELASTHYPER:
+        return launch_cell<MAT_HYPER, STIFF>(ctx, A);
     }
     return fail(ctx, B200S_ERR_INVALID, "material not set");
   }
@@ -1177,6 +1204,7 @@ extern "C"
     }
     for (auto& e : ctx->ev) cudaEventCreate(&e);
     for (auto& e : ctx->kev) cudaEventCreate(&e);
+    for (auto& e : ctx->ev_la) cudaEventCreate(&e);
     cudaStreamCreateWithFlags(&ctx->zero_stream, cudaStreamNonBlocking);
     for (auto& e : ctx->ev_zero_done) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_eval_start, cudaEventDisableTiming);
@@ -1200,6 +1228,13 @@ extern "C"
     if (ctx->zero_stream) cudaStreamDestroy(ctx->zero_stream);
     dfree(ctx->d_u_row), dfree(ctx->d_u_col), dfree(ctx->d_send_lid), dfree(ctx->d_recv_lid);
     dfree(ctx->d_sendbuf), dfree(ctx->d_recvbuf), dfree(ctx->d_err);
+    dfree(ctx->d_hyper), dfree(ctx->d_dN_gp), dfree(ctx->d_w), dfree(ctx->d_dN_cen), dfree(ctx->d_N_mass);
+    dfree(ctx->d_dN_mass), dfree(ctx->d_w_mass), dfree(ctx->d_ele_is_row), dfree(ctx->d_mass);
+    dfree(ctx->d_f_inertia), dfree(ctx->d_acc_row), dfree(ctx->d_acc_col), dfree(ctx->d_energy);
+    dfree(ctx->d_xmat), dfree(ctx->d_la_x), dfree(ctx->d_la_y), dfree(ctx->d_toggle);
+    for (auto& v : ctx->d_cg) dfree(v);
+    dfree(ctx->d_cg_s), dfree(ctx->d_cg_hist);
+    for (auto& e : ctx->ev_la) cudaEventDestroy(e);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
     for (auto& e : ctx->ev) cudaEventDestroy(e);
     for (auto& e : ctx->kev) cudaEventDestroy(e);
@@ -1242,6 +1277,16 @@ extern "C"
     if (to_device(ctx, &ctx->dconn, conn, n_col_eles * T.nn)) return B200S_ERR_CUDA;
     if (to_device(ctx, &ctx->d_u_col, (const double*)nullptr, 3 * n_col_nodes)) return B200S_ERR_CUDA;
     CK(cudaMemsetAsync(ctx->d_u_col, 0, sizeof(double) * 3 * n_col_nodes, ctx->stream));
+    ctx->ngp = T.ngp, ctx->ngp_mass = T.ngp_mass;
+    if (to_device(ctx, &ctx->d_dN_gp, T.dN_gp.data(), (int64_t)T.dN_gp.size()) ||
+        to_device(ctx, &ctx->d_w, T.w.data(), (int64_t)T.w.size()) ||
+        to_device(ctx, &ctx->d_dN_cen, T.dN_cen.data(), (int64_t)T.dN_cen.size()) ||
+        to_device(ctx, &ctx->d_N_mass, T.N_mass.data(), (int64_t)T.N_mass.size()) ||
+        to_device(ctx, &ctx->d_dN_mass, T.dN_mass.data(), (int64_t)T.dN_mass.size()) ||
+        to_device(ctx, &ctx->d_w_mass, T.w_mass.data(), (int64_t)T.w_mass.size()))
+      return B200S_ERR_CUDA;
+    CK(cudaStreamSynchronize(ctx->stream));  // T is a local
+    dfree(ctx->d_ele_is_row), dfree(ctx->d_acc_col);
     if (celltype == B200S_HEX8)
     {
       Hex8Const h;
@@ -1403,6 +1448,29 @@ extern "C"
     CK(cudaStreamSynchronize(ctx->stream));
     cudaFree(d_flag);
     CK(cudaGetLastError());
+    // buffers of the optional actions are sized by the graph: drop stale ones
+    dfree(ctx->d_mass), dfree(ctx->d_f_inertia), dfree(ctx->d_acc_row), dfree(ctx->d_xmat);
+    dfree(ctx->d_la_x), dfree(ctx->d_la_y), dfree(ctx->d_toggle);
+    for (auto& v : ctx->d_cg) dfree(v);
+    if (!flag)
+    {
+      // matrix column count and the node-blocked pattern test of the fast multiply
+      std::vector<int32_t> cb(ncn);
+      CK(cudaMemcpy(cb.data(), ctx->d_node_colbase, sizeof(int32_t) * ncn, cudaMemcpyDeviceToHost));
+      int32_t mx = -1;
+      for (int32_t v : cb) mx = v > mx ? v : mx;
+      ctx->n_mat_cols = (int64_t)mx + 3;
+      int* d_f3 = nullptr;
+      int f3 = 0;
+      CK(cudaMalloc((void**)&d_f3, sizeof(int)));
+      CK(cudaMemsetAsync(d_f3, 0, sizeof(int), ctx->stream));
+      k_check_node3<<<nblk(32 * ncn), 256, 0, ctx->stream>>>(ncn, ctx->d_node_row, d_colind, d_f3);
+      ctx->launches += 1;
+      CK(cudaMemcpyAsync(&f3, d_f3, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      cudaFree(d_f3);
+      ctx->node3_ok = (f3 == 0);
+    }
     if (flag)
     {
       dfree(ctx->d_pos);
@@ -1424,17 +1492,17 @@ extern "C"
     if (ctx->celltype < 0) return fail(ctx, B200S_ERR_INVALID, "set_mesh must precede set_graph");
     cudaSetDevice(ctx->device);
     // stage the caller's (host or device) arrays on the device; they are only needed to build the map
-    int64_t* d_rowptr = nullptr;
-    int32_t *d_colind = nullptr, *d_r = nullptr, *d_c = nullptr;
+    // the graph stays on the device: apply_dirichlet / multiply need it after the map is built
+    int32_t *d_r = nullptr, *d_c = nullptr;
     int64_t nnz = 0;
     CK(cudaMemcpy(&nnz, rowptr + n_rows, sizeof(int64_t), cudaMemcpyDefault));
     int rc = 0;
-    rc |= to_device(ctx, &d_rowptr, rowptr, n_rows + 1);
-    rc |= to_device(ctx, &d_colind, colind, nnz);
+    rc |= to_device(ctx, &ctx->d_rowptr, rowptr, n_rows + 1);
+    rc |= to_device(ctx, &ctx->d_colind, colind, nnz);
     rc |= to_device(ctx, &d_r, dof_row_lid, 3 * ctx->n_col_nodes);
     rc |= to_device(ctx, &d_c, dof_col_lid, 3 * ctx->n_col_nodes);
-    if (!rc) rc = install_graph(ctx, n_rows, d_rowptr, d_colind, d_r, d_c);
-    cudaFree(d_rowptr), cudaFree(d_colind), cudaFree(d_r), cudaFree(d_c);
+    if (!rc) rc = install_graph(ctx, n_rows, ctx->d_rowptr, ctx->d_colind, d_r, d_c);
+    cudaFree(d_r), cudaFree(d_c);
     return rc ? (rc < 0 ? rc : B200S_ERR_CUDA) : B200S_OK;
   }
 
@@ -1535,6 +1603,7 @@ extern "C"
     SYM(Recv, "ncclRecv");
     SYM(GroupStart, "ncclGroupStart");
     SYM(GroupEnd, "ncclGroupEnd");
+    SYM(AllReduce, "ncclAllReduce");
     SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
     return 0;
@@ -1581,23 +1650,82 @@ extern "C"
     return B200S_OK;
   }
 
-  // ---- evaluate -----------------------------------------------------------------------------------
-  int b200s_evaluate_async(b200s_ctx* ctx, int action)
+  static inline bool action_has_stiffness(int a)
   {
-    if (!ctx) return B200S_ERR_INVALID;
-    if (!ctx->d_pos || ctx->matkind < 0)
-      return fail(ctx, B200S_ERR_INVALID, "set_mesh, set_material and set_graph must precede evaluate");
-    cudaSetDevice(ctx->device);
+    return a == B200S_ACTION_NLNSTIFF || a == B200S_ACTION_NLNSTIFFMASS || a == B200S_ACTION_NLNSTIFFLMASS;
+  }
+  static inline bool action_has_mass(int a)
+  {
+    return a == B200S_ACTION_NLNSTIFFMASS || a == B200S_ACTION_NLNSTIFFLMASS ||
+           a == B200S_ACTION_INTERNALINERTIAFORCE;
+  }
+  static int import_row_to_col(b200s_ctx* ctx, const double* d_src_row, double* d_dst, bool to_matcol);
+
+  // mass matrix (second system matrix, same graph) and inertia force M_e * acc of the mass actions
+  // (4C_solid_ele_evaluate.cpp:116-159).  The "acceleration" state is optional: without it only the
+  // mass matrix is produced (the reference skips the product for an empty elevec2, :36-47).
+  static int launch_mass(b200s_ctx* ctx, int action)
+  {
     cudaStream_t st = ctx->stream;
-    const bool stiff = action == B200S_ACTION_NLNSTIFF;
-    ctx->last_action = action;
-    CK(cudaEventRecord(ctx->ev[1], st));
-    // set_state("displacement"): ghost import, then owned part
+    const bool assemble = action != B200S_ACTION_INTERNALINERTIAFORCE;
+    if (assemble)
+    {
+      if (!ctx->d_mass && to_device(ctx, &ctx->d_mass, (const double*)nullptr, ctx->nnz)) return B200S_ERR_CUDA;
+      CK(cudaMemsetAsync(ctx->d_mass, 0, sizeof(double) * (size_t)ctx->nnz, st));
+    }
+    if (!ctx->d_f_inertia && to_device(ctx, &ctx->d_f_inertia, (const double*)nullptr, ctx->n_rows))
+      return B200S_ERR_CUDA;
+    CK(cudaMemsetAsync(ctx->d_f_inertia, 0, sizeof(double) * (size_t)ctx->n_rows, st));
+    if (ctx->d_acc_row)
+    {
+      if (!ctx->d_acc_col && to_device(ctx, &ctx->d_acc_col, (const double*)nullptr, 3 * ctx->n_col_nodes))
+        return B200S_ERR_CUDA;
+      const int rc = import_row_to_col(ctx, ctx->d_acc_row, ctx->d_acc_col, false);
+      if (rc) return rc;
+    }
+    MassArgs M;
+    M.X = ctx->dX, M.conn = ctx->dconn, M.pos = ctx->d_pos, M.node_row = ctx->d_node_row;
+    M.acc = ctx->d_acc_row ? ctx->d_acc_col : nullptr;
+    M.N_mass = ctx->d_N_mass, M.dN_mass = ctx->d_dN_mass, M.w_mass = ctx->d_w_mass;
+    M.dN_gp = ctx->d_dN_gp, M.w = ctx->d_w;
+    M.density = ctx->density, M.n_ele = ctx->n_col_eles;
+    M.nn = ctx->nn, M.ngp = ctx->ngp, M.ngp_mass = ctx->ngp_mass, M.pos_stride = ctx->pos_stride;
+    // internalinertiaforce uses the consistent element mass matrix (:140-158)
+    M.lumped = action == B200S_ACTION_NLNSTIFFLMASS;
+    M.mass_vals = assemble ? ctx->d_mass : nullptr;
+    M.f_inertia = ctx->d_f_inertia;
+    const unsigned grid = nblk(ctx->n_col_eles * ctx->nn, 128);
+    if (grid)
+    {
+      switch (ctx->celltype)
+      {
+        case B200S_HEX8:
+          k_mass_assemble<8><<<grid, 128, 0, st>>>(M);
+          break;
+        case B200S_HEX27:
+          k_mass_assemble<27><<<grid, 128, 0, st>>>(M);
+          break;
+        case B200S_TET10:
+          k_mass_assemble<10><<<grid, 128, 0, st>>>(M);
+          break;
+      }
+      ctx->launches += 1;
+    }
+    return B200S_OK;
+  }
+
+  // Import of a row-map vector to the column map (Epetra_Import of Discretization::set_state,
+  // 4C_fem_discretization.cpp:612-665; the same import Epetra_CrsMatrix::Multiply does for x).
+  // to_matcol == false: dst is indexed by column-node lid (3 per node);
+  // to_matcol == true : dst is indexed by the matrix-local column id (node_colbase + d).
+  static int import_row_to_col(b200s_ctx* ctx, const double* d_src_row, double* d_dst, bool to_matcol)
+  {
+    cudaStream_t st = ctx->stream;
     if (ctx->n_nbr > 0)
     {
       if (!ctx->comm) return fail(ctx, B200S_ERR_COMM, "halo set but no communicator");
       const int64_t ns = ctx->send_off[ctx->n_nbr], nr = ctx->recv_off[ctx->n_nbr];
-      if (ns) k_pack_halo<<<nblk(3 * ns), 256, 0, st>>>(ns, ctx->d_send_lid, ctx->d_u_row, ctx->d_sendbuf);
+      if (ns) k_pack_halo<<<nblk(3 * ns), 256, 0, st>>>(ns, ctx->d_send_lid, d_src_row, ctx->d_sendbuf);
       ctx->nccl.GroupStart();
       for (int n = 0; n < ctx->n_nbr; ++n)
       {
@@ -1612,12 +1740,47 @@ extern "C"
       }
       const int rc = ctx->nccl.GroupEnd();
       if (rc) return fail(ctx, B200S_ERR_COMM, "halo exchange: %s", ctx->nccl.GetErrorString(rc));
-      if (nr) k_unpack_halo<<<nblk(3 * nr), 256, 0, st>>>(nr, ctx->d_recv_lid, ctx->d_recvbuf, ctx->d_u_col);
+      if (nr)
+      {
+        if (to_matcol)
+          k_unpack_halo_matcol<<<nblk(3 * nr), 256, 0, st>>>(
+              nr, ctx->d_recv_lid, ctx->d_node_colbase, ctx->d_recvbuf, d_dst);
+        else
+          k_unpack_halo<<<nblk(3 * nr), 256, 0, st>>>(nr, ctx->d_recv_lid, ctx->d_recvbuf, d_dst);
+      }
       ctx->launches += (ns > 0) + (nr > 0);
     }
-    k_row_to_col<<<nblk(3 * ctx->n_col_nodes), 256, 0, st>>>(
-        ctx->n_col_nodes, ctx->d_node_row, ctx->d_u_row, ctx->d_u_col);
+    if (to_matcol)
+      k_row_to_matcol<<<nblk(3 * ctx->n_col_nodes), 256, 0, st>>>(
+          ctx->n_col_nodes, ctx->d_node_row, ctx->d_node_colbase, d_src_row, d_dst);
+    else
+      k_row_to_col<<<nblk(3 * ctx->n_col_nodes), 256, 0, st>>>(
+          ctx->n_col_nodes, ctx->d_node_row, d_src_row, d_dst);
     ctx->launches += 1;
+    return B200S_OK;
+  }
+
+  // ---- evaluate -----------------------------------------------------------------------------------
+  int b200s_evaluate_async(b200s_ctx* ctx, int action)
+  {
+    if (!ctx) return B200S_ERR_INVALID;
+    if (!ctx->d_pos || ctx->matkind < 0)
+      return fail(ctx, B200S_ERR_INVALID, "set_mesh, set_material and set_graph must precede evaluate");
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    if (action < B200S_ACTION_INTERNALFORCE || action > B200S_ACTION_INTERNALINERTIAFORCE)
+      return fail(ctx, B200S_ERR_INVALID, "unknown action %d", action);
+    const bool stiff = action_has_stiffness(action);
+    const bool mass = action_has_mass(action);
+    if (mass && !(ctx->density > 0.0))
+      return fail(ctx, B200S_ERR_INVALID, "mass actions need b200s_set_density (density > 0)");
+    ctx->last_action = action;
+    CK(cudaEventRecord(ctx->ev[1], st));
+    // set_state("displacement"): ghost import, then owned part
+    {
+      const int rc = import_row_to_col(ctx, ctx->d_u_row, ctx->d_u_col, false);
+      if (rc) return rc;
+    }
     CK(cudaEventRecord(ctx->ev[2], st));
     // stiff.zero(); fint.put_scalar(0)
     if (stiff)
@@ -1660,6 +1823,11 @@ extern "C"
     if (rc) return rc;
     CK(cudaEventRecord(ctx->kev[2 * ctx->kev_pending + 1], st));
     ctx->kev_pending += 1;
+    if (mass)
+    {
+      const int mrc = launch_mass(ctx, action);
+      if (mrc) return mrc;
+    }
     if (ctx->check_finite)
     {
       if (stiff)
@@ -1724,7 +1892,7 @@ extern "C"
       CK(cudaMemcpyAsync(ctx->d_u_row, u_row, sizeof(double) * (size_t)ctx->n_rows, cudaMemcpyDefault, st));
     int rc = b200s_evaluate_async(ctx, action);
     if (rc) return rc;
-    if (K_values && action == B200S_ACTION_NLNSTIFF && K_values != ctx->d_vals)
+    if (K_values && action_has_stiffness(action) && K_values != ctx->d_vals)
       CK(cudaMemcpyAsync(K_values, ctx->d_vals, sizeof(double) * (size_t)ctx->nnz, cudaMemcpyDefault, st));
     if (f_row && f_row != ctx->d_f)
       CK(cudaMemcpyAsync(f_row, ctx->d_f, sizeof(double) * (size_t)ctx->n_rows, cudaMemcpyDefault, st));
@@ -1754,6 +1922,357 @@ extern "C"
     if (sum_ms) *sum_ms = ctx->ktime_sum_ms;
     if (count) *count = ctx->ktime_count;
     if (reset) ctx->ktime_sum_ms = 0.0, ctx->ktime_count = 0;
+    return B200S_OK;
+  }
+
+  // ---- further materials / states -------------------------------------------------------------------
+  int b200s_set_material_elasthyper(b200s_ctx* ctx, int n_summands, const int32_t* kinds,
+      const int32_t* modes, const double* params)
+  {
+    if (!ctx || !kinds || !params || n_summands < 1) return B200S_ERR_INVALID;
+    if (n_summands > HYPER_MAX_SUMMANDS)
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "at most %d summands on the device path", HYPER_MAX_SUMMANDS);
+    cudaSetDevice(ctx->device);
+    HyperMat hm{};
+    hm.n = n_summands, hm.uses_modified = 0;
+    for (int k = 0; k < n_summands; ++k)
+    {
+      if (summand_num_params(kinds[k]) < 0)
+        return fail(ctx, B200S_ERR_UNSUPPORTED, "summand kind %d is not on the device path", kinds[k]);
+      if (!make_summand(kinds[k], params + 4 * k, modes ? modes[k] : 0, hm.s[k]))
+        return fail(ctx, B200S_ERR_INVALID, "summand %d (kind %d): parameters rejected", k, kinds[k]);
+      if (summand_is_modified(kinds[k])) hm.uses_modified = 1;
+    }
+    ctx->hm = hm;
+    if (to_device(ctx, &ctx->d_hyper, &ctx->hm, 1)) return B200S_ERR_CUDA;
+    CK(cudaStreamSynchronize(ctx->stream));
+    MatParams mp{};
+    for (double& v : mp.p) v = 0.0;
+    mp.hyper = ctx->d_hyper;
+    ctx->matkind = B200S_MAT_ELASTHYPER, ctx->mp = mp;
+    dfree(ctx->d_per_ele);
+    return B200S_OK;
+  }
+
+  int b200s_set_density(b200s_ctx* ctx, double density)
+  {
+    if (!ctx) return B200S_ERR_INVALID;
+    if (!(density >= 0.0)) return fail(ctx, B200S_ERR_INVALID, "density must be >= 0");
+    ctx->density = density;
+    return B200S_OK;
+  }
+
+  int b200s_set_row_elements(b200s_ctx* ctx, const uint8_t* is_row)
+  {
+    if (!ctx) return B200S_ERR_INVALID;
+    if (ctx->celltype < 0) return fail(ctx, B200S_ERR_INVALID, "set_mesh must precede set_row_elements");
+    cudaSetDevice(ctx->device);
+    dfree(ctx->d_ele_is_row);
+    if (!is_row) return B200S_OK;
+    if (to_device(ctx, &ctx->d_ele_is_row, is_row, ctx->n_col_eles)) return B200S_ERR_CUDA;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B200S_OK;
+  }
+
+  int b200s_set_state(b200s_ctx* ctx, const char* name, const double* v_row)
+  {
+    if (!ctx || !name || !v_row) return B200S_ERR_INVALID;
+    if (ctx->n_rows <= 0) return fail(ctx, B200S_ERR_INVALID, "set_graph must precede set_state");
+    cudaSetDevice(ctx->device);
+    double* dst = nullptr;
+    if (!strcmp(name, "displacement"))
+      dst = ctx->d_u_row;
+    else if (!strcmp(name, "acceleration"))
+    {
+      if (!ctx->d_acc_row && to_device(ctx, &ctx->d_acc_row, (const double*)nullptr, ctx->n_rows))
+        return B200S_ERR_CUDA;
+      dst = ctx->d_acc_row;
+    }
+    else
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "state '%s' is not used on the device path", name);
+    if (v_row != dst)
+      CK(cudaMemcpyAsync(dst, v_row, sizeof(double) * (size_t)ctx->n_rows, cudaMemcpyDefault, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B200S_OK;
+  }
+
+  double* b200s_device_mass_values(b200s_ctx* ctx) { return ctx ? ctx->d_mass : nullptr; }
+  double* b200s_device_f_inertia(b200s_ctx* ctx) { return ctx ? ctx->d_f_inertia : nullptr; }
+
+  int b200s_get_mass(b200s_ctx* ctx, double* M_values, double* f_inertia)
+  {
+    if (!ctx) return B200S_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    if (M_values)
+    {
+      if (!ctx->d_mass) return fail(ctx, B200S_ERR_INVALID, "no mass matrix evaluated yet");
+      CK(cudaMemcpyAsync(M_values, ctx->d_mass, sizeof(double) * (size_t)ctx->nnz, cudaMemcpyDefault, ctx->stream));
+    }
+    if (f_inertia)
+    {
+      if (!ctx->d_f_inertia) return fail(ctx, B200S_ERR_INVALID, "no inertia force evaluated yet");
+      CK(cudaMemcpyAsync(f_inertia, ctx->d_f_inertia, sizeof(double) * (size_t)ctx->n_rows, cudaMemcpyDefault,
+          ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B200S_OK;
+  }
+
+  // ---- struct_calc_stress / struct_calc_energy --------------------------------------------------------
+  static int launch_post(b200s_ctx* ctx, int stress_type, int strain_type, double* d_stress,
+      double* d_strain, double* d_energy)
+  {
+    if (ctx->celltype < 0 || ctx->matkind < 0)
+      return fail(ctx, B200S_ERR_INVALID, "set_mesh and set_material must precede this action");
+    PostArgs P;
+    P.X = ctx->dX, P.u = ctx->d_u_col, P.conn = ctx->dconn, P.per_ele_param = ctx->d_per_ele;
+    P.ele_id = ctx->d_ele_id, P.ele_is_row = ctx->d_ele_is_row;
+    P.dN_gp = ctx->d_dN_gp, P.dN_cen = ctx->d_dN_cen, P.w = ctx->d_w, P.mp = ctx->mp;
+    P.n_ele = ctx->n_col_eles, P.nn = ctx->nn, P.ngp = ctx->ngp;
+    P.fbar = ctx->tech == B200S_TECH_FBAR;
+    P.stress_type = stress_type, P.strain_type = strain_type;
+    P.stress = d_stress, P.strain = d_strain, P.energy = d_energy;
+    const unsigned grid = nblk(ctx->n_col_eles * ctx->ngp, 128);
+    if (!grid) return B200S_OK;
+    switch (ctx->matkind)
+    {
+      case B200S_MAT_COUP_NEOHOOKE:
+        k_post_points<MAT_COUP_NEOHOOKE><<<grid, 128, 0, ctx->stream>>>(P);
+        break;
+      case B200S_MAT_ISO_VOL:
+        k_post_points<MAT_ISO_VOL><<<grid, 128, 0, ctx->stream>>>(P);
+        break;
+      case B200S_MAT_SVK:
+        k_post_points<MAT_SVK><<<grid, 128, 0, ctx->stream>>>(P);
+        break;
+      case B200S_MAT_ELASTHYPER:
+        k_post_points<MAT_HYPER><<<grid, 128, 0, ctx->stream>>>(P);
+        break;
+      default:
+        return fail(ctx, B200S_ERR_INVALID, "material not set");
+    }
+    ctx->launches += 1;
+    return B200S_OK;
+  }
+
+  int b200s_calc_stress(b200s_ctx* ctx, int stress_type, int strain_type, double* stress_out,
+      double* strain_out)
+  {
+    if (!ctx) return B200S_ERR_INVALID;
+    if (stress_type < B200S_STRESS_NONE || stress_type > B200S_STRESS_CAUCHY ||
+        strain_type < B200S_STRAIN_NONE || strain_type > B200S_STRAIN_EA)
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "stress/strain output type %d/%d has no device kernel",
+          stress_type, strain_type);
+    if (ctx->n_rows <= 0) return fail(ctx, B200S_ERR_INVALID, "set_graph must precede calc_stress");
+    cudaSetDevice(ctx->device);
+    const size_t n = (size_t)ctx->n_col_eles * ctx->ngp * 6;
+    double *d_s = nullptr, *d_e = nullptr;
+    const bool want_s = stress_out && stress_type != B200S_STRESS_NONE;
+    const bool want_e = strain_out && strain_type != B200S_STRAIN_NONE;
+    if (want_s) CK(cudaMalloc((void**)&d_s, sizeof(double) * (n ? n : 1)));
+    if (want_e) CK(cudaMalloc((void**)&d_e, sizeof(double) * (n ? n : 1)));
+    int rc = import_row_to_col(ctx, ctx->d_u_row, ctx->d_u_col, false);
+    if (!rc) rc = launch_post(ctx, stress_type, strain_type, d_s, d_e, nullptr);
+    if (!rc && want_s && cudaMemcpyAsync(stress_out, d_s, sizeof(double) * n, cudaMemcpyDefault, ctx->stream))
+      rc = B200S_ERR_CUDA;
+    if (!rc && want_e && cudaMemcpyAsync(strain_out, d_e, sizeof(double) * n, cudaMemcpyDefault, ctx->stream))
+      rc = B200S_ERR_CUDA;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && !rc)
+      rc = fail(ctx, B200S_ERR_CUDA, "calc_stress: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d_s), cudaFree(d_e);
+    return rc;
+  }
+
+  int b200s_calc_energy(b200s_ctx* ctx, double* energy_out)
+  {
+    if (!ctx || !energy_out) return B200S_ERR_INVALID;
+    if (ctx->n_rows <= 0) return fail(ctx, B200S_ERR_INVALID, "set_graph must precede calc_energy");
+    if (ctx->nranks > 1 && !ctx->d_ele_is_row)
+      return fail(ctx, B200S_ERR_INVALID,
+          "calc_energy on a partitioned mesh needs b200s_set_row_elements (row elements only)");
+    cudaSetDevice(ctx->device);
+    if (!ctx->d_energy && to_device(ctx, &ctx->d_energy, (const double*)nullptr, 1)) return B200S_ERR_CUDA;
+    CK(cudaMemsetAsync(ctx->d_energy, 0, sizeof(double), ctx->stream));
+    int rc = import_row_to_col(ctx, ctx->d_u_row, ctx->d_u_col, false);
+    if (!rc) rc = launch_post(ctx, B200S_STRESS_NONE, B200S_STRAIN_NONE, nullptr, nullptr, ctx->d_energy);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(energy_out, ctx->d_energy, sizeof(double), cudaMemcpyDefault, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return B200S_OK;
+  }
+
+  // ---- the step after the path: Dirichlet conditions and products on the device ---------------------
+  // stages a row-map vector that may live on the host
+  static int stage_row_vector(b200s_ctx* ctx, double** slot, const double* src)
+  {
+    if (!*slot && to_device(ctx, slot, (const double*)nullptr, ctx->n_rows)) return B200S_ERR_CUDA;
+    if (src != *slot)
+      CK(cudaMemcpyAsync(*slot, src, sizeof(double) * (size_t)ctx->n_rows, cudaMemcpyDefault, ctx->stream));
+    return B200S_OK;
+  }
+  static double* matrix_values(b200s_ctx* ctx, int which)
+  {
+    return which == B200S_MATRIX_MASS ? ctx->d_mass : ctx->d_vals;
+  }
+
+  int b200s_apply_dirichlet(b200s_ctx* ctx, int which, const double* dbctoggle_row, int diagonalblock)
+  {
+    if (!ctx || !dbctoggle_row) return B200S_ERR_INVALID;
+    if (!ctx->d_rowptr || !ctx->d_colind || !matrix_values(ctx, which))
+      return fail(ctx, B200S_ERR_INVALID, "apply_dirichlet needs an assembled matrix");
+    cudaSetDevice(ctx->device);
+    if (stage_row_vector(ctx, &ctx->d_toggle, dbctoggle_row)) return B200S_ERR_CUDA;
+    k_apply_dirichlet<<<nblk(32 * ctx->n_rows), 256, 0, ctx->stream>>>(ctx->n_rows, ctx->d_rowptr,
+        ctx->d_colind, ctx->d_toggle, diagonalblock, matrix_values(ctx, which));
+    ctx->launches += 1;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return B200S_OK;
+  }
+
+  int b200s_apply_dirichlet_to_system(b200s_ctx* ctx, double* x_row, double* b_row,
+      const double* dbcval_row, const double* dbctoggle_row)
+  {
+    if (!ctx || !dbcval_row || !dbctoggle_row || (!x_row && !b_row)) return B200S_ERR_INVALID;
+    if (ctx->n_rows <= 0) return fail(ctx, B200S_ERR_INVALID, "set_graph first");
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    const size_t bytes = sizeof(double) * (size_t)ctx->n_rows;
+    // toggle in d_toggle, values in d_la_y, the vectors pass through d_la_x one after the other
+    if (stage_row_vector(ctx, &ctx->d_toggle, dbctoggle_row)) return B200S_ERR_CUDA;
+    if (stage_row_vector(ctx, &ctx->d_la_y, dbcval_row)) return B200S_ERR_CUDA;
+    for (double* v : {x_row, b_row})
+    {
+      if (!v) continue;
+      if (stage_row_vector(ctx, &ctx->d_la_x, v)) return B200S_ERR_CUDA;
+      k_dirichlet_to_system<<<nblk(ctx->n_rows), 256, 0, st>>>(ctx->n_rows, ctx->d_toggle, ctx->d_la_y,
+          ctx->d_la_x, nullptr);
+      ctx->launches += 1;
+      CK(cudaMemcpyAsync(v, ctx->d_la_x, bytes, cudaMemcpyDefault, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    return B200S_OK;
+  }
+
+  // y = A x on device vectors (x on the row map = domain map); dot/w as in the kernels
+  static int multiply_device(b200s_ctx* ctx, int which, const double* d_x_row, double* d_y_row,
+      const double* d_w, double* d_dot)
+  {
+    const double* vals = matrix_values(ctx, which);
+    if (!ctx->d_rowptr || !ctx->d_colind || !vals)
+      return fail(ctx, B200S_ERR_INVALID, "multiply needs an assembled matrix");
+    if (!ctx->d_xmat && to_device(ctx, &ctx->d_xmat, (const double*)nullptr, ctx->n_mat_cols))
+      return B200S_ERR_CUDA;
+    const int rc = import_row_to_col(ctx, d_x_row, ctx->d_xmat, true);
+    if (rc) return rc;
+    if (ctx->node3_ok)
+      k_spmv_node3<<<nblk(32 * ctx->n_col_nodes), 256, 0, ctx->stream>>>(ctx->n_col_nodes, ctx->d_node_row,
+          ctx->d_colind, vals, ctx->d_xmat, d_y_row, d_w, d_dot);
+    else
+      k_spmv_csr<<<nblk(32 * ctx->n_rows), 256, 0, ctx->stream>>>(ctx->n_rows, ctx->d_rowptr, ctx->d_colind,
+          vals, ctx->d_xmat, d_y_row, d_w, d_dot);
+    ctx->launches += 1;
+    return B200S_OK;
+  }
+
+  int b200s_multiply(b200s_ctx* ctx, int which, const double* x_row, double* y_row)
+  {
+    if (!ctx || !x_row || !y_row) return B200S_ERR_INVALID;
+    if (ctx->n_rows <= 0) return fail(ctx, B200S_ERR_INVALID, "set_graph first");
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    if (stage_row_vector(ctx, &ctx->d_la_x, x_row)) return B200S_ERR_CUDA;
+    if (!ctx->d_la_y && to_device(ctx, &ctx->d_la_y, (const double*)nullptr, ctx->n_rows)) return B200S_ERR_CUDA;
+    CK(cudaEventRecord(ctx->ev_la[0], st));
+    const int rc = multiply_device(ctx, which, ctx->d_la_x, ctx->d_la_y, nullptr, nullptr);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev_la[1], st));
+    CK(cudaMemcpyAsync(y_row, ctx->d_la_y, sizeof(double) * (size_t)ctx->n_rows, cudaMemcpyDefault, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev_la[0], ctx->ev_la[1]);
+    ctx->last_spmv_ms = ms;
+    return B200S_OK;
+  }
+  double b200s_last_multiply_ms(const b200s_ctx* ctx) { return ctx ? ctx->last_spmv_ms : 0.0; }
+
+  int b200s_solve_cg(b200s_ctx* ctx, const double* b_row, double* x_row, double rtol, int maxit,
+      int* iters_out, double* relres_out)
+  {
+    if (!ctx || !b_row || !x_row || maxit < 1) return B200S_ERR_INVALID;
+    if (ctx->n_rows <= 0 || !ctx->d_vals) return fail(ctx, B200S_ERR_INVALID, "no assembled matrix");
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    const int64_t n = ctx->n_rows, nrn = n / 3;
+    const size_t bytes = sizeof(double) * (size_t)n;
+    for (int i = 0; i < 4; ++i)
+      if (!ctx->d_cg[i] && to_device(ctx, &ctx->d_cg[i], (const double*)nullptr, n)) return B200S_ERR_CUDA;
+    if (!ctx->d_cg[4] && to_device(ctx, &ctx->d_cg[4], (const double*)nullptr, 3 * n)) return B200S_ERR_CUDA;
+    if (!ctx->d_cg_s && to_device(ctx, &ctx->d_cg_s, (const double*)nullptr, 4)) return B200S_ERR_CUDA;
+    if (ctx->cg_hist_len < maxit + 1)
+    {
+      dfree(ctx->d_cg_hist);
+      if (to_device(ctx, &ctx->d_cg_hist, (const double*)nullptr, maxit + 1)) return B200S_ERR_CUDA;
+      ctx->cg_hist_len = maxit + 1;
+    }
+    double *r = ctx->d_cg[0], *z = ctx->d_cg[1], *p = ctx->d_cg[2], *Ap = ctx->d_cg[3], *dinv = ctx->d_cg[4];
+    double* s = ctx->d_cg_s;
+    // x0 = caller's x (initial guess), b staged in d_la_y, x in d_la_x
+    if (stage_row_vector(ctx, &ctx->d_la_x, x_row)) return B200S_ERR_CUDA;
+    if (stage_row_vector(ctx, &ctx->d_la_y, b_row)) return B200S_ERR_CUDA;
+    double* x = ctx->d_la_x;
+    const double* b = ctx->d_la_y;
+    auto allreduce = [&](double* v, int cnt) -> int
+    {
+      if (ctx->nranks <= 1 || !ctx->comm) return 0;
+      const int rc = ctx->nccl.AllReduce(v, v, (size_t)cnt, /*ncclDouble*/ 8, /*ncclSum*/ 0, ctx->comm, st);
+      return rc ? fail(ctx, B200S_ERR_COMM, "allreduce: %s", ctx->nccl.GetErrorString(rc)) : 0;
+    };
+    k_block_diag_inverse<<<nblk(ctx->n_col_nodes), 256, 0, st>>>(
+        ctx->n_col_nodes, ctx->d_node_row, ctx->d_colind, ctx->d_vals, dinv);
+    CK(cudaMemsetAsync(s, 0, 4 * sizeof(double), st));
+    int rc = multiply_device(ctx, B200S_MATRIX_STIFFNESS, x, Ap, nullptr, nullptr);
+    if (rc) return rc;
+    k_residual<<<nblk(n), 256, 0, st>>>(n, b, Ap, r);
+    k_cg_update<<<nblk(nrn), 256, 0, st>>>(nrn, dinv, p, Ap, x, r, z, s, 1);
+    if (allreduce(s + 2, 2)) return B200S_ERR_COMM;
+    k_cg_direction<<<nblk(n), 256, 0, st>>>(n, z, p, s, 1);
+    k_cg_roll<<<1, 1, 0, st>>>(s, ctx->d_cg_hist, 0);
+    ctx->launches += 5;
+    double rr0 = 0.0, rr = 0.0;
+    CK(cudaMemcpyAsync(&rr0, ctx->d_cg_hist, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    rr = rr0;
+    int it = 0;
+    const int check = 8;  // convergence is read back every `check` iterations (no sync in between)
+    while (it < maxit && rr0 > 0.0 && std::sqrt(rr / rr0) > rtol)
+    {
+      const int stop = it + check < maxit ? it + check : maxit;
+      for (; it < stop; ++it)
+      {
+        rc = multiply_device(ctx, B200S_MATRIX_STIFFNESS, p, Ap, p, s);
+        if (rc) return rc;
+        if (allreduce(s, 1)) return B200S_ERR_COMM;
+        k_cg_update<<<nblk(nrn), 256, 0, st>>>(nrn, dinv, p, Ap, x, r, z, s, 0);
+        if (allreduce(s + 2, 2)) return B200S_ERR_COMM;
+        k_cg_direction<<<nblk(n), 256, 0, st>>>(n, z, p, s, 0);
+        k_cg_roll<<<1, 1, 0, st>>>(s, ctx->d_cg_hist, it + 1);
+        ctx->launches += 3;
+      }
+      CK(cudaMemcpyAsync(&rr, ctx->d_cg_hist + it, sizeof(double), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (!(rr == rr)) break;  // NaN: breakdown (indefinite matrix)
+    }
+    CK(cudaMemcpyAsync(x_row, x, bytes, cudaMemcpyDefault, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (iters_out) *iters_out = it;
+    const double rel = rr0 > 0.0 ? std::sqrt(rr / rr0) : 0.0;
+    if (relres_out) *relres_out = rel;
+    if (!(rel == rel)) return fail(ctx, B200S_ERR_NONFINITE, "CG breakdown after %d iterations", it);
     return B200S_OK;
   }
 

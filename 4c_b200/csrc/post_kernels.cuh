@@ -1,0 +1,318 @@
+// post_kernels.cuh -- the element actions around the force/stiffness hot path:
+//   struct_calc_stress   SolidEleCalc::calculate_stress          (4C_solid_ele_calc.cpp:416-476)
+//   struct_calc_energy   SolidEleCalc::calculate_internal_energy (4C_solid_ele_calc.cpp:365-414)
+//   mass matrix / inertia force of struct_calc_nlnstiffmass, struct_calc_nlnstifflmass and
+//   struct_calc_internalinertiaforce (4C_solid_ele_evaluate.cpp:116-159; add_mass_matrix,
+//   4C_solid_ele_calc_lib.hpp:1221-1238; the branch for a mass rule that differs from the stiffness
+//   rule, 4C_solid_ele_calc.cpp:151-153,228-236,265-280)
+// None of them is per-Newton-iteration work; they are written for simplicity: one thread per
+// (element, Gauss point) resp. (element, row node), generic in the cell type through tables in
+// global memory.  The point functions are __host__ __device__ so the CPU suite can check them.
+#pragma once
+
+#include <stdint.h>
+
+#include "hex8_kernel.cuh"
+#include "solid_math.cuh"
+
+namespace b200s
+{
+  enum StressType  // FourC::Solid::StressType
+  {
+    STRESS_NONE = 0,
+    STRESS_2PK = 1,
+    STRESS_CAUCHY = 2
+  };
+  enum StrainType  // FourC::Solid::StrainType (strain_log needs an eigen decomposition: CPU path)
+  {
+    STRAIN_NONE = 0,
+    STRAIN_GL = 1,
+    STRAIN_EA = 2
+  };
+
+  struct PostArgs
+  {
+    const double* X;              // 3*n_col_nodes
+    const double* u;              // 3*n_col_nodes (column map)
+    const int32_t* conn;          // n_ele*nn, device element order
+    const double* per_ele_param;  // nullptr or n_ele (device order)
+    const int32_t* ele_id;        // nullptr or device element -> caller's column element
+    const uint8_t* ele_is_row;    // nullptr (all) or n_ele flags in the CALLER's numbering
+    const double* dN_gp;          // [ngp][nn][3]
+    const double* dN_cen;         // [nn][3] (F-bar)
+    const double* w;              // [ngp]
+    MatParams mp;
+    int64_t n_ele;
+    int nn, ngp;
+    int fbar;
+    int stress_type, strain_type;
+    double* stress;  // [caller element][gp][6] or nullptr
+    double* strain;  // same
+    double* energy;  // one double, accumulated over row elements, or nullptr
+  };
+
+  // J, det J and F at one parametric point from the tabulated dN[k*3+a]
+  // (evaluate_jacobian_mapping / evaluate_deformation_gradient, calc_lib.hpp:499-516,646-660)
+  B2_HD double point_kinematics(int nn, const double* dN, const double* X, const double* u,
+      const int32_t* ce, double* F)
+  {
+    double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, iJ[9];
+    for (int k = 0; k < nn; ++k)
+    {
+      const double* x = X + 3 * (int64_t)ce[k];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) J[a + 3 * b] += dN[3 * k + a] * x[b];
+    }
+    const double detJ = inv3(iJ, J);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) F[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    for (int k = 0; k < nn; ++k)
+    {
+      const double* uk = u + 3 * (int64_t)ce[k];
+      double G[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+        G[a] = iJ[a] * dN[3 * k] + iJ[a + 3] * dN[3 * k + 1] + iJ[a + 6] * dN[3 * k + 2];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) F[a + 3 * b] += uk[a] * G[b];
+    }
+    return detJ;
+  }
+
+  // One Gauss point of calculate_stress / calculate_internal_energy.  Returns psi * integration
+  // factor (0 when want_energy is false); stress6 / strain6 in the reference's row layout
+  // [xx,yy,zz,xy,yz,xz] (assemble_symmetric_tensor_to_matrix_row, calc_lib_io.hpp:41-70).
+  template <int MAT>
+  B2_HD double post_point(const PostArgs& A, int64_t e, int g, bool want_energy, double* stress6,
+      double* strain6)
+  {
+    const int32_t* ce = A.conn + e * A.nn;
+    double F[9];
+    const double detJ = point_kinematics(A.nn, A.dN_gp + (size_t)g * A.nn * 3, A.X, A.u, ce, F);
+    if (A.fbar)
+    {
+      // F_bar = (det F_0 / det F)^(1/3) F  (4C_solid_ele_calc_fbar.hpp:103-112, lib_fbar.hpp:47-51)
+      double F0[9];
+      point_kinematics(A.nn, A.dN_cen, A.X, A.u, ce, F0);
+      const double fb = pow(det3(F0) / det3(F), 1.0 / 3.0);
+#pragma unroll
+      for (int i = 0; i < 9; ++i) F[i] *= fb;
+    }
+    double C[6], S[6], Cm[21];
+    right_cauchy_green(F, C);
+    MatParams mp = A.mp;
+    if (A.per_ele_param != nullptr) mp.p[0] = A.per_ele_param[e];
+    if (stress6 != nullptr && A.stress_type != STRESS_NONE)
+    {
+      material_evaluate<MAT>(mp, C, S, Cm);
+      if (A.stress_type == STRESS_2PK)
+      {
+#pragma unroll
+        for (int v = 0; v < 6; ++v) stress6[v] = S[v];
+      }
+      else
+      {
+        // sigma = F S F^T / det F  (Solid::Utils::pk2_to_cauchy, 4C_solid_ele_utils.hpp:41-54)
+        double P[9];
+        first_piola(F, S, P);
+        const double idet = 1.0 / det3(F);
+#pragma unroll
+        for (int v = 0; v < 6; ++v)
+        {
+          const int a = va(v), b = vb(v);
+          stress6[v] = (P[a] * F[b] + P[a + 3] * F[b + 3] + P[a + 6] * F[b + 6]) * idet;
+        }
+      }
+    }
+    if (strain6 != nullptr && A.strain_type != STRAIN_NONE)
+    {
+      double E[6];
+#pragma unroll
+      for (int v = 0; v < 6; ++v) E[v] = 0.5 * (C[v] - (v < 3 ? 1.0 : 0.0));
+      if (A.strain_type == STRAIN_GL)
+      {
+#pragma unroll
+        for (int v = 0; v < 6; ++v) strain6[v] = E[v];
+      }
+      else
+      {
+        // e = F^-T E F^-1  (green_lagrange_to_euler_almansi, 4C_solid_ele_utils.hpp:64-79)
+        double iF[9], T[9];
+        inv3(iF, F);
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int b = 0; b < 3; ++b)  // T = E iF
+            T[a + 3 * b] = E[vg(a, 0)] * iF[0 + 3 * b] + E[vg(a, 1)] * iF[1 + 3 * b] + E[vg(a, 2)] * iF[2 + 3 * b];
+#pragma unroll
+        for (int v = 0; v < 6; ++v)
+        {
+          const int a = va(v), b = vb(v);
+          strain6[v] = iF[0 + 3 * a] * T[0 + 3 * b] + iF[1 + 3 * a] * T[1 + 3 * b] + iF[2 + 3 * a] * T[2 + 3 * b];
+        }
+      }
+    }
+    if (!want_energy) return 0.0;
+    return material_strain_energy<MAT>(mp, C) * (detJ * A.w[g]);
+  }
+
+  struct MassArgs
+  {
+    const double* X;
+    const int32_t* conn;      // device element order
+    const int32_t* pos;       // scatter map of the stiffness graph
+    const NodeRow* node_row;
+    const double* acc;        // nullptr or 3*n_col_nodes acceleration on the column map
+    const double* N_mass;     // [ngp_mass][nn]
+    const double* dN_mass;    // [ngp_mass][nn][3]
+    const double* w_mass;     // [ngp_mass]
+    const double* dN_gp;      // stiffness rule (only read when the rules differ)
+    const double* w;
+    double density;           // Mat::So3Material::density()
+    int64_t n_ele;
+    int nn, ngp, ngp_mass, pos_stride;
+    int lumped;               // struct_calc_nlnstifflmass: lump_matrix (row sums on the diagonal)
+    double* mass_vals;        // nnz or nullptr
+    double* f_inertia;        // n_rows or nullptr (needs acc)
+  };
+
+  B2_HD double point_detJ(int nn, const double* dN, const double* X, const int32_t* ce)
+  {
+    double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < nn; ++k)
+    {
+      const double* x = X + 3 * (int64_t)ce[k];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) J[a + 3 * b] += dN[3 * k + a] * x[b];
+    }
+    return det3(J);
+  }
+
+  // Row node i of the element mass matrix: m[j] = sum_gp rho N_i N_j detJ w (the same scalar on the
+  // three dof diagonals of block (i,j)).
+  template <int NN>
+  B2_HD void mass_row(const MassArgs& A, int64_t e, int i, double* m)
+  {
+    const int32_t* ce = A.conn + e * NN;
+    double rho = A.density;
+    if (A.ngp_mass != A.ngp)
+    {
+      // rules differ: density = element mass / element volume over the stiffness rule
+      // (4C_solid_ele_calc.cpp:230-234,277)
+      double em = 0.0, ev = 0.0;
+      for (int g = 0; g < A.ngp; ++g)
+      {
+        const double fac = point_detJ(NN, A.dN_gp + (size_t)g * NN * 3, A.X, ce) * A.w[g];
+        em += A.density * fac;
+        ev += fac;
+      }
+      rho = em / ev;
+    }
+#pragma unroll
+    for (int j = 0; j < NN; ++j) m[j] = 0.0;
+    for (int g = 0; g < A.ngp_mass; ++g)
+    {
+      const double fac = point_detJ(NN, A.dN_mass + (size_t)g * NN * 3, A.X, ce) * A.w_mass[g];
+      const double* N = A.N_mass + (size_t)g * NN;
+      const double ifactor = N[i] * fac * rho;
+#pragma unroll
+      for (int j = 0; j < NN; ++j) m[j] += N[j] * ifactor;
+    }
+  }
+
+  // scatter of one mass row + inertia force of the row node (owner-computes, as the stiffness)
+  template <int NN>
+  B2_HD void mass_scatter(const MassArgs& A, int64_t e, int i, const double* m)
+  {
+    const int32_t* ce = A.conn + e * NN;
+    const NodeRow nr = A.node_row[ce[i]];
+    if (nr.rowstart < 0) return;  // row node not owned
+    if (A.lumped)
+    {
+      // lump_matrix (4C_solid_ele_utils.cpp): every row keeps its row sum on the diagonal
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < NN; ++j) s += m[j];
+      if (A.mass_vals)
+      {
+        const int64_t base = nr.rowstart + A.pos[e * A.pos_stride + i * NN + i];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) B2_RED_ADD(A.mass_vals + base + (int64_t)d * nr.rowlen + d, s);
+      }
+      if (A.f_inertia && A.acc)
+      {
+        const double* a = A.acc + 3 * (int64_t)ce[i];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) B2_RED_ADD(A.f_inertia + nr.frow + d, s * a[d]);
+      }
+      return;
+    }
+    double fi[3] = {0, 0, 0};
+    for (int j = 0; j < NN; ++j)
+    {
+      if (A.mass_vals)
+      {
+        const int64_t base = nr.rowstart + A.pos[e * A.pos_stride + i * NN + j];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) B2_RED_ADD(A.mass_vals + base + (int64_t)d * nr.rowlen + d, m[j]);
+      }
+      if (A.acc)
+      {
+        const double* a = A.acc + 3 * (int64_t)ce[j];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) fi[d] += m[j] * a[d];
+      }
+    }
+    if (A.f_inertia && A.acc)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) B2_RED_ADD(A.f_inertia + nr.frow + d, fi[d]);
+  }
+
+#if defined(__CUDACC__)
+  template <int MAT>
+  __global__ void __launch_bounds__(128) k_post_points(const PostArgs A)
+  {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e = t / A.ngp;
+    const int g = (int)(t - e * A.ngp);
+    double psi = 0.0;
+    if (e < A.n_ele)
+    {
+      const int64_t eid = A.ele_id ? A.ele_id[e] : e;
+      const bool row = A.ele_is_row == nullptr || A.ele_is_row[eid] != 0;
+      double s6[6], e6[6];
+      psi = post_point<MAT>(A, e, g, A.energy != nullptr && row, A.stress ? s6 : nullptr,
+          A.strain ? e6 : nullptr);
+      if (A.stress && A.stress_type != STRESS_NONE)
+#pragma unroll
+        for (int v = 0; v < 6; ++v) A.stress[(eid * A.ngp + g) * 6 + v] = s6[v];
+      if (A.strain && A.strain_type != STRAIN_NONE)
+#pragma unroll
+        for (int v = 0; v < 6; ++v) A.strain[(eid * A.ngp + g) * 6 + v] = e6[v];
+    }
+    if (A.energy != nullptr)
+    {
+      for (int o = 16; o > 0; o >>= 1) psi += __shfl_xor_sync(0xffffffffu, psi, o);
+      if ((threadIdx.x & 31) == 0 && psi != 0.0) atomicAdd(A.energy, psi);
+    }
+  }
+
+  template <int NN>
+  __global__ void __launch_bounds__(128) k_mass_assemble(const MassArgs A)
+  {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e = t / NN;
+    const int i = (int)(t - e * NN);
+    if (e >= A.n_ele) return;
+    double m[NN];
+    mass_row<NN>(A, e, i, m);
+    mass_scatter<NN>(A, e, i, m);
+  }
+#endif
+}  // namespace b200s

@@ -25,6 +25,14 @@ namespace b200s
     std::vector<double> dN_gp;    // [ngp][nn][3]  dN_k/dxi_a at Gauss point g
     std::vector<double> dN_node;  // [nn][nn][3]   same at the element nodes (Jacobian check)
     std::vector<double> w;        // [ngp]
+    // mass-matrix rule (DisTypeToOptGaussRule, 4C_fem_general_element_integration_select.hpp:37-67:
+    // hex_8point, hex_27point, tet_11point) -- equals the stiffness rule except for tet10
+    int ngp_mass = 0;
+    std::vector<double> N_mass;   // [ngp_mass][nn]     shape function values
+    std::vector<double> dN_mass;  // [ngp_mass][nn][3]
+    std::vector<double> w_mass;   // [ngp_mass]
+    std::vector<double> N_gp;     // [ngp][nn] values at the stiffness rule's points
+    std::vector<double> dN_cen;   // [nn][3] derivatives at the element centroid (F-bar, EAS)
   };
 
   namespace detail
@@ -91,6 +99,38 @@ namespace b200s
           for (int a = 0; a < 3; ++a) dN[3 * k + a] = D[k][a];
       }
     }
+
+    // N[k] at xi (same celltype ids); 4C_fem_general_utils_fem_shapefunctions.hpp hex8 :61-79,
+    // hex27 :198-238, tet10 :252-267
+    inline void shape0(int celltype, const double* xi, double* N)
+    {
+      const double r = xi[0], s = xi[1], t = xi[2];
+      if (celltype == 0)
+      {
+        const double(*c)[3] = hex_nodes();
+        for (int k = 0; k < 8; ++k)
+          N[k] = 0.125 * (1.0 + c[k][0] * r) * (1.0 + c[k][1] * s) * (1.0 + c[k][2] * t);
+      }
+      else if (celltype == 1)
+      {
+        const double(*c)[3] = hex_nodes();
+        double L[3][3];
+        for (int d = 0; d < 3; ++d)
+        {
+          const double x = xi[d];
+          L[d][0] = 0.5 * x * (x - 1.0), L[d][1] = 1.0 - x * x, L[d][2] = 0.5 * x * (x + 1.0);
+        }
+        for (int k = 0; k < 27; ++k)
+          N[k] = L[0][(int)c[k][0] + 1] * L[1][(int)c[k][1] + 1] * L[2][(int)c[k][2] + 1];
+      }
+      else
+      {
+        const double u = 1.0 - r - s - t;
+        N[0] = u * (2.0 * u - 1.0), N[1] = r * (2.0 * r - 1.0), N[2] = s * (2.0 * s - 1.0);
+        N[3] = t * (2.0 * t - 1.0), N[4] = 4.0 * r * u, N[5] = 4.0 * r * s, N[6] = 4.0 * s * u;
+        N[7] = 4.0 * t * u, N[8] = 4.0 * r * t, N[9] = 4.0 * s * t;
+      }
+    }
   }  // namespace detail
 
   inline CellTables make_cell_tables(int celltype)
@@ -136,6 +176,35 @@ namespace b200s
     T.dN_node.resize((size_t)T.nn * T.nn * 3);
     const double(*nc)[3] = celltype == 2 ? detail::tet_nodes() : hc;
     for (int k = 0; k < T.nn; ++k) detail::deriv1(celltype, nc[k], &T.dN_node[(size_t)k * T.nn * 3]);
+    T.N_gp.resize((size_t)T.ngp * T.nn);
+    for (int q = 0; q < T.ngp; ++q) detail::shape0(celltype, &gxi[3 * q], &T.N_gp[(size_t)q * T.nn]);
+    // mass rule
+    std::vector<double> mxi = gxi;
+    T.w_mass = T.w, T.ngp_mass = T.ngp;
+    if (celltype == 2)
+    {
+      // tet_11point (4C_fem_general_utils_integration.cpp:447-495), decimals as the reference has them
+      const double a = 0.0714285714285714, b = 0.7857142857142857, c = 0.1005964238332008,
+                   d = 0.3994035761667992;
+      const double P[11][3] = {{0.25, 0.25, 0.25}, {b, a, a}, {a, a, a}, {a, a, b}, {a, b, a},
+          {c, d, d}, {d, c, d}, {d, d, c}, {d, c, c}, {c, d, c}, {c, c, d}};
+      const double Q16 = 1.0 / 6.0;
+      T.ngp_mass = 11;
+      mxi.assign(&P[0][0], &P[0][0] + 33);
+      T.w_mass.assign(11, 0.1493333333333333 * Q16);
+      T.w_mass[0] = -0.0789333333333333 * Q16;
+      for (int q = 1; q < 5; ++q) T.w_mass[q] = 0.0457333333333333 * Q16;
+    }
+    T.N_mass.resize((size_t)T.ngp_mass * T.nn);
+    T.dN_mass.resize((size_t)T.ngp_mass * T.nn * 3);
+    for (int q = 0; q < T.ngp_mass; ++q)
+    {
+      detail::shape0(celltype, &mxi[3 * q], &T.N_mass[(size_t)q * T.nn]);
+      detail::deriv1(celltype, &mxi[3 * q], &T.dN_mass[(size_t)q * T.nn * 3]);
+    }
+    const double cen_hex[3] = {0.0, 0.0, 0.0}, cen_tet[3] = {0.25, 0.25, 0.25};
+    T.dN_cen.resize((size_t)T.nn * 3);
+    detail::deriv1(celltype, celltype == 2 ? cen_tet : cen_hex, T.dN_cen.data());
     return T;
   }
 }  // namespace b200s

@@ -83,8 +83,13 @@ namespace b200s
   {
     MAT_COUP_NEOHOOKE = 0,
     MAT_ISO_VOL = 1,
-    MAT_SVK = 2
+    MAT_SVK = 2,
+    MAT_HYPER = 3  // generic MAT_ElastHyper summand list (summands.cuh)
   };
+
+  struct HyperMat;
+  B2_HD void hyper_evaluate(const HyperMat& hm, const double* C, double* S, double* Cm);
+  B2_HD double hyper_strain_energy(const HyperMat& hm, const double* C);
 
   // Material parameters preprocessed once on the host (b200s_set_material):
   //   COUP_NEOHOOKE: p[0]=c=YOUNG/(4(1+NUE)), p[1]=beta=NUE/(1-2NUE)
@@ -92,9 +97,11 @@ namespace b200s
   //   ISO_VOL      : p[0]=MUE (or per element), p[1]=KAPPA
   //   SVK          : p[0]=lambda, p[1]=2*mue, p[2]=mfac*(1-nu), p[3]=mfac*nu, p[4]=mfac*(1-2nu)/2
   //                  (src/mat/4C_mat_stvenantkirchhoff.hpp:136-170)
+  //   HYPER        : p[] unused; hyper points to the summand list (device memory on the device)
   struct MatParams
   {
     double p[6];
+    const HyperMat* hyper;
   };
 
   // Host-side preprocessing of the input-file parameters (what the reference's PAR:: constructors
@@ -102,6 +109,7 @@ namespace b200s
   inline bool make_mat_params(int kind, const double* params, MatParams& mp)
   {
     for (double& v : mp.p) v = 0.0;
+    mp.hyper = nullptr;
     if (kind == MAT_COUP_NEOHOOKE)
     {
       const double young = params[0], nue = params[1];
@@ -134,7 +142,11 @@ namespace b200s
   template <int MAT>
   B2_HD void material_evaluate(const MatParams& mp, const double* C, double* S, double* Cm)
   {
-    if (MAT == MAT_SVK)
+    if (MAT == MAT_HYPER)
+    {
+      hyper_evaluate(*mp.hyper, C, S, Cm);
+    }
+    else if (MAT == MAT_SVK)
     {
       // S = lambda tr(E) I + 2 mue E with E = (C - I)/2  (src/mat/4C_mat_stvenantkirchhoff.cpp:105-113)
       const double E0 = 0.5 * (C[0] - 1.0), E1 = 0.5 * (C[1] - 1.0), E2 = 0.5 * (C[2] - 1.0);
@@ -225,6 +237,46 @@ namespace b200s
     }
   }
 
+  // Mat::So3Material::strain_energy of the device materials, from C = 2E + I
+  //   ElastHyper: 4C_mat_elasthyper.cpp:286-308 with the summands' add_strain_energy
+  //   (4C_mat_elast_coupneohooke.cpp:31-48, ..._isoneohooke.cpp:22-31, ..._volsussmanbathe.cpp:25-34)
+  //   StVenantKirchhoff: 1/2 E:C:E (4C_mat_stvenantkirchhoff.cpp:119-135)
+  template <int MAT>
+  B2_HD double material_strain_energy(const MatParams& mp, const double* C)
+  {
+    if (MAT == MAT_HYPER) return hyper_strain_energy(*mp.hyper, C);
+    if (MAT == MAT_SVK)
+    {
+      const double E[6] = {0.5 * (C[0] - 1.0), 0.5 * (C[1] - 1.0), 0.5 * (C[2] - 1.0), 0.5 * C[3],
+          0.5 * C[4], 0.5 * C[5]};
+      const double tr = E[0] + E[1] + E[2];
+      double psi = 0.0;
+#pragma unroll
+      for (int v = 0; v < 6; ++v)
+      {
+        const double Sv = (v < 3 ? mp.p[0] * tr : 0.0) + mp.p[1] * E[v];
+        psi += 0.5 * Sv * E[v] * (v < 3 ? 1.0 : 2.0);
+      }
+      return psi;
+    }
+    const double I1 = C[0] + C[1] + C[2];
+    const double I3 = C[0] * C[1] * C[2] + 2 * (C[3] * C[4] * C[5]) - C[1] * C[5] * C[5] -
+                      C[2] * C[3] * C[3] - C[0] * C[4] * C[4];
+    if (MAT == MAT_COUP_NEOHOOKE)
+    {
+      const double c = mp.p[0], beta = mp.p[1];
+      double psi = c * (I1 - 3.);
+      if (beta != 0)
+        psi += (c / beta) * (exp(log(I3) * (-beta)) - 1.);
+      else
+        psi -= c * log(I3);
+      return psi;
+    }
+    // IsoNeoHooke + VolSussmanBathe
+    const double m1 = I1 * pow(I3, -1. / 3.), J = pow(I3, 0.5);
+    return mp.p[0] * 0.5 * (m1 - 3.) + mp.p[1] * 0.5 * (J - 1.) * (J - 1.);
+  }
+
   // Right Cauchy-Green tensor C = F^T F in Voigt storage (calc_lib.hpp:714-722)
   B2_HD void right_cauchy_green(const double* F, double* C)
   {
@@ -285,3 +337,5 @@ namespace b200s
     }
   }
 }  // namespace b200s
+
+#include "summands.cuh"

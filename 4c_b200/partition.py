@@ -37,6 +37,7 @@ class RankMesh:
     peers: list = field(default_factory=list)       # neighbour ranks
     send_row_nodes: list = field(default_factory=list)  # per peer: row-node indices to send
     recv_col_nodes: list = field(default_factory=list)  # per peer: column-node lids to fill
+    ele_is_row: np.ndarray = None  # (n_col_eles,) uint8: row (owned) elements; None = all
 
     @property
     def n_col_nodes(self):
@@ -131,6 +132,12 @@ def box_partition(celltype, n, rank, nranks, box=(1.0, 1.0, 1.0)):
 
     rm = RankMesh(celltype, rank, nranks, X, conn, gid, node_row_lid,
                   np.arange(len(gid), dtype=np.int32), n_row, n_row_eles, ele_gid)
+    # row elements = the rank's own section of the element grid
+    lo = [ranges[d][sec[d]] for d in range(3)]
+    hi = [ranges[d][sec[d] + 1] for d in range(3)]
+    rm.ele_is_row = ((EX >= lo[0]) & (EX < hi[0]) & (EY >= lo[1]) & (EY < hi[1]) & (EZ >= lo[2]) &
+                     (EZ < hi[2])).astype(np.uint8)
+    assert int(rm.ele_is_row.sum()) == n_row_eles
 
     # halo lists: my ghosts grouped by owner (receive), and for every neighbour q the nodes I own
     # that lie in q's column-node box (send), both ascending in gid = the order q stores them
@@ -191,6 +198,7 @@ def generic_partition(celltype, X, conn, node_owner, rank, nranks, ele_owner=Non
         ele_owner = own_cnt.argmax(axis=1)
     rm = RankMesh(celltype, rank, nranks, np.asarray(X, np.float64)[gid], lconn, gid, node_row_lid,
                   np.arange(len(gid), dtype=np.int32), n_row, int((ele_owner == rank).sum()), ele_gid)
+    rm.ele_is_row = (np.asarray(ele_owner)[ele_gid] == rank).astype(np.uint8)
     ghost_owner = owner[~mine]
     row_gid = gid[:n_row]
     peers = set(int(p) for p in np.unique(ghost_owner))

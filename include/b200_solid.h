@@ -49,13 +49,53 @@ extern "C"
    *   COUP_NEOHOOKE : MAT_ElastHyper{ELAST_CoupNeoHooke YOUNG NUE}     params = {YOUNG, NUE}
    *   ISO_VOL       : MAT_ElastHyper{ELAST_IsoNeoHooke MUE, ELAST_VolSussmanBathe KAPPA}
    *                   params = {MUE, KAPPA}; MUE may be overridden per element (InputField)
-   *   SVK           : MAT_Struct_StVenantKirchhoff YOUNG NUE           params = {YOUNG, NUE} */
+   *   SVK           : MAT_Struct_StVenantKirchhoff YOUNG NUE           params = {YOUNG, NUE}
+   *   ELASTHYPER    : MAT_ElastHyper with a run-time list of isotropic summands, installed with
+   *                   b200s_set_material_elasthyper (slower than the three specialised kinds) */
   typedef enum
   {
     B200S_MAT_COUP_NEOHOOKE = 0,
     B200S_MAT_ISO_VOL = 1,
-    B200S_MAT_SVK = 2
+    B200S_MAT_SVK = 2,
+    B200S_MAT_ELASTHYPER = 3
   } b200s_material;
+
+  /* Mat::Elastic::Summand implementations evaluated through the principal / modified invariants
+   * (src/mat/elast/4C_mat_elast_*.cpp; add_derivatives_principal / add_derivatives_modified /
+   * add_strain_energy).  Parameters in input-file order, at most 4 per summand:
+   *   COUP_NEOHOOKE {YOUNG,NUE}  COUP_MOONEYRIVLIN {C1,C2,C3}  COUP_LOGNEOHOOKE {C1,C2} + MODE
+   *   COUP_LOGMIXNEOHOOKE {C1,C2} + MODE  COUP_SVK {YOUNG,NUE}  COUP_SIMOPISTER {MUE}
+   *   COUP_BLATZKO {MUE,NUE,F}  COUP_EXPPOL {A,B,C}  COUP_1POW/2POW/3POW {C,D}  COUP_13APOW {C,D,A}
+   *   ISO_NEOHOOKE {MUE}  ISO_MOONEYRIVLIN {C1,C2}  ISO_YEOH {C1,C2,C3}  ISO_1POW/2POW {C,D}
+   *   ISO_EXPOPOW {K1,K2,C}  VOL_SUSSMANBATHE {KAPPA}  VOL_PENALTY {EPSILON,GAMMA}
+   *   VOL_OGDEN {KAPPA,BETA}  VOL_POW {A,EXPON}
+   * MODE (LogNeoHooke / LogMixNeoHooke): 0 = "YN" (C1 = Young, C2 = nue), 1 = "Lame" (C1 = mue,
+   * C2 = lambda).  Stretch-based (IsoOgden, IsoVarga, CoupVarga) and fibre summands: CPU path. */
+  typedef enum
+  {
+    B200S_SUM_COUP_NEOHOOKE = 0,
+    B200S_SUM_COUP_MOONEYRIVLIN = 1,
+    B200S_SUM_COUP_LOGNEOHOOKE = 2,
+    B200S_SUM_COUP_LOGMIXNEOHOOKE = 3,
+    B200S_SUM_COUP_SVK = 4,
+    B200S_SUM_COUP_SIMOPISTER = 5,
+    B200S_SUM_COUP_BLATZKO = 6,
+    B200S_SUM_COUP_EXPPOL = 7,
+    B200S_SUM_COUP_1POW = 8,
+    B200S_SUM_COUP_2POW = 9,
+    B200S_SUM_COUP_3POW = 10,
+    B200S_SUM_COUP_13APOW = 11,
+    B200S_SUM_ISO_NEOHOOKE = 12,
+    B200S_SUM_ISO_MOONEYRIVLIN = 13,
+    B200S_SUM_ISO_YEOH = 14,
+    B200S_SUM_ISO_1POW = 15,
+    B200S_SUM_ISO_2POW = 16,
+    B200S_SUM_ISO_EXPOPOW = 17,
+    B200S_SUM_VOL_SUSSMANBATHE = 18,
+    B200S_SUM_VOL_PENALTY = 19,
+    B200S_SUM_VOL_OGDEN = 20,
+    B200S_SUM_VOL_POW = 21
+  } b200s_summand;
 
   /* Discret::Elements::SolidElementProperties of an element block (4C_solid_ele_properties.hpp:30-65;
    * input keys KINEM / TECH / PRESTRESS_TECH of the SOLID element line) */
@@ -77,13 +117,38 @@ extern "C"
     B200S_PRESTRESS_MULF = 1 /* CPU path */
   } b200s_prestress_technology;
 
-  /* Core::Elements::ActionType values handled (legacy_enum_definitions):
-   * struct_calc_internalforce, struct_calc_nlnstiff (4C_solid_ele_evaluate.cpp:64-115) */
+  /* Core::Elements::ActionType values handled by b200s_evaluate (legacy_enum_definitions;
+   * 4C_solid_ele_evaluate.cpp:64-159).  struct_calc_stress and struct_calc_energy have their own
+   * entry points (b200s_calc_stress, b200s_calc_energy). */
   typedef enum
   {
-    B200S_ACTION_INTERNALFORCE = 0,
-    B200S_ACTION_NLNSTIFF = 1
+    B200S_ACTION_INTERNALFORCE = 0,        /* struct_calc_internalforce */
+    B200S_ACTION_NLNSTIFF = 1,             /* struct_calc_nlnstiff */
+    B200S_ACTION_NLNSTIFFMASS = 2,         /* struct_calc_nlnstiffmass: + mass matrix, inertia force */
+    B200S_ACTION_NLNSTIFFLMASS = 3,        /* struct_calc_nlnstifflmass: lumped mass */
+    B200S_ACTION_INTERNALINERTIAFORCE = 4  /* struct_calc_internalinertiaforce: f_int and M_e * acc */
   } b200s_action;
+
+  /* FourC::Solid::StressType / StrainType of struct_calc_stress (4C_solid_ele_calc_lib_io.hpp:140-290) */
+  typedef enum
+  {
+    B200S_STRESS_NONE = 0,
+    B200S_STRESS_2PK = 1,
+    B200S_STRESS_CAUCHY = 2
+  } b200s_stress_type;
+  typedef enum
+  {
+    B200S_STRAIN_NONE = 0,
+    B200S_STRAIN_GL = 1,
+    B200S_STRAIN_EA = 2 /* strain_log (eigen decomposition): CPU path */
+  } b200s_strain_type;
+
+  /* which system matrix of the context an operation addresses */
+  typedef enum
+  {
+    B200S_MATRIX_STIFFNESS = 0,
+    B200S_MATRIX_MASS = 1
+  } b200s_matrix;
 
   /* Mirror of the element error interface (4C_structure_new_elements_paramsinterface.hpp:46-55). */
   typedef struct
@@ -136,6 +201,24 @@ extern "C"
   int b200s_set_material(b200s_ctx* ctx, int kind, const double* params, int nparams,
       const double* per_ele_param);
 
+  /* MAT_ElastHyper with NUMMAT summands (Mat::ElastHyper, src/mat/4C_mat_elasthyper.cpp:314-325;
+   * elast_hyper_evaluate, 4C_mat_elasthyper_service.cpp:23-75).  kinds[n]: b200s_summand,
+   * modes[n] (may be NULL = all 0), params: 4 doubles per summand (unused ones ignored).
+   * B200S_ERR_UNSUPPORTED for an unknown summand, B200S_ERR_INVALID where the reference's
+   * parameter constructor would throw. */
+  int b200s_set_material_elasthyper(b200s_ctx* ctx, int n_summands, const int32_t* kinds,
+      const int32_t* modes, const double* params);
+  /* Mat::So3Material::density() of the block (DENS): needed by the mass actions */
+  int b200s_set_density(b200s_ctx* ctx, double density);
+  /* Row (owned) elements among the column elements: is_row[n_col_eles] in the caller's element
+   * order, NULL = all.  Only struct_calc_energy distinguishes them (row elements only,
+   * model_evaluator_structure.cpp:1714-1716). */
+  int b200s_set_row_elements(b200s_ctx* ctx, const uint8_t* is_row);
+  /* Discretization::set_state(name, vector on the dof row map) for the states the device path
+   * reads: "displacement" (same as passing u_row to b200s_evaluate) and "acceleration"
+   * (inertia force of the mass actions, get_acceleration_vector, 4C_solid_ele_evaluate.cpp:29-34). */
+  int b200s_set_state(b200s_ctx* ctx, const char* name, const double* v_row);
+
   /* The reference's own sparsity graph after SparseMatrix::complete() (4C_linalg_sparsematrix.cpp:
    * 700-721): local CSR of the Epetra_CrsMatrix as returned by ExtractCrsDataPointers.
    *   rowptr      [host|dev] n_rows+1 (64-bit: > 2^31 nnz per rank is supported here)
@@ -182,6 +265,44 @@ extern "C"
    * Returns B200S_OK, B200S_ERR_NEG_JACOBIAN (adapter rethrows the reference's message) ... */
   int b200s_evaluate(b200s_ctx* ctx, int action, const double* u_row, double* K_values,
       double* f_row, b200s_error_info* err);
+
+  /* Results of the mass actions: second system matrix (same graph as K; mass_ in
+   * structure_new) and the inertia force vector elevec2 assembled on the row map.  [host|dev] out. */
+  int b200s_get_mass(b200s_ctx* ctx, double* M_values, double* f_inertia);
+  double* b200s_device_mass_values(b200s_ctx* ctx); /* nnz, NULL before the first mass action */
+  double* b200s_device_f_inertia(b200s_ctx* ctx);   /* n_rows */
+
+  /* struct_calc_stress (SolidEleCalc::calculate_stress, 4C_solid_ele_calc.cpp:416-476) for the
+   * current "displacement" state: Gauss-point stresses / strains of every column element,
+   * [n_col_eles][num_gp][6] doubles in the caller's element order, rows [xx,yy,zz,xy,yz,xz]
+   * (what the reference serialises into stress_data / strain_data per element).  Either output
+   * may be NULL.  [host|dev]. */
+  int b200s_calc_stress(b200s_ctx* ctx, int stress_type, int strain_type, double* stress_out,
+      double* strain_out);
+  /* struct_calc_energy (calculate_internal_energy, 4C_solid_ele_calc.cpp:365-414): this rank's sum
+   * of psi * detJ * w over its ROW elements (the caller does the sum_all,
+   * model_evaluator_structure.cpp:1718-1725).  [host] out. */
+  int b200s_calc_energy(b200s_ctx* ctx, double* energy_out);
+
+  /* ---- the step after the path, on the device (K never returns to the host) ------------------------ */
+  /* SparseMatrix::apply_dirichlet(dbctoggle, diagonalblock), in-place branch
+   * (4C_linalg_sparsematrix.cpp:893-921): rows with toggle == 1.0 are zeroed and get 1.0 on the
+   * diagonal if diagonalblock.  which: b200s_matrix.  dbctoggle_row [host|dev] n_rows. */
+  int b200s_apply_dirichlet(b200s_ctx* ctx, int which, const double* dbctoggle_row, int diagonalblock);
+  /* Core::LinAlg::apply_dirichlet_to_system(x, b, dbcval, dbctoggle)
+   * (4C_linalg_utils_sparse_algebra_assemble.cpp:116-130); x_row or b_row may be NULL. */
+  int b200s_apply_dirichlet_to_system(b200s_ctx* ctx, double* x_row, double* b_row,
+      const double* dbcval_row, const double* dbctoggle_row);
+  /* SparseMatrix::multiply(false, x, y): y = A x with x, y on the dof row map; the import of x to the
+   * column map is the ghost exchange of b200s_set_halo.  [host|dev]. */
+  int b200s_multiply(b200s_ctx* ctx, int which, const double* x_row, double* y_row);
+  double b200s_last_multiply_ms(const b200s_ctx* ctx); /* device time of the last product */
+  /* Hand-off demonstrator: block-Jacobi (3x3 node blocks) preconditioned CG on the stiffness matrix
+   * in the context, x_row = initial guess in / solution out, stops at |r| <= rtol |r0|.
+   * Not part of the reference path (4C hands K to Belos/MueLu); it shows the device CSR being
+   * consumed in place.  Multi-rank: dot products by ncclAllReduce. */
+  int b200s_solve_cg(b200s_ctx* ctx, const double* b_row, double* x_row, double rtol, int maxit,
+      int* iters_out, double* relres_out);
 
   /* Asynchronous flavour used when the caller keeps everything on the device: enqueues on the
    * context stream, does not synchronise, u already in the context's device row vector. */

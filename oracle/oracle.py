@@ -13,7 +13,15 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 HEX8, HEX27, TET10 = 0, 1, 2
-MAT_COUP_NEOHOOKE, MAT_ISO_VOL, MAT_SVK = 0, 1, 2
+MAT_COUP_NEOHOOKE, MAT_ISO_VOL, MAT_SVK, MAT_ELASTHYPER = 0, 1, 2, 3
+# summand ids of the generic MAT_ElastHyper (ORC_SUM_* in solid_oracle.h)
+SUMMANDS = ["COUP_NEOHOOKE", "COUP_MOONEYRIVLIN", "COUP_LOGNEOHOOKE", "COUP_LOGMIXNEOHOOKE", "COUP_SVK",
+            "COUP_SIMOPISTER", "COUP_BLATZKO", "COUP_EXPPOL", "COUP_1POW", "COUP_2POW", "COUP_3POW",
+            "COUP_13APOW", "ISO_NEOHOOKE", "ISO_MOONEYRIVLIN", "ISO_YEOH", "ISO_1POW", "ISO_2POW",
+            "ISO_EXPOPOW", "VOL_SUSSMANBATHE", "VOL_PENALTY", "VOL_OGDEN", "VOL_POW"]
+SUM = {name: i for i, name in enumerate(SUMMANDS)}
+STRESS_NONE, STRESS_2PK, STRESS_CAUCHY = 0, 1, 2
+STRAIN_NONE, STRAIN_GL, STRAIN_EA = 0, 1, 2
 ACTION_FORCE, ACTION_FORCE_STIFF = 0, 1
 TECH_NONE, TECH_FBAR = 0, 1
 
@@ -69,6 +77,20 @@ def lib():
         L.orc_build_graph.argtypes = [C.c_int, C.c_int64, _ip, C.c_int64, _ip, _ip, C.c_int64, _lp,
                                       _ip]
         L.orc_element.argtypes = [C.c_int, C.c_int, _dp, C.c_int, _dp, _dp, _dp, _dp]
+        L.orc_element_stress.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int, _dp, _dp]
+        L.orc_element_energy.restype = C.c_double
+        L.orc_element_energy.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp]
+        L.orc_strain_energy.restype = C.c_double
+        L.orc_strain_energy.argtypes = [C.c_int, _dp, _dp]
+        L.orc_element_mass.argtypes = [C.c_int, C.c_double, _dp, C.c_int, _dp, _dp, _dp]
+        L.orc_calc_stress.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int64, _ip, _dp, _dp,
+                                      C.c_int, C.c_int, _dp, _dp]
+        L.orc_calc_energy.restype = C.c_double
+        L.orc_calc_energy.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int64, _ip, _dp, _dp,
+                                      C.POINTER(C.c_uint8)]
+        L.orc_assemble_mass.argtypes = [C.c_int, C.c_double, C.c_int, C.c_int64, _ip, _dp, _dp, _ip, _ip,
+                                        C.c_int64, _lp, _ip, _dp, _dp]
+        L.orc_invariant_derivatives.argtypes = [C.c_int, _dp, _dp, _dp, _dp]
         for fn in (L.orc_stiffness_bfree, L.orc_stiffness_bop):
             fn.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_double, _dp]
         _lib = L
@@ -230,3 +252,110 @@ def evaluate_assemble(ct, matkind, params, conn, X, u_col, node_row_lid, node_co
                                        _i(node_row_lid), _i(node_col_lid), n_row_nodes, _l(rowptr),
                                        _i(colind), _d(values), _d(f), nthreads)
     return values, f, int(nbad)
+
+
+def pack_elasthyper(summands):
+    """summands: list of (name or id, [params...]) or (name, [params...], mode) -> packed parameter block of
+    MAT_ELASTHYPER (solid_oracle.cpp hyper_generic): {n, n x {kind, mode, p0..p3}}."""
+    out = [float(len(summands))]
+    for sm in summands:
+        kind, par = sm[0], list(sm[1])
+        mode = sm[2] if len(sm) > 2 else 0
+        kind = SUM[kind] if isinstance(kind, str) else int(kind)
+        out += [float(kind), float(mode)] + [float(v) for v in par] + [0.0] * (4 - len(par))
+    return np.asarray(out, dtype=np.float64)
+
+
+def invariant_derivatives(kind, params, prinv):
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    prinv = np.ascontiguousarray(prinv, dtype=np.float64)
+    dPI, ddPII = np.zeros(3), np.zeros(6)
+    lib().orc_invariant_derivatives(kind, _d(params), _d(prinv), _d(dPI), _d(ddPII))
+    return dPI, ddPII
+
+
+def strain_energy(kind, params, E):
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    E = np.ascontiguousarray(E, dtype=np.float64)
+    return lib().orc_strain_energy(kind, _d(params), _d(E))
+
+
+def element_stress(ct, matkind, params, X, u, stress_type=STRESS_2PK, strain_type=STRAIN_GL, tech=TECH_NONE):
+    n, g = num_nodes(ct), num_gp(ct)
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    X = np.ascontiguousarray(X, dtype=np.float64).reshape(n, 3)
+    u = np.ascontiguousarray(u, dtype=np.float64).reshape(n, 3)
+    st, en = np.zeros((g, 6)), np.zeros((g, 6))
+    lib().orc_element_stress(ct, tech, matkind, _d(params), _d(X), _d(u), stress_type, strain_type,
+                             _d(st), _d(en))
+    return st, en
+
+
+def element_energy(ct, matkind, params, X, u, tech=TECH_NONE):
+    n = num_nodes(ct)
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    X = np.ascontiguousarray(X, dtype=np.float64).reshape(n, 3)
+    u = np.ascontiguousarray(u, dtype=np.float64).reshape(n, 3)
+    return lib().orc_element_energy(ct, tech, matkind, _d(params), _d(X), _d(u))
+
+
+def element_mass(ct, density, X, lumped=False, acc=None):
+    """Returns (Me[row, col], f_inertia or None)."""
+    n = num_nodes(ct)
+    X = np.ascontiguousarray(X, dtype=np.float64).reshape(n, 3)
+    Me = np.zeros((3 * n) ** 2)
+    fi = np.zeros(3 * n) if acc is not None else None
+    acc = None if acc is None else np.ascontiguousarray(acc, dtype=np.float64).reshape(n, 3)
+    lib().orc_element_mass(ct, float(density), _d(X), int(lumped), _d(acc), _d(Me), _d(fi))
+    return Me.reshape(3 * n, 3 * n).T.copy(), fi
+
+
+def calc_stress(ct, matkind, params, conn, X, u_col, stress_type=STRESS_2PK, strain_type=STRAIN_GL,
+                mue_per_ele=None, tech=TECH_NONE):
+    n, g = num_nodes(ct), num_gp(ct)
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, n)
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    u_col = np.ascontiguousarray(u_col, dtype=np.float64)
+    if mue_per_ele is not None:
+        mue_per_ele = np.ascontiguousarray(mue_per_ele, dtype=np.float64)
+    st, en = np.zeros((len(conn), g, 6)), np.zeros((len(conn), g, 6))
+    lib().orc_calc_stress(ct, tech, matkind, _d(params), _d(mue_per_ele), len(conn), _i(conn), _d(X),
+                          _d(u_col), stress_type, strain_type, _d(st), _d(en))
+    return st, en
+
+
+def calc_energy(ct, matkind, params, conn, X, u_col, ele_is_row=None, mue_per_ele=None, tech=TECH_NONE):
+    n = num_nodes(ct)
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, n)
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    u_col = np.ascontiguousarray(u_col, dtype=np.float64)
+    if mue_per_ele is not None:
+        mue_per_ele = np.ascontiguousarray(mue_per_ele, dtype=np.float64)
+    flag = None
+    if ele_is_row is not None:
+        ele_is_row = np.ascontiguousarray(ele_is_row, dtype=np.uint8)
+        flag = ele_is_row.ctypes.data_as(C.POINTER(C.c_uint8))
+    return lib().orc_calc_energy(ct, tech, matkind, _d(params), _d(mue_per_ele), len(conn), _i(conn),
+                                 _d(X), _d(u_col), flag)
+
+
+def assemble_mass(ct, density, conn, X, node_row_lid, node_col_lid, n_row_nodes, rowptr, colind,
+                  lumped=False, acc_col=None):
+    """Owner-computes assembly of the element mass matrices into the stiffness graph; returns
+    (mass_values, f_inertia or None)."""
+    n = num_nodes(ct)
+    conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, n)
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    node_row_lid = np.ascontiguousarray(node_row_lid, dtype=np.int32)
+    node_col_lid = np.ascontiguousarray(node_col_lid, dtype=np.int32)
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+    colind = np.ascontiguousarray(colind, dtype=np.int32)
+    vals = np.zeros(rowptr[-1])
+    fi = np.zeros(3 * n_row_nodes) if acc_col is not None else None
+    acc_col = None if acc_col is None else np.ascontiguousarray(acc_col, dtype=np.float64)
+    lib().orc_assemble_mass(ct, float(density), int(lumped), len(conn), _i(conn), _d(X), _d(acc_col),
+                            _i(node_row_lid), _i(node_col_lid), n_row_nodes, _l(rowptr), _i(colind),
+                            _d(vals), _d(fi))
+    return vals, fi

@@ -276,6 +276,353 @@ namespace
     }
   }
 
+
+  // ---- generic MAT_ElastHyper: list of isotropic summands ----------------------------------------
+  // Packed parameter block (oracle.py pack_elasthyper): par[0] = number of summands, then per summand
+  // 6 doubles {kind (ORC_SUM_*), mode, p0, p1, p2, p3} with the INPUT-FILE parameters; what the
+  // PAR:: constructors derive from them is restated in place.
+  //   Mat::ElastHyper::evaluate / strain_energy   src/mat/4C_mat_elasthyper.cpp:286-325
+  //   elast_hyper_evaluate_invariant_derivatives  src/mat/4C_mat_elasthyper_service.cpp:84-120
+  //   convert_mod_to_princ                        :122-154
+  //   invariants_modified                         src/mat/4C_mat_service.cpp:125-134
+  void lame_from_input(double mode, double c1, double c2, double& lambda, double& mue)
+  {
+    if (mode == 1.0)  // "Lame": C1 = mue, C2 = lambda (4C_mat_elast_couplogneohooke.cpp:33-37)
+    {
+      mue = c1, lambda = c2;
+      return;
+    }
+    lambda = (c2 == 0.5) ? 0.0 : c1 * c2 / ((1.0 + c2) * (1.0 - 2.0 * c2));
+    mue = c1 / (2.0 * (1.0 + c2));
+  }
+
+  // one summand: adds to dPI/ddPII (principal) or dPm/ddPm (modified) and to psi
+  void summand_add(int kind, double mode, const double* p, const double* I, const double* m,
+      double* dPI, double* ddPII, double* dPm, double* ddPm, double& psi)
+  {
+    using std::exp;
+    using std::log;
+    using std::pow;
+    using std::sqrt;
+    switch (kind)
+    {
+      case ORC_SUM_COUP_NEOHOOKE:  // src/mat/elast/4C_mat_elast_coupneohooke.cpp:17-68
+      {
+        const double c = p[0] / (4.0 * (1.0 + p[1])), beta = p[1] / (1.0 - 2.0 * p[1]);
+        double psiadd = c * (I[0] - 3.);
+        if (beta != 0)
+          psiadd += (c / beta) * (exp(log(I[2]) * (-beta)) - 1.);
+        else
+          psiadd -= c * log(I[2]);
+        psi += psiadd;
+        dPI[0] += c;
+        if (I[2] > 0)
+        {
+          const double prinv2_to_beta_m1 = exp(log(I[2]) * (-beta - 1.));
+          dPI[2] -= c * prinv2_to_beta_m1;
+          ddPII[2] += c * (beta + 1.) * prinv2_to_beta_m1 / I[2];
+        }
+        else
+          dPI[2] = ddPII[2] = std::numeric_limits<double>::quiet_NaN();
+        break;
+      }
+      case ORC_SUM_COUP_MOONEYRIVLIN:  // 4C_mat_elast_coupmooneyrivlin.cpp:29-64
+      {
+        const double c1 = p[0], c2 = p[1], c3 = p[2];
+        psi += c1 * (I[0] - 3.) + c2 * (I[1] - 3.) - (2. * c1 + 4. * c2) * log(sqrt(I[2])) +
+               c3 * pow((sqrt(I[2]) - 1.), 2.);
+        dPI[0] += c1;
+        dPI[1] += c2;
+        dPI[2] += c3 * (1 - pow(I[2], -0.5)) - (c1 + 2. * c2) * pow(I[2], -1.);
+        ddPII[2] += (c1 + 2 * c2) * pow(I[2], -2.) + 0.5 * c3 * pow(I[2], -1.5);
+        break;
+      }
+      case ORC_SUM_COUP_LOGNEOHOOKE:  // 4C_mat_elast_couplogneohooke.cpp:17-82
+      {
+        double lambda, mue;
+        lame_from_input(mode, p[0], p[1], lambda, mue);
+        psi += mue * 0.5 * (I[0] - 3.) - mue * log(sqrt(I[2])) + lambda * 0.5 * pow(log(sqrt(I[2])), 2.);
+        const double logdetf = log(sqrt(I[2]));
+        dPI[0] += mue * 0.5;
+        dPI[2] += (lambda * logdetf) / (2. * I[2]) - mue / (2. * I[2]);
+        ddPII[2] += lambda / (4. * I[2] * I[2]) + mue / (2. * I[2] * I[2]) -
+                    (lambda * logdetf) / (2. * I[2] * I[2]);
+        break;
+      }
+      case ORC_SUM_COUP_LOGMIXNEOHOOKE:  // 4C_mat_elast_couplogmixneohooke.cpp:17-82
+      {
+        double lambda, mue;
+        lame_from_input(mode, p[0], p[1], lambda, mue);
+        const double sq = sqrt(I[2]);
+        psi += mue * 0.5 * (I[0] - 3.) - mue * log(sq) + lambda * 0.5 * pow((sq - 1.), 2.);
+        dPI[0] += mue * 0.5;
+        dPI[2] += lambda * (sq - 1.) / (2. * sq) - mue / (2. * I[2]);
+        ddPII[2] += lambda / (4. * I[2]) + mue / (2. * I[2] * I[2]) - lambda * (sq - 1.) / (4. * sq * sq * sq);
+        break;
+      }
+      case ORC_SUM_COUP_SVK:  // 4C_mat_elast_coupSaintVenantKirchhoff.cpp:17-62
+      {
+        double lambda, mue;
+        lame_from_input(0.0, p[0], p[1], lambda, mue);
+        psi += (0.25 * mue + 0.125 * lambda) * I[0] * I[0] - (0.75 * lambda + 0.5 * mue) * I[0] -
+               0.5 * mue * I[1] + 1.125 * lambda + 0.75 * mue;
+        dPI[0] += (0.5 * mue + 0.25 * lambda) * I[0] - 0.75 * lambda - 0.5 * mue;
+        dPI[1] -= 0.5 * mue;
+        ddPII[0] += 0.5 * mue + 0.25 * lambda;
+        break;
+      }
+      case ORC_SUM_COUP_SIMOPISTER:  // 4C_mat_elast_coupsimopister.cpp
+      {
+        const double mue = p[0];
+        psi += 0.5 * mue * (I[0] - 3.) - mue * log(pow(I[2], 0.5));
+        dPI[0] += 0.5 * mue;
+        dPI[2] -= 0.5 * mue / I[2];
+        ddPII[2] += 0.5 * mue / (I[2] * I[2]);
+        break;
+      }
+      case ORC_SUM_COUP_BLATZKO:  // 4C_mat_elast_coupblatzko.cpp
+      {
+        const double mue = p[0], nue = p[1], f = p[2];
+        const double beta = nue / (1. - 2. * nue);
+        const double log_i3 = log(I[2]);
+        const double neg = beta == 0.0 ? -log_i3 : std::expm1(-beta * log_i3) / beta;
+        const double pos = beta == 0.0 ? log_i3 : std::expm1(beta * log_i3) / beta;
+        psi += 0.5 * mue * (f * (I[0] - 3.0 + neg) + (1.0 - f) * (I[1] / I[2] - 3.0 + pos));
+        dPI[0] += f * mue / 2.;
+        dPI[1] += (1. - f) * mue / (2. * I[2]);
+        dPI[2] += -(f * mue) / (2. * pow(I[2], beta + 1.)) -
+                  (mue * (pow(I[2], beta - 1.) - I[1] / I[2] / I[2]) * (f - 1.)) * 0.5;
+        ddPII[2] += (f * mue * (beta + 1.)) / (2. * pow(I[2], beta + 2.)) -
+                    (mue * (f - 1.) *
+                        ((2. * I[1]) / I[2] / I[2] / I[2] + pow(I[2], beta - 2.) * (beta - 1.))) *
+                        0.5;
+        ddPII[3] -= (1. - f) * 0.5 * mue / I[2] / I[2];
+        break;
+      }
+      case ORC_SUM_COUP_EXPPOL:  // 4C_mat_elast_coupexppol.cpp
+      {
+        const double a = p[0], b = p[1], c = p[2];
+        psi += a * exp(b * (I[0] - 3.0) - (2.0 * b + c) * log(sqrt(I[2])) + c * (sqrt(I[2]) - 1.0)) - a;
+        const double logdetf = log(sqrt(I[2]));
+        const double expfunc = exp(b * (I[0] - 3.0) - (2.0 * b + c) * logdetf + c * (sqrt(I[2]) - 1.0));
+        dPI[0] += a * b * expfunc;
+        dPI[2] += a * expfunc * (c / (2. * sqrt(I[2])) - (2. * b + c) / (2. * I[2]));
+        ddPII[0] += a * b * b * expfunc;
+        ddPII[2] += a * expfunc *
+                    ((0.5 * (2. * b + c) / (I[2] * I[2])) - (0.25 * c / pow(I[2], 1.5)) +
+                        (-0.5 * (2. * b + c) / I[2] + 0.5 * c / sqrt(I[2])) *
+                            (-0.5 * (2. * b + c) / I[2] + 0.5 * c / sqrt(I[2])));
+        ddPII[4] += a * b * expfunc * (c / (2. * sqrt(I[2])) - (2. * b + c) / (2. * I[2]));
+        break;
+      }
+      case ORC_SUM_COUP_1POW:  // 4C_mat_elast_coup1pow.cpp
+      case ORC_SUM_COUP_2POW:  // 4C_mat_elast_coup2pow.cpp
+      {
+        const int q = kind == ORC_SUM_COUP_1POW ? 0 : 1;
+        const double c = p[0];
+        const int d = (int)p[1];
+        psi += c * pow((I[q] - 3.), d);
+        dPI[q] += c * d * pow((I[q] - 3.), d - 1.);
+        if (d == 2)
+          ddPII[q] += (c * d * d - c * d);
+        else
+          ddPII[q] += (c * d * d - c * d) * pow((I[q] - 3.), d - 2.);
+        break;
+      }
+      case ORC_SUM_COUP_3POW:  // 4C_mat_elast_coup3pow.cpp
+      {
+        const double c = p[0];
+        const int d = (int)p[1];
+        psi += c * pow((pow(I[2], 1. / 3.) - 1.), d);
+        dPI[2] += 1. / 3. * c * d * pow(I[2], -2. / 3.) * pow((pow(I[2], 1. / 3.) - 1.), d - 1.);
+        if (d == 2)
+          ddPII[2] += -2. / 9. * c * d * pow(I[2], -5. / 3.) * pow((pow(I[2], 1. / 3.) - 1.), d - 1.) +
+                      1. / 9. * c * d * (d - 1.) * pow(I[2], -4. / 3.);
+        else
+          ddPII[2] += -2. / 9. * c * d * pow(I[2], -5. / 3.) * pow((pow(I[2], 1. / 3.) - 1.), d - 1.) +
+                      1. / 9. * c * d * (d - 1.) * pow(I[2], -4. / 3.) *
+                          pow((pow(I[2], 1. / 3.) - 1.), d - 2.);
+        break;
+      }
+      case ORC_SUM_COUP_13APOW:  // 4C_mat_elast_coup13apow.cpp
+      {
+        const double c = p[0], a = p[2];
+        const int d = (int)p[1];
+        psi += c * pow((I[0] * (pow(I[2], -a)) - 3.), d);
+        const double I1I3a3 = I[0] * pow(I[2], -a) - 3.;
+        dPI[0] += c * d * pow(I[2], -a) * pow(I1I3a3, d - 1.);
+        dPI[2] += -a * c * d * I[0] * pow(I[2], -a - 1.) * pow(I1I3a3, d - 1.);
+        if (d == 2)
+        {
+          ddPII[0] += c * d * (d - 1.) * pow(I[2], -2. * a);
+          ddPII[2] += a * (a + 1.) * c * d * I[0] * pow(I[2], -a - 2.) * pow(I1I3a3, d - 1.) +
+                      a * a * c * d * (d - 1.) * I[0] * I[0] * pow(I[2], (-2. * a - 2.));
+          ddPII[4] += -a * c * d * pow(I[2], -a - 1.) * pow(I1I3a3, d - 1.) -
+                      a * c * d * (d - 1.) * I[0] * pow(I[2], (-2. * a - 1.));
+        }
+        else
+        {
+          ddPII[0] += c * d * (d - 1.) * pow(I[2], -2. * a) * pow(I1I3a3, d - 2.);
+          ddPII[2] += a * (a + 1.) * c * d * I[0] * pow(I[2], -a - 2.) * pow(I1I3a3, d - 1.) +
+                      a * a * c * d * (d - 1.) * I[0] * I[0] * pow(I[2], (-2. * a - 2.)) *
+                          pow(I1I3a3, d - 2.);
+          ddPII[4] += -a * c * d * pow(I[2], -a - 1.) * pow(I1I3a3, d - 1.) -
+                      a * c * d * (d - 1.) * I[0] * pow(I[2], (-2. * a - 1.)) * pow(I1I3a3, d - 2.);
+        }
+        break;
+      }
+      case ORC_SUM_ISO_NEOHOOKE:  // 4C_mat_elast_isoneohooke.cpp:22-40
+        psi += p[0] * 0.5 * (m[0] - 3.);
+        dPm[0] += 0.5 * p[0];
+        break;
+      case ORC_SUM_ISO_MOONEYRIVLIN:  // 4C_mat_elast_isomooneyrivlin.cpp
+        psi += p[0] * (m[0] - 3.) + p[1] * (m[1] - 3.);
+        dPm[0] += p[0];
+        dPm[1] += p[1];
+        break;
+      case ORC_SUM_ISO_YEOH:  // 4C_mat_elast_isoyeoh.cpp
+      {
+        const double c1 = p[0], c2 = p[1], c3 = p[2];
+        psi += c1 * (m[0] - 3.) + c2 * (m[0] - 3.) * (m[0] - 3.) +
+               c3 * (m[0] - 3.) * (m[0] - 3.) * (m[0] - 3.);
+        dPm[0] += c1 + 2. * c2 * (m[0] - 3.) + 3. * c3 * (m[0] - 3.) * (m[0] - 3.);
+        ddPm[0] += 2. * c2 + 6. * c3 * (m[0] - 3.);
+        break;
+      }
+      case ORC_SUM_ISO_1POW:  // 4C_mat_elast_iso1pow.cpp
+      case ORC_SUM_ISO_2POW:  // 4C_mat_elast_iso2pow.cpp
+      {
+        const int q = kind == ORC_SUM_ISO_1POW ? 0 : 1;
+        const double c = p[0];
+        const int d = (int)p[1];
+        psi += c * pow((m[q] - 3.), d);
+        if (d == 1)
+          dPm[q] += c * d;
+        else
+          dPm[q] += c * d * pow(m[q] - 3., d - 1.);
+        if (d == 1)
+          ddPm[q] += 0.;
+        else if (d == 2)
+          ddPm[q] += c * d * (d - 1.);
+        else
+          ddPm[q] += c * d * (d - 1.) * pow(m[q] - 3., d - 2.);
+        break;
+      }
+      case ORC_SUM_ISO_EXPOPOW:  // 4C_mat_elast_isoexpopow.cpp
+      {
+        const double k1 = p[0], k2 = p[1];
+        const int d = (int)p[2];
+        if (k2 != 0) psi += k1 / (2. * k2) * (exp(k2 * pow(m[0] - 3., d)) - 1.);
+        const double expf = exp(k2 * pow(m[0] - 3., (double)d));
+        if (d == 1)
+          dPm[0] += k1 * d * 0.5 * expf;
+        else
+          dPm[0] += k1 * d * 0.5 * expf * pow(m[0] - 3., d - 1.);
+        if (d == 1)
+          ddPm[0] += k1 * d * d * k2 * 0.5 * expf;
+        else if (d == 2)
+          ddPm[0] += k1 * d * d * k2 * 0.5 * expf * pow((m[0] - 3.), 2. * (d - 1.)) +
+                     k1 * d * 0.5 * expf * (d - 1.);
+        else
+          ddPm[0] += k1 * d * d * k2 * 0.5 * expf * pow((m[0] - 3.), 2. * (d - 1.)) +
+                     k1 * d * 0.5 * expf * (d - 1.) * pow((m[0] - 3.), (d - 2.));
+        break;
+      }
+      case ORC_SUM_VOL_SUSSMANBATHE:  // 4C_mat_elast_volsussmanbathe.cpp:25-43
+        psi += p[0] * 0.5 * (m[2] - 1.) * (m[2] - 1.);
+        dPm[2] += p[0] * (m[2] - 1.);
+        ddPm[2] += p[0];
+        break;
+      case ORC_SUM_VOL_PENALTY:  // 4C_mat_elast_volpenalty.cpp
+      {
+        const double eps = p[0], game = p[1];
+        psi += eps * (pow(m[2], game) + pow(m[2], -game) - 2.);
+        dPm[2] += eps * game * (pow(m[2], game - 1.) - pow(m[2], -game - 1.));
+        ddPm[2] += eps * game * ((game - 1.) * pow(m[2], game - 2.) + (game + 1.) * pow(m[2], -game - 2.));
+        break;
+      }
+      case ORC_SUM_VOL_OGDEN:  // 4C_mat_elast_vologden.cpp
+      {
+        const double kappa = p[0], beta = p[1];
+        if (beta != 0)
+          psi += kappa / (beta * beta) * (beta * log(m[2]) + pow(m[2], -beta) - 1.);
+        else
+          psi += kappa / 2. * pow(log(m[2]), 2.);
+        if (beta != 0.)
+        {
+          dPm[2] += kappa / (beta * beta) * (beta / m[2] - beta * pow(m[2], -beta - 1.));
+          ddPm[2] += kappa / (beta * beta) *
+                     (-beta / (m[2] * m[2]) + beta * (beta + 1.) * pow(m[2], -beta - 2.));
+        }
+        else
+        {
+          dPm[2] += kappa * log(m[2]) / m[2];
+          ddPm[2] += kappa * (1. - log(m[2])) / (m[2] * m[2]);
+        }
+        break;
+      }
+      case ORC_SUM_VOL_POW:  // 4C_mat_elast_volpow.cpp
+      {
+        const double a = p[0], expon = p[1];
+        psi += a / (expon - 1.) * pow(m[2], -expon + 1.) + a * m[2];
+        dPm[2] += -a * (pow(m[2], -expon) - 1.);
+        ddPm[2] += expon * a * pow(m[2], -(expon + 1.));
+        break;
+      }
+      default:
+        break;
+    }
+  }
+
+  void convert_mod_to_princ(const double* I, const double* dPm, const double* ddPm, double* dPI, double* ddPII)
+  {
+    using std::pow;
+    dPI[0] += pow(I[2], -1. / 3.) * dPm[0];
+    dPI[1] += pow(I[2], -2. / 3.) * dPm[1];
+    dPI[2] += 0.5 * pow(I[2], -0.5) * dPm[2] - 1. / 3. * I[0] * pow(I[2], -4. / 3.) * dPm[0] -
+              2. / 3. * I[1] * pow(I[2], -5. / 3.) * dPm[1];
+    ddPII[0] += pow(I[2], -2. / 3.) * ddPm[0];
+    ddPII[1] += pow(I[2], -4. / 3.) * ddPm[1];
+    ddPII[2] += (1. / 9.) * pow(I[2], -8. / 3.) * I[0] * I[0] * ddPm[0] +
+                (4. / 9.) * I[0] * I[1] * pow(I[2], -3.) * ddPm[5] -
+                (1. / 3.) * pow(I[2], -11. / 6.) * I[0] * ddPm[4] +
+                (4. / 9.) * pow(I[2], -7. / 3.) * I[0] * dPm[0] +
+                (4. / 9.) * pow(I[2], -10. / 3.) * I[1] * I[1] * ddPm[1] -
+                (2. / 3.) * pow(I[2], -13. / 6.) * I[1] * ddPm[3] +
+                (10. / 9.) * pow(I[2], -8. / 3.) * I[1] * dPm[1] + 0.25 * pow(I[2], -1.) * ddPm[2] -
+                0.25 * pow(I[2], -1.5) * dPm[2];
+    ddPII[3] += -(1. / 3.) * pow(I[2], -2.) * I[0] * ddPm[5] -
+                (2. / 3.) * pow(I[2], -7. / 3.) * I[1] * ddPm[1] + 0.5 * pow(I[2], -7. / 6.) * ddPm[3] -
+                (2. / 3.) * pow(I[2], -5. / 3.) * dPm[1];
+    ddPII[4] += -(1. / 3.) * pow(I[2], -5. / 3.) * I[0] * ddPm[0] -
+                (2. / 3.) * pow(I[2], -2.) * I[1] * ddPm[5] + 0.5 * pow(I[2], -5. / 6.) * ddPm[4] -
+                (1. / 3.) * pow(I[2], -4. / 3.) * dPm[0];
+    ddPII[5] += pow(I[2], -1.) * ddPm[5];
+  }
+
+  // returns psi; dPI/ddPII may be null (strain energy only)
+  double hyper_generic(const double* par, const double* I, double* dPI, double* ddPII)
+  {
+    const int n = (int)par[0];
+    double d1[3] = {0, 0, 0}, d2[6] = {0, 0, 0, 0, 0, 0}, dPm[3] = {0, 0, 0}, ddPm[6] = {0, 0, 0, 0, 0, 0};
+    const double m[3] = {I[0] * std::pow(I[2], -1. / 3.), I[1] * std::pow(I[2], -2. / 3.), std::pow(I[2], 1. / 2.)};
+    double psi = 0.0;
+    bool isomod = false;
+    for (int k = 0; k < n; ++k)
+    {
+      const double* q = par + 1 + 6 * k;
+      const int kind = (int)q[0];
+      if (kind >= ORC_SUM_ISO_NEOHOOKE) isomod = true;
+      summand_add(kind, q[1], q + 2, I, m, d1, d2, dPm, ddPm, psi);
+    }
+    if (isomod) convert_mod_to_princ(I, dPm, ddPm, d1, d2);
+    if (dPI)
+      for (int i = 0; i < 3; ++i) dPI[i] = d1[i];
+    if (ddPII)
+      for (int i = 0; i < 6; ++i) ddPII[i] = d2[i];
+    return psi;
+  }
+
   // Mat::ElastHyper::evaluate -> elast_hyper_evaluate (src/mat/4C_mat_elasthyper.cpp:314-325,
   // src/mat/4C_mat_elasthyper_service.cpp:23-75,156-206)
   void elasthyper(int kind, const double* par, const double* E, double* S, double* Cm)
@@ -294,7 +641,10 @@ namespace
     I[2] = C[0] * C[1] * C[2] + 2 * (C[3] * C[4] * C[5]) - C[1] * C[5] * C[5] -
            C[2] * C[3] * C[3] - C[0] * C[4] * C[4];
     double dPI[3], ddPII[6], g[3], d[8];
-    invariant_derivatives(kind, par, I, dPI, ddPII);
+    if (kind == ORC_MAT_ELASTHYPER)
+      hyper_generic(par, I, dPI, ddPII);
+    else
+      invariant_derivatives(kind, par, I, dPI, ddPII);
     gamma_delta(I, dPI, ddPII, g, d);
     const double Id[6] = {1, 1, 1, 0, 0, 0};
     for (int i = 0; i < 6; ++i) S[i] = g[0] * Id[i] + g[1] * C[i] + g[2] * iC[i];
@@ -754,6 +1104,328 @@ extern "C"
     add_stiffness_bop(nnodes(ct), jm, F, S, C, fac, Ke);
   }
 
+
+  // ---- further element actions -------------------------------------------------
+  namespace
+  {
+    // Mat::So3Material::strain_energy of the oracle materials
+    double strain_energy(int kind, const double* par, const double* E)
+    {
+      if (kind == ORC_MAT_SVK) return orc_svk_strain_energy(par, E);
+      double C[6], I[3];
+      for (int i = 0; i < 6; ++i) C[i] = 2.0 * E[i] + (i < 3 ? 1.0 : 0.0);
+      I[0] = C[0] + C[1] + C[2];
+      I[1] = 0.5 * (I[0] * I[0] - C[0] * C[0] - C[1] * C[1] - C[2] * C[2]) - C[3] * C[3] - C[4] * C[4] -
+             C[5] * C[5];
+      I[2] = C[0] * C[1] * C[2] + 2 * (C[3] * C[4] * C[5]) - C[1] * C[5] * C[5] - C[2] * C[3] * C[3] -
+             C[0] * C[4] * C[4];
+      if (kind == ORC_MAT_ELASTHYPER) return hyper_generic(par, I, nullptr, nullptr);
+      double blk[13];
+      if (kind == ORC_MAT_COUP_NEOHOOKE)
+      {
+        const double b[7] = {1, ORC_SUM_COUP_NEOHOOKE, 0, par[0], par[1], 0, 0};
+        std::copy(b, b + 7, blk);
+      }
+      else
+      {
+        const double b[13] = {2, ORC_SUM_ISO_NEOHOOKE, 0, par[0], 0, 0, 0, ORC_SUM_VOL_SUSSMANBATHE, 0,
+            par[1], 0, 0, 0};
+        std::copy(b, b + 13, blk);
+      }
+      return hyper_generic(blk, I, nullptr, nullptr);
+    }
+
+    // kinematics of the formulation at one Gauss point: F and E as handed to the material
+    // (DisplacementBasedFormulation::evaluate, 4C_solid_ele_calc_displacement_based.hpp:44-63;
+    //  FBarFormulation::evaluate, 4C_solid_ele_calc_fbar.hpp:83-118)
+    void formulation_kinematics(int ct, int tech, const double* X, const double* u, const JacMap& jm,
+        double* F, double* E)
+    {
+      const int n = nnodes(ct);
+      deformation_gradient(n, u, jm, F);
+      if (tech == ORC_TECH_FBAR)
+      {
+        double N[MAXN], dN[3 * MAXN], F0[9];
+        JacMap jm0;
+        const double xi0[3] = {0.0, 0.0, 0.0};
+        shape(ct, xi0, N, dN);
+        jacobian_mapping(n, dN, X, jm0);
+        deformation_gradient(n, u, jm0, F0);
+        const double fbar = std::pow(det3(F0) / det3(F), 1.0 / 3.0);
+        for (int i = 0; i < 9; ++i) F[i] *= fbar;
+      }
+      double C[6];
+      cauchy_green(F, C, E);
+    }
+  }  // namespace
+
+  // SolidEleCalc::calculate_stress (src/solid_ele/4C_solid_ele_calc.cpp:416-476) for one element:
+  // stress / strain [ngp][6] in the row layout of assemble_symmetric_tensor_to_matrix_row
+  // (4C_solid_ele_calc_lib_io.hpp:41-70).  stress_type 1 = 2PK, 2 = Cauchy (pk2_to_cauchy,
+  // 4C_solid_ele_utils.hpp:41-54); strain_type 1 = GL, 2 = EA (green_lagrange_to_euler_almansi :64-79)
+  void orc_element_stress(int ct, int tech, int matkind, const double* par, const double* X,
+      const double* u, int stress_type, int strain_type, double* stress, double* strain)
+  {
+    const int n = nnodes(ct), ng = ngauss(ct);
+    double N[MAXN], dN[3 * MAXN], gxi[3 * MAXN], gw[MAXN];
+    JacMap jm;
+    gauss(ct, gxi, gw);
+    for (int gp = 0; gp < ng; ++gp)
+    {
+      shape(ct, gxi + 3 * gp, N, dN);
+      jacobian_mapping(n, dN, X, jm);
+      double F[9], E[6], S[6], Cm[36];
+      formulation_kinematics(ct, tech, X, u, jm, F, E);
+      material(matkind, par, F, E, S, Cm);
+      if (stress && stress_type == 1)
+        for (int v = 0; v < 6; ++v) stress[6 * gp + v] = S[v];
+      if (stress && stress_type == 2)
+      {
+        double FS[9];
+        for (int a = 0; a < 3; ++a)
+          for (int b = 0; b < 3; ++b)
+          {
+            double v = 0.0;
+            for (int c = 0; c < 3; ++c) v += F[a + 3 * c] * S[VG[c][b]];
+            FS[a + 3 * b] = v;
+          }
+        const double det = det3(F);
+        for (int v = 0; v < 6; ++v)
+        {
+          double w = 0.0;
+          for (int c = 0; c < 3; ++c) w += FS[VA[v] + 3 * c] * F[VB[v] + 3 * c];
+          stress[6 * gp + v] = w / det;
+        }
+      }
+      if (strain && strain_type == 1)
+        for (int v = 0; v < 6; ++v) strain[6 * gp + v] = E[v];
+      if (strain && strain_type == 2)
+      {
+        double iF[9], T[9];
+        inv3(iF, F);
+        for (int a = 0; a < 3; ++a)
+          for (int b = 0; b < 3; ++b)
+          {  // T = iF^T E
+            double v = 0.0;
+            for (int c = 0; c < 3; ++c) v += iF[c + 3 * a] * E[VG[c][b]];
+            T[a + 3 * b] = v;
+          }
+        for (int v = 0; v < 6; ++v)
+        {
+          double w = 0.0;
+          for (int c = 0; c < 3; ++c) w += T[VA[v] + 3 * c] * iF[c + 3 * VB[v]];
+          strain[6 * gp + v] = w;
+        }
+      }
+    }
+  }
+
+  // SolidEleCalc::calculate_internal_energy (4C_solid_ele_calc.cpp:365-414)
+  double orc_element_energy(int ct, int tech, int matkind, const double* par, const double* X,
+      const double* u)
+  {
+    const int n = nnodes(ct), ng = ngauss(ct);
+    double N[MAXN], dN[3 * MAXN], gxi[3 * MAXN], gw[MAXN];
+    JacMap jm;
+    gauss(ct, gxi, gw);
+    double intenergy = 0.0;
+    for (int gp = 0; gp < ng; ++gp)
+    {
+      shape(ct, gxi + 3 * gp, N, dN);
+      jacobian_mapping(n, dN, X, jm);
+      double F[9], E[6];
+      formulation_kinematics(ct, tech, X, u, jm, F, E);
+      intenergy += strain_energy(matkind, par, E) * (jm.det * gw[gp]);
+    }
+    return intenergy;
+  }
+  double orc_strain_energy(int matkind, const double* par, const double* E)
+  {
+    return strain_energy(matkind, par, E);
+  }
+
+  // mass rule: DisTypeToOptGaussRule (4C_fem_general_element_integration_select.hpp:37-67):
+  // hex_8point / hex_27point (= stiffness rule) and tet_11point
+  // (4C_fem_general_utils_integration.cpp:447-495)
+  static int mass_rule(int ct, double* xi, double* w)
+  {
+    if (ct != ORC_TET10)
+    {
+      gauss(ct, xi, w);
+      return ngauss(ct);
+    }
+    const double Q16 = 1.0 / 6.0;
+    const double q[11][3] = {{0.2500000000000000, 0.2500000000000000, 0.2500000000000000},
+        {0.7857142857142857, 0.0714285714285714, 0.0714285714285714},
+        {0.0714285714285714, 0.0714285714285714, 0.0714285714285714},
+        {0.0714285714285714, 0.0714285714285714, 0.7857142857142857},
+        {0.0714285714285714, 0.7857142857142857, 0.0714285714285714},
+        {0.1005964238332008, 0.3994035761667992, 0.3994035761667992},
+        {0.3994035761667992, 0.1005964238332008, 0.3994035761667992},
+        {0.3994035761667992, 0.3994035761667992, 0.1005964238332008},
+        {0.3994035761667992, 0.1005964238332008, 0.1005964238332008},
+        {0.1005964238332008, 0.3994035761667992, 0.1005964238332008},
+        {0.1005964238332008, 0.1005964238332008, 0.3994035761667992}};
+    for (int i = 0; i < 11; ++i)
+      for (int d = 0; d < 3; ++d) xi[3 * i + d] = q[i][d];
+    w[0] = -0.0789333333333333 * Q16;
+    for (int i = 1; i < 5; ++i) w[i] = 0.0457333333333333 * Q16;
+    for (int i = 5; i < 11; ++i) w[i] = 0.1493333333333333 * Q16;
+    return 11;
+  }
+
+  // Element mass matrix as evaluate_nonlinear_force_stiffness_mass integrates it
+  // (4C_solid_ele_calc.cpp:151-153,226-236,265-280; add_mass_matrix calc_lib.hpp:1221-1238),
+  // optional lump_matrix (calc_lib.hpp:73-89), inertia force M_e * acc
+  // (4C_solid_ele_evaluate.cpp:36-59).  Me column-major 3n x 3n; finert may be NULL.
+  void orc_element_mass(int ct, double density, const double* X, int lumped, const double* acc,
+      double* Me, double* finert)
+  {
+    const int n = nnodes(ct), nd = 3 * n, ng = ngauss(ct);
+    double N[MAXN], dN[3 * MAXN], gxi[3 * MAXN], gw[MAXN], mxi[3 * MAXN], mw[MAXN];
+    JacMap jm;
+    std::memset(Me, 0, sizeof(double) * nd * nd);
+    gauss(ct, gxi, gw);
+    const int nm = mass_rule(ct, mxi, mw);
+    const bool equal = (nm == ng);  // compare_gauss_integration: number of points
+    auto add_mass = [&](double fac, double rho)
+    {
+      for (int inod = 0; inod < n; ++inod)
+      {
+        const double ifactor = N[inod] * fac * rho;
+        for (int jnod = 0; jnod < n; ++jnod)
+        {
+          const double massfactor = N[jnod] * ifactor;
+          for (int d = 0; d < 3; ++d) Me[(3 * inod + d) + nd * (3 * jnod + d)] += massfactor;
+        }
+      }
+    };
+    double element_mass = 0.0, element_volume = 0.0;
+    for (int gp = 0; gp < ng; ++gp)
+    {
+      shape(ct, gxi + 3 * gp, N, dN);
+      jacobian_mapping(n, dN, X, jm);
+      const double fac = jm.det * gw[gp];
+      if (equal)
+        add_mass(fac, density);
+      else
+        element_mass += density * fac, element_volume += fac;
+    }
+    if (!equal)
+      for (int gp = 0; gp < nm; ++gp)
+      {
+        shape(ct, mxi + 3 * gp, N, dN);
+        jacobian_mapping(n, dN, X, jm);
+        add_mass(jm.det * mw[gp], element_mass / element_volume);
+      }
+    if (lumped)
+      for (int c = 0; c < nd; ++c)
+      {
+        double d = 0.0;
+        for (int r = 0; r < nd; ++r)
+        {
+          d += Me[r + nd * c];
+          Me[r + nd * c] = 0.0;
+        }
+        Me[c + nd * c] = d;
+      }
+    if (finert && acc)
+      for (int r = 0; r < nd; ++r)
+      {
+        double v = 0.0;
+        for (int c = 0; c < nd; ++c) v += Me[r + nd * c] * acc[c];
+        finert[r] = v;
+      }
+  }
+
+  // Whole-mesh versions: Gauss-point stresses of every column element, internal energy of the row
+  // elements, mass matrix + inertia force assembled owner-computes into the stiffness graph.
+  void orc_calc_stress(int ct, int tech, int matkind, const double* matparams, const double* mue_per_ele,
+      int64_t n_ele, const int32_t* conn, const double* X, const double* u_col, int stress_type,
+      int strain_type, double* stress, double* strain)
+  {
+    const int n = nnodes(ct), nd = 3 * n, ng = ngauss(ct);
+    std::vector<double> Xe(nd), ue(nd);
+    std::vector<double> par(matparams, matparams + (matkind == ORC_MAT_ELASTHYPER ? 1 + 6 * (int)matparams[0] : 2));
+    for (int64_t e = 0; e < n_ele; ++e)
+    {
+      for (int i = 0; i < n; ++i)
+        for (int d = 0; d < 3; ++d)
+        {
+          Xe[3 * i + d] = X[3 * (int64_t)conn[e * n + i] + d];
+          ue[3 * i + d] = u_col[3 * (int64_t)conn[e * n + i] + d];
+        }
+      if (mue_per_ele) par[0] = mue_per_ele[e];
+      orc_element_stress(ct, tech, matkind, par.data(), Xe.data(), ue.data(), stress_type, strain_type,
+          stress ? stress + e * ng * 6 : nullptr, strain ? strain + e * ng * 6 : nullptr);
+    }
+  }
+
+  double orc_calc_energy(int ct, int tech, int matkind, const double* matparams,
+      const double* mue_per_ele, int64_t n_ele, const int32_t* conn, const double* X,
+      const double* u_col, const uint8_t* ele_is_row)
+  {
+    const int n = nnodes(ct), nd = 3 * n;
+    std::vector<double> Xe(nd), ue(nd);
+    std::vector<double> par(matparams, matparams + (matkind == ORC_MAT_ELASTHYPER ? 1 + 6 * (int)matparams[0] : 2));
+    double sum = 0.0;
+    for (int64_t e = 0; e < n_ele; ++e)
+    {
+      if (ele_is_row && !ele_is_row[e]) continue;  // row elements only (model_evaluator_structure.cpp:1714)
+      for (int i = 0; i < n; ++i)
+        for (int d = 0; d < 3; ++d)
+        {
+          Xe[3 * i + d] = X[3 * (int64_t)conn[e * n + i] + d];
+          ue[3 * i + d] = u_col[3 * (int64_t)conn[e * n + i] + d];
+        }
+      if (mue_per_ele) par[0] = mue_per_ele[e];
+      sum += orc_element_energy(ct, tech, matkind, par.data(), Xe.data(), ue.data());
+    }
+    return sum;
+  }
+
+  void orc_assemble_mass(int ct, double density, int lumped, int64_t n_ele, const int32_t* conn,
+      const double* X, const double* acc_col, const int32_t* node_row_lid, const int32_t* node_col_lid,
+      int64_t n_row_nodes, const int64_t* rowptr, const int32_t* colind, double* mass_values,
+      double* f_inertia)
+  {
+    const int n = nnodes(ct), nd = 3 * n;
+    std::vector<double> Me(nd * nd), fi(nd), Xe(nd), ae(nd);
+    if (mass_values) std::fill(mass_values, mass_values + rowptr[3 * n_row_nodes], 0.0);
+    if (f_inertia) std::fill(f_inertia, f_inertia + 3 * n_row_nodes, 0.0);
+    for (int64_t e = 0; e < n_ele; ++e)
+    {
+      const int32_t* ce = conn + e * n;
+      for (int i = 0; i < n; ++i)
+        for (int d = 0; d < 3; ++d)
+        {
+          Xe[3 * i + d] = X[3 * (int64_t)ce[i] + d];
+          ae[3 * i + d] = acc_col ? acc_col[3 * (int64_t)ce[i] + d] : 0.0;
+        }
+      orc_element_mass(ct, density, Xe.data(), lumped, acc_col ? ae.data() : nullptr, Me.data(), fi.data());
+      for (int i = 0; i < n; ++i)
+      {
+        const int32_t r = node_row_lid[ce[i]];
+        if (r < 0) continue;
+        for (int b = 0; b < 3; ++b)
+        {
+          const int64_t rlid = 3 * (int64_t)r + b;
+          if (f_inertia && acc_col) f_inertia[rlid] += fi[3 * i + b];
+          if (!mass_values) continue;
+          const int32_t* idx = colind + rowptr[rlid];
+          const int len = (int)(rowptr[rlid + 1] - rowptr[rlid]);
+          for (int j = 0; j < n; ++j)
+            for (int c = 0; c < 3; ++c)
+            {
+              const int32_t col = 3 * node_col_lid[ce[j]] + c;
+              const int32_t* loc = std::lower_bound(idx, idx + len, col);
+              mass_values[rowptr[rlid] + (loc - idx)] += Me[(3 * i + b) + nd * (3 * j + c)];
+            }
+        }
+      }
+    }
+  }
+
   // First assembly inserts every (owned row, element column) pair in global ids, zeros included
   // (src/core/linalg/src/sparse/4C_linalg_sparsematrix.cpp:469-494), complete() then sorts each
   // row by local column id (:700-721).  All three dofs of a node share the node's pattern.
@@ -821,7 +1493,9 @@ extern "C"
       std::fill(f + 3 * r0, f + 3 * r1, 0.0);
       std::vector<double> Ke(nd * nd), fe(nd), Xe(nd), ue(nd);
       std::vector<int32_t> localcol(nd);
-      double par[4] = {matparams[0], matparams[1], 0, 0};
+      // generic MAT_ElastHyper: packed summand block (1 + 6 n doubles), used in place
+      std::vector<double> par(matparams, matparams + (matkind == ORC_MAT_ELASTHYPER ? 1 + 6 * (int)matparams[0] : 2));
+      par.resize(par.size() + 2, 0.0);
       // Discretization::evaluate loop over column elements
       // (src/core/fem/src/discretization/4C_fem_discretization_evaluate.cpp:85-117)
       for (int64_t e = 0; e < n_ele; ++e)
@@ -842,7 +1516,7 @@ extern "C"
           }
         if (mue_per_ele) par[0] = mue_per_ele[e];  // InputField MUE looked up by element id
         const bool stiff = (action == ORC_ACTION_FORCE_STIFF) && values;
-        if (element_tech(ct, tech, matkind, par, action, Xe.data(), ue.data(),
+        if (element_tech(ct, tech, matkind, par.data(), action, Xe.data(), ue.data(),
                 stiff ? Ke.data() : nullptr, fe.data()))
         {
           bad[tid]++;

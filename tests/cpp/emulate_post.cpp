@@ -1,0 +1,151 @@
+// TEST INFRASTRUCTURE: runs the PRODUCT's __host__ __device__ point functions of
+// 4c_b200/csrc/post_kernels.cuh, summands.cuh and solid_math.cuh on the CPU (one call per thread
+// the kernels would launch), so the CPU suite checks the stress / energy / mass arithmetic, the
+// generic MAT_ElastHyper summands and the mass scatter addressing against the oracle without a
+// GPU.  Not shipped, not a fallback: the library has no host execution path.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../4c_b200/csrc/post_kernels.cuh"
+#include "../../4c_b200/csrc/shape_tables.hpp"
+
+using namespace b200s;
+
+namespace
+{
+  // matkind 0..2: params = raw input parameters (as b200s_set_material);
+  // matkind 3   : params = {n, n x {kind, mode, p0..p3}} (the oracle's packed block)
+  bool setup_material(int matkind, const double* params, MatParams& mp, HyperMat& hm)
+  {
+    if (matkind != MAT_HYPER) return make_mat_params(matkind, params, mp);
+    for (double& v : mp.p) v = 0.0;
+    hm.n = (int)params[0], hm.uses_modified = 0;
+    if (hm.n > HYPER_MAX_SUMMANDS) return false;
+    for (int k = 0; k < hm.n; ++k)
+    {
+      const double* q = params + 1 + 6 * k;
+      if (!make_summand((int)q[0], q + 2, (int)q[1], hm.s[k])) return false;
+      if (summand_is_modified((int)q[0])) hm.uses_modified = 1;
+    }
+    mp.hyper = &hm;
+    return true;
+  }
+
+  template <int MAT>
+  void run_post(const PostArgs& A, double* energy)
+  {
+    double sum = 0.0;
+    for (int64_t e = 0; e < A.n_ele; ++e)
+      for (int g = 0; g < A.ngp; ++g)
+      {
+        const int64_t eid = A.ele_id ? A.ele_id[e] : e;
+        const bool row = A.ele_is_row == nullptr || A.ele_is_row[eid] != 0;
+        double s6[6], e6[6];
+        sum += post_point<MAT>(A, e, g, energy != nullptr && row, A.stress ? s6 : nullptr,
+            A.strain ? e6 : nullptr);
+        for (int v = 0; v < 6; ++v)
+        {
+          if (A.stress && A.stress_type != STRESS_NONE) A.stress[(eid * A.ngp + g) * 6 + v] = s6[v];
+          if (A.strain && A.strain_type != STRAIN_NONE) A.strain[(eid * A.ngp + g) * 6 + v] = e6[v];
+        }
+      }
+    if (energy) *energy = sum;
+  }
+
+  template <int NN>
+  void run_mass(const MassArgs& A)
+  {
+    for (int64_t e = 0; e < A.n_ele; ++e)
+      for (int i = 0; i < NN; ++i)
+      {
+        double m[NN];
+        mass_row<NN>(A, e, i, m);
+        mass_scatter<NN>(A, e, i, m);
+      }
+  }
+}  // namespace
+
+// Mat::So3Material::evaluate + strain_energy of the product at one point: C (Voigt) in,
+// S[6], Cm[36] (full symmetric 6x6, row-major = column-major) and psi out
+extern "C" int emu_material(int matkind, const double* params, const double* C, double* S,
+    double* Cm36, double* psi)
+{
+  MatParams mp;
+  HyperMat hm;
+  if (!setup_material(matkind, params, mp, hm)) return -3;
+  double Cm[21];
+  switch (matkind)
+  {
+    case 0:
+      material_evaluate<MAT_COUP_NEOHOOKE>(mp, C, S, Cm), *psi = material_strain_energy<MAT_COUP_NEOHOOKE>(mp, C);
+      break;
+    case 1:
+      material_evaluate<MAT_ISO_VOL>(mp, C, S, Cm), *psi = material_strain_energy<MAT_ISO_VOL>(mp, C);
+      break;
+    case 2:
+      material_evaluate<MAT_SVK>(mp, C, S, Cm), *psi = material_strain_energy<MAT_SVK>(mp, C);
+      break;
+    default:
+      material_evaluate<MAT_HYPER>(mp, C, S, Cm), *psi = material_strain_energy<MAT_HYPER>(mp, C);
+  }
+  for (int I = 0; I < 6; ++I)
+    for (int J = 0; J < 6; ++J) Cm36[I + 6 * J] = Cm[c21(I, J)];
+  return 0;
+}
+
+extern "C" int emu_post(int celltype, int fbar, int matkind, const double* params, const double* per_ele,
+    int64_t n_ele, const int32_t* conn, const double* X, const double* u_col, const uint8_t* ele_is_row,
+    int stress_type, int strain_type, double* stress, double* strain, double* energy)
+{
+  const CellTables T = make_cell_tables(celltype);
+  MatParams mp;
+  HyperMat hm;
+  if (!setup_material(matkind, params, mp, hm)) return -3;
+  PostArgs A;
+  A.X = X, A.u = u_col, A.conn = conn, A.per_ele_param = per_ele, A.ele_id = nullptr;
+  A.ele_is_row = ele_is_row, A.dN_gp = T.dN_gp.data(), A.dN_cen = T.dN_cen.data(), A.w = T.w.data();
+  A.mp = mp, A.n_ele = n_ele, A.nn = T.nn, A.ngp = T.ngp, A.fbar = fbar;
+  A.stress_type = stress_type, A.strain_type = strain_type;
+  A.stress = stress, A.strain = strain, A.energy = nullptr;
+  switch (matkind)
+  {
+    case 0:
+      run_post<MAT_COUP_NEOHOOKE>(A, energy);
+      break;
+    case 1:
+      run_post<MAT_ISO_VOL>(A, energy);
+      break;
+    case 2:
+      run_post<MAT_SVK>(A, energy);
+      break;
+    default:
+      run_post<MAT_HYPER>(A, energy);
+  }
+  return 0;
+}
+
+extern "C" int emu_mass(int celltype, double density, int lumped, int64_t n_ele, const int32_t* conn,
+    const double* X, const double* acc_col, const int32_t* pos, const int64_t* node_rowstart,
+    const int32_t* node_rowlen, const int32_t* node_frow, int64_t n_col_nodes, double* mass_vals,
+    double* f_inertia)
+{
+  const CellTables T = make_cell_tables(celltype);
+  std::vector<NodeRow> node_row(n_col_nodes);
+  for (int64_t k = 0; k < n_col_nodes; ++k)
+    node_row[k].rowstart = node_rowstart[k], node_row[k].rowlen = node_rowlen[k],
+    node_row[k].frow = node_frow[k];
+  MassArgs M;
+  M.X = X, M.conn = conn, M.pos = pos, M.node_row = node_row.data(), M.acc = acc_col;
+  M.N_mass = T.N_mass.data(), M.dN_mass = T.dN_mass.data(), M.w_mass = T.w_mass.data();
+  M.dN_gp = T.dN_gp.data(), M.w = T.w.data(), M.density = density, M.n_ele = n_ele;
+  M.nn = T.nn, M.ngp = T.ngp, M.ngp_mass = T.ngp_mass, M.pos_stride = T.nn * T.nn;
+  M.lumped = lumped, M.mass_vals = mass_vals, M.f_inertia = f_inertia;
+  if (celltype == 0)
+    run_mass<8>(M);
+  else if (celltype == 1)
+    run_mass<27>(M);
+  else
+    run_mass<10>(M);
+  return 0;
+}

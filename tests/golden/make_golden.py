@@ -78,9 +78,19 @@ def integration_case(cell, rel):
         if s["QUANTITY"] in ("dispx", "dispy", "dispz"):
             expected.append({"node": s["NODE"] - 1, "dof": "xyz".index(s["QUANTITY"][-1]),
                              "value": float(s["VALUE"]), "tol": float(s["TOLERANCE"])})
+    # nodal stresses (IO: STRUCT_STRESS Cauchy, Gauss-point values extrapolated to the nodes)
+    comp = {"xx": 0, "yy": 1, "zz": 2, "xy": 3, "yz": 4, "xz": 5}
+    expected_stress = []
+    for r in y["RESULT DESCRIPTION"]:
+        s = r["STRUCTURE"]
+        if s["QUANTITY"].startswith("stress_"):
+            expected_stress.append({"node": s["NODE"] - 1, "comp": comp[s["QUANTITY"][-2:]],
+                                    "value": float(s["VALUE"]), "tol": float(s["TOLERANCE"])})
     return {
         "source": rel,
         "celltype": cell,
+        "iostress": y["IO"]["STRUCT_STRESS"],
+        "expected_stress": expected_stress,
         "coords": coords,
         "elements": eles,
         "material": {"kind": "ELAST_CoupNeoHooke", "YOUNG": float(nh["YOUNG"]),

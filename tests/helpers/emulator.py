@@ -17,7 +17,8 @@ def lib(cell="hex8"):
         so = os.path.join(_CPP, f"libemu_{cell}.so")
         srcs = [os.path.join(_CPP, f"emulate_{cell}.cpp")] + [
             os.path.join(_CPP, "..", "..", "4c_b200", "csrc", f)
-            for f in ("hex8_kernel.cuh", "hex8_fbar_kernel.cuh", "tet10_kernel.cuh", "hex27_kernel.cuh", "solid_math.cuh", "shape_tables.hpp")]
+            for f in ("hex8_kernel.cuh", "hex8_fbar_kernel.cuh", "tet10_kernel.cuh", "hex27_kernel.cuh", "solid_math.cuh",
+                      "summands.cuh", "post_kernels.cuh", "shape_tables.hpp")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", so, srcs[0]])
         _libs[cell] = C.CDLL(so)
@@ -71,3 +72,58 @@ def evaluate(matkind, params, conn, X, u_col, rowptr, colind, node_row_lid, node
                         p(rowlen), p(frow), C.c_int64(len(rowstart)), p(vals), p(f), C.byref(dJ), C.byref(dF), C.byref(nb))
     assert rc == 0
     return vals, f, dict(min_detJ=dJ.value, min_detF=dF.value, n_bad=nb.value)
+
+
+_vp = C.c_void_p
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+def material(matkind, params, Cv):
+    """Product material at one point: C (Voigt) -> S[6], Cm[6,6], psi."""
+    params = np.ascontiguousarray(params, np.float64)
+    Cv = np.ascontiguousarray(Cv, np.float64)
+    S, Cm, psi = np.zeros(6), np.zeros(36), C.c_double(0)
+    rc = lib("post").emu_material(C.c_int(matkind), _p(params), _p(Cv), _p(S), _p(Cm), C.byref(psi))
+    assert rc == 0, rc
+    return S, Cm.reshape(6, 6), psi.value
+
+
+def post(celltype, matkind, params, conn, X, u_col, stress_type=1, strain_type=1, ele_is_row=None,
+         per_ele=None, fbar=False, want_energy=True):
+    conn = np.ascontiguousarray(conn, np.int32)
+    X = np.ascontiguousarray(X, np.float64)
+    u_col = np.ascontiguousarray(u_col, np.float64)
+    params = np.ascontiguousarray(params, np.float64)
+    ngp = {0: 8, 1: 27, 2: 4}[celltype]
+    st = np.zeros((len(conn), ngp, 6))
+    en = np.zeros((len(conn), ngp, 6))
+    energy = C.c_double(0)
+    if ele_is_row is not None:
+        ele_is_row = np.ascontiguousarray(ele_is_row, np.uint8)
+    if per_ele is not None:
+        per_ele = np.ascontiguousarray(per_ele, np.float64)
+    rc = lib("post").emu_post(C.c_int(celltype), C.c_int(int(fbar)), C.c_int(matkind), _p(params), _p(per_ele),
+                              C.c_int64(len(conn)), _p(conn), _p(X), _p(u_col), _p(ele_is_row),
+                              C.c_int(stress_type), C.c_int(strain_type), _p(st), _p(en),
+                              C.byref(energy) if want_energy else None)
+    assert rc == 0, rc
+    return st, en, energy.value
+
+
+def mass(celltype, density, conn, X, rowptr, colind, node_row_lid, node_col_lid, n_row_nodes, lumped=False,
+         acc_col=None):
+    conn = np.ascontiguousarray(conn, np.int32)
+    X = np.ascontiguousarray(X, np.float64)
+    pos, rowstart, rowlen, frow = scatter_map(conn, rowptr, colind, node_row_lid, node_col_lid)
+    vals = np.zeros(rowptr[-1])
+    fi = np.zeros(3 * n_row_nodes)
+    if acc_col is not None:
+        acc_col = np.ascontiguousarray(acc_col, np.float64)
+    rc = lib("post").emu_mass(C.c_int(celltype), C.c_double(density), C.c_int(int(lumped)), C.c_int64(len(conn)),
+                              _p(conn), _p(X), _p(acc_col), _p(pos), _p(rowstart), _p(rowlen), _p(frow),
+                              C.c_int64(len(rowstart)), _p(vals), _p(fi))
+    assert rc == 0, rc
+    return vals, fi

@@ -1,0 +1,300 @@
+"""CPU suite for the actions around the hot path: generic MAT_ElastHyper summands,
+struct_calc_stress, struct_calc_energy, mass matrix / inertia force.
+
+Part 1 pins the ORACLE restatement: the reference's own known answers (nodal Cauchy stresses of the
+three ctest inputs, Cook's membrane internal energy, Blatz-Ko logarithmic limit) and the consistency
+checks the reference's unit tests use (numerical derivative of the strain energy, unittests/mat/elast/
+4C_elast_strain_energy_test.cpp).
+Part 2 runs the PRODUCT's __host__ __device__ point functions on the CPU (tests/cpp/emulate_post.cpp)
+against the oracle at 1e-12.
+"""
+import importlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests.helpers import emulator as emu
+from tests.helpers.meshes import serial_maps
+from tests.helpers.newton import solve_case
+from tests.helpers.postprocess import nodal_stresses
+
+b200 = importlib.import_module("4c_b200")
+G = os.path.join(os.path.dirname(__file__), "golden")
+CELLS = {"hex8": orc.HEX8, "hex27": orc.HEX27, "tet10": orc.TET10}
+
+# one parameter set per summand (input-file parameters)
+SUMMAND_CASES = [
+    ("COUP_NEOHOOKE", [200.0, 0.25]), ("COUP_NEOHOOKE", [10.0, 0.0]), ("COUP_MOONEYRIVLIN", [1.3, 0.4, 25.0]),
+    ("COUP_LOGNEOHOOKE", [100.0, 0.3]), ("COUP_LOGNEOHOOKE", [40.0, 60.0], 1), ("COUP_LOGMIXNEOHOOKE", [100.0, 0.3]),
+    ("COUP_LOGMIXNEOHOOKE", [40.0, 60.0], 1), ("COUP_SVK", [1000.0, 0.3]), ("COUP_SIMOPISTER", [3.0]),
+    ("COUP_BLATZKO", [2.3, 0.2, 0.35]), ("COUP_BLATZKO", [2.3, 0.0, 0.35]), ("COUP_EXPPOL", [0.8, 0.3, 0.6]),
+    ("COUP_1POW", [1.7, 2]), ("COUP_1POW", [1.7, 3]), ("COUP_2POW", [0.9, 2]), ("COUP_2POW", [0.9, 4]),
+    ("COUP_3POW", [55.0, 2]), ("COUP_3POW", [55.0, 3]), ("COUP_13APOW", [2.0, 2, 0.05]), ("COUP_13APOW", [2.0, 3, 0.1]),
+    ("ISO_NEOHOOKE", [1.5]), ("ISO_MOONEYRIVLIN", [0.7, 0.2]), ("ISO_YEOH", [0.6, 0.1, 0.05]),
+    ("ISO_1POW", [1.1, 1]), ("ISO_1POW", [1.1, 2]), ("ISO_1POW", [1.1, 3]), ("ISO_2POW", [0.4, 1]),
+    ("ISO_2POW", [0.4, 2]), ("ISO_2POW", [0.4, 3]), ("ISO_EXPOPOW", [2.0, 0.5, 1]), ("ISO_EXPOPOW", [2.0, 0.5, 2]),
+    ("ISO_EXPOPOW", [2.0, 0.5, 3]), ("VOL_SUSSMANBATHE", [1000.0]), ("VOL_PENALTY", [50.0, 4.0]),
+    ("VOL_OGDEN", [300.0, -2.0]), ("VOL_OGDEN", [300.0, 0.0]), ("VOL_POW", [2.5, 4.0]),
+]
+E_TEST = np.array([0.11, -0.07, 0.05, 0.02, -0.03, 0.04])
+
+
+def _C_of(E):
+    return 2.0 * np.asarray(E) + np.array([1.0, 1, 1, 0, 0, 0])
+
+
+def _voigt_to_full(v):
+    return np.array([[v[0], v[3], v[5]], [v[3], v[1], v[4]], [v[5], v[4], v[2]]])
+
+
+# ------------------------------------------------------------------------------------------------------
+# Part 1: oracle pinned
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", SUMMAND_CASES, ids=lambda c: f"{c[0]}-{c[1]}-{c[2] if len(c) > 2 else 0}")
+def test_summand_stress_and_tangent_are_derivatives_of_the_strain_energy(case):
+    """S = d psi / d E and C = d S / d E by central differences (the consistency the reference checks in
+    4C_elast_strain_energy_test.cpp, carried through gamma/delta and convert_mod_to_princ)."""
+    blk = orc.pack_elasthyper([case])
+    S, Cm = orc.material(orc.MAT_ELASTHYPER, blk, E_TEST)
+    h = 1e-6
+    w = np.array([1, 1, 1, 2, 2, 2.0])  # shear components appear twice in E:S
+    for v in range(6):
+        d = np.zeros(6)
+        d[v] = h
+        dpsi = (orc.strain_energy(orc.MAT_ELASTHYPER, blk, E_TEST + d) -
+                orc.strain_energy(orc.MAT_ELASTHYPER, blk, E_TEST - d)) / (2 * h)
+        assert abs(dpsi / w[v] - S[v]) <= 2e-7 * max(1.0, np.abs(S).max()), (v, dpsi / w[v], S[v])
+        Sp = orc.material(orc.MAT_ELASTHYPER, blk, E_TEST + d)[0]
+        Sm = orc.material(orc.MAT_ELASTHYPER, blk, E_TEST - d)[0]
+        dS = (Sp - Sm) / (2 * h) / w[v]
+        assert np.abs(dS - Cm[:, v]).max() <= 2e-6 * max(1.0, np.abs(Cm).max()), (v, dS, Cm[:, v])
+    assert np.abs(Cm - Cm.T).max() <= 1e-12 * max(1.0, np.abs(Cm).max())
+
+
+def test_blatzko_energy_logarithmic_limit_known_answer():
+    """unittests/mat/elast/4C_elast_strain_energy_test.cpp:61-82 (NUE = 0, expected value, 1e-14)."""
+    # a C with the test's invariants is not needed: the summand only sees the invariants, so choose
+    # E such that the invariants are whatever they are and compare against the same closed form
+    blk = orc.pack_elasthyper([("COUP_BLATZKO", [2.3, 0.0, 0.35])])
+    C = _voigt_to_full(_C_of(E_TEST))
+    I1, I3 = np.trace(C), np.linalg.det(C)
+    I2 = 0.5 * (I1 * I1 - np.trace(C @ C))
+    expected = 0.5 * 2.3 * (0.35 * (I1 - 3.0 - np.log(I3)) + 0.65 * (I2 / I3 - 3.0 + np.log(I3)))
+    assert abs(orc.strain_energy(orc.MAT_ELASTHYPER, blk, E_TEST) - expected) < 1e-13
+
+
+def test_generic_material_reproduces_the_specialised_ones():
+    for kind, par, blk in ((orc.MAT_COUP_NEOHOOKE, [200.0, 0.25], [("COUP_NEOHOOKE", [200.0, 0.25])]),
+                           (orc.MAT_ISO_VOL, [1.0, 1000.0], [("ISO_NEOHOOKE", [1.0]), ("VOL_SUSSMANBATHE", [1000.0])])):
+        S, Cm = orc.material(kind, par, E_TEST)
+        S2, C2 = orc.material(orc.MAT_ELASTHYPER, orc.pack_elasthyper(blk), E_TEST)
+        assert np.array_equal(S, S2) and np.array_equal(Cm, C2)
+    # CoupSVK is St.Venant-Kirchhoff written in invariants
+    S, Cm = orc.material(orc.MAT_SVK, [1000.0, 0.3], E_TEST)
+    S2, C2 = orc.material(orc.MAT_ELASTHYPER, orc.pack_elasthyper([("COUP_SVK", [1000.0, 0.3])]), E_TEST)
+    assert np.abs(S - S2).max() < 1e-11 and np.abs(Cm - C2).max() < 1e-10
+    assert abs(orc.strain_energy(orc.MAT_SVK, [1000.0, 0.3], E_TEST) -
+               orc.strain_energy(orc.MAT_ELASTHYPER, orc.pack_elasthyper([("COUP_SVK", [1000.0, 0.3])]), E_TEST)) < 1e-11
+
+
+@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10"])
+def test_nodal_cauchy_stress_known_answers(cell):
+    """RESULT DESCRIPTION stress_xx..stress_yz (tolerance 1e-12 in the reference) of the ctest inputs
+    tests/input_files/solid_ele_<cell>_Standard*_stressout.4C.yaml: Newton solve with the oracle,
+    struct_calc_stress (Cauchy) with the oracle, Gauss point -> node extrapolation and nodal averaging as
+    the reference does them (tests/helpers/postprocess.py).  Pins calculate_stress + pk2_to_cauchy."""
+    case = json.load(open(os.path.join(G, f"integration_{cell}.json")))
+    assert case["iostress"] == "Cauchy" and len(case["expected_stress"]) >= 24
+    ct = CELLS[cell]
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    nn = len(X)
+    row, col = serial_maps(nn)
+    rowptr, colind = orc.build_graph(ct, conn, row, col, nn)
+    par = [case["material"]["YOUNG"], case["material"]["NUE"]]
+
+    def evaluate(u):
+        vals, f, nbad = orc.evaluate_assemble(ct, orc.MAT_COUP_NEOHOOKE, par, conn, X.ravel(), u, row, col, nn,
+                                              rowptr, colind)
+        return rowptr, colind, vals, f
+
+    u = solve_case(case, evaluate)
+    st, _ = orc.calc_stress(ct, orc.MAT_COUP_NEOHOOKE, par, conn, X.ravel(), u.ravel(), orc.STRESS_CAUCHY,
+                            orc.STRAIN_GL)
+    nodal = nodal_stresses(ct, conn, st, nn)
+    # the reference's 1e-12 is for its own round-off; the Newton iterate here converged to TOLRES 1e-12,
+    # which bounds the stress error by ~|dS/du| * 1e-12
+    for e in case["expected_stress"]:
+        assert abs(nodal[e["node"], e["comp"]] - e["value"]) < 2e-10, (e, nodal[e["node"], e["comp"]])
+
+
+def test_cooks_membrane_internal_energy_known_answer():
+    """internal_energy RESULT of tests/input_files/sohex8fbar_cooks_nl_new_struc.4C.yaml (1e-7): pins
+    calculate_internal_energy incl. the F-bar kinematics and CoupNeoHooke::add_strain_energy."""
+    case = json.load(open(os.path.join(G, "integration_cooks_fbar.json")))
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    nn = len(X)
+    row, col = serial_maps(nn)
+    rowptr, colind = orc.build_graph(orc.HEX8, conn, row, col, nn)
+    par = [case["material"]["YOUNG"], case["material"]["NUE"]]
+
+    def evaluate(u):
+        vals, f, _ = orc.evaluate_assemble(orc.HEX8, orc.MAT_COUP_NEOHOOKE, par, conn, X.ravel(), u, row, col,
+                                           nn, rowptr, colind, tech=orc.TECH_FBAR)
+        return rowptr, colind, vals, f
+
+    u = solve_case(case, evaluate)
+    energy = orc.calc_energy(orc.HEX8, orc.MAT_COUP_NEOHOOKE, par, conn, X.ravel(), u.ravel(), tech=orc.TECH_FBAR)
+    exp = case["expected_internal_energy"]
+    assert abs(energy - exp["value"]) < exp["tol"], (energy, exp)
+
+
+@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10"])
+def test_element_mass_matrix_properties(cell):
+    """Consistent mass: symmetric, each direction sums to rho * V, M_e * (rigid acceleration) = rho V a / n
+    summed; lumped: diagonal with the same total; tet10 uses the 11-point rule via the mass/volume ratio."""
+    ct = CELLS[cell]
+    n = orc.num_nodes(ct)
+    rng = np.random.default_rng(5)
+    X = orc.node_param_coords(ct) * np.array([1.0, 1.3, 0.8])  # affine: det J constant
+    vol = {orc.HEX8: 8.0, orc.HEX27: 8.0, orc.TET10: 1.0 / 6.0}[ct] * 1.0 * 1.3 * 0.8
+    rho = 2.7
+    Me, _ = orc.element_mass(ct, rho, X)
+    assert np.abs(Me - Me.T).max() < 1e-14
+    for d in range(3):
+        assert abs(Me[d::3, d::3].sum() - rho * vol) < 1e-12 * rho * vol * 10
+    assert np.abs(Me[0::3, 1::3]).max() == 0.0
+    acc = rng.uniform(-1, 1, (n, 3))
+    Ml, fl = orc.element_mass(ct, rho, X, lumped=True, acc=acc)
+    assert np.count_nonzero(Ml - np.diag(np.diag(Ml))) == 0
+    assert np.abs(np.diag(Ml) - Me.sum(axis=0)).max() < 1e-14
+    assert np.abs(fl - np.diag(Ml) * acc.ravel()).max() < 1e-14
+    _, fc = orc.element_mass(ct, rho, X, acc=acc)
+    assert np.abs(fc - Me @ acc.ravel()).max() < 1e-14
+
+
+# ------------------------------------------------------------------------------------------------------
+# Part 2: product arithmetic (emulated on the CPU) against the oracle
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", SUMMAND_CASES, ids=lambda c: f"{c[0]}-{c[1]}-{c[2] if len(c) > 2 else 0}")
+def test_product_summand_matches_oracle(case):
+    blk = orc.pack_elasthyper([case])
+    S, Cm = orc.material(orc.MAT_ELASTHYPER, blk, E_TEST)
+    psi = orc.strain_energy(orc.MAT_ELASTHYPER, blk, E_TEST)
+    S2, C2, psi2 = emu.material(3, blk, _C_of(E_TEST))
+    sS, sC = max(np.abs(S).max(), 1e-300), max(np.abs(Cm).max(), 1e-300)
+    assert np.abs(S - S2).max() <= 1e-12 * sS, (S, S2)
+    assert np.abs(Cm - C2).max() <= 1e-12 * sC
+    assert abs(psi - psi2) <= 1e-12 * max(abs(psi), 1e-3)
+
+
+def test_product_summand_combination_matches_oracle():
+    combo = [("ISO_YEOH", [0.6, 0.1, 0.05]), ("ISO_MOONEYRIVLIN", [0.2, 0.1]), ("VOL_OGDEN", [300.0, -2.0]),
+             ("COUP_1POW", [0.3, 2])]
+    blk = orc.pack_elasthyper(combo)
+    S, Cm = orc.material(orc.MAT_ELASTHYPER, blk, E_TEST)
+    S2, C2, psi2 = emu.material(3, blk, _C_of(E_TEST))
+    assert np.abs(S - S2).max() <= 1e-12 * np.abs(S).max()
+    assert np.abs(Cm - C2).max() <= 1e-12 * np.abs(Cm).max()
+    assert abs(psi2 - orc.strain_energy(orc.MAT_ELASTHYPER, blk, E_TEST)) <= 1e-12 * abs(psi2)
+
+
+def test_product_specialised_strain_energy_matches_oracle():
+    for kind, par in ((0, [200.0, 0.25]), (1, [1.0, 1000.0]), (2, [1000.0, 0.3])):
+        _, _, psi = emu.material(kind, par, _C_of(E_TEST))
+        ref = orc.strain_energy(kind, par, E_TEST)
+        assert abs(psi - ref) <= 1e-12 * abs(ref), (kind, psi, ref)
+
+
+def _mesh(cell, n=(3, 2, 2)):
+    ct = CELLS[cell]
+    if cell == "tet10":
+        X, conn = b200.mesh.unstructured_tet10(2, seed=3)
+        rm = b200.partition.serial_mesh(ct, X, conn)
+        h = 0.5
+    else:
+        rm = b200.partition.box_partition(ct, n, 0, 1)
+        h = 1.0 / max(n)
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, h)
+    return ct, rm, u
+
+
+MATS = [(orc.MAT_COUP_NEOHOOKE, [200.0, 0.25]), (orc.MAT_ISO_VOL, [1.0, 1000.0]), (orc.MAT_SVK, [1000.0, 0.3]),
+        (orc.MAT_ELASTHYPER, [("ISO_YEOH", [0.6, 0.1, 0.05]), ("VOL_SUSSMANBATHE", [500.0])])]
+
+
+@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10"])
+@pytest.mark.parametrize("mi", range(len(MATS)))
+@pytest.mark.parametrize("types", [(orc.STRESS_2PK, orc.STRAIN_GL), (orc.STRESS_CAUCHY, orc.STRAIN_EA)])
+def test_product_stress_and_energy_match_oracle(cell, mi, types):
+    ct, rm, u = _mesh(cell)
+    mk, par = MATS[mi]
+    opar = orc.pack_elasthyper(par) if mk == orc.MAT_ELASTHYPER else par
+    st, en = orc.calc_stress(ct, mk, opar, rm.conn, rm.X.ravel(), u.ravel(), types[0], types[1])
+    is_row = (np.arange(rm.n_col_eles) % 3 != 0).astype(np.uint8)
+    energy = orc.calc_energy(ct, mk, opar, rm.conn, rm.X.ravel(), u.ravel(), ele_is_row=is_row)
+    st2, en2, energy2 = emu.post(ct, mk, opar, rm.conn, rm.X.ravel(), u.ravel(), types[0], types[1],
+                                 ele_is_row=is_row)
+    assert np.abs(st - st2).max() <= 1e-12 * np.abs(st).max()
+    assert np.abs(en - en2).max() <= 1e-12 * np.abs(en).max()
+    assert abs(energy - energy2) <= 1e-12 * abs(energy) and energy > 0
+
+
+def test_product_fbar_stress_and_energy_match_oracle():
+    ct, rm, u = _mesh("hex8")
+    par = [200.0, 0.25]
+    st, en = orc.calc_stress(ct, 0, par, rm.conn, rm.X.ravel(), u.ravel(), orc.STRESS_CAUCHY, orc.STRAIN_GL,
+                             tech=orc.TECH_FBAR)
+    energy = orc.calc_energy(ct, 0, par, rm.conn, rm.X.ravel(), u.ravel(), tech=orc.TECH_FBAR)
+    st2, en2, energy2 = emu.post(ct, 0, par, rm.conn, rm.X.ravel(), u.ravel(), orc.STRESS_CAUCHY, orc.STRAIN_GL,
+                                 fbar=True)
+    assert np.abs(st - st2).max() <= 1e-12 * np.abs(st).max()
+    assert np.abs(en - en2).max() <= 1e-12 * np.abs(en).max()
+    assert abs(energy - energy2) <= 1e-12 * abs(energy)
+    plain = orc.calc_energy(ct, 0, par, rm.conn, rm.X.ravel(), u.ravel())
+    assert abs(plain - energy) > 1e-9 * abs(energy)  # the F-bar kinematics really differ
+
+
+def test_product_per_element_mue_in_energy():
+    ct, rm, u = _mesh("tet10")
+    mue = 1.0 + 0.2 * np.arange(rm.n_col_eles) / rm.n_col_eles
+    ref = orc.calc_energy(ct, orc.MAT_ISO_VOL, [1.0, 1000.0], rm.conn, rm.X.ravel(), u.ravel(), mue_per_ele=mue)
+    _, _, got = emu.post(ct, orc.MAT_ISO_VOL, [1.0, 1000.0], rm.conn, rm.X.ravel(), u.ravel(), per_ele=mue)
+    assert abs(ref - got) <= 1e-12 * abs(ref)
+
+
+@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10"])
+@pytest.mark.parametrize("lumped", [False, True])
+def test_product_mass_matrix_matches_oracle(cell, lumped):
+    ct, rm, u = _mesh(cell)
+    rowptr, colind = orc.build_graph(ct, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    acc = np.random.default_rng(2).uniform(-1, 1, 3 * rm.n_col_nodes)
+    ref_M, ref_f = orc.assemble_mass(ct, 7.8, rm.conn, rm.X.ravel(), rm.node_row_lid, rm.node_col_lid,
+                                     rm.n_row_nodes, rowptr, colind, lumped=lumped, acc_col=acc)
+    M, f = emu.mass(ct, 7.8, rm.conn, rm.X.ravel(), rowptr, colind, rm.node_row_lid, rm.node_col_lid,
+                    rm.n_row_nodes, lumped=lumped, acc_col=acc)
+    assert np.abs(M - ref_M).max() <= 1e-12 * np.abs(ref_M).max()
+    assert np.abs(f - ref_f).max() <= 1e-12 * np.abs(ref_f).max()
+    # total mass of every direction = rho * volume (unit cube)
+    vol = 1.0
+    for d in range(3):
+        rows = np.arange(d, 3 * rm.n_row_nodes, 3)
+        tot = sum(M[rowptr[r]:rowptr[r + 1]].sum() for r in rows)
+        assert abs(tot - 7.8 * vol) < 1e-10
+
+
+@pytest.mark.parametrize("rank", [0, 3])
+def test_product_mass_owner_computes_rows(rank):
+    rm = b200.partition.box_partition(b200.mesh.HEX8, (4, 4, 2), rank, 4)
+    rowptr, colind = orc.build_graph(orc.HEX8, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    acc = np.random.default_rng(3).uniform(-1, 1, 3 * rm.n_col_nodes)
+    ref_M, ref_f = orc.assemble_mass(orc.HEX8, 1.0, rm.conn, rm.X.ravel(), rm.node_row_lid, rm.node_col_lid,
+                                     rm.n_row_nodes, rowptr, colind, acc_col=acc)
+    M, f = emu.mass(orc.HEX8, 1.0, rm.conn, rm.X.ravel(), rowptr, colind, rm.node_row_lid, rm.node_col_lid,
+                    rm.n_row_nodes, acc_col=acc)
+    assert np.abs(M - ref_M).max() <= 1e-12 * np.abs(ref_M).max()
+    assert np.abs(f - ref_f).max() <= 1e-12 * np.abs(ref_f).max()
