@@ -77,6 +77,13 @@ class DeviceAssembler:
         rc, err = self.ctx.evaluate(act, self._u, K, f, check=check)
         return K, f, err
 
+    def evaluate_resident(self, action="struct_calc_nlnstiff", check=True):
+        """Like evaluate, but K stays in the context's device CSR (for apply_dirichlet / multiply /
+        solve_cg): returns (None, f, error_info); only vectors cross the ABI."""
+        f = np.empty(self.n_rows)
+        rc, err = self.ctx.evaluate(ACTIONS[action], self._u, None, f, check=check)
+        return None, f, err
+
     def mass(self, want_matrix=True):
         """(M_values, f_inertia) of the last mass action."""
         return self.ctx.get_mass(want_matrix=want_matrix)

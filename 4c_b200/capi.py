@@ -42,7 +42,7 @@ SYMBOLS = [
     "b200s_set_material_elasthyper", "b200s_set_density", "b200s_set_row_elements", "b200s_set_state",
     "b200s_get_mass", "b200s_device_mass_values", "b200s_device_f_inertia", "b200s_calc_stress",
     "b200s_calc_energy", "b200s_apply_dirichlet", "b200s_apply_dirichlet_to_system", "b200s_multiply",
-    "b200s_last_multiply_ms", "b200s_solve_cg",
+    "b200s_last_multiply_ms", "b200s_solve_cg", "b200s_get_values",
 ]
 
 
@@ -114,6 +114,7 @@ def load():
         getattr(L, fn).argtypes = [vp]
         getattr(L, fn).restype = vp
     L.b200s_calc_stress.argtypes = [vp, i32, i32, vp, vp]
+    L.b200s_get_values.argtypes = [vp, i32, vp]
     L.b200s_calc_energy.argtypes = [vp, C.POINTER(dbl)]
     L.b200s_apply_dirichlet.argtypes = [vp, i32, vp, i32]
     L.b200s_apply_dirichlet_to_system.argtypes = [vp, vp, vp, vp, vp]
@@ -213,6 +214,11 @@ class Context:
         fi = np.empty(self.n_rows) if want_inertia else None
         self._ck(self.L.b200s_get_mass(self.h, _ptr(M), _ptr(fi)))
         return M, fi
+
+    def get_values(self, which=MATRIX_STIFFNESS):
+        v = np.empty(self.nnz)
+        self._ck(self.L.b200s_get_values(self.h, which, _ptr(v)))
+        return v
 
     def calc_stress(self, num_gp, stress_type=STRESS_2PK, strain_type=STRAIN_GL):
         st = np.empty((self.n_col_eles, num_gp, 6)) if stress_type != STRESS_NONE else None

@@ -1997,6 +1997,16 @@ extern "C"
   }
 
   double* b200s_device_mass_values(b200s_ctx* ctx) { return ctx ? ctx->d_mass : nullptr; }
+  int b200s_get_values(b200s_ctx* ctx, int which, double* values_out)
+  {
+    if (!ctx || !values_out) return B200S_ERR_INVALID;
+    const double* src = which == B200S_MATRIX_MASS ? ctx->d_mass : ctx->d_vals;
+    if (!src || ctx->nnz <= 0) return fail(ctx, B200S_ERR_INVALID, "matrix %d has not been assembled", which);
+    cudaSetDevice(ctx->device);
+    CK(cudaMemcpyAsync(values_out, src, sizeof(double) * (size_t)ctx->nnz, cudaMemcpyDefault, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B200S_OK;
+  }
   double* b200s_device_f_inertia(b200s_ctx* ctx) { return ctx ? ctx->d_f_inertia : nullptr; }
 
   int b200s_get_mass(b200s_ctx* ctx, double* M_values, double* f_inertia)

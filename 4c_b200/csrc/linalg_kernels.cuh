@@ -183,7 +183,7 @@ namespace b200s
     double rz = 0.0, rr = 0.0;
     if (k < n_row_nodes)
     {
-      const double alpha = first ? 0.0 : s[1] / s[0];
+      const double alpha = (first || s[0] == 0.0) ? 0.0 : s[1] / s[0];  // p.Ap == 0: converged exactly
       double rv[3];
 #pragma unroll
       for (int d = 0; d < 3; ++d)
@@ -224,7 +224,7 @@ namespace b200s
   {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double beta = first ? 0.0 : s[2] / s[1];
+    const double beta = (first || s[1] == 0.0) ? 0.0 : s[2] / s[1];
     p[i] = fma(beta, p[i], z[i]);
   }
   // after the direction update: s[1] = s[2]; s[0] = s[2] = s[3] = 0; history[it] = r.r

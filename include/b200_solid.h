@@ -270,6 +270,9 @@ extern "C"
    * structure_new) and the inertia force vector elevec2 assembled on the row map.  [host|dev] out. */
   int b200s_get_mass(b200s_ctx* ctx, double* M_values, double* f_inertia);
   double* b200s_device_mass_values(b200s_ctx* ctx); /* nnz, NULL before the first mass action */
+  /* Copy of the CSR values of a system matrix of the context (b200s_matrix) as they are now, e.g.
+   * after b200s_apply_dirichlet: what ExtractCrsDataPointers would show.  [host|dev] out, nnz. */
+  int b200s_get_values(b200s_ctx* ctx, int which, double* values_out);
   double* b200s_device_f_inertia(b200s_ctx* ctx);   /* n_rows */
 
   /* struct_calc_stress (SolidEleCalc::calculate_stress, 4C_solid_ele_calc.cpp:416-476) for the

@@ -1,0 +1,306 @@
+"""GPU parity tests of the actions around the hot path, through the C ABI against the
+oracle: generic MAT_ElastHyper inside the evaluate+assemble kernels, struct_calc_stress,
+struct_calc_energy, the mass actions, and the device-resident linear algebra (apply_dirichlet,
+multiply, CG hand-off).  Tolerance 1e-12 in the norms stated per test."""
+import importlib
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import oracle as orc
+from tests.helpers.neumann import neumann_load
+
+pytestmark = pytest.mark.gpu
+b200 = importlib.import_module("4c_b200")
+capi = b200.capi
+G = os.path.join(os.path.dirname(__file__), "golden")
+RTOL = 1e-12
+CELLS = {"hex8": orc.HEX8, "hex27": orc.HEX27, "tet10": orc.TET10}
+HYPER = [("ISO_YEOH", [0.6, 0.1, 0.05]), ("ISO_MOONEYRIVLIN", [0.2, 0.1]), ("VOL_OGDEN", [300.0, -2.0]),
+         ("COUP_1POW", [0.3, 2])]
+MATS = [(capi.MAT_COUP_NEOHOOKE, [200.0, 0.25]), (capi.MAT_ISO_VOL, [1.0, 1000.0]), (capi.MAT_SVK, [1000.0, 0.3]),
+        (capi.MAT_ELASTHYPER, HYPER)]
+
+
+def _mesh(cell, n=(5, 4, 3), rank=0, nranks=1):
+    ct = CELLS[cell]
+    if cell == "tet10":
+        X, conn = b200.mesh.unstructured_tet10(3, seed=3)
+        rm = b200.partition.serial_mesh(ct, X, conn)
+        h = 1.0 / 3
+    else:
+        rm = b200.partition.box_partition(ct, n, rank, nranks)
+        h = 1.0 / max(n)
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, h)
+    return ct, rm, u
+
+
+def _opar(mk, par):
+    return orc.pack_elasthyper(par) if mk == capi.MAT_ELASTHYPER else par
+
+
+@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10"])
+def test_generic_elasthyper_evaluate_matches_oracle(cell):
+    ct, rm, u = _mesh(cell)
+    asm = b200.DeviceAssembler(rm, capi.MAT_ELASTHYPER, HYPER)
+    rowptr, colind = asm.graph()
+    asm.set_state("displacement", u[:rm.n_row_nodes].ravel())
+    K, f, err = asm.evaluate("struct_calc_nlnstiff")
+    rK, rf, nbad = orc.evaluate_assemble(ct, orc.MAT_ELASTHYPER, orc.pack_elasthyper(HYPER), rm.conn, rm.X.ravel(),
+                                         u.ravel(), rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, rowptr,
+                                         colind, nthreads=4)
+    ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
+    assert ok and nbad == 0, (wK, wf)
+    asm.close()
+
+
+def test_generic_elasthyper_fbar_and_specialised_equivalence():
+    """F-bar kernel with the summand list; and the list {CoupNeoHooke} gives the specialised kernel's K."""
+    ct, rm, u = _mesh("hex8")
+    one = [("COUP_NEOHOOKE", [200.0, 0.25])]
+    a = b200.DeviceAssembler(rm, capi.MAT_ELASTHYPER, one, tech=capi.TECH_FBAR)
+    b = b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, [200.0, 0.25], tech=capi.TECH_FBAR)
+    rowptr, colind = a.graph()
+    for asm in (a, b):
+        asm.set_state("displacement", u.ravel())
+    Ka, fa, _ = a.evaluate()
+    Kb, fb, _ = b.evaluate()
+    ok, wK, wf = b200.parity_report(rowptr, Ka, Kb, fa, fb, RTOL)
+    assert ok, (wK, wf)
+    a.close(), b.close()
+
+
+def test_unknown_summand_is_rejected():
+    ct, rm, u = _mesh("hex8", (2, 2, 2))
+    ctx = capi.Context(0)
+    ctx.set_mesh(ct, rm.X, rm.conn)
+    with pytest.raises(capi.B200SolidError) as ei:
+        ctx.set_material_elasthyper([(99, [1.0])])
+    assert ei.value.code == capi.ERR_UNSUPPORTED
+    with pytest.raises(capi.B200SolidError) as ei:
+        ctx.set_material_elasthyper([("COUP_1POW", [1.0, 1])])  # the reference throws for D < 2
+    assert ei.value.code == capi.ERR_INVALID
+    ctx.close()
+
+
+@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10"])
+@pytest.mark.parametrize("mi", range(len(MATS)))
+def test_calc_stress_and_energy_match_oracle(cell, mi):
+    ct, rm, u = _mesh(cell)
+    mk, par = MATS[mi]
+    rm.ele_is_row = (np.arange(rm.n_col_eles) % 3 != 0).astype(np.uint8)
+    asm = b200.DeviceAssembler(rm, mk, par)
+    asm.set_state("displacement", u[:rm.n_row_nodes].ravel())
+    for io, types in ((("2pk", "gl"), (orc.STRESS_2PK, orc.STRAIN_GL)),
+                      (("cauchy", "ea"), (orc.STRESS_CAUCHY, orc.STRAIN_EA))):
+        st, en = asm.calc_stress(*io)
+        rst, ren = orc.calc_stress(ct, mk, _opar(mk, par), rm.conn, rm.X.ravel(), u.ravel(), types[0], types[1])
+        assert np.abs(st - rst).max() <= RTOL * np.abs(rst).max()
+        assert np.abs(en - ren).max() <= RTOL * np.abs(ren).max()
+    energy = asm.calc_energy()
+    ref = orc.calc_energy(ct, mk, _opar(mk, par), rm.conn, rm.X.ravel(), u.ravel(), ele_is_row=rm.ele_is_row)
+    assert abs(energy - ref) <= 1e-11 * abs(ref), (energy, ref)  # atomic summation order
+    asm.close()
+
+
+def test_calc_stress_fbar_and_per_element_mue():
+    ct, rm, u = _mesh("hex8")
+    asm = b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, [200.0, 0.25], tech=capi.TECH_FBAR)
+    asm.set_state("displacement", u.ravel())
+    st, en = asm.calc_stress("cauchy", "gl")
+    rst, ren = orc.calc_stress(ct, 0, [200.0, 0.25], rm.conn, rm.X.ravel(), u.ravel(), orc.STRESS_CAUCHY,
+                               orc.STRAIN_GL, tech=orc.TECH_FBAR)
+    assert np.abs(st - rst).max() <= RTOL * np.abs(rst).max() and np.abs(en - ren).max() <= RTOL * np.abs(ren).max()
+    e = asm.calc_energy()
+    re_ = orc.calc_energy(ct, 0, [200.0, 0.25], rm.conn, rm.X.ravel(), u.ravel(), tech=orc.TECH_FBAR)
+    assert abs(e - re_) <= 1e-11 * abs(re_)
+    asm.close()
+    ct, rm, u = _mesh("tet10")
+    mue = 1.0 + 0.2 * np.arange(rm.n_col_eles) / rm.n_col_eles
+    asm = b200.DeviceAssembler(rm, capi.MAT_ISO_VOL, [1.0, 1000.0], per_ele_param=mue)
+    asm.set_state("displacement", u.ravel())
+    st, _ = asm.calc_stress("2pk", "none")
+    rst, _ = orc.calc_stress(ct, 1, [1.0, 1000.0], rm.conn, rm.X.ravel(), u.ravel(), orc.STRESS_2PK, orc.STRAIN_NONE,
+                             mue_per_ele=mue)
+    assert np.abs(st - rst).max() <= RTOL * np.abs(rst).max()
+    asm.close()
+
+
+@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10"])
+@pytest.mark.parametrize("action", ["struct_calc_nlnstiffmass", "struct_calc_nlnstifflmass",
+                                    "struct_calc_internalinertiaforce"])
+def test_mass_actions_match_oracle(cell, action):
+    ct, rm, u = _mesh(cell)
+    asm = b200.DeviceAssembler(rm, capi.MAT_SVK, [1000.0, 0.3], density=7.8)
+    rowptr, colind = asm.graph()
+    acc = np.random.default_rng(2).uniform(-1, 1, 3 * rm.n_col_nodes)
+    asm.set_state("displacement", u[:rm.n_row_nodes].ravel())
+    asm.set_state("acceleration", acc[:3 * rm.n_row_nodes])
+    K, f, _ = asm.evaluate(action)
+    stiff = action != "struct_calc_internalinertiaforce"
+    rK, rf, _ = orc.evaluate_assemble(ct, orc.MAT_SVK, [1000.0, 0.3], rm.conn, rm.X.ravel(), u.ravel(),
+                                      rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, rowptr, colind,
+                                      action=orc.ACTION_FORCE_STIFF if stiff else orc.ACTION_FORCE)
+    if stiff:
+        ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
+        assert ok, (wK, wf)
+    else:
+        assert K is None and np.abs(f - rf).max() <= RTOL * np.abs(rf).max()
+    lumped = action == "struct_calc_nlnstifflmass"
+    rM, rfi = orc.assemble_mass(ct, 7.8, rm.conn, rm.X.ravel(), rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes,
+                                rowptr, colind, lumped=lumped, acc_col=acc)
+    M, fi = asm.mass(want_matrix=stiff)
+    if stiff:
+        assert np.abs(M - rM).max() <= RTOL * np.abs(rM).max()
+    assert np.abs(fi - rfi).max() <= RTOL * np.abs(rfi).max()
+    asm.close()
+
+
+def test_mass_action_needs_density():
+    ct, rm, u = _mesh("hex8", (2, 2, 2))
+    asm = b200.DeviceAssembler(rm, capi.MAT_SVK, [1000.0, 0.3])
+    asm.set_state("displacement", u.ravel())
+    with pytest.raises(capi.B200SolidError) as ei:
+        asm.evaluate("struct_calc_nlnstiffmass")
+    assert ei.value.code == capi.ERR_INVALID
+    asm.close()
+
+
+def _csr(rowptr, colind, vals, ncols):
+    return sp.csr_matrix((vals, colind, rowptr), shape=(len(rowptr) - 1, ncols))
+
+
+@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10"])
+def test_apply_dirichlet_and_multiply_match_host_csr(cell):
+    """SparseMatrix::apply_dirichlet (in-place branch) and multiply on the device-resident K against
+    scipy on the host copy of the same values (bitwise for the Dirichlet rows, 1e-12 for the product)."""
+    ct, rm, u = _mesh(cell)
+    asm = b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, [200.0, 0.25])
+    rowptr, colind = asm.graph()
+    asm.set_state("displacement", u.ravel())
+    K, f, _ = asm.evaluate()
+    n = asm.n_rows
+    rng = np.random.default_rng(4)
+    x = rng.uniform(-1, 1, n)
+    A = _csr(rowptr, colind, K, n)
+    y = asm.ctx.multiply(x)
+    ref = A @ x
+    assert np.abs(y - ref).max() <= RTOL * np.abs(ref).max()
+    toggle = (rng.uniform(0, 1, n) < 0.2).astype(np.float64)
+    asm.ctx.apply_dirichlet(toggle, diagonalblock=True)
+    Kd = asm.ctx.get_values()
+    ref_K = K.copy()
+    rows = np.repeat(np.arange(n), np.diff(rowptr))
+    dbc = toggle[rows] == 1.0
+    ref_K[dbc] = 0.0
+    ref_K[dbc & (colind == rows)] = 1.0
+    assert np.array_equal(Kd, ref_K)
+    y2 = asm.ctx.multiply(x)
+    ref2 = _csr(rowptr, colind, ref_K, n) @ x
+    assert np.abs(y2 - ref2).max() <= RTOL * np.abs(ref2).max()
+    # apply_dirichlet_to_system on host vectors
+    xv, bv, val = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    x0, b0 = xv.copy(), bv.copy()
+    asm.ctx.apply_dirichlet_to_system(xv, bv, val, toggle)
+    assert np.array_equal(xv, np.where(toggle == 1.0, val, x0)) and np.array_equal(bv, np.where(toggle == 1.0, val, b0))
+    asm.close()
+
+
+def test_multiply_general_csr_route_and_mass_matrix():
+    """A caller-supplied graph with an extra, non-blocked column forces the general CSR kernel; the mass
+    matrix is addressed with which=MATRIX_MASS."""
+    ct, rm, u = _mesh("hex8", (4, 3, 2))
+    rowptr0, colind0 = orc.build_graph(ct, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    # one extra (never assembled) column in the three rows of row node 0, e.g. a coupling entry of another
+    # element block: the rows are no longer made of column triplets
+    extra = max(set(range(asm_cols := 3 * rm.n_col_nodes)) - set(colind0[rowptr0[0]:rowptr0[1]].tolist()))
+    rows = []
+    for r in range(len(rowptr0) - 1):
+        c = colind0[rowptr0[r]:rowptr0[r + 1]]
+        rows.append(np.sort(np.append(c, extra)) if r < 3 else c)
+    rowptr = np.concatenate([[0], np.cumsum([len(c) for c in rows])]).astype(np.int64)
+    colind = np.concatenate(rows).astype(np.int32)
+    asm = b200.DeviceAssembler(rm, capi.MAT_SVK, [1000.0, 0.3], graph=(rowptr, colind), density=2.0)
+    asm.set_state("displacement", u.ravel())
+    K, f, _ = asm.evaluate("struct_calc_nlnstiffmass")
+    rK, rf, _ = orc.evaluate_assemble(ct, orc.MAT_SVK, [1000.0, 0.3], rm.conn, rm.X.ravel(), u.ravel(),
+                                      rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, rowptr, colind)
+    ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
+    assert ok, (wK, wf)
+    M, _ = asm.mass()
+    x = np.random.default_rng(9).uniform(-1, 1, asm.n_rows)
+    yK = asm.ctx.multiply(x)
+    refK = _csr(rowptr, colind, K, asm.n_rows) @ x
+    assert np.abs(yK - refK).max() <= RTOL * np.abs(refK).max()
+    yM = asm.ctx.multiply(x, which=capi.MATRIX_MASS)
+    ref = _csr(rowptr, colind, M, asm.n_rows) @ x
+    assert np.abs(yM - ref).max() <= RTOL * np.abs(ref).max()
+    asm.close()
+
+
+def test_golden_hex8_newton_with_device_resident_linear_algebra():
+    """The reference's hex8 ctest input solved with K never leaving the device: evaluate, apply_dirichlet
+    and the CG hand-off all operate on the context's CSR; only vectors cross the ABI.  Displacements
+    against the RESULT DESCRIPTION known answers (CG tolerance bounds the error: 1e-9 here)."""
+    case = json.load(open(os.path.join(G, "integration_hex8.json")))
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    rm = b200.partition.serial_mesh(orc.HEX8, X, conn)
+    par = [case["material"]["YOUNG"], case["material"]["NUE"]]
+    asm = b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, par)
+    nn = len(X)
+    toggle = np.zeros(3 * nn)
+    for k in case["dirichlet_nodes"]:
+        toggle[3 * k:3 * k + 3] = 1.0
+    u = np.zeros(3 * nn)
+    t = 0.0
+    for _ in range(case["numstep"]):
+        t += case["timestep"]
+        fext = neumann_load(case, t)
+        for it in range(30):
+            asm.set_state("displacement", u)
+            _, fint, _ = asm.evaluate_resident("struct_calc_nlnstiff")
+            rhs = -(fint - fext)
+            asm.ctx.apply_dirichlet(toggle, True)
+            du0 = np.zeros(3 * nn)
+            asm.ctx.apply_dirichlet_to_system(du0, rhs, np.zeros(3 * nn), toggle)
+            du, iters, rel = asm.ctx.solve_cg(rhs, du0, rtol=1e-13, maxit=500)
+            u += du
+            if np.linalg.norm(du) < 1e-11:
+                break
+        else:
+            raise AssertionError("Newton did not converge")
+    u = u.reshape(nn, 3)
+    for e in case["expected_disp"]:
+        assert abs(u[e["node"], e["dof"]] - e["value"]) < 1e-9, (e, u[e["node"], e["dof"]])
+    asm.close()
+
+
+def test_cg_handoff_on_a_larger_block():
+    """K of a 12x10x8 Neo-Hooke block with one face clamped: CG on the device against scipy's direct solve."""
+    import scipy.sparse.linalg as spla
+    ct, rm, u = _mesh("hex8", (12, 10, 8))
+    asm = b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, [200.0, 0.25])
+    rowptr, colind = asm.graph()
+    asm.set_state("displacement", 0.2 * u.ravel())
+    K, f, _ = asm.evaluate()
+    n = asm.n_rows
+    toggle = np.repeat((rm.X[:, 0] < 1e-12).astype(np.float64), 3)
+    asm.ctx.apply_dirichlet(toggle, True)
+    b = np.random.default_rng(1).uniform(-1, 1, n)
+    b[toggle == 1.0] = 0.0
+    x, iters, rel = asm.ctx.solve_cg(b, rtol=1e-12, maxit=2000)
+    rows = np.repeat(np.arange(n), np.diff(rowptr))
+    Kd = K.copy()
+    dbc = toggle[rows] == 1.0
+    Kd[dbc] = 0.0
+    Kd[dbc & (colind == rows)] = 1.0
+    # the Dirichlet-row-only modification is unsymmetric; with zero rhs on those rows CG stays in the
+    # subspace x_dbc = 0 where the operator is symmetric positive definite
+    ref = spla.spsolve(_csr(rowptr, colind, Kd, n).tocsc(), b)
+    assert rel <= 1e-12 and iters < 2000
+    assert np.abs(x - ref).max() <= 1e-8 * np.abs(ref).max(), (iters, rel)
+    asm.close()
