@@ -23,7 +23,7 @@ NUM_GP = {capi.HEX8: 8, capi.HEX27: 27, capi.TET10: 4}
 
 class DeviceAssembler:
     def __init__(self, rank_mesh, matkind, matparams, device=0, per_ele_param=None, graph=None,
-                 tech=capi.TECH_NONE, density=None):
+                 tech=capi.TECH_NONE, density=None, prestress=capi.PRESTRESS_NONE):
         """rank_mesh: partition.RankMesh.  graph: (rowptr, colind) from the reference's matrix, or
         None to build the FillComplete-equivalent graph on the device.  tech: element technology of
         the block (TECH key of the SOLID element line).  matkind MAT_ELASTHYPER: matparams is the
@@ -31,8 +31,8 @@ class DeviceAssembler:
         rm = self.rm = rank_mesh
         self.ctx = capi.Context(device, rm.rank, rm.nranks)
         self.ctx.set_mesh(rm.celltype, rm.X, rm.conn)
-        if tech != capi.TECH_NONE:
-            self.ctx.set_element_properties(tech=tech)
+        if tech != capi.TECH_NONE or prestress != capi.PRESTRESS_NONE:
+            self.ctx.set_element_properties(tech=tech, prestress=prestress)
         if matkind == capi.MAT_ELASTHYPER:
             self.ctx.set_material_elasthyper(matparams)
         else:
@@ -83,6 +83,10 @@ class DeviceAssembler:
         f = np.empty(self.n_rows)
         rc, err = self.ctx.evaluate(ACTIONS[action], self._u, None, f, check=check)
         return None, f, err
+
+    def update_prestress(self):
+        """struct_update_prestress for the current displacement state (PRESTRESS_TECH mulf)."""
+        self.ctx.update_prestress()
 
     def mass(self, want_matrix=True):
         """(M_values, f_inertia) of the last mass action."""

@@ -43,6 +43,7 @@ SYMBOLS = [
     "b200s_get_mass", "b200s_device_mass_values", "b200s_device_f_inertia", "b200s_calc_stress",
     "b200s_calc_energy", "b200s_apply_dirichlet", "b200s_apply_dirichlet_to_system", "b200s_multiply",
     "b200s_last_multiply_ms", "b200s_solve_cg", "b200s_get_values",
+    "b200s_update_prestress", "b200s_gp_history_size", "b200s_get_gp_history", "b200s_set_gp_history",
 ]
 
 
@@ -115,6 +116,11 @@ def load():
         getattr(L, fn).restype = vp
     L.b200s_calc_stress.argtypes = [vp, i32, i32, vp, vp]
     L.b200s_get_values.argtypes = [vp, i32, vp]
+    L.b200s_update_prestress.argtypes = [vp]
+    L.b200s_gp_history_size.argtypes = [vp]
+    L.b200s_gp_history_size.restype = i64
+    L.b200s_get_gp_history.argtypes = [vp, vp]
+    L.b200s_set_gp_history.argtypes = [vp, vp]
     L.b200s_calc_energy.argtypes = [vp, C.POINTER(dbl)]
     L.b200s_apply_dirichlet.argtypes = [vp, i32, vp, i32]
     L.b200s_apply_dirichlet_to_system.argtypes = [vp, vp, vp, vp, vp]
@@ -214,6 +220,19 @@ class Context:
         fi = np.empty(self.n_rows) if want_inertia else None
         self._ck(self.L.b200s_get_mass(self.h, _ptr(M), _ptr(fi)))
         return M, fi
+
+    def update_prestress(self):
+        self._ck(self.L.b200s_update_prestress(self.h))
+
+    def get_gp_history(self):
+        h = np.empty(self.L.b200s_gp_history_size(self.h))
+        self._ck(self.L.b200s_get_gp_history(self.h, _ptr(h)))
+        return h
+
+    def set_gp_history(self, hist):
+        h = np.ascontiguousarray(hist, np.float64).ravel()
+        assert h.size == self.L.b200s_gp_history_size(self.h)
+        self._ck(self.L.b200s_set_gp_history(self.h, _ptr(h)))
 
     def get_values(self, which=MATRIX_STIFFNESS):
         v = np.empty(self.nnz)

@@ -141,14 +141,16 @@ namespace b200s
   }  // namespace hex8
 
   // TECH 0: displacement based (4 warps, 2 CTAs/SM); TECH 1: F-bar (7 warps, 1 CTA/SM, more shared
-  // memory per warp and the full non-symmetric block row per lane, hex8_fbar_kernel.cuh)
+  // memory per warp and the full non-symmetric block row per lane, hex8_fbar_kernel.cuh);
+  // TECH 2: displacement based with MULF prestress (TECH 0 with the history-based deformation gradient)
   template <int MAT, bool STIFF, int TECH>
-  __global__ void __launch_bounds__((TECH ? HEX8_FBAR_WARPS : HEX8_WARPS) * 32, TECH ? 1 : 2)
+  __global__ void __launch_bounds__((TECH == 1 ? HEX8_FBAR_WARPS : HEX8_WARPS) * 32, TECH == 1 ? 1 : 2)
       k_hex8_eval_assemble(const EvalArgs A)
   {
-    constexpr int WARPS = TECH ? HEX8_FBAR_WARPS : HEX8_WARPS;
-    constexpr size_t warp_bytes = TECH ? hex8_fbar_warp_bytes : hex8_warp_bytes;
-    constexpr int MP_SIZE = TECH ? hex8fbar::MP_SIZE : hex8::MP_SIZE;
+    constexpr bool FBAR = TECH == 1, MULF = TECH == 2;
+    constexpr int WARPS = FBAR ? HEX8_FBAR_WARPS : HEX8_WARPS;
+    constexpr size_t warp_bytes = FBAR ? hex8_fbar_warp_bytes : hex8_warp_bytes;
+    constexpr int MP_SIZE = FBAR ? hex8fbar::MP_SIZE : hex8::MP_SIZE;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* tab_gp = reinterpret_cast<double*>(smem_raw);
     double* tab_node = tab_gp + hex8::TAB_SIZE;
@@ -167,8 +169,8 @@ namespace b200s
     S.mp = reinterpret_cast<double*>(wbase);
     S.g = S.mp + MP_SIZE;
     S.xu = S.g + hex8::G_SIZE;
-    if (TECH) S.h0 = S.xu + hex8::XU_SIZE;
-    S.nrow = reinterpret_cast<NodeRow*>(S.xu + hex8::XU_SIZE + (TECH ? hex8fbar::H0_SIZE : 0));
+    if (FBAR) S.h0 = S.xu + hex8::XU_SIZE;
+    S.nrow = reinterpret_cast<NodeRow*>(S.xu + hex8::XU_SIZE + (FBAR ? hex8fbar::H0_SIZE : 0));
     S.pos = reinterpret_cast<int32_t*>(S.nrow + hex8::EPW * hex8::NN);
 
     const int64_t n_tiles = (A.n_ele + hex8::EPW - 1) / hex8::EPW;
@@ -198,10 +200,10 @@ namespace b200s
       double out54[54];
       double dJ, dF;
       bool neg;
-      if (TECH)
+      if (FBAR)
         hex8fbar::phase1<MAT, STIFF>(A, S, tab_gp, wgt, lane, e0, out54, dJ, dF, neg);
       else
-        hex8::phase1<MAT, STIFF>(A, S, tab_gp, tab_node, wgt, lane, e0, out54, dJ, dF, neg);
+        hex8::phase1<MAT, STIFF, MULF>(A, S, tab_gp, tab_node, wgt, lane, e0, out54, dJ, dF, neg);
       if (e0 + (lane >> 3) < A.n_ele)
       {
         detJ_min = fmin(detJ_min, dJ);
@@ -221,13 +223,13 @@ namespace b200s
       cp_async_commit();
       hex8::phase1_store<STIFF>(S, lane, out54);
       __syncwarp();
-      double Kacc[TECH ? 8 : 5][9], facc[3];
-      if (TECH)
+      double Kacc[FBAR ? 8 : 5][9], facc[3];
+      if (FBAR)
         hex8fbar::phase2<STIFF>(S, lane, Kacc, facc);
       else
         hex8::phase2<STIFF>(S, lane, Kacc, facc);
       __syncwarp();  // M/Pw/G are dead: K_e / f_e staging overwrites them
-      if (TECH)
+      if (FBAR)
         hex8fbar::stage_ke<STIFF>(S, lane, Kacc, facc);
       else
         hex8::stage_ke<STIFF>(S, lane, Kacc, facc);
@@ -312,7 +314,7 @@ namespace b200s
     }
   }  // namespace tet10
 
-  template <int MAT, bool STIFF>
+  template <int MAT, bool STIFF, bool MULF>
   __global__ void __launch_bounds__(TET10_WARPS * 32, 2) k_tet10_eval_assemble(const EvalArgs A)
   {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -363,7 +365,7 @@ namespace b200s
       const bool neg = live && !(dJn > 0.0);
       double out54[54];
       double dJ, dF;
-      tet10::phase1<MAT, STIFF>(A, S, tab_gp, wgt, lane, e0, out54, dJ, dF);
+      tet10::phase1<MAT, STIFF, MULF>(A, S, tab_gp, wgt, lane, e0, out54, dJ, dF);
       if (live)
       {
         detJ_min = fmin(detJ_min, fmin(dJn, dJ));
@@ -460,7 +462,7 @@ namespace b200s
     }
   }  // namespace hex27
 
-  template <int MAT, bool STIFF>
+  template <int MAT, bool STIFF, bool MULF>
   __global__ void __launch_bounds__(HEX27_PAIRS * 64, 1) k_hex27_eval_assemble(const EvalArgs A)
   {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -512,7 +514,7 @@ namespace b200s
       {
         double out54[54];
         double dJ, dF;
-        hex27::phase1<MAT, STIFF>(A, S, tab_gp, wgt, my_gp, e, out54, dJ, dF);
+        hex27::phase1<MAT, STIFF, MULF>(A, S, tab_gp, wgt, my_gp, e, out54, dJ, dF);
         detJ_min = fmin(detJ_min, dJ);
         detF_min = fmin(detF_min, dF);
       }
@@ -951,6 +953,8 @@ struct b200s_ctx
   int32_t* dconn = nullptr;
   // SolidElementProperties of the block (4C_solid_ele_properties.hpp:55-65)
   int tech = B200S_TECH_NONE;
+  int prestress = B200S_PRESTRESS_NONE;
+  double* d_gp_hist = nullptr;  // MULF: n_col_eles * ngp * MULF_HIST doubles, device element order
   // material
   int matkind = -1;
   MatParams mp{};
@@ -1082,6 +1086,24 @@ namespace
     ctx->kev_pending = 0;
   }
 
+  // fresh MulfHistoryData of every Gauss point (inverse_jacobian of the reference configuration,
+  // deformation_gradient = I): what the reference sets up lazily at the first evaluate
+  // (4C_solid_ele_calc_mulf.hpp:56-60)
+  int mulf_allocate(b200s_ctx* ctx)
+  {
+    const int64_t n = ctx->n_col_eles * ctx->ngp;
+    if (to_device(ctx, &ctx->d_gp_hist, (const double*)nullptr, n * MULF_HIST)) return B200S_ERR_CUDA;
+    if (n > 0)
+    {
+      k_mulf_init<<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->n_col_eles, ctx->nn, ctx->ngp, ctx->dconn, ctx->dX,
+          ctx->d_dN_gp, ctx->d_gp_hist);
+      ctx->launches += 1;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return 0;
+  }
+
   template <int MAT, bool STIFF>
   static int launch_hex8(b200s_ctx* ctx, const EvalArgs& A)
   {
@@ -1098,7 +1120,8 @@ namespace
       ctx->launches += 1;
       return 0;
     }
-    auto kern = k_hex8_eval_assemble<MAT, STIFF, 0>;
+    auto kern = ctx->prestress == B200S_PRESTRESS_MULF ? k_hex8_eval_assemble<MAT, STIFF, 2>
+                                                       : k_hex8_eval_assemble<MAT, STIFF, 0>;
     // per device and cheap: set on every launch (a process may hold contexts on several GPUs)
     if (set_smem_attr(kern, hex8_smem_bytes))
       return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", hex8_smem_bytes);
@@ -1115,7 +1138,8 @@ namespace
   template <int MAT, bool STIFF>
   static int launch_tet10(b200s_ctx* ctx, const EvalArgs& A)
   {
-    auto kern = k_tet10_eval_assemble<MAT, STIFF>;
+    auto kern = ctx->prestress == B200S_PRESTRESS_MULF ? k_tet10_eval_assemble<MAT, STIFF, true>
+                                                       : k_tet10_eval_assemble<MAT, STIFF, false>;
     // per device and cheap: set on every launch (a process may hold contexts on several GPUs)
     if (set_smem_attr(kern, tet10_smem_bytes))
       return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", tet10_smem_bytes);
@@ -1132,7 +1156,8 @@ namespace
   template <int MAT, bool STIFF>
   static int launch_hex27(b200s_ctx* ctx, const EvalArgs& A)
   {
-    auto kern = k_hex27_eval_assemble<MAT, STIFF>;
+    auto kern = ctx->prestress == B200S_PRESTRESS_MULF ? k_hex27_eval_assemble<MAT, STIFF, true>
+                                                       : k_hex27_eval_assemble<MAT, STIFF, false>;
     // per device and cheap: set on every launch (a process may hold contexts on several GPUs)
     if (set_smem_attr(kern, hex27_smem_bytes))
       return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", hex27_smem_bytes);
@@ -1228,6 +1253,7 @@ extern "C"
     if (ctx->zero_stream) cudaStreamDestroy(ctx->zero_stream);
     dfree(ctx->d_u_row), dfree(ctx->d_u_col), dfree(ctx->d_send_lid), dfree(ctx->d_recv_lid);
     dfree(ctx->d_sendbuf), dfree(ctx->d_recvbuf), dfree(ctx->d_err);
+    dfree(ctx->d_gp_hist);
     dfree(ctx->d_hyper), dfree(ctx->d_dN_gp), dfree(ctx->d_w), dfree(ctx->d_dN_cen), dfree(ctx->d_N_mass);
     dfree(ctx->d_dN_mass), dfree(ctx->d_w_mass), dfree(ctx->d_ele_is_row), dfree(ctx->d_mass);
     dfree(ctx->d_f_inertia), dfree(ctx->d_acc_row), dfree(ctx->d_acc_col), dfree(ctx->d_energy);
@@ -1286,7 +1312,8 @@ extern "C"
         to_device(ctx, &ctx->d_w_mass, T.w_mass.data(), (int64_t)T.w_mass.size()))
       return B200S_ERR_CUDA;
     CK(cudaStreamSynchronize(ctx->stream));  // T is a local
-    dfree(ctx->d_ele_is_row), dfree(ctx->d_acc_col);
+    dfree(ctx->d_ele_is_row), dfree(ctx->d_acc_col), dfree(ctx->d_gp_hist);
+    if (ctx->prestress == B200S_PRESTRESS_MULF && mulf_allocate(ctx)) return B200S_ERR_CUDA;
     if (celltype == B200S_HEX8)
     {
       Hex8Const h;
@@ -1366,9 +1393,13 @@ extern "C"
     if (!ctx) return B200S_ERR_INVALID;
     if (kinem_type != B200S_KINEM_NONLINEAR_TOTLAG)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "kinematic type %d has no device kernel", kinem_type);
-    if (prestress_technology != B200S_PRESTRESS_NONE)
+    if (prestress_technology != B200S_PRESTRESS_NONE && prestress_technology != B200S_PRESTRESS_MULF)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "prestress technology %d has no device kernel",
           prestress_technology);
+    // MulfFBarFormulation (4C_solid_ele_calc_mulf_fbar.hpp) stays on the CPU path
+    if (prestress_technology == B200S_PRESTRESS_MULF && element_technology != B200S_TECH_NONE)
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "MULF prestress with element technology %d has no device kernel",
+          element_technology);
     if (element_technology != B200S_TECH_NONE && element_technology != B200S_TECH_FBAR)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "element technology %d has no device kernel",
           element_technology);
@@ -1376,6 +1407,14 @@ extern "C"
     if (element_technology == B200S_TECH_FBAR && ctx->celltype >= 0 && ctx->celltype != B200S_HEX8)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "F-bar is a hex8 technology");
     ctx->tech = element_technology;
+    const bool fresh = prestress_technology == B200S_PRESTRESS_MULF && ctx->prestress != B200S_PRESTRESS_MULF;
+    ctx->prestress = prestress_technology;
+    if (prestress_technology != B200S_PRESTRESS_MULF) dfree(ctx->d_gp_hist);
+    if ((fresh || !ctx->d_gp_hist) && prestress_technology == B200S_PRESTRESS_MULF && ctx->celltype >= 0)
+    {
+      cudaSetDevice(ctx->device);
+      if (mulf_allocate(ctx)) return B200S_ERR_CUDA;
+    }
     return B200S_OK;
   }
 
@@ -1814,6 +1853,9 @@ extern "C"
     EvalArgs A;
     A.X = ctx->dX, A.u = ctx->d_u_col, A.conn = ctx->dconn, A.pos = ctx->d_pos;
     A.node_row = ctx->d_node_row, A.per_ele_param = ctx->d_per_ele, A.ele_id = ctx->d_ele_id;
+    A.gp_hist = ctx->d_gp_hist;
+    if (ctx->prestress == B200S_PRESTRESS_MULF && !ctx->d_gp_hist)
+      return fail(ctx, B200S_ERR_INVALID, "MULF history missing (set_mesh after set_element_properties?)");
     A.vals = ctx->d_vals, A.f = ctx->d_f, A.err = ctx->d_err, A.mp = ctx->mp;
     A.n_ele = ctx->n_col_eles;
     A.scatter_mode = ctx->scatter_mode;
@@ -2038,6 +2080,7 @@ extern "C"
     P.X = ctx->dX, P.u = ctx->d_u_col, P.conn = ctx->dconn, P.per_ele_param = ctx->d_per_ele;
     P.ele_id = ctx->d_ele_id, P.ele_is_row = ctx->d_ele_is_row;
     P.dN_gp = ctx->d_dN_gp, P.dN_cen = ctx->d_dN_cen, P.w = ctx->d_w, P.mp = ctx->mp;
+    P.gp_hist = ctx->prestress == B200S_PRESTRESS_MULF ? ctx->d_gp_hist : nullptr;
     P.n_ele = ctx->n_col_eles, P.nn = ctx->nn, P.ngp = ctx->ngp;
     P.fbar = ctx->tech == B200S_TECH_FBAR;
     P.stress_type = stress_type, P.strain_type = strain_type;
@@ -2110,6 +2153,68 @@ extern "C"
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
     return B200S_OK;
+  }
+
+  // ---- MULF prestress: struct_update_prestress and the Gauss-point history (restart) ------------------
+  int b200s_update_prestress(b200s_ctx* ctx)
+  {
+    if (!ctx) return B200S_ERR_INVALID;
+    if (ctx->prestress != B200S_PRESTRESS_MULF || !ctx->d_gp_hist)
+      return fail(ctx, B200S_ERR_UNSUPPORTED,
+          "Your element evaluation does not allow to update prestress. You may need to add MULF to your "
+          "element line definitions.");
+    if (ctx->n_rows <= 0) return fail(ctx, B200S_ERR_INVALID, "set_graph must precede update_prestress");
+    cudaSetDevice(ctx->device);
+    const int rc = import_row_to_col(ctx, ctx->d_u_row, ctx->d_u_col, false);
+    if (rc) return rc;
+    const int64_t n = ctx->n_col_eles * ctx->ngp;
+    if (n > 0)
+    {
+      k_mulf_update<<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->n_col_eles, ctx->nn, ctx->ngp, ctx->dconn, ctx->dX,
+          ctx->d_u_col, ctx->d_dN_gp, ctx->d_gp_hist);
+      ctx->launches += 1;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return B200S_OK;
+  }
+
+  int64_t b200s_gp_history_size(const b200s_ctx* ctx)
+  {
+    if (!ctx || ctx->prestress != B200S_PRESTRESS_MULF) return 0;
+    return ctx->n_col_eles * ctx->ngp * MULF_HIST;
+  }
+
+  static int history_copy(b200s_ctx* ctx, double* caller, int to_caller)
+  {
+    if (!ctx || !caller) return B200S_ERR_INVALID;
+    if (ctx->prestress != B200S_PRESTRESS_MULF || !ctx->d_gp_hist)
+      return fail(ctx, B200S_ERR_INVALID, "the element block has no Gauss-point history");
+    cudaSetDevice(ctx->device);
+    const int64_t n = b200s_gp_history_size(ctx);
+    const int per_ele = ctx->ngp * MULF_HIST;
+    double* tmp = nullptr;
+    CK(cudaMalloc((void**)&tmp, sizeof(double) * (size_t)(n ? n : 1)));
+    int rc = B200S_OK;
+    if (to_caller)
+    {
+      k_hist_permute<<<nblk(n), 256, 0, ctx->stream>>>(ctx->n_col_eles, per_ele, ctx->d_ele_id, ctx->d_gp_hist, tmp, 1);
+      if (cudaMemcpyAsync(caller, tmp, sizeof(double) * (size_t)n, cudaMemcpyDefault, ctx->stream)) rc = B200S_ERR_CUDA;
+    }
+    else
+    {
+      if (cudaMemcpyAsync(tmp, caller, sizeof(double) * (size_t)n, cudaMemcpyDefault, ctx->stream)) rc = B200S_ERR_CUDA;
+      k_hist_permute<<<nblk(n), 256, 0, ctx->stream>>>(ctx->n_col_eles, per_ele, ctx->d_ele_id, tmp, ctx->d_gp_hist, 0);
+    }
+    ctx->launches += 1;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = B200S_ERR_CUDA;
+    cudaFree(tmp);
+    return rc ? fail(ctx, rc, "history copy failed") : B200S_OK;
+  }
+  int b200s_get_gp_history(b200s_ctx* ctx, double* hist_out) { return history_copy(ctx, hist_out, 1); }
+  int b200s_set_gp_history(b200s_ctx* ctx, const double* hist_in)
+  {
+    return history_copy(ctx, const_cast<double*>(hist_in), 0);
   }
 
   // ---- the step after the path: Dirichlet conditions and products on the device ---------------------

@@ -147,7 +147,7 @@ namespace b200s
     }
 
     // ---- phase 1: Gauss point g -----------------------------------------------------------------
-    template <int MAT, bool STIFF>
+    template <int MAT, bool STIFF, bool MULF = false>
     B2_HD void phase1(const EvalArgs& A, const PairSmem& S, const double* tab_gp, const double* wgt,
         int g, int64_t e, double* out54, double& detJ_gp, double& detF_gp)
     {
@@ -183,6 +183,8 @@ namespace b200s
           for (int b = 0; b < 3; ++b) F[a + 3 * b] = fma(ua, Gk[b], F[a + 3 * b]);
         }
       }
+      if (MULF && e < A.n_ele)
+        mulf_deformation_gradient<NN>(A.gp_hist + (e * NGP + g) * MULF_HIST, dN, xu + NDOF, F);
       detF_gp = det3(F);
 
       double C[6], Sv[6], Cm[21];

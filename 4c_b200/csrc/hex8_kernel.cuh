@@ -60,6 +60,7 @@ namespace b200s
     const NodeRow* node_row;      // n_col_nodes: CSR rows of the node's three dofs
     const double* per_ele_param;  // nullptr or n_ele (indexed like conn, i.e. in device order)
     const int32_t* ele_id;        // nullptr or n_ele: caller's column-element index of device element e
+    const double* gp_hist;        // MULF only: n_ele * ngp * MULF_HIST doubles in device element order
     double* vals;                 // nnz (may be nullptr for force only)
     double* f;                    // n_rows
     ErrWord* err;
@@ -159,7 +160,7 @@ namespace b200s
     // tab_gp / tab_node: dN tables with row stride TAB_STRIDE; wgt: Gauss weights.
     // Results: G to S.g, (M, Pw) kept in registers `out54` for the caller to store after a
     // __syncwarp() (the staging area they overwrite is still being read by other lanes).
-    template <int MAT, bool STIFF>
+    template <int MAT, bool STIFF, bool MULF = false>
     B2_HD void phase1(const EvalArgs& A, const WarpSmem& S, const double* tab_gp,
         const double* tab_node, const double* wgt, int lane, int64_t e0, double* out54,
         double& detJ_min, double& detF_min, bool& neg_jac)
@@ -215,6 +216,8 @@ namespace b200s
           for (int b = 0; b < 3; ++b) F[a + 3 * b] += ua * Gk[b];
         }
       }
+      if (MULF && e < A.n_ele)  // MulfFormulation::evaluate: only F changes, the gradients stay
+        mulf_deformation_gradient<NN>(A.gp_hist + (e * NGP + g) * MULF_HIST, dN, xu + 24, F);
       detF_min = det3(F);
 
       // material: So3Material::evaluate(F, E=(C-I)/2) -> S, Cm (calc_lib.hpp:976-989)

@@ -41,6 +41,7 @@ namespace b200s
     const double* dN_gp;          // [ngp][nn][3]
     const double* dN_cen;         // [nn][3] (F-bar)
     const double* w;              // [ngp]
+    const double* gp_hist;        // nullptr or MULF history (device element order)
     MatParams mp;
     int64_t n_ele;
     int nn, ngp;
@@ -83,6 +84,69 @@ namespace b200s
     return detJ;
   }
 
+  B2_HD double point_detJ_rt(int nn, const double* dN, const double* X, const int32_t* ce)
+  {
+    double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < nn; ++k)
+    {
+      const double* x = X + 3 * (int64_t)ce[k];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) J[a + 3 * b] += dN[3 * k + a] * x[b];
+    }
+    return det3(J);
+  }
+
+  // MULF flavour of point_kinematics with run-time node count: F = (I + u (iJ_hist dN)^T) F_hist, returns
+  // det J of the reference mapping; Fd_out (may be null) receives F_delta
+  B2_HD double point_kinematics_mulf(int nn, const double* dN, const double* X, const double* u,
+      const int32_t* ce, const double* h, double* F, double* Fd_out)
+  {
+    const double detJ = point_detJ_rt(nn, dN, X, ce);
+    double Fd[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Fd[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    for (int k = 0; k < nn; ++k)
+    {
+      const double* uk = u + 3 * (int64_t)ce[k];
+      double Nh[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+        Nh[a] = fma(h[a + 6], dN[3 * k + 2], fma(h[a + 3], dN[3 * k + 1], h[a] * dN[3 * k]));
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) Fd[a + 3 * b] = fma(uk[a], Nh[b], Fd[a + 3 * b]);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+        F[a + 3 * b] = fma(Fd[a + 6], h[9 + 2 + 3 * b], fma(Fd[a + 3], h[9 + 1 + 3 * b], Fd[a] * h[9 + 3 * b]));
+    if (Fd_out)
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Fd_out[i] = Fd[i];
+    return detJ;
+  }
+
+  // MulfFormulation::update_prestress at one Gauss point (4C_solid_ele_calc_mulf.hpp:124-143):
+  // deformation_gradient <- F of the current state, inverse_jacobian <- F_delta^-T inverse_jacobian
+  B2_HD void mulf_update_point(int nn, const double* dN, const double* X, const double* u,
+      const int32_t* ce, double* h)
+  {
+    double F[9], Fd[9], iFd[9], niJ[9];
+    point_kinematics_mulf(nn, dN, X, u, ce, h, F, Fd);
+    inv3(iFd, Fd);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+        niJ[a + 3 * b] = iFd[3 * a] * h[3 * b] + iFd[1 + 3 * a] * h[1 + 3 * b] + iFd[2 + 3 * a] * h[2 + 3 * b];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) h[i] = niJ[i], h[9 + i] = F[i];
+  }
+
   // One Gauss point of calculate_stress / calculate_internal_energy.  Returns psi * integration
   // factor (0 when want_energy is false); stress6 / strain6 in the reference's row layout
   // [xx,yy,zz,xy,yz,xz] (assemble_symmetric_tensor_to_matrix_row, calc_lib_io.hpp:41-70).
@@ -92,7 +156,10 @@ namespace b200s
   {
     const int32_t* ce = A.conn + e * A.nn;
     double F[9];
-    const double detJ = point_kinematics(A.nn, A.dN_gp + (size_t)g * A.nn * 3, A.X, A.u, ce, F);
+    const double detJ =
+        A.gp_hist ? point_kinematics_mulf(A.nn, A.dN_gp + (size_t)g * A.nn * 3, A.X, A.u, ce,
+                        A.gp_hist + (e * A.ngp + g) * MULF_HIST, F, nullptr)
+                  : point_kinematics(A.nn, A.dN_gp + (size_t)g * A.nn * 3, A.X, A.u, ce, F);
     if (A.fbar)
     {
       // F_bar = (det F_0 / det F)^(1/3) F  (4C_solid_ele_calc_fbar.hpp:103-112, lib_fbar.hpp:47-51)
@@ -275,6 +342,56 @@ namespace b200s
   }
 
 #if defined(__CUDACC__)
+  __global__ void __launch_bounds__(128) k_mulf_init(int64_t n_ele, int nn, int ngp, const int32_t* conn,
+      const double* X, const double* dN_gp, double* hist)
+  {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e = t / ngp;
+    const int g = (int)(t - e * ngp);
+    if (e >= n_ele) return;
+    const int32_t* ce = conn + e * nn;
+    const double* dN = dN_gp + (size_t)g * nn * 3;
+    double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, iJ[9];
+    for (int k = 0; k < nn; ++k)
+    {
+      const double* x = X + 3 * (int64_t)ce[k];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) J[a + 3 * b] += dN[3 * k + a] * x[b];
+    }
+    inv3(iJ, J);
+    double* h = hist + t * MULF_HIST;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) h[i] = iJ[i], h[9 + i] = (i % 4 == 0) ? 1.0 : 0.0;
+  }
+
+  // struct_update_prestress (SolidEleCalc::update_prestress, 4C_solid_ele_calc.cpp:478-519)
+  __global__ void __launch_bounds__(128) k_mulf_update(int64_t n_ele, int nn, int ngp, const int32_t* conn,
+      const double* X, const double* u, const double* dN_gp, double* hist)
+  {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e = t / ngp;
+    const int g = (int)(t - e * ngp);
+    if (e >= n_ele) return;
+    mulf_update_point(nn, dN_gp + (size_t)g * nn * 3, X, u, conn + e * nn, hist + t * MULF_HIST);
+  }
+
+  // history in the caller's element numbering <-> device element order (restart pack / unpack)
+  __global__ void k_hist_permute(int64_t n_ele, int per_ele, const int32_t* ele_id, const double* src,
+      double* dst, int to_caller)
+  {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_ele * per_ele) return;
+    const int64_t e = t / per_ele;
+    const int64_t r = t - e * per_ele;
+    const int64_t ec = ele_id ? ele_id[e] : e;
+    if (to_caller)
+      dst[ec * per_ele + r] = src[t];
+    else
+      dst[t] = src[ec * per_ele + r];
+  }
+
   template <int MAT>
   __global__ void __launch_bounds__(128) k_post_points(const PostArgs A)
   {

@@ -277,6 +277,43 @@ namespace b200s
     return mp.p[0] * 0.5 * (m1 - 3.) + mp.p[1] * 0.5 * (J - 1.) * (J - 1.);
   }
 
+  // MULF prestress (PRESTRESS_TECH mulf): Gauss-point history = MulfHistoryData without the set-up
+  // flag (the device initialises it at b200s_set_element_properties): h[0..8] inverse_jacobian,
+  // h[9..17] deformation_gradient, both column-major (a + 3 b).
+  constexpr int MULF_HIST = 18;
+  // F_delta = I + u (iJ_hist dN)^T  (evaluate_mulf_deformation_gradient_update,
+  // 4C_solid_ele_calc_lib_mulf.hpp:41-60); dN[k*3+a], u[k*3+a]
+  template <int NN>
+  B2_HD void mulf_delta_deformation_gradient(const double* h, const double* dN, const double* u, double* Fd)
+  {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Fd[i] = (i % 4 == 0) ? 1.0 : 0.0;
+#pragma unroll 2
+    for (int k = 0; k < NN; ++k)
+    {
+      double Nh[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+        Nh[a] = fma(h[a + 6], dN[3 * k + 2], fma(h[a + 3], dN[3 * k + 1], h[a] * dN[3 * k]));
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) Fd[a + 3 * b] = fma(u[3 * k + a], Nh[b], Fd[a + 3 * b]);
+    }
+  }
+  // F = F_delta F_hist (evaluate_mulf_spatial_material_mapping, lib_mulf.hpp:62-90)
+  template <int NN>
+  B2_HD void mulf_deformation_gradient(const double* h, const double* dN, const double* u, double* F)
+  {
+    double Fd[9];
+    mulf_delta_deformation_gradient<NN>(h, dN, u, Fd);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+        F[a + 3 * b] = fma(Fd[a + 6], h[9 + 2 + 3 * b], fma(Fd[a + 3], h[9 + 1 + 3 * b], Fd[a] * h[9 + 3 * b]));
+  }
+
   // Right Cauchy-Green tensor C = F^T F in Voigt storage (calc_lib.hpp:714-722)
   B2_HD void right_cauchy_green(const double* F, double* C)
   {

@@ -114,7 +114,7 @@ extern "C"
   typedef enum
   {
     B200S_PRESTRESS_NONE = 0,
-    B200S_PRESTRESS_MULF = 1 /* CPU path */
+    B200S_PRESTRESS_MULF = 1 /* 4C_solid_ele_calc_mulf.hpp (displacement based only; mulf + fbar: CPU path) */
   } b200s_prestress_technology;
 
   /* Core::Elements::ActionType values handled by b200s_evaluate (legacy_enum_definitions;
@@ -286,6 +286,22 @@ extern "C"
    * of psi * detJ * w over its ROW elements (the caller does the sum_all,
    * model_evaluator_structure.cpp:1718-1725).  [host] out. */
   int b200s_calc_energy(b200s_ctx* ctx, double* energy_out);
+
+  /* ---- MULF prestress (PRESTRESS_TECH mulf) --------------------------------------------------------- */
+  /* struct_update_prestress (Solid<3>::evaluate -> SolidEleCalc::update_prestress,
+   * 4C_solid_ele_calc.cpp:478-519; MulfFormulation::update_prestress, 4C_solid_ele_calc_mulf.hpp:
+   * 124-143) for the current "displacement" state: every Gauss point stores the current deformation
+   * gradient and pulls its inverse Jacobian forward.  The caller resets the displacements afterwards
+   * (Solid::IMPLICIT::PreStress::post_update).  B200S_ERR_UNSUPPORTED (reference: FOUR_C_THROW) when
+   * the block was not set up with B200S_PRESTRESS_MULF. */
+  int b200s_update_prestress(b200s_ctx* ctx);
+  /* Gauss-point history of the block = what MulfFormulation::pack / unpack write for restart
+   * (4C_solid_ele_calc_mulf.hpp:112-122): per column element (caller's order) and Gauss point 18
+   * doubles {inverse_jacobian[9], deformation_gradient[9]}, column-major 3x3 each.
+   * b200s_gp_history_size: number of doubles (0 without history).  [host|dev]. */
+  int64_t b200s_gp_history_size(const b200s_ctx* ctx);
+  int b200s_get_gp_history(b200s_ctx* ctx, double* hist_out);
+  int b200s_set_gp_history(b200s_ctx* ctx, const double* hist_in);
 
   /* ---- the step after the path, on the device (K never returns to the host) ------------------------ */
   /* SparseMatrix::apply_dirichlet(dbctoggle, diagonalblock), in-place branch

@@ -20,10 +20,12 @@ SUMMANDS = ["COUP_NEOHOOKE", "COUP_MOONEYRIVLIN", "COUP_LOGNEOHOOKE", "COUP_LOGM
             "COUP_13APOW", "ISO_NEOHOOKE", "ISO_MOONEYRIVLIN", "ISO_YEOH", "ISO_1POW", "ISO_2POW",
             "ISO_EXPOPOW", "VOL_SUSSMANBATHE", "VOL_PENALTY", "VOL_OGDEN", "VOL_POW"]
 SUM = {name: i for i, name in enumerate(SUMMANDS)}
+SUM.update({"COUP_ANISOEXPO": 100, "FIBER": 101})  # oracle only, see solid_oracle.h
 STRESS_NONE, STRESS_2PK, STRESS_CAUCHY = 0, 1, 2
 STRAIN_NONE, STRAIN_GL, STRAIN_EA = 0, 1, 2
 ACTION_FORCE, ACTION_FORCE_STIFF = 0, 1
-TECH_NONE, TECH_FBAR = 0, 1
+TECH_NONE, TECH_FBAR, TECH_MULF = 0, 1, 2
+MULF_HIST = 19
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -73,6 +75,12 @@ def lib():
         L.orc_evaluate_assemble_tech.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int,
                                                  C.c_int64, _ip, C.c_int64, _dp, _dp, _ip, _ip,
                                                  C.c_int64, _lp, _ip, _dp, _dp, C.c_int]
+        L.orc_evaluate_assemble_hist.restype = C.c_int64
+        L.orc_evaluate_assemble_hist.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int,
+                                                 C.c_int64, _ip, C.c_int64, _dp, _dp, _ip, _ip,
+                                                 C.c_int64, _lp, _ip, _dp, _dp, C.c_int, _dp]
+        L.orc_mulf_init_history.argtypes = [C.c_int64, _dp]
+        L.orc_update_prestress.argtypes = [C.c_int, C.c_int64, _ip, _dp, _dp, _dp]
         L.orc_element_tech.argtypes = [C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp, _dp, _dp]
         L.orc_build_graph.argtypes = [C.c_int, C.c_int64, _ip, C.c_int64, _ip, _ip, C.c_int64, _lp,
                                       _ip]
@@ -222,7 +230,7 @@ def build_graph(ct, conn, node_row_lid, node_col_lid, n_row_nodes):
 
 def evaluate_assemble(ct, matkind, params, conn, X, u_col, node_row_lid, node_col_lid, n_row_nodes,
                       rowptr, colind, action=ACTION_FORCE_STIFF, mue_per_ele=None, nthreads=1,
-                      impl="oracle", tech=TECH_NONE):
+                      impl="oracle", tech=TECH_NONE, hist=None):
     """impl="oracle": plain restatement; impl="ref": element arithmetic by the reference's headers."""
     n = num_nodes(ct)
     params = np.ascontiguousarray(params, dtype=np.float64)
@@ -247,10 +255,13 @@ def evaluate_assemble(ct, matkind, params, conn, X, u_col, node_row_lid, node_co
                                                _l(rowptr), _i(colind), _d(gxi), _d(gw), len(gw),
                                                _d(values), _d(f), nthreads)
         return values, f, int(nbad)
-    nbad = lib().orc_evaluate_assemble_tech(ct, tech, matkind, _d(params), _d(mue_per_ele), action,
-                                       conn.shape[0], _i(conn), len(node_row_lid), _d(X), _d(u_col),
-                                       _i(node_row_lid), _i(node_col_lid), n_row_nodes, _l(rowptr),
-                                       _i(colind), _d(values), _d(f), nthreads)
+    if hist is not None:
+        assert hist.dtype == np.float64 and hist.flags["C_CONTIGUOUS"] and nthreads == 1
+    nbad = lib().orc_evaluate_assemble_hist(ct, tech, matkind, _d(params), _d(mue_per_ele), action,
+                                            conn.shape[0], _i(conn), len(node_row_lid), _d(X), _d(u_col),
+                                            _i(node_row_lid), _i(node_col_lid), n_row_nodes, _l(rowptr),
+                                            _i(colind), _d(values), _d(f), nthreads, _d(hist))
+    assert nbad >= 0, "ORC_TECH_MULF needs a history array"
     return values, f, int(nbad)
 
 
@@ -359,3 +370,20 @@ def assemble_mass(ct, density, conn, X, node_row_lid, node_col_lid, n_row_nodes,
                             _i(node_row_lid), _i(node_col_lid), n_row_nodes, _l(rowptr), _i(colind),
                             _d(vals), _d(fi))
     return vals, fi
+
+
+def mulf_new_history(ct, n_ele):
+    """Fresh MulfHistoryData of every Gauss point: (n_ele, ngp, MULF_HIST)."""
+    h = np.zeros((n_ele, num_gp(ct), MULF_HIST))
+    lib().orc_mulf_init_history(n_ele * num_gp(ct), _d(h))
+    return h
+
+
+def update_prestress(ct, conn, X, u_col, hist):
+    """struct_update_prestress: in place on hist."""
+    n = num_nodes(ct)
+    conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, n)
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    u_col = np.ascontiguousarray(u_col, dtype=np.float64)
+    assert hist.dtype == np.float64 and hist.flags["C_CONTIGUOUS"]
+    lib().orc_update_prestress(ct, len(conn), _i(conn), _d(X), _d(u_col), _d(hist))

@@ -600,6 +600,42 @@ namespace
     ddPII[5] += pow(I[2], -1.) * ddPm[5];
   }
 
+  // ELAST_CoupAnisoExpo with one element fibre (ORACLE ONLY: the reference's MULF known answers use
+  // it, so the oracle needs it to pin its MULF restatement; the device path does not have it).
+  // Packed as two consecutive entries: {ORC_SUM_COUP_ANISOEXPO, 0, K1, K2, K1COMP, K2COMP} and
+  // {ORC_SUM_FIBER, 0, a0, a1, a2, 0} with the element's FIBER1.  Structural tensor A = a (x) a
+  // ("Standard" strategy), scalar product 1
+  // (src/mat/elast/4C_mat_elast_coupanisoexpobase.cpp:36-62,128-160, ..._coupanisoexpo.cpp:18-21).
+  void aniso_expo_add(const double* par, const double* C, double* S, double* Cm, double* psi)
+  {
+    const int n = (int)par[0];
+    for (int k = 0; k + 1 < n; ++k)
+    {
+      const double* q = par + 1 + 6 * k;
+      if ((int)q[0] != ORC_SUM_COUP_ANISOEXPO) continue;
+      const double* fq = q + 6;
+      if ((int)fq[0] != ORC_SUM_FIBER) continue;
+      const double* a = fq + 2;
+      double A[6];
+      for (int v = 0; v < 6; ++v) A[v] = a[VA[v]] * a[VB[v]];
+      double I4 = 0.0;
+      for (int v = 0; v < 6; ++v) I4 += C[v] * A[v] * (v < 3 ? 1.0 : 2.0);
+      const double scalarProduct = 1.0;
+      double k1 = q[2], k2 = q[3];
+      if (I4 < 1.0) k1 = q[4], k2 = q[5];
+      if (psi) *psi += (k1 / (2.0 * k2)) * (std::exp(k2 * (I4 - scalarProduct) * (I4 - scalarProduct)) - 1.0);
+      if (S)
+      {
+        const double gamma = 2. * (k1 * (I4 - scalarProduct) * std::exp(k2 * std::pow((I4 - scalarProduct), 2)));
+        for (int v = 0; v < 6; ++v) S[v] += gamma * A[v];
+        const double delta = 2. * (1. + 2. * k2 * std::pow((I4 - scalarProduct), 2)) * 2. * k1 *
+                             std::exp(k2 * std::pow((I4 - scalarProduct), 2));
+        for (int I = 0; I < 6; ++I)
+          for (int J = 0; J < 6; ++J) Cm[I + 6 * J] += delta * A[I] * A[J];
+      }
+    }
+  }
+
   // returns psi; dPI/ddPII may be null (strain energy only)
   double hyper_generic(const double* par, const double* I, double* dPI, double* ddPII)
   {
@@ -612,7 +648,7 @@ namespace
     {
       const double* q = par + 1 + 6 * k;
       const int kind = (int)q[0];
-      if (kind >= ORC_SUM_ISO_NEOHOOKE) isomod = true;
+      if (kind >= ORC_SUM_ISO_NEOHOOKE && kind <= ORC_SUM_VOL_POW) isomod = true;
       summand_add(kind, q[1], q + 2, I, m, d1, d2, dPm, ddPm, psi);
     }
     if (isomod) convert_mod_to_princ(I, dPm, ddPm, d1, d2);
@@ -666,6 +702,7 @@ namespace
         v += d[7] * 0.5 * ((a == c && b == e ? 1.0 : 0.0) + (a == e && b == c ? 1.0 : 0.0));
         Cm[Iv + 6 * Jv] = v;
       }
+    if (kind == ORC_MAT_ELASTHYPER) aniso_expo_add(par, C, S, Cm, nullptr);
   }
 
   // Mat::StVenantKirchhoff::evaluate (src/mat/4C_mat_stvenantkirchhoff.cpp:105-113,
@@ -1026,9 +1063,114 @@ namespace
     return 0;
   }
 
-  int element_tech(int ct, int tech, int matkind, const double* par, int action, const double* X,
-      const double* u, double* Ke, double* fe)
+  // ---- SolidEleCalc<celltype, MulfFormulation>  (src/solid_ele/4C_solid_ele_calc_mulf.hpp:36-148,
+  //      src/solid_ele/4C_solid_ele_calc_lib_mulf.hpp:26-92)
+  // Gauss-point history (MulfHistoryData), ORC_MULF_HIST doubles per point:
+  //   [0..8] inverse_jacobian (a + 3 b), [9..17] deformation_gradient (a + 3 b), [18] is_setup
+  // A fresh history is {identity, identity, 0}; orc_mulf_init_history writes it.
+  void mulf_kinematics(int n, const double* dN, const double* u, const JacMap& jm, double* h,
+      double* Fdelta, double* F)
   {
+    if (h[18] == 0.0)  // calc_mulf.hpp:56-60
+    {
+      for (int i = 0; i < 9; ++i) h[i] = jm.iJ[i];
+      h[18] = 1.0;
+    }
+    // evaluate_mulf_deformation_gradient_update (lib_mulf.hpp:41-60)
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) Fdelta[a + 3 * b] = (a == b) ? 1.0 : 0.0;
+    for (int k = 0; k < n; ++k)
+    {
+      double Nh[3];
+      for (int a = 0; a < 3; ++a)
+      {
+        double v = 0.0;
+        for (int b = 0; b < 3; ++b) v += h[a + 3 * b] * dN[b + 3 * k];
+        Nh[a] = v;
+      }
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) Fdelta[a + 3 * b] += u[3 * k + a] * Nh[b];
+    }
+    // F = F_delta * F_history (lib_mulf.hpp:76-77)
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b)
+      {
+        double v = 0.0;
+        for (int c = 0; c < 3; ++c) v += Fdelta[a + 3 * c] * h[9 + c + 3 * b];
+        F[a + 3 * b] = v;
+      }
+  }
+
+  int element_mulf(int ct, int matkind, const double* par, int action, const double* X,
+      const double* u, double* hist, double* Ke, double* fe)
+  {
+    const int n = nnodes(ct), nd = 3 * n, ng = ngauss(ct);
+    double N[MAXN], dN[3 * MAXN];
+    JacMap jm;
+    if (Ke) std::memset(Ke, 0, sizeof(double) * nd * nd);
+    std::memset(fe, 0, sizeof(double) * nd);
+    int err = 0;
+    for (int k = 0; k < n; ++k)
+    {
+      double xi[3];
+      node_ref(ct, k, xi);
+      shape(ct, xi, N, dN);
+      jacobian_mapping(n, dN, X, jm);
+      if (!(jm.det > 0)) err = 1;
+    }
+    if (err) return 1;
+    double gxi[3 * MAXN], gw[MAXN];
+    gauss(ct, gxi, gw);
+    for (int gp = 0; gp < ng; ++gp)
+    {
+      shape(ct, gxi + 3 * gp, N, dN);
+      jacobian_mapping(n, dN, X, jm);
+      const double fac = jm.det * gw[gp];
+      double Fd[9], F[9], C[6], E[6], S[6], Cm[36];
+      mulf_kinematics(n, dN, u, jm, hist + ORC_MULF_HIST * gp, Fd, F);
+      cauchy_green(F, C, E);
+      material(matkind, par, F, E, S, Cm);
+      // add_internal_force_vector(Bop, stress) / add_elastic_stiffness_matrix(Bop, stress) +
+      // add_geometric_stiffness_matrix with the B-operator of the UNMODIFIED reference gradients and
+      // the MULF deformation gradient (calc_mulf.hpp:74-79,84-110); the B-free forms are the same
+      // operator (unit test 4C_solid_ele_calc_lib_test.cpp:243-343)
+      add_force(n, jm, F, S, fac, fe);
+      if (action == ORC_ACTION_FORCE_STIFF && Ke) add_stiffness_bop(n, jm, F, S, Cm, fac, Ke);
+    }
+    return 0;
+  }
+
+  // SolidEleCalc::update_prestress (4C_solid_ele_calc.cpp:478-519) with
+  // MulfFormulation::update_prestress (calc_mulf.hpp:124-143)
+  void element_update_prestress(int ct, const double* X, const double* u, double* hist)
+  {
+    const int n = nnodes(ct), ng = ngauss(ct);
+    double N[MAXN], dN[3 * MAXN], gxi[3 * MAXN], gw[MAXN];
+    JacMap jm;
+    gauss(ct, gxi, gw);
+    for (int gp = 0; gp < ng; ++gp)
+    {
+      shape(ct, gxi + 3 * gp, N, dN);
+      jacobian_mapping(n, dN, X, jm);
+      double* h = hist + ORC_MULF_HIST * gp;
+      double Fd[9], F[9], iFd[9], niJ[9];
+      mulf_kinematics(n, dN, u, jm, h, Fd, F);  // evaluate(): deformation_gradient of this state
+      inv3(iFd, Fd);
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b)
+        {
+          double v = 0.0;
+          for (int c = 0; c < 3; ++c) v += iFd[c + 3 * a] * h[c + 3 * b];
+          niJ[a + 3 * b] = v;
+        }
+      for (int i = 0; i < 9; ++i) h[9 + i] = F[i], h[i] = niJ[i];
+    }
+  }
+
+  int element_tech(int ct, int tech, int matkind, const double* par, int action, const double* X,
+      const double* u, double* Ke, double* fe, double* hist = nullptr)
+  {
+    if (tech == ORC_TECH_MULF) return element_mulf(ct, matkind, par, action, X, u, hist, Ke, fe);
     if (tech == ORC_TECH_FBAR) return element_fbar(ct, matkind, par, action, X, u, Ke, fe);
     return element(ct, matkind, par, action, X, u, Ke, fe);
   }
@@ -1119,7 +1261,12 @@ extern "C"
              C[5] * C[5];
       I[2] = C[0] * C[1] * C[2] + 2 * (C[3] * C[4] * C[5]) - C[1] * C[5] * C[5] - C[2] * C[3] * C[3] -
              C[0] * C[4] * C[4];
-      if (kind == ORC_MAT_ELASTHYPER) return hyper_generic(par, I, nullptr, nullptr);
+      if (kind == ORC_MAT_ELASTHYPER)
+      {
+        double psi = hyper_generic(par, I, nullptr, nullptr);
+        aniso_expo_add(par, C, nullptr, nullptr, &psi);
+        return psi;
+      }
       double blk[13];
       if (kind == ORC_MAT_COUP_NEOHOOKE)
       {
@@ -1479,7 +1626,49 @@ extern "C"
       const int32_t* node_col_lid, int64_t n_row_nodes, const int64_t* rowptr,
       const int32_t* colind, double* values, double* f, int nthreads)
   {
+    return orc_evaluate_assemble_hist(ct, tech, matkind, matparams, mue_per_ele, action, n_ele, conn,
+        n_col_nodes, X, u_col, node_row_lid, node_col_lid, n_row_nodes, rowptr, colind, values, f,
+        nthreads, nullptr);
+  }
+
+  void orc_mulf_init_history(int64_t n_points, double* hist)
+  {
+    for (int64_t p = 0; p < n_points; ++p)
+    {
+      double* h = hist + ORC_MULF_HIST * p;
+      for (int i = 0; i < 9; ++i) h[i] = h[9 + i] = (i % 4 == 0) ? 1.0 : 0.0;
+      h[18] = 0.0;
+    }
+  }
+
+  // struct_update_prestress over the column elements (model_evaluator_structure.cpp:1608-1642)
+  void orc_update_prestress(int ct, int64_t n_ele, const int32_t* conn, const double* X,
+      const double* u_col, double* hist)
+  {
+    const int n = nnodes(ct), nd = 3 * n, ng = ngauss(ct);
+    std::vector<double> Xe(nd), ue(nd);
+    for (int64_t e = 0; e < n_ele; ++e)
+    {
+      for (int i = 0; i < n; ++i)
+        for (int d = 0; d < 3; ++d)
+        {
+          Xe[3 * i + d] = X[3 * (int64_t)conn[e * n + i] + d];
+          ue[3 * i + d] = u_col[3 * (int64_t)conn[e * n + i] + d];
+        }
+      element_update_prestress(ct, Xe.data(), ue.data(), hist + (int64_t)ORC_MULF_HIST * ng * e);
+    }
+  }
+
+  // hist: Gauss-point history of the column elements (n_ele * ngp * ORC_MULF_HIST), required for
+  // ORC_TECH_MULF (use nthreads = 1: the first evaluate initialises it)
+  int64_t orc_evaluate_assemble_hist(int ct, int tech, int matkind, const double* matparams,
+      const double* mue_per_ele, int action, int64_t n_ele, const int32_t* conn,
+      int64_t n_col_nodes, const double* X, const double* u_col, const int32_t* node_row_lid,
+      const int32_t* node_col_lid, int64_t n_row_nodes, const int64_t* rowptr,
+      const int32_t* colind, double* values, double* f, int nthreads, double* hist)
+  {
     (void)n_col_nodes;
+    if (tech == ORC_TECH_MULF && hist == nullptr) return -1;
     const int n = nnodes(ct), nd = 3 * n;
     if (nthreads < 1) nthreads = 1;
     std::vector<int64_t> bad(nthreads, 0);
@@ -1514,10 +1703,19 @@ extern "C"
             Xe[3 * i + d] = X[3 * (int64_t)ce[i] + d];
             ue[3 * i + d] = u_col[3 * (int64_t)ce[i] + d];  // extract_values via lm
           }
-        if (mue_per_ele) par[0] = mue_per_ele[e];  // InputField MUE looked up by element id
+        if (mue_per_ele && matkind == ORC_MAT_ELASTHYPER)
+        {
+          // element fibres (FIBER1 of the element line): 3 doubles per element into the ORC_SUM_FIBER entry
+          for (int k = 0; k < (int)par[0]; ++k)
+            if ((int)par[1 + 6 * k] == ORC_SUM_FIBER)
+              for (int d = 0; d < 3; ++d) par[1 + 6 * k + 2 + d] = mue_per_ele[3 * e + d];
+        }
+        else if (mue_per_ele)
+          par[0] = mue_per_ele[e];  // InputField MUE looked up by element id
         const bool stiff = (action == ORC_ACTION_FORCE_STIFF) && values;
         if (element_tech(ct, tech, matkind, par.data(), action, Xe.data(), ue.data(),
-                stiff ? Ke.data() : nullptr, fe.data()))
+                stiff ? Ke.data() : nullptr, fe.data(),
+                hist ? hist + (int64_t)ORC_MULF_HIST * ngauss(ct) * e : nullptr))
         {
           bad[tid]++;
           continue;

@@ -16,7 +16,8 @@ using namespace b200s;
 template <int MAT, bool STIFF, int TECH>
 static void run(const EvalArgs& A, double* min_detJ, double* min_detF, int64_t* n_bad)
 {
-  constexpr int MP_SIZE = TECH ? hex8fbar::MP_SIZE : hex8::MP_SIZE;
+  constexpr bool FBAR = TECH == 1, MULF = TECH == 2;  // as in k_hex8_eval_assemble
+  constexpr int MP_SIZE = FBAR ? hex8fbar::MP_SIZE : hex8::MP_SIZE;
   const CellTables T = make_cell_tables(0);
   std::vector<double> tab_gp(hex8::TAB_SIZE, 0.0), tab_node(hex8::TAB_SIZE, 0.0);
   for (int t = 0; t < 8 * 24; ++t)
@@ -24,7 +25,7 @@ static void run(const EvalArgs& A, double* min_detJ, double* min_detF, int64_t* 
     tab_gp[(t / 24) * hex8::TAB_STRIDE + (t % 24)] = T.dN_gp[t];
     tab_node[(t / 24) * hex8::TAB_STRIDE + (t % 24)] = T.dN_node[t];
   }
-  std::vector<double> sm((TECH ? hex8fbar::WARP_DOUBLES : hex8::WARP_DOUBLES) + 2, 0.0);
+  std::vector<double> sm((FBAR ? hex8fbar::WARP_DOUBLES : hex8::WARP_DOUBLES) + 2, 0.0);
   std::vector<NodeRow> nrow(hex8::EPW * hex8::NN);
   std::vector<int32_t> posbuf(hex8::EPW * hex8::NN * hex8::NN);
   hex8::WarpSmem S;
@@ -32,12 +33,12 @@ static void run(const EvalArgs& A, double* min_detJ, double* min_detF, int64_t* 
   S.mp = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sm.data()) + 15) & ~uintptr_t(15));
   S.g = S.mp + MP_SIZE;
   S.xu = S.g + hex8::G_SIZE;
-  if (TECH) S.h0 = S.xu + hex8::XU_SIZE;
+  if (FBAR) S.h0 = S.xu + hex8::XU_SIZE;
   S.nrow = nrow.data(), S.pos = posbuf.data();
   *min_detJ = 1e300, *min_detF = 1e300, *n_bad = 0;
   const int64_t n_tiles = (A.n_ele + hex8::EPW - 1) / hex8::EPW;
   static double out54[32][54];
-  static double Kacc[32][TECH ? 8 : 5][9], facc[32][3];
+  static double Kacc[32][FBAR ? 8 : 5][9], facc[32][3];
   for (int64_t tile = 0; tile < n_tiles; ++tile)
   {
     const int64_t e0 = tile * hex8::EPW;
@@ -47,11 +48,11 @@ static void run(const EvalArgs& A, double* min_detJ, double* min_detF, int64_t* 
     {
       double dJ, dF;
       bool neg;
-      if (TECH)
+      if (FBAR)
         hex8fbar::phase1<MAT, STIFF>(
             A, S, tab_gp.data(), T.w.data(), lane, e0, out54[lane], dJ, dF, neg);
       else
-        hex8::phase1<MAT, STIFF>(A, S, tab_gp.data(), tab_node.data(), T.w.data(), lane, e0,
+        hex8::phase1<MAT, STIFF, MULF>(A, S, tab_gp.data(), tab_node.data(), T.w.data(), lane, e0,
             out54[lane], dJ, dF, neg);
       if (e0 + (lane >> 3) < A.n_ele)
       {
@@ -62,7 +63,7 @@ static void run(const EvalArgs& A, double* min_detJ, double* min_detF, int64_t* 
     }
     for (bool b : negel) *n_bad += b;
     for (int lane = 0; lane < 32; ++lane) hex8::phase1_store<STIFF>(S, lane, out54[lane]);
-    if constexpr (TECH != 0)
+    if constexpr (FBAR)
     {
       for (int lane = 0; lane < 32; ++lane) hex8fbar::phase2<STIFF>(S, lane, Kacc[lane], facc[lane]);
       for (int lane = 0; lane < 32; ++lane) hex8fbar::stage_ke<STIFF>(S, lane, Kacc[lane], facc[lane]);
@@ -79,7 +80,8 @@ static void run(const EvalArgs& A, double* min_detJ, double* min_detF, int64_t* 
 static int emu_hex8_tech(int tech, int matkind, const double* params, const double* per_ele, int stiff,
     int64_t n_ele, const int32_t* conn, const double* X, const double* u_col, const int32_t* pos,
     const int64_t* node_rowstart, const int32_t* node_rowlen, const int32_t* node_frow,
-    int64_t n_col_nodes, double* vals, double* f, double* min_detJ, double* min_detF, int64_t* n_bad)
+    int64_t n_col_nodes, double* vals, double* f, double* min_detJ, double* min_detF, int64_t* n_bad,
+    const double* gp_hist = nullptr)
 {
   std::vector<NodeRow> node_row(n_col_nodes);
   for (int64_t k = 0; k < n_col_nodes; ++k)
@@ -87,11 +89,16 @@ static int emu_hex8_tech(int tech, int matkind, const double* params, const doub
     node_row[k].frow = node_frow[k];
   EvalArgs A;
   A.X = X, A.u = u_col, A.conn = conn, A.pos = pos, A.node_row = node_row.data();
-  A.per_ele_param = per_ele, A.ele_id = nullptr;
+  A.per_ele_param = per_ele, A.ele_id = nullptr, A.gp_hist = nullptr;
   A.vals = vals, A.f = f, A.err = nullptr, A.n_ele = n_ele, A.scatter_mode = 0;
   if (!make_mat_params(matkind, params, A.mp)) return -3;
+  A.gp_hist = gp_hist;
 #define RUN(M)                                                  \
-  if (tech && stiff)                                            \
+  if (tech == 2 && stiff)                                       \
+    run<M, true, 2>(A, min_detJ, min_detF, n_bad);              \
+  else if (tech == 2)                                           \
+    run<M, false, 2>(A, min_detJ, min_detF, n_bad);             \
+  else if (tech && stiff)                                       \
     run<M, true, 1>(A, min_detJ, min_detF, n_bad);              \
   else if (tech)                                                \
     run<M, false, 1>(A, min_detJ, min_detF, n_bad);             \
@@ -130,4 +137,15 @@ extern "C" int emu_hex8fbar(int matkind, const double* params, const double* per
 {
   return emu_hex8_tech(1, matkind, params, per_ele, stiff, n_ele, conn, X, u_col, pos, node_rowstart,
       node_rowlen, node_frow, n_col_nodes, vals, f, min_detJ, min_detF, n_bad);
+}
+
+// MULF variant (TECH 2 of k_hex8_eval_assemble): gp_hist = n_ele * 8 * 18 doubles
+extern "C" int emu_hex8mulf(int matkind, const double* params, const double* per_ele, int stiff,
+    int64_t n_ele, const int32_t* conn, const double* X, const double* u_col, const int32_t* pos,
+    const int64_t* node_rowstart, const int32_t* node_rowlen, const int32_t* node_frow,
+    int64_t n_col_nodes, double* vals, double* f, double* min_detJ, double* min_detF, int64_t* n_bad,
+    const double* gp_hist)
+{
+  return emu_hex8_tech(2, matkind, params, per_ele, stiff, n_ele, conn, X, u_col, pos, node_rowstart,
+      node_rowlen, node_frow, n_col_nodes, vals, f, min_detJ, min_detF, n_bad, gp_hist);
 }

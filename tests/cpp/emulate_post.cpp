@@ -96,7 +96,7 @@ extern "C" int emu_material(int matkind, const double* params, const double* C, 
 
 extern "C" int emu_post(int celltype, int fbar, int matkind, const double* params, const double* per_ele,
     int64_t n_ele, const int32_t* conn, const double* X, const double* u_col, const uint8_t* ele_is_row,
-    int stress_type, int strain_type, double* stress, double* strain, double* energy)
+    int stress_type, int strain_type, double* stress, double* strain, double* energy, const double* gp_hist)
 {
   const CellTables T = make_cell_tables(celltype);
   MatParams mp;
@@ -105,7 +105,7 @@ extern "C" int emu_post(int celltype, int fbar, int matkind, const double* param
   PostArgs A;
   A.X = X, A.u = u_col, A.conn = conn, A.per_ele_param = per_ele, A.ele_id = nullptr;
   A.ele_is_row = ele_is_row, A.dN_gp = T.dN_gp.data(), A.dN_cen = T.dN_cen.data(), A.w = T.w.data();
-  A.mp = mp, A.n_ele = n_ele, A.nn = T.nn, A.ngp = T.ngp, A.fbar = fbar;
+  A.mp = mp, A.n_ele = n_ele, A.nn = T.nn, A.ngp = T.ngp, A.fbar = fbar, A.gp_hist = gp_hist;
   A.stress_type = stress_type, A.strain_type = strain_type;
   A.stress = stress, A.strain = strain, A.energy = nullptr;
   switch (matkind)
@@ -147,5 +147,31 @@ extern "C" int emu_mass(int celltype, double density, int lumped, int64_t n_ele,
     run_mass<27>(M);
   else
     run_mass<10>(M);
+  return 0;
+}
+
+// MULF history: fresh set-up (what k_mulf_init does) and struct_update_prestress (k_mulf_update)
+extern "C" int emu_mulf_history(int celltype, int update, int64_t n_ele, const int32_t* conn, const double* X,
+    const double* u_col, double* hist)
+{
+  const CellTables T = make_cell_tables(celltype);
+  for (int64_t e = 0; e < n_ele; ++e)
+    for (int g = 0; g < T.ngp; ++g)
+    {
+      double* h = hist + (e * T.ngp + g) * MULF_HIST;
+      const double* dN = T.dN_gp.data() + (size_t)g * T.nn * 3;
+      const int32_t* ce = conn + e * T.nn;
+      if (update)
+        mulf_update_point(T.nn, dN, X, u_col, ce, h);
+      else
+      {
+        double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, iJ[9];
+        for (int k = 0; k < T.nn; ++k)
+          for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) J[a + 3 * b] += dN[3 * k + a] * X[3 * (int64_t)ce[k] + b];
+        inv3(iJ, J);
+        for (int i = 0; i < 9; ++i) h[i] = iJ[i], h[9 + i] = (i % 4 == 0) ? 1.0 : 0.0;
+      }
+    }
   return 0;
 }

@@ -10,6 +10,8 @@ What it writes
           tests/input_files/solid_ele_hex8_Standard_eas_none_stressout.4C.yaml
           tests/input_files/solid_ele_hex27_Standard_stressout.4C.yaml
           tests/input_files/solid_ele_tet10_Standard_stressout.4C.yaml
+  integration_<cell>_mulf.json : MULF prestress inputs tests/input_files/solid_ele_<cell>_Standard_mulf.4C.yaml
+        (CoupNeoHooke + CoupAnisoExpo element fibre, PRESTRESSTIME 1) with their nodal displacements
   integration_cooks_fbar.json : Cook's membrane with 64 F-bar hex8 elements
           tests/input_files/sohex8fbar_cooks_nl_new_struc.4C.yaml (dispy of node 162, 1e-8)
   unit_known_answers.json : known answers of unittests/mat/4C_elasthyper_service_test.cpp:36-155,
@@ -101,6 +103,62 @@ def integration_case(cell, rel):
                     "FUNCT1": y["FUNCT1"][0]["SYMBOLIC_FUNCTION_OF_SPACE_TIME"],
                     "FUNCT2": y["FUNCT2"][0]["SYMBOLIC_FUNCTION_OF_SPACE_TIME"]},
         "timestep": float(sd["TIMESTEP"]), "numstep": int(sd["NUMSTEP"]),
+        "tolres": float(sd["TOLRES"]), "toldisp": float(sd["TOLDISP"]),
+        "expected_disp": expected,
+    }
+
+
+def mulf_case(cell, rel):
+    """MULF prestress ctest input: one element block with MAT_ElastHyper{CoupNeoHooke, CoupAnisoExpo},
+    element fibre FIBER1, PRESTRESS MULF until PRESTRESSTIME; known answers = nodal displacements."""
+    with open(os.path.join(REF, rel)) as fh:
+        y = yaml.safe_load(fh)
+    nodes = {}
+    for line in y["NODE COORDS"]:
+        m = re.match(r"NODE\s+(\d+)\s+COORD\s+(\S+)\s+(\S+)\s+(\S+)", line)
+        nodes[int(m.group(1))] = [float(m.group(i)) for i in (2, 3, 4)]
+    coords = [nodes[i + 1] for i in range(max(nodes))]
+    eles, fibers = [], []
+    for line in y["STRUCTURE ELEMENTS"]:
+        tok = line.split()
+        assert tok[1] == "SOLID" and tok[2].lower() == cell and "PRESTRESS_TECH mulf" in line
+        k = 3
+        conn = []
+        while tok[k] != "MAT":
+            conn.append(int(tok[k]) - 1)
+            k += 1
+        eles.append(conn)
+        f = tok.index("FIBER1")
+        fibers.append([float(tok[f + 1]), float(tok[f + 2]), float(tok[f + 3])])
+    surf = {1: [], 2: []}
+    for line in y["DSURF-NODE TOPOLOGY"]:
+        m = re.match(r"NODE\s+(\d+)\s+DSURFACE\s+(\d+)", line)
+        surf[int(m.group(2))].append(int(m.group(1)) - 1)
+    mats = {m["MAT"]: m for m in y["MATERIALS"]}
+    eh = mats[1]["MAT_ElastHyper"]
+    summands = []
+    for mid in eh["MATIDS"]:
+        (name, par), = [(k, v) for k, v in mats[mid].items() if k != "MAT"]
+        summands.append({"name": name, "params": par})
+    dbc = y["DESIGN SURF DIRICH CONDITIONS"][0]
+    neu = y["DESIGN SURF NEUMANN CONDITIONS"][0]
+    assert dbc["E"] == 1 and neu["E"] == 2
+    sd = y["STRUCTURAL DYNAMIC"]
+    assert sd["PRESTRESS"].lower() == "mulf"
+    expected = []
+    for r in y["RESULT DESCRIPTION"]:
+        s = r["STRUCTURE"]
+        if s["QUANTITY"] in ("dispx", "dispy", "dispz"):
+            expected.append({"node": s["NODE"] - 1, "dof": "xyz".index(s["QUANTITY"][-1]),
+                             "value": float(s["VALUE"]), "tol": float(s["TOLERANCE"])})
+    return {
+        "source": rel, "celltype": cell, "coords": coords, "elements": eles, "fibers": fibers,
+        "summands": summands, "dirichlet_nodes": sorted(surf[1]), "neumann_nodes": sorted(surf[2]),
+        "neumann": {"ONOFF": neu["ONOFF"], "VAL": neu["VAL"], "FUNCT": neu["FUNCT"],
+                    "FUNCT1": y["FUNCT1"][0]["SYMBOLIC_FUNCTION_OF_SPACE_TIME"],
+                    "FUNCT2": y["FUNCT2"][0]["SYMBOLIC_FUNCTION_OF_SPACE_TIME"]},
+        "timestep": float(sd["TIMESTEP"]), "numstep": int(sd["NUMSTEP"]),
+        "prestresstime": float(sd["PRESTRESSTIME"]),
         "tolres": float(sd["TOLRES"]), "toldisp": float(sd["TOLDISP"]),
         "expected_disp": expected,
     }
@@ -243,6 +301,9 @@ if __name__ == "__main__":
             ("cooks_fbar", "tests/input_files/sohex8fbar_cooks_nl_new_struc.4C.yaml", "fbar"),):
         with open(os.path.join(HERE, f"integration_{name}.json"), "w") as fh:
             json.dump(cooks_case(rel, tech), fh)
+    for cell in ("hex8", "hex27", "tet10"):
+        with open(os.path.join(HERE, f"integration_{cell}_mulf.json"), "w") as fh:
+            json.dump(mulf_case(cell, f"tests/input_files/solid_ele_{cell}_Standard_mulf.4C.yaml"), fh, indent=1)
     with open(os.path.join(HERE, "unit_known_answers.json"), "w") as fh:
         json.dump(unit_known_answers(), fh, indent=1)
     np.savez_compressed(os.path.join(HERE, "ref_elements.npz"), **ref_elements())

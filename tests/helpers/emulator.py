@@ -12,7 +12,7 @@ _libs = {}
 
 
 def lib(cell="hex8"):
-    cell = {"hex8fbar": "hex8"}.get(cell, cell)
+    cell = {"hex8fbar": "hex8", "hex8mulf": "hex8"}.get(cell, cell)
     if cell not in _libs:
         so = os.path.join(_CPP, f"libemu_{cell}.so")
         srcs = [os.path.join(_CPP, f"emulate_{cell}.cpp")] + [
@@ -54,7 +54,7 @@ def scatter_map(conn, rowptr, colind, node_row_lid, node_col_lid):
 
 
 def evaluate(matkind, params, conn, X, u_col, rowptr, colind, node_row_lid, node_col_lid, n_row_nodes,
-             stiff=True, per_ele=None, cell="hex8"):
+             stiff=True, per_ele=None, cell="hex8", gp_hist=None):
     conn = np.ascontiguousarray(conn, np.int32)
     X = np.ascontiguousarray(X, np.float64)
     u_col = np.ascontiguousarray(u_col, np.float64)
@@ -69,7 +69,8 @@ def evaluate(matkind, params, conn, X, u_col, rowptr, colind, node_row_lid, node
         per_ele = np.ascontiguousarray(per_ele, np.float64)
     rc = getattr(lib(cell), f"emu_{cell}")(C.c_int(matkind), p(params), p(per_ele), C.c_int(int(stiff)),
                         C.c_int64(conn.shape[0]), p(conn), p(X), p(u_col), p(pos), p(rowstart),
-                        p(rowlen), p(frow), C.c_int64(len(rowstart)), p(vals), p(f), C.byref(dJ), C.byref(dF), C.byref(nb))
+                        p(rowlen), p(frow), C.c_int64(len(rowstart)), p(vals), p(f), C.byref(dJ), C.byref(dF), C.byref(nb),
+                        *([p(np.ascontiguousarray(gp_hist, np.float64))] if cell == "hex8mulf" else []))
     assert rc == 0
     return vals, f, dict(min_detJ=dJ.value, min_detF=dF.value, n_bad=nb.value)
 
@@ -91,8 +92,24 @@ def material(matkind, params, Cv):
     return S, Cm.reshape(6, 6), psi.value
 
 
+def mulf_history(celltype, conn, X, u_col=None, hist=None):
+    """hist is None: fresh history (n_ele, ngp, 18); else struct_update_prestress in place for state u_col."""
+    conn = np.ascontiguousarray(conn, np.int32)
+    X = np.ascontiguousarray(X, np.float64)
+    ngp = {0: 8, 1: 27, 2: 4}[celltype]
+    update = hist is not None
+    if hist is None:
+        hist = np.zeros((len(conn), ngp, 18))
+    u = None if u_col is None else np.ascontiguousarray(u_col, np.float64)
+    assert hist.flags["C_CONTIGUOUS"]
+    rc = lib("post").emu_mulf_history(C.c_int(celltype), C.c_int(int(update)), C.c_int64(len(conn)), _p(conn), _p(X),
+                                      _p(u), _p(hist))
+    assert rc == 0
+    return hist
+
+
 def post(celltype, matkind, params, conn, X, u_col, stress_type=1, strain_type=1, ele_is_row=None,
-         per_ele=None, fbar=False, want_energy=True):
+         per_ele=None, fbar=False, want_energy=True, gp_hist=None):
     conn = np.ascontiguousarray(conn, np.int32)
     X = np.ascontiguousarray(X, np.float64)
     u_col = np.ascontiguousarray(u_col, np.float64)
@@ -108,7 +125,8 @@ def post(celltype, matkind, params, conn, X, u_col, stress_type=1, strain_type=1
     rc = lib("post").emu_post(C.c_int(celltype), C.c_int(int(fbar)), C.c_int(matkind), _p(params), _p(per_ele),
                               C.c_int64(len(conn)), _p(conn), _p(X), _p(u_col), _p(ele_is_row),
                               C.c_int(stress_type), C.c_int(strain_type), _p(st), _p(en),
-                              C.byref(energy) if want_energy else None)
+                              C.byref(energy) if want_energy else None,
+                              None if gp_hist is None else _p(np.ascontiguousarray(gp_hist, np.float64)))
     assert rc == 0, rc
     return st, en, energy.value
 

@@ -11,8 +11,14 @@ from .meshes import csr_to_dense
 from .neumann import neumann_load
 
 
-def solve_case(case, evaluate, max_iter=30):
-    """evaluate(u_flat) -> (rowptr, colind, values, fint). Returns converged displacement (nn,3)."""
+def solve_case(case, evaluate, max_iter=30, update_prestress=None):
+    """evaluate(u_flat) -> (rowptr, colind, values, fint). Returns converged displacement (nn,3).
+
+    update_prestress(u_flat): PRESTRESS MULF.  While the time reached by a step is <= PRESTRESSTIME
+    (the state has already been advanced when update_step_element runs; confirmed by the known answers:
+    PRESTRESSTIME 1 with TIMESTEP 0.5 gives two MULF steps) the converged step ends with the element
+    action struct_update_prestress and the displacements are reset to zero (src/structure_new/src/model_evaluator/4C_structure_new_model_evaluator_structure.cpp:
+    1608-1642, src/structure_new/src/implicit/4C_structure_new_impl_prestress.cpp:94-108)."""
     nn = len(case["coords"])
     fixed = np.zeros(3 * nn, bool)
     for n in case["dirichlet_nodes"]:
@@ -39,4 +45,7 @@ def solve_case(case, evaluate, max_iter=30):
                 break
         else:
             raise RuntimeError(f"Newton did not converge at t={t}: |r|={rnorm}")
+        if update_prestress is not None and t <= case["prestresstime"] + 1.0e-15:
+            update_prestress(u)
+            u = np.zeros(3 * nn)
     return u.reshape(nn, 3)

@@ -304,3 +304,98 @@ def test_cg_handoff_on_a_larger_block():
     assert rel <= 1e-12 and iters < 2000
     assert np.abs(x - ref).max() <= 1e-8 * np.abs(ref).max(), (iters, rel)
     asm.close()
+
+
+# ------------------------------------------------------------------------------------------------------
+# MULF prestress (PRESTRESS_TECH mulf)
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10"])
+@pytest.mark.parametrize("mi", [0, 3])
+def test_mulf_evaluate_update_and_history_match_oracle(cell, mi):
+    ct, rm, u = _mesh(cell)
+    mk, par = MATS[mi]
+    asm = b200.DeviceAssembler(rm, mk, par, prestress=capi.PRESTRESS_MULF)
+    rowptr, colind = asm.graph()
+    ohist = orc.mulf_new_history(ct, rm.n_col_eles)
+    maps = (rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, rowptr, colind)
+    ngp = orc.num_gp(ct)
+    for scale in (1.0, -0.6, 0.3):
+        us = scale * u.ravel()
+        asm.set_state("displacement", us[:3 * rm.n_row_nodes])
+        K, f, _ = asm.evaluate("struct_calc_nlnstiff")
+        rK, rf, nbad = orc.evaluate_assemble(ct, mk, _opar(mk, par), rm.conn, rm.X.ravel(), us, *maps,
+                                             tech=orc.TECH_MULF, hist=ohist)
+        ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
+        assert ok and nbad == 0, (scale, wK, wf)
+        _, f2, _ = asm.evaluate("struct_calc_internalforce")
+        assert np.abs(f2 - rf).max() <= RTOL * np.abs(rf).max()
+        asm.update_prestress()
+        orc.update_prestress(ct, rm.conn, rm.X.ravel(), us, ohist)
+        h = asm.ctx.get_gp_history().reshape(rm.n_col_eles, ngp, 18)
+        assert np.abs(h - ohist[:, :, :18]).max() <= 1e-13 * np.abs(ohist).max()
+    # restart: a second context that unpacks the history continues identically
+    asm2 = b200.DeviceAssembler(rm, mk, par, prestress=capi.PRESTRESS_MULF)
+    asm2.ctx.set_gp_history(asm.ctx.get_gp_history())
+    us = 0.2 * u.ravel()
+    for a in (asm, asm2):
+        a.set_state("displacement", us[:3 * rm.n_row_nodes])
+    Ka, fa, _ = asm.evaluate()
+    Kb, fb, _ = asm2.evaluate()
+    assert np.array_equal(fa, fb) and np.abs(Ka - Kb).max() <= 1e-13 * np.abs(Ka).max()
+    # stresses see the prestressed state
+    st, _ = asm.calc_stress("2pk", "none")
+    asm.set_state("displacement", 0.0 * us[:3 * rm.n_row_nodes])
+    st0, _ = asm.calc_stress("2pk", "none")
+    assert np.abs(st0).max() > 1e-3 and np.abs(st - st0).max() > 1e-6
+    asm.close(), asm2.close()
+
+
+def test_mulf_prestressing_procedure_through_cuda_path():
+    """The reference's MULF ctest procedure (two prestress load steps with update + displacement reset,
+    then ordinary load steps) with the CUDA path inside the Newton loop, against the same procedure with
+    the oracle (whose MULF restatement is pinned to the reference's known answers with the fibre material
+    of those inputs; the device block uses the isotropic part only)."""
+    from tests.helpers.newton import solve_case
+    case = json.load(open(os.path.join(G, "integration_hex8_mulf.json")))
+    case = dict(case, numstep=4)
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    rm = b200.partition.serial_mesh(orc.HEX8, X, conn)
+    nh = case["summands"][0]["params"]
+    par = [nh["YOUNG"], nh["NUE"]]
+    nn = len(X)
+    asm = b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, par, prestress=capi.PRESTRESS_MULF)
+    rowptr, colind = asm.graph()
+    ohist = orc.mulf_new_history(orc.HEX8, len(conn))
+
+    def ev_dev(u):
+        asm.set_state("displacement", u)
+        K, f, _ = asm.evaluate()
+        return rowptr, colind, K, f
+
+    def up_dev(u):
+        asm.set_state("displacement", u)
+        asm.update_prestress()
+
+    def ev_orc(u):
+        K, f, _ = orc.evaluate_assemble(orc.HEX8, 0, par, conn, X.ravel(), u, rm.node_row_lid, rm.node_col_lid, nn,
+                                        rowptr, colind, tech=orc.TECH_MULF, hist=ohist)
+        return rowptr, colind, K, f
+
+    u_dev = solve_case(case, ev_dev, update_prestress=up_dev)
+    u_orc = solve_case(case, ev_orc, update_prestress=lambda u: orc.update_prestress(orc.HEX8, conn, X.ravel(), u, ohist))
+    assert np.abs(u_dev - u_orc).max() < 1e-10 and np.abs(u_orc).max() > 0.05
+    asm.close()
+
+
+def test_update_prestress_needs_mulf_and_mulf_fbar_is_rejected():
+    ct, rm, u = _mesh("hex8", (2, 2, 2))
+    asm = b200.DeviceAssembler(rm, capi.MAT_SVK, [1000.0, 0.3])
+    asm.set_state("displacement", u.ravel())
+    with pytest.raises(capi.B200SolidError) as ei:
+        asm.update_prestress()
+    assert ei.value.code == capi.ERR_UNSUPPORTED
+    with pytest.raises(capi.B200SolidError) as ei:
+        asm.ctx.set_element_properties(tech=capi.TECH_FBAR, prestress=capi.PRESTRESS_MULF)
+    assert ei.value.code == capi.ERR_UNSUPPORTED
+    asm.close()

@@ -298,3 +298,112 @@ def test_product_mass_owner_computes_rows(rank):
                     rm.n_row_nodes, acc_col=acc)
     assert np.abs(M - ref_M).max() <= 1e-12 * np.abs(ref_M).max()
     assert np.abs(f - ref_f).max() <= 1e-12 * np.abs(ref_f).max()
+
+
+# ------------------------------------------------------------------------------------------------------
+# MULF prestress
+# ------------------------------------------------------------------------------------------------------
+def _mulf_material(case, e=0):
+    nh, fib = case["summands"][0]["params"], case["summands"][1]["params"]
+    assert case["summands"][0]["name"] == "ELAST_CoupNeoHooke" and case["summands"][1]["name"] == "ELAST_CoupAnisoExpo"
+    return orc.pack_elasthyper([("COUP_NEOHOOKE", [nh["YOUNG"], nh["NUE"]]),
+                                ("COUP_ANISOEXPO", [fib["K1"], fib["K2"], fib["K1COMP"], fib["K2COMP"]]),
+                                ("FIBER", case["fibers"][e])])
+
+
+@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10"])
+def test_mulf_prestress_known_answers(cell):
+    """RESULT DESCRIPTION displacements (1e-12) of tests/input_files/solid_ele_<cell>_Standard_mulf.4C.yaml:
+    two MULF load steps (update_prestress + displacement reset), then eight ordinary steps.  Pins the
+    oracle's MulfFormulation restatement (history set-up, F = F_delta F_hist, prestress update)."""
+    case = json.load(open(os.path.join(G, f"integration_{cell}_mulf.json")))
+    ct = CELLS[cell]
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    fibers = np.asarray(case["fibers"], float)  # FIBER1 per element
+    nn = len(X)
+    row, col = serial_maps(nn)
+    rowptr, colind = orc.build_graph(ct, conn, row, col, nn)
+    par = _mulf_material(case)
+    hist = orc.mulf_new_history(ct, len(conn))
+
+    def evaluate(u):
+        vals, f, nbad = orc.evaluate_assemble(ct, orc.MAT_ELASTHYPER, par, conn, X.ravel(), u, row, col, nn,
+                                              rowptr, colind, tech=orc.TECH_MULF, hist=hist,
+                                              mue_per_ele=fibers.ravel())
+        assert nbad == 0
+        return rowptr, colind, vals, f
+
+    u = solve_case(case, evaluate, update_prestress=lambda uu: orc.update_prestress(ct, conn, X.ravel(), uu, hist))
+    assert len(case["expected_disp"]) >= 12
+    for e in case["expected_disp"]:
+        assert abs(u[e["node"], e["dof"]] - e["value"]) < 1e-11, (e, u[e["node"], e["dof"]])
+
+
+def test_mulf_update_keeps_the_stress_state():
+    """After struct_update_prestress and the displacement reset the element sees the same deformation
+    gradient (F_delta = I, F = F_hist), hence the same internal force."""
+    ct, rm, u = _mesh("hex8")
+    rowptr, colind = orc.build_graph(ct, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    hist = orc.mulf_new_history(ct, rm.n_col_eles)
+    args = (ct, orc.MAT_COUP_NEOHOOKE, [200.0, 0.25], rm.conn, rm.X.ravel())
+    maps = (rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, rowptr, colind)
+    K0, f0, _ = orc.evaluate_assemble(*args, u.ravel(), *maps, tech=orc.TECH_MULF, hist=hist)
+    Kp, fp, _ = orc.evaluate_assemble(*args, u.ravel(), *maps)
+    assert np.abs(K0 - Kp).max() <= 1e-12 * np.abs(Kp).max()  # fresh history = displacement based
+    orc.update_prestress(ct, rm.conn, rm.X.ravel(), u.ravel(), hist)
+    K1, f1, _ = orc.evaluate_assemble(*args, 0.0 * u.ravel(), *maps, tech=orc.TECH_MULF, hist=hist)
+    assert np.abs(f1 - f0).max() <= 1e-12 * np.abs(f0).max()
+
+
+def test_product_mulf_matches_oracle():
+    """hex8 kernel phases with the MULF deformation gradient (TECH 2), the history set-up and
+    struct_update_prestress of the product (emulated on the CPU) against the oracle, over two prestress
+    updates with different displacement states."""
+    ct, rm, u = _mesh("hex8")
+    rowptr, colind = orc.build_graph(ct, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    par = [200.0, 0.25]
+    ohist = orc.mulf_new_history(ct, rm.n_col_eles)
+    phist = emu.mulf_history(ct, rm.conn, rm.X.ravel())
+    maps = (rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    for scale in (1.0, -0.6, 0.3):
+        us = scale * u.ravel()
+        rK, rf, _ = orc.evaluate_assemble(ct, 0, par, rm.conn, rm.X.ravel(), us, *maps, rowptr, colind,
+                                          tech=orc.TECH_MULF, hist=ohist)
+        K, f, _ = emu.evaluate(0, par, rm.conn, rm.X.ravel(), us, rowptr, colind, *maps, cell="hex8mulf",
+                               gp_hist=phist)
+        ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, 1e-12)
+        assert ok, (scale, wK, wf)
+        # stress / energy with the history
+        rst, _ = orc_calc_stress_mulf(ct, par, rm, us, ohist)
+        st, _, en = emu.post(ct, 0, par, rm.conn, rm.X.ravel(), us, orc.STRESS_CAUCHY, orc.STRAIN_GL, gp_hist=phist)
+        assert np.abs(st - rst).max() <= 1e-12 * np.abs(rst).max()
+        orc.update_prestress(ct, rm.conn, rm.X.ravel(), us, ohist)
+        emu.mulf_history(ct, rm.conn, rm.X.ravel(), us, phist)
+        assert np.abs(phist - ohist[:, :, :18]).max() <= 1e-13 * np.abs(ohist).max()
+
+
+def orc_calc_stress_mulf(ct, par, rm, us, hist):
+    """Cauchy stresses of the oracle's MULF state: F = F_delta F_hist is what evaluate_assemble sees; the
+    oracle's calc_stress has no history argument, so recompute from the history here."""
+    ngp = orc.num_gp(ct)
+    gxi, _ = orc.gauss(ct)
+    out = np.zeros((rm.n_col_eles, ngp, 6))
+    for e in range(rm.n_col_eles):
+        ce = rm.conn[e]
+        ue = us.reshape(-1, 3)[ce]
+        for g in range(ngp):
+            _, dN = orc.shape(ct, gxi[g])                  # dN[a, k]
+            h = hist[e, g]
+            iJh = h[:9].reshape(3, 3).T                    # column-major (a + 3 b)
+            Fh = h[9:18].reshape(3, 3).T
+            Nh = iJh @ dN                                  # (3, n)
+            F = (np.eye(3) + ue.T @ Nh.T) @ Fh
+            C = F.T @ F
+            E = 0.5 * (C - np.eye(3))
+            Ev = np.array([E[0, 0], E[1, 1], E[2, 2], E[0, 1], E[1, 2], E[0, 2]])
+            S, _ = orc.material(0, par, Ev)
+            Sf = _voigt_to_full(S)
+            sig = F @ Sf @ F.T / np.linalg.det(F)
+            out[e, g] = [sig[0, 0], sig[1, 1], sig[2, 2], sig[0, 1], sig[1, 2], sig[0, 2]]
+    return out, None
