@@ -341,7 +341,8 @@ def test_mulf_evaluate_update_and_history_match_oracle(cell, mi):
         a.set_state("displacement", us[:3 * rm.n_row_nodes])
     Ka, fa, _ = asm.evaluate()
     Kb, fb, _ = asm2.evaluate()
-    assert np.array_equal(fa, fb) and np.abs(Ka - Kb).max() <= 1e-13 * np.abs(Ka).max()
+    # (atomic scatter order differs between runs: equal to round-off, not bitwise)
+    assert np.abs(fa - fb).max() <= 1e-13 * np.abs(fa).max() and np.abs(Ka - Kb).max() <= 1e-13 * np.abs(Ka).max()
     # stresses see the prestressed state
     st, _ = asm.calc_stress("2pk", "none")
     asm.set_state("displacement", 0.0 * us[:3 * rm.n_row_nodes])
