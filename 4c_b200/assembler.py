@@ -84,6 +84,10 @@ class DeviceAssembler:
         rc, err = self.ctx.evaluate(ACTIONS[action], self._u, None, f, check=check)
         return None, f, err
 
+    def recover(self, du_row, step_length=1.0):
+        """struct_calc_recover with the Newton direction as "residual displacement" (EAS alpha update)."""
+        self.ctx.recover(np.ascontiguousarray(du_row, np.float64).ravel(), step_length)
+
     def update_prestress(self):
         """struct_update_prestress for the current displacement state (PRESTRESS_TECH mulf)."""
         self.ctx.update_prestress()

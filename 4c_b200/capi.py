@@ -44,6 +44,7 @@ SYMBOLS = [
     "b200s_calc_energy", "b200s_apply_dirichlet", "b200s_apply_dirichlet_to_system", "b200s_multiply",
     "b200s_last_multiply_ms", "b200s_solve_cg", "b200s_get_values",
     "b200s_update_prestress", "b200s_gp_history_size", "b200s_get_gp_history", "b200s_set_gp_history",
+    "b200s_recover", "b200s_element_history_size", "b200s_get_element_history", "b200s_set_element_history",
 ]
 
 
@@ -117,6 +118,11 @@ def load():
     L.b200s_calc_stress.argtypes = [vp, i32, i32, vp, vp]
     L.b200s_get_values.argtypes = [vp, i32, vp]
     L.b200s_update_prestress.argtypes = [vp]
+    L.b200s_recover.argtypes = [vp, vp, dbl]
+    L.b200s_element_history_size.argtypes = [vp]
+    L.b200s_element_history_size.restype = i64
+    L.b200s_get_element_history.argtypes = [vp, vp]
+    L.b200s_set_element_history.argtypes = [vp, vp]
     L.b200s_gp_history_size.argtypes = [vp]
     L.b200s_gp_history_size.restype = i64
     L.b200s_get_gp_history.argtypes = [vp, vp]
@@ -223,6 +229,20 @@ class Context:
 
     def update_prestress(self):
         self._ck(self.L.b200s_update_prestress(self.h))
+
+    def recover(self, du_row, step_length=1.0):
+        du = np.ascontiguousarray(du_row, np.float64)
+        self._ck(self.L.b200s_recover(self.h, _ptr(du), float(step_length)))
+
+    def get_element_history(self):
+        h = np.empty(self.L.b200s_element_history_size(self.h))
+        self._ck(self.L.b200s_get_element_history(self.h, _ptr(h)))
+        return h
+
+    def set_element_history(self, hist):
+        h = np.ascontiguousarray(hist, np.float64).ravel()
+        assert h.size == self.L.b200s_element_history_size(self.h)
+        self._ck(self.L.b200s_set_element_history(self.h, _ptr(h)))
 
     def get_gp_history(self):
         h = np.empty(self.L.b200s_gp_history_size(self.h))

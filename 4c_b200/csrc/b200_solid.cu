@@ -15,6 +15,7 @@
 #include "../../include/b200_solid.h"
 #include "hex8_kernel.cuh"
 #include "hex8_fbar_kernel.cuh"
+#include "hex8_eas_kernel.cuh"
 #include "tet10_kernel.cuh"
 #include "hex27_kernel.cuh"
 #include "post_kernels.cuh"
@@ -31,6 +32,7 @@ namespace b200s
     double dN_gp[8 * 24];
     double dN_node[8 * 24];
     double w[8];
+    double xi_gp[8 * 3];  // parameter coordinates of the Gauss points (EAS shape functions)
   };
   __constant__ Hex8Const c_hex8;
   struct Tet10Const
@@ -257,6 +259,105 @@ namespace b200s
         atomicMin(&A.err->first_bad, bad);
         atomicAdd(&A.err->n_neg_jac, (unsigned long long)nbad);
       }
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------------
+  // hex8 EAS evaluate + assemble kernel (hex8_eas_kernel.cuh): one warp per element, persistent grid
+  // ------------------------------------------------------------------------------------------------
+  constexpr int HEX8_EAS_WARPS = 4;
+  template <int NEAS>
+  constexpr size_t hex8_eas_smem_bytes()
+  {
+    return hex8_table_bytes + 24 * 8 + HEX8_EAS_WARPS * (size_t)((hex8eas::Layout<NEAS>::BYTES + 15) & ~15);
+  }
+  template <int MAT, bool STIFF, int NEAS>
+  __global__ void __launch_bounds__(HEX8_EAS_WARPS * 32, 2) k_hex8_eas_eval_assemble(const EvalArgs A, double* hist)
+  {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* tab_gp = reinterpret_cast<double*>(smem_raw);
+    double* wgt = tab_gp + 2 * hex8::TAB_SIZE;
+    double* gxi = wgt + 8;
+    for (int t = threadIdx.x; t < 8 * 24; t += blockDim.x)
+      tab_gp[(t / 24) * hex8::TAB_STRIDE + (t % 24)] = c_hex8.dN_gp[t];
+    if (threadIdx.x < 8) wgt[threadIdx.x] = c_hex8.w[threadIdx.x];
+    if (threadIdx.x < 24) gxi[threadIdx.x] = c_hex8.xi_gp[threadIdx.x];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr size_t wbytes = (hex8eas::Layout<NEAS>::BYTES + 15) & ~15;
+    unsigned char* wbase = smem_raw + hex8_table_bytes + 24 * 8 + warp * wbytes;
+    double* sm = reinterpret_cast<double*>(wbase);
+    NodeRow* nrow = reinterpret_cast<NodeRow*>(sm + hex8eas::Layout<NEAS>::DOUBLES);
+    int32_t* pos = reinterpret_cast<int32_t*>(nrow + 8);
+    double detJ_min = 1e300, detF_min = 1e300;
+    long long bad = LLONG_MAX;
+    unsigned int nbad = 0;
+    constexpr int HS = hex8eas::hist_size(NEAS);
+    for (int64_t e = (int64_t)blockIdx.x * HEX8_EAS_WARPS + warp; e < A.n_ele; e += (int64_t)gridDim.x * HEX8_EAS_WARPS)
+    {
+      bool neg = false;
+      hex8eas::element<MAT, STIFF, NEAS>(A, sm, nrow, pos, tab_gp, wgt, gxi, lane, e, hist + e * HS, detJ_min,
+          detF_min, neg);
+      if (__ballot_sync(0xffffffffu, neg))
+      {
+        ++nbad;
+        const long long id = A.ele_id ? (long long)A.ele_id[e] : (long long)e;
+        bad = min(bad, id);
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      detJ_min = fmin(detJ_min, __shfl_xor_sync(0xffffffffu, detJ_min, o));
+      detF_min = fmin(detF_min, __shfl_xor_sync(0xffffffffu, detF_min, o));
+    }
+    if (lane == 0)
+    {
+      atomic_min_double(&A.err->min_detJ, detJ_min);
+      atomic_min_double(&A.err->min_detF, detF_min);
+      if (nbad)
+      {
+        atomicMin(&A.err->first_bad, bad);
+        atomicAdd(&A.err->n_neg_jac, (unsigned long long)nbad);
+      }
+    }
+  }
+
+  // struct_calc_recover, default step (SolidEleCalc::recover, 4C_solid_ele_calc.cpp:284-314; update_alpha,
+  // 4C_solid_ele_calc_eas_helpers.hpp:166-190): alpha_inc = -invKaa (s + Kda^T du), alpha += step alpha_inc.
+  // One warp per element, lane a = EAS parameter; du = "residual displacement" on the column map.
+  template <int NEAS>
+  __global__ void __launch_bounds__(128) k_eas_recover(int64_t n_ele, const int32_t* conn, const double* du_col,
+      double step_length, double* hist)
+  {
+    const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (e >= n_ele) return;
+    double* h = hist + e * hex8eas::hist_size(NEAS);
+    double* alpha_inc = h;
+    double* alpha = h + NEAS;
+    const double* s = h + 2 * NEAS;
+    const double* invKaa = h + 3 * NEAS;
+    const double* Kda = invKaa + NEAS * NEAS;
+    // du of the element's 24 dofs: lane r < 24
+    double du = 0.0;
+    if (lane < 24) du = du_col[3 * (int64_t)conn[e * 8 + lane / 3] + lane % 3];
+    double tmp = 0.0;  // (s + Kda^T du)(a) in lane a
+    for (int r = 0; r < 24; ++r)
+    {
+      const double dr = __shfl_sync(0xffffffffu, du, r);
+      if (lane < NEAS) tmp = fma(Kda[r + 24 * lane], dr, tmp);
+    }
+    if (lane < NEAS) tmp += s[lane];
+    double inc = 0.0;
+    for (int c = 0; c < NEAS; ++c)
+    {
+      const double tc = __shfl_sync(0xffffffffu, tmp, c);
+      if (lane < NEAS) inc = fma(invKaa[lane + NEAS * c], tc, inc);
+    }
+    if (lane < NEAS)
+    {
+      alpha_inc[lane] = -inc;
+      alpha[lane] += step_length * (-inc);
     }
   }
 
@@ -955,6 +1056,9 @@ struct b200s_ctx
   int tech = B200S_TECH_NONE;
   int prestress = B200S_PRESTRESS_NONE;
   double* d_gp_hist = nullptr;  // MULF: n_col_eles * ngp * MULF_HIST doubles, device element order
+  double* d_eas_hist = nullptr; // EAS: n_col_eles * hex8eas::hist_size(neas) doubles, device element order
+  double* d_du_row = nullptr;   // "residual displacement" state (struct_calc_recover)
+  double* d_du_col = nullptr;
   // material
   int matkind = -1;
   MatParams mp{};
@@ -1086,6 +1190,17 @@ namespace
     ctx->kev_pending = 0;
   }
 
+  inline int eas_neas(int tech) { return tech == B200S_TECH_EAS_MILD ? 9 : (tech == B200S_TECH_EAS_FULL ? 21 : 0); }
+  // fresh EASHistoryData of every element: all zero (4C_solid_ele_calc_eas_helpers.hpp:98-112)
+  int eas_allocate(b200s_ctx* ctx)
+  {
+    const int64_t n = ctx->n_col_eles * hex8eas::hist_size(eas_neas(ctx->tech));
+    if (to_device(ctx, &ctx->d_eas_hist, (const double*)nullptr, n)) return B200S_ERR_CUDA;
+    CK(cudaMemsetAsync(ctx->d_eas_hist, 0, sizeof(double) * (size_t)(n > 0 ? n : 1), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  }
+
   // fresh MulfHistoryData of every Gauss point (inverse_jacobian of the reference configuration,
   // deformation_gradient = I): what the reference sets up lazily at the first evaluate
   // (4C_solid_ele_calc_mulf.hpp:56-60)
@@ -1104,9 +1219,27 @@ namespace
     return 0;
   }
 
+  template <int MAT, bool STIFF, int NEAS>
+  static int launch_hex8_eas(b200s_ctx* ctx, const EvalArgs& A)
+  {
+    auto kern = k_hex8_eas_eval_assemble<MAT, STIFF, NEAS>;
+    constexpr size_t bytes = hex8_eas_smem_bytes<NEAS>();
+    if (set_smem_attr(kern, bytes)) return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", bytes);
+    if (!ctx->d_eas_hist) return fail(ctx, B200S_ERR_INVALID, "EAS history missing");
+    int64_t grid = (A.n_ele + HEX8_EAS_WARPS - 1) / HEX8_EAS_WARPS;
+    const int64_t cap = (int64_t)ctx->n_sm * 2;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, HEX8_EAS_WARPS * 32, bytes, ctx->stream>>>(A, ctx->d_eas_hist);
+    ctx->launches += 1;
+    return 0;
+  }
+
   template <int MAT, bool STIFF>
   static int launch_hex8(b200s_ctx* ctx, const EvalArgs& A)
   {
+    if (ctx->tech == B200S_TECH_EAS_MILD) return launch_hex8_eas<MAT, STIFF, 9>(ctx, A);
+    if (ctx->tech == B200S_TECH_EAS_FULL) return launch_hex8_eas<MAT, STIFF, 21>(ctx, A);
     if (ctx->tech == B200S_TECH_FBAR)
     {
       auto kern = k_hex8_eval_assemble<MAT, STIFF, 1>;
@@ -1253,7 +1386,7 @@ extern "C"
     if (ctx->zero_stream) cudaStreamDestroy(ctx->zero_stream);
     dfree(ctx->d_u_row), dfree(ctx->d_u_col), dfree(ctx->d_send_lid), dfree(ctx->d_recv_lid);
     dfree(ctx->d_sendbuf), dfree(ctx->d_recvbuf), dfree(ctx->d_err);
-    dfree(ctx->d_gp_hist);
+    dfree(ctx->d_gp_hist), dfree(ctx->d_eas_hist), dfree(ctx->d_du_row), dfree(ctx->d_du_col);
     dfree(ctx->d_hyper), dfree(ctx->d_dN_gp), dfree(ctx->d_w), dfree(ctx->d_dN_cen), dfree(ctx->d_N_mass);
     dfree(ctx->d_dN_mass), dfree(ctx->d_w_mass), dfree(ctx->d_ele_is_row), dfree(ctx->d_mass);
     dfree(ctx->d_f_inertia), dfree(ctx->d_acc_row), dfree(ctx->d_acc_col), dfree(ctx->d_energy);
@@ -1312,14 +1445,17 @@ extern "C"
         to_device(ctx, &ctx->d_w_mass, T.w_mass.data(), (int64_t)T.w_mass.size()))
       return B200S_ERR_CUDA;
     CK(cudaStreamSynchronize(ctx->stream));  // T is a local
-    dfree(ctx->d_ele_is_row), dfree(ctx->d_acc_col), dfree(ctx->d_gp_hist);
+    dfree(ctx->d_ele_is_row), dfree(ctx->d_acc_col), dfree(ctx->d_gp_hist), dfree(ctx->d_eas_hist);
+    dfree(ctx->d_du_col);
     if (ctx->prestress == B200S_PRESTRESS_MULF && mulf_allocate(ctx)) return B200S_ERR_CUDA;
+    if (eas_neas(ctx->tech) && eas_allocate(ctx)) return B200S_ERR_CUDA;
     if (celltype == B200S_HEX8)
     {
       Hex8Const h;
       memcpy(h.dN_gp, T.dN_gp.data(), sizeof h.dN_gp);
       memcpy(h.dN_node, T.dN_node.data(), sizeof h.dN_node);
       memcpy(h.w, T.w.data(), sizeof h.w);
+      memcpy(h.xi_gp, T.xi_gp.data(), sizeof h.xi_gp);
       CK(cudaMemcpyToSymbolAsync(c_hex8, &h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
       CK(cudaStreamSynchronize(ctx->stream));
     }
@@ -1400,13 +1536,21 @@ extern "C"
     if (prestress_technology == B200S_PRESTRESS_MULF && element_technology != B200S_TECH_NONE)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "MULF prestress with element technology %d has no device kernel",
           element_technology);
-    if (element_technology != B200S_TECH_NONE && element_technology != B200S_TECH_FBAR)
+    if (element_technology < B200S_TECH_NONE || element_technology > B200S_TECH_EAS_FULL)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "element technology %d has no device kernel",
           element_technology);
-    // the reference offers F-bar for hex8 (and pyramid5) only (4C_solid_ele_factory_lib.hpp)
-    if (element_technology == B200S_TECH_FBAR && ctx->celltype >= 0 && ctx->celltype != B200S_HEX8)
-      return fail(ctx, B200S_ERR_UNSUPPORTED, "F-bar is a hex8 technology");
+    // the reference offers F-bar and EAS for hex8 only among the device cell types
+    // (4C_solid_ele_factory_lib.hpp)
+    if (element_technology != B200S_TECH_NONE && ctx->celltype >= 0 && ctx->celltype != B200S_HEX8)
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "F-bar and EAS are hex8 technologies");
+    const bool eas_fresh = eas_neas(element_technology) != eas_neas(ctx->tech) || !ctx->d_eas_hist;
     ctx->tech = element_technology;
+    if (!eas_neas(ctx->tech)) dfree(ctx->d_eas_hist);
+    if (eas_neas(ctx->tech) && eas_fresh && ctx->celltype >= 0)
+    {
+      cudaSetDevice(ctx->device);
+      if (eas_allocate(ctx)) return B200S_ERR_CUDA;
+    }
     const bool fresh = prestress_technology == B200S_PRESTRESS_MULF && ctx->prestress != B200S_PRESTRESS_MULF;
     ctx->prestress = prestress_technology;
     if (prestress_technology != B200S_PRESTRESS_MULF) dfree(ctx->d_gp_hist);
@@ -2076,6 +2220,8 @@ extern "C"
   {
     if (ctx->celltype < 0 || ctx->matkind < 0)
       return fail(ctx, B200S_ERR_INVALID, "set_mesh and set_material must precede this action");
+    if (eas_neas(ctx->tech))
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "stress / energy output of EAS elements stays on the CPU path");
     PostArgs P;
     P.X = ctx->dX, P.u = ctx->d_u_col, P.conn = ctx->dconn, P.per_ele_param = ctx->d_per_ele;
     P.ele_id = ctx->d_ele_id, P.ele_is_row = ctx->d_ele_is_row;
@@ -2185,26 +2331,65 @@ extern "C"
     return ctx->n_col_eles * ctx->ngp * MULF_HIST;
   }
 
-  static int history_copy(b200s_ctx* ctx, double* caller, int to_caller)
+  // ---- EAS: struct_calc_recover and the element history ---------------------------------------------
+  int b200s_recover(b200s_ctx* ctx, const double* du_row, double step_length)
+  {
+    if (!ctx || !du_row) return B200S_ERR_INVALID;
+    if (ctx->n_rows <= 0) return fail(ctx, B200S_ERR_INVALID, "set_graph must precede recover");
+    const int neas = eas_neas(ctx->tech);
+    if (!neas) return B200S_OK;  // formulations without condensed variables: nothing to recover
+    if (!ctx->d_eas_hist) return fail(ctx, B200S_ERR_INVALID, "EAS history missing");
+    cudaSetDevice(ctx->device);
+    if (!ctx->d_du_row && to_device(ctx, &ctx->d_du_row, (const double*)nullptr, ctx->n_rows)) return B200S_ERR_CUDA;
+    if (!ctx->d_du_col && to_device(ctx, &ctx->d_du_col, (const double*)nullptr, 3 * ctx->n_col_nodes))
+      return B200S_ERR_CUDA;
+    if (du_row != ctx->d_du_row)
+      CK(cudaMemcpyAsync(ctx->d_du_row, du_row, sizeof(double) * (size_t)ctx->n_rows, cudaMemcpyDefault, ctx->stream));
+    const int rc = import_row_to_col(ctx, ctx->d_du_row, ctx->d_du_col, false);
+    if (rc) return rc;
+    const unsigned grid = nblk(32 * ctx->n_col_eles, 128);
+    if (grid)
+    {
+      if (neas == 9)
+        k_eas_recover<9><<<grid, 128, 0, ctx->stream>>>(ctx->n_col_eles, ctx->dconn, ctx->d_du_col, step_length,
+            ctx->d_eas_hist);
+      else
+        k_eas_recover<21><<<grid, 128, 0, ctx->stream>>>(ctx->n_col_eles, ctx->dconn, ctx->d_du_col, step_length,
+            ctx->d_eas_hist);
+      ctx->launches += 1;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return B200S_OK;
+  }
+
+  int64_t b200s_element_history_size(const b200s_ctx* ctx)
+  {
+    if (!ctx || !eas_neas(ctx->tech)) return 0;
+    return ctx->n_col_eles * hex8eas::hist_size(eas_neas(ctx->tech));
+  }
+
+  static int history_copy(b200s_ctx* ctx, double* caller, int to_caller, int element_level = 0)
   {
     if (!ctx || !caller) return B200S_ERR_INVALID;
-    if (ctx->prestress != B200S_PRESTRESS_MULF || !ctx->d_gp_hist)
-      return fail(ctx, B200S_ERR_INVALID, "the element block has no Gauss-point history");
+    double* d_hist = element_level ? ctx->d_eas_hist : ctx->d_gp_hist;
+    if (!d_hist || (element_level ? !eas_neas(ctx->tech) : ctx->prestress != B200S_PRESTRESS_MULF))
+      return fail(ctx, B200S_ERR_INVALID, "the element block has no %s history", element_level ? "element" : "Gauss-point");
     cudaSetDevice(ctx->device);
-    const int64_t n = b200s_gp_history_size(ctx);
-    const int per_ele = ctx->ngp * MULF_HIST;
+    const int64_t n = element_level ? b200s_element_history_size(ctx) : b200s_gp_history_size(ctx);
+    const int per_ele = element_level ? hex8eas::hist_size(eas_neas(ctx->tech)) : ctx->ngp * MULF_HIST;
     double* tmp = nullptr;
     CK(cudaMalloc((void**)&tmp, sizeof(double) * (size_t)(n ? n : 1)));
     int rc = B200S_OK;
     if (to_caller)
     {
-      k_hist_permute<<<nblk(n), 256, 0, ctx->stream>>>(ctx->n_col_eles, per_ele, ctx->d_ele_id, ctx->d_gp_hist, tmp, 1);
+      k_hist_permute<<<nblk(n), 256, 0, ctx->stream>>>(ctx->n_col_eles, per_ele, ctx->d_ele_id, d_hist, tmp, 1);
       if (cudaMemcpyAsync(caller, tmp, sizeof(double) * (size_t)n, cudaMemcpyDefault, ctx->stream)) rc = B200S_ERR_CUDA;
     }
     else
     {
       if (cudaMemcpyAsync(tmp, caller, sizeof(double) * (size_t)n, cudaMemcpyDefault, ctx->stream)) rc = B200S_ERR_CUDA;
-      k_hist_permute<<<nblk(n), 256, 0, ctx->stream>>>(ctx->n_col_eles, per_ele, ctx->d_ele_id, tmp, ctx->d_gp_hist, 0);
+      k_hist_permute<<<nblk(n), 256, 0, ctx->stream>>>(ctx->n_col_eles, per_ele, ctx->d_ele_id, tmp, d_hist, 0);
     }
     ctx->launches += 1;
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = B200S_ERR_CUDA;
@@ -2215,6 +2400,11 @@ extern "C"
   int b200s_set_gp_history(b200s_ctx* ctx, const double* hist_in)
   {
     return history_copy(ctx, const_cast<double*>(hist_in), 0);
+  }
+  int b200s_get_element_history(b200s_ctx* ctx, double* hist_out) { return history_copy(ctx, hist_out, 1, 1); }
+  int b200s_set_element_history(b200s_ctx* ctx, const double* hist_in)
+  {
+    return history_copy(ctx, const_cast<double*>(hist_in), 0, 1);
   }
 
   // ---- the step after the path: Dirichlet conditions and products on the device ---------------------

@@ -33,6 +33,7 @@ namespace b200s
     std::vector<double> w_mass;   // [ngp_mass]
     std::vector<double> N_gp;     // [ngp][nn] values at the stiffness rule's points
     std::vector<double> dN_cen;   // [nn][3] derivatives at the element centroid (F-bar, EAS)
+    std::vector<double> xi_gp;    // [ngp][3] parameter coordinates of the stiffness rule's points (EAS)
   };
 
   namespace detail
@@ -176,6 +177,7 @@ namespace b200s
     T.dN_node.resize((size_t)T.nn * T.nn * 3);
     const double(*nc)[3] = celltype == 2 ? detail::tet_nodes() : hc;
     for (int k = 0; k < T.nn; ++k) detail::deriv1(celltype, nc[k], &T.dN_node[(size_t)k * T.nn * 3]);
+    T.xi_gp = gxi;
     T.N_gp.resize((size_t)T.ngp * T.nn);
     for (int q = 0; q < T.ngp; ++q) detail::shape0(celltype, &gxi[3 * q], &T.N_gp[(size_t)q * T.nn]);
     // mass rule

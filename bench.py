@@ -48,6 +48,19 @@ WORKLOADS = {
                       flops=63.8e3 + 8 * (1152 + 576 + 288 + 72 + 40) + 600, bytes=2304.0,
                       kernel="k_hex8_eval_assemble<COUP_NEOHOOKE,STIFF,FBAR>", default_n=100,
                       metric="hex8 F-bar Neo-Hooke element evaluate+assemble (force + tangent stiffness into CSR), FP64"),
+    # Section 8(f) row 1: EAS hex8 on the config-2 mesh.  Model = hex8 model + per Gauss point C*Mtilde (72 n),
+    # Kaa (12 n^2), Kda (288 n), s (12 n) and per element the inverse (2 n^3), Kda*Kaa^-1 (48 n^2), the
+    # condensed stiffness (1152 n) and force (48 n), n = 9 / 21 enhanced strain parameters.
+    "hex8_eas_mild": dict(config="2 mesh, TECH eas_mild (SURVEY 8f.1)", cell="HEX8", mat="MAT_COUP_NEOHOOKE",
+                          par=[200.0, 0.25], matname="CoupNeoHooke (E=200, nu=0.25), EAS mild", tech="TECH_EAS_MILD",
+                          flops=63.8e3 + 8 * 4320 + 16146, bytes=2304.0 + 2 * 8 * 324,
+                          kernel="k_hex8_eas_eval_assemble<COUP_NEOHOOKE,STIFF,9>", default_n=100,
+                          metric="hex8 EAS (mild) Neo-Hooke element evaluate+assemble (force + tangent stiffness into CSR), FP64"),
+    "hex8_eas_full": dict(config="2 mesh, TECH eas_full (SURVEY 8f.1)", cell="HEX8", mat="MAT_COUP_NEOHOOKE",
+                          par=[200.0, 0.25], matname="CoupNeoHooke (E=200, nu=0.25), EAS full", tech="TECH_EAS_FULL",
+                          flops=63.8e3 + 8 * 13104 + 64890, bytes=2304.0 + 2 * 8 * 1008,
+                          kernel="k_hex8_eas_eval_assemble<COUP_NEOHOOKE,STIFF,21>", default_n=100,
+                          metric="hex8 EAS (full) Neo-Hooke element evaluate+assemble (force + tangent stiffness into CSR), FP64"),
     "tet10": dict(config="4", cell="TET10", mat="MAT_ISO_VOL", par=[1.0, 1000.0],
                   matname="IsoNeoHooke mu=1 + VolSussmanBathe kappa=1000", flops=43.3e3, bytes=3300.0,
                   kernel="k_tet10_eval_assemble<ISO_VOL,STIFF>", default_n=87,
@@ -172,6 +185,7 @@ class CpuArm:
         self.tech = getattr(orc, wl.get("tech", "TECH_NONE"))
         if self.tech != orc.TECH_NONE:  # oracle/_ref covers the displacement-based formulation only
             self.kind, self.impl = "port", "oracle"
+        self.hist = None
         if wl["cell"] == "TET10":
             X, conn = b200.mesh.unstructured_tet10(n_sample)
             self.rm = b200.partition.serial_mesh(b200.mesh.TET10, X, conn)
@@ -184,13 +198,17 @@ class CpuArm:
         self.graph = orc.build_graph(self.ct, self.rm.conn, self.rm.node_row_lid, self.rm.node_col_lid,
                                      self.rm.n_row_nodes)
         self.n_sample = n_sample
+        if self.tech in (orc.TECH_EAS_MILD, orc.TECH_EAS_FULL):
+            self.hist = orc.eas_new_history(self.tech, self.rm.n_col_eles)
 
     def step(self, threads):
+        if self.hist is not None:
+            threads = 1  # the oracle's history-carrying formulations are evaluated by one thread
         rm, orc = self.rm, self.orc
         t = time.perf_counter()
         orc.evaluate_assemble(self.ct, self.mk, self.wl["par"], rm.conn, rm.X.ravel(), self.u.ravel(),
                               rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, self.graph[0], self.graph[1],
-                              nthreads=threads, impl=self.impl, tech=self.tech)
+                              nthreads=threads, impl=self.impl, tech=self.tech, hist=self.hist)
         return time.perf_counter() - t
 
     def describe(self):
@@ -199,10 +217,17 @@ class CpuArm:
                 f"owner-computes assembly")
 
 
+def cpu_threads(wl, threads):
+    """History-carrying formulations (EAS) run on one thread in the oracle."""
+    return 1 if "EAS" in wl.get("tech", "") else threads
+
+
 def cpu_sample_size(wl, threads, target_s):
     """Mesh edge parameter so that one CPU step takes about target_s (hex8: 33k elements/s/thread with
     oracle/_ref measured; scaled by the flop model for the other cells)."""
+    threads = cpu_threads(wl, threads)
     rate = {"HEX8": 30e3, "TET10": 7e3, "HEX27": 1.3e3}[wl["cell"]]  # elements/s/thread, measured
+    rate *= 63.8e3 / wl["flops"] if wl["cell"] == "HEX8" else 1.0
     ne = rate * max(threads, 1) * 0.7 * target_s
     if wl["cell"] == "TET10":
         ne /= 6.0
@@ -229,7 +254,8 @@ def run_reference(args):
         "config": {"workload": f"BASELINE config {wl['config']} ({wl['cell'].lower()}, {wl['matname']}); "
                                "each step is a bounded sample: " + arm.describe(),
                    "l2": "n/a (CPU)"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": arm.kind, "sample": arm.describe()},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cpu_threads(wl, threads), "kind": arm.kind,
+                         "sample": arm.describe()},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -389,7 +415,7 @@ def run_b200(args):
             arm = CpuArm(wl, cpu_sample_size(wl, threads, 3.0))
             arm.step(threads)
             ts = [arm.step(threads) for _ in range(3)]
-            cpu = {"value": arm.rm.n_col_eles / float(np.median(ts)), "unit": UNIT, "cores": threads,
+            cpu = {"value": arm.rm.n_col_eles / float(np.median(ts)), "unit": UNIT, "cores": cpu_threads(wl, threads),
                    "kind": arm.kind, "sample": arm.describe() + ", median of 3 after 1 warm-up"}
             arm1 = CpuArm(wl, cpu_sample_size(wl, 1, 2.0))      # also P = 1
             arm1.step(1)

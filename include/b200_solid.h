@@ -108,8 +108,8 @@ extern "C"
   {
     B200S_TECH_NONE = 0,
     B200S_TECH_FBAR = 1,     /* hex8: 4C_solid_ele_calc_fbar.hpp */
-    B200S_TECH_EAS_MILD = 2, /* CPU path */
-    B200S_TECH_EAS_FULL = 3  /* CPU path */
+    B200S_TECH_EAS_MILD = 2, /* hex8, 9 enhanced strain parameters: 4C_solid_ele_calc_eas.hpp */
+    B200S_TECH_EAS_FULL = 3  /* hex8, 21 parameters */
   } b200s_element_technology;
   typedef enum
   {
@@ -302,6 +302,21 @@ extern "C"
   int64_t b200s_gp_history_size(const b200s_ctx* ctx);
   int b200s_get_gp_history(b200s_ctx* ctx, double* hist_out);
   int b200s_set_gp_history(b200s_ctx* ctx, const double* hist_in);
+
+  /* ---- EAS (TECH eas_mild / eas_full): condensed element variables ------------------------------------ */
+  /* struct_calc_recover (Solid::ModelEvaluator::Structure::run_recover, model_evaluator_structure.cpp:
+   * 1482-1509; SolidEleCalc::recover default step, 4C_solid_ele_calc.cpp:284-314): after every Newton
+   * update the caller passes the Newton direction ("residual displacement", dof row map, [host|dev]) and
+   * the step length; every element updates alpha += step * (-Kaa^-1 (s + Kda^T du)) from the matrices its
+   * last evaluate stored.  A no-op (B200S_OK) for formulations without condensed variables.  The
+   * line-search correction (correct_condensed_variables_for_linesearch) is not on the device path. */
+  int b200s_recover(b200s_ctx* ctx, const double* du_row, double step_length);
+  /* Element history of the block = what EASFormulation::pack / unpack write for restart
+   * (4C_solid_ele_calc_eas.hpp:266-288, without old_step_length): per column element (caller's order)
+   * alpha_inc[n], alpha[n], s[n], invKaa[n*n], Kda[24*n], matrices column-major, n = 9 or 21. */
+  int64_t b200s_element_history_size(const b200s_ctx* ctx);
+  int b200s_get_element_history(b200s_ctx* ctx, double* hist_out);
+  int b200s_set_element_history(b200s_ctx* ctx, const double* hist_in);
 
   /* ---- the step after the path, on the device (K never returns to the host) ------------------------ */
   /* SparseMatrix::apply_dirichlet(dbctoggle, diagonalblock), in-place branch

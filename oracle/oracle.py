@@ -24,7 +24,7 @@ SUM.update({"COUP_ANISOEXPO": 100, "FIBER": 101})  # oracle only, see solid_orac
 STRESS_NONE, STRESS_2PK, STRESS_CAUCHY = 0, 1, 2
 STRAIN_NONE, STRAIN_GL, STRAIN_EA = 0, 1, 2
 ACTION_FORCE, ACTION_FORCE_STIFF = 0, 1
-TECH_NONE, TECH_FBAR, TECH_MULF = 0, 1, 2
+TECH_NONE, TECH_FBAR, TECH_MULF, TECH_EAS_MILD, TECH_EAS_FULL = 0, 1, 2, 3, 4
 MULF_HIST = 19
 
 _dp = C.POINTER(C.c_double)
@@ -79,6 +79,8 @@ def lib():
         L.orc_evaluate_assemble_hist.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int,
                                                  C.c_int64, _ip, C.c_int64, _dp, _dp, _ip, _ip,
                                                  C.c_int64, _lp, _ip, _dp, _dp, C.c_int, _dp]
+        L.orc_eas_hist_size.restype = C.c_int64
+        L.orc_eas_recover.argtypes = [C.c_int, C.c_int64, _ip, _dp, C.c_double, _dp]
         L.orc_mulf_init_history.argtypes = [C.c_int64, _dp]
         L.orc_update_prestress.argtypes = [C.c_int, C.c_int64, _ip, _dp, _dp, _dp]
         L.orc_element_tech.argtypes = [C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp, _dp, _dp]
@@ -387,3 +389,16 @@ def update_prestress(ct, conn, X, u_col, hist):
     u_col = np.ascontiguousarray(u_col, dtype=np.float64)
     assert hist.dtype == np.float64 and hist.flags["C_CONTIGUOUS"]
     lib().orc_update_prestress(ct, len(conn), _i(conn), _d(X), _d(u_col), _d(hist))
+
+
+def eas_new_history(tech, n_ele):
+    """Fresh EASHistoryData of every element: zeros (n_ele, orc_eas_hist_size)."""
+    return np.zeros((n_ele, lib().orc_eas_hist_size(tech)))
+
+
+def eas_recover(tech, conn, du_col, hist, step_length=1.0):
+    """struct_calc_recover (default step): in place on hist."""
+    conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, 8)
+    du_col = np.ascontiguousarray(du_col, dtype=np.float64)
+    assert hist.dtype == np.float64 and hist.flags["C_CONTIGUOUS"]
+    lib().orc_eas_recover(tech, len(conn), _i(conn), _d(du_col), float(step_length), _d(hist))

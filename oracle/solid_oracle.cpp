@@ -1167,9 +1167,253 @@ namespace
     }
   }
 
+
+  // ---- SolidEleCalc<hex8, EASFormulation<eastype_h8_9 | eastype_h8_21>>
+  //      (src/solid_ele/4C_solid_ele_calc_eas.hpp:44-290, 4C_solid_ele_calc_eas_helpers.hpp,
+  //       driver 4C_solid_ele_calc.cpp:137-314)
+  // Element history (EASHistoryData / EasIterationData, in the order pack() writes it, eas.hpp:266-275),
+  // orc_eas_hist_size(neas) doubles: alpha_inc[neas], alpha[neas], s[neas], invKaa[neas x neas],
+  // Kda[24 x neas] (both column-major).  A fresh history is all zero.
+  int eas_num(int tech) { return tech == ORC_TECH_EAS_MILD ? 9 : 21; }
+
+  // dense inverse by Gauss-Jordan with partial pivoting (the reference calls LAPACK getrf/getri through
+  // FixedSizeSerialDenseSolver::invert; same operator up to round-off)
+  void dense_inverse(int n, double* A /*column-major, in place*/)
+  {
+    std::vector<double> M(n * 2 * n, 0.0);  // [A | I], row-major
+    for (int r = 0; r < n; ++r)
+    {
+      for (int c = 0; c < n; ++c) M[r * 2 * n + c] = A[r + n * c];
+      M[r * 2 * n + n + r] = 1.0;
+    }
+    for (int c = 0; c < n; ++c)
+    {
+      int piv = c;
+      for (int r = c + 1; r < n; ++r)
+        if (std::fabs(M[r * 2 * n + c]) > std::fabs(M[piv * 2 * n + c])) piv = r;
+      if (piv != c)
+        for (int k = 0; k < 2 * n; ++k) std::swap(M[c * 2 * n + k], M[piv * 2 * n + k]);
+      const double d = 1.0 / M[c * 2 * n + c];
+      for (int k = 0; k < 2 * n; ++k) M[c * 2 * n + k] *= d;
+      for (int r = 0; r < n; ++r)
+      {
+        if (r == c) continue;
+        const double f = M[r * 2 * n + c];
+        if (f != 0.0)
+          for (int k = 0; k < 2 * n; ++k) M[r * 2 * n + k] -= f * M[c * 2 * n + k];
+      }
+    }
+    for (int r = 0; r < n; ++r)
+      for (int c = 0; c < n; ++c) A[r + n * c] = M[r * 2 * n + n + c];
+  }
+
+  // evaluate_voigt_transformation_matrix at the centroid (4C_solid_ele_calc_lib.hpp:1451-1518):
+  // T0invT (6x6 column-major, strain-like Voigt), jacobian_(a,b) = J[a + 3 b]
+  void eas_centroid_transformation(int ct, const double* X, double* T0invT, double& detJ0)
+  {
+    const int n = nnodes(ct);
+    double N[MAXN], dN[3 * MAXN];
+    JacMap jm;
+    const double xi0[3] = {0.0, 0.0, 0.0};
+    shape(ct, xi0, N, dN);
+    jacobian_mapping(n, dN, X, jm);
+    detJ0 = jm.det;
+    auto J = [&](int a, int b) { return jm.J[a + 3 * b]; };
+    double* T = T0invT;
+    auto at = [&](int r, int c) -> double& { return T[r + 6 * c]; };
+    for (int c = 0; c < 3; ++c)
+    {
+      at(0, c) = J(0, c) * J(0, c);
+      at(1, c) = J(1, c) * J(1, c);
+      at(2, c) = J(2, c) * J(2, c);
+      at(3, c) = 2 * J(0, c) * J(1, c);
+      at(4, c) = 2 * J(1, c) * J(2, c);
+      at(5, c) = 2 * J(0, c) * J(2, c);
+    }
+    const int pa[3] = {0, 1, 0}, pb[3] = {1, 2, 2};  // columns 3,4,5 pair the jacobian columns (0,1),(1,2),(0,2)
+    for (int q = 0; q < 3; ++q)
+    {
+      const int a = pa[q], b = pb[q], c = 3 + q;
+      at(0, c) = J(0, a) * J(0, b);
+      at(1, c) = J(1, a) * J(1, b);
+      at(2, c) = J(2, a) * J(2, b);
+      at(3, c) = J(0, a) * J(1, b) + J(1, a) * J(0, b);
+      at(4, c) = J(1, a) * J(2, b) + J(2, a) * J(1, b);
+      at(5, c) = J(0, a) * J(2, b) + J(2, a) * J(0, b);
+    }
+    dense_inverse(6, T);
+  }
+
+  // evaluate_eas_shape_functions_parameter_space (eas_helpers.hpp:205-275): M 6 x neas column-major
+  void eas_shape_functions(int neas, const double* xi, double* M)
+  {
+    std::fill(M, M + 6 * neas, 0.0);
+    auto at = [&](int r, int c) -> double& { return M[r + 6 * c]; };
+    at(0, 0) = xi[0], at(1, 1) = xi[1], at(2, 2) = xi[2];
+    at(3, 3) = xi[0], at(3, 4) = xi[1], at(4, 5) = xi[1], at(4, 6) = xi[2], at(5, 7) = xi[0], at(5, 8) = xi[2];
+    if (neas == 21)
+    {
+      at(0, 15) = xi[0] * xi[1], at(0, 16) = xi[0] * xi[2];
+      at(1, 17) = xi[0] * xi[1], at(1, 18) = xi[1] * xi[2];
+      at(2, 19) = xi[0] * xi[2], at(2, 20) = xi[1] * xi[2];
+      at(3, 9) = xi[0] * xi[2], at(3, 10) = xi[1] * xi[2];
+      at(4, 11) = xi[0] * xi[1], at(4, 12) = xi[0] * xi[2];
+      at(5, 13) = xi[0] * xi[1], at(5, 14) = xi[1] * xi[2];
+    }
+  }
+
+  // Gauss-point kinematics of the EAS formulation (evaluate_eas_kinematics, eas_helpers.hpp:405-448):
+  // Mtilde = detJ0/detJ T0invT M, E_enh = E(F) + stress-like(Mtilde alpha)
+  void eas_point(int neas, const double* T0invT, double detJ0, double detJ, const double* xi,
+      const double* alpha, const double* F, double* Mtilde, double* E_enh)
+  {
+    double M[6 * 21];
+    eas_shape_functions(neas, xi, M);
+    for (int c = 0; c < neas; ++c)
+      for (int r = 0; r < 6; ++r)
+      {
+        double v = 0.0;
+        for (int k = 0; k < 6; ++k) v += T0invT[r + 6 * k] * M[k + 6 * c];
+        Mtilde[r + 6 * c] = (detJ0 / detJ) * v;
+      }
+    double C[6], E[6];
+    cauchy_green(F, C, E);
+    for (int r = 0; r < 6; ++r)
+    {
+      double v = 0.0;
+      for (int c = 0; c < neas; ++c) v += Mtilde[r + 6 * c] * alpha[c];
+      E_enh[r] = E[r] + (r < 3 ? v : 0.5 * v);  // Voigt::Strains::to_stress_like
+    }
+  }
+
+  int element_eas(int ct, int tech, int matkind, const double* par, int action, const double* X,
+      const double* u, double* hist, double* Ke, double* fe)
+  {
+    if (ct != ORC_HEX8) return 2;
+    const int n = nnodes(ct), nd = 3 * n, ng = ngauss(ct), neas = eas_num(tech);
+    double* alpha = hist + neas;
+    double* s = hist + 2 * neas;
+    double* invKaa = hist + 3 * neas;
+    double* Kda = invKaa + neas * neas;
+    double N[MAXN], dN[3 * MAXN];
+    JacMap jm;
+    if (Ke) std::memset(Ke, 0, sizeof(double) * nd * nd);
+    std::memset(fe, 0, sizeof(double) * nd);
+    // prepare(): centroid transformation (eas.hpp:66-70)
+    double T0invT[36], detJ0;
+    eas_centroid_transformation(ct, X, T0invT, detJ0);
+    // reset_condensed_variable_integration (eas.hpp:168-175)
+    std::fill(invKaa, invKaa + neas * neas, 0.0);
+    std::fill(Kda, Kda + nd * neas, 0.0);
+    std::fill(s, s + neas, 0.0);
+    int err = 0;
+    for (int k = 0; k < n; ++k)
+    {
+      double xi[3];
+      node_ref(ct, k, xi);
+      shape(ct, xi, N, dN);
+      jacobian_mapping(n, dN, X, jm);
+      if (!(jm.det > 0)) err = 1;
+    }
+    if (err) return 1;
+    double gxi[3 * MAXN], gw[MAXN];
+    gauss(ct, gxi, gw);
+    std::vector<double> B(6 * nd), cmatM(6 * neas), Mt(6 * neas);
+    for (int gp = 0; gp < ng; ++gp)
+    {
+      shape(ct, gxi + 3 * gp, N, dN);
+      jacobian_mapping(n, dN, X, jm);
+      const double fac = jm.det * gw[gp];
+      double F[9], E[6], S[6], Cm[36];
+      deformation_gradient(n, u, jm, F);
+      strain_gradient(n, jm, F, B.data());
+      eas_point(neas, T0invT, detJ0, jm.det, gxi + 3 * gp, alpha, F, Mt.data(), E);
+      // the materials on this path use the GL strain only; the enhanced deformation gradient
+      // (compute_deformation_gradient_from_gl_strains) is not needed by them
+      material(matkind, par, F, E, S, Cm);
+      // integrate_eas (eas_helpers.hpp:352-371)
+      for (int c = 0; c < neas; ++c)
+        for (int r = 0; r < 6; ++r)
+        {
+          double v = 0.0;
+          for (int k = 0; k < 6; ++k) v += Cm[r + 6 * k] * Mt[k + 6 * c];
+          cmatM[r + 6 * c] = v;
+        }
+      for (int c = 0; c < neas; ++c)
+      {
+        for (int r = 0; r < neas; ++r)
+        {
+          double v = 0.0;
+          for (int k = 0; k < 6; ++k) v += Mt[k + 6 * r] * cmatM[k + 6 * c];
+          invKaa[r + neas * c] += fac * v;
+        }
+        for (int r = 0; r < nd; ++r)
+        {
+          double v = 0.0;
+          for (int k = 0; k < 6; ++k) v += B[k + 6 * r] * cmatM[k + 6 * c];
+          Kda[r + nd * c] += fac * v;
+        }
+        double v = 0.0;
+        for (int k = 0; k < 6; ++k) v += Mt[k + 6 * c] * S[k];
+        s[c] += fac * v;
+      }
+      add_force(n, jm, F, S, fac, fe);
+      if (action == ORC_ACTION_FORCE_STIFF && Ke) add_stiffness_bop(n, jm, F, S, Cm, fac, Ke);
+    }
+    // prepare_condensed_contribution (eas.hpp:188-203) and the two condensed contributions (:245-263)
+    dense_inverse(neas, invKaa);
+    std::vector<double> mKdaiKaa(nd * neas);
+    for (int r = 0; r < nd; ++r)
+      for (int c = 0; c < neas; ++c)
+      {
+        double v = 0.0;
+        for (int k = 0; k < neas; ++k) v += Kda[r + nd * k] * invKaa[k + neas * c];
+        mKdaiKaa[r + nd * c] = -v;
+      }
+    for (int r = 0; r < nd; ++r)
+    {
+      double v = 0.0;
+      for (int c = 0; c < neas; ++c) v += mKdaiKaa[r + nd * c] * s[c];
+      fe[r] += v;
+    }
+    if (action == ORC_ACTION_FORCE_STIFF && Ke)
+      for (int r = 0; r < nd; ++r)
+        for (int c = 0; c < nd; ++c)
+        {
+          double v = 0.0;
+          for (int k = 0; k < neas; ++k) v += mKdaiKaa[r + nd * k] * Kda[c + nd * k];
+          Ke[r + nd * c] += v;
+        }
+    return 0;
+  }
+
+  // SolidEleCalc::recover, default step (4C_solid_ele_calc.cpp:284-314; update_alpha,
+  // eas_helpers.hpp:166-190): alpha_inc = -invKaa (s + Kda^T du), alpha += step_length alpha_inc
+  void element_eas_recover(int tech, const double* du, double step_length, double* hist)
+  {
+    const int neas = eas_num(tech), nd = 24;
+    double* alpha_inc = hist;
+    double* alpha = hist + neas;
+    const double* s = hist + 2 * neas;
+    const double* invKaa = hist + 3 * neas;
+    const double* Kda = invKaa + neas * neas;
+    std::vector<double> tmp(s, s + neas);
+    for (int c = 0; c < neas; ++c)
+      for (int r = 0; r < nd; ++r) tmp[c] += Kda[r + nd * c] * du[r];
+    for (int r = 0; r < neas; ++r)
+    {
+      double v = 0.0;
+      for (int c = 0; c < neas; ++c) v += invKaa[r + neas * c] * tmp[c];
+      alpha_inc[r] = -v;
+    }
+    for (int r = 0; r < neas; ++r) alpha[r] += step_length * alpha_inc[r];
+  }
+
   int element_tech(int ct, int tech, int matkind, const double* par, int action, const double* X,
       const double* u, double* Ke, double* fe, double* hist = nullptr)
   {
+    if (tech == ORC_TECH_EAS_MILD || tech == ORC_TECH_EAS_FULL)
+      return element_eas(ct, tech, matkind, par, action, X, u, hist, Ke, fe);
     if (tech == ORC_TECH_MULF) return element_mulf(ct, matkind, par, action, X, u, hist, Ke, fe);
     if (tech == ORC_TECH_FBAR) return element_fbar(ct, matkind, par, action, X, u, Ke, fe);
     return element(ct, matkind, par, action, X, u, Ke, fe);
@@ -1631,6 +1875,26 @@ extern "C"
         nthreads, nullptr);
   }
 
+  int64_t orc_eas_hist_size(int tech)
+  {
+    const int neas = eas_num(tech);
+    return 3 * neas + neas * neas + 24 * neas;
+  }
+  // struct_calc_recover over the column elements with the Newton increment on the column map
+  // (Solid::ModelEvaluator::Structure::run_recover, model_evaluator_structure.cpp:1482-1509)
+  void orc_eas_recover(int tech, int64_t n_ele, const int32_t* conn, const double* du_col,
+      double step_length, double* hist)
+  {
+    const int64_t per = orc_eas_hist_size(tech);
+    double due[24];
+    for (int64_t e = 0; e < n_ele; ++e)
+    {
+      for (int i = 0; i < 8; ++i)
+        for (int d = 0; d < 3; ++d) due[3 * i + d] = du_col[3 * (int64_t)conn[e * 8 + i] + d];
+      element_eas_recover(tech, due, step_length, hist + per * e);
+    }
+  }
+
   void orc_mulf_init_history(int64_t n_points, double* hist)
   {
     for (int64_t p = 0; p < n_points; ++p)
@@ -1668,7 +1932,10 @@ extern "C"
       const int32_t* colind, double* values, double* f, int nthreads, double* hist)
   {
     (void)n_col_nodes;
-    if (tech == ORC_TECH_MULF && hist == nullptr) return -1;
+    const bool needs_hist = tech == ORC_TECH_MULF || tech == ORC_TECH_EAS_MILD || tech == ORC_TECH_EAS_FULL;
+    if (needs_hist && hist == nullptr) return -1;
+    const int64_t hist_per_ele = tech == ORC_TECH_MULF ? (int64_t)ORC_MULF_HIST * ngauss(ct)
+                                                       : (needs_hist ? orc_eas_hist_size(tech) : 0);
     const int n = nnodes(ct), nd = 3 * n;
     if (nthreads < 1) nthreads = 1;
     std::vector<int64_t> bad(nthreads, 0);
@@ -1715,7 +1982,7 @@ extern "C"
         const bool stiff = (action == ORC_ACTION_FORCE_STIFF) && values;
         if (element_tech(ct, tech, matkind, par.data(), action, Xe.data(), ue.data(),
                 stiff ? Ke.data() : nullptr, fe.data(),
-                hist ? hist + (int64_t)ORC_MULF_HIST * ngauss(ct) * e : nullptr))
+                hist ? hist + hist_per_ele * e : nullptr))
         {
           bad[tid]++;
           continue;

@@ -12,6 +12,9 @@ What it writes
           tests/input_files/solid_ele_tet10_Standard_stressout.4C.yaml
   integration_<cell>_mulf.json : MULF prestress inputs tests/input_files/solid_ele_<cell>_Standard_mulf.4C.yaml
         (CoupNeoHooke + CoupAnisoExpo element fibre, PRESTRESSTIME 1) with their nodal displacements
+  integration_hex8_eas_full.json / _eas_mild.json : TECH eas_full / eas_mild hex8 inputs
+        tests/input_files/solid_ele_hex8_Standard_eas_{full_stressout_cauchy_strainout_ea,mild_stressout_2pk_strainout_gl}.4C.yaml
+        (same fibre material) with nodal displacements, stresses and strains
   integration_cooks_fbar.json : Cook's membrane with 64 F-bar hex8 elements
           tests/input_files/sohex8fbar_cooks_nl_new_struc.4C.yaml (dispy of node 162, 1e-8)
   unit_known_answers.json : known answers of unittests/mat/4C_elasthyper_service_test.cpp:36-155,
@@ -108,7 +111,7 @@ def integration_case(cell, rel):
     }
 
 
-def mulf_case(cell, rel):
+def mulf_case(cell, rel, tech=None):
     """MULF prestress ctest input: one element block with MAT_ElastHyper{CoupNeoHooke, CoupAnisoExpo},
     element fibre FIBER1, PRESTRESS MULF until PRESTRESSTIME; known answers = nodal displacements."""
     with open(os.path.join(REF, rel)) as fh:
@@ -121,7 +124,8 @@ def mulf_case(cell, rel):
     eles, fibers = [], []
     for line in y["STRUCTURE ELEMENTS"]:
         tok = line.split()
-        assert tok[1] == "SOLID" and tok[2].lower() == cell and "PRESTRESS_TECH mulf" in line
+        assert tok[1] == "SOLID" and tok[2].lower() == cell
+        assert (f"TECH {tech}" in line) if tech else ("PRESTRESS_TECH mulf" in line)
         k = 3
         conn = []
         while tok[k] != "MAT":
@@ -144,7 +148,23 @@ def mulf_case(cell, rel):
     neu = y["DESIGN SURF NEUMANN CONDITIONS"][0]
     assert dbc["E"] == 1 and neu["E"] == 2
     sd = y["STRUCTURAL DYNAMIC"]
-    assert sd["PRESTRESS"].lower() == "mulf"
+    assert tech or sd["PRESTRESS"].lower() == "mulf"
+    vol = None
+    if "DESIGN VOL NEUMANN CONDITIONS" in y:
+        vn = y["DESIGN VOL NEUMANN CONDITIONS"][0]
+        vol_nodes = sorted(int(re.match(r"NODE\s+(\d+)\s+DVOL\s+(\d+)", l).group(1)) - 1
+                           for l in y["DVOL-NODE TOPOLOGY"]
+                           if int(re.match(r"NODE\s+(\d+)\s+DVOL\s+(\d+)", l).group(2)) == vn["E"])
+        assert vol_nodes == list(range(len(coords)))  # the volume load acts on every element
+        vol = {"ONOFF": vn["ONOFF"], "VAL": vn["VAL"], "FUNCT": vn["FUNCT"]}
+    comp = {"xx": 0, "yy": 1, "zz": 2, "xy": 3, "yz": 4, "xz": 5}
+    expected_stress, expected_strain = [], []
+    for r in y["RESULT DESCRIPTION"]:
+        s = r["STRUCTURE"]
+        for key, lst in (("stress_", expected_stress), ("strain_", expected_strain)):
+            if s["QUANTITY"].startswith(key):
+                lst.append({"node": s["NODE"] - 1, "comp": comp[s["QUANTITY"][-2:]],
+                            "value": float(s["VALUE"]), "tol": float(s["TOLERANCE"])})
     expected = []
     for r in y["RESULT DESCRIPTION"]:
         s = r["STRUCTURE"]
@@ -158,9 +178,10 @@ def mulf_case(cell, rel):
                     "FUNCT1": y["FUNCT1"][0]["SYMBOLIC_FUNCTION_OF_SPACE_TIME"],
                     "FUNCT2": y["FUNCT2"][0]["SYMBOLIC_FUNCTION_OF_SPACE_TIME"]},
         "timestep": float(sd["TIMESTEP"]), "numstep": int(sd["NUMSTEP"]),
-        "prestresstime": float(sd["PRESTRESSTIME"]),
+        "prestresstime": float(sd.get("PRESTRESSTIME", -1.0)), "tech": tech, "vol_neumann": vol,
+        "iostress": y["IO"].get("STRUCT_STRESS"), "iostrain": y["IO"].get("STRUCT_STRAIN"),
         "tolres": float(sd["TOLRES"]), "toldisp": float(sd["TOLDISP"]),
-        "expected_disp": expected,
+        "expected_disp": expected, "expected_stress": expected_stress, "expected_strain": expected_strain,
     }
 
 
@@ -304,6 +325,10 @@ if __name__ == "__main__":
     for cell in ("hex8", "hex27", "tet10"):
         with open(os.path.join(HERE, f"integration_{cell}_mulf.json"), "w") as fh:
             json.dump(mulf_case(cell, f"tests/input_files/solid_ele_{cell}_Standard_mulf.4C.yaml"), fh, indent=1)
+    for tech, rel in (("eas_full", "tests/input_files/solid_ele_hex8_Standard_eas_full_stressout_cauchy_strainout_ea.4C.yaml"),
+                      ("eas_mild", "tests/input_files/solid_ele_hex8_Standard_eas_mild_stressout_2pk_strainout_gl.4C.yaml")):
+        with open(os.path.join(HERE, f"integration_hex8_{tech}.json"), "w") as fh:
+            json.dump(mulf_case("hex8", rel, tech), fh, indent=1)
     with open(os.path.join(HERE, "unit_known_answers.json"), "w") as fh:
         json.dump(unit_known_answers(), fh, indent=1)
     np.savez_compressed(os.path.join(HERE, "ref_elements.npz"), **ref_elements())

@@ -60,8 +60,46 @@ def _rule(kind):
     return x, w
 
 
+def _funct(fid, gp, time):
+    if fid == 1:
+        return time
+    if fid == 2:
+        return (gp[0] + 1) * (gp[1] + 2) * (gp[2] + 3)
+    return 1.0
+
+
+def volume_neumann_load(case, time):
+    """DESIGN VOL NEUMANN CONDITIONS: dead body load integrated with the stiffness Gauss rule, functions
+    evaluated at the reference coordinates of the Gauss point
+    (src/solid_ele/4C_solid_ele_neumann_evaluator.cpp:43-123)."""
+    from oracle import oracle as orc
+    ct = {"hex8": orc.HEX8, "hex27": orc.HEX27, "tet10": orc.TET10}[case["celltype"]]
+    X = np.asarray(case["coords"], float)
+    vn = case["vol_neumann"]
+    gxi, gw = orc.gauss(ct)
+    f = np.zeros(3 * len(X))
+    for conn in case["elements"]:
+        x = X[conn]
+        for xi, w in zip(gxi, gw):
+            N, dN = orc.shape(ct, xi)          # dN[a, k]
+            detJ = np.linalg.det(dN @ x)
+            gp = N @ x
+            for dof in range(3):
+                if vn["ONOFF"][dof]:
+                    fac = vn["VAL"][dof] * _funct(vn["FUNCT"][dof], gp, time) * detJ * w
+                    for a, nid in enumerate(conn):
+                        f[3 * nid + dof] += N[a] * fac
+    return f
+
+
 def neumann_load(case, time):
     """External force vector (3*nnode) of the golden case at total time `time`."""
+    if case.get("vol_neumann"):
+        return _surface_neumann_load(case, time) + volume_neumann_load(case, time)
+    return _surface_neumann_load(case, time)
+
+
+def _surface_neumann_load(case, time):
     cell = case["celltype"]
     X = np.asarray(case["coords"], float)
     nset = set(case["neumann_nodes"])

@@ -11,8 +11,12 @@ from .meshes import csr_to_dense
 from .neumann import neumann_load
 
 
-def solve_case(case, evaluate, max_iter=30, update_prestress=None):
+def solve_case(case, evaluate, max_iter=30, update_prestress=None, recover=None):
     """evaluate(u_flat) -> (rowptr, colind, values, fint). Returns converged displacement (nn,3).
+
+    recover(du_flat): element action struct_calc_recover after every Newton update with the Newton
+    direction as "residual displacement" (Solid::ModelEvaluator::Structure::run_post_compute_x / run_recover,
+    model_evaluator_structure.cpp:1482-1509): condensed element variables (EAS alpha) follow the step.
 
     update_prestress(u_flat): PRESTRESS MULF.  While the time reached by a step is <= PRESTRESSTIME
     (the state has already been advanced when update_step_element runs; confirmed by the known answers:
@@ -38,6 +42,8 @@ def solve_case(case, evaluate, max_iter=30, update_prestress=None):
             du = np.zeros(3 * nn)
             du[free] = np.linalg.solve(K[np.ix_(free, free)], -res[free])
             u += du
+            if recover is not None:
+                recover(du)
             rowptr, colind, values, fint = evaluate(u)
             rnorm = np.linalg.norm((fint - fext)[free])
             ok_r, ok_d = rnorm < case["tolres"], np.linalg.norm(du) < case["toldisp"]

@@ -407,3 +407,35 @@ def orc_calc_stress_mulf(ct, par, rm, us, hist):
             sig = F @ Sf @ F.T / np.linalg.det(F)
             out[e, g] = [sig[0, 0], sig[1, 1], sig[2, 2], sig[0, 1], sig[1, 2], sig[0, 2]]
     return out, None
+
+
+# ------------------------------------------------------------------------------------------------------
+# EAS hex8 (TECH eas_mild / eas_full)
+# ------------------------------------------------------------------------------------------------------
+EAS_TECH = {"eas_mild": orc.TECH_EAS_MILD, "eas_full": orc.TECH_EAS_FULL}
+
+
+@pytest.mark.parametrize("tech", ["eas_mild", "eas_full"])
+def test_eas_known_answers(tech):
+    """RESULT DESCRIPTION displacements (1e-12) of the reference's TECH eas_mild / eas_full hex8 inputs:
+    Newton with struct_calc_recover after every update.  Pins the oracle's EASFormulation restatement
+    (centroid transformation, enhanced strains, static condensation, alpha update)."""
+    case = json.load(open(os.path.join(G, f"integration_hex8_{tech}.json")))
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    nn = len(X)
+    row, col = serial_maps(nn)
+    rowptr, colind = orc.build_graph(orc.HEX8, conn, row, col, nn)
+    par = _mulf_material(case)
+    hist = orc.eas_new_history(EAS_TECH[tech], len(conn))
+
+    def evaluate(u):
+        vals, f, nbad = orc.evaluate_assemble(orc.HEX8, orc.MAT_ELASTHYPER, par, conn, X.ravel(), u, row, col, nn,
+                                              rowptr, colind, tech=EAS_TECH[tech], hist=hist)
+        assert nbad == 0
+        return rowptr, colind, vals, f
+
+    u = solve_case(case, evaluate, recover=lambda du: orc.eas_recover(EAS_TECH[tech], conn, du, hist))
+    assert len(case["expected_disp"]) >= 12
+    for e in case["expected_disp"]:
+        assert abs(u[e["node"], e["dof"]] - e["value"]) < 1e-11, (e, u[e["node"], e["dof"]])
