@@ -224,7 +224,12 @@ namespace b200s
   {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double beta = (first || s[1] == 0.0) ? 0.0 : s[2] / s[1];
+    if (first)
+    {
+      p[i] = z[i];  // p is uninitialised memory here: 0 * NaN would poison it
+      return;
+    }
+    const double beta = (s[1] == 0.0) ? 0.0 : s[2] / s[1];
     p[i] = fma(beta, p[i], z[i]);
   }
   // after the direction update: s[1] = s[2]; s[0] = s[2] = s[3] = 0; history[it] = r.r
