@@ -272,7 +272,8 @@ namespace b200s
     return hex8_table_bytes + 24 * 8 + HEX8_EAS_WARPS * (size_t)((hex8eas::Layout<NEAS>::BYTES + 15) & ~15);
   }
   template <int MAT, bool STIFF, int NEAS>
-  __global__ void __launch_bounds__(HEX8_EAS_WARPS * 32, 2) k_hex8_eas_eval_assemble(const EvalArgs A, double* hist)
+  __global__ void __launch_bounds__(HEX8_EAS_WARPS * 32, 2)
+      k_hex8_eas_eval_assemble(const EvalArgs A, double* hist, const double* t0tab)
   {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* tab_gp = reinterpret_cast<double*>(smem_raw);
@@ -296,8 +297,8 @@ namespace b200s
     for (int64_t e = (int64_t)blockIdx.x * HEX8_EAS_WARPS + warp; e < A.n_ele; e += (int64_t)gridDim.x * HEX8_EAS_WARPS)
     {
       bool neg = false;
-      hex8eas::element<MAT, STIFF, NEAS>(A, sm, nrow, pos, tab_gp, wgt, gxi, lane, e, hist + e * HS, detJ_min,
-          detF_min, neg);
+      hex8eas::element<MAT, STIFF, NEAS>(A, sm, nrow, pos, tab_gp, wgt, gxi, lane, e, hist + e * HS,
+          t0tab + e * hex8eas::T0_STRIDE, detJ_min, detF_min, neg);
       if (__ballot_sync(0xffffffffu, neg))
       {
         ++nbad;
@@ -320,6 +321,16 @@ namespace b200s
         atomicAdd(&A.err->n_neg_jac, (unsigned long long)nbad);
       }
     }
+  }
+
+  // EAS set-up: centroid transformation of every element (reference geometry only)
+  __global__ void __launch_bounds__(128) k_eas_centroid(int64_t n_ele, const int32_t* conn, const double* X, double* t0tab)
+  {
+    __shared__ double aug[4][72];
+    const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (e >= n_ele) return;  // warp-uniform
+    hex8eas::centroid_transformation(X, conn + e * 8, aug[warp], lane, t0tab + e * hex8eas::T0_STRIDE);
   }
 
   // struct_calc_recover, default step (SolidEleCalc::recover, 4C_solid_ele_calc.cpp:284-314; update_alpha,
@@ -1057,6 +1068,7 @@ struct b200s_ctx
   int prestress = B200S_PRESTRESS_NONE;
   double* d_gp_hist = nullptr;  // MULF: n_col_eles * ngp * MULF_HIST doubles, device element order
   double* d_eas_hist = nullptr; // EAS: n_col_eles * hex8eas::hist_size(neas) doubles, device element order
+  double* d_eas_t0 = nullptr;   // EAS: T0invT[36] + detJ0 per element (stride hex8eas::T0_STRIDE)
   double* d_du_row = nullptr;   // "residual displacement" state (struct_calc_recover)
   double* d_du_col = nullptr;
   // material
@@ -1197,7 +1209,15 @@ namespace
     const int64_t n = ctx->n_col_eles * hex8eas::hist_size(eas_neas(ctx->tech));
     if (to_device(ctx, &ctx->d_eas_hist, (const double*)nullptr, n)) return B200S_ERR_CUDA;
     CK(cudaMemsetAsync(ctx->d_eas_hist, 0, sizeof(double) * (size_t)(n > 0 ? n : 1), ctx->stream));
+    if (to_device(ctx, &ctx->d_eas_t0, (const double*)nullptr, ctx->n_col_eles * hex8eas::T0_STRIDE)) return B200S_ERR_CUDA;
+    if (ctx->n_col_eles > 0)
+    {
+      k_eas_centroid<<<nblk(32 * ctx->n_col_eles, 128), 128, 0, ctx->stream>>>(ctx->n_col_eles, ctx->dconn, ctx->dX,
+          ctx->d_eas_t0);
+      ctx->launches += 1;
+    }
     CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
     return 0;
   }
 
@@ -1230,7 +1250,7 @@ namespace
     const int64_t cap = (int64_t)ctx->n_sm * 2;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, HEX8_EAS_WARPS * 32, bytes, ctx->stream>>>(A, ctx->d_eas_hist);
+    kern<<<(unsigned)grid, HEX8_EAS_WARPS * 32, bytes, ctx->stream>>>(A, ctx->d_eas_hist, ctx->d_eas_t0);
     ctx->launches += 1;
     return 0;
   }
@@ -1387,6 +1407,7 @@ extern "C"
     dfree(ctx->d_u_row), dfree(ctx->d_u_col), dfree(ctx->d_send_lid), dfree(ctx->d_recv_lid);
     dfree(ctx->d_sendbuf), dfree(ctx->d_recvbuf), dfree(ctx->d_err);
     dfree(ctx->d_gp_hist), dfree(ctx->d_eas_hist), dfree(ctx->d_du_row), dfree(ctx->d_du_col);
+    dfree(ctx->d_eas_t0);
     dfree(ctx->d_hyper), dfree(ctx->d_dN_gp), dfree(ctx->d_w), dfree(ctx->d_dN_cen), dfree(ctx->d_N_mass);
     dfree(ctx->d_dN_mass), dfree(ctx->d_w_mass), dfree(ctx->d_ele_is_row), dfree(ctx->d_mass);
     dfree(ctx->d_f_inertia), dfree(ctx->d_acc_row), dfree(ctx->d_acc_col), dfree(ctx->d_energy);

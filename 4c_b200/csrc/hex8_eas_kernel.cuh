@@ -7,10 +7,11 @@
 //
 // Mapping: one warp = one element.  Lane r < 24 owns dof row r of the element: column r of the
 // B-operator, row r of K_dd (24 doubles) and of K_da (NEAS doubles) live in its registers; lane
-// a < NEAS owns EAS parameter a: column a of Mtilde, row a of K_aa.  Per Gauss point every lane
-// evaluates the (cheap) kinematics and the material redundantly, writes its column of  w C B  and
-// w C Mtilde  to shared memory, and after a __syncwarp accumulates its rows against those columns
-// (broadcast loads).  After the 8 Gauss points: K_aa is inverted in shared memory by the warp
+// a < NEAS owns EAS parameter a: column a of Mtilde, row a of K_aa.  Phase 1: lane g < 8 evaluates
+// Gauss point g once (Jacobian, dN/dX, F, enhanced strain, material) and leaves F, w S, w C, dN/dX in
+// shared memory.  Phase 2, per Gauss point: every lane forms its column of B and Mtilde, writes its
+// column of  w C B  and  w C Mtilde  to shared memory, and after a __syncwarp accumulates its rows
+// against those columns (broadcast loads).  After the 8 Gauss points: K_aa is inverted in shared memory by the warp
 // (Gauss-Jordan with partial pivoting, the operator LAPACK's getrf/getri gives the reference), the
 // element history {s, K_aa^-1, K_da} goes to HBM for struct_calc_recover, the condensed
 // contributions  f -= K_da K_aa^-1 s,  K_dd -= K_da K_aa^-1 K_da^T  are applied row-wise, and K_e / f_e
@@ -37,16 +38,12 @@ namespace b200s
 #if defined(__CUDACC__)
     // one non-zero per column of the parametric EAS shape function matrix M(xi)
     // (evaluate_eas_shape_functions_parameter_space, eas_helpers.hpp:205-275): Voigt row and monomial
-    __device__ __forceinline__ int m_row(int c)
+    // (0 r, 1 s, 2 t, 3 rs, 4 rt, 5 st) of column c
+    __constant__ int c_eas_row[21] = {0, 1, 2, 3, 3, 4, 4, 5, 5, 3, 3, 4, 4, 5, 5, 0, 0, 1, 1, 2, 2};
+    __constant__ int c_eas_mono[21] = {0, 1, 2, 0, 1, 1, 2, 0, 2, 4, 5, 3, 4, 3, 5, 3, 4, 3, 5, 4, 5};
+    __device__ __forceinline__ double monomial(int m, double r, double s, double t)
     {
-      constexpr int t[21] = {0, 1, 2, 3, 3, 4, 4, 5, 5, 3, 3, 4, 4, 5, 5, 0, 0, 1, 1, 2, 2};
-      return t[c];
-    }
-    __device__ __forceinline__ double m_val(int c, double r, double s, double t)
-    {
-      constexpr int mono[21] = {0, 1, 2, 0, 1, 1, 2, 0, 2, 4, 5, 3, 4, 3, 5, 3, 4, 3, 5, 4, 5};
-      const double v[6] = {r, s, t, r * s, r * t, s * t};
-      return v[mono[c]];
+      return m == 0 ? r : m == 1 ? s : m == 2 ? t : m == 3 ? r * s : m == 4 ? r * t : s * t;
     }
 
     // shared memory of one warp, in doubles
@@ -58,34 +55,39 @@ namespace b200s
       static constexpr int T0 = XU + 48;                  // T0invT 6x6 column-major
       static constexpr int ALPHA = T0 + 36;               // alpha[NA]
       static constexpr int SG = ALPHA + NA;               // s vector after the loop [NA]
-      static constexpr int GALL = SG + NA;                // G_k(a) of the current Gauss point [24]
-      static constexpr int CB = GALL + 24;                // w C B      6 x 24, [k + 6 r]
+      static constexpr int CB = SG + NA;                  // w C B      6 x 24, [k + 6 r]
       static constexpr int CM = CB + 144;                 // w C Mtilde 6 x NEAS, [k + 6 a]
-      static constexpr int WORK = CM + 6 * NA;            // post-loop work area
-      //   augmented [Kaa | I] NEAS x 2 NEAS row-major, later invKaa NEAS x NEAS [k*NEAS + a]
+      // per Gauss point, written once by lane g before the loop: F[9], w S[6], w Cm[21], G[24], scale
+      static constexpr int GP = CM + 6 * NA;
+      static constexpr int GP_STRIDE = 62;
+      static constexpr int GP_F = 0, GP_S = 9, GP_C = 15, GP_G = 36, GP_SCALE = 60;
+      static constexpr int WORK = GP + NGP * GP_STRIDE;   // post-loop work area
+      //   Kaa NEAS x NEAS row-major, inverted in place
       static constexpr int AUG = WORK;
-      static constexpr int KDA = AUG + 2 * NEAS * NEAS + (2 * NEAS * NEAS & 1);  // Kda 24 x NEAS [r*NEAS + a]
+      static constexpr int KDA = AUG + NEAS * NEAS + (NEAS * NEAS & 1);          // Kda 24 x NEAS [r*NEAS + a]
       static constexpr int KE = KDA + ND * NEAS + (ND * NEAS & 1);               // K_e 24 x 24 row-major, f_e behind
       static constexpr int DOUBLES = KE + 576 + 24;
       static constexpr int BYTES = DOUBLES * 8 + NN * 16 + NN * NN * 4;          // + NodeRow[8] + pos[64]
     };
 
     // In-place inverse of the n x n matrix in the left half of the row-major augmented [A | I]
-    // (n x 2n) in shared memory, by the whole warp: Gauss-Jordan with partial pivoting.  On return the
-    // right half holds A^-1.  A singular pivot is used as it is (the reference ignores the LAPACK
-    // error, solve_for_inverse_ignoring_errors).
+    // (n x 2n, n <= 32) in shared memory, by the whole warp: Gauss-Jordan with partial pivoting (pivot
+    // search as a warp arg-max).  On return the right half holds A^-1.  A singular pivot is used as it is
+    // (the reference ignores the LAPACK error, solve_for_inverse_ignoring_errors).
     __device__ __forceinline__ void warp_gauss_jordan(int n, double* aug, int lane)
     {
       const int w = 2 * n;
       for (int c = 0; c < n; ++c)
       {
-        // pivot search (every lane reads the same column: uniform result)
-        int piv = c;
-        double best = fabs(aug[c * w + c]);
-        for (int r = c + 1; r < n; ++r)
+        // pivot: largest |a(r, c)|, r >= c; ties to the lowest row like a sequential search
+        double best = (lane >= c && lane < n) ? fabs(aug[lane * w + c]) : -1.0;
+        int piv = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
         {
-          const double v = fabs(aug[r * w + c]);
-          if (v > best) best = v, piv = r;
+          const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int op = __shfl_xor_sync(0xffffffffu, piv, o);
+          if (ob > best || (ob == best && op < piv)) best = ob, piv = op;
         }
         if (piv != c)
           for (int k = lane; k < w; k += 32)
@@ -99,24 +101,102 @@ namespace b200s
         __syncwarp();
         for (int k = lane; k < w; k += 32) aug[c * w + k] *= d;
         __syncwarp();
-        // eliminate column c from every other row; lane = row, so each lane reads its factor first
-        for (int r = lane; r < n; r += 32)
+        // eliminate column c from every other row; lane = row
+        if (lane < n && lane != c)
         {
-          if (r == c) continue;
-          const double f = aug[r * w + c];
+          const double f = aug[lane * w + c];
           if (f != 0.0)
-            for (int k = 0; k < w; ++k) aug[r * w + k] = fma(-f, aug[c * w + k], aug[r * w + k]);
+            for (int k = 0; k < w; ++k) aug[lane * w + k] = fma(-f, aug[c * w + k], aug[lane * w + k]);
         }
         __syncwarp();
       }
     }
+
+    // In-place inverse of a symmetric positive definite n x n matrix (row-major, n <= 32) in shared memory
+    // by the warp, lane = row: Gauss-Jordan without pivoting (two __syncwarp per step).  K_aa = sum w Mt^T C Mt
+    // is positive definite whenever the material tangent is; the reference's LU with partial pivoting
+    // (solve_for_inverse_ignoring_errors) gives the same operator up to round-off then.
+    __device__ __forceinline__ void warp_spd_inverse(int n, double* a, int lane)
+    {
+      for (int c = 0; c < n; ++c)
+      {
+        const double d = 1.0 / a[c * n + c];
+        if (lane < n && lane != c)
+        {
+          const double f = a[lane * n + c] * d;
+          for (int k = 0; k < n; ++k)
+            if (k != c) a[lane * n + k] = fma(-f, a[c * n + k], a[lane * n + k]);
+          a[lane * n + c] = -f;
+        }
+        __syncwarp();
+        if (lane < n) a[c * n + lane] = (lane == c) ? d : a[c * n + lane] * d;
+        __syncwarp();
+      }
+    }
+
+    // Set-up (once per mesh): T0invT (6x6 column-major) and det J0 of one element into t0[0..35], t0[36]
+    // (evaluate_centroid_transformation, eas_helpers.hpp:118-133); aug = 72 doubles of shared memory
+    __device__ __forceinline__ void centroid_transformation(const double* X, const int32_t* ce, double* aug,
+        int lane, double* t0)
+    {
+      double J0[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) J0[i] = 0.0;
+#pragma unroll
+      for (int k = 0; k < NN; ++k)
+      {
+        const double* x = X + 3 * (int64_t)ce[k];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+        {
+          const double dn = 0.125 * hex8fbar::sgn(k, a);
+#pragma unroll
+          for (int b = 0; b < 3; ++b) J0[a + 3 * b] = fma(dn, x[b], J0[a + 3 * b]);
+        }
+      }
+      // T^T in strain-like Voigt notation (calc_lib.hpp:1456-1508) into the augmented work area (6 x 12);
+      // lane c writes column c (static register indices: the column loop is unrolled)
+#pragma unroll
+      for (int c = 0; c < 6; ++c)
+      {
+        if (lane != c) continue;
+        double col[6];
+        if (c < 3)
+        {
+          col[0] = J0[0 + 3 * c] * J0[0 + 3 * c], col[1] = J0[1 + 3 * c] * J0[1 + 3 * c];
+          col[2] = J0[2 + 3 * c] * J0[2 + 3 * c], col[3] = 2 * J0[0 + 3 * c] * J0[1 + 3 * c];
+          col[4] = 2 * J0[1 + 3 * c] * J0[2 + 3 * c], col[5] = 2 * J0[0 + 3 * c] * J0[2 + 3 * c];
+        }
+        else
+        {
+          const int a = (c == 4) ? 1 : 0, b = (c == 3) ? 1 : 2;
+          col[0] = J0[0 + 3 * a] * J0[0 + 3 * b], col[1] = J0[1 + 3 * a] * J0[1 + 3 * b];
+          col[2] = J0[2 + 3 * a] * J0[2 + 3 * b];
+          col[3] = J0[0 + 3 * a] * J0[1 + 3 * b] + J0[1 + 3 * a] * J0[0 + 3 * b];
+          col[4] = J0[1 + 3 * a] * J0[2 + 3 * b] + J0[2 + 3 * a] * J0[1 + 3 * b];
+          col[5] = J0[0 + 3 * a] * J0[2 + 3 * b] + J0[2 + 3 * a] * J0[0 + 3 * b];
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+        {
+          aug[r * 12 + c] = col[r];
+          aug[r * 12 + 6 + c] = (r == c) ? 1.0 : 0.0;
+        }
+      }
+      __syncwarp();
+      warp_gauss_jordan(6, aug, lane);
+      for (int t = lane; t < 36; t += 32) t0[(t % 6) + 6 * (t / 6)] = aug[(t % 6) * 12 + 6 + (t / 6)];
+      if (lane == 0) t0[36] = det3(J0);
+      __syncwarp();
+    }
+    constexpr int T0_STRIDE = 40;  // doubles per element in the precomputed table
 
     // The warp's work on one element.  sm: the warp's shared memory (Layout<NEAS>), hist: the element's
     // history block in HBM.
     template <int MAT, bool STIFF, int NEAS>
     __device__ __forceinline__ void element(const EvalArgs& A, double* sm, NodeRow* nrow, int32_t* pos,
         const double* tab_gp /*[g][k*3+a], stride TAB_STRIDE*/, const double* wgt, const double* gxi /*[g][3]*/,
-        int lane, int64_t e, double* hist, double& detJ_min, double& detF_min, bool& neg_jac)
+        int lane, int64_t e, double* hist, const double* t0tab, double& detJ_min, double& detF_min, bool& neg_jac)
     {
       using L = Layout<NEAS>;
       double* xu = sm + L::XU;
@@ -139,96 +219,37 @@ namespace b200s
       if (lane < NEAS) alpha[lane] = hist[NEAS + lane];
       __syncwarp();
 
-      // ---- prepare: centroid transformation (eas.hpp:66-70) -------------------------------------------
-      double detJ0;
-      {
-        double J0[9];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) J0[i] = 0.0;
-#pragma unroll
-        for (int k = 0; k < NN; ++k)
-#pragma unroll
-          for (int a = 0; a < 3; ++a)
-          {
-            const double dn = 0.125 * hex8fbar::sgn(k, a);
-#pragma unroll
-            for (int b = 0; b < 3; ++b) J0[a + 3 * b] = fma(dn, xu[3 * k + b], J0[a + 3 * b]);
-          }
-        detJ0 = det3(J0);
-        // T^T in strain-like Voigt notation (calc_lib.hpp:1456-1508) into the augmented work area
-        double* aug = sm + L::AUG;  // 6 x 12
-        if (lane < 6)
-        {
-          const int c = lane;
-          double col[6];
-          if (c < 3)
-          {
-            col[0] = J0[0 + 3 * c] * J0[0 + 3 * c], col[1] = J0[1 + 3 * c] * J0[1 + 3 * c];
-            col[2] = J0[2 + 3 * c] * J0[2 + 3 * c], col[3] = 2 * J0[0 + 3 * c] * J0[1 + 3 * c];
-            col[4] = 2 * J0[1 + 3 * c] * J0[2 + 3 * c], col[5] = 2 * J0[0 + 3 * c] * J0[2 + 3 * c];
-          }
-          else
-          {
-            const int a = (c == 4) ? 1 : 0, b = (c == 3) ? 1 : 2;
-            col[0] = J0[0 + 3 * a] * J0[0 + 3 * b], col[1] = J0[1 + 3 * a] * J0[1 + 3 * b];
-            col[2] = J0[2 + 3 * a] * J0[2 + 3 * b];
-            col[3] = J0[0 + 3 * a] * J0[1 + 3 * b] + J0[1 + 3 * a] * J0[0 + 3 * b];
-            col[4] = J0[1 + 3 * a] * J0[2 + 3 * b] + J0[2 + 3 * a] * J0[1 + 3 * b];
-            col[5] = J0[0 + 3 * a] * J0[2 + 3 * b] + J0[2 + 3 * a] * J0[0 + 3 * b];
-          }
-#pragma unroll
-          for (int r = 0; r < 6; ++r)
-          {
-            aug[r * 12 + c] = col[r];
-            aug[r * 12 + 6 + c] = (r == c) ? 1.0 : 0.0;
-          }
-        }
-        __syncwarp();
-        warp_gauss_jordan(6, aug, lane);
-        for (int t = lane; t < 36; t += 32) T0[(t % 6) + 6 * (t / 6)] = aug[(t % 6) * 12 + 6 + (t / 6)];
-        __syncwarp();
-      }
+      // ---- prepare: centroid transformation (eas.hpp:66-70), precomputed per element at set-up ---------
+      for (int t = lane; t < 36; t += 32) T0[t] = t0tab[t];
+      const double detJ0 = t0tab[36];
+      __syncwarp();
 
-      // nodal Jacobian check (calc_lib.hpp:543-562): lane < 8 = node
+      // ---- phase 1: lane g < 8 = Gauss point g (and element node g for the Jacobian check) -----------------
+      if (lane < NGP)
       {
-        double J[9];
-        const int g = lane & 7;
-        const double sr = 0.5 * hex8fbar::sgn(g, 0), ss = 0.5 * hex8fbar::sgn(g, 1), st = 0.5 * hex8fbar::sgn(g, 2);
-        const double *xq = xu + 3 * g, *xr = xu + 3 * (g ^ 1), *xs = xu + 3 * (g ^ 3), *xt = xu + 3 * (g ^ 4);
-#pragma unroll
-        for (int b = 0; b < 3; ++b)
-        {
-          J[0 + 3 * b] = sr * (xq[b] - xr[b]);
-          J[1 + 3 * b] = ss * (xq[b] - xs[b]);
-          J[2 + 3 * b] = st * (xq[b] - xt[b]);
-        }
-        const double dn = det3(J);
-        neg_jac = !(dn > 0.0);
-        detJ_min = fmin(detJ_min, dn);
-      }
-
-      // ---- Gauss loop ----------------------------------------------------------------------------------
-      const int r_ = lane < ND ? lane : 0;      // dof row of this lane (lanes >= 24 shadow row 0, results unused)
-      const int ni = r_ / 3, ei = r_ - 3 * ni;  // node and direction of the row
-      const int a_ = lane < NEAS ? lane : 0;    // EAS parameter of this lane
-      const int arow = m_row(a_);
-      double Kdd[ND], Kda[NEAS], Kaa[NEAS], facc = 0.0, sacc = 0.0;
-#pragma unroll
-      for (int c = 0; c < ND; ++c) Kdd[c] = 0.0;
-#pragma unroll
-      for (int c = 0; c < NEAS; ++c) Kda[c] = 0.0, Kaa[c] = 0.0;
-
-#pragma unroll 1
-      for (int g = 0; g < NGP; ++g)
-      {
-        const double* dN = tab_gp + g * hex8::TAB_STRIDE;
+        const int g = lane;
         double J[9], iJ[9];
+        {
+          // ensure_positive_jacobian_determinant_at_element_nodes (calc_lib.hpp:543-562), corner form
+          const double sr = 0.5 * hex8fbar::sgn(g, 0), ss = 0.5 * hex8fbar::sgn(g, 1), st = 0.5 * hex8fbar::sgn(g, 2);
+          const double *xq = xu + 3 * g, *xr = xu + 3 * (g ^ 1), *xs = xu + 3 * (g ^ 3), *xt = xu + 3 * (g ^ 4);
+#pragma unroll
+          for (int b = 0; b < 3; ++b)
+          {
+            J[0 + 3 * b] = sr * (xq[b] - xr[b]);
+            J[1 + 3 * b] = ss * (xq[b] - xs[b]);
+            J[2 + 3 * b] = st * (xq[b] - xt[b]);
+          }
+          const double dn = det3(J);
+          neg_jac = !(dn > 0.0);
+          detJ_min = fmin(detJ_min, dn);
+        }
+        const double* dN = tab_gp + g * hex8::TAB_STRIDE;
         hex8::jacobian(dN, xu, J);
         const double detJ = inv3(iJ, J);
         detJ_min = fmin(detJ_min, detJ);
-        // F = I + u G^T (redundant in every lane), G_i of the lane's own node
+        double* gp = sm + L::GP + g * L::GP_STRIDE;
         double F[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-        double Gi[3] = {0, 0, 0}, Gl[3] = {0, 0, 0};  // of the row's node / of node (lane & 7)
 #pragma unroll
         for (int k = 0; k < NN; ++k)
         {
@@ -236,34 +257,20 @@ namespace b200s
 #pragma unroll
           for (int a = 0; a < 3; ++a)
             Gk[a] = iJ[a] * dN[3 * k] + iJ[a + 3] * dN[3 * k + 1] + iJ[a + 6] * dN[3 * k + 2];
-          if (k == ni) Gi[0] = Gk[0], Gi[1] = Gk[1], Gi[2] = Gk[2];
-          if ((lane & 7) == k) Gl[0] = Gk[0], Gl[1] = Gk[1], Gl[2] = Gk[2];
 #pragma unroll
           for (int a = 0; a < 3; ++a)
           {
+            gp[L::GP_G + 3 * k + a] = Gk[a];
             const double ua = xu[24 + 3 * k + a];
 #pragma unroll
             for (int b = 0; b < 3; ++b) F[a + 3 * b] += ua * Gk[b];
           }
         }
         detF_min = fmin(detF_min, det3(F));
-
-        // column r of the B-operator (evaluate_strain_gradient, calc_lib.hpp:777-826), strain-like rows
-        double Bc[6];
-        Bc[0] = F[ei] * Gi[0], Bc[1] = F[ei + 3] * Gi[1], Bc[2] = F[ei + 6] * Gi[2];
-        Bc[3] = F[ei] * Gi[1] + F[ei + 3] * Gi[0];
-        Bc[4] = F[ei + 3] * Gi[2] + F[ei + 6] * Gi[1];
-        Bc[5] = F[ei + 6] * Gi[0] + F[ei] * Gi[2];
-
-        // Mtilde = detJ0/detJ T0invT M(xi): column a of this lane, and Mtilde alpha for the strain
+        // E_enh = E + stress-like(Mtilde alpha), Mtilde = detJ0/detJ T0invT M(xi)
+        // (evaluate_eas_kinematics, eas_helpers.hpp:405-448); C_enh = C + 2 (...), shear rows halved
         const double xr = gxi[3 * g], xs = gxi[3 * g + 1], xt = gxi[3 * g + 2];
         const double scale = detJ0 / detJ;
-        double Mc[6];
-        {
-          const double mv = scale * m_val(a_, xr, xs, xt);
-#pragma unroll
-          for (int k = 0; k < 6; ++k) Mc[k] = mv * T0[k + 6 * arow];
-        }
         double C[6];
         right_cauchy_green(F, C);
         {
@@ -273,11 +280,8 @@ namespace b200s
           {
             constexpr int rows[21] = {0, 1, 2, 3, 3, 4, 4, 5, 5, 3, 3, 4, 4, 5, 5, 0, 0, 1, 1, 2, 2};
             constexpr int mono[21] = {0, 1, 2, 0, 1, 1, 2, 0, 2, 4, 5, 3, 4, 3, 5, 3, 4, 3, 5, 4, 5};
-            const double mon = mono[c] == 0 ? xr : mono[c] == 1 ? xs : mono[c] == 2 ? xt
-                             : mono[c] == 3 ? xr * xs : mono[c] == 4 ? xr * xt : xs * xt;
-            v[rows[c]] = fma(mon, alpha[c], v[rows[c]]);
+            v[rows[c]] = fma(monomial(mono[c], xr, xs, xt), alpha[c], v[rows[c]]);
           }
-          // E_enh = E + stress-like(Mtilde alpha); C_enh = 2 E_enh + I = C + 2 (...)  (shear rows halved)
 #pragma unroll
           for (int k = 0; k < 6; ++k)
           {
@@ -292,23 +296,67 @@ namespace b200s
         if (A.per_ele_param != nullptr) mp.p[0] = A.per_ele_param[e];
         material_evaluate<MAT>(mp, C, Sv, Cm);
         const double w = detJ * wgt[g];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) gp[L::GP_F + i] = F[i];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) gp[L::GP_S + i] = w * Sv[i];
+#pragma unroll
+        for (int i = 0; i < 21; ++i) gp[L::GP_C + i] = w * Cm[i];
+        gp[L::GP_SCALE] = scale;
+      }
+      __syncwarp();
 
+      // ---- phase 2: Gauss loop, lane = dof row r (< 24) and EAS parameter a (< NEAS) -----------------------
+      const int r_ = lane < ND ? lane : 0;      // lanes >= 24 shadow row 0, results unused
+      const int ni = r_ / 3, ei = r_ - 3 * ni;  // node and direction of the row
+      const int a_ = lane < NEAS ? lane : 0;
+      const int arow = c_eas_row[a_], amono = c_eas_mono[a_];
+      double Kdd[ND], Kda[NEAS], Kaa[NEAS], facc = 0.0, sacc = 0.0;
+#pragma unroll
+      for (int c = 0; c < ND; ++c) Kdd[c] = 0.0;
+#pragma unroll
+      for (int c = 0; c < NEAS; ++c) Kda[c] = 0.0, Kaa[c] = 0.0;
+
+#pragma unroll 1
+      for (int g = 0; g < NGP; ++g)
+      {
+        const double* gp = sm + L::GP + g * L::GP_STRIDE;
+        const double* Gi = gp + L::GP_G + 3 * ni;
+        const double Fe0 = gp[L::GP_F + ei], Fe1 = gp[L::GP_F + ei + 3], Fe2 = gp[L::GP_F + ei + 6];
+        const double G0 = Gi[0], G1 = Gi[1], G2 = Gi[2];
+        // column r of the B-operator (evaluate_strain_gradient, calc_lib.hpp:777-826), strain-like rows
+        double Bc[6];
+        Bc[0] = Fe0 * G0, Bc[1] = Fe1 * G1, Bc[2] = Fe2 * G2;
+        Bc[3] = Fe0 * G1 + Fe1 * G0;
+        Bc[4] = Fe1 * G2 + Fe2 * G1;
+        Bc[5] = Fe2 * G0 + Fe0 * G2;
+        // column a of Mtilde
+        double Mc[6];
+        {
+          const double mv = gp[L::GP_SCALE] * monomial(amono, gxi[3 * g], gxi[3 * g + 1], gxi[3 * g + 2]);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) Mc[k] = mv * T0[k + 6 * arow];
+        }
         // columns of  w C B  and  w C Mtilde  (integrate_eas: cmatM, eas_helpers.hpp:352-371)
         double CBc[6], CMc[6];
-#pragma unroll
-        for (int I = 0; I < 6; ++I)
         {
-          double tb = 0.0, tm = 0.0;
+          double Cm[21];
 #pragma unroll
-          for (int Jv = 0; Jv < 6; ++Jv)
+          for (int i = 0; i < 21; ++i) Cm[i] = gp[L::GP_C + i];
+#pragma unroll
+          for (int I = 0; I < 6; ++I)
           {
-            tb = fma(Cm[c21(I, Jv)], Bc[Jv], tb);
-            tm = fma(Cm[c21(I, Jv)], Mc[Jv], tm);
+            double tb = 0.0, tm = 0.0;
+#pragma unroll
+            for (int Jv = 0; Jv < 6; ++Jv)
+            {
+              tb = fma(Cm[c21(I, Jv)], Bc[Jv], tb);
+              tm = fma(Cm[c21(I, Jv)], Mc[Jv], tm);
+            }
+            CBc[I] = tb, CMc[I] = tm;
           }
-          CBc[I] = w * tb, CMc[I] = w * tm;
         }
-        __syncwarp();  // previous Gauss point's CB / CM / G fully consumed
-        if (lane < NN) sm[L::GALL + 3 * lane] = Gl[0], sm[L::GALL + 3 * lane + 1] = Gl[1], sm[L::GALL + 3 * lane + 2] = Gl[2];
+        __syncwarp();  // previous Gauss point's CB / CM fully consumed
         if (lane < ND)
 #pragma unroll
           for (int I = 0; I < 6; ++I) sm[L::CB + I + 6 * lane] = CBc[I];
@@ -317,17 +365,20 @@ namespace b200s
           for (int I = 0; I < 6; ++I) sm[L::CM + I + 6 * lane] = CMc[I];
         __syncwarp();
 
-        // force and EAS residual: f_r += w B_r . S, s_a += w Mtilde_a . S
-        double bs = 0.0, ms = 0.0;
+        // force and EAS residual: f_r += B_r . (w S), s_a += Mtilde_a . (w S)
+        double wS[6];
 #pragma unroll
-        for (int I = 0; I < 6; ++I) bs = fma(Bc[I], Sv[I], bs), ms = fma(Mc[I], Sv[I], ms);
-        facc = fma(w, bs, facc);
-        sacc = fma(w, ms, sacc);
+        for (int I = 0; I < 6; ++I) wS[I] = gp[L::GP_S + I];
+#pragma unroll
+        for (int I = 0; I < 6; ++I) facc = fma(Bc[I], wS[I], facc), sacc = fma(Mc[I], wS[I], sacc);
         // K_da(r, a) += B_r . (w C Mtilde_a);  K_aa(a, a') += Mtilde_a . (w C Mtilde_a')
 #pragma unroll
         for (int c = 0; c < NEAS; ++c)
         {
-          const double* cm = sm + L::CM + 6 * c;
+          // three 128-bit broadcast loads per column (columns are 48 bytes apart, 16-byte aligned)
+          const d2* cm2 = reinterpret_cast<const d2*>(sm + L::CM + 6 * c);
+          const d2 q0 = cm2[0], q1 = cm2[1], q2 = cm2[2];
+          const double cm[6] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y};
           double t1 = 0.0, t2 = 0.0;
 #pragma unroll
           for (int I = 0; I < 6; ++I) t1 = fma(Bc[I], cm[I], t1), t2 = fma(Mc[I], cm[I], t2);
@@ -335,28 +386,27 @@ namespace b200s
         }
         if (STIFF)
         {
-          // elastic: K_dd(r, c) += B_r . (w C B_c); geometric: K_dd(3i+b, 3j+b) += w G_i.S.G_j
+          // elastic: K_dd(r, c) += B_r . (w C B_c); geometric: K_dd(3i+b, 3j+b) += G_i.(w S).G_j
           double gi[3];
 #pragma unroll
-          for (int d = 0; d < 3; ++d)
-            gi[d] = w * (Gi[0] * Sv[vg(0, d)] + Gi[1] * Sv[vg(1, d)] + Gi[2] * Sv[vg(2, d)]);
+          for (int d = 0; d < 3; ++d) gi[d] = G0 * wS[vg(0, d)] + G1 * wS[vg(1, d)] + G2 * wS[vg(2, d)];
 #pragma unroll
           for (int c = 0; c < ND; ++c)
           {
-            const double* cb = sm + L::CB + 6 * c;
-            double t = 0.0;
-#pragma unroll
-            for (int I = 0; I < 6; ++I) t = fma(Bc[I], cb[I], t);
-            Kdd[c] += t;
+            const d2* cb2 = reinterpret_cast<const d2*>(sm + L::CB + 6 * c);
+            const d2 q0 = cb2[0], q1 = cb2[1], q2 = cb2[2];
+            // two independent chains per column
+            const double t = fma(Bc[2], q1.x, fma(Bc[1], q0.y, Bc[0] * q0.x));
+            const double v = fma(Bc[5], q2.y, fma(Bc[4], q2.x, Bc[3] * q1.y));
+            Kdd[c] += t + v;
           }
 #pragma unroll
           for (int j = 0; j < NN; ++j)
           {
-            const double* gj = sm + L::GALL + 3 * j;
+            const double* gj = gp + L::GP_G + 3 * j;
             const double sg = gi[0] * gj[0] + gi[1] * gj[1] + gi[2] * gj[2];
 #pragma unroll
-            for (int b = 0; b < 3; ++b)
-              if (b == ei) Kdd[3 * j + b] += sg;
+            for (int b = 0; b < 3; ++b) Kdd[3 * j + b] += (b == ei) ? sg : 0.0;  // select, no divergent branch
           }
         }
       }
@@ -369,18 +419,14 @@ namespace b200s
       if (lane < NEAS)
       {
 #pragma unroll
-        for (int c = 0; c < NEAS; ++c)
-        {
-          aug[lane * 2 * NEAS + c] = Kaa[c];
-          aug[lane * 2 * NEAS + NEAS + c] = (c == lane) ? 1.0 : 0.0;
-        }
+        for (int c = 0; c < NEAS; ++c) aug[lane * NEAS + c] = Kaa[c];
         sS[lane] = sacc;
       }
       if (lane < ND)
 #pragma unroll
         for (int c = 0; c < NEAS; ++c) KdaS[lane * NEAS + c] = Kda[c];
       __syncwarp();
-      warp_gauss_jordan(NEAS, aug, lane);
+      warp_spd_inverse(NEAS, aug, lane);
       // history for struct_calc_recover: s, invKaa (column-major), Kda (column-major)
       {
         double* h_s = hist + 2 * NEAS;
@@ -388,7 +434,7 @@ namespace b200s
         double* h_kda = h_inv + NEAS * NEAS;
         if (lane < NEAS) h_s[lane] = sS[lane];
         for (int t = lane; t < NEAS * NEAS; t += 32)  // t = r + NEAS c
-          h_inv[t] = aug[(t % NEAS) * 2 * NEAS + NEAS + t / NEAS];
+          h_inv[t] = aug[(t % NEAS) * NEAS + t / NEAS];
         for (int t = lane; t < ND * NEAS; t += 32)  // t = r + 24 c
           h_kda[t] = KdaS[(t % ND) * NEAS + t / ND];
       }
@@ -399,7 +445,7 @@ namespace b200s
 #pragma unroll
       for (int k = 0; k < NEAS; ++k)
       {
-        const double* row = aug + k * 2 * NEAS + NEAS;
+        const double* row = aug + k * NEAS;
 #pragma unroll
         for (int a = 0; a < NEAS; ++a) mK[a] = fma(-Kda[k], row[a], mK[a]);
       }
