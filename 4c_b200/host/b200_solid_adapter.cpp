@@ -29,7 +29,7 @@ namespace B200Solid
   {
     const bool cell = celltype == B200S_HEX8 || celltype == B200S_HEX27 || celltype == B200S_TET10;
     const bool mat = material_kind == B200S_MAT_COUP_NEOHOOKE || material_kind == B200S_MAT_ISO_VOL ||
-                     material_kind == B200S_MAT_SVK;
+                     material_kind == B200S_MAT_SVK || material_kind == B200S_MAT_ELASTHYPER;
     return cell && mat;
   }
 
@@ -84,6 +84,61 @@ namespace B200Solid
     b200s_error_info info;
     std::memset(&info, 0, sizeof info);
     check(b200s_evaluate(ctx_, (int)action, u_row_, crs_values, f_row, &info));
+  }
+
+  void DeviceElementBlock::set_material_elasthyper(const std::vector<std::int32_t>& kinds,
+      const std::vector<std::int32_t>& modes, const std::vector<double>& params4, double density)
+  {
+    check(b200s_set_material_elasthyper(ctx_, (int)kinds.size(), kinds.data(), modes.empty() ? nullptr : modes.data(),
+        params4.data()));
+    if (density > 0.0) check(b200s_set_density(ctx_, density));
+  }
+
+  void DeviceElementBlock::set_element_properties(int kinem, int tech, int prestress)
+  {
+    check(b200s_set_element_properties(ctx_, kinem, tech, prestress));
+  }
+
+  void DeviceElementBlock::set_row_elements(const std::uint8_t* is_row) { check(b200s_set_row_elements(ctx_, is_row)); }
+
+  void DeviceElementBlock::set_state(const char* name, const double* v_row)
+  {
+    if (!std::strcmp(name, "displacement")) u_row_ = v_row;
+    check(b200s_set_state(ctx_, name, v_row));
+  }
+
+  void DeviceElementBlock::get_mass(double* mass_values, double* f_inertia)
+  {
+    check(b200s_get_mass(ctx_, mass_values, f_inertia));
+  }
+
+  void DeviceElementBlock::calc_stress(int stress_type, int strain_type, double* stress, double* strain)
+  {
+    check(b200s_calc_stress(ctx_, stress_type, strain_type, stress, strain));
+  }
+
+  double DeviceElementBlock::calc_energy()
+  {
+    double e = 0.0;
+    check(b200s_calc_energy(ctx_, &e));
+    return e;
+  }
+
+  void DeviceElementBlock::update_prestress() { check(b200s_update_prestress(ctx_)); }
+
+  void DeviceElementBlock::recover(const double* du_row, double step_length)
+  {
+    check(b200s_recover(ctx_, du_row, step_length));
+  }
+
+  void DeviceElementBlock::apply_dirichlet(const double* dbctoggle_row, bool diagonalblock)
+  {
+    check(b200s_apply_dirichlet(ctx_, B200S_MATRIX_STIFFNESS, dbctoggle_row, diagonalblock ? 1 : 0));
+  }
+
+  void DeviceElementBlock::multiply(const double* x_row, double* y_row)
+  {
+    check(b200s_multiply(ctx_, B200S_MATRIX_STIFFNESS, x_row, y_row));
   }
 
   std::int64_t DeviceElementBlock::nnz() const { return b200s_nnz(ctx_); }

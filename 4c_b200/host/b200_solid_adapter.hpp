@@ -28,7 +28,10 @@ namespace B200Solid
   enum class Action
   {
     struct_calc_internalforce = B200S_ACTION_INTERNALFORCE,
-    struct_calc_nlnstiff = B200S_ACTION_NLNSTIFF
+    struct_calc_nlnstiff = B200S_ACTION_NLNSTIFF,
+    struct_calc_nlnstiffmass = B200S_ACTION_NLNSTIFFMASS,
+    struct_calc_nlnstifflmass = B200S_ACTION_NLNSTIFFLMASS,
+    struct_calc_internalinertiaforce = B200S_ACTION_INTERNALINERTIAFORCE
   };
 
   /// What 4C throws: Core::Exception (FOUR_C_THROW).  Stand-in so that unit tests can
@@ -90,6 +93,12 @@ namespace B200Solid
     /// Mat::So3Material of the block: kind + parameters (+ optional per-element field, see
     /// 4C_mat_elast_isoneohooke.cpp:15-18)
     void set_material(int kind, const std::vector<double>& params, const double* per_element = nullptr);
+    /// MAT_ElastHyper with a summand list (b200s_summand ids, 4 input parameters each) and DENS
+    void set_material_elasthyper(const std::vector<std::int32_t>& kinds, const std::vector<std::int32_t>& modes,
+        const std::vector<double>& params4, double density = 0.0);
+    /// Discret::Elements::SolidElementProperties of the block (KINEM / TECH / PRESTRESS_TECH)
+    void set_element_properties(int kinem, int tech, int prestress);
+    void set_row_elements(const std::uint8_t* is_row);
     void set_graph(const ElementBlockView& block, const CrsView& crs);
     void set_import(const ImportView& imp);
     void init_communicator(const char* nccl_id128);  // id from rank 0's nccl_unique_id(), MPI_Bcast by 4C
@@ -101,6 +110,18 @@ namespace B200Solid
     /// crs.values (zero + assemble) and f_row with the device result.  Throws Exception with the
     /// reference's message text on det J <= 0.
     void evaluate(Action action, double* crs_values, double* f_row);
+    /// further states by name, e.g. "acceleration" (mass actions)
+    void set_state(const char* name, const double* v_row);
+    /// results of the mass actions: mass_->values, inertia force
+    void get_mass(double* mass_values, double* f_inertia);
+    /// struct_calc_stress / struct_calc_energy / struct_update_prestress / struct_calc_recover
+    void calc_stress(int stress_type, int strain_type, double* stress, double* strain);
+    double calc_energy();
+    void update_prestress();
+    void recover(const double* du_row, double step_length);
+    /// SparseMatrix::apply_dirichlet / multiply on the device-resident stiffness
+    void apply_dirichlet(const double* dbctoggle_row, bool diagonalblock = true);
+    void multiply(const double* x_row, double* y_row);
 
     std::int64_t nnz() const;
     std::int64_t n_rows() const;
