@@ -23,7 +23,7 @@ NUM_GP = {capi.HEX8: 8, capi.HEX27: 27, capi.TET10: 4}
 
 class DeviceAssembler:
     def __init__(self, rank_mesh, matkind, matparams, device=0, per_ele_param=None, graph=None,
-                 tech=capi.TECH_NONE, density=None, prestress=capi.PRESTRESS_NONE):
+                 tech=capi.TECH_NONE, density=None, prestress=capi.PRESTRESS_NONE, fibers=None):
         """rank_mesh: partition.RankMesh.  graph: (rowptr, colind) from the reference's matrix, or
         None to build the FillComplete-equivalent graph on the device.  tech: element technology of
         the block (TECH key of the SOLID element line).  matkind MAT_ELASTHYPER: matparams is the
@@ -37,6 +37,8 @@ class DeviceAssembler:
             self.ctx.set_material_elasthyper(matparams)
         else:
             self.ctx.set_material(matkind, matparams, per_ele_param)
+        if fibers is not None:  # FIBER1 per column element
+            self.ctx.set_element_fibers(fibers)
         if density is not None:
             self.ctx.set_density(density)
         if getattr(rm, "ele_is_row", None) is not None:

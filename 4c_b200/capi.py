@@ -23,7 +23,7 @@ MATRIX_STIFFNESS, MATRIX_MASS = 0, 1
 SUMMANDS = ["COUP_NEOHOOKE", "COUP_MOONEYRIVLIN", "COUP_LOGNEOHOOKE", "COUP_LOGMIXNEOHOOKE", "COUP_SVK",
             "COUP_SIMOPISTER", "COUP_BLATZKO", "COUP_EXPPOL", "COUP_1POW", "COUP_2POW", "COUP_3POW",
             "COUP_13APOW", "ISO_NEOHOOKE", "ISO_MOONEYRIVLIN", "ISO_YEOH", "ISO_1POW", "ISO_2POW",
-            "ISO_EXPOPOW", "VOL_SUSSMANBATHE", "VOL_PENALTY", "VOL_OGDEN", "VOL_POW"]
+            "ISO_EXPOPOW", "VOL_SUSSMANBATHE", "VOL_PENALTY", "VOL_OGDEN", "VOL_POW", "COUP_ANISOEXPO"]
 SUM = {name: i for i, name in enumerate(SUMMANDS)}
 KINEM_NONLINEAR_TOTLAG, KINEM_LINEAR = 0, 1
 TECH_NONE, TECH_FBAR, TECH_EAS_MILD, TECH_EAS_FULL = 0, 1, 2, 3
@@ -45,6 +45,7 @@ SYMBOLS = [
     "b200s_last_multiply_ms", "b200s_solve_cg", "b200s_get_values",
     "b200s_update_prestress", "b200s_gp_history_size", "b200s_get_gp_history", "b200s_set_gp_history",
     "b200s_recover", "b200s_element_history_size", "b200s_get_element_history", "b200s_set_element_history",
+    "b200s_set_element_fibers",
 ]
 
 
@@ -109,6 +110,7 @@ def load():
     L.b200s_version.restype = C.c_char_p
     L.b200s_set_material_elasthyper.argtypes = [vp, i32, vp, vp, vp]
     L.b200s_set_density.argtypes = [vp, dbl]
+    L.b200s_set_element_fibers.argtypes = [vp, vp]
     L.b200s_set_row_elements.argtypes = [vp, vp]
     L.b200s_set_state.argtypes = [vp, C.c_char_p, vp]
     L.b200s_get_mass.argtypes = [vp, vp, vp]
@@ -209,6 +211,10 @@ class Context:
         for k, s in enumerate(summands):
             par[k, :len(s[1])] = s[1]
         self._ck(self.L.b200s_set_material_elasthyper(self.h, len(summands), _ptr(kinds), _ptr(modes), _ptr(par)))
+
+    def set_element_fibers(self, fiber1):
+        f = None if fiber1 is None else np.ascontiguousarray(fiber1, np.float64).reshape(self.n_col_eles, 3)
+        self._ck(self.L.b200s_set_element_fibers(self.h, _ptr(f)))
 
     def set_density(self, density):
         self._ck(self.L.b200s_set_density(self.h, float(density)))

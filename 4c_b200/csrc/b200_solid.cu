@@ -1077,6 +1077,7 @@ struct b200s_ctx
   double* d_per_ele = nullptr;
   HyperMat hm{};                // generic MAT_ElastHyper summand list (host copy)
   HyperMat* d_hyper = nullptr;  // ... and on the device (MatParams::hyper)
+  double* d_fibers = nullptr;   // unit element fibres FIBER1, 3 per column element, device element order
   double density = 0.0;         // Mat::So3Material::density()
   // cell tables in global memory for the post / mass kernels (post_kernels.cuh)
   int ngp = 0, ngp_mass = 0;
@@ -1202,6 +1203,13 @@ namespace
     ctx->kev_pending = 0;
   }
 
+  inline bool material_needs_fibers(const b200s_ctx* ctx)
+  {
+    if (ctx->matkind != B200S_MAT_ELASTHYPER) return false;
+    for (int k = 0; k < ctx->hm.n; ++k)
+      if (summand_needs_fiber(ctx->hm.s[k].kind)) return true;
+    return false;
+  }
   inline int eas_neas(int tech) { return tech == B200S_TECH_EAS_MILD ? 9 : (tech == B200S_TECH_EAS_FULL ? 21 : 0); }
   // fresh EASHistoryData of every element: all zero (4C_solid_ele_calc_eas_helpers.hpp:98-112)
   int eas_allocate(b200s_ctx* ctx)
@@ -1407,7 +1415,7 @@ extern "C"
     dfree(ctx->d_u_row), dfree(ctx->d_u_col), dfree(ctx->d_send_lid), dfree(ctx->d_recv_lid);
     dfree(ctx->d_sendbuf), dfree(ctx->d_recvbuf), dfree(ctx->d_err);
     dfree(ctx->d_gp_hist), dfree(ctx->d_eas_hist), dfree(ctx->d_du_row), dfree(ctx->d_du_col);
-    dfree(ctx->d_eas_t0);
+    dfree(ctx->d_eas_t0), dfree(ctx->d_fibers);
     dfree(ctx->d_hyper), dfree(ctx->d_dN_gp), dfree(ctx->d_w), dfree(ctx->d_dN_cen), dfree(ctx->d_N_mass);
     dfree(ctx->d_dN_mass), dfree(ctx->d_w_mass), dfree(ctx->d_ele_is_row), dfree(ctx->d_mass);
     dfree(ctx->d_f_inertia), dfree(ctx->d_acc_row), dfree(ctx->d_acc_col), dfree(ctx->d_energy);
@@ -1467,7 +1475,7 @@ extern "C"
       return B200S_ERR_CUDA;
     CK(cudaStreamSynchronize(ctx->stream));  // T is a local
     dfree(ctx->d_ele_is_row), dfree(ctx->d_acc_col), dfree(ctx->d_gp_hist), dfree(ctx->d_eas_hist);
-    dfree(ctx->d_du_col);
+    dfree(ctx->d_du_col), dfree(ctx->d_fibers);
     if (ctx->prestress == B200S_PRESTRESS_MULF && mulf_allocate(ctx)) return B200S_ERR_CUDA;
     if (eas_neas(ctx->tech) && eas_allocate(ctx)) return B200S_ERR_CUDA;
     if (celltype == B200S_HEX8)
@@ -2018,7 +2026,9 @@ extern "C"
     EvalArgs A;
     A.X = ctx->dX, A.u = ctx->d_u_col, A.conn = ctx->dconn, A.pos = ctx->d_pos;
     A.node_row = ctx->d_node_row, A.per_ele_param = ctx->d_per_ele, A.ele_id = ctx->d_ele_id;
-    A.gp_hist = ctx->d_gp_hist;
+    A.gp_hist = ctx->d_gp_hist, A.fibers = ctx->d_fibers;
+    if (material_needs_fibers(ctx) && !ctx->d_fibers)
+      return fail(ctx, B200S_ERR_INVALID, "the material has a fibre summand: b200s_set_element_fibers first");
     if (ctx->prestress == B200S_PRESTRESS_MULF && !ctx->d_gp_hist)
       return fail(ctx, B200S_ERR_INVALID, "MULF history missing (set_mesh after set_element_properties?)");
     A.vals = ctx->d_vals, A.f = ctx->d_f, A.err = ctx->d_err, A.mp = ctx->mp;
@@ -2161,6 +2171,38 @@ extern "C"
     return B200S_OK;
   }
 
+  int b200s_set_element_fibers(b200s_ctx* ctx, const double* fiber1)
+  {
+    if (!ctx) return B200S_ERR_INVALID;
+    if (ctx->celltype < 0) return fail(ctx, B200S_ERR_INVALID, "set_mesh must precede set_element_fibers");
+    cudaSetDevice(ctx->device);
+    dfree(ctx->d_fibers);
+    if (!fiber1) return B200S_OK;
+    // read_fibers normalises the input vectors (src/solid_ele/4C_solid_ele_fiber.cpp:66-69)
+    const int64_t n = ctx->n_col_eles;
+    std::vector<double> h(3 * (size_t)(n > 0 ? n : 1));
+    CK(cudaMemcpy(h.data(), fiber1, sizeof(double) * 3 * (size_t)n, cudaMemcpyDefault));
+    for (int64_t e = 0; e < n; ++e)
+    {
+      const double nrm = std::sqrt(h[3 * e] * h[3 * e] + h[3 * e + 1] * h[3 * e + 1] + h[3 * e + 2] * h[3 * e + 2]);
+      if (!(nrm > 0.0)) return fail(ctx, B200S_ERR_INVALID, "element %lld has a zero fibre vector", (long long)e);
+      for (int d = 0; d < 3; ++d) h[3 * e + d] /= nrm;
+    }
+    double* tmp = nullptr;
+    if (to_device(ctx, &tmp, h.data(), 3 * n)) return B200S_ERR_CUDA;
+    if (to_device(ctx, &ctx->d_fibers, (const double*)nullptr, 3 * n)) return B200S_ERR_CUDA;
+    if (n > 0)
+    {
+      // caller's element order -> device (locality) order
+      k_hist_permute<<<nblk(3 * n), 256, 0, ctx->stream>>>(n, 3, ctx->d_ele_id, tmp, ctx->d_fibers, 0);
+      ctx->launches += 1;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(tmp);
+    CK(cudaGetLastError());
+    return B200S_OK;
+  }
+
   int b200s_set_density(b200s_ctx* ctx, double density)
   {
     if (!ctx) return B200S_ERR_INVALID;
@@ -2243,8 +2285,11 @@ extern "C"
       return fail(ctx, B200S_ERR_INVALID, "set_mesh and set_material must precede this action");
     if (eas_neas(ctx->tech))
       return fail(ctx, B200S_ERR_UNSUPPORTED, "stress / energy output of EAS elements stays on the CPU path");
+    if (material_needs_fibers(ctx) && !ctx->d_fibers)
+      return fail(ctx, B200S_ERR_INVALID, "the material has a fibre summand: b200s_set_element_fibers first");
     PostArgs P;
     P.X = ctx->dX, P.u = ctx->d_u_col, P.conn = ctx->dconn, P.per_ele_param = ctx->d_per_ele;
+    P.fibers = ctx->d_fibers;
     P.ele_id = ctx->d_ele_id, P.ele_is_row = ctx->d_ele_is_row;
     P.dN_gp = ctx->d_dN_gp, P.dN_cen = ctx->d_dN_cen, P.w = ctx->d_w, P.mp = ctx->mp;
     P.gp_hist = ctx->prestress == B200S_PRESTRESS_MULF ? ctx->d_gp_hist : nullptr;

@@ -191,6 +191,7 @@ namespace b200s
       right_cauchy_green(F, C);
       MatParams mp = A.mp;
       if (A.per_ele_param != nullptr && e < A.n_ele) mp.p[0] = A.per_ele_param[e];
+      if (MAT == MAT_HYPER && A.fibers != nullptr && e < A.n_ele) mp.fiber = A.fibers + 3 * e;
       material_evaluate<MAT>(mp, C, Sv, Cm);
 
       const double w = detJ * wgt[g];

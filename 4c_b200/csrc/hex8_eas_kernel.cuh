@@ -294,6 +294,7 @@ namespace b200s
         double Sv[6], Cm[21];
         MatParams mp = A.mp;
         if (A.per_ele_param != nullptr) mp.p[0] = A.per_ele_param[e];
+        if (MAT == MAT_HYPER && A.fibers != nullptr) mp.fiber = A.fibers + 3 * e;
         material_evaluate<MAT>(mp, C, Sv, Cm);
         const double w = detJ * wgt[g];
 #pragma unroll

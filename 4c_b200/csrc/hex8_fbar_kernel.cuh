@@ -156,6 +156,7 @@ namespace b200s
       }
       MatParams mp = A.mp;
       if (A.per_ele_param != nullptr && e < A.n_ele) mp.p[0] = A.per_ele_param[e];
+      if (MAT == MAT_HYPER && A.fibers != nullptr && e < A.n_ele) mp.fiber = A.fibers + 3 * e;
       material_evaluate<MAT>(mp, Cbar, Sv, Cm);
 
       // force / geometric stiffness carry w/fbar, the elastic stiffness w*fbar (fbar.hpp:152-176)

@@ -60,6 +60,7 @@ namespace b200s
     const NodeRow* node_row;      // n_col_nodes: CSR rows of the node's three dofs
     const double* per_ele_param;  // nullptr or n_ele (indexed like conn, i.e. in device order)
     const int32_t* ele_id;        // nullptr or n_ele: caller's column-element index of device element e
+    const double* fibers;         // nullptr or 3*n_ele unit fibre vectors (FIBER1), device element order
     const double* gp_hist;        // MULF only: n_ele * ngp * MULF_HIST doubles in device element order
     double* vals;                 // nnz (may be nullptr for force only)
     double* f;                    // n_rows
@@ -225,6 +226,7 @@ namespace b200s
       right_cauchy_green(F, C);
       MatParams mp = A.mp;
       if (A.per_ele_param != nullptr && e < A.n_ele) mp.p[0] = A.per_ele_param[e];
+      if (MAT == MAT_HYPER && A.fibers != nullptr && e < A.n_ele) mp.fiber = A.fibers + 3 * e;
       material_evaluate<MAT>(mp, C, Sv, Cm);
 
       // integration factor (calc_lib.hpp:1270-1280), folded into S and Cm once

@@ -36,6 +36,7 @@ namespace b200s
     const double* u;              // 3*n_col_nodes (column map)
     const int32_t* conn;          // n_ele*nn, device element order
     const double* per_ele_param;  // nullptr or n_ele (device order)
+    const double* fibers;         // nullptr or 3*n_ele unit fibre vectors (device order)
     const int32_t* ele_id;        // nullptr or device element -> caller's column element
     const uint8_t* ele_is_row;    // nullptr (all) or n_ele flags in the CALLER's numbering
     const double* dN_gp;          // [ngp][nn][3]
@@ -173,6 +174,7 @@ namespace b200s
     right_cauchy_green(F, C);
     MatParams mp = A.mp;
     if (A.per_ele_param != nullptr) mp.p[0] = A.per_ele_param[e];
+    if (MAT == MAT_HYPER && A.fibers != nullptr) mp.fiber = A.fibers + 3 * e;
     if (stress6 != nullptr && A.stress_type != STRESS_NONE)
     {
       material_evaluate<MAT>(mp, C, S, Cm);

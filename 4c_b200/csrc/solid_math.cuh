@@ -88,8 +88,8 @@ namespace b200s
   };
 
   struct HyperMat;
-  B2_HD void hyper_evaluate(const HyperMat& hm, const double* C, double* S, double* Cm);
-  B2_HD double hyper_strain_energy(const HyperMat& hm, const double* C);
+  B2_HD void hyper_evaluate(const HyperMat& hm, const double* fiber, const double* C, double* S, double* Cm);
+  B2_HD double hyper_strain_energy(const HyperMat& hm, const double* fiber, const double* C);
 
   // Material parameters preprocessed once on the host (b200s_set_material):
   //   COUP_NEOHOOKE: p[0]=c=YOUNG/(4(1+NUE)), p[1]=beta=NUE/(1-2NUE)
@@ -102,6 +102,7 @@ namespace b200s
   {
     double p[6];
     const HyperMat* hyper;
+    const double* fiber;  // HYPER with a fibre summand: the element's unit fibre vector (3 doubles)
   };
 
   // Host-side preprocessing of the input-file parameters (what the reference's PAR:: constructors
@@ -109,7 +110,7 @@ namespace b200s
   inline bool make_mat_params(int kind, const double* params, MatParams& mp)
   {
     for (double& v : mp.p) v = 0.0;
-    mp.hyper = nullptr;
+    mp.hyper = nullptr, mp.fiber = nullptr;
     if (kind == MAT_COUP_NEOHOOKE)
     {
       const double young = params[0], nue = params[1];
@@ -144,7 +145,7 @@ namespace b200s
   {
     if (MAT == MAT_HYPER)
     {
-      hyper_evaluate(*mp.hyper, C, S, Cm);
+      hyper_evaluate(*mp.hyper, mp.fiber, C, S, Cm);
     }
     else if (MAT == MAT_SVK)
     {
@@ -244,7 +245,7 @@ namespace b200s
   template <int MAT>
   B2_HD double material_strain_energy(const MatParams& mp, const double* C)
   {
-    if (MAT == MAT_HYPER) return hyper_strain_energy(*mp.hyper, C);
+    if (MAT == MAT_HYPER) return hyper_strain_energy(*mp.hyper, mp.fiber, C);
     if (MAT == MAT_SVK)
     {
       const double E[6] = {0.5 * (C[0] - 1.0), 0.5 * (C[1] - 1.0), 0.5 * (C[2] - 1.0), 0.5 * C[3],

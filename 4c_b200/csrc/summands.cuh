@@ -39,7 +39,8 @@ namespace b200s
     SUM_VOL_PENALTY = 19,        // EPSILON GAMMA
     SUM_VOL_OGDEN = 20,          // KAPPA BETA
     SUM_VOL_POW = 21,            // A EXPON
-    SUM_COUNT = 22
+    SUM_COUP_ANISOEXPO = 22,     // K1 K2 K1COMP K2COMP: one exponential fibre family on the element fibre FIBER1
+    SUM_COUNT = 23
   };
 
   constexpr int HYPER_MAX_SUMMANDS = 8;
@@ -56,7 +57,8 @@ namespace b200s
     HyperSummand s[HYPER_MAX_SUMMANDS];
   };
 
-  inline bool summand_is_modified(int kind) { return kind >= SUM_ISO_NEOHOOKE && kind < SUM_COUNT; }
+  inline bool summand_is_modified(int kind) { return kind >= SUM_ISO_NEOHOOKE && kind <= SUM_VOL_POW; }
+  inline bool summand_needs_fiber(int kind) { return kind == SUM_COUP_ANISOEXPO; }
 
   // What the reference's PAR:: constructors do once per summand: input-file parameters -> p[].
   // mode (only LogNeoHooke / LogMixNeoHooke): 0 = "YN", 1 = "Lame".  Returns false when the
@@ -114,6 +116,9 @@ namespace b200s
       case SUM_ISO_YEOH:
         s.p[0] = in[0], s.p[1] = in[1], s.p[2] = in[2];
         return true;
+      case SUM_COUP_ANISOEXPO:  // GAMMA / INIT / STR_TENS_ID: element fibres, standard structural tensor only
+        s.p[0] = in[0], s.p[1] = in[1], s.p[2] = in[2], s.p[3] = in[3];
+        return true;
       case SUM_COUP_SIMOPISTER:
       case SUM_ISO_NEOHOOKE:
       case SUM_VOL_SUSSMANBATHE:
@@ -143,6 +148,8 @@ namespace b200s
       case SUM_ISO_YEOH:
       case SUM_ISO_EXPOPOW:
         return 3;
+      case SUM_COUP_ANISOEXPO:
+        return 4;
       default:
         return (kind >= 0 && kind < SUM_COUNT) ? 2 : -1;
     }
@@ -436,10 +443,44 @@ namespace b200s
            C[0] * C[4] * C[4];
   }
 
+  // ELAST_CoupAnisoExpo summands (src/mat/elast/4C_mat_elast_coupanisoexpobase.cpp:36-62,128-160): one
+  // fibre family on the element's unit fibre a, structural tensor A = a (x) a, I4 = C : A, scalar product 1.
+  // Adds to S / Cm (when not null) and to psi (when not null).
+  B2_HD void hyper_add_fibers(const HyperMat& hm, const double* fiber, const double* C, double* S, double* Cm,
+      double* psi)
+  {
+    if (fiber == nullptr) return;
+    for (int k = 0; k < hm.n; ++k)
+    {
+      if (hm.s[k].kind != SUM_COUP_ANISOEXPO) continue;
+      const double* p = hm.s[k].p;
+      double Av[6];
+#pragma unroll
+      for (int v = 0; v < 6; ++v) Av[v] = fiber[va(v)] * fiber[vb(v)];
+      double I4 = 0.0;
+#pragma unroll
+      for (int v = 0; v < 6; ++v) I4 += C[v] * Av[v] * (v < 3 ? 1.0 : 2.0);
+      const double k1 = I4 < 1.0 ? p[2] : p[0], k2 = I4 < 1.0 ? p[3] : p[1];
+      const double x = I4 - 1.0, ef = exp(k2 * x * x);
+      if (psi) *psi += (k1 / (2.0 * k2)) * (ef - 1.0);
+      if (S)
+      {
+        const double gamma = 2. * (k1 * x * ef);
+        const double delta = 2. * (1. + 2. * k2 * x * x) * 2. * k1 * ef;
+#pragma unroll
+        for (int v = 0; v < 6; ++v) S[v] += gamma * Av[v];
+#pragma unroll
+        for (int P = 0; P < 6; ++P)
+#pragma unroll
+          for (int Q = P; Q < 6; ++Q) Cm[c21(P, Q)] += delta * Av[P] * Av[Q];
+      }
+    }
+  }
+
   // Mat::ElastHyper::evaluate for the generic summand list: S[6], Cm[21] from C (Voigt)
   // (elast_hyper_add_isotropic_stress_cmat, 4C_mat_elasthyper_service.cpp:156-206;
   //  calculate_gamma_delta :417-435)
-  B2_HD void hyper_evaluate(const HyperMat& hm, const double* C, double* S, double* Cm)
+  B2_HD void hyper_evaluate(const HyperMat& hm, const double* fiber, const double* C, double* S, double* Cm)
   {
     double I[3], iC[6], dPI[3], ddPII[6];
     invariants_principal(C, I);
@@ -469,14 +510,16 @@ namespace b200s
         if (P == Q) v += P < 3 ? d7 : 0.5 * d7;  // symmetric identity 1/2 (d_ac d_be + d_ae d_bc)
         Cm[c21(P, Q)] = v;
       }
+    hyper_add_fibers(hm, fiber, C, S, Cm, nullptr);
   }
 
   // Mat::ElastHyper::strain_energy (4C_mat_elasthyper.cpp:286-308)
-  B2_HD double hyper_strain_energy(const HyperMat& hm, const double* C)
+  B2_HD double hyper_strain_energy(const HyperMat& hm, const double* fiber, const double* C)
   {
     double I[3], dPI[3], ddPII[6], psi = 0.0;
     invariants_principal(C, I);
     hyper_invariant_derivatives(hm, I, dPI, ddPII, &psi);
+    hyper_add_fibers(hm, fiber, C, nullptr, nullptr, &psi);
     return psi;
   }
 }  // namespace b200s

@@ -70,7 +70,8 @@ extern "C"
    *   ISO_EXPOPOW {K1,K2,C}  VOL_SUSSMANBATHE {KAPPA}  VOL_PENALTY {EPSILON,GAMMA}
    *   VOL_OGDEN {KAPPA,BETA}  VOL_POW {A,EXPON}
    * MODE (LogNeoHooke / LogMixNeoHooke): 0 = "YN" (C1 = Young, C2 = nue), 1 = "Lame" (C1 = mue,
-   * C2 = lambda).  Stretch-based (IsoOgden, IsoVarga, CoupVarga) and fibre summands: CPU path. */
+   * C2 = lambda).  Stretch-based summands (IsoOgden, IsoVarga, CoupVarga) and fibre summands other than
+   * COUP_ANISOEXPO: CPU path. */
   typedef enum
   {
     B200S_SUM_COUP_NEOHOOKE = 0,
@@ -94,7 +95,10 @@ extern "C"
     B200S_SUM_VOL_SUSSMANBATHE = 18,
     B200S_SUM_VOL_PENALTY = 19,
     B200S_SUM_VOL_OGDEN = 20,
-    B200S_SUM_VOL_POW = 21
+    B200S_SUM_VOL_POW = 21,
+    B200S_SUM_COUP_ANISOEXPO = 22 /* {K1,K2,K1COMP,K2COMP}: ELAST_CoupAnisoExpo on the element fibre FIBER1
+                                     (INIT 1, standard structural tensor strategy; needs
+                                     b200s_set_element_fibers) */
   } b200s_summand;
 
   /* Discret::Elements::SolidElementProperties of an element block (4C_solid_ele_properties.hpp:30-65;
@@ -208,6 +212,10 @@ extern "C"
    * parameter constructor would throw. */
   int b200s_set_material_elasthyper(b200s_ctx* ctx, int n_summands, const int32_t* kinds,
       const int32_t* modes, const double* params);
+  /* Element fibres (FIBER1 of the SOLID element line, Discret::Elements::read_fibers,
+   * src/solid_ele/4C_solid_ele_fiber.cpp:45-73; Mat::Anisotropy::set_element_fibers): 3 doubles per
+   * column element in the caller's order, normalised here like the reference does.  [host|dev]. */
+  int b200s_set_element_fibers(b200s_ctx* ctx, const double* fiber1);
   /* Mat::So3Material::density() of the block (DENS): needed by the mass actions */
   int b200s_set_density(b200s_ctx* ctx, double density);
   /* Row (owned) elements among the column elements: is_row[n_col_eles] in the caller's element

@@ -615,7 +615,9 @@ namespace
       if ((int)q[0] != ORC_SUM_COUP_ANISOEXPO) continue;
       const double* fq = q + 6;
       if ((int)fq[0] != ORC_SUM_FIBER) continue;
-      const double* a = fq + 2;
+      // read_fibers normalises the input vector (src/solid_ele/4C_solid_ele_fiber.cpp:66-69)
+      const double nrm = std::sqrt(fq[2] * fq[2] + fq[3] * fq[3] + fq[4] * fq[4]);
+      const double a[3] = {fq[2] / nrm, fq[3] / nrm, fq[4] / nrm};
       double A[6];
       for (int v = 0; v < 6; ++v) A[v] = a[VA[v]] * a[VB[v]];
       double I4 = 0.0;

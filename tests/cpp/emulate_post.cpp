@@ -4,6 +4,7 @@
 // generic MAT_ElastHyper summands and the mass scatter addressing against the oracle without a
 // GPU.  Not shipped, not a fallback: the library has no host execution path.
 #include <cstdint>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -16,17 +17,32 @@ namespace
 {
   // matkind 0..2: params = raw input parameters (as b200s_set_material);
   // matkind 3   : params = {n, n x {kind, mode, p0..p3}} (the oracle's packed block)
+  // the oracle's block may carry its fibre material as {100: CoupAnisoExpo}{101: fibre vector}: the product's
+  // summand id is SUM_COUP_ANISOEXPO and the (normalised) fibre goes through MatParams::fiber
+  double g_fiber[3];
   bool setup_material(int matkind, const double* params, MatParams& mp, HyperMat& hm)
   {
     if (matkind != MAT_HYPER) return make_mat_params(matkind, params, mp);
     for (double& v : mp.p) v = 0.0;
-    hm.n = (int)params[0], hm.uses_modified = 0;
-    if (hm.n > HYPER_MAX_SUMMANDS) return false;
-    for (int k = 0; k < hm.n; ++k)
+    mp.fiber = nullptr;
+    const int n = (int)params[0];
+    hm.n = 0, hm.uses_modified = 0;
+    for (int k = 0; k < n; ++k)
     {
       const double* q = params + 1 + 6 * k;
-      if (!make_summand((int)q[0], q + 2, (int)q[1], hm.s[k])) return false;
-      if (summand_is_modified((int)q[0])) hm.uses_modified = 1;
+      int kind = (int)q[0];
+      if (kind == 101)
+      {
+        const double nrm = std::sqrt(q[2] * q[2] + q[3] * q[3] + q[4] * q[4]);
+        for (int d = 0; d < 3; ++d) g_fiber[d] = q[2 + d] / nrm;
+        mp.fiber = g_fiber;
+        continue;
+      }
+      if (kind == 100) kind = SUM_COUP_ANISOEXPO;
+      if (hm.n >= HYPER_MAX_SUMMANDS) return false;
+      if (!make_summand(kind, q + 2, (int)q[1], hm.s[hm.n])) return false;
+      if (summand_is_modified(kind)) hm.uses_modified = 1;
+      hm.n += 1;
     }
     mp.hyper = &hm;
     return true;
@@ -103,7 +119,7 @@ extern "C" int emu_post(int celltype, int fbar, int matkind, const double* param
   HyperMat hm;
   if (!setup_material(matkind, params, mp, hm)) return -3;
   PostArgs A;
-  A.X = X, A.u = u_col, A.conn = conn, A.per_ele_param = per_ele, A.ele_id = nullptr;
+  A.X = X, A.u = u_col, A.conn = conn, A.per_ele_param = per_ele, A.ele_id = nullptr, A.fibers = nullptr;
   A.ele_is_row = ele_is_row, A.dN_gp = T.dN_gp.data(), A.dN_cen = T.dN_cen.data(), A.w = T.w.data();
   A.mp = mp, A.n_ele = n_ele, A.nn = T.nn, A.ngp = T.ngp, A.fbar = fbar, A.gp_hist = gp_hist;
   A.stress_type = stress_type, A.strain_type = strain_type;

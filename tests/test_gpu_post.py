@@ -517,3 +517,88 @@ def test_eas_is_hex8_only_and_recover_is_a_noop_without_eas():
     asm = b200.DeviceAssembler(rm, capi.MAT_SVK, [1000.0, 0.3])
     asm.recover(np.zeros(asm.n_rows))
     asm.close()
+
+
+# ------------------------------------------------------------------------------------------------------
+# The reference's own MULF / EAS ctest inputs (fibre material) through the CUDA path
+# ------------------------------------------------------------------------------------------------------
+def _fibre_material(case):
+    nh, fib = case["summands"][0]["params"], case["summands"][1]["params"]
+    return [("COUP_NEOHOOKE", [nh["YOUNG"], nh["NUE"]]),
+            ("COUP_ANISOEXPO", [fib["K1"], fib["K2"], fib["K1COMP"], fib["K2COMP"]])]
+
+
+@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10"])
+def test_reference_mulf_known_answers_through_cuda_path(cell):
+    """RESULT DESCRIPTION displacements (reference tolerance 1e-12) of tests/input_files/
+    solid_ele_<cell>_Standard_mulf.4C.yaml with the CUDA path doing every evaluate and prestress update:
+    MAT_ElastHyper{CoupNeoHooke, CoupAnisoExpo} on the element fibres, PRESTRESS_TECH mulf."""
+    from tests.helpers.newton import solve_case
+    case = json.load(open(os.path.join(G, f"integration_{cell}_mulf.json")))
+    ct = CELLS[cell]
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    rm = b200.partition.serial_mesh(ct, X, conn)
+    asm = b200.DeviceAssembler(rm, capi.MAT_ELASTHYPER, _fibre_material(case), prestress=capi.PRESTRESS_MULF,
+                               fibers=np.asarray(case["fibers"], float))
+    rowptr, colind = asm.graph()
+
+    def ev(u):
+        asm.set_state("displacement", u)
+        K, f, _ = asm.evaluate()
+        return rowptr, colind, K, f
+
+    def up(u):
+        asm.set_state("displacement", u)
+        asm.update_prestress()
+
+    u = solve_case(case, ev, update_prestress=up)
+    assert len(case["expected_disp"]) >= 12
+    for e in case["expected_disp"]:
+        assert abs(u[e["node"], e["dof"]] - e["value"]) < 1e-10, (e, u[e["node"], e["dof"]])
+    asm.close()
+
+
+@pytest.mark.parametrize("tech", ["eas_mild", "eas_full"])
+def test_reference_eas_known_answers_through_cuda_path(tech):
+    """RESULT DESCRIPTION displacements of the reference's TECH eas_mild / eas_full hex8 inputs with the
+    CUDA path doing every evaluate and struct_calc_recover (fibre material on the device)."""
+    from tests.helpers.newton import solve_case
+    case = json.load(open(os.path.join(G, f"integration_hex8_{tech}.json")))
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    rm = b200.partition.serial_mesh(orc.HEX8, X, conn)
+    asm = b200.DeviceAssembler(rm, capi.MAT_ELASTHYPER, _fibre_material(case), tech=EAS[tech][0],
+                               fibers=np.asarray(case["fibers"], float))
+    rowptr, colind = asm.graph()
+
+    def ev(u):
+        asm.set_state("displacement", u)
+        K, f, _ = asm.evaluate()
+        return rowptr, colind, K, f
+
+    u = solve_case(case, ev, recover=lambda du: asm.recover(du, 1.0))
+    for e in case["expected_disp"]:
+        assert abs(u[e["node"], e["dof"]] - e["value"]) < 1e-10, (e, u[e["node"], e["dof"]])
+    asm.close()
+
+
+def test_fibre_material_needs_fibres_and_stress_output_matches_oracle():
+    ct, rm, u = _mesh("hex8")
+    mat = [("COUP_NEOHOOKE", [10.0, 0.25]), ("COUP_ANISOEXPO", [100.0, 1.0, 0.0, 1.0])]
+    asm = b200.DeviceAssembler(rm, capi.MAT_ELASTHYPER, mat)
+    asm.set_state("displacement", u.ravel())
+    with pytest.raises(capi.B200SolidError) as ei:
+        asm.evaluate()
+    assert ei.value.code == capi.ERR_INVALID
+    rng = np.random.default_rng(3)
+    fib = rng.uniform(-1, 1, (rm.n_col_eles, 3)) + np.array([2.0, 0, 0])  # not normalised on purpose
+    asm.ctx.set_element_fibers(fib)
+    rowptr, colind = asm.graph()
+    K, f, _ = asm.evaluate()
+    opar = orc.pack_elasthyper(mat + [("FIBER", [1.0, 0.0, 0.0])])
+    rK, rf, _ = orc.evaluate_assemble(ct, orc.MAT_ELASTHYPER, opar, rm.conn, rm.X.ravel(), u.ravel(), rm.node_row_lid,
+                                      rm.node_col_lid, rm.n_row_nodes, rowptr, colind, mue_per_ele=fib.ravel())
+    ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
+    assert ok, (wK, wf)
+    asm.close()

@@ -439,3 +439,33 @@ def test_eas_known_answers(tech):
     assert len(case["expected_disp"]) >= 12
     for e in case["expected_disp"]:
         assert abs(u[e["node"], e["dof"]] - e["value"]) < 1e-11, (e, u[e["node"], e["dof"]])
+
+
+# ------------------------------------------------------------------------------------------------------
+# fibre summand ELAST_CoupAnisoExpo
+# ------------------------------------------------------------------------------------------------------
+FIBER_BLOCK = [("COUP_NEOHOOKE", [10.0, 0.25]), ("COUP_ANISOEXPO", [100.0, 1.0, 0.0, 1.0]), ("FIBER", [0.6, 0.7, 0.2])]
+
+
+def test_fibre_summand_is_consistent_and_product_matches_oracle():
+    """S = d psi / d E, C = d S / d E for the oracle's CoupAnisoExpo (tension branch and compression branch
+    K1COMP = 0), and the product's summand (emulated) against it.  The oracle's summand is additionally
+    pinned by the MULF / EAS known answers above, which all use it."""
+    for E in (E_TEST, -0.5 * E_TEST):
+        blk = orc.pack_elasthyper(FIBER_BLOCK)
+        S, Cm = orc.material(orc.MAT_ELASTHYPER, blk, E)
+        h = 1e-6
+        w = np.array([1, 1, 1, 2, 2, 2.0])
+        for v in range(6):
+            d = np.zeros(6)
+            d[v] = h
+            dpsi = (orc.strain_energy(orc.MAT_ELASTHYPER, blk, E + d) - orc.strain_energy(orc.MAT_ELASTHYPER, blk, E - d)) / (2 * h)
+            assert abs(dpsi / w[v] - S[v]) <= 2e-7 * max(1.0, np.abs(S).max())
+            dS = (orc.material(orc.MAT_ELASTHYPER, blk, E + d)[0] - orc.material(orc.MAT_ELASTHYPER, blk, E - d)[0]) / (2 * h) / w[v]
+            assert np.abs(dS - Cm[:, v]).max() <= 2e-6 * max(1.0, np.abs(Cm).max())
+        S2, C2, psi2 = emu.material(3, blk, _C_of(E))
+        assert np.abs(S - S2).max() <= 1e-12 * np.abs(S).max() and np.abs(Cm - C2).max() <= 1e-12 * np.abs(Cm).max()
+        assert abs(psi2 - orc.strain_energy(orc.MAT_ELASTHYPER, blk, E)) <= 1e-12 * max(abs(psi2), 1e-6)
+    # the fibre really contributes in tension
+    iso = orc.material(orc.MAT_ELASTHYPER, orc.pack_elasthyper(FIBER_BLOCK[:1]), E_TEST)[0]
+    assert np.abs(orc.material(orc.MAT_ELASTHYPER, orc.pack_elasthyper(FIBER_BLOCK), E_TEST)[0] - iso).max() > 1.0
