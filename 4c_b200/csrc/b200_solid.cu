@@ -1091,6 +1091,7 @@ struct b200s_ctx
   // linear algebra on the assembled matrix (linalg_kernels.cuh)
   int64_t n_mat_cols = 0;
   bool node3_ok = false;
+  int32_t* d_blkcol = nullptr;  // node-blocked layout: one column id per 3x3 block (nnz / 9)
   double *d_xmat = nullptr, *d_la_x = nullptr, *d_la_y = nullptr, *d_toggle = nullptr;
   double *d_cg[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // r z p Ap dinv(3x)
   double *d_cg_s = nullptr, *d_cg_hist = nullptr;
@@ -1415,7 +1416,7 @@ extern "C"
     dfree(ctx->d_u_row), dfree(ctx->d_u_col), dfree(ctx->d_send_lid), dfree(ctx->d_recv_lid);
     dfree(ctx->d_sendbuf), dfree(ctx->d_recvbuf), dfree(ctx->d_err);
     dfree(ctx->d_gp_hist), dfree(ctx->d_eas_hist), dfree(ctx->d_du_row), dfree(ctx->d_du_col);
-    dfree(ctx->d_eas_t0), dfree(ctx->d_fibers);
+    dfree(ctx->d_eas_t0), dfree(ctx->d_fibers), dfree(ctx->d_blkcol);
     dfree(ctx->d_hyper), dfree(ctx->d_dN_gp), dfree(ctx->d_w), dfree(ctx->d_dN_cen), dfree(ctx->d_N_mass);
     dfree(ctx->d_dN_mass), dfree(ctx->d_w_mass), dfree(ctx->d_ele_is_row), dfree(ctx->d_mass);
     dfree(ctx->d_f_inertia), dfree(ctx->d_acc_row), dfree(ctx->d_acc_col), dfree(ctx->d_energy);
@@ -1682,6 +1683,14 @@ extern "C"
       CK(cudaStreamSynchronize(ctx->stream));
       cudaFree(d_f3);
       ctx->node3_ok = (f3 == 0);
+      dfree(ctx->d_blkcol);
+      if (ctx->node3_ok)
+      {
+        if (to_device(ctx, &ctx->d_blkcol, (const int32_t*)nullptr, nnz / 9 + 1)) return B200S_ERR_CUDA;
+        k_build_blkcol<<<nblk(32 * ncn), 256, 0, ctx->stream>>>(ncn, ctx->d_node_row, d_colind, ctx->d_blkcol);
+        ctx->launches += 1;
+        CK(cudaStreamSynchronize(ctx->stream));
+      }
     }
     if (flag)
     {
@@ -2540,7 +2549,7 @@ extern "C"
     if (rc) return rc;
     if (ctx->node3_ok)
       k_spmv_node3<<<nblk(32 * ctx->n_col_nodes), 256, 0, ctx->stream>>>(ctx->n_col_nodes, ctx->d_node_row,
-          ctx->d_colind, vals, ctx->d_xmat, d_y_row, d_w, d_dot);
+          ctx->d_blkcol, vals, ctx->d_xmat, d_y_row, d_w, d_dot);
     else
       k_spmv_csr<<<nblk(32 * ctx->n_rows), 256, 0, ctx->stream>>>(ctx->n_rows, ctx->d_rowptr, ctx->d_colind,
           vals, ctx->d_xmat, d_y_row, d_w, d_dot);

@@ -87,8 +87,8 @@ namespace b200s
   // step -- one column index per 9 values, 8.4 bytes per non-zero instead of 12.
   // Row nodes are the column nodes with frow >= 0 (owned), visited in column-node order.
   __global__ void __launch_bounds__(256) k_spmv_node3(int64_t n_col_nodes, const NodeRow* node_row,
-      const int32_t* colind, const double* vals, const double* x_mat, double* y, const double* w,
-      double* dot)
+      const int32_t* colind /* block column ids, k_build_blkcol */, const double* vals, const double* x_mat,
+      double* y, const double* w, double* dot)
   {
     const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -99,11 +99,12 @@ namespace b200s
     const double* v0 = vals + nr.rowstart;
     const double* v1 = v0 + nr.rowlen;
     const double* v2 = v1 + nr.rowlen;
-    const int32_t* ci = colind + nr.rowstart;
+    // one column id per 3x3 block: rows of a node are consecutive, so rowstart / 9 is the block offset
+    const int32_t* ci = colind + nr.rowstart / 9;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
     for (int q = lane; q < nblk; q += 32)
     {
-      const int32_t c = ci[3 * q];
+      const int32_t c = ci[q];
       const double x0 = __ldg(x_mat + c), x1 = __ldg(x_mat + c + 1), x2 = __ldg(x_mat + c + 2);
       a0 = fma(v0[3 * q + 2], x2, fma(v0[3 * q + 1], x1, fma(v0[3 * q], x0, a0)));
       a1 = fma(v1[3 * q + 2], x2, fma(v1[3 * q + 1], x1, fma(v1[3 * q], x0, a1)));
@@ -122,6 +123,18 @@ namespace b200s
     }
   }
 
+  // compressed column ids of the node-blocked layout: first column of every 3x3 block, nnz / 9 entries
+  __global__ void k_build_blkcol(int64_t n_col_nodes, const NodeRow* node_row, const int32_t* colind,
+      int32_t* blkcol)
+  {
+    const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (k >= n_col_nodes) return;
+    const NodeRow nr = node_row[k];
+    if (nr.frow < 0) return;
+    for (int q = lane; q < nr.rowlen / 3; q += 32) blkcol[nr.rowstart / 9 + q] = colind[nr.rowstart + 3 * q];
+  }
+
   // checks the node-blocked pattern k_spmv_node3 relies on; flag |= 1 otherwise
   __global__ void k_check_node3(int64_t n_col_nodes, const NodeRow* node_row, const int32_t* colind,
       int* flag)
@@ -131,7 +144,7 @@ namespace b200s
     if (k >= n_col_nodes) return;
     const NodeRow nr = node_row[k];
     if (nr.frow < 0) return;
-    bool bad = (nr.rowlen % 3) != 0;
+    bool bad = (nr.rowlen % 3) != 0 || (nr.rowstart % 9) != 0;
     const int32_t* ci = colind + nr.rowstart;
     for (int q = lane; q < nr.rowlen && !bad; q += 32)
     {
