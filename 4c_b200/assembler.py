@@ -23,7 +23,8 @@ NUM_GP = {capi.HEX8: 8, capi.HEX27: 27, capi.TET10: 4}
 
 class DeviceAssembler:
     def __init__(self, rank_mesh, matkind, matparams, device=0, per_ele_param=None, graph=None,
-                 tech=capi.TECH_NONE, density=None, prestress=capi.PRESTRESS_NONE, fibers=None):
+                 tech=capi.TECH_NONE, density=None, prestress=capi.PRESTRESS_NONE, fibers=None,
+                 kinem=capi.KINEM_NONLINEAR_TOTLAG):
         """rank_mesh: partition.RankMesh.  graph: (rowptr, colind) from the reference's matrix, or
         None to build the FillComplete-equivalent graph on the device.  tech: element technology of
         the block (TECH key of the SOLID element line).  matkind MAT_ELASTHYPER: matparams is the
@@ -31,8 +32,8 @@ class DeviceAssembler:
         rm = self.rm = rank_mesh
         self.ctx = capi.Context(device, rm.rank, rm.nranks)
         self.ctx.set_mesh(rm.celltype, rm.X, rm.conn)
-        if tech != capi.TECH_NONE or prestress != capi.PRESTRESS_NONE:
-            self.ctx.set_element_properties(tech=tech, prestress=prestress)
+        if tech != capi.TECH_NONE or prestress != capi.PRESTRESS_NONE or kinem != capi.KINEM_NONLINEAR_TOTLAG:
+            self.ctx.set_element_properties(kinem=kinem, tech=tech, prestress=prestress)
         if matkind == capi.MAT_ELASTHYPER:
             self.ctx.set_material_elasthyper(matparams)
         else:

@@ -12,14 +12,31 @@
 #include <string>
 #include <vector>
 
+// Translation-unit partitioning: the ~100 heavy kernel instantiations make one nvcc run take ~3 minutes, so
+// __graft_entry__.build_library compiles this file five times in parallel with -DB200S_PART=0..4 (core + ABI,
+// hex8, hex8 EAS, tet10, hex27) and links the objects.  Without the macro everything is one translation unit.
+// (nvcc --split-compile was measured: 3x faster to build but 8-25 % slower kernels.)
+#define B200S_PART_CORE 0
+#define B200S_PART_HEX8 1
+#define B200S_PART_EAS 2
+#define B200S_PART_TET10 3
+#define B200S_PART_HEX27 4
+#ifndef B200S_PART
+#define B200S_HAS(p) 1
+#else
+#define B200S_HAS(p) (B200S_PART == (p))
+#endif
+
 #include "../../include/b200_solid.h"
 #include "hex8_kernel.cuh"
 #include "hex8_fbar_kernel.cuh"
 #include "hex8_eas_kernel.cuh"
 #include "tet10_kernel.cuh"
 #include "hex27_kernel.cuh"
+#if B200S_HAS(B200S_PART_CORE)
 #include "post_kernels.cuh"
 #include "linalg_kernels.cuh"
+#endif
 #include "shape_tables.hpp"
 
 namespace b200s
@@ -34,21 +51,21 @@ namespace b200s
     double w[8];
     double xi_gp[8 * 3];  // parameter coordinates of the Gauss points (EAS shape functions)
   };
-  __constant__ Hex8Const c_hex8;
+  static __constant__ Hex8Const c_hex8;  // one copy per translation unit that launches hex8 kernels
   struct Tet10Const
   {
     double dN_gp[4 * 30];
     double dN_node[10 * 30];
     double w[4];
   };
-  __constant__ Tet10Const c_tet10;
+  static __constant__ Tet10Const c_tet10;
   struct Hex27Const
   {
     double dN_gp[27 * 81];
     double w[28];
     hex27::IntTables it;
   };
-  __device__ Hex27Const c_hex27;  // global memory (17.8 KB): copied to shared memory once per CTA
+  static __device__ Hex27Const c_hex27;  // global memory (17.8 KB): copied to shared memory once per CTA
 
   // ------------------------------------------------------------------------------------------------
   // hex8 evaluate + assemble kernel (see hex8_kernel.cuh for the phase structure)
@@ -142,14 +159,16 @@ namespace b200s
     }
   }  // namespace hex8
 
+#if B200S_HAS(B200S_PART_HEX8)
   // TECH 0: displacement based (4 warps, 2 CTAs/SM); TECH 1: F-bar (7 warps, 1 CTA/SM, more shared
   // memory per warp and the full non-symmetric block row per lane, hex8_fbar_kernel.cuh);
-  // TECH 2: displacement based with MULF prestress (TECH 0 with the history-based deformation gradient)
+  // TECH 2: displacement based with MULF prestress (TECH 0 with the history-based deformation gradient);
+  // TECH 3: displacement based with linear kinematics (KINEM linear)
   template <int MAT, bool STIFF, int TECH>
   __global__ void __launch_bounds__((TECH == 1 ? HEX8_FBAR_WARPS : HEX8_WARPS) * 32, TECH == 1 ? 1 : 2)
       k_hex8_eval_assemble(const EvalArgs A)
   {
-    constexpr bool FBAR = TECH == 1, MULF = TECH == 2;
+    constexpr bool FBAR = TECH == 1, MULF = TECH == 2, LINEAR = TECH == 3;
     constexpr int WARPS = FBAR ? HEX8_FBAR_WARPS : HEX8_WARPS;
     constexpr size_t warp_bytes = FBAR ? hex8_fbar_warp_bytes : hex8_warp_bytes;
     constexpr int MP_SIZE = FBAR ? hex8fbar::MP_SIZE : hex8::MP_SIZE;
@@ -205,7 +224,7 @@ namespace b200s
       if (FBAR)
         hex8fbar::phase1<MAT, STIFF>(A, S, tab_gp, wgt, lane, e0, out54, dJ, dF, neg);
       else
-        hex8::phase1<MAT, STIFF, MULF>(A, S, tab_gp, tab_node, wgt, lane, e0, out54, dJ, dF, neg);
+        hex8::phase1<MAT, STIFF, MULF, LINEAR>(A, S, tab_gp, tab_node, wgt, lane, e0, out54, dJ, dF, neg);
       if (e0 + (lane >> 3) < A.n_ele)
       {
         detJ_min = fmin(detJ_min, dJ);
@@ -262,6 +281,8 @@ namespace b200s
     }
   }
 
+#endif  // B200S_PART_HEX8
+
   // ------------------------------------------------------------------------------------------------
   // hex8 EAS evaluate + assemble kernel (hex8_eas_kernel.cuh): one warp per element, persistent grid
   // ------------------------------------------------------------------------------------------------
@@ -271,6 +292,7 @@ namespace b200s
   {
     return hex8_table_bytes + 24 * 8 + HEX8_EAS_WARPS * (size_t)((hex8eas::Layout<NEAS>::BYTES + 15) & ~15);
   }
+#if B200S_HAS(B200S_PART_EAS)
   template <int MAT, bool STIFF, int NEAS>
   __global__ void __launch_bounds__(HEX8_EAS_WARPS * 32, 2)
       k_hex8_eas_eval_assemble(const EvalArgs A, double* hist, const double* t0tab)
@@ -372,6 +394,8 @@ namespace b200s
     }
   }
 
+#endif  // B200S_PART_EAS
+
   // ------------------------------------------------------------------------------------------------
   // tet10 evaluate + assemble kernel (see tet10_kernel.cuh; same gather pipeline as hex8)
   // ------------------------------------------------------------------------------------------------
@@ -426,7 +450,9 @@ namespace b200s
     }
   }  // namespace tet10
 
-  template <int MAT, bool STIFF, bool MULF>
+#if B200S_HAS(B200S_PART_TET10)
+  // FORM 0: displacement based, 1: MULF prestress, 2: KINEM linear
+  template <int MAT, bool STIFF, int FORM>
   __global__ void __launch_bounds__(TET10_WARPS * 32, 2) k_tet10_eval_assemble(const EvalArgs A)
   {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -477,7 +503,7 @@ namespace b200s
       const bool neg = live && !(dJn > 0.0);
       double out54[54];
       double dJ, dF;
-      tet10::phase1<MAT, STIFF, MULF>(A, S, tab_gp, wgt, lane, e0, out54, dJ, dF);
+      tet10::phase1<MAT, STIFF, FORM == 1, FORM == 2>(A, S, tab_gp, wgt, lane, e0, out54, dJ, dF);
       if (live)
       {
         detJ_min = fmin(detJ_min, fmin(dJn, dJ));
@@ -527,6 +553,8 @@ namespace b200s
     }
   }
 
+#endif  // B200S_PART_TET10
+
   // ------------------------------------------------------------------------------------------------
   // hex27 evaluate + assemble kernel (see hex27_kernel.cuh): CTA = 4 warp pairs, one element per pair
   // ------------------------------------------------------------------------------------------------
@@ -574,7 +602,9 @@ namespace b200s
     }
   }  // namespace hex27
 
-  template <int MAT, bool STIFF, bool MULF>
+#if B200S_HAS(B200S_PART_HEX27)
+  // FORM 0: displacement based, 1: MULF prestress, 2: KINEM linear
+  template <int MAT, bool STIFF, int FORM>
   __global__ void __launch_bounds__(HEX27_PAIRS * 64, 1) k_hex27_eval_assemble(const EvalArgs A)
   {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -626,7 +656,7 @@ namespace b200s
       {
         double out54[54];
         double dJ, dF;
-        hex27::phase1<MAT, STIFF, MULF>(A, S, tab_gp, wgt, my_gp, e, out54, dJ, dF);
+        hex27::phase1<MAT, STIFF, FORM == 1, FORM == 2>(A, S, tab_gp, wgt, my_gp, e, out54, dJ, dF);
         detJ_min = fmin(detJ_min, dJ);
         detF_min = fmin(detF_min, dF);
       }
@@ -690,6 +720,9 @@ namespace b200s
     }
   }
 
+#endif  // B200S_PART_HEX27
+
+#if B200S_HAS(B200S_PART_CORE)
   // ------------------------------------------------------------------------------------------------
   // set-up kernels
   // ------------------------------------------------------------------------------------------------
@@ -1028,6 +1061,7 @@ namespace b200s
       atomicAdd(buf + idx, 1.0);
     }
   }
+#endif  // B200S_PART_CORE
 }  // namespace b200s
 
 using namespace b200s;
@@ -1066,6 +1100,7 @@ struct b200s_ctx
   // SolidElementProperties of the block (4C_solid_ele_properties.hpp:55-65)
   int tech = B200S_TECH_NONE;
   int prestress = B200S_PRESTRESS_NONE;
+  int kinem = B200S_KINEM_NONLINEAR_TOTLAG;
   double* d_gp_hist = nullptr;  // MULF: n_col_eles * ngp * MULF_HIST doubles, device element order
   double* d_eas_hist = nullptr; // EAS: n_col_eles * hex8eas::hist_size(neas) doubles, device element order
   double* d_eas_t0 = nullptr;   // EAS: T0invT[36] + detJ0 per element (stride hex8eas::T0_STRIDE)
@@ -1141,7 +1176,8 @@ struct b200s_ctx
 
 namespace
 {
-  int fail(b200s_ctx* c, int code, const char* fmt, ...)
+  // (static: nvcc derives the anonymous-namespace name from the source file, which all parts share)
+  static int fail(b200s_ctx* c, int code, const char* fmt, ...)
   {
     char buf[512];
     va_list ap;
@@ -1185,6 +1221,37 @@ namespace
   }
 }  // namespace
 
+// Entry points of the kernel translation units (each defined in exactly one part, see the top of the file)
+namespace b200s_parts
+{
+  int launch_hex8(b200s_ctx* ctx, const EvalArgs& A, bool stiff);      // TECH none / fbar, MULF, KINEM linear
+  int launch_hex8_eas(b200s_ctx* ctx, const EvalArgs& A, bool stiff);  // TECH eas_mild / eas_full
+  int launch_tet10(b200s_ctx* ctx, const EvalArgs& A, bool stiff);
+  int launch_hex27(b200s_ctx* ctx, const EvalArgs& A, bool stiff);
+  int set_tables_hex8(b200s_ctx* ctx, const Hex8Const& h);      // constant tables of the part's kernels
+  int set_tables_hex8_eas(b200s_ctx* ctx, const Hex8Const& h);
+  int set_tables_tet10(b200s_ctx* ctx, const Tet10Const& h);
+  int set_tables_hex27(b200s_ctx* ctx, const Hex27Const& h);
+  int eas_centroid(b200s_ctx* ctx);                              // set-up: T0^-T, det J0 of every element
+  int eas_recover(b200s_ctx* ctx, int neas, double step_length); // struct_calc_recover
+}  // namespace b200s_parts
+
+// material switch of a part's launch function template
+#define B200S_DISPATCH_MATERIAL(fn)                                                                     \
+  switch (ctx->matkind)                                                                                 \
+  {                                                                                                     \
+    case B200S_MAT_COUP_NEOHOOKE:                                                                       \
+      return stiff ? fn<MAT_COUP_NEOHOOKE, true>(ctx, A) : fn<MAT_COUP_NEOHOOKE, false>(ctx, A);        \
+    case B200S_MAT_ISO_VOL:                                                                             \
+      return stiff ? fn<MAT_ISO_VOL, true>(ctx, A) : fn<MAT_ISO_VOL, false>(ctx, A);                    \
+    case B200S_MAT_SVK:                                                                                 \
+      return stiff ? fn<MAT_SVK, true>(ctx, A) : fn<MAT_SVK, false>(ctx, A);                            \
+    case B200S_MAT_ELASTHYPER:                                                                          \
+      return stiff ? fn<MAT_HYPER, true>(ctx, A) : fn<MAT_HYPER, false>(ctx, A);                        \
+  }                                                                                                     \
+  return fail(ctx, B200S_ERR_INVALID, "material not set")
+
+#if B200S_HAS(B200S_PART_CORE)
 namespace
 {
   // element-kernel durations: one CUDA event pair per evaluate on the context stream, harvested at
@@ -1219,12 +1286,7 @@ namespace
     if (to_device(ctx, &ctx->d_eas_hist, (const double*)nullptr, n)) return B200S_ERR_CUDA;
     CK(cudaMemsetAsync(ctx->d_eas_hist, 0, sizeof(double) * (size_t)(n > 0 ? n : 1), ctx->stream));
     if (to_device(ctx, &ctx->d_eas_t0, (const double*)nullptr, ctx->n_col_eles * hex8eas::T0_STRIDE)) return B200S_ERR_CUDA;
-    if (ctx->n_col_eles > 0)
-    {
-      k_eas_centroid<<<nblk(32 * ctx->n_col_eles, 128), 128, 0, ctx->stream>>>(ctx->n_col_eles, ctx->dconn, ctx->dX,
-          ctx->d_eas_t0);
-      ctx->launches += 1;
-    }
+    if (ctx->n_col_eles > 0 && b200s_parts::eas_centroid(ctx)) return B200S_ERR_CUDA;
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
     return 0;
@@ -1248,6 +1310,12 @@ namespace
     return 0;
   }
 
+}  // namespace
+#endif  // B200S_PART_CORE
+
+#if B200S_HAS(B200S_PART_EAS)
+namespace
+{
   template <int MAT, bool STIFF, int NEAS>
   static int launch_hex8_eas(b200s_ctx* ctx, const EvalArgs& A)
   {
@@ -1265,10 +1333,50 @@ namespace
   }
 
   template <int MAT, bool STIFF>
-  static int launch_hex8(b200s_ctx* ctx, const EvalArgs& A)
+  static int launch_hex8_eas_any(b200s_ctx* ctx, const EvalArgs& A)
   {
-    if (ctx->tech == B200S_TECH_EAS_MILD) return launch_hex8_eas<MAT, STIFF, 9>(ctx, A);
-    if (ctx->tech == B200S_TECH_EAS_FULL) return launch_hex8_eas<MAT, STIFF, 21>(ctx, A);
+    return ctx->tech == B200S_TECH_EAS_MILD ? launch_hex8_eas<MAT, STIFF, 9>(ctx, A)
+                                            : launch_hex8_eas<MAT, STIFF, 21>(ctx, A);
+  }
+}  // namespace
+namespace b200s_parts
+{
+  int launch_hex8_eas(b200s_ctx* ctx, const EvalArgs& A, bool stiff) { B200S_DISPATCH_MATERIAL(launch_hex8_eas_any); }
+  int set_tables_hex8_eas(b200s_ctx* ctx, const Hex8Const& h)
+  {
+    CK(cudaMemcpyToSymbolAsync(c_hex8, &h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  }
+  int eas_centroid(b200s_ctx* ctx)
+  {
+    k_eas_centroid<<<nblk(32 * ctx->n_col_eles, 128), 128, 0, ctx->stream>>>(ctx->n_col_eles, ctx->dconn, ctx->dX,
+        ctx->d_eas_t0);
+    ctx->launches += 1;
+    return 0;
+  }
+  int eas_recover(b200s_ctx* ctx, int neas, double step_length)
+  {
+    const unsigned grid = nblk(32 * ctx->n_col_eles, 128);
+    if (!grid) return 0;
+    if (neas == 9)
+      k_eas_recover<9><<<grid, 128, 0, ctx->stream>>>(ctx->n_col_eles, ctx->dconn, ctx->d_du_col, step_length,
+          ctx->d_eas_hist);
+    else
+      k_eas_recover<21><<<grid, 128, 0, ctx->stream>>>(ctx->n_col_eles, ctx->dconn, ctx->d_du_col, step_length,
+          ctx->d_eas_hist);
+    ctx->launches += 1;
+    return 0;
+  }
+}  // namespace b200s_parts
+#endif  // B200S_PART_EAS
+
+#if B200S_HAS(B200S_PART_HEX8)
+namespace
+{
+  template <int MAT, bool STIFF>
+  static int launch_hex8_t(b200s_ctx* ctx, const EvalArgs& A)
+  {
     if (ctx->tech == B200S_TECH_FBAR)
     {
       auto kern = k_hex8_eval_assemble<MAT, STIFF, 1>;
@@ -1282,8 +1390,10 @@ namespace
       ctx->launches += 1;
       return 0;
     }
-    auto kern = ctx->prestress == B200S_PRESTRESS_MULF ? k_hex8_eval_assemble<MAT, STIFF, 2>
-                                                       : k_hex8_eval_assemble<MAT, STIFF, 0>;
+    auto kern = ctx->prestress == B200S_PRESTRESS_MULF
+                    ? k_hex8_eval_assemble<MAT, STIFF, 2>
+                    : (ctx->kinem == B200S_KINEM_LINEAR ? k_hex8_eval_assemble<MAT, STIFF, 3>
+                                                        : k_hex8_eval_assemble<MAT, STIFF, 0>);
     // per device and cheap: set on every launch (a process may hold contexts on several GPUs)
     if (set_smem_attr(kern, hex8_smem_bytes))
       return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", hex8_smem_bytes);
@@ -1297,11 +1407,29 @@ namespace
     return 0;
   }
 
-  template <int MAT, bool STIFF>
-  static int launch_tet10(b200s_ctx* ctx, const EvalArgs& A)
+}  // namespace
+namespace b200s_parts
+{
+  int launch_hex8(b200s_ctx* ctx, const EvalArgs& A, bool stiff) { B200S_DISPATCH_MATERIAL(launch_hex8_t); }
+  int set_tables_hex8(b200s_ctx* ctx, const Hex8Const& h)
   {
-    auto kern = ctx->prestress == B200S_PRESTRESS_MULF ? k_tet10_eval_assemble<MAT, STIFF, true>
-                                                       : k_tet10_eval_assemble<MAT, STIFF, false>;
+    CK(cudaMemcpyToSymbolAsync(c_hex8, &h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  }
+}  // namespace b200s_parts
+#endif  // B200S_PART_HEX8
+
+#if B200S_HAS(B200S_PART_TET10)
+namespace
+{
+  template <int MAT, bool STIFF>
+  static int launch_tet10_t(b200s_ctx* ctx, const EvalArgs& A)
+  {
+    auto kern = ctx->prestress == B200S_PRESTRESS_MULF
+                    ? k_tet10_eval_assemble<MAT, STIFF, 1>
+                    : (ctx->kinem == B200S_KINEM_LINEAR ? k_tet10_eval_assemble<MAT, STIFF, 2>
+                                                        : k_tet10_eval_assemble<MAT, STIFF, 0>);
     // per device and cheap: set on every launch (a process may hold contexts on several GPUs)
     if (set_smem_attr(kern, tet10_smem_bytes))
       return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", tet10_smem_bytes);
@@ -1315,11 +1443,29 @@ namespace
     return 0;
   }
 
-  template <int MAT, bool STIFF>
-  static int launch_hex27(b200s_ctx* ctx, const EvalArgs& A)
+}  // namespace
+namespace b200s_parts
+{
+  int launch_tet10(b200s_ctx* ctx, const EvalArgs& A, bool stiff) { B200S_DISPATCH_MATERIAL(launch_tet10_t); }
+  int set_tables_tet10(b200s_ctx* ctx, const Tet10Const& h)
   {
-    auto kern = ctx->prestress == B200S_PRESTRESS_MULF ? k_hex27_eval_assemble<MAT, STIFF, true>
-                                                       : k_hex27_eval_assemble<MAT, STIFF, false>;
+    CK(cudaMemcpyToSymbolAsync(c_tet10, &h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  }
+}  // namespace b200s_parts
+#endif  // B200S_PART_TET10
+
+#if B200S_HAS(B200S_PART_HEX27)
+namespace
+{
+  template <int MAT, bool STIFF>
+  static int launch_hex27_t(b200s_ctx* ctx, const EvalArgs& A)
+  {
+    auto kern = ctx->prestress == B200S_PRESTRESS_MULF
+                    ? k_hex27_eval_assemble<MAT, STIFF, 1>
+                    : (ctx->kinem == B200S_KINEM_LINEAR ? k_hex27_eval_assemble<MAT, STIFF, 2>
+                                                        : k_hex27_eval_assemble<MAT, STIFF, 0>);
     // per device and cheap: set on every launch (a process may hold contexts on several GPUs)
     if (set_smem_attr(kern, hex27_smem_bytes))
       return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", hex27_smem_bytes);
@@ -1331,38 +1477,40 @@ namespace
     return 0;
   }
 
-  template <int MAT, bool STIFF>
-  static int launch_cell(b200s_ctx* ctx, const EvalArgs& A)
+}  // namespace
+namespace b200s_parts
+{
+  int launch_hex27(b200s_ctx* ctx, const EvalArgs& A, bool stiff) { B200S_DISPATCH_MATERIAL(launch_hex27_t); }
+  int set_tables_hex27(b200s_ctx* ctx, const Hex27Const& h)
   {
+    CK(cudaMemcpyToSymbolAsync(c_hex27, &h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  }
+}  // namespace b200s_parts
+#endif  // B200S_PART_HEX27
+
+#if B200S_HAS(B200S_PART_CORE)
+namespace
+{
+  template <bool STIFF>
+  static int launch_eval(b200s_ctx* ctx, const EvalArgs& A)
+  {
+    if (ctx->matkind < 0) return fail(ctx, B200S_ERR_INVALID, "material not set");
     if (ctx->tech != B200S_TECH_NONE && ctx->celltype != B200S_HEX8)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "element technology %d needs hex8", ctx->tech);
     switch (ctx->celltype)
     {
       case B200S_HEX27:
-        return launch_hex27<MAT, STIFF>(ctx, A);
+        return b200s_parts::launch_hex27(ctx, A, STIFF);
       case B200S_HEX8:
-        return launch_hex8<MAT, STIFF>(ctx, A);
+        if (ctx->tech == B200S_TECH_EAS_MILD || ctx->tech == B200S_TECH_EAS_FULL)
+          return b200s_parts::launch_hex8_eas(ctx, A, STIFF);
+        return b200s_parts::launch_hex8(ctx, A, STIFF);
       case B200S_TET10:
-        return launch_tet10<MAT, STIFF>(ctx, A);
+        return b200s_parts::launch_tet10(ctx, A, STIFF);
     }
     return fail(ctx, B200S_ERR_UNSUPPORTED, "cell type %d has no device kernel", ctx->celltype);
-  }
-
-  template <bool STIFF>
-  static int launch_eval(b200s_ctx* ctx, const EvalArgs& A)
-  {
-    switch (ctx->matkind)
-    {
-      case B200S_MAT_COUP_NEOHOOKE:
-        return launch_cell<MAT_COUP_NEOHOOKE, STIFF>(ctx, A);
-      case B200S_MAT_ISO_VOL:
-        return launch_cell<MAT_ISO_VOL, STIFF>(ctx, A);
-      case B200S_MAT_SVK:
-        return launch_cell<MAT_SVK, STIFF>(ctx, A);
-      case B200S_MAT_ELASTHYPER:
-        return launch_cell<MAT_HYPER, STIFF>(ctx, A);
-    }
-    return fail(ctx, B200S_ERR_INVALID, "material not set");
   }
 
 }  // namespace
@@ -1486,8 +1634,7 @@ extern "C"
       memcpy(h.dN_node, T.dN_node.data(), sizeof h.dN_node);
       memcpy(h.w, T.w.data(), sizeof h.w);
       memcpy(h.xi_gp, T.xi_gp.data(), sizeof h.xi_gp);
-      CK(cudaMemcpyToSymbolAsync(c_hex8, &h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
-      CK(cudaStreamSynchronize(ctx->stream));
+      if (b200s_parts::set_tables_hex8(ctx, h) || b200s_parts::set_tables_hex8_eas(ctx, h)) return B200S_ERR_CUDA;
     }
     else if (celltype == B200S_HEX27)
     {
@@ -1503,8 +1650,7 @@ extern "C"
         h.it.abc[k] = a | (b << 2) | (c << 4);
         h.it.node_of[a + 3 * b + 9 * c] = k;
       }
-      CK(cudaMemcpyToSymbolAsync(c_hex27, &h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
-      CK(cudaStreamSynchronize(ctx->stream));
+      if (b200s_parts::set_tables_hex27(ctx, h)) return B200S_ERR_CUDA;
     }
     else if (celltype == B200S_TET10)
     {
@@ -1512,8 +1658,7 @@ extern "C"
       memcpy(h.dN_gp, T.dN_gp.data(), sizeof h.dN_gp);
       memcpy(h.dN_node, T.dN_node.data(), sizeof h.dN_node);
       memcpy(h.w, T.w.data(), sizeof h.w);
-      CK(cudaMemcpyToSymbolAsync(c_tet10, &h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
-      CK(cudaStreamSynchronize(ctx->stream));
+      if (b200s_parts::set_tables_tet10(ctx, h)) return B200S_ERR_CUDA;
     }
     dfree(ctx->d_ele_id);
     if (ctx->reorder && n_col_eles > 1)
@@ -1557,8 +1702,12 @@ extern "C"
       int prestress_technology)
   {
     if (!ctx) return B200S_ERR_INVALID;
-    if (kinem_type != B200S_KINEM_NONLINEAR_TOTLAG)
+    if (kinem_type != B200S_KINEM_NONLINEAR_TOTLAG && kinem_type != B200S_KINEM_LINEAR)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "kinematic type %d has no device kernel", kinem_type);
+    // linear kinematics with F-bar / EAS / MULF (e.g. EASFormulation<..., linear>): CPU path
+    if (kinem_type == B200S_KINEM_LINEAR &&
+        (element_technology != B200S_TECH_NONE || prestress_technology != B200S_PRESTRESS_NONE))
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "KINEM linear with an element technology or prestress has no device kernel");
     if (prestress_technology != B200S_PRESTRESS_NONE && prestress_technology != B200S_PRESTRESS_MULF)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "prestress technology %d has no device kernel",
           prestress_technology);
@@ -1573,6 +1722,7 @@ extern "C"
     // (4C_solid_ele_factory_lib.hpp)
     if (element_technology != B200S_TECH_NONE && ctx->celltype >= 0 && ctx->celltype != B200S_HEX8)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "F-bar and EAS are hex8 technologies");
+    ctx->kinem = kinem_type;
     const bool eas_fresh = eas_neas(element_technology) != eas_neas(ctx->tech) || !ctx->d_eas_hist;
     ctx->tech = element_technology;
     if (!eas_neas(ctx->tech)) dfree(ctx->d_eas_hist);
@@ -2036,6 +2186,7 @@ extern "C"
     A.X = ctx->dX, A.u = ctx->d_u_col, A.conn = ctx->dconn, A.pos = ctx->d_pos;
     A.node_row = ctx->d_node_row, A.per_ele_param = ctx->d_per_ele, A.ele_id = ctx->d_ele_id;
     A.gp_hist = ctx->d_gp_hist, A.fibers = ctx->d_fibers;
+    A.linear = ctx->kinem == B200S_KINEM_LINEAR;
     if (material_needs_fibers(ctx) && !ctx->d_fibers)
       return fail(ctx, B200S_ERR_INVALID, "the material has a fibre summand: b200s_set_element_fibers first");
     if (ctx->prestress == B200S_PRESTRESS_MULF && !ctx->d_gp_hist)
@@ -2304,6 +2455,7 @@ extern "C"
     P.gp_hist = ctx->prestress == B200S_PRESTRESS_MULF ? ctx->d_gp_hist : nullptr;
     P.n_ele = ctx->n_col_eles, P.nn = ctx->nn, P.ngp = ctx->ngp;
     P.fbar = ctx->tech == B200S_TECH_FBAR;
+    P.linear = ctx->kinem == B200S_KINEM_LINEAR;
     P.stress_type = stress_type, P.strain_type = strain_type;
     P.stress = d_stress, P.strain = d_strain, P.energy = d_energy;
     const unsigned grid = nblk(ctx->n_col_eles * ctx->ngp, 128);
@@ -2422,17 +2574,7 @@ extern "C"
       CK(cudaMemcpyAsync(ctx->d_du_row, du_row, sizeof(double) * (size_t)ctx->n_rows, cudaMemcpyDefault, ctx->stream));
     const int rc = import_row_to_col(ctx, ctx->d_du_row, ctx->d_du_col, false);
     if (rc) return rc;
-    const unsigned grid = nblk(32 * ctx->n_col_eles, 128);
-    if (grid)
-    {
-      if (neas == 9)
-        k_eas_recover<9><<<grid, 128, 0, ctx->stream>>>(ctx->n_col_eles, ctx->dconn, ctx->d_du_col, step_length,
-            ctx->d_eas_hist);
-      else
-        k_eas_recover<21><<<grid, 128, 0, ctx->stream>>>(ctx->n_col_eles, ctx->dconn, ctx->d_du_col, step_length,
-            ctx->d_eas_hist);
-      ctx->launches += 1;
-    }
+    if (b200s_parts::eas_recover(ctx, neas, step_length)) return B200S_ERR_CUDA;
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
     return B200S_OK;
@@ -2789,3 +2931,4 @@ extern "C"
     if (p) cudaFreeHost(p);
   }
 }
+#endif  // B200S_PART_CORE

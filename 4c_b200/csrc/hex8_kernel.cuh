@@ -67,6 +67,8 @@ namespace b200s
     ErrWord* err;
     MatParams mp;
     int64_t n_ele;
+    int linear;        // KINEM linear (solid_math.cuh linear_kinematics): a template parameter of the element
+                       // kernels (the headline path pays nothing); this flag only labels the launch
     int scatter_mode;  // 0: red.global.add (product); 1: skip scatter, 2: plain stores (both only
                        // for profiling the cost split, results are then meaningless)
   };
@@ -161,7 +163,7 @@ namespace b200s
     // tab_gp / tab_node: dN tables with row stride TAB_STRIDE; wgt: Gauss weights.
     // Results: G to S.g, (M, Pw) kept in registers `out54` for the caller to store after a
     // __syncwarp() (the staging area they overwrite is still being read by other lanes).
-    template <int MAT, bool STIFF, bool MULF = false>
+    template <int MAT, bool STIFF, bool MULF = false, bool LINEAR = false>
     B2_HD void phase1(const EvalArgs& A, const WarpSmem& S, const double* tab_gp,
         const double* tab_node, const double* wgt, int lane, int64_t e0, double* out54,
         double& detJ_min, double& detF_min, bool& neg_jac)
@@ -224,6 +226,7 @@ namespace b200s
       // material: So3Material::evaluate(F, E=(C-I)/2) -> S, Cm (calc_lib.hpp:976-989)
       double C[6], Sv[6], Cm[21];
       right_cauchy_green(F, C);
+      if (LINEAR) linear_kinematics(F, C);  // compile-time in this kernel (TECH 3): the headline path pays nothing
       MatParams mp = A.mp;
       if (A.per_ele_param != nullptr && e < A.n_ele) mp.p[0] = A.per_ele_param[e];
       if (MAT == MAT_HYPER && A.fibers != nullptr && e < A.n_ele) mp.fiber = A.fibers + 3 * e;
@@ -237,7 +240,13 @@ namespace b200s
       {
 #pragma unroll
         for (int v = 0; v < 21; ++v) Cm[v] *= w;
-        material_geometric_operator(F, Sv, Cm, out54);
+        if (LINEAR)
+        {
+          const double zero[6] = {0, 0, 0, 0, 0, 0};  // no geometric stiffness
+          material_geometric_operator(F, zero, Cm, out54);
+        }
+        else
+          material_geometric_operator(F, Sv, Cm, out54);
       }
       first_piola(F, Sv, out54 + 45);
     }

@@ -46,7 +46,7 @@ namespace b200s
     MatParams mp;
     int64_t n_ele;
     int nn, ngp;
-    int fbar;
+    int fbar, linear;
     int stress_type, strain_type;
     double* stress;  // [caller element][gp][6] or nullptr
     double* strain;  // same
@@ -172,6 +172,7 @@ namespace b200s
     }
     double C[6], S[6], Cm[21];
     right_cauchy_green(F, C);
+    if (A.linear) linear_kinematics(F, C);
     MatParams mp = A.mp;
     if (A.per_ele_param != nullptr) mp.p[0] = A.per_ele_param[e];
     if (MAT == MAT_HYPER && A.fibers != nullptr) mp.fiber = A.fibers + 3 * e;

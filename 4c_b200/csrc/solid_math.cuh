@@ -278,6 +278,24 @@ namespace b200s
     return mp.p[0] * 0.5 * (m1 - 3.) + mp.p[1] * 0.5 * (J - 1.) * (J - 1.);
   }
 
+  // KINEM linear (DisplacementBasedLinearKinematicsFormulation, 4C_solid_ele_calc_displacement_based_
+  // linear_kinematics.hpp:44-62,122-150): the material sees E = sym(grad u) (evaluate_linear_gl_strain,
+  // calc_lib.hpp:752-761) and the identity as deformation gradient; force = S dN w, stiffness =
+  // dN C dN w without geometric term.  In: F = I + grad u.  Out: C = 2 E_lin + I for the material and
+  // F = I, so that the nonlinear operators with a zero geometric stress give exactly those terms.
+  B2_HD void linear_kinematics(double* F, double* C)
+  {
+#pragma unroll
+    for (int v = 0; v < 6; ++v)
+    {
+      const int a = va(v), b = vb(v);
+      // H = F - I; 2 E_lin = H + H^T
+      C[v] = (a == b) ? (2.0 * (F[a + 3 * a] - 1.0) + 1.0) : (F[a + 3 * b] + F[b + 3 * a]);
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) F[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  }
+
   // MULF prestress (PRESTRESS_TECH mulf): Gauss-point history = MulfHistoryData without the set-up
   // flag (the device initialises it at b200s_set_element_properties): h[0..8] inverse_jacobian,
   // h[9..17] deformation_gradient, both column-major (a + 3 b).

@@ -122,7 +122,7 @@ namespace b200s
     }
 
     // ---- phase 1: lanes (el, g < 4) run one Gauss point each --------------------------------------
-    template <int MAT, bool STIFF, bool MULF = false>
+    template <int MAT, bool STIFF, bool MULF = false, bool LINEAR = false>
     B2_HD void phase1(const EvalArgs& A, const WarpSmem& S, const double* tab_gp, const double* wgt,
         int lane, int64_t e0, double* out54, double& detJ_gp, double& detF_gp)
     {
@@ -161,6 +161,7 @@ namespace b200s
 
       double C[6], Sv[6], Cm[21];
       right_cauchy_green(F, C);
+      if (LINEAR) linear_kinematics(F, C);
       MatParams mp = A.mp;
       if (A.per_ele_param != nullptr && e < A.n_ele) mp.p[0] = A.per_ele_param[e];
       if (MAT == MAT_HYPER && A.fibers != nullptr && e < A.n_ele) mp.fiber = A.fibers + 3 * e;
@@ -173,7 +174,13 @@ namespace b200s
       {
 #pragma unroll
         for (int v = 0; v < 21; ++v) Cm[v] *= w;
-        material_geometric_operator(F, Sv, Cm, out54);
+        if (LINEAR)
+        {
+          const double zero[6] = {0, 0, 0, 0, 0, 0};  // no geometric stiffness
+          material_geometric_operator(F, zero, Cm, out54);
+        }
+        else
+          material_geometric_operator(F, Sv, Cm, out54);
       }
       first_piola(F, Sv, out54 + 45);
     }

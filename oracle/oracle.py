@@ -24,7 +24,7 @@ SUM.update({"COUP_ANISOEXPO": 100, "FIBER": 101})  # oracle only, see solid_orac
 STRESS_NONE, STRESS_2PK, STRESS_CAUCHY = 0, 1, 2
 STRAIN_NONE, STRAIN_GL, STRAIN_EA = 0, 1, 2
 ACTION_FORCE, ACTION_FORCE_STIFF = 0, 1
-TECH_NONE, TECH_FBAR, TECH_MULF, TECH_EAS_MILD, TECH_EAS_FULL = 0, 1, 2, 3, 4
+TECH_NONE, TECH_FBAR, TECH_MULF, TECH_EAS_MILD, TECH_EAS_FULL, TECH_LINEAR = 0, 1, 2, 3, 4, 5
 MULF_HIST = 19
 
 _dp = C.POINTER(C.c_double)

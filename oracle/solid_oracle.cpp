@@ -903,6 +903,63 @@ namespace
     return 0;
   }
 
+  // ---- SolidEleCalc<celltype, DisplacementBasedLinearKinematicsFormulation>
+  //      (src/solid_ele/4C_solid_ele_calc_displacement_based_linear_kinematics.hpp:44-62,101-150)
+  int element_linear(int ct, int matkind, const double* par, int action, const double* X,
+      const double* u, double* Ke, double* fe)
+  {
+    const int n = nnodes(ct), nd = 3 * n, ng = ngauss(ct);
+    double N[MAXN], dN[3 * MAXN];
+    JacMap jm;
+    if (Ke) std::memset(Ke, 0, sizeof(double) * nd * nd);
+    std::memset(fe, 0, sizeof(double) * nd);
+    int err = 0;
+    for (int k = 0; k < n; ++k)
+    {
+      double xi[3];
+      node_ref(ct, k, xi);
+      shape(ct, xi, N, dN);
+      jacobian_mapping(n, dN, X, jm);
+      if (!(jm.det > 0)) err = 1;
+    }
+    if (err) return 1;
+    double gxi[3 * MAXN], gw[MAXN];
+    gauss(ct, gxi, gw);
+    const double Id[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int gp = 0; gp < ng; ++gp)
+    {
+      shape(ct, gxi + 3 * gp, N, dN);
+      jacobian_mapping(n, dN, X, jm);
+      const double fac = jm.det * gw[gp];
+      // evaluate_linear_gl_strain (calc_lib.hpp:752-761): H = u N_XYZ^T, E = 1/2 (H + H^T)
+      double H[9], E[6], S[6], Cm[36];
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b)
+        {
+          double v = 0.0;
+          for (int k = 0; k < n; ++k) v += u[3 * k + a] * jm.G[k][b];
+          H[a + 3 * b] = v;
+        }
+      for (int v = 0; v < 6; ++v) E[v] = 0.5 * (H[VA[v] + 3 * VB[v]] + H[VB[v] + 3 * VA[v]]);
+      material(matkind, par, Id, E, S, Cm);
+      // add_internal_force_vector(jacobian_mapping, F = I, pk2) (:122-131)
+      add_force(n, jm, Id, S, fac, fe);
+      if (!(action == ORC_ACTION_FORCE_STIFF && Ke)) continue;
+      // add_stiffness_matrix (:133-150): K_ij(b,c) += sum_ad N_XYZ_i(a) C(a,b,c,d) N_XYZ_j(d) w
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j)
+          for (int b = 0; b < 3; ++b)
+            for (int c = 0; c < 3; ++c)
+            {
+              double v = 0.0;
+              for (int a = 0; a < 3; ++a)
+                for (int d = 0; d < 3; ++d) v += jm.G[i][a] * Cm[VG[a][b] + 6 * VG[c][d]] * jm.G[j][d];
+              Ke[(3 * i + b) + nd * (3 * j + c)] += fac * v;
+            }
+    }
+    return 0;
+  }
+
   // evaluate_strain_gradient (src/solid_ele/4C_solid_ele_calc_lib.hpp:777-826): B-operator, 6 x 3n
   // column-major, rows in the order [00,11,22,01,12,02] (strain-like: shear rows hold both terms)
   void strain_gradient(int n, const JacMap& jm, const double* F, double* B)
@@ -1416,6 +1473,7 @@ namespace
   {
     if (tech == ORC_TECH_EAS_MILD || tech == ORC_TECH_EAS_FULL)
       return element_eas(ct, tech, matkind, par, action, X, u, hist, Ke, fe);
+    if (tech == ORC_TECH_LINEAR) return element_linear(ct, matkind, par, action, X, u, Ke, fe);
     if (tech == ORC_TECH_MULF) return element_mulf(ct, matkind, par, action, X, u, hist, Ke, fe);
     if (tech == ORC_TECH_FBAR) return element_fbar(ct, matkind, par, action, X, u, Ke, fe);
     return element(ct, matkind, par, action, X, u, Ke, fe);
@@ -1536,6 +1594,13 @@ extern "C"
     {
       const int n = nnodes(ct);
       deformation_gradient(n, u, jm, F);
+      if (tech == ORC_TECH_LINEAR)
+      {
+        for (int v = 0; v < 6; ++v)
+          E[v] = 0.5 * ((F[VA[v] + 3 * VB[v]] - (v < 3 ? 1.0 : 0.0)) + (F[VB[v] + 3 * VA[v]] - (v < 3 ? 1.0 : 0.0)));
+        for (int i = 0; i < 9; ++i) F[i] = (i % 4 == 0) ? 1.0 : 0.0;
+        return;
+      }
       if (tech == ORC_TECH_FBAR)
       {
         double N[MAXN], dN[3 * MAXN], F0[9];

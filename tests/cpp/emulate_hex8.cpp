@@ -16,7 +16,7 @@ using namespace b200s;
 template <int MAT, bool STIFF, int TECH>
 static void run(const EvalArgs& A, double* min_detJ, double* min_detF, int64_t* n_bad)
 {
-  constexpr bool FBAR = TECH == 1, MULF = TECH == 2;  // as in k_hex8_eval_assemble
+  constexpr bool FBAR = TECH == 1, MULF = TECH == 2, LINEAR = TECH == 3;  // as in k_hex8_eval_assemble
   constexpr int MP_SIZE = FBAR ? hex8fbar::MP_SIZE : hex8::MP_SIZE;
   const CellTables T = make_cell_tables(0);
   std::vector<double> tab_gp(hex8::TAB_SIZE, 0.0), tab_node(hex8::TAB_SIZE, 0.0);
@@ -52,7 +52,7 @@ static void run(const EvalArgs& A, double* min_detJ, double* min_detF, int64_t* 
         hex8fbar::phase1<MAT, STIFF>(
             A, S, tab_gp.data(), T.w.data(), lane, e0, out54[lane], dJ, dF, neg);
       else
-        hex8::phase1<MAT, STIFF, MULF>(A, S, tab_gp.data(), tab_node.data(), T.w.data(), lane, e0,
+        hex8::phase1<MAT, STIFF, MULF, LINEAR>(A, S, tab_gp.data(), tab_node.data(), T.w.data(), lane, e0,
             out54[lane], dJ, dF, neg);
       if (e0 + (lane >> 3) < A.n_ele)
       {
@@ -89,12 +89,17 @@ static int emu_hex8_tech(int tech, int matkind, const double* params, const doub
     node_row[k].frow = node_frow[k];
   EvalArgs A;
   A.X = X, A.u = u_col, A.conn = conn, A.pos = pos, A.node_row = node_row.data();
-  A.per_ele_param = per_ele, A.ele_id = nullptr, A.gp_hist = nullptr, A.fibers = nullptr;
+  A.per_ele_param = per_ele, A.ele_id = nullptr, A.gp_hist = nullptr, A.fibers = nullptr, A.linear = 0;
   A.vals = vals, A.f = f, A.err = nullptr, A.n_ele = n_ele, A.scatter_mode = 0;
   if (!make_mat_params(matkind, params, A.mp)) return -3;
   A.gp_hist = gp_hist;
+  if (tech == 3) A.linear = 1;
 #define RUN(M)                                                  \
-  if (tech == 2 && stiff)                                       \
+  if (tech == 3 && stiff)                                       \
+    run<M, true, 3>(A, min_detJ, min_detF, n_bad);              \
+  else if (tech == 3)                                           \
+    run<M, false, 3>(A, min_detJ, min_detF, n_bad);             \
+  else if (tech == 2 && stiff)                                  \
     run<M, true, 2>(A, min_detJ, min_detF, n_bad);              \
   else if (tech == 2)                                           \
     run<M, false, 2>(A, min_detJ, min_detF, n_bad);             \
@@ -148,4 +153,14 @@ extern "C" int emu_hex8mulf(int matkind, const double* params, const double* per
 {
   return emu_hex8_tech(2, matkind, params, per_ele, stiff, n_ele, conn, X, u_col, pos, node_rowstart,
       node_rowlen, node_frow, n_col_nodes, vals, f, min_detJ, min_detF, n_bad, gp_hist);
+}
+
+// KINEM linear (EvalArgs::linear)
+extern "C" int emu_hex8linear(int matkind, const double* params, const double* per_ele, int stiff,
+    int64_t n_ele, const int32_t* conn, const double* X, const double* u_col, const int32_t* pos,
+    const int64_t* node_rowstart, const int32_t* node_rowlen, const int32_t* node_frow,
+    int64_t n_col_nodes, double* vals, double* f, double* min_detJ, double* min_detF, int64_t* n_bad)
+{
+  return emu_hex8_tech(3, matkind, params, per_ele, stiff, n_ele, conn, X, u_col, pos, node_rowstart,
+      node_rowlen, node_frow, n_col_nodes, vals, f, min_detJ, min_detF, n_bad);
 }

@@ -121,7 +121,8 @@ extern "C" int emu_post(int celltype, int fbar, int matkind, const double* param
   PostArgs A;
   A.X = X, A.u = u_col, A.conn = conn, A.per_ele_param = per_ele, A.ele_id = nullptr, A.fibers = nullptr;
   A.ele_is_row = ele_is_row, A.dN_gp = T.dN_gp.data(), A.dN_cen = T.dN_cen.data(), A.w = T.w.data();
-  A.mp = mp, A.n_ele = n_ele, A.nn = T.nn, A.ngp = T.ngp, A.fbar = fbar, A.gp_hist = gp_hist;
+  A.mp = mp, A.n_ele = n_ele, A.nn = T.nn, A.ngp = T.ngp, A.fbar = fbar == 1, A.linear = fbar == 2;
+  A.gp_hist = gp_hist;
   A.stress_type = stress_type, A.strain_type = strain_type;
   A.stress = stress, A.strain = strain, A.energy = nullptr;
   switch (matkind)

@@ -552,7 +552,7 @@ def test_golden_cooks_membrane_fbar_through_cuda_path():
 
 def test_unsupported_element_properties_are_rejected():
     ctx = capi.Context(0)
-    for kw in (dict(tech=7), dict(prestress=2), dict(kinem=capi.KINEM_LINEAR)):
+    for kw in (dict(tech=7), dict(prestress=2), dict(kinem=5)):
         with pytest.raises(capi.B200SolidError) as ei:
             ctx.set_element_properties(**kw)
         assert ei.value.code == capi.ERR_UNSUPPORTED

@@ -602,3 +602,31 @@ def test_fibre_material_needs_fibres_and_stress_output_matches_oracle():
     ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
     assert ok, (wK, wf)
     asm.close()
+
+
+# ------------------------------------------------------------------------------------------------------
+# KINEM linear
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10"])
+@pytest.mark.parametrize("mi", [2, 0])
+def test_linear_kinematics_match_oracle(cell, mi):
+    ct, rm, u = _mesh(cell)
+    mk, par = MATS[mi]
+    asm = b200.DeviceAssembler(rm, mk, par, kinem=capi.KINEM_LINEAR)
+    rowptr, colind = asm.graph()
+    asm.set_state("displacement", u.ravel())
+    K, f, _ = asm.evaluate()
+    rK, rf, _ = orc.evaluate_assemble(ct, mk, par, rm.conn, rm.X.ravel(), u.ravel(), rm.node_row_lid, rm.node_col_lid,
+                                      rm.n_row_nodes, rowptr, colind, tech=orc.TECH_LINEAR)
+    ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
+    assert ok, (wK, wf)
+    st, en = asm.calc_stress("cauchy", "gl")
+    rst, ren = orc.calc_stress(ct, mk, par, rm.conn, rm.X.ravel(), u.ravel(), orc.STRESS_CAUCHY, orc.STRAIN_GL,
+                               tech=orc.TECH_LINEAR)
+    assert np.abs(st - rst).max() <= RTOL * np.abs(rst).max() and np.abs(en - ren).max() <= RTOL * np.abs(ren).max()
+    asm.close()
+    ctx = capi.Context(0)
+    with pytest.raises(capi.B200SolidError) as ei:
+        ctx.set_element_properties(kinem=capi.KINEM_LINEAR, tech=capi.TECH_FBAR)
+    assert ei.value.code == capi.ERR_UNSUPPORTED
+    ctx.close()

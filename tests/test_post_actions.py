@@ -469,3 +469,36 @@ def test_fibre_summand_is_consistent_and_product_matches_oracle():
     # the fibre really contributes in tension
     iso = orc.material(orc.MAT_ELASTHYPER, orc.pack_elasthyper(FIBER_BLOCK[:1]), E_TEST)[0]
     assert np.abs(orc.material(orc.MAT_ELASTHYPER, orc.pack_elasthyper(FIBER_BLOCK), E_TEST)[0] - iso).max() > 1.0
+
+
+# ------------------------------------------------------------------------------------------------------
+# KINEM linear
+# ------------------------------------------------------------------------------------------------------
+def test_linear_kinematics_oracle_properties_and_product():
+    """Small-strain formulation: K does not depend on u for St.Venant-Kirchhoff, f = K u exactly, K is
+    symmetric; the product's hex8 kernel with the linear flag (emulated) and the post path against it."""
+    ct, rm, u = _mesh("hex8")
+    rowptr, colind = orc.build_graph(ct, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    maps = (rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    par = [1000.0, 0.3]
+    K1, f1, _ = orc.evaluate_assemble(ct, orc.MAT_SVK, par, rm.conn, rm.X.ravel(), u.ravel(), *maps, rowptr, colind,
+                                      tech=orc.TECH_LINEAR)
+    K2, _, _ = orc.evaluate_assemble(ct, orc.MAT_SVK, par, rm.conn, rm.X.ravel(), 0.0 * u.ravel(), *maps, rowptr, colind,
+                                     tech=orc.TECH_LINEAR)
+    assert np.abs(K1 - K2).max() <= 1e-13 * np.abs(K1).max()
+    import scipy.sparse as sp
+    A = sp.csr_matrix((K1, colind, rowptr), shape=(3 * rm.n_row_nodes,) * 2)
+    assert np.abs(A @ u.ravel() - f1).max() <= 1e-12 * np.abs(f1).max()
+    assert abs(A - A.T).max() <= 1e-12 * np.abs(K1).max()
+    for mk, mpar in ((orc.MAT_SVK, par), (orc.MAT_COUP_NEOHOOKE, [200.0, 0.25])):
+        rK, rf, _ = orc.evaluate_assemble(ct, mk, mpar, rm.conn, rm.X.ravel(), u.ravel(), *maps, rowptr, colind,
+                                          tech=orc.TECH_LINEAR)
+        K, f, _ = emu.evaluate(mk, mpar, rm.conn, rm.X.ravel(), u.ravel(), rowptr, colind, *maps, cell="hex8linear")
+        ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, 1e-12)
+        assert ok, (mk, wK, wf)
+        st, en = orc.calc_stress(ct, mk, mpar, rm.conn, rm.X.ravel(), u.ravel(), orc.STRESS_CAUCHY, orc.STRAIN_GL,
+                                 tech=orc.TECH_LINEAR)
+        e_ref = orc.calc_energy(ct, mk, mpar, rm.conn, rm.X.ravel(), u.ravel(), tech=orc.TECH_LINEAR)
+        st2, en2, e2 = emu.post(ct, mk, mpar, rm.conn, rm.X.ravel(), u.ravel(), orc.STRESS_CAUCHY, orc.STRAIN_GL, fbar=2)
+        assert np.abs(st - st2).max() <= 1e-12 * np.abs(st).max() and np.abs(en - en2).max() <= 1e-12 * np.abs(en).max()
+        assert abs(e_ref - e2) <= 1e-12 * abs(e_ref)
