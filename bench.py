@@ -73,8 +73,9 @@ WORKLOADS = {
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the element kernel at the workload's default
 # size, from the committed ncu captures profiles/r01e_ncu_metrics_<workload>.csv (same bench.py command)
-NCU_TRAFFIC_BYTES = {"hex8": 2695288832 + 2235513856, "tet10": 20888573696 + 17315611904,
-                     "hex27": 25082223616 + 24644916992}
+NCU_TRAFFIC_BYTES = {"hex8": 2694710016 + 2248577536, "tet10": 20888573696 + 17315611904,
+                     "hex27": 25082223616 + 24644916992, "hex8_eas_full": 3559638528 + 10256551424}
+NCU_TRAFFIC_FILE = {"hex8": "r01h_ncu_metrics_hex8.csv", "hex8_eas_full": "r01h_ncu_metrics_hex8_eas_full.csv"}
 
 
 def host_threads():
@@ -405,7 +406,8 @@ def run_b200(args):
             "kernel_ms": k_ms, "kernel_launches_timed": kcnt,
             "traffic": args.traffic_bytes if args.traffic_bytes is not None else (
                 NCU_TRAFFIC_BYTES.get(args.workload) if per_gpu_n == wl["default_n"] else None),
-            "traffic_source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01e_ncu_metrics_{args.workload}.csv",
+            "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/"
+                              + NCU_TRAFFIC_FILE.get(args.workload, f"r01e_ncu_metrics_{args.workload}.csv"),
             "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": ach_gbs / peaks["hbm_gbs"], "peak_source": peak_src},
         }
