@@ -287,6 +287,7 @@ namespace b200s
   // hex8 EAS evaluate + assemble kernel (hex8_eas_kernel.cuh): one warp per element, persistent grid
   // ------------------------------------------------------------------------------------------------
   constexpr int HEX8_EAS_WARPS = 4;
+  constexpr int HEX8_EAS_CTAS_PER_SM = 3;  // 12 warps / SM: 170 registers, 15 KB shared memory per warp
   template <int NEAS>
   constexpr size_t hex8_eas_smem_bytes()
   {
@@ -294,7 +295,7 @@ namespace b200s
   }
 #if B200S_HAS(B200S_PART_EAS)
   template <int MAT, bool STIFF, int NEAS>
-  __global__ void __launch_bounds__(HEX8_EAS_WARPS * 32, 2)
+  __global__ void __launch_bounds__(HEX8_EAS_WARPS * 32, HEX8_EAS_CTAS_PER_SM)
       k_hex8_eas_eval_assemble(const EvalArgs A, double* hist, const double* t0tab)
   {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1324,7 +1325,7 @@ namespace
     if (set_smem_attr(kern, bytes)) return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", bytes);
     if (!ctx->d_eas_hist) return fail(ctx, B200S_ERR_INVALID, "EAS history missing");
     int64_t grid = (A.n_ele + HEX8_EAS_WARPS - 1) / HEX8_EAS_WARPS;
-    const int64_t cap = (int64_t)ctx->n_sm * 2;
+    const int64_t cap = (int64_t)ctx->n_sm * HEX8_EAS_CTAS_PER_SM;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, HEX8_EAS_WARPS * 32, bytes, ctx->stream>>>(A, ctx->d_eas_hist, ctx->d_eas_t0);

@@ -61,12 +61,14 @@ namespace b200s
       static constexpr int GP = CM + 6 * NA;
       static constexpr int GP_STRIDE = 62;
       static constexpr int GP_F = 0, GP_S = 9, GP_C = 15, GP_G = 36, GP_SCALE = 60;
-      static constexpr int WORK = GP + NGP * GP_STRIDE;   // post-loop work area
-      //   Kaa NEAS x NEAS row-major, inverted in place
-      static constexpr int AUG = WORK;
-      static constexpr int KDA = AUG + NEAS * NEAS + (NEAS * NEAS & 1);          // Kda 24 x NEAS [r*NEAS + a]
-      static constexpr int KE = KDA + ND * NEAS + (ND * NEAS & 1);               // K_e 24 x 24 row-major, f_e behind
-      static constexpr int DOUBLES = KE + 576 + 24;
+      static constexpr int LOOP_END = GP + NGP * GP_STRIDE;
+      // K_e 24 x 24 row-major with f_e behind: staged after the Gauss loop, aliases CB / CM / GP (dead then)
+      static constexpr int KE = CB;
+      static_assert(KE + 576 + 24 <= LOOP_END, "K_e staging fits into the dead Gauss-loop buffers");
+      // post-loop work area: Kaa NEAS x NEAS row-major, inverted in place, and Kda 24 x NEAS [r*NEAS + a]
+      static constexpr int AUG = LOOP_END;
+      static constexpr int KDA = AUG + NEAS * NEAS + (NEAS * NEAS & 1);
+      static constexpr int DOUBLES = KDA + ND * NEAS + (ND * NEAS & 1);
       static constexpr int BYTES = DOUBLES * 8 + NN * 16 + NN * NN * 4;          // + NodeRow[8] + pos[64]
     };
 
@@ -132,6 +134,60 @@ namespace b200s
         if (lane < n) a[c * n + lane] = (lane == c) ? d : a[c * n + lane] * d;
         __syncwarp();
       }
+    }
+
+    // Shared-memory flavour with a compile-time size: the k loop is unrolled and branch free (the pivot
+    // column is overwritten afterwards), the step loop stays rolled to keep the code small.
+    template <int N>
+    __device__ __forceinline__ void warp_spd_inverse_t(double* a, int lane)
+    {
+#pragma unroll 1
+      for (int c = 0; c < N; ++c)
+      {
+        const double d = 1.0 / a[c * N + c];
+        if (lane < N && lane != c)
+        {
+          const double f = a[lane * N + c] * d;
+          const double* pr = a + c * N;
+          double* row = a + lane * N;
+#pragma unroll
+          for (int k = 0; k < N; ++k) row[k] = fma(-f, pr[k], row[k]);
+          row[c] = -f;
+        }
+        __syncwarp();
+        if (lane < N) a[c * N + lane] = (lane == c) ? d : a[c * N + lane] * d;
+        __syncwarp();
+      }
+    }
+
+    // The same inverse with the rows in registers: lane r holds row r of the matrix in a[] (lanes >= N hold
+    // anything and are ignored).  Per elimination step the pivot lane publishes its scaled row through a
+    // double-buffered 2 N shared-memory scratch (one __syncwarp per step); every index is a compile-time
+    // constant after unrolling, so a[] never leaves the register file.  On return a[] is row `lane` of A^-1.
+    template <int N>
+    __device__ __forceinline__ void warp_spd_inverse_reg(double (&a)[N], double* scratch, int lane)
+    {
+#pragma unroll
+      for (int c = 0; c < N; ++c)
+      {
+        double* buf = scratch + (c & 1) * N;
+        if (lane == c)
+        {
+          const double d = 1.0 / a[c];
+#pragma unroll
+          for (int k = 0; k < N; ++k) a[k] = (k == c) ? d : a[k] * d;
+#pragma unroll
+          for (int k = 0; k < N; ++k) buf[k] = a[k];
+        }
+        __syncwarp();
+        if (lane != c)
+        {
+          const double f = a[c];
+#pragma unroll
+          for (int k = 0; k < N; ++k) a[k] = (k == c) ? -f * buf[c] : fma(-f, buf[k], a[k]);
+        }
+      }
+      __syncwarp();
     }
 
     // Set-up (once per mesh): T0invT (6x6 column-major) and det J0 of one element into t0[0..35], t0[36]
@@ -307,90 +363,163 @@ namespace b200s
       }
       __syncwarp();
 
-      // ---- phase 2: Gauss loop, lane = dof row r (< 24) and EAS parameter a (< NEAS) -----------------------
+      // ---- phase 2: lane = dof row r (< 24) and EAS parameter a (< NEAS) -------------------------------------
+      // Two passes over the Gauss points so that the register-resident rows never coexist: first K_da, K_aa,
+      // f and s (42 accumulators), condensation operator mK = -K_da K_aa^-1 (21), then K_dd (24).
       const int r_ = lane < ND ? lane : 0;      // lanes >= 24 shadow row 0, results unused
       const int ni = r_ / 3, ei = r_ - 3 * ni;  // node and direction of the row
       const int a_ = lane < NEAS ? lane : 0;
       const int arow = c_eas_row[a_], amono = c_eas_mono[a_];
-      double Kdd[ND], Kda[NEAS], Kaa[NEAS], facc = 0.0, sacc = 0.0;
-#pragma unroll
-      for (int c = 0; c < ND; ++c) Kdd[c] = 0.0;
-#pragma unroll
-      for (int c = 0; c < NEAS; ++c) Kda[c] = 0.0, Kaa[c] = 0.0;
-
-#pragma unroll 1
-      for (int g = 0; g < NGP; ++g)
+      double facc = 0.0;
+      double mK[NEAS];
+      double* aug = sm + L::AUG;
+      double* KdaS = sm + L::KDA;
+      double* sS = sm + L::SG;
       {
-        const double* gp = sm + L::GP + g * L::GP_STRIDE;
-        const double* Gi = gp + L::GP_G + 3 * ni;
-        const double Fe0 = gp[L::GP_F + ei], Fe1 = gp[L::GP_F + ei + 3], Fe2 = gp[L::GP_F + ei + 6];
-        const double G0 = Gi[0], G1 = Gi[1], G2 = Gi[2];
-        // column r of the B-operator (evaluate_strain_gradient, calc_lib.hpp:777-826), strain-like rows
-        double Bc[6];
-        Bc[0] = Fe0 * G0, Bc[1] = Fe1 * G1, Bc[2] = Fe2 * G2;
-        Bc[3] = Fe0 * G1 + Fe1 * G0;
-        Bc[4] = Fe1 * G2 + Fe2 * G1;
-        Bc[5] = Fe2 * G0 + Fe0 * G2;
-        // column a of Mtilde
-        double Mc[6];
-        {
-          const double mv = gp[L::GP_SCALE] * monomial(amono, gxi[3 * g], gxi[3 * g + 1], gxi[3 * g + 2]);
+        double Kda[NEAS], Kaa[NEAS], sacc = 0.0;
 #pragma unroll
-          for (int k = 0; k < 6; ++k) Mc[k] = mv * T0[k + 6 * arow];
-        }
-        // columns of  w C B  and  w C Mtilde  (integrate_eas: cmatM, eas_helpers.hpp:352-371)
-        double CBc[6], CMc[6];
+        for (int c = 0; c < NEAS; ++c) Kda[c] = 0.0, Kaa[c] = 0.0;
+#pragma unroll 1
+        for (int g = 0; g < NGP; ++g)
         {
-          double Cm[21];
+          const double* gp = sm + L::GP + g * L::GP_STRIDE;
+          const double* Gi = gp + L::GP_G + 3 * ni;
+          const double Fe0 = gp[L::GP_F + ei], Fe1 = gp[L::GP_F + ei + 3], Fe2 = gp[L::GP_F + ei + 6];
+          const double G0 = Gi[0], G1 = Gi[1], G2 = Gi[2];
+          // column r of the B-operator (evaluate_strain_gradient, calc_lib.hpp:777-826), strain-like rows
+          double Bc[6];
+          Bc[0] = Fe0 * G0, Bc[1] = Fe1 * G1, Bc[2] = Fe2 * G2;
+          Bc[3] = Fe0 * G1 + Fe1 * G0;
+          Bc[4] = Fe1 * G2 + Fe2 * G1;
+          Bc[5] = Fe2 * G0 + Fe0 * G2;
+          // column a of Mtilde and of  w C Mtilde  (integrate_eas: cmatM, eas_helpers.hpp:352-371)
+          double Mc[6], CMc[6];
+          {
+            const double mv = gp[L::GP_SCALE] * monomial(amono, gxi[3 * g], gxi[3 * g + 1], gxi[3 * g + 2]);
 #pragma unroll
-          for (int i = 0; i < 21; ++i) Cm[i] = gp[L::GP_C + i];
+            for (int k = 0; k < 6; ++k) Mc[k] = mv * T0[k + 6 * arow];
+#pragma unroll
+            for (int I = 0; I < 6; ++I)
+            {
+              double tm = 0.0;
+#pragma unroll
+              for (int Jv = 0; Jv < 6; ++Jv) tm = fma(gp[L::GP_C + c21(I, Jv)], Mc[Jv], tm);
+              CMc[I] = tm;
+            }
+          }
+          __syncwarp();  // previous Gauss point's CM fully consumed
+          if (lane < NEAS)
+#pragma unroll
+            for (int I = 0; I < 6; ++I) sm[L::CM + I + 6 * lane] = CMc[I];
+          __syncwarp();
+          // force and EAS residual: f_r += B_r . (w S), s_a += Mtilde_a . (w S)
 #pragma unroll
           for (int I = 0; I < 6; ++I)
           {
-            double tb = 0.0, tm = 0.0;
+            const double ws = gp[L::GP_S + I];
+            facc = fma(Bc[I], ws, facc), sacc = fma(Mc[I], ws, sacc);
+          }
+          // K_da(r, a) += B_r . (w C Mtilde_a);  K_aa(a, a') += Mtilde_a . (w C Mtilde_a')
 #pragma unroll
-            for (int Jv = 0; Jv < 6; ++Jv)
-            {
-              tb = fma(Cm[c21(I, Jv)], Bc[Jv], tb);
-              tm = fma(Cm[c21(I, Jv)], Mc[Jv], tm);
-            }
-            CBc[I] = tb, CMc[I] = tm;
+          for (int c = 0; c < NEAS; ++c)
+          {
+            const d2* cm2 = reinterpret_cast<const d2*>(sm + L::CM + 6 * c);
+            const d2 q0 = cm2[0], q1 = cm2[1], q2 = cm2[2];
+            const double cm[6] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y};
+            double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+            for (int I = 0; I < 6; ++I) t1 = fma(Bc[I], cm[I], t1), t2 = fma(Mc[I], cm[I], t2);
+            Kda[c] += t1, Kaa[c] += t2;
           }
         }
-        __syncwarp();  // previous Gauss point's CB / CM fully consumed
-        if (lane < ND)
-#pragma unroll
-          for (int I = 0; I < 6; ++I) sm[L::CB + I + 6 * lane] = CBc[I];
-        if (lane < NEAS)
-#pragma unroll
-          for (int I = 0; I < 6; ++I) sm[L::CM + I + 6 * lane] = CMc[I];
         __syncwarp();
 
-        // force and EAS residual: f_r += B_r . (w S), s_a += Mtilde_a . (w S)
-        double wS[6];
+        // ---- condensation operator ---------------------------------------------------------------------
+        if (lane < NEAS) sS[lane] = sacc;
+        if (lane < ND)
 #pragma unroll
-        for (int I = 0; I < 6; ++I) wS[I] = gp[L::GP_S + I];
-#pragma unroll
-        for (int I = 0; I < 6; ++I) facc = fma(Bc[I], wS[I], facc), sacc = fma(Mc[I], wS[I], sacc);
-        // K_da(r, a) += B_r . (w C Mtilde_a);  K_aa(a, a') += Mtilde_a . (w C Mtilde_a')
-#pragma unroll
-        for (int c = 0; c < NEAS; ++c)
+          for (int c = 0; c < NEAS; ++c) KdaS[lane * NEAS + c] = Kda[c];
+        // K_aa^-1 into `aug` (row-major).  9 x 9: rows stay in the registers of their lanes (fully unrolled);
+        // 21 x 21: in shared memory with a rolled step loop (measured: the unrolled register form is slower
+        // there, 34.9 vs 32.9 ms, the 441-FMA update no longer fits the instruction cache together with the rest)
+        if (NEAS <= 9)
         {
-          // three 128-bit broadcast loads per column (columns are 48 bytes apart, 16-byte aligned)
-          const d2* cm2 = reinterpret_cast<const d2*>(sm + L::CM + 6 * c);
-          const d2 q0 = cm2[0], q1 = cm2[1], q2 = cm2[2];
-          const double cm[6] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y};
-          double t1 = 0.0, t2 = 0.0;
+          warp_spd_inverse_reg<NEAS>(Kaa, aug, lane);  // scratch = the first 2 NEAS doubles of aug
+          if (lane < NEAS)
 #pragma unroll
-          for (int I = 0; I < 6; ++I) t1 = fma(Bc[I], cm[I], t1), t2 = fma(Mc[I], cm[I], t2);
-          Kda[c] += t1, Kaa[c] += t2;
+            for (int c = 0; c < NEAS; ++c) aug[lane * NEAS + c] = Kaa[c];
+          __syncwarp();
         }
-        if (STIFF)
+        else
         {
+          if (lane < NEAS)
+#pragma unroll
+            for (int c = 0; c < NEAS; ++c) aug[lane * NEAS + c] = Kaa[c];
+          __syncwarp();
+          warp_spd_inverse_t<NEAS>(aug, lane);
+        }
+        // history for struct_calc_recover: s, invKaa (column-major), Kda (column-major)
+        {
+          double* h_s = hist + 2 * NEAS;
+          double* h_inv = hist + 3 * NEAS;
+          double* h_kda = h_inv + NEAS * NEAS;
+          if (lane < NEAS) h_s[lane] = sS[lane];
+          for (int t = lane; t < NEAS * NEAS; t += 32)  // t = r + NEAS c
+            h_inv[t] = aug[(t % NEAS) * NEAS + t / NEAS];
+          for (int t = lane; t < ND * NEAS; t += 32)  // t = r + 24 c
+            h_kda[t] = KdaS[(t % ND) * NEAS + t / ND];
+        }
+        // mK(r, a) = -sum_k Kda(r, k) invKaa(k, a)   (prepare_condensed_contribution, eas.hpp:188-203)
+#pragma unroll
+        for (int a = 0; a < NEAS; ++a) mK[a] = 0.0;
+#pragma unroll
+        for (int k = 0; k < NEAS; ++k)
+        {
+          const double* row = aug + k * NEAS;
+#pragma unroll
+          for (int a = 0; a < NEAS; ++a) mK[a] = fma(-Kda[k], row[a], mK[a]);
+        }
+        // f_r += mK(r,:) s   (eas.hpp:245-253)
+#pragma unroll
+        for (int a = 0; a < NEAS; ++a) facc = fma(mK[a], sS[a], facc);
+      }
+
+      // ---- K_dd: second pass over the Gauss points, then K_dd(r, c) += mK(r,:) Kda(c,:)  (eas.hpp:255-263) ---
+      double Kdd[ND];
+      if (STIFF)
+      {
+#pragma unroll
+        for (int c = 0; c < ND; ++c) Kdd[c] = 0.0;
+#pragma unroll 1
+        for (int g = 0; g < NGP; ++g)
+        {
+          const double* gp = sm + L::GP + g * L::GP_STRIDE;
+          const double* Gi = gp + L::GP_G + 3 * ni;
+          const double Fe0 = gp[L::GP_F + ei], Fe1 = gp[L::GP_F + ei + 3], Fe2 = gp[L::GP_F + ei + 6];
+          const double G0 = Gi[0], G1 = Gi[1], G2 = Gi[2];
+          double Bc[6], CBc[6];
+          Bc[0] = Fe0 * G0, Bc[1] = Fe1 * G1, Bc[2] = Fe2 * G2;
+          Bc[3] = Fe0 * G1 + Fe1 * G0;
+          Bc[4] = Fe1 * G2 + Fe2 * G1;
+          Bc[5] = Fe2 * G0 + Fe0 * G2;
+#pragma unroll
+          for (int I = 0; I < 6; ++I)
+          {
+            double tb = 0.0;
+#pragma unroll
+            for (int Jv = 0; Jv < 6; ++Jv) tb = fma(gp[L::GP_C + c21(I, Jv)], Bc[Jv], tb);
+            CBc[I] = tb;
+          }
+          __syncwarp();  // previous Gauss point's CB fully consumed
+          if (lane < ND)
+#pragma unroll
+            for (int I = 0; I < 6; ++I) sm[L::CB + I + 6 * lane] = CBc[I];
+          __syncwarp();
           // elastic: K_dd(r, c) += B_r . (w C B_c); geometric: K_dd(3i+b, 3j+b) += G_i.(w S).G_j
           double gi[3];
 #pragma unroll
-          for (int d = 0; d < 3; ++d) gi[d] = G0 * wS[vg(0, d)] + G1 * wS[vg(1, d)] + G2 * wS[vg(2, d)];
+          for (int d = 0; d < 3; ++d)
+            gi[d] = G0 * gp[L::GP_S + vg(0, d)] + G1 * gp[L::GP_S + vg(1, d)] + G2 * gp[L::GP_S + vg(2, d)];
 #pragma unroll
           for (int c = 0; c < ND; ++c)
           {
@@ -410,50 +539,6 @@ namespace b200s
             for (int b = 0; b < 3; ++b) Kdd[3 * j + b] += (b == ei) ? sg : 0.0;  // select, no divergent branch
           }
         }
-      }
-      __syncwarp();
-
-      // ---- condensation ----------------------------------------------------------------------------------
-      double* aug = sm + L::AUG;
-      double* KdaS = sm + L::KDA;
-      double* sS = sm + L::SG;
-      if (lane < NEAS)
-      {
-#pragma unroll
-        for (int c = 0; c < NEAS; ++c) aug[lane * NEAS + c] = Kaa[c];
-        sS[lane] = sacc;
-      }
-      if (lane < ND)
-#pragma unroll
-        for (int c = 0; c < NEAS; ++c) KdaS[lane * NEAS + c] = Kda[c];
-      __syncwarp();
-      warp_spd_inverse(NEAS, aug, lane);
-      // history for struct_calc_recover: s, invKaa (column-major), Kda (column-major)
-      {
-        double* h_s = hist + 2 * NEAS;
-        double* h_inv = hist + 3 * NEAS;
-        double* h_kda = h_inv + NEAS * NEAS;
-        if (lane < NEAS) h_s[lane] = sS[lane];
-        for (int t = lane; t < NEAS * NEAS; t += 32)  // t = r + NEAS c
-          h_inv[t] = aug[(t % NEAS) * NEAS + t / NEAS];
-        for (int t = lane; t < ND * NEAS; t += 32)  // t = r + 24 c
-          h_kda[t] = KdaS[(t % ND) * NEAS + t / ND];
-      }
-      // mK(r, a) = -sum_k Kda(r, k) invKaa(k, a)   (prepare_condensed_contribution, eas.hpp:188-203)
-      double mK[NEAS];
-#pragma unroll
-      for (int a = 0; a < NEAS; ++a) mK[a] = 0.0;
-#pragma unroll
-      for (int k = 0; k < NEAS; ++k)
-      {
-        const double* row = aug + k * NEAS;
-#pragma unroll
-        for (int a = 0; a < NEAS; ++a) mK[a] = fma(-Kda[k], row[a], mK[a]);
-      }
-      // f_r += mK(r,:) s ; K_dd(r, c) += mK(r,:) Kda(c,:)   (eas.hpp:245-263)
-#pragma unroll
-      for (int a = 0; a < NEAS; ++a) facc = fma(mK[a], sS[a], facc);
-      if (STIFF)
 #pragma unroll
         for (int c = 0; c < ND; ++c)
         {
@@ -463,6 +548,8 @@ namespace b200s
           for (int a = 0; a < NEAS; ++a) t = fma(mK[a], kc[a], t);
           Kdd[c] += t;
         }
+      }
+      __syncwarp();  // every lane is done with CB / GP: the K_e staging overwrites them
       // ---- stage + scatter (as hex8::scatter, one element) -----------------------------------------------
       double* Ke = sm + L::KE;
       double* fe = Ke + 576;
