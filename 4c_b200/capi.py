@@ -45,7 +45,7 @@ SYMBOLS = [
     "b200s_last_multiply_ms", "b200s_solve_cg", "b200s_get_values",
     "b200s_update_prestress", "b200s_gp_history_size", "b200s_get_gp_history", "b200s_set_gp_history",
     "b200s_recover", "b200s_element_history_size", "b200s_get_element_history", "b200s_set_element_history",
-    "b200s_set_element_fibers",
+    "b200s_set_element_fibers", "b200s_recover_linesearch", "b200s_update_step", "b200s_reset_step",
 ]
 
 
@@ -121,6 +121,9 @@ def load():
     L.b200s_get_values.argtypes = [vp, i32, vp]
     L.b200s_update_prestress.argtypes = [vp]
     L.b200s_recover.argtypes = [vp, vp, dbl]
+    L.b200s_recover_linesearch.argtypes = [vp, dbl]
+    L.b200s_update_step.argtypes = [vp]
+    L.b200s_reset_step.argtypes = [vp]
     L.b200s_element_history_size.argtypes = [vp]
     L.b200s_element_history_size.restype = i64
     L.b200s_get_element_history.argtypes = [vp, vp]
@@ -239,6 +242,15 @@ class Context:
     def recover(self, du_row, step_length=1.0):
         du = np.ascontiguousarray(du_row, np.float64)
         self._ck(self.L.b200s_recover(self.h, _ptr(du), float(step_length)))
+
+    def recover_linesearch(self, new_step_length):
+        self._ck(self.L.b200s_recover_linesearch(self.h, float(new_step_length)))
+
+    def update_step(self):
+        self._ck(self.L.b200s_update_step(self.h))
+
+    def reset_step(self):
+        self._ck(self.L.b200s_reset_step(self.h))
 
     def get_element_history(self):
         h = np.empty(self.L.b200s_element_history_size(self.h))

@@ -1105,6 +1105,8 @@ struct b200s_ctx
   double* d_gp_hist = nullptr;  // MULF: n_col_eles * ngp * MULF_HIST doubles, device element order
   double* d_eas_hist = nullptr; // EAS: n_col_eles * hex8eas::hist_size(neas) doubles, device element order
   double* d_eas_t0 = nullptr;   // EAS: T0invT[36] + detJ0 per element (stride hex8eas::T0_STRIDE)
+  double* d_hist_old = nullptr; // old_history_data_ of the block (struct_calc_update_istep / _reset_istep)
+  double eas_old_step_length = 1.0;  // EASHistoryData::old_step_length
   double* d_du_row = nullptr;   // "residual displacement" state (struct_calc_recover)
   double* d_du_col = nullptr;
   // material
@@ -1117,7 +1119,7 @@ struct b200s_ctx
   double density = 0.0;         // Mat::So3Material::density()
   // cell tables in global memory for the post / mass kernels (post_kernels.cuh)
   int ngp = 0, ngp_mass = 0;
-  double *d_dN_gp = nullptr, *d_w = nullptr, *d_dN_cen = nullptr;
+  double *d_dN_gp = nullptr, *d_w = nullptr, *d_dN_cen = nullptr, *d_xi_gp = nullptr;
   double *d_N_mass = nullptr, *d_dN_mass = nullptr, *d_w_mass = nullptr;
   uint8_t* d_ele_is_row = nullptr;  // caller numbering; nullptr = every column element is a row element
   // mass matrix / inertia force (struct_calc_nlnstiffmass & co.)
@@ -1565,7 +1567,8 @@ extern "C"
     dfree(ctx->d_u_row), dfree(ctx->d_u_col), dfree(ctx->d_send_lid), dfree(ctx->d_recv_lid);
     dfree(ctx->d_sendbuf), dfree(ctx->d_recvbuf), dfree(ctx->d_err);
     dfree(ctx->d_gp_hist), dfree(ctx->d_eas_hist), dfree(ctx->d_du_row), dfree(ctx->d_du_col);
-    dfree(ctx->d_eas_t0), dfree(ctx->d_fibers), dfree(ctx->d_blkcol);
+    dfree(ctx->d_eas_t0), dfree(ctx->d_fibers), dfree(ctx->d_blkcol), dfree(ctx->d_hist_old);
+    dfree(ctx->d_xi_gp);
     dfree(ctx->d_hyper), dfree(ctx->d_dN_gp), dfree(ctx->d_w), dfree(ctx->d_dN_cen), dfree(ctx->d_N_mass);
     dfree(ctx->d_dN_mass), dfree(ctx->d_w_mass), dfree(ctx->d_ele_is_row), dfree(ctx->d_mass);
     dfree(ctx->d_f_inertia), dfree(ctx->d_acc_row), dfree(ctx->d_acc_col), dfree(ctx->d_energy);
@@ -1619,13 +1622,14 @@ extern "C"
     if (to_device(ctx, &ctx->d_dN_gp, T.dN_gp.data(), (int64_t)T.dN_gp.size()) ||
         to_device(ctx, &ctx->d_w, T.w.data(), (int64_t)T.w.size()) ||
         to_device(ctx, &ctx->d_dN_cen, T.dN_cen.data(), (int64_t)T.dN_cen.size()) ||
+        to_device(ctx, &ctx->d_xi_gp, T.xi_gp.data(), (int64_t)T.xi_gp.size()) ||
         to_device(ctx, &ctx->d_N_mass, T.N_mass.data(), (int64_t)T.N_mass.size()) ||
         to_device(ctx, &ctx->d_dN_mass, T.dN_mass.data(), (int64_t)T.dN_mass.size()) ||
         to_device(ctx, &ctx->d_w_mass, T.w_mass.data(), (int64_t)T.w_mass.size()))
       return B200S_ERR_CUDA;
     CK(cudaStreamSynchronize(ctx->stream));  // T is a local
     dfree(ctx->d_ele_is_row), dfree(ctx->d_acc_col), dfree(ctx->d_gp_hist), dfree(ctx->d_eas_hist);
-    dfree(ctx->d_du_col), dfree(ctx->d_fibers);
+    dfree(ctx->d_du_col), dfree(ctx->d_fibers), dfree(ctx->d_hist_old);
     if (ctx->prestress == B200S_PRESTRESS_MULF && mulf_allocate(ctx)) return B200S_ERR_CUDA;
     if (eas_neas(ctx->tech) && eas_allocate(ctx)) return B200S_ERR_CUDA;
     if (celltype == B200S_HEX8)
@@ -1724,6 +1728,7 @@ extern "C"
     if (element_technology != B200S_TECH_NONE && ctx->celltype >= 0 && ctx->celltype != B200S_HEX8)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "F-bar and EAS are hex8 technologies");
     ctx->kinem = kinem_type;
+    dfree(ctx->d_hist_old);
     const bool eas_fresh = eas_neas(element_technology) != eas_neas(ctx->tech) || !ctx->d_eas_hist;
     ctx->tech = element_technology;
     if (!eas_neas(ctx->tech)) dfree(ctx->d_eas_hist);
@@ -2444,8 +2449,6 @@ extern "C"
   {
     if (ctx->celltype < 0 || ctx->matkind < 0)
       return fail(ctx, B200S_ERR_INVALID, "set_mesh and set_material must precede this action");
-    if (eas_neas(ctx->tech))
-      return fail(ctx, B200S_ERR_UNSUPPORTED, "stress / energy output of EAS elements stays on the CPU path");
     if (material_needs_fibers(ctx) && !ctx->d_fibers)
       return fail(ctx, B200S_ERR_INVALID, "the material has a fibre summand: b200s_set_element_fibers first");
     PostArgs P;
@@ -2454,6 +2457,12 @@ extern "C"
     P.ele_id = ctx->d_ele_id, P.ele_is_row = ctx->d_ele_is_row;
     P.dN_gp = ctx->d_dN_gp, P.dN_cen = ctx->d_dN_cen, P.w = ctx->d_w, P.mp = ctx->mp;
     P.gp_hist = ctx->prestress == B200S_PRESTRESS_MULF ? ctx->d_gp_hist : nullptr;
+    P.eas_neas = eas_neas(ctx->tech);
+    P.eas_hist_size = P.eas_neas ? hex8eas::hist_size(P.eas_neas) : 0;
+    P.eas_t0_stride = hex8eas::T0_STRIDE;
+    P.eas_hist = ctx->d_eas_hist, P.eas_t0 = ctx->d_eas_t0, P.xi_gp = ctx->d_xi_gp;
+    if (P.eas_neas && (!ctx->d_eas_hist || !ctx->d_eas_t0))
+      return fail(ctx, B200S_ERR_INVALID, "EAS history missing");
     P.n_ele = ctx->n_col_eles, P.nn = ctx->nn, P.ngp = ctx->ngp;
     P.fbar = ctx->tech == B200S_TECH_FBAR;
     P.linear = ctx->kinem == B200S_KINEM_LINEAR;
@@ -2576,10 +2585,55 @@ extern "C"
     const int rc = import_row_to_col(ctx, ctx->d_du_row, ctx->d_du_col, false);
     if (rc) return rc;
     if (b200s_parts::eas_recover(ctx, neas, step_length)) return B200S_ERR_CUDA;
+    ctx->eas_old_step_length = step_length;
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
     return B200S_OK;
   }
+
+  // correct_condensed_variables_for_linesearch (4C_solid_ele_calc_eas.hpp:228-243; correct_alpha,
+  // eas_helpers.hpp:192-199): alpha += (new - old step length) * alpha_inc
+  int b200s_recover_linesearch(b200s_ctx* ctx, double new_step_length)
+  {
+    if (!ctx) return B200S_ERR_INVALID;
+    const int neas = eas_neas(ctx->tech);
+    if (!neas) return B200S_OK;
+    if (!ctx->d_eas_hist) return fail(ctx, B200S_ERR_INVALID, "EAS history missing");
+    cudaSetDevice(ctx->device);
+    const int hs = hex8eas::hist_size(neas);
+    k_eas_correct_alpha<<<nblk(ctx->n_col_eles * neas), 256, 0, ctx->stream>>>(ctx->n_col_eles, neas, hs,
+        new_step_length - ctx->eas_old_step_length, ctx->d_eas_hist);
+    ctx->launches += 1;
+    ctx->eas_old_step_length = new_step_length;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return B200S_OK;
+  }
+
+  // struct_calc_update_istep / struct_calc_reset_istep (SolidEleCalc::update :317-363 and
+  // reset_to_last_converged :570-575 of 4C_solid_ele_calc.cpp): old_history_data_ = history_data_ and back.
+  // The materials on the device path have no history of their own (So3Material::update / reset_step are
+  // no-ops for them), so only the element (EAS) / Gauss-point (MULF) history is involved.
+  static int history_snapshot(b200s_ctx* ctx, int restore)
+  {
+    if (!ctx) return B200S_ERR_INVALID;
+    double* cur = eas_neas(ctx->tech) ? ctx->d_eas_hist : (ctx->prestress == B200S_PRESTRESS_MULF ? ctx->d_gp_hist : nullptr);
+    if (!cur) return B200S_OK;  // formulations without history: nothing to do
+    const int64_t n = eas_neas(ctx->tech) ? ctx->n_col_eles * hex8eas::hist_size(eas_neas(ctx->tech))
+                                          : ctx->n_col_eles * ctx->ngp * MULF_HIST;
+    cudaSetDevice(ctx->device);
+    if (!ctx->d_hist_old)
+    {
+      if (restore) return fail(ctx, B200S_ERR_INVALID, "reset_step before the first update_step");
+      if (to_device(ctx, &ctx->d_hist_old, (const double*)nullptr, n)) return B200S_ERR_CUDA;
+    }
+    CK(cudaMemcpyAsync(restore ? cur : ctx->d_hist_old, restore ? ctx->d_hist_old : cur, sizeof(double) * (size_t)n,
+        cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B200S_OK;
+  }
+  int b200s_update_step(b200s_ctx* ctx) { return history_snapshot(ctx, 0); }
+  int b200s_reset_step(b200s_ctx* ctx) { return history_snapshot(ctx, 1); }
 
   int64_t b200s_element_history_size(const b200s_ctx* ctx)
   {

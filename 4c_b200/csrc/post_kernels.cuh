@@ -43,6 +43,12 @@ namespace b200s
     const double* dN_cen;         // [nn][3] (F-bar)
     const double* w;              // [ngp]
     const double* gp_hist;        // nullptr or MULF history (device element order)
+    // EAS hex8 (eas_neas = 9 / 21, else 0): element history (alpha at [neas..2 neas)), the precomputed
+    // centroid transformation (T0invT[36], detJ0; stride eas_t0_stride) and the Gauss point coordinates
+    int eas_neas, eas_hist_size, eas_t0_stride;
+    const double* eas_hist;
+    const double* eas_t0;
+    const double* xi_gp;          // [ngp][3]
     MatParams mp;
     int64_t n_ele;
     int nn, ngp;
@@ -148,6 +154,73 @@ namespace b200s
     for (int i = 0; i < 9; ++i) h[i] = niJ[i], h[9 + i] = F[i];
   }
 
+  // Square root U and inverse square root of a symmetric positive definite 3x3 (Voigt in, full column-major
+  // out) by the Denman-Beavers iteration Y <- (Y + Z^-1)/2, Z <- (Z + Y^-1)/2 (Y -> C^1/2, Z -> C^-1/2;
+  // quadratic convergence, 12 steps reach round-off for the stretches met here).  The reference takes the
+  // root through an eigen decomposition (compute_deformation_gradient_from_gl_strains,
+  // 4C_solid_ele_calc_lib.hpp:1566-1595); same tensor.
+  B2_HD void sqrt_sym3(const double* Cv, double* U, double* iU)
+  {
+    double Y[9], Z[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) Y[a + 3 * b] = Cv[vg(a, b)];
+    for (int it = 0; it < 12; ++it)
+    {
+      double iY[9], iZ[9];
+      inv3(iY, Y);
+      inv3(iZ, Z);
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+      {
+        Y[i] = 0.5 * (Y[i] + iZ[i]);
+        Z[i] = 0.5 * (Z[i] + iY[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) U[i] = Y[i], iU[i] = Z[i];
+  }
+
+  // EAS kinematics at one Gauss point of a hex8 (evaluate_eas_kinematics, 4C_solid_ele_calc_eas_helpers.hpp:
+  // 405-448): C <- C_enh = C + 2 stress-like(Mtilde alpha); with want_F also F <- F_enh = R U_enh,
+  // R = F U^-1 (compute_deformation_gradient_from_gl_strains)
+  B2_HD void eas_enhance(const PostArgs& A, int64_t e, int g, double detJ, bool want_F, double* F, double* C)
+  {
+    const double* t0 = A.eas_t0 + e * A.eas_t0_stride;
+    const double* alpha = A.eas_hist + e * A.eas_hist_size + A.eas_neas;
+    const double r = A.xi_gp[3 * g], s = A.xi_gp[3 * g + 1], t = A.xi_gp[3 * g + 2];
+    const double scale = t0[36] / detJ;
+    const int rows[21] = {0, 1, 2, 3, 3, 4, 4, 5, 5, 3, 3, 4, 4, 5, 5, 0, 0, 1, 1, 2, 2};
+    const double mono[21] = {r, s, t, r, s, s, t, r, t, r * t, s * t, r * s, r * t, r * s, s * t, r * s, r * t,
+        r * s, s * t, r * t, s * t};
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    for (int c = 0; c < A.eas_neas; ++c) v[rows[c]] += mono[c] * alpha[c];
+    double Cd[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) Cd[k] = C[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+    {
+      double q = 0.0;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) q += t0[k + 6 * j] * v[j];
+      C[k] += (k < 3 ? 2.0 : 1.0) * scale * q;
+    }
+    if (!want_F) return;
+    double U[9], iU[9], Ue[9], iUe[9], R[9];
+    sqrt_sym3(Cd, U, iU);
+    sqrt_sym3(C, Ue, iUe);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) R[a + 3 * b] = F[a] * iU[3 * b] + F[a + 3] * iU[1 + 3 * b] + F[a + 6] * iU[2 + 3 * b];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) F[a + 3 * b] = R[a] * Ue[3 * b] + R[a + 3] * Ue[1 + 3 * b] + R[a + 6] * Ue[2 + 3 * b];
+  }
+
   // One Gauss point of calculate_stress / calculate_internal_energy.  Returns psi * integration
   // factor (0 when want_energy is false); stress6 / strain6 in the reference's row layout
   // [xx,yy,zz,xy,yz,xz] (assemble_symmetric_tensor_to_matrix_row, calc_lib_io.hpp:41-70).
@@ -173,6 +246,9 @@ namespace b200s
     double C[6], S[6], Cm[21];
     right_cauchy_green(F, C);
     if (A.linear) linear_kinematics(F, C);
+    if (A.eas_neas)
+      eas_enhance(A, e, g, detJ,
+          (stress6 != nullptr && A.stress_type == STRESS_CAUCHY) || (strain6 != nullptr && A.strain_type == STRAIN_EA), F, C);
     MatParams mp = A.mp;
     if (A.per_ele_param != nullptr) mp.p[0] = A.per_ele_param[e];
     if (MAT == MAT_HYPER && A.fibers != nullptr) mp.fiber = A.fibers + 3 * e;
@@ -378,6 +454,16 @@ namespace b200s
     const int g = (int)(t - e * ngp);
     if (e >= n_ele) return;
     mulf_update_point(nn, dN_gp + (size_t)g * nn * 3, X, u, conn + e * nn, hist + t * MULF_HIST);
+  }
+
+  // EAS line-search correction: alpha += dstep * alpha_inc (history block = {alpha_inc[n], alpha[n], ...})
+  __global__ void k_eas_correct_alpha(int64_t n_ele, int neas, int hist_size, double dstep, double* hist)
+  {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_ele * neas) return;
+    double* h = hist + (t / neas) * hist_size;
+    const int a = (int)(t % neas);
+    h[neas + a] = fma(dstep, h[a], h[neas + a]);
   }
 
   // history in the caller's element numbering <-> device element order (restart pack / unpack)

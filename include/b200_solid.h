@@ -288,7 +288,8 @@ extern "C"
    * current "displacement" state: Gauss-point stresses / strains of every column element,
    * [n_col_eles][num_gp][6] doubles in the caller's element order, rows [xx,yy,zz,xy,yz,xz]
    * (what the reference serialises into stress_data / strain_data per element).  Either output
-   * may be NULL.  [host|dev]. */
+   * may be NULL.  [host|dev].  EAS blocks: the enhanced strain / stress, Cauchy and Euler-Almansi through
+   * the enhanced deformation gradient F = R U_enh (4C_solid_ele_calc_lib.hpp:1566-1595). */
   int b200s_calc_stress(b200s_ctx* ctx, int stress_type, int strain_type, double* stress_out,
       double* strain_out);
   /* struct_calc_energy (calculate_internal_energy, 4C_solid_ele_calc.cpp:365-414): this rank's sum
@@ -320,6 +321,14 @@ extern "C"
    * last evaluate stored.  A no-op (B200S_OK) for formulations without condensed variables.  The
    * line-search correction (correct_condensed_variables_for_linesearch) is not on the device path. */
   int b200s_recover(b200s_ctx* ctx, const double* du_row, double step_length);
+  /* Non-default step of struct_calc_recover (correct_condensed_variables_for_linesearch,
+   * 4C_solid_ele_calc_eas.hpp:228-243): alpha += (new_step_length - old_step_length) * alpha_inc. */
+  int b200s_recover_linesearch(b200s_ctx* ctx, double new_step_length);
+  /* struct_calc_update_istep / struct_calc_reset_istep (SolidEleCalc::update / reset_to_last_converged,
+   * 4C_solid_ele_calc.cpp:317-363,570-575): snapshot of the block's history at a converged step and the
+   * way back after a failed one.  No-ops for formulations without history. */
+  int b200s_update_step(b200s_ctx* ctx);
+  int b200s_reset_step(b200s_ctx* ctx);
   /* Element history of the block = what EASFormulation::pack / unpack write for restart
    * (4C_solid_ele_calc_eas.hpp:266-288, without old_step_length): per column element (caller's order)
    * alpha_inc[n], alpha[n], s[n], invKaa[n*n], Kda[24*n], matrices column-major, n = 9 or 21. */

@@ -79,6 +79,7 @@ def lib():
         L.orc_evaluate_assemble_hist.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int,
                                                  C.c_int64, _ip, C.c_int64, _dp, _dp, _ip, _ip,
                                                  C.c_int64, _lp, _ip, _dp, _dp, C.c_int, _dp]
+        L.orc_set_output_history.argtypes = [_dp]
         L.orc_eas_hist_size.restype = C.c_int64
         L.orc_eas_recover.argtypes = [C.c_int, C.c_int64, _ip, _dp, C.c_double, _dp]
         L.orc_mulf_init_history.argtypes = [C.c_int64, _dp]
@@ -324,7 +325,7 @@ def element_mass(ct, density, X, lumped=False, acc=None):
 
 
 def calc_stress(ct, matkind, params, conn, X, u_col, stress_type=STRESS_2PK, strain_type=STRAIN_GL,
-                mue_per_ele=None, tech=TECH_NONE):
+                mue_per_ele=None, tech=TECH_NONE, hist=None):
     n, g = num_nodes(ct), num_gp(ct)
     params = np.ascontiguousarray(params, dtype=np.float64)
     conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, n)
@@ -333,12 +334,14 @@ def calc_stress(ct, matkind, params, conn, X, u_col, stress_type=STRESS_2PK, str
     if mue_per_ele is not None:
         mue_per_ele = np.ascontiguousarray(mue_per_ele, dtype=np.float64)
     st, en = np.zeros((len(conn), g, 6)), np.zeros((len(conn), g, 6))
+    lib().orc_set_output_history(_d(hist))
     lib().orc_calc_stress(ct, tech, matkind, _d(params), _d(mue_per_ele), len(conn), _i(conn), _d(X),
                           _d(u_col), stress_type, strain_type, _d(st), _d(en))
+    lib().orc_set_output_history(None)
     return st, en
 
 
-def calc_energy(ct, matkind, params, conn, X, u_col, ele_is_row=None, mue_per_ele=None, tech=TECH_NONE):
+def calc_energy(ct, matkind, params, conn, X, u_col, ele_is_row=None, mue_per_ele=None, tech=TECH_NONE, hist=None):
     n = num_nodes(ct)
     params = np.ascontiguousarray(params, dtype=np.float64)
     conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, n)
@@ -350,8 +353,11 @@ def calc_energy(ct, matkind, params, conn, X, u_col, ele_is_row=None, mue_per_el
     if ele_is_row is not None:
         ele_is_row = np.ascontiguousarray(ele_is_row, dtype=np.uint8)
         flag = ele_is_row.ctypes.data_as(C.POINTER(C.c_uint8))
-    return lib().orc_calc_energy(ct, tech, matkind, _d(params), _d(mue_per_ele), len(conn), _i(conn),
-                                 _d(X), _d(u_col), flag)
+    lib().orc_set_output_history(_d(hist))
+    e = lib().orc_calc_energy(ct, tech, matkind, _d(params), _d(mue_per_ele), len(conn), _i(conn),
+                              _d(X), _d(u_col), flag)
+    lib().orc_set_output_history(None)
+    return e
 
 
 def assemble_mass(ct, density, conn, X, node_row_lid, node_col_lid, n_row_nodes, rowptr, colind,

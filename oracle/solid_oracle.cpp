@@ -1586,6 +1586,87 @@ extern "C"
       return hyper_generic(blk, I, nullptr, nullptr);
     }
 
+    // eigen decomposition of a symmetric 3x3 by cyclic Jacobi rotations (the reference calls
+    // Core::LinAlg::eig = LAPACK dsyev; same decomposition): A = V diag(w) V^T, V column-major
+    void sym_eig3(const double* Afull, double* w, double* V)
+    {
+      double A[9];
+      for (int i = 0; i < 9; ++i) A[i] = Afull[i], V[i] = (i % 4 == 0) ? 1.0 : 0.0;
+      for (int sweep = 0; sweep < 60; ++sweep)
+      {
+        const double off = std::fabs(A[3]) + std::fabs(A[6]) + std::fabs(A[7]);
+        if (off < 1e-300) break;
+        for (int p = 0; p < 2; ++p)
+          for (int q = p + 1; q < 3; ++q)
+          {
+            const double apq = A[p + 3 * q];
+            if (apq == 0.0) continue;
+            const double theta = (A[q + 3 * q] - A[p + 3 * p]) / (2.0 * apq);
+            const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+            const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+            for (int k = 0; k < 3; ++k)
+            {
+              const double akp = A[k + 3 * p], akq = A[k + 3 * q];
+              A[k + 3 * p] = c * akp - s * akq, A[k + 3 * q] = s * akp + c * akq;
+            }
+            for (int k = 0; k < 3; ++k)
+            {
+              const double apk = A[p + 3 * k], aqk = A[q + 3 * k];
+              A[p + 3 * k] = c * apk - s * aqk, A[q + 3 * k] = s * apk + c * aqk;
+            }
+            for (int k = 0; k < 3; ++k)
+            {
+              const double vkp = V[k + 3 * p], vkq = V[k + 3 * q];
+              V[k + 3 * p] = c * vkp - s * vkq, V[k + 3 * q] = s * vkp + c * vkq;
+            }
+          }
+      }
+      for (int i = 0; i < 3; ++i) w[i] = A[i + 3 * i];
+    }
+    // pure stretch tensor U = C^(1/2) (compute_pure_stretch_tensor, 4C_solid_ele_calc_lib.hpp:1577-1586)
+    void pure_stretch(const double* Cv, double* U)
+    {
+      double Cf[9], w[3], V[9];
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) Cf[a + 3 * b] = Cv[VG[a][b]];
+      sym_eig3(Cf, w, V);
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b)
+        {
+          double v = 0.0;
+          for (int k = 0; k < 3; ++k) v += V[a + 3 * k] * std::sqrt(w[k]) * V[b + 3 * k];
+          U[a + 3 * b] = v;
+        }
+    }
+    // compute_deformation_gradient_from_gl_strains (calc_lib.hpp:1566-1595): F_enh = R U_enh, R = F U^-1
+    void enhanced_deformation_gradient(const double* F, const double* E_enh, double* Fenh)
+    {
+      double C[6], Ce[6], U[9], iU[9], Ue[9], R[9];
+      cauchy_green(F, C, nullptr);
+      for (int v = 0; v < 6; ++v) Ce[v] = 2.0 * E_enh[v] + (v < 3 ? 1.0 : 0.0);
+      pure_stretch(C, U);
+      pure_stretch(Ce, Ue);
+      inv3(iU, U);
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b)
+        {
+          double v = 0.0;
+          for (int k = 0; k < 3; ++k) v += F[a + 3 * k] * iU[k + 3 * b];
+          R[a + 3 * b] = v;
+        }
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b)
+        {
+          double v = 0.0;
+          for (int k = 0; k < 3; ++k) v += R[a + 3 * k] * Ue[k + 3 * b];
+          Fenh[a + 3 * b] = v;
+        }
+    }
+
+    // element history of the EAS formulations for the output actions (set by orc_set_output_history)
+    const double* g_eas_hist = nullptr;
+    const double* g_xi = nullptr;  // parameter coordinates of the Gauss point being evaluated
+
     // kinematics of the formulation at one Gauss point: F and E as handed to the material
     // (DisplacementBasedFormulation::evaluate, 4C_solid_ele_calc_displacement_based.hpp:44-63;
     //  FBarFormulation::evaluate, 4C_solid_ele_calc_fbar.hpp:83-118)
@@ -1594,6 +1675,17 @@ extern "C"
     {
       const int n = nnodes(ct);
       deformation_gradient(n, u, jm, F);
+      if (tech == ORC_TECH_EAS_MILD || tech == ORC_TECH_EAS_FULL)
+      {
+        // EASFormulation::evaluate (4C_solid_ele_calc_eas.hpp:72-88): enhanced GL strain and deformation gradient
+        const int neas = eas_num(tech);
+        double T0invT[36], detJ0, Mt[6 * 21], Fenh[9];
+        eas_centroid_transformation(ct, X, T0invT, detJ0);
+        eas_point(neas, T0invT, detJ0, jm.det, g_xi, g_eas_hist + neas, F, Mt, E);
+        enhanced_deformation_gradient(F, E, Fenh);
+        for (int i = 0; i < 9; ++i) F[i] = Fenh[i];
+        return;
+      }
       if (tech == ORC_TECH_LINEAR)
       {
         for (int v = 0; v < 6; ++v)
@@ -1617,6 +1709,11 @@ extern "C"
     }
   }  // namespace
 
+  // history of all elements for the output actions of history-carrying formulations (EAS): set before
+  // orc_calc_stress / orc_calc_energy, NULL afterwards
+  static const double* g_output_hist = nullptr;
+  void orc_set_output_history(const double* hist) { g_output_hist = hist; }
+
   // SolidEleCalc::calculate_stress (src/solid_ele/4C_solid_ele_calc.cpp:416-476) for one element:
   // stress / strain [ngp][6] in the row layout of assemble_symmetric_tensor_to_matrix_row
   // (4C_solid_ele_calc_lib_io.hpp:41-70).  stress_type 1 = 2PK, 2 = Cauchy (pk2_to_cauchy,
@@ -1633,6 +1730,7 @@ extern "C"
       shape(ct, gxi + 3 * gp, N, dN);
       jacobian_mapping(n, dN, X, jm);
       double F[9], E[6], S[6], Cm[36];
+      g_xi = gxi + 3 * gp;
       formulation_kinematics(ct, tech, X, u, jm, F, E);
       material(matkind, par, F, E, S, Cm);
       if (stress && stress_type == 1)
@@ -1692,6 +1790,7 @@ extern "C"
       shape(ct, gxi + 3 * gp, N, dN);
       jacobian_mapping(n, dN, X, jm);
       double F[9], E[6];
+      g_xi = gxi + 3 * gp;
       formulation_kinematics(ct, tech, X, u, jm, F, E);
       intenergy += strain_energy(matkind, par, E) * (jm.det * gw[gp]);
     }
@@ -1814,6 +1913,8 @@ extern "C"
           ue[3 * i + d] = u_col[3 * (int64_t)conn[e * n + i] + d];
         }
       if (mue_per_ele) par[0] = mue_per_ele[e];
+      if (g_output_hist && (tech == ORC_TECH_EAS_MILD || tech == ORC_TECH_EAS_FULL))
+        g_eas_hist = g_output_hist + orc_eas_hist_size(tech) * e;
       orc_element_stress(ct, tech, matkind, par.data(), Xe.data(), ue.data(), stress_type, strain_type,
           stress ? stress + e * ng * 6 : nullptr, strain ? strain + e * ng * 6 : nullptr);
     }
@@ -1837,6 +1938,8 @@ extern "C"
           ue[3 * i + d] = u_col[3 * (int64_t)conn[e * n + i] + d];
         }
       if (mue_per_ele) par[0] = mue_per_ele[e];
+      if (g_output_hist && (tech == ORC_TECH_EAS_MILD || tech == ORC_TECH_EAS_FULL))
+        g_eas_hist = g_output_hist + orc_eas_hist_size(tech) * e;
       sum += orc_element_energy(ct, tech, matkind, par.data(), Xe.data(), ue.data());
     }
     return sum;

@@ -123,6 +123,8 @@ extern "C" int emu_post(int celltype, int fbar, int matkind, const double* param
   A.ele_is_row = ele_is_row, A.dN_gp = T.dN_gp.data(), A.dN_cen = T.dN_cen.data(), A.w = T.w.data();
   A.mp = mp, A.n_ele = n_ele, A.nn = T.nn, A.ngp = T.ngp, A.fbar = fbar == 1, A.linear = fbar == 2;
   A.gp_hist = gp_hist;
+  A.eas_neas = 0, A.eas_hist_size = 0, A.eas_t0_stride = 0, A.eas_hist = nullptr, A.eas_t0 = nullptr;
+  A.xi_gp = T.xi_gp.data();
   A.stress_type = stress_type, A.strain_type = strain_type;
   A.stress = stress, A.strain = strain, A.energy = nullptr;
   switch (matkind)

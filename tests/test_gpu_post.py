@@ -580,6 +580,16 @@ def test_reference_eas_known_answers_through_cuda_path(tech):
     u = solve_case(case, ev, recover=lambda du: asm.recover(du, 1.0))
     for e in case["expected_disp"]:
         assert abs(u[e["node"], e["dof"]] - e["value"]) < 1e-10, (e, u[e["node"], e["dof"]])
+    # nodal stresses / strains of the same inputs from the device's struct_calc_stress (eas_mild: 2PK + GL,
+    # eas_full: Cauchy + Euler-Almansi through the enhanced deformation gradient)
+    from tests.helpers.postprocess import nodal_stresses
+    asm.set_state("displacement", u.ravel())
+    st, en = asm.calc_stress(case["iostress"].lower(), case["iostrain"].lower())
+    ns, ne = nodal_stresses(orc.HEX8, conn, st, len(X)), nodal_stresses(orc.HEX8, conn, en, len(X))
+    for e in case["expected_stress"]:
+        assert abs(ns[e["node"], e["comp"]] - e["value"]) < 1e-8, (e, ns[e["node"], e["comp"]])
+    for e in case["expected_strain"]:
+        assert abs(ne[e["node"], e["comp"]] - e["value"]) < 1e-9, (e, ne[e["node"], e["comp"]])
     asm.close()
 
 
@@ -630,3 +640,67 @@ def test_linear_kinematics_match_oracle(cell, mi):
         ctx.set_element_properties(kinem=capi.KINEM_LINEAR, tech=capi.TECH_FBAR)
     assert ei.value.code == capi.ERR_UNSUPPORTED
     ctx.close()
+
+
+def test_eas_linesearch_correction_and_step_update_reset():
+    """correct_condensed_variables_for_linesearch: alpha += (new - old step) * alpha_inc; struct_calc_update_istep /
+    struct_calc_reset_istep: snapshot and restore of the element history (EAS) and Gauss-point history (MULF)."""
+    ct, rm, u = _mesh("hex8")
+    asm = b200.DeviceAssembler(rm, capi.MAT_SVK, [1000.0, 0.3], tech=capi.TECH_EAS_MILD)
+    asm.set_state("displacement", u.ravel())
+    asm.evaluate()
+    du = 1e-3 * np.random.default_rng(4).uniform(-1, 1, asm.n_rows)
+    asm.recover(du, 1.0)
+    h1 = asm.ctx.get_element_history().reshape(rm.n_col_eles, -1)
+    asm.ctx.update_step()
+    asm.ctx.recover_linesearch(0.25)
+    h2 = asm.ctx.get_element_history().reshape(rm.n_col_eles, -1)
+    assert np.abs(h2[:, 9:18] - (h1[:, 9:18] - 0.75 * h1[:, :9])).max() <= 1e-15 * np.abs(h1[:, 9:18]).max()
+    assert np.array_equal(h2[:, :9], h1[:, :9]) and np.array_equal(h2[:, 18:], h1[:, 18:])
+    asm.ctx.reset_step()
+    assert np.array_equal(asm.ctx.get_element_history().reshape(rm.n_col_eles, -1), h1)
+    asm.close()
+    asm = b200.DeviceAssembler(rm, capi.MAT_SVK, [1000.0, 0.3], prestress=capi.PRESTRESS_MULF)
+    asm.set_state("displacement", u.ravel())
+    asm.update_prestress()
+    g1 = asm.ctx.get_gp_history()
+    asm.ctx.update_step()
+    asm.set_state("displacement", -0.5 * u.ravel())
+    asm.update_prestress()
+    assert np.abs(asm.ctx.get_gp_history() - g1).max() > 1e-6
+    asm.ctx.reset_step()
+    assert np.array_equal(asm.ctx.get_gp_history(), g1)
+    asm.close()
+    plain = b200.DeviceAssembler(rm, capi.MAT_SVK, [1000.0, 0.3])
+    plain.ctx.update_step(), plain.ctx.reset_step(), plain.ctx.recover_linesearch(0.5)  # no-ops
+    plain.close()
+
+
+@pytest.mark.parametrize("tech", ["eas_mild", "eas_full"])
+def test_eas_stress_and_energy_output_match_oracle(tech):
+    ct, rm, u = _mesh("hex8", (5, 4, 3))
+    dt, ot = EAS[tech]
+    mk, par = MATS[0]
+    asm = b200.DeviceAssembler(rm, mk, par, tech=dt)
+    rowptr, colind = asm.graph()
+    ohist = orc.eas_new_history(ot, rm.n_col_eles)
+    us = u.ravel().copy()
+    asm.set_state("displacement", us)
+    asm.evaluate()
+    orc.evaluate_assemble(ct, mk, par, rm.conn, rm.X.ravel(), us, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes,
+                          rowptr, colind, tech=ot, hist=ohist)
+    du = 1e-4 * np.random.default_rng(6).uniform(-1, 1, us.size)
+    asm.recover(du, 1.0)
+    orc.eas_recover(ot, rm.conn, du, ohist, 1.0)
+    us = us + du
+    asm.set_state("displacement", us)
+    assert np.abs(ohist[:, 9 if tech == "eas_mild" else 21:][:, :5]).max() > 0  # alpha is not trivially zero
+    for io, types in ((("2pk", "gl"), (orc.STRESS_2PK, orc.STRAIN_GL)), (("cauchy", "ea"), (orc.STRESS_CAUCHY, orc.STRAIN_EA))):
+        st, en = asm.calc_stress(*io)
+        rst, ren = orc.calc_stress(ct, mk, par, rm.conn, rm.X.ravel(), us, types[0], types[1], tech=ot, hist=ohist)
+        assert np.abs(st - rst).max() <= 1e-10 * np.abs(rst).max(), (io, np.abs(st - rst).max() / np.abs(rst).max())
+        assert np.abs(en - ren).max() <= 1e-10 * np.abs(ren).max(), (io, np.abs(en - ren).max() / np.abs(ren).max())
+    e_dev = asm.calc_energy()
+    e_ref = orc.calc_energy(ct, mk, par, rm.conn, rm.X.ravel(), us, tech=ot, hist=ohist)
+    assert abs(e_dev - e_ref) <= 1e-10 * abs(e_ref)
+    asm.close()

@@ -439,6 +439,19 @@ def test_eas_known_answers(tech):
     assert len(case["expected_disp"]) >= 12
     for e in case["expected_disp"]:
         assert abs(u[e["node"], e["dof"]] - e["value"]) < 1e-11, (e, u[e["node"], e["dof"]])
+    # nodal stresses / strains of the same inputs (eas_mild: 2PK + GL, eas_full: Cauchy + Euler-Almansi through the
+    # enhanced deformation gradient): pins calculate_stress of the EAS formulation
+    st_type = {"2PK": orc.STRESS_2PK, "Cauchy": orc.STRESS_CAUCHY}[case["iostress"]]
+    en_type = {"GL": orc.STRAIN_GL, "EA": orc.STRAIN_EA}[case["iostrain"]]
+    st, en = orc.calc_stress(orc.HEX8, orc.MAT_ELASTHYPER, par, conn, X.ravel(), u.ravel(), st_type, en_type,
+                             tech=EAS_TECH[tech], hist=hist)
+    nodal_s = nodal_stresses(orc.HEX8, conn, st, nn)
+    nodal_e = nodal_stresses(orc.HEX8, conn, en, nn)
+    assert len(case["expected_stress"]) >= 20 and len(case["expected_strain"]) >= 20
+    for e in case["expected_stress"]:
+        assert abs(nodal_s[e["node"], e["comp"]] - e["value"]) < 1e-9, (e, nodal_s[e["node"], e["comp"]])
+    for e in case["expected_strain"]:
+        assert abs(nodal_e[e["node"], e["comp"]] - e["value"]) < 1e-10, (e, nodal_e[e["node"], e["comp"]])
 
 
 # ------------------------------------------------------------------------------------------------------
