@@ -109,6 +109,22 @@ class DeviceAssembler:
         """struct_calc_energy: internal energy of this rank's row elements."""
         return self.ctx.calc_energy()
 
+    def add_surface_neumann(self, neumann_type, face_nodes, onoff, val):
+        """One DESIGN SURF NEUMANN CONDITIONS entry; face_nodes in column-node lids of this rank
+        (every face of the condition geometry all of whose nodes are column nodes here). Returns its id."""
+        t = {"live": capi.NEUMANN_LIVE, "pseudo_orthopressure": capi.NEUMANN_PSEUDO_ORTHOPRESSURE,
+             "orthopressure": capi.NEUMANN_ORTHOPRESSURE}[neumann_type.lower()]
+        return self.ctx.add_surface_neumann(t, face_nodes, onoff, val)
+
+    def add_volume_neumann(self, onoff, val, ele_ids=None):
+        return self.ctx.add_volume_neumann(onoff, val, ele_ids)
+
+    def evaluate_neumann(self, u_row=None, loadlin=False, mulf_active=False):
+        """Discretization::evaluate_neumann on the block: external force on the row map; with loadlin the
+        orthopressure load stiffness is added to the stiffness values resident in the context."""
+        flags = (capi.NEUMANN_LOADLIN if loadlin else 0) | (capi.NEUMANN_MULF_ACTIVE if mulf_active else 0)
+        return self.ctx.evaluate_neumann(u_row, flags)
+
     def close(self):
         self.ctx.close()
 

@@ -19,6 +19,8 @@ ACTION_INTERNALFORCE, ACTION_NLNSTIFF, ACTION_NLNSTIFFMASS, ACTION_NLNSTIFFLMASS
 STRESS_NONE, STRESS_2PK, STRESS_CAUCHY = 0, 1, 2
 STRAIN_NONE, STRAIN_GL, STRAIN_EA = 0, 1, 2
 MATRIX_STIFFNESS, MATRIX_MASS = 0, 1
+NEUMANN_LIVE, NEUMANN_PSEUDO_ORTHOPRESSURE, NEUMANN_ORTHOPRESSURE = 0, 1, 2
+NEUMANN_LOADLIN, NEUMANN_MULF_ACTIVE = 1, 2
 # b200s_summand ids (include/b200_solid.h), by name
 SUMMANDS = ["COUP_NEOHOOKE", "COUP_MOONEYRIVLIN", "COUP_LOGNEOHOOKE", "COUP_LOGMIXNEOHOOKE", "COUP_SVK",
             "COUP_SIMOPISTER", "COUP_BLATZKO", "COUP_EXPPOL", "COUP_1POW", "COUP_2POW", "COUP_3POW",
@@ -46,6 +48,8 @@ SYMBOLS = [
     "b200s_update_prestress", "b200s_gp_history_size", "b200s_get_gp_history", "b200s_set_gp_history",
     "b200s_recover", "b200s_element_history_size", "b200s_get_element_history", "b200s_set_element_history",
     "b200s_set_element_fibers", "b200s_recover_linesearch", "b200s_update_step", "b200s_reset_step",
+    "b200s_add_surface_neumann", "b200s_add_volume_neumann", "b200s_clear_neumann", "b200s_neumann_gp_count",
+    "b200s_neumann_gp_coords", "b200s_set_neumann_factors", "b200s_evaluate_neumann", "b200s_device_fext",
 ]
 
 
@@ -139,6 +143,16 @@ def load():
     L.b200s_last_multiply_ms.argtypes = [vp]
     L.b200s_last_multiply_ms.restype = dbl
     L.b200s_solve_cg.argtypes = [vp, vp, vp, dbl, i32, C.POINTER(i32), C.POINTER(dbl)]
+    L.b200s_add_surface_neumann.argtypes = [vp, i32, i64, vp, vp, vp]
+    L.b200s_add_volume_neumann.argtypes = [vp, i64, vp, vp, vp]
+    L.b200s_clear_neumann.argtypes = [vp]
+    L.b200s_neumann_gp_count.argtypes = [vp, i32]
+    L.b200s_neumann_gp_count.restype = i64
+    L.b200s_neumann_gp_coords.argtypes = [vp, i32, i32, vp]
+    L.b200s_set_neumann_factors.argtypes = [vp, i32, vp, vp]
+    L.b200s_evaluate_neumann.argtypes = [vp, vp, i32, vp]
+    L.b200s_device_fext.argtypes = [vp]
+    L.b200s_device_fext.restype = vp
     _lib = L
     return L
 
@@ -287,6 +301,48 @@ class Context:
         e = C.c_double(0)
         self._ck(self.L.b200s_calc_energy(self.h, C.byref(e)))
         return e.value
+
+    # ---- external loads (Discretization::evaluate_neumann) ----
+    def add_surface_neumann(self, neumann_type, face_nodes, onoff, val):
+        f = np.ascontiguousarray(face_nodes, np.int32)
+        o = np.ascontiguousarray(onoff, np.int32)
+        v = np.ascontiguousarray(val, np.float64)
+        assert len(o) >= 3 and len(v) >= 3
+        rc = self.L.b200s_add_surface_neumann(self.h, int(neumann_type), len(f), _ptr(f), _ptr(o), _ptr(v))
+        if rc < 0:
+            self._ck(rc)
+        return rc
+
+    def add_volume_neumann(self, onoff, val, ele_ids=None):
+        o = np.ascontiguousarray(onoff, np.int32)
+        v = np.ascontiguousarray(val, np.float64)
+        e = None if ele_ids is None else np.ascontiguousarray(ele_ids, np.int32)
+        rc = self.L.b200s_add_volume_neumann(self.h, 0 if e is None else len(e), _ptr(e), _ptr(o), _ptr(v))
+        if rc < 0:
+            self._ck(rc)
+        return rc
+
+    def clear_neumann(self):
+        self._ck(self.L.b200s_clear_neumann(self.h))
+
+    def neumann_gp_coords(self, cond, flags=0):
+        n = self.L.b200s_neumann_gp_count(self.h, int(cond))
+        if n < 0:
+            raise B200SolidError(ERR_INVALID, f"no Neumann condition {cond}")
+        out = np.zeros((n, 3))
+        self._ck(self.L.b200s_neumann_gp_coords(self.h, int(cond), int(flags), _ptr(out)))
+        return out
+
+    def set_neumann_factors(self, cond, dof_fac=None, gp_fac=None):
+        d = None if dof_fac is None else np.ascontiguousarray(dof_fac, np.float64)
+        g = None if gp_fac is None else np.ascontiguousarray(gp_fac, np.float64)
+        self._ck(self.L.b200s_set_neumann_factors(self.h, int(cond), _ptr(d), _ptr(g)))
+
+    def evaluate_neumann(self, u_row=None, flags=0):
+        u = None if u_row is None else np.ascontiguousarray(u_row, np.float64)
+        f = np.zeros(self.n_rows)
+        self._ck(self.L.b200s_evaluate_neumann(self.h, _ptr(u), int(flags), _ptr(f)))
+        return f
 
     def apply_dirichlet(self, dbctoggle_row, diagonalblock=True, which=MATRIX_STIFFNESS):
         t = np.ascontiguousarray(dbctoggle_row, np.float64)

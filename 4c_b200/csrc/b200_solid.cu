@@ -36,6 +36,7 @@
 #if B200S_HAS(B200S_PART_CORE)
 #include "post_kernels.cuh"
 #include "linalg_kernels.cuh"
+#include "neumann_kernels.cuh"
 #endif
 #include "shape_tables.hpp"
 
@@ -1126,6 +1127,22 @@ struct b200s_ctx
   double *d_mass = nullptr, *d_f_inertia = nullptr, *d_acc_row = nullptr, *d_acc_col = nullptr;
   // post-processing outputs
   double* d_energy = nullptr;
+  // external loads (neumann_kernels.cuh)
+  struct NeumannCond
+  {
+    bool volume = false;
+    int kind = 0;
+    int64_t n = 0;                 // faces / loaded elements
+    int32_t* d_faces = nullptr;    // surface: [n][face_nn]
+    int32_t* d_ele_slot = nullptr; // volume: caller's element id -> index, nullptr = all
+    int onoff[3] = {0, 0, 0};
+    double val[3] = {0, 0, 0}, fac[3] = {1, 1, 1};
+    double* d_gp_fac = nullptr;
+  };
+  std::vector<NeumannCond> neumann;
+  int face_nn = 0, face_ngp = 0;
+  double *d_face_N = nullptr, *d_face_d0 = nullptr, *d_face_d1 = nullptr, *d_face_w = nullptr;
+  double *d_N_gp = nullptr, *d_fext = nullptr, *d_nm_row = nullptr, *d_nm_col = nullptr;
   // linear algebra on the assembled matrix (linalg_kernels.cuh)
   int64_t n_mat_cols = 0;
   bool node3_ok = false;
@@ -1569,6 +1586,9 @@ extern "C"
     dfree(ctx->d_gp_hist), dfree(ctx->d_eas_hist), dfree(ctx->d_du_row), dfree(ctx->d_du_col);
     dfree(ctx->d_eas_t0), dfree(ctx->d_fibers), dfree(ctx->d_blkcol), dfree(ctx->d_hist_old);
     dfree(ctx->d_xi_gp);
+    b200s_clear_neumann(ctx);
+    dfree(ctx->d_face_N), dfree(ctx->d_face_d0), dfree(ctx->d_face_d1), dfree(ctx->d_face_w);
+    dfree(ctx->d_N_gp), dfree(ctx->d_fext), dfree(ctx->d_nm_row), dfree(ctx->d_nm_col);
     dfree(ctx->d_hyper), dfree(ctx->d_dN_gp), dfree(ctx->d_w), dfree(ctx->d_dN_cen), dfree(ctx->d_N_mass);
     dfree(ctx->d_dN_mass), dfree(ctx->d_w_mass), dfree(ctx->d_ele_is_row), dfree(ctx->d_mass);
     dfree(ctx->d_f_inertia), dfree(ctx->d_acc_row), dfree(ctx->d_acc_col), dfree(ctx->d_energy);
@@ -1625,8 +1645,18 @@ extern "C"
         to_device(ctx, &ctx->d_xi_gp, T.xi_gp.data(), (int64_t)T.xi_gp.size()) ||
         to_device(ctx, &ctx->d_N_mass, T.N_mass.data(), (int64_t)T.N_mass.size()) ||
         to_device(ctx, &ctx->d_dN_mass, T.dN_mass.data(), (int64_t)T.dN_mass.size()) ||
-        to_device(ctx, &ctx->d_w_mass, T.w_mass.data(), (int64_t)T.w_mass.size()))
+        to_device(ctx, &ctx->d_w_mass, T.w_mass.data(), (int64_t)T.w_mass.size()) ||
+        to_device(ctx, &ctx->d_N_gp, T.N_gp.data(), (int64_t)T.N_gp.size()))
       return B200S_ERR_CUDA;
+    const FaceTables FT = make_face_tables(celltype);
+    ctx->face_nn = FT.nn, ctx->face_ngp = FT.ngp;
+    if (to_device(ctx, &ctx->d_face_N, FT.N.data(), (int64_t)FT.N.size()) ||
+        to_device(ctx, &ctx->d_face_d0, FT.d0.data(), (int64_t)FT.d0.size()) ||
+        to_device(ctx, &ctx->d_face_d1, FT.d1.data(), (int64_t)FT.d1.size()) ||
+        to_device(ctx, &ctx->d_face_w, FT.w.data(), (int64_t)FT.w.size()))
+      return B200S_ERR_CUDA;
+    b200s_clear_neumann(ctx);  // conditions refer to the previous mesh
+    dfree(ctx->d_nm_col);
     CK(cudaStreamSynchronize(ctx->stream));  // T is a local
     dfree(ctx->d_ele_is_row), dfree(ctx->d_acc_col), dfree(ctx->d_gp_hist), dfree(ctx->d_eas_hist);
     dfree(ctx->d_du_col), dfree(ctx->d_fibers), dfree(ctx->d_hist_old);
@@ -2692,6 +2722,239 @@ extern "C"
   {
     return which == B200S_MATRIX_MASS ? ctx->d_mass : ctx->d_vals;
   }
+
+  // ---- external loads (Discretization::evaluate_neumann on the element block) -----------------------
+  int b200s_clear_neumann(b200s_ctx* ctx)
+  {
+    if (!ctx) return B200S_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& c : ctx->neumann) dfree(c.d_faces), dfree(c.d_ele_slot), dfree(c.d_gp_fac);
+    ctx->neumann.clear();
+    return B200S_OK;
+  }
+
+  int b200s_add_surface_neumann(b200s_ctx* ctx, int neumann_type, int64_t n_faces, const int32_t* face_nodes,
+      const int32_t* onoff, const double* val)
+  {
+    if (!ctx || n_faces < 0 || (n_faces > 0 && !face_nodes) || !onoff || !val) return B200S_ERR_INVALID;
+    if (ctx->celltype < 0) return fail(ctx, B200S_ERR_INVALID, "set_mesh must precede add_surface_neumann");
+    if (neumann_type < B200S_NEUMANN_LIVE || neumann_type > B200S_NEUMANN_ORTHOPRESSURE)
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "Unknown type of SurfaceNeumann condition");
+    if (neumann_type != B200S_NEUMANN_LIVE && (onoff[0] != 1 || onoff[1] != 0 || onoff[2] != 0))
+      return fail(ctx, B200S_ERR_INVALID, "orthopressure on 1st dof only!");
+    for (int64_t t = 0; t < n_faces * ctx->face_nn; ++t)
+      if (face_nodes[t] < 0 || face_nodes[t] >= ctx->n_col_nodes)
+        return fail(ctx, B200S_ERR_INVALID, "face %lld: node id %d out of range", (long long)(t / ctx->face_nn),
+            face_nodes[t]);
+    cudaSetDevice(ctx->device);
+    b200s_ctx::NeumannCond c;
+    c.volume = false, c.kind = neumann_type, c.n = n_faces;
+    for (int d = 0; d < 3; ++d) c.onoff[d] = onoff[d], c.val[d] = val[d];
+    if (to_device(ctx, &c.d_faces, face_nodes, n_faces * ctx->face_nn)) return B200S_ERR_CUDA;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->neumann.push_back(c);
+    return (int)ctx->neumann.size() - 1;
+  }
+
+  int b200s_add_volume_neumann(b200s_ctx* ctx, int64_t n_eles, const int32_t* ele_ids, const int32_t* onoff,
+      const double* val)
+  {
+    if (!ctx || !onoff || !val || n_eles < 0) return B200S_ERR_INVALID;
+    if (ctx->celltype < 0) return fail(ctx, B200S_ERR_INVALID, "set_mesh must precede add_volume_neumann");
+    cudaSetDevice(ctx->device);
+    b200s_ctx::NeumannCond c;
+    c.volume = true, c.kind = B200S_NEUMANN_LIVE, c.n = ele_ids ? n_eles : ctx->n_col_eles;
+    for (int d = 0; d < 3; ++d) c.onoff[d] = onoff[d], c.val[d] = val[d];
+    if (ele_ids)
+    {
+      std::vector<int32_t> slot((size_t)ctx->n_col_eles, -1);
+      for (int64_t k = 0; k < n_eles; ++k)
+      {
+        if (ele_ids[k] < 0 || ele_ids[k] >= ctx->n_col_eles)
+          return fail(ctx, B200S_ERR_INVALID, "element id %d out of range", ele_ids[k]);
+        slot[ele_ids[k]] = (int32_t)k;
+      }
+      if (to_device(ctx, &c.d_ele_slot, slot.data(), ctx->n_col_eles)) return B200S_ERR_CUDA;
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->neumann.push_back(c);
+    return (int)ctx->neumann.size() - 1;
+  }
+
+  int64_t b200s_neumann_gp_count(const b200s_ctx* ctx, int cond)
+  {
+    if (!ctx || cond < 0 || cond >= (int)ctx->neumann.size()) return -1;
+    const auto& c = ctx->neumann[cond];
+    return c.n * (c.volume ? ctx->ngp : ctx->face_ngp);
+  }
+
+  int b200s_set_neumann_factors(b200s_ctx* ctx, int cond, const double* dof_fac, const double* gp_fac)
+  {
+    if (!ctx || cond < 0 || cond >= (int)ctx->neumann.size()) return B200S_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    auto& c = ctx->neumann[cond];
+    for (int d = 0; d < 3; ++d) c.fac[d] = dof_fac ? dof_fac[d] : 1.0;
+    if (!gp_fac)
+    {
+      CK(cudaStreamSynchronize(ctx->stream));
+      dfree(c.d_gp_fac);
+      return B200S_OK;
+    }
+    const int64_t n = 3 * b200s_neumann_gp_count(ctx, cond);
+    if (!c.d_gp_fac && to_device(ctx, &c.d_gp_fac, (const double*)nullptr, n)) return B200S_ERR_CUDA;
+    CK(cudaMemcpyAsync(c.d_gp_fac, gp_fac, sizeof(double) * (size_t)n, cudaMemcpyDefault, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B200S_OK;
+  }
+
+  // (static helpers of the entry points below)
+    static NeumannSurfArgs neumann_surface_args(b200s_ctx* ctx, const b200s_ctx::NeumannCond& c, const double* d_u_col,
+        int flags)
+    {
+      NeumannSurfArgs A;
+      A.T.nn = ctx->face_nn, A.T.ngp = ctx->face_ngp;
+      A.T.N = ctx->d_face_N, A.T.d0 = ctx->d_face_d0, A.T.d1 = ctx->d_face_d1, A.T.w = ctx->d_face_w;
+      A.X = ctx->dX;
+      // configuration (:127-178): material for Live and for an orthopressure while MULF is active
+      const bool material = c.kind == B200S_NEUMANN_LIVE ||
+                            (c.kind == B200S_NEUMANN_ORTHOPRESSURE && (flags & B200S_NEUMANN_MULF_ACTIVE));
+      A.u = material ? nullptr : d_u_col;
+      A.faces = c.d_faces, A.n_faces = c.n, A.kind = c.kind;
+      for (int d = 0; d < 3; ++d) A.onoff[d] = c.onoff[d], A.val[d] = c.val[d] * c.fac[d];
+      A.gp_fac = c.d_gp_fac;
+      A.node_row = ctx->d_node_row, A.node_colbase = ctx->d_node_colbase, A.colind = ctx->d_colind;
+      A.fext = ctx->d_fext;
+      const bool lin = c.kind == B200S_NEUMANN_ORTHOPRESSURE && (flags & B200S_NEUMANN_LOADLIN) && !material;
+      A.K = lin ? ctx->d_vals : nullptr;
+      return A;
+    }
+    static NeumannVolArgs neumann_volume_args(b200s_ctx* ctx, const b200s_ctx::NeumannCond& c)
+    {
+      NeumannVolArgs A;
+      A.X = ctx->dX, A.conn = ctx->dconn, A.ele_id = ctx->d_ele_id, A.ele_slot = c.d_ele_slot;
+      A.N_gp = ctx->d_N_gp, A.dN_gp = ctx->d_dN_gp, A.w = ctx->d_w;
+      A.n_ele = ctx->n_col_eles, A.nn = ctx->nn, A.ngp = ctx->ngp;
+      for (int d = 0; d < 3; ++d) A.onoff[d] = c.onoff[d], A.val[d] = c.val[d] * c.fac[d];
+      A.gp_fac = c.d_gp_fac;
+      A.node_row = ctx->d_node_row, A.fext = ctx->d_fext;
+      return A;
+    }
+    // column-map displacement the deformation dependent conditions act on
+    static int neumann_state(b200s_ctx* ctx, const double* u_row, const double** d_u_col)
+    {
+      if (!u_row)
+      {
+        const int rc = import_row_to_col(ctx, ctx->d_u_row, ctx->d_u_col, false);
+        *d_u_col = ctx->d_u_col;
+        return rc;
+      }
+      if (stage_row_vector(ctx, &ctx->d_nm_row, u_row)) return B200S_ERR_CUDA;
+      if (!ctx->d_nm_col)
+      {
+        if (to_device(ctx, &ctx->d_nm_col, (const double*)nullptr, 3 * ctx->n_col_nodes)) return B200S_ERR_CUDA;
+        CK(cudaMemsetAsync(ctx->d_nm_col, 0, sizeof(double) * 3 * (size_t)ctx->n_col_nodes, ctx->stream));
+      }
+      *d_u_col = ctx->d_nm_col;
+      return import_row_to_col(ctx, ctx->d_nm_row, ctx->d_nm_col, false);
+    }
+
+  int b200s_neumann_gp_coords(b200s_ctx* ctx, int cond, int flags, double* xyz_out)
+  {
+    if (!ctx || !xyz_out || cond < 0 || cond >= (int)ctx->neumann.size()) return B200S_ERR_INVALID;
+    if (ctx->n_rows <= 0) return fail(ctx, B200S_ERR_INVALID, "set_graph must precede neumann_gp_coords");
+    cudaSetDevice(ctx->device);
+    const auto& c = ctx->neumann[cond];
+    const int64_t n = b200s_neumann_gp_count(ctx, cond);
+    double* d_out = nullptr;
+    if (to_device(ctx, &d_out, (const double*)nullptr, 3 * n)) return B200S_ERR_CUDA;
+    int rc = B200S_OK;
+    if (c.volume)
+    {
+      NeumannVolArgs A = neumann_volume_args(ctx, c);
+      if (n) k_neumann_volume_gp_coords<<<nblk(ctx->n_col_eles * ctx->ngp), 256, 0, ctx->stream>>>(A, d_out);
+    }
+    else
+    {
+      const double* d_u_col = nullptr;
+      if (c.kind != B200S_NEUMANN_LIVE) rc = neumann_state(ctx, nullptr, &d_u_col);
+      NeumannSurfArgs A = neumann_surface_args(ctx, c, d_u_col, flags);
+      if (!rc && n) k_neumann_surface_gp_coords<<<nblk(n), 256, 0, ctx->stream>>>(A, d_out);
+    }
+    ctx->launches += 1;
+    cudaError_t e = cudaMemcpyAsync(xyz_out, d_out, sizeof(double) * 3 * (size_t)n, cudaMemcpyDefault, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(d_out);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(ctx, B200S_ERR_CUDA, "neumann_gp_coords: %s", cudaGetErrorString(e));
+    return B200S_OK;
+  }
+
+  int b200s_evaluate_neumann(b200s_ctx* ctx, const double* u_row, int flags, double* fext_row)
+  {
+    if (!ctx) return B200S_ERR_INVALID;
+    if (ctx->n_rows <= 0 || !ctx->d_node_row)
+      return fail(ctx, B200S_ERR_INVALID, "set_mesh and set_graph must precede evaluate_neumann");
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    if (!ctx->d_fext && to_device(ctx, &ctx->d_fext, (const double*)nullptr, ctx->n_rows)) return B200S_ERR_CUDA;
+    CK(cudaMemsetAsync(ctx->d_fext, 0, sizeof(double) * (size_t)ctx->n_rows, st));
+    bool needs_state = false, needs_matrix = false;
+    for (const auto& c : ctx->neumann)
+    {
+      if (!c.volume && c.kind != B200S_NEUMANN_LIVE) needs_state = true;
+      if (!c.volume && c.kind == B200S_NEUMANN_ORTHOPRESSURE && (flags & B200S_NEUMANN_LOADLIN)) needs_matrix = true;
+    }
+    if (needs_matrix && !ctx->d_vals)
+      return fail(ctx, B200S_ERR_INVALID, "load linearisation needs the stiffness matrix of this iteration");
+    const double* d_u_col = nullptr;
+    if (needs_state)
+    {
+      const int rc = neumann_state(ctx, u_row, &d_u_col);
+      if (rc) return rc;
+    }
+    int* d_flag = nullptr;
+    if (needs_matrix)
+    {
+      CK(cudaMalloc((void**)&d_flag, sizeof(int)));
+      CK(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+    }
+    for (const auto& c : ctx->neumann)
+    {
+      if (c.n == 0) continue;
+      if (c.volume)
+      {
+        NeumannVolArgs A = neumann_volume_args(ctx, c);
+        k_neumann_volume_force<<<nblk(ctx->n_col_eles * ctx->nn), 256, 0, st>>>(A);
+        ctx->launches += 1;
+        continue;
+      }
+      NeumannSurfArgs A = neumann_surface_args(ctx, c, d_u_col, flags);
+      k_neumann_surface_force<<<nblk(c.n * ctx->face_nn), 256, 0, st>>>(A);
+      ctx->launches += 1;
+      if (A.K)
+      {
+        k_neumann_surface_lin<<<nblk(c.n * ctx->face_nn * ctx->face_nn), 256, 0, st>>>(A, d_flag);
+        ctx->launches += 1;
+      }
+    }
+    int h_flag = 0;
+    cudaError_t e = cudaSuccess;
+    if (d_flag) e = cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && fext_row && fext_row != ctx->d_fext)
+      e = cudaMemcpyAsync(fext_row, ctx->d_fext, sizeof(double) * (size_t)ctx->n_rows, cudaMemcpyDefault, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (d_flag) cudaFree(d_flag);
+    if (e != cudaSuccess) return fail(ctx, B200S_ERR_CUDA, "evaluate_neumann: %s", cudaGetErrorString(e));
+    if (h_flag)
+      return fail(ctx, B200S_ERR_INVALID,
+          "a loaded face couples two nodes without an entry in the stiffness graph (face not on an element of the block?)");
+    return B200S_OK;
+  }
+  double* b200s_device_fext(b200s_ctx* ctx) { return ctx ? ctx->d_fext : nullptr; }
+
 
   int b200s_apply_dirichlet(b200s_ctx* ctx, int which, const double* dbctoggle_row, int diagonalblock)
   {

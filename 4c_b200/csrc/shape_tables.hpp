@@ -209,4 +209,83 @@ namespace b200s
     detail::deriv1(celltype, celltype == 2 ? cen_tet : cen_hex, T.dN_cen.data());
     return T;
   }
+  // Surface cells of the three solid cell types (hex8 -> quad4, hex27 -> quad9, tet10 -> tri6) at the
+  // Gauss rule SolidSurface uses (get_optimal_gauss_rule, src/solid_ele/4C_solid_ele_surface.cpp:58-76):
+  // shape functions 4C_fem_general_utils_fem_shapefunctions.hpp quad4 :2025, quad9 :2087, tri6 :2120 and
+  // their derivatives :2184,:2269,:2324; rules 4C_fem_general_utils_integration.cpp quad_4point :6151,
+  // quad_9point :6185, tri_6point :6374 (decimals as the reference has them).
+  struct FaceTables
+  {
+    int nn = 0, ngp = 0;
+    std::vector<double> N, d0, d1, w;  // [ngp][nn] x3, [ngp]
+  };
+
+  inline FaceTables make_face_tables(int celltype)
+  {
+    FaceTables T;
+    std::vector<double> xi;
+    if (celltype == 0)
+    {
+      const double g = 0.5773502691896;
+      T.nn = 4, T.ngp = 4;
+      xi = {-g, -g, g, -g, g, g, -g, g};
+      T.w.assign(4, 1.0);
+    }
+    else if (celltype == 1)
+    {
+      const double g = 0.7745966692415, w1 = 0.5555555555556, w2 = 0.8888888888889;
+      T.nn = 9, T.ngp = 9;
+      xi = {-g, -g, g, -g, g, g, -g, g, 0, -g, g, 0, 0, g, -g, 0, 0, 0};
+      T.w = {w1 * w1, w1 * w1, w1 * w1, w1 * w1, w2 * w1, w1 * w2, w2 * w1, w1 * w2, w2 * w2};
+    }
+    else
+    {
+      const double a = 0.0915762135098, b = 0.8168475729805, c = 0.4459484909160, d = 0.1081030181681;
+      const double wa = 0.0549758718277, wb = 0.1116907948390;
+      T.nn = 6, T.ngp = 6;
+      xi = {a, a, b, a, a, b, c, d, c, c, d, c};
+      T.w = {wa, wa, wa, wb, wb, wb};
+    }
+    T.N.resize((size_t)T.ngp * T.nn), T.d0.resize(T.N.size()), T.d1.resize(T.N.size());
+    for (int q = 0; q < T.ngp; ++q)
+    {
+      const double r = xi[2 * q], s = xi[2 * q + 1];
+      double* N = &T.N[(size_t)q * T.nn];
+      double* d0 = &T.d0[(size_t)q * T.nn];
+      double* d1 = &T.d1[(size_t)q * T.nn];
+      if (celltype == 0)
+      {
+        const double c[4][2] = {{-1, -1}, {1, -1}, {1, 1}, {-1, 1}};
+        for (int k = 0; k < 4; ++k)
+        {
+          N[k] = 0.25 * (1.0 + c[k][0] * r) * (1.0 + c[k][1] * s);
+          d0[k] = 0.25 * c[k][0] * (1.0 + c[k][1] * s);
+          d1[k] = 0.25 * c[k][1] * (1.0 + c[k][0] * r);
+        }
+      }
+      else if (celltype == 1)
+      {
+        const int c[9][2] = {{-1, -1}, {1, -1}, {1, 1}, {-1, 1}, {0, -1}, {1, 0}, {0, 1}, {-1, 0}, {0, 0}};
+        const double Lr[3] = {0.5 * r * (r - 1.0), 1.0 - r * r, 0.5 * r * (r + 1.0)};
+        const double Ls[3] = {0.5 * s * (s - 1.0), 1.0 - s * s, 0.5 * s * (s + 1.0)};
+        const double dLr[3] = {r - 0.5, -2.0 * r, r + 0.5};
+        const double dLs[3] = {s - 0.5, -2.0 * s, s + 0.5};
+        for (int k = 0; k < 9; ++k)
+        {
+          const int i = c[k][0] + 1, j = c[k][1] + 1;
+          N[k] = Lr[i] * Ls[j], d0[k] = dLr[i] * Ls[j], d1[k] = Lr[i] * dLs[j];
+        }
+      }
+      else
+      {
+        const double t1 = 1.0 - r - s, t2 = r, t3 = s;
+        const double n[6] = {t1 * (2.0 * t1 - 1.0), t2 * (2.0 * t2 - 1.0), t3 * (2.0 * t3 - 1.0),
+            4.0 * t2 * t1, 4.0 * t2 * t3, 4.0 * t3 * t1};
+        const double a0[6] = {-(4.0 * t1 - 1.0), 4.0 * t2 - 1.0, 0.0, 4.0 * (t1 - t2), 4.0 * t3, -4.0 * t3};
+        const double a1[6] = {-(4.0 * t1 - 1.0), 0.0, 4.0 * t3 - 1.0, -4.0 * t2, 4.0 * t2, 4.0 * (t1 - t3)};
+        for (int k = 0; k < 6; ++k) N[k] = n[k], d0[k] = a0[k], d1[k] = a1[k];
+      }
+    }
+    return T;
+  }
 }  // namespace b200s

@@ -131,6 +131,33 @@ namespace B200Solid
     check(b200s_recover(ctx_, du_row, step_length));
   }
 
+  int DeviceElementBlock::add_surface_neumann(b200s_neumann_type type, std::int64_t n_faces,
+      const std::int32_t* face_nodes, const std::int32_t* onoff, const double* val)
+  {
+    const int id = b200s_add_surface_neumann(ctx_, type, n_faces, face_nodes, onoff, val);
+    if (id < 0) check(id);
+    return id;
+  }
+
+  int DeviceElementBlock::add_volume_neumann(std::int64_t n_eles, const std::int32_t* ele_ids,
+      const std::int32_t* onoff, const double* val)
+  {
+    const int id = b200s_add_volume_neumann(ctx_, n_eles, ele_ids, onoff, val);
+    if (id < 0) check(id);
+    return id;
+  }
+
+  void DeviceElementBlock::set_neumann_factors(int cond, const double* dof_fac, const double* gp_fac)
+  {
+    check(b200s_set_neumann_factors(ctx_, cond, dof_fac, gp_fac));
+  }
+
+  void DeviceElementBlock::evaluate_neumann(double* fext_row, bool loadlin, bool mulf_active, const double* u_row)
+  {
+    const int flags = (loadlin ? B200S_NEUMANN_LOADLIN : 0) | (mulf_active ? B200S_NEUMANN_MULF_ACTIVE : 0);
+    check(b200s_evaluate_neumann(ctx_, u_row, flags, fext_row));
+  }
+
   void DeviceElementBlock::apply_dirichlet(const double* dbctoggle_row, bool diagonalblock)
   {
     check(b200s_apply_dirichlet(ctx_, B200S_MATRIX_STIFFNESS, dbctoggle_row, diagonalblock ? 1 : 0));

@@ -119,6 +119,16 @@ namespace B200Solid
     double calc_energy();
     void update_prestress();
     void recover(const double* du_row, double step_length);
+    /// Discretization::evaluate_neumann on the block (4C_fem_discretization_evaluate.cpp:264-297):
+    /// conditions of the block's faces / elements; functions of space and time are evaluated by the
+    /// caller's function manager and handed in as factors (set_neumann_factors).
+    int add_surface_neumann(b200s_neumann_type type, std::int64_t n_faces, const std::int32_t* face_nodes,
+        const std::int32_t* onoff, const double* val);
+    int add_volume_neumann(std::int64_t n_eles, const std::int32_t* ele_ids, const std::int32_t* onoff,
+        const double* val);
+    void set_neumann_factors(int cond, const double* dof_fac, const double* gp_fac);
+    /// fext_row overwritten; loadlin adds the orthopressure load stiffness to the resident stiffness
+    void evaluate_neumann(double* fext_row, bool loadlin, bool mulf_active = false, const double* u_row = nullptr);
     /// SparseMatrix::apply_dirichlet / multiply on the device-resident stiffness
     void apply_dirichlet(const double* dbctoggle_row, bool diagonalblock = true);
     void multiply(const double* x_row, double* y_row);

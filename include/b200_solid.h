@@ -155,6 +155,18 @@ extern "C"
     B200S_MATRIX_MASS = 1
   } b200s_matrix;
 
+  /* TYPE of a DESIGN SURF NEUMANN CONDITIONS entry (SolidSurface::evaluate_neumann,
+   * src/solid_ele/4C_solid_ele_surface_evaluate.cpp:61-106). */
+  typedef enum
+  {
+    B200S_NEUMANN_LIVE = 0,                 /* dead load on the material configuration */
+    B200S_NEUMANN_PSEUDO_ORTHOPRESSURE = 1, /* pressure on the last converged configuration, no linearisation */
+    B200S_NEUMANN_ORTHOPRESSURE = 2         /* follower pressure on the spatial configuration (LOADLIN) */
+  } b200s_neumann_type;
+  /* flags of b200s_evaluate_neumann */
+#define B200S_NEUMANN_LOADLIN 1     /* elemat1 != nullptr: add the load stiffness into the stiffness matrix */
+#define B200S_NEUMANN_MULF_ACTIVE 2 /* is_mulf_active(time): orthopressure acts on the material configuration */
+
   /* Mirror of the element error interface (4C_structure_new_elements_paramsinterface.hpp:46-55). */
   typedef struct
   {
@@ -335,6 +347,44 @@ extern "C"
   int64_t b200s_element_history_size(const b200s_ctx* ctx);
   int b200s_get_element_history(b200s_ctx* ctx, double* hist_out);
   int b200s_set_element_history(b200s_ctx* ctx, const double* hist_in);
+
+  /* ---- external loads: Discretization::evaluate_neumann restricted to the element block ------------- */
+  /* (4C_fem_discretization_evaluate.cpp:264-297: every Line/Surface/VolumeNeumann condition, every
+   * element of its geometry incl. ghosted ones, owner-computes assemble.)
+   * One DESIGN SURF NEUMANN CONDITIONS entry on faces of the block's elements:
+   *   face_nodes [host] n_faces * nodes_per_face column-node lids in the node order of the parent's
+   *              surface (quad4 / quad9 / tri6 for hex8 / hex27 / tet10; the order the reference's
+   *              boundary-element factory produces decides the sign of the orthopressure normal)
+   *   onoff, val [host] 3 entries (ONOFF, VAL; the orthopressure types use entry 0 only and fail like
+   *              the reference -- "orthopressure on 1st dof only!" -- otherwise)
+   * Returns the condition id (>= 0) or a negative b200s_status. */
+  int b200s_add_surface_neumann(b200s_ctx* ctx, int neumann_type, int64_t n_faces,
+      const int32_t* face_nodes, const int32_t* onoff, const double* val);
+  /* One DESIGN VOL NEUMANN CONDITIONS entry (dead body load, evaluate_neumann<celltype>,
+   * src/solid_ele/4C_solid_ele_neumann_evaluator.cpp:43-113).  ele_ids [host] n_eles column-element
+   * indices (set_mesh numbering) or NULL = every element of the block. */
+  int b200s_add_volume_neumann(b200s_ctx* ctx, int64_t n_eles, const int32_t* ele_ids,
+      const int32_t* onoff, const double* val);
+  int b200s_clear_neumann(b200s_ctx* ctx);
+  /* Functions of space and time stay with the host's function manager (FunctionOfSpaceTime::evaluate,
+   * 4C_solid_ele_surface_evaluate.cpp:296-303,339-352): the caller sets, per condition,
+   *   dof_fac [host] 3 factors (the value of the condition's time function per dof; NULL = 1) and
+   *   gp_fac  [host|dev] n_gp*3 factors per Gauss point and dof (NULL = 1), evaluated at the positions
+   *           b200s_neumann_gp_coords returns (material configuration; with B200S_NEUMANN_* flags the
+   *           configuration an orthopressure condition acts on, taken from the resident displacement).
+   * n_gp = b200s_neumann_gp_count = faces (or loaded elements) * Gauss points, face-major. */
+  int64_t b200s_neumann_gp_count(const b200s_ctx* ctx, int cond);
+  int b200s_neumann_gp_coords(b200s_ctx* ctx, int cond, int flags, double* xyz_out);
+  int b200s_set_neumann_factors(b200s_ctx* ctx, int cond, const double* dof_fac, const double* gp_fac);
+  /* Evaluate every condition: fext_row [host|dev] n_rows OVERWRITTEN with the external force
+   * (may be NULL: stays in b200s_device_fext).  u_row [host|dev] displacement the deformation
+   * dependent types act on ("displacement new" for orthopressure, the last converged "displacement"
+   * for pseudo_orthopressure); NULL = the displacement resident from the last evaluate / set_state.
+   * With B200S_NEUMANN_LOADLIN the linearisation of the orthopressure conditions is ADDED to the
+   * stiffness values in the context, i.e. call it after the b200s_evaluate of the iteration
+   * (apply_force_stiff_external after apply_force_stiff_internal) and before apply_dirichlet. */
+  int b200s_evaluate_neumann(b200s_ctx* ctx, const double* u_row, int flags, double* fext_row);
+  double* b200s_device_fext(b200s_ctx* ctx); /* n_rows, NULL before the first evaluate_neumann */
 
   /* ---- the step after the path, on the device (K never returns to the host) ------------------------ */
   /* SparseMatrix::apply_dirichlet(dbctoggle, diagonalblock), in-place branch

@@ -15,6 +15,8 @@ What it writes
   integration_hex8_eas_full.json / _eas_mild.json : TECH eas_full / eas_mild hex8 inputs
         tests/input_files/solid_ele_hex8_Standard_eas_{full_stressout_cauchy_strainout_ea,mild_stressout_2pk_strainout_gl}.4C.yaml
         (same fibre material) with nodal displacements, stresses and strains
+  integration_hex8_loadlin.json : tests/input_files/loadlin.4C.yaml, 300 hex8 EAS-full elements under a
+        follower pressure (TYPE orthopressure with LOADLIN); dispy of node 404 (1e-8)
   integration_cooks_fbar.json : Cook's membrane with 64 F-bar hex8 elements
           tests/input_files/sohex8fbar_cooks_nl_new_struc.4C.yaml (dispy of node 162, 1e-8)
   unit_known_answers.json : known answers of unittests/mat/4C_elasthyper_service_test.cpp:36-155,
@@ -185,6 +187,56 @@ def mulf_case(cell, rel, tech=None):
     }
 
 
+def loadlin_case(rel):
+    """tests/input_files/loadlin.4C.yaml: cantilever of 300 hex8 EAS-full elements (CoupNeoHooke) under a
+    follower pressure (DESIGN SURF NEUMANN CONDITIONS TYPE orthopressure, LOADLIN true), statics;
+    known answer = dispy of node 404."""
+    with open(os.path.join(REF, rel)) as fh:
+        y = yaml.safe_load(fh)
+    nodes = {}
+    for line in y["NODE COORDS"]:
+        m = re.match(r"NODE\s+(\d+)\s+COORD\s+(\S+)\s+(\S+)\s+(\S+)", line)
+        nodes[int(m.group(1))] = [float(m.group(i)) for i in (2, 3, 4)]
+    coords = [nodes[i + 1] for i in range(max(nodes))]
+    eles = []
+    for line in y["STRUCTURE ELEMENTS"]:
+        tok = line.split()
+        assert tok[1] == "SOLID" and tok[2] == "HEX8" and "KINEM nonlinear TECH eas_full" in line
+        eles.append([int(t) - 1 for t in tok[3:11]])
+    dbc, = y["DESIGN SURF DIRICH CONDITIONS"]
+    neu, = y["DESIGN SURF NEUMANN CONDITIONS"]
+    assert neu["TYPE"] == "orthopressure" and dbc["ONOFF"] == [1, 1, 1]
+    surf = {dbc["E"]: [], neu["E"]: []}
+    for line in y["DSURF-NODE TOPOLOGY"]:
+        m = re.match(r"NODE\s+(\d+)\s+DSURFACE\s+(\d+)", line)
+        if int(m.group(2)) in surf:
+            surf[int(m.group(2))].append(int(m.group(1)) - 1)
+    mats = {m["MAT"]: m for m in y["MATERIALS"]}
+    eh = mats[1]["MAT_ElastHyper"]
+    nh = mats[eh["MATIDS"][0]]["ELAST_CoupNeoHooke"]
+    var, = [f for f in y["FUNCT1"] if "VARIABLE" in f]
+    assert var["TYPE"] == "linearinterpolation"
+    sd = y["STRUCTURAL DYNAMIC"]
+    assert sd["DYNAMICTYPE"] == "Statics" and sd["LOADLIN"] is True
+    expected = []
+    for r in y["RESULT DESCRIPTION"]:
+        s = r["STRUCTURE"]
+        expected.append({"node": s["NODE"] - 1, "dof": "xyz".index(s["QUANTITY"][-1]),
+                         "value": float(s["VALUE"]), "tol": float(s["TOLERANCE"])})
+    return {
+        "source": rel, "celltype": "hex8", "tech": "eas_full", "coords": coords, "elements": eles,
+        "material": {"kind": "ELAST_CoupNeoHooke", "YOUNG": float(nh["YOUNG"]), "NUE": float(nh["NUE"])},
+        "dirichlet_nodes": sorted(surf[dbc["E"]]), "neumann_nodes": sorted(surf[neu["E"]]),
+        "neumann": {"TYPE": neu["TYPE"], "ONOFF": neu["ONOFF"][:3], "VAL": neu["VAL"][:3],
+                    "FUNCT": neu["FUNCT"][:3],
+                    "FUNCT1_TIMES": [float(v) for v in var["TIMES"]],
+                    "FUNCT1_VALUES": [float(v) for v in var["VALUES"]]},
+        "timestep": float(sd["TIMESTEP"]), "numstep": int(sd["NUMSTEP"]),
+        "tolres": float(sd["TOLRES"]), "toldisp": float(sd["TOLDISP"]),
+        "expected_disp": expected,
+    }
+
+
 def cooks_case(rel, tech):
     """Cook's membrane inputs (64 hex8, CoupNeoHooke nu=0.4999): several Dirichlet conditions with
     per-dof ONOFF, one dead surface load, known answer = dispy of node 162 (and internal energy)."""
@@ -329,6 +381,8 @@ if __name__ == "__main__":
                       ("eas_mild", "tests/input_files/solid_ele_hex8_Standard_eas_mild_stressout_2pk_strainout_gl.4C.yaml")):
         with open(os.path.join(HERE, f"integration_hex8_{tech}.json"), "w") as fh:
             json.dump(mulf_case("hex8", rel, tech), fh, indent=1)
+    with open(os.path.join(HERE, "integration_hex8_loadlin.json"), "w") as fh:
+        json.dump(loadlin_case("tests/input_files/loadlin.4C.yaml"), fh)
     with open(os.path.join(HERE, "unit_known_answers.json"), "w") as fh:
         json.dump(unit_known_answers(), fh, indent=1)
     np.savez_compressed(os.path.join(HERE, "ref_elements.npz"), **ref_elements())

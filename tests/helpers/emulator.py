@@ -18,7 +18,7 @@ def lib(cell="hex8"):
         srcs = [os.path.join(_CPP, f"emulate_{cell}.cpp")] + [
             os.path.join(_CPP, "..", "..", "4c_b200", "csrc", f)
             for f in ("hex8_kernel.cuh", "hex8_fbar_kernel.cuh", "tet10_kernel.cuh", "hex27_kernel.cuh", "solid_math.cuh",
-                      "summands.cuh", "post_kernels.cuh", "shape_tables.hpp")]
+                      "summands.cuh", "post_kernels.cuh", "neumann_kernels.cuh", "shape_tables.hpp")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", so, srcs[0]])
         _libs[cell] = C.CDLL(so)
@@ -146,3 +146,60 @@ def mass(celltype, density, conn, X, rowptr, colind, node_row_lid, node_col_lid,
                               C.c_int64(len(rowstart)), _p(vals), _p(fi))
     assert rc == 0, rc
     return vals, fi
+
+
+def _node_rows(rowptr, node_row_lid, node_col_lid):
+    """numpy version of k_node_rows: per column node (rowstart, rowlen, frow, colbase); lids per NODE."""
+    node_row_lid = np.asarray(node_row_lid)
+    ncn = len(node_row_lid)
+    rowstart = np.full(ncn, -1, np.int64)
+    rowlen = np.zeros(ncn, np.int32)
+    frow = np.full(ncn, -1, np.int32)
+    own = node_row_lid >= 0
+    r0 = 3 * node_row_lid[own].astype(np.int64)
+    rowptr = np.asarray(rowptr, np.int64)
+    rowstart[own] = rowptr[r0]
+    rowlen[own] = (rowptr[r0 + 1] - rowptr[r0]).astype(np.int32)
+    frow[own] = r0
+    colbase = np.ascontiguousarray(3 * np.asarray(node_col_lid), np.int32)
+    return rowstart, rowlen, frow, colbase
+
+
+def neumann_surface(celltype, kind, faces, X, u_col, onoff, val, rowptr, colind, node_row_lid, node_col_lid, n_rows,
+                    gp_fac=None, loadlin=False, want_gp=False):
+    """Product surface-load functions on the CPU: (fext, K values or None, gp positions or None, flag)."""
+    faces = np.ascontiguousarray(faces, np.int32)
+    X = np.ascontiguousarray(X, np.float64)
+    rowstart, rowlen, frow, colbase = _node_rows(rowptr, node_row_lid, node_col_lid)
+    colind = np.ascontiguousarray(colind, np.int32)
+    fext = np.zeros(n_rows)
+    K = np.zeros(int(rowptr[-1])) if loadlin else None
+    ngp = {0: 4, 1: 9, 2: 6}[celltype]
+    gp = np.zeros((len(faces), ngp, 3)) if want_gp else None
+    if u_col is not None:
+        u_col = np.ascontiguousarray(u_col, np.float64)
+    if gp_fac is not None:
+        gp_fac = np.ascontiguousarray(gp_fac, np.float64)
+    flag = lib("neumann").emu_neumann_surface(
+        C.c_int(celltype), C.c_int(kind), C.c_int64(len(faces)), _p(faces), _p(X), _p(u_col),
+        _p(np.ascontiguousarray(onoff, np.int32)), _p(np.ascontiguousarray(val, np.float64)), _p(gp_fac),
+        C.c_int64(len(rowstart)), _p(rowstart), _p(rowlen), _p(frow), _p(colbase), _p(colind), _p(fext), _p(K), _p(gp))
+    return fext, K, gp, flag
+
+
+def neumann_volume(celltype, conn, X, onoff, val, rowptr, node_row_lid, node_col_lid, n_rows, ele_slot=None,
+                   gp_fac=None):
+    conn = np.ascontiguousarray(conn, np.int32)
+    X = np.ascontiguousarray(X, np.float64)
+    rowstart, rowlen, frow, _ = _node_rows(rowptr, node_row_lid, node_col_lid)
+    fext = np.zeros(n_rows)
+    if ele_slot is not None:
+        ele_slot = np.ascontiguousarray(ele_slot, np.int32)
+    if gp_fac is not None:
+        gp_fac = np.ascontiguousarray(gp_fac, np.float64)
+    rc = lib("neumann").emu_neumann_volume(
+        C.c_int(celltype), C.c_int64(len(conn)), _p(conn), _p(X), _p(ele_slot),
+        _p(np.ascontiguousarray(onoff, np.int32)), _p(np.ascontiguousarray(val, np.float64)), _p(gp_fac),
+        C.c_int64(len(rowstart)), _p(rowstart), _p(rowlen), _p(frow), _p(fext))
+    assert rc == 0
+    return fext

@@ -55,6 +55,35 @@ def post_checks(rank, world, rm, asm, u, rowptr, colind):
     rM, rfi = orc.assemble_mass(orc.HEX8, 7.8, rm.conn, rm.X.ravel(), rm.node_row_lid, rm.node_col_lid, nr, rowptr,
                                 colind, acc_col=acc.ravel())
     assert np.abs(M - rM).max() <= 1e-12 * np.abs(rM).max() and np.abs(fi - rfi).max() <= 1e-12 * np.abs(rfi).max()
+    # --- follower pressure on the top face: ghost displacements through the halo, owner-computes rows ----
+    from tests.helpers import neumann as nm
+    case = {"celltype": "hex8", "coords": rm.X.tolist(), "elements": rm.conn.tolist(),
+            "neumann_nodes": np.nonzero(rm.X[:, 2] > 1.0 - 1e-9)[0].tolist(),
+            "neumann": {"ONOFF": [1, 0, 0], "VAL": [-0.7, 0, 0], "FUNCT": [0, 0, 0]}}
+    faces = nm.loaded_faces(case)
+    cond = asm.add_surface_neumann("orthopressure", faces, [1, 0, 0], [-0.7, 0, 0])
+    asm.set_state("displacement", uu[:nr].ravel())
+    asm.evaluate_resident("struct_calc_nlnstiff")
+    K0 = asm.ctx.get_values()
+    fext = asm.evaluate_neumann(loadlin=True)
+    dK = asm.ctx.get_values() - K0
+    if len(faces):
+        rf, rK = nm.orthopressure_load(case, uu.ravel(), 0.0, faces=faces)
+        own = np.nonzero(rm.node_row_lid >= 0)[0]
+        src = (3 * own[:, None] + np.arange(3)).ravel()                      # column-node dofs of the owned nodes
+        dst = (3 * rm.node_row_lid[own][:, None] + np.arange(3)).ravel()     # the rows they own
+        rf_row = np.zeros(n_rows)
+        rf_row[dst] = rf[src]
+        sel = np.empty(n_rows, np.int64)
+        sel[dst] = src
+        colperm = (3 * rm.node_col_lid[:, None] + np.arange(3)).ravel()      # column-node dof -> matrix column
+        P = sp.csr_matrix((np.ones(len(colperm)), (np.arange(len(colperm)), colperm)), shape=(len(colperm),) * 2)
+        ref_dK = nm.add_to_csr_values((rK.tocsr()[sel] @ P).tocsr(), rowptr, colind, np.zeros(len(colind)))
+        assert np.abs(fext - rf_row).max() <= 1e-12 * np.abs(rf).max(), (rank, "neumann f")
+        assert np.abs(dK - ref_dK).max() <= 1e-10 * np.abs(rK).max() + 1e-15 * np.abs(K0).max(), (rank, "neumann K")
+    else:
+        assert np.all(fext == 0.0) and np.all(dK == 0.0)
+    asm.ctx.clear_neumann()
     # --- Dirichlet + distributed CG on the resident K: residual through the distributed product -------
     # (tangent at a small strain state: CG needs a positive definite operator)
     asm.set_state("displacement", 0.1 * u[:nr].ravel())
@@ -69,7 +98,7 @@ def post_checks(rank, world, rm, asm, u, rowptr, colind):
     dist.all_reduce(nrm)
     true_rel = float(torch.sqrt(nrm[0] / nrm[1]))
     assert rel <= 1e-10 and true_rel <= 1e-8, (rank, iters, rel, true_rel)
-    print(f"MGPU_POST rank {rank}: multiply/energy/mass ok, CG {iters} iterations, recurrence residual {rel:.2e}, "
+    print(f"MGPU_POST rank {rank}: multiply/energy/mass/neumann({len(faces)} faces) ok, CG {iters} iterations, recurrence residual {rel:.2e}, "
           f"true residual {true_rel:.2e}", flush=True)
 
 

@@ -134,3 +134,82 @@ def _surface_neumann_load(case, time):
                     for a, nid in enumerate(ids):
                         f[3 * nid + dof] += N[a] * fac
     return f
+
+
+def loaded_faces(case):
+    """Faces of the condition geometry: every element surface whose nodes all belong to the condition's
+    node set, in the parent's surface node order (the boundary-element factory of the reference)."""
+    cell = case["celltype"]
+    nset = set(case["neumann_nodes"])
+    out = []
+    for conn in case["elements"]:
+        for face in FACES[cell]:
+            ids = [conn[k] for k in face]
+            if all(i in nset for i in ids):
+                out.append(ids)
+    return np.asarray(out, np.int32)
+
+
+def time_factor(case, time):
+    """FUNCT1 of the follower-load case: one linearinterpolation variable."""
+    n = case["neumann"]
+    return float(np.interp(time, n["FUNCT1_TIMES"], n["FUNCT1_VALUES"]))
+
+
+def orthopressure_load(case, u, time, loadlin=True, faces=None, material=False):
+    """TYPE orthopressure (4C_solid_ele_surface_evaluate.cpp:319-378): follower pressure on the spatial
+    configuration x = X + u, force N_a * (g1 x g2) * w * funct * VAL[0], and with LOADLIN the load
+    stiffness -N_a * d(g1 x g2)/dx * fac (analytical_d_surface_integration :502-547) as a scipy CSR matrix.
+    material=True: the configuration is the material one and there is no linearisation (MULF active,
+    :158-166; also what pseudo_orthopressure does on the last converged state when u is that state)."""
+    cell = case["celltype"]
+    X = np.asarray(case["coords"], float)
+    x_all = X if material else X + np.asarray(u, float).reshape(-1, 3)
+    kind, fn = {"hex8": ("quad4", _quad4), "hex27": ("quad9", _quad9), "tet10": ("tri6", _tri6)}[cell]
+    gx, gw = _rule(kind)
+    n = case["neumann"]
+    assert n["ONOFF"][0] == 1 and not any(n["ONOFF"][1:3]), "orthopressure on 1st dof only!"
+    val = n["VAL"][0] * (time_factor(case, time) if n["FUNCT"][0] else 1.0)
+    faces = loaded_faces(case) if faces is None else faces
+    nd = 3 * len(X)
+    f = np.zeros(nd)
+    lin = loadlin and not material
+    ri, ci, vi = [], [], []
+    eps = np.zeros((3, 3, 3))  # permutation symbol: (a x b)_i = eps_ijk a_j b_k
+    eps[0, 1, 2] = eps[1, 2, 0] = eps[2, 0, 1] = 1.0
+    eps[0, 2, 1] = eps[2, 1, 0] = eps[1, 0, 2] = -1.0
+    for ids in faces:
+        x = x_all[ids]
+        dofs = np.array([3 * i + d for i in ids for d in range(3)])
+        Ke = np.zeros((len(dofs), len(dofs)))
+        for (r, s), w in zip(gx, gw):
+            N, dN = fn(r, s)
+            g1, g2 = dN[0] @ x, dN[1] @ x
+            normal = np.cross(g1, g2)
+            fac = w * val
+            for a, nid in enumerate(ids):
+                f[3 * nid:3 * nid + 3] += N[a] * normal * fac
+            if lin:
+                # d(g1 x g2)_dim / d x_{b,k} = dN0_b (e_k x g2)_dim + dN1_b (g1 x e_k)_dim
+                A2 = np.einsum("ikm,m->ik", eps, g2)   # (e_k x g2)_i
+                A1 = np.einsum("imk,m->ik", eps, g1)   # (g1 x e_k)_i
+                Dn = (dN[0][None, :, None] * A2[:, None, :] + dN[1][None, :, None] * A1[:, None, :])
+                Dn = Dn.reshape(3, len(dofs))
+                Ke -= np.einsum("a,dj->adj", N, Dn).reshape(len(dofs), len(dofs)) * fac
+        if lin:
+            ri.append(np.repeat(dofs, len(dofs)))
+            ci.append(np.tile(dofs, len(dofs)))
+            vi.append(Ke.ravel())
+    if not lin:
+        return f, None
+    import scipy.sparse as sp
+    K = sp.coo_matrix((np.concatenate(vi), (np.concatenate(ri), np.concatenate(ci))), shape=(nd, nd)).tocsr()
+    return f, K
+
+
+def add_to_csr_values(K, rowptr, colind, values):
+    """values + the entries of the sparse matrix K at the CSR pattern (K's pattern must be contained)."""
+    rows = np.repeat(np.arange(len(rowptr) - 1), np.diff(rowptr))
+    add = np.asarray(K[rows, colind]).ravel()
+    assert abs(add).sum() >= abs(K).sum() * (1 - 1e-12)
+    return values + add

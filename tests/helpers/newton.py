@@ -11,12 +11,16 @@ from .meshes import csr_to_dense
 from .neumann import neumann_load
 
 
-def solve_case(case, evaluate, max_iter=30, update_prestress=None, recover=None):
+def solve_case(case, evaluate, max_iter=30, update_prestress=None, recover=None, external=None):
     """evaluate(u_flat) -> (rowptr, colind, values, fint). Returns converged displacement (nn,3).
 
     recover(du_flat): element action struct_calc_recover after every Newton update with the Newton
     direction as "residual displacement" (Solid::ModelEvaluator::Structure::run_post_compute_x / run_recover,
     model_evaluator_structure.cpp:1482-1509): condensed element variables (EAS alpha) follow the step.
+
+    external(u_flat, t, values) -> (fext, values'): deformation dependent loads (orthopressure with LOADLIN:
+    apply_force_stiff_external adds the load stiffness to the stiffness matrix of the iteration,
+    model_evaluator_structure.cpp:474-516); default is the dead load of the case.
 
     update_prestress(u_flat): PRESTRESS MULF.  While the time reached by a step is <= PRESTRESSTIME
     (the state has already been advanced when update_step_element runs; confirmed by the known answers:
@@ -34,17 +38,27 @@ def solve_case(case, evaluate, max_iter=30, update_prestress=None, recover=None)
     t = 0.0
     for _ in range(case["numstep"]):
         t += case["timestep"]
-        fext = neumann_load(case, t)
+        fext = neumann_load(case, t) if external is None else None
         for it in range(max_iter):
             rowptr, colind, values, fint = evaluate(u)
+            if external is not None:
+                fext, values = external(u, t, values)
             res = fint - fext
-            K = csr_to_dense(rowptr, colind, values, 3 * nn)
             du = np.zeros(3 * nn)
-            du[free] = np.linalg.solve(K[np.ix_(free, free)], -res[free])
+            if 3 * nn > 1500:
+                import scipy.sparse as sp
+                from scipy.sparse.linalg import spsolve
+                K = sp.csr_matrix((values, colind, rowptr), shape=(3 * nn, 3 * nn))
+                du[free] = spsolve(K[free][:, free].tocsc(), -res[free])
+            else:
+                K = csr_to_dense(rowptr, colind, values, 3 * nn)
+                du[free] = np.linalg.solve(K[np.ix_(free, free)], -res[free])
             u += du
             if recover is not None:
                 recover(du)
             rowptr, colind, values, fint = evaluate(u)
+            if external is not None:
+                fext, _ = external(u, t, None)
             rnorm = np.linalg.norm((fint - fext)[free])
             ok_r, ok_d = rnorm < case["tolres"], np.linalg.norm(du) < case["toldisp"]
             if (ok_r or ok_d) if combine_or else (ok_r and ok_d):
