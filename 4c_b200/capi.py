@@ -25,7 +25,8 @@ NEUMANN_LOADLIN, NEUMANN_MULF_ACTIVE = 1, 2
 SUMMANDS = ["COUP_NEOHOOKE", "COUP_MOONEYRIVLIN", "COUP_LOGNEOHOOKE", "COUP_LOGMIXNEOHOOKE", "COUP_SVK",
             "COUP_SIMOPISTER", "COUP_BLATZKO", "COUP_EXPPOL", "COUP_1POW", "COUP_2POW", "COUP_3POW",
             "COUP_13APOW", "ISO_NEOHOOKE", "ISO_MOONEYRIVLIN", "ISO_YEOH", "ISO_1POW", "ISO_2POW",
-            "ISO_EXPOPOW", "VOL_SUSSMANBATHE", "VOL_PENALTY", "VOL_OGDEN", "VOL_POW", "COUP_ANISOEXPO"]
+            "ISO_EXPOPOW", "VOL_SUSSMANBATHE", "VOL_PENALTY", "VOL_OGDEN", "VOL_POW", "COUP_ANISOEXPO",
+            "ISO_OGDEN", "COUP_VARGA", "ISO_VARGA"]
 SUM = {name: i for i, name in enumerate(SUMMANDS)}
 KINEM_NONLINEAR_TOTLAG, KINEM_LINEAR = 0, 1
 TECH_NONE, TECH_FBAR, TECH_EAS_MILD, TECH_EAS_FULL = 0, 1, 2, 3

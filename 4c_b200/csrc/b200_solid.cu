@@ -2556,6 +2556,10 @@ extern "C"
     if (ctx->nranks > 1 && !ctx->d_ele_is_row)
       return fail(ctx, B200S_ERR_INVALID,
           "calc_energy on a partitioned mesh needs b200s_set_row_elements (row elements only)");
+    if (ctx->matkind == B200S_MAT_ELASTHYPER)
+      for (int k = 0; k < ctx->hm.n; ++k)
+        if (summand_in_stretches(ctx->hm.s[k].kind))
+          return fail(ctx, B200S_ERR_UNSUPPORTED, "Summand does not support calculation of strain energy");
     cudaSetDevice(ctx->device);
     if (!ctx->d_energy && to_device(ctx, &ctx->d_energy, (const double*)nullptr, 1)) return B200S_ERR_CUDA;
     CK(cudaMemsetAsync(ctx->d_energy, 0, sizeof(double), ctx->stream));

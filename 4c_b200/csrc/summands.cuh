@@ -40,7 +40,11 @@ namespace b200s
     SUM_VOL_OGDEN = 20,          // KAPPA BETA
     SUM_VOL_POW = 21,            // A EXPON
     SUM_COUP_ANISOEXPO = 22,     // K1 K2 K1COMP K2COMP: one exponential fibre family on the element fibre FIBER1
-    SUM_COUNT = 23
+    // formulated in (modified) principal stretches: elast_hyper_add_response_stretches
+    SUM_ISO_OGDEN = 23,          // MUE ALPHA
+    SUM_COUP_VARGA = 24,         // MUE BETA             -> p = {2 mue - beta, beta}
+    SUM_ISO_VARGA = 25,          // MUE BETA             -> p = {2 mue - beta, beta}
+    SUM_COUNT = 26
   };
 
   constexpr int HYPER_MAX_SUMMANDS = 8;
@@ -59,6 +63,7 @@ namespace b200s
 
   inline bool summand_is_modified(int kind) { return kind >= SUM_ISO_NEOHOOKE && kind <= SUM_VOL_POW; }
   inline bool summand_needs_fiber(int kind) { return kind == SUM_COUP_ANISOEXPO; }
+  B2_HD bool summand_in_stretches(int kind) { return kind >= SUM_ISO_OGDEN && kind <= SUM_ISO_VARGA; }
 
   // What the reference's PAR:: constructors do once per summand: input-file parameters -> p[].
   // mode (only LogNeoHooke / LogMixNeoHooke): 0 = "YN", 1 = "Lame".  Returns false when the
@@ -127,7 +132,12 @@ namespace b200s
       case SUM_ISO_MOONEYRIVLIN:
       case SUM_VOL_OGDEN:
       case SUM_VOL_POW:
+      case SUM_ISO_OGDEN:
         s.p[0] = in[0], s.p[1] = in[1];
+        return true;
+      case SUM_COUP_VARGA:
+      case SUM_ISO_VARGA:
+        s.p[0] = 2.0 * in[0] - in[1], s.p[1] = in[1];
         return true;
     }
     return false;
@@ -477,6 +487,192 @@ namespace b200s
     }
   }
 
+  // Eigen decomposition of a symmetric 3x3 tensor in Voigt storage by cyclic Jacobi rotations
+  // (the reference calls Core::LinAlg::eig = LAPACK dsyev): C = sum_a w[a] n_a (x) n_a, n_a = V[. + 3a].
+  B2_HD void sym_eig3_voigt(const double* Cv, double* w, double* V)
+  {
+    double A[9];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) A[a + 3 * b] = Cv[vg(a, b)], V[a + 3 * b] = a == b ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 30; ++sweep)
+    {
+      if (fabs(A[3]) + fabs(A[6]) + fabs(A[7]) < 1e-300) break;
+      for (int p = 0; p < 2; ++p)
+        for (int q = p + 1; q < 3; ++q)
+        {
+          const double apq = A[p + 3 * q];
+          if (apq == 0.0) continue;
+          const double theta = (A[q + 3 * q] - A[p + 3 * p]) / (2.0 * apq);
+          const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+          const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+          for (int k = 0; k < 3; ++k)
+          {
+            const double akp = A[k + 3 * p], akq = A[k + 3 * q];
+            A[k + 3 * p] = c * akp - sn * akq, A[k + 3 * q] = sn * akp + c * akq;
+          }
+          for (int k = 0; k < 3; ++k)
+          {
+            const double apk = A[p + 3 * k], aqk = A[q + 3 * k];
+            A[p + 3 * k] = c * apk - sn * aqk, A[q + 3 * k] = sn * apk + c * aqk;
+          }
+          for (int k = 0; k < 3; ++k)
+          {
+            const double vkp = V[k + 3 * p], vkq = V[k + 3 * q];
+            V[k + 3 * p] = c * vkp - sn * vkq, V[k + 3 * q] = sn * vkp + c * vkq;
+          }
+        }
+    }
+    w[0] = A[0], w[1] = A[4], w[2] = A[8];
+  }
+
+  // Summands in principal stretches (ELAST_CoupVarga) and modified principal stretches (ELAST_IsoOgden,
+  // ELAST_IsoVarga): Mat::elast_hyper_add_response_stretches (4C_mat_elasthyper_service.cpp:208-386) with the
+  // coefficient functions of src/mat/elast/4C_mat_elast_{isoogden,coupvarga,isovarga}.cpp.  With the
+  // eigen-dyads D^a = n_a (x) n_a and T^ab = n_a (x) n_b + n_b (x) n_a the elasticity tensor of Holzapfel
+  // (6.180),(6.196) is  sum_ab f1_ab D^a (x) D^b + sum_{a<b} f2_ab T^ab (x) T^ab.  Adds to S[6], Cm[21].
+  B2_HD void hyper_add_stretches(const HyperMat& hm, const double* C, double* S, double* Cm)
+  {
+    bool princ = false, mod = false;
+    for (int k = 0; k < hm.n; ++k)
+    {
+      princ = princ || hm.s[k].kind == SUM_COUP_VARGA;
+      mod = mod || hm.s[k].kind == SUM_ISO_OGDEN || hm.s[k].kind == SUM_ISO_VARGA;
+    }
+    if (!princ && !mod) return;
+    double ev[3], N[9], lam[3];
+    sym_eig3_voigt(C, ev, N);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) lam[a] = sqrt(ev[a]);
+    double gam[3] = {0, 0, 0}, del[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    if (princ)
+      for (int k = 0; k < hm.n; ++k)
+      {
+        if (hm.s[k].kind != SUM_COUP_VARGA) continue;
+        const double al = hm.s[k].p[0], be = hm.s[k].p[1];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+        {
+          gam[a] += al - be / (lam[a] * lam[a]);
+          del[a][a] += 2.0 * be / (lam[a] * lam[a] * lam[a]);
+        }
+      }
+    if (mod)
+    {
+      const double j13 = pow(lam[0] * lam[1] * lam[2], -1.0 / 3.0);
+      double ml[3], mg[3] = {0, 0, 0}, md[3] = {0, 0, 0};  // modified stretches, dPsi/dml, d2Psi/dml2 (diagonal)
+#pragma unroll
+      for (int a = 0; a < 3; ++a) ml[a] = j13 * lam[a];
+      for (int k = 0; k < hm.n; ++k)
+      {
+        const double* p = hm.s[k].p;
+        if (hm.s[k].kind == SUM_ISO_OGDEN)
+        {
+          const double f = 2.0 * p[0] / p[1];
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+          {
+            mg[a] += f * pow(ml[a], p[1] - 1.0);
+            md[a] += f * (p[1] - 1.0) * pow(ml[a], p[1] - 2.0);
+          }
+        }
+        else if (hm.s[k].kind == SUM_ISO_VARGA)
+        {
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+          {
+            mg[a] += p[0] - p[1] / (ml[a] * ml[a]);
+            md[a] += 2.0 * p[1] / (ml[a] * ml[a] * ml[a]);
+          }
+        }
+      }
+      // d ml_a / d lam_b = J^(-1/3)/3 (3 delta_ab - ml_a / ml_b)
+      double B[3][3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) B[a][b] = (j13 / 3.0) * ((a == b ? 3.0 : 0.0) - ml[a] / ml[b]);
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) gam[b] += B[a][b] * mg[a];
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+        {
+          double v = 0.0;
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+          {
+            v += B[a][b] * md[a] * B[a][g];                  // Psi_,mm  m_,l  m_,l   (md is diagonal)
+            v += -mg[a] * B[a][b] / (3.0 * lam[g]);          // Psi_,m   m_,ll
+            if (g == a) v += -mg[a] * j13 / (3.0 * lam[b]);
+            if (b == g) v += mg[a] * j13 * lam[a] / (3.0 * lam[b] * lam[b]);
+          }
+          del[b][g] += v;
+        }
+    }
+    double prs[3], f1[3][3], f2[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) prs[a] = gam[a] / lam[a];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+      {
+        // the reference reads the upper triangle of delta (Voigt pairs 01, 12, 20)
+        const double d = (a == b) ? del[a][a] : ((a + b == 2) ? del[2][0] : del[a < b ? a : b][a < b ? b : a]);
+        f1[a][b] = d / (lam[a] * lam[b]) - (a == b ? gam[a] / (lam[a] * lam[a] * lam[a]) : 0.0);
+      }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+      {
+        f2[a][b] = 0.0;
+        if (a == b) continue;
+        // Voigt pair (al, be) of the reference: (0,1), (1,2), (2,0)
+        const int al = (a + b == 2) ? 2 : (a < b ? a : b), be = (a + b == 2) ? 0 : (a < b ? b : a);
+        if (fabs(lam[al] - lam[be]) < 1e-6)
+          f2[a][b] = (f1[be][be] - f1[al][be]) / 2.0;
+        else
+          f2[a][b] = (prs[be] - prs[al]) / (lam[be] * lam[be] - lam[al] * lam[al]);
+      }
+    double D[3][6], T[3][6];  // T: pairs (0,1), (1,2), (2,0)
+#pragma unroll
+    for (int v = 0; v < 6; ++v)
+    {
+      const int i = va(v), j = vb(v);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) D[a][v] = N[i + 3 * a] * N[j + 3 * a];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+      {
+        const int b = (a + 1) % 3;
+        T[a][v] = N[i + 3 * a] * N[j + 3 * b] + N[i + 3 * b] * N[j + 3 * a];
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < 6; ++v) S[v] += prs[0] * D[0][v] + prs[1] * D[1][v] + prs[2] * D[2][v];
+#pragma unroll
+    for (int P = 0; P < 6; ++P)
+#pragma unroll
+      for (int Q = P; Q < 6; ++Q)
+      {
+        double c = 0.0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+        {
+#pragma unroll
+          for (int b = 0; b < 3; ++b) c += f1[a][b] * D[a][P] * D[b][Q];
+          c += f2[a][(a + 1) % 3] * T[a][P] * T[a][Q];
+        }
+        Cm[c21(P, Q)] += c;
+      }
+  }
+
   // Mat::ElastHyper::evaluate for the generic summand list: S[6], Cm[21] from C (Voigt)
   // (elast_hyper_add_isotropic_stress_cmat, 4C_mat_elasthyper_service.cpp:156-206;
   //  calculate_gamma_delta :417-435)
@@ -510,6 +706,7 @@ namespace b200s
         if (P == Q) v += P < 3 ? d7 : 0.5 * d7;  // symmetric identity 1/2 (d_ac d_be + d_ae d_bc)
         Cm[c21(P, Q)] = v;
       }
+    hyper_add_stretches(hm, C, S, Cm);
     hyper_add_fibers(hm, fiber, C, S, Cm, nullptr);
   }
 

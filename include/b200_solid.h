@@ -96,9 +96,16 @@ extern "C"
     B200S_SUM_VOL_PENALTY = 19,
     B200S_SUM_VOL_OGDEN = 20,
     B200S_SUM_VOL_POW = 21,
-    B200S_SUM_COUP_ANISOEXPO = 22 /* {K1,K2,K1COMP,K2COMP}: ELAST_CoupAnisoExpo on the element fibre FIBER1
-                                     (INIT 1, standard structural tensor strategy; needs
-                                     b200s_set_element_fibers) */
+    B200S_SUM_COUP_ANISOEXPO = 22, /* {K1,K2,K1COMP,K2COMP}: ELAST_CoupAnisoExpo on the element fibre FIBER1
+                                      (INIT 1, standard structural tensor strategy; needs
+                                      b200s_set_element_fibers) */
+    /* summands in (modified) principal stretches: Mat::elast_hyper_add_response_stretches
+     * (src/mat/4C_mat_elasthyper_service.cpp:208-386).  Like in the reference they have no strain energy:
+     * b200s_calc_energy returns B200S_ERR_UNSUPPORTED ("Summand does not support calculation of strain
+     * energy", src/mat/elast/4C_mat_elast_summand.hpp:127-139). */
+    B200S_SUM_ISO_OGDEN = 23,  /* {MUE, ALPHA}  ELAST_IsoOgden  */
+    B200S_SUM_COUP_VARGA = 24, /* {MUE, BETA}   ELAST_CoupVarga */
+    B200S_SUM_ISO_VARGA = 25   /* {MUE, BETA}   ELAST_IsoVarga  */
   } b200s_summand;
 
   /* Discret::Elements::SolidElementProperties of an element block (4C_solid_ele_properties.hpp:30-65;

@@ -20,6 +20,7 @@ SUMMANDS = ["COUP_NEOHOOKE", "COUP_MOONEYRIVLIN", "COUP_LOGNEOHOOKE", "COUP_LOGM
             "COUP_13APOW", "ISO_NEOHOOKE", "ISO_MOONEYRIVLIN", "ISO_YEOH", "ISO_1POW", "ISO_2POW",
             "ISO_EXPOPOW", "VOL_SUSSMANBATHE", "VOL_PENALTY", "VOL_OGDEN", "VOL_POW"]
 SUM = {name: i for i, name in enumerate(SUMMANDS)}
+SUM.update({"ISO_OGDEN": 23, "COUP_VARGA": 24, "ISO_VARGA": 25})  # principal-stretch summands
 SUM.update({"COUP_ANISOEXPO": 100, "FIBER": 101})  # oracle only, see solid_oracle.h
 STRESS_NONE, STRESS_2PK, STRESS_CAUCHY = 0, 1, 2
 STRAIN_NONE, STRAIN_GL, STRAIN_EA = 0, 1, 2

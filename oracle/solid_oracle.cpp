@@ -661,6 +661,198 @@ namespace
     return psi;
   }
 
+  // eigen decomposition of a symmetric 3x3 by cyclic Jacobi rotations (the reference calls
+  // Core::LinAlg::eig = LAPACK dsyev; same decomposition): A = V diag(w) V^T, V column-major
+  void sym_eig3(const double* Afull, double* w, double* V)
+  {
+    double A[9];
+    for (int i = 0; i < 9; ++i) A[i] = Afull[i], V[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 60; ++sweep)
+    {
+      const double off = std::fabs(A[3]) + std::fabs(A[6]) + std::fabs(A[7]);
+      if (off < 1e-300) break;
+      for (int p = 0; p < 2; ++p)
+        for (int q = p + 1; q < 3; ++q)
+        {
+          const double apq = A[p + 3 * q];
+          if (apq == 0.0) continue;
+          const double theta = (A[q + 3 * q] - A[p + 3 * p]) / (2.0 * apq);
+          const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+          const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+          for (int k = 0; k < 3; ++k)
+          {
+            const double akp = A[k + 3 * p], akq = A[k + 3 * q];
+            A[k + 3 * p] = c * akp - s * akq, A[k + 3 * q] = s * akp + c * akq;
+          }
+          for (int k = 0; k < 3; ++k)
+          {
+            const double apk = A[p + 3 * k], aqk = A[q + 3 * k];
+            A[p + 3 * k] = c * apk - s * aqk, A[q + 3 * k] = s * apk + c * aqk;
+          }
+          for (int k = 0; k < 3; ++k)
+          {
+            const double vkp = V[k + 3 * p], vkq = V[k + 3 * q];
+            V[k + 3 * p] = c * vkp - s * vkq, V[k + 3 * q] = s * vkp + c * vkq;
+          }
+        }
+    }
+    for (int i = 0; i < 3; ++i) w[i] = A[i + 3 * i];
+  }
+
+  // add_coefficients_stretches_modified of ELAST_IsoOgden (4C_mat_elast_isoogden.cpp:24-50) and
+  // ELAST_IsoVarga (4C_mat_elast_isovarga.cpp): first / second derivatives w.r.t. the modified stretches
+  void stretch_coefficients_modified(int kind, const double* p, const double* modstr, double* mg, double* md)
+  {
+    if (kind == ORC_SUM_ISO_OGDEN)
+    {
+      const double mue = p[0], alpha = p[1];
+      for (int i = 0; i < 3; ++i)
+      {
+        mg[i] += 2 * mue / alpha * std::pow(modstr[i], alpha - 1);
+        md[i] += 2 * mue / alpha * (alpha - 1) * std::pow(modstr[i], alpha - 2);
+      }
+    }
+    else if (kind == ORC_SUM_ISO_VARGA)
+    {
+      const double alpha = 2.0 * p[0] - p[1], beta = p[1];
+      for (int i = 0; i < 3; ++i)
+      {
+        mg[i] += alpha - beta / (modstr[i] * modstr[i]);
+        md[i] += 2.0 * beta / (modstr[i] * modstr[i] * modstr[i]);
+      }
+    }
+  }
+
+  // Mat::elast_hyper_add_response_stretches (src/mat/4C_mat_elasthyper_service.cpp:208-386) for the summands
+  // formulated in principal stretches (ELAST_CoupVarga, 4C_mat_elast_coupvarga.cpp) or modified principal
+  // stretches (ELAST_IsoOgden, 4C_mat_elast_isoogden.cpp:24-50; ELAST_IsoVarga, 4C_mat_elast_isovarga.cpp);
+  // stretches_modified: src/mat/4C_mat_service.cpp:156-164.  Adds to S and Cm; returns false if the block
+  // holds no such summand.
+  bool stretch_response_add(const double* par, const double* C, double* S, double* Cm)
+  {
+    const int n = (int)par[0];
+    bool princ = false, mod = false;
+    for (int k = 0; k < n; ++k)
+    {
+      const int kind = (int)par[1 + 6 * k];
+      princ = princ || kind == ORC_SUM_COUP_VARGA;
+      mod = mod || kind == ORC_SUM_ISO_OGDEN || kind == ORC_SUM_ISO_VARGA;
+    }
+    if (!princ && !mod) return false;
+    double Cf[9], ev[3], N[9];
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) Cf[a + 3 * b] = C[VG[a][b]];
+    sym_eig3(Cf, ev, N);  // N(i, al) = N[i + 3 * al]
+    double prstr[3], modstr[3];
+    for (int i = 0; i < 3; ++i) prstr[i] = std::sqrt(ev[i]);
+    const double detF = prstr[0] * prstr[1] * prstr[2];
+    for (int i = 0; i < 3; ++i) modstr[i] = std::pow(detF, -1.0 / 3.0) * prstr[i];
+    double gamma[3] = {0, 0, 0}, delta[6] = {0, 0, 0, 0, 0, 0};
+    if (princ)
+      for (int k = 0; k < n; ++k)
+      {
+        const double* q = par + 1 + 6 * k;
+        if ((int)q[0] != ORC_SUM_COUP_VARGA) continue;
+        const double alpha = 2.0 * q[2] - q[3], beta = q[3];
+        for (int i = 0; i < 3; ++i)
+        {
+          gamma[i] += alpha - beta / (prstr[i] * prstr[i]);
+          delta[i] += 2.0 * beta / (prstr[i] * prstr[i] * prstr[i]);
+        }
+      }
+    if (mod)
+    {
+      const double detF13 = std::pow(detF, -1.0 / 3.0);
+      double mg[3] = {0, 0, 0}, md[6] = {0, 0, 0, 0, 0, 0};
+      for (int k = 0; k < n; ++k)
+      {
+        const double* q = par + 1 + 6 * k;
+        const int kind = (int)q[0];
+        stretch_coefficients_modified(kind, q + 2, modstr, mg, md);
+      }
+      double modbypr[3][3];
+      for (int al = 0; al < 3; ++al)
+      {
+        for (int be = 0; be < 3; ++be) modbypr[al][be] = -modstr[al] / modstr[be];
+        modbypr[al][al] += 3.0;
+      }
+      for (int al = 0; al < 3; ++al)
+        for (int be = 0; be < 3; ++be) modbypr[al][be] *= detF13 / 3.0;
+      for (int be = 0; be < 3; ++be)
+        for (int al = 0; al < 3; ++al) gamma[be] += modbypr[al][be] * mg[al];
+      const double mdt[3][3] = {{md[0], md[3], md[5]}, {md[3], md[1], md[4]}, {md[5], md[4], md[2]}};
+      double aux[3][3], dt[3][3];
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+        {
+          aux[i][j] = 0.0;
+          for (int k = 0; k < 3; ++k) aux[i][j] += modbypr[k][i] * mdt[k][j];
+        }
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+        {
+          dt[i][j] = 0.0;
+          for (int k = 0; k < 3; ++k) dt[i][j] += aux[i][k] * modbypr[k][j];
+        }
+      for (int be = 0; be < 3; ++be)
+        for (int ga = 0; ga < 3; ++ga)
+        {
+          double v = 0.0;
+          for (int al = 0; al < 3; ++al)
+          {
+            v += -mg[al] * modbypr[al][be] / (3.0 * prstr[ga]);
+            if (ga == al) v += -mg[al] * detF13 / (3.0 * prstr[be]);
+            if (be == ga) v += mg[al] * detF13 * prstr[al] / (3.0 * prstr[be] * prstr[be]);
+          }
+          dt[be][ga] += v;
+        }
+      delta[0] += dt[0][0], delta[1] += dt[1][1], delta[2] += dt[2][2];
+      delta[3] += dt[0][1], delta[4] += dt[1][2], delta[5] += dt[2][0];
+    }
+    // principal 2nd Piola-Kirchhoff stresses and the stress tensor
+    double prsts[3];
+    for (int al = 0; al < 3; ++al)
+    {
+      prsts[al] = gamma[al] / prstr[al];
+      for (int v = 0; v < 6; ++v) S[v] += prsts[al] * N[VA[v] + 3 * al] * N[VB[v] + 3 * al];
+    }
+    double f1[6], f2[6] = {0, 0, 0, 0, 0, 0};
+    for (int albe = 0; albe < 6; ++albe)
+    {
+      const int al = VA[albe], be = VB[albe];
+      f1[albe] = delta[albe] / (prstr[al] * prstr[be]);
+      if (albe < 3) f1[albe] -= gamma[al] / (prstr[be] * prstr[al] * prstr[al]);
+    }
+    for (int albe = 3; albe < 6; ++albe)
+    {
+      const int al = VA[albe], be = VB[albe];
+      if (std::fabs(prstr[al] - prstr[be]) < 1e-6)
+        f2[albe] = (f1[be] - f1[albe]) / 2.0;
+      else
+        f2[albe] = (prsts[be] - prsts[al]) / (prstr[be] * prstr[be] - prstr[al] * prstr[al]);
+    }
+    auto n_ = [&](int i, int al) { return N[i + 3 * al]; };
+    for (int kl = 0; kl < 6; ++kl)
+      for (int ij = 0; ij < 6; ++ij)
+      {
+        const int k = VA[kl], l = VB[kl], i = VA[ij], j = VB[ij];
+        double c = 0.0;
+        for (int albe = 0; albe < 6; ++albe)
+        {
+          const int al = VA[albe], be = VB[albe];
+          c += f1[albe] * n_(i, al) * n_(j, al) * n_(k, be) * n_(l, be);
+          if (albe >= 3)
+          {
+            c += f1[albe] * n_(i, be) * n_(j, be) * n_(k, al) * n_(l, al);
+            c += f2[albe] * (n_(i, al) * n_(j, be) * n_(k, al) * n_(l, be) + n_(i, al) * n_(j, be) * n_(k, be) * n_(l, al) +
+                             n_(i, be) * n_(j, al) * n_(k, be) * n_(l, al) + n_(i, be) * n_(j, al) * n_(k, al) * n_(l, be));
+          }
+        }
+        Cm[ij + 6 * kl] += c;
+      }
+    return true;
+  }
+
   // Mat::ElastHyper::evaluate -> elast_hyper_evaluate (src/mat/4C_mat_elasthyper.cpp:314-325,
   // src/mat/4C_mat_elasthyper_service.cpp:23-75,156-206)
   void elasthyper(int kind, const double* par, const double* E, double* S, double* Cm)
@@ -704,6 +896,7 @@ namespace
         v += d[7] * 0.5 * ((a == c && b == e ? 1.0 : 0.0) + (a == e && b == c ? 1.0 : 0.0));
         Cm[Iv + 6 * Jv] = v;
       }
+    if (kind == ORC_MAT_ELASTHYPER) stretch_response_add(par, C, S, Cm);
     if (kind == ORC_MAT_ELASTHYPER) aniso_expo_add(par, C, S, Cm, nullptr);
   }
 
@@ -1490,6 +1683,16 @@ extern "C"
   {
     for (int k = 0; k < nnodes(ct); ++k) node_ref(ct, k, xi + 3 * k);
   }
+  // test hook: add_coefficients_stretches_modified of one summand (pins ELAST_IsoOgden against
+  // unittests/mat/elast/4C_elast_isoogden_test.cpp:44-68)
+  void orc_test_stretch_coefficients_modified(int kind, const double* p, const double* modstr, double* modgamma,
+      double* moddelta)
+  {
+    for (int i = 0; i < 3; ++i) modgamma[i] = 0.0;
+    for (int i = 0; i < 6; ++i) moddelta[i] = 0.0;
+    stretch_coefficients_modified(kind, p, modstr, modgamma, moddelta);
+  }
+
   void orc_material(
       int kind, const double* par, const double* F, const double* E, double* S, double* C)
   {
@@ -1586,43 +1789,6 @@ extern "C"
       return hyper_generic(blk, I, nullptr, nullptr);
     }
 
-    // eigen decomposition of a symmetric 3x3 by cyclic Jacobi rotations (the reference calls
-    // Core::LinAlg::eig = LAPACK dsyev; same decomposition): A = V diag(w) V^T, V column-major
-    void sym_eig3(const double* Afull, double* w, double* V)
-    {
-      double A[9];
-      for (int i = 0; i < 9; ++i) A[i] = Afull[i], V[i] = (i % 4 == 0) ? 1.0 : 0.0;
-      for (int sweep = 0; sweep < 60; ++sweep)
-      {
-        const double off = std::fabs(A[3]) + std::fabs(A[6]) + std::fabs(A[7]);
-        if (off < 1e-300) break;
-        for (int p = 0; p < 2; ++p)
-          for (int q = p + 1; q < 3; ++q)
-          {
-            const double apq = A[p + 3 * q];
-            if (apq == 0.0) continue;
-            const double theta = (A[q + 3 * q] - A[p + 3 * p]) / (2.0 * apq);
-            const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
-            const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
-            for (int k = 0; k < 3; ++k)
-            {
-              const double akp = A[k + 3 * p], akq = A[k + 3 * q];
-              A[k + 3 * p] = c * akp - s * akq, A[k + 3 * q] = s * akp + c * akq;
-            }
-            for (int k = 0; k < 3; ++k)
-            {
-              const double apk = A[p + 3 * k], aqk = A[q + 3 * k];
-              A[p + 3 * k] = c * apk - s * aqk, A[q + 3 * k] = s * apk + c * aqk;
-            }
-            for (int k = 0; k < 3; ++k)
-            {
-              const double vkp = V[k + 3 * p], vkq = V[k + 3 * q];
-              V[k + 3 * p] = c * vkp - s * vkq, V[k + 3 * q] = s * vkp + c * vkq;
-            }
-          }
-      }
-      for (int i = 0; i < 3; ++i) w[i] = A[i + 3 * i];
-    }
     // pure stretch tensor U = C^(1/2) (compute_pure_stretch_tensor, 4C_solid_ele_calc_lib.hpp:1577-1586)
     void pure_stretch(const double* Cv, double* U)
     {

@@ -17,6 +17,8 @@ What it writes
         (same fibre material) with nodal displacements, stresses and strains
   integration_hex8_loadlin.json : tests/input_files/loadlin.4C.yaml, 300 hex8 EAS-full elements under a
         follower pressure (TYPE orthopressure with LOADLIN); dispy of node 404 (1e-8)
+  integration_hex8_isoogden.json : tests/input_files/elasthyper_isoogden.4C.yaml, MAT_ElastHyper{ELAST_IsoOgden,
+        ELAST_VolOgden} (principal-stretch formulation) under prescribed displacements; nodal Cauchy stresses
   integration_cooks_fbar.json : Cook's membrane with 64 F-bar hex8 elements
           tests/input_files/sohex8fbar_cooks_nl_new_struc.4C.yaml (dispy of node 162, 1e-8)
   unit_known_answers.json : known answers of unittests/mat/4C_elasthyper_service_test.cpp:36-155,
@@ -237,6 +239,49 @@ def loadlin_case(rel):
     }
 
 
+def isoogden_case(rel):
+    """tests/input_files/elasthyper_isoogden.4C.yaml: three cubes of 8 hex8 each, MAT_ElastHyper{IsoOgden, VolOgden},
+    driven by prescribed displacements (compression, extension, shear); known answers = nodal Cauchy stresses."""
+    with open(os.path.join(REF, rel)) as fh:
+        y = yaml.safe_load(fh)
+    ids, coords = [], []
+    for line in y["NODE COORDS"]:
+        m = re.match(r"NODE\s+(\d+)\s+COORD\s+(\S+)\s+(\S+)\s+(\S+)", line)
+        ids.append(int(m.group(1)))
+        coords.append([float(m.group(i)) for i in (2, 3, 4)])
+    index = {g: k for k, g in enumerate(ids)}
+    eles = []
+    for line in y["STRUCTURE ELEMENTS"]:
+        tok = line.split()
+        assert tok[1] == "SOLID" and tok[2] == "HEX8" and line.rstrip('"').endswith("KINEM nonlinear")
+        eles.append([index[int(t)] for t in tok[3:11]])
+    surf = {}
+    for line in y["DSURF-NODE TOPOLOGY"]:
+        m = re.match(r"NODE\s+(\d+)\s+DSURFACE\s+(\d+)", line)
+        surf.setdefault(int(m.group(2)), []).append(index[int(m.group(1))])
+    dirichlet = [{"nodes": sorted(surf[c["E"]]), "ONOFF": c["ONOFF"], "VAL": c["VAL"], "FUNCT": c["FUNCT"]}
+                 for c in y["DESIGN SURF DIRICH CONDITIONS"]]
+    functs = {}
+    for k in (1, 2, 3):
+        var, = [f for f in y[f"FUNCT{k}"] if "VARIABLE" in f]
+        assert var["TYPE"] == "linearinterpolation"
+        functs[str(k)] = {"TIMES": [float(v) for v in var["TIMES"]], "VALUES": [float(v) for v in var["VALUES"]]}
+    mats = {m["MAT"]: m for m in y["MATERIALS"]}
+    summands = []
+    for mid in mats[1]["MAT_ElastHyper"]["MATIDS"]:
+        (name, par), = [(k, v) for k, v in mats[mid].items() if k != "MAT"]
+        summands.append({"name": name, "params": par})
+    comp = {"xx": 0, "yy": 1, "zz": 2, "xy": 3, "yz": 4, "xz": 5}
+    expected = [{"node": index[r["STRUCTURE"]["NODE"]], "comp": comp[r["STRUCTURE"]["QUANTITY"][-2:]],
+                 "value": float(r["STRUCTURE"]["VALUE"]), "tol": float(r["STRUCTURE"]["TOLERANCE"])}
+                for r in y["RESULT DESCRIPTION"]]
+    sd = y["STRUCTURAL DYNAMIC"]
+    return {"source": rel, "celltype": "hex8", "coords": coords, "elements": eles, "summands": summands,
+            "dirichlet": dirichlet, "functs": functs, "iostress": y["IO"]["STRUCT_STRESS"],
+            "timestep": float(sd["TIMESTEP"]), "numstep": int(sd["NUMSTEP"]),
+            "tolres": float(sd["TOLRES"]), "toldisp": float(sd["TOLDISP"]), "expected_stress": expected}
+
+
 def cooks_case(rel, tech):
     """Cook's membrane inputs (64 hex8, CoupNeoHooke nu=0.4999): several Dirichlet conditions with
     per-dof ONOFF, one dead surface load, known answer = dispy of node 162 (and internal energy)."""
@@ -383,6 +428,8 @@ if __name__ == "__main__":
             json.dump(mulf_case("hex8", rel, tech), fh, indent=1)
     with open(os.path.join(HERE, "integration_hex8_loadlin.json"), "w") as fh:
         json.dump(loadlin_case("tests/input_files/loadlin.4C.yaml"), fh)
+    with open(os.path.join(HERE, "integration_hex8_isoogden.json"), "w") as fh:
+        json.dump(isoogden_case("tests/input_files/elasthyper_isoogden.4C.yaml"), fh)
     with open(os.path.join(HERE, "unit_known_answers.json"), "w") as fh:
         json.dump(unit_known_answers(), fh, indent=1)
     np.savez_compressed(os.path.join(HERE, "ref_elements.npz"), **ref_elements())

@@ -69,3 +69,42 @@ def solve_case(case, evaluate, max_iter=30, update_prestress=None, recover=None,
             update_prestress(u)
             u = np.zeros(3 * nn)
     return u.reshape(nn, 3)
+
+
+def solve_prescribed_displacement_case(case, evaluate, max_iter=30):
+    """Statics driven by DESIGN SURF DIRICH CONDITIONS with time functions only (no external load): every
+    step sets the prescribed dofs to VAL * FUNCT(t) (Core::FE::evaluate_dirichlet) and iterates the free
+    ones on f_int = 0.  case["dirichlet"]: [{nodes, ONOFF, VAL, FUNCT}], case["functs"][id] =
+    linearinterpolation {TIMES, VALUES}."""
+    nn = len(case["coords"])
+    fixed = np.zeros(3 * nn, bool)
+    for c in case["dirichlet"]:
+        for n in c["nodes"]:
+            for d in range(3):
+                if c["ONOFF"][d]:
+                    fixed[3 * n + d] = True
+    free = ~fixed
+    u = np.zeros(3 * nn)
+    t = 0.0
+    for _ in range(case["numstep"]):
+        t += case["timestep"]
+        for c in case["dirichlet"]:
+            for d in range(3):
+                if not c["ONOFF"][d]:
+                    continue
+                f = case["functs"][str(c["FUNCT"][d])] if c["FUNCT"][d] else None
+                fac = 1.0 if f is None else float(np.interp(t, f["TIMES"], f["VALUES"]))
+                for n in c["nodes"]:
+                    u[3 * n + d] = c["VAL"][d] * fac
+        for it in range(max_iter):
+            rowptr, colind, values, fint = evaluate(u)
+            K = csr_to_dense(rowptr, colind, values, 3 * nn)
+            du = np.zeros(3 * nn)
+            du[free] = np.linalg.solve(K[np.ix_(free, free)], -fint[free])
+            u += du
+            rowptr, colind, values, fint = evaluate(u)
+            if np.linalg.norm(fint[free]) < case["tolres"] and np.linalg.norm(du) < case["toldisp"]:
+                break
+        else:
+            raise RuntimeError(f"Newton did not converge at t={t}: |r|={np.linalg.norm(fint[free])}")
+    return u.reshape(nn, 3)

@@ -704,3 +704,67 @@ def test_eas_stress_and_energy_output_match_oracle(tech):
     e_ref = orc.calc_energy(ct, mk, par, rm.conn, rm.X.ravel(), us, tech=ot, hist=ohist)
     assert abs(e_dev - e_ref) <= 1e-10 * abs(e_ref)
     asm.close()
+
+
+# ------------------------------------------------------------------------------------------------------
+# summands in (modified) principal stretches: ELAST_IsoOgden, ELAST_CoupVarga, ELAST_IsoVarga
+# ------------------------------------------------------------------------------------------------------
+STRETCH = [("ISO_OGDEN", [0.8, 4.0]), ("COUP_VARGA", [1.0, 0.3]), ("ISO_VARGA", [2.0, 0.7]), ("VOL_SUSSMANBATHE", [50.0])]
+
+
+@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10"])
+def test_stretch_summands_evaluate_and_stress_match_oracle(cell):
+    ct, rm, u = _mesh(cell)
+    asm = b200.DeviceAssembler(rm, capi.MAT_ELASTHYPER, STRETCH)
+    rowptr, colind = asm.graph()
+    asm.set_state("displacement", u.ravel())
+    K, f, err = asm.evaluate("struct_calc_nlnstiff")
+    opar = orc.pack_elasthyper(STRETCH)
+    rK, rf, nbad = orc.evaluate_assemble(ct, orc.MAT_ELASTHYPER, opar, rm.conn, rm.X.ravel(), u.ravel(), rm.node_row_lid,
+                                         rm.node_col_lid, rm.n_row_nodes, rowptr, colind, nthreads=4)
+    ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
+    assert ok and nbad == 0, (wK, wf)
+    st, en = asm.calc_stress("cauchy", "ea")
+    rst, ren = orc.calc_stress(ct, orc.MAT_ELASTHYPER, opar, rm.conn, rm.X.ravel(), u.ravel(), orc.STRESS_CAUCHY,
+                               orc.STRAIN_EA)
+    assert np.abs(st - rst).max() <= RTOL * np.abs(rst).max() and np.abs(en - ren).max() <= RTOL * np.abs(ren).max()
+    # like the reference: "Summand does not support calculation of strain energy" (4C_mat_elast_summand.hpp:127-139)
+    with pytest.raises(capi.B200SolidError) as ei:
+        asm.calc_energy()
+    assert ei.value.code == capi.ERR_UNSUPPORTED and "strain energy" in str(ei.value)
+    # the undeformed state: three equal stretches, the reference's limit branch (a lone Varga term is not
+    # stress free there, so the force is compared too)
+    asm.set_state("displacement", 0.0 * u.ravel())
+    K0, f0, _ = asm.evaluate()
+    rK0, rf0, _ = orc.evaluate_assemble(ct, orc.MAT_ELASTHYPER, opar, rm.conn, rm.X.ravel(), 0.0 * u.ravel(),
+                                      rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, rowptr, colind, nthreads=4)
+    assert np.abs(f0 - rf0).max() <= 1e-9 * np.abs(K0).max()
+    assert np.abs(K0 - rK0).max() <= 1e-9 * np.abs(rK0).max()
+    asm.close()
+
+
+def test_reference_isoogden_known_answers_through_cuda_path():
+    """Nodal Cauchy stresses of tests/input_files/elasthyper_isoogden.4C.yaml (MAT_ElastHyper{IsoOgden, VolOgden},
+    prescribed displacements) with the device doing every evaluate and the stress output."""
+    from tests.helpers.newton import solve_prescribed_displacement_case
+    from tests.helpers.postprocess import nodal_stresses
+    from tests.test_stretch_summands import case_material
+    case = json.load(open(os.path.join(G, "integration_hex8_isoogden.json")))
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    rm = b200.partition.serial_mesh(orc.HEX8, X, conn)
+    asm = b200.DeviceAssembler(rm, capi.MAT_ELASTHYPER, case_material(case))
+    rowptr, colind = asm.graph()
+
+    def ev(u):
+        asm.set_state("displacement", u)
+        K, f, _ = asm.evaluate()
+        return rowptr, colind, K, f
+
+    u = solve_prescribed_displacement_case(case, ev)
+    asm.set_state("displacement", u.ravel())
+    st, _ = asm.calc_stress("cauchy", "none")
+    ns = nodal_stresses(orc.HEX8, conn, st, len(X))
+    for e in case["expected_stress"]:
+        assert abs(ns[e["node"], e["comp"]] - e["value"]) < 1e-6, (e, ns[e["node"], e["comp"]])
+    asm.close()
