@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib4c_b200_solid.so")
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NEG_JACOBIAN, ERR_NONFINITE, ERR_COMM = -1, -2, -3, -4, -5, -6
 HEX8, HEX27, TET10 = 0, 1, 2
-MAT_COUP_NEOHOOKE, MAT_ISO_VOL, MAT_SVK, MAT_ELASTHYPER = 0, 1, 2, 3
+MAT_COUP_NEOHOOKE, MAT_ISO_VOL, MAT_SVK, MAT_ELASTHYPER, MAT_DRUCKER_PRAGER = 0, 1, 2, 3, 4
 ACTION_INTERNALFORCE, ACTION_NLNSTIFF, ACTION_NLNSTIFFMASS, ACTION_NLNSTIFFLMASS, ACTION_INTERNALINERTIAFORCE = 0, 1, 2, 3, 4
 STRESS_NONE, STRESS_2PK, STRESS_CAUCHY = 0, 1, 2
 STRAIN_NONE, STRAIN_GL, STRAIN_EA = 0, 1, 2
@@ -51,6 +51,7 @@ SYMBOLS = [
     "b200s_set_element_fibers", "b200s_recover_linesearch", "b200s_update_step", "b200s_reset_step",
     "b200s_add_surface_neumann", "b200s_add_volume_neumann", "b200s_clear_neumann", "b200s_neumann_gp_count",
     "b200s_neumann_gp_coords", "b200s_set_neumann_factors", "b200s_evaluate_neumann", "b200s_device_fext",
+    "b200s_material_history_size", "b200s_get_material_history", "b200s_set_material_history",
 ]
 
 
@@ -154,8 +155,17 @@ def load():
     L.b200s_evaluate_neumann.argtypes = [vp, vp, i32, vp]
     L.b200s_device_fext.argtypes = [vp]
     L.b200s_device_fext.restype = vp
+    L.b200s_material_history_size.argtypes = [vp]
+    L.b200s_material_history_size.restype = i64
+    L.b200s_get_material_history.argtypes = [vp, vp]
+    L.b200s_set_material_history.argtypes = [vp, vp]
     _lib = L
     return L
+
+
+def drucker_prager_params(YOUNG, NUE, ISOHARD, TOL, C, ETA, XI, ETABAR, MAXITER=50, TANG="consistent", **_):
+    """Parameter block of MAT_DRUCKER_PRAGER from the keys of the MAT_Struct_DruckerPrager input line."""
+    return np.array([YOUNG, NUE, ISOHARD, TOL, C, ETA, XI, ETABAR, MAXITER, 0.0 if TANG == "elastic" else 1.0], float)
 
 
 def _ptr(a):
@@ -276,6 +286,17 @@ class Context:
         h = np.ascontiguousarray(hist, np.float64).ravel()
         assert h.size == self.L.b200s_element_history_size(self.h)
         self._ck(self.L.b200s_set_element_history(self.h, _ptr(h)))
+
+    def get_material_history(self):
+        """History material state, (n_col_eles, num_gp, 14) flattened: Mat::PlasticDruckerPrager::pack."""
+        h = np.empty(self.L.b200s_material_history_size(self.h))
+        self._ck(self.L.b200s_get_material_history(self.h, _ptr(h)))
+        return h
+
+    def set_material_history(self, hist):
+        h = np.ascontiguousarray(hist, np.float64).ravel()
+        assert h.size == self.L.b200s_material_history_size(self.h)
+        self._ck(self.L.b200s_set_material_history(self.h, _ptr(h)))
 
     def get_gp_history(self):
         h = np.empty(self.L.b200s_gp_history_size(self.h))

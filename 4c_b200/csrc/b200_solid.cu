@@ -1127,6 +1127,8 @@ struct b200s_ctx
   double *d_mass = nullptr, *d_f_inertia = nullptr, *d_acc_row = nullptr, *d_acc_col = nullptr;
   // post-processing outputs
   double* d_energy = nullptr;
+  // history material (history_materials.cuh): preprocessed parameters and the Gauss-point state store
+  double *d_mat_ext = nullptr, *d_mat_hist = nullptr;
   // external loads (neumann_kernels.cuh)
   struct NeumannCond
   {
@@ -1312,6 +1314,19 @@ namespace
     return 0;
   }
 
+  // fresh history of a history material: what Mat::PlasticDruckerPrager::setup(numgp) does per element
+  // (src/mat/4C_mat_plasticdruckerprager.cpp:109-117): zero plastic strains at every Gauss point
+  int material_history_allocate(b200s_ctx* ctx)
+  {
+    dfree(ctx->d_mat_hist);
+    if (ctx->matkind != B200S_MAT_DRUCKER_PRAGER || ctx->celltype < 0) return 0;
+    const int64_t n = ctx->n_col_eles * ctx->ngp * DP_HIST;
+    if (to_device(ctx, &ctx->d_mat_hist, (const double*)nullptr, n)) return B200S_ERR_CUDA;
+    CK(cudaMemsetAsync(ctx->d_mat_hist, 0, sizeof(double) * (size_t)(n > 0 ? n : 1), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  }
+
   // fresh MulfHistoryData of every Gauss point (inverse_jacobian of the reference configuration,
   // deformation_gradient = I): what the reference sets up lazily at the first evaluate
   // (4C_solid_ele_calc_mulf.hpp:56-60)
@@ -1397,6 +1412,7 @@ namespace
   template <int MAT, bool STIFF>
   static int launch_hex8_t(b200s_ctx* ctx, const EvalArgs& A)
   {
+    if constexpr (MAT != MAT_DP)
     if (ctx->tech == B200S_TECH_FBAR)
     {
       auto kern = k_hex8_eval_assemble<MAT, STIFF, 1>;
@@ -1410,10 +1426,17 @@ namespace
       ctx->launches += 1;
       return 0;
     }
-    auto kern = ctx->prestress == B200S_PRESTRESS_MULF
-                    ? k_hex8_eval_assemble<MAT, STIFF, 2>
-                    : (ctx->kinem == B200S_KINEM_LINEAR ? k_hex8_eval_assemble<MAT, STIFF, 3>
-                                                        : k_hex8_eval_assemble<MAT, STIFF, 0>);
+    // history materials (MAT_DP) exist for KINEM linear only: one kernel instead of four
+    auto kern = [&]
+    {
+      if constexpr (MAT == MAT_DP)
+        return k_hex8_eval_assemble<MAT, STIFF, 3>;
+      else
+        return ctx->prestress == B200S_PRESTRESS_MULF
+                   ? k_hex8_eval_assemble<MAT, STIFF, 2>
+                   : (ctx->kinem == B200S_KINEM_LINEAR ? k_hex8_eval_assemble<MAT, STIFF, 3>
+                                                       : k_hex8_eval_assemble<MAT, STIFF, 0>);
+    }();
     // per device and cheap: set on every launch (a process may hold contexts on several GPUs)
     if (set_smem_attr(kern, hex8_smem_bytes))
       return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", hex8_smem_bytes);
@@ -1430,7 +1453,12 @@ namespace
 }  // namespace
 namespace b200s_parts
 {
-  int launch_hex8(b200s_ctx* ctx, const EvalArgs& A, bool stiff) { B200S_DISPATCH_MATERIAL(launch_hex8_t); }
+  int launch_hex8(b200s_ctx* ctx, const EvalArgs& A, bool stiff)
+  {
+    if (ctx->matkind == B200S_MAT_DRUCKER_PRAGER)
+      return stiff ? launch_hex8_t<MAT_DP, true>(ctx, A) : launch_hex8_t<MAT_DP, false>(ctx, A);
+    B200S_DISPATCH_MATERIAL(launch_hex8_t);
+  }
   int set_tables_hex8(b200s_ctx* ctx, const Hex8Const& h)
   {
     CK(cudaMemcpyToSymbolAsync(c_hex8, &h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
@@ -1446,10 +1474,16 @@ namespace
   template <int MAT, bool STIFF>
   static int launch_tet10_t(b200s_ctx* ctx, const EvalArgs& A)
   {
-    auto kern = ctx->prestress == B200S_PRESTRESS_MULF
-                    ? k_tet10_eval_assemble<MAT, STIFF, 1>
-                    : (ctx->kinem == B200S_KINEM_LINEAR ? k_tet10_eval_assemble<MAT, STIFF, 2>
-                                                        : k_tet10_eval_assemble<MAT, STIFF, 0>);
+    auto kern = [&]
+    {
+      if constexpr (MAT == MAT_DP)
+        return k_tet10_eval_assemble<MAT, STIFF, 2>;
+      else
+        return ctx->prestress == B200S_PRESTRESS_MULF
+                   ? k_tet10_eval_assemble<MAT, STIFF, 1>
+                   : (ctx->kinem == B200S_KINEM_LINEAR ? k_tet10_eval_assemble<MAT, STIFF, 2>
+                                                       : k_tet10_eval_assemble<MAT, STIFF, 0>);
+    }();
     // per device and cheap: set on every launch (a process may hold contexts on several GPUs)
     if (set_smem_attr(kern, tet10_smem_bytes))
       return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", tet10_smem_bytes);
@@ -1466,7 +1500,12 @@ namespace
 }  // namespace
 namespace b200s_parts
 {
-  int launch_tet10(b200s_ctx* ctx, const EvalArgs& A, bool stiff) { B200S_DISPATCH_MATERIAL(launch_tet10_t); }
+  int launch_tet10(b200s_ctx* ctx, const EvalArgs& A, bool stiff)
+  {
+    if (ctx->matkind == B200S_MAT_DRUCKER_PRAGER)
+      return stiff ? launch_tet10_t<MAT_DP, true>(ctx, A) : launch_tet10_t<MAT_DP, false>(ctx, A);
+    B200S_DISPATCH_MATERIAL(launch_tet10_t);
+  }
   int set_tables_tet10(b200s_ctx* ctx, const Tet10Const& h)
   {
     CK(cudaMemcpyToSymbolAsync(c_tet10, &h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
@@ -1482,10 +1521,16 @@ namespace
   template <int MAT, bool STIFF>
   static int launch_hex27_t(b200s_ctx* ctx, const EvalArgs& A)
   {
-    auto kern = ctx->prestress == B200S_PRESTRESS_MULF
-                    ? k_hex27_eval_assemble<MAT, STIFF, 1>
-                    : (ctx->kinem == B200S_KINEM_LINEAR ? k_hex27_eval_assemble<MAT, STIFF, 2>
-                                                        : k_hex27_eval_assemble<MAT, STIFF, 0>);
+    auto kern = [&]
+    {
+      if constexpr (MAT == MAT_DP)
+        return k_hex27_eval_assemble<MAT, STIFF, 2>;
+      else
+        return ctx->prestress == B200S_PRESTRESS_MULF
+                   ? k_hex27_eval_assemble<MAT, STIFF, 1>
+                   : (ctx->kinem == B200S_KINEM_LINEAR ? k_hex27_eval_assemble<MAT, STIFF, 2>
+                                                       : k_hex27_eval_assemble<MAT, STIFF, 0>);
+    }();
     // per device and cheap: set on every launch (a process may hold contexts on several GPUs)
     if (set_smem_attr(kern, hex27_smem_bytes))
       return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", hex27_smem_bytes);
@@ -1500,7 +1545,12 @@ namespace
 }  // namespace
 namespace b200s_parts
 {
-  int launch_hex27(b200s_ctx* ctx, const EvalArgs& A, bool stiff) { B200S_DISPATCH_MATERIAL(launch_hex27_t); }
+  int launch_hex27(b200s_ctx* ctx, const EvalArgs& A, bool stiff)
+  {
+    if (ctx->matkind == B200S_MAT_DRUCKER_PRAGER)
+      return stiff ? launch_hex27_t<MAT_DP, true>(ctx, A) : launch_hex27_t<MAT_DP, false>(ctx, A);
+    B200S_DISPATCH_MATERIAL(launch_hex27_t);
+  }
   int set_tables_hex27(b200s_ctx* ctx, const Hex27Const& h)
   {
     CK(cudaMemcpyToSymbolAsync(c_hex27, &h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
@@ -1586,6 +1636,7 @@ extern "C"
     dfree(ctx->d_gp_hist), dfree(ctx->d_eas_hist), dfree(ctx->d_du_row), dfree(ctx->d_du_col);
     dfree(ctx->d_eas_t0), dfree(ctx->d_fibers), dfree(ctx->d_blkcol), dfree(ctx->d_hist_old);
     dfree(ctx->d_xi_gp);
+    dfree(ctx->d_mat_ext), dfree(ctx->d_mat_hist);
     b200s_clear_neumann(ctx);
     dfree(ctx->d_face_N), dfree(ctx->d_face_d0), dfree(ctx->d_face_d1), dfree(ctx->d_face_w);
     dfree(ctx->d_N_gp), dfree(ctx->d_fext), dfree(ctx->d_nm_row), dfree(ctx->d_nm_col);
@@ -1662,6 +1713,7 @@ extern "C"
     dfree(ctx->d_du_col), dfree(ctx->d_fibers), dfree(ctx->d_hist_old);
     if (ctx->prestress == B200S_PRESTRESS_MULF && mulf_allocate(ctx)) return B200S_ERR_CUDA;
     if (eas_neas(ctx->tech) && eas_allocate(ctx)) return B200S_ERR_CUDA;
+    if (material_history_allocate(ctx)) return B200S_ERR_CUDA;
     if (celltype == B200S_HEX8)
     {
       Hex8Const h;
@@ -1784,6 +1836,25 @@ extern "C"
     if (!ctx || !params || nparams < 2) return B200S_ERR_INVALID;
     cudaSetDevice(ctx->device);
     MatParams mp{};
+    if (kind == B200S_MAT_DRUCKER_PRAGER)
+    {
+      if (nparams < 10 || per_ele_param)
+        return fail(ctx, B200S_ERR_INVALID,
+            "MAT_Struct_DruckerPrager: 10 parameters {YOUNG NUE ISOHARD TOL C ETA XI ETABAR MAXITER TANG}");
+      double q[DP_NPAR];
+      if (!make_drucker_prager(params, q))
+        return fail(ctx, B200S_ERR_UNSUPPORTED,
+            "MAT_Struct_DruckerPrager: the consistent tangent with ETA != ETABAR is not major-symmetric; the device "
+            "kernels keep a symmetric constitutive tensor (use TANG elastic, or keep this block on the CPU loop)");
+      for (double& v : mp.p) v = 0.0;
+      if (to_device(ctx, &ctx->d_mat_ext, q, DP_NPAR)) return B200S_ERR_CUDA;
+      CK(cudaStreamSynchronize(ctx->stream));  // q is a local
+      mp.ext = ctx->d_mat_ext;
+      ctx->matkind = kind, ctx->mp = mp;
+      dfree(ctx->d_per_ele);
+      return material_history_allocate(ctx) ? B200S_ERR_CUDA : B200S_OK;
+    }
+    dfree(ctx->d_mat_hist);
     if (!make_mat_params(kind, params, mp))
       return fail(ctx, B200S_ERR_UNSUPPORTED, "material kind %d is not on the device path", kind);
     if (per_ele_param && kind != B200S_MAT_ISO_VOL)
@@ -2221,12 +2292,19 @@ extern "C"
     EvalArgs A;
     A.X = ctx->dX, A.u = ctx->d_u_col, A.conn = ctx->dconn, A.pos = ctx->d_pos;
     A.node_row = ctx->d_node_row, A.per_ele_param = ctx->d_per_ele, A.ele_id = ctx->d_ele_id;
-    A.gp_hist = ctx->d_gp_hist, A.fibers = ctx->d_fibers;
+    A.gp_hist = ctx->d_gp_hist, A.fibers = ctx->d_fibers, A.mat_hist = ctx->d_mat_hist;
     A.linear = ctx->kinem == B200S_KINEM_LINEAR;
     if (material_needs_fibers(ctx) && !ctx->d_fibers)
       return fail(ctx, B200S_ERR_INVALID, "the material has a fibre summand: b200s_set_element_fibers first");
     if (ctx->prestress == B200S_PRESTRESS_MULF && !ctx->d_gp_hist)
       return fail(ctx, B200S_ERR_INVALID, "MULF history missing (set_mesh after set_element_properties?)");
+    if (ctx->matkind == B200S_MAT_DRUCKER_PRAGER)
+    {
+      if (ctx->kinem != B200S_KINEM_LINEAR || ctx->tech != B200S_TECH_NONE || ctx->prestress != B200S_PRESTRESS_NONE)
+        return fail(ctx, B200S_ERR_UNSUPPORTED,
+            "MAT_Struct_DruckerPrager is a small-strain material: KINEM linear without element technology / prestress");
+      if (!ctx->d_mat_hist) return fail(ctx, B200S_ERR_INVALID, "material history missing (set_mesh first)");
+    }
     A.vals = ctx->d_vals, A.f = ctx->d_f, A.err = ctx->d_err, A.mp = ctx->mp;
     A.n_ele = ctx->n_col_eles;
     A.scatter_mode = ctx->scatter_mode;
@@ -2363,7 +2441,7 @@ extern "C"
     for (double& v : mp.p) v = 0.0;
     mp.hyper = ctx->d_hyper;
     ctx->matkind = B200S_MAT_ELASTHYPER, ctx->mp = mp;
-    dfree(ctx->d_per_ele);
+    dfree(ctx->d_per_ele), dfree(ctx->d_mat_hist);
     return B200S_OK;
   }
 
@@ -2487,6 +2565,7 @@ extern "C"
     P.ele_id = ctx->d_ele_id, P.ele_is_row = ctx->d_ele_is_row;
     P.dN_gp = ctx->d_dN_gp, P.dN_cen = ctx->d_dN_cen, P.w = ctx->d_w, P.mp = ctx->mp;
     P.gp_hist = ctx->prestress == B200S_PRESTRESS_MULF ? ctx->d_gp_hist : nullptr;
+    P.mat_hist = ctx->d_mat_hist;
     P.eas_neas = eas_neas(ctx->tech);
     P.eas_hist_size = P.eas_neas ? hex8eas::hist_size(P.eas_neas) : 0;
     P.eas_t0_stride = hex8eas::T0_STRIDE;
@@ -2513,6 +2592,11 @@ extern "C"
         break;
       case B200S_MAT_ELASTHYPER:
         k_post_points<MAT_HYPER><<<grid, 128, 0, ctx->stream>>>(P);
+        break;
+      case B200S_MAT_DRUCKER_PRAGER:
+        if (d_energy) return fail(ctx, B200S_ERR_UNSUPPORTED, "MAT_Struct_DruckerPrager has no strain energy");
+        if (!P.linear) return fail(ctx, B200S_ERR_UNSUPPORTED, "MAT_Struct_DruckerPrager needs KINEM linear");
+        k_post_points<MAT_DP><<<grid, 128, 0, ctx->stream>>>(P);
         break;
       default:
         return fail(ctx, B200S_ERR_INVALID, "material not set");
@@ -2666,8 +2750,38 @@ extern "C"
     CK(cudaStreamSynchronize(ctx->stream));
     return B200S_OK;
   }
-  int b200s_update_step(b200s_ctx* ctx) { return history_snapshot(ctx, 0); }
-  int b200s_reset_step(b200s_ctx* ctx) { return history_snapshot(ctx, 1); }
+  // history material: last <- current (update) or current <- last (reset), in place
+  static int material_history_commit(b200s_ctx* ctx, int restore)
+  {
+    if (!ctx->d_mat_hist) return B200S_OK;
+    cudaSetDevice(ctx->device);
+    const int64_t np = ctx->n_col_eles * ctx->ngp;
+    if (np > 0)
+    {
+      k_material_history_commit<<<nblk(np * (DP_HIST / 2)), 256, 0, ctx->stream>>>(np, DP_HIST, DP_HIST / 2, restore,
+          ctx->d_mat_hist);
+      ctx->launches += 1;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return B200S_OK;
+  }
+  int b200s_update_step(b200s_ctx* ctx)
+  {
+    if (!ctx) return B200S_ERR_INVALID;
+    const int rc = material_history_commit(ctx, 0);
+    return rc ? rc : history_snapshot(ctx, 0);
+  }
+  int b200s_reset_step(b200s_ctx* ctx)
+  {
+    if (!ctx) return B200S_ERR_INVALID;
+    const int rc = material_history_commit(ctx, 1);
+    return rc ? rc : history_snapshot(ctx, 1);
+  }
+  int64_t b200s_material_history_size(const b200s_ctx* ctx)
+  {
+    return (ctx && ctx->d_mat_hist) ? ctx->n_col_eles * ctx->ngp * DP_HIST : 0;
+  }
 
   int64_t b200s_element_history_size(const b200s_ctx* ctx)
   {
@@ -2678,12 +2792,17 @@ extern "C"
   static int history_copy(b200s_ctx* ctx, double* caller, int to_caller, int element_level = 0)
   {
     if (!ctx || !caller) return B200S_ERR_INVALID;
-    double* d_hist = element_level ? ctx->d_eas_hist : ctx->d_gp_hist;
-    if (!d_hist || (element_level ? !eas_neas(ctx->tech) : ctx->prestress != B200S_PRESTRESS_MULF))
-      return fail(ctx, B200S_ERR_INVALID, "the element block has no %s history", element_level ? "element" : "Gauss-point");
+    // element_level: 0 MULF Gauss-point history, 1 EAS element history, 2 material history
+    double* d_hist = element_level == 2 ? ctx->d_mat_hist : (element_level ? ctx->d_eas_hist : ctx->d_gp_hist);
+    if (!d_hist || (element_level == 2 ? false
+                                       : (element_level ? !eas_neas(ctx->tech) : ctx->prestress != B200S_PRESTRESS_MULF)))
+      return fail(ctx, B200S_ERR_INVALID, "the element block has no %s history",
+          element_level == 2 ? "material" : (element_level ? "element" : "Gauss-point"));
     cudaSetDevice(ctx->device);
-    const int64_t n = element_level ? b200s_element_history_size(ctx) : b200s_gp_history_size(ctx);
-    const int per_ele = element_level ? hex8eas::hist_size(eas_neas(ctx->tech)) : ctx->ngp * MULF_HIST;
+    const int64_t n = element_level == 2 ? b200s_material_history_size(ctx)
+                                         : (element_level ? b200s_element_history_size(ctx) : b200s_gp_history_size(ctx));
+    const int per_ele = element_level == 2 ? ctx->ngp * DP_HIST
+                                           : (element_level ? hex8eas::hist_size(eas_neas(ctx->tech)) : ctx->ngp * MULF_HIST);
     double* tmp = nullptr;
     CK(cudaMalloc((void**)&tmp, sizeof(double) * (size_t)(n ? n : 1)));
     int rc = B200S_OK;
@@ -2706,6 +2825,11 @@ extern "C"
   int b200s_set_gp_history(b200s_ctx* ctx, const double* hist_in)
   {
     return history_copy(ctx, const_cast<double*>(hist_in), 0);
+  }
+  int b200s_get_material_history(b200s_ctx* ctx, double* hist_out) { return history_copy(ctx, hist_out, 1, 2); }
+  int b200s_set_material_history(b200s_ctx* ctx, const double* hist_in)
+  {
+    return history_copy(ctx, const_cast<double*>(hist_in), 0, 2);
   }
   int b200s_get_element_history(b200s_ctx* ctx, double* hist_out) { return history_copy(ctx, hist_out, 1, 1); }
   int b200s_set_element_history(b200s_ctx* ctx, const double* hist_in)

@@ -62,6 +62,7 @@ namespace b200s
     const int32_t* ele_id;        // nullptr or n_ele: caller's column-element index of device element e
     const double* fibers;         // nullptr or 3*n_ele unit fibre vectors (FIBER1), device element order
     const double* gp_hist;        // MULF only: n_ele * ngp * MULF_HIST doubles in device element order
+    double* mat_hist;             // history material (MAT_DP): n_ele * ngp * DP_HIST doubles, device element order
     double* vals;                 // nnz (may be nullptr for force only)
     double* f;                    // n_rows
     ErrWord* err;
@@ -230,6 +231,7 @@ namespace b200s
       MatParams mp = A.mp;
       if (A.per_ele_param != nullptr && e < A.n_ele) mp.p[0] = A.per_ele_param[e];
       if (MAT == MAT_HYPER && A.fibers != nullptr && e < A.n_ele) mp.fiber = A.fibers + 3 * e;
+      if (MAT == MAT_DP && A.mat_hist != nullptr && e < A.n_ele) mp.hist = A.mat_hist + (e * NGP + g) * DP_HIST;
       material_evaluate<MAT>(mp, C, Sv, Cm);
 
       // integration factor (calc_lib.hpp:1270-1280), folded into S and Cm once

@@ -43,6 +43,7 @@ namespace b200s
     const double* dN_cen;         // [nn][3] (F-bar)
     const double* w;              // [ngp]
     const double* gp_hist;        // nullptr or MULF history (device element order)
+    double* mat_hist;         // history material: n_ele * ngp * DP_HIST (device element order) or nullptr
     // EAS hex8 (eas_neas = 9 / 21, else 0): element history (alpha at [neas..2 neas)), the precomputed
     // centroid transformation (T0invT[36], detJ0; stride eas_t0_stride) and the Gauss point coordinates
     int eas_neas, eas_hist_size, eas_t0_stride;
@@ -252,6 +253,7 @@ namespace b200s
     MatParams mp = A.mp;
     if (A.per_ele_param != nullptr) mp.p[0] = A.per_ele_param[e];
     if (MAT == MAT_HYPER && A.fibers != nullptr) mp.fiber = A.fibers + 3 * e;
+    if (MAT == MAT_DP && A.mat_hist != nullptr) mp.hist = A.mat_hist + (e * A.ngp + g) * DP_HIST;
     if (stress6 != nullptr && A.stress_type != STRESS_NONE)
     {
       material_evaluate<MAT>(mp, C, S, Cm);
@@ -519,6 +521,22 @@ namespace b200s
     double m[NN];
     mass_row<NN>(A, e, i, m);
     mass_scatter<NN>(A, e, i, m);
+  }
+#endif
+
+#if defined(__CUDACC__)
+  // Mat::PlasticDruckerPrager::update for every Gauss point: last <- current (or, restore = 1, the reverse:
+  // reset_to_last_converged discards the iterate)
+  __global__ void k_material_history_commit(int64_t n_points, int stride, int half, int restore, double* hist)
+  {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_points * half) return;
+    double* h = hist + (t / half) * stride;
+    const int i = (int)(t % half);
+    if (restore)
+      h[half + i] = h[i];
+    else
+      h[i] = h[half + i];
   }
 #endif
 }  // namespace b200s

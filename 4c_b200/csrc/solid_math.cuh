@@ -84,11 +84,13 @@ namespace b200s
     MAT_COUP_NEOHOOKE = 0,
     MAT_ISO_VOL = 1,
     MAT_SVK = 2,
-    MAT_HYPER = 3  // generic MAT_ElastHyper summand list (summands.cuh)
+    MAT_HYPER = 3, // generic MAT_ElastHyper summand list (summands.cuh)
+    MAT_DP = 4     // MAT_Struct_DruckerPrager, a history material (history_materials.cuh); KINEM linear only
   };
 
   struct HyperMat;
   B2_HD void hyper_evaluate(const HyperMat& hm, const double* fiber, const double* C, double* S, double* Cm);
+  B2_HD void drucker_prager_evaluate(const double* q, double* hist, const double* C, double* S, double* Cm);
   B2_HD double hyper_strain_energy(const HyperMat& hm, const double* fiber, const double* C);
 
   // Material parameters preprocessed once on the host (b200s_set_material):
@@ -103,6 +105,8 @@ namespace b200s
     double p[6];
     const HyperMat* hyper;
     const double* fiber;  // HYPER with a fibre summand: the element's unit fibre vector (3 doubles)
+    const double* ext;    // history materials: preprocessed parameter block in device memory
+    double* hist;         // history materials: state of the Gauss point being evaluated (set by the kernel)
   };
 
   // Host-side preprocessing of the input-file parameters (what the reference's PAR:: constructors
@@ -110,7 +114,7 @@ namespace b200s
   inline bool make_mat_params(int kind, const double* params, MatParams& mp)
   {
     for (double& v : mp.p) v = 0.0;
-    mp.hyper = nullptr, mp.fiber = nullptr;
+    mp.hyper = nullptr, mp.fiber = nullptr, mp.ext = nullptr, mp.hist = nullptr;
     if (kind == MAT_COUP_NEOHOOKE)
     {
       const double young = params[0], nue = params[1];
@@ -146,6 +150,10 @@ namespace b200s
     if (MAT == MAT_HYPER)
     {
       hyper_evaluate(*mp.hyper, mp.fiber, C, S, Cm);
+    }
+    else if (MAT == MAT_DP)
+    {
+      drucker_prager_evaluate(mp.ext, mp.hist, C, S, Cm);
     }
     else if (MAT == MAT_SVK)
     {
@@ -246,6 +254,7 @@ namespace b200s
   B2_HD double material_strain_energy(const MatParams& mp, const double* C)
   {
     if (MAT == MAT_HYPER) return hyper_strain_energy(*mp.hyper, mp.fiber, C);
+    if (MAT == MAT_DP) return 0.0;  // no strain energy in the reference; rejected on the host
     if (MAT == MAT_SVK)
     {
       const double E[6] = {0.5 * (C[0] - 1.0), 0.5 * (C[1] - 1.0), 0.5 * (C[2] - 1.0), 0.5 * C[3],
@@ -395,3 +404,4 @@ namespace b200s
 }  // namespace b200s
 
 #include "summands.cuh"
+#include "history_materials.cuh"

@@ -158,6 +158,12 @@ namespace B200Solid
     check(b200s_evaluate_neumann(ctx_, u_row, flags, fext_row));
   }
 
+  void DeviceElementBlock::update_step() { check(b200s_update_step(ctx_)); }
+  void DeviceElementBlock::reset_step() { check(b200s_reset_step(ctx_)); }
+  std::int64_t DeviceElementBlock::material_history_size() const { return b200s_material_history_size(ctx_); }
+  void DeviceElementBlock::get_material_history(double* hist) { check(b200s_get_material_history(ctx_, hist)); }
+  void DeviceElementBlock::set_material_history(const double* hist) { check(b200s_set_material_history(ctx_, hist)); }
+
   void DeviceElementBlock::apply_dirichlet(const double* dbctoggle_row, bool diagonalblock)
   {
     check(b200s_apply_dirichlet(ctx_, B200S_MATRIX_STIFFNESS, dbctoggle_row, diagonalblock ? 1 : 0));

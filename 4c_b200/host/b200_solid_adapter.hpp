@@ -129,6 +129,13 @@ namespace B200Solid
     void set_neumann_factors(int cond, const double* dof_fac, const double* gp_fac);
     /// fext_row overwritten; loadlin adds the orthopressure load stiffness to the resident stiffness
     void evaluate_neumann(double* fext_row, bool loadlin, bool mulf_active = false, const double* u_row = nullptr);
+    /// struct_calc_update_istep / struct_calc_reset_istep (element and material history) and restart of the
+    /// material state store (Mat::PlasticDruckerPrager::pack / unpack)
+    void update_step();
+    void reset_step();
+    std::int64_t material_history_size() const;
+    void get_material_history(double* hist) ;
+    void set_material_history(const double* hist);
     /// SparseMatrix::apply_dirichlet / multiply on the device-resident stiffness
     void apply_dirichlet(const double* dbctoggle_row, bool diagonalblock = true);
     void multiply(const double* x_row, double* y_row);

@@ -51,13 +51,22 @@ extern "C"
    *                   params = {MUE, KAPPA}; MUE may be overridden per element (InputField)
    *   SVK           : MAT_Struct_StVenantKirchhoff YOUNG NUE           params = {YOUNG, NUE}
    *   ELASTHYPER    : MAT_ElastHyper with a run-time list of isotropic summands, installed with
-   *                   b200s_set_material_elasthyper (slower than the three specialised kinds) */
+   *                   b200s_set_material_elasthyper (slower than the three specialised kinds)
+   *   DRUCKER_PRAGER: MAT_Struct_DruckerPrager (src/mat/4C_mat_plasticdruckerprager.cpp), a HISTORY material:
+   *                   params = {YOUNG, NUE, ISOHARD, TOL, C, ETA, XI, ETABAR, MAXITER, TANG (0 elastic,
+   *                   1 consistent)}; small strains, i.e. KINEM linear blocks only.  Plastic strain and
+   *                   accumulated plastic strain of every Gauss point (last converged + current iterate) live
+   *                   in the context: b200s_update_step = Mat::PlasticDruckerPrager::update(),
+   *                   b200s_reset_step discards the iterate, b200s_get/set_material_history = pack/unpack.
+   *                   The consistent tangent needs ETA == ETABAR (otherwise it is not major-symmetric and
+   *                   b200s_set_material returns B200S_ERR_UNSUPPORTED; TANG elastic always works). */
   typedef enum
   {
     B200S_MAT_COUP_NEOHOOKE = 0,
     B200S_MAT_ISO_VOL = 1,
     B200S_MAT_SVK = 2,
-    B200S_MAT_ELASTHYPER = 3
+    B200S_MAT_ELASTHYPER = 3,
+    B200S_MAT_DRUCKER_PRAGER = 4
   } b200s_material;
 
   /* Mat::Elastic::Summand implementations evaluated through the principal / modified invariants
@@ -392,6 +401,15 @@ extern "C"
    * (apply_force_stiff_external after apply_force_stiff_internal) and before apply_dirichlet. */
   int b200s_evaluate_neumann(b200s_ctx* ctx, const double* u_row, int flags, double* fext_row);
   double* b200s_device_fext(b200s_ctx* ctx); /* n_rows, NULL before the first evaluate_neumann */
+
+  /* ---- history materials: restart of the Gauss-point state store ------------------------------------- */
+  /* Mat::PlasticDruckerPrager::pack / unpack (4C_mat_plasticdruckerprager.cpp:63-107): per column element
+   * (set_mesh numbering) and Gauss point 14 doubles {strainpllast[6], strainbarpllast, strainplcurr[6],
+   * strainbarplcurr}, tensor components 00,11,22,01,12,02.  size = n_col_eles * num_gp * 14 doubles,
+   * 0 for a material without history.  [host|dev] */
+  int64_t b200s_material_history_size(const b200s_ctx* ctx);
+  int b200s_get_material_history(b200s_ctx* ctx, double* hist_out);
+  int b200s_set_material_history(b200s_ctx* ctx, const double* hist_in);
 
   /* ---- the step after the path, on the device (K never returns to the host) ------------------------ */
   /* SparseMatrix::apply_dirichlet(dbctoggle, diagonalblock), in-place branch

@@ -13,7 +13,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 HEX8, HEX27, TET10 = 0, 1, 2
-MAT_COUP_NEOHOOKE, MAT_ISO_VOL, MAT_SVK, MAT_ELASTHYPER = 0, 1, 2, 3
+MAT_COUP_NEOHOOKE, MAT_ISO_VOL, MAT_SVK, MAT_ELASTHYPER, MAT_DRUCKER_PRAGER = 0, 1, 2, 3, 4
+DP_HIST = 14  # {strainpllast[6], strainbarpllast, strainplcurr[6], strainbarplcurr} per Gauss point
 # summand ids of the generic MAT_ElastHyper (ORC_SUM_* in solid_oracle.h)
 SUMMANDS = ["COUP_NEOHOOKE", "COUP_MOONEYRIVLIN", "COUP_LOGNEOHOOKE", "COUP_LOGMIXNEOHOOKE", "COUP_SVK",
             "COUP_SIMOPISTER", "COUP_BLATZKO", "COUP_EXPPOL", "COUP_1POW", "COUP_2POW", "COUP_3POW",
@@ -173,6 +174,25 @@ def material(kind, params, E, F=None):
     Cm = np.zeros(36)
     lib().orc_material(kind, _d(params), _d(F), _d(E), _d(S), _d(Cm))
     return S, Cm.reshape(6, 6).T.copy()  # Cm[I,J]
+
+
+def drucker_prager_params(YOUNG, NUE, ISOHARD, TOL, C, ETA, XI, ETABAR, MAXITER=50, TANG="consistent", **_):
+    """Parameter block of MAT_DRUCKER_PRAGER from the keys of MAT_Struct_DruckerPrager."""
+    return np.array([YOUNG, NUE, ISOHARD, TOL, C, ETA, XI, ETABAR, MAXITER, 0.0 if TANG == "elastic" else 1.0], float)
+
+
+def material_hist(kind, params, E, hist=None):
+    """History material at one point: E tensor components [00,11,22,01,12,02]; hist (DP_HIST,) updated in place."""
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    E = np.ascontiguousarray(E, dtype=np.float64)
+    S, Cm = np.zeros(6), np.zeros(36)
+    lib().orc_material_hist(kind, _d(params), _d(E), _d(hist), _d(S), _d(Cm))
+    return S, Cm.reshape(6, 6).T.copy()
+
+
+def material_update(kind, hist):
+    """Mat::...::update(): current -> last for every Gauss point of hist (n, DP_HIST)."""
+    lib().orc_material_update(kind, C.c_int64(hist.size // DP_HIST), _d(hist))
 
 
 def element(ct, matkind, params, X, u, action=ACTION_FORCE_STIFF, tech=TECH_NONE):

@@ -916,11 +916,146 @@ namespace
     for (int i = 3; i < 6; ++i) Cm[i + 6 * i] = mfac * 0.5 * (1.0 - 2.0 * nu);
   }
 
+  // Mat::PlasticDruckerPrager::evaluate (src/mat/4C_mat_plasticdruckerprager.cpp:168-263) with
+  // setup_cmat_elasto_plastic_cone / _apex (:127-166), the return-mapping residuals (:293-319) and
+  // Core::Utils::solve_local_newton (src/core/utils/src/numerics/4C_utils_local_newton.hpp:194-223).
+  // E, S: tensor components [00,11,22,01,12,02]; Cm 6x6 (NOT major-symmetric for ETA != ETABAR).
+  // hist: {strainpllast[6], strainbarpllast, strainplcurr[6], strainbarplcurr} or null (virgin point).
+  void drucker_prager(const double* par, double* hist, const double* E, double* S, double* Cm)
+  {
+    const double young = par[0], nu = par[1], Hiso = par[2], abstol = par[3], cohesion = par[4], eta = par[5],
+                 xi = par[6], etabar = par[7];
+    const int itermax = (int)par[8];
+    const bool consistent = par[9] != 0.0;
+    const double G = young / (2.0 * (1.0 + nu)), kappa = young / (3.0 * (1.0 - 2.0 * nu));
+    const double id2[6] = {1, 1, 1, 0, 0, 0};
+    double pl_last[6] = {0, 0, 0, 0, 0, 0}, bar_last = 0.0;
+    if (hist)
+    {
+      for (int i = 0; i < 6; ++i) pl_last[i] = hist[i];
+      bar_last = hist[6];
+    }
+    double trial[6], dev[6], devstress[6];
+    for (int i = 0; i < 6; ++i) trial[i] = E[i] - pl_last[i];
+    const double tr = trial[0] + trial[1] + trial[2];
+    for (int i = 0; i < 6; ++i) dev[i] = trial[i] - id2[i] * (tr / 3.0);
+    double p = kappa * tr;
+    const double p_trial = p;
+    for (int i = 0; i < 6; ++i) devstress[i] = 2.0 * G * dev[i];
+    auto ddot = [](const double* a, const double* b)
+    {
+      double v = 0.0;
+      for (int i = 0; i < 6; ++i) v += a[i] * b[i] * (i < 3 ? 1.0 : 2.0);
+      return v;
+    };
+    const double J2 = 0.5 * ddot(devstress, devstress);
+    double strainbar_p = bar_last;
+    const double Phi_trial = std::sqrt(J2) + eta * p_trial - xi * (cohesion + Hiso * strainbar_p);
+    double Dgamma = 0.0, dstrainv = 0.0;
+    double pl_curr[6], bar_curr;
+    auto newton = [&](auto fun, double x0, double tol)
+    {
+      double x = x0;
+      auto rd = fun(x);
+      int it = 0;
+      while (std::fabs(rd.first) > tol)
+      {
+        if (it > itermax) break;  // the reference throws
+        x -= rd.first / rd.second;
+        rd = fun(x);
+        ++it;
+      }
+      return x;
+    };
+    if (Phi_trial / std::fabs(cohesion) > abstol)
+    {
+      Dgamma = newton(
+          [&](double x)
+          {
+            return std::make_pair(Phi_trial - x * (G + eta * kappa * etabar) - (xi * xi * x * Hiso),
+                -G - (kappa * etabar * eta) - (xi * xi * Hiso));
+          },
+          Dgamma, abstol * cohesion);
+      if ((std::sqrt(J2) - G * Dgamma) / std::fabs(cohesion) < abstol)
+      {
+        strainbar_p = bar_last;
+        const double alpha = xi / eta, beta = xi / etabar;
+        dstrainv = newton(
+            [&](double x)
+            {
+              return std::make_pair(beta * cohesion + beta * strainbar_p * Hiso - p_trial + x * (alpha * beta * Hiso + kappa),
+                  xi * xi / eta / etabar * Hiso + kappa);
+            },
+            dstrainv, abstol * cohesion);
+        strainbar_p = bar_last + xi / eta * dstrainv;
+        p = p_trial - kappa * dstrainv;
+        for (int i = 0; i < 6; ++i) devstress[i] = 0.0;
+      }
+      else
+      {
+        strainbar_p = bar_last + xi * Dgamma;
+        const double f = 1.0 - G * Dgamma / std::sqrt(J2);
+        for (int i = 0; i < 6; ++i) devstress[i] *= f;
+        p = p_trial - kappa * etabar * Dgamma;
+      }
+      for (int i = 0; i < 6; ++i) S[i] = devstress[i] + p * id2[i];
+      for (int i = 0; i < 6; ++i) pl_curr[i] = E[i] - (devstress[i] * (1.0 / (2.0 * G)) + id2[i] * (p / (3.0 * kappa)));
+      bar_curr = strainbar_p;
+    }
+    else
+    {
+      for (int i = 0; i < 6; ++i) S[i] = devstress[i] + p * id2[i], pl_curr[i] = pl_last[i];
+      bar_curr = bar_last;
+    }
+    if (hist)
+    {
+      for (int i = 0; i < 6; ++i) hist[7 + i] = pl_curr[i];
+      hist[13] = bar_curr;
+    }
+    if (Phi_trial > 0.0 && consistent)
+    {
+      // tensors in Voigt rows/columns of tensor components: Is(I,J) = 1 (normal), 1/2 (shear)
+      if (dstrainv != 0.0)
+      {
+        const double epfac = kappa * (1.0 - kappa / (kappa + xi / eta * xi / etabar * Hiso));
+        for (int I = 0; I < 6; ++I)
+          for (int J = 0; J < 6; ++J) Cm[I + 6 * J] = epfac * id2[I] * id2[J];
+      }
+      else
+      {
+        const double nd = std::sqrt(ddot(dev, dev));
+        double D[6];
+        for (int i = 0; i < 6; ++i) D[i] = dev[i] / nd;
+        const double A = 1.0 / (G + kappa * etabar * eta + xi * xi * Hiso);
+        const double epfac = 2.0 * G * (1.0 - Dgamma / (std::sqrt(2.0) * nd));
+        const double epfac2 = 2.0 * G * (Dgamma / (std::sqrt(2.0) * nd) - G * A);
+        const double epfac3 = -std::sqrt(2.0) * G * A * kappa;
+        const double epfac4 = kappa * (1.0 - kappa * eta * etabar * A);
+        for (int I = 0; I < 6; ++I)
+          for (int J = 0; J < 6; ++J)
+          {
+            const double Is = (I == J) ? (I < 3 ? 1.0 : 0.5) : 0.0;
+            const double Idev = Is - id2[I] * id2[J] / 3.0;
+            Cm[I + 6 * J] = epfac * Idev + epfac2 * D[I] * D[J] + epfac3 * (eta * D[I] * id2[J] + etabar * id2[I] * D[J]) +
+                            epfac4 * id2[I] * id2[J];
+          }
+      }
+    }
+    else
+    {
+      double Sdummy[6];
+      svk(par, E, Sdummy, Cm);  // StVenantKirchhoff::evaluate_stress_linearization(young, nu)
+    }
+  }
+
+  thread_local double* g_material_hist = nullptr;  // history of the point being evaluated (set by the element loop)
   void material(int kind, const double* par, const double* /*F*/, const double* E, double* S,
       double* Cm)
   {
     if (kind == ORC_MAT_SVK)
       svk(par, E, S, Cm);
+    else if (kind == ORC_MAT_DRUCKER_PRAGER)
+      drucker_prager(par, g_material_hist, E, S, Cm);
     else
       elasthyper(kind, par, E, S, Cm);
   }
@@ -1099,7 +1234,7 @@ namespace
   // ---- SolidEleCalc<celltype, DisplacementBasedLinearKinematicsFormulation>
   //      (src/solid_ele/4C_solid_ele_calc_displacement_based_linear_kinematics.hpp:44-62,101-150)
   int element_linear(int ct, int matkind, const double* par, int action, const double* X,
-      const double* u, double* Ke, double* fe)
+      const double* u, double* Ke, double* fe, double* hist = nullptr)
   {
     const int n = nnodes(ct), nd = 3 * n, ng = ngauss(ct);
     double N[MAXN], dN[3 * MAXN];
@@ -1134,7 +1269,9 @@ namespace
           H[a + 3 * b] = v;
         }
       for (int v = 0; v < 6; ++v) E[v] = 0.5 * (H[VA[v] + 3 * VB[v]] + H[VB[v] + 3 * VA[v]]);
+      g_material_hist = (hist && matkind == ORC_MAT_DRUCKER_PRAGER) ? hist + ORC_DP_HIST * gp : nullptr;
       material(matkind, par, Id, E, S, Cm);
+      g_material_hist = nullptr;
       // add_internal_force_vector(jacobian_mapping, F = I, pk2) (:122-131)
       add_force(n, jm, Id, S, fac, fe);
       if (!(action == ORC_ACTION_FORCE_STIFF && Ke)) continue;
@@ -1666,7 +1803,7 @@ namespace
   {
     if (tech == ORC_TECH_EAS_MILD || tech == ORC_TECH_EAS_FULL)
       return element_eas(ct, tech, matkind, par, action, X, u, hist, Ke, fe);
-    if (tech == ORC_TECH_LINEAR) return element_linear(ct, matkind, par, action, X, u, Ke, fe);
+    if (tech == ORC_TECH_LINEAR) return element_linear(ct, matkind, par, action, X, u, Ke, fe, hist);
     if (tech == ORC_TECH_MULF) return element_mulf(ct, matkind, par, action, X, u, hist, Ke, fe);
     if (tech == ORC_TECH_FBAR) return element_fbar(ct, matkind, par, action, X, u, Ke, fe);
     return element(ct, matkind, par, action, X, u, Ke, fe);
@@ -1693,6 +1830,19 @@ extern "C"
     stretch_coefficients_modified(kind, p, modstr, modgamma, moddelta);
   }
 
+  void orc_material_hist(int kind, const double* par, const double* E, double* hist, double* S, double* C)
+  {
+    const double Id[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    g_material_hist = hist;
+    material(kind, par, Id, E, S, C);
+    g_material_hist = nullptr;
+  }
+  void orc_material_update(int kind, int64_t n_points, double* hist)
+  {
+    if (kind != ORC_MAT_DRUCKER_PRAGER) return;
+    for (int64_t k = 0; k < n_points; ++k)
+      for (int i = 0; i < 7; ++i) hist[ORC_DP_HIST * k + i] = hist[ORC_DP_HIST * k + 7 + i];
+  }
   void orc_material(
       int kind, const double* par, const double* F, const double* E, double* S, double* C)
   {
@@ -2268,10 +2418,13 @@ extern "C"
       const int32_t* colind, double* values, double* f, int nthreads, double* hist)
   {
     (void)n_col_nodes;
-    const bool needs_hist = tech == ORC_TECH_MULF || tech == ORC_TECH_EAS_MILD || tech == ORC_TECH_EAS_FULL;
+    const bool mat_hist = matkind == ORC_MAT_DRUCKER_PRAGER;  // history material: small strains only
+    if (mat_hist && tech != ORC_TECH_LINEAR) return -1;
+    const bool needs_hist = tech == ORC_TECH_MULF || tech == ORC_TECH_EAS_MILD || tech == ORC_TECH_EAS_FULL || mat_hist;
     if (needs_hist && hist == nullptr) return -1;
-    const int64_t hist_per_ele = tech == ORC_TECH_MULF ? (int64_t)ORC_MULF_HIST * ngauss(ct)
-                                                       : (needs_hist ? orc_eas_hist_size(tech) : 0);
+    const int64_t hist_per_ele = mat_hist ? (int64_t)ORC_DP_HIST * ngauss(ct)
+                                 : tech == ORC_TECH_MULF ? (int64_t)ORC_MULF_HIST * ngauss(ct)
+                                                         : (needs_hist ? orc_eas_hist_size(tech) : 0);
     const int n = nnodes(ct), nd = 3 * n;
     if (nthreads < 1) nthreads = 1;
     std::vector<int64_t> bad(nthreads, 0);
@@ -2286,7 +2439,8 @@ extern "C"
       std::vector<double> Ke(nd * nd), fe(nd), Xe(nd), ue(nd);
       std::vector<int32_t> localcol(nd);
       // generic MAT_ElastHyper: packed summand block (1 + 6 n doubles), used in place
-      std::vector<double> par(matparams, matparams + (matkind == ORC_MAT_ELASTHYPER ? 1 + 6 * (int)matparams[0] : 2));
+      std::vector<double> par(matparams, matparams + (matkind == ORC_MAT_ELASTHYPER ? 1 + 6 * (int)matparams[0]
+                                                      : (matkind == ORC_MAT_DRUCKER_PRAGER ? 10 : 2)));
       par.resize(par.size() + 2, 0.0);
       // Discretization::evaluate loop over column elements
       // (src/core/fem/src/discretization/4C_fem_discretization_evaluate.cpp:85-117)

@@ -77,7 +77,7 @@ extern "C" int emu_hex27(int matkind, const double* params, const double* per_el
     std::memcpy(&pos2[e * hex27::POS_STRIDE], pos + e * 729, 729 * sizeof(int32_t));
   EvalArgs A;
   A.X = X, A.u = u_col, A.conn = conn, A.pos = pos2.data(), A.node_row = node_row.data();
-  A.per_ele_param = per_ele, A.ele_id = nullptr, A.gp_hist = nullptr, A.fibers = nullptr, A.linear = 0;
+  A.per_ele_param = per_ele, A.ele_id = nullptr, A.gp_hist = nullptr, A.fibers = nullptr, A.linear = 0, A.mat_hist = nullptr;
   A.vals = vals, A.f = f, A.err = nullptr, A.n_ele = n_ele, A.scatter_mode = 0;
   if (!make_mat_params(matkind, params, A.mp)) return -3;
 #define RUN(M)                                                  \

@@ -89,7 +89,7 @@ static int emu_hex8_tech(int tech, int matkind, const double* params, const doub
     node_row[k].frow = node_frow[k];
   EvalArgs A;
   A.X = X, A.u = u_col, A.conn = conn, A.pos = pos, A.node_row = node_row.data();
-  A.per_ele_param = per_ele, A.ele_id = nullptr, A.gp_hist = nullptr, A.fibers = nullptr, A.linear = 0;
+  A.per_ele_param = per_ele, A.ele_id = nullptr, A.gp_hist = nullptr, A.fibers = nullptr, A.linear = 0, A.mat_hist = nullptr;
   A.vals = vals, A.f = f, A.err = nullptr, A.n_ele = n_ele, A.scatter_mode = 0;
   if (!make_mat_params(matkind, params, A.mp)) return -3;
   A.gp_hist = gp_hist;
@@ -163,4 +163,31 @@ extern "C" int emu_hex8linear(int matkind, const double* params, const double* p
 {
   return emu_hex8_tech(3, matkind, params, per_ele, stiff, n_ele, conn, X, u_col, pos, node_rowstart,
       node_rowlen, node_frow, n_col_nodes, vals, f, min_detJ, min_detF, n_bad);
+}
+
+// KINEM linear hex8 block with the history material MAT_Struct_DruckerPrager: mat_hist = n_ele * 8 * DP_HIST doubles
+// (updated in place like the kernel does); in10 = input-file parameters
+extern "C" int emu_hex8_drucker_prager(const double* in10, int stiff, int64_t n_ele, const int32_t* conn,
+    const double* X, const double* u_col, const int32_t* pos, const int64_t* node_rowstart, const int32_t* node_rowlen,
+    const int32_t* node_frow, int64_t n_col_nodes, double* vals, double* f, double* mat_hist)
+{
+  std::vector<NodeRow> node_row(n_col_nodes);
+  for (int64_t k = 0; k < n_col_nodes; ++k)
+    node_row[k].rowstart = node_rowstart[k], node_row[k].rowlen = node_rowlen[k], node_row[k].frow = node_frow[k];
+  double q[DP_NPAR];
+  if (!make_drucker_prager(in10, q)) return -3;
+  EvalArgs A;
+  A.X = X, A.u = u_col, A.conn = conn, A.pos = pos, A.node_row = node_row.data();
+  A.per_ele_param = nullptr, A.ele_id = nullptr, A.gp_hist = nullptr, A.fibers = nullptr, A.linear = 1;
+  A.mat_hist = mat_hist;
+  A.vals = vals, A.f = f, A.err = nullptr, A.n_ele = n_ele, A.scatter_mode = 0;
+  for (double& v : A.mp.p) v = 0.0;
+  A.mp.hyper = nullptr, A.mp.fiber = nullptr, A.mp.ext = q, A.mp.hist = nullptr;
+  double dj = 1e300, df = 1e300;
+  int64_t bad = 0;
+  if (stiff)
+    run<MAT_DP, true, 3>(A, &dj, &df, &bad);
+  else
+    run<MAT_DP, false, 3>(A, &dj, &df, &bad);
+  return (int)bad;
 }

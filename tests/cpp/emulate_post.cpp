@@ -110,6 +110,22 @@ extern "C" int emu_material(int matkind, const double* params, const double* C, 
   return 0;
 }
 
+// MAT_Struct_DruckerPrager of the product at one point: in10 = input-file parameters {YOUNG NUE ISOHARD TOL C ETA
+// XI ETABAR MAXITER TANG}, hist = DP_HIST doubles (updated in place) or null; returns -3 for parameters the device
+// rejects (non-symmetric consistent tangent)
+extern "C" int emu_drucker_prager(const double* in10, double* hist, const double* C, double* S, double* Cm36)
+{
+  double q[DP_NPAR], Cm[21];
+  if (!make_drucker_prager(in10, q)) return -3;
+  MatParams mp;
+  for (double& v : mp.p) v = 0.0;
+  mp.hyper = nullptr, mp.fiber = nullptr, mp.ext = q, mp.hist = hist;
+  material_evaluate<MAT_DP>(mp, C, S, Cm);
+  for (int I = 0; I < 6; ++I)
+    for (int J = 0; J < 6; ++J) Cm36[I + 6 * J] = Cm[c21(I, J)];
+  return 0;
+}
+
 extern "C" int emu_post(int celltype, int fbar, int matkind, const double* params, const double* per_ele,
     int64_t n_ele, const int32_t* conn, const double* X, const double* u_col, const uint8_t* ele_is_row,
     int stress_type, int strain_type, double* stress, double* strain, double* energy, const double* gp_hist)
@@ -123,6 +139,7 @@ extern "C" int emu_post(int celltype, int fbar, int matkind, const double* param
   A.ele_is_row = ele_is_row, A.dN_gp = T.dN_gp.data(), A.dN_cen = T.dN_cen.data(), A.w = T.w.data();
   A.mp = mp, A.n_ele = n_ele, A.nn = T.nn, A.ngp = T.ngp, A.fbar = fbar == 1, A.linear = fbar == 2;
   A.gp_hist = gp_hist;
+  A.mat_hist = nullptr;
   A.eas_neas = 0, A.eas_hist_size = 0, A.eas_t0_stride = 0, A.eas_hist = nullptr, A.eas_t0 = nullptr;
   A.xi_gp = T.xi_gp.data();
   A.stress_type = stress_type, A.strain_type = strain_type;

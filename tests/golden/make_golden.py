@@ -19,6 +19,8 @@ What it writes
         follower pressure (TYPE orthopressure with LOADLIN); dispy of node 404 (1e-8)
   integration_hex8_isoogden.json : tests/input_files/elasthyper_isoogden.4C.yaml, MAT_ElastHyper{ELAST_IsoOgden,
         ELAST_VolOgden} (principal-stretch formulation) under prescribed displacements; nodal Cauchy stresses
+  integration_hex8_druckerprager_RetToCone[_elastic_tang].json : tests/input_files/mat_druckerprager_RetToCone*.4C.yaml,
+        40 hex8 KINEM linear elements with the history material MAT_Struct_DruckerPrager under nodal forces
   integration_cooks_fbar.json : Cook's membrane with 64 F-bar hex8 elements
           tests/input_files/sohex8fbar_cooks_nl_new_struc.4C.yaml (dispy of node 162, 1e-8)
   unit_known_answers.json : known answers of unittests/mat/4C_elasthyper_service_test.cpp:36-155,
@@ -282,6 +284,44 @@ def isoogden_case(rel):
             "tolres": float(sd["TOLRES"]), "toldisp": float(sd["TOLDISP"]), "expected_stress": expected}
 
 
+def druckerprager_case(rel):
+    """tests/input_files/mat_druckerprager_RetToCone[_elastic_tang].4C.yaml: cantilever of 40 hex8 KINEM linear
+    elements, MAT_Struct_DruckerPrager (history material), nodal forces (DESIGN POINT NEUMANN) growing with t,
+    statics; known answers = tip displacements."""
+    with open(os.path.join(REF, rel)) as fh:
+        y = yaml.safe_load(fh)
+    ids, coords = [], []
+    for line in y["NODE COORDS"]:
+        m = re.match(r"NODE\s+(\d+)\s+COORD\s+(\S+)\s+(\S+)\s+(\S+)", line)
+        ids.append(int(m.group(1)))
+        coords.append([float(m.group(i)) for i in (2, 3, 4)])
+    index = {g: k for k, g in enumerate(ids)}
+    eles = []
+    for line in y["STRUCTURE ELEMENTS"]:
+        tok = line.split()
+        assert tok[1] == "SOLID" and tok[2] == "HEX8" and "KINEM linear" in line
+        eles.append([index[int(t)] for t in tok[3:11]])
+    dbc, = y["DESIGN SURF DIRICH CONDITIONS"]
+    pn, = y["DESIGN POINT NEUMANN CONDITIONS"]
+    assert dbc["ONOFF"] == [1, 1, 1] and dbc["VAL"] == [0, 0, 0]
+    dnodes = [index[int(re.match(r"NODE\s+(\d+)\s+DNODE\s+(\d+)", l).group(1))] for l in y["DNODE-NODE TOPOLOGY"]
+              if int(re.match(r"NODE\s+(\d+)\s+DNODE\s+(\d+)", l).group(2)) == pn["E"]]
+    snodes = [index[int(re.match(r"NODE\s+(\d+)\s+DSURFACE\s+(\d+)", l).group(1))] for l in y["DSURF-NODE TOPOLOGY"]
+              if int(re.match(r"NODE\s+(\d+)\s+DSURFACE\s+(\d+)", l).group(2)) == dbc["E"]]
+    assert y["FUNCT1"][0]["SYMBOLIC_FUNCTION_OF_TIME"] == "t"
+    mat = dict(y["MATERIALS"][0]["MAT_Struct_DruckerPrager"])
+    mat = {k: (float(v) if k != "TANG" else v) for k, v in mat.items()}
+    sd = y["STRUCTURAL DYNAMIC"]
+    expected = [{"node": index[r["STRUCTURE"]["NODE"]], "dof": "xyz".index(r["STRUCTURE"]["QUANTITY"][-1]),
+                 "value": float(r["STRUCTURE"]["VALUE"]), "tol": float(r["STRUCTURE"]["TOLERANCE"])}
+                for r in y["RESULT DESCRIPTION"]]
+    return {"source": rel, "celltype": "hex8", "kinem": "linear", "coords": coords, "elements": eles, "material": mat,
+            "dirichlet_nodes": sorted(snodes),
+            "point_neumann": {"nodes": sorted(dnodes), "ONOFF": pn["ONOFF"], "VAL": pn["VAL"], "FUNCT": pn["FUNCT"]},
+            "timestep": float(sd["TIMESTEP"]), "numstep": int(sd["NUMSTEP"]),
+            "tolres": float(sd["TOLRES"]), "toldisp": float(sd["TOLDISP"]), "expected_disp": expected}
+
+
 def cooks_case(rel, tech):
     """Cook's membrane inputs (64 hex8, CoupNeoHooke nu=0.4999): several Dirichlet conditions with
     per-dof ONOFF, one dead surface load, known answer = dispy of node 162 (and internal energy)."""
@@ -430,6 +470,9 @@ if __name__ == "__main__":
         json.dump(loadlin_case("tests/input_files/loadlin.4C.yaml"), fh)
     with open(os.path.join(HERE, "integration_hex8_isoogden.json"), "w") as fh:
         json.dump(isoogden_case("tests/input_files/elasthyper_isoogden.4C.yaml"), fh)
+    for name in ("RetToCone", "RetToCone_elastic_tang"):
+        with open(os.path.join(HERE, f"integration_hex8_druckerprager_{name}.json"), "w") as fh:
+            json.dump(druckerprager_case(f"tests/input_files/mat_druckerprager_{name}.4C.yaml"), fh)
     with open(os.path.join(HERE, "unit_known_answers.json"), "w") as fh:
         json.dump(unit_known_answers(), fh, indent=1)
     np.savez_compressed(os.path.join(HERE, "ref_elements.npz"), **ref_elements())

@@ -18,7 +18,7 @@ def lib(cell="hex8"):
         srcs = [os.path.join(_CPP, f"emulate_{cell}.cpp")] + [
             os.path.join(_CPP, "..", "..", "4c_b200", "csrc", f)
             for f in ("hex8_kernel.cuh", "hex8_fbar_kernel.cuh", "tet10_kernel.cuh", "hex27_kernel.cuh", "solid_math.cuh",
-                      "summands.cuh", "post_kernels.cuh", "neumann_kernels.cuh", "shape_tables.hpp")]
+                      "summands.cuh", "history_materials.cuh", "post_kernels.cuh", "neumann_kernels.cuh", "shape_tables.hpp")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", so, srcs[0]])
         _libs[cell] = C.CDLL(so)
@@ -203,3 +203,29 @@ def neumann_volume(celltype, conn, X, onoff, val, rowptr, node_row_lid, node_col
         C.c_int64(len(rowstart)), _p(rowstart), _p(rowlen), _p(frow), _p(fext))
     assert rc == 0
     return fext
+
+
+def drucker_prager(in10, Cv, hist=None):
+    """Product MAT_Struct_DruckerPrager at one point: (S, Cm) or None if the device rejects the parameters."""
+    in10 = np.ascontiguousarray(in10, np.float64)
+    Cv = np.ascontiguousarray(Cv, np.float64)
+    S, Cm = np.zeros(6), np.zeros(36)
+    rc = lib("post").emu_drucker_prager(_p(in10), _p(hist), _p(Cv), _p(S), _p(Cm))
+    if rc == -3:
+        return None
+    assert rc == 0
+    return S, Cm.reshape(6, 6)
+
+
+def hex8_drucker_prager(in10, conn, X, u_col, rowptr, colind, node_row_lid, node_col_lid, n_row_nodes, mat_hist,
+                        stiff=True):
+    """Emulated KINEM linear hex8 kernel with the history material; mat_hist (n_ele, 8, 14) updated in place."""
+    conn = np.ascontiguousarray(conn, np.int32)
+    pos, rowstart, rowlen, frow = scatter_map(conn, rowptr, colind, node_row_lid, node_col_lid)
+    vals, f = np.zeros(rowptr[-1]), np.zeros(3 * n_row_nodes)
+    rc = lib("hex8").emu_hex8_drucker_prager(
+        _p(np.ascontiguousarray(in10, np.float64)), C.c_int(int(stiff)), C.c_int64(len(conn)), _p(conn),
+        _p(np.ascontiguousarray(X, np.float64)), _p(np.ascontiguousarray(u_col, np.float64)), _p(pos), _p(rowstart),
+        _p(rowlen), _p(frow), C.c_int64(len(rowstart)), _p(vals), _p(f), _p(mat_hist))
+    assert rc == 0, rc
+    return vals, f

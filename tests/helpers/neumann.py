@@ -213,3 +213,15 @@ def add_to_csr_values(K, rowptr, colind, values):
     add = np.asarray(K[rows, colind]).ravel()
     assert abs(add).sum() >= abs(K).sum() * (1 - 1e-12)
     return values + add
+
+
+def point_neumann_load(case, time):
+    """DESIGN POINT NEUMANN CONDITIONS (Discretization::evaluate_neumann, 4C_fem_discretization_evaluate.cpp:
+    205-256): VAL * FUNCT(t) on every node of the condition; FUNCT1 = t."""
+    pn = case["point_neumann"]
+    f = np.zeros(3 * len(case["coords"]))
+    for n in pn["nodes"]:
+        for d in range(3):
+            if pn["ONOFF"][d]:
+                f[3 * n + d] += pn["VAL"][d] * (time if pn["FUNCT"][d] == 1 else 1.0)
+    return f

@@ -11,7 +11,7 @@ from .meshes import csr_to_dense
 from .neumann import neumann_load
 
 
-def solve_case(case, evaluate, max_iter=30, update_prestress=None, recover=None, external=None):
+def solve_case(case, evaluate, max_iter=30, update_prestress=None, recover=None, external=None, update_step=None):
     """evaluate(u_flat) -> (rowptr, colind, values, fint). Returns converged displacement (nn,3).
 
     recover(du_flat): element action struct_calc_recover after every Newton update with the Newton
@@ -21,6 +21,9 @@ def solve_case(case, evaluate, max_iter=30, update_prestress=None, recover=None,
     external(u_flat, t, values) -> (fext, values'): deformation dependent loads (orthopressure with LOADLIN:
     apply_force_stiff_external adds the load stiffness to the stiffness matrix of the iteration,
     model_evaluator_structure.cpp:474-516); default is the dead load of the case.
+
+    update_step(u_flat): end of a converged time step (update_step_element -> struct_calc_update_istep:
+    history materials commit their current state, Mat::...::update()).
 
     update_prestress(u_flat): PRESTRESS MULF.  While the time reached by a step is <= PRESTRESSTIME
     (the state has already been advanced when update_step_element runs; confirmed by the known answers:
@@ -65,6 +68,8 @@ def solve_case(case, evaluate, max_iter=30, update_prestress=None, recover=None,
                 break
         else:
             raise RuntimeError(f"Newton did not converge at t={t}: |r|={rnorm}")
+        if update_step is not None:
+            update_step(u)
         if update_prestress is not None and t <= case["prestresstime"] + 1.0e-15:
             update_prestress(u)
             u = np.zeros(3 * nn)

@@ -768,3 +768,123 @@ def test_reference_isoogden_known_answers_through_cuda_path():
     for e in case["expected_stress"]:
         assert abs(ns[e["node"], e["comp"]] - e["value"]) < 1e-6, (e, ns[e["node"], e["comp"]])
     asm.close()
+
+
+# ------------------------------------------------------------------------------------------------------
+# history material on the device GP-state store: MAT_Struct_DruckerPrager (KINEM linear)
+# ------------------------------------------------------------------------------------------------------
+DP_MAT = dict(YOUNG=10.0, NUE=0.3, ISOHARD=0.5, TOL=1e-12, C=0.05, ETA=0.2, XI=0.25, ETABAR=0.2)
+
+
+@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10"])
+@pytest.mark.parametrize("tang", ["consistent", "elastic"])
+def test_history_material_evaluate_and_state_store_match_oracle(cell, tang):
+    ct, rm, u = _mesh(cell)
+    u = 4.0 * u.ravel()                                   # well into the plastic range
+    par = capi.drucker_prager_params(**dict(DP_MAT, TANG=tang))
+    asm = b200.DeviceAssembler(rm, capi.MAT_DRUCKER_PRAGER, par, kinem=capi.KINEM_LINEAR)
+    rowptr, colind = asm.graph()
+    ngp = {"hex8": 8, "hex27": 27, "tet10": 4}[cell]
+    h_o = np.zeros((rm.n_col_eles, ngp, orc.DP_HIST))
+    assert asm.ctx.get_material_history().size == h_o.size and not asm.ctx.get_material_history().any()
+    for fac in (1.0, 0.6, 1.5):                            # load, commit, unload, commit, reload beyond
+        asm.set_state("displacement", fac * u)
+        K, f, _ = asm.evaluate()
+        rK, rf, nbad = orc.evaluate_assemble(ct, orc.MAT_DRUCKER_PRAGER, par, rm.conn, rm.X.ravel(), fac * u,
+                                             rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, rowptr, colind,
+                                             tech=orc.TECH_LINEAR, hist=h_o)
+        ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
+        assert ok and nbad == 0, (fac, wK, wf)
+        h_d = asm.ctx.get_material_history().reshape(h_o.shape)
+        assert np.abs(h_d - h_o).max() <= 1e-12 * np.abs(h_o).max()
+        assert (h_o[:, :, 13] > 0).mean() > 0.2
+        # struct_calc_internalforce leaves the same iterate
+        _, f2, _ = asm.evaluate("struct_calc_internalforce")
+        assert np.abs(f2 - rf).max() <= RTOL * np.abs(rf).max()
+        asm.ctx.update_step()
+        orc.material_update(orc.MAT_DRUCKER_PRAGER, h_o)
+    h_conv = asm.ctx.get_material_history().reshape(h_o.shape)
+    assert np.array_equal(h_conv[:, :, :7], h_conv[:, :, 7:])
+    # reset_step discards the iterate of a rejected step; restart = get / set of the state store
+    asm.set_state("displacement", 2.5 * u)
+    asm.evaluate()
+    assert not np.array_equal(asm.ctx.get_material_history(), h_conv.ravel())
+    asm.ctx.reset_step()
+    assert np.array_equal(asm.ctx.get_material_history(), h_conv.ravel())
+    asm2 = b200.DeviceAssembler(rm, capi.MAT_DRUCKER_PRAGER, par, kinem=capi.KINEM_LINEAR)
+    asm2.ctx.set_material_history(h_conv)
+    asm2.set_state("displacement", 0.9 * u)
+    asm.set_state("displacement", 0.9 * u)
+    Ka, fa, _ = asm.evaluate()
+    Kb, fb, _ = asm2.evaluate()
+    assert np.abs(fa - fb).max() <= 1e-13 * np.abs(fa).max() and np.abs(Ka - Kb).max() <= 1e-13 * np.abs(Ka).max()
+    # stress output of the current iterate (linear kinematics: Cauchy == 2PK of the small-strain model)
+    st, en = asm.calc_stress("2pk", "gl")
+    S_ref = np.zeros_like(st)
+    Xc, uc = rm.X[rm.conn], (0.9 * u).reshape(-1, 3)[rm.conn]
+    gxi, _ = orc.gauss(ct)
+    for g, xi in enumerate(gxi):
+        _, dN = orc.shape(ct, xi)
+        for e in range(rm.n_col_eles):
+            Gx = np.linalg.solve(dN @ Xc[e], dN)          # N_XYZ = J^-1 dN, (3, nn)
+            H = uc[e].T @ Gx.T                            # displacement gradient
+            E = 0.5 * (H + H.T)
+            h = h_conv[e, g].copy()
+            S_ref[e, g], _ = orc.material_hist(orc.MAT_DRUCKER_PRAGER, par, [E[0, 0], E[1, 1], E[2, 2], E[0, 1], E[1, 2], E[0, 2]], h)
+    assert np.abs(st - S_ref).max() <= 1e-11 * np.abs(S_ref).max()
+    with pytest.raises(capi.B200SolidError) as ei:
+        asm.calc_energy()
+    assert ei.value.code == capi.ERR_UNSUPPORTED
+    asm.close()
+    asm2.close()
+
+
+def test_history_material_restrictions():
+    ct, rm, u = _mesh("hex8")
+    par = capi.drucker_prager_params(**DP_MAT)
+    asm = b200.DeviceAssembler(rm, capi.MAT_DRUCKER_PRAGER, par)          # nonlinear kinematics
+    asm.set_state("displacement", u.ravel())
+    with pytest.raises(capi.B200SolidError) as ei:
+        asm.evaluate()
+    assert ei.value.code == capi.ERR_UNSUPPORTED and "KINEM linear" in str(ei.value)
+    # non-associative consistent tangent: not major-symmetric
+    with pytest.raises(capi.B200SolidError) as ei:
+        asm.ctx.set_material(capi.MAT_DRUCKER_PRAGER, capi.drucker_prager_params(**dict(DP_MAT, ETABAR=0.4)))
+    assert ei.value.code == capi.ERR_UNSUPPORTED and "symmetric" in str(ei.value)
+    asm.ctx.set_material(capi.MAT_DRUCKER_PRAGER, capi.drucker_prager_params(**dict(DP_MAT, ETABAR=0.4, TANG="elastic")))
+    with pytest.raises(capi.B200SolidError):
+        asm.ctx.set_material(capi.MAT_DRUCKER_PRAGER, [10.0, 0.3])      # too few parameters
+    # a material without history has no state store
+    asm.ctx.set_material(capi.MAT_SVK, [1000.0, 0.3])
+    assert asm.ctx.L.b200s_material_history_size(asm.ctx.h) == 0
+    with pytest.raises(capi.B200SolidError) as ei:
+        asm.ctx.get_material_history()
+    assert ei.value.code == capi.ERR_INVALID
+    asm.close()
+
+
+def test_reference_druckerprager_known_answers_through_cuda_path():
+    """Tip displacements (1e-10) of tests/input_files/mat_druckerprager_RetToCone_elastic_tang.4C.yaml with the
+    device doing every evaluate and the history commits (20 load steps, 68 yielding Gauss points)."""
+    from tests.helpers.newton import solve_case
+    from tests.helpers.neumann import point_neumann_load
+    case = json.load(open(os.path.join(G, "integration_hex8_druckerprager_RetToCone_elastic_tang.json")))
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    rm = b200.partition.serial_mesh(orc.HEX8, X, conn)
+    asm = b200.DeviceAssembler(rm, capi.MAT_DRUCKER_PRAGER, capi.drucker_prager_params(**case["material"]),
+                               kinem=capi.KINEM_LINEAR)
+    rowptr, colind = asm.graph()
+
+    def ev(u):
+        asm.set_state("displacement", u)
+        K, f, _ = asm.evaluate()
+        return rowptr, colind, K, f
+
+    u = solve_case(case, ev, max_iter=400, external=lambda u, t, v: (point_neumann_load(case, t), v),
+                   update_step=lambda u: asm.ctx.update_step())
+    h = asm.ctx.get_material_history().reshape(len(conn), 8, orc.DP_HIST)
+    assert int((h[:, :, 6] > 0).sum()) == 68
+    for e in case["expected_disp"]:
+        assert abs(u[e["node"], e["dof"]] - e["value"]) < 1e-10, (e, u[e["node"], e["dof"]])
+    asm.close()
