@@ -25,14 +25,23 @@ def _free_port():
     return p
 
 
+def _launch(world, args):
+    """torchrun on a free rendezvous port; a port that got taken between the probe and the bind is retried."""
+    for attempt in range(3):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+               "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+               os.path.join(ROOT, "tests", "helpers", "mgpu_worker.py")] + args
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+        if r.returncode == 0 or "EADDRINUSE" not in r.stderr:
+            break
+    return r
+
+
 @pytest.mark.parametrize("world,n", [(2, (12, 7, 5)), (4, (10, 9, 6)), (8, (10, 8, 8))])
 def test_nccl_halo_rows_match_oracle(world, n):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(ROOT, "tests", "helpers", "mgpu_worker.py"), ",".join(map(str, n))]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    r = _launch(world, [",".join(map(str, n))])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("MGPU_OK") == world, r.stdout[-3000:]
 
@@ -43,9 +52,6 @@ def test_nccl_actions_around_the_path(world, n):
     all-reduced dot products on a partitioned mesh."""
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(ROOT, "tests", "helpers", "mgpu_worker.py"), ",".join(map(str, n)), "post"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    r = _launch(world, [",".join(map(str, n)), "post"])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("MGPU_OK") == world and r.stdout.count("MGPU_POST") == world, r.stdout[-3000:]
