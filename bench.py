@@ -61,6 +61,16 @@ WORKLOADS = {
                           flops=63.8e3 + 8 * 13104 + 64890, bytes=2304.0 + 2 * 8 * 1008,
                           kernel="k_hex8_eas_eval_assemble<COUP_NEOHOOKE,STIFF,21>", default_n=100,
                           metric="hex8 EAS (full) Neo-Hooke element evaluate+assemble (force + tangent stiffness into CSR), FP64"),
+    # Section 8(f) row 4: history material on the device Gauss-point state store, KINEM linear hex8 on the config-2
+    # mesh.  Model = hex8 model with M = ~150 flops (elastic predictor + return mapping + tangent); bytes add the
+    # state store: 7 doubles read (last converged) + 7 written (current iterate) per Gauss point.
+    "hex8_dp": dict(config="2 mesh, KINEM linear, MAT_Struct_DruckerPrager (SURVEY 8f.4)", cell="HEX8",
+                    mat="MAT_DRUCKER_PRAGER", par=[10.0, 0.3, 0.5, 1e-12, 2e-3, 0.2, 0.25, 0.2, 50, 1.0],
+                    matname="Drucker-Prager (E=10, nu=0.3, H=0.5, c=2e-3, eta=etabar=0.2, xi=0.25), KINEM linear",
+                    tech="TECH_LINEAR", kinem="KINEM_LINEAR",
+                    flops=8 * (62 * 64 + 228 * 8 + 1183 + 150), bytes=2304.0 + 8 * 14 * 8,
+                    kernel="k_hex8_eval_assemble<DP,STIFF,LINEAR>", default_n=100,
+                    metric="hex8 Drucker-Prager (history material) element evaluate+assemble (force + tangent stiffness into CSR), FP64"),
     "tet10": dict(config="4", cell="TET10", mat="MAT_ISO_VOL", par=[1.0, 1000.0],
                   matname="IsoNeoHooke mu=1 + VolSussmanBathe kappa=1000", flops=43.3e3, bytes=3300.0,
                   kernel="k_tet10_eval_assemble<ISO_VOL,STIFF>", default_n=87,
@@ -201,6 +211,8 @@ class CpuArm:
         self.n_sample = n_sample
         if self.tech in (orc.TECH_EAS_MILD, orc.TECH_EAS_FULL):
             self.hist = orc.eas_new_history(self.tech, self.rm.n_col_eles)
+        if wl["mat"] == "MAT_DRUCKER_PRAGER":
+            self.hist = np.zeros((self.rm.n_col_eles, 8, orc.DP_HIST))
 
     def step(self, threads):
         if self.hist is not None:
@@ -220,7 +232,7 @@ class CpuArm:
 
 def cpu_threads(wl, threads):
     """History-carrying formulations (EAS) run on one thread in the oracle."""
-    return 1 if "EAS" in wl.get("tech", "") else threads
+    return 1 if ("EAS" in wl.get("tech", "") or wl["mat"] == "MAT_DRUCKER_PRAGER") else threads
 
 
 def cpu_sample_size(wl, threads, target_s):
@@ -298,7 +310,8 @@ def run_b200(args):
     per_gpu_n = args.per_gpu_n or wl["default_n"]
     rm, u, mesh_label = build_rank(wl, per_gpu_n, rank, world, args.strong)
     asm = b200.DeviceAssembler(rm, getattr(capi, wl["mat"]), wl["par"], device=local,
-                               tech=getattr(capi, wl.get("tech", "TECH_NONE")))
+                               tech=getattr(capi, wl.get("tech", "TECH_NONE")) if "kinem" not in wl else capi.TECH_NONE,
+                               kinem=getattr(capi, wl.get("kinem", "KINEM_NONLINEAR_TOTLAG")))
     ctx = asm.ctx
     if world > 1:
         uid = [ctx.nccl_unique_id() if rank == 0 else None]
