@@ -1145,6 +1145,7 @@ struct b200s_ctx
   int face_nn = 0, face_ngp = 0;
   double *d_face_N = nullptr, *d_face_d0 = nullptr, *d_face_d1 = nullptr, *d_face_w = nullptr;
   double *d_N_gp = nullptr, *d_fext = nullptr, *d_nm_row = nullptr, *d_nm_col = nullptr;
+  int* d_nm_flag = nullptr;  // set by k_neumann_surface_lin when a face pair has no graph entry
   // linear algebra on the assembled matrix (linalg_kernels.cuh)
   int64_t n_mat_cols = 0;
   bool node3_ok = false;
@@ -1639,7 +1640,7 @@ extern "C"
     dfree(ctx->d_mat_ext), dfree(ctx->d_mat_hist);
     b200s_clear_neumann(ctx);
     dfree(ctx->d_face_N), dfree(ctx->d_face_d0), dfree(ctx->d_face_d1), dfree(ctx->d_face_w);
-    dfree(ctx->d_N_gp), dfree(ctx->d_fext), dfree(ctx->d_nm_row), dfree(ctx->d_nm_col);
+    dfree(ctx->d_N_gp), dfree(ctx->d_fext), dfree(ctx->d_nm_row), dfree(ctx->d_nm_col), dfree(ctx->d_nm_flag);
     dfree(ctx->d_hyper), dfree(ctx->d_dN_gp), dfree(ctx->d_w), dfree(ctx->d_dN_cen), dfree(ctx->d_N_mass);
     dfree(ctx->d_dN_mass), dfree(ctx->d_w_mass), dfree(ctx->d_ele_is_row), dfree(ctx->d_mass);
     dfree(ctx->d_f_inertia), dfree(ctx->d_acc_row), dfree(ctx->d_acc_col), dfree(ctx->d_energy);
@@ -3045,7 +3046,8 @@ extern "C"
     int* d_flag = nullptr;
     if (needs_matrix)
     {
-      CK(cudaMalloc((void**)&d_flag, sizeof(int)));
+      if (!ctx->d_nm_flag && to_device(ctx, &ctx->d_nm_flag, (const int*)nullptr, 1)) return B200S_ERR_CUDA;
+      d_flag = ctx->d_nm_flag;
       CK(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
     }
     for (const auto& c : ctx->neumann)
@@ -3074,7 +3076,6 @@ extern "C"
       e = cudaMemcpyAsync(fext_row, ctx->d_fext, sizeof(double) * (size_t)ctx->n_rows, cudaMemcpyDefault, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e == cudaSuccess) e = cudaGetLastError();
-    if (d_flag) cudaFree(d_flag);
     if (e != cudaSuccess) return fail(ctx, B200S_ERR_CUDA, "evaluate_neumann: %s", cudaGetErrorString(e));
     if (h_flag)
       return fail(ctx, B200S_ERR_INVALID,
