@@ -313,6 +313,9 @@ def run_b200(args):
                                tech=getattr(capi, wl.get("tech", "TECH_NONE")) if "kinem" not in wl else capi.TECH_NONE,
                                kinem=getattr(capi, wl.get("kinem", "KINEM_NONLINEAR_TOTLAG")))
     ctx = asm.ctx
+    for kv in args.option or []:          # library options, e.g. --option lazy_zero=0
+        k, v = kv.split("=")
+        ctx.set_option(k, float(v))
     if world > 1:
         uid = [ctx.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -486,6 +489,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--option", action="append", help="library option key=value (b200s_set_option), repeatable")
     ap.add_argument("--workload", default="hex8", choices=sorted(WORKLOADS),
                     help="hex8 = BASELINE config 2 (default, the headline), tet10 = config 4, hex27 = config 3")
     ap.add_argument("--per-gpu-n", type=int, default=0,
