@@ -196,7 +196,20 @@ namespace b200s
 
       // evaluate_jacobian_mapping at Gauss point g (calc_lib.hpp:499-516)
       const double* dN = tab_gp + g * TAB_STRIDE;
-      jacobian(dN, xu, J);
+      // the eight lanes of an element read the same X and u: 128-bit loads halve the shared-memory wavefronts
+      double xr[24], ur[24];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+      for (int p = 0; p < 12; ++p)
+      {
+        const d2 tx = *reinterpret_cast<const d2*>(xu + 2 * p);  // xu is 16-byte aligned (XU_ESTRIDE even)
+        const d2 tu = *reinterpret_cast<const d2*>(xu + 24 + 2 * p);
+        xr[2 * p] = tx.x, xr[2 * p + 1] = tx.y, ur[2 * p] = tu.x, ur[2 * p + 1] = tu.y;
+      }
+#else
+      for (int p = 0; p < 24; ++p) xr[p] = xu[p], ur[p] = xu[24 + p];
+#endif
+      jacobian(dN, xr, J);
       const double detJ = inv3(iJ, J);  // same expression as det3(J)
       neg_jac = !(detJ_node > 0.0) && (e < A.n_ele);
       detJ_min = fmin(detJ_node, detJ);
@@ -215,7 +228,7 @@ namespace b200s
         for (int a = 0; a < 3; ++a)
         {
           Gout[3 * k + a] = Gk[a];
-          const double ua = xu[24 + 3 * k + a];
+          const double ua = ur[3 * k + a];
 #pragma unroll
           for (int b = 0; b < 3; ++b) F[a + 3 * b] += ua * Gk[b];
         }
