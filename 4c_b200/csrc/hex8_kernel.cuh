@@ -79,7 +79,7 @@ namespace b200s
     constexpr int NN = 8, NGP = 8, EPW = 4;  // nodes, Gauss points, elements per warp
     // shared-memory geometry (in doubles); strides chosen so that 64/128-bit accesses of a warp
     // fall on distinct banks (see DESIGN.md "shared memory layout")
-    constexpr int TAB_STRIDE = 25;                 // per Gauss point / node row of a dN table
+    constexpr int TAB_STRIDE = 26;                 // per Gauss point / node row of a dN table (even: rows 16-byte aligned)
     constexpr int TAB_SIZE = 8 * TAB_STRIDE;       // one table
     constexpr int MP_PAIRS = 27;                   // 45 M + 9 Pw = 54 doubles = 27 x double2
     constexpr int MP_SLOTS = EPW * 9;              // slot = el*9 + g (9: pad)
@@ -195,7 +195,18 @@ namespace b200s
       const double detJ_node = det3(J);
 
       // evaluate_jacobian_mapping at Gauss point g (calc_lib.hpp:499-516)
-      const double* dN = tab_gp + g * TAB_STRIDE;
+      const double* dNs = tab_gp + g * TAB_STRIDE;
+      double dN[24];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+      for (int p = 0; p < 12; ++p)
+      {
+        const d2 t = *reinterpret_cast<const d2*>(dNs + 2 * p);
+        dN[2 * p] = t.x, dN[2 * p + 1] = t.y;
+      }
+#else
+      for (int p = 0; p < 24; ++p) dN[p] = dNs[p];
+#endif
       // the eight lanes of an element read the same X and u: 128-bit loads halve the shared-memory wavefronts
       double xr[24], ur[24];
 #if defined(__CUDA_ARCH__)
