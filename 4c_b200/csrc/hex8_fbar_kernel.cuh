@@ -194,7 +194,8 @@ namespace b200s
     }
 
     // ---- phase 2: lane = row node i, full block row -------------------------------------------
-    // Kacc[j][b + 3c] = K_ij(b,c), facc = f_i
+    // Kacc[k][b + 3c] = K_ij(b,c) with j = (i + k) mod 8 (rotated like the displacement-based kernel: the
+    // staging stores of the eight lanes of an element then fall on distinct banks), facc = f_i
     template <bool STIFF>
     B2_HD void phase2(const hex8::WarpSmem& S, int lane, double (*Kacc)[9], double* facc)
     {
@@ -254,15 +255,16 @@ namespace b200s
               for (int b = 0; b < 3; ++b) out[b][3 * d + c] = fma(-v[b], fi, out[b][3 * d + c]);
             }
 #pragma unroll
-          for (int j = 0; j < NN; ++j)
+          for (int k = 0; k < NN; ++k)
           {
+            const int j = (i + k) & 7;
             const double Gj[3] = {Gg[3 * j], Gg[3 * j + 1], Gg[3 * j + 2]};
 #pragma unroll
             for (int b = 0; b < 3; ++b)
 #pragma unroll
               for (int c = 0; c < 3; ++c)
-                Kacc[j][b + 3 * c] = fma(out[b][6 + c], Gj[2],
-                    fma(out[b][3 + c], Gj[1], fma(out[b][c], Gj[0], Kacc[j][b + 3 * c])));
+                Kacc[k][b + 3 * c] = fma(out[b][6 + c], Gj[2],
+                    fma(out[b][3 + c], Gj[1], fma(out[b][c], Gj[0], Kacc[k][b + 3 * c])));
           }
         }
       }
@@ -271,13 +273,13 @@ namespace b200s
         // centroid half: K_ij(b,c) += V_i(b) h0_j(c)
         const double* h0 = S.h0 + el * 24;
 #pragma unroll
-        for (int j = 0; j < NN; ++j)
+        for (int k = 0; k < NN; ++k)
 #pragma unroll
           for (int c = 0; c < 3; ++c)
           {
-            const double h = h0[3 * j + c];
+            const double h = h0[3 * ((i + k) & 7) + c];
 #pragma unroll
-            for (int b = 0; b < 3; ++b) Kacc[j][b + 3 * c] = fma(Vacc[b], h, Kacc[j][b + 3 * c]);
+            for (int b = 0; b < 3; ++b) Kacc[k][b + 3 * c] = fma(Vacc[b], h, Kacc[k][b + 3 * c]);
           }
       }
     }
@@ -292,11 +294,14 @@ namespace b200s
       if (!STIFF) return;
       double* Ke = S.mp + el * hex8::KE_ESTRIDE;
 #pragma unroll
-      for (int j = 0; j < NN; ++j)
+      for (int k = 0; k < NN; ++k)
+      {
+        const int j = (i + k) & 7;
 #pragma unroll
         for (int b = 0; b < 3; ++b)
 #pragma unroll
-          for (int c = 0; c < 3; ++c) Ke[(3 * i + b) * 24 + 3 * j + c] = Kacc[j][b + 3 * c];
+          for (int c = 0; c < 3; ++c) Ke[(3 * i + b) * 24 + 3 * j + c] = Kacc[k][b + 3 * c];
+      }
     }
   }  // namespace hex8fbar
 }  // namespace b200s
