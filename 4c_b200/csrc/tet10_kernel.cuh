@@ -31,7 +31,12 @@ namespace b200s
     constexpr int G_SIZE = EPW * G_ESTRIDE;
     constexpr int XU_ESTRIDE = 62;                  // gathered X[k*3+d], u at +30
     constexpr int XU_SIZE = EPW * XU_ESTRIDE;
-    constexpr int KE_ESTRIDE = NDOF * NDOF + 14;    // staged K_e per element (914 = 2 mod 16: bank offset 4)
+    // staged K_e: row stride 32.  With j = (i + k) mod 10 the direct store of lane i lands on bank pair
+    // (3*32 + 3) i + 3 k = 3 i + const (mod 16), the wrapped column blocks (j - 10: -30 doubles = +2) can only meet a
+    // lane i + 6, which is wrapped as well, and the transposed store (row 3 j + c) wraps by a multiple of 16:
+    // both are conflict free inside an element (stride 30 gave 13 i and 2-way conflicts on up to four lanes).
+    constexpr int KE_RS = 32;
+    constexpr int KE_ESTRIDE = NDOF * KE_RS + 2;    // per element (962 = 2 mod 16)
     constexpr int FE_OFFSET = EPW * KE_ESTRIDE;
     constexpr int STAGE_SIZE = FE_OFFSET + EPW * NDOF + 2;  // M/Pw/G alias the front of the stage
     static_assert(MP_SIZE + G_SIZE <= STAGE_SIZE, "M/Pw/G live inside the K_e staging area");
@@ -284,8 +289,8 @@ namespace b200s
 #pragma unroll
           for (int c = 0; c < 3; ++c)
           {
-            Ke[(3 * i + b) * NDOF + 3 * j + c] = Kacc[k][b + 3 * c];
-            if (k > 0) Ke[(3 * j + c) * NDOF + 3 * i + b] = Kacc[k][b + 3 * c];  // K_ji = K_ij^T
+            Ke[(3 * i + b) * KE_RS + 3 * j + c] = Kacc[k][b + 3 * c];
+            if (k > 0) Ke[(3 * j + c) * KE_RS + 3 * i + b] = Kacc[k][b + 3 * c];  // K_ji = K_ij^T
           }
       }
     }
@@ -314,9 +319,9 @@ namespace b200s
           const NodeRow r = nr[i];
           if (r.rowstart < 0) continue;
           double* dst = A.vals + (r.rowstart + pos[i * NN] + cl);
-          B2_RED_ADD(dst, Ke[(3 * i) * NDOF]);
-          B2_RED_ADD(dst + r.rowlen, Ke[(3 * i + 1) * NDOF]);
-          B2_RED_ADD(dst + 2 * (int64_t)r.rowlen, Ke[(3 * i + 2) * NDOF]);
+          B2_RED_ADD(dst, Ke[(3 * i) * KE_RS]);
+          B2_RED_ADD(dst + r.rowlen, Ke[(3 * i + 1) * KE_RS]);
+          B2_RED_ADD(dst + 2 * (int64_t)r.rowlen, Ke[(3 * i + 2) * KE_RS]);
         }
       }
     }
