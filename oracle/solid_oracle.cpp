@@ -606,6 +606,21 @@ namespace
   // {ORC_SUM_FIBER, 0, a0, a1, a2, 0} with the element's FIBER1.  Structural tensor A = a (x) a
   // ("Standard" strategy), scalar product 1
   // (src/mat/elast/4C_mat_elast_coupanisoexpobase.cpp:36-62,128-160, ..._coupanisoexpo.cpp:18-21).
+  // CoupAnisoExpoBase at one point for a general structural tensor A (Voigt, tensor components) and scalar
+  // product (src/mat/elast/4C_mat_elast_coupanisoexpobase.cpp:46-113): I4 = C : A, compression parameters for
+  // I4 < 1; returns psi, dPsi/dI4 and d2Psi/dI4^2
+  void aniso_expo_point(const double* k /*K1 K2 K1COMP K2COMP*/, const double* A, double scalarProduct, const double* C,
+      double* psi, double* dPI, double* ddPII)
+  {
+    double I4 = 0.0;
+    for (int v = 0; v < 6; ++v) I4 += C[v] * A[v] * (v < 3 ? 1.0 : 2.0);
+    double k1 = k[0], k2 = k[1];
+    if (I4 < 1.0) k1 = k[2], k2 = k[3];
+    *psi = (k1 / (2.0 * k2)) * (std::exp(k2 * (I4 - scalarProduct) * (I4 - scalarProduct)) - 1.0);
+    *dPI = k1 * (I4 - scalarProduct) * std::exp(k2 * (I4 - scalarProduct) * (I4 - scalarProduct));
+    *ddPII = (1.0 + 2.0 * k2 * std::pow((I4 - scalarProduct), 2)) * k1 * std::exp(k2 * std::pow((I4 - scalarProduct), 2));
+  }
+
   void aniso_expo_add(const double* par, const double* C, double* S, double* Cm, double* psi)
   {
     const int n = (int)par[0];
@@ -615,23 +630,20 @@ namespace
       if ((int)q[0] != ORC_SUM_COUP_ANISOEXPO) continue;
       const double* fq = q + 6;
       if ((int)fq[0] != ORC_SUM_FIBER) continue;
-      // read_fibers normalises the input vector (src/solid_ele/4C_solid_ele_fiber.cpp:66-69)
+      // read_fibers normalises the input vector (src/solid_ele/4C_solid_ele_fiber.cpp:66-69); element fibres give the
+      // structural tensor a (x) a and scalar product 1 (unittests/mat/elast/4C_elast_coupanisoexpo_elementfibers_test.cpp)
       const double nrm = std::sqrt(fq[2] * fq[2] + fq[3] * fq[3] + fq[4] * fq[4]);
       const double a[3] = {fq[2] / nrm, fq[3] / nrm, fq[4] / nrm};
       double A[6];
       for (int v = 0; v < 6; ++v) A[v] = a[VA[v]] * a[VB[v]];
-      double I4 = 0.0;
-      for (int v = 0; v < 6; ++v) I4 += C[v] * A[v] * (v < 3 ? 1.0 : 2.0);
-      const double scalarProduct = 1.0;
-      double k1 = q[2], k2 = q[3];
-      if (I4 < 1.0) k1 = q[4], k2 = q[5];
-      if (psi) *psi += (k1 / (2.0 * k2)) * (std::exp(k2 * (I4 - scalarProduct) * (I4 - scalarProduct)) - 1.0);
+      double w, dPI, ddPII;
+      aniso_expo_point(q + 2, A, 1.0, C, &w, &dPI, &ddPII);
+      if (psi) *psi += w;
       if (S)
       {
-        const double gamma = 2. * (k1 * (I4 - scalarProduct) * std::exp(k2 * std::pow((I4 - scalarProduct), 2)));
+        // add_stress_aniso_principal (:115-160): S += 2 dPI A, C += 4 ddPII A (x) A
+        const double gamma = 2. * dPI, delta = 4. * ddPII;
         for (int v = 0; v < 6; ++v) S[v] += gamma * A[v];
-        const double delta = 2. * (1. + 2. * k2 * std::pow((I4 - scalarProduct), 2)) * 2. * k1 *
-                             std::exp(k2 * std::pow((I4 - scalarProduct), 2));
         for (int I = 0; I < 6; ++I)
           for (int J = 0; J < 6; ++J) Cm[I + 6 * J] += delta * A[I] * A[J];
       }
@@ -1830,6 +1842,13 @@ extern "C"
     stretch_coefficients_modified(kind, p, modstr, modgamma, moddelta);
   }
 
+  // test hook: CoupAnisoExpoBase for a given structural tensor / scalar product
+  // (pins the summand against unittests/mat/elast/4C_elast_coupanisoexpobase_test.cpp:146-230)
+  void orc_test_aniso_expo(const double* k4, const double* A6, double scalar_product, const double* C6, double* psi,
+      double* dPI, double* ddPII)
+  {
+    aniso_expo_point(k4, A6, scalar_product, C6, psi, dPI, ddPII);
+  }
   void orc_material_hist(int kind, const double* par, const double* E, double* hist, double* S, double* C)
   {
     const double Id[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};

@@ -460,6 +460,37 @@ def test_eas_known_answers(tech):
 FIBER_BLOCK = [("COUP_NEOHOOKE", [10.0, 0.25]), ("COUP_ANISOEXPO", [100.0, 1.0, 0.0, 1.0]), ("FIBER", [0.6, 0.7, 0.2])]
 
 
+def test_fibre_summand_unit_known_answers_of_the_reference():
+    """unittests/mat/elast/4C_elast_coupanisoexpobase_test.cpp:146-230: strain energy, dPsi/dI4 and d2Psi/dI4^2 of
+    CoupAnisoExpoBase (K1 1.2, K2 1.3, K1COMP 1.4, K2COMP 1.5) for two structural tensors sym(a (x) b) with scalar
+    product a.b and two right Cauchy-Green tensors (tension and compression branch), 1e-10.  The element-fibre
+    summand of the oracle / product is the special case a = b (scalar product 1,
+    4C_elast_coupanisoexpo_elementfibers_test.cpp:70-92)."""
+    import ctypes as C
+    L = orc.lib()
+    dp = C.POINTER(C.c_double)
+    L.orc_test_aniso_expo.argtypes = [dp, dp, C.c_double, dp, dp, dp, dp]
+    k = np.array([1.2, 1.3, 1.4, 1.5])
+    fa = [np.array([0.469809238649817, 0.872502871778232, 0.134231211042805]),
+          np.array([0.245358246032859, 0.858753861115007, 0.449823451060242])]
+    fb = [np.array([0.071428571428571, 0.142857142857143, 0.214285714285714]),
+          np.array([0.068965517241379, 0.103448275862069, 0.137931034482759])]
+    Cs = [np.array([1.484, 2.3, 1.84, 0.22, 0.3214, 0.523]), np.array([0.516, 0.3, 0.16, 0.022, 0.03214, 0.0523])]
+    ref = {(0, 0): (3.3970087043259376 - 3.3, 0.6000375695574949, 2.329771574299716),
+           (1, 0): (3.308930242120174 - 3.3, -0.1603915791546372, 1.4808816133878135),
+           (0, 1): (3.358837786011725 - 3.3, 0.4435645526048857, 1.9509145858930543),
+           (1, 1): (3.3088538178019045 - 3.3, -0.15968456768492822, 1.480185139428871)}
+    for gp in (0, 1):
+        T = 0.5 * (np.outer(fa[gp], fb[gp]) + np.outer(fb[gp], fa[gp]))
+        A = np.array([T[0, 0], T[1, 1], T[2, 2], T[0, 1], T[1, 2], T[0, 2]])
+        for ci, Cv in enumerate(Cs):
+            psi, d1, d2 = C.c_double(), C.c_double(), C.c_double()
+            L.orc_test_aniso_expo(k.ctypes.data_as(dp), A.ctypes.data_as(dp), float(fa[gp] @ fb[gp]),
+                                  Cv.ctypes.data_as(dp), C.byref(psi), C.byref(d1), C.byref(d2))
+            r = ref[(ci, gp)]
+            assert abs(psi.value - r[0]) < 1e-10 and abs(d1.value - r[1]) < 1e-10 and abs(d2.value - r[2]) < 1e-10
+
+
 def test_fibre_summand_is_consistent_and_product_matches_oracle():
     """S = d psi / d E, C = d S / d E for the oracle's CoupAnisoExpo (tension branch and compression branch
     K1COMP = 0), and the product's summand (emulated) against it.  The oracle's summand is additionally
