@@ -2049,6 +2049,48 @@ extern "C"
   static const double* g_output_hist = nullptr;
   void orc_set_output_history(const double* hist) { g_output_hist = hist; }
 
+  // Solid::Utils::pk2_to_cauchy (src/solid_ele/4C_solid_ele_utils.hpp:41-54): sigma = F S F^T / det F
+  void stress_pk2_to_cauchy(const double* F, const double* S, double* out)
+  {
+    double FS[9];
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b)
+      {
+        double v = 0.0;
+        for (int c = 0; c < 3; ++c) v += F[a + 3 * c] * S[VG[c][b]];
+        FS[a + 3 * b] = v;
+      }
+    const double det = det3(F);
+    for (int v = 0; v < 6; ++v)
+    {
+      double w = 0.0;
+      for (int c = 0; c < 3; ++c) w += FS[VA[v] + 3 * c] * F[VB[v] + 3 * c];
+      out[v] = w / det;
+    }
+  }
+  // Solid::Utils::green_lagrange_to_euler_almansi (:64-79): e = F^-T E F^-1
+  void strain_gl_to_euler_almansi(const double* F, const double* E, double* out)
+  {
+    double iF[9], T[9];
+    inv3(iF, F);
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b)
+      {  // T = iF^T E
+        double v = 0.0;
+        for (int c = 0; c < 3; ++c) v += iF[c + 3 * a] * E[VG[c][b]];
+        T[a + 3 * b] = v;
+      }
+    for (int v = 0; v < 6; ++v)
+    {
+      double w = 0.0;
+      for (int c = 0; c < 3; ++c) w += T[VA[v] + 3 * c] * iF[c + 3 * VB[v]];
+      out[v] = w;
+    }
+  }
+  // test hooks for unittests/solid_ele/4C_solid_ele_utils_test.cpp
+  void orc_test_pk2_to_cauchy(const double* F, const double* S, double* out) { stress_pk2_to_cauchy(F, S, out); }
+  void orc_test_gl_to_euler_almansi(const double* F, const double* E, double* out) { strain_gl_to_euler_almansi(F, E, out); }
+
   // SolidEleCalc::calculate_stress (src/solid_ele/4C_solid_ele_calc.cpp:416-476) for one element:
   // stress / strain [ngp][6] in the row layout of assemble_symmetric_tensor_to_matrix_row
   // (4C_solid_ele_calc_lib_io.hpp:41-70).  stress_type 1 = 2PK, 2 = Cauchy (pk2_to_cauchy,
@@ -2072,41 +2114,13 @@ extern "C"
         for (int v = 0; v < 6; ++v) stress[6 * gp + v] = S[v];
       if (stress && stress_type == 2)
       {
-        double FS[9];
-        for (int a = 0; a < 3; ++a)
-          for (int b = 0; b < 3; ++b)
-          {
-            double v = 0.0;
-            for (int c = 0; c < 3; ++c) v += F[a + 3 * c] * S[VG[c][b]];
-            FS[a + 3 * b] = v;
-          }
-        const double det = det3(F);
-        for (int v = 0; v < 6; ++v)
-        {
-          double w = 0.0;
-          for (int c = 0; c < 3; ++c) w += FS[VA[v] + 3 * c] * F[VB[v] + 3 * c];
-          stress[6 * gp + v] = w / det;
-        }
+        stress_pk2_to_cauchy(F, S, stress + 6 * gp);
       }
       if (strain && strain_type == 1)
         for (int v = 0; v < 6; ++v) strain[6 * gp + v] = E[v];
       if (strain && strain_type == 2)
       {
-        double iF[9], T[9];
-        inv3(iF, F);
-        for (int a = 0; a < 3; ++a)
-          for (int b = 0; b < 3; ++b)
-          {  // T = iF^T E
-            double v = 0.0;
-            for (int c = 0; c < 3; ++c) v += iF[c + 3 * a] * E[VG[c][b]];
-            T[a + 3 * b] = v;
-          }
-        for (int v = 0; v < 6; ++v)
-        {
-          double w = 0.0;
-          for (int c = 0; c < 3; ++c) w += T[VA[v] + 3 * c] * iF[c + 3 * VB[v]];
-          strain[6 * gp + v] = w;
-        }
+        strain_gl_to_euler_almansi(F, E, strain + 6 * gp);
       }
     }
   }

@@ -888,3 +888,22 @@ def test_reference_druckerprager_known_answers_through_cuda_path():
     for e in case["expected_disp"]:
         assert abs(u[e["node"], e["dof"]] - e["value"]) < 1e-10, (e, u[e["node"], e["dof"]])
     asm.close()
+
+
+def test_reference_strain_measure_known_answer_through_cuda_path():
+    """unittests/solid_ele/4C_solid_ele_utils_test.cpp:26-50: Euler-Almansi strain of a given deformation gradient (1e-13),
+    here as struct_calc_stress output of a unit hex8 cube under the homogeneous deformation u = (F - I) X."""
+    F = np.array([[1.1, 0.2, 0.5], [0.14, 1.2, 0.3], [0.05, 0.2, 1.3]])
+    ea_ref = np.array([0.055233442151184, 0.101134166403205, 0.104112596224498, 0.0913211447369115,
+                       0.1073842904312605, 0.157679374545429])
+    X = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
+    u = X @ (F - np.eye(3)).T
+    rm = b200.partition.serial_mesh(orc.HEX8, X, np.arange(8, dtype=np.int32)[None, :])
+    asm = b200.DeviceAssembler(rm, capi.MAT_SVK, [1000.0, 0.3])
+    asm.set_state("displacement", u.ravel())
+    st, en = asm.calc_stress("cauchy", "ea")
+    assert np.abs(en[0] - ea_ref).max() < 1e-13
+    rst, _ = orc.calc_stress(orc.HEX8, orc.MAT_SVK, [1000.0, 0.3], rm.conn, X.ravel(), u.ravel(), orc.STRESS_CAUCHY,
+                             orc.STRAIN_NONE)
+    assert np.abs(st - rst).max() <= RTOL * np.abs(rst).max()
+    asm.close()

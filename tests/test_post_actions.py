@@ -460,6 +460,49 @@ def test_eas_known_answers(tech):
 FIBER_BLOCK = [("COUP_NEOHOOKE", [10.0, 0.25]), ("COUP_ANISOEXPO", [100.0, 1.0, 0.0, 1.0]), ("FIBER", [0.6, 0.7, 0.2])]
 
 
+def _v6(M):
+    return np.array([M[0][0], M[1][1], M[2][2], M[0][1], M[1][2], M[0][2]], float)
+
+
+def test_stress_strain_measure_unit_known_answers_of_the_reference():
+    """unittests/solid_ele/4C_solid_ele_utils_test.cpp:26-87: green_lagrange_to_euler_almansi (1e-13) and pk2_to_cauchy
+    (1e-12) for a given deformation gradient.  The oracle's conversions directly; the product's through
+    struct_calc_stress on a unit hex8 cube under the homogeneous deformation u = (F - I) X, whose Green-Lagrange
+    strain is the unit test's input."""
+    import ctypes as C
+    F = np.array([[1.1, 0.2, 0.5], [0.14, 1.2, 0.3], [0.05, 0.2, 1.3]])
+    E = _v6([[0.11605, 0.199, 0.3285], [0.199, 0.26, 0.36], [0.3285, 0.36, 0.515]])
+    ea_ref = _v6([[0.055233442151184, 0.0913211447369115, 0.157679374545429],
+                  [0.0913211447369115, 0.101134166403205, 0.1073842904312605],
+                  [0.157679374545429, 0.1073842904312605, 0.104112596224498]])
+    S = _v6([[283.6946919505318, 142.72731871521245, 278.020938548381],
+             [142.72731871521245, 195.86721709838096, 182.86374040756576],
+             [278.020938548381, 182.86374040756576, 202.01904686970775]])
+    cauchy_ref = _v6([[504.0646185061422, 340.6815203116966, 411.0514636046741],
+                      [340.6815203116966, 317.85764952017706, 306.97914008976466],
+                      [411.0514636046741, 306.97914008976466, 302.4131750725638]])
+    L, dp = orc.lib(), C.POINTER(C.c_double)
+    Fc = np.ascontiguousarray(F.T).ravel()                  # column-major a + 3 b
+    out = np.zeros(6)
+    L.orc_test_gl_to_euler_almansi(Fc.ctypes.data_as(dp), E.ctypes.data_as(dp), out.ctypes.data_as(dp))
+    assert np.abs(out - ea_ref).max() < 1e-13
+    L.orc_test_pk2_to_cauchy(Fc.ctypes.data_as(dp), S.ctypes.data_as(dp), out.ctypes.data_as(dp))
+    assert np.abs(out - cauchy_ref).max() < 1e-12
+    # product (emulated) and oracle element paths: homogeneous deformation of the unit cube
+    X = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
+    u = X @ (F - np.eye(3)).T
+    conn = np.arange(8, dtype=np.int32)[None, :]
+    par = [1000.0, 0.3]
+    _, en_o = orc.calc_stress(orc.HEX8, orc.MAT_SVK, par, conn, X.ravel(), u.ravel(), orc.STRESS_CAUCHY, orc.STRAIN_EA)
+    st_p, en_p, _ = emu.post(orc.HEX8, orc.MAT_SVK, par, conn, X.ravel(), u.ravel(), stress_type=orc.STRESS_CAUCHY,
+                             strain_type=orc.STRAIN_EA)
+    assert np.abs(en_o[0] - ea_ref).max() < 1e-13 and np.abs(en_p[0] - ea_ref).max() < 1e-13
+    # Cauchy stress of the same state: sigma = F S F^T / det F with the material's own S (St.Venant-Kirchhoff of E)
+    S_svk, _ = orc.material(orc.MAT_SVK, par, E)
+    L.orc_test_pk2_to_cauchy(Fc.ctypes.data_as(dp), np.ascontiguousarray(S_svk).ctypes.data_as(dp), out.ctypes.data_as(dp))
+    assert np.abs(st_p[0] - out).max() <= 1e-12 * np.abs(out).max()
+
+
 def test_fibre_summand_unit_known_answers_of_the_reference():
     """unittests/mat/elast/4C_elast_coupanisoexpobase_test.cpp:146-230: strain energy, dPsi/dI4 and d2Psi/dI4^2 of
     CoupAnisoExpoBase (K1 1.2, K2 1.3, K1COMP 1.4, K2COMP 1.5) for two structural tensors sym(a (x) b) with scalar
