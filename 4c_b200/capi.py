@@ -52,6 +52,8 @@ SYMBOLS = [
     "b200s_add_surface_neumann", "b200s_add_volume_neumann", "b200s_clear_neumann", "b200s_neumann_gp_count",
     "b200s_neumann_gp_coords", "b200s_set_neumann_factors", "b200s_evaluate_neumann", "b200s_device_fext",
     "b200s_material_history_size", "b200s_get_material_history", "b200s_set_material_history",
+    "b200s_get_value_rows", "b200s_get_f_rows", "b200s_eas_old_step_length", "b200s_set_eas_old_step_length",
+    "b200s_attach_block", "b200s_host_alloc_near", "b200s_last_evaluate_info",
 ]
 
 
@@ -159,6 +161,15 @@ def load():
     L.b200s_material_history_size.restype = i64
     L.b200s_get_material_history.argtypes = [vp, vp]
     L.b200s_set_material_history.argtypes = [vp, vp]
+    L.b200s_get_value_rows.argtypes = [vp, i32, i64, i64, vp, vp, vp]
+    L.b200s_get_f_rows.argtypes = [vp, i64, i64, vp]
+    L.b200s_eas_old_step_length.argtypes = [vp]
+    L.b200s_eas_old_step_length.restype = dbl
+    L.b200s_set_eas_old_step_length.argtypes = [vp, dbl]
+    L.b200s_attach_block.argtypes = [vp, vp]
+    L.b200s_host_alloc_near.argtypes = [i32, i64, C.POINTER(i32)]
+    L.b200s_host_alloc_near.restype = vp
+    L.b200s_last_evaluate_info.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -312,6 +323,37 @@ class Context:
         v = np.empty(self.nnz)
         self._ck(self.L.b200s_get_values(self.h, which, _ptr(v)))
         return v
+
+    def get_value_rows(self, row0, row1, which=MATRIX_STIFFNESS, want_values=True):
+        """(rowptr relative to the first entry, colind, values) of the local rows [row0,row1) of the resident CSR."""
+        rp = np.zeros(row1 - row0 + 1, np.int64)
+        self._ck(self.L.b200s_get_value_rows(self.h, which, row0, row1, None, None, _ptr(rp)))
+        ci = np.zeros(int(rp[-1]), np.int32)
+        v = np.zeros(int(rp[-1])) if want_values else None
+        self._ck(self.L.b200s_get_value_rows(self.h, which, row0, row1, _ptr(v), _ptr(ci), None))
+        return rp, ci, v
+
+    def get_f_rows(self, row0, row1):
+        f = np.zeros(row1 - row0)
+        self._ck(self.L.b200s_get_f_rows(self.h, row0, row1, _ptr(f)))
+        return f
+
+    def attach_block(self, primary):
+        """This context becomes a further element block of `primary`'s system matrix (b200s_attach_block)."""
+        self._ck(self.L.b200s_attach_block(self.h, primary.h))
+        self._primary = primary  # keep it alive
+
+    def last_evaluate_info(self):
+        o = np.zeros(5, np.int64)
+        self._ck(self.L.b200s_last_evaluate_info(self.h, _ptr(o)))
+        return dict(kernel_launches=int(o[0]), pipeline_chunks=int(o[1]), halo_overlapped=int(o[2]),
+                    row_phases=int(o[3]), ghost_elements=int(o[4]))
+
+    def eas_old_step_length(self):
+        return self.L.b200s_eas_old_step_length(self.h)
+
+    def set_eas_old_step_length(self, v):
+        self._ck(self.L.b200s_set_eas_old_step_length(self.h, float(v)))
 
     def calc_stress(self, num_gp, stress_type=STRESS_2PK, strain_type=STRAIN_GL):
         st = np.empty((self.n_col_eles, num_gp, 6)) if stress_type != STRESS_NONE else None

@@ -3,7 +3,12 @@
 #include <cub/cub.cuh>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges are no-ops unless a profiler injects itself
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
+#include <cctype>
 #include <climits>
 #include <cmath>
 #include <cstdarg>
@@ -805,6 +810,79 @@ namespace b200s
     if (t >= n_ele * nn) return;
     conn_out[t] = conn_in[(int64_t)idx[t / nn] * nn + (t % nn)];
   }
+  // ---- element segments (install_graph): see b200s_ctx::seg_begin ----------------------------------
+  // row boundaries of P phases holding about nnz / P entries each
+  __global__ void k_phase_rows(int P, int64_t n_rows, const int64_t* rowptr, int64_t* phase_row, int64_t* phase_off)
+  {
+    const int k = threadIdx.x;
+    if (k > P) return;
+    int64_t r = k == 0 ? 0 : n_rows;
+    if (k > 0 && k < P)
+    {
+      const int64_t target = (int64_t)((double)rowptr[n_rows] * k / P);
+      int64_t lo = 0, hi = n_rows;
+      while (lo < hi)
+      {
+        const int64_t mid = (lo + hi) >> 1;
+        if (rowptr[mid] < target)
+          lo = mid + 1;
+        else
+          hi = mid;
+      }
+      r = lo;
+    }
+    phase_row[k] = r, phase_off[k] = rowptr[r];
+  }
+  // key 0: the element holds a ghost node; 1 + phase of its lowest owned row otherwise.  n_spread counts the
+  // elements whose owned nodes span more than two phases (a row numbering without spatial locality).
+  __global__ void k_segment_keys(int nn, int64_t n_ele, const int32_t* conn, const NodeRow* node_row, int P,
+      const int64_t* phase_row, uint32_t* keys, int32_t* idx, unsigned long long* n_spread)
+  {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_ele) return;
+    int pmin = INT_MAX, pmax = -1;
+    bool ghost = false;
+    for (int k = 0; k < nn; ++k)
+    {
+      const int32_t fr = node_row[conn[e * nn + k]].frow;
+      if (fr < 0)
+      {
+        ghost = true;
+        continue;
+      }
+      int ph = 0;
+      while (ph + 1 < P && phase_row[ph + 1] <= fr) ++ph;
+      pmin = ph < pmin ? ph : pmin, pmax = ph > pmax ? ph : pmax;
+    }
+    keys[e] = (ghost || pmax < 0) ? 0u : (uint32_t)(1 + pmin);
+    idx[e] = (int32_t)e;
+    if (pmax - pmin > 1) atomicAdd(n_spread, 1ull);
+  }
+  __global__ void k_segment_bounds(int n_seg, int64_t n, const uint32_t* sorted_keys, int64_t* seg_begin)
+  {
+    const int s = threadIdx.x;
+    if (s > n_seg) return;
+    int64_t lo = 0, hi = n;
+    while (lo < hi)
+    {
+      const int64_t mid = (lo + hi) >> 1;
+      if (sorted_keys[mid] < (uint32_t)s)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    seg_begin[s] = lo;
+  }
+  // out[e] = in[perm[e]] for rows of `width` items
+  template <class T>
+  __global__ void k_permute_rows(int64_t n, int width, const int32_t* perm, const T* in, T* out)
+  {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * width) return;
+    const int64_t e = t / width;
+    out[t] = in[(int64_t)perm[e] * width + (t - e * width)];
+  }
+
   __global__ void k_gather_double(int64_t n, const double* src, const int32_t* idx, double* dst)
   {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1092,7 +1170,8 @@ struct NcclApi
 struct b200s_ctx
 {
   int device = 0, rank = 0, nranks = 1, n_sm = 148;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // stream every call of this context enqueues on (an attached block: the primary's)
+  cudaStream_t own_stream = nullptr;  // the stream created (and destroyed) with this context
   std::string err;
   // mesh
   int celltype = -1, nn = 0, pos_stride = 0;
@@ -1107,7 +1186,8 @@ struct b200s_ctx
   double* d_eas_hist = nullptr; // EAS: n_col_eles * hex8eas::hist_size(neas) doubles, device element order
   double* d_eas_t0 = nullptr;   // EAS: T0invT[36] + detJ0 per element (stride hex8eas::T0_STRIDE)
   double* d_hist_old = nullptr; // old_history_data_ of the block (struct_calc_update_istep / _reset_istep)
-  double eas_old_step_length = 1.0;  // EASHistoryData::old_step_length
+  double eas_old_step_length = 1.0;  // EASHistoryData::old_step_length (the same value in every element)
+  double eas_old_step_length_snap = 1.0;  // ... of old_history_data_ (struct_calc_update_istep)
   double* d_du_row = nullptr;   // "residual displacement" state (struct_calc_recover)
   double* d_du_col = nullptr;
   // material
@@ -1150,6 +1230,7 @@ struct b200s_ctx
   int64_t n_mat_cols = 0;
   bool node3_ok = false;
   int32_t* d_blkcol = nullptr;  // node-blocked layout: one column id per 3x3 block (nnz / 9)
+  int32_t* d_row_diagcol = nullptr;  // matrix-local column id of every row's diagonal entry
   double *d_xmat = nullptr, *d_la_x = nullptr, *d_la_y = nullptr, *d_toggle = nullptr;
   double *d_cg[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // r z p Ap dinv(3x)
   double *d_cg_s = nullptr, *d_cg_hist = nullptr;
@@ -1172,6 +1253,22 @@ struct b200s_ctx
   bool vals_zeroed[2] = {false, false};
   cudaStream_t zero_stream = nullptr;
   cudaEvent_t ev_zero_done[2] = {}, ev_eval_start = nullptr;
+  // element segments in device element order (chosen at install_graph, see order_elements_for_graph):
+  //   segment 0            elements holding a ghost node: the only ones that read halo-imported displacements
+  //   segments 1..n_phases the others by ROW PHASE = contiguous CSR row range (about equal nnz) of their lowest
+  //                        owned node: once the segments 0..k+1 are evaluated, the rows of phase k are complete
+  //                        and can travel to the host while the later segments are still being evaluated
+  int n_phases = 1;
+  bool segmented = false;              // false: one segment holding everything (option reorder = 0, tiny meshes)
+  std::vector<int64_t> seg_begin;      // n_phases + 2 element offsets
+  std::vector<int64_t> phase_row;      // n_phases + 1 row boundaries
+  std::vector<int64_t> phase_off;      // rowptr[phase_row[k]]
+  cudaStream_t copy_stream = nullptr, halo_stream = nullptr;
+  static constexpr int MAX_PHASES = 64;
+  cudaEvent_t ev_phase[MAX_PHASES] = {}, ev_fork = nullptr, ev_halo_done = nullptr, ev_copy_done = nullptr;
+  // element block attached to another context's system matrix (b200s_attach_block): graph, values, f, the
+  // displacement vectors, stream and communicator are the primary's (not owned here)
+  b200s_ctx* primary = nullptr;
   // halo
   int n_nbr = 0;
   std::vector<int32_t> peer;
@@ -1182,10 +1279,12 @@ struct b200s_ctx
   void* comm = nullptr;
   // errors / timers
   ErrWord* d_err = nullptr;
-  ErrWord* h_err = nullptr;  // pinned
+  ErrWord* h_err = nullptr;       // pinned; D2H target only (read at b200s_synchronize)
+  ErrWord* h_err_init = nullptr;  // pinned constant: the reset word every evaluate copies to d_err
   cudaEvent_t ev[7] = {};
   static constexpr int RING = 64;       // element-kernel event pairs not yet harvested
   cudaEvent_t kev[2 * RING] = {};
+  bool kev_first[RING] = {};  // pair belongs to the first element-kernel launch of an evaluate
   int kev_pending = 0;
   double ktime_sum_ms = 0.0;
   int64_t ktime_count = 0;
@@ -1195,6 +1294,10 @@ struct b200s_ctx
   bool timed_h2d = false, timed_d2h = false;
   // options
   int check_finite = 0, ctas_per_sm = 2, scatter_mode = 0, reorder = 1, double_buffer = 0;
+  int pipeline_phases = 12;  // row phases of the host-destination pipeline (1 = off)
+  int overlap_halo = 1;      // ghost import on a side stream while the elements without ghost nodes are evaluated
+  // what the last evaluate did (bench / tests): launches of the element kernel, overlapped D2H chunks
+  int last_kernel_launches = 0, last_pipeline_chunks = 0, last_halo_overlapped = 0;
 };
 
 namespace
@@ -1287,11 +1390,40 @@ namespace
       cudaEventSynchronize(ctx->kev[2 * i + 1]);
       if (cudaEventElapsedTime(&ms, ctx->kev[2 * i], ctx->kev[2 * i + 1]) == cudaSuccess)
       {
-        ctx->ktime_sum_ms += ms, ctx->ktime_count += 1;
-        ctx->timers[2] = ms;
+        // an evaluate may consist of several launches (segments): their times add up, the count is per evaluate
+        ctx->ktime_sum_ms += ms, ctx->ktime_count += ctx->kev_first[i] ? 1 : 0;
+        ctx->timers[2] = ctx->kev_first[i] ? ms : ctx->timers[2] + ms;
       }
     }
     ctx->kev_pending = 0;
+  }
+
+  // an attached element block borrows these from its primary: forget them before the context frees its own
+  void detach_shared(b200s_ctx* ctx)
+  {
+    ctx->d_rowptr = nullptr, ctx->d_colind = nullptr, ctx->d_node_row = nullptr, ctx->d_node_colbase = nullptr;
+    ctx->d_row_diagcol = nullptr, ctx->d_blkcol = nullptr;
+    ctx->d_vals_buf[0] = ctx->d_vals_buf[1] = nullptr, ctx->d_vals = nullptr;
+    ctx->d_f = nullptr, ctx->d_u_row = nullptr, ctx->d_u_col = nullptr;
+    ctx->comm = nullptr, ctx->n_nbr = 0;
+    ctx->stream = ctx->own_stream;
+    ctx->primary = nullptr;
+    ctx->n_rows = 0, ctx->nnz = 0;
+  }
+
+  // per-element arrays follow the device element order: out[e] = in[perm[e]]
+  template <class T>
+  static int permute_array(b200s_ctx* ctx, T*& arr, int64_t n, int width, const int32_t* d_perm)
+  {
+    if (!arr || n <= 0 || width <= 0) return 0;
+    T* out = nullptr;
+    CK(cudaMalloc((void**)&out, sizeof(T) * (size_t)n * width));
+    k_permute_rows<T><<<nblk(n * width), 256, 0, ctx->stream>>>(n, width, d_perm, arr, out);
+    ctx->launches += 1;
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(arr);
+    arr = out;
+    return 0;
   }
 
   inline bool material_needs_fibers(const b200s_ctx* ctx)
@@ -1305,6 +1437,7 @@ namespace
   // fresh EASHistoryData of every element: all zero (4C_solid_ele_calc_eas_helpers.hpp:98-112)
   int eas_allocate(b200s_ctx* ctx)
   {
+    ctx->eas_old_step_length = ctx->eas_old_step_length_snap = 1.0;
     const int64_t n = ctx->n_col_eles * hex8eas::hist_size(eas_neas(ctx->tech));
     if (to_device(ctx, &ctx->d_eas_hist, (const double*)nullptr, n)) return B200S_ERR_CUDA;
     CK(cudaMemsetAsync(ctx->d_eas_hist, 0, sizeof(double) * (size_t)(n > 0 ? n : 1), ctx->stream));
@@ -1363,7 +1496,8 @@ namespace
     const int64_t cap = (int64_t)ctx->n_sm * HEX8_EAS_CTAS_PER_SM;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, HEX8_EAS_WARPS * 32, bytes, ctx->stream>>>(A, ctx->d_eas_hist, ctx->d_eas_t0);
+    kern<<<(unsigned)grid, HEX8_EAS_WARPS * 32, bytes, ctx->stream>>>(A,
+        ctx->d_eas_hist + A.e_begin * hex8eas::hist_size(NEAS), ctx->d_eas_t0 + A.e_begin * hex8eas::T0_STRIDE);
     ctx->launches += 1;
     return 0;
   }
@@ -1601,17 +1735,30 @@ extern "C"
     ctx->device = device, ctx->rank = rank, ctx->nranks = nranks;
     cudaSetDevice(device);
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        (ctx->stream = ctx->own_stream) == nullptr ||
         cudaMalloc((void**)&ctx->d_err, sizeof(ErrWord)) != cudaSuccess ||
-        cudaMallocHost((void**)&ctx->h_err, sizeof(ErrWord)) != cudaSuccess)
+        cudaMallocHost((void**)&ctx->h_err, 2 * sizeof(ErrWord)) != cudaSuccess)
     {
       delete ctx;
       return B200S_ERR_CUDA;
+    }
+    ctx->h_err_init = ctx->h_err + 1;
+    for (ErrWord* w : {ctx->h_err, ctx->h_err_init})
+    {
+      w->n_neg_jac = 0, w->first_bad = LLONG_MAX;
+      w->min_detJ = 1e300, w->min_detF = 1e300, w->n_nonfinite = 0;
     }
     for (auto& e : ctx->ev) cudaEventCreate(&e);
     for (auto& e : ctx->kev) cudaEventCreate(&e);
     for (auto& e : ctx->ev_la) cudaEventCreate(&e);
     cudaStreamCreateWithFlags(&ctx->zero_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->halo_stream, cudaStreamNonBlocking);
+    for (auto& e : ctx->ev_phase) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_halo_done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_copy_done, cudaEventDisableTiming);
     for (auto& e : ctx->ev_zero_done) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_eval_start, cudaEventDisableTiming);
     *out = ctx;
@@ -1623,6 +1770,11 @@ extern "C"
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream), cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->halo_stream) cudaStreamSynchronize(ctx->halo_stream), cudaStreamDestroy(ctx->halo_stream);
+    for (auto& e : ctx->ev_phase) cudaEventDestroy(e);
+    cudaEventDestroy(ctx->ev_fork), cudaEventDestroy(ctx->ev_halo_done), cudaEventDestroy(ctx->ev_copy_done);
+    if (ctx->primary) detach_shared(ctx);  // the primary owns graph, values, vectors, stream and communicator
     if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
     dfree(ctx->dX), dfree(ctx->dconn), dfree(ctx->d_per_ele), dfree(ctx->d_rowptr);
     dfree(ctx->d_colind), dfree(ctx->d_pos), dfree(ctx->d_node_row), dfree(ctx->d_ele_id);
@@ -1636,6 +1788,7 @@ extern "C"
     dfree(ctx->d_sendbuf), dfree(ctx->d_recvbuf), dfree(ctx->d_err);
     dfree(ctx->d_gp_hist), dfree(ctx->d_eas_hist), dfree(ctx->d_du_row), dfree(ctx->d_du_col);
     dfree(ctx->d_eas_t0), dfree(ctx->d_fibers), dfree(ctx->d_blkcol), dfree(ctx->d_hist_old);
+    dfree(ctx->d_row_diagcol);
     dfree(ctx->d_xi_gp);
     dfree(ctx->d_mat_ext), dfree(ctx->d_mat_hist);
     b200s_clear_neumann(ctx);
@@ -1651,7 +1804,7 @@ extern "C"
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
     for (auto& e : ctx->ev) cudaEventDestroy(e);
     for (auto& e : ctx->kev) cudaEventDestroy(e);
-    cudaStreamDestroy(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
   }
 
@@ -1670,6 +1823,10 @@ extern "C"
       ctx->reorder = value != 0;
     else if (!strcmp(key, "double_buffer"))  // takes effect at the next set_graph / build_graph
       ctx->double_buffer = value != 0;
+    else if (!strcmp(key, "pipeline_phases"))  // takes effect at the next set_graph / build_graph
+      ctx->pipeline_phases = (int)value;
+    else if (!strcmp(key, "overlap_halo"))
+      ctx->overlap_halo = value != 0;
     else
       return fail(ctx, B200S_ERR_INVALID, "unknown option %s", key);
     return B200S_OK;
@@ -1680,6 +1837,7 @@ extern "C"
   {
     if (!ctx || !X || !conn || n_col_nodes <= 0 || n_col_eles < 0) return B200S_ERR_INVALID;
     cudaSetDevice(ctx->device);
+    if (ctx->primary) detach_shared(ctx);  // a new mesh: attach again afterwards
     if (celltype != B200S_HEX8 && celltype != B200S_TET10 && celltype != B200S_HEX27)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "cell type %d is not on the device path", celltype);
     if (n_col_nodes > INT32_MAX / 3) return fail(ctx, B200S_ERR_INVALID, "too many column nodes");
@@ -1712,9 +1870,8 @@ extern "C"
     CK(cudaStreamSynchronize(ctx->stream));  // T is a local
     dfree(ctx->d_ele_is_row), dfree(ctx->d_acc_col), dfree(ctx->d_gp_hist), dfree(ctx->d_eas_hist);
     dfree(ctx->d_du_col), dfree(ctx->d_fibers), dfree(ctx->d_hist_old);
-    if (ctx->prestress == B200S_PRESTRESS_MULF && mulf_allocate(ctx)) return B200S_ERR_CUDA;
-    if (eas_neas(ctx->tech) && eas_allocate(ctx)) return B200S_ERR_CUDA;
-    if (material_history_allocate(ctx)) return B200S_ERR_CUDA;
+    // per-element data of the previous mesh (caller's numbering of THAT mesh): the caller sets it again
+    dfree(ctx->d_per_ele);
     if (celltype == B200S_HEX8)
     {
       Hex8Const h;
@@ -1780,8 +1937,13 @@ extern "C"
       cudaFree(d_box), cudaFree(k0), cudaFree(k1), cudaFree(i0), cudaFree(tmp);
     }
     CK(cudaStreamSynchronize(ctx->stream));
-    // graph-dependent data is stale now
-    dfree(ctx->d_pos);
+    // histories are indexed by the DEVICE element index: build them only now that dconn / d_ele_id are in
+    // their final (locality) order -- also when set_element_properties / set_material came first
+    if (ctx->prestress == B200S_PRESTRESS_MULF && mulf_allocate(ctx)) return B200S_ERR_CUDA;
+    if (eas_neas(ctx->tech) && eas_allocate(ctx)) return B200S_ERR_CUDA;
+    if (material_history_allocate(ctx)) return B200S_ERR_CUDA;
+    // graph-dependent data is stale now (build_graph / set_graph must follow)
+    dfree(ctx->d_pos), dfree(ctx->d_rowptr), dfree(ctx->d_colind);
     ctx->nnz = 0, ctx->n_rows = 0;
     return B200S_OK;
   }
@@ -1843,6 +2005,10 @@ extern "C"
         return fail(ctx, B200S_ERR_INVALID,
             "MAT_Struct_DruckerPrager: 10 parameters {YOUNG NUE ISOHARD TOL C ETA XI ETABAR MAXITER TANG}");
       double q[DP_NPAR];
+      if (params[4] == 0.0 || params[5] == 0.0 || params[7] == 0.0)
+        return fail(ctx, B200S_ERR_INVALID,
+            "MAT_Struct_DruckerPrager: C, ETA and ETABAR must be non-zero (the yield function is normalised by the "
+            "cohesion and the return mapping divides by the friction parameters)");
       if (!make_drucker_prager(params, q))
         return fail(ctx, B200S_ERR_UNSUPPORTED,
             "MAT_Struct_DruckerPrager: the consistent tangent with ETA != ETABAR is not major-symmetric; the device "
@@ -1882,9 +2048,127 @@ extern "C"
     return B200S_OK;
   }
 
+  // Element segments for the graph just installed (b200s_ctx::seg_begin): stable sort of the locality
+  // (Morton) order of set_mesh by {holds a ghost node, row phase of the lowest owned node}.  Needs
+  // ctx->d_node_row and ctx->d_rowptr; re-orders every per-element array that already exists.
+  static int order_elements_for_graph(b200s_ctx* ctx)
+  {
+    const int64_t n = ctx->n_col_eles;
+    ctx->segmented = false, ctx->n_phases = 1;
+    ctx->seg_begin = {0, 0, n};
+    ctx->phase_row = {0, ctx->n_rows};
+    ctx->phase_off = {0, ctx->nnz};
+    if (!ctx->reorder || n <= 1 || !ctx->d_rowptr) return 0;
+    cudaStream_t st = ctx->stream;
+    int P = ctx->pipeline_phases < 1 ? 1 : (ctx->pipeline_phases > b200s_ctx::MAX_PHASES - 2 ? b200s_ctx::MAX_PHASES - 2
+                                                                                              : ctx->pipeline_phases);
+    while (P > 1 && ctx->nnz / P < (1 << 21)) --P;  // at least 16 MB of values per phase
+    int64_t *d_prow = nullptr, *d_poff = nullptr, *d_seg = nullptr;
+    uint32_t *k0 = nullptr, *k1 = nullptr;
+    int32_t *i0 = nullptr, *perm = nullptr;
+    unsigned long long* d_spread = nullptr;
+    void* tmp = nullptr;
+    CK(cudaMalloc((void**)&d_prow, 8 * b200s_ctx::MAX_PHASES));
+    CK(cudaMalloc((void**)&d_poff, 8 * b200s_ctx::MAX_PHASES));
+    CK(cudaMalloc((void**)&d_seg, 8 * (b200s_ctx::MAX_PHASES + 2)));
+    CK(cudaMalloc((void**)&d_spread, 8));
+    CK(cudaMalloc((void**)&k0, 4 * (size_t)n));
+    CK(cudaMalloc((void**)&k1, 4 * (size_t)n));
+    CK(cudaMalloc((void**)&i0, 4 * (size_t)n));
+    CK(cudaMalloc((void**)&perm, 4 * (size_t)n));
+    for (int attempt = 0; attempt < 2; ++attempt)
+    {
+      unsigned long long spread = 0;
+      k_phase_rows<<<1, b200s_ctx::MAX_PHASES, 0, st>>>(P, ctx->n_rows, ctx->d_rowptr, d_prow, d_poff);
+      CK(cudaMemsetAsync(d_spread, 0, 8, st));
+      k_segment_keys<<<nblk(n), 256, 0, st>>>(ctx->nn, n, ctx->dconn, ctx->d_node_row, P, d_prow, k0, i0, d_spread);
+      ctx->launches += 2;
+      CK(cudaMemcpyAsync(&spread, d_spread, 8, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      // rows numbered without spatial locality (e.g. randomly renumbered nodes): row phases would scatter
+      // every phase over the whole mesh and cost the L2 locality of the Morton order -- one phase then
+      if (P > 1 && spread > (unsigned long long)(n / 8))
+      {
+        P = 1;
+        continue;
+      }
+      break;
+    }
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, k0, k1, i0, perm, n, 0, 8, st);
+    CK(cudaMalloc(&tmp, tb));
+    cub::DeviceRadixSort::SortPairs(tmp, tb, k0, k1, i0, perm, n, 0, 8, st);  // stable: Morton order inside a segment
+    k_segment_bounds<<<1, 128, 0, st>>>(P + 1, n, k1, d_seg);
+    ctx->launches += 1;
+    ctx->n_phases = P;
+    ctx->seg_begin.assign((size_t)P + 2, 0);
+    ctx->phase_row.assign((size_t)P + 1, 0);
+    ctx->phase_off.assign((size_t)P + 1, 0);
+    CK(cudaMemcpyAsync(ctx->seg_begin.data(), d_seg, 8 * (size_t)(P + 2), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->phase_row.data(), d_prow, 8 * (size_t)(P + 1), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->phase_off.data(), d_poff, 8 * (size_t)(P + 1), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    ctx->seg_begin[(size_t)P + 1] = n;
+    const int neas = eas_neas(ctx->tech);
+    const int hist_w = neas ? hex8eas::hist_size(neas) : ctx->ngp * MULF_HIST;
+    int rc = permute_array(ctx, ctx->dconn, n, ctx->nn, perm);
+    if (!rc)
+    {
+      if (ctx->d_ele_id)
+        rc = permute_array(ctx, ctx->d_ele_id, n, 1, perm);
+      else
+      {
+        CK(cudaMalloc((void**)&ctx->d_ele_id, 4 * (size_t)n));
+        CK(cudaMemcpyAsync(ctx->d_ele_id, perm, 4 * (size_t)n, cudaMemcpyDeviceToDevice, st));
+      }
+    }
+    if (!rc) rc = permute_array(ctx, ctx->d_per_ele, n, 1, perm);
+    if (!rc) rc = permute_array(ctx, ctx->d_fibers, n, 3, perm);
+    if (!rc) rc = permute_array(ctx, ctx->d_gp_hist, n, ctx->ngp * MULF_HIST, perm);
+    if (!rc) rc = permute_array(ctx, ctx->d_eas_hist, n, neas ? hex8eas::hist_size(neas) : 0, perm);
+    if (!rc) rc = permute_array(ctx, ctx->d_eas_t0, n, hex8eas::T0_STRIDE, perm);
+    if (!rc) rc = permute_array(ctx, ctx->d_hist_old, n, hist_w, perm);
+    if (!rc) rc = permute_array(ctx, ctx->d_mat_hist, n, ctx->ngp * DP_HIST, perm);
+    CK(cudaStreamSynchronize(st));
+    cudaFree(d_prow), cudaFree(d_poff), cudaFree(d_seg), cudaFree(d_spread), cudaFree(k0), cudaFree(k1);
+    cudaFree(i0), cudaFree(perm), cudaFree(tmp);
+    if (rc) return B200S_ERR_CUDA;
+    ctx->segmented = true;
+    return 0;
+  }
+
+  // element -> CSR slot map of this context's element block against the graph in ctx->d_colind / d_node_row
+  static int install_block_map(b200s_ctx* ctx)
+  {
+    if (order_elements_for_graph(ctx)) return B200S_ERR_CUDA;
+    ctx->pos_stride = ctx->celltype == B200S_HEX27 ? hex27::POS_STRIDE : ctx->nn * ctx->nn;
+    if (to_device(ctx, &ctx->d_pos, (const int32_t*)nullptr, ctx->n_col_eles * ctx->pos_stride))
+      return B200S_ERR_CUDA;
+    if (!ctx->d_nm_flag && to_device(ctx, &ctx->d_nm_flag, (const int*)nullptr, 1)) return B200S_ERR_CUDA;
+    CK(cudaMemsetAsync(ctx->d_nm_flag, 0, sizeof(int), ctx->stream));
+    k_build_scatter_map<<<nblk(ctx->n_col_eles * ctx->nn), 256, 0, ctx->stream>>>(ctx->nn,
+        ctx->pos_stride, ctx->n_col_eles, ctx->dconn, ctx->d_colind, ctx->d_node_row, ctx->d_node_colbase, ctx->d_pos,
+        ctx->d_nm_flag);
+    ctx->launches += 1;
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, ctx->d_nm_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    if (flag)
+    {
+      dfree(ctx->d_pos);
+      return fail(ctx, B200S_ERR_UNSUPPORTED,
+          "graph layout outside the fast assembly path (flag 8: an element column is missing / not contiguous in "
+          "an owned row)");
+    }
+    return B200S_OK;
+  }
+
   static int install_graph(b200s_ctx* ctx, int64_t n_rows, const int64_t* d_rowptr,
       const int32_t* d_colind, const int32_t* d_dof_row_lid, const int32_t* d_dof_col_lid)
   {
+    if (ctx->primary) return fail(ctx, B200S_ERR_INVALID, "an attached element block uses its primary's graph");
     const int64_t ncn = ctx->n_col_nodes;
     int64_t nnz = 0;
     CK(cudaMemcpyAsync(&nnz, d_rowptr + n_rows, sizeof(int64_t), cudaMemcpyDefault, ctx->stream));
@@ -1892,9 +2176,6 @@ extern "C"
     ctx->n_rows = n_rows, ctx->nnz = nnz;
     if (to_device(ctx, &ctx->d_node_row, (const NodeRow*)nullptr, ncn)) return B200S_ERR_CUDA;
     if (to_device(ctx, &ctx->d_node_colbase, (const int32_t*)nullptr, ncn)) return B200S_ERR_CUDA;
-    ctx->pos_stride = ctx->celltype == B200S_HEX27 ? hex27::POS_STRIDE : ctx->nn * ctx->nn;
-    if (to_device(ctx, &ctx->d_pos, (const int32_t*)nullptr, ctx->n_col_eles * ctx->pos_stride))
-      return B200S_ERR_CUDA;
     if (ctx->zero_stream) cudaStreamSynchronize(ctx->zero_stream);
     dfree(ctx->d_vals_buf[1]);
     if (to_device(ctx, &ctx->d_vals_buf[0], (const double*)nullptr, nnz)) return B200S_ERR_CUDA;
@@ -1910,10 +2191,7 @@ extern "C"
     CK(cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
     k_node_rows<<<nblk(ncn), 256, 0, ctx->stream>>>(ncn, d_dof_row_lid, d_dof_col_lid, d_rowptr,
         n_rows, ctx->d_node_row, ctx->d_node_colbase, d_flag);
-    k_build_scatter_map<<<nblk(ctx->n_col_eles * ctx->nn), 256, 0, ctx->stream>>>(ctx->nn,
-        ctx->pos_stride, ctx->n_col_eles, ctx->dconn, d_colind, ctx->d_node_row, ctx->d_node_colbase, ctx->d_pos,
-        d_flag);
-    ctx->launches += 2;
+    ctx->launches += 1;
     int flag = 0;
     CK(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1922,43 +2200,55 @@ extern "C"
     // buffers of the optional actions are sized by the graph: drop stale ones
     dfree(ctx->d_mass), dfree(ctx->d_f_inertia), dfree(ctx->d_acc_row), dfree(ctx->d_xmat);
     dfree(ctx->d_la_x), dfree(ctx->d_la_y), dfree(ctx->d_toggle);
+    dfree(ctx->d_fext), dfree(ctx->d_nm_row), dfree(ctx->d_du_row);
     for (auto& v : ctx->d_cg) dfree(v);
-    if (!flag)
-    {
-      // matrix column count and the node-blocked pattern test of the fast multiply
-      std::vector<int32_t> cb(ncn);
-      CK(cudaMemcpy(cb.data(), ctx->d_node_colbase, sizeof(int32_t) * ncn, cudaMemcpyDeviceToHost));
-      int32_t mx = -1;
-      for (int32_t v : cb) mx = v > mx ? v : mx;
-      ctx->n_mat_cols = (int64_t)mx + 3;
-      int* d_f3 = nullptr;
-      int f3 = 0;
-      CK(cudaMalloc((void**)&d_f3, sizeof(int)));
-      CK(cudaMemsetAsync(d_f3, 0, sizeof(int), ctx->stream));
-      k_check_node3<<<nblk(32 * ncn), 256, 0, ctx->stream>>>(ncn, ctx->d_node_row, d_colind, d_f3);
-      ctx->launches += 1;
-      CK(cudaMemcpyAsync(&f3, d_f3, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-      CK(cudaStreamSynchronize(ctx->stream));
-      cudaFree(d_f3);
-      ctx->node3_ok = (f3 == 0);
-      dfree(ctx->d_blkcol);
-      if (ctx->node3_ok)
-      {
-        if (to_device(ctx, &ctx->d_blkcol, (const int32_t*)nullptr, nnz / 9 + 1)) return B200S_ERR_CUDA;
-        k_build_blkcol<<<nblk(32 * ncn), 256, 0, ctx->stream>>>(ncn, ctx->d_node_row, d_colind, ctx->d_blkcol);
-        ctx->launches += 1;
-        CK(cudaStreamSynchronize(ctx->stream));
-      }
-    }
+    dfree(ctx->d_cg_hist);
+    ctx->cg_hist_len = 0;
     if (flag)
     {
       dfree(ctx->d_pos);
       ctx->nnz = 0;
       return fail(ctx, B200S_ERR_UNSUPPORTED,
           "graph layout outside the fast assembly path (flags 0x%x: 1 col dofs of a node not "
-          "contiguous, 2 row dofs not contiguous, 4 unequal row lengths of a node, 8 element column "
-          "missing / not contiguous in an owned row)",
+          "contiguous, 2 row dofs not contiguous, 4 unequal row lengths of a node)",
           flag);
+    }
+    {
+      const int rc = install_block_map(ctx);
+      if (rc)
+      {
+        ctx->nnz = 0;
+        return rc;
+      }
+    }
+    // matrix column count and the node-blocked pattern test of the fast multiply
+    std::vector<int32_t> cb(ncn);
+    CK(cudaMemcpy(cb.data(), ctx->d_node_colbase, sizeof(int32_t) * ncn, cudaMemcpyDeviceToHost));
+    int32_t mx = -1;
+    for (int32_t v : cb) mx = v > mx ? v : mx;
+    ctx->n_mat_cols = (int64_t)mx + 3;
+    if (to_device(ctx, &ctx->d_row_diagcol, (const int32_t*)nullptr, n_rows)) return B200S_ERR_CUDA;
+    CK(cudaMemsetAsync(ctx->d_row_diagcol, 0xff, sizeof(int32_t) * (size_t)n_rows, ctx->stream));
+    k_row_diag_col<<<nblk(3 * ncn), 256, 0, ctx->stream>>>(ncn, ctx->d_node_row, ctx->d_node_colbase,
+        ctx->d_row_diagcol);
+    ctx->launches += 1;
+    int* d_f3 = nullptr;
+    int f3 = 0;
+    CK(cudaMalloc((void**)&d_f3, sizeof(int)));
+    CK(cudaMemsetAsync(d_f3, 0, sizeof(int), ctx->stream));
+    k_check_node3<<<nblk(32 * ncn), 256, 0, ctx->stream>>>(ncn, ctx->d_node_row, d_colind, d_f3);
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(&f3, d_f3, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_f3);
+    ctx->node3_ok = (f3 == 0);
+    dfree(ctx->d_blkcol);
+    if (ctx->node3_ok)
+    {
+      if (to_device(ctx, &ctx->d_blkcol, (const int32_t*)nullptr, nnz / 9 + 1)) return B200S_ERR_CUDA;
+      k_build_blkcol<<<nblk(32 * ncn), 256, 0, ctx->stream>>>(ncn, ctx->d_node_row, d_colind, ctx->d_blkcol);
+      ctx->launches += 1;
+      CK(cudaStreamSynchronize(ctx->stream));
     }
     return B200S_OK;
   }
@@ -1969,6 +2259,7 @@ extern "C"
     if (!ctx || !rowptr || !colind || !dof_row_lid || !dof_col_lid || n_rows <= 0)
       return B200S_ERR_INVALID;
     if (ctx->celltype < 0) return fail(ctx, B200S_ERR_INVALID, "set_mesh must precede set_graph");
+    if (ctx->primary) return fail(ctx, B200S_ERR_INVALID, "an attached element block uses its primary's graph");
     cudaSetDevice(ctx->device);
     // stage the caller's (host or device) arrays on the device; they are only needed to build the map
     // the graph stays on the device: apply_dirichlet / multiply need it after the map is built
@@ -1990,6 +2281,7 @@ extern "C"
   {
     if (!ctx || !node_row_lid || !node_col_lid || n_row_nodes <= 0) return B200S_ERR_INVALID;
     if (ctx->celltype < 0) return fail(ctx, B200S_ERR_INVALID, "set_mesh must precede build_graph");
+    if (ctx->primary) return fail(ctx, B200S_ERR_INVALID, "an attached element block uses its primary's graph");
     cudaSetDevice(ctx->device);
     cudaStream_t st = ctx->stream;
     const int nn = ctx->nn;
@@ -2062,6 +2354,52 @@ extern "C"
       CK(cudaMemcpy(rowptr_out, ctx->d_rowptr, sizeof(int64_t) * (ctx->n_rows + 1), cudaMemcpyDefault));
     if (colind_out)
       CK(cudaMemcpy(colind_out, ctx->d_colind, sizeof(int32_t) * ctx->nnz, cudaMemcpyDefault));
+    return B200S_OK;
+  }
+
+  // Element block `ctx` (its own set_mesh / set_element_properties / set_material; the SAME column nodes as the
+  // primary) assembles into the primary's system matrix.
+  int b200s_attach_block(b200s_ctx* ctx, b200s_ctx* primary)
+  {
+    if (!ctx || !primary || ctx == primary) return B200S_ERR_INVALID;
+    if (primary->primary) return fail(ctx, B200S_ERR_INVALID, "attach to the primary context, not to another attached block");
+    if (ctx->celltype < 0) return fail(ctx, B200S_ERR_INVALID, "set_mesh must precede attach_block");
+    if (!primary->d_rowptr || !primary->d_node_row || primary->nnz <= 0)
+      return fail(ctx, B200S_ERR_INVALID, "the primary context has no graph yet (set_graph / build_graph first)");
+    if (ctx->device != primary->device || ctx->n_col_nodes != primary->n_col_nodes)
+      return fail(ctx, B200S_ERR_INVALID,
+          "an attached block lives on the primary's device and uses the primary's column nodes (%lld here, %lld there)",
+          (long long)ctx->n_col_nodes, (long long)primary->n_col_nodes);
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->primary)
+      detach_shared(ctx);
+    else
+    {
+      // drop an own graph, if any
+      if (ctx->zero_stream) cudaStreamSynchronize(ctx->zero_stream);
+      dfree(ctx->d_rowptr), dfree(ctx->d_colind), dfree(ctx->d_node_row), dfree(ctx->d_node_colbase);
+      dfree(ctx->d_row_diagcol), dfree(ctx->d_blkcol), dfree(ctx->d_vals_buf[0]), dfree(ctx->d_vals_buf[1]);
+      dfree(ctx->d_f), dfree(ctx->d_u_row), dfree(ctx->d_u_col);
+      if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
+      ctx->comm = nullptr, ctx->n_nbr = 0;
+    }
+    ctx->primary = primary;
+    ctx->stream = primary->stream;
+    ctx->d_rowptr = primary->d_rowptr, ctx->d_colind = primary->d_colind;
+    ctx->d_node_row = primary->d_node_row, ctx->d_node_colbase = primary->d_node_colbase;
+    ctx->d_row_diagcol = primary->d_row_diagcol, ctx->d_blkcol = primary->d_blkcol;
+    ctx->d_vals = primary->d_vals, ctx->d_f = primary->d_f;
+    ctx->d_u_row = primary->d_u_row, ctx->d_u_col = primary->d_u_col;
+    ctx->n_rows = primary->n_rows, ctx->nnz = primary->nnz;
+    ctx->n_mat_cols = primary->n_mat_cols, ctx->node3_ok = primary->node3_ok;
+    ctx->rank = primary->rank, ctx->nranks = primary->nranks;
+    const int rc = install_block_map(ctx);
+    if (rc)
+    {
+      detach_shared(ctx);
+      return rc;
+    }
     return B200S_OK;
   }
 
@@ -2139,6 +2477,7 @@ extern "C"
            a == B200S_ACTION_INTERNALINERTIAFORCE;
   }
   static int import_row_to_col(b200s_ctx* ctx, const double* d_src_row, double* d_dst, bool to_matcol);
+  static double* matrix_values(b200s_ctx* ctx, int which);
 
   // mass matrix (second system matrix, same graph) and inertia force M_e * acc of the mass actions
   // (4C_solid_ele_evaluate.cpp:116-159).  The "acceleration" state is optional: without it only the
@@ -2197,38 +2536,41 @@ extern "C"
   // 4C_fem_discretization.cpp:612-665; the same import Epetra_CrsMatrix::Multiply does for x).
   // to_matcol == false: dst is indexed by column-node lid (3 per node);
   // to_matcol == true : dst is indexed by the matrix-local column id (node_colbase + d).
-  static int import_row_to_col(b200s_ctx* ctx, const double* d_src_row, double* d_dst, bool to_matcol)
+  // Two halves writing disjoint entries of dst: the ghost part (pack, ncclSend/Recv group, unpack) and the owned
+  // part; evaluate runs the first on a side stream while the elements without ghost nodes are evaluated.
+  static int import_ghosts(b200s_ctx* ctx, const double* d_src_row, double* d_dst, bool to_matcol, cudaStream_t st)
   {
-    cudaStream_t st = ctx->stream;
-    if (ctx->n_nbr > 0)
+    if (ctx->n_nbr <= 0) return B200S_OK;
+    if (!ctx->comm) return fail(ctx, B200S_ERR_COMM, "halo set but no communicator");
+    const int64_t ns = ctx->send_off[ctx->n_nbr], nr = ctx->recv_off[ctx->n_nbr];
+    if (ns) k_pack_halo<<<nblk(3 * ns), 256, 0, st>>>(ns, ctx->d_send_lid, d_src_row, ctx->d_sendbuf);
+    ctx->nccl.GroupStart();
+    for (int n = 0; n < ctx->n_nbr; ++n)
     {
-      if (!ctx->comm) return fail(ctx, B200S_ERR_COMM, "halo set but no communicator");
-      const int64_t ns = ctx->send_off[ctx->n_nbr], nr = ctx->recv_off[ctx->n_nbr];
-      if (ns) k_pack_halo<<<nblk(3 * ns), 256, 0, st>>>(ns, ctx->d_send_lid, d_src_row, ctx->d_sendbuf);
-      ctx->nccl.GroupStart();
-      for (int n = 0; n < ctx->n_nbr; ++n)
-      {
-        const int64_t s0 = ctx->send_off[n], s1 = ctx->send_off[n + 1];
-        const int64_t r0 = ctx->recv_off[n], r1 = ctx->recv_off[n + 1];
-        if (s1 > s0)
-          ctx->nccl.Send(ctx->d_sendbuf + 3 * s0, (size_t)(3 * (s1 - s0)), /*ncclDouble*/ 8,
-              ctx->peer[n], ctx->comm, st);
-        if (r1 > r0)
-          ctx->nccl.Recv(ctx->d_recvbuf + 3 * r0, (size_t)(3 * (r1 - r0)), 8, ctx->peer[n],
-              ctx->comm, st);
-      }
-      const int rc = ctx->nccl.GroupEnd();
-      if (rc) return fail(ctx, B200S_ERR_COMM, "halo exchange: %s", ctx->nccl.GetErrorString(rc));
-      if (nr)
-      {
-        if (to_matcol)
-          k_unpack_halo_matcol<<<nblk(3 * nr), 256, 0, st>>>(
-              nr, ctx->d_recv_lid, ctx->d_node_colbase, ctx->d_recvbuf, d_dst);
-        else
-          k_unpack_halo<<<nblk(3 * nr), 256, 0, st>>>(nr, ctx->d_recv_lid, ctx->d_recvbuf, d_dst);
-      }
-      ctx->launches += (ns > 0) + (nr > 0);
+      const int64_t s0 = ctx->send_off[n], s1 = ctx->send_off[n + 1];
+      const int64_t r0 = ctx->recv_off[n], r1 = ctx->recv_off[n + 1];
+      if (s1 > s0)
+        ctx->nccl.Send(ctx->d_sendbuf + 3 * s0, (size_t)(3 * (s1 - s0)), /*ncclDouble*/ 8,
+            ctx->peer[n], ctx->comm, st);
+      if (r1 > r0)
+        ctx->nccl.Recv(ctx->d_recvbuf + 3 * r0, (size_t)(3 * (r1 - r0)), 8, ctx->peer[n],
+            ctx->comm, st);
     }
+    const int rc = ctx->nccl.GroupEnd();
+    if (rc) return fail(ctx, B200S_ERR_COMM, "halo exchange: %s", ctx->nccl.GetErrorString(rc));
+    if (nr)
+    {
+      if (to_matcol)
+        k_unpack_halo_matcol<<<nblk(3 * nr), 256, 0, st>>>(
+            nr, ctx->d_recv_lid, ctx->d_node_colbase, ctx->d_recvbuf, d_dst);
+      else
+        k_unpack_halo<<<nblk(3 * nr), 256, 0, st>>>(nr, ctx->d_recv_lid, ctx->d_recvbuf, d_dst);
+    }
+    ctx->launches += (ns > 0) + (nr > 0);
+    return B200S_OK;
+  }
+  static int import_owned(b200s_ctx* ctx, const double* d_src_row, double* d_dst, bool to_matcol, cudaStream_t st)
+  {
     if (to_matcol)
       k_row_to_matcol<<<nblk(3 * ctx->n_col_nodes), 256, 0, st>>>(
           ctx->n_col_nodes, ctx->d_node_row, ctx->d_node_colbase, d_src_row, d_dst);
@@ -2238,14 +2580,68 @@ extern "C"
     ctx->launches += 1;
     return B200S_OK;
   }
+  static int import_row_to_col(b200s_ctx* ctx, const double* d_src_row, double* d_dst, bool to_matcol)
+  {
+    const int rc = import_ghosts(ctx, d_src_row, d_dst, to_matcol, ctx->stream);
+    return rc ? rc : import_owned(ctx, d_src_row, d_dst, to_matcol, ctx->stream);
+  }
 
   // ---- evaluate -----------------------------------------------------------------------------------
-  int b200s_evaluate_async(b200s_ctx* ctx, int action)
+  // arguments of one element-kernel launch over the device elements [e_begin, e_begin + count)
+  static EvalArgs make_eval_args(b200s_ctx* ctx, int64_t e_begin, int64_t count)
   {
-    if (!ctx) return B200S_ERR_INVALID;
+    EvalArgs A;
+    A.X = ctx->dX, A.u = ctx->d_u_col, A.node_row = ctx->d_node_row;
+    A.conn = ctx->dconn + e_begin * ctx->nn;
+    A.pos = ctx->d_pos + e_begin * ctx->pos_stride;
+    A.per_ele_param = ctx->d_per_ele ? ctx->d_per_ele + e_begin : nullptr;
+    A.ele_id = ctx->d_ele_id ? ctx->d_ele_id + e_begin : nullptr;
+    A.fibers = ctx->d_fibers ? ctx->d_fibers + 3 * e_begin : nullptr;
+    A.gp_hist = ctx->d_gp_hist ? ctx->d_gp_hist + e_begin * ctx->ngp * MULF_HIST : nullptr;
+    A.mat_hist = ctx->d_mat_hist ? ctx->d_mat_hist + e_begin * ctx->ngp * DP_HIST : nullptr;
+    A.linear = ctx->kinem == B200S_KINEM_LINEAR;
+    A.vals = ctx->d_vals, A.f = ctx->d_f, A.err = ctx->d_err, A.mp = ctx->mp;
+    A.n_ele = count;
+    A.scatter_mode = ctx->scatter_mode;
+    A.e_begin = e_begin;
+    return A;
+  }
+
+  // one element-kernel launch over a range of device elements, bracketed by an event pair of the timing ring
+  static int launch_segment(b200s_ctx* ctx, bool stiff, int64_t e_begin, int64_t e_end, bool& first)
+  {
+    if (e_end <= e_begin) return B200S_OK;
+    cudaStream_t st = ctx->stream;
+    if (ctx->kev_pending == b200s_ctx::RING) harvest_kernel_times(ctx);
+    const EvalArgs A = make_eval_args(ctx, e_begin, e_end - e_begin);
+    CK(cudaEventRecord(ctx->kev[2 * ctx->kev_pending], st));
+    const int rc = stiff ? launch_eval<true>(ctx, A) : launch_eval<false>(ctx, A);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->kev[2 * ctx->kev_pending + 1], st));
+    ctx->kev_first[ctx->kev_pending] = first;
+    first = false;
+    ctx->kev_pending += 1;
+    ctx->last_kernel_launches += 1;
+    return B200S_OK;
+  }
+
+  static bool is_host_pointer(const void* p)
+  {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
+    {
+      cudaGetLastError();
+      return true;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeUnregistered;
+  }
+
+  // K_dst / f_dst: optional destinations of the result (b200s_evaluate); a HOST K_dst is filled phase by phase
+  // while the later element segments are still being evaluated.
+  static int evaluate_impl(b200s_ctx* ctx, int action, double* K_dst, double* f_dst)
+  {
     if (!ctx->d_pos || ctx->matkind < 0)
       return fail(ctx, B200S_ERR_INVALID, "set_mesh, set_material and set_graph must precede evaluate");
-    cudaSetDevice(ctx->device);
     cudaStream_t st = ctx->stream;
     if (action < B200S_ACTION_INTERNALFORCE || action > B200S_ACTION_INTERNALINERTIAFORCE)
       return fail(ctx, B200S_ERR_INVALID, "unknown action %d", action);
@@ -2253,48 +2649,6 @@ extern "C"
     const bool mass = action_has_mass(action);
     if (mass && !(ctx->density > 0.0))
       return fail(ctx, B200S_ERR_INVALID, "mass actions need b200s_set_density (density > 0)");
-    ctx->last_action = action;
-    CK(cudaEventRecord(ctx->ev[1], st));
-    // set_state("displacement"): ghost import, then owned part
-    {
-      const int rc = import_row_to_col(ctx, ctx->d_u_row, ctx->d_u_col, false);
-      if (rc) return rc;
-    }
-    CK(cudaEventRecord(ctx->ev[2], st));
-    // stiff.zero(); fint.put_scalar(0)
-    if (stiff)
-    {
-      const size_t vbytes = sizeof(double) * (size_t)ctx->nnz;
-      if (ctx->d_vals_buf[1])
-      {
-        // this evaluate fills the buffer that was cleared during the previous one (or clears it now,
-        // the first time); meanwhile the side stream clears the buffer holding the previous result,
-        // once everything enqueued so far (e.g. its copy to the host) has finished
-        const int use = ctx->vals_cur ^ 1, idle = ctx->vals_cur;
-        CK(cudaEventRecord(ctx->ev_eval_start, st));
-        if (ctx->vals_zeroed[use])
-          CK(cudaStreamWaitEvent(st, ctx->ev_zero_done[use], 0));
-        else
-          CK(cudaMemsetAsync(ctx->d_vals_buf[use], 0, vbytes, st));
-        CK(cudaStreamWaitEvent(ctx->zero_stream, ctx->ev_eval_start, 0));
-        CK(cudaMemsetAsync(ctx->d_vals_buf[idle], 0, vbytes, ctx->zero_stream));
-        CK(cudaEventRecord(ctx->ev_zero_done[idle], ctx->zero_stream));
-        ctx->vals_zeroed[idle] = true, ctx->vals_zeroed[use] = false;
-        ctx->vals_cur = use, ctx->d_vals = ctx->d_vals_buf[use];
-      }
-      else
-        CK(cudaMemsetAsync(ctx->d_vals, 0, vbytes, st));
-    }
-    CK(cudaMemsetAsync(ctx->d_f, 0, sizeof(double) * (size_t)ctx->n_rows, st));
-    ctx->h_err->n_neg_jac = 0, ctx->h_err->first_bad = LLONG_MAX;
-    ctx->h_err->min_detJ = 1e300, ctx->h_err->min_detF = 1e300, ctx->h_err->n_nonfinite = 0;
-    CK(cudaMemcpyAsync(ctx->d_err, ctx->h_err, sizeof(ErrWord), cudaMemcpyHostToDevice, st));
-    CK(cudaEventRecord(ctx->ev[3], st));
-    EvalArgs A;
-    A.X = ctx->dX, A.u = ctx->d_u_col, A.conn = ctx->dconn, A.pos = ctx->d_pos;
-    A.node_row = ctx->d_node_row, A.per_ele_param = ctx->d_per_ele, A.ele_id = ctx->d_ele_id;
-    A.gp_hist = ctx->d_gp_hist, A.fibers = ctx->d_fibers, A.mat_hist = ctx->d_mat_hist;
-    A.linear = ctx->kinem == B200S_KINEM_LINEAR;
     if (material_needs_fibers(ctx) && !ctx->d_fibers)
       return fail(ctx, B200S_ERR_INVALID, "the material has a fibre summand: b200s_set_element_fibers first");
     if (ctx->prestress == B200S_PRESTRESS_MULF && !ctx->d_gp_hist)
@@ -2306,19 +2660,129 @@ extern "C"
             "MAT_Struct_DruckerPrager is a small-strain material: KINEM linear without element technology / prestress");
       if (!ctx->d_mat_hist) return fail(ctx, B200S_ERR_INVALID, "material history missing (set_mesh first)");
     }
-    A.vals = ctx->d_vals, A.f = ctx->d_f, A.err = ctx->d_err, A.mp = ctx->mp;
-    A.n_ele = ctx->n_col_eles;
-    A.scatter_mode = ctx->scatter_mode;
-    if (ctx->kev_pending == b200s_ctx::RING) harvest_kernel_times(ctx);
-    CK(cudaEventRecord(ctx->kev[2 * ctx->kev_pending], st));
-    const int rc = stiff ? launch_eval<true>(ctx, A) : launch_eval<false>(ctx, A);
-    if (rc) return rc;
-    CK(cudaEventRecord(ctx->kev[2 * ctx->kev_pending + 1], st));
-    ctx->kev_pending += 1;
+    // an attached block adds into its primary's matrix: the primary's evaluate of this iteration has imported
+    // the state and zeroed K / f
+    const bool accumulate = ctx->primary != nullptr;
+    if (accumulate)
+    {
+      b200s_ctx* pr = ctx->primary;
+      ctx->d_vals = pr->d_vals;  // follows the primary's buffer switch (option double_buffer)
+      if (mass) return fail(ctx, B200S_ERR_UNSUPPORTED, "mass actions of an attached block: evaluate them on the primary");
+    }
+    ctx->last_action = action;
+    ctx->last_kernel_launches = 0, ctx->last_pipeline_chunks = 0, ctx->last_halo_overlapped = 0;
+    const int64_t n_ele = ctx->n_col_eles;
+    const int64_t n_ghost_eles = ctx->segmented ? ctx->seg_begin[1] : 0;
+    // pipeline: host destination for K, at least two non-empty phases
+    const bool pipeline = stiff && K_dst && ctx->segmented && ctx->n_phases > 1 && ctx->pipeline_phases > 1 &&
+                          !mass && !ctx->check_finite && is_host_pointer(K_dst);
+    // overlap of the ghost import with the elements that do not read it
+    const bool overlap = !accumulate && !pipeline && ctx->n_nbr > 0 && ctx->segmented && ctx->overlap_halo &&
+                         n_ghost_eles < n_ele;
+    nvtxRangePushA("b200s_evaluate");
+    CK(cudaEventRecord(ctx->ev[1], st));
+    if (!accumulate)
+    {
+      // set_state("displacement"): ghost import, then owned part
+      nvtxRangePushA("halo");
+      int rc;
+      if (overlap)
+      {
+        CK(cudaEventRecord(ctx->ev_fork, st));
+        CK(cudaStreamWaitEvent(ctx->halo_stream, ctx->ev_fork, 0));
+        rc = import_ghosts(ctx, ctx->d_u_row, ctx->d_u_col, false, ctx->halo_stream);
+        CK(cudaEventRecord(ctx->ev_halo_done, ctx->halo_stream));
+        if (!rc) rc = import_owned(ctx, ctx->d_u_row, ctx->d_u_col, false, st);
+        ctx->last_halo_overlapped = 1;
+      }
+      else
+        rc = import_row_to_col(ctx, ctx->d_u_row, ctx->d_u_col, false);
+      nvtxRangePop();
+      if (rc)
+      {
+        nvtxRangePop();
+        return rc;
+      }
+    }
+    CK(cudaEventRecord(ctx->ev[2], st));
+    // stiff.zero(); fint.put_scalar(0)
+    if (!accumulate)
+    {
+      nvtxRangePushA("zero");
+      if (stiff)
+      {
+        const size_t vbytes = sizeof(double) * (size_t)ctx->nnz;
+        if (ctx->d_vals_buf[1])
+        {
+          // this evaluate fills the buffer that was cleared during the previous one (or clears it now,
+          // the first time); meanwhile the side stream clears the buffer holding the previous result,
+          // once everything enqueued so far (e.g. its copy to the host) has finished
+          const int use = ctx->vals_cur ^ 1, idle = ctx->vals_cur;
+          CK(cudaEventRecord(ctx->ev_eval_start, st));
+          if (ctx->vals_zeroed[use])
+            CK(cudaStreamWaitEvent(st, ctx->ev_zero_done[use], 0));
+          else
+            CK(cudaMemsetAsync(ctx->d_vals_buf[use], 0, vbytes, st));
+          CK(cudaStreamWaitEvent(ctx->zero_stream, ctx->ev_eval_start, 0));
+          CK(cudaMemsetAsync(ctx->d_vals_buf[idle], 0, vbytes, ctx->zero_stream));
+          CK(cudaEventRecord(ctx->ev_zero_done[idle], ctx->zero_stream));
+          ctx->vals_zeroed[idle] = true, ctx->vals_zeroed[use] = false;
+          ctx->vals_cur = use, ctx->d_vals = ctx->d_vals_buf[use];
+        }
+        else
+          CK(cudaMemsetAsync(ctx->d_vals, 0, vbytes, st));
+      }
+      CK(cudaMemsetAsync(ctx->d_f, 0, sizeof(double) * (size_t)ctx->n_rows, st));
+      nvtxRangePop();
+    }
+    // reset word from a constant pinned source: h_err itself may still be the target of the previous
+    // (asynchronous) evaluate's read-back
+    CK(cudaMemcpyAsync(ctx->d_err, ctx->h_err_init, sizeof(ErrWord), cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->ev[3], st));
+    nvtxRangePushA("element kernels");
+    bool first = true;
+    int rc = B200S_OK;
+    if (overlap)
+    {
+      // elements without ghost nodes while the halo travels, the others once it has arrived
+      rc = launch_segment(ctx, stiff, n_ghost_eles, n_ele, first);
+      CK(cudaStreamWaitEvent(st, ctx->ev_halo_done, 0));
+      if (!rc) rc = launch_segment(ctx, stiff, 0, n_ghost_eles, first);
+    }
+    else if (pipeline)
+    {
+      // segment 0 (ghost-node elements) first, then phase by phase; the rows of phase k are complete after
+      // segment k + 1 and leave on the copy stream while the next segments are evaluated
+      rc = launch_segment(ctx, stiff, 0, n_ghost_eles, first);
+      for (int k = 0; k < ctx->n_phases && !rc; ++k)
+      {
+        rc = launch_segment(ctx, stiff, ctx->seg_begin[(size_t)k + 1], ctx->seg_begin[(size_t)k + 2], first);
+        const int64_t o0 = ctx->phase_off[(size_t)k], o1 = ctx->phase_off[(size_t)k + 1];
+        if (rc || o1 <= o0) continue;
+        CK(cudaEventRecord(ctx->ev_phase[k], st));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_phase[k], 0));
+        CK(cudaMemcpyAsync(K_dst + o0, ctx->d_vals + o0, sizeof(double) * (size_t)(o1 - o0), cudaMemcpyDeviceToHost,
+            ctx->copy_stream));
+        ctx->last_pipeline_chunks += 1;
+      }
+      CK(cudaEventRecord(ctx->ev_copy_done, ctx->copy_stream));
+    }
+    else
+      rc = launch_segment(ctx, stiff, 0, n_ele, first);
+    nvtxRangePop();
+    if (rc)
+    {
+      nvtxRangePop();
+      return rc;
+    }
     if (mass)
     {
       const int mrc = launch_mass(ctx, action);
-      if (mrc) return mrc;
+      if (mrc)
+      {
+        nvtxRangePop();
+        return mrc;
+      }
     }
     if (ctx->check_finite)
     {
@@ -2329,8 +2793,28 @@ extern "C"
     }
     CK(cudaEventRecord(ctx->ev[4], st));
     CK(cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(ErrWord), cudaMemcpyDeviceToHost, st));
+    // results to the caller's buffers
+    if (K_dst && stiff && K_dst != ctx->d_vals)
+    {
+      nvtxRangePushA("d2h");
+      if (pipeline)
+        CK(cudaStreamWaitEvent(st, ctx->ev_copy_done, 0));  // the context stream ends after the last chunk
+      else
+        CK(cudaMemcpyAsync(K_dst, ctx->d_vals, sizeof(double) * (size_t)ctx->nnz, cudaMemcpyDefault, st));
+      nvtxRangePop();
+    }
+    if (f_dst && f_dst != ctx->d_f)
+      CK(cudaMemcpyAsync(f_dst, ctx->d_f, sizeof(double) * (size_t)ctx->n_rows, cudaMemcpyDefault, st));
     CK(cudaGetLastError());
+    nvtxRangePop();
     return B200S_OK;
+  }
+
+  int b200s_evaluate_async(b200s_ctx* ctx, int action)
+  {
+    if (!ctx) return B200S_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    return evaluate_impl(ctx, action, nullptr, nullptr);
   }
 
   int b200s_synchronize(b200s_ctx* ctx, b200s_error_info* err)
@@ -2381,13 +2865,13 @@ extern "C"
     ctx->timed_h2d = u_row != nullptr, ctx->timed_d2h = (K_values || f_row);
     CK(cudaEventRecord(ctx->ev[0], st));
     if (u_row && u_row != ctx->d_u_row)
+    {
+      nvtxRangePushA("h2d");
       CK(cudaMemcpyAsync(ctx->d_u_row, u_row, sizeof(double) * (size_t)ctx->n_rows, cudaMemcpyDefault, st));
-    int rc = b200s_evaluate_async(ctx, action);
+      nvtxRangePop();
+    }
+    const int rc = evaluate_impl(ctx, action, K_values, f_row);
     if (rc) return rc;
-    if (K_values && action_has_stiffness(action) && K_values != ctx->d_vals)
-      CK(cudaMemcpyAsync(K_values, ctx->d_vals, sizeof(double) * (size_t)ctx->nnz, cudaMemcpyDefault, st));
-    if (f_row && f_row != ctx->d_f)
-      CK(cudaMemcpyAsync(f_row, ctx->d_f, sizeof(double) * (size_t)ctx->n_rows, cudaMemcpyDefault, st));
     CK(cudaEventRecord(ctx->ev[5], st));
     return b200s_synchronize(ctx, err);
   }
@@ -2532,6 +3016,46 @@ extern "C"
     return B200S_OK;
   }
   double* b200s_device_f_inertia(b200s_ctx* ctx) { return ctx ? ctx->d_f_inertia : nullptr; }
+
+  // rows [row0,row1) of the resident CSR: what ExtractMyRowView would show for those rows
+  int b200s_get_value_rows(b200s_ctx* ctx, int which, int64_t row0, int64_t row1, double* values_out,
+      int32_t* colind_out, int64_t* rowptr_out)
+  {
+    if (!ctx || row0 < 0 || row1 < row0) return B200S_ERR_INVALID;
+    if (!ctx->d_rowptr || row1 > ctx->n_rows) return fail(ctx, B200S_ERR_INVALID, "rows [%lld,%lld) outside the graph",
+        (long long)row0, (long long)row1);
+    cudaSetDevice(ctx->device);
+    const int64_t nr = row1 - row0;
+    std::vector<int64_t> rp((size_t)nr + 1);
+    CK(cudaMemcpyAsync(rp.data(), ctx->d_rowptr + row0, sizeof(int64_t) * (size_t)(nr + 1), cudaMemcpyDeviceToHost,
+        ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int64_t lo = rp[0], n = rp[(size_t)nr] - lo;
+    if (rowptr_out)
+    {
+      for (auto& v : rp) v -= lo;  // offsets relative to the first returned entry
+      CK(cudaMemcpyAsync(rowptr_out, rp.data(), sizeof(int64_t) * (size_t)(nr + 1), cudaMemcpyDefault, ctx->stream));
+    }
+    if (values_out && n > 0)
+    {
+      const double* src = matrix_values(ctx, which);
+      if (!src) return fail(ctx, B200S_ERR_INVALID, "matrix %d has not been assembled", which);
+      CK(cudaMemcpyAsync(values_out, src + lo, sizeof(double) * (size_t)n, cudaMemcpyDefault, ctx->stream));
+    }
+    if (colind_out && n > 0)
+      CK(cudaMemcpyAsync(colind_out, ctx->d_colind + lo, sizeof(int32_t) * (size_t)n, cudaMemcpyDefault, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B200S_OK;
+  }
+  int b200s_get_f_rows(b200s_ctx* ctx, int64_t row0, int64_t row1, double* f_out)
+  {
+    if (!ctx || !f_out || row0 < 0 || row1 < row0) return B200S_ERR_INVALID;
+    if (!ctx->d_f || row1 > ctx->n_rows) return fail(ctx, B200S_ERR_INVALID, "rows outside the residual vector");
+    cudaSetDevice(ctx->device);
+    CK(cudaMemcpyAsync(f_out, ctx->d_f + row0, sizeof(double) * (size_t)(row1 - row0), cudaMemcpyDefault, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B200S_OK;
+  }
 
   int b200s_get_mass(b200s_ctx* ctx, double* M_values, double* f_inertia)
   {
@@ -2743,11 +3267,27 @@ extern "C"
     cudaSetDevice(ctx->device);
     if (!ctx->d_hist_old)
     {
-      if (restore) return fail(ctx, B200S_ERR_INVALID, "reset_step before the first update_step");
+      if (restore)
+      {
+        // no converged step yet: old_history_data_ is still the default-constructed history
+        // (4C_solid_ele_calc.cpp:570-575), i.e. zero EAS parameters / the reference-configuration MULF history
+        if (eas_neas(ctx->tech))
+        {
+          CK(cudaMemsetAsync(cur, 0, sizeof(double) * (size_t)(n > 0 ? n : 1), ctx->stream));
+          ctx->eas_old_step_length = 1.0;
+          CK(cudaStreamSynchronize(ctx->stream));
+          return B200S_OK;
+        }
+        return mulf_allocate(ctx) ? B200S_ERR_CUDA : B200S_OK;
+      }
       if (to_device(ctx, &ctx->d_hist_old, (const double*)nullptr, n)) return B200S_ERR_CUDA;
     }
     CK(cudaMemcpyAsync(restore ? cur : ctx->d_hist_old, restore ? ctx->d_hist_old : cur, sizeof(double) * (size_t)n,
         cudaMemcpyDeviceToDevice, ctx->stream));
+    if (restore)
+      ctx->eas_old_step_length = ctx->eas_old_step_length_snap;
+    else
+      ctx->eas_old_step_length_snap = ctx->eas_old_step_length;
     CK(cudaStreamSynchronize(ctx->stream));
     return B200S_OK;
   }
@@ -2821,6 +3361,13 @@ extern "C"
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = B200S_ERR_CUDA;
     cudaFree(tmp);
     return rc ? fail(ctx, rc, "history copy failed") : B200S_OK;
+  }
+  double b200s_eas_old_step_length(const b200s_ctx* ctx) { return ctx ? ctx->eas_old_step_length : 1.0; }
+  int b200s_set_eas_old_step_length(b200s_ctx* ctx, double step_length)
+  {
+    if (!ctx) return B200S_ERR_INVALID;
+    ctx->eas_old_step_length = step_length;
+    return B200S_OK;
   }
   int b200s_get_gp_history(b200s_ctx* ctx, double* hist_out) { return history_copy(ctx, hist_out, 1); }
   int b200s_set_gp_history(b200s_ctx* ctx, const double* hist_in)
@@ -3092,11 +3639,18 @@ extern "C"
       return fail(ctx, B200S_ERR_INVALID, "apply_dirichlet needs an assembled matrix");
     cudaSetDevice(ctx->device);
     if (stage_row_vector(ctx, &ctx->d_toggle, dbctoggle_row)) return B200S_ERR_CUDA;
+    if (!ctx->d_nm_flag && to_device(ctx, &ctx->d_nm_flag, (const int*)nullptr, 1)) return B200S_ERR_CUDA;
+    CK(cudaMemsetAsync(ctx->d_nm_flag, 0, sizeof(int), ctx->stream));
     k_apply_dirichlet<<<nblk(32 * ctx->n_rows), 256, 0, ctx->stream>>>(ctx->n_rows, ctx->d_rowptr,
-        ctx->d_colind, ctx->d_toggle, diagonalblock, matrix_values(ctx, which));
+        ctx->d_colind, ctx->d_row_diagcol, ctx->d_toggle, diagonalblock, matrix_values(ctx, which), ctx->d_nm_flag);
     ctx->launches += 1;
+    int missing = 0;
+    CK(cudaMemcpyAsync(&missing, ctx->d_nm_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
+    if (missing)
+      return fail(ctx, B200S_ERR_INVALID, "apply_dirichlet: %d Dirichlet rows have no diagonal entry in the graph",
+          missing);
     return B200S_OK;
   }
 
@@ -3201,7 +3755,7 @@ extern "C"
       return rc ? fail(ctx, B200S_ERR_COMM, "allreduce: %s", ctx->nccl.GetErrorString(rc)) : 0;
     };
     k_block_diag_inverse<<<nblk(ctx->n_col_nodes), 256, 0, st>>>(
-        ctx->n_col_nodes, ctx->d_node_row, ctx->d_colind, ctx->d_vals, dinv);
+        ctx->n_col_nodes, ctx->d_node_row, ctx->d_node_colbase, ctx->d_colind, ctx->d_vals, dinv);
     CK(cudaMemsetAsync(s, 0, 4 * sizeof(double), st));
     int rc = multiply_device(ctx, B200S_MATRIX_STIFFNESS, x, Ap, nullptr, nullptr);
     if (rc) return rc;
@@ -3367,15 +3921,108 @@ extern "C"
     return B200S_OK;
   }
 
+  // ---- pinned host staging ----------------------------------------------------------------------------
+  // NUMA node of a CUDA device (sysfs numa_node of its PCI function), -1 if unknown / single node
+  static int device_numa_node(int device)
+  {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) return -1;
+    for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+  }
+  struct HostBlock
+  {
+    void* p;
+    size_t bytes;
+    bool mapped;  // mmap + cudaHostRegister (NUMA placed) instead of cudaMallocHost
+  };
+  static std::vector<HostBlock>& host_blocks()
+  {
+    static std::vector<HostBlock> v;
+    return v;
+  }
+
   void* b200s_host_alloc(int64_t bytes)
   {
     void* p = nullptr;
-    if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) return nullptr;
+    if (bytes <= 0 || cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) return nullptr;
+    host_blocks().push_back({p, (size_t)bytes, false});
     return p;
   }
+
+  // Pinned staging memory placed on the NUMA node the GPU hangs off: with one rank per GPU every rank DMAs its
+  // K values (GBs per Newton iteration) into host memory, and pages that all sit on one socket serialise the
+  // ranks on that socket's memory controllers and the inter-socket link.  mmap + mbind(MPOL_BIND) + first touch
+  // + cudaHostRegister; falls back to cudaMallocHost when the node is unknown or binding is not permitted.
+  void* b200s_host_alloc_near(int device, int64_t bytes, int* numa_node_out)
+  {
+    if (numa_node_out) *numa_node_out = -1;
+    if (bytes <= 0) return nullptr;
+    const int node = device_numa_node(device);
+    if (node >= 0 && node < 1024)
+    {
+      const size_t len = ((size_t)bytes + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+      void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+      if (p != MAP_FAILED)
+      {
+        unsigned long mask[16] = {0};
+        mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+        const long rc = syscall(SYS_mbind, p, len, /*MPOL_BIND*/ 2, mask, (unsigned long)(8 * sizeof mask), 0ul);
+        if (rc == 0)
+        {
+          madvise(p, len, MADV_HUGEPAGE);
+          for (size_t o = 0; o < len; o += 4096) ((volatile char*)p)[o] = 0;  // first touch on the bound node
+          cudaSetDevice(device);
+          if (cudaHostRegister(p, len, cudaHostRegisterPortable) == cudaSuccess)
+          {
+            host_blocks().push_back({p, len, true});
+            if (numa_node_out) *numa_node_out = node;
+            return p;
+          }
+          cudaGetLastError();
+        }
+        munmap(p, len);
+      }
+    }
+    return b200s_host_alloc(bytes);
+  }
+
   void b200s_host_free(void* p)
   {
-    if (p) cudaFreeHost(p);
+    if (!p) return;
+    auto& v = host_blocks();
+    for (size_t i = 0; i < v.size(); ++i)
+      if (v[i].p == p)
+      {
+        if (v[i].mapped)
+        {
+          cudaHostUnregister(p);
+          munmap(p, v[i].bytes);
+        }
+        else
+          cudaFreeHost(p);
+        v.erase(v.begin() + (long)i);
+        return;
+      }
+    cudaFreeHost(p);
+  }
+
+  // what the last evaluate did: out[0] element-kernel launches, [1] value chunks copied to the host while later
+  // segments were still being evaluated, [2] 1 if the ghost import ran beside the interior elements,
+  // [3] row phases of the installed graph, [4] elements holding a ghost node
+  int b200s_last_evaluate_info(const b200s_ctx* ctx, int64_t* out5)
+  {
+    if (!ctx || !out5) return B200S_ERR_INVALID;
+    out5[0] = ctx->last_kernel_launches, out5[1] = ctx->last_pipeline_chunks, out5[2] = ctx->last_halo_overlapped;
+    out5[3] = ctx->n_phases, out5[4] = ctx->segmented && ctx->seg_begin.size() > 1 ? ctx->seg_begin[1] : 0;
+    return B200S_OK;
   }
 }
 #endif  // B200S_PART_CORE

@@ -72,6 +72,9 @@ namespace b200s
                        // kernels (the headline path pays nothing); this flag only labels the launch
     int scatter_mode;  // 0: red.global.add (product); 1: skip scatter, 2: plain stores (both only
                        // for profiling the cost split, results are then meaningless)
+    int64_t e_begin = 0;  // first device element of this launch's segment: every per-element pointer above is
+                          // already offset by it (the kernels index from 0); launch wrappers with further
+                          // per-element arrays (EAS history) use it
   };
 
   namespace hex8

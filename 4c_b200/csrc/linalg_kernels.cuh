@@ -17,17 +17,37 @@
 namespace b200s
 {
 #if defined(__CUDACC__)
-  // one warp per CSR row: rows flagged 1.0 are zeroed; diagonalblock puts 1.0 on the diagonal
-  // (local column id == local row id: owned dofs lead the column map)
+  // matrix-local column id of every owned row's own dof (the diagonal entry): the column map need not list
+  // the owned dofs first / in row order, so "column id == row lid" is not assumed
+  __global__ void k_row_diag_col(int64_t n_col_nodes, const NodeRow* node_row, const int32_t* node_colbase,
+      int32_t* row_diagcol)
+  {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3 * n_col_nodes) return;
+    const int64_t k = t / 3;
+    const int d = (int)(t - 3 * k);
+    const int32_t fr = node_row[k].frow;
+    if (fr >= 0) row_diagcol[fr + d] = node_colbase[k] + d;
+  }
+
+  // one warp per CSR row: rows flagged 1.0 are zeroed; diagonalblock puts 1.0 on the diagonal.  missing counts
+  // toggled rows without a diagonal entry in the graph (the caller reports them instead of leaving a zero row).
   __global__ void k_apply_dirichlet(int64_t n_rows, const int64_t* rowptr, const int32_t* colind,
-      const double* toggle, int diagonalblock, double* vals)
+      const int32_t* row_diagcol, const double* toggle, int diagonalblock, double* vals, int* missing)
   {
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= n_rows || toggle[row] != 1.0) return;
     const int64_t s = rowptr[row], t = rowptr[row + 1];
+    const int32_t dc = row_diagcol[row];
+    bool found = false;
     for (int64_t q = s + lane; q < t; q += 32)
-      vals[q] = (diagonalblock && colind[q] == (int32_t)row) ? 1.0 : 0.0;
+    {
+      const bool diag = colind[q] == dc;
+      found |= diag;
+      vals[q] = (diagonalblock && diag) ? 1.0 : 0.0;
+    }
+    if (diagonalblock && !__any_sync(0xffffffffu, found) && lane == 0) atomicAdd(missing, 1);
   }
 
   __global__ void k_dirichlet_to_system(int64_t n, const double* toggle, const double* dbcval,
@@ -157,7 +177,7 @@ namespace b200s
 
   // inverse of the 3x3 diagonal block of every owned node (block-Jacobi preconditioner);
   // a singular block falls back to the identity
-  __global__ void k_block_diag_inverse(int64_t n_col_nodes, const NodeRow* node_row,
+  __global__ void k_block_diag_inverse(int64_t n_col_nodes, const NodeRow* node_row, const int32_t* node_colbase,
       const int32_t* colind, const double* vals, double* dinv /*9 per row node, at 3*frow*/)
   {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -165,17 +185,18 @@ namespace b200s
     const NodeRow nr = node_row[k];
     if (nr.frow < 0) return;
     const int32_t* ci = colind + nr.rowstart;
+    const int32_t dc = node_colbase[k];  // matrix-local column id of the node's first dof
     int lo = 0, hi = nr.rowlen;
     while (lo < hi)
     {
       const int mid = (lo + hi) >> 1;
-      if (ci[mid] < nr.frow)
+      if (ci[mid] < dc)
         lo = mid + 1;
       else
         hi = mid;
     }
     double m[9], o[9];
-    bool ok = lo + 3 <= nr.rowlen && ci[lo] == nr.frow;
+    bool ok = lo + 3 <= nr.rowlen && ci[lo] == dc;
     if (ok)
     {
       for (int b = 0; b < 3; ++b)

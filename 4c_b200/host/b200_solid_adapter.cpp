@@ -33,6 +33,39 @@ namespace B200Solid
     return cell && mat;
   }
 
+  bool DeviceElementBlock::supported(int celltype, int kinem, int tech, int prestress, int material_kind)
+  {
+    const bool cell = celltype == B200S_HEX8 || celltype == B200S_HEX27 || celltype == B200S_TET10;
+    if (!cell) return false;
+    const bool hyper = material_kind == B200S_MAT_COUP_NEOHOOKE || material_kind == B200S_MAT_ISO_VOL ||
+                       material_kind == B200S_MAT_SVK || material_kind == B200S_MAT_ELASTHYPER;
+    if (kinem == B200S_KINEM_LINEAR)
+    {
+      // displacement based, small strains: the hyperelastic kinds and the history material
+      if (tech != B200S_TECH_NONE || prestress != B200S_PRESTRESS_NONE) return false;
+      return hyper || material_kind == B200S_MAT_DRUCKER_PRAGER;
+    }
+    if (kinem != B200S_KINEM_NONLINEAR_TOTLAG || !hyper) return false;
+    if (prestress == B200S_PRESTRESS_MULF) return tech == B200S_TECH_NONE;  // MULF + F-bar: CPU loop
+    if (prestress != B200S_PRESTRESS_NONE) return false;
+    if (tech == B200S_TECH_NONE) return true;
+    // F-bar and EAS are hex8 technologies (4C_solid_ele_factory_lib.hpp)
+    return celltype == B200S_HEX8 &&
+           (tech == B200S_TECH_FBAR || tech == B200S_TECH_EAS_MILD || tech == B200S_TECH_EAS_FULL);
+  }
+
+  void DeviceElementBlock::attach_to(DeviceElementBlock& primary)
+  {
+    check(b200s_attach_block(ctx_, primary.ctx_));
+    attached_ = true;
+  }
+
+  double* DeviceElementBlock::alloc_staging(int device, std::int64_t n_doubles)
+  {
+    return static_cast<double*>(b200s_host_alloc_near(device, 8 * n_doubles, nullptr));
+  }
+  void DeviceElementBlock::free_staging(double* p) { b200s_host_free(p); }
+
   void DeviceElementBlock::set_block(const ElementBlockView& b)
   {
     check(b200s_set_mesh(ctx_, b.celltype, b.n_col_nodes, b.X, b.n_col_eles, b.conn));
@@ -80,10 +113,11 @@ namespace B200Solid
 
   void DeviceElementBlock::evaluate(Action action, double* crs_values, double* f_row)
   {
-    if (!u_row_) throw Exception(B200S_ERR_INVALID, "set_state(\"displacement\") must precede evaluate");
+    // an attached block reads the state its primary imported in this iteration
+    if (!u_row_ && !attached_) throw Exception(B200S_ERR_INVALID, "set_state(\"displacement\") must precede evaluate");
     b200s_error_info info;
     std::memset(&info, 0, sizeof info);
-    check(b200s_evaluate(ctx_, (int)action, u_row_, crs_values, f_row, &info));
+    check(b200s_evaluate(ctx_, (int)action, attached_ ? nullptr : u_row_, crs_values, f_row, &info));
   }
 
   void DeviceElementBlock::set_material_elasthyper(const std::vector<std::int32_t>& kinds,

@@ -88,6 +88,19 @@ namespace B200Solid
 
     /// true if (cell type, material) are on the device path; otherwise the caller keeps the CPU loop
     static bool supported(int celltype, int material_kind);
+    /// The full capability matrix of the device path = which SolidCalcVariant / So3Material combinations of the
+    /// reference's factory (4C_solid_ele_factory.cpp:252-305) have a kernel: cell type x KINEM x TECH x
+    /// PRESTRESS_TECH x material kind.  Anything else keeps the CPU element loop.
+    static bool supported(int celltype, int kinem, int tech, int prestress, int material_kind);
+    /// This block assembles into `primary`'s system matrix (several cell types / MAT ids in one discretization,
+    /// 4C_fem_discretization_evaluate.cpp:85-117): call after set_block / set_element_properties / set_material
+    /// of this block and after the primary's set_graph with the graph of the WHOLE matrix.  Per Newton
+    /// iteration evaluate the primary first, then the attached blocks; pass crs_values / f_row to the last one.
+    void attach_to(DeviceElementBlock& primary);
+    /// Pinned staging buffer on the NUMA node of this block's GPU (for Epetra value arrays the adapter copies
+    /// into; b200s_host_alloc_near)
+    static double* alloc_staging(int device, std::int64_t n_doubles);
+    static void free_staging(double* p);
 
     void set_block(const ElementBlockView& block);
     /// Mat::So3Material of the block: kind + parameters (+ optional per-element field, see
@@ -148,5 +161,6 @@ namespace B200Solid
     void check(int rc) const;
     b200s_ctx* ctx_ = nullptr;
     const double* u_row_ = nullptr;
+    bool attached_ = false;
   };
 }  // namespace B200Solid

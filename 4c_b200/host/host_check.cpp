@@ -50,6 +50,52 @@ int main()
     }
     std::printf("HOST_ADAPTER_OK fmax=%.3g asym=%.3g rowsum=%.3g kmax=%.3g\n", fmax, asym, rowsum, kmax);
     const bool ok = fmax < 1e-13 && asym < 1e-13 * kmax && rowsum < 1e-12 * kmax && kmax > 0.1;
+    // two element blocks (two MAT ids in the reference's terms) assembling into one matrix give the same K as one
+    // block holding both elements (same material in both blocks here)
+    bool blocks_ok = false;
+    {
+      const double X2[36] = {0, 0, 0, 1, 0, 0, 1, 1, 0, 0, 1, 0, 0, 0, 1, 1, 0, 1, 1, 1, 1, 0, 1, 1,
+          0, 0, 2.1, 1, 0, 2, 1.1, 1, 2, 0, 1, 2.2};
+      const std::int32_t conn2[16] = {0, 1, 2, 3, 4, 5, 6, 7, 4, 5, 6, 7, 8, 9, 10, 11};
+      std::vector<std::int32_t> lid2(36);
+      for (int i = 0; i < 36; ++i) lid2[i] = i;
+      // graph of the two-element mesh: nodes 0-3 see 0-7, nodes 4-7 see all, nodes 8-11 see 4-11
+      std::vector<int> off2(37, 0), ind2;
+      for (int r = 0; r < 36; ++r)
+      {
+        const int node = r / 3, lo = node < 4 ? 0 : (node < 8 ? 0 : 12), hi = node < 4 ? 24 : 36;
+        for (int c = lo; c < hi; ++c) ind2.push_back(c);
+        off2[r + 1] = (int)ind2.size();
+      }
+      std::vector<double> u2(36), Ka(ind2.size()), Kb(ind2.size()), fa(36), fb(36);
+      for (int i = 0; i < 36; ++i) u2[i] = 0.01 * std::sin(1.7 * i);
+      CrsView crs2;
+      crs2.n_rows = 36, crs2.index_offset = off2.data(), crs2.indices = ind2.data();
+      ElementBlockView all, lower, upper;
+      all.celltype = B200S_HEX8, all.n_col_nodes = 12, all.X = X2, all.n_col_eles = 2, all.conn = conn2;
+      all.dof_row_lid = lid2.data(), all.dof_col_lid = lid2.data();
+      lower = all, upper = all;
+      lower.n_col_eles = 1, upper.n_col_eles = 1, upper.conn = conn2 + 8;
+      DeviceElementBlock one(0, 0, 1), pa(0, 0, 1), pb(0, 0, 1);
+      one.set_block(all), one.set_material(B200S_MAT_COUP_NEOHOOKE, {10.0, 0.25}), one.set_graph(all, crs2);
+      one.set_state(u2.data());
+      one.evaluate(Action::struct_calc_nlnstiff, Ka.data(), fa.data());
+      pa.set_block(lower), pa.set_material(B200S_MAT_COUP_NEOHOOKE, {10.0, 0.25}), pa.set_graph(all, crs2);
+      pb.set_block(upper), pb.set_material(B200S_MAT_COUP_NEOHOOKE, {10.0, 0.25}), pb.attach_to(pa);
+      pa.set_state(u2.data());
+      pa.evaluate(Action::struct_calc_nlnstiff, nullptr, nullptr);
+      pb.evaluate(Action::struct_calc_nlnstiff, Kb.data(), fb.data());
+      double dk = 0, df = 0, km = 0;
+      for (size_t i = 0; i < Ka.size(); ++i) dk = std::fmax(dk, std::fabs(Ka[i] - Kb[i])), km = std::fmax(km, std::fabs(Ka[i]));
+      for (int i = 0; i < 36; ++i) df = std::fmax(df, std::fabs(fa[i] - fb[i]));
+      blocks_ok = dk < 1e-13 * km && df < 1e-13 * km && km > 0.1;
+      std::printf("HOST_ADAPTER_BLOCKS dk=%.3g df=%.3g kmax=%.3g\n", dk, df, km);
+      if (!DeviceElementBlock::supported(B200S_HEX8, B200S_KINEM_LINEAR, B200S_TECH_NONE, B200S_PRESTRESS_NONE,
+              B200S_MAT_DRUCKER_PRAGER) ||
+          DeviceElementBlock::supported(B200S_TET10, B200S_KINEM_NONLINEAR_TOTLAG, B200S_TECH_FBAR, B200S_PRESTRESS_NONE,
+              B200S_MAT_SVK))
+        blocks_ok = false;
+    }
     // inverted element: the reference throws
     double Xbad[24];
     for (int i = 0; i < 24; ++i) Xbad[i] = X[i];
@@ -67,7 +113,7 @@ int main()
       thrown = e.code() == B200S_ERR_NEG_JACOBIAN;
       std::printf("expected throw: %s\n", e.what());
     }
-    return ok && thrown ? 0 : 1;
+    return ok && thrown && blocks_ok ? 0 : 1;
   }
   catch (const Exception& e)
   {

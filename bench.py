@@ -18,6 +18,7 @@ header-only tensor/shape-function code; falls back to the oracle port) on all ho
 Nothing here reads /root/reference.
 """
 import argparse
+import ctypes as C
 import importlib
 import json
 import os
@@ -81,11 +82,36 @@ WORKLOADS = {
 }
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the element kernel at the workload's default
-# size, from the committed ncu captures profiles/r01e_ncu_metrics_<workload>.csv (same bench.py command)
-NCU_TRAFFIC_BYTES = {"hex8": 2694710016 + 2248577536, "tet10": 20888573696 + 17315611904,
-                     "hex27": 25082223616 + 24644916992, "hex8_eas_full": 3559638528 + 10256551424}
-NCU_TRAFFIC_FILE = {"hex8": "r01h_ncu_metrics_hex8.csv", "hex8_eas_full": "r01h_ncu_metrics_hex8_eas_full.csv"}
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the element kernel, PARSED from the newest
+    committed ncu metrics CSV of this workload (profiles/r<NN>*_ncu_metrics_<workload>.csv, written by
+    `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,... --csv` around this very bench command; median
+    over the captured launches).  Returns (bytes or None, file name or None)."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_ncu_metrics_{workload}.csv")))
+    for path in reversed(files):
+        per_launch = {}
+        try:
+            with open(path, newline="") as fh:
+                rows = [r for r in csv.reader(l for l in fh if l.startswith('"'))]
+        except OSError:
+            continue
+        if not rows:
+            continue
+        hdr = rows[0]
+        try:
+            ik, im, iv, ii = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
+        except ValueError:
+            continue
+        for r in rows[1:]:
+            if "eval_assemble" not in r[ik] or not r[im].startswith("dram__bytes_"):
+                continue
+            if r[im] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                per_launch[r[ii]] = per_launch.get(r[ii], 0.0) + float(r[iv].replace(",", ""))
+        if per_launch:
+            return float(np.median(list(per_launch.values()))), os.path.basename(path)
+    return None, None
 
 
 def host_threads():
@@ -279,6 +305,90 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
+PARITY_WORKLOADS = ("hex8", "hex8_fbar", "tet10", "hex27")
+
+
+def parity_record(args, wl, ctx, rm, u, world, dist, torch, n_random=150, n_interface=50):
+    """Driver-visible correctness at every N: AFTER the timed regions every rank compares the CSR rows of ~200
+    owned nodes (random ones plus nodes of elements that hold ghost nodes, i.e. rows fed by halo-imported
+    displacements) of the K resident from its last evaluate with the CPU oracle evaluated on the elements
+    touching those nodes (oracle/sampled_rows.py; the oracle is the checker, never timed)."""
+    if args.no_parity:
+        return {"ok": None, "skipped": "--no-parity"}
+    if args.workload not in PARITY_WORKLOADS:
+        return {"ok": None, "skipped": "history-carrying formulation: covered by tests/test_gpu_post.py"}
+    from oracle import oracle as orc
+    from oracle import sampled_rows
+    b200 = importlib.import_module("4c_b200")
+    capi = b200.capi
+    h_u = np.ascontiguousarray(u[:rm.n_row_nodes].ravel())
+    ctx.evaluate(capi.ACTION_NLNSTIFF, h_u, None, None)   # K resident for exactly this state
+    nodes = sampled_rows.pick_nodes(rm, n_random, n_interface if world > 1 else 0, seed=17 + rm.rank)
+    tech = getattr(orc, wl.get("tech", "TECH_NONE"))
+    r = sampled_rows.check(ctx, rm, getattr(orc, wl["cell"]), getattr(orc, wl["mat"]), wl["par"], u, nodes,
+                           rtol=1e-12, tech=tech, nthreads=min(8, host_threads()))
+    v = torch.tensor([0.0 if r["ok"] else 1.0, r["worst_blockrow_ratio"], r["worst_entry_rel"], r["worst_f_ratio"],
+                      float(r["nodes"]), float(r["entries"])], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        mx = v.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = v.clone()
+        dist.all_reduce(sm)
+        v = torch.cat([mx[:4], sm[4:]])
+    v = v.tolist()
+    return {"ok": v[0] == 0.0, "worst": v[1], "worst_entry_rel": v[2], "worst_f": v[3], "rtol": 1e-12,
+            "norm": "worst = max |a-b| / (rtol * max-abs of the node's 3 CSR rows) (SURVEY 8d, <= 1 passes); "
+                    "worst_entry_rel = max |a-b| / max(|a|,|b|) over entries above 1e-6 of that scale",
+            "rows_checked": int(3 * v[4]), "entries_checked": int(v[5]), "ranks_checked": world,
+            "pattern": "bit-exact colind/rowptr of the sampled rows vs the oracle's FillComplete restatement",
+            "ghost_fed_rows": world > 1}
+
+
+def run_config5(args, wl, rank, world, local, barrier, dist, torch):
+    """BASELINE config 5: 400^3 = 64 M hex8 Neo-Hooke elements on 8 B200 (200^3 row elements per rank, nnz/rank
+    1.97e9 > 2^31), device-resident timing + sampled-row parity.  No e2e leg: the host staging of 8 x 15.8 GB of
+    CSR values is not a sensible benchmark of this box's host."""
+    b200 = importlib.import_module("4c_b200")
+    capi = b200.capi
+    rm, u, label = build_rank(wl, 200, rank, world, False)
+    asm = b200.DeviceAssembler(rm, getattr(capi, wl["mat"]), wl["par"], device=local)
+    ctx = asm.ctx
+    uid = [ctx.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ctx.comm_init_nccl(uid[0])
+    h_u = np.ascontiguousarray(u[:rm.n_row_nodes].ravel())
+    ctx.evaluate(capi.ACTION_NLNSTIFF, h_u, None, None)
+    stream = torch.cuda.ExternalStream(ctx.device_ptrs()["stream"], device=torch.device("cuda", local))
+    for _ in range(args.warmup):
+        ctx.evaluate_async(capi.ACTION_NLNSTIFF)
+    ctx.synchronize()
+    ctx.kernel_time(reset=True)
+    steps = max(3, min(args.steps, 10))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(steps):
+        ctx.evaluate_async(capi.ACTION_NLNSTIFF)
+    e1.record(stream)
+    e1.synchronize()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ctx.synchronize()
+    ksum, kcnt = ctx.kernel_time(reset=True)
+    info = ctx.last_evaluate_info()
+    parity = parity_record(args, wl, ctx, rm, u, world, dist, torch)
+    tot = torch.tensor([rm.n_row_eles, rm.n_col_eles], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tot)
+    out = {"workload": f"BASELINE config 5: {label}, {wl['matname']}, {int(tot[0])} elements, nnz/rank={asm.nnz}",
+           "value": float(tot[0]) * steps / (float(ms) * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+           "ms_per_step": float(ms) / steps, "kernel_ms_rank0": ksum / max(kcnt, 1),
+           "halo_overlapped": bool(info["halo_overlapped"]), "ghost_elements_rank0": info["ghost_elements"],
+           "parity": parity}
+    asm.close()
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -333,7 +443,11 @@ def run_b200(args):
     if 8 * (nnz + 2 * n_rows) * world > 0.5 * avail:
         raise SystemExit(f"host staging of {8 * nnz * world / 1e9:.1f} GB of CSR values does not fit the host "
                          f"({avail / 1e9:.1f} GB available): choose a smaller --per-gpu-n")
-    hb = {k: capi.load().b200s_host_alloc(8 * sz) for k, sz in (("u", n_rows), ("K", nnz), ("f", n_rows))}
+    # pinned staging on the NUMA node of this rank's GPU (b200s_host_alloc_near; --host-alloc plain = cudaMallocHost)
+    hb, numa_node = {}, C.c_int(-1)
+    for k, sz in (("u", n_rows), ("K", nnz), ("f", n_rows)):
+        hb[k] = (capi.load().b200s_host_alloc_near(local, 8 * sz, C.byref(numa_node)) if args.host_alloc == "near"
+                 else capi.load().b200s_host_alloc(8 * sz))
     if not all(hb.values()):
         raise SystemExit("pinned host allocation failed")
     h_u = np.ctypeslib.as_array((capi.C.c_double * n_rows).from_address(hb["u"]))
@@ -350,9 +464,11 @@ def run_b200(args):
         e1.record(stream)
         e1.synchronize()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        own = e0.elapsed_time(e1)
+        ms = torch.tensor([own], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        timed.own_ms = own
         return float(ms.item())
 
     def step_dev():
@@ -379,6 +495,15 @@ def run_b200(args):
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, e2e_steps)
+    e2e_info = ctx.last_evaluate_info()
+    # per-rank device->host rate of the K values during the e2e steps (every rank's own clock)
+    own_gbs = torch.tensor([8.0 * (nnz + n_rows) * e2e_steps / (timed.own_ms * 1e-3) / 1e9, float(numa_node.value)],
+                           dtype=torch.float64, device="cuda")
+    all_gbs = [torch.zeros_like(own_gbs) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(all_gbs, own_gbs)
+    else:
+        all_gbs = [own_gbs]
     # ---- the step after the path with K resident on the device -----------------
     # e2e_resident: same blocking call, host u in / host f out, K stays in the context's CSR for
     # b200s_apply_dirichlet / b200s_multiply / a device solver; multiply: y = K x on that CSR.
@@ -397,6 +522,12 @@ def run_b200(args):
     t1 = sampler.mark() if sampler else 0
     clocks = sampler.stop(t0, t1) if sampler else None
 
+    parity = parity_record(args, wl, ctx, rm, u, world, dist if world > 1 else None, torch)
+    halo_info = None
+    if world > 1:
+        ctx.evaluate_async(capi.ACTION_NLNSTIFF)
+        ctx.synchronize()
+        halo_info = ctx.last_evaluate_info()
     tot_eles = torch.tensor([rm.n_row_eles, rm.n_col_eles], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tot_eles)
@@ -407,23 +538,28 @@ def run_b200(args):
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
-        fp64_tf, fp64_mhz = capi.measure_fp64_peak(local)
+        dfma_tf, fp64_mhz = capi.measure_fp64_peak(local)
+        dmma_tf = capi.microbench(1, 0, local)
+        fp64_tf = max(dfma_tf, dmma_tf)   # the FP64 pipe's peak is whichever instruction stream reaches more
         k_ms = ksum / max(kcnt, 1)
+        traffic, tfile = (args.traffic_bytes, "--traffic-bytes") if args.traffic_bytes is not None else (
+            ncu_traffic(args.workload) if per_gpu_n == wl["default_n"] and world == 1 else (None, None))
+        traffic_src = (f"ncu dram__bytes_read.sum + dram__bytes_write.sum per launch (median), parsed from profiles/{tfile}"
+                       if traffic is not None else "no committed ncu capture for this workload/size")
         eps_kernel = rm.n_col_eles / (k_ms * 1e-3)      # elements this rank's kernel evaluates per second
         ach_tf = FLOPS_PER_ELE * eps_kernel / 1e12
         ach_gbs = BYTES_PER_ELE * eps_kernel / 1e9
         roof = {
             "bound": "fp64", "kernel": wl["kernel"],
             "achieved": ach_tf, "peak": fp64_tf, "unit": "TFLOP/s", "frac": ach_tf / fp64_tf,
-            "peak_source": "DFMA microbenchmark run in this process (b200s_measure_fp64_peak, implied "
-                           f"{fp64_mhz:.0f} MHz); MEASURED_PEAKS.json holds no FP64 figure",
+            "peak_source": f"max of two microbenchmarks run in this process: DFMA loop {dfma_tf:.1f} TFLOP/s, DMMA "
+                           f"m8n8k4 loop {dmma_tf:.1f} TFLOP/s (148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2); "
+                           "MEASURED_PEAKS.json holds no FP64 figure",
             "model": f"SURVEY 8(d): {FLOPS_PER_ELE / 1e3:.1f} kflop and {BYTES_PER_ELE:.0f} B per {wl['cell'].lower()} "
                      "element (algorithmic, full non-symmetric K_e)",
             "kernel_ms": k_ms, "kernel_launches_timed": kcnt,
-            "traffic": args.traffic_bytes if args.traffic_bytes is not None else (
-                NCU_TRAFFIC_BYTES.get(args.workload) if per_gpu_n == wl["default_n"] else None),
-            "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/"
-                              + NCU_TRAFFIC_FILE.get(args.workload, f"r01e_ncu_metrics_{args.workload}.csv"),
+            "traffic": traffic, "traffic_source": traffic_src,
+            "algorithmic_bytes_per_launch": BYTES_PER_ELE * rm.n_col_eles,
             "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": ach_gbs / peaks["hbm_gbs"], "peak_source": peak_src},
         }
@@ -453,7 +589,12 @@ def run_b200(args):
             },
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * n_rows * world,
                     "d2h_bytes_per_step": 8 * (nnz + n_rows) * world, "ms_per_step": ms_e2e / e2e_steps,
-                    "steps": e2e_steps, "api": "b200s_evaluate(ctx, NLNSTIFF, u_host, K_values_host, f_host) with pinned host buffers"},
+                    "steps": e2e_steps, "api": "b200s_evaluate(ctx, NLNSTIFF, u_host, K_values_host, f_host) with pinned host buffers",
+                    "pipeline": {"row_phases": e2e_info["row_phases"], "chunks_overlapped": e2e_info["pipeline_chunks"],
+                                 "kernel_launches_per_step": e2e_info["kernel_launches"]},
+                    "host_alloc": args.host_alloc,
+                    "per_rank": [{"rank": r, "bytes_per_s_gb": round(float(g[0]), 2), "numa_node": int(g[1])}
+                                 for r, g in enumerate(all_gbs)]},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,
@@ -474,10 +615,21 @@ def run_b200(args):
         }
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        line["parity"] = parity
+        if halo_info:
+            line["config"]["halo"] = {"overlapped_with_interior_elements": bool(halo_info["halo_overlapped"]),
+                                      "ghost_elements_rank0": halo_info["ghost_elements"],
+                                      "kernel_launches_per_step": halo_info["kernel_launches"]}
     for p in hb.values():
         capi.load().b200s_host_free(p)
     asm.close()
+    # BASELINE config 5 proper (64 M hex8 elements on 8 GPUs = 200^3 per rank): an extra device-resident run
+    if world == 8 and args.workload == "hex8" and not args.strong and not args.per_gpu_n and not args.no_config5:
+        c5 = run_config5(args, wl, rank, world, local, barrier, dist, torch)
+        if rank == 0:
+            line["config5"] = c5
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -498,6 +650,10 @@ def main():
     ap.add_argument("--strong", action="store_true",
                     help="strong scaling: --per-gpu-n is the edge of the WHOLE mesh, cut into N boxes")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sampled-row parity record")
+    ap.add_argument("--no-config5", action="store_true", help="at --gpus 8: skip the extra 200^3-per-rank run")
+    ap.add_argument("--host-alloc", default="near", choices=["near", "plain"],
+                    help="pinned staging of the e2e leg: on the GPU's NUMA node (default) or plain cudaMallocHost")
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram bytes per launch of the element kernel from the committed ncu capture (profiles/)")
     args = ap.parse_args()

@@ -207,7 +207,14 @@ extern "C"
    * start of every evaluate; 1 = two buffers, the zero() of the next Newton iteration's matrix runs on a
    * side stream while the current evaluate fills the other buffer and b200s_device_values() alternates
    * between two addresses -- measured on B200: the concurrent memset slows the element kernel by as much
-   * as it saves (2.46 vs 2.48 ms per step), hence off; takes effect at the next set_graph / build_graph), "ctas_per_sm" and "scatter_mode" (tuning / profiling only). */
+   * as it saves (2.46 vs 2.48 ms per step), hence off; takes effect at the next set_graph / build_graph),
+   * "pipeline_phases" (default 12; at the next set_graph / build_graph the elements are grouped by the CSR
+   * row range -- about nnz / phases entries each -- of their lowest owned node, so that b200s_evaluate with a
+   * HOST K_values copies the rows of a finished phase while the next phases are still being evaluated;
+   * 1 = one phase, no overlap; meshes whose row numbering has no spatial locality get one phase),
+   * "overlap_halo" (default 1: with a halo, the ghost import runs on a side stream beside the elements that
+   * hold no ghost node; 0 = in-stream before a single launch), "ctas_per_sm" and "scatter_mode" (tuning /
+   * profiling only). */
   int b200s_set_option(b200s_ctx* ctx, const char* key, double value);
 
   /* ---- set-up (once per discretization) ------------------------------------------------------ */
@@ -270,6 +277,19 @@ extern "C"
   int b200s_set_graph(b200s_ctx* ctx, int64_t n_rows, const int64_t* rowptr, const int32_t* colind,
       const int32_t* dof_row_lid, const int32_t* dof_col_lid);
 
+  /* Several element blocks, one system matrix.  Discretization::evaluate assembles ANY mix of cell types,
+   * formulations and MAT ids into the same SparseMatrix (4C_fem_discretization_evaluate.cpp:85-117); a
+   * context evaluates ONE block (cell type, SolidElementProperties, material).  b200s_attach_block makes
+   * `ctx` a further block of `primary`'s matrix: after its own b200s_set_mesh (the SAME column nodes, in the
+   * same order, as the primary; its own column elements), b200s_set_element_properties and material calls,
+   * attach builds the block's element -> CSR slot map against the primary's graph (which must hold every
+   * coupling of the block's elements: pass the matrix graph of the whole discretization to the primary's
+   * b200s_set_graph) and from then on the block shares the primary's CSR values, residual, displacement
+   * vectors, stream and communicator.  Per Newton iteration: b200s_evaluate on the primary first (state import,
+   * zero, its elements), then on every attached block (its elements are ADDED; u_row is ignored / may be NULL);
+   * K_values / f_row given to the LAST call receive the sum.  Destroy attached blocks before their primary. */
+  int b200s_attach_block(b200s_ctx* ctx, b200s_ctx* primary);
+
   /* Ghost-displacement halo = the Epetra_Import of Discretization::set_state
    * (4C_fem_discretization.cpp:653-661), rank-local view (Epetra_Import::ExportLIDs / RemoteLIDs /
    * ExportPIDs).  For each neighbour n in [0,n_nbr): peer rank peer[n],
@@ -311,6 +331,15 @@ extern "C"
    * after b200s_apply_dirichlet: what ExtractCrsDataPointers would show.  [host|dev] out, nnz. */
   int b200s_get_values(b200s_ctx* ctx, int which, double* values_out);
   double* b200s_device_f_inertia(b200s_ctx* ctx);   /* n_rows */
+  /* Rows [row0,row1) of a resident system matrix (which: b200s_matrix) and of the residual: the values
+   * Epetra_CrsMatrix::ExtractMyRowView (4C_linalg_sparsematrix.cpp:386-447 writes through it) would show
+   * for those local rows, without moving the whole matrix -- the at-scale parity tests and bench.py's
+   * `parity` record sample rows with it (BASELINE configs 3 and 5 hold > 2^31 non-zeros per rank).
+   *   values_out [host|dev] rowptr[row1]-rowptr[row0] doubles, colind_out likewise (int32), rowptr_out
+   *   row1-row0+1 offsets relative to the first returned entry; each may be NULL. */
+  int b200s_get_value_rows(b200s_ctx* ctx, int which, int64_t row0, int64_t row1, double* values_out,
+      int32_t* colind_out, int64_t* rowptr_out);
+  int b200s_get_f_rows(b200s_ctx* ctx, int64_t row0, int64_t row1, double* f_out);
 
   /* struct_calc_stress (SolidEleCalc::calculate_stress, 4C_solid_ele_calc.cpp:416-476) for the
    * current "displacement" state: Gauss-point stresses / strains of every column element,
@@ -354,7 +383,8 @@ extern "C"
   int b200s_recover_linesearch(b200s_ctx* ctx, double new_step_length);
   /* struct_calc_update_istep / struct_calc_reset_istep (SolidEleCalc::update / reset_to_last_converged,
    * 4C_solid_ele_calc.cpp:317-363,570-575): snapshot of the block's history at a converged step and the
-   * way back after a failed one.  No-ops for formulations without history. */
+   * way back after a failed one (before the first update_step: back to the fresh, default-constructed
+   * history).  No-ops for formulations without history. */
   int b200s_update_step(b200s_ctx* ctx);
   int b200s_reset_step(b200s_ctx* ctx);
   /* Element history of the block = what EASFormulation::pack / unpack write for restart
@@ -363,6 +393,11 @@ extern "C"
   int64_t b200s_element_history_size(const b200s_ctx* ctx);
   int b200s_get_element_history(b200s_ctx* ctx, double* hist_out);
   int b200s_set_element_history(b200s_ctx* ctx, const double* hist_in);
+  /* EASHistoryData::old_step_length (4C_solid_ele_calc_eas.hpp:36,270,281): the reference packs it per
+   * element, but every element holds the same value (the step length of the last recover), so the block
+   * keeps one scalar; it is part of the update_step / reset_step snapshot and of the restart data. */
+  double b200s_eas_old_step_length(const b200s_ctx* ctx);
+  int b200s_set_eas_old_step_length(b200s_ctx* ctx, double step_length);
 
   /* ---- external loads: Discretization::evaluate_neumann restricted to the element block ------------- */
   /* (4C_fem_discretization_evaluate.cpp:264-297: every Line/Surface/VolumeNeumann condition, every
@@ -478,9 +513,18 @@ extern "C"
    * over a `size`-byte buffer. */
   int b200s_microbench(int device, int which, int64_t size, double* result);
 
-  /* Pinned host memory for the adapter's staging of u / values / f. */
+  /* Pinned host memory for the adapter's staging of u / values / f (what the adapter copies into / out of
+   * Epetra's own arrays, or registers them).  b200s_host_alloc_near places the pages on the NUMA node of the
+   * given device (mmap + mbind + cudaHostRegister; *numa_node_out = that node, -1 when it fell back to a
+   * plain cudaMallocHost): with one rank per GPU the K values of all ranks (GBs per Newton iteration) must
+   * not land on one socket. */
   void* b200s_host_alloc(int64_t bytes);
+  void* b200s_host_alloc_near(int device, int64_t bytes, int* numa_node_out);
   void b200s_host_free(void* p);
+  /* Diagnostics of the last evaluate: out5[0] element-kernel launches, [1] chunks of K copied to the host
+   * while later element segments were still being evaluated, [2] 1 if the ghost import overlapped the
+   * elements without ghost nodes, [3] row phases of the installed graph, [4] elements holding a ghost node. */
+  int b200s_last_evaluate_info(const b200s_ctx* ctx, int64_t* out5);
 
   const char* b200s_version(void);
 

@@ -1,0 +1,341 @@
+"""GPU parity at BASELINE.json's own sizes (configs 3, 4 and 5: more than 2^31 non-zeros per rank for 3 and 5,
+64-bit CSR offsets) through row sampling, plus the library features added in round 2: the host-destination
+pipeline (rows of finished phases travel while later element segments are evaluated), several element blocks
+in one system matrix (b200s_attach_block), call-order independence of set_element_properties / set_mesh, and
+struct_calc_reset_istep before the first update.  Tolerance 1e-12 (north_star); CSR pattern bit-exact."""
+import ctypes
+import importlib
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from oracle import sampled_rows
+
+pytestmark = pytest.mark.gpu
+b200 = importlib.import_module("4c_b200")
+capi = b200.capi
+RTOL = 1e-12
+
+
+def _cudart():
+    for name in ("libcudart.so", "libcudart.so.12", "libcudart.so.13"):
+        try:
+            return ctypes.CDLL(name)
+        except OSError:
+            continue
+    import torch  # torch ships its own copy
+    import glob
+    import os
+    cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "cuda_runtime", "lib", "libcudart.so*"))
+    return ctypes.CDLL(cands[0])
+
+
+def _write_device(ptr, arr):
+    """Host array -> device memory owned by the library (harness only: stands in for the NCCL halo when ONE
+    rank of a partition is tested alone)."""
+    arr = np.ascontiguousarray(arr, np.float64)
+    rt = _cudart()
+    rt.cudaMemcpy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+    rc = rt.cudaMemcpy(ctypes.c_void_p(ptr), ctypes.c_void_p(arr.ctypes.data), arr.nbytes, 1)
+    assert rc == 0, rc
+
+
+def _report(tag, r):
+    print(f"{tag}: sampled-row parity worst block-row ratio {r['worst_blockrow_ratio']:.3g}, worst pure relative "
+          f"error {r['worst_entry_rel']:.3g} (entries > {r['entry_floor']:g} x row scale), f ratio {r['worst_f_ratio']:.3g}, "
+          f"{r['nodes']} nodes, {r['entries']} entries")
+
+
+# ---- BASELINE config 3: 80^3 hex27 St.Venant-Kirchhoff, nnz = 2.36e9 > 2^31 ------------------------------
+def test_config3_hex27_sampled_rows_at_full_size():
+    n = (80, 80, 80)
+    rm = b200.partition.box_partition(b200.mesh.HEX27, n, 0, 1, box=(0.8, 0.8, 0.8))
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 0.01)
+    par = [1000.0, 0.3]
+    asm = b200.DeviceAssembler(rm, capi.MAT_SVK, par)
+    assert asm.nnz > 2 ** 31
+    asm.set_state("displacement", u.ravel())
+    _, f, err = asm.evaluate_resident()
+    assert err.n_neg_jacobian == 0
+    assert np.abs(f.reshape(-1, 3).sum(axis=0)).max() < 1e-9 * np.abs(f).max() * np.sqrt(len(f))
+    # nodes spread over the whole row range, incl. the last rows (offsets beyond 2^31)
+    rng = np.random.default_rng(3)
+    nodes = np.unique(np.concatenate([rng.choice(rm.n_row_nodes, 120, replace=False),
+                                      np.arange(rm.n_row_nodes - 30, rm.n_row_nodes)]))
+    r = sampled_rows.check(asm.ctx, rm, orc.HEX27, orc.MAT_SVK, par, u, nodes, RTOL, nthreads=8)
+    _report("config 3", r)
+    assert r["ok"], r
+    rp, _, _ = asm.ctx.get_value_rows(asm.n_rows - 3, asm.n_rows, want_values=False)
+    assert rp[-1] > 0
+    asm.close()
+
+
+# ---- BASELINE config 4: 3.95 M unstructured tet10, nearly incompressible iso/vol Neo-Hooke -----------------
+def test_config4_tet10_sampled_rows_at_full_size():
+    X, conn = b200.mesh.unstructured_tet10(87)
+    rm = b200.partition.serial_mesh(b200.mesh.TET10, X, conn)
+    assert rm.n_col_eles == 6 * 87 ** 3
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 1.0 / 87)
+    par = [1.0, 1000.0]
+    asm = b200.DeviceAssembler(rm, capi.MAT_ISO_VOL, par)
+    asm.set_state("displacement", u.ravel())
+    _, f, err = asm.evaluate_resident()
+    assert err.n_neg_jacobian == 0 and 0.7 < err.min_detF < 1.3
+    assert np.abs(f.reshape(-1, 3).sum(axis=0)).max() < 1e-9 * np.abs(f).max() * np.sqrt(len(f))
+    nodes = sampled_rows.pick_nodes(rm, 200, 0, seed=4)
+    r = sampled_rows.check(asm.ctx, rm, orc.TET10, orc.MAT_ISO_VOL, par, u, nodes, RTOL, nthreads=8)
+    _report("config 4", r)
+    assert r["ok"], r
+    asm.close()
+
+
+# ---- BASELINE config 5: one 200^3 rank of the 400^3 = 64 M element hex8 mesh on 8 ranks ---------------------
+def test_config5_one_rank_of_8_sampled_rows():
+    """Rank 0 of the 8-way box partition of 400^3 hex8 elements: 8.12 M column elements (one ghost layer on three
+    sides), nnz 1.97e9.  The NCCL halo is replaced by writing the exact ghost displacements into the column
+    vector (the halo itself is covered by tests/test_gpu_multirank.py and by bench.py's parity record at N > 1)."""
+    n = (400, 400, 400)
+    rm = b200.partition.box_partition(b200.mesh.HEX8, n, 0, 8, box=(4.0, 4.0, 4.0))
+    assert rm.n_row_eles == 200 ** 3 and rm.n_col_eles == 201 ** 3
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 4.0, 0.01)
+    par = [200.0, 0.25]
+    ctx = capi.Context(0)   # a lone context: no communicator, the ghosts are written below
+    ctx.set_mesh(rm.celltype, rm.X, rm.conn)
+    ctx.set_material(capi.MAT_COUP_NEOHOOKE, par)
+    nnz = ctx.build_graph(rm.n_row_nodes, rm.node_row_lid, rm.node_col_lid)
+    assert nnz > 1.9e9
+    _write_device(ctx.device_ptrs()["u_col"], u.ravel())
+    u_row = np.ascontiguousarray(u[:rm.n_row_nodes].ravel())
+    rc, err = ctx.evaluate(capi.ACTION_NLNSTIFF, u_row, None, None)
+    assert err.n_neg_jacobian == 0 and 0.7 < err.min_detF < 1.3
+    info = ctx.last_evaluate_info()
+    assert info["ghost_elements"] == 201 ** 3 - 200 ** 3, info
+    nodes = sampled_rows.pick_nodes(rm, 150, 60, seed=5)
+    r = sampled_rows.check(ctx, rm, orc.HEX8, orc.MAT_COUP_NEOHOOKE, par, u, nodes, RTOL, nthreads=8)
+    _report("config 5 (rank 0 of 8)", r)
+    assert r["ok"], r
+    ctx.close()
+
+
+# ---- host-destination pipeline --------------------------------------------------------------------------------
+@pytest.mark.parametrize("cell,n,mk,par", [("HEX8", (40, 36, 30), capi.MAT_COUP_NEOHOOKE, [200.0, 0.25]),
+                                           ("HEX27", (12, 10, 9), capi.MAT_SVK, [1000.0, 0.3])])
+def test_pipelined_host_copy_matches_resident_result(cell, n, mk, par):
+    rm = b200.partition.box_partition(getattr(b200.mesh, cell), n, 0, 1)
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 1.0 / max(n))
+    asm = b200.DeviceAssembler(rm, mk, par)
+    rowptr, colind = asm.graph()
+    asm.set_state("displacement", u.ravel())
+    K, f, _ = asm.evaluate()                       # host K: pipelined copy
+    info = asm.ctx.last_evaluate_info()
+    assert info["row_phases"] > 1 and info["pipeline_chunks"] == info["row_phases"], info
+    assert info["kernel_launches"] >= info["row_phases"]
+    rK, rf, nbad = orc.evaluate_assemble(getattr(orc, cell), mk, par, rm.conn, rm.X.ravel(), u.ravel(), rm.node_row_lid,
+                                         rm.node_col_lid, rm.n_row_nodes, rowptr, colind, nthreads=8)
+    ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
+    assert ok and nbad == 0, (wK, wf)
+    # the monolithic launch (K stays on the device) gives the same matrix
+    asm.evaluate_resident()
+    assert asm.ctx.last_evaluate_info()["kernel_launches"] == 1
+    K2 = asm.ctx.get_values()
+    ok, wK, _ = b200.parity_report(rowptr, K2, rK, f, rf, RTOL)
+    assert ok, wK
+    # one phase: no overlap, same numbers
+    ctx = capi.Context(0)
+    ctx.set_option("pipeline_phases", 1)
+    ctx.set_mesh(rm.celltype, rm.X, rm.conn)
+    ctx.set_material(mk, par)
+    ctx.build_graph(rm.n_row_nodes, rm.node_row_lid, rm.node_col_lid)
+    K3, f3 = np.empty(asm.nnz), np.empty(asm.n_rows)
+    ctx.evaluate(capi.ACTION_NLNSTIFF, np.ascontiguousarray(u.ravel()), K3, f3)
+    assert ctx.last_evaluate_info()["pipeline_chunks"] == 0
+    ok, wK, wf = b200.parity_report(rowptr, K3, rK, f3, rf, RTOL)
+    assert ok, (wK, wf)
+    ctx.close()
+    asm.close()
+
+
+def test_random_row_numbering_gets_one_phase():
+    """Randomly renumbered tet10 nodes: row ranges have no spatial locality, the pipeline must not reorder by them."""
+    X, conn = b200.mesh.unstructured_tet10(16)
+    rm = b200.partition.serial_mesh(b200.mesh.TET10, X, conn)
+    asm = b200.DeviceAssembler(rm, capi.MAT_ISO_VOL, [1.0, 1000.0])
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 1.0 / 16)
+    asm.set_state("displacement", u.ravel())
+    asm.evaluate()
+    assert asm.ctx.last_evaluate_info()["row_phases"] == 1
+    asm.close()
+
+
+# ---- several element blocks in one system matrix ---------------------------------------------------------------
+def _union_graph(blocks, n_row_nodes, n_col_nodes):
+    """FillComplete of the matrix all blocks assemble into: node-blocked CSR (rows of a node share the pattern,
+    columns ascending) from the node adjacency of every block."""
+    import scipy.sparse as sp
+    A = sp.csr_matrix((n_row_nodes, n_col_nodes), dtype=np.int8)
+    for conn in blocks:
+        nn = conn.shape[1]
+        r = np.repeat(conn, nn, axis=1).ravel()
+        c = np.tile(conn, (1, nn)).ravel()
+        keep = r < n_row_nodes
+        A = A + sp.csr_matrix((np.ones(keep.sum(), np.int8), (r[keep], c[keep])), shape=A.shape)
+    A.sum_duplicates()
+    A.sort_indices()
+    cnt = np.diff(A.indptr)
+    rowptr = np.zeros(3 * n_row_nodes + 1, np.int64)
+    rowptr[1:] = np.cumsum(np.repeat(3 * cnt, 3))
+    colind = np.empty(rowptr[-1], np.int32)
+    for r in range(n_row_nodes):
+        cols = (3 * A.indices[A.indptr[r]:A.indptr[r + 1]][:, None] + np.arange(3)).ravel()
+        for d in range(3):
+            colind[rowptr[3 * r + d]:rowptr[3 * r + d + 1]] = cols
+    return rowptr, colind
+
+
+def test_two_cell_types_and_two_materials_in_one_matrix():
+    """hex27 elements (SVK) in the lower half, hex8 elements (two MAT ids: CoupNeoHooke / iso-vol split) on the fine
+    grid of the upper half, all on the node set of the hex27 grid: the three blocks assemble into ONE CSR like the
+    reference's element loop does for any mix of element types and MAT ids
+    (4C_fem_discretization_evaluate.cpp:85-117)."""
+    n = (4, 3, 4)
+    X, conn27 = b200.mesh.structured_hex(b200.mesh.HEX27, n)
+    nx, ny, nz = n
+    e27 = np.arange(len(conn27))
+    lower = (e27 // (nx * ny)) < nz // 2
+    blkA = conn27[lower]
+    # fine hex8 cells of the upper half on the (2n+1)^3 node grid
+    gx, gy, gz = 2 * nx + 1, 2 * ny + 1, 2 * nz + 1
+    cells = [(i, j, k) for k in range(nz, 2 * nz) for j in range(2 * ny) for i in range(2 * nx)]
+    off = [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)]
+    c8 = np.array([[((k + c) * gy + (j + b)) * gx + (i + a) for a, b, c in off] for i, j, k in cells], np.int32)
+    blkB, blkC = c8[0::2], c8[1::2]
+    nnodes = len(X)
+    ids = np.arange(nnodes, dtype=np.int32)
+    rowptr, colind = _union_graph([blkA, blkB, blkC], nnodes, nnodes)
+    u = 2.0 * b200.mesh.displacement_field(X, ids, 1.0, 0.1)
+    mats = [(capi.HEX27, blkA, capi.MAT_SVK, [1000.0, 0.3]), (capi.HEX8, blkB, capi.MAT_COUP_NEOHOOKE, [200.0, 0.25]),
+            (capi.HEX8, blkC, capi.MAT_ISO_VOL, [1.0, 1000.0])]
+    d = np.arange(3, dtype=np.int32)
+    dof = (3 * ids[:, None] + d).astype(np.int32).ravel()
+    ctxs = []
+    for k, (ct, conn, mk, par) in enumerate(mats):
+        c = capi.Context(0)
+        c.set_mesh(ct, X, conn)
+        c.set_material(mk, par)
+        if k == 0:
+            c.set_graph(rowptr, colind, dof, dof)
+        else:
+            c.attach_block(ctxs[0])
+        ctxs.append(c)
+    u_row = np.ascontiguousarray(u.ravel())
+    K, f = np.empty(rowptr[-1]), np.empty(3 * nnodes)
+    ctxs[0].evaluate(capi.ACTION_NLNSTIFF, u_row, None, None)
+    ctxs[1].evaluate(capi.ACTION_NLNSTIFF, None, None, None)
+    ctxs[2].evaluate(capi.ACTION_NLNSTIFF, None, K, f)       # the last block hands out the sum
+    rK, rf = np.zeros_like(K), np.zeros_like(f)
+    for ct, conn, mk, par in mats:
+        k_, f_, nbad = orc.evaluate_assemble(ct, mk, par, conn, X.ravel(), u.ravel(), ids, ids, nnodes, rowptr, colind)
+        assert nbad == 0
+        rK += k_
+        rf += f_
+    ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
+    assert ok, (wK, wf)
+    # a block whose couplings are missing from the primary's graph is refused
+    far = capi.Context(0)
+    far.set_mesh(capi.HEX8, X, np.array([[0, 1, 2, 3, nnodes - 4, nnodes - 3, nnodes - 2, nnodes - 1]], np.int32))
+    far.set_material(capi.MAT_SVK, [1.0, 0.3])
+    with pytest.raises(capi.B200SolidError) as ei:
+        far.attach_block(ctxs[0])
+    assert ei.value.code == capi.ERR_UNSUPPORTED
+    far.close()
+    for c in reversed(ctxs):
+        c.close()
+
+
+# ---- call order: element properties before the mesh (device element order is final only after set_mesh) --------
+@pytest.mark.parametrize("tech,prestress", [(capi.TECH_EAS_MILD, capi.PRESTRESS_NONE), (capi.TECH_NONE, capi.PRESTRESS_MULF)])
+def test_properties_before_mesh_on_a_graded_mesh(tech, prestress):
+    n = (7, 6, 5)
+    rm = b200.partition.box_partition(b200.mesh.HEX8, n, 0, 1)
+    X = rm.X.copy()
+    X[:, 0] = X[:, 0] ** 1.7 * 1.3            # graded and stretched: every element has its own Jacobian
+    X[:, 1] = X[:, 1] * (1.0 + 0.4 * X[:, 2])
+    rm.X = X
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 0.1)
+    par = [200.0, 0.25]
+    res = []
+    for order in ("mesh_first", "properties_first", "mesh_twice"):
+        ctx = capi.Context(0)
+        if order == "properties_first":
+            ctx.set_element_properties(tech=tech, prestress=prestress)
+            ctx.set_mesh(rm.celltype, rm.X, rm.conn)
+        else:
+            ctx.set_mesh(rm.celltype, rm.X[::-1].copy() if order == "mesh_twice" else rm.X, rm.conn)
+            ctx.set_element_properties(tech=tech, prestress=prestress)
+            if order == "mesh_twice":
+                ctx.set_mesh(rm.celltype, rm.X, rm.conn)
+        ctx.set_material(capi.MAT_COUP_NEOHOOKE, par)
+        nnz = ctx.build_graph(rm.n_row_nodes, rm.node_row_lid, rm.node_col_lid)
+        K, f = np.empty(nnz), np.empty(3 * rm.n_row_nodes)
+        ctx.evaluate(capi.ACTION_NLNSTIFF, np.ascontiguousarray(u.ravel()), K, f)
+        res.append((K, f))
+        ctx.close()
+    for K, f in res[1:]:
+        assert np.abs(K - res[0][0]).max() <= 1e-12 * np.abs(res[0][0]).max()
+        assert np.abs(f - res[0][1]).max() <= 1e-12 * np.abs(res[0][1]).max()
+
+
+def test_reset_step_before_first_update_restores_fresh_history():
+    n = (4, 3, 3)
+    rm = b200.partition.box_partition(b200.mesh.HEX8, n, 0, 1)
+    u = 2.0 * b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 0.2)
+    asm = b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, [200.0, 0.25], tech=capi.TECH_EAS_MILD)
+    asm.set_state("displacement", u.ravel())
+    K0, f0, _ = asm.evaluate()
+    asm.recover(0.3 * u[:rm.n_row_nodes].ravel(), 0.5)   # alpha moves away from zero, old_step_length = 0.5
+    assert asm.ctx.eas_old_step_length() == 0.5
+    assert np.abs(asm.ctx.get_element_history()).max() > 0
+    asm.ctx.reset_step()                                   # diverged first step: back to the fresh history
+    assert asm.ctx.eas_old_step_length() == 1.0
+    h = asm.ctx.get_element_history().reshape(rm.n_col_eles, -1)
+    assert np.abs(h[:, :18]).max() == 0.0                   # alpha_inc, alpha
+    K1, f1, _ = asm.evaluate()
+    assert np.abs(K1 - K0).max() <= 1e-12 * np.abs(K0).max() and np.abs(f1 - f0).max() <= 1e-12 * np.abs(f0).max()
+    # snapshot / restore carries old_step_length
+    asm.recover(0.3 * u[:rm.n_row_nodes].ravel(), 0.25)
+    asm.ctx.update_step()
+    asm.ctx.recover_linesearch(0.75)
+    asm.ctx.reset_step()
+    assert asm.ctx.eas_old_step_length() == 0.25
+    asm.close()
+
+
+def test_dirichlet_diagonal_with_permuted_column_map():
+    """Matrix-local column ids that do not list the owned dofs in row order: the 1.0 of apply_dirichlet must still
+    land on the diagonal entry."""
+    import scipy.sparse as sp
+    n = (3, 3, 2)
+    rm = b200.partition.box_partition(b200.mesh.HEX8, n, 0, 1)
+    nn = rm.n_col_nodes
+    perm = np.random.default_rng(7).permutation(nn).astype(np.int32)      # column-node id of node k
+    rowptr0, colind0 = orc.build_graph(orc.HEX8, rm.conn, rm.node_row_lid, perm, rm.n_row_nodes)
+    d = np.arange(3, dtype=np.int32)
+    dof_row = (3 * np.arange(nn, dtype=np.int32)[:, None] + d).ravel()
+    dof_col = (3 * perm[:, None] + d).astype(np.int32).ravel()
+    ctx = capi.Context(0)
+    ctx.set_mesh(rm.celltype, rm.X, rm.conn)
+    ctx.set_material(capi.MAT_SVK, [1000.0, 0.3])
+    ctx.set_graph(rowptr0, colind0, dof_row, dof_col)
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 0.2)
+    ctx.evaluate(capi.ACTION_NLNSTIFF, np.ascontiguousarray(u.ravel()), None, None)
+    tog = np.zeros(3 * nn)
+    tog[[0, 7, 20, 3 * nn - 1]] = 1.0
+    ctx.apply_dirichlet(tog, True)
+    K = ctx.get_values()
+    A = sp.csr_matrix((K, colind0, rowptr0), shape=(3 * nn, 3 * nn)).toarray()
+    for r in np.nonzero(tog)[0]:
+        node, dd = divmod(int(r), 3)
+        row = A[r]
+        assert row[3 * perm[node] + dd] == 1.0 and np.count_nonzero(row) == 1
+    ctx.close()
