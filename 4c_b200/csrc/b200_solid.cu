@@ -2814,6 +2814,7 @@ extern "C"
   {
     if (!ctx) return B200S_ERR_INVALID;
     cudaSetDevice(ctx->device);
+    ctx->timed_h2d = ctx->timed_d2h = false;  // no copies in this flavour: timers[4], [5] read 0
     return evaluate_impl(ctx, action, nullptr, nullptr);
   }
 
