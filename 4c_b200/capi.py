@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib4c_b200_solid.so")
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NEG_JACOBIAN, ERR_NONFINITE, ERR_COMM = -1, -2, -3, -4, -5, -6
 HEX8, HEX27, TET10 = 0, 1, 2
-MAT_COUP_NEOHOOKE, MAT_ISO_VOL, MAT_SVK, MAT_ELASTHYPER, MAT_DRUCKER_PRAGER = 0, 1, 2, 3, 4
+MAT_COUP_NEOHOOKE, MAT_ISO_VOL, MAT_SVK, MAT_ELASTHYPER, MAT_DRUCKER_PRAGER, MAT_VISCONEOHOOKE = 0, 1, 2, 3, 4, 5
 ACTION_INTERNALFORCE, ACTION_NLNSTIFF, ACTION_NLNSTIFFMASS, ACTION_NLNSTIFFLMASS, ACTION_INTERNALINERTIAFORCE = 0, 1, 2, 3, 4
 STRESS_NONE, STRESS_2PK, STRESS_CAUCHY = 0, 1, 2
 STRAIN_NONE, STRAIN_GL, STRAIN_EA = 0, 1, 2
@@ -53,7 +53,7 @@ SYMBOLS = [
     "b200s_neumann_gp_coords", "b200s_set_neumann_factors", "b200s_evaluate_neumann", "b200s_device_fext",
     "b200s_material_history_size", "b200s_get_material_history", "b200s_set_material_history",
     "b200s_get_value_rows", "b200s_get_f_rows", "b200s_eas_old_step_length", "b200s_set_eas_old_step_length",
-    "b200s_attach_block", "b200s_host_alloc_near", "b200s_last_evaluate_info",
+    "b200s_attach_block", "b200s_host_alloc_near", "b200s_last_evaluate_info", "b200s_set_time_step_size",
 ]
 
 
@@ -170,6 +170,7 @@ def load():
     L.b200s_host_alloc_near.argtypes = [i32, i64, C.POINTER(i32)]
     L.b200s_host_alloc_near.restype = vp
     L.b200s_last_evaluate_info.argtypes = [vp, vp]
+    L.b200s_set_time_step_size.argtypes = [vp, dbl]
     _lib = L
     return L
 
@@ -254,6 +255,9 @@ class Context:
     def set_element_fibers(self, fiber1):
         f = None if fiber1 is None else np.ascontiguousarray(fiber1, np.float64).reshape(self.n_col_eles, 3)
         self._ck(self.L.b200s_set_element_fibers(self.h, _ptr(f)))
+
+    def set_time_step_size(self, dt):
+        self._ck(self.L.b200s_set_time_step_size(self.h, float(dt)))
 
     def set_density(self, density):
         self._ck(self.L.b200s_set_density(self.h, float(density)))

@@ -1198,6 +1198,9 @@ struct b200s_ctx
   HyperMat* d_hyper = nullptr;  // ... and on the device (MatParams::hyper)
   double* d_fibers = nullptr;   // unit element fibres FIBER1, 3 per column element, device element order
   double density = 0.0;         // Mat::So3Material::density()
+  double visco_in[6] = {0, 0, 0, 0, 0, 0};  // MAT_VISCONEOHOOKE input-file parameters
+  double dt = 0.0;              // EvaluationContext::time_step_size
+  bool dt_set = false;
   // cell tables in global memory for the post / mass kernels (post_kernels.cuh)
   int ngp = 0, ngp_mass = 0;
   double *d_dN_gp = nullptr, *d_w = nullptr, *d_dN_cen = nullptr, *d_xi_gp = nullptr;
@@ -1448,13 +1451,18 @@ namespace
     return 0;
   }
 
+  // history doubles per Gauss point of the block's material
+  inline int mat_hist_per_gp(const b200s_ctx* ctx)
+  {
+    return ctx->matkind == B200S_MAT_DRUCKER_PRAGER ? DP_HIST : (ctx->matkind == B200S_MAT_VISCONEOHOOKE ? VISCO_HIST : 0);
+  }
   // fresh history of a history material: what Mat::PlasticDruckerPrager::setup(numgp) does per element
   // (src/mat/4C_mat_plasticdruckerprager.cpp:109-117): zero plastic strains at every Gauss point
   int material_history_allocate(b200s_ctx* ctx)
   {
     dfree(ctx->d_mat_hist);
-    if (ctx->matkind != B200S_MAT_DRUCKER_PRAGER || ctx->celltype < 0) return 0;
-    const int64_t n = ctx->n_col_eles * ctx->ngp * DP_HIST;
+    if (mat_hist_per_gp(ctx) == 0 || ctx->celltype < 0) return 0;
+    const int64_t n = ctx->n_col_eles * ctx->ngp * mat_hist_per_gp(ctx);
     if (to_device(ctx, &ctx->d_mat_hist, (const double*)nullptr, n)) return B200S_ERR_CUDA;
     CK(cudaMemsetAsync(ctx->d_mat_hist, 0, sizeof(double) * (size_t)(n > 0 ? n : 1), ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1511,7 +1519,12 @@ namespace
 }  // namespace
 namespace b200s_parts
 {
-  int launch_hex8_eas(b200s_ctx* ctx, const EvalArgs& A, bool stiff) { B200S_DISPATCH_MATERIAL(launch_hex8_eas_any); }
+  int launch_hex8_eas(b200s_ctx* ctx, const EvalArgs& A, bool stiff)
+  {
+    if (ctx->matkind == B200S_MAT_VISCONEOHOOKE)
+      return stiff ? launch_hex8_eas_any<MAT_VISCO, true>(ctx, A) : launch_hex8_eas_any<MAT_VISCO, false>(ctx, A);
+    B200S_DISPATCH_MATERIAL(launch_hex8_eas_any);
+  }
   int set_tables_hex8_eas(b200s_ctx* ctx, const Hex8Const& h)
   {
     CK(cudaMemcpyToSymbolAsync(c_hex8, &h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
@@ -1547,7 +1560,7 @@ namespace
   template <int MAT, bool STIFF>
   static int launch_hex8_t(b200s_ctx* ctx, const EvalArgs& A)
   {
-    if constexpr (MAT != MAT_DP)
+    if constexpr (MAT != MAT_DP && MAT != MAT_VISCO)
     if (ctx->tech == B200S_TECH_FBAR)
     {
       auto kern = k_hex8_eval_assemble<MAT, STIFF, 1>;
@@ -1561,11 +1574,14 @@ namespace
       ctx->launches += 1;
       return 0;
     }
-    // history materials (MAT_DP) exist for KINEM linear only: one kernel instead of four
+    // history materials exist for one formulation each (MAT_DP: KINEM linear, MAT_VISCO: nonlinear total
+    // Lagrangean): one kernel instead of four
     auto kern = [&]
     {
       if constexpr (MAT == MAT_DP)
         return k_hex8_eval_assemble<MAT, STIFF, 3>;
+      else if constexpr (MAT == MAT_VISCO)
+        return k_hex8_eval_assemble<MAT, STIFF, 0>;
       else
         return ctx->prestress == B200S_PRESTRESS_MULF
                    ? k_hex8_eval_assemble<MAT, STIFF, 2>
@@ -1592,6 +1608,8 @@ namespace b200s_parts
   {
     if (ctx->matkind == B200S_MAT_DRUCKER_PRAGER)
       return stiff ? launch_hex8_t<MAT_DP, true>(ctx, A) : launch_hex8_t<MAT_DP, false>(ctx, A);
+    if (ctx->matkind == B200S_MAT_VISCONEOHOOKE)
+      return stiff ? launch_hex8_t<MAT_VISCO, true>(ctx, A) : launch_hex8_t<MAT_VISCO, false>(ctx, A);
     B200S_DISPATCH_MATERIAL(launch_hex8_t);
   }
   int set_tables_hex8(b200s_ctx* ctx, const Hex8Const& h)
@@ -1613,6 +1631,8 @@ namespace
     {
       if constexpr (MAT == MAT_DP)
         return k_tet10_eval_assemble<MAT, STIFF, 2>;
+      else if constexpr (MAT == MAT_VISCO)
+        return k_tet10_eval_assemble<MAT, STIFF, 0>;
       else
         return ctx->prestress == B200S_PRESTRESS_MULF
                    ? k_tet10_eval_assemble<MAT, STIFF, 1>
@@ -1639,6 +1659,8 @@ namespace b200s_parts
   {
     if (ctx->matkind == B200S_MAT_DRUCKER_PRAGER)
       return stiff ? launch_tet10_t<MAT_DP, true>(ctx, A) : launch_tet10_t<MAT_DP, false>(ctx, A);
+    if (ctx->matkind == B200S_MAT_VISCONEOHOOKE)
+      return stiff ? launch_tet10_t<MAT_VISCO, true>(ctx, A) : launch_tet10_t<MAT_VISCO, false>(ctx, A);
     B200S_DISPATCH_MATERIAL(launch_tet10_t);
   }
   int set_tables_tet10(b200s_ctx* ctx, const Tet10Const& h)
@@ -1660,6 +1682,8 @@ namespace
     {
       if constexpr (MAT == MAT_DP)
         return k_hex27_eval_assemble<MAT, STIFF, 2>;
+      else if constexpr (MAT == MAT_VISCO)
+        return k_hex27_eval_assemble<MAT, STIFF, 0>;
       else
         return ctx->prestress == B200S_PRESTRESS_MULF
                    ? k_hex27_eval_assemble<MAT, STIFF, 1>
@@ -1684,6 +1708,8 @@ namespace b200s_parts
   {
     if (ctx->matkind == B200S_MAT_DRUCKER_PRAGER)
       return stiff ? launch_hex27_t<MAT_DP, true>(ctx, A) : launch_hex27_t<MAT_DP, false>(ctx, A);
+    if (ctx->matkind == B200S_MAT_VISCONEOHOOKE)
+      return stiff ? launch_hex27_t<MAT_VISCO, true>(ctx, A) : launch_hex27_t<MAT_VISCO, false>(ctx, A);
     B200S_DISPATCH_MATERIAL(launch_hex27_t);
   }
   int set_tables_hex27(b200s_ctx* ctx, const Hex27Const& h)
@@ -2021,6 +2047,23 @@ extern "C"
       dfree(ctx->d_per_ele);
       return material_history_allocate(ctx) ? B200S_ERR_CUDA : B200S_OK;
     }
+    if (kind == B200S_MAT_VISCONEOHOOKE)
+    {
+      if (nparams < 6 || per_ele_param)
+        return fail(ctx, B200S_ERR_INVALID,
+            "MAT_VISCONEOHOOKE: 6 parameters {YOUNGS_SLOW POISSON DENS YOUNGS_FAST RELAX THETA}");
+      for (double& v : mp.p) v = 0.0;
+      mp.hyper = nullptr, mp.fiber = nullptr, mp.ext = nullptr, mp.hist = nullptr;
+      if (params[3] < params[0]) return fail(ctx, B200S_ERR_INVALID, "Wrong ratio between fast and slow Young's modulus");
+      if (!(params[4] > 0.0)) return fail(ctx, B200S_ERR_INVALID, "Relaxation time tau has to be positive!");
+      for (int i = 0; i < 6; ++i) ctx->visco_in[i] = params[i];
+      make_visco_neohooke(ctx->visco_in, ctx->dt, mp.p);
+      const bool fresh = ctx->matkind != kind || !ctx->d_mat_hist;
+      ctx->matkind = kind, ctx->mp = mp;
+      if (params[2] > 0.0) ctx->density = params[2];
+      dfree(ctx->d_per_ele);
+      return (fresh && material_history_allocate(ctx)) ? B200S_ERR_CUDA : B200S_OK;
+    }
     dfree(ctx->d_mat_hist);
     if (!make_mat_params(kind, params, mp))
       return fail(ctx, B200S_ERR_UNSUPPORTED, "material kind %d is not on the device path", kind);
@@ -2129,7 +2172,7 @@ extern "C"
     if (!rc) rc = permute_array(ctx, ctx->d_eas_hist, n, neas ? hex8eas::hist_size(neas) : 0, perm);
     if (!rc) rc = permute_array(ctx, ctx->d_eas_t0, n, hex8eas::T0_STRIDE, perm);
     if (!rc) rc = permute_array(ctx, ctx->d_hist_old, n, hist_w, perm);
-    if (!rc) rc = permute_array(ctx, ctx->d_mat_hist, n, ctx->ngp * DP_HIST, perm);
+    if (!rc) rc = permute_array(ctx, ctx->d_mat_hist, n, ctx->ngp * mat_hist_per_gp(ctx), perm);
     CK(cudaStreamSynchronize(st));
     cudaFree(d_prow), cudaFree(d_poff), cudaFree(d_seg), cudaFree(d_spread), cudaFree(k0), cudaFree(k1);
     cudaFree(i0), cudaFree(perm), cudaFree(tmp);
@@ -2598,7 +2641,7 @@ extern "C"
     A.ele_id = ctx->d_ele_id ? ctx->d_ele_id + e_begin : nullptr;
     A.fibers = ctx->d_fibers ? ctx->d_fibers + 3 * e_begin : nullptr;
     A.gp_hist = ctx->d_gp_hist ? ctx->d_gp_hist + e_begin * ctx->ngp * MULF_HIST : nullptr;
-    A.mat_hist = ctx->d_mat_hist ? ctx->d_mat_hist + e_begin * ctx->ngp * DP_HIST : nullptr;
+    A.mat_hist = ctx->d_mat_hist ? ctx->d_mat_hist + e_begin * ctx->ngp * mat_hist_per_gp(ctx) : nullptr;
     A.linear = ctx->kinem == B200S_KINEM_LINEAR;
     A.vals = ctx->d_vals, A.f = ctx->d_f, A.err = ctx->d_err, A.mp = ctx->mp;
     A.n_ele = count;
@@ -2658,6 +2701,18 @@ extern "C"
       if (ctx->kinem != B200S_KINEM_LINEAR || ctx->tech != B200S_TECH_NONE || ctx->prestress != B200S_PRESTRESS_NONE)
         return fail(ctx, B200S_ERR_UNSUPPORTED,
             "MAT_Struct_DruckerPrager is a small-strain material: KINEM linear without element technology / prestress");
+      if (!ctx->d_mat_hist) return fail(ctx, B200S_ERR_INVALID, "material history missing (set_mesh first)");
+    }
+    if (ctx->matkind == B200S_MAT_VISCONEOHOOKE)
+    {
+      const bool eas = ctx->tech == B200S_TECH_EAS_MILD || ctx->tech == B200S_TECH_EAS_FULL;
+      if (ctx->kinem != B200S_KINEM_NONLINEAR_TOTLAG || (ctx->tech != B200S_TECH_NONE && !eas) ||
+          ctx->prestress != B200S_PRESTRESS_NONE)
+        return fail(ctx, B200S_ERR_UNSUPPORTED,
+            "MAT_VISCONEOHOOKE on the device: KINEM nonlinear, TECH none or eas_mild / eas_full, no prestress");
+      if (!ctx->dt_set)
+        return fail(ctx, B200S_ERR_INVALID,
+            "Time step size not given in evaluation context. (b200s_set_time_step_size)");
       if (!ctx->d_mat_hist) return fail(ctx, B200S_ERR_INVALID, "material history missing (set_mesh first)");
     }
     // an attached block adds into its primary's matrix: the primary's evaluate of this iteration has imported
@@ -2971,6 +3026,15 @@ extern "C"
     return B200S_OK;
   }
 
+  int b200s_set_time_step_size(b200s_ctx* ctx, double dt)
+  {
+    if (!ctx) return B200S_ERR_INVALID;
+    if (!(dt >= 0.0)) return fail(ctx, B200S_ERR_INVALID, "time step size must be >= 0");
+    ctx->dt = dt, ctx->dt_set = true;
+    if (ctx->matkind == B200S_MAT_VISCONEOHOOKE) make_visco_neohooke(ctx->visco_in, dt, ctx->mp.p);
+    return B200S_OK;
+  }
+
   int b200s_set_row_elements(b200s_ctx* ctx, const uint8_t* is_row)
   {
     if (!ctx) return B200S_ERR_INVALID;
@@ -3118,6 +3182,11 @@ extern "C"
         break;
       case B200S_MAT_ELASTHYPER:
         k_post_points<MAT_HYPER><<<grid, 128, 0, ctx->stream>>>(P);
+        break;
+      case B200S_MAT_VISCONEOHOOKE:
+        if (d_energy) return fail(ctx, B200S_ERR_UNSUPPORTED, "MAT_VISCONEOHOOKE has no strain energy");
+        if (!ctx->dt_set) return fail(ctx, B200S_ERR_INVALID, "Time step size not given in evaluation context.");
+        k_post_points<MAT_VISCO><<<grid, 128, 0, ctx->stream>>>(P);
         break;
       case B200S_MAT_DRUCKER_PRAGER:
         if (d_energy) return fail(ctx, B200S_ERR_UNSUPPORTED, "MAT_Struct_DruckerPrager has no strain energy");
@@ -3300,8 +3369,11 @@ extern "C"
     const int64_t np = ctx->n_col_eles * ctx->ngp;
     if (np > 0)
     {
-      k_material_history_commit<<<nblk(np * (DP_HIST / 2)), 256, 0, ctx->stream>>>(np, DP_HIST, DP_HIST / 2, restore,
-          ctx->d_mat_hist);
+      // update: last <- current (Mat::ViscoNeoHooke::update additionally clears the current iterate, :197-216);
+      // reset: current <- last
+      const int H = mat_hist_per_gp(ctx);
+      k_material_history_commit<<<nblk(np * (H / 2)), 256, 0, ctx->stream>>>(np, H, H / 2,
+          restore ? 1 : (ctx->matkind == B200S_MAT_VISCONEOHOOKE ? 2 : 0), ctx->d_mat_hist);
       ctx->launches += 1;
     }
     CK(cudaStreamSynchronize(ctx->stream));
@@ -3322,7 +3394,7 @@ extern "C"
   }
   int64_t b200s_material_history_size(const b200s_ctx* ctx)
   {
-    return (ctx && ctx->d_mat_hist) ? ctx->n_col_eles * ctx->ngp * DP_HIST : 0;
+    return (ctx && ctx->d_mat_hist) ? ctx->n_col_eles * ctx->ngp * mat_hist_per_gp(ctx) : 0;
   }
 
   int64_t b200s_element_history_size(const b200s_ctx* ctx)
@@ -3343,7 +3415,7 @@ extern "C"
     cudaSetDevice(ctx->device);
     const int64_t n = element_level == 2 ? b200s_material_history_size(ctx)
                                          : (element_level ? b200s_element_history_size(ctx) : b200s_gp_history_size(ctx));
-    const int per_ele = element_level == 2 ? ctx->ngp * DP_HIST
+    const int per_ele = element_level == 2 ? ctx->ngp * mat_hist_per_gp(ctx)
                                            : (element_level ? hex8eas::hist_size(eas_neas(ctx->tech)) : ctx->ngp * MULF_HIST);
     double* tmp = nullptr;
     CK(cudaMalloc((void**)&tmp, sizeof(double) * (size_t)(n ? n : 1)));

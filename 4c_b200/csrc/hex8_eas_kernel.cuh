@@ -351,6 +351,8 @@ namespace b200s
         MatParams mp = A.mp;
         if (A.per_ele_param != nullptr) mp.p[0] = A.per_ele_param[e];
         if (MAT == MAT_HYPER && A.fibers != nullptr) mp.fiber = A.fibers + 3 * e;
+        if (material_hist_doubles(MAT) > 0 && A.mat_hist != nullptr)
+          mp.hist = A.mat_hist + (e * 8 + g) * material_hist_doubles(MAT);
         material_evaluate<MAT>(mp, C, Sv, Cm);
         const double w = detJ * wgt[g];
 #pragma unroll

@@ -258,7 +258,8 @@ namespace b200s
       MatParams mp = A.mp;
       if (A.per_ele_param != nullptr && e < A.n_ele) mp.p[0] = A.per_ele_param[e];
       if (MAT == MAT_HYPER && A.fibers != nullptr && e < A.n_ele) mp.fiber = A.fibers + 3 * e;
-      if (MAT == MAT_DP && A.mat_hist != nullptr && e < A.n_ele) mp.hist = A.mat_hist + (e * NGP + g) * DP_HIST;
+      if (material_hist_doubles(MAT) > 0 && A.mat_hist != nullptr && e < A.n_ele)
+        mp.hist = A.mat_hist + (e * NGP + g) * material_hist_doubles(MAT);
       material_evaluate<MAT>(mp, C, Sv, Cm);
 
       // integration factor (calc_lib.hpp:1270-1280), folded into S and Cm once

@@ -152,4 +152,79 @@ namespace b200s
     }
   }
 
+  // ---- MAT_VISCONEOHOOKE ----------------------------------------------------------------------------------------
+  // Mat::ViscoNeoHooke::evaluate (src/mat/4C_mat_visconeohooke.cpp:222-405, GEN_MAXWELL branch): compressible
+  // Neo-Hooke on the fast modulus, W = mue/2 (I1 I3^-1/3 - 3) + kappa/2 (J - 1)^2; the deviatoric stress relaxes
+  // through one Maxwell branch integrated with the one-step-theta rule
+  //   Q^(n+1) = artscalar2 [ artscalar1 Q^n + S_dev^(n+1) - S_dev^n ],
+  //   S = S_vol + alpha0 S_dev + (1 - alpha0) Q,   C = C_vol + scalarvisco C_dev   (major-symmetric).
+  // History per Gauss point (VISCO_HIST doubles, the pack order :97-104): histstresslast[6], artstresslast[6],
+  // histstresscurr[6], artstresscurr[6]; update() (:197-216): last <- current, current <- 0.  The scalars depend on
+  // the time step size (EvaluationContext::time_step_size, b200s_set_time_step_size).
+  constexpr int VISCO_HIST = 24;
+  // in: {YOUNGS_SLOW, POISSON, DENS, YOUNGS_FAST, RELAX, THETA}; false where setup() throws (:185-189)
+  inline bool make_visco_neohooke(const double* in, double dt, double* p6)
+  {
+    const double E_s = in[0], nue = in[1], E_f = in[3], theta = in[5];
+    double tau = in[4];
+    if (E_f < E_s || !(tau > 0.0)) return false;
+    if (E_f > E_s) tau = tau * E_s / (E_f - E_s);
+    const double alpha0 = E_s / E_f, alpha1 = 1.0 - alpha0;
+    const double lambda = nue * E_f / ((1.0 + nue) * (1.0 - 2.0 * nue));
+    const double mue = E_f / (2.0 * (1.0 + nue));
+    p6[0] = alpha0, p6[1] = mue, p6[2] = lambda + 2.0 / 3.0 * mue;
+    p6[3] = (tau - dt + theta * dt) / tau;
+    p6[4] = tau / (tau + theta * dt);
+    p6[5] = alpha0 + alpha1 * tau / (tau + theta * dt);
+    return true;
+  }
+
+  // C (tensor components 00,11,22,01,12,02) in; S[6], Cm[21] out; hist = state of this point or nullptr
+  B2_HD void visco_neohooke_evaluate(const double* p, double* hist, const double* C, double* S, double* Cm)
+  {
+    const double alpha0 = p[0], mue = p[1], kappa = p[2], art1 = p[3], art2 = p[4], scalarvisco = p[5];
+    const double alpha1 = 1.0 - alpha0;
+    const double I1 = C[0] + C[1] + C[2];
+    const double I3 = C[0] * C[1] * C[2] + 2.0 * C[3] * C[4] * C[5] - C[1] * C[5] * C[5] - C[2] * C[3] * C[3] -
+                      C[0] * C[4] * C[4];
+    const double J = sqrt(I3);
+    const double I3invcubroot = pow(I3, -1.0 / 3.0);
+    double Ci[6] = {C[1] * C[2] - C[4] * C[4], C[0] * C[2] - C[5] * C[5], C[0] * C[1] - C[3] * C[3],
+        C[5] * C[4] - C[3] * C[2], C[3] * C[5] - C[0] * C[4], C[3] * C[4] - C[5] * C[1]};
+    const double inv = 1.0 / I3;
+#pragma unroll
+    for (int v = 0; v < 6; ++v) Ci[v] *= inv;
+#pragma unroll
+    for (int v = 0; v < 6; ++v)
+    {
+      const double idv = v < 3 ? 1.0 : 0.0;
+      const double sdev = mue * I3invcubroot * (idv - 1.0 / 3.0 * I1 * Ci[v]);
+      const double S_n = hist ? hist[v] : 0.0, Q_n = hist ? hist[6 + v] : 0.0;
+      const double Q = art2 * (art1 * Q_n + sdev - S_n);
+      if (hist) hist[12 + v] = sdev, hist[18 + v] = Q;
+      S[v] = kappa * (J - 1.0) * J * Ci[v] + alpha0 * sdev + alpha1 * Q;
+    }
+    const double scalar1 = 2.0 * kappa * J * J - kappa * J;
+    const double scalar2 = -2.0 * kappa * J * J + 2.0 * kappa * J;
+    const double scalar3 = 2.0 / 3.0 * mue * I3invcubroot * I1;
+    const double scalar4 = 2.0 / 3.0 * mue * I3invcubroot;
+    const double cH = scalar2 + scalarvisco * scalar3, cCC = scalar1 + scalarvisco * scalar3 / 3.0,
+                 cIC = -scalarvisco * scalar4;
+    constexpr int va[6] = {0, 1, 2, 0, 1, 0}, vb[6] = {0, 1, 2, 1, 2, 2};
+    constexpr int vg[3][3] = {{0, 3, 5}, {3, 1, 4}, {5, 4, 2}};
+#pragma unroll
+    for (int P = 0; P < 6; ++P)
+#pragma unroll
+      for (int Q = P; Q < 6; ++Q)
+      {
+        // holzapfel_product: 1/2 (Cinv_ac Cinv_bd + Cinv_ad Cinv_bc)
+        const double H = 0.5 * (Ci[vg[va[P]][va[Q]]] * Ci[vg[vb[P]][vb[Q]]] + Ci[vg[va[P]][vb[Q]]] * Ci[vg[vb[P]][va[Q]]]);
+        const double iP = P < 3 ? 1.0 : 0.0, iQ = Q < 3 ? 1.0 : 0.0;
+        Cm[c21(P, Q)] = cH * H + cCC * Ci[P] * Ci[Q] + cIC * (iP * Ci[Q] + iQ * Ci[P]);
+      }
+  }
+
+  // history doubles per Gauss point of a material kind (0: no history)
+  B2_HD constexpr int material_hist_doubles(int mat) { return mat == MAT_DP ? DP_HIST : (mat == MAT_VISCO ? VISCO_HIST : 0); }
+
 }  // namespace b200s

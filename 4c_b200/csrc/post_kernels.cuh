@@ -253,7 +253,8 @@ namespace b200s
     MatParams mp = A.mp;
     if (A.per_ele_param != nullptr) mp.p[0] = A.per_ele_param[e];
     if (MAT == MAT_HYPER && A.fibers != nullptr) mp.fiber = A.fibers + 3 * e;
-    if (MAT == MAT_DP && A.mat_hist != nullptr) mp.hist = A.mat_hist + (e * A.ngp + g) * DP_HIST;
+    if (material_hist_doubles(MAT) > 0 && A.mat_hist != nullptr)
+      mp.hist = A.mat_hist + (e * A.ngp + g) * material_hist_doubles(MAT);
     if (stress6 != nullptr && A.stress_type != STRESS_NONE)
     {
       material_evaluate<MAT>(mp, C, S, Cm);
@@ -533,10 +534,14 @@ namespace b200s
     if (t >= n_points * half) return;
     double* h = hist + (t / half) * stride;
     const int i = (int)(t % half);
-    if (restore)
+    // restore 0: last <- current; 1: current <- last; 2: last <- current and current <- 0
+    if (restore == 1)
       h[half + i] = h[i];
     else
+    {
       h[i] = h[half + i];
+      if (restore == 2) h[half + i] = 0.0;
+    }
   }
 #endif
 }  // namespace b200s

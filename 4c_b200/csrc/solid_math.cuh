@@ -85,12 +85,14 @@ namespace b200s
     MAT_ISO_VOL = 1,
     MAT_SVK = 2,
     MAT_HYPER = 3, // generic MAT_ElastHyper summand list (summands.cuh)
-    MAT_DP = 4     // MAT_Struct_DruckerPrager, a history material (history_materials.cuh); KINEM linear only
+    MAT_DP = 4,    // MAT_Struct_DruckerPrager, a history material (history_materials.cuh); KINEM linear only
+    MAT_VISCO = 5  // MAT_VISCONEOHOOKE, a finite-strain history material (history_materials.cuh)
   };
 
   struct HyperMat;
   B2_HD void hyper_evaluate(const HyperMat& hm, const double* fiber, const double* C, double* S, double* Cm);
   B2_HD void drucker_prager_evaluate(const double* q, double* hist, const double* C, double* S, double* Cm);
+  B2_HD void visco_neohooke_evaluate(const double* p, double* hist, const double* C, double* S, double* Cm);
   B2_HD double hyper_strain_energy(const HyperMat& hm, const double* fiber, const double* C);
 
   // Material parameters preprocessed once on the host (b200s_set_material):
@@ -100,6 +102,8 @@ namespace b200s
   //   SVK          : p[0]=lambda, p[1]=2*mue, p[2]=mfac*(1-nu), p[3]=mfac*nu, p[4]=mfac*(1-2nu)/2
   //                  (src/mat/4C_mat_stvenantkirchhoff.hpp:136-170)
   //   HYPER        : p[] unused; hyper points to the summand list (device memory on the device)
+  //   VISCO        : p[0]=alpha0=E_s/E_f, p[1]=mue, p[2]=kappa (fast modulus), p[3]=artscalar1, p[4]=artscalar2,
+  //                  p[5]=scalarvisco -- functions of the time step size (history_materials.cuh make_visco_neohooke)
   struct MatParams
   {
     double p[6];
@@ -154,6 +158,10 @@ namespace b200s
     else if (MAT == MAT_DP)
     {
       drucker_prager_evaluate(mp.ext, mp.hist, C, S, Cm);
+    }
+    else if (MAT == MAT_VISCO)
+    {
+      visco_neohooke_evaluate(mp.p, mp.hist, C, S, Cm);
     }
     else if (MAT == MAT_SVK)
     {
@@ -254,7 +262,7 @@ namespace b200s
   B2_HD double material_strain_energy(const MatParams& mp, const double* C)
   {
     if (MAT == MAT_HYPER) return hyper_strain_energy(*mp.hyper, mp.fiber, C);
-    if (MAT == MAT_DP) return 0.0;  // no strain energy in the reference; rejected on the host
+    if (MAT == MAT_DP || MAT == MAT_VISCO) return 0.0;  // no strain energy in the reference; rejected on the host
     if (MAT == MAT_SVK)
     {
       const double E[6] = {0.5 * (C[0] - 1.0), 0.5 * (C[1] - 1.0), 0.5 * (C[2] - 1.0), 0.5 * C[3],

@@ -59,14 +59,22 @@ extern "C"
    *                   in the context: b200s_update_step = Mat::PlasticDruckerPrager::update(),
    *                   b200s_reset_step discards the iterate, b200s_get/set_material_history = pack/unpack.
    *                   The consistent tangent needs ETA == ETABAR (otherwise it is not major-symmetric and
-   *                   b200s_set_material returns B200S_ERR_UNSUPPORTED; TANG elastic always works). */
+   *                   b200s_set_material returns B200S_ERR_UNSUPPORTED; TANG elastic always works).
+   *   VISCONEOHOOKE : MAT_VISCONEOHOOKE (src/mat/4C_mat_visconeohooke.cpp), a finite-strain HISTORY material:
+   *                   params = {YOUNGS_SLOW, POISSON, DENS, YOUNGS_FAST, RELAX, THETA}; compressible Neo-Hooke on
+   *                   the fast modulus whose deviatoric stress relaxes through one Maxwell branch (one-step-theta
+   *                   rule over the time step given with b200s_set_time_step_size).  KINEM nonlinear blocks, TECH
+   *                   none (hex8 / hex27 / tet10) or eas_mild / eas_full (hex8).  24 doubles of state per Gauss
+   *                   point (last converged and current {S_dev, Q}); b200s_update_step =
+   *                   Mat::ViscoNeoHooke::update(), b200s_get/set_material_history = pack/unpack. */
   typedef enum
   {
     B200S_MAT_COUP_NEOHOOKE = 0,
     B200S_MAT_ISO_VOL = 1,
     B200S_MAT_SVK = 2,
     B200S_MAT_ELASTHYPER = 3,
-    B200S_MAT_DRUCKER_PRAGER = 4
+    B200S_MAT_DRUCKER_PRAGER = 4,
+    B200S_MAT_VISCONEOHOOKE = 5
   } b200s_material;
 
   /* Mat::Elastic::Summand implementations evaluated through the principal / modified invariants
@@ -254,6 +262,9 @@ extern "C"
   int b200s_set_element_fibers(b200s_ctx* ctx, const double* fiber1);
   /* Mat::So3Material::density() of the block (DENS): needed by the mass actions */
   int b200s_set_density(b200s_ctx* ctx, double density);
+  /* EvaluationContext::time_step_size of the coming evaluates (4C_mat_visconeohooke.cpp:238-240): rate-dependent
+   * materials only; without it their evaluate fails like the reference's FOUR_C_ASSERT. */
+  int b200s_set_time_step_size(b200s_ctx* ctx, double dt);
   /* Row (owned) elements among the column elements: is_row[n_col_eles] in the caller's element
    * order, NULL = all.  Only struct_calc_energy distinguishes them (row elements only,
    * model_evaluator_structure.cpp:1714-1716). */
@@ -440,8 +451,10 @@ extern "C"
   /* ---- history materials: restart of the Gauss-point state store ------------------------------------- */
   /* Mat::PlasticDruckerPrager::pack / unpack (4C_mat_plasticdruckerprager.cpp:63-107): per column element
    * (set_mesh numbering) and Gauss point 14 doubles {strainpllast[6], strainbarpllast, strainplcurr[6],
-   * strainbarplcurr}, tensor components 00,11,22,01,12,02.  size = n_col_eles * num_gp * 14 doubles,
-   * 0 for a material without history.  [host|dev] */
+   * strainbarplcurr}, tensor components 00,11,22,01,12,02.  Mat::ViscoNeoHooke::pack / unpack
+   * (4C_mat_visconeohooke.cpp:80-158): 24 doubles {histstresslast[6], artstresslast[6], histstresscurr[6],
+   * artstresscurr[6]}.  size = n_col_eles * num_gp * (14 | 24) doubles, 0 for a material without history.
+   * [host|dev] */
   int64_t b200s_material_history_size(const b200s_ctx* ctx);
   int b200s_get_material_history(b200s_ctx* ctx, double* hist_out);
   int b200s_set_material_history(b200s_ctx* ctx, const double* hist_in);

@@ -13,8 +13,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 HEX8, HEX27, TET10 = 0, 1, 2
-MAT_COUP_NEOHOOKE, MAT_ISO_VOL, MAT_SVK, MAT_ELASTHYPER, MAT_DRUCKER_PRAGER = 0, 1, 2, 3, 4
+MAT_COUP_NEOHOOKE, MAT_ISO_VOL, MAT_SVK, MAT_ELASTHYPER, MAT_DRUCKER_PRAGER, MAT_VISCONEOHOOKE = 0, 1, 2, 3, 4, 5
 DP_HIST = 14  # {strainpllast[6], strainbarpllast, strainplcurr[6], strainbarplcurr} per Gauss point
+VISCO_HIST = 24  # {histstresslast[6], artstresslast[6], histstresscurr[6], artstresscurr[6]} per Gauss point
 # summand ids of the generic MAT_ElastHyper (ORC_SUM_* in solid_oracle.h)
 SUMMANDS = ["COUP_NEOHOOKE", "COUP_MOONEYRIVLIN", "COUP_LOGNEOHOOKE", "COUP_LOGMIXNEOHOOKE", "COUP_SVK",
             "COUP_SIMOPISTER", "COUP_BLATZKO", "COUP_EXPPOL", "COUP_1POW", "COUP_2POW", "COUP_3POW",
@@ -82,6 +83,10 @@ def lib():
                                                  C.c_int64, _ip, C.c_int64, _dp, _dp, _ip, _ip,
                                                  C.c_int64, _lp, _ip, _dp, _dp, C.c_int, _dp]
         L.orc_set_output_history.argtypes = [_dp]
+        L.orc_set_material_history.argtypes = [_dp]
+        L.orc_set_element_material_history.argtypes = [_dp]
+        L.orc_material_hist.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp]
+        L.orc_material_update.argtypes = [C.c_int, C.c_int64, _dp]
         L.orc_eas_hist_size.restype = C.c_int64
         L.orc_eas_recover.argtypes = [C.c_int, C.c_int64, _ip, _dp, C.c_double, _dp]
         L.orc_mulf_init_history.argtypes = [C.c_int64, _dp]
@@ -191,8 +196,29 @@ def material_hist(kind, params, E, hist=None):
 
 
 def material_update(kind, hist):
-    """Mat::...::update(): current -> last for every Gauss point of hist (n, DP_HIST)."""
-    lib().orc_material_update(kind, C.c_int64(hist.size // DP_HIST), _d(hist))
+    """Mat::...::update(): current -> last for every Gauss point of hist (n, DP_HIST or VISCO_HIST)."""
+    per = VISCO_HIST if kind == MAT_VISCONEOHOOKE else DP_HIST
+    lib().orc_material_update(kind, C.c_int64(hist.size // per), _d(hist))
+
+
+def visco_neohooke_params(YOUNGS_SLOW, POISSON, DENS, YOUNGS_FAST, RELAX, THETA, dt, **_):
+    """Parameter block of MAT_VISCONEOHOOKE from the keys of the input line + the time step size."""
+    return np.array([YOUNGS_SLOW, POISSON, DENS, YOUNGS_FAST, RELAX, THETA, dt], float)
+
+
+def set_material_history(mat_hist):
+    """History store of a finite-strain history material for the element loops: (n_ele, ngp, VISCO_HIST) float64,
+    C-contiguous, updated in place; None switches it off.  Keep the array alive while it is installed."""
+    if mat_hist is not None:
+        assert mat_hist.dtype == np.float64 and mat_hist.flags["C_CONTIGUOUS"]
+    lib().orc_set_material_history(_d(mat_hist))
+
+
+def set_element_material_history(mat_hist):
+    """Same for single-element calls (element / element_tech): (ngp, VISCO_HIST)."""
+    if mat_hist is not None:
+        assert mat_hist.dtype == np.float64 and mat_hist.flags["C_CONTIGUOUS"]
+    lib().orc_set_element_material_history(_d(mat_hist))
 
 
 def element(ct, matkind, params, X, u, action=ACTION_FORCE_STIFF, tech=TECH_NONE):

@@ -1060,7 +1060,68 @@ namespace
     }
   }
 
+  // Mat::ViscoNeoHooke::evaluate (src/mat/4C_mat_visconeohooke.cpp:222-405, the GEN_MAXWELL branch that is
+  // compiled in): compressible Neo-Hooke W = mue/2 (I1 I3^-1/3 - 3) + kappa/2 (J - 1)^2 on the FAST modulus, the
+  // deviatoric stress relaxing through one Maxwell branch integrated with the one-step-theta rule
+  //   Q^(n+1) = tau/(tau + theta dt) [ (tau - dt + theta dt)/tau Q^n + S_dev^(n+1) - S_dev^n ].
+  // par: {YOUNGS_SLOW, POISSON, DENS, YOUNGS_FAST, RELAX, THETA, dt (EvaluationContext::time_step_size)}.
+  // E, S: tensor components [00,11,22,01,12,02]; Cm 6x6 column-major in the same (stress-like) index pairs.
+  // hist (ORC_VISCO_HIST = 24): {histstresslast[6], artstresslast[6], histstresscurr[6], artstresscurr[6]}, the
+  // pack order (:97-104); null = virgin point, nothing stored.
+  void visco_neohooke(const double* par, double* hist, const double* E, double* S, double* Cm)
+  {
+    const double E_s = par[0], nue = par[1], E_f = par[3], theta = par[5], dt = par[6];
+    double tau = par[4];
+    if (E_f > E_s) tau = tau * E_s / (E_f - E_s);  // algorithmic relaxation time (:244-249)
+    const double alpha0 = E_s / E_f, alpha1 = 1.0 - alpha0;
+    const double lambda = nue * E_f / ((1.0 + nue) * (1.0 - 2.0 * nue));
+    const double mue = E_f / (2.0 * (1.0 + nue));
+    const double kappa = lambda + 2.0 / 3.0 * mue;
+    const double artscalar1 = (tau - dt + theta * dt) / tau;
+    const double artscalar2 = tau / (tau + theta * dt);
+    const double scalarvisco = alpha0 + alpha1 * tau / (tau + theta * dt);
+    const double Id[6] = {1, 1, 1, 0, 0, 0};
+    double c[6];  // right Cauchy-Green, tensor components (the reference's strain-like C(3..5) are 2 c[3..5])
+    for (int v = 0; v < 6; ++v) c[v] = 2.0 * E[v] + Id[v];
+    const double I1 = c[0] + c[1] + c[2];
+    const double I3 = c[0] * c[1] * c[2] + 2.0 * c[3] * c[4] * c[5] - c[1] * c[5] * c[5] - c[2] * c[3] * c[3] -
+                      c[0] * c[4] * c[4];
+    const double J = std::sqrt(I3);
+    const double I3invcubroot = std::pow(I3, -1.0 / 3.0);
+    double Cinv[6] = {c[1] * c[2] - c[4] * c[4], c[0] * c[2] - c[5] * c[5], c[0] * c[1] - c[3] * c[3],
+        c[5] * c[4] - c[3] * c[2], c[3] * c[5] - c[0] * c[4], c[3] * c[4] - c[5] * c[1]};
+    for (double& v : Cinv) v *= 1.0 / I3;
+    double SDevEla[6], Q[6];
+    for (int v = 0; v < 6; ++v)
+    {
+      S[v] = kappa * (J - 1.0) * J * Cinv[v];                                    // volumetric part
+      SDevEla[v] = mue * I3invcubroot * (Id[v] - 1.0 / 3.0 * I1 * Cinv[v]);       // 2 dW_dev/dC
+      const double S_n = hist ? hist[v] : 0.0, Q_n = hist ? hist[6 + v] : 0.0;
+      Q[v] = artscalar2 * (artscalar1 * Q_n + SDevEla[v] - S_n);
+      if (hist) hist[12 + v] = SDevEla[v], hist[18 + v] = Q[v];
+      S[v] += alpha0 * SDevEla[v] + alpha1 * Q[v];
+    }
+    const double scalar1 = 2.0 * kappa * J * J - kappa * J;
+    const double scalar2 = -2.0 * kappa * J * J + 2.0 * kappa * J;
+    const double scalar3 = 2.0 / 3.0 * mue * I3invcubroot * I1;
+    const double scalar4 = 2.0 / 3.0 * mue * I3invcubroot;
+    for (int I = 0; I < 6; ++I)
+      for (int Jv = 0; Jv < 6; ++Jv)
+      {
+        const int a = VA[I], b = VB[I], cc = VA[Jv], d = VB[Jv];
+        // holzapfel_product: 1/2 (Cinv_ac Cinv_bd + Cinv_ad Cinv_bc)
+        const double H = 0.5 * (Cinv[VG[a][cc]] * Cinv[VG[b][d]] + Cinv[VG[a][d]] * Cinv[VG[b][cc]]);
+        Cm[I + 6 * Jv] = (scalar2 + scalarvisco * scalar3) * H + scalar1 * Cinv[I] * Cinv[Jv] +
+                         scalarvisco * (-scalar4) * (Id[I] * Cinv[Jv] + Id[Jv] * Cinv[I]) +
+                         scalarvisco * scalar3 * Cinv[I] * Cinv[Jv] / 3.0;
+      }
+  }
+
   thread_local double* g_material_hist = nullptr;  // history of the point being evaluated (set by the element loop)
+  // finite-strain history material in the nonlinear / EAS element loops: history block of the element being
+  // evaluated (ORC_VISCO_HIST doubles per Gauss point) or null
+  thread_local double* g_element_material_hist = nullptr;
+  double* g_material_hist_base = nullptr;  // orc_set_material_history: [n_ele][ngp][ORC_VISCO_HIST]
   void material(int kind, const double* par, const double* /*F*/, const double* E, double* S,
       double* Cm)
   {
@@ -1068,6 +1129,8 @@ namespace
       svk(par, E, S, Cm);
     else if (kind == ORC_MAT_DRUCKER_PRAGER)
       drucker_prager(par, g_material_hist, E, S, Cm);
+    else if (kind == ORC_MAT_VISCONEOHOOKE)
+      visco_neohooke(par, g_material_hist, E, S, Cm);
     else
       elasthyper(kind, par, E, S, Cm);
   }
@@ -1236,7 +1299,11 @@ namespace
         C[v] = s;
         E[v] = 0.5 * (s - (v < 3 ? 1.0 : 0.0));
       }
+      g_material_hist = (g_element_material_hist && matkind == ORC_MAT_VISCONEOHOOKE)
+                            ? g_element_material_hist + ORC_VISCO_HIST * gp
+                            : nullptr;
       material(matkind, par, F, E, S, Cm);
+      g_material_hist = nullptr;
       add_force(n, jm, F, S, fac, fe);
       if (action == ORC_ACTION_FORCE_STIFF && Ke) add_stiffness_bfree(n, jm, F, S, Cm, fac, Ke);
     }
@@ -1731,7 +1798,11 @@ namespace
       eas_point(neas, T0invT, detJ0, jm.det, gxi + 3 * gp, alpha, F, Mt.data(), E);
       // the materials on this path use the GL strain only; the enhanced deformation gradient
       // (compute_deformation_gradient_from_gl_strains) is not needed by them
+      g_material_hist = (g_element_material_hist && matkind == ORC_MAT_VISCONEOHOOKE)
+                            ? g_element_material_hist + ORC_VISCO_HIST * gp
+                            : nullptr;
       material(matkind, par, F, E, S, Cm);
+      g_material_hist = nullptr;
       // integrate_eas (eas_helpers.hpp:352-371)
       for (int c = 0; c < neas; ++c)
         for (int r = 0; r < 6; ++r)
@@ -1858,10 +1929,19 @@ extern "C"
   }
   void orc_material_update(int kind, int64_t n_points, double* hist)
   {
+    if (kind == ORC_MAT_VISCONEOHOOKE)  // Mat::ViscoNeoHooke::update (:197-216): last <- current, current <- 0
+      for (int64_t k = 0; k < n_points; ++k)
+        for (int i = 0; i < 12; ++i)
+        {
+          hist[ORC_VISCO_HIST * k + i] = hist[ORC_VISCO_HIST * k + 12 + i];
+          hist[ORC_VISCO_HIST * k + 12 + i] = 0.0;
+        }
     if (kind != ORC_MAT_DRUCKER_PRAGER) return;
     for (int64_t k = 0; k < n_points; ++k)
       for (int i = 0; i < 7; ++i) hist[ORC_DP_HIST * k + i] = hist[ORC_DP_HIST * k + 7 + i];
   }
+  void orc_set_material_history(double* mat_hist) { g_material_hist_base = mat_hist; }
+  void orc_set_element_material_history(double* mat_hist) { g_element_material_hist = mat_hist; }
   void orc_material(
       int kind, const double* par, const double* F, const double* E, double* S, double* C)
   {
@@ -2473,7 +2553,9 @@ extern "C"
       std::vector<int32_t> localcol(nd);
       // generic MAT_ElastHyper: packed summand block (1 + 6 n doubles), used in place
       std::vector<double> par(matparams, matparams + (matkind == ORC_MAT_ELASTHYPER ? 1 + 6 * (int)matparams[0]
-                                                      : (matkind == ORC_MAT_DRUCKER_PRAGER ? 10 : 2)));
+                                                      : (matkind == ORC_MAT_DRUCKER_PRAGER
+                                                                ? 10
+                                                                : (matkind == ORC_MAT_VISCONEOHOOKE ? 7 : 2))));
       par.resize(par.size() + 2, 0.0);
       // Discretization::evaluate loop over column elements
       // (src/core/fem/src/discretization/4C_fem_discretization_evaluate.cpp:85-117)
@@ -2503,9 +2585,12 @@ extern "C"
         else if (mue_per_ele)
           par[0] = mue_per_ele[e];  // InputField MUE looked up by element id
         const bool stiff = (action == ORC_ACTION_FORCE_STIFF) && values;
-        if (element_tech(ct, tech, matkind, par.data(), action, Xe.data(), ue.data(),
-                stiff ? Ke.data() : nullptr, fe.data(),
-                hist ? hist + hist_per_ele * e : nullptr))
+        g_element_material_hist =
+            g_material_hist_base ? g_material_hist_base + (int64_t)ORC_VISCO_HIST * ngauss(ct) * e : nullptr;
+        const int ele_err = element_tech(ct, tech, matkind, par.data(), action, Xe.data(), ue.data(),
+            stiff ? Ke.data() : nullptr, fe.data(), hist ? hist + hist_per_ele * e : nullptr);
+        g_element_material_hist = nullptr;
+        if (ele_err)
         {
           bad[tid]++;
           continue;

@@ -191,3 +191,29 @@ extern "C" int emu_hex8_drucker_prager(const double* in10, int stiff, int64_t n_
     run<MAT_DP, false, 3>(A, &dj, &df, &bad);
   return (int)bad;
 }
+
+// nonlinear hex8 block with the finite-strain history material MAT_VISCONEOHOOKE: mat_hist = n_ele * 8 * VISCO_HIST
+// doubles (updated in place like the kernel does); in6 = input-file parameters, dt = time step size
+extern "C" int emu_hex8_visco(const double* in6, double dt, int stiff, int64_t n_ele, const int32_t* conn,
+    const double* X, const double* u_col, const int32_t* pos, const int64_t* node_rowstart, const int32_t* node_rowlen,
+    const int32_t* node_frow, int64_t n_col_nodes, double* vals, double* f, double* mat_hist)
+{
+  std::vector<NodeRow> node_row(n_col_nodes);
+  for (int64_t k = 0; k < n_col_nodes; ++k)
+    node_row[k].rowstart = node_rowstart[k], node_row[k].rowlen = node_rowlen[k], node_row[k].frow = node_frow[k];
+  EvalArgs A;
+  A.X = X, A.u = u_col, A.conn = conn, A.pos = pos, A.node_row = node_row.data();
+  A.per_ele_param = nullptr, A.ele_id = nullptr, A.gp_hist = nullptr, A.fibers = nullptr, A.linear = 0;
+  A.mat_hist = mat_hist;
+  A.vals = vals, A.f = f, A.err = nullptr, A.n_ele = n_ele, A.scatter_mode = 0;
+  for (double& v : A.mp.p) v = 0.0;
+  if (!make_visco_neohooke(in6, dt, A.mp.p)) return -3;
+  A.mp.hyper = nullptr, A.mp.fiber = nullptr, A.mp.ext = nullptr, A.mp.hist = nullptr;
+  double dj = 1e300, df = 1e300;
+  int64_t bad = 0;
+  if (stiff)
+    run<MAT_VISCO, true, 0>(A, &dj, &df, &bad);
+  else
+    run<MAT_VISCO, false, 0>(A, &dj, &df, &bad);
+  return (int)bad;
+}

@@ -110,6 +110,21 @@ extern "C" int emu_material(int matkind, const double* params, const double* C, 
   return 0;
 }
 
+// MAT_VISCONEOHOOKE of the product at one point: in6 = {YOUNGS_SLOW POISSON DENS YOUNGS_FAST RELAX THETA}, dt = time
+// step size, hist = VISCO_HIST doubles (updated in place) or null; -3 for parameters setup() rejects
+extern "C" int emu_visco_neohooke(const double* in6, double dt, double* hist, const double* C, double* S, double* Cm36)
+{
+  MatParams mp;
+  for (double& v : mp.p) v = 0.0;
+  if (!make_visco_neohooke(in6, dt, mp.p)) return -3;
+  mp.hyper = nullptr, mp.fiber = nullptr, mp.ext = nullptr, mp.hist = hist;
+  double Cm[21];
+  material_evaluate<MAT_VISCO>(mp, C, S, Cm);
+  for (int I = 0; I < 6; ++I)
+    for (int J = 0; J < 6; ++J) Cm36[I + 6 * J] = Cm[c21(I, J)];
+  return 0;
+}
+
 // MAT_Struct_DruckerPrager of the product at one point: in10 = input-file parameters {YOUNG NUE ISOHARD TOL C ETA
 // XI ETABAR MAXITER TANG}, hist = DP_HIST doubles (updated in place) or null; returns -3 for parameters the device
 // rejects (non-symmetric consistent tangent)

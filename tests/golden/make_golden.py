@@ -322,6 +322,54 @@ def druckerprager_case(rel):
             "tolres": float(sd["TOLRES"]), "toldisp": float(sd["TOLDISP"]), "expected_disp": expected}
 
 
+def visco_creep_case(rel):
+    """tests/input_files/viscoNeoHooke_creep.4C.yaml: unit cube of 64 hex8 EAS-mild elements, MAT_VISCONEOHOOKE (finite-strain
+    history material), constant surface traction, symmetry Dirichlet conditions per dof, default time integration of
+    STRUCTURAL DYNAMIC (GenAlpha, rho_inf = 1, no damping, consistent mass with DENS 1e-10), 100 steps of 0.1."""
+    with open(os.path.join(REF, rel)) as fh:
+        y = yaml.safe_load(fh)
+    ids, coords = [], []
+    for line in y["NODE COORDS"]:
+        m = re.match(r"NODE\s+(\d+)\s+COORD\s+(\S+)\s+(\S+)\s+(\S+)", line)
+        ids.append(int(m.group(1)))
+        coords.append([float(m.group(i)) for i in (2, 3, 4)])
+    index = {g: k for k, g in enumerate(ids)}
+    eles = []
+    for line in y["STRUCTURE ELEMENTS"]:
+        tok = line.split()
+        assert tok[1] == "SOLID" and tok[2] == "HEX8" and "KINEM nonlinear TECH eas_mild" in line and "MAT 1" in line
+        eles.append([index[int(t)] for t in tok[3:11]])
+    topo = {"DNODE": {}, "DLINE": {}, "DSURFACE": {}}
+    for key, kind in (("DNODE-NODE TOPOLOGY", "DNODE"), ("DLINE-NODE TOPOLOGY", "DLINE"), ("DSURF-NODE TOPOLOGY", "DSURFACE")):
+        for line in y.get(key, []):
+            m = re.match(r"NODE\s+(\d+)\s+" + kind + r"\s+(\d+)", line)
+            topo[kind].setdefault(int(m.group(2)), []).append(index[int(m.group(1))])
+    fixed = set()
+    for key, kind in (("DESIGN POINT DIRICH CONDITIONS", "DNODE"), ("DESIGN LINE DIRICH CONDITIONS", "DLINE"),
+                      ("DESIGN SURF DIRICH CONDITIONS", "DSURFACE")):
+        for c in y.get(key, []):
+            assert all(v == 0 for v in c["VAL"])
+            for n in topo[kind][c["E"]]:
+                for d in range(3):
+                    if c["ONOFF"][d]:
+                        fixed.add(3 * n + d)
+    neu, = y["DESIGN SURF NEUMANN CONDITIONS"]
+    assert all(f == 0 for f in neu["FUNCT"])
+    mat = {k: float(v) for k, v in y["MATERIALS"][0]["MAT_VISCONEOHOOKE"].items()}
+    sd = y["STRUCTURAL DYNAMIC"]
+    assert "DYNAMICTYPE" not in sd and "DAMPING" not in sd and "GENALPHA" not in y   # the defaults named above
+    expected = [{"node": index[r["STRUCTURE"]["NODE"]], "dof": "xyz".index(r["STRUCTURE"]["QUANTITY"][-1]),
+                 "value": float(r["STRUCTURE"]["VALUE"]), "tol": float(r["STRUCTURE"]["TOLERANCE"])}
+                for r in y["RESULT DESCRIPTION"]]
+    return {"source": rel, "celltype": "hex8", "tech": "eas_mild", "coords": coords, "elements": eles, "material": mat,
+            "dirichlet_nodes": [], "dirichlet_dofs": sorted(fixed),
+            "neumann_nodes": sorted(topo["DSURFACE"][neu["E"]]),
+            "neumann": {"ONOFF": neu["ONOFF"][:3], "VAL": neu["VAL"][:3], "FUNCT": neu["FUNCT"][:3], "FUNCT1": "t", "FUNCT2": None},
+            "timestep": float(sd["TIMESTEP"]), "numstep": int(sd["NUMSTEP"]), "toldisp": float(sd["TOLDISP"]),
+            "genalpha": {"rho_inf": 1.0, "genavg": "TrLike", "damping": "None", "predict": "ConstDis", "lumpmass": False},
+            "expected_disp": expected}
+
+
 def cooks_case(rel, tech):
     """Cook's membrane inputs (64 hex8, CoupNeoHooke nu=0.4999): several Dirichlet conditions with
     per-dof ONOFF, one dead surface load, known answer = dispy of node 162 (and internal energy)."""
@@ -473,6 +521,8 @@ if __name__ == "__main__":
     for name in ("RetToCone", "RetToCone_elastic_tang"):
         with open(os.path.join(HERE, f"integration_hex8_druckerprager_{name}.json"), "w") as fh:
             json.dump(druckerprager_case(f"tests/input_files/mat_druckerprager_{name}.4C.yaml"), fh)
+    with open(os.path.join(HERE, "integration_hex8_visco_creep.json"), "w") as fh:
+        json.dump(visco_creep_case("tests/input_files/viscoNeoHooke_creep.4C.yaml"), fh)
     with open(os.path.join(HERE, "unit_known_answers.json"), "w") as fh:
         json.dump(unit_known_answers(), fh, indent=1)
     np.savez_compressed(os.path.join(HERE, "ref_elements.npz"), **ref_elements())

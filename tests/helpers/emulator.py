@@ -229,3 +229,31 @@ def hex8_drucker_prager(in10, conn, X, u_col, rowptr, colind, node_row_lid, node
         _p(rowlen), _p(frow), C.c_int64(len(rowstart)), _p(vals), _p(f), _p(mat_hist))
     assert rc == 0, rc
     return vals, f
+
+
+def visco_neohooke(in6, dt, Cv, hist=None):
+    """Product MAT_VISCONEOHOOKE at one point: (S, Cm); hist (24,) updated in place or None."""
+    in6 = np.ascontiguousarray(in6, np.float64)
+    Cv = np.ascontiguousarray(Cv, np.float64)
+    S, Cm = np.zeros(6), np.zeros(36)
+    L = lib("post")
+    L.emu_visco_neohooke.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = L.emu_visco_neohooke(_p(in6), float(dt), _p(hist), _p(Cv), _p(S), _p(Cm))
+    if rc == -3:
+        return None
+    assert rc == 0
+    return S, Cm.reshape(6, 6)
+
+
+def hex8_visco(in6, dt, conn, X, u_col, rowptr, colind, node_row_lid, node_col_lid, n_row_nodes, mat_hist, stiff=True):
+    """Emulated nonlinear hex8 kernel with MAT_VISCONEOHOOKE; mat_hist (n_ele, 8, 24) updated in place."""
+    conn = np.ascontiguousarray(conn, np.int32)
+    pos, rowstart, rowlen, frow = scatter_map(conn, rowptr, colind, node_row_lid, node_col_lid)
+    vals, f = np.zeros(rowptr[-1]), np.zeros(3 * n_row_nodes)
+    L = lib("hex8")
+    L.emu_hex8_visco.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int64] + [C.c_void_p] * 7 + [C.c_int64] + [C.c_void_p] * 3
+    rc = L.emu_hex8_visco(_p(np.ascontiguousarray(in6, np.float64)), float(dt), int(stiff), len(conn), _p(conn),
+                          _p(np.ascontiguousarray(X, np.float64)), _p(np.ascontiguousarray(u_col, np.float64)), _p(pos),
+                          _p(rowstart), _p(rowlen), _p(frow), len(rowstart), _p(vals), _p(f), _p(mat_hist))
+    assert rc == 0, rc
+    return vals, f

@@ -113,3 +113,69 @@ def solve_prescribed_displacement_case(case, evaluate, max_iter=30):
         else:
             raise RuntimeError(f"Newton did not converge at t={t}: |r|={np.linalg.norm(fint[free])}")
     return u.reshape(nn, 3)
+
+
+def solve_genalpha_case(case, evaluate, mass_values, recover=None, update_step=None, max_iter=25, trace=None):
+    """Generalised-alpha time integration around the hot path, as structure_new runs it for DYNAMICTYPE GenAlpha
+    (the default of STRUCTURAL DYNAMIC) with GENAVG TrLike, no damping and the ConstDis predictor:
+      coefficients from RHO_INF        4C_structure_new_impl_genalpha.cpp:59,175-190
+      Newmark update of v, a           :205-250, 460-510
+      residual  (1-a_f)(f_int - f_ext)_{n+1} + a_f (f_int - f_ext)_n + M ((1-a_m) a_{n+1} + a_m a_n)
+                                        :264-262,326-344; model_evaluator_structure.cpp:277-300,1539-1570
+      Jacobian  (1-a_f) K + (1-a_m)/(beta dt^2) M                                            :346-360
+      consistent initial acceleration  M a_0 = f_ext(0) - f_int(0)  (equilibrate_initial_state)
+    evaluate(u_flat) -> (rowptr, colind, K values, f_int); mass_values: CSR values of M on the same graph.
+    recover(du) / update_step(u): as in solve_case.  Returns the displacement (nn,3) after numstep steps."""
+    import scipy.sparse as sp
+    from scipy.sparse.linalg import splu
+    nn = len(case["coords"])
+    ndof = 3 * nn
+    fixed = np.zeros(ndof, bool)
+    for n in case.get("dirichlet_nodes", []):
+        fixed[3 * n:3 * n + 3] = True
+    fixed[case.get("dirichlet_dofs", [])] = True
+    free = np.nonzero(~fixed)[0]
+    rho = case["genalpha"]["rho_inf"]
+    am, af = (2.0 * rho - 1.0) / (rho + 1.0), rho / (rho + 1.0)
+    beta, gamma = 0.25 * (1.0 - am + af) ** 2, 0.5 - am + af
+    dt = case["timestep"]
+    d, v = np.zeros(ndof), np.zeros(ndof)
+    rowptr, colind, Kv, fint_n = evaluate(d)
+    M = sp.csr_matrix((mass_values, colind, rowptr), shape=(ndof, ndof))
+    Mff = M[free][:, free].tocsc()
+    t = 0.0
+    fext_n = neumann_load(case, t)
+    a = np.zeros(ndof)
+    a[free] = splu(Mff).solve((fext_n - fint_n)[free])
+    for step in range(case["numstep"]):
+        t += dt
+        fext = neumann_load(case, t)
+        const_vel = (beta - gamma) / beta * v + (2.0 * beta - gamma) * dt / (2.0 * beta) * a - gamma / (beta * dt) * d
+        const_acc = (2.0 * beta - 1.0) / (2.0 * beta) * a - v / (beta * dt) - d / (beta * dt * dt)
+        dn = d.copy()        # predictor ConstDis
+        for it in range(max_iter):
+            rowptr, colind, Kv, fint = evaluate(dn)
+            an = const_acc + dn / (beta * dt * dt)
+            an[fixed] = 0.0
+            R = (1.0 - af) * (fint - fext) + af * (fint_n - fext_n) + M @ ((1.0 - am) * an + am * a)
+            rnorm = np.linalg.norm(R[free])
+            if it > 0 and np.linalg.norm(du) < 1e-13 * max(1.0, np.linalg.norm(dn)) + 1e-16:
+                break
+            K = sp.csr_matrix((Kv, colind, rowptr), shape=(ndof, ndof))
+            Keff = ((1.0 - af) * K + (1.0 - am) / (beta * dt * dt) * M)[free][:, free].tocsc()
+            du = np.zeros(ndof)
+            du[free] = splu(Keff).solve(-R[free])
+            dn += du
+            if recover is not None:
+                recover(du)
+        else:
+            raise RuntimeError(f"GenAlpha Newton did not converge at t={t}: |r|={rnorm}")
+        vn = const_vel + gamma / (beta * dt) * dn
+        an = const_acc + dn / (beta * dt * dt)
+        vn[fixed], an[fixed] = 0.0, 0.0
+        d, v, a, fint_n, fext_n = dn, vn, an, fint, fext
+        if update_step is not None:
+            update_step(d)
+        if trace is not None:
+            trace.append((t, d.copy()))
+    return d.reshape(nn, 3)
