@@ -119,6 +119,39 @@ namespace b200s
   // all but the most recently committed group are complete
   __device__ __forceinline__ void cp_async_wait_but_last() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
+  // TMA bulk copy (cp.async.bulk, SASS UBLKCP) of a contiguous, 16-byte aligned block global -> shared, completion
+  // signalled on an mbarrier (complete_tx); issued by ONE lane, awaited by all lanes of the warp
+  __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+  {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __device__ __forceinline__ void tma_bulk_load(void* smem, const void* gmem, unsigned bytes, uint64_t* bar)
+  {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    // earlier generic-proxy reads of the destination (the previous tile's scatter) are ordered before the
+    // async-proxy write
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem)),
+                 "l"(gmem), "r"(bytes), "r"(b)
+                 : "memory");
+  }
+  __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+  {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned done = 0;
+    while (!done)
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(b), "r"(parity)
+          : "memory");
+  }
+
   namespace hex8
   {
     // node id handled by this lane (element e0 + lane/8, local node lane%8) or -1 beyond the mesh
@@ -146,15 +179,26 @@ namespace b200s
         cp_async8(xu + 24 + d, gu + d);
       }
     }
-    // CSR row info of this lane's node and the tile's 4 x 64 scatter-map entries (2 x 16 bytes/lane)
+    // CSR row info of this lane's node and the tile's 4 x 64 scatter-map entries (2 x 16 bytes/lane); with TMA the
+    // tile's map (1 KB, contiguous) is ONE bulk copy issued by lane 0 and awaited on the warp's mbarrier
+    template <bool TMA = false>
     __device__ __forceinline__ void issue_rowpos(
-        const EvalArgs& A, const WarpSmem& S, int lane, int node, int64_t tile)
+        const EvalArgs& A, const WarpSmem& S, int lane, int node, int64_t tile, uint64_t* bar = nullptr)
     {
       if (node >= 0)
         cp_async16(S.nrow + lane, A.node_row + node);
       else
         S.nrow[lane].rowstart = -1, S.nrow[lane].rowlen = 0, S.nrow[lane].frow = -1;
       const int64_t e0 = tile * EPW;
+      if (TMA)
+      {
+        if (lane == 0)
+        {
+          const int64_t live = A.n_ele - e0 < EPW ? A.n_ele - e0 : EPW;
+          tma_bulk_load(S.pos, A.pos + e0 * (NN * NN), (unsigned)(live * NN * NN * 4), bar);
+        }
+        return;
+      }
 #pragma unroll
       for (int h = 0; h < 2; ++h)
       {
@@ -170,7 +214,9 @@ namespace b200s
   // memory per warp and the full non-symmetric block row per lane, hex8_fbar_kernel.cuh);
   // TECH 2: displacement based with MULF prestress (TECH 0 with the history-based deformation gradient);
   // TECH 3: displacement based with linear kinematics (KINEM linear)
-  template <int MAT, bool STIFF, int TECH>
+  // TMA: the tile's scatter map is staged with cp.async.bulk + mbarrier instead of 64 cp.async (A/B variant,
+  // option "tma_gather"; instantiated for the headline combination only)
+  template <int MAT, bool STIFF, int TECH, bool TMA = false>
   __global__ void __launch_bounds__((TECH == 1 ? HEX8_FBAR_WARPS : HEX8_WARPS) * 32, TECH == 1 ? 1 : 2)
       k_hex8_eval_assemble(const EvalArgs A)
   {
@@ -199,6 +245,14 @@ namespace b200s
     if (FBAR) S.h0 = S.xu + hex8::XU_SIZE;
     S.nrow = reinterpret_cast<NodeRow*>(S.xu + hex8::XU_SIZE + (FBAR ? hex8fbar::H0_SIZE : 0));
     S.pos = reinterpret_cast<int32_t*>(S.nrow + hex8::EPW * hex8::NN);
+    // the warp's mbarrier (TMA variant) lives in the 16 spare bytes behind the scatter map
+    uint64_t* bar = reinterpret_cast<uint64_t*>(S.pos + hex8::EPW * hex8::NN * hex8::NN);
+    unsigned bar_parity = 0;
+    if (TMA)
+    {
+      if (lane == 0) mbar_init(bar, 1);
+      __syncwarp();
+    }
 
     const int64_t n_tiles = (A.n_ele + hex8::EPW - 1) / hex8::EPW;
     const int64_t wstride = (int64_t)gridDim.x * WARPS;
@@ -213,7 +267,7 @@ namespace b200s
     // may be empty (no next tile), which keeps the wait_group arithmetic uniform.
     if (tile < n_tiles) hex8::issue_xu(A, S, lane, node_next);
     cp_async_commit();
-    if (tile < n_tiles) hex8::issue_rowpos(A, S, lane, node_next, tile);
+    if (tile < n_tiles) hex8::issue_rowpos<TMA>(A, S, lane, node_next, tile, bar);
     cp_async_commit();
     node_next = hex8::load_node(A, lane, tile + wstride, n_tiles);
 
@@ -261,10 +315,15 @@ namespace b200s
       else
         hex8::stage_ke<STIFF>(S, lane, Kacc, facc);
       cp_async_wait_but_last();  // row info / scatter map of this tile landed
+      if (TMA)
+      {
+        mbar_wait(bar, bar_parity);  // ... the map through the bulk copy's transaction count
+        bar_parity ^= 1u;
+      }
       __syncwarp();
       if (A.scatter_mode == 0) hex8::scatter<STIFF>(A, S, lane, e0);
       __syncwarp();  // row info / scatter map consumed: refill for the next tile
-      if (tile + wstride < n_tiles) hex8::issue_rowpos(A, S, lane, node_next, tile + wstride);
+      if (tile + wstride < n_tiles) hex8::issue_rowpos<TMA>(A, S, lane, node_next, tile + wstride, bar);
       cp_async_commit();
       node_next = node_next2;
     }
@@ -525,11 +584,12 @@ namespace b200s
             const long long id = A.ele_id ? (long long)A.ele_id[e0 + el] : (long long)(e0 + el);
             bad = min(bad, id);
           }
+      // M / Pw go to shared memory right away: nobody reads that area during phase 1 (the previous tile's staged
+      // K_e was consumed before the barrier that ended its scatter), and out54 need not stay live across the refill
+      tet10::phase1_store<STIFF>(S, lane, out54);
       __syncwarp();
       if (tile + wstride < n_tiles) tet10::issue_xu(A, S, lane, node_next);
       cp_async_commit();
-      tet10::phase1_store<STIFF>(S, lane, out54);
-      __syncwarp();
       double Kacc[tet10::NBLK][9], facc[3];
       tet10::phase2<STIFF>(S, lane, Kacc, facc);
       __syncwarp();
@@ -1297,6 +1357,7 @@ struct b200s_ctx
   bool timed_h2d = false, timed_d2h = false;
   // options
   int check_finite = 0, ctas_per_sm = 2, scatter_mode = 0, reorder = 1, double_buffer = 0;
+  int tma_gather = 0;        // hex8 headline kernel: scatter map staged by a TMA bulk copy (A/B variant)
   int pipeline_phases = 12;  // row phases of the host-destination pipeline (1 = off)
   int overlap_halo = 1;      // ghost import on a side stream while the elements without ghost nodes are evaluated
   // what the last evaluate did (bench / tests): launches of the element kernel, overlapped D2H chunks
@@ -1588,6 +1649,9 @@ namespace
                    : (ctx->kinem == B200S_KINEM_LINEAR ? k_hex8_eval_assemble<MAT, STIFF, 3>
                                                        : k_hex8_eval_assemble<MAT, STIFF, 0>);
     }();
+    if constexpr (MAT == MAT_COUP_NEOHOOKE && STIFF)
+      if (ctx->tma_gather && ctx->prestress != B200S_PRESTRESS_MULF && ctx->kinem != B200S_KINEM_LINEAR)
+        kern = k_hex8_eval_assemble<MAT, STIFF, 0, true>;
     // per device and cheap: set on every launch (a process may hold contexts on several GPUs)
     if (set_smem_attr(kern, hex8_smem_bytes))
       return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", hex8_smem_bytes);
@@ -1853,6 +1917,8 @@ extern "C"
       ctx->pipeline_phases = (int)value;
     else if (!strcmp(key, "overlap_halo"))
       ctx->overlap_halo = value != 0;
+    else if (!strcmp(key, "tma_gather"))
+      ctx->tma_gather = value != 0;
     else
       return fail(ctx, B200S_ERR_INVALID, "unknown option %s", key);
     return B200S_OK;

@@ -95,7 +95,7 @@ namespace b200s
     constexpr int FE_OFFSET = EPW * KE_ESTRIDE;    // staged f_e (EPW*24) behind the K_e's
     constexpr int WARP_DOUBLES = MP_SIZE + G_SIZE + XU_SIZE;
     static_assert(FE_OFFSET + EPW * 24 <= MP_SIZE + G_SIZE, "K_e/f_e staging aliases M/Pw/G");
-    constexpr int WARP_BYTES = WARP_DOUBLES * 8 + EPW * NN * 16 + EPW * NN * NN * 4;
+    constexpr int WARP_BYTES = WARP_DOUBLES * 8 + EPW * NN * 16 + EPW * NN * NN * 4 + 16;  // + 16: the warp's mbarrier
 
     struct WarpSmem
     {

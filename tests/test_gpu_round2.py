@@ -339,3 +339,104 @@ def test_dirichlet_diagonal_with_permuted_column_map():
         row = A[r]
         assert row[3 * perm[node] + dd] == 1.0 and np.count_nonzero(row) == 1
     ctx.close()
+
+
+# ---- MAT_VISCONEOHOOKE: finite-strain history material on the device Gauss-point state store ---------------------
+VISCO = dict(YOUNGS_SLOW=100.0, POISSON=0.3, DENS=1e-10, YOUNGS_FAST=250.0, RELAX=10.0, THETA=0.5)
+VISCO6 = [VISCO[k] for k in ("YOUNGS_SLOW", "POISSON", "DENS", "YOUNGS_FAST", "RELAX", "THETA")]
+
+
+@pytest.mark.parametrize("cell,n,tech", [("HEX8", (6, 5, 4), "none"), ("HEX27", (3, 2, 2), "none"), ("TET10", 3, "none"),
+                                         ("HEX8", (5, 4, 3), "eas_mild"), ("HEX8", (4, 3, 3), "eas_full")])
+def test_visco_neohooke_matches_oracle_over_steps(cell, n, tech):
+    """Two time steps with a state commit in between and a changed displacement: K, f and the stored state of the
+    CUDA path against the oracle (pinned to the reference's creep known answer, tests/test_visco_material.py)."""
+    ct = getattr(orc, cell)
+    if cell == "TET10":
+        X, conn = b200.mesh.unstructured_tet10(n)
+        rm = b200.partition.serial_mesh(b200.mesh.TET10, X, conn)
+        h = 1.0 / n
+    else:
+        rm = b200.partition.box_partition(getattr(b200.mesh, cell), n, 0, 1)
+        h = 1.0 / max(n)
+    u = 2.0 * b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, h)
+    dt = 0.2
+    par = orc.visco_neohooke_params(dt=dt, **VISCO)
+    otech = {"none": orc.TECH_NONE, "eas_mild": orc.TECH_EAS_MILD, "eas_full": orc.TECH_EAS_FULL}[tech]
+    dtech = {"none": capi.TECH_NONE, "eas_mild": capi.TECH_EAS_MILD, "eas_full": capi.TECH_EAS_FULL}[tech]
+    asm = b200.DeviceAssembler(rm, capi.MAT_VISCONEOHOOKE, VISCO6, tech=dtech)
+    rowptr, colind = asm.graph()
+    ngp = orc.num_gp(ct)
+    mh = np.zeros((rm.n_col_eles, ngp, orc.VISCO_HIST))
+    eas = orc.eas_new_history(otech, rm.n_col_eles) if tech != "none" else None
+    # without a time step size the evaluate fails like the reference's assertion
+    asm.set_state("displacement", u.ravel())
+    rc, _ = asm.ctx.evaluate(capi.ACTION_NLNSTIFF, asm._u, None, None, check=False)
+    assert rc == capi.ERR_INVALID
+    asm.ctx.set_time_step_size(dt)
+    assert asm.ctx.L.b200s_material_history_size(asm.ctx.h) == mh.size
+    for step, fac in enumerate((1.0, 1.4)):
+        asm.set_state("displacement", (fac * u).ravel())
+        K, f, err = asm.evaluate()
+        orc.set_material_history(mh)
+        rK, rf, nbad = orc.evaluate_assemble(ct, orc.MAT_VISCONEOHOOKE, par, rm.conn, rm.X.ravel(), (fac * u).ravel(),
+                                             rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, rowptr, colind, tech=otech,
+                                             hist=eas)
+        orc.set_material_history(None)
+        ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, 1e-12 if tech == "none" else 1e-11)
+        assert ok and nbad == 0 and err.n_neg_jacobian == 0, (step, wK, wf)
+        dh = asm.ctx.get_material_history().reshape(mh.shape)
+        assert np.abs(dh - mh).max() <= 1e-12 * np.abs(mh).max()
+        asm.ctx.update_step()
+        orc.material_update(orc.MAT_VISCONEOHOOKE, mh)
+        dh = asm.ctx.get_material_history().reshape(mh.shape)
+        assert np.abs(dh[..., 12:]).max() == 0.0 and np.abs(dh[..., :12] - mh[..., :12]).max() <= 1e-12 * np.abs(mh).max()
+    # restart: the state store round-trips through get / set (caller's element numbering)
+    blob = asm.ctx.get_material_history()
+    asm2 = b200.DeviceAssembler(rm, capi.MAT_VISCONEOHOOKE, VISCO6, tech=dtech)
+    asm2.ctx.set_time_step_size(dt)
+    asm2.ctx.set_material_history(blob)
+    if tech != "none":
+        asm2.ctx.set_element_history(asm.ctx.get_element_history())
+    for a in (asm, asm2):
+        a.set_state("displacement", (1.7 * u).ravel())
+    K1, f1, _ = asm.evaluate()
+    K2, f2, _ = asm2.evaluate()
+    assert np.abs(K1 - K2).max() <= 1e-12 * np.abs(K1).max() and np.abs(f1 - f2).max() <= 1e-12 * np.abs(f1).max()
+    asm.close()
+    asm2.close()
+
+
+def test_reference_visco_creep_known_answer_through_cuda_path():
+    """tests/input_files/viscoNeoHooke_creep.4C.yaml with the CUDA path inside the generalised-alpha loop: device EAS-mild
+    kernel with MAT_VISCONEOHOOKE, consistent mass matrix from the device mass action, struct_calc_recover and the
+    state commit on the device; RESULT DESCRIPTION displacements of node 122 (tolerance 1e-9)."""
+    import json
+    import os
+    from tests.helpers.newton import solve_genalpha_case
+    case = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "integration_hex8_visco_creep.json")))
+    X = np.array(case["coords"])
+    conn = np.array(case["elements"], np.int32)
+    rm = b200.partition.serial_mesh(b200.mesh.HEX8, X, conn)
+    m = case["material"]
+    in6 = [m[k] for k in ("YOUNGS_SLOW", "POISSON", "DENS", "YOUNGS_FAST", "RELAX", "THETA")]
+    asm = b200.DeviceAssembler(rm, capi.MAT_VISCONEOHOOKE, in6, tech=capi.TECH_EAS_MILD, density=m["DENS"])
+    asm.ctx.set_time_step_size(case["timestep"])
+    rowptr, colind = asm.graph()
+    asm.set_state("displacement", np.zeros(asm.n_rows))
+    asm.evaluate("struct_calc_nlnstiffmass")
+    Mv, _ = asm.mass(want_matrix=True)
+    Mo, _ = orc.assemble_mass(orc.HEX8, m["DENS"], conn, X.ravel(), rm.node_row_lid, rm.node_col_lid, len(X), rowptr, colind)
+    assert np.abs(Mv - Mo).max() <= 1e-12 * np.abs(Mo).max()
+
+    def evaluate(u):
+        asm.set_state("displacement", u)
+        K, f, _ = asm.evaluate()
+        return rowptr, colind, K, f
+
+    u = solve_genalpha_case(case, evaluate, Mv, recover=lambda du: asm.recover(du),
+                            update_step=lambda u: asm.ctx.update_step())
+    for e in case["expected_disp"]:
+        assert abs(u[e["node"], e["dof"]] - e["value"]) < e["tol"], (e, u[e["node"], e["dof"]])
+    assert abs(u[121, 0] - 0.0006320013656913447) < 1e-11
+    asm.close()

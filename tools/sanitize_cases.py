@@ -12,6 +12,7 @@ b200 = importlib.import_module("4c_b200")
 capi = b200.capi
 
 CASES = [("hex8", "HEX8", (7, 6, 5), capi.MAT_COUP_NEOHOOKE, [200.0, 0.25], {}),
+         ("hex8 tma", "HEX8", (7, 6, 5), capi.MAT_COUP_NEOHOOKE, [200.0, 0.25], {}),   # option tma_gather = 1
          ("hex8 fbar", "HEX8", (6, 5, 4), capi.MAT_COUP_NEOHOOKE, [200.0, 0.25], dict(tech=capi.TECH_FBAR)),
          ("hex8 eas_mild", "HEX8", (5, 4, 4), capi.MAT_COUP_NEOHOOKE, [200.0, 0.25], dict(tech=capi.TECH_EAS_MILD)),
          ("hex8 eas_full", "HEX8", (5, 4, 3), capi.MAT_SVK, [1000.0, 0.3], dict(tech=capi.TECH_EAS_FULL)),
@@ -31,6 +32,8 @@ for name, cell, n, mk, par, kw in CASES:
         h = 1.0 / max(n)
     u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, h)
     asm = b200.DeviceAssembler(rm, mk, par, **kw)
+    if name.endswith("tma"):
+        asm.ctx.set_option("tma_gather", 1)
     asm.set_state("displacement", u.ravel())
     K, f, err = asm.evaluate("struct_calc_nlnstiff")
     _, f2, _ = asm.evaluate("struct_calc_internalforce")
