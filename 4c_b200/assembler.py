@@ -24,13 +24,15 @@ NUM_GP = {capi.HEX8: 8, capi.HEX27: 27, capi.TET10: 4}
 class DeviceAssembler:
     def __init__(self, rank_mesh, matkind, matparams, device=0, per_ele_param=None, graph=None,
                  tech=capi.TECH_NONE, density=None, prestress=capi.PRESTRESS_NONE, fibers=None,
-                 kinem=capi.KINEM_NONLINEAR_TOTLAG):
+                 kinem=capi.KINEM_NONLINEAR_TOTLAG, options=None):
         """rank_mesh: partition.RankMesh.  graph: (rowptr, colind) from the reference's matrix, or
         None to build the FillComplete-equivalent graph on the device.  tech: element technology of
         the block (TECH key of the SOLID element line).  matkind MAT_ELASTHYPER: matparams is the
         summand list [(name, [params]), ...].  density: DENS of the material (mass actions)."""
         rm = self.rm = rank_mesh
         self.ctx = capi.Context(device, rm.rank, rm.nranks)
+        for k, v in (options or {}).items():   # library options that act at set_mesh / set_graph (b200s_set_option)
+            self.ctx.set_option(k, v)
         self.ctx.set_mesh(rm.celltype, rm.X, rm.conn)
         if tech != capi.TECH_NONE or prestress != capi.PRESTRESS_NONE or kinem != capi.KINEM_NONLINEAR_TOTLAG:
             self.ctx.set_element_properties(kinem=kinem, tech=tech, prestress=prestress)

@@ -54,6 +54,7 @@ SYMBOLS = [
     "b200s_material_history_size", "b200s_get_material_history", "b200s_set_material_history",
     "b200s_get_value_rows", "b200s_get_f_rows", "b200s_eas_old_step_length", "b200s_set_eas_old_step_length",
     "b200s_attach_block", "b200s_host_alloc_near", "b200s_last_evaluate_info", "b200s_set_time_step_size",
+    "b200s_last_d2h_value_bytes", "b200s_symmetric_transfer_status", "b200s_debug_element_order",
 ]
 
 
@@ -171,6 +172,11 @@ def load():
     L.b200s_host_alloc_near.restype = vp
     L.b200s_last_evaluate_info.argtypes = [vp, vp]
     L.b200s_set_time_step_size.argtypes = [vp, dbl]
+    L.b200s_debug_element_order.argtypes = [vp, vp]
+    L.b200s_last_d2h_value_bytes.argtypes = [vp]
+    L.b200s_last_d2h_value_bytes.restype = i64
+    L.b200s_symmetric_transfer_status.argtypes = [vp]
+    L.b200s_symmetric_transfer_status.restype = C.c_char_p
     _lib = L
     return L
 
@@ -352,6 +358,17 @@ class Context:
         self._ck(self.L.b200s_last_evaluate_info(self.h, _ptr(o)))
         return dict(kernel_launches=int(o[0]), pipeline_chunks=int(o[1]), halo_overlapped=int(o[2]),
                     row_phases=int(o[3]), ghost_elements=int(o[4]))
+
+    def element_order(self):
+        o = np.zeros(self.n_col_eles, np.int32)
+        self._ck(self.L.b200s_debug_element_order(self.h, _ptr(o)))
+        return o
+
+    def last_d2h_value_bytes(self):
+        return self.L.b200s_last_d2h_value_bytes(self.h)
+
+    def symmetric_transfer_status(self):
+        return self.L.b200s_symmetric_transfer_status(self.h).decode()
 
     def eas_old_step_length(self):
         return self.L.b200s_eas_old_step_length(self.h)

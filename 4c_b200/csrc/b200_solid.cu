@@ -9,13 +9,22 @@
 #include <unistd.h>
 
 #include <cctype>
+#include <algorithm>
 #include <climits>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 // Translation-unit partitioning: the ~100 heavy kernel instantiations make one nvcc run take ~3 minutes, so
 // __graft_entry__.build_library compiles this file five times in parallel with -DB200S_PART=0..4 (core + ABI,
@@ -40,6 +49,7 @@
 #include "hex27_kernel.cuh"
 #if B200S_HAS(B200S_PART_CORE)
 #include "post_kernels.cuh"
+#include "generic_kernel.cuh"
 #include "linalg_kernels.cuh"
 #include "neumann_kernels.cuh"
 #endif
@@ -584,12 +594,13 @@ namespace b200s
             const long long id = A.ele_id ? (long long)A.ele_id[e0 + el] : (long long)(e0 + el);
             bad = min(bad, id);
           }
-      // M / Pw go to shared memory right away: nobody reads that area during phase 1 (the previous tile's staged
-      // K_e was consumed before the barrier that ended its scatter), and out54 need not stay live across the refill
-      tet10::phase1_store<STIFF>(S, lane, out54);
       __syncwarp();
+      // (order measured: storing M / Pw BEFORE the refill below -- same SASS apart from the position of the six
+      // LDGSTS -- costs 14.6 -> 23.1 ms and doubles the DRAM traffic on config 4; profiles/r02_summary.md)
       if (tile + wstride < n_tiles) tet10::issue_xu(A, S, lane, node_next);
       cp_async_commit();
+      tet10::phase1_store<STIFF>(S, lane, out54);
+      __syncwarp();
       double Kacc[tet10::NBLK][9], facc[3];
       tet10::phase2<STIFF>(S, lane, Kacc, facc);
       __syncwarp();
@@ -889,7 +900,7 @@ namespace b200s
         else
           hi = mid;
       }
-      r = lo;
+      r = lo - lo % 3;  // node-aligned where the three rows of a node are 3 r', 3 r' + 1, 3 r' + 2
     }
     phase_row[k] = r, phase_off[k] = rowptr[r];
   }
@@ -941,6 +952,21 @@ namespace b200s
     if (t >= n * width) return;
     const int64_t e = t / width;
     out[t] = in[(int64_t)perm[e] * width + (t - e * width)];
+  }
+
+  // block-upper transfer: the upper part (column node >= row node) of the three CSR rows of every row node of
+  // [node0, node1) -> packed, row node by row node, dof row by dof row (3 * nu contiguous doubles each)
+  __global__ void k_pack_upper(int64_t node0, int64_t node1, const int64_t* csr_start, const int32_t* nb,
+      const int32_t* dp, const int64_t* up_start, const double* vals, double* packed)
+  {
+    const int64_t r = node0 + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= node1) return;
+    const int len = 3 * nb[r], lo = 3 * dp[r], nu3 = len - lo;
+    const double* src = vals + csr_start[r] + lo;
+    double* dst = packed + up_start[r];
+    for (int b = 0; b < 3; ++b)
+      for (int q = lane; q < nu3; q += 32) dst[b * nu3 + q] = src[(int64_t)b * len + q];
   }
 
   __global__ void k_gather_double(int64_t n, const double* src, const int32_t* idx, double* dst)
@@ -1227,6 +1253,7 @@ struct NcclApi
   const char* (*GetErrorString)(int) = nullptr;
 };
 
+struct SymTransfer;
 struct b200s_ctx
 {
   int device = 0, rank = 0, nranks = 1, n_sm = 148;
@@ -1263,7 +1290,8 @@ struct b200s_ctx
   bool dt_set = false;
   // cell tables in global memory for the post / mass kernels (post_kernels.cuh)
   int ngp = 0, ngp_mass = 0;
-  double *d_dN_gp = nullptr, *d_w = nullptr, *d_dN_cen = nullptr, *d_xi_gp = nullptr;
+  double *d_dN_gp = nullptr, *d_w = nullptr, *d_dN_cen = nullptr, *d_xi_gp = nullptr, *d_dN_node = nullptr;
+  bool general_tangent = false;  // the material's tangent has no major symmetry: generic_kernel.cuh evaluates the block
   double *d_N_mass = nullptr, *d_dN_mass = nullptr, *d_w_mass = nullptr;
   uint8_t* d_ele_is_row = nullptr;  // caller numbering; nullptr = every column element is a row element
   // mass matrix / inertia force (struct_calc_nlnstiffmass & co.)
@@ -1312,6 +1340,8 @@ struct b200s_ctx
   // stiff.zero() of the NEXT Newton iteration overlapped with this iteration's evaluate: two value
   // buffers, the idle one is cleared on a side stream while the element kernel fills the other
   double* d_vals_buf[2] = {nullptr, nullptr};
+  static constexpr size_t ZERO_BLOCK = 64u << 20;
+  void* d_zero = nullptr;         // option double_buffer = 2: source of the copy-engine zeroing
   int vals_cur = 0;               // d_vals == d_vals_buf[vals_cur]: result of the last evaluate
   bool vals_zeroed[2] = {false, false};
   cudaStream_t zero_stream = nullptr;
@@ -1329,6 +1359,10 @@ struct b200s_ctx
   cudaStream_t copy_stream = nullptr, halo_stream = nullptr;
   static constexpr int MAX_PHASES = 64;
   cudaEvent_t ev_phase[MAX_PHASES] = {}, ev_fork = nullptr, ev_halo_done = nullptr, ev_copy_done = nullptr;
+  // block-upper transfer of a symmetric K with a threaded host-side mirror (option symmetric_transfer)
+  struct SymTransfer* sym = nullptr;
+  int symmetric_transfer = 0, host_threads = 0, nt_stores = 1;
+  int64_t last_d2h_bytes = 0;  // bytes of K values that crossed PCIe in the last b200s_evaluate
   // element block attached to another context's system matrix (b200s_attach_block): graph, values, f, the
   // displacement vectors, stream and communicator are the primary's (not owned here)
   b200s_ctx* primary = nullptr;
@@ -1357,6 +1391,7 @@ struct b200s_ctx
   bool timed_h2d = false, timed_d2h = false;
   // options
   int check_finite = 0, ctas_per_sm = 2, scatter_mode = 0, reorder = 1, double_buffer = 0;
+  int segments = 1;          // 0: keep the plain locality order of set_mesh (no ghost / row-phase segments)
   int tma_gather = 0;        // hex8 headline kernel: scatter map staged by a TMA bulk copy (A/B variant)
   int pipeline_phases = 12;  // row phases of the host-destination pipeline (1 = off)
   int overlap_halo = 1;      // ghost import on a side stream while the elements without ghost nodes are evaluated
@@ -1442,8 +1477,245 @@ namespace b200s_parts
   return fail(ctx, B200S_ERR_INVALID, "material not set")
 
 #if B200S_HAS(B200S_PART_CORE)
+// ---- block-upper transfer of a symmetric K (option symmetric_transfer) ------------------------------------------
+// For formulations whose K_e is symmetric (everything on the device path except F-bar) only the blocks with column
+// node >= row node cross PCIe (ghost columns follow the owned ones in the column map, so they are all included); a
+// small pool of host threads writes the full CSR rows into the caller's array: the upper part of a row is copied,
+// a lower block (i,j) is the transpose of the upper block (j,i) of an earlier row.  Sums of the same element
+// contributions in another order: equal to rounding, well inside the 1e-12 parity bound.
+struct HostPool
+{
+  std::vector<std::thread> th;
+  std::mutex m;
+  std::condition_variable cv, cv_done;
+  std::deque<std::function<void()>> q;
+  int busy = 0;
+  bool stop = false;
+  void start(int n)
+  {
+    for (int i = 0; i < n; ++i)
+      th.emplace_back([this]
+          {
+            for (;;)
+            {
+              std::function<void()> f;
+              {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [this] { return stop || !q.empty(); });
+                if (stop && q.empty()) return;
+                f = std::move(q.front());
+                q.pop_front();
+                ++busy;
+              }
+              f();
+              {
+                std::lock_guard<std::mutex> lk(m);
+                --busy;
+              }
+              cv_done.notify_all();
+            }
+          });
+  }
+  void submit(std::function<void()> f)
+  {
+    {
+      std::lock_guard<std::mutex> lk(m);
+      q.push_back(std::move(f));
+    }
+    cv.notify_one();
+  }
+  void wait()
+  {
+    std::unique_lock<std::mutex> lk(m);
+    cv_done.wait(lk, [this] { return q.empty() && busy == 0; });
+  }
+  ~HostPool()
+  {
+    {
+      std::lock_guard<std::mutex> lk(m);
+      stop = true;
+    }
+    cv.notify_all();
+    for (auto& t : th) t.join();
+  }
+};
+
+struct SymTransfer
+{
+  bool usable = false;
+  std::string why;               // reason when not usable
+  int64_t n_row_nodes = 0, n_packed = 0;  // packed doubles
+  // per row node (row lid of dof 0 = 3 r): blocks per row, index of the diagonal block, first CSR entry, first packed
+  // double, first entry of the lower-block tables
+  std::vector<int32_t> nb, dp;
+  std::vector<int64_t> csr_start, up_start, low_start;
+  // per lower block: packed offset of the transposed source block (dof row 0) and the source's row stride 3 nu_j
+  std::vector<int64_t> moff;
+  std::vector<int32_t> mstride;
+  std::vector<int64_t> phase_node;  // row-node boundaries of the row phases
+  double *d_packed = nullptr, *h_packed = nullptr;
+  int64_t *d_csr_start = nullptr, *d_up_start = nullptr;
+  int32_t *d_nb = nullptr, *d_dp = nullptr;
+  cudaEvent_t ev_arrive[b200s_ctx::MAX_PHASES] = {};
+  HostPool pool;
+  int n_threads = 0;
+  ~SymTransfer()
+  {
+    cudaFree(d_packed), cudaFree(d_csr_start), cudaFree(d_up_start), cudaFree(d_nb), cudaFree(d_dp);
+    if (h_packed) cudaFreeHost(h_packed);
+    for (auto& e : ev_arrive)
+      if (e) cudaEventDestroy(e);
+  }
+};
+
 namespace
 {
+  inline void store_stream(double* p, double v, bool nt)
+  {
+#if defined(__x86_64__)
+    if (nt)
+    {
+      long long bits;
+      memcpy(&bits, &v, 8);
+      _mm_stream_si64(reinterpret_cast<long long*>(p), bits);  // no read-for-ownership of the destination line
+      return;
+    }
+#endif
+    (void)nt;
+    *p = v;
+  }
+
+  // full CSR rows of the row nodes [r0, r1) from the packed upper blocks
+  void sym_unpack_rows(const SymTransfer& T, int64_t r0, int64_t r1, double* K, bool nt)
+  {
+    const double* P = T.h_packed;
+    for (int64_t r = r0; r < r1; ++r)
+    {
+      const int nb = T.nb[r], dp = T.dp[r], nu3 = 3 * (nb - dp), len = 3 * nb;
+      const int64_t* mo = T.moff.data() + T.low_start[r];
+      const int32_t* ms = T.mstride.data() + T.low_start[r];
+      for (int b = 0; b < 3; ++b)
+      {
+        double* dst = K + T.csr_start[r] + (int64_t)b * len;
+        // K_ij(b,c) = K_ji(c,b): row c of the source block row, column 3 pos + b
+        for (int k = 0; k < dp; ++k)
+        {
+          const double* src = P + mo[k] + b;
+          const int64_t st = ms[k];
+          store_stream(dst + 3 * k, src[0], nt);
+          store_stream(dst + 3 * k + 1, src[st], nt);
+          store_stream(dst + 3 * k + 2, src[2 * st], nt);
+        }
+        const double* up = P + T.up_start[r] + (int64_t)b * nu3;
+        double* du = dst + 3 * dp;
+        for (int q = 0; q < nu3; ++q) store_stream(du + q, up[q], nt);
+      }
+    }
+#if defined(__x86_64__)
+    if (nt) _mm_sfence();
+#endif
+  }
+
+  // tables of the block-upper transfer for the graph installed in ctx (once per graph)
+  int sym_prepare(b200s_ctx* ctx)
+  {
+    delete ctx->sym;
+    SymTransfer* T = ctx->sym = new SymTransfer;
+    auto no = [&](const char* why)
+    {
+      T->usable = false, T->why = why;
+      return 0;
+    };
+    if (!ctx->node3_ok || !ctx->d_blkcol) return no("the graph is not node-blocked");
+    if (!ctx->segmented) return no("elements are not grouped by row phase (option reorder = 0)");
+    if (ctx->n_rows % 3) return no("rows are not node-blocked");
+    const int64_t ncn = ctx->n_col_nodes, nrn = ctx->n_rows / 3;
+    std::vector<NodeRow> nr((size_t)ncn);
+    std::vector<int32_t> cb((size_t)ncn), blk((size_t)(ctx->nnz / 9 + 1));
+    CK(cudaMemcpy(nr.data(), ctx->d_node_row, sizeof(NodeRow) * (size_t)ncn, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(cb.data(), ctx->d_node_colbase, 4 * (size_t)ncn, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(blk.data(), ctx->d_blkcol, 4 * (size_t)(ctx->nnz / 9), cudaMemcpyDeviceToHost));
+    T->n_row_nodes = nrn;
+    T->nb.assign((size_t)nrn, -1), T->dp.assign((size_t)nrn, 0);
+    T->csr_start.assign((size_t)nrn, 0), T->up_start.assign((size_t)nrn + 1, 0), T->low_start.assign((size_t)nrn + 1, 0);
+    for (int64_t k = 0; k < ncn; ++k)
+    {
+      if (nr[(size_t)k].frow < 0) continue;
+      const int32_t fr = nr[(size_t)k].frow;
+      // owned dofs must carry their row lid as matrix column id (Epetra's column map lists the owned ids first, in
+      // row-map order) and the rows of a node must be 3 r, 3 r + 1, 3 r + 2
+      if (fr % 3 || cb[(size_t)k] != fr) return no("column ids of owned dofs differ from their row ids");
+      const int64_t r = fr / 3;
+      T->nb[(size_t)r] = nr[(size_t)k].rowlen / 3, T->csr_start[(size_t)r] = nr[(size_t)k].rowstart;
+    }
+    for (int64_t r = 0; r < nrn; ++r)
+    {
+      if (T->nb[(size_t)r] < 0) return no("a row node without CSR rows");
+      const int32_t* bl = blk.data() + T->csr_start[(size_t)r] / 9;
+      const int nb = T->nb[(size_t)r];
+      const int dp = (int)(std::lower_bound(bl, bl + nb, (int32_t)(3 * r)) - bl);
+      if (dp >= nb || bl[dp] != 3 * r) return no("a row without diagonal block");
+      T->dp[(size_t)r] = dp;
+      T->up_start[(size_t)r + 1] = T->up_start[(size_t)r] + 9 * (int64_t)(nb - dp);
+      T->low_start[(size_t)r + 1] = T->low_start[(size_t)r] + dp;
+    }
+    T->n_packed = T->up_start[(size_t)nrn];
+    T->moff.resize((size_t)T->low_start[(size_t)nrn]), T->mstride.resize((size_t)T->low_start[(size_t)nrn]);
+    bool pattern_ok = true;
+    const int nt = ctx->host_threads > 0 ? ctx->host_threads : (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    {
+      std::vector<std::thread> th;
+      std::mutex mm;
+      for (int t = 0; t < nt; ++t)
+        th.emplace_back([&, t]
+            {
+              bool ok = true;
+              for (int64_t r = nrn * t / nt; r < nrn * (t + 1) / nt; ++r)
+              {
+                const int32_t* bl = blk.data() + T->csr_start[(size_t)r] / 9;
+                for (int k = 0; k < T->dp[(size_t)r]; ++k)
+                {
+                  const int64_t j = bl[k] / 3;  // owned: column id = row id
+                  const int32_t* bj = blk.data() + T->csr_start[(size_t)j] / 9;
+                  const int nbj = T->nb[(size_t)j], dpj = T->dp[(size_t)j];
+                  const int pos = (int)(std::lower_bound(bj + dpj, bj + nbj, (int32_t)(3 * r)) - (bj + dpj));
+                  if (pos >= nbj - dpj || bj[dpj + pos] != 3 * r)
+                  {
+                    ok = false;  // structurally unsymmetric pattern
+                    continue;
+                  }
+                  T->moff[(size_t)(T->low_start[(size_t)r] + k)] = T->up_start[(size_t)j] + 3 * pos;
+                  T->mstride[(size_t)(T->low_start[(size_t)r] + k)] = 3 * (nbj - dpj);
+                }
+              }
+              if (!ok)
+              {
+                std::lock_guard<std::mutex> lk(mm);
+                pattern_ok = false;
+              }
+            });
+      for (auto& t : th) t.join();
+    }
+    if (!pattern_ok) return no("the sparsity pattern is not structurally symmetric");
+    T->phase_node.resize(ctx->phase_row.size());
+    for (size_t k = 0; k < ctx->phase_row.size(); ++k)
+    {
+      if (ctx->phase_row[k] % 3) return no("row phases are not node-aligned");
+      T->phase_node[k] = ctx->phase_row[k] / 3;
+    }
+    if (to_device(ctx, &T->d_csr_start, T->csr_start.data(), nrn) || to_device(ctx, &T->d_up_start, T->up_start.data(), nrn) ||
+        to_device(ctx, &T->d_nb, T->nb.data(), nrn) || to_device(ctx, &T->d_dp, T->dp.data(), nrn))
+      return B200S_ERR_CUDA;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMalloc((void**)&T->d_packed, 8 * (size_t)std::max<int64_t>(T->n_packed, 1)));
+    CK(cudaMallocHost((void**)&T->h_packed, 8 * (size_t)std::max<int64_t>(T->n_packed, 1)));
+    for (auto& e : T->ev_arrive) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    T->n_threads = nt;
+    T->pool.start(nt);
+    T->usable = true;
+    return 0;
+  }
+
   // element-kernel durations: one CUDA event pair per evaluate on the context stream, harvested at
   // the next synchronize (or when the ring is full) so that a timed loop needs no per-step sync
   void harvest_kernel_times(b200s_ctx* ctx)
@@ -1788,10 +2060,40 @@ namespace b200s_parts
 #if B200S_HAS(B200S_PART_CORE)
 namespace
 {
+  // blocks whose tangent has no major symmetry (generic_kernel.cuh)
+  static int launch_generic(b200s_ctx* ctx, const EvalArgs& A, bool stiff)
+  {
+    GenericArgs Ga;
+    Ga.A = A;
+    Ga.dN_gp = ctx->d_dN_gp, Ga.dN_node = ctx->d_dN_node, Ga.w = ctx->d_w;
+    Ga.nn = ctx->nn, Ga.ngp = ctx->ngp, Ga.pos_stride = ctx->pos_stride, Ga.stiff = stiff;
+    const unsigned grid = nblk(A.n_ele * ctx->nn, 64);
+    if (!grid) return 0;
+    if (ctx->matkind != B200S_MAT_DRUCKER_PRAGER)
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "general-tangent kernel: material kind %d", ctx->matkind);
+    switch (ctx->celltype)
+    {
+      case B200S_HEX8:
+        k_generic_eval_assemble<MAT_DP, 8><<<grid, 64, 0, ctx->stream>>>(Ga);
+        break;
+      case B200S_TET10:
+        k_generic_eval_assemble<MAT_DP, 10><<<grid, 64, 0, ctx->stream>>>(Ga);
+        break;
+      case B200S_HEX27:
+        k_generic_eval_assemble<MAT_DP, 27><<<grid, 64, 0, ctx->stream>>>(Ga);
+        break;
+      default:
+        return fail(ctx, B200S_ERR_UNSUPPORTED, "cell type %d has no device kernel", ctx->celltype);
+    }
+    ctx->launches += 1;
+    return 0;
+  }
+
   template <bool STIFF>
   static int launch_eval(b200s_ctx* ctx, const EvalArgs& A)
   {
     if (ctx->matkind < 0) return fail(ctx, B200S_ERR_INVALID, "material not set");
+    if (ctx->general_tangent) return launch_generic(ctx, A, STIFF);
     if (ctx->tech != B200S_TECH_NONE && ctx->celltype != B200S_HEX8)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "element technology %d needs hex8", ctx->tech);
     switch (ctx->celltype)
@@ -1864,12 +2166,15 @@ extern "C"
     if (ctx->halo_stream) cudaStreamSynchronize(ctx->halo_stream), cudaStreamDestroy(ctx->halo_stream);
     for (auto& e : ctx->ev_phase) cudaEventDestroy(e);
     cudaEventDestroy(ctx->ev_fork), cudaEventDestroy(ctx->ev_halo_done), cudaEventDestroy(ctx->ev_copy_done);
+    delete ctx->sym;
+    ctx->sym = nullptr;
     if (ctx->primary) detach_shared(ctx);  // the primary owns graph, values, vectors, stream and communicator
     if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
     dfree(ctx->dX), dfree(ctx->dconn), dfree(ctx->d_per_ele), dfree(ctx->d_rowptr);
     dfree(ctx->d_colind), dfree(ctx->d_pos), dfree(ctx->d_node_row), dfree(ctx->d_ele_id);
     if (ctx->zero_stream) cudaStreamSynchronize(ctx->zero_stream);
     dfree(ctx->d_node_colbase), dfree(ctx->d_vals_buf[0]), dfree(ctx->d_vals_buf[1]), dfree(ctx->d_f);
+    dfree(ctx->d_zero);
     ctx->d_vals = nullptr;
     for (auto& e : ctx->ev_zero_done) cudaEventDestroy(e);
     cudaEventDestroy(ctx->ev_eval_start);
@@ -1879,7 +2184,7 @@ extern "C"
     dfree(ctx->d_gp_hist), dfree(ctx->d_eas_hist), dfree(ctx->d_du_row), dfree(ctx->d_du_col);
     dfree(ctx->d_eas_t0), dfree(ctx->d_fibers), dfree(ctx->d_blkcol), dfree(ctx->d_hist_old);
     dfree(ctx->d_row_diagcol);
-    dfree(ctx->d_xi_gp);
+    dfree(ctx->d_xi_gp), dfree(ctx->d_dN_node);
     dfree(ctx->d_mat_ext), dfree(ctx->d_mat_hist);
     b200s_clear_neumann(ctx);
     dfree(ctx->d_face_N), dfree(ctx->d_face_d0), dfree(ctx->d_face_d1), dfree(ctx->d_face_w);
@@ -1912,13 +2217,25 @@ extern "C"
     else if (!strcmp(key, "reorder"))  // takes effect at the next set_mesh
       ctx->reorder = value != 0;
     else if (!strcmp(key, "double_buffer"))  // takes effect at the next set_graph / build_graph
-      ctx->double_buffer = value != 0;
+      ctx->double_buffer = (int)value;  // 0 off, 1 memset on a side stream, 2 copy-engine zeroing on a side stream
     else if (!strcmp(key, "pipeline_phases"))  // takes effect at the next set_graph / build_graph
       ctx->pipeline_phases = (int)value;
     else if (!strcmp(key, "overlap_halo"))
       ctx->overlap_halo = value != 0;
     else if (!strcmp(key, "tma_gather"))
       ctx->tma_gather = value != 0;
+    else if (!strcmp(key, "segments"))  // takes effect at the next set_graph / build_graph
+      ctx->segments = value != 0;
+    else if (!strcmp(key, "symmetric_transfer"))
+      ctx->symmetric_transfer = value != 0;
+    else if (!strcmp(key, "host_threads"))  // takes effect when the transfer tables are (re)built
+    {
+      ctx->host_threads = (int)value;
+      delete ctx->sym;
+      ctx->sym = nullptr;
+    }
+    else if (!strcmp(key, "nt_stores"))
+      ctx->nt_stores = value != 0;
     else
       return fail(ctx, B200S_ERR_INVALID, "unknown option %s", key);
     return B200S_OK;
@@ -1944,6 +2261,7 @@ extern "C"
     if (to_device(ctx, &ctx->d_dN_gp, T.dN_gp.data(), (int64_t)T.dN_gp.size()) ||
         to_device(ctx, &ctx->d_w, T.w.data(), (int64_t)T.w.size()) ||
         to_device(ctx, &ctx->d_dN_cen, T.dN_cen.data(), (int64_t)T.dN_cen.size()) ||
+        to_device(ctx, &ctx->d_dN_node, T.dN_node.data(), (int64_t)T.dN_node.size()) ||
         to_device(ctx, &ctx->d_xi_gp, T.xi_gp.data(), (int64_t)T.xi_gp.size()) ||
         to_device(ctx, &ctx->d_N_mass, T.N_mass.data(), (int64_t)T.N_mass.size()) ||
         to_device(ctx, &ctx->d_dN_mass, T.dN_mass.data(), (int64_t)T.dN_mass.size()) ||
@@ -2101,10 +2419,9 @@ extern "C"
         return fail(ctx, B200S_ERR_INVALID,
             "MAT_Struct_DruckerPrager: C, ETA and ETABAR must be non-zero (the yield function is normalised by the "
             "cohesion and the return mapping divides by the friction parameters)");
-      if (!make_drucker_prager(params, q))
-        return fail(ctx, B200S_ERR_UNSUPPORTED,
-            "MAT_Struct_DruckerPrager: the consistent tangent with ETA != ETABAR is not major-symmetric; the device "
-            "kernels keep a symmetric constitutive tensor (use TANG elastic, or keep this block on the CPU loop)");
+      if (!make_drucker_prager(params, q)) return fail(ctx, B200S_ERR_INVALID, "MAT_Struct_DruckerPrager: parameters rejected");
+      // the non-associative consistent tangent (ETA != ETABAR) has no major symmetry: general kernel
+      ctx->general_tangent = !drucker_prager_tangent_is_symmetric(params);
       for (double& v : mp.p) v = 0.0;
       if (to_device(ctx, &ctx->d_mat_ext, q, DP_NPAR)) return B200S_ERR_CUDA;
       CK(cudaStreamSynchronize(ctx->stream));  // q is a local
@@ -2113,6 +2430,7 @@ extern "C"
       dfree(ctx->d_per_ele);
       return material_history_allocate(ctx) ? B200S_ERR_CUDA : B200S_OK;
     }
+    ctx->general_tangent = false;
     if (kind == B200S_MAT_VISCONEOHOOKE)
     {
       if (nparams < 6 || per_ele_param)
@@ -2167,7 +2485,7 @@ extern "C"
     ctx->seg_begin = {0, 0, n};
     ctx->phase_row = {0, ctx->n_rows};
     ctx->phase_off = {0, ctx->nnz};
-    if (!ctx->reorder || n <= 1 || !ctx->d_rowptr) return 0;
+    if (!ctx->reorder || !ctx->segments || n <= 1 || !ctx->d_rowptr) return 0;
     cudaStream_t st = ctx->stream;
     int P = ctx->pipeline_phases < 1 ? 1 : (ctx->pipeline_phases > b200s_ctx::MAX_PHASES - 2 ? b200s_ctx::MAX_PHASES - 2
                                                                                               : ctx->pipeline_phases);
@@ -2278,6 +2596,8 @@ extern "C"
       const int32_t* d_colind, const int32_t* d_dof_row_lid, const int32_t* d_dof_col_lid)
   {
     if (ctx->primary) return fail(ctx, B200S_ERR_INVALID, "an attached element block uses its primary's graph");
+    delete ctx->sym;  // transfer tables of the previous graph
+    ctx->sym = nullptr;
     const int64_t ncn = ctx->n_col_nodes;
     int64_t nnz = 0;
     CK(cudaMemcpyAsync(&nnz, d_rowptr + n_rows, sizeof(int64_t), cudaMemcpyDefault, ctx->stream));
@@ -2797,6 +3117,13 @@ extern "C"
     // pipeline: host destination for K, at least two non-empty phases
     const bool pipeline = stiff && K_dst && ctx->segmented && ctx->n_phases > 1 && ctx->pipeline_phases > 1 &&
                           !mass && !ctx->check_finite && is_host_pointer(K_dst);
+    // block-upper transfer: symmetric K_e (every device formulation but F-bar), tables usable for this graph
+    bool symmetric = pipeline && ctx->symmetric_transfer && !accumulate && ctx->tech != B200S_TECH_FBAR;
+    if (symmetric)
+    {
+      if (!ctx->sym && sym_prepare(ctx)) return fail(ctx, B200S_ERR_CUDA, "symmetric transfer: set-up failed");
+      symmetric = ctx->sym->usable;
+    }
     // overlap of the ghost import with the elements that do not read it
     const bool overlap = !accumulate && !pipeline && ctx->n_nbr > 0 && ctx->segmented && ctx->overlap_halo &&
                          n_ghost_eles < n_ele;
@@ -2845,7 +3172,24 @@ extern "C"
           else
             CK(cudaMemsetAsync(ctx->d_vals_buf[use], 0, vbytes, st));
           CK(cudaStreamWaitEvent(ctx->zero_stream, ctx->ev_eval_start, 0));
-          CK(cudaMemsetAsync(ctx->d_vals_buf[idle], 0, vbytes, ctx->zero_stream));
+          if (ctx->double_buffer == 2)
+          {
+            // zeros by the copy engine: device-to-device copies from a small (L2 resident) zero block, so that the
+            // clearing neither occupies SMs nor competes for their L1TEX with the element kernel
+            if (!ctx->d_zero)
+            {
+              CK(cudaMalloc((void**)&ctx->d_zero, b200s_ctx::ZERO_BLOCK));
+              CK(cudaMemsetAsync(ctx->d_zero, 0, b200s_ctx::ZERO_BLOCK, ctx->zero_stream));
+            }
+            for (size_t o = 0; o < vbytes; o += b200s_ctx::ZERO_BLOCK)
+            {
+              const size_t nb = vbytes - o < b200s_ctx::ZERO_BLOCK ? vbytes - o : b200s_ctx::ZERO_BLOCK;
+              CK(cudaMemcpyAsync((char*)ctx->d_vals_buf[idle] + o, ctx->d_zero, nb, cudaMemcpyDeviceToDevice,
+                  ctx->zero_stream));
+            }
+          }
+          else
+            CK(cudaMemsetAsync(ctx->d_vals_buf[idle], 0, vbytes, ctx->zero_stream));
           CK(cudaEventRecord(ctx->ev_zero_done[idle], ctx->zero_stream));
           ctx->vals_zeroed[idle] = true, ctx->vals_zeroed[use] = false;
           ctx->vals_cur = use, ctx->d_vals = ctx->d_vals_buf[use];
@@ -2880,6 +3224,23 @@ extern "C"
         rc = launch_segment(ctx, stiff, ctx->seg_begin[(size_t)k + 1], ctx->seg_begin[(size_t)k + 2], first);
         const int64_t o0 = ctx->phase_off[(size_t)k], o1 = ctx->phase_off[(size_t)k + 1];
         if (rc || o1 <= o0) continue;
+        if (symmetric)
+        {
+          // only the blocks with column node >= row node travel; the host threads write the full rows (below)
+          SymTransfer& T = *ctx->sym;
+          const int64_t n0 = T.phase_node[(size_t)k], n1 = T.phase_node[(size_t)k + 1];
+          const int64_t p0 = T.up_start[(size_t)n0], p1 = T.up_start[(size_t)n1];
+          k_pack_upper<<<nblk(32 * (n1 - n0)), 256, 0, st>>>(n0, n1, T.d_csr_start, T.d_nb, T.d_dp, T.d_up_start,
+              ctx->d_vals, T.d_packed);
+          ctx->launches += 1;
+          CK(cudaEventRecord(ctx->ev_phase[k], st));
+          CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_phase[k], 0));
+          CK(cudaMemcpyAsync(T.h_packed + p0, T.d_packed + p0, sizeof(double) * (size_t)(p1 - p0), cudaMemcpyDeviceToHost,
+              ctx->copy_stream));
+          CK(cudaEventRecord(T.ev_arrive[k], ctx->copy_stream));
+          ctx->last_pipeline_chunks += 1;
+          continue;
+        }
         CK(cudaEventRecord(ctx->ev_phase[k], st));
         CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_phase[k], 0));
         CK(cudaMemcpyAsync(K_dst + o0, ctx->d_vals + o0, sizeof(double) * (size_t)(o1 - o0), cudaMemcpyDeviceToHost,
@@ -2927,6 +3288,31 @@ extern "C"
     if (f_dst && f_dst != ctx->d_f)
       CK(cudaMemcpyAsync(f_dst, ctx->d_f, sizeof(double) * (size_t)ctx->n_rows, cudaMemcpyDefault, st));
     CK(cudaGetLastError());
+    if (K_dst && stiff) ctx->last_d2h_bytes = 8 * (symmetric ? ctx->sym->n_packed : ctx->nnz);
+    if (symmetric)
+    {
+      // host side of the block-upper transfer: as the packed rows of a phase arrive, the pool writes the full
+      // CSR rows of that phase (lower blocks = transposes of upper blocks of earlier rows) while the next phases
+      // are still being evaluated and copied
+      nvtxRangePushA("host mirror");
+      SymTransfer& T = *ctx->sym;
+      const bool nt = ctx->nt_stores != 0;
+      for (int k = 0; k < ctx->n_phases; ++k)
+      {
+        const int64_t n0 = T.phase_node[(size_t)k], n1 = T.phase_node[(size_t)k + 1];
+        if (ctx->phase_off[(size_t)k + 1] <= ctx->phase_off[(size_t)k] || n1 <= n0) continue;
+        CK(cudaEventSynchronize(T.ev_arrive[k]));
+        const int64_t chunk = std::max<int64_t>(256, (n1 - n0 + 2 * T.n_threads - 1) / (2 * T.n_threads));
+        for (int64_t r = n0; r < n1; r += chunk)
+        {
+          const int64_t r1 = std::min(n1, r + chunk);
+          const SymTransfer* Tp = &T;
+          T.pool.submit([Tp, r, r1, K_dst, nt] { sym_unpack_rows(*Tp, r, r1, K_dst, nt); });
+        }
+      }
+      T.pool.wait();
+      nvtxRangePop();
+    }
     nvtxRangePop();
     return B200S_OK;
   }
@@ -3048,6 +3434,7 @@ extern "C"
     for (double& v : mp.p) v = 0.0;
     mp.hyper = ctx->d_hyper;
     ctx->matkind = B200S_MAT_ELASTHYPER, ctx->mp = mp;
+    ctx->general_tangent = false;
     dfree(ctx->d_per_ele), dfree(ctx->d_mat_hist);
     return B200S_OK;
   }
@@ -4153,6 +4540,25 @@ extern "C"
     cudaFreeHost(p);
   }
 
+  // diagnostics: device element order (caller's column-element index of every device element)
+  int b200s_debug_element_order(b200s_ctx* ctx, int32_t* out)
+  {
+    if (!ctx || !out) return B200S_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    if (!ctx->d_ele_id)
+    {
+      for (int64_t e = 0; e < ctx->n_col_eles; ++e) out[e] = (int32_t)e;
+      return B200S_OK;
+    }
+    CK(cudaMemcpy(out, ctx->d_ele_id, 4 * (size_t)ctx->n_col_eles, cudaMemcpyDeviceToHost));
+    return B200S_OK;
+  }
+  int64_t b200s_last_d2h_value_bytes(const b200s_ctx* ctx) { return ctx ? ctx->last_d2h_bytes : 0; }
+  const char* b200s_symmetric_transfer_status(const b200s_ctx* ctx)
+  {
+    if (!ctx || !ctx->sym) return "not prepared";
+    return ctx->sym->usable ? "in use" : ctx->sym->why.c_str();
+  }
   // what the last evaluate did: out[0] element-kernel launches, [1] value chunks copied to the host while later
   // segments were still being evaluated, [2] 1 if the ghost import ran beside the interior elements,
   // [3] row phases of the installed graph, [4] elements holding a ghost node

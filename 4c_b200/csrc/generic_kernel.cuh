@@ -1,0 +1,187 @@
+// generic_kernel.cuh -- general evaluate + assemble for constitutive tensors WITHOUT major symmetry.
+//
+// The fast element kernels (hex8 / tet10 / hex27) carry the 21 unique entries of a major-symmetric tangent and exploit
+// the symmetry of K_e.  A material whose algorithmic tangent is not symmetric -- the non-associative consistent tangent
+// of MAT_Struct_DruckerPrager (ETA != ETABAR, src/mat/4C_mat_plasticdruckerprager.cpp:127-150) -- gives a
+// non-symmetric K_e = sum_gp B^T C B w, which the reference assembles entry by entry like any other
+// (add_stiffness_matrix, src/solid_ele/4C_solid_ele_calc_lib.hpp:1124-1151; linear kinematics:
+// 4C_solid_ele_calc_displacement_based_linear_kinematics.hpp:133-150).  This kernel is the plain route for such blocks:
+// one thread per (element, row node i) computes the whole block row K_i,: (3 x 3 nn) and f_i and adds them into the CSR
+// rows of node i.  Table driven (any cell with nn <= NN nodes), total Lagrangean or linear kinematics; throughput is
+// not the point here (every thread of an element repeats the Gauss-point work), correctness and coverage are.
+#pragma once
+
+#include "hex8_kernel.cuh"
+#include "solid_math.cuh"
+
+namespace b200s
+{
+  struct GenericArgs
+  {
+    EvalArgs A;             // mesh, state, graph, outputs as for the fast kernels (pointers already offset)
+    const double* dN_gp;    // [ngp][nn][3]
+    const double* dN_node;  // [nn][nn][3] (Jacobian check) or nullptr
+    const double* w;        // [ngp]
+    int nn, ngp, pos_stride, stiff;
+  };
+
+  // S[6], Cm36[I + 6 J] of the block's material at one point (C = tensor components 00,11,22,01,12,02)
+  template <int MAT>
+  B2_HD void material_evaluate_full(const MatParams& mp, const double* C, double* S, double* Cm36)
+  {
+    if (MAT == MAT_DP)
+      drucker_prager_evaluate_t<true>(mp.ext, mp.hist, C, S, Cm36);
+    else
+    {
+      double Cm[21];
+      material_evaluate<MAT>(mp, C, S, Cm);
+#pragma unroll
+      for (int I = 0; I < 6; ++I)
+#pragma unroll
+        for (int J = 0; J < 6; ++J) Cm36[I + 6 * J] = Cm[c21(I < J ? I : J, I < J ? J : I)];
+    }
+  }
+
+  // block row i of K_e and f_i of element e (device element index); Krow[j][b + 3 c] = K_ij(b, c)
+  template <int MAT, int NN>
+  B2_HD bool generic_block_row(const GenericArgs& Ga, int64_t e, int i, double (*Krow)[9], double* fi, double& detJ_min,
+      double& detF_min)
+  {
+    const EvalArgs& A = Ga.A;
+    const int nn = Ga.nn;
+    constexpr int vg[3][3] = {{0, 3, 5}, {3, 1, 4}, {5, 4, 2}};
+    double X[NN][3], u[NN][3], G[NN][3];
+    const int32_t* ce = A.conn + e * nn;
+    for (int k = 0; k < nn; ++k)
+      for (int d = 0; d < 3; ++d) X[k][d] = A.X[3 * (int64_t)ce[k] + d], u[k][d] = A.u[3 * (int64_t)ce[k] + d];
+    for (int j = 0; j < nn; ++j)
+      for (int q = 0; q < 9; ++q) Krow[j][q] = 0.0;
+    fi[0] = fi[1] = fi[2] = 0.0;
+    bool neg = false;
+    // ensure_positive_jacobian_determinant_at_element_nodes (calc_lib.hpp:543-562): node i of this thread
+    if (Ga.dN_node)
+    {
+      double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      const double* dN = Ga.dN_node + (size_t)i * nn * 3;
+      for (int k = 0; k < nn; ++k)
+        for (int a = 0; a < 3; ++a)
+          for (int b = 0; b < 3; ++b) J[a + 3 * b] = fma(dN[3 * k + a], X[k][b], J[a + 3 * b]);
+      const double dj = det3(J);
+      detJ_min = fmin(detJ_min, dj);
+      neg = !(dj > 0.0);
+    }
+    for (int g = 0; g < Ga.ngp; ++g)
+    {
+      const double* dN = Ga.dN_gp + (size_t)g * nn * 3;
+      double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, iJ[9];
+      for (int k = 0; k < nn; ++k)
+        for (int a = 0; a < 3; ++a)
+          for (int b = 0; b < 3; ++b) J[a + 3 * b] = fma(dN[3 * k + a], X[k][b], J[a + 3 * b]);
+      const double detJ = inv3(iJ, J);
+      detJ_min = fmin(detJ_min, detJ);
+      double F[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+      for (int k = 0; k < nn; ++k)
+      {
+        for (int a = 0; a < 3; ++a)
+          G[k][a] = fma(iJ[a + 6], dN[3 * k + 2], fma(iJ[a + 3], dN[3 * k + 1], iJ[a] * dN[3 * k]));
+        for (int a = 0; a < 3; ++a)
+          for (int b = 0; b < 3; ++b) F[a + 3 * b] = fma(u[k][a], G[k][b], F[a + 3 * b]);
+      }
+      detF_min = fmin(detF_min, det3(F));
+      double C[6], S[6], Cm[36];
+      right_cauchy_green(F, C);
+      if (A.linear) linear_kinematics(F, C);  // E = sym(grad u), F = I
+      MatParams mp = A.mp;
+      if (A.per_ele_param != nullptr) mp.p[0] = A.per_ele_param[e];
+      if (MAT == MAT_HYPER && A.fibers != nullptr) mp.fiber = A.fibers + 3 * e;
+      if (material_hist_doubles(MAT) > 0 && A.mat_hist != nullptr)
+        mp.hist = A.mat_hist + (e * Ga.ngp + g) * material_hist_doubles(MAT);  // every thread of the element writes the same state
+      material_evaluate_full<MAT>(mp, C, S, Cm);
+      const double w = detJ * Ga.w[g];
+      // f_i(b) += w sum_a (F S)(b, a) G_i(a)
+      for (int b = 0; b < 3; ++b)
+      {
+        double v = 0.0;
+        for (int a = 0; a < 3; ++a)
+        {
+          double fs = 0.0;
+          for (int c = 0; c < 3; ++c) fs = fma(F[b + 3 * c], S[vg[c][a]], fs);
+          v = fma(fs, G[i][a], v);
+        }
+        fi[b] = fma(w, v, fi[b]);
+      }
+      if (!Ga.stiff) continue;
+      // T1[b][f][d] = sum_{a,e} G_i(a) F(b,e) C[(a e)][(f d)];  V[b][c][d] = w (sum_f T1[b][f][d] F(c,f) + delta_bc sum_a G_i(a) S(a,d))
+      double V[3][3][3];
+      for (int b = 0; b < 3; ++b)
+      {
+        double T1[3][3];
+        for (int f = 0; f < 3; ++f)
+          for (int d = 0; d < 3; ++d)
+          {
+            double v = 0.0;
+            for (int a = 0; a < 3; ++a)
+              for (int ee = 0; ee < 3; ++ee) v = fma(G[i][a] * F[b + 3 * ee], Cm[vg[a][ee] + 6 * vg[f][d]], v);
+            T1[f][d] = v;
+          }
+        for (int c = 0; c < 3; ++c)
+          for (int d = 0; d < 3; ++d)
+            V[b][c][d] = w * (T1[0][d] * F[c] + T1[1][d] * F[c + 3] + T1[2][d] * F[c + 6]);
+      }
+      if (!A.linear)
+        for (int d = 0; d < 3; ++d)
+        {
+          const double sg = w * (G[i][0] * S[vg[0][d]] + G[i][1] * S[vg[1][d]] + G[i][2] * S[vg[2][d]]);
+          for (int b = 0; b < 3; ++b) V[b][b][d] += sg;
+        }
+      for (int j = 0; j < nn; ++j)
+        for (int b = 0; b < 3; ++b)
+          for (int c = 0; c < 3; ++c)
+            Krow[j][b + 3 * c] = fma(V[b][c][2], G[j][2], fma(V[b][c][1], G[j][1], fma(V[b][c][0], G[j][0], Krow[j][b + 3 * c])));
+    }
+    return neg;
+  }
+
+#if defined(__CUDACC__)
+  __device__ __forceinline__ void atomic_min_double_generic(double* addr, double v)
+  {
+    unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+    unsigned long long old = *a;
+    while (__longlong_as_double((long long)old) > v)
+    {
+      const unsigned long long assumed = old;
+      old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+      if (old == assumed) break;
+    }
+  }
+
+  template <int MAT, int NN>
+  __global__ void __launch_bounds__(64) k_generic_eval_assemble(const GenericArgs Ga)
+  {
+    const EvalArgs& A = Ga.A;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e = t / Ga.nn;
+    const int i = (int)(t - e * Ga.nn);
+    if (e >= A.n_ele) return;
+    double Krow[NN][9], fi[3], dj = 1e300, df = 1e300;
+    const bool neg = generic_block_row<MAT, NN>(Ga, e, i, Krow, fi, dj, df);
+    atomic_min_double_generic(&A.err->min_detJ, dj);
+    atomic_min_double_generic(&A.err->min_detF, df);
+    if (neg)
+    {
+      const long long id = A.ele_id ? (long long)A.ele_id[e] : (long long)e;
+      atomicMin(&A.err->first_bad, id);
+      atomicAdd(&A.err->n_neg_jac, 1ull);  // counts offending nodes here; > 0 is what the caller tests
+    }
+    const NodeRow nr = A.node_row[A.conn[e * Ga.nn + i]];
+    if (nr.rowstart < 0) return;  // row node not owned (lmrowowner != myrank)
+    for (int b = 0; b < 3; ++b) atomicAdd(A.f + nr.frow + b, fi[b]);
+    if (!Ga.stiff) return;
+    const int32_t* pos = A.pos + e * Ga.pos_stride + i * Ga.nn;
+    for (int j = 0; j < Ga.nn; ++j)
+      for (int b = 0; b < 3; ++b)
+        for (int c = 0; c < 3; ++c)
+          atomicAdd(A.vals + nr.rowstart + (int64_t)b * nr.rowlen + pos[j] + c, Krow[j][b + 3 * c]);
+  }
+#endif
+}  // namespace b200s

@@ -13,10 +13,10 @@
 //   [7..12] plastic strain, current iterate  [13] accumulated plastic strain, current iterate
 // tensor components in the order 00,11,22,01,12,02.
 //
-// The element kernels keep the constitutive tensor as the 21 entries of a major-symmetric 6x6 matrix, so the
-// consistent tangent is available for ETA == ETABAR (associative in the volumetric part: the cone tangent
-// eta D(x)1 + etabar 1(x)D is symmetric) and the elastic tangent (TANG elastic) always; the non-associative
-// consistent tangent is rejected at b200s_set_material (the converged states are the same with either).
+// The fast element kernels keep the constitutive tensor as the 21 entries of a major-symmetric 6x6 matrix: they
+// serve ETA == ETABAR (the cone tangent eta D(x)1 + etabar 1(x)D is symmetric then) and the elastic tangent (TANG
+// elastic).  The non-associative consistent tangent (ETA != ETABAR, what the reference's RetToCone ctest uses) has
+// no major symmetry: such blocks run through the general kernel of generic_kernel.cuh (full 6x6 tangent, full K_e).
 #pragma once
 
 #include "solid_math.cuh"
@@ -35,12 +35,18 @@ namespace b200s
     q[9] = in[9] != 0.0 ? 1.0 : 0.0;
     const double mfac = young / ((1.0 + nu) * (1.0 - 2.0 * nu));
     q[10] = mfac * (1.0 - nu), q[11] = mfac * nu, q[12] = mfac * 0.5 * (1.0 - 2.0 * nu);
-    // symmetric tangent storage: see the header of this file
-    return !(q[9] != 0.0 && in[5] != in[7]) && in[4] != 0.0 && in[5] != 0.0 && in[7] != 0.0;
+    return in[4] != 0.0 && in[5] != 0.0 && in[7] != 0.0;
   }
+  // the consistent tangent is major-symmetric only for ETA == ETABAR; otherwise the block is evaluated by the general
+  // (full 6x6 tangent, full K_e) kernel of generic_kernel.cuh
+  inline bool drucker_prager_tangent_is_symmetric(const double* in) { return !(in[9] != 0.0 && in[5] != in[7]); }
 
-  // C = 2 E + I (Voigt) in; S[6], Cm[21] out; hist = history of this point or nullptr (virgin, nothing stored)
-  B2_HD void drucker_prager_evaluate(const double* q, double* hist, const double* C, double* S, double* Cm)
+  // C = 2 E + I (Voigt) in; S[6] and the tangent out: FULL = false: Cm[21] (upper triangle, valid for ETA == ETABAR
+  // or the elastic tangent), FULL = true: Cm[36], entry [I][J] at I + 6 J like the reference's 6x6 view
+  // (setup_cmat_elasto_plastic_cone :127-150: eta D(x)1 + etabar 1(x)D is not symmetric for ETA != ETABAR);
+  // hist = history of this point or nullptr (virgin, nothing stored)
+  template <bool FULL>
+  B2_HD void drucker_prager_evaluate_t(const double* q, double* hist, const double* C, double* S, double* Cm)
   {
     const double G = q[0], kappa = q[1], Hiso = q[2], abstol = q[3], coh = q[4], eta = q[5], xi = q[6], etabar = q[7];
     const int itermax = (int)q[8];
@@ -115,14 +121,19 @@ namespace b200s
       }
       hist[13] = bar;
     }
+    // tangent entry (P, Q): the upper triangle of a symmetric matrix or the full 6x6
+    auto slot = [](int P, int Q) { return FULL ? P + 6 * Q : c21(P < Q ? P : Q, P < Q ? Q : P); };
 #pragma unroll
-    for (int i = 0; i < 21; ++i) Cm[i] = 0.0;
+    for (int i = 0; i < (FULL ? 36 : 21); ++i) Cm[i] = 0.0;
     if (Phi > 0.0 && q[9] != 0.0)
     {
       if (dstrainv != 0.0)
       {
         const double ep = kappa * (1.0 - kappa / (kappa + xi / eta * xi / etabar * Hiso));
-        Cm[c21(0, 0)] = Cm[c21(1, 1)] = Cm[c21(2, 2)] = Cm[c21(0, 1)] = Cm[c21(0, 2)] = Cm[c21(1, 2)] = ep;
+#pragma unroll
+        for (int P = 0; P < 3; ++P)
+#pragma unroll
+          for (int Q = FULL ? 0 : P; Q < 3; ++Q) Cm[slot(P, Q)] = ep;
       }
       else
       {
@@ -130,26 +141,32 @@ namespace b200s
         const double A = 1.0 / (G + kappa * etabar * eta + xi * xi * Hiso);
         const double r = Dgamma / (sqrt(2.0) * nd);
         const double f1 = 2.0 * G * (1.0 - r), f2 = 2.0 * G * (r - G * A);
-        const double f3 = -sqrt(2.0) * G * A * kappa * eta;   // eta == etabar (make_drucker_prager)
+        const double f3 = -sqrt(2.0) * G * A * kappa;
         const double f4 = kappa * (1.0 - kappa * eta * etabar * A);
 #pragma unroll
         for (int P = 0; P < 6; ++P)
 #pragma unroll
-          for (int Q = P; Q < 6; ++Q)
+          for (int Q = FULL ? 0 : P; Q < 6; ++Q)
           {
             const double iP = P < 3 ? 1.0 : 0.0, iQ = Q < 3 ? 1.0 : 0.0;
             const double Is = (P == Q) ? (P < 3 ? 1.0 : 0.5) : 0.0;
-            Cm[c21(P, Q)] = f1 * (Is - iP * iQ / 3.0) + f2 * (d[P] / nd) * (d[Q] / nd) +
-                            f3 * ((d[P] / nd) * iQ + iP * (d[Q] / nd)) + f4 * iP * iQ;
+            Cm[slot(P, Q)] = f1 * (Is - iP * iQ / 3.0) + f2 * (d[P] / nd) * (d[Q] / nd) +
+                             f3 * (eta * (d[P] / nd) * iQ + etabar * iP * (d[Q] / nd)) + f4 * iP * iQ;
           }
       }
     }
     else
     {
-      Cm[c21(0, 0)] = Cm[c21(1, 1)] = Cm[c21(2, 2)] = q[10];
-      Cm[c21(0, 1)] = Cm[c21(0, 2)] = Cm[c21(1, 2)] = q[11];
-      Cm[c21(3, 3)] = Cm[c21(4, 4)] = Cm[c21(5, 5)] = q[12];
+#pragma unroll
+      for (int P = 0; P < 3; ++P)
+#pragma unroll
+        for (int Q = FULL ? 0 : P; Q < 3; ++Q) Cm[slot(P, Q)] = P == Q ? q[10] : q[11];
+      Cm[slot(3, 3)] = Cm[slot(4, 4)] = Cm[slot(5, 5)] = q[12];
     }
+  }
+  B2_HD void drucker_prager_evaluate(const double* q, double* hist, const double* C, double* S, double* Cm)
+  {
+    drucker_prager_evaluate_t<false>(q, hist, C, S, Cm);
   }
 
   // ---- MAT_VISCONEOHOOKE ----------------------------------------------------------------------------------------

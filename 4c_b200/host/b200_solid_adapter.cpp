@@ -45,7 +45,12 @@ namespace B200Solid
       if (tech != B200S_TECH_NONE || prestress != B200S_PRESTRESS_NONE) return false;
       return hyper || material_kind == B200S_MAT_DRUCKER_PRAGER;
     }
-    if (kinem != B200S_KINEM_NONLINEAR_TOTLAG || !hyper) return false;
+    if (kinem != B200S_KINEM_NONLINEAR_TOTLAG) return false;
+    // finite-strain history material: displacement based (all three cells) or EAS (hex8), no prestress
+    if (material_kind == B200S_MAT_VISCONEOHOOKE)
+      return prestress == B200S_PRESTRESS_NONE &&
+             (tech == B200S_TECH_NONE || (celltype == B200S_HEX8 && (tech == B200S_TECH_EAS_MILD || tech == B200S_TECH_EAS_FULL)));
+    if (!hyper) return false;
     if (prestress == B200S_PRESTRESS_MULF) return tech == B200S_TECH_NONE;  // MULF + F-bar: CPU loop
     if (prestress != B200S_PRESTRESS_NONE) return false;
     if (tech == B200S_TECH_NONE) return true;

@@ -421,11 +421,9 @@ def run_b200(args):
     rm, u, mesh_label = build_rank(wl, per_gpu_n, rank, world, args.strong)
     asm = b200.DeviceAssembler(rm, getattr(capi, wl["mat"]), wl["par"], device=local,
                                tech=getattr(capi, wl.get("tech", "TECH_NONE")) if "kinem" not in wl else capi.TECH_NONE,
-                               kinem=getattr(capi, wl.get("kinem", "KINEM_NONLINEAR_TOTLAG")))
+                               kinem=getattr(capi, wl.get("kinem", "KINEM_NONLINEAR_TOTLAG")),
+                               options={kv.split("=")[0]: float(kv.split("=")[1]) for kv in args.option or []})
     ctx = asm.ctx
-    for kv in args.option or []:          # library options, e.g. --option lazy_zero=0
-        k, v = kv.split("=")
-        ctx.set_option(k, float(v))
     if world > 1:
         uid = [ctx.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)

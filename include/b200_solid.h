@@ -58,8 +58,8 @@ extern "C"
    *                   accumulated plastic strain of every Gauss point (last converged + current iterate) live
    *                   in the context: b200s_update_step = Mat::PlasticDruckerPrager::update(),
    *                   b200s_reset_step discards the iterate, b200s_get/set_material_history = pack/unpack.
-   *                   The consistent tangent needs ETA == ETABAR (otherwise it is not major-symmetric and
-   *                   b200s_set_material returns B200S_ERR_UNSUPPORTED; TANG elastic always works).
+   *                   With ETA != ETABAR the consistent tangent is not major-symmetric: such blocks are evaluated
+   *                   by the general kernel (full 6x6 tangent, full K_e; slower than the symmetric fast path).
    *   VISCONEOHOOKE : MAT_VISCONEOHOOKE (src/mat/4C_mat_visconeohooke.cpp), a finite-strain HISTORY material:
    *                   params = {YOUNGS_SLOW, POISSON, DENS, YOUNGS_FAST, RELAX, THETA}; compressible Neo-Hooke on
    *                   the fast modulus whose deviatoric stress relaxes through one Maxwell branch (one-step-theta
@@ -220,6 +220,13 @@ extern "C"
    * row range -- about nnz / phases entries each -- of their lowest owned node, so that b200s_evaluate with a
    * HOST K_values copies the rows of a finished phase while the next phases are still being evaluated;
    * 1 = one phase, no overlap; meshes whose row numbering has no spatial locality get one phase),
+   * "symmetric_transfer" (default 0; with a HOST K_values and a formulation whose K_e is symmetric -- everything on
+   * the device path except TECH fbar -- only the 3x3 blocks with column node >= row node cross PCIe, about half
+   * of the bytes, and a pool of "host_threads" threads (default: all, at most 32) writes the full CSR rows into
+   * K_values: the upper part of a row is copied, a lower block is the transpose of an upper block of an earlier
+   * row; "nt_stores" (default 1) uses non-temporal stores for that.  Needs a node-blocked, structurally symmetric
+   * graph whose owned column ids equal the row ids; otherwise the full transfer is used,
+   * b200s_symmetric_transfer_status says why),
    * "overlap_halo" (default 1: with a halo, the ghost import runs on a side stream beside the elements that
    * hold no ghost node; 0 = in-stream before a single launch), "ctas_per_sm" and "scatter_mode" (tuning /
    * profiling only). */
@@ -538,6 +545,12 @@ extern "C"
    * while later element segments were still being evaluated, [2] 1 if the ghost import overlapped the
    * elements without ghost nodes, [3] row phases of the installed graph, [4] elements holding a ghost node. */
   int b200s_last_evaluate_info(const b200s_ctx* ctx, int64_t* out5);
+  /* Bytes of CSR values that crossed PCIe in the last b200s_evaluate with a host K_values, and whether the
+   * block-upper transfer (option "symmetric_transfer") is in use for the installed graph (else: why not). */
+  /* Diagnostics: the device element order, out[n_col_eles] = caller's column-element index of device element e. */
+  int b200s_debug_element_order(b200s_ctx* ctx, int32_t* out);
+  int64_t b200s_last_d2h_value_bytes(const b200s_ctx* ctx);
+  const char* b200s_symmetric_transfer_status(const b200s_ctx* ctx);
 
   const char* b200s_version(void);
 

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../4c_b200/csrc/post_kernels.cuh"
+#include "../../4c_b200/csrc/generic_kernel.cuh"
 #include "../../4c_b200/csrc/shape_tables.hpp"
 
 using namespace b200s;
@@ -130,15 +131,68 @@ extern "C" int emu_visco_neohooke(const double* in6, double dt, double* hist, co
 // rejects (non-symmetric consistent tangent)
 extern "C" int emu_drucker_prager(const double* in10, double* hist, const double* C, double* S, double* Cm36)
 {
-  double q[DP_NPAR], Cm[21];
+  double q[DP_NPAR];
   if (!make_drucker_prager(in10, q)) return -3;
   MatParams mp;
   for (double& v : mp.p) v = 0.0;
   mp.hyper = nullptr, mp.fiber = nullptr, mp.ext = q, mp.hist = hist;
+  if (!drucker_prager_tangent_is_symmetric(in10))
+  {
+    // ETA != ETABAR with the consistent tangent: the general kernel's material call (full 6x6)
+    material_evaluate_full<MAT_DP>(mp, C, S, Cm36);
+    return 1;
+  }
+  double Cm[21];
   material_evaluate<MAT_DP>(mp, C, S, Cm);
   for (int I = 0; I < 6; ++I)
     for (int J = 0; J < 6; ++J) Cm36[I + 6 * J] = Cm[c21(I, J)];
   return 0;
+}
+
+// The general (non-symmetric tangent) kernel of generic_kernel.cuh stepped on the host: one call of generic_block_row
+// per (element, row node) and the kernel's scatter.  celltype 0 hex8 / 1 hex27 / 2 tet10, KINEM linear,
+// MAT_Struct_DruckerPrager with its state store (n_ele * ngp * DP_HIST, updated in place).
+template <int NN>
+static int run_generic_dp(const GenericArgs& Ga)
+{
+  const EvalArgs& A = Ga.A;
+  int bad = 0;
+  for (int64_t e = 0; e < A.n_ele; ++e)
+    for (int i = 0; i < Ga.nn; ++i)
+    {
+      double Krow[NN][9], fi[3], dj = 1e300, df = 1e300;
+      if (generic_block_row<MAT_DP, NN>(Ga, e, i, Krow, fi, dj, df)) ++bad;
+      const NodeRow nr = A.node_row[A.conn[e * Ga.nn + i]];
+      if (nr.rowstart < 0) continue;
+      for (int b = 0; b < 3; ++b) A.f[nr.frow + b] += fi[b];
+      if (!Ga.stiff) continue;
+      const int32_t* pos = A.pos + e * Ga.pos_stride + i * Ga.nn;
+      for (int j = 0; j < Ga.nn; ++j)
+        for (int b = 0; b < 3; ++b)
+          for (int c = 0; c < 3; ++c) A.vals[nr.rowstart + (int64_t)b * nr.rowlen + pos[j] + c] += Krow[j][b + 3 * c];
+    }
+  return bad;
+}
+extern "C" int emu_generic_drucker_prager(int celltype, const double* in10, int stiff, int64_t n_ele, const int32_t* conn,
+    const double* X, const double* u_col, const int32_t* pos, int pos_stride, const int64_t* node_rowstart,
+    const int32_t* node_rowlen, const int32_t* node_frow, int64_t n_col_nodes, double* vals, double* f, double* mat_hist)
+{
+  std::vector<NodeRow> node_row(n_col_nodes);
+  for (int64_t k = 0; k < n_col_nodes; ++k)
+    node_row[k].rowstart = node_rowstart[k], node_row[k].rowlen = node_rowlen[k], node_row[k].frow = node_frow[k];
+  double q[DP_NPAR];
+  if (!make_drucker_prager(in10, q)) return -3;
+  const CellTables T = make_cell_tables(celltype);
+  GenericArgs Ga;
+  EvalArgs& A = Ga.A;
+  A.X = X, A.u = u_col, A.conn = conn, A.pos = pos, A.node_row = node_row.data();
+  A.per_ele_param = nullptr, A.ele_id = nullptr, A.gp_hist = nullptr, A.fibers = nullptr, A.linear = 1;
+  A.mat_hist = mat_hist, A.vals = vals, A.f = f, A.err = nullptr, A.n_ele = n_ele, A.scatter_mode = 0;
+  for (double& v : A.mp.p) v = 0.0;
+  A.mp.hyper = nullptr, A.mp.fiber = nullptr, A.mp.ext = q, A.mp.hist = nullptr;
+  Ga.dN_gp = T.dN_gp.data(), Ga.dN_node = T.dN_node.data(), Ga.w = T.w.data();
+  Ga.nn = T.nn, Ga.ngp = T.ngp, Ga.pos_stride = pos_stride, Ga.stiff = stiff;
+  return T.nn == 8 ? run_generic_dp<8>(Ga) : (T.nn == 10 ? run_generic_dp<10>(Ga) : run_generic_dp<27>(Ga));
 }
 
 extern "C" int emu_post(int celltype, int fbar, int matkind, const double* params, const double* per_ele,

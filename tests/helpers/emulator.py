@@ -213,8 +213,8 @@ def drucker_prager(in10, Cv, hist=None):
     rc = lib("post").emu_drucker_prager(_p(in10), _p(hist), _p(Cv), _p(S), _p(Cm))
     if rc == -3:
         return None
-    assert rc == 0
-    return S, Cm.reshape(6, 6)
+    assert rc in (0, 1)   # 1: the full (non-symmetric) tangent of the general kernel, stored [I + 6 J]
+    return S, (Cm.reshape(6, 6).T.copy() if rc == 1 else Cm.reshape(6, 6))
 
 
 def hex8_drucker_prager(in10, conn, X, u_col, rowptr, colind, node_row_lid, node_col_lid, n_row_nodes, mat_hist,
@@ -255,5 +255,25 @@ def hex8_visco(in6, dt, conn, X, u_col, rowptr, colind, node_row_lid, node_col_l
     rc = L.emu_hex8_visco(_p(np.ascontiguousarray(in6, np.float64)), float(dt), int(stiff), len(conn), _p(conn),
                           _p(np.ascontiguousarray(X, np.float64)), _p(np.ascontiguousarray(u_col, np.float64)), _p(pos),
                           _p(rowstart), _p(rowlen), _p(frow), len(rowstart), _p(vals), _p(f), _p(mat_hist))
+    assert rc == 0, rc
+    return vals, f
+
+
+def generic_drucker_prager(celltype, in10, conn, X, u_col, rowptr, colind, node_row_lid, node_col_lid, n_row_nodes, mat_hist,
+                           stiff=True):
+    """Emulated general-tangent kernel (generic_kernel.cuh), KINEM linear, MAT_Struct_DruckerPrager with a tangent
+    without major symmetry; mat_hist (n_ele, ngp, 14) updated in place."""
+    conn = np.ascontiguousarray(conn, np.int32)
+    nn = conn.shape[1]
+    pos, rowstart, rowlen, frow = scatter_map(conn, rowptr, colind, node_row_lid, node_col_lid)
+    pos = np.ascontiguousarray(pos.reshape(len(conn), -1))
+    vals, f = np.zeros(rowptr[-1]), np.zeros(3 * n_row_nodes)
+    L = lib("post")
+    L.emu_generic_drucker_prager.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int64] + [C.c_void_p] * 4 + [C.c_int] + \
+        [C.c_void_p] * 3 + [C.c_int64] + [C.c_void_p] * 3
+    rc = L.emu_generic_drucker_prager(int(celltype), _p(np.ascontiguousarray(in10, np.float64)), int(stiff), len(conn), _p(conn),
+                                      _p(np.ascontiguousarray(X, np.float64)), _p(np.ascontiguousarray(u_col, np.float64)),
+                                      _p(pos), pos.shape[1], _p(rowstart), _p(rowlen), _p(frow), len(rowstart), _p(vals),
+                                      _p(f), _p(mat_hist))
     assert rc == 0, rc
     return vals, f

@@ -847,11 +847,12 @@ def test_history_material_restrictions():
     with pytest.raises(capi.B200SolidError) as ei:
         asm.evaluate()
     assert ei.value.code == capi.ERR_UNSUPPORTED and "KINEM linear" in str(ei.value)
-    # non-associative consistent tangent: not major-symmetric
-    with pytest.raises(capi.B200SolidError) as ei:
-        asm.ctx.set_material(capi.MAT_DRUCKER_PRAGER, capi.drucker_prager_params(**dict(DP_MAT, ETABAR=0.4)))
-    assert ei.value.code == capi.ERR_UNSUPPORTED and "symmetric" in str(ei.value)
+    # non-associative consistent tangent: accepted (general-tangent kernel); zero friction parameters are not
+    asm.ctx.set_material(capi.MAT_DRUCKER_PRAGER, capi.drucker_prager_params(**dict(DP_MAT, ETABAR=0.4)))
     asm.ctx.set_material(capi.MAT_DRUCKER_PRAGER, capi.drucker_prager_params(**dict(DP_MAT, ETABAR=0.4, TANG="elastic")))
+    with pytest.raises(capi.B200SolidError) as ei:
+        asm.ctx.set_material(capi.MAT_DRUCKER_PRAGER, capi.drucker_prager_params(**dict(DP_MAT, ETA=0.0)))
+    assert ei.value.code == capi.ERR_INVALID and "non-zero" in str(ei.value)
     with pytest.raises(capi.B200SolidError):
         asm.ctx.set_material(capi.MAT_DRUCKER_PRAGER, [10.0, 0.3])      # too few parameters
     # a material without history has no state store
@@ -863,12 +864,45 @@ def test_history_material_restrictions():
     asm.close()
 
 
-def test_reference_druckerprager_known_answers_through_cuda_path():
-    """Tip displacements (1e-10) of tests/input_files/mat_druckerprager_RetToCone_elastic_tang.4C.yaml with the
-    device doing every evaluate and the history commits (20 load steps, 68 yielding Gauss points)."""
+@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10"])
+def test_unsymmetric_tangent_block_matches_oracle(cell):
+    """MAT_Struct_DruckerPrager with ETA != ETABAR and the consistent tangent (no major symmetry, K not symmetric):
+    the general-tangent kernel against the oracle, incl. the state store over a commit."""
+    ct, rm, u = _mesh(cell)
+    u = 4.0 * u.ravel()
+    par = capi.drucker_prager_params(**dict(DP_MAT, ETA=0.1, ETABAR=0.25))
+    asm = b200.DeviceAssembler(rm, capi.MAT_DRUCKER_PRAGER, par, kinem=capi.KINEM_LINEAR)
+    rowptr, colind = asm.graph()
+    ngp = {"hex8": 8, "hex27": 27, "tet10": 4}[cell]
+    h_o = np.zeros((rm.n_col_eles, ngp, orc.DP_HIST))
+    for fac in (1.0, 1.5):
+        asm.set_state("displacement", fac * u)
+        K, f, _ = asm.evaluate()
+        rK, rf, nbad = orc.evaluate_assemble(ct, orc.MAT_DRUCKER_PRAGER, par, rm.conn, rm.X.ravel(), fac * u,
+                                             rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, rowptr, colind,
+                                             tech=orc.TECH_LINEAR, hist=h_o)
+        ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
+        assert ok and nbad == 0, (fac, wK, wf)
+        h_d = asm.ctx.get_material_history().reshape(h_o.shape)
+        assert np.abs(h_d - h_o).max() <= 1e-12 * np.abs(h_o).max()
+        _, f2, _ = asm.evaluate("struct_calc_internalforce")
+        assert np.abs(f2 - rf).max() <= RTOL * np.abs(rf).max()
+        asm.ctx.update_step()
+        orc.material_update(orc.MAT_DRUCKER_PRAGER, h_o)
+    import scipy.sparse as sp
+    A = sp.csr_matrix((K, colind, rowptr), shape=(asm.n_rows, asm.n_rows))
+    assert abs(A - A.T).max() > 1e-6 * np.abs(K).max()
+    asm.close()
+
+
+@pytest.mark.parametrize("name", ["RetToCone_elastic_tang", "RetToCone"])
+def test_reference_druckerprager_known_answers_through_cuda_path(name):
+    """Tip displacements (1e-10) of tests/input_files/mat_druckerprager_RetToCone[_elastic_tang].4C.yaml with the
+    device doing every evaluate and the history commits (20 load steps, 68 yielding Gauss points).  RetToCone
+    itself uses the non-associative consistent tangent (ETA 0.1, ETABAR 0.25): general-tangent kernel."""
     from tests.helpers.newton import solve_case
     from tests.helpers.neumann import point_neumann_load
-    case = json.load(open(os.path.join(G, "integration_hex8_druckerprager_RetToCone_elastic_tang.json")))
+    case = json.load(open(os.path.join(G, f"integration_hex8_druckerprager_{name}.json")))
     X = np.asarray(case["coords"], float)
     conn = np.asarray(case["elements"], np.int32)
     rm = b200.partition.serial_mesh(orc.HEX8, X, conn)

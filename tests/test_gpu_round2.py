@@ -440,3 +440,57 @@ def test_reference_visco_creep_known_answer_through_cuda_path():
         assert abs(u[e["node"], e["dof"]] - e["value"]) < e["tol"], (e, u[e["node"], e["dof"]])
     assert abs(u[121, 0] - 0.0006320013656913447) < 1e-11
     asm.close()
+
+
+# ---- block-upper transfer of a symmetric K with the threaded host mirror -------------------------------------------
+@pytest.mark.parametrize("cell,n,mk,par,tech", [("HEX8", (40, 36, 30), capi.MAT_COUP_NEOHOOKE, [200.0, 0.25], capi.TECH_NONE),
+                                                ("HEX27", (12, 10, 9), capi.MAT_SVK, [1000.0, 0.3], capi.TECH_NONE),
+                                                ("HEX8", (30, 28, 26), capi.MAT_ISO_VOL, [1.0, 1000.0], capi.TECH_EAS_MILD)])
+@pytest.mark.parametrize("nt_stores,threads", [(1, 0), (0, 3)])
+def test_symmetric_transfer_matches_oracle(cell, n, mk, par, tech, nt_stores, threads):
+    rm = b200.partition.box_partition(getattr(b200.mesh, cell), n, 0, 1)
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 1.0 / max(n))
+    asm = b200.DeviceAssembler(rm, mk, par, tech=tech,
+                               options={"symmetric_transfer": 1, "nt_stores": nt_stores, "host_threads": threads})
+    rowptr, colind = asm.graph()
+    asm.set_state("displacement", u.ravel())
+    K = np.full(asm.nnz, np.nan)
+    f = np.empty(asm.n_rows)
+    asm.ctx.evaluate(capi.ACTION_NLNSTIFF, asm._u, K, f)
+    assert asm.ctx.symmetric_transfer_status() == "in use", asm.ctx.symmetric_transfer_status()
+    moved = asm.ctx.last_d2h_value_bytes()
+    assert 0.5 * 8 * asm.nnz < moved < 0.6 * 8 * asm.nnz, (moved, 8 * asm.nnz)
+    otech = {capi.TECH_NONE: orc.TECH_NONE, capi.TECH_EAS_MILD: orc.TECH_EAS_MILD}[tech]
+    hist = orc.eas_new_history(otech, rm.n_col_eles) if tech != capi.TECH_NONE else None
+    rK, rf, nbad = orc.evaluate_assemble(getattr(orc, cell), mk, par, rm.conn, rm.X.ravel(), u.ravel(), rm.node_row_lid,
+                                         rm.node_col_lid, rm.n_row_nodes, rowptr, colind, tech=otech, hist=hist,
+                                         nthreads=1 if hist is not None else 8)
+    assert np.isfinite(K).all()                                   # every entry of the full CSR was written
+    ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL if tech == capi.TECH_NONE else 1e-10)
+    assert ok and nbad == 0, (wK, wf)
+    # off-diagonal node blocks are exact transposes by construction (the diagonal 3x3 blocks travel whole)
+    import scipy.sparse as sp
+    A = sp.csr_matrix((K, colind, rowptr), shape=(asm.n_rows, asm.n_rows))
+    D = abs(A - A.T).tocoo()
+    off = (D.row // 3) != (D.col // 3)
+    assert D.data[off].max(initial=0.0) == 0.0
+    assert D.data.max(initial=0.0) <= 1e-13 * np.abs(K).max()
+    asm.close()
+
+
+def test_symmetric_transfer_is_refused_for_fbar():
+    """F-bar has a non-symmetric K_e: the option is ignored, the whole matrix travels."""
+    n = (40, 36, 30)
+    rm = b200.partition.box_partition(b200.mesh.HEX8, n, 0, 1)
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 1.0 / max(n))
+    asm = b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, [200.0, 0.25], tech=capi.TECH_FBAR, options={"symmetric_transfer": 1})
+    rowptr, colind = asm.graph()
+    asm.set_state("displacement", u.ravel())
+    K, f, _ = asm.evaluate()
+    assert asm.ctx.last_d2h_value_bytes() == 8 * asm.nnz
+    rK, rf, nbad = orc.evaluate_assemble(orc.HEX8, orc.MAT_COUP_NEOHOOKE, [200.0, 0.25], rm.conn, rm.X.ravel(), u.ravel(),
+                                         rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, rowptr, colind, tech=orc.TECH_FBAR,
+                                         nthreads=8)
+    ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
+    assert ok and nbad == 0, (wK, wf)
+    asm.close()

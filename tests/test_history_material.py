@@ -127,10 +127,54 @@ def test_product_point_matches_oracle(name, tang):
     assert np.abs(S3 - orc.material_hist(DP, in10, E)[0]).max() <= 1e-13 * np.abs(S3).max()
 
 
-def test_product_rejects_the_unsymmetric_tangent_only():
-    C = C_of(STRAINS["cone"])
-    assert emu.drucker_prager(orc.drucker_prager_params(**dict(UNIT, ETA=0.4)), C) is None
-    assert emu.drucker_prager(orc.drucker_prager_params(**dict(UNIT, ETA=0.4, TANG="elastic")), C) is not None
+def test_product_unsymmetric_tangent_matches_oracle():
+    """ETA != ETABAR with the consistent tangent: no major symmetry (the reference's RetToCone ctest input is of this
+    kind).  The product evaluates such blocks with the general kernel's full 6x6 tangent."""
+    in10 = orc.drucker_prager_params(**dict(UNIT, ETA=0.4))
+    for name in STRAINS:
+        E = STRAINS[name]
+        h_o, h_p = np.zeros(orc.DP_HIST), np.zeros(orc.DP_HIST)
+        S, Cm = orc.material_hist(DP, in10, E, h_o)
+        S2, C2 = emu.drucker_prager(in10, C_of(E), h_p)
+        assert np.abs(S - S2).max() <= 1e-13 * max(np.abs(S).max(), 1e-3)
+        assert np.abs(Cm - C2).max() <= 1e-13 * np.abs(Cm).max(), name
+        assert np.abs(h_o - h_p).max() <= 1e-14 * max(np.abs(h_o).max(), 1.0)
+    Sc, Cc = emu.drucker_prager(in10, C_of(STRAINS["cone"]), None)
+    assert np.abs(Cc - Cc.T).max() > 1e-3 * np.abs(Cc).max()          # really unsymmetric on the cone
+    assert emu.drucker_prager(orc.drucker_prager_params(**dict(UNIT, ETA=0.4, TANG="elastic")), C_of(STRAINS["cone"])) is not None
+
+
+@pytest.mark.parametrize("cell,n", [("HEX8", (3, 2, 2)), ("TET10", 2), ("HEX27", (2, 1, 1))])
+def test_general_tangent_kernel_matches_oracle(cell, n):
+    """generic_kernel.cuh stepped on the CPU: K (not symmetric), f and the state store for the non-associative
+    consistent tangent, against the oracle, over load / commit / reload."""
+    ct = getattr(orc, cell)
+    if cell == "TET10":
+        X, conn = b200.mesh.unstructured_tet10(n)
+        rm = b200.partition.serial_mesh(b200.mesh.TET10, X, conn)
+    else:
+        rm = b200.partition.box_partition(getattr(b200.mesh, cell), n, 0, 1)
+    u = np.asarray(b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 0.4), float).ravel()
+    rowptr, colind = orc.build_graph(ct, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    in10 = orc.drucker_prager_params(YOUNG=10.0, NUE=0.3, ISOHARD=0.5, TOL=1e-12, C=0.05, ETA=0.1, XI=0.25, ETABAR=0.25)
+    ngp = orc.num_gp(ct)
+    h_o = np.zeros((rm.n_col_eles, ngp, orc.DP_HIST))
+    h_p = np.zeros_like(h_o)
+    for fac in (1.0, 1.5):
+        rK, rf, nbad = orc.evaluate_assemble(ct, DP, in10, rm.conn, rm.X.ravel(), fac * u, rm.node_row_lid, rm.node_col_lid,
+                                             rm.n_row_nodes, rowptr, colind, tech=orc.TECH_LINEAR, hist=h_o)
+        K, f = emu.generic_drucker_prager(rm.celltype, in10, rm.conn, rm.X.ravel(), fac * u, rowptr, colind, rm.node_row_lid,
+                                          rm.node_col_lid, rm.n_row_nodes, h_p)
+        assert nbad == 0
+        assert np.abs(K - rK).max() <= 1e-12 * np.abs(rK).max()
+        assert np.abs(f - rf).max() <= 1e-12 * np.abs(rf).max()
+        assert np.abs(h_o - h_p).max() <= 1e-13 * np.abs(h_o).max()
+        assert (h_o[:, :, 13] > 0).sum() > 4
+        orc.material_update(DP, h_o)
+        h_p[:, :, :7] = h_p[:, :, 7:]
+    import scipy.sparse as sp
+    A = sp.csr_matrix((rK, colind, rowptr), shape=(3 * rm.n_row_nodes,) * 2)
+    assert abs(A - A.T).max() > 1e-6 * np.abs(rK).max()                 # the assembled K is not symmetric
 
 
 def test_product_kernel_with_state_store_matches_oracle():
