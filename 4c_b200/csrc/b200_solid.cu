@@ -30,6 +30,9 @@
 // __graft_entry__.build_library compiles this file five times in parallel with -DB200S_PART=0..4 (core + ABI,
 // hex8, hex8 EAS, tet10, hex27) and links the objects.  Without the macro everything is one translation unit.
 // (nvcc --split-compile was measured: 3x faster to build but 8-25 % slower kernels.)
+#ifndef B200S_TET10_SPLIT_PHASE1
+#define B200S_TET10_SPLIT_PHASE1 0  // 1: operator M formed after the X/u refill (see tet10_kernel.cuh phase1a / phase1b)
+#endif
 #define B200S_PART_CORE 0
 #define B200S_PART_HEX8 1
 #define B200S_PART_EAS 2
@@ -577,9 +580,15 @@ namespace b200s
       // nodal Jacobian check: lane = (element, node)
       const double dJn = tet10::node_jacobian_det(S, tab_node, lane);
       const bool neg = live && !(dJn > 0.0);
+#if B200S_TET10_SPLIT_PHASE1
+      double Fg[9], Sg[6], Cg[21];
+      double dJ, dF;
+      tet10::phase1a<MAT, STIFF, FORM == 1, FORM == 2>(A, S, tab_gp, wgt, lane, e0, Fg, Sg, Cg, dJ, dF);
+#else
       double out54[54];
       double dJ, dF;
       tet10::phase1<MAT, STIFF, FORM == 1, FORM == 2>(A, S, tab_gp, wgt, lane, e0, out54, dJ, dF);
+#endif
       if (live)
       {
         detJ_min = fmin(detJ_min, fmin(dJn, dJ));
@@ -599,7 +608,11 @@ namespace b200s
       // LDGSTS -- costs 14.6 -> 23.1 ms and doubles the DRAM traffic on config 4; profiles/r02_summary.md)
       if (tile + wstride < n_tiles) tet10::issue_xu(A, S, lane, node_next);
       cp_async_commit();
+#if B200S_TET10_SPLIT_PHASE1
+      tet10::phase1b<STIFF, FORM == 2>(S, lane, Fg, Sg, Cg);
+#else
       tet10::phase1_store<STIFF>(S, lane, out54);
+#endif
       __syncwarp();
       double Kacc[tet10::NBLK][9], facc[3];
       tet10::phase2<STIFF>(S, lane, Kacc, facc);

@@ -192,6 +192,89 @@ namespace b200s
       first_piola(F, Sv, out54 + 45);
     }
 
+    // ---- phase 1 split in two (device kernel): the first half ends with the material response kept in registers
+    // (F, w S, w C = 36 doubles), the second half -- after the X/u refill has been issued -- forms the operator M
+    // and P w and stores them; the 54 operator entries never have to stay live across the refill.
+    template <int MAT, bool STIFF, bool MULF = false, bool LINEAR = false>
+    B2_HD void phase1a(const EvalArgs& A, const WarpSmem& S, const double* tab_gp, const double* wgt, int lane,
+        int64_t e0, double* F, double* Sv, double* Cm, double& detJ_gp, double& detF_gp)
+    {
+      const int el = lane / NN, g = lane - el * NN;
+      detJ_gp = detF_gp = 1e300;
+      if (el >= EPW || g >= NGP) return;
+      const int64_t e = e0 + el;
+      const double* xu = S.xu + el * XU_ESTRIDE;
+      double J[9], iJ[9];
+      const double* dN = tab_gp + g * TAB_STRIDE;
+      jacobian(dN, xu, J);
+      const double detJ = inv3(iJ, J);
+      detJ_gp = detJ;
+#pragma unroll
+      for (int q = 0; q < 9; ++q) F[q] = (q % 4 == 0) ? 1.0 : 0.0;
+      double* Gout = S.g + el * G_ESTRIDE + g * G_GSTRIDE;
+#pragma unroll
+      for (int k = 0; k < NN; ++k)
+      {
+        double Gk[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+          Gk[a] = fma(iJ[a + 6], dN[3 * k + 2], fma(iJ[a + 3], dN[3 * k + 1], iJ[a] * dN[3 * k]));
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+        {
+          Gout[3 * k + a] = Gk[a];
+          const double ua = xu[NDOF + 3 * k + a];
+#pragma unroll
+          for (int b = 0; b < 3; ++b) F[a + 3 * b] = fma(ua, Gk[b], F[a + 3 * b]);
+        }
+      }
+      if (MULF && e < A.n_ele)
+        mulf_deformation_gradient<NN>(A.gp_hist + (e * NGP + g) * MULF_HIST, dN, xu + NDOF, F);
+      detF_gp = det3(F);
+      double C[6];
+      right_cauchy_green(F, C);
+      if (LINEAR) linear_kinematics(F, C);
+      MatParams mp = A.mp;
+      if (A.per_ele_param != nullptr && e < A.n_ele) mp.p[0] = A.per_ele_param[e];
+      if (MAT == MAT_HYPER && A.fibers != nullptr && e < A.n_ele) mp.fiber = A.fibers + 3 * e;
+      if (material_hist_doubles(MAT) > 0 && A.mat_hist != nullptr && e < A.n_ele)
+        mp.hist = A.mat_hist + (e * NGP + g) * material_hist_doubles(MAT);
+      material_evaluate<MAT>(mp, C, Sv, Cm);
+      const double w = detJ * wgt[g];
+#pragma unroll
+      for (int v = 0; v < 6; ++v) Sv[v] *= w;
+      if (STIFF)
+      {
+#pragma unroll
+        for (int v = 0; v < 21; ++v) Cm[v] *= w;
+      }
+    }
+    template <bool STIFF, bool LINEAR = false>
+    B2_HD void phase1b(const WarpSmem& S, int lane, const double* F, const double* Sv, const double* Cm)
+    {
+      const int el = lane / NN, g = lane - el * NN;
+      if (el >= EPW || g >= NGP) return;
+      double out54[54];
+      if (STIFF)
+      {
+        if (LINEAR)
+        {
+          const double zero[6] = {0, 0, 0, 0, 0, 0};  // no geometric stiffness
+          material_geometric_operator(F, zero, Cm, out54);
+        }
+        else
+          material_geometric_operator(F, Sv, Cm, out54);
+      }
+      first_piola(F, Sv, out54 + 45);
+#pragma unroll
+      for (int p = STIFF ? 0 : 22; p < MP_PAIRS; ++p)
+      {
+        double* dst = S.mp + mp_index(p, el, g);
+        dst[0] = out54[2 * p];
+        dst[1] = out54[2 * p + 1];
+      }
+    }
+
     template <bool STIFF>
     B2_HD void phase1_store(const WarpSmem& S, int lane, const double* out54)
     {
