@@ -2073,7 +2073,34 @@ namespace b200s_parts
 #if B200S_HAS(B200S_PART_CORE)
 namespace
 {
-  // blocks whose tangent has no major symmetry (generic_kernel.cuh)
+  // blocks evaluated by the table-driven general kernel (generic_kernel.cuh): tangents without major symmetry, and
+  // the cell types without a specialised kernel (tet4, hex20)
+  template <int MAT>
+  static int launch_generic_mat(b200s_ctx* ctx, const GenericArgs& Ga, unsigned grid)
+  {
+    switch (ctx->nn)
+    {
+      case 4:
+        k_generic_eval_assemble<MAT, 4><<<grid, 64, 0, ctx->stream>>>(Ga);
+        break;
+      case 8:
+        k_generic_eval_assemble<MAT, 8><<<grid, 64, 0, ctx->stream>>>(Ga);
+        break;
+      case 10:
+        k_generic_eval_assemble<MAT, 10><<<grid, 64, 0, ctx->stream>>>(Ga);
+        break;
+      case 20:
+        k_generic_eval_assemble<MAT, 20><<<grid, 64, 0, ctx->stream>>>(Ga);
+        break;
+      case 27:
+        k_generic_eval_assemble<MAT, 27><<<grid, 64, 0, ctx->stream>>>(Ga);
+        break;
+      default:
+        return fail(ctx, B200S_ERR_UNSUPPORTED, "cell type %d has no device kernel", ctx->celltype);
+    }
+    ctx->launches += 1;
+    return 0;
+  }
   static int launch_generic(b200s_ctx* ctx, const EvalArgs& A, bool stiff)
   {
     GenericArgs Ga;
@@ -2082,31 +2109,33 @@ namespace
     Ga.nn = ctx->nn, Ga.ngp = ctx->ngp, Ga.pos_stride = ctx->pos_stride, Ga.stiff = stiff;
     const unsigned grid = nblk(A.n_ele * ctx->nn, 64);
     if (!grid) return 0;
-    if (ctx->matkind != B200S_MAT_DRUCKER_PRAGER)
-      return fail(ctx, B200S_ERR_UNSUPPORTED, "general-tangent kernel: material kind %d", ctx->matkind);
-    switch (ctx->celltype)
+    if (ctx->tech != B200S_TECH_NONE || ctx->prestress != B200S_PRESTRESS_NONE)
+      return fail(ctx, B200S_ERR_UNSUPPORTED,
+          "the general kernel evaluates displacement-based blocks only (no element technology / prestress)");
+    switch (ctx->matkind)
     {
-      case B200S_HEX8:
-        k_generic_eval_assemble<MAT_DP, 8><<<grid, 64, 0, ctx->stream>>>(Ga);
-        break;
-      case B200S_TET10:
-        k_generic_eval_assemble<MAT_DP, 10><<<grid, 64, 0, ctx->stream>>>(Ga);
-        break;
-      case B200S_HEX27:
-        k_generic_eval_assemble<MAT_DP, 27><<<grid, 64, 0, ctx->stream>>>(Ga);
-        break;
-      default:
-        return fail(ctx, B200S_ERR_UNSUPPORTED, "cell type %d has no device kernel", ctx->celltype);
+      case B200S_MAT_COUP_NEOHOOKE:
+        return launch_generic_mat<MAT_COUP_NEOHOOKE>(ctx, Ga, grid);
+      case B200S_MAT_ISO_VOL:
+        return launch_generic_mat<MAT_ISO_VOL>(ctx, Ga, grid);
+      case B200S_MAT_SVK:
+        return launch_generic_mat<MAT_SVK>(ctx, Ga, grid);
+      case B200S_MAT_ELASTHYPER:
+        return launch_generic_mat<MAT_HYPER>(ctx, Ga, grid);
+      case B200S_MAT_DRUCKER_PRAGER:
+        return launch_generic_mat<MAT_DP>(ctx, Ga, grid);
+      case B200S_MAT_VISCONEOHOOKE:
+        return launch_generic_mat<MAT_VISCO>(ctx, Ga, grid);
     }
-    ctx->launches += 1;
-    return 0;
+    return fail(ctx, B200S_ERR_UNSUPPORTED, "general kernel: material kind %d", ctx->matkind);
   }
 
   template <bool STIFF>
   static int launch_eval(b200s_ctx* ctx, const EvalArgs& A)
   {
     if (ctx->matkind < 0) return fail(ctx, B200S_ERR_INVALID, "material not set");
-    if (ctx->general_tangent) return launch_generic(ctx, A, STIFF);
+    if (ctx->general_tangent || ctx->celltype == B200S_TET4 || ctx->celltype == B200S_HEX20)
+      return launch_generic(ctx, A, STIFF);
     if (ctx->tech != B200S_TECH_NONE && ctx->celltype != B200S_HEX8)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "element technology %d needs hex8", ctx->tech);
     switch (ctx->celltype)
@@ -2260,7 +2289,8 @@ extern "C"
     if (!ctx || !X || !conn || n_col_nodes <= 0 || n_col_eles < 0) return B200S_ERR_INVALID;
     cudaSetDevice(ctx->device);
     if (ctx->primary) detach_shared(ctx);  // a new mesh: attach again afterwards
-    if (celltype != B200S_HEX8 && celltype != B200S_TET10 && celltype != B200S_HEX27)
+    if (celltype != B200S_HEX8 && celltype != B200S_TET10 && celltype != B200S_HEX27 && celltype != B200S_TET4 &&
+        celltype != B200S_HEX20)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "cell type %d is not on the device path", celltype);
     if (n_col_nodes > INT32_MAX / 3) return fail(ctx, B200S_ERR_INVALID, "too many column nodes");
     const CellTables T = make_cell_tables(celltype);
@@ -2395,6 +2425,8 @@ extern "C"
     // (4C_solid_ele_factory_lib.hpp)
     if (element_technology != B200S_TECH_NONE && ctx->celltype >= 0 && ctx->celltype != B200S_HEX8)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "F-bar and EAS are hex8 technologies");
+    if (prestress_technology != B200S_PRESTRESS_NONE && (ctx->celltype == B200S_TET4 || ctx->celltype == B200S_HEX20))
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "MULF prestress of tet4 / hex20 blocks has no device kernel");
     ctx->kinem = kinem_type;
     dfree(ctx->d_hist_old);
     const bool eas_fresh = eas_neas(element_technology) != eas_neas(ctx->tech) || !ctx->d_eas_hist;
@@ -2967,6 +2999,12 @@ extern "C"
           break;
         case B200S_TET10:
           k_mass_assemble<10><<<grid, 128, 0, st>>>(M);
+          break;
+        case B200S_TET4:
+          k_mass_assemble<4><<<grid, 128, 0, st>>>(M);
+          break;
+        case B200S_HEX20:
+          k_mass_assemble<20><<<grid, 128, 0, st>>>(M);
           break;
       }
       ctx->launches += 1;
@@ -4487,11 +4525,17 @@ extern "C"
     static std::vector<HostBlock> v;
     return v;
   }
+  static std::mutex& host_blocks_mutex()  // contexts of several ranks may live in one process (threads)
+  {
+    static std::mutex m;
+    return m;
+  }
 
   void* b200s_host_alloc(int64_t bytes)
   {
     void* p = nullptr;
     if (bytes <= 0 || cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lk(host_blocks_mutex());
     host_blocks().push_back({p, (size_t)bytes, false});
     return p;
   }
@@ -4521,6 +4565,7 @@ extern "C"
           cudaSetDevice(device);
           if (cudaHostRegister(p, len, cudaHostRegisterPortable) == cudaSuccess)
           {
+            std::lock_guard<std::mutex> lk(host_blocks_mutex());
             host_blocks().push_back({p, len, true});
             if (numa_node_out) *numa_node_out = node;
             return p;
@@ -4536,21 +4581,25 @@ extern "C"
   void b200s_host_free(void* p)
   {
     if (!p) return;
-    auto& v = host_blocks();
-    for (size_t i = 0; i < v.size(); ++i)
-      if (v[i].p == p)
-      {
-        if (v[i].mapped)
+    HostBlock blk{p, 0, false};
+    {
+      std::lock_guard<std::mutex> lk(host_blocks_mutex());
+      auto& v = host_blocks();
+      for (size_t i = 0; i < v.size(); ++i)
+        if (v[i].p == p)
         {
-          cudaHostUnregister(p);
-          munmap(p, v[i].bytes);
+          blk = v[i];
+          v.erase(v.begin() + (long)i);
+          break;
         }
-        else
-          cudaFreeHost(p);
-        v.erase(v.begin() + (long)i);
-        return;
-      }
-    cudaFreeHost(p);
+    }
+    if (blk.mapped)
+    {
+      cudaHostUnregister(p);
+      munmap(p, blk.bytes);
+    }
+    else
+      cudaFreeHost(p);
   }
 
   // diagnostics: device element order (caller's column-element index of every device element)

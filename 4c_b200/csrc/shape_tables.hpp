@@ -88,6 +88,42 @@ namespace b200s
           dN[3 * k + 2] = L[0][a] * L[1][b] * dL[2][e];
         }
       }
+      else if (celltype == 3)
+      {
+        // tet4 (4C_fem_general_utils_fem_shapefunctions.hpp:813-830)
+        const double D[4][3] = {{-1, -1, -1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+        for (int k = 0; k < 4; ++k)
+          for (int a = 0; a < 3; ++a) dN[3 * k + a] = D[k][a];
+      }
+      else if (celltype == 4)
+      {
+        // hex20 serendipity (:607-705): corners 1/8 c_a f_b f_e (2 f_a + f_b + f_e - 5), f_d = 1 + c_d x_d;
+        // mid-edge node on an edge along a: -1/2 x_a f_b f_e, 1/4 (1 - x_a^2) c_b f_e, 1/4 (1 - x_a^2) f_b c_e
+        const double(*c)[3] = hex_nodes();
+        for (int k = 0; k < 20; ++k)
+        {
+          if (k < 8)
+          {
+            const double f[3] = {1.0 + c[k][0] * r, 1.0 + c[k][1] * s, 1.0 + c[k][2] * t};
+            for (int a = 0; a < 3; ++a)
+            {
+              const int b = (a + 1) % 3, e = (a + 2) % 3;
+              dN[3 * k + a] = 0.125 * c[k][a] * f[b] * f[e] * (2.0 * f[a] + f[b] + f[e] - 5.0);
+            }
+          }
+          else
+          {
+            int a = 0;
+            for (int d = 0; d < 3; ++d)
+              if (c[k][d] == 0.0) a = d;
+            const int b = (a + 1) % 3, e = (a + 2) % 3;
+            const double q = 1.0 - xi[a] * xi[a], fb = 1.0 + c[k][b] * xi[b], fe = 1.0 + c[k][e] * xi[e];
+            dN[3 * k + a] = -0.5 * xi[a] * fb * fe;
+            dN[3 * k + b] = 0.25 * q * c[k][b] * fe;
+            dN[3 * k + e] = 0.25 * q * fb * c[k][e];
+          }
+        }
+      }
       else
       {
         const double u = 1.0 - r - s - t;
@@ -124,6 +160,30 @@ namespace b200s
         for (int k = 0; k < 27; ++k)
           N[k] = L[0][(int)c[k][0] + 1] * L[1][(int)c[k][1] + 1] * L[2][(int)c[k][2] + 1];
       }
+      else if (celltype == 3)
+      {
+        N[0] = 1.0 - r - s - t, N[1] = r, N[2] = s, N[3] = t;  // tet4 (:239-251)
+      }
+      else if (celltype == 4)
+      {
+        const double(*c)[3] = hex_nodes();  // hex20 (:146-197)
+        for (int k = 0; k < 20; ++k)
+        {
+          if (k < 8)
+          {
+            const double f[3] = {1.0 + c[k][0] * r, 1.0 + c[k][1] * s, 1.0 + c[k][2] * t};
+            N[k] = 0.125 * f[0] * f[1] * f[2] * (f[0] + f[1] + f[2] - 5.0);
+          }
+          else
+          {
+            int a = 0;
+            for (int d = 0; d < 3; ++d)
+              if (c[k][d] == 0.0) a = d;
+            const int b = (a + 1) % 3, e = (a + 2) % 3;
+            N[k] = 0.25 * (1.0 - xi[a] * xi[a]) * (1.0 + c[k][b] * xi[b]) * (1.0 + c[k][e] * xi[e]);
+          }
+        }
+      }
       else
       {
         const double u = 1.0 - r - s - t;
@@ -137,8 +197,10 @@ namespace b200s
   inline CellTables make_cell_tables(int celltype)
   {
     CellTables T;
-    T.nn = celltype == 0 ? 8 : (celltype == 1 ? 27 : 10);
-    T.ngp = celltype == 0 ? 8 : (celltype == 1 ? 27 : 4);
+    // celltype 0 hex8, 1 hex27, 2 tet10, 3 tet4, 4 hex20; stiffness rules hex_8point, hex_27point (hex27 and hex20),
+    // tet_4point (tet10), tet_1point (tet4) (4C_solid_ele_calc_lib_integration.hpp:43-64)
+    T.nn = celltype == 0 ? 8 : (celltype == 1 ? 27 : (celltype == 3 ? 4 : (celltype == 4 ? 20 : 10)));
+    T.ngp = celltype == 0 ? 8 : ((celltype == 1 || celltype == 4) ? 27 : (celltype == 3 ? 1 : 4));
     std::vector<double> gxi(3 * T.ngp);
     T.w.resize(T.ngp);
     const double(*hc)[3] = detail::hex_nodes();
@@ -151,7 +213,12 @@ namespace b200s
         T.w[q] = 1.0;
       }
     }
-    else if (celltype == 1)
+    else if (celltype == 3)
+    {
+      gxi[0] = gxi[1] = gxi[2] = 0.25;  // tet_1point (4C_fem_general_utils_integration.cpp:322-330)
+      T.w[0] = 1.0 / 6.0;
+    }
+    else if (celltype == 1 || celltype == 4)
     {
       // truncated decimals exactly as the reference has them
       const double xi3 = 0.7745966692415, w1 = 0.5555555555556, w2 = 0.8888888888889;
@@ -175,7 +242,7 @@ namespace b200s
     T.dN_gp.resize((size_t)T.ngp * T.nn * 3);
     for (int q = 0; q < T.ngp; ++q) detail::deriv1(celltype, &gxi[3 * q], &T.dN_gp[(size_t)q * T.nn * 3]);
     T.dN_node.resize((size_t)T.nn * T.nn * 3);
-    const double(*nc)[3] = celltype == 2 ? detail::tet_nodes() : hc;
+    const double(*nc)[3] = (celltype == 2 || celltype == 3) ? detail::tet_nodes() : hc;
     for (int k = 0; k < T.nn; ++k) detail::deriv1(celltype, nc[k], &T.dN_node[(size_t)k * T.nn * 3]);
     T.xi_gp = gxi;
     T.N_gp.resize((size_t)T.ngp * T.nn);
@@ -183,6 +250,15 @@ namespace b200s
     // mass rule
     std::vector<double> mxi = gxi;
     T.w_mass = T.w, T.ngp_mass = T.ngp;
+    if (celltype == 3)
+    {
+      // DisTypeToOptGaussRule<tet4> = tet_4point (:331-352)
+      const double pa = (5.0 + 3.0 * std::sqrt(5.0)) / 20.0, pb = (5.0 - std::sqrt(5.0)) / 20.0;
+      const double P[4][3] = {{pb, pb, pb}, {pa, pb, pb}, {pb, pa, pb}, {pb, pb, pa}};
+      T.ngp_mass = 4;
+      mxi.assign(&P[0][0], &P[0][0] + 12);
+      T.w_mass.assign(4, 1.0 / 24.0);
+    }
     if (celltype == 2)
     {
       // tet_11point (4C_fem_general_utils_integration.cpp:447-495), decimals as the reference has them
@@ -206,7 +282,7 @@ namespace b200s
     }
     const double cen_hex[3] = {0.0, 0.0, 0.0}, cen_tet[3] = {0.25, 0.25, 0.25};
     T.dN_cen.resize((size_t)T.nn * 3);
-    detail::deriv1(celltype, celltype == 2 ? cen_tet : cen_hex, T.dN_cen.data());
+    detail::deriv1(celltype, (celltype == 2 || celltype == 3) ? cen_tet : cen_hex, T.dN_cen.data());
     return T;
   }
   // Surface cells of the three solid cell types (hex8 -> quad4, hex27 -> quad9, tet10 -> tri6) at the
@@ -235,6 +311,21 @@ namespace b200s
     {
       const double g = 0.7745966692415, w1 = 0.5555555555556, w2 = 0.8888888888889;
       T.nn = 9, T.ngp = 9;
+      xi = {-g, -g, g, -g, g, g, -g, g, 0, -g, g, 0, 0, g, -g, 0, 0, 0};
+      T.w = {w1 * w1, w1 * w1, w1 * w1, w1 * w1, w2 * w1, w1 * w2, w2 * w1, w1 * w2, w2 * w2};
+    }
+    else if (celltype == 3)
+    {
+      // tet4 -> tri3 at tri_3point (:6341-6355)
+      T.nn = 3, T.ngp = 3;
+      xi = {1.0 / 6.0, 1.0 / 6.0, 2.0 / 3.0, 1.0 / 6.0, 1.0 / 6.0, 2.0 / 3.0};
+      T.w.assign(3, 1.0 / 6.0);
+    }
+    else if (celltype == 4)
+    {
+      // hex20 -> quad8 at quad_9point
+      const double g = 0.7745966692415, w1 = 0.5555555555556, w2 = 0.8888888888889;
+      T.nn = 8, T.ngp = 9;
       xi = {-g, -g, g, -g, g, g, -g, g, 0, -g, g, 0, 0, g, -g, 0, 0, 0};
       T.w = {w1 * w1, w1 * w1, w1 * w1, w1 * w1, w2 * w1, w1 * w2, w2 * w1, w1 * w2, w2 * w2};
     }
@@ -274,6 +365,39 @@ namespace b200s
         {
           const int i = c[k][0] + 1, j = c[k][1] + 1;
           N[k] = Lr[i] * Ls[j], d0[k] = dLr[i] * Ls[j], d1[k] = Lr[i] * dLs[j];
+        }
+      }
+      else if (celltype == 3)
+      {
+        N[0] = 1.0 - r - s, N[1] = r, N[2] = s;  // tri3 (:2110-2119, 2312-2323)
+        d0[0] = -1.0, d0[1] = 1.0, d0[2] = 0.0;
+        d1[0] = -1.0, d1[1] = 0.0, d1[2] = 1.0;
+      }
+      else if (celltype == 4)
+      {
+        // quad8 serendipity (:2049-2086): corner k 1/4 [f_r f_s - (1 - r^2) f_s - (1 - s^2) f_r], mid-side nodes
+        // 1/2 (1 - r^2) f_s (on s = -+1) and 1/2 (1 - s^2) f_r (on r = +-1)
+        const double c[4][2] = {{-1, -1}, {1, -1}, {1, 1}, {-1, 1}}, m[4][2] = {{0, -1}, {1, 0}, {0, 1}, {-1, 0}};
+        const double r2 = 1.0 - r * r, s2 = 1.0 - s * s;
+        for (int k = 0; k < 4; ++k)
+        {
+          const double fr = 1.0 + c[k][0] * r, fs = 1.0 + c[k][1] * s;
+          N[k] = 0.25 * (fr * fs - (r2 * fs + s2 * fr));
+          d0[k] = 0.25 * (c[k][0] * fs - (-2.0 * r * fs + s2 * c[k][0]));
+          d1[k] = 0.25 * (fr * c[k][1] - (r2 * c[k][1] - 2.0 * s * fr));
+        }
+        for (int k = 0; k < 4; ++k)
+        {
+          if (m[k][0] == 0.0)
+          {
+            const double fs = 1.0 + m[k][1] * s;
+            N[4 + k] = 0.5 * r2 * fs, d0[4 + k] = -r * fs, d1[4 + k] = 0.5 * r2 * m[k][1];
+          }
+          else
+          {
+            const double fr = 1.0 + m[k][0] * r;
+            N[4 + k] = 0.5 * s2 * fr, d0[4 + k] = 0.5 * s2 * m[k][0], d1[4 + k] = -s * fr;
+          }
         }
       }
       else

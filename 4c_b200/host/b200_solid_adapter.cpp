@@ -35,8 +35,10 @@ namespace B200Solid
 
   bool DeviceElementBlock::supported(int celltype, int kinem, int tech, int prestress, int material_kind)
   {
-    const bool cell = celltype == B200S_HEX8 || celltype == B200S_HEX27 || celltype == B200S_TET10;
+    const bool general_cell = celltype == B200S_TET4 || celltype == B200S_HEX20;  // general kernel: displacement based only
+    const bool cell = celltype == B200S_HEX8 || celltype == B200S_HEX27 || celltype == B200S_TET10 || general_cell;
     if (!cell) return false;
+    if (general_cell && (tech != B200S_TECH_NONE || prestress != B200S_PRESTRESS_NONE)) return false;
     const bool hyper = material_kind == B200S_MAT_COUP_NEOHOOKE || material_kind == B200S_MAT_ISO_VOL ||
                        material_kind == B200S_MAT_SVK || material_kind == B200S_MAT_ELASTHYPER;
     if (kinem == B200S_KINEM_LINEAR)

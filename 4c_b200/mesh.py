@@ -9,8 +9,8 @@ seeded permutation (config 4).
 """
 import numpy as np
 
-HEX8, HEX27, TET10 = 0, 1, 2
-NODES = {HEX8: 8, HEX27: 27, TET10: 10}
+HEX8, HEX27, TET10, TET4, HEX20 = 0, 1, 2, 3, 4
+NODES = {HEX8: 8, HEX27: 27, TET10: 10, TET4: 4, HEX20: 20}
 
 # node order of hex27 in parameter space (first 8 = hex8);
 # 4C_fem_general_utils_local_connectivity_matrices.hpp:291
@@ -95,6 +95,31 @@ def unstructured_tet10(n, seed=4321, jitter=0.2, renumber=True, box=(1.0, 1.0, 1
         conn = pn[conn]
         conn = conn[rng.permutation(ne)]
     return X, conn.astype(np.int32)
+
+
+def unstructured_tet4(n, seed=4321, jitter=0.2, renumber=True, box=(1.0, 1.0, 1.0)):
+    """The corner-node (linear) version of unstructured_tet10: same cells, jitter and renumbering recipe."""
+    X10, c10 = unstructured_tet10(n, seed, jitter, renumber=False, box=box)
+    nc = (n + 1) ** 3                      # corner nodes come first in the un-renumbered tet10 mesh
+    X, conn = X10[:nc], c10[:, :4].astype(np.int64)
+    if renumber:
+        rng = np.random.default_rng(seed + 1)
+        pn = rng.permutation(nc)
+        Xn = np.empty_like(X)
+        Xn[pn] = X
+        X, conn = Xn, pn[conn][rng.permutation(len(conn))]
+    return X, conn.astype(np.int32)
+
+
+def structured_hex20(n, box=(1.0, 1.0, 1.0)):
+    """Serendipity version of the structured hex27 mesh: the first 20 nodes of every hex27 element (corners and
+    mid-edge nodes, 4C_fem_general_utils_local_connectivity_matrices.hpp), unused grid nodes removed."""
+    X27, c27 = structured_hex(HEX27, n, box)
+    c = c27[:, :20]
+    used = np.unique(c)
+    new = np.full(len(X27), -1, np.int64)
+    new[used] = np.arange(len(used))
+    return X27[used], new[c].astype(np.int32)
 
 
 def _hash_uniform(idx, seed):

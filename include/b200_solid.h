@@ -42,7 +42,12 @@ extern "C"
   {
     B200S_HEX8 = 0,
     B200S_HEX27 = 1,
-    B200S_TET10 = 2
+    B200S_TET10 = 2,
+    /* displacement-based blocks of further cell types (create_solid_calculation_interface,
+     * 4C_solid_ele_factory.hpp:36-38,79-89) run through the table-driven general kernel (no specialised
+     * fast kernel; KINEM nonlinear / linear, every material kind, no element technology / prestress): */
+    B200S_TET4 = 3, /* tet_1point stiffness rule, tet_4point mass rule */
+    B200S_HEX20 = 4 /* hex_27point */
   } b200s_celltype;
 
   /* Mat::So3Material implementations on the device path (Core::Materials::MaterialType):

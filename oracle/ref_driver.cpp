@@ -327,6 +327,10 @@ extern "C"
       run.template operator()<CT::hex8>();
     else if (ct == 1)
       run.template operator()<CT::hex27>();
+    else if (ct == 3)
+      run.template operator()<CT::tet4>();
+    else if (ct == 4)
+      run.template operator()<CT::hex20>();
     else
       run.template operator()<CT::tet10>();
   }
@@ -346,6 +350,10 @@ extern "C"
       run.template operator()<CT::hex8>();
     else if (ct == 1)
       run.template operator()<CT::hex27>();
+    else if (ct == 3)
+      run.template operator()<CT::tet4>();
+    else if (ct == 4)
+      run.template operator()<CT::hex20>();
     else
       run.template operator()<CT::tet10>();
   }
@@ -365,6 +373,8 @@ extern "C"
   {
     if (ct == 0) return element<CT::hex8>(matkind, par, action, X, u, gxi, gw, ngp, Ke, fe);
     if (ct == 1) return element<CT::hex27>(matkind, par, action, X, u, gxi, gw, ngp, Ke, fe);
+    if (ct == 3) return element<CT::tet4>(matkind, par, action, X, u, gxi, gw, ngp, Ke, fe);
+    if (ct == 4) return element<CT::hex20>(matkind, par, action, X, u, gxi, gw, ngp, Ke, fe);
     return element<CT::tet10>(matkind, par, action, X, u, gxi, gw, ngp, Ke, fe);
   }
 
@@ -475,6 +485,10 @@ extern "C"
       run.template operator()<CT::hex8>();
     else if (ct == 1)
       run.template operator()<CT::hex27>();
+    else if (ct == 3)
+      run.template operator()<CT::tet4>();
+    else if (ct == 4)
+      run.template operator()<CT::hex20>();
     else
       run.template operator()<CT::tet10>();
   }

@@ -29,12 +29,21 @@ namespace
   const double tet10_ref[10][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0.5, 0, 0},
       {0.5, 0.5, 0}, {0, 0.5, 0}, {0, 0, 0.5}, {0.5, 0, 0.5}, {0, 0.5, 0.5}};
 
-  int nnodes(int ct) { return ct == ORC_HEX8 ? 8 : (ct == ORC_HEX27 ? 27 : 10); }
-  int ngauss(int ct) { return ct == ORC_HEX8 ? 8 : (ct == ORC_HEX27 ? 27 : 4); }
+  int nnodes(int ct)
+  {
+    return ct == ORC_HEX8 ? 8 : (ct == ORC_HEX27 ? 27 : (ct == ORC_TET4 ? 4 : (ct == ORC_HEX20 ? 20 : 10)));
+  }
+  // stiffness rule (get_gauss_rule_stiffness_matrix, 4C_solid_ele_calc_lib_integration.hpp:43-64): hex_8point,
+  // hex_27point (hex27 AND hex20), tet_4point (tet10), tet_1point (tet4)
+  int ngauss(int ct)
+  {
+    return ct == ORC_HEX8 ? 8 : ((ct == ORC_HEX27 || ct == ORC_HEX20) ? 27 : (ct == ORC_TET4 ? 1 : 4));
+  }
 
   void node_ref(int ct, int k, double* xi)
   {
-    const double* p = (ct == ORC_TET10) ? tet10_ref[k] : hex27_ref[k];  // hex8 = first 8 of hex27
+    // hex8 / hex20 = first 8 / 20 of hex27, tet4 = first 4 of tet10
+    const double* p = (ct == ORC_TET10 || ct == ORC_TET4) ? tet10_ref[k] : hex27_ref[k];
     xi[0] = p[0], xi[1] = p[1], xi[2] = p[2];
   }
 
@@ -76,6 +85,49 @@ namespace
         dN[2 + 3 * k] = Lr[a] * Ls[b] * dLt[c];
       }
     }
+    else if (ct == ORC_TET4)
+    {
+      // linear tetrahedron (shapefunctions.hpp:239-251, 813-830)
+      N[0] = 1.0 - r - s - t, N[1] = r, N[2] = s, N[3] = t;
+      const double D[4][3] = {{-1, -1, -1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+      for (int k = 0; k < 4; ++k)
+        for (int a = 0; a < 3; ++a) dN[a + 3 * k] = D[k][a];
+    }
+    else if (ct == ORC_HEX20)
+    {
+      // 20-node serendipity hexahedron (shapefunctions.hpp:146-197, 607-705): corner k
+      //   N = 1/8 (1 + r_k r)(1 + s_k s)(1 + t_k t)((1 + r_k r) + (1 + s_k s) + (1 + t_k t) - 5),
+      // mid-edge node on an edge along direction a: 1/4 (1 - xi_a^2) (1 + x_b x_b^k)(1 + x_c x_c^k)
+      for (int k = 0; k < 20; ++k)
+      {
+        const double c[3] = {hex27_ref[k][0], hex27_ref[k][1], hex27_ref[k][2]};
+        const double x[3] = {r, s, t};
+        if (k < 8)
+        {
+          const double f[3] = {1.0 + c[0] * r, 1.0 + c[1] * s, 1.0 + c[2] * t};
+          const double sum = f[0] + f[1] + f[2] - 5.0;
+          N[k] = 0.125 * f[0] * f[1] * f[2] * sum;
+          for (int a = 0; a < 3; ++a)
+          {
+            const int b = (a + 1) % 3, e = (a + 2) % 3;
+            // d/dx_a [f_a f_b f_e (f_a + f_b + f_e - 5)] = c_a f_b f_e (2 f_a + f_b + f_e - 5)
+            dN[a + 3 * k] = 0.125 * c[a] * f[b] * f[e] * (2.0 * f[a] + f[b] + f[e] - 5.0);
+          }
+        }
+        else
+        {
+          int a = 0;  // the direction with node coordinate 0
+          for (int d = 0; d < 3; ++d)
+            if (c[d] == 0.0) a = d;
+          const int b = (a + 1) % 3, e = (a + 2) % 3;
+          const double q = 1.0 - x[a] * x[a], fb = 1.0 + c[b] * x[b], fe = 1.0 + c[e] * x[e];
+          N[k] = 0.25 * q * fb * fe;
+          dN[a + 3 * k] = -0.5 * x[a] * fb * fe;
+          dN[b + 3 * k] = 0.25 * q * c[b] * fe;
+          dN[e + 3 * k] = 0.25 * q * fb * c[e];
+        }
+      }
+    }
     else
     {
       const double u = 1.0 - r - s - t;
@@ -108,7 +160,13 @@ namespace
         w[q] = 1.0;
       }
     }
-    else if (ct == ORC_HEX27)
+    else if (ct == ORC_TET4)
+    {
+      // tet_1point (4C_fem_general_utils_integration.cpp:322-330)
+      xi[0] = xi[1] = xi[2] = 0.25;
+      w[0] = 1.0 / 6.0;
+    }
+    else if (ct == ORC_HEX27 || ct == ORC_HEX20)
     {
       const double xi3 = 0.7745966692415;
       const double w1 = 0.5555555555556, w2 = 0.8888888888889;
@@ -2235,6 +2293,12 @@ extern "C"
   // (4C_fem_general_utils_integration.cpp:447-495)
   static int mass_rule(int ct, double* xi, double* w)
   {
+    if (ct == ORC_TET4)
+    {
+      // DisTypeToOptGaussRule<tet4> = tet_4point (:331-352): the points of tet10's stiffness rule
+      gauss(ORC_TET10, xi, w);
+      return 4;
+    }
     if (ct != ORC_TET10)
     {
       gauss(ct, xi, w);

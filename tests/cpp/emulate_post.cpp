@@ -152,6 +152,63 @@ extern "C" int emu_drucker_prager(const double* in10, double* hist, const double
 // The general (non-symmetric tangent) kernel of generic_kernel.cuh stepped on the host: one call of generic_block_row
 // per (element, row node) and the kernel's scatter.  celltype 0 hex8 / 1 hex27 / 2 tet10, KINEM linear,
 // MAT_Struct_DruckerPrager with its state store (n_ele * ngp * DP_HIST, updated in place).
+template <int MAT, int NN>
+static int run_generic(const GenericArgs& Ga)
+{
+  const EvalArgs& A = Ga.A;
+  int bad = 0;
+  for (int64_t e = 0; e < A.n_ele; ++e)
+    for (int i = 0; i < Ga.nn; ++i)
+    {
+      double Krow[NN][9], fi[3], dj = 1e300, df = 1e300;
+      if (generic_block_row<MAT, NN>(Ga, e, i, Krow, fi, dj, df)) ++bad;
+      const NodeRow nr = A.node_row[A.conn[e * Ga.nn + i]];
+      if (nr.rowstart < 0) continue;
+      for (int b = 0; b < 3; ++b) A.f[nr.frow + b] += fi[b];
+      if (!Ga.stiff) continue;
+      const int32_t* pos = A.pos + e * Ga.pos_stride + i * Ga.nn;
+      for (int j = 0; j < Ga.nn; ++j)
+        for (int b = 0; b < 3; ++b)
+          for (int c = 0; c < 3; ++c) A.vals[nr.rowstart + (int64_t)b * nr.rowlen + pos[j] + c] += Krow[j][b + 3 * c];
+    }
+  return bad;
+}
+template <int MAT>
+static int run_generic_nn(const GenericArgs& Ga)
+{
+  switch (Ga.nn)
+  {
+    case 4: return run_generic<MAT, 4>(Ga);
+    case 8: return run_generic<MAT, 8>(Ga);
+    case 10: return run_generic<MAT, 10>(Ga);
+    case 20: return run_generic<MAT, 20>(Ga);
+    default: return run_generic<MAT, 27>(Ga);
+  }
+}
+// The general kernel for the hyperelastic kinds 0..2 (tet4 / hex20 blocks run through it): celltype as in
+// shape_tables.hpp (0 hex8, 1 hex27, 2 tet10, 3 tet4, 4 hex20), linear != 0 = KINEM linear
+extern "C" int emu_generic(int celltype, int matkind, const double* params, int linear, int stiff, int64_t n_ele,
+    const int32_t* conn, const double* X, const double* u_col, const int32_t* pos, int pos_stride,
+    const int64_t* node_rowstart, const int32_t* node_rowlen, const int32_t* node_frow, int64_t n_col_nodes, double* vals,
+    double* f)
+{
+  std::vector<NodeRow> node_row(n_col_nodes);
+  for (int64_t k = 0; k < n_col_nodes; ++k)
+    node_row[k].rowstart = node_rowstart[k], node_row[k].rowlen = node_rowlen[k], node_row[k].frow = node_frow[k];
+  const CellTables T = make_cell_tables(celltype);
+  GenericArgs Ga;
+  EvalArgs& A = Ga.A;
+  A.X = X, A.u = u_col, A.conn = conn, A.pos = pos, A.node_row = node_row.data();
+  A.per_ele_param = nullptr, A.ele_id = nullptr, A.gp_hist = nullptr, A.fibers = nullptr, A.linear = linear;
+  A.mat_hist = nullptr, A.vals = vals, A.f = f, A.err = nullptr, A.n_ele = n_ele, A.scatter_mode = 0;
+  if (!make_mat_params(matkind, params, A.mp)) return -3;
+  Ga.dN_gp = T.dN_gp.data(), Ga.dN_node = T.dN_node.data(), Ga.w = T.w.data();
+  Ga.nn = T.nn, Ga.ngp = T.ngp, Ga.pos_stride = pos_stride, Ga.stiff = stiff;
+  if (matkind == MAT_COUP_NEOHOOKE) return run_generic_nn<MAT_COUP_NEOHOOKE>(Ga);
+  if (matkind == MAT_ISO_VOL) return run_generic_nn<MAT_ISO_VOL>(Ga);
+  return run_generic_nn<MAT_SVK>(Ga);
+}
+
 template <int NN>
 static int run_generic_dp(const GenericArgs& Ga)
 {

@@ -48,6 +48,8 @@ CASES = {
     "hex8": "tests/input_files/solid_ele_hex8_Standard_eas_none_stressout.4C.yaml",
     "hex27": "tests/input_files/solid_ele_hex27_Standard_stressout.4C.yaml",
     "tet10": "tests/input_files/solid_ele_tet10_Standard_stressout.4C.yaml",
+    "tet4": "tests/input_files/solid_ele_tet4_Standard_stressout.4C.yaml",
+    "hex20": "tests/input_files/solid_ele_hex20_Standard_stressout.4C.yaml",
 }
 
 
@@ -465,7 +467,8 @@ def ref_elements():
     out = {}
     mats = {orc.MAT_COUP_NEOHOOKE: [200.0, 0.25], orc.MAT_ISO_VOL: [1.0, 1000.0],
             orc.MAT_SVK: [1000.0, 0.3]}
-    for ct, name in ((orc.HEX8, "hex8"), (orc.HEX27, "hex27"), (orc.TET10, "tet10")):
+    # (new cells are appended so that the random stream of the earlier fixtures stays what it was)
+    for ct, name in ((orc.HEX8, "hex8"), (orc.HEX27, "hex27"), (orc.TET10, "tet10"), (orc.TET4, "tet4"), (orc.HEX20, "hex20")):
         n = orc.num_nodes(ct)
         X = orc.node_param_coords(ct) * np.array([1.0, 1.1, 1.2]) + 0.05 * rng.uniform(-1, 1, (n, 3))
         u = 0.04 * rng.uniform(-1, 1, (n, 3))

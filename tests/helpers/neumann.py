@@ -14,7 +14,9 @@ HEX27_FACES = [[0, 3, 2, 1, 11, 10, 9, 8, 20], [0, 1, 5, 4, 8, 13, 16, 12, 21],
                [1, 2, 6, 5, 9, 14, 17, 13, 22], [2, 3, 7, 6, 10, 15, 18, 14, 23],
                [0, 4, 7, 3, 12, 19, 15, 11, 24], [4, 5, 6, 7, 16, 17, 18, 19, 25]]
 TET10_FACES = [[0, 1, 3, 4, 8, 7], [1, 2, 3, 5, 9, 8], [0, 3, 2, 7, 9, 6], [0, 2, 1, 6, 5, 4]]
-FACES = {"hex8": HEX8_FACES, "hex27": HEX27_FACES, "tet10": TET10_FACES}
+TET4_FACES = [f[:3] for f in TET10_FACES]     # tri3: the corners of the tri6 faces
+HEX20_FACES = [f[:8] for f in HEX27_FACES]    # quad8: corners + mid-edge nodes of the quad9 faces
+FACES = {"hex8": HEX8_FACES, "hex27": HEX27_FACES, "tet10": TET10_FACES, "tet4": TET4_FACES, "hex20": HEX20_FACES}
 
 
 def _quad4(r, s):
@@ -45,7 +47,39 @@ def _tri6(r, s):
     return N, dN
 
 
+def _tri3(r, s):
+    N = np.array([1 - r - s, r, s])
+    dN = np.array([[-1.0, 1.0, 0.0], [-1.0, 0.0, 1.0]])
+    return N, dN
+
+
+def _quad8(r, s):
+    """8-node serendipity quadrilateral (4C_fem_general_utils_fem_shapefunctions.hpp:2049-2086): corner k
+    1/4 [(1 + r_k r)(1 + s_k s) - (1 - r^2)(1 + s_k s) - (1 - s^2)(1 + r_k r)], mid-side nodes 1/2 (1 - r^2)(1 + s_k s) ..."""
+    c = [(-1, -1), (1, -1), (1, 1), (-1, 1)]
+    N, d0, d1 = np.zeros(8), np.zeros(8), np.zeros(8)
+    r2, s2 = 1 - r * r, 1 - s * s
+    for k, (a, b) in enumerate(c):
+        fr, fs = 1 + a * r, 1 + b * s
+        N[k] = 0.25 * (fr * fs - (r2 * fs + s2 * fr))
+        d0[k] = 0.25 * (a * fs - (-2 * r * fs + s2 * a))
+        d1[k] = 0.25 * (fr * b - (r2 * b - 2 * s * fr))
+    mids = [(0, -1), (1, 0), (0, 1), (-1, 0)]
+    for k, (a, b) in enumerate(mids):
+        if a == 0:
+            fs = 1 + b * s
+            N[4 + k], d0[4 + k], d1[4 + k] = 0.5 * r2 * fs, -r * fs, 0.5 * r2 * b
+        else:
+            fr = 1 + a * r
+            N[4 + k], d0[4 + k], d1[4 + k] = 0.5 * s2 * fr, 0.5 * s2 * a, -s * fr
+    return N, np.stack([d0, d1])
+
+
 def _rule(kind):
+    if kind == "tri3":   # tri_3point (4C_fem_general_utils_integration.cpp:6341-6355)
+        return np.array([[1 / 6, 1 / 6], [2 / 3, 1 / 6], [1 / 6, 2 / 3]]), np.full(3, 1 / 6)
+    if kind == "quad8":  # get_optimal_gauss_rule(quad8) = quad_9point
+        return _rule("quad9")
     if kind == "quad4":
         g = 0.5773502691896
         return np.array([[-g, -g], [g, -g], [g, g], [-g, g]]), np.ones(4)
@@ -103,7 +137,8 @@ def _surface_neumann_load(case, time):
     cell = case["celltype"]
     X = np.asarray(case["coords"], float)
     nset = set(case["neumann_nodes"])
-    kind, fn = {"hex8": ("quad4", _quad4), "hex27": ("quad9", _quad9), "tet10": ("tri6", _tri6)}[cell]
+    kind, fn = {"hex8": ("quad4", _quad4), "hex27": ("quad9", _quad9), "tet10": ("tri6", _tri6),
+                "tet4": ("tri3", _tri3), "hex20": ("quad8", _quad8)}[cell]
     gx, gw = _rule(kind)
     val, onoff, funct = case["neumann"]["VAL"], case["neumann"]["ONOFF"], case["neumann"]["FUNCT"]
     assert case["neumann"]["FUNCT1"] == "t"
@@ -165,7 +200,8 @@ def orthopressure_load(case, u, time, loadlin=True, faces=None, material=False):
     cell = case["celltype"]
     X = np.asarray(case["coords"], float)
     x_all = X if material else X + np.asarray(u, float).reshape(-1, 3)
-    kind, fn = {"hex8": ("quad4", _quad4), "hex27": ("quad9", _quad9), "tet10": ("tri6", _tri6)}[cell]
+    kind, fn = {"hex8": ("quad4", _quad4), "hex27": ("quad9", _quad9), "tet10": ("tri6", _tri6),
+                "tet4": ("tri3", _tri3), "hex20": ("quad8", _quad8)}[cell]
     gx, gw = _rule(kind)
     n = case["neumann"]
     assert n["ONOFF"][0] == 1 and not any(n["ONOFF"][1:3]), "orthopressure on 1st dof only!"

@@ -1,0 +1,58 @@
+"""tet4 and hex20 displacement-based blocks (create_solid_calculation_interface instantiates them next to hex8 / hex27 /
+tet10, src/solid_ele/4C_solid_ele_factory.hpp:36-38,79-89): on the device they run through the table-driven general
+kernel (generic_kernel.cuh).  Oracle pins: shape functions vs the reference's own headers, element matrices vs
+oracle/_ref fixtures and the RESULT DESCRIPTION displacements of solid_ele_tet4_Standard_stressout.4C.yaml /
+solid_ele_hex20_Standard_stressout.4C.yaml (tests/test_oracle_golden.py).  Here: the PRODUCT's tables and general-kernel
+arithmetic stepped on the CPU against the oracle."""
+import importlib
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests.helpers import emulator as emu
+
+b200 = importlib.import_module("4c_b200")
+MATS = {orc.MAT_COUP_NEOHOOKE: [200.0, 0.25], orc.MAT_ISO_VOL: [1.0, 1000.0], orc.MAT_SVK: [1000.0, 0.3]}
+
+
+def _mesh(cell):
+    if cell == "tet4":
+        X, conn = b200.mesh.unstructured_tet4(3)
+        return orc.TET4, b200.partition.serial_mesh(b200.mesh.TET4, X, conn), 1.0 / 3
+    X, conn = b200.mesh.structured_hex20((2, 2, 1))
+    return orc.HEX20, b200.partition.serial_mesh(b200.mesh.HEX20, X, conn), 0.5
+
+
+@pytest.mark.parametrize("cell", ["tet4", "hex20"])
+@pytest.mark.parametrize("mk", list(MATS))
+@pytest.mark.parametrize("linear", [False, True])
+def test_emulated_general_kernel_matches_oracle(cell, mk, linear):
+    ct, rm, h = _mesh(cell)
+    u = 2.0 * b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, h)
+    rowptr, colind = orc.build_graph(ct, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    rK, rf, nbad = orc.evaluate_assemble(ct, mk, MATS[mk], rm.conn, rm.X.ravel(), u.ravel(), rm.node_row_lid, rm.node_col_lid,
+                                         rm.n_row_nodes, rowptr, colind, tech=orc.TECH_LINEAR if linear else orc.TECH_NONE)
+    K, f = emu.generic(rm.celltype, mk, MATS[mk], rm.conn, rm.X.ravel(), u.ravel(), rowptr, colind, rm.node_row_lid,
+                       rm.node_col_lid, rm.n_row_nodes, linear=linear)
+    ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, 1e-12)
+    assert ok and nbad == 0, (wK, wf)
+
+
+def test_general_kernel_equals_fast_kernels_on_their_cells():
+    """The general kernel on hex8 / tet10 / hex27 gives what the oracle gives there too (same tables as the fast path)."""
+    for cell, n in (("HEX8", (2, 2, 2)), ("TET10", 2), ("HEX27", (1, 1, 2))):
+        ct = getattr(orc, cell)
+        if cell == "TET10":
+            X, conn = b200.mesh.unstructured_tet10(n)
+            rm = b200.partition.serial_mesh(b200.mesh.TET10, X, conn)
+        else:
+            rm = b200.partition.box_partition(getattr(b200.mesh, cell), n, 0, 1)
+        u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 0.4)
+        rowptr, colind = orc.build_graph(ct, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+        rK, rf, _ = orc.evaluate_assemble(ct, orc.MAT_COUP_NEOHOOKE, [200.0, 0.25], rm.conn, rm.X.ravel(), u.ravel(),
+                                          rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, rowptr, colind)
+        K, f = emu.generic(rm.celltype, orc.MAT_COUP_NEOHOOKE, [200.0, 0.25], rm.conn, rm.X.ravel(), u.ravel(), rowptr, colind,
+                           rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+        ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, 1e-12)
+        assert ok, (cell, wK, wf)

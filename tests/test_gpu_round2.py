@@ -499,3 +499,110 @@ def test_symmetric_transfer_is_refused_for_fbar():
     ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
     assert ok and nbad == 0, (wK, wf)
     asm.close()
+
+
+# ---- tet4 and hex20 blocks (general kernel; src/solid_ele/4C_solid_ele_factory.hpp:36-38 instantiates them) ----
+GEN_MATS = {capi.MAT_COUP_NEOHOOKE: [200.0, 0.25], capi.MAT_ISO_VOL: [1.0, 1000.0], capi.MAT_SVK: [1000.0, 0.3]}
+
+
+def _general_mesh(cell, n=None):
+    if cell == "tet4":
+        X, conn = b200.mesh.unstructured_tet4(n or 5)
+        return orc.TET4, b200.partition.serial_mesh(b200.mesh.TET4, X, conn), 1.0 / (n or 5)
+    X, conn = b200.mesh.structured_hex20(n or (4, 3, 3))
+    return orc.HEX20, b200.partition.serial_mesh(b200.mesh.HEX20, X, conn), 0.3
+
+
+@pytest.mark.parametrize("cell", ["tet4", "hex20"])
+@pytest.mark.parametrize("mk", list(GEN_MATS))
+@pytest.mark.parametrize("kinem", [capi.KINEM_NONLINEAR_TOTLAG, capi.KINEM_LINEAR])
+def test_tet4_hex20_match_oracle(cell, mk, kinem):
+    ct, rm, h = _general_mesh(cell)
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, h)
+    asm = b200.DeviceAssembler(rm, mk, GEN_MATS[mk], kinem=kinem)
+    rowptr, colind = asm.graph()
+    o = orc.build_graph(ct, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    assert rowptr.tobytes() == o[0].tobytes() and colind.tobytes() == o[1].tobytes()
+    asm.set_state("displacement", u.ravel())
+    K, f, err = asm.evaluate()
+    rK, rf, nbad = orc.evaluate_assemble(ct, mk, GEN_MATS[mk], rm.conn, rm.X.ravel(), u.ravel(), rm.node_row_lid,
+                                         rm.node_col_lid, rm.n_row_nodes, rowptr, colind, nthreads=4,
+                                         tech=orc.TECH_LINEAR if kinem == capi.KINEM_LINEAR else orc.TECH_NONE)
+    ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
+    assert ok and nbad == 0 and err.n_neg_jacobian == 0, (wK, wf)
+    _, f2, _ = asm.evaluate("struct_calc_internalforce")
+    assert np.abs(f2 - rf).max() <= RTOL * np.abs(rf).max()
+    asm.close()
+
+
+@pytest.mark.parametrize("cell", ["tet4", "hex20"])
+def test_tet4_hex20_mass_stress_energy(cell):
+    ct, rm, h = _general_mesh(cell)
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, h)
+    asm = b200.DeviceAssembler(rm, capi.MAT_SVK, [1000.0, 0.3], density=7.8)
+    rowptr, colind = asm.graph()
+    acc = np.random.default_rng(2).uniform(-1, 1, 3 * rm.n_col_nodes)
+    asm.set_state("displacement", u.ravel())
+    asm.set_state("acceleration", acc)
+    for action, lumped in (("struct_calc_nlnstiffmass", False), ("struct_calc_nlnstifflmass", True)):
+        K, f, _ = asm.evaluate(action)
+        rK, rf, _ = orc.evaluate_assemble(ct, orc.MAT_SVK, [1000.0, 0.3], rm.conn, rm.X.ravel(), u.ravel(),
+                                          rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, rowptr, colind)
+        ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
+        assert ok, (wK, wf)
+        rM, rfi = orc.assemble_mass(ct, 7.8, rm.conn, rm.X.ravel(), rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes,
+                                    rowptr, colind, lumped=lumped, acc_col=acc)
+        M, fi = asm.mass()
+        assert np.abs(M - rM).max() <= RTOL * np.abs(rM).max()
+        assert np.abs(fi - rfi).max() <= RTOL * np.abs(rfi).max()
+    st, en = asm.calc_stress("cauchy", "ea")
+    rst, ren = orc.calc_stress(ct, orc.MAT_SVK, [1000.0, 0.3], rm.conn, rm.X.ravel(), u.ravel(), orc.STRESS_CAUCHY,
+                               orc.STRAIN_EA)
+    assert st.shape == rst.shape
+    assert np.abs(st - rst).max() <= RTOL * np.abs(rst).max() and np.abs(en - ren).max() <= RTOL * np.abs(ren).max()
+    e = asm.calc_energy()
+    re_ = orc.calc_energy(ct, orc.MAT_SVK, [1000.0, 0.3], rm.conn, rm.X.ravel(), u.ravel())
+    assert abs(e - re_) <= 1e-11 * abs(re_)
+    asm.close()
+
+
+@pytest.mark.parametrize("cell", ["tet4", "hex20"])
+def test_reference_tet4_hex20_known_answers_through_cuda_path(cell):
+    """RESULT DESCRIPTION displacements of tests/input_files/solid_ele_{tet4,hex20}_Standard_stressout.4C.yaml."""
+    import json
+    import os
+    from tests.helpers.newton import solve_case
+    case = json.load(open(os.path.join(os.path.dirname(__file__), "golden", f"integration_{cell}.json")))
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    rm = b200.partition.serial_mesh(b200.mesh.TET4 if cell == "tet4" else b200.mesh.HEX20, X, conn)
+    mat = case["material"]
+    asm = b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, [mat["YOUNG"], mat["NUE"]])
+    rowptr, colind = asm.graph()
+
+    def evaluate(u):
+        asm.set_state("displacement", u)
+        K, f, _ = asm.evaluate()
+        return rowptr, colind, K, f
+
+    u = solve_case(case, evaluate)
+    assert len(case["expected_disp"]) >= 12
+    for e in case["expected_disp"]:
+        assert abs(u[e["node"], e["dof"]] - e["value"]) < e["tol"], e
+    asm.close()
+
+
+def test_tet4_inverted_element_is_reported():
+    ct, rm, h = _general_mesh("tet4", 2)
+    X = rm.X.copy()
+    c = rm.conn[3]
+    X[c[0]], X[c[1]] = X[c[1]].copy(), X[c[0]].copy()   # swaps orientation of every tet at these two nodes
+    rm2 = b200.partition.serial_mesh(b200.mesh.TET4, X, rm.conn)
+    asm = b200.DeviceAssembler(rm2, capi.MAT_SVK, [1000.0, 0.3])
+    asm.set_state("displacement", np.zeros(3 * rm2.n_row_nodes))
+    rowptr, colind = asm.graph()
+    K, f, err = asm.evaluate(check=False)
+    _, _, nbad = orc.evaluate_assemble(ct, orc.MAT_SVK, [1000.0, 0.3], rm2.conn, rm2.X.ravel(), np.zeros(3 * rm2.n_col_nodes),
+                                       rm2.node_row_lid, rm2.node_col_lid, rm2.n_row_nodes, rowptr, colind)
+    assert nbad > 0 and err.n_neg_jacobian == nbad
+    asm.close()

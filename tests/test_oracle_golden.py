@@ -13,7 +13,7 @@ from tests.helpers.newton import solve_case
 G = os.path.join(os.path.dirname(__file__), "golden")
 KA = json.load(open(os.path.join(G, "unit_known_answers.json")))
 REFEL = np.load(os.path.join(G, "ref_elements.npz"))
-CELLS = {"hex8": orc.HEX8, "hex27": orc.HEX27, "tet10": orc.TET10}
+CELLS = {"hex8": orc.HEX8, "hex27": orc.HEX27, "tet10": orc.TET10, "tet4": orc.TET4, "hex20": orc.HEX20}
 
 
 def _dp(a):
@@ -98,7 +98,7 @@ def test_bfree_equals_boperator_stiffness(cell):
         assert np.abs(Kf - Kr).max() < k["tol"]
 
 
-@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10"])
+@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10", "tet4", "hex20"])
 @pytest.mark.parametrize("mk", [orc.MAT_COUP_NEOHOOKE, orc.MAT_ISO_VOL, orc.MAT_SVK])
 def test_oracle_matches_reference_header_fixtures(cell, mk):
     """oracle == oracle/_ref outputs committed in tests/golden/ref_elements.npz."""
@@ -115,7 +115,7 @@ def test_oracle_matches_reference_header_fixtures(cell, mk):
 
 
 @pytest.mark.skipif(orc.ref_lib() is None, reason="oracle/_ref not built (no /root/reference)")
-@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10"])
+@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10", "tet4", "hex20"])
 def test_shape_functions_match_reference_headers(cell):
     import ctypes as C
     ct = CELLS[cell]
@@ -152,7 +152,7 @@ def test_element_tangent_is_derivative_of_force():
             assert np.abs(Ke - Ke.T).max() < 1e-12 * np.abs(Ke).max()
 
 
-@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10"])
+@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10", "tet4", "hex20"])
 def test_integration_known_answers(cell):
     """RESULT DESCRIPTION displacements (1e-12) of the reference's ctest inputs, reproduced by the
     oracle's evaluate+assemble inside a Newton loop (tests/golden/integration_*.json)."""
