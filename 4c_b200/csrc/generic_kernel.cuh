@@ -58,17 +58,21 @@ namespace b200s
       for (int q = 0; q < 9; ++q) Krow[j][q] = 0.0;
     fi[0] = fi[1] = fi[2] = 0.0;
     bool neg = false;
-    // ensure_positive_jacobian_determinant_at_element_nodes (calc_lib.hpp:543-562): node i of this thread
-    if (Ga.dN_node)
+    // ensure_positive_jacobian_determinant_at_element_nodes (calc_lib.hpp:543-562): the thread of row node 0 checks
+    // every node of the element, so that offending ELEMENTS are counted once (as the fast kernels and the oracle do)
+    if (Ga.dN_node && i == 0)
     {
-      double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-      const double* dN = Ga.dN_node + (size_t)i * nn * 3;
-      for (int k = 0; k < nn; ++k)
-        for (int a = 0; a < 3; ++a)
-          for (int b = 0; b < 3; ++b) J[a + 3 * b] = fma(dN[3 * k + a], X[k][b], J[a + 3 * b]);
-      const double dj = det3(J);
-      detJ_min = fmin(detJ_min, dj);
-      neg = !(dj > 0.0);
+      for (int q = 0; q < nn; ++q)
+      {
+        double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        const double* dN = Ga.dN_node + (size_t)q * nn * 3;
+        for (int k = 0; k < nn; ++k)
+          for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) J[a + 3 * b] = fma(dN[3 * k + a], X[k][b], J[a + 3 * b]);
+        const double dj = det3(J);
+        detJ_min = fmin(detJ_min, dj);
+        neg = neg || !(dj > 0.0);
+      }
     }
     for (int g = 0; g < Ga.ngp; ++g)
     {
@@ -171,7 +175,7 @@ namespace b200s
     {
       const long long id = A.ele_id ? (long long)A.ele_id[e] : (long long)e;
       atomicMin(&A.err->first_bad, id);
-      atomicAdd(&A.err->n_neg_jac, 1ull);  // counts offending nodes here; > 0 is what the caller tests
+      atomicAdd(&A.err->n_neg_jac, 1ull);
     }
     const NodeRow nr = A.node_row[A.conn[e * Ga.nn + i]];
     if (nr.rowstart < 0) return;  // row node not owned (lmrowowner != myrank)
