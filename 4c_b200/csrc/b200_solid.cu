@@ -48,6 +48,7 @@
 #include "hex8_kernel.cuh"
 #include "hex8_fbar_kernel.cuh"
 #include "hex8_eas_kernel.cuh"
+#include "hex8_eas_mma_kernel.cuh"
 #include "tet10_kernel.cuh"
 #include "hex27_kernel.cuh"
 #if B200S_HAS(B200S_PART_CORE)
@@ -399,6 +400,66 @@ namespace b200s
     {
       bool neg = false;
       hex8eas::element<MAT, STIFF, NEAS>(A, sm, nrow, pos, tab_gp, wgt, gxi, lane, e, hist + e * HS,
+          t0tab + e * hex8eas::T0_STRIDE, detJ_min, detF_min, neg);
+      if (__ballot_sync(0xffffffffu, neg))
+      {
+        ++nbad;
+        const long long id = A.ele_id ? (long long)A.ele_id[e] : (long long)e;
+        bad = min(bad, id);
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      detJ_min = fmin(detJ_min, __shfl_xor_sync(0xffffffffu, detJ_min, o));
+      detF_min = fmin(detF_min, __shfl_xor_sync(0xffffffffu, detF_min, o));
+    }
+    if (lane == 0)
+    {
+      atomic_min_double(&A.err->min_detJ, detJ_min);
+      atomic_min_double(&A.err->min_detF, detF_min);
+      if (nbad)
+      {
+        atomicMin(&A.err->first_bad, bad);
+        atomicAdd(&A.err->n_neg_jac, (unsigned long long)nbad);
+      }
+    }
+  }
+
+  // The same element on the FP64 tensor cores (hex8_eas_mma_kernel.cuh); 10 warps per SM at 21 KB of shared memory each
+  constexpr int HEX8_EASM_WARPS = 5;
+  constexpr int HEX8_EASM_CTAS_PER_SM = 2;
+  template <int NEAS>
+  constexpr size_t hex8_easm_smem_bytes()
+  {
+    return hex8_table_bytes + 24 * 8 + HEX8_EASM_WARPS * (size_t)((hex8eas::MmaLayout<NEAS>::BYTES + 15) & ~15);
+  }
+  template <int MAT, bool STIFF, int NEAS>
+  __global__ void __launch_bounds__(HEX8_EASM_WARPS * 32, HEX8_EASM_CTAS_PER_SM)
+      k_hex8_eas_mma_eval_assemble(const EvalArgs A, double* hist, const double* t0tab)
+  {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* tab_gp = reinterpret_cast<double*>(smem_raw);
+    double* wgt = tab_gp + 2 * hex8::TAB_SIZE;
+    double* gxi = wgt + 8;
+    for (int t = threadIdx.x; t < 8 * 24; t += blockDim.x)
+      tab_gp[(t / 24) * hex8::TAB_STRIDE + (t % 24)] = c_hex8.dN_gp[t];
+    if (threadIdx.x < 8) wgt[threadIdx.x] = c_hex8.w[threadIdx.x];
+    if (threadIdx.x < 24) gxi[threadIdx.x] = c_hex8.xi_gp[threadIdx.x];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr size_t wbytes = (hex8eas::MmaLayout<NEAS>::BYTES + 15) & ~15;
+    unsigned char* wbase = smem_raw + hex8_table_bytes + 24 * 8 + warp * wbytes;
+    double* sm = reinterpret_cast<double*>(wbase);
+    NodeRow* nrow = reinterpret_cast<NodeRow*>(sm + hex8eas::MmaLayout<NEAS>::DOUBLES);
+    int32_t* pos = reinterpret_cast<int32_t*>(nrow + 8);
+    double detJ_min = 1e300, detF_min = 1e300;
+    long long bad = LLONG_MAX;
+    unsigned int nbad = 0;
+    constexpr int HS = hex8eas::hist_size(NEAS);
+    for (int64_t e = (int64_t)blockIdx.x * HEX8_EASM_WARPS + warp; e < A.n_ele; e += (int64_t)gridDim.x * HEX8_EASM_WARPS)
+    {
+      bool neg = false;
+      hex8eas::element_mma<MAT, STIFF, NEAS>(A, sm, nrow, pos, tab_gp, wgt, gxi, lane, e, hist + e * HS,
           t0tab + e * hex8eas::T0_STRIDE, detJ_min, detF_min, neg);
       if (__ballot_sync(0xffffffffu, neg))
       {
@@ -1406,6 +1467,7 @@ struct b200s_ctx
   int check_finite = 0, ctas_per_sm = 2, scatter_mode = 0, reorder = 1, double_buffer = 0;
   int segments = 1;          // 0: keep the plain locality order of set_mesh (no ghost / row-phase segments)
   int tma_gather = 0;        // hex8 headline kernel: scatter map staged by a TMA bulk copy (A/B variant)
+  int eas_mma = 1;           // hex8 EAS: element matrices on the FP64 tensor cores (0: warp-per-element FMA kernel)
   int pipeline_phases = 12;  // row phases of the host-destination pipeline (1 = off)
   int overlap_halo = 1;      // ghost import on a side stream while the elements without ghost nodes are evaluated
   // what the last evaluate did (bench / tests): launches of the element kernel, overlapped D2H chunks
@@ -1842,10 +1904,24 @@ namespace
   template <int MAT, bool STIFF, int NEAS>
   static int launch_hex8_eas(b200s_ctx* ctx, const EvalArgs& A)
   {
+    if (!ctx->d_eas_hist) return fail(ctx, B200S_ERR_INVALID, "EAS history missing");
+    if (ctx->eas_mma)
+    {
+      auto kern = k_hex8_eas_mma_eval_assemble<MAT, STIFF, NEAS>;
+      constexpr size_t bytes = hex8_easm_smem_bytes<NEAS>();
+      if (set_smem_attr(kern, bytes)) return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", bytes);
+      int64_t grid = (A.n_ele + HEX8_EASM_WARPS - 1) / HEX8_EASM_WARPS;
+      const int64_t cap = (int64_t)ctx->n_sm * HEX8_EASM_CTAS_PER_SM;
+      if (grid > cap) grid = cap;
+      if (grid < 1) grid = 1;
+      kern<<<(unsigned)grid, HEX8_EASM_WARPS * 32, bytes, ctx->stream>>>(A,
+          ctx->d_eas_hist + A.e_begin * hex8eas::hist_size(NEAS), ctx->d_eas_t0 + A.e_begin * hex8eas::T0_STRIDE);
+      ctx->launches += 1;
+      return 0;
+    }
     auto kern = k_hex8_eas_eval_assemble<MAT, STIFF, NEAS>;
     constexpr size_t bytes = hex8_eas_smem_bytes<NEAS>();
     if (set_smem_attr(kern, bytes)) return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", bytes);
-    if (!ctx->d_eas_hist) return fail(ctx, B200S_ERR_INVALID, "EAS history missing");
     int64_t grid = (A.n_ele + HEX8_EAS_WARPS - 1) / HEX8_EAS_WARPS;
     const int64_t cap = (int64_t)ctx->n_sm * HEX8_EAS_CTAS_PER_SM;
     if (grid > cap) grid = cap;
@@ -2266,6 +2342,8 @@ extern "C"
       ctx->overlap_halo = value != 0;
     else if (!strcmp(key, "tma_gather"))
       ctx->tma_gather = value != 0;
+    else if (!strcmp(key, "eas_mma"))
+      ctx->eas_mma = value != 0;
     else if (!strcmp(key, "segments"))  // takes effect at the next set_graph / build_graph
       ctx->segments = value != 0;
     else if (!strcmp(key, "symmetric_transfer"))

@@ -606,3 +606,34 @@ def test_tet4_inverted_element_is_reported():
                                        rm2.node_row_lid, rm2.node_col_lid, rm2.n_row_nodes, rowptr, colind)
     assert nbad > 0 and err.n_neg_jacobian == nbad
     asm.close()
+
+
+# ---- hex8 EAS: tensor-core (DMMA) kernel against the warp-per-element FMA kernel and the oracle ----
+@pytest.mark.parametrize("tech,otech", [(capi.TECH_EAS_MILD, orc.TECH_EAS_MILD), (capi.TECH_EAS_FULL, orc.TECH_EAS_FULL)])
+@pytest.mark.parametrize("mk", [capi.MAT_COUP_NEOHOOKE, capi.MAT_SVK])
+def test_eas_tensor_core_kernel_matches_fma_kernel_and_oracle(tech, otech, mk):
+    rm = b200.partition.box_partition(b200.mesh.HEX8, (7, 6, 5), 0, 1)
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 0.2)
+    par = GEN_MATS[mk]
+    res = {}
+    for mma in (1, 0):
+        asm = b200.DeviceAssembler(rm, mk, par, tech=tech, options={"eas_mma": mma})
+        rowptr, colind = asm.graph()
+        asm.set_state("displacement", u.ravel())
+        K, f, err = asm.evaluate()
+        _, f2, _ = asm.evaluate("struct_calc_internalforce")
+        assert err.n_neg_jacobian == 0
+        assert np.abs(f2 - f).max() <= 1e-13 * np.abs(f).max()
+        res[mma] = (K, f, asm.ctx.get_element_history().copy())
+        asm.close()
+    ohist = orc.eas_new_history(otech, rm.n_col_eles)
+    rK, rf, nbad = orc.evaluate_assemble(orc.HEX8, mk, par, rm.conn, rm.X.ravel(), u.ravel(), rm.node_row_lid, rm.node_col_lid,
+                                         rm.n_row_nodes, rowptr, colind, tech=otech, hist=ohist, nthreads=4)
+    for mma in (1, 0):
+        ok, wK, wf = b200.parity_report(rowptr, res[mma][0], rK, res[mma][1], rf, 1e-10)
+        print("eas_mma", mma, "worst K", wK * 1e-10, "worst f", wf * 1e-10)
+        assert ok and nbad == 0, (mma, wK, wf)
+    ok, wK, wf = b200.parity_report(rowptr, res[1][0], res[0][0], res[1][1], res[0][1], 1e-10)
+    assert ok, (wK, wf)
+    h1, h0 = res[1][2].reshape(ohist.shape), res[0][2].reshape(ohist.shape)
+    assert np.abs(h1 - h0).max() <= 1e-8 * np.abs(h0).max()
