@@ -425,18 +425,23 @@ namespace b200s
     }
   }
 
-  // The same element on the FP64 tensor cores (hex8_eas_mma_kernel.cuh); 10 warps per SM at 21 KB of shared memory each
-  constexpr int HEX8_EASM_WARPS = 5;
-  constexpr int HEX8_EASM_CTAS_PER_SM = 2;
+  // The same element on the FP64 tensor cores (hex8_eas_mma_kernel.cuh).  The gather of the next element (node ids one
+  // more element ahead in a register) is in flight as cp.async copies while the warp works on the current one.
   template <int NEAS>
-  constexpr size_t hex8_easm_smem_bytes()
+  struct EasMmaCfg
   {
-    return hex8_table_bytes + 24 * 8 + HEX8_EASM_WARPS * (size_t)((hex8eas::MmaLayout<NEAS>::BYTES + 15) & ~15);
-  }
+    static constexpr int WARPS = NEAS > 12 ? 6 : 7;  // x 2 CTAs per SM: 12 warps (17.9 KB each) / 14 warps (15.8 KB)
+    static constexpr int CTAS = 2;
+    static constexpr size_t WBYTES = ((size_t)hex8eas::MmaLayout<NEAS>::BYTES + 15) & ~(size_t)15;
+    static constexpr size_t SMEM = hex8_table_bytes + 24 * 8 + WARPS * WBYTES;
+  };
   template <int MAT, bool STIFF, int NEAS>
-  __global__ void __launch_bounds__(HEX8_EASM_WARPS * 32, HEX8_EASM_CTAS_PER_SM)
+  __global__ void __launch_bounds__(EasMmaCfg<NEAS>::WARPS * 32, EasMmaCfg<NEAS>::CTAS)
       k_hex8_eas_mma_eval_assemble(const EvalArgs A, double* hist, const double* t0tab)
   {
+    using L = hex8eas::MmaLayout<NEAS>;
+    constexpr int WARPS = EasMmaCfg<NEAS>::WARPS;
+    constexpr int HS = hex8eas::hist_size(NEAS);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* tab_gp = reinterpret_cast<double*>(smem_raw);
     double* wgt = tab_gp + 2 * hex8::TAB_SIZE;
@@ -447,20 +452,53 @@ namespace b200s
     if (threadIdx.x < 24) gxi[threadIdx.x] = c_hex8.xi_gp[threadIdx.x];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr size_t wbytes = (hex8eas::MmaLayout<NEAS>::BYTES + 15) & ~15;
-    unsigned char* wbase = smem_raw + hex8_table_bytes + 24 * 8 + warp * wbytes;
-    double* sm = reinterpret_cast<double*>(wbase);
-    NodeRow* nrow = reinterpret_cast<NodeRow*>(sm + hex8eas::MmaLayout<NEAS>::DOUBLES);
-    int32_t* pos = reinterpret_cast<int32_t*>(nrow + 8);
+    double* sm = reinterpret_cast<double*>(smem_raw + hex8_table_bytes + 24 * 8 + warp * EasMmaCfg<NEAS>::WBYTES);
     double detJ_min = 1e300, detF_min = 1e300;
     long long bad = LLONG_MAX;
     unsigned int nbad = 0;
-    constexpr int HS = hex8eas::hist_size(NEAS);
-    for (int64_t e = (int64_t)blockIdx.x * HEX8_EASM_WARPS + warp; e < A.n_ele; e += (int64_t)gridDim.x * HEX8_EASM_WARPS)
+    const int64_t stride = (int64_t)gridDim.x * WARPS;
+    int64_t e = (int64_t)blockIdx.x * WARPS + warp;
+    // stage `buf` <- element `el` whose node ids the lanes < 8 hold in `node`
+    auto issue = [&](int buf, int64_t el, int32_t node)
     {
+      double* st = sm + buf * L::STAGE;
+      if (lane < 8)
+      {
+        const double* gx = A.X + 3 * (int64_t)node;
+        const double* gu = A.u + 3 * (int64_t)node;
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+        {
+          cp_async8(st + L::ST_XU + 3 * lane + d, gx + d);
+          cp_async8(st + L::ST_XU + 24 + 3 * lane + d, gu + d);
+        }
+        cp_async16(reinterpret_cast<NodeRow*>(st + L::ST_NROW) + lane, A.node_row + node);
+      }
+      if (lane < 16) cp_async16(reinterpret_cast<int32_t*>(st + L::ST_POS) + 4 * lane, A.pos + el * 64 + 4 * lane);
+      if (lane < 20) cp_async16(st + L::ST_T0 + 2 * lane, t0tab + el * hex8eas::T0_STRIDE + 2 * lane);
+      if (lane < NEAS) cp_async8(st + L::ST_ALPHA + lane, hist + el * HS + NEAS + lane);
+    };
+    int32_t node1 = 0;  // node ids of element e + stride
+    if (e < A.n_ele)
+    {
+      const int32_t node0 = lane < 8 ? A.conn[e * 8 + lane] : 0;
+      if (lane < 8 && e + stride < A.n_ele) node1 = A.conn[(e + stride) * 8 + lane];
+      issue(0, e, node0);
+    }
+    cp_async_commit();
+    int buf = 0;
+    for (; e < A.n_ele; e += stride, buf ^= 1)
+    {
+      int32_t node2 = 0;
+      if (lane < 8 && e + 2 * stride < A.n_ele) node2 = A.conn[(e + 2 * stride) * 8 + lane];
+      if (e + stride < A.n_ele) issue(buf ^ 1, e + stride, node1);
+      cp_async_commit();
+      node1 = node2;
+      cp_async_wait_but_last();  // this element's stage landed (the next one may still fly)
+      __syncwarp();
       bool neg = false;
-      hex8eas::element_mma<MAT, STIFF, NEAS>(A, sm, nrow, pos, tab_gp, wgt, gxi, lane, e, hist + e * HS,
-          t0tab + e * hex8eas::T0_STRIDE, detJ_min, detF_min, neg);
+      hex8eas::element_mma<MAT, STIFF, NEAS>(A, sm, sm + buf * L::STAGE, tab_gp,
+          wgt, gxi, lane, e, hist + e * HS, detJ_min, detF_min, neg);
       if (__ballot_sync(0xffffffffu, neg))
       {
         ++nbad;
@@ -1908,13 +1946,13 @@ namespace
     if (ctx->eas_mma)
     {
       auto kern = k_hex8_eas_mma_eval_assemble<MAT, STIFF, NEAS>;
-      constexpr size_t bytes = hex8_easm_smem_bytes<NEAS>();
-      if (set_smem_attr(kern, bytes)) return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", bytes);
-      int64_t grid = (A.n_ele + HEX8_EASM_WARPS - 1) / HEX8_EASM_WARPS;
-      const int64_t cap = (int64_t)ctx->n_sm * HEX8_EASM_CTAS_PER_SM;
+      using Cfg = EasMmaCfg<NEAS>;
+      if (set_smem_attr(kern, Cfg::SMEM)) return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", Cfg::SMEM);
+      int64_t grid = (A.n_ele + Cfg::WARPS - 1) / Cfg::WARPS;
+      const int64_t cap = (int64_t)ctx->n_sm * Cfg::CTAS;
       if (grid > cap) grid = cap;
       if (grid < 1) grid = 1;
-      kern<<<(unsigned)grid, HEX8_EASM_WARPS * 32, bytes, ctx->stream>>>(A,
+      kern<<<(unsigned)grid, Cfg::WARPS * 32, Cfg::SMEM, ctx->stream>>>(A,
           ctx->d_eas_hist + A.e_begin * hex8eas::hist_size(NEAS), ctx->d_eas_t0 + A.e_begin * hex8eas::T0_STRIDE);
       ctx->launches += 1;
       return 0;

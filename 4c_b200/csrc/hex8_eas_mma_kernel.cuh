@@ -20,8 +20,10 @@
 // warp_spd_inverse_rot).
 //
 // Work per element (one warp):
-//   gather, phase 1 (lane g < 8 = Gauss point g)             as hex8_eas_kernel.cuh
-//   4 x { build P, Q of two Gauss points (12 rows) in shared memory: one (Gauss point, column) item per lane;
+//   gather: cp.async into a double-buffered stage, one element ahead (issued by the kernel around element_mma)
+//   phase 1 (lane g < 8 = Gauss point g)                      as hex8_eas_kernel.cuh
+//   4 x { build P, Q of two Gauss points (12 rows) in shared memory: per point 30 lanes push the 24 columns of B and
+//         the 6 columns of T0invT through w C (hoisted into registers), then the Mtilde columns are scaled copies;
 //         3 k-steps: 2 NT fragment loads, NT (NT + 1) / 2 DMMA }
 //   geometric 8 x 8 (6 DMMA), K_aa / K_da / s / f from the accumulators to shared memory (K_da also to the history),
 //   K_aa^-1, history, mK (DMMA), f, K_dd += mK K_da^T (DMMA), stage K_e, scatter (as hex8::scatter).
@@ -62,29 +64,32 @@ namespace b200s
       static constexpr int LDK = NEAS > 12 ? 28 : 20;     // K_da, mK, K_aa^-1 row stride (12 / 4 mod 16)
       static_assert(LD >= NCP && (LD % 16 == 12 || LD % 16 == 4), "P / Q row stride");
       static_assert(LDK >= 8 * NAT && LDK >= 4 * NK && (LDK % 16 == 12 || LDK % 16 == 4), "K_da / mK row stride");
-      static constexpr int XU = 0;                        // X[24], u[24]
-      static constexpr int T0 = XU + 48;                  // T0invT 6x6 column-major
-      static constexpr int ALPHA = T0 + 36;               // alpha[NA]
-      static constexpr int SG = ALPHA + NA;               // s[NA]
+      // gather stage (double buffered by the kernel, filled with cp.async one element ahead): X[24], u[24], T0invT 6x6
+      // column-major + detJ0 (40), alpha[NA], NodeRow[8], pos[64]
+      static constexpr int ST_XU = 0, ST_T0 = 48, ST_ALPHA = 88, ST_NROW = ST_ALPHA + NA, ST_POS = ST_NROW + 2 * NN;
+      static constexpr int STAGE = ST_POS + NN * NN / 2;   // doubles per stage
+      static constexpr int SG = 2 * STAGE;                // s[NA]
       static constexpr int FE = SG + NA;                  // f_e[24]
       static constexpr int BUF = FE + ND;                 // pivot row exchange of the inverse, 2 x NA
-      // Gauss-loop buffers: per Gauss point F[9], w S[6], w C[21], G[24], scale (as Layout<NEAS>), then P, Q of a pair
-      static constexpr int GP = BUF + 2 * NA;
+      static constexpr int CT = BUF + 2 * NA;             // w C T0invT of the two Gauss points of a pair: [gg][q][I]
+      // Gauss-loop buffers: per Gauss point w C[21] (16-byte aligned), F[9], w S[6], G[24], scale; then P, Q of a pair
+      static constexpr int GP = CT + 72;
       static constexpr int GP_STRIDE = 62;
-      static constexpr int GP_F = 0, GP_S = 9, GP_C = 15, GP_G = 36, GP_SCALE = 60;
+      static constexpr int GP_C = 0, GP_F = 22, GP_S = 31, GP_G = 37, GP_SCALE = 61;
       static constexpr int PM = GP + NGP * GP_STRIDE;
       static constexpr int QM = PM + 12 * LD;
       static constexpr int LOOP_END = QM + 12 * LD;
-      // after the loop (GP / P / Q dead): K_aa then K_aa^-1 (4 NK rows), K_da
+      static_assert(GP % 2 == 0 && GP_STRIDE % 2 == 0, "w C is read with 128-bit loads");
+      // after the loop (GP / P / Q dead): K_aa, then [K_aa^-1 | K_aa^-1 s] (4 NK rows), then mK (24 rows); K_da behind;
+      // K_e (24 x 26) is staged over the front once both are consumed
       static constexpr int AUG = GP;
-      static constexpr int KDA = AUG + 4 * NK * LDK;
-      static_assert(KDA + ND * LDK <= LOOP_END, "K_aa^-1 and K_da fit into the dead Gauss-loop buffers");
-      // mK (24 x LDK), later K_e 24 x 26
-      static constexpr int MK = LOOP_END;
-      static constexpr int KE = MK, KE_RS = 26;
-      static constexpr int R2 = ND * LDK > ND * KE_RS ? ND * LDK : ND * KE_RS;
-      static constexpr int DOUBLES = MK + R2;
-      static constexpr int BYTES = DOUBLES * 8 + NN * 16 + NN * NN * 4;  // + NodeRow[8] + pos[64]
+      static constexpr int MK = AUG;
+      static constexpr int KDA = AUG + ND * LDK;
+      static constexpr int KE = GP, KE_RS = 26;
+      static_assert(4 * NK <= ND && KDA + ND * LDK <= LOOP_END && KE + ND * KE_RS <= LOOP_END,
+          "post-loop work areas fit into the dead Gauss-loop buffers");
+      static constexpr int DOUBLES = LOOP_END;
+      static constexpr int BYTES = DOUBLES * 8;
     };
 
     // In-place inverse of a symmetric positive definite N x N matrix, lane r holds row r in a[] (lanes >= N pass
@@ -127,13 +132,11 @@ namespace b200s
     // phase 1 of both EAS kernels: lane g < 8 = Gauss point g (and element node g for the Jacobian check); leaves
     // F, w S, w C, dN/dX and detJ0 / detJ in the Gauss point's block of shared memory (layout LT)
     template <int MAT, int NEAS, class LT>
-    __device__ __forceinline__ void gauss_points(const EvalArgs& A, double* sm, const double* tab_gp, const double* wgt,
-        const double* gxi, int lane, int64_t e, double detJ0, double& detJ_min, double& detF_min, bool& neg_jac)
+    __device__ __forceinline__ void gauss_points(const EvalArgs& A, double* sm, const double* xu, const double* T0,
+        const double* alpha, const double* tab_gp, const double* wgt, const double* gxi, int lane, int64_t e, double detJ0,
+        double& detJ_min, double& detF_min, bool& neg_jac)
     {
       if (lane >= NGP) return;
-      const double* xu = sm + LT::XU;
-      const double* T0 = sm + LT::T0;
-      const double* alpha = sm + LT::ALPHA;
       const int g = lane;
       double J[9], iJ[9];
       {
@@ -214,37 +217,23 @@ namespace b200s
       gp[LT::GP_SCALE] = scale;
     }
 
+    // The warp's work on one element whose gather stage (X, u, T0invT, detJ0, alpha, row info, scatter map) is in shared
+    // memory; sm: the warp's work area (MmaLayout<NEAS>), hist: the element's history block in HBM.
     template <int MAT, bool STIFF, int NEAS>
-    __device__ __forceinline__ void element_mma(const EvalArgs& A, double* sm, NodeRow* nrow, int32_t* pos,
+    __device__ __forceinline__ void element_mma(const EvalArgs& A, double* sm, const double* stage,
         const double* tab_gp /*[g][k*3+a], stride TAB_STRIDE*/, const double* wgt, const double* gxi /*[g][3]*/,
-        int lane, int64_t e, double* hist, const double* t0tab, double& detJ_min, double& detF_min, bool& neg_jac)
+        int lane, int64_t e, double* hist, double& detJ_min, double& detF_min, bool& neg_jac)
     {
       using L = MmaLayout<NEAS>;
       constexpr int NT = L::NT, LD = L::LD, LDK = L::LDK, NK = L::NK, NAT = L::NAT;
-      double* xu = sm + L::XU;
-      double* T0 = sm + L::T0;
-      double* alpha = sm + L::ALPHA;
+      const double* xu = stage + L::ST_XU;
+      const double* T0 = stage + L::ST_T0;
+      const double* alpha = stage + L::ST_ALPHA;
+      const NodeRow* nrow = reinterpret_cast<const NodeRow*>(stage + L::ST_NROW);
+      const int32_t* pos = reinterpret_cast<const int32_t*>(stage + L::ST_POS);
       const int lq = lane >> 2, lr = lane & 3;  // fragment coordinates: "group" and "thread in group"
 
-      // ---- gather ----------------------------------------------------------------------------------
-      if (lane < NN)
-      {
-        const int64_t node = A.conn[e * NN + lane];
-#pragma unroll
-        for (int d = 0; d < 3; ++d)
-        {
-          xu[3 * lane + d] = A.X[3 * node + d];
-          xu[24 + 3 * lane + d] = A.u[3 * node + d];
-        }
-        nrow[lane] = A.node_row[node];
-      }
-      for (int t = lane; t < NN * NN; t += 32) pos[t] = A.pos[e * (NN * NN) + t];
-      if (lane < NEAS) alpha[lane] = hist[NEAS + lane];
-      for (int t = lane; t < 36; t += 32) T0[t] = t0tab[t];
-      const double detJ0 = t0tab[36];
-      __syncwarp();
-
-      gauss_points<MAT, NEAS, L>(A, sm, tab_gp, wgt, gxi, lane, e, detJ0, detJ_min, detF_min, neg_jac);
+      gauss_points<MAT, NEAS, L>(A, sm, xu, T0, alpha, tab_gp, wgt, gxi, lane, e, T0[36], detJ_min, detF_min, neg_jac);
       __syncwarp();
 
       // ---- S = P^T Q over the Gauss points, two at a time ------------------------------------------------------
@@ -258,46 +247,83 @@ namespace b200s
 #pragma unroll 1
       for (int pr = 0; pr < NGP / 2; ++pr)
       {
-        // one (Gauss point of the pair, column) item per lane and round
+        // per Gauss point of the pair one round of 30 lanes: the 24 columns of the B-operator and the 6 columns of
+        // T0invT go through  q = (w C) p  (w C hoisted into registers: 11 loads, then six independent FMA chains)
+        double* CT = sm + L::CT;
 #pragma unroll 1
-        for (int it = lane; it < 2 * L::NCU; it += 32)
+        for (int gg = 0; gg < 2; ++gg)
         {
-          const int gg = it >= L::NCU ? 1 : 0;
-          const int col = it - gg * L::NCU;
           const int g = 2 * pr + gg;
           const double* gp = sm + L::GP + g * L::GP_STRIDE;
-          double pc[6];
-          if (col < ND)
+          if (lane < ND + 6)
           {
-            // column of the B-operator (evaluate_strain_gradient, calc_lib.hpp:777-826), strain-like rows
-            const int ni = col / 3, ei = col - 3 * ni;
-            const double* Gi = gp + L::GP_G + 3 * ni;
-            const double Fe0 = gp[L::GP_F + ei], Fe1 = gp[L::GP_F + ei + 3], Fe2 = gp[L::GP_F + ei + 6];
-            const double G0 = Gi[0], G1 = Gi[1], G2 = Gi[2];
-            pc[0] = Fe0 * G0, pc[1] = Fe1 * G1, pc[2] = Fe2 * G2;
-            pc[3] = Fe0 * G1 + Fe1 * G0;
-            pc[4] = Fe1 * G2 + Fe2 * G1;
-            pc[5] = Fe2 * G0 + Fe0 * G2;
-          }
-          else
-          {
-            // column of Mtilde = detJ0 / detJ T0invT M(xi) (eas_helpers.hpp:352-371)
-            const int a = col - ND;
-            const int arow = c_eas_row[a];
-            const double mv = gp[L::GP_SCALE] * monomial(c_eas_mono[a], gxi[3 * g], gxi[3 * g + 1], gxi[3 * g + 2]);
+            double cw[22];
+            {
+              const d2* c2 = reinterpret_cast<const d2*>(gp + L::GP_C);
 #pragma unroll
-            for (int k = 0; k < 6; ++k) pc[k] = mv * T0[k + 6 * arow];
+              for (int i = 0; i < 11; ++i)
+              {
+                const d2 t = c2[i];
+                cw[2 * i] = t.x, cw[2 * i + 1] = t.y;
+              }
+            }
+            double pc[6];
+            if (lane < ND)
+            {
+              // column of the B-operator (evaluate_strain_gradient, calc_lib.hpp:777-826), strain-like rows
+              const int ni = lane / 3, ei = lane - 3 * ni;
+              const double* Gi = gp + L::GP_G + 3 * ni;
+              const double Fe0 = gp[L::GP_F + ei], Fe1 = gp[L::GP_F + ei + 3], Fe2 = gp[L::GP_F + ei + 6];
+              const double G0 = Gi[0], G1 = Gi[1], G2 = Gi[2];
+              pc[0] = Fe0 * G0, pc[1] = Fe1 * G1, pc[2] = Fe2 * G2;
+              pc[3] = Fe0 * G1 + Fe1 * G0;
+              pc[4] = Fe1 * G2 + Fe2 * G1;
+              pc[5] = Fe2 * G0 + Fe0 * G2;
+            }
+            else
+            {
+#pragma unroll
+              for (int k = 0; k < 6; ++k) pc[k] = T0[k + 6 * (lane - ND)];
+            }
+            double qc[6];
+#pragma unroll
+            for (int I = 0; I < 6; ++I) qc[I] = cw[c21(I, 0)] * pc[0];
+#pragma unroll
+            for (int Jv = 1; Jv < 6; ++Jv)
+#pragma unroll
+              for (int I = 0; I < 6; ++I) qc[I] = fma(cw[c21(I, Jv)], pc[Jv], qc[I]);
+            if (lane < ND)
+            {
+#pragma unroll
+              for (int I = 0; I < 6; ++I)
+              {
+                Pm[(6 * gg + I) * LD + lane] = pc[I];
+                Qm[(6 * gg + I) * LD + lane] = qc[I];
+              }
+            }
+            else
+            {
+#pragma unroll
+              for (int I = 0; I < 6; ++I) CT[(6 * gg + lane - ND) * 6 + I] = qc[I];
+            }
           }
-          double* pd = Pm + 6 * gg * LD + col;
-          double* qd = Qm + 6 * gg * LD + col;
+        }
+        __syncwarp();
+        // columns of Mtilde = detJ0 / detJ T0invT M(xi) (one non-zero per column of M: eas_helpers.hpp:205-275, 352-371):
+        // p = mv T0invT(:, row), q = mv (w C T0invT)(:, row)
+        for (int it = lane; it < 2 * NEAS; it += 32)
+        {
+          const int gg = it >= NEAS ? 1 : 0;
+          const int a = it - gg * NEAS;
+          const int g = 2 * pr + gg;
+          const int arow = c_eas_row[a];
+          const double mv = sm[L::GP + g * L::GP_STRIDE + L::GP_SCALE] *
+                            monomial(c_eas_mono[a], gxi[3 * g], gxi[3 * g + 1], gxi[3 * g + 2]);
 #pragma unroll
           for (int I = 0; I < 6; ++I)
           {
-            double t = 0.0;
-#pragma unroll
-            for (int Jv = 0; Jv < 6; ++Jv) t = fma(gp[L::GP_C + c21(I, Jv)], pc[Jv], t);
-            pd[I * LD] = pc[I];
-            qd[I * LD] = t;
+            Pm[(6 * gg + I) * LD + ND + a] = mv * T0[I + 6 * arow];
+            Qm[(6 * gg + I) * LD + ND + a] = mv * CT[(6 * gg + arow) * 6 + I];
           }
         }
         // column CF: w S in Q, zero in P; the padding columns behind it are zero in both
@@ -452,6 +478,7 @@ namespace b200s
       {
         // ---- K_dd += mK K_da^T  (eas.hpp:255-263): mK through shared memory into A fragments ---------------------------
         double* MkS = sm + L::MK;
+        __syncwarp();  // [K_aa^-1 | K_aa^-1 s] consumed by every lane: mK is staged over it
 #pragma unroll
         for (int tm = 0; tm < 3; ++tm)
 #pragma unroll

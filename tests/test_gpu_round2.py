@@ -628,7 +628,7 @@ def test_eas_tensor_core_kernel_matches_fma_kernel_and_oracle(tech, otech, mk):
         asm.close()
     ohist = orc.eas_new_history(otech, rm.n_col_eles)
     rK, rf, nbad = orc.evaluate_assemble(orc.HEX8, mk, par, rm.conn, rm.X.ravel(), u.ravel(), rm.node_row_lid, rm.node_col_lid,
-                                         rm.n_row_nodes, rowptr, colind, tech=otech, hist=ohist, nthreads=4)
+                                         rm.n_row_nodes, rowptr, colind, tech=otech, hist=ohist)
     for mma in (1, 0):
         ok, wK, wf = b200.parity_report(rowptr, res[mma][0], rK, res[mma][1], rf, 1e-10)
         print("eas_mma", mma, "worst K", wK * 1e-10, "worst f", wf * 1e-10)
