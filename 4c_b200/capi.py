@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib4c_b200_solid.so")
+LIB_PATH = os.environ.get("B200S_LIB") or os.path.join(_HERE, "lib4c_b200_solid.so")  # B200S_LIB: A/B builds (tools/)
 
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NEG_JACOBIAN, ERR_NONFINITE, ERR_COMM = -1, -2, -3, -4, -5, -6

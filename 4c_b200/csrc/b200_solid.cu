@@ -430,7 +430,15 @@ namespace b200s
   template <int NEAS>
   struct EasMmaCfg
   {
-    static constexpr int WARPS = NEAS > 12 ? 6 : 7;  // x 2 CTAs per SM: 12 warps (17.9 KB each) / 14 warps (15.8 KB)
+#ifndef B200S_EASM_WARPS_MILD
+#define B200S_EASM_WARPS_MILD 6
+#endif
+#ifndef B200S_EASM_WARPS_FULL
+#define B200S_EASM_WARPS_FULL 6
+#endif
+    // x 2 CTAs per SM = 12 warps for both sizes (measured: eas_mild with 14 warps at 128 registers spills, 11.2 ms against
+    // 10.6 ms with 12 warps at 168; eas_full with 10 warps 21.1 ms against 17.7 ms with 12)
+    static constexpr int WARPS = NEAS > 12 ? B200S_EASM_WARPS_FULL : B200S_EASM_WARPS_MILD;
     static constexpr int CTAS = 2;
     static constexpr size_t WBYTES = ((size_t)hex8eas::MmaLayout<NEAS>::BYTES + 15) & ~(size_t)15;
     static constexpr size_t SMEM = hex8_table_bytes + 24 * 8 + WARPS * WBYTES;
@@ -462,18 +470,13 @@ namespace b200s
     auto issue = [&](int buf, int64_t el, int32_t node)
     {
       double* st = sm + buf * L::STAGE;
-      if (lane < 8)
+      const int32_t nk = __shfl_sync(0xffffffffu, node, lane < 24 ? lane / 3 : 0);  // node of dof `lane`
+      if (lane < 24)
       {
-        const double* gx = A.X + 3 * (int64_t)node;
-        const double* gu = A.u + 3 * (int64_t)node;
-#pragma unroll
-        for (int d = 0; d < 3; ++d)
-        {
-          cp_async8(st + L::ST_XU + 3 * lane + d, gx + d);
-          cp_async8(st + L::ST_XU + 24 + 3 * lane + d, gu + d);
-        }
-        cp_async16(reinterpret_cast<NodeRow*>(st + L::ST_NROW) + lane, A.node_row + node);
+        cp_async8(st + L::ST_XU + lane, A.X + 3 * (int64_t)nk + (lane - 3 * (lane / 3)));
+        cp_async8(st + L::ST_XU + 24 + lane, A.u + 3 * (int64_t)nk + (lane - 3 * (lane / 3)));
       }
+      if (lane < 8) cp_async16(reinterpret_cast<NodeRow*>(st + L::ST_NROW) + lane, A.node_row + node);
       if (lane < 16) cp_async16(reinterpret_cast<int32_t*>(st + L::ST_POS) + 4 * lane, A.pos + el * 64 + 4 * lane);
       if (lane < 20) cp_async16(st + L::ST_T0 + 2 * lane, t0tab + el * hex8eas::T0_STRIDE + 2 * lane);
       if (lane < NEAS) cp_async8(st + L::ST_ALPHA + lane, hist + el * HS + NEAS + lane);

@@ -96,11 +96,12 @@ namespace b200s
     // zeros).  Gauss-Jordan without pivoting like warp_spd_inverse_t, but the rows live in registers although the step
     // loop stays rolled: every step rotates the row by one place (the update of entry k is written to place k - 1, the
     // new pivot-column entry goes to the last place), so that the pivot column always sits in a[0] and no register
-    // is indexed dynamically; after N steps the rotation is the identity.  The pivot lane publishes its row through
-    // the double-buffered scratch `buf` (2 N doubles): one __syncwarp per step.
+    // is indexed dynamically; after N steps the rotation is the identity.  The pivot lane publishes its row through the
+    // double-buffered scratch `buf` (2 N doubles): one __syncwarp per step.
     template <int N>
     __device__ __forceinline__ void warp_spd_inverse_rot(double (&a)[N], double* buf, int lane)
     {
+      double scale = 1.0;  // the row of a lane that has been the pivot is kept unscaled: true row = scale * a[]
 #pragma unroll 1
       for (int c = 0; c < N; ++c)
       {
@@ -111,21 +112,18 @@ namespace b200s
           for (int k = 0; k < N; ++k) b[k] = a[k];
         }
         __syncwarp();
+        // a(r, k) -= (a(r, c) / a(c, c)) a(c, k) is linear in row r, so it acts on the unscaled rows as it stands; the
+        // pivot lane passes f = 0, rotates, and from now on carries the factor 1 / a(c, c)
+        const bool piv = lane == c;
         const double d = 1.0 / b[0];
-        if (lane == c)
-        {
+        const double f = piv ? 0.0 : a[0] * d;
 #pragma unroll
-          for (int k = 1; k < N; ++k) a[k - 1] = a[k] * d;
-          a[N - 1] = d;
-        }
-        else
-        {
-          const double f = a[0] * d;
-#pragma unroll
-          for (int k = 1; k < N; ++k) a[k - 1] = fma(-f, b[k], a[k]);
-          a[N - 1] = -f;
-        }
+        for (int k = 1; k < N; ++k) a[k - 1] = fma(-f, b[k], a[k]);
+        a[N - 1] = piv ? 1.0 : -f;
+        scale = piv ? d : scale;
       }
+#pragma unroll
+      for (int k = 0; k < N; ++k) a[k] *= scale;
       __syncwarp();
     }
 
@@ -244,6 +242,23 @@ namespace b200s
         for (int tn = 0; tn < NT; ++tn) acc[tm][tn][0] = acc[tm][tn][1] = 0.0;
       double* Pm = sm + L::PM;
       double* Qm = sm + L::QM;
+      // column CF of P and the padding columns behind it in P and Q are zero for the whole element
+      for (int t = lane; t < 12 * (L::NCP - L::CF); t += 32)
+      {
+        const int kk = t / (L::NCP - L::CF), c = L::CF + (t - kk * (L::NCP - L::CF));
+        Pm[kk * LD + c] = 0.0;
+        if (c > L::CF) Qm[kk * LD + c] = 0.0;
+      }
+      // Mtilde column 16 r + (lane & 15) of this lane: Voigt row and monomial of its non-zero (-1: the w S column, -2: idle)
+      constexpr int MR = (NEAS + 1 + 15) / 16;
+      int m_row[MR], m_mono[MR];
+#pragma unroll
+      for (int r = 0; r < MR; ++r)
+      {
+        const int a = 16 * r + (lane & 15);
+        m_row[r] = a < NEAS ? c_eas_row[a < NEAS ? a : 0] : (a == NEAS ? -1 : -2);
+        m_mono[r] = c_eas_mono[a < NEAS ? a : 0];
+      }
 #pragma unroll 1
       for (int pr = 0; pr < NGP / 2; ++pr)
       {
@@ -310,28 +325,31 @@ namespace b200s
         }
         __syncwarp();
         // columns of Mtilde = detJ0 / detJ T0invT M(xi) (one non-zero per column of M: eas_helpers.hpp:205-275, 352-371):
-        // p = mv T0invT(:, row), q = mv (w C T0invT)(:, row)
-        for (int it = lane; it < 2 * NEAS; it += 32)
+        // p = mv T0invT(:, row), q = mv (w C T0invT)(:, row); one half warp per Gauss point of the pair, the lane behind
+        // the last Mtilde column writes w S into column CF of Q
         {
-          const int gg = it >= NEAS ? 1 : 0;
-          const int a = it - gg * NEAS;
-          const int g = 2 * pr + gg;
-          const int arow = c_eas_row[a];
-          const double mv = sm[L::GP + g * L::GP_STRIDE + L::GP_SCALE] *
-                            monomial(c_eas_mono[a], gxi[3 * g], gxi[3 * g + 1], gxi[3 * g + 2]);
+          const int gg = lane >> 4, g = 2 * pr + gg;
+          const double* gp = sm + L::GP + g * L::GP_STRIDE;
+          const double xr = gxi[3 * g], xs = gxi[3 * g + 1], xt = gxi[3 * g + 2], sc = gp[L::GP_SCALE];
 #pragma unroll
-          for (int I = 0; I < 6; ++I)
+          for (int r = 0; r < MR; ++r)
           {
-            Pm[(6 * gg + I) * LD + ND + a] = mv * T0[I + 6 * arow];
-            Qm[(6 * gg + I) * LD + ND + a] = mv * CT[(6 * gg + arow) * 6 + I];
+            double* pd = Pm + 6 * gg * LD + ND + 16 * r + (lane & 15);
+            double* qd = Qm + 6 * gg * LD + ND + 16 * r + (lane & 15);
+            if (m_row[r] >= 0)
+            {
+              const double mv = sc * monomial(m_mono[r], xr, xs, xt);
+              const double* t0c = T0 + 6 * m_row[r];
+              const double* ctc = CT + (6 * gg + m_row[r]) * 6;
+#pragma unroll
+              for (int I = 0; I < 6; ++I) pd[I * LD] = mv * t0c[I], qd[I * LD] = mv * ctc[I];
+            }
+            else if (m_row[r] == -1)
+            {
+#pragma unroll
+              for (int I = 0; I < 6; ++I) qd[I * LD] = gp[L::GP_S + I];
+            }
           }
-        }
-        // column CF: w S in Q, zero in P; the padding columns behind it are zero in both
-        for (int t = lane; t < 12 * (L::NCP - L::CF); t += 32)
-        {
-          const int kk = t / (L::NCP - L::CF), c = L::CF + (t - kk * (L::NCP - L::CF));
-          Pm[kk * LD + c] = 0.0;
-          Qm[kk * LD + c] = (c == L::CF) ? sm[L::GP + (2 * pr + kk / 6) * L::GP_STRIDE + L::GP_S + kk % 6] : 0.0;
         }
         __syncwarp();
 #pragma unroll
