@@ -49,6 +49,16 @@ namespace b200s
           : "d"(a), "d"(b));
     }
 
+    // 1 / x without the slow path of the IEEE division: hardware estimate (relative error < 2^-20) and two Newton steps,
+    // a result within an ulp or two; used for the pivots of K_aa^-1, whose operator is defined up to round-off anyway
+    __device__ __forceinline__ double fast_rcp(double x)
+    {
+      double r;
+      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+      r = fma(fma(-x, r, 1.0), r, r);
+      return fma(fma(-x, r, 1.0), r, r);
+    }
+
     // shared memory of one warp, in doubles
     template <int NEAS>
     struct MmaLayout
@@ -115,7 +125,7 @@ namespace b200s
         // a(r, k) -= (a(r, c) / a(c, c)) a(c, k) is linear in row r, so it acts on the unscaled rows as it stands; the
         // pivot lane passes f = 0, rotates, and from now on carries the factor 1 / a(c, c)
         const bool piv = lane == c;
-        const double d = 1.0 / b[0];
+        const double d = fast_rcp(b[0]);
         const double f = piv ? 0.0 : a[0] * d;
 #pragma unroll
         for (int k = 1; k < N; ++k) a[k - 1] = fma(-f, b[k], a[k]);
@@ -158,21 +168,24 @@ namespace b200s
       detJ_min = fmin(detJ_min, detJ);
       double* gp = sm + LT::GP + g * LT::GP_STRIDE;
       double F[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+      double G[24];  // kept in registers until X, u and the shape function table are consumed: no load of this loop has to
+                     // be ordered behind a store it might alias with
 #pragma unroll
       for (int k = 0; k < NN; ++k)
       {
-        double Gk[3];
 #pragma unroll
-        for (int a = 0; a < 3; ++a) Gk[a] = iJ[a] * dN[3 * k] + iJ[a + 3] * dN[3 * k + 1] + iJ[a + 6] * dN[3 * k + 2];
+        for (int a = 0; a < 3; ++a)
+          G[3 * k + a] = iJ[a] * dN[3 * k] + iJ[a + 3] * dN[3 * k + 1] + iJ[a + 6] * dN[3 * k + 2];
 #pragma unroll
         for (int a = 0; a < 3; ++a)
         {
-          gp[LT::GP_G + 3 * k + a] = Gk[a];
           const double ua = xu[24 + 3 * k + a];
 #pragma unroll
-          for (int b = 0; b < 3; ++b) F[a + 3 * b] += ua * Gk[b];
+          for (int b = 0; b < 3; ++b) F[a + 3 * b] += ua * G[3 * k + b];
         }
       }
+#pragma unroll
+      for (int i = 0; i < 24; ++i) gp[LT::GP_G + i] = G[i];
       detF_min = fmin(detF_min, det3(F));
       // E_enh = E + stress-like(Mtilde alpha), Mtilde = detJ0/detJ T0invT M(xi)
       // (evaluate_eas_kinematics, eas_helpers.hpp:405-448); C_enh = C + 2 (...), shear rows halved
@@ -341,13 +354,19 @@ namespace b200s
               const double mv = sc * monomial(m_mono[r], xr, xs, xt);
               const double* t0c = T0 + 6 * m_row[r];
               const double* ctc = CT + (6 * gg + m_row[r]) * 6;
+              double pv[6], qv[6];  // all loads before the first store (the compiler has to assume aliasing)
 #pragma unroll
-              for (int I = 0; I < 6; ++I) pd[I * LD] = mv * t0c[I], qd[I * LD] = mv * ctc[I];
+              for (int I = 0; I < 6; ++I) pv[I] = t0c[I], qv[I] = ctc[I];
+#pragma unroll
+              for (int I = 0; I < 6; ++I) pd[I * LD] = mv * pv[I], qd[I * LD] = mv * qv[I];
             }
             else if (m_row[r] == -1)
             {
+              double qv[6];
 #pragma unroll
-              for (int I = 0; I < 6; ++I) qd[I * LD] = gp[L::GP_S + I];
+              for (int I = 0; I < 6; ++I) qv[I] = gp[L::GP_S + I];
+#pragma unroll
+              for (int I = 0; I < 6; ++I) qd[I * LD] = qv[I];
             }
           }
         }
