@@ -132,6 +132,7 @@ namespace b200s
   __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
   // all but the most recently committed group are complete
   __device__ __forceinline__ void cp_async_wait_but_last() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+  __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
   // TMA bulk copy (cp.async.bulk, SASS UBLKCP) of a contiguous, 16-byte aligned block global -> shared, completion
   // signalled on an mbarrier (complete_tx); issued by ONE lane, awaited by all lanes of the warp
@@ -441,7 +442,7 @@ namespace b200s
     static constexpr int WARPS = NEAS > 12 ? B200S_EASM_WARPS_FULL : B200S_EASM_WARPS_MILD;
     static constexpr int CTAS = 2;
     static constexpr size_t WBYTES = ((size_t)hex8eas::MmaLayout<NEAS>::BYTES + 15) & ~(size_t)15;
-    static constexpr size_t SMEM = hex8_table_bytes + 24 * 8 + WARPS * WBYTES;
+    static constexpr size_t SMEM = hex8_table_bytes + 72 * 8 + WARPS * WBYTES;
   };
   template <int MAT, bool STIFF, int NEAS>
   __global__ void __launch_bounds__(EasMmaCfg<NEAS>::WARPS * 32, EasMmaCfg<NEAS>::CTAS)
@@ -458,9 +459,15 @@ namespace b200s
       tab_gp[(t / 24) * hex8::TAB_STRIDE + (t % 24)] = c_hex8.dN_gp[t];
     if (threadIdx.x < 8) wgt[threadIdx.x] = c_hex8.w[threadIdx.x];
     if (threadIdx.x < 24) gxi[threadIdx.x] = c_hex8.xi_gp[threadIdx.x];
+    // gxi[24 + 8 m + g]: monomial m (r, s, t, rs, rt, st) of the EAS shape functions at Gauss point g
+    if (threadIdx.x < 48)
+    {
+      const int g = threadIdx.x & 7;
+      gxi[24 + threadIdx.x] = hex8eas::monomial(threadIdx.x >> 3, c_hex8.xi_gp[3 * g], c_hex8.xi_gp[3 * g + 1], c_hex8.xi_gp[3 * g + 2]);
+    }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* sm = reinterpret_cast<double*>(smem_raw + hex8_table_bytes + 24 * 8 + warp * EasMmaCfg<NEAS>::WBYTES);
+    double* sm = reinterpret_cast<double*>(smem_raw + hex8_table_bytes + 72 * 8 + warp * EasMmaCfg<NEAS>::WBYTES);
     double detJ_min = 1e300, detF_min = 1e300;
     long long bad = LLONG_MAX;
     unsigned int nbad = 0;
@@ -481,27 +488,43 @@ namespace b200s
       if (lane < 20) cp_async16(st + L::ST_T0 + 2 * lane, t0tab + el * hex8eas::T0_STRIDE + 2 * lane);
       if (lane < NEAS) cp_async8(st + L::ST_ALPHA + lane, hist + el * HS + NEAS + lane);
     };
-    int32_t node1 = 0;  // node ids of element e + stride
+    // The node ids of an element travel one more element ahead, as a cp.async into the stage that is being worked on:
+    // group(e) = { stage of element e + stride, node ids of element e + 2 stride }.
+    auto fetch_conn = [&](int buf, int64_t el)
+    {
+      if (lane < 2) cp_async16(reinterpret_cast<int32_t*>(sm + buf * L::STAGE + L::ST_CONN) + 4 * lane, A.conn + el * 8 + 4 * lane);
+    };
     if (e < A.n_ele)
     {
       const int32_t node0 = lane < 8 ? A.conn[e * 8 + lane] : 0;
-      if (lane < 8 && e + stride < A.n_ele) node1 = A.conn[(e + stride) * 8 + lane];
       issue(0, e, node0);
+      if (e + stride < A.n_ele) fetch_conn(1, e + stride);
     }
     cp_async_commit();
+    // Mtilde column 16 r + (lane & 15) of this lane: Voigt row and monomial of its non-zero (-1: the w S column, -2: idle)
+    int m_row[NEAS > 12 ? 2 : 1], m_mono[NEAS > 12 ? 2 : 1];
+#pragma unroll
+    for (int r = 0; r < (NEAS > 12 ? 2 : 1); ++r)
+    {
+      const int a = 16 * r + (lane & 15);
+      m_row[r] = a < NEAS ? hex8eas::c_eas_row[a < NEAS ? a : 0] : (a == NEAS ? -1 : -2);
+      m_mono[r] = hex8eas::c_eas_mono[a < NEAS ? a : 0];
+    }
     int buf = 0;
     for (; e < A.n_ele; e += stride, buf ^= 1)
     {
-      int32_t node2 = 0;
-      if (lane < 8 && e + 2 * stride < A.n_ele) node2 = A.conn[(e + 2 * stride) * 8 + lane];
-      if (e + stride < A.n_ele) issue(buf ^ 1, e + stride, node1);
-      cp_async_commit();
-      node1 = node2;
-      cp_async_wait_but_last();  // this element's stage landed (the next one may still fly)
+      cp_async_wait_all();  // this element's stage and the node ids of the next element landed
       __syncwarp();
+      if (e + stride < A.n_ele)
+      {
+        const int32_t node1 = lane < 8 ? reinterpret_cast<const int32_t*>(sm + (buf ^ 1) * L::STAGE + L::ST_CONN)[lane] : 0;
+        issue(buf ^ 1, e + stride, node1);
+        if (e + 2 * stride < A.n_ele) fetch_conn(buf, e + 2 * stride);
+      }
+      cp_async_commit();
       bool neg = false;
-      hex8eas::element_mma<MAT, STIFF, NEAS>(A, sm, sm + buf * L::STAGE, tab_gp,
-          wgt, gxi, lane, e, hist + e * HS, detJ_min, detF_min, neg);
+      hex8eas::element_mma<MAT, STIFF, NEAS>(A, sm, sm + buf * L::STAGE, tab_gp, wgt, gxi, m_row, m_mono, lane, e,
+          hist + e * HS, detJ_min, detF_min, neg);
       if (__ballot_sync(0xffffffffu, neg))
       {
         ++nbad;

@@ -75,9 +75,10 @@ namespace b200s
       static_assert(LD >= NCP && (LD % 16 == 12 || LD % 16 == 4), "P / Q row stride");
       static_assert(LDK >= 8 * NAT && LDK >= 4 * NK && (LDK % 16 == 12 || LDK % 16 == 4), "K_da / mK row stride");
       // gather stage (double buffered by the kernel, filled with cp.async one element ahead): X[24], u[24], T0invT 6x6
-      // column-major + detJ0 (40), alpha[NA], NodeRow[8], pos[64]
+      // column-major + detJ0 (40), alpha[NA], NodeRow[8], pos[64], conn[8]
       static constexpr int ST_XU = 0, ST_T0 = 48, ST_ALPHA = 88, ST_NROW = ST_ALPHA + NA, ST_POS = ST_NROW + 2 * NN;
-      static constexpr int STAGE = ST_POS + NN * NN / 2;   // doubles per stage
+      static constexpr int ST_CONN = ST_POS + NN * NN / 2;  // node ids of the element after the next one (kernel)
+      static constexpr int STAGE = ST_CONN + NN / 2;       // doubles per stage
       static constexpr int SG = 2 * STAGE;                // s[NA]
       static constexpr int FE = SG + NA;                  // f_e[24]
       static constexpr int BUF = FE + ND;                 // pivot row exchange of the inverse, 2 x NA
@@ -233,8 +234,11 @@ namespace b200s
     template <int MAT, bool STIFF, int NEAS>
     __device__ __forceinline__ void element_mma(const EvalArgs& A, double* sm, const double* stage,
         const double* tab_gp /*[g][k*3+a], stride TAB_STRIDE*/, const double* wgt, const double* gxi /*[g][3]*/,
-        int lane, int64_t e, double* hist, double& detJ_min, double& detF_min, bool& neg_jac)
+        const int (&m_row)[(NEAS + 1 + 15) / 16], const int (&m_mono)[(NEAS + 1 + 15) / 16], int lane, int64_t e,
+        double* hist, double& detJ_min, double& detF_min, bool& neg_jac)
     {
+      // m_row[r], m_mono[r]: Mtilde column 16 r + (lane & 15) of this lane -- Voigt row (-1: the w S column, -2: idle) and
+      // monomial of its non-zero; gxi[24 + 8 m + g]: monomial m at Gauss point g
       using L = MmaLayout<NEAS>;
       constexpr int NT = L::NT, LD = L::LD, LDK = L::LDK, NK = L::NK, NAT = L::NAT;
       const double* xu = stage + L::ST_XU;
@@ -262,16 +266,7 @@ namespace b200s
         Pm[kk * LD + c] = 0.0;
         if (c > L::CF) Qm[kk * LD + c] = 0.0;
       }
-      // Mtilde column 16 r + (lane & 15) of this lane: Voigt row and monomial of its non-zero (-1: the w S column, -2: idle)
       constexpr int MR = (NEAS + 1 + 15) / 16;
-      int m_row[MR], m_mono[MR];
-#pragma unroll
-      for (int r = 0; r < MR; ++r)
-      {
-        const int a = 16 * r + (lane & 15);
-        m_row[r] = a < NEAS ? c_eas_row[a < NEAS ? a : 0] : (a == NEAS ? -1 : -2);
-        m_mono[r] = c_eas_mono[a < NEAS ? a : 0];
-      }
 #pragma unroll 1
       for (int pr = 0; pr < NGP / 2; ++pr)
       {
@@ -343,7 +338,7 @@ namespace b200s
         {
           const int gg = lane >> 4, g = 2 * pr + gg;
           const double* gp = sm + L::GP + g * L::GP_STRIDE;
-          const double xr = gxi[3 * g], xs = gxi[3 * g + 1], xt = gxi[3 * g + 2], sc = gp[L::GP_SCALE];
+          const double sc = gp[L::GP_SCALE];
 #pragma unroll
           for (int r = 0; r < MR; ++r)
           {
@@ -351,7 +346,7 @@ namespace b200s
             double* qd = Qm + 6 * gg * LD + ND + 16 * r + (lane & 15);
             if (m_row[r] >= 0)
             {
-              const double mv = sc * monomial(m_mono[r], xr, xs, xt);
+              const double mv = sc * gxi[24 + 8 * m_mono[r] + g];
               const double* t0c = T0 + 6 * m_row[r];
               const double* ctc = CT + (6 * gg + m_row[r]) * 6;
               double pv[6], qv[6];  // all loads before the first store (the compiler has to assume aliasing)
