@@ -55,12 +55,12 @@ WORKLOADS = {
     "hex8_eas_mild": dict(config="2 mesh, TECH eas_mild (SURVEY 8f.1)", cell="HEX8", mat="MAT_COUP_NEOHOOKE",
                           par=[200.0, 0.25], matname="CoupNeoHooke (E=200, nu=0.25), EAS mild", tech="TECH_EAS_MILD",
                           flops=63.8e3 + 8 * 4320 + 16146, bytes=2304.0 + 2 * 8 * 324,
-                          kernel="k_hex8_eas_eval_assemble<COUP_NEOHOOKE,STIFF,9>", default_n=100,
+                          kernel="k_hex8_eas_mma_eval_assemble<COUP_NEOHOOKE,STIFF,9> (FP64 tensor cores; option eas_mma=0: k_hex8_eas_eval_assemble)", default_n=100,
                           metric="hex8 EAS (mild) Neo-Hooke element evaluate+assemble (force + tangent stiffness into CSR), FP64"),
     "hex8_eas_full": dict(config="2 mesh, TECH eas_full (SURVEY 8f.1)", cell="HEX8", mat="MAT_COUP_NEOHOOKE",
                           par=[200.0, 0.25], matname="CoupNeoHooke (E=200, nu=0.25), EAS full", tech="TECH_EAS_FULL",
                           flops=63.8e3 + 8 * 13104 + 64890, bytes=2304.0 + 2 * 8 * 1008,
-                          kernel="k_hex8_eas_eval_assemble<COUP_NEOHOOKE,STIFF,21>", default_n=100,
+                          kernel="k_hex8_eas_mma_eval_assemble<COUP_NEOHOOKE,STIFF,21> (FP64 tensor cores; option eas_mma=0: k_hex8_eas_eval_assemble)", default_n=100,
                           metric="hex8 EAS (full) Neo-Hooke element evaluate+assemble (force + tangent stiffness into CSR), FP64"),
     # Section 8(f) row 4: history material on the device Gauss-point state store, KINEM linear hex8 on the config-2
     # mesh.  Model = hex8 model with M = ~150 flops (elastic predictor + return mapping + tangent); bytes add the

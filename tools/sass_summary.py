@@ -1,5 +1,5 @@
 """SASS / resource listing of the element kernels for profiles/: per kernel the counts of the instructions that
-matter for this path (DFMA / DMUL / DADD, LDS / STS, LDGSTS = cp.async, UBLKCP = TMA bulk copy, SYNCS = mbarrier,
+matter for this path (DMMA = FP64 tensor-core mma.sync m8n8k4, DFMA / DMUL / DADD, LDS / STS, LDGSTS = cp.async, UBLKCP = TMA bulk copy, SYNCS = mbarrier,
 RED / ATOM, local-memory LDL / STL = spills, BAR), plus registers / shared memory / stack from the cubin.
     python tools/sass_summary.py > profiles/r02_sass_summary.md        (no GPU needed)"""
 import collections
@@ -14,11 +14,13 @@ WANT = [("hex8 headline <CoupNeoHooke, STIFF>", r"k_hex8_eval_assembleILi0ELb1EL
         ("hex8 headline, TMA map staging", r"k_hex8_eval_assembleILi0ELb1ELi0ELb1E"),
         ("hex8 F-bar", r"k_hex8_eval_assembleILi0ELb1ELi1ELb0E"),
         ("hex8 MAT_VISCONEOHOOKE", r"k_hex8_eval_assembleILi5ELb1ELi0ELb0E"),
-        ("hex8 EAS mild", r"k_hex8_eas_eval_assembleILi0ELb1ELi9E"),
-        ("hex8 EAS full", r"k_hex8_eas_eval_assembleILi0ELb1ELi21E"),
+        ("hex8 EAS mild, tensor-core kernel (default)", r"k_hex8_eas_mma_eval_assembleILi0ELb1ELi9E"),
+        ("hex8 EAS full, tensor-core kernel (default)", r"k_hex8_eas_mma_eval_assembleILi0ELb1ELi21E"),
+        ("hex8 EAS mild, FMA kernel (option eas_mma = 0)", r"k_hex8_eas_eval_assembleILi0ELb1ELi9E"),
+        ("hex8 EAS full, FMA kernel (option eas_mma = 0)", r"k_hex8_eas_eval_assembleILi0ELb1ELi21E"),
         ("tet10 <iso/vol, STIFF>", r"k_tet10_eval_assembleILi1ELb1ELi0E"),
         ("hex27 <SVK, STIFF>", r"k_hex27_eval_assembleILi2ELb1ELi0E")]
-OPS = ["DFMA", "DMUL", "DADD", "MUFU", "LDS", "STS", "LDGSTS", "UBLKCP", "SYNCS", "LDG", "STG", "RED", "ATOM", "LDL", "STL",
+OPS = ["DMMA", "DFMA", "DMUL", "DADD", "MUFU", "LDS", "STS", "LDGSTS", "UBLKCP", "SYNCS", "LDG", "STG", "RED", "ATOM", "LDL", "STL",
        "BAR", "SHFL", "WARPSYNC"]
 
 
