@@ -2220,6 +2220,12 @@ namespace
   {
     switch (ctx->nn)
     {
+      case 5:
+        k_generic_eval_assemble<MAT, 5><<<grid, 64, 0, ctx->stream>>>(Ga);
+        break;
+      case 6:
+        k_generic_eval_assemble<MAT, 6><<<grid, 64, 0, ctx->stream>>>(Ga);
+        break;
       case 4:
         k_generic_eval_assemble<MAT, 4><<<grid, 64, 0, ctx->stream>>>(Ga);
         break;
@@ -2270,12 +2276,17 @@ namespace
     return fail(ctx, B200S_ERR_UNSUPPORTED, "general kernel: material kind %d", ctx->matkind);
   }
 
+  // cell types that only the table-driven general kernel hosts
+  static bool is_general_cell(int ct)
+  {
+    return ct == B200S_TET4 || ct == B200S_HEX20 || ct == B200S_WEDGE6 || ct == B200S_PYRAMID5;
+  }
+
   template <bool STIFF>
   static int launch_eval(b200s_ctx* ctx, const EvalArgs& A)
   {
     if (ctx->matkind < 0) return fail(ctx, B200S_ERR_INVALID, "material not set");
-    if (ctx->general_tangent || ctx->celltype == B200S_TET4 || ctx->celltype == B200S_HEX20)
-      return launch_generic(ctx, A, STIFF);
+    if (ctx->general_tangent || is_general_cell(ctx->celltype)) return launch_generic(ctx, A, STIFF);
     if (ctx->tech != B200S_TECH_NONE && ctx->celltype != B200S_HEX8)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "element technology %d needs hex8", ctx->tech);
     switch (ctx->celltype)
@@ -2431,8 +2442,7 @@ extern "C"
     if (!ctx || !X || !conn || n_col_nodes <= 0 || n_col_eles < 0) return B200S_ERR_INVALID;
     cudaSetDevice(ctx->device);
     if (ctx->primary) detach_shared(ctx);  // a new mesh: attach again afterwards
-    if (celltype != B200S_HEX8 && celltype != B200S_TET10 && celltype != B200S_HEX27 && celltype != B200S_TET4 &&
-        celltype != B200S_HEX20)
+    if (celltype != B200S_HEX8 && celltype != B200S_TET10 && celltype != B200S_HEX27 && !is_general_cell(celltype))
       return fail(ctx, B200S_ERR_UNSUPPORTED, "cell type %d is not on the device path", celltype);
     if (n_col_nodes > INT32_MAX / 3) return fail(ctx, B200S_ERR_INVALID, "too many column nodes");
     const CellTables T = make_cell_tables(celltype);
@@ -2567,8 +2577,8 @@ extern "C"
     // (4C_solid_ele_factory_lib.hpp)
     if (element_technology != B200S_TECH_NONE && ctx->celltype >= 0 && ctx->celltype != B200S_HEX8)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "F-bar and EAS are hex8 technologies");
-    if (prestress_technology != B200S_PRESTRESS_NONE && (ctx->celltype == B200S_TET4 || ctx->celltype == B200S_HEX20))
-      return fail(ctx, B200S_ERR_UNSUPPORTED, "MULF prestress of tet4 / hex20 blocks has no device kernel");
+    if (prestress_technology != B200S_PRESTRESS_NONE && is_general_cell(ctx->celltype))
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "MULF prestress of tet4 / hex20 / wedge6 / pyramid5 blocks has no device kernel");
     ctx->kinem = kinem_type;
     dfree(ctx->d_hist_old);
     const bool eas_fresh = eas_neas(element_technology) != eas_neas(ctx->tech) || !ctx->d_eas_hist;
@@ -3147,6 +3157,12 @@ extern "C"
           break;
         case B200S_HEX20:
           k_mass_assemble<20><<<grid, 128, 0, st>>>(M);
+          break;
+        case B200S_WEDGE6:
+          k_mass_assemble<6><<<grid, 128, 0, st>>>(M);
+          break;
+        case B200S_PYRAMID5:
+          k_mass_assemble<5><<<grid, 128, 0, st>>>(M);
           break;
       }
       ctx->launches += 1;
@@ -4134,6 +4150,8 @@ extern "C"
   {
     if (!ctx || n_faces < 0 || (n_faces > 0 && !face_nodes) || !onoff || !val) return B200S_ERR_INVALID;
     if (ctx->celltype < 0) return fail(ctx, B200S_ERR_INVALID, "set_mesh must precede add_surface_neumann");
+    if (ctx->face_nn == 0)
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "surface loads on wedge6 / pyramid5 blocks (two surface shapes) have no device kernel");
     if (neumann_type < B200S_NEUMANN_LIVE || neumann_type > B200S_NEUMANN_ORTHOPRESSURE)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "Unknown type of SurfaceNeumann condition");
     if (neumann_type != B200S_NEUMANN_LIVE && (onoff[0] != 1 || onoff[1] != 0 || onoff[2] != 0))

@@ -88,6 +88,33 @@ namespace b200s
           dN[3 * k + 2] = L[0][a] * L[1][b] * dL[2][e];
         }
       }
+      else if (celltype == 5)
+      {
+        // wedge6 (:877-903): triangle coordinates r, s, 1 - r - s times (1 -+ t) / 2
+        const double tri[3] = {r, s, 1.0 - r - s}, dr[3] = {1.0, 0.0, -1.0}, ds[3] = {0.0, 1.0, -1.0};
+        for (int k = 0; k < 6; ++k)
+        {
+          const double sg = k < 3 ? -1.0 : 1.0, lin = 0.5 * (1.0 + sg * t);
+          dN[3 * k + 0] = dr[k % 3] * lin, dN[3 * k + 1] = ds[k % 3] * lin, dN[3 * k + 2] = 0.5 * sg * tri[k % 3];
+        }
+      }
+      else if (celltype == 6)
+      {
+        // pyramid5 (:976-1018): bilinear base minus t plus / minus the rational term r s t / (1 - t); at the apex the
+        // reference replaces the three derivatives of that term by 1
+        const bool apex = !(std::fabs(t - 1.0) > 1e-14);
+        const double qr = apex ? 1.0 : s * t / (1.0 - t), qs = apex ? 1.0 : r * t / (1.0 - t),
+                     qt = apex ? 1.0 : r * s / ((1.0 - t) * (1.0 - t));
+        const double c[4][2] = {{-1, -1}, {1, -1}, {1, 1}, {-1, 1}};
+        for (int k = 0; k < 4; ++k)
+        {
+          const double sg = c[k][0] * c[k][1];
+          dN[3 * k + 0] = 0.25 * (c[k][0] * (1.0 + c[k][1] * s) + sg * qr);
+          dN[3 * k + 1] = 0.25 * (c[k][1] * (1.0 + c[k][0] * r) + sg * qs);
+          dN[3 * k + 2] = 0.25 * (sg * qt - 1.0);
+        }
+        dN[12] = 0.0, dN[13] = 0.0, dN[14] = 1.0;
+      }
       else if (celltype == 3)
       {
         // tet4 (4C_fem_general_utils_fem_shapefunctions.hpp:813-830)
@@ -164,6 +191,18 @@ namespace b200s
       {
         N[0] = 1.0 - r - s - t, N[1] = r, N[2] = s, N[3] = t;  // tet4 (:239-251)
       }
+      else if (celltype == 5)
+      {
+        const double tri[3] = {r, s, 1.0 - r - s};  // wedge6 (:268-279)
+        for (int k = 0; k < 6; ++k) N[k] = tri[k % 3] * 0.5 * (k < 3 ? 1.0 - t : 1.0 + t);
+      }
+      else if (celltype == 6)
+      {
+        const double q = !(std::fabs(t - 1.0) > 1e-14) ? 0.0 : r * s * t / (1.0 - t);  // pyramid5 (:320-348)
+        const double c[4][2] = {{-1, -1}, {1, -1}, {1, 1}, {-1, 1}};
+        for (int k = 0; k < 4; ++k) N[k] = 0.25 * ((1.0 + c[k][0] * r) * (1.0 + c[k][1] * s) - t + c[k][0] * c[k][1] * q);
+        N[4] = t;
+      }
       else if (celltype == 4)
       {
         const double(*c)[3] = hex_nodes();  // hex20 (:146-197)
@@ -199,8 +238,10 @@ namespace b200s
     CellTables T;
     // celltype 0 hex8, 1 hex27, 2 tet10, 3 tet4, 4 hex20; stiffness rules hex_8point, hex_27point (hex27 and hex20),
     // tet_4point (tet10), tet_1point (tet4) (4C_solid_ele_calc_lib_integration.hpp:43-64)
-    T.nn = celltype == 0 ? 8 : (celltype == 1 ? 27 : (celltype == 3 ? 4 : (celltype == 4 ? 20 : 10)));
-    T.ngp = celltype == 0 ? 8 : ((celltype == 1 || celltype == 4) ? 27 : (celltype == 3 ? 1 : 4));
+    // 5 wedge6 (wedge_6point), 6 pyramid5 (pyramid_8point): DisTypeToOptGaussRule for stiffness and mass
+    // (4C_fem_general_element_integration_select.hpp:68-82)
+    T.nn = celltype == 0 ? 8 : (celltype == 1 ? 27 : (celltype == 3 ? 4 : (celltype == 4 ? 20 : (celltype == 5 ? 6 : (celltype == 6 ? 5 : 10)))));
+    T.ngp = celltype == 0 ? 8 : ((celltype == 1 || celltype == 4) ? 27 : (celltype == 3 ? 1 : (celltype == 5 ? 6 : (celltype == 6 ? 8 : 4))));
     std::vector<double> gxi(3 * T.ngp);
     T.w.resize(T.ngp);
     const double(*hc)[3] = detail::hex_nodes();
@@ -217,6 +258,28 @@ namespace b200s
     {
       gxi[0] = gxi[1] = gxi[2] = 0.25;  // tet_1point (4C_fem_general_utils_integration.cpp:322-330)
       T.w[0] = 1.0 / 6.0;
+    }
+    else if (celltype == 5)
+    {
+      // wedge_6point (:5992-6026): the 3-point triangle rule at t = +-1/sqrt(3)
+      const double g = 1.0 / std::sqrt(3.0), a = 2.0 / 3.0, b = 1.0 / 6.0;
+      const double tri[3][2] = {{a, b}, {b, a}, {b, b}};
+      for (int q = 0; q < 6; ++q)
+      {
+        gxi[3 * q] = tri[q % 3][0], gxi[3 * q + 1] = tri[q % 3][1], gxi[3 * q + 2] = q < 3 ? g : -g;
+        T.w[q] = b;
+      }
+    }
+    else if (celltype == 6)
+    {
+      // pyramid_8point (:6092-6132), decimals as the reference has them
+      const double a1 = 0.26318405556971, a2 = 0.50661630334979, t1 = 0.54415184401122, t2 = 0.12251482265544;
+      for (int q = 0; q < 8; ++q)
+      {
+        const double a = (q & 1) ? a2 : a1;
+        gxi[3 * q] = q < 4 ? -a : a, gxi[3 * q + 1] = (q & 2) ? a : -a, gxi[3 * q + 2] = (q & 1) ? t2 : t1;
+        T.w[q] = (q & 1) ? 0.23254745125351 : 0.10078588207983;
+      }
     }
     else if (celltype == 1 || celltype == 4)
     {
@@ -242,7 +305,12 @@ namespace b200s
     T.dN_gp.resize((size_t)T.ngp * T.nn * 3);
     for (int q = 0; q < T.ngp; ++q) detail::deriv1(celltype, &gxi[3 * q], &T.dN_gp[(size_t)q * T.nn * 3]);
     T.dN_node.resize((size_t)T.nn * T.nn * 3);
-    const double(*nc)[3] = (celltype == 2 || celltype == 3) ? detail::tet_nodes() : hc;
+    // nodal parameter coordinates as the reference tabulates them (4C_fem_general_utils_local_connectivity_matrices.hpp:
+    // wedge6 reads the first rows of the wedge18 table :321-325, pyramid5 :318-319)
+    static const double wedge_nodes[6][3] = {{0, 0, -1}, {1, 0, -1}, {0, 1, -1}, {0, 0, 1}, {1, 0, 1}, {0, 1, 1}};
+    static const double pyramid_nodes[5][3] = {{-1, -1, 0}, {1, -1, 0}, {1, 1, 0}, {-1, 1, 0}, {0, 0, 1}};
+    const double(*nc)[3] = (celltype == 2 || celltype == 3) ? detail::tet_nodes()
+                           : (celltype == 5 ? wedge_nodes : (celltype == 6 ? pyramid_nodes : hc));
     for (int k = 0; k < T.nn; ++k) detail::deriv1(celltype, nc[k], &T.dN_node[(size_t)k * T.nn * 3]);
     T.xi_gp = gxi;
     T.N_gp.resize((size_t)T.ngp * T.nn);
@@ -280,9 +348,11 @@ namespace b200s
       detail::shape0(celltype, &mxi[3 * q], &T.N_mass[(size_t)q * T.nn]);
       detail::deriv1(celltype, &mxi[3 * q], &T.dN_mass[(size_t)q * T.nn * 3]);
     }
-    const double cen_hex[3] = {0.0, 0.0, 0.0}, cen_tet[3] = {0.25, 0.25, 0.25};
+    const double cen_hex[3] = {0.0, 0.0, 0.0}, cen_tet[3] = {0.25, 0.25, 0.25}, cen_wedge[3] = {1.0 / 3.0, 1.0 / 3.0, 0.0},
+                 cen_pyramid[3] = {0.0, 0.0, 0.25};
     T.dN_cen.resize((size_t)T.nn * 3);
-    detail::deriv1(celltype, (celltype == 2 || celltype == 3) ? cen_tet : cen_hex, T.dN_cen.data());
+    detail::deriv1(celltype, (celltype == 2 || celltype == 3) ? cen_tet : (celltype == 5 ? cen_wedge : (celltype == 6 ? cen_pyramid : cen_hex)),
+        T.dN_cen.data());
     return T;
   }
   // Surface cells of the three solid cell types (hex8 -> quad4, hex27 -> quad9, tet10 -> tri6) at the
@@ -299,6 +369,7 @@ namespace b200s
   inline FaceTables make_face_tables(int celltype)
   {
     FaceTables T;
+    if (celltype == 5 || celltype == 6) return T;  // wedge6 / pyramid5 have two surface shapes: no single face table
     std::vector<double> xi;
     if (celltype == 0)
     {

@@ -35,7 +35,8 @@ namespace B200Solid
 
   bool DeviceElementBlock::supported(int celltype, int kinem, int tech, int prestress, int material_kind)
   {
-    const bool general_cell = celltype == B200S_TET4 || celltype == B200S_HEX20;  // general kernel: displacement based only
+    // general kernel: displacement based only
+    const bool general_cell = celltype == B200S_TET4 || celltype == B200S_HEX20 || celltype == B200S_WEDGE6 || celltype == B200S_PYRAMID5;
     const bool cell = celltype == B200S_HEX8 || celltype == B200S_HEX27 || celltype == B200S_TET10 || general_cell;
     if (!cell) return false;
     if (general_cell && (tech != B200S_TECH_NONE || prestress != B200S_PRESTRESS_NONE)) return false;

@@ -9,8 +9,8 @@ seeded permutation (config 4).
 """
 import numpy as np
 
-HEX8, HEX27, TET10, TET4, HEX20 = 0, 1, 2, 3, 4
-NODES = {HEX8: 8, HEX27: 27, TET10: 10, TET4: 4, HEX20: 20}
+HEX8, HEX27, TET10, TET4, HEX20, WEDGE6, PYRAMID5 = 0, 1, 2, 3, 4, 5, 6
+NODES = {HEX8: 8, HEX27: 27, TET10: 10, TET4: 4, HEX20: 20, WEDGE6: 6, PYRAMID5: 5}
 
 # node order of hex27 in parameter space (first 8 = hex8);
 # 4C_fem_general_utils_local_connectivity_matrices.hpp:291
@@ -120,6 +120,37 @@ def structured_hex20(n, box=(1.0, 1.0, 1.0)):
     new = np.full(len(X27), -1, np.int64)
     new[used] = np.arange(len(used))
     return X27[used], new[c].astype(np.int32)
+
+
+def structured_wedge6(n, box=(1.0, 1.0, 1.0), jitter=0.15, seed=77):
+    """Every cell of the structured hex8 grid split into two wedges along the diagonal of its bottom face (node order of
+    the wedge6 shape functions: bottom triangle, then the top triangle above it), interior nodes jittered."""
+    X, c8 = structured_hex(HEX8, n, box)
+    X = _jitter_interior(X, n, box, jitter, seed)
+    w = np.concatenate([c8[:, [0, 1, 2, 4, 5, 6]], c8[:, [0, 2, 3, 4, 6, 7]]])
+    return X, np.ascontiguousarray(w, np.int32)
+
+
+def structured_pyramid5(n, box=(1.0, 1.0, 1.0), jitter=0.15, seed=78):
+    """Every cell of the structured hex8 grid split into six pyramids with the cell centre as the apex; the base
+    quadrilaterals are ordered so that the mapping has a positive Jacobian (outward faces of the hex8 seen from the apex)."""
+    X, c8 = structured_hex(HEX8, n, box)
+    X = _jitter_interior(X, n, box, jitter, seed)
+    cen = X[c8].mean(axis=1)
+    apex = len(X) + np.arange(len(c8))
+    faces = [[0, 1, 2, 3], [4, 7, 6, 5], [0, 4, 5, 1], [1, 5, 6, 2], [2, 6, 7, 3], [3, 7, 4, 0]]
+    p = np.concatenate([np.column_stack([c8[:, f], apex]) for f in faces])
+    return np.concatenate([X, cen]), np.ascontiguousarray(p, np.int32)
+
+
+def _jitter_interior(X, n, box, jitter, seed):
+    n = (n,) * 3 if np.isscalar(n) else tuple(n)
+    h = np.array(box, float) / np.array(n, float)
+    rng = np.random.default_rng(seed)
+    X = X.copy()
+    inner = np.all((X > 1e-12) & (X < np.array(box) - 1e-12), axis=1)
+    X[inner] += jitter * h * rng.uniform(-1, 1, (int(inner.sum()), 3))
+    return X
 
 
 def _hash_uniform(idx, seed):

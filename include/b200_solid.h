@@ -47,7 +47,9 @@ extern "C"
      * 4C_solid_ele_factory.hpp:36-38,79-89) run through the table-driven general kernel (no specialised
      * fast kernel; KINEM nonlinear / linear, every material kind, no element technology / prestress): */
     B200S_TET4 = 3, /* tet_1point stiffness rule, tet_4point mass rule */
-    B200S_HEX20 = 4 /* hex_27point */
+    B200S_HEX20 = 4, /* hex_27point */
+    B200S_WEDGE6 = 5,  /* wedge_6point; general kernel, no surface loads (two surface shapes) */
+    B200S_PYRAMID5 = 6 /* pyramid_8point, the reference's rational shape functions; general kernel, no surface loads */
   } b200s_celltype;
 
   /* Mat::So3Material implementations on the device path (Core::Materials::MaterialType):

@@ -12,7 +12,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-HEX8, HEX27, TET10, TET4, HEX20 = 0, 1, 2, 3, 4
+HEX8, HEX27, TET10, TET4, HEX20, WEDGE6, PYRAMID5 = 0, 1, 2, 3, 4, 5, 6
 MAT_COUP_NEOHOOKE, MAT_ISO_VOL, MAT_SVK, MAT_ELASTHYPER, MAT_DRUCKER_PRAGER, MAT_VISCONEOHOOKE = 0, 1, 2, 3, 4, 5
 DP_HIST = 14  # {strainpllast[6], strainbarpllast, strainplcurr[6], strainbarplcurr} per Gauss point
 VISCO_HIST = 24  # {histstresslast[6], artstresslast[6], histstresscurr[6], artstresscurr[6]} per Gauss point

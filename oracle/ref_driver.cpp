@@ -331,6 +331,10 @@ extern "C"
       run.template operator()<CT::tet4>();
     else if (ct == 4)
       run.template operator()<CT::hex20>();
+    else if (ct == 5)
+      run.template operator()<CT::wedge6>();
+    else if (ct == 6)
+      run.template operator()<CT::pyramid5>();
     else
       run.template operator()<CT::tet10>();
   }
@@ -354,6 +358,10 @@ extern "C"
       run.template operator()<CT::tet4>();
     else if (ct == 4)
       run.template operator()<CT::hex20>();
+    else if (ct == 5)
+      run.template operator()<CT::wedge6>();
+    else if (ct == 6)
+      run.template operator()<CT::pyramid5>();
     else
       run.template operator()<CT::tet10>();
   }
@@ -375,6 +383,8 @@ extern "C"
     if (ct == 1) return element<CT::hex27>(matkind, par, action, X, u, gxi, gw, ngp, Ke, fe);
     if (ct == 3) return element<CT::tet4>(matkind, par, action, X, u, gxi, gw, ngp, Ke, fe);
     if (ct == 4) return element<CT::hex20>(matkind, par, action, X, u, gxi, gw, ngp, Ke, fe);
+    if (ct == 5) return element<CT::wedge6>(matkind, par, action, X, u, gxi, gw, ngp, Ke, fe);
+    if (ct == 6) return element<CT::pyramid5>(matkind, par, action, X, u, gxi, gw, ngp, Ke, fe);
     return element<CT::tet10>(matkind, par, action, X, u, gxi, gw, ngp, Ke, fe);
   }
 
@@ -489,6 +499,10 @@ extern "C"
       run.template operator()<CT::tet4>();
     else if (ct == 4)
       run.template operator()<CT::hex20>();
+    else if (ct == 5)
+      run.template operator()<CT::wedge6>();
+    else if (ct == 6)
+      run.template operator()<CT::pyramid5>();
     else
       run.template operator()<CT::tet10>();
   }

@@ -29,21 +29,35 @@ namespace
   const double tet10_ref[10][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0.5, 0, 0},
       {0.5, 0.5, 0}, {0, 0.5, 0}, {0, 0, 0.5}, {0.5, 0, 0.5}, {0, 0.5, 0.5}};
 
+  // wedge6 / pyramid5: nodal parameter coordinates as the reference tabulates them
+  // (4C_fem_general_utils_local_connectivity_matrices.hpp:318-325,564-598: wedge6 reads the first six rows of the wedge18
+  // table, whose corner order (0,0),(1,0),(0,1) is NOT the order of the wedge6 shape functions r, s, 1-r-s -- the
+  // nodal Jacobian check therefore visits the corners in a permuted order, which changes nothing for the check)
+  const double wedge6_ref[6][3] = {{0, 0, -1}, {1, 0, -1}, {0, 1, -1}, {0, 0, 1}, {1, 0, 1}, {0, 1, 1}};
+  const double pyramid5_ref[5][3] = {{-1, -1, 0}, {1, -1, 0}, {1, 1, 0}, {-1, 1, 0}, {0, 0, 1}};
+
   int nnodes(int ct)
   {
+    if (ct == ORC_WEDGE6) return 6;
+    if (ct == ORC_PYRAMID5) return 5;
     return ct == ORC_HEX8 ? 8 : (ct == ORC_HEX27 ? 27 : (ct == ORC_TET4 ? 4 : (ct == ORC_HEX20 ? 20 : 10)));
   }
   // stiffness rule (get_gauss_rule_stiffness_matrix, 4C_solid_ele_calc_lib_integration.hpp:43-64): hex_8point,
   // hex_27point (hex27 AND hex20), tet_4point (tet10), tet_1point (tet4)
+  // wedge6: wedge_6point, pyramid5: pyramid_8point (DisTypeToOptGaussRule,
+  // 4C_fem_general_element_integration_select.hpp:68-82), for stiffness and mass
   int ngauss(int ct)
   {
+    if (ct == ORC_WEDGE6) return 6;
+    if (ct == ORC_PYRAMID5) return 8;
     return ct == ORC_HEX8 ? 8 : ((ct == ORC_HEX27 || ct == ORC_HEX20) ? 27 : (ct == ORC_TET4 ? 1 : 4));
   }
 
   void node_ref(int ct, int k, double* xi)
   {
     // hex8 / hex20 = first 8 / 20 of hex27, tet4 = first 4 of tet10
-    const double* p = (ct == ORC_TET10 || ct == ORC_TET4) ? tet10_ref[k] : hex27_ref[k];
+    const double* p = (ct == ORC_TET10 || ct == ORC_TET4) ? tet10_ref[k]
+                      : (ct == ORC_WEDGE6 ? wedge6_ref[k] : (ct == ORC_PYRAMID5 ? pyramid5_ref[k] : hex27_ref[k]));
     xi[0] = p[0], xi[1] = p[1], xi[2] = p[2];
   }
 
@@ -84,6 +98,40 @@ namespace
         dN[1 + 3 * k] = Lr[a] * Lt[c] * dLs[b];
         dN[2 + 3 * k] = Lr[a] * Ls[b] * dLt[c];
       }
+    }
+    else if (ct == ORC_WEDGE6)
+    {
+      // linear wedge (shapefunctions.hpp:268-279, 877-903): triangle coordinates r, s, 1-r-s times (1 -+ t)/2
+      const double tri[3] = {r, s, 1.0 - r - s};
+      const double dtri[3][2] = {{1, 0}, {0, 1}, {-1, -1}};
+      for (int k = 0; k < 6; ++k)
+      {
+        const int c = k % 3;
+        const double sg = k < 3 ? -1.0 : 1.0, lin = 0.5 * (1.0 + sg * t);
+        N[k] = tri[c] * lin;
+        dN[0 + 3 * k] = dtri[c][0] * lin;
+        dN[1 + 3 * k] = dtri[c][1] * lin;
+        dN[2 + 3 * k] = 0.5 * sg * tri[c];
+      }
+    }
+    else if (ct == ORC_PYRAMID5)
+    {
+      // pyramid with the rational term r s t / (1 - t) (shapefunctions.hpp:320-348, 976-1018); at the apex (|t - 1| <= 1e-14)
+      // the reference sets the term to 0 in the functions and its three derivatives to 1
+      const bool apex = !(std::fabs(t - 1.0) > 1e-14);
+      const double q = apex ? 0.0 : r * s * t / (1.0 - t);
+      const double qr = apex ? 1.0 : s * t / (1.0 - t), qs = apex ? 1.0 : r * t / (1.0 - t),
+                   qt = apex ? 1.0 : r * s / ((1.0 - t) * (1.0 - t));
+      for (int k = 0; k < 4; ++k)
+      {
+        const double rk = pyramid5_ref[k][0], sk = pyramid5_ref[k][1], sg = rk * sk;  // +1, -1, +1, -1
+        N[k] = 0.25 * ((1.0 + rk * r) * (1.0 + sk * s) - t + sg * q);
+        dN[0 + 3 * k] = 0.25 * (rk * (1.0 + sk * s) + sg * qr);
+        dN[1 + 3 * k] = 0.25 * (sk * (1.0 + rk * r) + sg * qs);
+        dN[2 + 3 * k] = 0.25 * (sg * qt - 1.0);
+      }
+      N[4] = t;
+      dN[0 + 12] = 0.0, dN[1 + 12] = 0.0, dN[2 + 12] = 1.0;
     }
     else if (ct == ORC_TET4)
     {
@@ -158,6 +206,31 @@ namespace
       {
         for (int d = 0; d < 3; ++d) xi[3 * q + d] = hex27_ref[q][d] * g;
         w[q] = 1.0;
+      }
+    }
+    else if (ct == ORC_WEDGE6)
+    {
+      // wedge_6point (4C_fem_general_utils_integration.cpp:5992-6026): the 3-point triangle rule at t = +-1/sqrt(3)
+      const double g = 1.0 / std::sqrt(3.0), a = 2.0 / 3.0, b = 1.0 / 6.0;
+      const double T[3][2] = {{a, b}, {b, a}, {b, b}};
+      for (int q = 0; q < 6; ++q)
+      {
+        xi[3 * q] = T[q % 3][0], xi[3 * q + 1] = T[q % 3][1], xi[3 * q + 2] = q < 3 ? g : -g;
+        w[q] = b;
+      }
+    }
+    else if (ct == ORC_PYRAMID5)
+    {
+      // pyramid_8point (4C_fem_general_utils_integration.cpp:6092-6132), decimals as tabulated there
+      const double a1 = 0.26318405556971, a2 = 0.50661630334979, t1 = 0.54415184401122, t2 = 0.12251482265544;
+      const double w1 = 0.10078588207983, w2 = 0.23254745125351;
+      for (int q = 0; q < 8; ++q)
+      {
+        const double a = (q & 1) ? a2 : a1;
+        xi[3 * q] = (q < 4 ? -a : a);
+        xi[3 * q + 1] = ((q & 2) ? a : -a);
+        xi[3 * q + 2] = (q & 1) ? t2 : t1;
+        w[q] = (q & 1) ? w2 : w1;
       }
     }
     else if (ct == ORC_TET4)

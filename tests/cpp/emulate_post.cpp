@@ -179,6 +179,8 @@ static int run_generic_nn(const GenericArgs& Ga)
   switch (Ga.nn)
   {
     case 4: return run_generic<MAT, 4>(Ga);
+    case 5: return run_generic<MAT, 5>(Ga);
+    case 6: return run_generic<MAT, 6>(Ga);
     case 8: return run_generic<MAT, 8>(Ga);
     case 10: return run_generic<MAT, 10>(Ga);
     case 20: return run_generic<MAT, 20>(Ga);

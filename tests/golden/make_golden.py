@@ -50,6 +50,8 @@ CASES = {
     "tet10": "tests/input_files/solid_ele_tet10_Standard_stressout.4C.yaml",
     "tet4": "tests/input_files/solid_ele_tet4_Standard_stressout.4C.yaml",
     "hex20": "tests/input_files/solid_ele_hex20_Standard_stressout.4C.yaml",
+    "wedge6": "tests/input_files/solid_ele_wedge6_Standard_stressout.4C.yaml",
+    "pyramid5": "tests/input_files/solid_ele_pyramid5_Standard_stressout.4C.yaml",
 }
 
 
@@ -468,7 +470,8 @@ def ref_elements():
     mats = {orc.MAT_COUP_NEOHOOKE: [200.0, 0.25], orc.MAT_ISO_VOL: [1.0, 1000.0],
             orc.MAT_SVK: [1000.0, 0.3]}
     # (new cells are appended so that the random stream of the earlier fixtures stays what it was)
-    for ct, name in ((orc.HEX8, "hex8"), (orc.HEX27, "hex27"), (orc.TET10, "tet10"), (orc.TET4, "tet4"), (orc.HEX20, "hex20")):
+    for ct, name in ((orc.HEX8, "hex8"), (orc.HEX27, "hex27"), (orc.TET10, "tet10"), (orc.TET4, "tet4"), (orc.HEX20, "hex20"),
+                     (orc.WEDGE6, "wedge6"), (orc.PYRAMID5, "pyramid5")):
         n = orc.num_nodes(ct)
         X = orc.node_param_coords(ct) * np.array([1.0, 1.1, 1.2]) + 0.05 * rng.uniform(-1, 1, (n, 3))
         u = 0.04 * rng.uniform(-1, 1, (n, 3))

@@ -16,7 +16,12 @@ HEX27_FACES = [[0, 3, 2, 1, 11, 10, 9, 8, 20], [0, 1, 5, 4, 8, 13, 16, 12, 21],
 TET10_FACES = [[0, 1, 3, 4, 8, 7], [1, 2, 3, 5, 9, 8], [0, 3, 2, 7, 9, 6], [0, 2, 1, 6, 5, 4]]
 TET4_FACES = [f[:3] for f in TET10_FACES]     # tri3: the corners of the tri6 faces
 HEX20_FACES = [f[:8] for f in HEX27_FACES]    # quad8: corners + mid-edge nodes of the quad9 faces
-FACES = {"hex8": HEX8_FACES, "hex27": HEX27_FACES, "tet10": TET10_FACES, "tet4": TET4_FACES, "hex20": HEX20_FACES}
+# wedge6: three quad4 then two tri3 surfaces, pyramid5: the quad4 base then four tri3 surfaces
+# (4C_fem_general_utils_local_connectivity_matrices.hpp:68-86, .cpp:697-765: first corners of the wedge18 tables)
+WEDGE6_FACES = [[0, 1, 4, 3], [1, 2, 5, 4], [2, 0, 3, 5], [2, 1, 0], [5, 3, 4]]
+PYRAMID5_FACES = [[0, 3, 2, 1], [0, 1, 4], [1, 2, 4], [2, 3, 4], [0, 4, 3]]
+FACES = {"hex8": HEX8_FACES, "hex27": HEX27_FACES, "tet10": TET10_FACES, "tet4": TET4_FACES, "hex20": HEX20_FACES,
+         "wedge6": WEDGE6_FACES, "pyramid5": PYRAMID5_FACES}
 
 
 def _quad4(r, s):
@@ -137,9 +142,8 @@ def _surface_neumann_load(case, time):
     cell = case["celltype"]
     X = np.asarray(case["coords"], float)
     nset = set(case["neumann_nodes"])
-    kind, fn = {"hex8": ("quad4", _quad4), "hex27": ("quad9", _quad9), "tet10": ("tri6", _tri6),
-                "tet4": ("tri3", _tri3), "hex20": ("quad8", _quad8)}[cell]
-    gx, gw = _rule(kind)
+    kinds = {"hex8": ("quad4", _quad4), "hex27": ("quad9", _quad9), "tet10": ("tri6", _tri6),
+             "tet4": ("tri3", _tri3), "hex20": ("quad8", _quad8)}
     val, onoff, funct = case["neumann"]["VAL"], case["neumann"]["ONOFF"], case["neumann"]["FUNCT"]
     assert case["neumann"]["FUNCT1"] == "t"
     assert case["neumann"]["FUNCT2"] in ("(x+1)*(y+2)*(z+3)", None)
@@ -150,6 +154,8 @@ def _surface_neumann_load(case, time):
             if not all(i in nset for i in ids):
                 continue
             x = X[ids]
+            kind, fn = kinds[cell] if cell in kinds else (("tri3", _tri3) if len(face) == 3 else ("quad4", _quad4))
+            gx, gw = _rule(kind)
             for (r, s), w in zip(gx, gw):
                 N, dN = fn(r, s)
                 dx = dN @ x  # (2,3)

@@ -1,4 +1,4 @@
-"""tet4 and hex20 displacement-based blocks (create_solid_calculation_interface instantiates them next to hex8 / hex27 /
+"""tet4, hex20, wedge6 and pyramid5 displacement-based blocks (create_solid_calculation_interface instantiates them next to hex8 / hex27 /
 tet10, src/solid_ele/4C_solid_ele_factory.hpp:36-38,79-89): on the device they run through the table-driven general
 kernel (generic_kernel.cuh).  Oracle pins: shape functions vs the reference's own headers, element matrices vs
 oracle/_ref fixtures and the RESULT DESCRIPTION displacements of solid_ele_tet4_Standard_stressout.4C.yaml /
@@ -20,11 +20,17 @@ def _mesh(cell):
     if cell == "tet4":
         X, conn = b200.mesh.unstructured_tet4(3)
         return orc.TET4, b200.partition.serial_mesh(b200.mesh.TET4, X, conn), 1.0 / 3
+    if cell == "wedge6":
+        X, conn = b200.mesh.structured_wedge6((3, 2, 2))
+        return orc.WEDGE6, b200.partition.serial_mesh(b200.mesh.WEDGE6, X, conn), 1.0 / 3
+    if cell == "pyramid5":
+        X, conn = b200.mesh.structured_pyramid5((2, 2, 2))
+        return orc.PYRAMID5, b200.partition.serial_mesh(b200.mesh.PYRAMID5, X, conn), 0.25
     X, conn = b200.mesh.structured_hex20((2, 2, 1))
     return orc.HEX20, b200.partition.serial_mesh(b200.mesh.HEX20, X, conn), 0.5
 
 
-@pytest.mark.parametrize("cell", ["tet4", "hex20"])
+@pytest.mark.parametrize("cell", ["tet4", "hex20", "wedge6", "pyramid5"])
 @pytest.mark.parametrize("mk", list(MATS))
 @pytest.mark.parametrize("linear", [False, True])
 def test_emulated_general_kernel_matches_oracle(cell, mk, linear):

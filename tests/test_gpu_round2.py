@@ -509,11 +509,17 @@ def _general_mesh(cell, n=None):
     if cell == "tet4":
         X, conn = b200.mesh.unstructured_tet4(n or 5)
         return orc.TET4, b200.partition.serial_mesh(b200.mesh.TET4, X, conn), 1.0 / (n or 5)
+    if cell == "wedge6":
+        X, conn = b200.mesh.structured_wedge6(n or (5, 4, 3))
+        return orc.WEDGE6, b200.partition.serial_mesh(b200.mesh.WEDGE6, X, conn), 0.25
+    if cell == "pyramid5":
+        X, conn = b200.mesh.structured_pyramid5(n or (4, 3, 3))
+        return orc.PYRAMID5, b200.partition.serial_mesh(b200.mesh.PYRAMID5, X, conn), 0.25
     X, conn = b200.mesh.structured_hex20(n or (4, 3, 3))
     return orc.HEX20, b200.partition.serial_mesh(b200.mesh.HEX20, X, conn), 0.3
 
 
-@pytest.mark.parametrize("cell", ["tet4", "hex20"])
+@pytest.mark.parametrize("cell", ["tet4", "hex20", "wedge6", "pyramid5"])
 @pytest.mark.parametrize("mk", list(GEN_MATS))
 @pytest.mark.parametrize("kinem", [capi.KINEM_NONLINEAR_TOTLAG, capi.KINEM_LINEAR])
 def test_tet4_hex20_match_oracle(cell, mk, kinem):
@@ -535,7 +541,7 @@ def test_tet4_hex20_match_oracle(cell, mk, kinem):
     asm.close()
 
 
-@pytest.mark.parametrize("cell", ["tet4", "hex20"])
+@pytest.mark.parametrize("cell", ["tet4", "hex20", "wedge6", "pyramid5"])
 def test_tet4_hex20_mass_stress_energy(cell):
     ct, rm, h = _general_mesh(cell)
     u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, h)
@@ -566,16 +572,16 @@ def test_tet4_hex20_mass_stress_energy(cell):
     asm.close()
 
 
-@pytest.mark.parametrize("cell", ["tet4", "hex20"])
+@pytest.mark.parametrize("cell", ["tet4", "hex20", "wedge6", "pyramid5"])
 def test_reference_tet4_hex20_known_answers_through_cuda_path(cell):
-    """RESULT DESCRIPTION displacements of tests/input_files/solid_ele_{tet4,hex20}_Standard_stressout.4C.yaml."""
+    """RESULT DESCRIPTION displacements of tests/input_files/solid_ele_{tet4,hex20,wedge6,pyramid5}_Standard_stressout.4C.yaml."""
     import json
     import os
     from tests.helpers.newton import solve_case
     case = json.load(open(os.path.join(os.path.dirname(__file__), "golden", f"integration_{cell}.json")))
     X = np.asarray(case["coords"], float)
     conn = np.asarray(case["elements"], np.int32)
-    rm = b200.partition.serial_mesh(b200.mesh.TET4 if cell == "tet4" else b200.mesh.HEX20, X, conn)
+    rm = b200.partition.serial_mesh(getattr(b200.mesh, cell.upper()), X, conn)
     mat = case["material"]
     asm = b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, [mat["YOUNG"], mat["NUE"]])
     rowptr, colind = asm.graph()
@@ -637,3 +643,18 @@ def test_eas_tensor_core_kernel_matches_fma_kernel_and_oracle(tech, otech, mk):
     assert ok, (wK, wf)
     h1, h0 = res[1][2].reshape(ohist.shape), res[0][2].reshape(ohist.shape)
     assert np.abs(h1 - h0).max() <= 1e-8 * np.abs(h0).max()
+
+
+def test_wedge6_pyramid5_surface_loads_are_refused():
+    """Cells with two surface shapes have no face table on the device: the library says so instead of integrating a
+    wrong shape (volume loads work)."""
+    ct, rm, h = _general_mesh("wedge6", (2, 2, 2))
+    asm = b200.DeviceAssembler(rm, capi.MAT_SVK, [1000.0, 0.3])
+    with pytest.raises(capi.B200SolidError) as ei:
+        asm.add_surface_neumann("live", np.zeros((1, 4), np.int32), [1, 0, 0], [1.0, 0.0, 0.0])
+    assert ei.value.code == capi.ERR_UNSUPPORTED
+    c = asm.add_volume_neumann([1, 0, 0], [1.0, 0.0, 0.0])
+    asm.ctx.set_neumann_factors(c, [1.0, 1.0, 1.0])
+    f = asm.evaluate_neumann()
+    assert abs(f.reshape(-1, 3)[:, 0].sum() - 1.0) < 1e-12   # unit cube, unit body force
+    asm.close()
