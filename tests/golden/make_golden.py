@@ -55,7 +55,11 @@ CASES = {
 }
 
 
-def integration_case(cell, rel):
+# KINEM linear + MAT_Struct_StVenantKirchhoff: the reference's own small-strain ctest inputs
+LINEAR_CELLS = ("hex8", "hex20", "hex27", "tet4", "pyramid5")
+
+
+def integration_case(cell, rel, linear=False):
     with open(os.path.join(REF, rel)) as fh:
         y = yaml.safe_load(fh)
     nodes = {}
@@ -73,16 +77,19 @@ def integration_case(cell, rel):
         while tok[k] != "MAT":
             conn.append(int(tok[k]) - 1)
             k += 1
-        assert "nonlinear" in line
+        assert ("KINEM nonlinear" in line) != linear and ("KINEM linear" in line) == linear
         eles.append(conn)
     surf = {1: [], 2: []}
     for line in y["DSURF-NODE TOPOLOGY"]:
         m = re.match(r"NODE\s+(\d+)\s+DSURFACE\s+(\d+)", line)
         surf[int(m.group(2))].append(int(m.group(1)) - 1)
     mats = {m["MAT"]: m for m in y["MATERIALS"]}
-    eh = mats[1]["MAT_ElastHyper"]
-    assert eh["NUMMAT"] == 1
-    nh = mats[eh["MATIDS"][0]]["ELAST_CoupNeoHooke"]
+    if "MAT_Struct_StVenantKirchhoff" in mats[1]:  # the *_Standard_linear inputs
+        matkind, nh = "MAT_Struct_StVenantKirchhoff", mats[1]["MAT_Struct_StVenantKirchhoff"]
+    else:
+        eh = mats[1]["MAT_ElastHyper"]
+        assert eh["NUMMAT"] == 1
+        matkind, nh = "ELAST_CoupNeoHooke", mats[eh["MATIDS"][0]]["ELAST_CoupNeoHooke"]
     dbc = y["DESIGN SURF DIRICH CONDITIONS"][0]
     neu = y["DESIGN SURF NEUMANN CONDITIONS"][0]
     assert dbc["E"] == 1 and neu["E"] == 2
@@ -101,15 +108,21 @@ def integration_case(cell, rel):
         if s["QUANTITY"].startswith("stress_"):
             expected_stress.append({"node": s["NODE"] - 1, "comp": comp[s["QUANTITY"][-2:]],
                                     "value": float(s["VALUE"]), "tol": float(s["TOLERANCE"])})
+    extra = {}
+    if "DESIGN VOL NEUMANN CONDITIONS" in y:  # body load on every element (DVOL 1 = all nodes)
+        vn = y["DESIGN VOL NEUMANN CONDITIONS"][0]
+        assert vn["E"] == 1 and len(y["DVOL-NODE TOPOLOGY"]) == nn
+        extra["vol_neumann"] = {"ONOFF": vn["ONOFF"], "VAL": vn["VAL"], "FUNCT": vn["FUNCT"]}
     return {
+        **extra,
         "source": rel,
         "celltype": cell,
         "iostress": y["IO"]["STRUCT_STRESS"],
         "expected_stress": expected_stress,
         "coords": coords,
         "elements": eles,
-        "material": {"kind": "ELAST_CoupNeoHooke", "YOUNG": float(nh["YOUNG"]),
-                     "NUE": float(nh["NUE"])},
+        "material": {"kind": matkind, "YOUNG": float(nh["YOUNG"]), "NUE": float(nh["NUE"])},
+        "kinem": "linear" if linear else "nonlinear",
         "dirichlet_nodes": sorted(surf[1]),
         "neumann_nodes": sorted(surf[2]),
         "neumann": {"ONOFF": neu["ONOFF"], "VAL": neu["VAL"], "FUNCT": neu["FUNCT"],
@@ -509,6 +522,9 @@ if __name__ == "__main__":
     for cell, rel in CASES.items():
         with open(os.path.join(HERE, f"integration_{cell}.json"), "w") as fh:
             json.dump(integration_case(cell, rel), fh, indent=1)
+    for cell in LINEAR_CELLS:
+        with open(os.path.join(HERE, f"integration_{cell}_linear.json"), "w") as fh:
+            json.dump(integration_case(cell, f"tests/input_files/solid_ele_{cell}_Standard_linear.4C.yaml", linear=True), fh, indent=1)
     for name, rel, tech in (
             ("cooks_fbar", "tests/input_files/sohex8fbar_cooks_nl_new_struc.4C.yaml", "fbar"),):
         with open(os.path.join(HERE, f"integration_{name}.json"), "w") as fh:

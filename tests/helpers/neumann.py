@@ -112,7 +112,8 @@ def volume_neumann_load(case, time):
     evaluated at the reference coordinates of the Gauss point
     (src/solid_ele/4C_solid_ele_neumann_evaluator.cpp:43-123)."""
     from oracle import oracle as orc
-    ct = {"hex8": orc.HEX8, "hex27": orc.HEX27, "tet10": orc.TET10}[case["celltype"]]
+    ct = {"hex8": orc.HEX8, "hex27": orc.HEX27, "tet10": orc.TET10, "tet4": orc.TET4, "hex20": orc.HEX20,
+          "wedge6": orc.WEDGE6, "pyramid5": orc.PYRAMID5}[case["celltype"]]
     X = np.asarray(case["coords"], float)
     vn = case["vol_neumann"]
     gxi, gw = orc.gauss(ct)

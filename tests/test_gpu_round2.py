@@ -658,3 +658,31 @@ def test_wedge6_pyramid5_surface_loads_are_refused():
     f = asm.evaluate_neumann()
     assert abs(f.reshape(-1, 3)[:, 0].sum() - 1.0) < 1e-12   # unit cube, unit body force
     asm.close()
+
+
+@pytest.mark.parametrize("cell", ["hex8", "hex20", "hex27", "tet4", "pyramid5"])
+def test_reference_linear_kinematics_known_answers_through_cuda_path(cell):
+    """KINEM linear + MAT_Struct_StVenantKirchhoff: RESULT DESCRIPTION displacements (1e-12) of the reference's
+    solid_ele_<cell>_Standard_linear.4C.yaml (surface + volume load) with K and f from the device kernels."""
+    import json
+    import os
+    from tests.helpers.newton import solve_case
+    case = json.load(open(os.path.join(os.path.dirname(__file__), "golden", f"integration_{cell}_linear.json")))
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    rm = b200.partition.serial_mesh(getattr(b200.mesh, cell.upper()), X, conn)
+    mat = case["material"]
+    assert mat["kind"] == "MAT_Struct_StVenantKirchhoff" and case["kinem"] == "linear"
+    asm = b200.DeviceAssembler(rm, capi.MAT_SVK, [mat["YOUNG"], mat["NUE"]], kinem=capi.KINEM_LINEAR)
+    rowptr, colind = asm.graph()
+
+    def evaluate(u):
+        asm.set_state("displacement", u)
+        K, f, _ = asm.evaluate()
+        return rowptr, colind, K, f
+
+    u = solve_case(case, evaluate)
+    assert len(case["expected_disp"]) >= 12
+    for e in case["expected_disp"]:
+        assert abs(u[e["node"], e["dof"]] - e["value"]) < e["tol"], e
+    asm.close()

@@ -232,3 +232,29 @@ def test_assembly_threads_equal_serial():
     b = orc.evaluate_assemble(orc.TET10, orc.MAT_ISO_VOL, [1.0, 1000.0], conn, X.ravel(), u, row,
                               col, nn, rowptr, colind, nthreads=3)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("cell", ["hex8", "hex20", "hex27", "tet4", "pyramid5"])
+def test_linear_kinematics_known_answers(cell):
+    """KINEM linear + MAT_Struct_StVenantKirchhoff: RESULT DESCRIPTION displacements (1e-12) of the reference's
+    solid_ele_<cell>_Standard_linear.4C.yaml, reproduced by the oracle's small-strain path (tech = TECH_LINEAR)."""
+    case = json.load(open(os.path.join(G, f"integration_{cell}_linear.json")))
+    assert case["kinem"] == "linear" and case["material"]["kind"] == "MAT_Struct_StVenantKirchhoff"
+    ct = CELLS[cell]
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    nn = len(X)
+    row, col = serial_maps(nn)
+    rowptr, colind = orc.build_graph(ct, conn, row, col, nn)
+    par = [case["material"]["YOUNG"], case["material"]["NUE"]]
+
+    def evaluate(u):
+        vals, f, nbad = orc.evaluate_assemble(ct, orc.MAT_SVK, par, conn, X.ravel(), u, row, col, nn, rowptr, colind,
+                                              tech=orc.TECH_LINEAR)
+        assert nbad == 0
+        return rowptr, colind, vals, f
+
+    u = solve_case(case, evaluate)
+    assert len(case["expected_disp"]) >= 12
+    for e in case["expected_disp"]:
+        assert abs(u[e["node"], e["dof"]] - e["value"]) < e["tol"], (e, u[e["node"], e["dof"]])
