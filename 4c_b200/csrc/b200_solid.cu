@@ -2255,9 +2255,8 @@ namespace
     Ga.nn = ctx->nn, Ga.ngp = ctx->ngp, Ga.pos_stride = ctx->pos_stride, Ga.stiff = stiff;
     const unsigned grid = nblk(A.n_ele * ctx->nn, 64);
     if (!grid) return 0;
-    if (ctx->tech != B200S_TECH_NONE || ctx->prestress != B200S_PRESTRESS_NONE)
-      return fail(ctx, B200S_ERR_UNSUPPORTED,
-          "the general kernel evaluates displacement-based blocks only (no element technology / prestress)");
+    if (ctx->tech != B200S_TECH_NONE)
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "the general kernel evaluates displacement-based blocks only (no element technology)");
     switch (ctx->matkind)
     {
       case B200S_MAT_COUP_NEOHOOKE:
@@ -2577,8 +2576,6 @@ extern "C"
     // (4C_solid_ele_factory_lib.hpp)
     if (element_technology != B200S_TECH_NONE && ctx->celltype >= 0 && ctx->celltype != B200S_HEX8)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "F-bar and EAS are hex8 technologies");
-    if (prestress_technology != B200S_PRESTRESS_NONE && is_general_cell(ctx->celltype))
-      return fail(ctx, B200S_ERR_UNSUPPORTED, "MULF prestress of tet4 / hex20 / wedge6 / pyramid5 blocks has no device kernel");
     ctx->kinem = kinem_type;
     dfree(ctx->d_hist_old);
     const bool eas_fresh = eas_neas(element_technology) != eas_neas(ctx->tech) || !ctx->d_eas_hist;

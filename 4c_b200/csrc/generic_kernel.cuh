@@ -91,6 +91,9 @@ namespace b200s
         for (int a = 0; a < 3; ++a)
           for (int b = 0; b < 3; ++b) F[a + 3 * b] = fma(u[k][a], G[k][b], F[a + 3 * b]);
       }
+      // PRESTRESS_TECH mulf: F = (I + u (J_hist^-1 dN)^T) F_hist (4C_solid_ele_calc_lib_mulf.hpp:41-90); everything else
+      // of the formulation is the displacement-based one
+      if (A.gp_hist != nullptr) mulf_deformation_gradient<NN>(A.gp_hist + (e * Ga.ngp + g) * MULF_HIST, dN, &u[0][0], F);
       detF_min = fmin(detF_min, det3(F));
       double C[6], S[6], Cm[36];
       right_cauchy_green(F, C);

@@ -39,7 +39,7 @@ namespace B200Solid
     const bool general_cell = celltype == B200S_TET4 || celltype == B200S_HEX20 || celltype == B200S_WEDGE6 || celltype == B200S_PYRAMID5;
     const bool cell = celltype == B200S_HEX8 || celltype == B200S_HEX27 || celltype == B200S_TET10 || general_cell;
     if (!cell) return false;
-    if (general_cell && (tech != B200S_TECH_NONE || prestress != B200S_PRESTRESS_NONE)) return false;
+    if (general_cell && tech != B200S_TECH_NONE) return false;
     const bool hyper = material_kind == B200S_MAT_COUP_NEOHOOKE || material_kind == B200S_MAT_ISO_VOL ||
                        material_kind == B200S_MAT_SVK || material_kind == B200S_MAT_ELASTHYPER;
     if (kinem == B200S_KINEM_LINEAR)

@@ -192,7 +192,7 @@ static int run_generic_nn(const GenericArgs& Ga)
 extern "C" int emu_generic(int celltype, int matkind, const double* params, int linear, int stiff, int64_t n_ele,
     const int32_t* conn, const double* X, const double* u_col, const int32_t* pos, int pos_stride,
     const int64_t* node_rowstart, const int32_t* node_rowlen, const int32_t* node_frow, int64_t n_col_nodes, double* vals,
-    double* f)
+    double* f, const double* gp_hist)
 {
   std::vector<NodeRow> node_row(n_col_nodes);
   for (int64_t k = 0; k < n_col_nodes; ++k)
@@ -201,7 +201,7 @@ extern "C" int emu_generic(int celltype, int matkind, const double* params, int 
   GenericArgs Ga;
   EvalArgs& A = Ga.A;
   A.X = X, A.u = u_col, A.conn = conn, A.pos = pos, A.node_row = node_row.data();
-  A.per_ele_param = nullptr, A.ele_id = nullptr, A.gp_hist = nullptr, A.fibers = nullptr, A.linear = linear;
+  A.per_ele_param = nullptr, A.ele_id = nullptr, A.gp_hist = gp_hist, A.fibers = nullptr, A.linear = linear;
   A.mat_hist = nullptr, A.vals = vals, A.f = f, A.err = nullptr, A.n_ele = n_ele, A.scatter_mode = 0;
   if (!make_mat_params(matkind, params, A.mp)) return -3;
   Ga.dN_gp = T.dN_gp.data(), Ga.dN_node = T.dN_node.data(), Ga.w = T.w.data();

@@ -529,7 +529,7 @@ if __name__ == "__main__":
             ("cooks_fbar", "tests/input_files/sohex8fbar_cooks_nl_new_struc.4C.yaml", "fbar"),):
         with open(os.path.join(HERE, f"integration_{name}.json"), "w") as fh:
             json.dump(cooks_case(rel, tech), fh)
-    for cell in ("hex8", "hex27", "tet10"):
+    for cell in ("hex8", "hex27", "tet10", "tet4", "hex20", "wedge6", "pyramid5"):
         with open(os.path.join(HERE, f"integration_{cell}_mulf.json"), "w") as fh:
             json.dump(mulf_case(cell, f"tests/input_files/solid_ele_{cell}_Standard_mulf.4C.yaml"), fh, indent=1)
     for tech, rel in (("eas_full", "tests/input_files/solid_ele_hex8_Standard_eas_full_stressout_cauchy_strainout_ea.4C.yaml"),

@@ -17,7 +17,7 @@ def lib(cell="hex8"):
         so = os.path.join(_CPP, f"libemu_{cell}.so")
         srcs = [os.path.join(_CPP, f"emulate_{cell}.cpp")] + [
             os.path.join(_CPP, "..", "..", "4c_b200", "csrc", f)
-            for f in ("hex8_kernel.cuh", "hex8_fbar_kernel.cuh", "tet10_kernel.cuh", "hex27_kernel.cuh", "solid_math.cuh",
+            for f in ("hex8_kernel.cuh", "hex8_fbar_kernel.cuh", "tet10_kernel.cuh", "hex27_kernel.cuh", "generic_kernel.cuh", "solid_math.cuh",
                       "summands.cuh", "history_materials.cuh", "post_kernels.cuh", "neumann_kernels.cuh", "shape_tables.hpp")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", so, srcs[0]])
@@ -96,7 +96,7 @@ def mulf_history(celltype, conn, X, u_col=None, hist=None):
     """hist is None: fresh history (n_ele, ngp, 18); else struct_update_prestress in place for state u_col."""
     conn = np.ascontiguousarray(conn, np.int32)
     X = np.ascontiguousarray(X, np.float64)
-    ngp = {0: 8, 1: 27, 2: 4}[celltype]
+    ngp = {0: 8, 1: 27, 2: 4, 3: 1, 4: 27, 5: 6, 6: 8}[celltype]
     update = hist is not None
     if hist is None:
         hist = np.zeros((len(conn), ngp, 18))
@@ -280,7 +280,7 @@ def generic_drucker_prager(celltype, in10, conn, X, u_col, rowptr, colind, node_
 
 
 def generic(celltype, matkind, params, conn, X, u_col, rowptr, colind, node_row_lid, node_col_lid, n_row_nodes, linear=False,
-            stiff=True):
+            stiff=True, gp_hist=None):
     """Emulated general kernel (generic_kernel.cuh) for the hyperelastic kinds 0..2 and any cell type of
     shape_tables.hpp (tet4 / hex20 blocks run through it on the device)."""
     conn = np.ascontiguousarray(conn, np.int32)
@@ -289,10 +289,10 @@ def generic(celltype, matkind, params, conn, X, u_col, rowptr, colind, node_row_
     vals, f = np.zeros(rowptr[-1]), np.zeros(3 * n_row_nodes)
     L = lib("post")
     L.emu_generic.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 4 + [C.c_int] + \
-        [C.c_void_p] * 3 + [C.c_int64] + [C.c_void_p] * 2
+        [C.c_void_p] * 3 + [C.c_int64] + [C.c_void_p] * 3
     rc = L.emu_generic(int(celltype), int(matkind), _p(np.ascontiguousarray(params, np.float64)), int(linear), int(stiff),
                        len(conn), _p(conn), _p(np.ascontiguousarray(X, np.float64)),
                        _p(np.ascontiguousarray(u_col, np.float64)), _p(pos), pos.shape[1], _p(rowstart), _p(rowlen),
-                       _p(frow), len(rowstart), _p(vals), _p(f))
+                       _p(frow), len(rowstart), _p(vals), _p(f), _p(gp_hist))
     assert rc == 0, rc
     return vals, f

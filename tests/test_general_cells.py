@@ -62,3 +62,29 @@ def test_general_kernel_equals_fast_kernels_on_their_cells():
                            rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
         ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, 1e-12)
         assert ok, (cell, wK, wf)
+
+
+@pytest.mark.parametrize("cell", ["tet4", "hex20", "wedge6", "pyramid5"])
+def test_emulated_general_kernel_mulf_matches_oracle(cell):
+    """PRESTRESS_TECH mulf on the general cells (MulfFormulation is instantiated for every displacement-based cell,
+    src/solid_ele/4C_solid_ele_factory.hpp:59-60; ctests solid_ele_{tet4,hex20,wedge6,pyramid5}_Standard_mulf): the general
+    kernel with the MULF deformation gradient, the history set-up and struct_update_prestress of the product (stepped
+    on the CPU) against the oracle over two prestress updates."""
+    ct, rm, h = _mesh(cell)
+    u = 2.0 * b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, h)
+    rowptr, colind = orc.build_graph(ct, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    par = [200.0, 0.25]
+    ohist = orc.mulf_new_history(ct, rm.n_col_eles)
+    phist = emu.mulf_history(rm.celltype, rm.conn, rm.X.ravel())
+    maps = (rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    for scale in (1.0, -0.6, 0.3):
+        us = scale * u.ravel()
+        rK, rf, nbad = orc.evaluate_assemble(ct, orc.MAT_COUP_NEOHOOKE, par, rm.conn, rm.X.ravel(), us, *maps, rowptr, colind,
+                                             tech=orc.TECH_MULF, hist=ohist)
+        K, f = emu.generic(rm.celltype, orc.MAT_COUP_NEOHOOKE, par, rm.conn, rm.X.ravel(), us, rowptr, colind, *maps,
+                           gp_hist=phist)
+        ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, 1e-12)
+        assert ok and nbad == 0, (scale, wK, wf)
+        orc.update_prestress(ct, rm.conn, rm.X.ravel(), us, ohist)
+        emu.mulf_history(rm.celltype, rm.conn, rm.X.ravel(), us, phist)
+        assert np.abs(phist - ohist[:, :, :18]).max() <= 1e-13 * np.abs(ohist).max()

@@ -686,3 +686,63 @@ def test_reference_linear_kinematics_known_answers_through_cuda_path(cell):
     for e in case["expected_disp"]:
         assert abs(u[e["node"], e["dof"]] - e["value"]) < e["tol"], e
     asm.close()
+
+
+# ---- PRESTRESS_TECH mulf on the general cells (MulfFormulation: src/solid_ele/4C_solid_ele_factory.hpp:59-60) ----
+@pytest.mark.parametrize("cell", ["tet4", "hex20", "wedge6", "pyramid5"])
+def test_general_cells_mulf_evaluate_update_and_history_match_oracle(cell):
+    ct, rm, h = _general_mesh(cell)
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, h)
+    mk, par = capi.MAT_COUP_NEOHOOKE, [200.0, 0.25]
+    asm = b200.DeviceAssembler(rm, mk, par, prestress=capi.PRESTRESS_MULF)
+    rowptr, colind = asm.graph()
+    ohist = orc.mulf_new_history(ct, rm.n_col_eles)
+    maps = (rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, rowptr, colind)
+    ngp = orc.num_gp(ct)
+    for scale in (1.0, -0.6, 0.3):
+        us = scale * u.ravel()
+        asm.set_state("displacement", us[:3 * rm.n_row_nodes])
+        K, f, _ = asm.evaluate("struct_calc_nlnstiff")
+        rK, rf, nbad = orc.evaluate_assemble(ct, mk, par, rm.conn, rm.X.ravel(), us, *maps, tech=orc.TECH_MULF, hist=ohist)
+        ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
+        assert ok and nbad == 0, (scale, wK, wf)
+        _, f2, _ = asm.evaluate("struct_calc_internalforce")
+        assert np.abs(f2 - rf).max() <= RTOL * np.abs(rf).max()
+        asm.update_prestress()
+        orc.update_prestress(ct, rm.conn, rm.X.ravel(), us, ohist)
+        hh = asm.ctx.get_gp_history().reshape(rm.n_col_eles, ngp, 18)
+        assert np.abs(hh - ohist[:, :, :18]).max() <= 1e-13 * np.abs(ohist).max()
+    asm.close()
+
+
+@pytest.mark.parametrize("cell", ["tet4", "hex20", "wedge6", "pyramid5"])
+def test_reference_general_cells_mulf_known_answers_through_cuda_path(cell):
+    """RESULT DESCRIPTION displacements of tests/input_files/solid_ele_{tet4,hex20,wedge6,pyramid5}_Standard_mulf.4C.yaml
+    (MAT_ElastHyper{CoupNeoHooke, CoupAnisoExpo} on the element fibres, two prestress steps + eight load steps) with the
+    CUDA path doing every evaluate and prestress update."""
+    import json
+    import os
+    from tests.helpers.newton import solve_case
+    case = json.load(open(os.path.join(os.path.dirname(__file__), "golden", f"integration_{cell}_mulf.json")))
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    rm = b200.partition.serial_mesh(getattr(b200.mesh, cell.upper()), X, conn)
+    nh, fib = case["summands"][0]["params"], case["summands"][1]["params"]
+    mat = [("COUP_NEOHOOKE", [nh["YOUNG"], nh["NUE"]]), ("COUP_ANISOEXPO", [fib["K1"], fib["K2"], fib["K1COMP"], fib["K2COMP"]])]
+    asm = b200.DeviceAssembler(rm, capi.MAT_ELASTHYPER, mat, prestress=capi.PRESTRESS_MULF, fibers=np.asarray(case["fibers"], float))
+    rowptr, colind = asm.graph()
+
+    def ev(u):
+        asm.set_state("displacement", u)
+        K, f, _ = asm.evaluate()
+        return rowptr, colind, K, f
+
+    def up(u):
+        asm.set_state("displacement", u)
+        asm.update_prestress()
+
+    u = solve_case(case, ev, update_prestress=up)
+    assert len(case["expected_disp"]) >= 12
+    for e in case["expected_disp"]:
+        assert abs(u[e["node"], e["dof"]] - e["value"]) < 1e-10, (e, u[e["node"], e["dof"]])
+    asm.close()

@@ -311,13 +311,13 @@ def _mulf_material(case, e=0):
                                 ("FIBER", case["fibers"][e])])
 
 
-@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10"])
+@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10", "tet4", "hex20", "wedge6", "pyramid5"])
 def test_mulf_prestress_known_answers(cell):
     """RESULT DESCRIPTION displacements (1e-12) of tests/input_files/solid_ele_<cell>_Standard_mulf.4C.yaml:
     two MULF load steps (update_prestress + displacement reset), then eight ordinary steps.  Pins the
     oracle's MulfFormulation restatement (history set-up, F = F_delta F_hist, prestress update)."""
     case = json.load(open(os.path.join(G, f"integration_{cell}_mulf.json")))
-    ct = CELLS[cell]
+    ct = getattr(orc, cell.upper())
     X = np.asarray(case["coords"], float)
     conn = np.asarray(case["elements"], np.int32)
     fibers = np.asarray(case["fibers"], float)  # FIBER1 per element
