@@ -1407,7 +1407,9 @@ struct b200s_ctx
   int tech = B200S_TECH_NONE;
   int prestress = B200S_PRESTRESS_NONE;
   int kinem = B200S_KINEM_NONLINEAR_TOTLAG;
-  double* d_gp_hist = nullptr;  // MULF: n_col_eles * ngp * MULF_HIST doubles, device element order
+  double* d_gp_hist = nullptr;  // MULF: n_col_eles * mulf_points * MULF_HIST doubles, device element order (mulf_points = ngp,
+                                // + 1 with TECH fbar: the element's global history at the centroid follows its Gauss points)
+  double* d_dN_pts = nullptr;   // [ngp + 1][nn][3]: d_dN_gp followed by d_dN_cen (history set-up / update of MULF + F-bar)
   double* d_eas_hist = nullptr; // EAS: n_col_eles * hex8eas::hist_size(neas) doubles, device element order
   double* d_eas_t0 = nullptr;   // EAS: T0invT[36] + detJ0 per element (stride hex8eas::T0_STRIDE)
   double* d_hist_old = nullptr; // old_history_data_ of the block (struct_calc_update_istep / _reset_istep)
@@ -1430,6 +1432,7 @@ struct b200s_ctx
   int ngp = 0, ngp_mass = 0;
   double *d_dN_gp = nullptr, *d_w = nullptr, *d_dN_cen = nullptr, *d_xi_gp = nullptr, *d_dN_node = nullptr;
   bool general_tangent = false;  // the material's tangent has no major symmetry: generic_kernel.cuh evaluates the block
+  bool general_kernel = false;   // option "general_kernel": every block through generic_kernel.cuh (A/B, tests)
   double *d_N_mass = nullptr, *d_dN_mass = nullptr, *d_w_mass = nullptr;
   uint8_t* d_ele_is_row = nullptr;  // caller numbering; nullptr = every column element is a row element
   // mass matrix / inertia force (struct_calc_nlnstiffmass & co.)
@@ -1909,6 +1912,9 @@ namespace
     return false;
   }
   inline int eas_neas(int tech) { return tech == B200S_TECH_EAS_MILD ? 9 : (tech == B200S_TECH_EAS_FULL ? 21 : 0); }
+  // MulfHistoryData per element: one per Gauss point, with TECH fbar one more for the centroid (GlobalHistory of
+  // MulfFBarFormulation, 4C_solid_ele_calc_mulf_fbar.hpp:112-116)
+  inline int mulf_points(const b200s_ctx* ctx) { return ctx->ngp + (ctx->tech == B200S_TECH_FBAR ? 1 : 0); }
   // fresh EASHistoryData of every element: all zero (4C_solid_ele_calc_eas_helpers.hpp:98-112)
   int eas_allocate(b200s_ctx* ctx)
   {
@@ -1946,12 +1952,12 @@ namespace
   // (4C_solid_ele_calc_mulf.hpp:56-60)
   int mulf_allocate(b200s_ctx* ctx)
   {
-    const int64_t n = ctx->n_col_eles * ctx->ngp;
+    const int64_t n = ctx->n_col_eles * mulf_points(ctx);
     if (to_device(ctx, &ctx->d_gp_hist, (const double*)nullptr, n * MULF_HIST)) return B200S_ERR_CUDA;
     if (n > 0)
     {
-      k_mulf_init<<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->n_col_eles, ctx->nn, ctx->ngp, ctx->dconn, ctx->dX,
-          ctx->d_dN_gp, ctx->d_gp_hist);
+      k_mulf_init<<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->n_col_eles, ctx->nn, mulf_points(ctx), ctx->dconn, ctx->dX,
+          ctx->d_dN_pts, ctx->d_gp_hist);
       ctx->launches += 1;
     }
     CK(cudaStreamSynchronize(ctx->stream));
@@ -2253,10 +2259,13 @@ namespace
     Ga.A = A;
     Ga.dN_gp = ctx->d_dN_gp, Ga.dN_node = ctx->d_dN_node, Ga.w = ctx->d_w;
     Ga.nn = ctx->nn, Ga.ngp = ctx->ngp, Ga.pos_stride = ctx->pos_stride, Ga.stiff = stiff;
+    // TECH fbar (hex8, pyramid5; with PRESTRESS_TECH mulf: MulfFBarFormulation)
+    Ga.dN_cen = ctx->tech == B200S_TECH_FBAR ? ctx->d_dN_cen : nullptr;
+    Ga.hist_pts = mulf_points(ctx);
     const unsigned grid = nblk(A.n_ele * ctx->nn, 64);
     if (!grid) return 0;
-    if (ctx->tech != B200S_TECH_NONE)
-      return fail(ctx, B200S_ERR_UNSUPPORTED, "the general kernel evaluates displacement-based blocks only (no element technology)");
+    if (ctx->tech != B200S_TECH_NONE && ctx->tech != B200S_TECH_FBAR)
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "the general kernel evaluates displacement-based and F-bar blocks only (no EAS)");
     switch (ctx->matkind)
     {
       case B200S_MAT_COUP_NEOHOOKE:
@@ -2285,7 +2294,9 @@ namespace
   static int launch_eval(b200s_ctx* ctx, const EvalArgs& A)
   {
     if (ctx->matkind < 0) return fail(ctx, B200S_ERR_INVALID, "material not set");
-    if (ctx->general_tangent || is_general_cell(ctx->celltype)) return launch_generic(ctx, A, STIFF);
+    if (ctx->general_tangent || ctx->general_kernel || is_general_cell(ctx->celltype) ||
+        (ctx->tech == B200S_TECH_FBAR && ctx->prestress == B200S_PRESTRESS_MULF))
+      return launch_generic(ctx, A, STIFF);
     if (ctx->tech != B200S_TECH_NONE && ctx->celltype != B200S_HEX8)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "element technology %d needs hex8", ctx->tech);
     switch (ctx->celltype)
@@ -2381,7 +2392,7 @@ extern "C"
     b200s_clear_neumann(ctx);
     dfree(ctx->d_face_N), dfree(ctx->d_face_d0), dfree(ctx->d_face_d1), dfree(ctx->d_face_w);
     dfree(ctx->d_N_gp), dfree(ctx->d_fext), dfree(ctx->d_nm_row), dfree(ctx->d_nm_col), dfree(ctx->d_nm_flag);
-    dfree(ctx->d_hyper), dfree(ctx->d_dN_gp), dfree(ctx->d_w), dfree(ctx->d_dN_cen), dfree(ctx->d_N_mass);
+    dfree(ctx->d_hyper), dfree(ctx->d_dN_gp), dfree(ctx->d_w), dfree(ctx->d_dN_cen), dfree(ctx->d_N_mass), dfree(ctx->d_dN_pts);
     dfree(ctx->d_dN_mass), dfree(ctx->d_w_mass), dfree(ctx->d_ele_is_row), dfree(ctx->d_mass);
     dfree(ctx->d_f_inertia), dfree(ctx->d_acc_row), dfree(ctx->d_acc_col), dfree(ctx->d_energy);
     dfree(ctx->d_xmat), dfree(ctx->d_la_x), dfree(ctx->d_la_y), dfree(ctx->d_toggle);
@@ -2414,6 +2425,8 @@ extern "C"
       ctx->pipeline_phases = (int)value;
     else if (!strcmp(key, "overlap_halo"))
       ctx->overlap_halo = value != 0;
+    else if (!strcmp(key, "general_kernel"))  // A/B and tests: route every block through the table-driven general kernel
+      ctx->general_kernel = value != 0;
     else if (!strcmp(key, "tma_gather"))
       ctx->tma_gather = value != 0;
     else if (!strcmp(key, "eas_mma"))
@@ -2455,6 +2468,7 @@ extern "C"
     if (to_device(ctx, &ctx->d_dN_gp, T.dN_gp.data(), (int64_t)T.dN_gp.size()) ||
         to_device(ctx, &ctx->d_w, T.w.data(), (int64_t)T.w.size()) ||
         to_device(ctx, &ctx->d_dN_cen, T.dN_cen.data(), (int64_t)T.dN_cen.size()) ||
+        to_device(ctx, &ctx->d_dN_pts, (const double*)nullptr, (int64_t)(T.dN_gp.size() + T.dN_cen.size())) ||
         to_device(ctx, &ctx->d_dN_node, T.dN_node.data(), (int64_t)T.dN_node.size()) ||
         to_device(ctx, &ctx->d_xi_gp, T.xi_gp.data(), (int64_t)T.xi_gp.size()) ||
         to_device(ctx, &ctx->d_N_mass, T.N_mass.data(), (int64_t)T.N_mass.size()) ||
@@ -2462,6 +2476,8 @@ extern "C"
         to_device(ctx, &ctx->d_w_mass, T.w_mass.data(), (int64_t)T.w_mass.size()) ||
         to_device(ctx, &ctx->d_N_gp, T.N_gp.data(), (int64_t)T.N_gp.size()))
       return B200S_ERR_CUDA;
+    CK(cudaMemcpyAsync(ctx->d_dN_pts, ctx->d_dN_gp, 8 * T.dN_gp.size(), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_dN_pts + T.dN_gp.size(), ctx->d_dN_cen, 8 * T.dN_cen.size(), cudaMemcpyDeviceToDevice, ctx->stream));
     const FaceTables FT = make_face_tables(celltype);
     ctx->face_nn = FT.nn, ctx->face_ngp = FT.ngp;
     if (to_device(ctx, &ctx->d_face_N, FT.N.data(), (int64_t)FT.N.size()) ||
@@ -2565,8 +2581,10 @@ extern "C"
     if (prestress_technology != B200S_PRESTRESS_NONE && prestress_technology != B200S_PRESTRESS_MULF)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "prestress technology %d has no device kernel",
           prestress_technology);
-    // MulfFBarFormulation (4C_solid_ele_calc_mulf_fbar.hpp) stays on the CPU path
-    if (prestress_technology == B200S_PRESTRESS_MULF && element_technology != B200S_TECH_NONE)
+    // MulfFBarFormulation (4C_solid_ele_calc_mulf_fbar.hpp: hex8, pyramid5) runs through the general kernel; MULF with
+    // EAS does not exist in the reference (4C_solid_ele_factory_lib.hpp)
+    if (prestress_technology == B200S_PRESTRESS_MULF && element_technology != B200S_TECH_NONE &&
+        element_technology != B200S_TECH_FBAR)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "MULF prestress with element technology %d has no device kernel",
           element_technology);
     if (element_technology < B200S_TECH_NONE || element_technology > B200S_TECH_EAS_FULL)
@@ -2574,8 +2592,10 @@ extern "C"
           element_technology);
     // the reference offers F-bar and EAS for hex8 only among the device cell types
     // (4C_solid_ele_factory_lib.hpp)
-    if (element_technology != B200S_TECH_NONE && ctx->celltype >= 0 && ctx->celltype != B200S_HEX8)
-      return fail(ctx, B200S_ERR_UNSUPPORTED, "F-bar and EAS are hex8 technologies");
+    if (element_technology != B200S_TECH_NONE && ctx->celltype >= 0 && ctx->celltype != B200S_HEX8 &&
+        !(element_technology == B200S_TECH_FBAR && ctx->celltype == B200S_PYRAMID5))
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "F-bar is a hex8 / pyramid5 technology, EAS a hex8 technology");
+    const int old_points = mulf_points(ctx);
     ctx->kinem = kinem_type;
     dfree(ctx->d_hist_old);
     const bool eas_fresh = eas_neas(element_technology) != eas_neas(ctx->tech) || !ctx->d_eas_hist;
@@ -2586,7 +2606,8 @@ extern "C"
       cudaSetDevice(ctx->device);
       if (eas_allocate(ctx)) return B200S_ERR_CUDA;
     }
-    const bool fresh = prestress_technology == B200S_PRESTRESS_MULF && ctx->prestress != B200S_PRESTRESS_MULF;
+    const bool fresh = prestress_technology == B200S_PRESTRESS_MULF &&
+                       (ctx->prestress != B200S_PRESTRESS_MULF || mulf_points(ctx) != old_points);
     ctx->prestress = prestress_technology;
     if (prestress_technology != B200S_PRESTRESS_MULF) dfree(ctx->d_gp_hist);
     if ((fresh || !ctx->d_gp_hist) && prestress_technology == B200S_PRESTRESS_MULF && ctx->celltype >= 0)
@@ -2732,7 +2753,7 @@ extern "C"
     CK(cudaGetLastError());
     ctx->seg_begin[(size_t)P + 1] = n;
     const int neas = eas_neas(ctx->tech);
-    const int hist_w = neas ? hex8eas::hist_size(neas) : ctx->ngp * MULF_HIST;
+    const int hist_w = neas ? hex8eas::hist_size(neas) : mulf_points(ctx) * MULF_HIST;
     int rc = permute_array(ctx, ctx->dconn, n, ctx->nn, perm);
     if (!rc)
     {
@@ -2746,7 +2767,7 @@ extern "C"
     }
     if (!rc) rc = permute_array(ctx, ctx->d_per_ele, n, 1, perm);
     if (!rc) rc = permute_array(ctx, ctx->d_fibers, n, 3, perm);
-    if (!rc) rc = permute_array(ctx, ctx->d_gp_hist, n, ctx->ngp * MULF_HIST, perm);
+    if (!rc) rc = permute_array(ctx, ctx->d_gp_hist, n, mulf_points(ctx) * MULF_HIST, perm);
     if (!rc) rc = permute_array(ctx, ctx->d_eas_hist, n, neas ? hex8eas::hist_size(neas) : 0, perm);
     if (!rc) rc = permute_array(ctx, ctx->d_eas_t0, n, hex8eas::T0_STRIDE, perm);
     if (!rc) rc = permute_array(ctx, ctx->d_hist_old, n, hist_w, perm);
@@ -3232,7 +3253,7 @@ extern "C"
     A.per_ele_param = ctx->d_per_ele ? ctx->d_per_ele + e_begin : nullptr;
     A.ele_id = ctx->d_ele_id ? ctx->d_ele_id + e_begin : nullptr;
     A.fibers = ctx->d_fibers ? ctx->d_fibers + 3 * e_begin : nullptr;
-    A.gp_hist = ctx->d_gp_hist ? ctx->d_gp_hist + e_begin * ctx->ngp * MULF_HIST : nullptr;
+    A.gp_hist = ctx->d_gp_hist ? ctx->d_gp_hist + e_begin * mulf_points(ctx) * MULF_HIST : nullptr;
     A.mat_hist = ctx->d_mat_hist ? ctx->d_mat_hist + e_begin * ctx->ngp * mat_hist_per_gp(ctx) : nullptr;
     A.linear = ctx->kinem == B200S_KINEM_LINEAR;
     A.vals = ctx->d_vals, A.f = ctx->d_f, A.err = ctx->d_err, A.mp = ctx->mp;
@@ -3814,6 +3835,7 @@ extern "C"
     P.ele_id = ctx->d_ele_id, P.ele_is_row = ctx->d_ele_is_row;
     P.dN_gp = ctx->d_dN_gp, P.dN_cen = ctx->d_dN_cen, P.w = ctx->d_w, P.mp = ctx->mp;
     P.gp_hist = ctx->prestress == B200S_PRESTRESS_MULF ? ctx->d_gp_hist : nullptr;
+    P.hist_pts = mulf_points(ctx);
     P.mat_hist = ctx->d_mat_hist;
     P.eas_neas = eas_neas(ctx->tech);
     P.eas_hist_size = P.eas_neas ? hex8eas::hist_size(P.eas_neas) : 0;
@@ -3922,11 +3944,12 @@ extern "C"
     cudaSetDevice(ctx->device);
     const int rc = import_row_to_col(ctx, ctx->d_u_row, ctx->d_u_col, false);
     if (rc) return rc;
-    const int64_t n = ctx->n_col_eles * ctx->ngp;
+    // MulfFBarFormulation::update_prestress: the centroid history is updated like a Gauss point's (mulf_fbar.hpp:245-277)
+    const int64_t n = ctx->n_col_eles * mulf_points(ctx);
     if (n > 0)
     {
-      k_mulf_update<<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->n_col_eles, ctx->nn, ctx->ngp, ctx->dconn, ctx->dX,
-          ctx->d_u_col, ctx->d_dN_gp, ctx->d_gp_hist);
+      k_mulf_update<<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->n_col_eles, ctx->nn, mulf_points(ctx), ctx->dconn, ctx->dX,
+          ctx->d_u_col, ctx->d_dN_pts, ctx->d_gp_hist);
       ctx->launches += 1;
     }
     CK(cudaStreamSynchronize(ctx->stream));
@@ -3937,7 +3960,7 @@ extern "C"
   int64_t b200s_gp_history_size(const b200s_ctx* ctx)
   {
     if (!ctx || ctx->prestress != B200S_PRESTRESS_MULF) return 0;
-    return ctx->n_col_eles * ctx->ngp * MULF_HIST;
+    return ctx->n_col_eles * mulf_points(ctx) * MULF_HIST;
   }
 
   // ---- EAS: struct_calc_recover and the element history ---------------------------------------------
@@ -3992,7 +4015,7 @@ extern "C"
     double* cur = eas_neas(ctx->tech) ? ctx->d_eas_hist : (ctx->prestress == B200S_PRESTRESS_MULF ? ctx->d_gp_hist : nullptr);
     if (!cur) return B200S_OK;  // formulations without history: nothing to do
     const int64_t n = eas_neas(ctx->tech) ? ctx->n_col_eles * hex8eas::hist_size(eas_neas(ctx->tech))
-                                          : ctx->n_col_eles * ctx->ngp * MULF_HIST;
+                                          : ctx->n_col_eles * mulf_points(ctx) * MULF_HIST;
     cudaSetDevice(ctx->device);
     if (!ctx->d_hist_old)
     {
@@ -4075,7 +4098,7 @@ extern "C"
     const int64_t n = element_level == 2 ? b200s_material_history_size(ctx)
                                          : (element_level ? b200s_element_history_size(ctx) : b200s_gp_history_size(ctx));
     const int per_ele = element_level == 2 ? ctx->ngp * mat_hist_per_gp(ctx)
-                                           : (element_level ? hex8eas::hist_size(eas_neas(ctx->tech)) : ctx->ngp * MULF_HIST);
+                                           : (element_level ? hex8eas::hist_size(eas_neas(ctx->tech)) : mulf_points(ctx) * MULF_HIST);
     double* tmp = nullptr;
     CK(cudaMalloc((void**)&tmp, sizeof(double) * (size_t)(n ? n : 1)));
     int rc = B200S_OK;

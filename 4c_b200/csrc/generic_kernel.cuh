@@ -22,7 +22,9 @@ namespace b200s
     const double* dN_gp;    // [ngp][nn][3]
     const double* dN_node;  // [nn][nn][3] (Jacobian check) or nullptr
     const double* w;        // [ngp]
+    const double* dN_cen;   // [nn][3] at the element centroid: TECH fbar (nullptr otherwise)
     int nn, ngp, pos_stride, stiff;
+    int hist_pts;           // MULF histories per element: ngp, or ngp + 1 with TECH fbar (the centroid's follows the points')
   };
 
   // S[6], Cm36[I + 6 J] of the block's material at one point (C = tensor components 00,11,22,01,12,02)
@@ -74,6 +76,31 @@ namespace b200s
         neg = neg || !(dj > 0.0);
       }
     }
+    // TECH fbar, FBarFormulation::prepare (4C_solid_ele_calc_fbar.hpp:58-66; MulfFBarFormulation::prepare,
+    // 4C_solid_ele_calc_mulf_fbar.hpp:118-149): Jacobian mapping and deformation gradient at the centroid;
+    // H0[k][c] = sum_d F0^-1(d,c) N_XYZ_0(d,k) is the centroid half of the H-operator (lib_fbar.hpp:71-104)
+    const bool fbar = Ga.dN_cen != nullptr;
+    double detF0 = 1.0, H0[NN][3];
+    if (fbar)
+    {
+      double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, iJ[9], F0[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, iF0[9];
+      for (int k = 0; k < nn; ++k)
+        for (int a = 0; a < 3; ++a)
+          for (int b = 0; b < 3; ++b) J[a + 3 * b] = fma(Ga.dN_cen[3 * k + a], X[k][b], J[a + 3 * b]);
+      inv3(iJ, J);
+      for (int k = 0; k < nn; ++k)
+      {
+        for (int a = 0; a < 3; ++a)
+          G[k][a] = fma(iJ[a + 6], Ga.dN_cen[3 * k + 2], fma(iJ[a + 3], Ga.dN_cen[3 * k + 1], iJ[a] * Ga.dN_cen[3 * k]));
+        for (int a = 0; a < 3; ++a)
+          for (int b = 0; b < 3; ++b) F0[a + 3 * b] = fma(u[k][a], G[k][b], F0[a + 3 * b]);
+      }
+      if (A.gp_hist != nullptr)
+        mulf_deformation_gradient<NN>(A.gp_hist + (e * Ga.hist_pts + Ga.ngp) * MULF_HIST, Ga.dN_cen, &u[0][0], F0);
+      detF0 = inv3(iF0, F0);
+      for (int k = 0; k < nn; ++k)
+        for (int c = 0; c < 3; ++c) H0[k][c] = iF0[3 * c] * G[k][0] + iF0[1 + 3 * c] * G[k][1] + iF0[2 + 3 * c] * G[k][2];
+    }
     for (int g = 0; g < Ga.ngp; ++g)
     {
       const double* dN = Ga.dN_gp + (size_t)g * nn * 3;
@@ -93,10 +120,20 @@ namespace b200s
       }
       // PRESTRESS_TECH mulf: F = (I + u (J_hist^-1 dN)^T) F_hist (4C_solid_ele_calc_lib_mulf.hpp:41-90); everything else
       // of the formulation is the displacement-based one
-      if (A.gp_hist != nullptr) mulf_deformation_gradient<NN>(A.gp_hist + (e * Ga.ngp + g) * MULF_HIST, dN, &u[0][0], F);
-      detF_min = fmin(detF_min, det3(F));
-      double C[6], S[6], Cm[36];
+      if (A.gp_hist != nullptr) mulf_deformation_gradient<NN>(A.gp_hist + (e * Ga.hist_pts + g) * MULF_HIST, dN, &u[0][0], F);
+      double C[6], S[6], Cm[36], iF[9], Cu[6], fb = 1.0;
+      const double detF = fbar ? inv3(iF, F) : det3(F);
+      detF_min = fmin(detF_min, detF);
       right_cauchy_green(F, C);
+      if (fbar)
+      {
+        // evaluate_fbar_factor (lib_fbar.hpp:47-51); the material sees F_bar = fb F, i.e. C_bar = fb^2 C (fbar.hpp:103-112)
+        fb = pow(detF0 / detF, 1.0 / 3.0);
+        double Fb[9];
+        for (int q = 0; q < 9; ++q) Fb[q] = fb * F[q];
+        for (int q = 0; q < 6; ++q) Cu[q] = C[q];
+        right_cauchy_green(Fb, C);
+      }
       if (A.linear) linear_kinematics(F, C);  // E = sym(grad u), F = I
       MatParams mp = A.mp;
       if (A.per_ele_param != nullptr) mp.p[0] = A.per_ele_param[e];
@@ -104,8 +141,11 @@ namespace b200s
       if (material_hist_doubles(MAT) > 0 && A.mat_hist != nullptr)
         mp.hist = A.mat_hist + (e * Ga.ngp + g) * material_hist_doubles(MAT);  // every thread of the element writes the same state
       material_evaluate_full<MAT>(mp, C, S, Cm);
-      const double w = detJ * Ga.w[g];
-      // f_i(b) += w sum_a (F S)(b, a) G_i(a)
+      const double w0 = detJ * Ga.w[g];
+      // F-bar: force and geometric stiffness with fac / fbar, elastic stiffness with fac * fbar (fbar.hpp:152-176)
+      const double w = w0 * fb, ws = w0 / fb;
+      // f_i(b) += ws sum_a (F S)(b, a) G_i(a)
+      double bS[3];
       for (int b = 0; b < 3; ++b)
       {
         double v = 0.0;
@@ -115,7 +155,8 @@ namespace b200s
           for (int c = 0; c < 3; ++c) fs = fma(F[b + 3 * c], S[vg[c][a]], fs);
           v = fma(fs, G[i][a], v);
         }
-        fi[b] = fma(w, v, fi[b]);
+        bS[b] = v;
+        fi[b] = fma(ws, v, fi[b]);
       }
       if (!Ga.stiff) continue;
       // T1[b][f][d] = sum_{a,e} G_i(a) F(b,e) C[(a e)][(f d)];  V[b][c][d] = w (sum_f T1[b][f][d] F(c,f) + delta_bc sum_a G_i(a) S(a,d))
@@ -138,13 +179,43 @@ namespace b200s
       if (!A.linear)
         for (int d = 0; d < 3; ++d)
         {
-          const double sg = w * (G[i][0] * S[vg[0][d]] + G[i][1] * S[vg[1][d]] + G[i][2] * S[vg[2][d]]);
+          const double sg = ws * (G[i][0] * S[vg[0][d]] + G[i][1] * S[vg[1][d]] + G[i][2] * S[vg[2][d]]);
           for (int b = 0; b < 3; ++b) V[b][b][d] += sg;
         }
       for (int j = 0; j < nn; ++j)
         for (int b = 0; b < 3; ++b)
           for (int c = 0; c < 3; ++c)
             Krow[j][b + 3 * c] = fma(V[b][c][2], G[j][2], fma(V[b][c][1], G[j][1], fma(V[b][c][0], G[j][0], Krow[j][b + 3 * c])));
+      if (fbar)
+      {
+        // add_fbar_stiffness_matrix (lib_fbar.hpp:121-160): K_ij(b,c) += Hop_j(c) (B_i^T ccg fac fbar / 3 - B_i^T S fac / fbar / 3)(b),
+        // ccg = cmat : C with the Cauchy-Green tensor of the unscaled F, Hop_j(c) = H0_j(c) - sum_d F^-1(d,c) N_XYZ(d,j)
+        double ccg[6];
+        for (int I = 0; I < 6; ++I)
+        {
+          double v = 0.0;
+          for (int J2 = 0; J2 < 6; ++J2) v = fma(Cm[I + 6 * J2] * (J2 < 3 ? 1.0 : 2.0), Cu[J2], v);
+          ccg[I] = v;
+        }
+        double t[3];
+        for (int b = 0; b < 3; ++b)
+        {
+          double v = 0.0;
+          for (int a = 0; a < 3; ++a)
+          {
+            double fc = 0.0;
+            for (int c = 0; c < 3; ++c) fc = fma(F[b + 3 * c], ccg[vg[c][a]], fc);
+            v = fma(fc, G[i][a], v);
+          }
+          t[b] = (w / 3.0) * v - (ws / 3.0) * bS[b];
+        }
+        for (int j = 0; j < nn; ++j)
+          for (int c = 0; c < 3; ++c)
+          {
+            const double hop = H0[j][c] - (iF[3 * c] * G[j][0] + iF[1 + 3 * c] * G[j][1] + iF[2 + 3 * c] * G[j][2]);
+            for (int b = 0; b < 3; ++b) Krow[j][b + 3 * c] = fma(hop, t[b], Krow[j][b + 3 * c]);
+          }
+      }
     }
     return neg;
   }

@@ -42,7 +42,8 @@ namespace b200s
     const double* dN_gp;          // [ngp][nn][3]
     const double* dN_cen;         // [nn][3] (F-bar)
     const double* w;              // [ngp]
-    const double* gp_hist;        // nullptr or MULF history (device element order)
+    const double* gp_hist;        // nullptr or MULF history (device element order), hist_pts points per element
+    int hist_pts;                 // ngp, or ngp + 1 for MULF + F-bar (the centroid history follows the Gauss points)
     double* mat_hist;         // history material: n_ele * ngp * DP_HIST (device element order) or nullptr
     // EAS hex8 (eas_neas = 9 / 21, else 0): element history (alpha at [neas..2 neas)), the precomputed
     // centroid transformation (T0invT[36], detJ0; stride eas_t0_stride) and the Gauss point coordinates
@@ -233,13 +234,16 @@ namespace b200s
     double F[9];
     const double detJ =
         A.gp_hist ? point_kinematics_mulf(A.nn, A.dN_gp + (size_t)g * A.nn * 3, A.X, A.u, ce,
-                        A.gp_hist + (e * A.ngp + g) * MULF_HIST, F, nullptr)
+                        A.gp_hist + (e * A.hist_pts + g) * MULF_HIST, F, nullptr)
                   : point_kinematics(A.nn, A.dN_gp + (size_t)g * A.nn * 3, A.X, A.u, ce, F);
     if (A.fbar)
     {
       // F_bar = (det F_0 / det F)^(1/3) F  (4C_solid_ele_calc_fbar.hpp:103-112, lib_fbar.hpp:47-51)
       double F0[9];
-      point_kinematics(A.nn, A.dN_cen, A.X, A.u, ce, F0);
+      if (A.gp_hist)  // MulfFBarFormulation: the centroid's own history (mulf_fbar.hpp:41-63)
+        point_kinematics_mulf(A.nn, A.dN_cen, A.X, A.u, ce, A.gp_hist + (e * A.hist_pts + A.ngp) * MULF_HIST, F0, nullptr);
+      else
+        point_kinematics(A.nn, A.dN_cen, A.X, A.u, ce, F0);
       const double fb = pow(det3(F0) / det3(F), 1.0 / 3.0);
 #pragma unroll
       for (int i = 0; i < 9; ++i) F[i] *= fb;

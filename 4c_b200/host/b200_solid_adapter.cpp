@@ -35,11 +35,11 @@ namespace B200Solid
 
   bool DeviceElementBlock::supported(int celltype, int kinem, int tech, int prestress, int material_kind)
   {
-    // general kernel: displacement based only
+    // general kernel: displacement based (+ MULF), pyramid5 also F-bar (+ MULF)
     const bool general_cell = celltype == B200S_TET4 || celltype == B200S_HEX20 || celltype == B200S_WEDGE6 || celltype == B200S_PYRAMID5;
     const bool cell = celltype == B200S_HEX8 || celltype == B200S_HEX27 || celltype == B200S_TET10 || general_cell;
     if (!cell) return false;
-    if (general_cell && tech != B200S_TECH_NONE) return false;
+    if (general_cell && tech != B200S_TECH_NONE && !(celltype == B200S_PYRAMID5 && tech == B200S_TECH_FBAR)) return false;
     const bool hyper = material_kind == B200S_MAT_COUP_NEOHOOKE || material_kind == B200S_MAT_ISO_VOL ||
                        material_kind == B200S_MAT_SVK || material_kind == B200S_MAT_ELASTHYPER;
     if (kinem == B200S_KINEM_LINEAR)
@@ -54,12 +54,14 @@ namespace B200Solid
       return prestress == B200S_PRESTRESS_NONE &&
              (tech == B200S_TECH_NONE || (celltype == B200S_HEX8 && (tech == B200S_TECH_EAS_MILD || tech == B200S_TECH_EAS_FULL)));
     if (!hyper) return false;
-    if (prestress == B200S_PRESTRESS_MULF) return tech == B200S_TECH_NONE;  // MULF + F-bar: CPU loop
+    // F-bar: hex8 and pyramid5, also with MULF (FbarEvaluators, FBarMulfEvaluators: 4C_solid_ele_factory.hpp:59-60,79-81)
+    const bool fbar_cell = celltype == B200S_HEX8 || celltype == B200S_PYRAMID5;
+    if (prestress == B200S_PRESTRESS_MULF) return tech == B200S_TECH_NONE || (tech == B200S_TECH_FBAR && fbar_cell);
     if (prestress != B200S_PRESTRESS_NONE) return false;
     if (tech == B200S_TECH_NONE) return true;
-    // F-bar and EAS are hex8 technologies (4C_solid_ele_factory_lib.hpp)
-    return celltype == B200S_HEX8 &&
-           (tech == B200S_TECH_FBAR || tech == B200S_TECH_EAS_MILD || tech == B200S_TECH_EAS_FULL);
+    if (tech == B200S_TECH_FBAR) return fbar_cell;
+    // EAS is a hex8 technology (4C_solid_ele_factory_lib.hpp)
+    return celltype == B200S_HEX8 && (tech == B200S_TECH_EAS_MILD || tech == B200S_TECH_EAS_FULL);
   }
 
   void DeviceElementBlock::attach_to(DeviceElementBlock& primary)

@@ -143,14 +143,16 @@ extern "C"
   typedef enum
   {
     B200S_TECH_NONE = 0,
-    B200S_TECH_FBAR = 1,     /* hex8: 4C_solid_ele_calc_fbar.hpp */
+    B200S_TECH_FBAR = 1,     /* hex8, pyramid5: 4C_solid_ele_calc_fbar.hpp (pyramid5 and the MULF combination: general kernel) */
     B200S_TECH_EAS_MILD = 2, /* hex8, 9 enhanced strain parameters: 4C_solid_ele_calc_eas.hpp */
     B200S_TECH_EAS_FULL = 3  /* hex8, 21 parameters */
   } b200s_element_technology;
   typedef enum
   {
     B200S_PRESTRESS_NONE = 0,
-    B200S_PRESTRESS_MULF = 1 /* 4C_solid_ele_calc_mulf.hpp (displacement based only; mulf + fbar: CPU path) */
+    B200S_PRESTRESS_MULF = 1 /* 4C_solid_ele_calc_mulf.hpp (every displacement-based cell); with B200S_TECH_FBAR:
+                                4C_solid_ele_calc_mulf_fbar.hpp (hex8, pyramid5) -- the Gauss-point history then carries one more
+                                MulfHistoryData per element, the global history at the centroid, after its Gauss points */
   } b200s_prestress_technology;
 
   /* Core::Elements::ActionType values handled by b200s_evaluate (legacy_enum_definitions;

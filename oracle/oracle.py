@@ -27,7 +27,7 @@ SUM.update({"COUP_ANISOEXPO": 100, "FIBER": 101})  # oracle only, see solid_orac
 STRESS_NONE, STRESS_2PK, STRESS_CAUCHY = 0, 1, 2
 STRAIN_NONE, STRAIN_GL, STRAIN_EA = 0, 1, 2
 ACTION_FORCE, ACTION_FORCE_STIFF = 0, 1
-TECH_NONE, TECH_FBAR, TECH_MULF, TECH_EAS_MILD, TECH_EAS_FULL, TECH_LINEAR = 0, 1, 2, 3, 4, 5
+TECH_NONE, TECH_FBAR, TECH_MULF, TECH_EAS_MILD, TECH_EAS_FULL, TECH_LINEAR, TECH_MULF_FBAR = 0, 1, 2, 3, 4, 5, 6
 MULF_HIST = 19
 
 _dp = C.POINTER(C.c_double)
@@ -91,6 +91,7 @@ def lib():
         L.orc_eas_recover.argtypes = [C.c_int, C.c_int64, _ip, _dp, C.c_double, _dp]
         L.orc_mulf_init_history.argtypes = [C.c_int64, _dp]
         L.orc_update_prestress.argtypes = [C.c_int, C.c_int64, _ip, _dp, _dp, _dp]
+        L.orc_update_prestress_fbar.argtypes = [C.c_int, C.c_int64, _ip, _dp, _dp, _dp]
         L.orc_element_tech.argtypes = [C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp, _dp, _dp]
         L.orc_build_graph.argtypes = [C.c_int, C.c_int64, _ip, C.c_int64, _ip, _ip, C.c_int64, _lp,
                                       _ip]
@@ -427,15 +428,23 @@ def assemble_mass(ct, density, conn, X, node_row_lid, node_col_lid, n_row_nodes,
     return vals, fi
 
 
-def mulf_new_history(ct, n_ele):
-    """Fresh MulfHistoryData of every Gauss point: (n_ele, ngp, MULF_HIST)."""
-    h = np.zeros((n_ele, num_gp(ct), MULF_HIST))
-    lib().orc_mulf_init_history(n_ele * num_gp(ct), _d(h))
+def mulf_new_history(ct, n_ele, fbar=False):
+    """Fresh MulfHistoryData of every Gauss point: (n_ele, ngp, MULF_HIST); fbar (MulfFBarFormulation): one more per
+    element, the global history at the centroid."""
+    npt = num_gp(ct) + (1 if fbar else 0)
+    h = np.zeros((n_ele, npt, MULF_HIST))
+    lib().orc_mulf_init_history(n_ele * npt, _d(h))
     return h
 
 
 def update_prestress(ct, conn, X, u_col, hist):
-    """struct_update_prestress: in place on hist."""
+    """struct_update_prestress: in place on hist (hist with ngp + 1 points per element: MulfFBarFormulation)."""
+    if hist.shape[1] == num_gp(ct) + 1:
+        n = num_nodes(ct)
+        conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, n)
+        lib().orc_update_prestress_fbar(ct, len(conn), _i(conn), _d(np.ascontiguousarray(X, dtype=np.float64)),
+                                        _d(np.ascontiguousarray(u_col, dtype=np.float64)), _d(hist))
+        return
     n = num_nodes(ct)
     conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, n)
     X = np.ascontiguousarray(X, dtype=np.float64)

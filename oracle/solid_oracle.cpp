@@ -1552,10 +1552,26 @@ namespace
     }
   }
 
-  // ---- SolidEleCalc<hex8, FBarFormulation>  (src/solid_ele/4C_solid_ele_calc_fbar.hpp:58-180,
-  //      src/solid_ele/4C_solid_ele_calc_lib_fbar.hpp:47-160)
+  // evaluate_parameter_coordinate_centroid (src/solid_ele/4C_solid_ele_calc_lib.hpp:281-334): hex / nurbs 0, tet 1/4,
+  // pyramid (0, 0, 1/4), wedge (1/3, 1/3, 0)
+  void centroid_xi(int ct, double* xi)
+  {
+    xi[0] = xi[1] = xi[2] = 0.0;
+    if (ct == ORC_TET4 || ct == ORC_TET10) xi[0] = xi[1] = xi[2] = 0.25;
+    if (ct == ORC_PYRAMID5) xi[2] = 0.25;
+    if (ct == ORC_WEDGE6) xi[0] = xi[1] = 1.0 / 3.0;
+  }
+
+  void mulf_kinematics(int n, const double* dN, const double* u, const JacMap& jm, double* h, double* Fdelta, double* F);
+
+  // ---- SolidEleCalc<hex8 | pyramid5, FBarFormulation>  (src/solid_ele/4C_solid_ele_calc_fbar.hpp:58-180,
+  //      src/solid_ele/4C_solid_ele_calc_lib_fbar.hpp:47-160) and, with hist != nullptr,
+  //      SolidEleCalc<hex8 | pyramid5, MulfFBarFormulation> (src/solid_ele/4C_solid_ele_calc_mulf_fbar.hpp:103-243):
+  //      hist = ngauss Gauss-point histories followed by the element's global (centroid) history, ORC_MULF_HIST each;
+  //      the deformation gradients at the points and at the centroid are the MULF ones, everything else -- B-operator and
+  //      H-operator on the reference gradients N_XYZ / N_XYZ_0, the three stiffness terms -- is the F-bar formulation.
   int element_fbar(int ct, int matkind, const double* par, int action, const double* X,
-      const double* u, double* Ke, double* fe)
+      const double* u, double* Ke, double* fe, double* hist = nullptr)
   {
     const int n = nnodes(ct), nd = 3 * n, ng = ngauss(ct);
     double N[MAXN], dN[3 * MAXN];
@@ -1563,12 +1579,16 @@ namespace
     if (Ke) std::memset(Ke, 0, sizeof(double) * nd * nd);
     std::memset(fe, 0, sizeof(double) * nd);
 
-    // prepare(): Jacobian mapping and deformation gradient at the element centroid (:58-66)
-    const double xi0[3] = {0.0, 0.0, 0.0};
+    // prepare(): Jacobian mapping and deformation gradient at the element centroid (:58-66; mulf_fbar.hpp:118-149)
+    double xi0[3];
+    centroid_xi(ct, xi0);
     shape(ct, xi0, N, dN);
     jacobian_mapping(n, dN, X, jm0);
-    double F0[9], iF0[9];
-    deformation_gradient(n, u, jm0, F0);
+    double F0[9], iF0[9], Fd0[9];
+    if (hist)
+      mulf_kinematics(n, dN, u, jm0, hist + ORC_MULF_HIST * ngauss(ct), Fd0, F0);
+    else
+      deformation_gradient(n, u, jm0, F0);
     const double detF0 = det3(F0);
     inv3(iF0, F0);
 
@@ -1591,8 +1611,11 @@ namespace
       shape(ct, gxi + 3 * gp, N, dN);
       jacobian_mapping(n, dN, X, jm);
       const double fac = jm.det * gw[gp];
-      double F[9], iF[9], C[6], Fbar[9], Cbar[6], Ebar[6], S[6], Cm[36];
-      deformation_gradient(n, u, jm, F);
+      double F[9], iF[9], C[6], Fbar[9], Cbar[6], Ebar[6], S[6], Cm[36], Fd[9];
+      if (hist)
+        mulf_kinematics(n, dN, u, jm, hist + ORC_MULF_HIST * gp, Fd, F);
+      else
+        deformation_gradient(n, u, jm, F);
       const double detF = det3(F);
       inv3(iF, F);
       // evaluate_fbar_factor (lib_fbar.hpp:47-51)
@@ -1667,8 +1690,7 @@ namespace
   // Gauss-point history (MulfHistoryData), ORC_MULF_HIST doubles per point:
   //   [0..8] inverse_jacobian (a + 3 b), [9..17] deformation_gradient (a + 3 b), [18] is_setup
   // A fresh history is {identity, identity, 0}; orc_mulf_init_history writes it.
-  void mulf_kinematics(int n, const double* dN, const double* u, const JacMap& jm, double* h,
-      double* Fdelta, double* F)
+  void mulf_kinematics(int n, const double* dN, const double* u, const JacMap& jm, double* h, double* Fdelta, double* F)
   {
     if (h[18] == 0.0)  // calc_mulf.hpp:56-60
     {
@@ -1741,13 +1763,16 @@ namespace
 
   // SolidEleCalc::update_prestress (4C_solid_ele_calc.cpp:478-519) with
   // MulfFormulation::update_prestress (calc_mulf.hpp:124-143)
-  void element_update_prestress(int ct, const double* X, const double* u, double* hist)
+  // with_centroid: MulfFBarFormulation::update_prestress (mulf_fbar.hpp:245-277) -- the same history update at every
+  // Gauss point and once more for the element's global history at the centroid (slot ngauss)
+  void element_update_prestress(int ct, const double* X, const double* u, double* hist, bool with_centroid = false)
   {
     const int n = nnodes(ct), ng = ngauss(ct);
-    double N[MAXN], dN[3 * MAXN], gxi[3 * MAXN], gw[MAXN];
+    double N[MAXN], dN[3 * MAXN], gxi[3 * MAXN + 3], gw[MAXN];
     JacMap jm;
     gauss(ct, gxi, gw);
-    for (int gp = 0; gp < ng; ++gp)
+    centroid_xi(ct, gxi + 3 * ng);
+    for (int gp = 0; gp < ng + (with_centroid ? 1 : 0); ++gp)
     {
       shape(ct, gxi + 3 * gp, N, dN);
       jacobian_mapping(n, dN, X, jm);
@@ -2020,6 +2045,7 @@ namespace
     if (tech == ORC_TECH_LINEAR) return element_linear(ct, matkind, par, action, X, u, Ke, fe, hist);
     if (tech == ORC_TECH_MULF) return element_mulf(ct, matkind, par, action, X, u, hist, Ke, fe);
     if (tech == ORC_TECH_FBAR) return element_fbar(ct, matkind, par, action, X, u, Ke, fe);
+    if (tech == ORC_TECH_MULF_FBAR) return element_fbar(ct, matkind, par, action, X, u, Ke, fe, hist);
     return element(ct, matkind, par, action, X, u, Ke, fe);
   }
 }  // namespace
@@ -2243,7 +2269,8 @@ extern "C"
       {
         double N[MAXN], dN[3 * MAXN], F0[9];
         JacMap jm0;
-        const double xi0[3] = {0.0, 0.0, 0.0};
+        double xi0[3];
+        centroid_xi(ct, xi0);
         shape(ct, xi0, N, dN);
         jacobian_mapping(n, dN, X, jm0);
         deformation_gradient(n, u, jm0, F0);
@@ -2642,6 +2669,23 @@ extern "C"
   }
 
   // struct_update_prestress over the column elements (model_evaluator_structure.cpp:1608-1642)
+  void orc_update_prestress_fbar(int ct, int64_t n_ele, const int32_t* conn, const double* X, const double* u_col,
+      double* hist)
+  {
+    // MulfFBarFormulation: ngauss + 1 histories per element (the last one is the global / centroid history)
+    const int n = nnodes(ct), nd = 3 * n, ng = ngauss(ct);
+    std::vector<double> Xe(nd), ue(nd);
+    for (int64_t e = 0; e < n_ele; ++e)
+    {
+      for (int i = 0; i < n; ++i)
+        for (int d = 0; d < 3; ++d)
+        {
+          Xe[3 * i + d] = X[3 * (int64_t)conn[e * n + i] + d];
+          ue[3 * i + d] = u_col[3 * (int64_t)conn[e * n + i] + d];
+        }
+      element_update_prestress(ct, Xe.data(), ue.data(), hist + (int64_t)ORC_MULF_HIST * (ng + 1) * e, true);
+    }
+  }
   void orc_update_prestress(int ct, int64_t n_ele, const int32_t* conn, const double* X,
       const double* u_col, double* hist)
   {
@@ -2670,9 +2714,11 @@ extern "C"
     (void)n_col_nodes;
     const bool mat_hist = matkind == ORC_MAT_DRUCKER_PRAGER;  // history material: small strains only
     if (mat_hist && tech != ORC_TECH_LINEAR) return -1;
-    const bool needs_hist = tech == ORC_TECH_MULF || tech == ORC_TECH_EAS_MILD || tech == ORC_TECH_EAS_FULL || mat_hist;
+    const bool needs_hist = tech == ORC_TECH_MULF || tech == ORC_TECH_MULF_FBAR || tech == ORC_TECH_EAS_MILD ||
+                            tech == ORC_TECH_EAS_FULL || mat_hist;
     if (needs_hist && hist == nullptr) return -1;
     const int64_t hist_per_ele = mat_hist ? (int64_t)ORC_DP_HIST * ngauss(ct)
+                                 : tech == ORC_TECH_MULF_FBAR ? (int64_t)ORC_MULF_HIST * (ngauss(ct) + 1)
                                  : tech == ORC_TECH_MULF ? (int64_t)ORC_MULF_HIST * ngauss(ct)
                                                          : (needs_hist ? orc_eas_hist_size(tech) : 0);
     const int n = nnodes(ct), nd = 3 * n;

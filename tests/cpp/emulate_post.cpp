@@ -192,7 +192,7 @@ static int run_generic_nn(const GenericArgs& Ga)
 extern "C" int emu_generic(int celltype, int matkind, const double* params, int linear, int stiff, int64_t n_ele,
     const int32_t* conn, const double* X, const double* u_col, const int32_t* pos, int pos_stride,
     const int64_t* node_rowstart, const int32_t* node_rowlen, const int32_t* node_frow, int64_t n_col_nodes, double* vals,
-    double* f, const double* gp_hist)
+    double* f, const double* gp_hist, int fbar)
 {
   std::vector<NodeRow> node_row(n_col_nodes);
   for (int64_t k = 0; k < n_col_nodes; ++k)
@@ -206,6 +206,7 @@ extern "C" int emu_generic(int celltype, int matkind, const double* params, int 
   if (!make_mat_params(matkind, params, A.mp)) return -3;
   Ga.dN_gp = T.dN_gp.data(), Ga.dN_node = T.dN_node.data(), Ga.w = T.w.data();
   Ga.nn = T.nn, Ga.ngp = T.ngp, Ga.pos_stride = pos_stride, Ga.stiff = stiff;
+  Ga.dN_cen = fbar ? T.dN_cen.data() : nullptr, Ga.hist_pts = T.ngp + (fbar ? 1 : 0);
   if (matkind == MAT_COUP_NEOHOOKE) return run_generic_nn<MAT_COUP_NEOHOOKE>(Ga);
   if (matkind == MAT_ISO_VOL) return run_generic_nn<MAT_ISO_VOL>(Ga);
   return run_generic_nn<MAT_SVK>(Ga);
@@ -251,6 +252,7 @@ extern "C" int emu_generic_drucker_prager(int celltype, const double* in10, int 
   A.mp.hyper = nullptr, A.mp.fiber = nullptr, A.mp.ext = q, A.mp.hist = nullptr;
   Ga.dN_gp = T.dN_gp.data(), Ga.dN_node = T.dN_node.data(), Ga.w = T.w.data();
   Ga.nn = T.nn, Ga.ngp = T.ngp, Ga.pos_stride = pos_stride, Ga.stiff = stiff;
+  Ga.dN_cen = nullptr, Ga.hist_pts = T.ngp;
   return T.nn == 8 ? run_generic_dp<8>(Ga) : (T.nn == 10 ? run_generic_dp<10>(Ga) : run_generic_dp<27>(Ga));
 }
 
@@ -266,7 +268,7 @@ extern "C" int emu_post(int celltype, int fbar, int matkind, const double* param
   A.X = X, A.u = u_col, A.conn = conn, A.per_ele_param = per_ele, A.ele_id = nullptr, A.fibers = nullptr;
   A.ele_is_row = ele_is_row, A.dN_gp = T.dN_gp.data(), A.dN_cen = T.dN_cen.data(), A.w = T.w.data();
   A.mp = mp, A.n_ele = n_ele, A.nn = T.nn, A.ngp = T.ngp, A.fbar = fbar == 1, A.linear = fbar == 2;
-  A.gp_hist = gp_hist;
+  A.gp_hist = gp_hist, A.hist_pts = T.ngp + ((gp_hist && fbar) ? 1 : 0);
   A.mat_hist = nullptr;
   A.eas_neas = 0, A.eas_hist_size = 0, A.eas_t0_stride = 0, A.eas_hist = nullptr, A.eas_t0 = nullptr;
   A.xi_gp = T.xi_gp.data();
@@ -316,14 +318,15 @@ extern "C" int emu_mass(int celltype, double density, int lumped, int64_t n_ele,
 
 // MULF history: fresh set-up (what k_mulf_init does) and struct_update_prestress (k_mulf_update)
 extern "C" int emu_mulf_history(int celltype, int update, int64_t n_ele, const int32_t* conn, const double* X,
-    const double* u_col, double* hist)
+    const double* u_col, double* hist, int with_centroid)
 {
   const CellTables T = make_cell_tables(celltype);
+  const int npt = T.ngp + (with_centroid ? 1 : 0);  // MULF + F-bar: the centroid history follows the Gauss points'
   for (int64_t e = 0; e < n_ele; ++e)
-    for (int g = 0; g < T.ngp; ++g)
+    for (int g = 0; g < npt; ++g)
     {
-      double* h = hist + (e * T.ngp + g) * MULF_HIST;
-      const double* dN = T.dN_gp.data() + (size_t)g * T.nn * 3;
+      double* h = hist + (e * npt + g) * MULF_HIST;
+      const double* dN = g < T.ngp ? T.dN_gp.data() + (size_t)g * T.nn * 3 : T.dN_cen.data();
       const int32_t* ce = conn + e * T.nn;
       if (update)
         mulf_update_point(T.nn, dN, X, u_col, ce, h);

@@ -536,6 +536,9 @@ if __name__ == "__main__":
                       ("eas_mild", "tests/input_files/solid_ele_hex8_Standard_eas_mild_stressout_2pk_strainout_gl.4C.yaml")):
         with open(os.path.join(HERE, f"integration_hex8_{tech}.json"), "w") as fh:
             json.dump(mulf_case("hex8", rel, tech), fh, indent=1)
+    for name, cell in (("pyramid5_fbar", "pyramid5"), ("hex8_fbar", "hex8"), ("hex8_mulf_fbar", "hex8")):
+        with open(os.path.join(HERE, f"integration_{name}.json"), "w") as fh:
+            json.dump(mulf_case(cell, f"tests/input_files/solid_ele_{cell}_Standard_{name[len(cell) + 1:]}.4C.yaml", "fbar"), fh, indent=1)
     with open(os.path.join(HERE, "integration_hex8_loadlin.json"), "w") as fh:
         json.dump(loadlin_case("tests/input_files/loadlin.4C.yaml"), fh)
     with open(os.path.join(HERE, "integration_hex8_isoogden.json"), "w") as fh:

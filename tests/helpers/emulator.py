@@ -92,18 +92,19 @@ def material(matkind, params, Cv):
     return S, Cm.reshape(6, 6), psi.value
 
 
-def mulf_history(celltype, conn, X, u_col=None, hist=None):
-    """hist is None: fresh history (n_ele, ngp, 18); else struct_update_prestress in place for state u_col."""
+def mulf_history(celltype, conn, X, u_col=None, hist=None, fbar=False):
+    """hist is None: fresh history (n_ele, ngp, 18); else struct_update_prestress in place for state u_col.
+    fbar: MULF + F-bar, ngp + 1 histories per element (the centroid's last)."""
     conn = np.ascontiguousarray(conn, np.int32)
     X = np.ascontiguousarray(X, np.float64)
     ngp = {0: 8, 1: 27, 2: 4, 3: 1, 4: 27, 5: 6, 6: 8}[celltype]
     update = hist is not None
     if hist is None:
-        hist = np.zeros((len(conn), ngp, 18))
+        hist = np.zeros((len(conn), ngp + (1 if fbar else 0), 18))
     u = None if u_col is None else np.ascontiguousarray(u_col, np.float64)
     assert hist.flags["C_CONTIGUOUS"]
     rc = lib("post").emu_mulf_history(C.c_int(celltype), C.c_int(int(update)), C.c_int64(len(conn)), _p(conn), _p(X),
-                                      _p(u), _p(hist))
+                                      _p(u), _p(hist), C.c_int(int(fbar)))
     assert rc == 0
     return hist
 
@@ -280,7 +281,7 @@ def generic_drucker_prager(celltype, in10, conn, X, u_col, rowptr, colind, node_
 
 
 def generic(celltype, matkind, params, conn, X, u_col, rowptr, colind, node_row_lid, node_col_lid, n_row_nodes, linear=False,
-            stiff=True, gp_hist=None):
+            stiff=True, gp_hist=None, fbar=False):
     """Emulated general kernel (generic_kernel.cuh) for the hyperelastic kinds 0..2 and any cell type of
     shape_tables.hpp (tet4 / hex20 blocks run through it on the device)."""
     conn = np.ascontiguousarray(conn, np.int32)
@@ -289,10 +290,10 @@ def generic(celltype, matkind, params, conn, X, u_col, rowptr, colind, node_row_
     vals, f = np.zeros(rowptr[-1]), np.zeros(3 * n_row_nodes)
     L = lib("post")
     L.emu_generic.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 4 + [C.c_int] + \
-        [C.c_void_p] * 3 + [C.c_int64] + [C.c_void_p] * 3
+        [C.c_void_p] * 3 + [C.c_int64] + [C.c_void_p] * 3 + [C.c_int]
     rc = L.emu_generic(int(celltype), int(matkind), _p(np.ascontiguousarray(params, np.float64)), int(linear), int(stiff),
                        len(conn), _p(conn), _p(np.ascontiguousarray(X, np.float64)),
                        _p(np.ascontiguousarray(u_col, np.float64)), _p(pos), pos.shape[1], _p(rowstart), _p(rowlen),
-                       _p(frow), len(rowstart), _p(vals), _p(f), _p(gp_hist))
+                       _p(frow), len(rowstart), _p(vals), _p(f), _p(gp_hist), int(fbar))
     assert rc == 0, rc
     return vals, f

@@ -88,3 +88,34 @@ def test_emulated_general_kernel_mulf_matches_oracle(cell):
         orc.update_prestress(ct, rm.conn, rm.X.ravel(), us, ohist)
         emu.mulf_history(rm.celltype, rm.conn, rm.X.ravel(), us, phist)
         assert np.abs(phist - ohist[:, :, :18]).max() <= 1e-13 * np.abs(ohist).max()
+
+
+@pytest.mark.parametrize("cell", ["hex8", "pyramid5"])
+@pytest.mark.parametrize("mulf", [False, True])
+def test_emulated_general_kernel_fbar_matches_oracle(cell, mulf):
+    """TECH fbar (FbarEvaluators = hex8, pyramid5) and TECH fbar + PRESTRESS_TECH mulf (FBarMulfEvaluators, the same two cells:
+    src/solid_ele/4C_solid_ele_factory.hpp:59-60,79-81) in the general kernel -- centroid mapping, F_bar, the three
+    stiffness terms of the non-symmetric F-bar tangent, for MULF the Gauss-point and centroid histories and their
+    update -- stepped on the CPU against the oracle."""
+    if cell == "hex8":
+        rm = b200.partition.box_partition(b200.mesh.HEX8, (2, 2, 2), 0, 1)
+        ct, h = orc.HEX8, 0.4
+    else:
+        ct, rm, h = _mesh(cell)
+    u = 2.0 * b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, h)
+    rowptr, colind = orc.build_graph(ct, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    maps = (rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    for mk, par in ((orc.MAT_COUP_NEOHOOKE, [200.0, 0.25]), (orc.MAT_ISO_VOL, [1.0, 1000.0])):
+        ohist = orc.mulf_new_history(ct, rm.n_col_eles, fbar=True) if mulf else None
+        phist = emu.mulf_history(rm.celltype, rm.conn, rm.X.ravel(), fbar=True) if mulf else None
+        for scale in (1.0, -0.6, 0.3):
+            us = scale * u.ravel()
+            rK, rf, nbad = orc.evaluate_assemble(ct, mk, par, rm.conn, rm.X.ravel(), us, *maps, rowptr, colind,
+                                                 tech=orc.TECH_MULF_FBAR if mulf else orc.TECH_FBAR, hist=ohist)
+            K, f = emu.generic(rm.celltype, mk, par, rm.conn, rm.X.ravel(), us, rowptr, colind, *maps, gp_hist=phist, fbar=True)
+            ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, 1e-12)
+            assert ok and nbad == 0, (mk, scale, wK, wf)
+            if mulf:
+                orc.update_prestress(ct, rm.conn, rm.X.ravel(), us, ohist)
+                emu.mulf_history(rm.celltype, rm.conn, rm.X.ravel(), us, phist, fbar=True)
+                assert np.abs(phist - ohist[:, :, :18]).max() <= 1e-13 * np.abs(ohist).max()

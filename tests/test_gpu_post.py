@@ -389,7 +389,7 @@ def test_mulf_prestressing_procedure_through_cuda_path():
     asm.close()
 
 
-def test_update_prestress_needs_mulf_and_mulf_fbar_is_rejected():
+def test_update_prestress_needs_mulf_and_mulf_eas_is_rejected():
     ct, rm, u = _mesh("hex8", (2, 2, 2))
     asm = b200.DeviceAssembler(rm, capi.MAT_SVK, [1000.0, 0.3])
     asm.set_state("displacement", u.ravel())
@@ -397,7 +397,7 @@ def test_update_prestress_needs_mulf_and_mulf_fbar_is_rejected():
         asm.update_prestress()
     assert ei.value.code == capi.ERR_UNSUPPORTED
     with pytest.raises(capi.B200SolidError) as ei:
-        asm.ctx.set_element_properties(tech=capi.TECH_FBAR, prestress=capi.PRESTRESS_MULF)
+        asm.ctx.set_element_properties(tech=capi.TECH_EAS_MILD, prestress=capi.PRESTRESS_MULF)
     assert ei.value.code == capi.ERR_UNSUPPORTED
     asm.close()
 

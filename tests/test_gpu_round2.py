@@ -746,3 +746,88 @@ def test_reference_general_cells_mulf_known_answers_through_cuda_path(cell):
     for e in case["expected_disp"]:
         assert abs(u[e["node"], e["dof"]] - e["value"]) < 1e-10, (e, u[e["node"], e["dof"]])
     asm.close()
+
+
+# ---- TECH fbar on pyramid5 and TECH fbar + PRESTRESS_TECH mulf (hex8, pyramid5) through the general kernel -----------
+def _fbar_mesh(cell):
+    if cell == "hex8":
+        return orc.HEX8, b200.partition.box_partition(b200.mesh.HEX8, (4, 3, 3), 0, 1), 0.25
+    return _general_mesh("pyramid5")
+
+
+@pytest.mark.parametrize("cell", ["hex8", "pyramid5"])
+@pytest.mark.parametrize("mulf", [False, True])
+def test_general_kernel_fbar_and_mulf_fbar_match_oracle(cell, mulf):
+    """FbarEvaluators / FBarMulfEvaluators = hex8, pyramid5 (src/solid_ele/4C_solid_ele_factory.hpp:59-60,79-81): K (not
+    symmetric), f, the histories after update_prestress and the stress output against the oracle; for hex8 without MULF the
+    general kernel (option general_kernel) also against the fast F-bar kernel."""
+    ct, rm, h = _fbar_mesh(cell)
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, h)
+    mk, par = capi.MAT_ISO_VOL, [1.0, 1000.0]
+    asm = b200.DeviceAssembler(rm, mk, par, tech=capi.TECH_FBAR, prestress=capi.PRESTRESS_MULF if mulf else capi.PRESTRESS_NONE,
+                               options={"general_kernel": 1})
+    rowptr, colind = asm.graph()
+    ohist = orc.mulf_new_history(ct, rm.n_col_eles, fbar=True) if mulf else None
+    maps = (rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, rowptr, colind)
+    for scale in (1.0, -0.6, 0.3):
+        us = scale * u.ravel()
+        asm.set_state("displacement", us[:3 * rm.n_row_nodes])
+        K, f, err = asm.evaluate("struct_calc_nlnstiff")
+        rK, rf, nbad = orc.evaluate_assemble(ct, mk, par, rm.conn, rm.X.ravel(), us, *maps,
+                                             tech=orc.TECH_MULF_FBAR if mulf else orc.TECH_FBAR, hist=ohist)
+        # after a prestress update the two histories differ by round-off (1e-13 below) and the nearly incompressible
+        # material (kappa / mue = 1000) amplifies that in p = kappa (J - 1): 1e-11 from the second state on
+        tol = RTOL if (not mulf or scale == 1.0) else 1e-11
+        ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, tol)
+        assert ok and nbad == 0 and err.n_neg_jacobian == 0, (scale, wK, wf)
+        _, f2, _ = asm.evaluate("struct_calc_internalforce")
+        assert np.abs(f2 - rf).max() <= tol * np.abs(rf).max()
+        if mulf:
+            asm.update_prestress()
+            orc.update_prestress(ct, rm.conn, rm.X.ravel(), us, ohist)
+            hh = asm.ctx.get_gp_history().reshape(rm.n_col_eles, orc.num_gp(ct) + 1, 18)
+            assert np.abs(hh - ohist[:, :, :18]).max() <= 1e-13 * np.abs(ohist).max()
+    if cell == "hex8" and not mulf:
+        fast = b200.DeviceAssembler(rm, mk, par, tech=capi.TECH_FBAR)
+        fast.set_state("displacement", us[:3 * rm.n_row_nodes])
+        Kf, ff, _ = fast.evaluate()
+        ok, wK, wf = b200.parity_report(rowptr, K, Kf, f, ff, RTOL)
+        assert ok, (wK, wf)
+        fast.close()
+    asm.close()
+
+
+@pytest.mark.parametrize("name", ["pyramid5_fbar", "hex8_mulf_fbar", "hex8_fbar"])
+def test_reference_fbar_known_answers_through_general_kernel(name):
+    """RESULT DESCRIPTION displacements of tests/input_files/solid_ele_pyramid5_Standard_fbar.4C.yaml,
+    solid_ele_hex8_Standard_mulf_fbar.4C.yaml and solid_ele_hex8_Standard_fbar.4C.yaml (fibre material) with the CUDA path
+    doing every evaluate and prestress update."""
+    import json
+    import os
+    from tests.helpers.newton import solve_case
+    case = json.load(open(os.path.join(os.path.dirname(__file__), "golden", f"integration_{name}.json")))
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    rm = b200.partition.serial_mesh(getattr(b200.mesh, case["celltype"].upper()), X, conn)
+    nh, fib = case["summands"][0]["params"], case["summands"][1]["params"]
+    mat = [("COUP_NEOHOOKE", [nh["YOUNG"], nh["NUE"]]), ("COUP_ANISOEXPO", [fib["K1"], fib["K2"], fib["K1COMP"], fib["K2COMP"]])]
+    mulf = case["prestresstime"] > 0
+    asm = b200.DeviceAssembler(rm, capi.MAT_ELASTHYPER, mat, tech=capi.TECH_FBAR,
+                               prestress=capi.PRESTRESS_MULF if mulf else capi.PRESTRESS_NONE,
+                               fibers=np.asarray(case["fibers"], float), options={"general_kernel": 1})
+    rowptr, colind = asm.graph()
+
+    def ev(u):
+        asm.set_state("displacement", u)
+        K, f, _ = asm.evaluate()
+        return rowptr, colind, K, f
+
+    def up(u):
+        asm.set_state("displacement", u)
+        asm.update_prestress()
+
+    u = solve_case(case, ev, update_prestress=up if mulf else None)
+    assert len(case["expected_disp"]) >= 12
+    for e in case["expected_disp"]:
+        assert abs(u[e["node"], e["dof"]] - e["value"]) < 1e-10, (e, u[e["node"], e["dof"]])
+    asm.close()

@@ -340,6 +340,38 @@ def test_mulf_prestress_known_answers(cell):
         assert abs(u[e["node"], e["dof"]] - e["value"]) < 1e-11, (e, u[e["node"], e["dof"]])
 
 
+@pytest.mark.parametrize("name", ["hex8_fbar", "pyramid5_fbar", "hex8_mulf_fbar"])
+def test_fbar_and_mulf_fbar_known_answers(name):
+    """RESULT DESCRIPTION displacements of tests/input_files/solid_ele_hex8_Standard_fbar, solid_ele_pyramid5_Standard_fbar
+    (FbarEvaluators = hex8, pyramid5: 4C_solid_ele_factory.hpp:59-60; the pyramid's centroid is (0, 0, 1/4)) and
+    solid_ele_hex8_Standard_mulf_fbar (MulfFBarFormulation: Gauss-point histories + the element's centroid history, two
+    prestress steps + two load steps).  Pins the oracle's F-bar / MULF F-bar restatement."""
+    case = json.load(open(os.path.join(G, f"integration_{name}.json")))
+    ct = getattr(orc, case["celltype"].upper())
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    fibers = np.asarray(case["fibers"], float)
+    nn = len(X)
+    row, col = serial_maps(nn)
+    rowptr, colind = orc.build_graph(ct, conn, row, col, nn)
+    par = _mulf_material(case)
+    mulf = case["prestresstime"] > 0
+    hist = orc.mulf_new_history(ct, len(conn), fbar=True) if mulf else None
+
+    def evaluate(u):
+        vals, f, nbad = orc.evaluate_assemble(ct, orc.MAT_ELASTHYPER, par, conn, X.ravel(), u, row, col, nn, rowptr, colind,
+                                              tech=orc.TECH_MULF_FBAR if mulf else orc.TECH_FBAR, hist=hist,
+                                              mue_per_ele=fibers.ravel())
+        assert nbad == 0
+        return rowptr, colind, vals, f
+
+    u = solve_case(case, evaluate,
+                   update_prestress=(lambda uu: orc.update_prestress(ct, conn, X.ravel(), uu, hist)) if mulf else None)
+    assert len(case["expected_disp"]) >= 12
+    for e in case["expected_disp"]:
+        assert abs(u[e["node"], e["dof"]] - e["value"]) < 1e-11, (e, u[e["node"], e["dof"]])
+
+
 def test_mulf_update_keeps_the_stress_state():
     """After struct_update_prestress and the displacement reset the element sees the same deformation
     gradient (F_delta = I, F = F_hist), hence the same internal force."""
