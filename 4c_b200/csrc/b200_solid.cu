@@ -2,6 +2,9 @@
 // declared in include/b200_solid.h.  sm_100a only; FP64 throughout; no CPU fallback.
 #include <cub/cub.cuh>
 #include <cuda_runtime.h>
+#ifndef B200S_L2_HINTS
+#define B200S_L2_HINTS 0  // experiment switch: bit 0 = evict-first loads of the scatter map, bit 1 = evict-last REDs
+#endif
 #include <dlfcn.h>
 #include <nvtx3/nvToolsExt.h>  // header-only: ranges are no-ops unless a profiler injects itself
 #include <sys/mman.h>
@@ -129,6 +132,21 @@ namespace b200s
                  "l"(gmem)
                  : "memory");
   }
+  // streaming variant for data read exactly once per evaluate (the element -> CSR-slot map): L2 evict-first, so that
+  // the map does not push partially accumulated CSR rows out of L2 (B200S_L2_HINTS bit 0; A/B in profiles/r02w_summary.md)
+  __device__ __forceinline__ void cp_async16_stream(void* smem, const void* gmem)
+  {
+#if (B200S_L2_HINTS & 1)
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem)),
+                 "l"(gmem), "l"(pol)
+                 : "memory");
+#else
+    cp_async16(smem, gmem);
+#endif
+  }
   __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
   // all but the most recently committed group are complete
   __device__ __forceinline__ void cp_async_wait_but_last() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
@@ -219,7 +237,7 @@ namespace b200s
       {
         const int chunk = lane + 32 * h;  // 16-byte chunk of the tile's 1 KB map; 16 chunks / element
         if (e0 + (chunk >> 4) < A.n_ele)
-          cp_async16(S.pos + 4 * chunk, A.pos + e0 * (NN * NN) + 4 * chunk);
+          cp_async16_stream(S.pos + 4 * chunk, A.pos + e0 * (NN * NN) + 4 * chunk);
       }
     }
   }  // namespace hex8
@@ -649,7 +667,7 @@ namespace b200s
       {
         const int chunk = lane + 32 * h;  // 16-byte chunk of the tile's 1200-byte map; 25 chunks / element
         if (chunk < POS_INTS / 4 && e0 + chunk / 25 < A.n_ele)
-          cp_async16(S.pos + 4 * chunk, A.pos + e0 * (NN * NN) + 4 * chunk);
+          cp_async16_stream(S.pos + 4 * chunk, A.pos + e0 * (NN * NN) + 4 * chunk);
       }
     }
   }  // namespace tet10

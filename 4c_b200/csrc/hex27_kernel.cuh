@@ -309,19 +309,37 @@ namespace b200s
       const int kk = SUB * s + t;
       const int k = NBLK * w + kk;
       const bool on = t < SUB && kk < NBLK && !(tr && k == 0);
-#pragma unroll 3
-      for (int i = 0; i < NN; ++i)
+      // three row nodes per step: their shared-memory reads (row info, map entry, staged block entries) first, then
+      // the REDs -- no branch between the loads, so their latencies overlap
+#pragma unroll 1
+      for (int i0 = 0; i0 < NN; i0 += 3)
       {
-        const NodeRow r = S.nrow[i];
-        if (r.rowstart < 0 || !on) continue;  // first condition is warp uniform
-        int j = tr ? i - k : i + k;
-        j = j < 0 ? j + NN : (j >= NN ? j - NN : j);
-        double* dst = A.vals + (r.rowstart + S.pos[i * NN + j] + c);
-        const double* src = tr ? stage + j * STAGE_LSTRIDE + 9 * t + c : stage + i * STAGE_LSTRIDE + 9 * t + 3 * c;
-        const int sb = tr ? 3 : 1;  // stride over the row dof b inside the staged block
-        B2_RED_ADD(dst, src[0]);
-        B2_RED_ADD(dst + r.rowlen, src[sb]);
-        B2_RED_ADD(dst + 2 * (int64_t)r.rowlen, src[2 * sb]);
+        int64_t off[3];
+        int32_t len[3];
+        double v[3][3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+        {
+          const int i = i0 + q;
+          const NodeRow r = S.nrow[i];
+          int j = tr ? i - k : i + k;
+          j = j < 0 ? j + NN : (j >= NN ? j - NN : j);
+          const bool act = on && r.rowstart >= 0;  // the row-ownership part is warp uniform
+          off[q] = act ? r.rowstart + S.pos[i * NN + (on ? j : 0)] + c : -1;
+          len[q] = r.rowlen;
+          const double* src = tr ? stage + j * STAGE_LSTRIDE + 9 * t + c : stage + i * STAGE_LSTRIDE + 9 * t + 3 * c;
+          const int sb = tr ? 3 : 1;  // stride over the row dof b inside the staged block
+          v[q][0] = on ? src[0] : 0.0, v[q][1] = on ? src[sb] : 0.0, v[q][2] = on ? src[2 * sb] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+          if (off[q] >= 0)
+          {
+            double* dst = A.vals + off[q];
+            B2_RED_ADD(dst, v[q][0]);
+            B2_RED_ADD(dst + len[q], v[q][1]);
+            B2_RED_ADD(dst + 2 * (int64_t)len[q], v[q][2]);
+          }
       }
     }
 

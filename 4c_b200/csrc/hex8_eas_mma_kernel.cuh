@@ -565,14 +565,30 @@ namespace b200s
         if (fr_ >= 0) atomicAdd(A.f + fr_ + cl, sm[L::FE + lane]);
         if (STIFF)
 #pragma unroll
-          for (int i = 0; i < NN; ++i)
+          for (int h = 0; h < NN; h += 4)
           {
-            const NodeRow nr = nrow[i];
-            if (nr.rowstart < 0) continue;
-            double* dst = A.vals + nr.rowstart + pos[i * NN + jl] + cl;
-            atomicAdd(dst, Ke[(3 * i) * L::KE_RS + lane]);
-            atomicAdd(dst + nr.rowlen, Ke[(3 * i + 1) * L::KE_RS + lane]);
-            atomicAdd(dst + 2 * (int64_t)nr.rowlen, Ke[(3 * i + 2) * L::KE_RS + lane]);
+            // the shared-memory reads of four row nodes first, then their REDs (no branch between the loads)
+            int64_t off[4];
+            int32_t len[4];
+            double v[4][3];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+            {
+              const NodeRow nr = nrow[h + i];
+              off[i] = nr.rowstart >= 0 ? nr.rowstart + pos[(h + i) * NN + jl] + cl : -1;  // -1: row node not owned
+              len[i] = nr.rowlen;
+#pragma unroll
+              for (int b = 0; b < 3; ++b) v[i][b] = Ke[(3 * (h + i) + b) * L::KE_RS + lane];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (off[i] >= 0)
+              {
+                double* dst = A.vals + off[i];
+                atomicAdd(dst, v[i][0]);
+                atomicAdd(dst + len[i], v[i][1]);
+                atomicAdd(dst + 2 * (int64_t)len[i], v[i][2]);
+              }
           }
       }
       __syncwarp();

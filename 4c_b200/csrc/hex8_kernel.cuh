@@ -361,7 +361,16 @@ namespace b200s
       }
     }
 
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(B200S_L2_HINTS) && (B200S_L2_HINTS & 2)
+    // experiment (profiles/r02w_summary.md): REDs into the CSR values with an L2 evict-last policy
+    __device__ __forceinline__ void red_add_keep(double* p, double v)
+    {
+      unsigned long long pol;
+      asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+      asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol));
+    }
+#define B2_RED_ADD(ptr, v) ::b200s::hex8::red_add_keep((ptr), (v))
+#elif defined(__CUDA_ARCH__)
 #define B2_RED_ADD(ptr, v) atomicAdd((ptr), (v))
 #else
 #define B2_RED_ADD(ptr, v) (*(ptr) += (v))

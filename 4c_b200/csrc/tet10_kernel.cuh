@@ -397,6 +397,11 @@ namespace b200s
         if (!STIFF) continue;
         const double* Ke = S.mp + el * KE_ESTRIDE + lane;
         const int32_t* pos = S.pos + el * (NN * NN) + jl;
+        // one row node per step, loads and REDs interleaved.  (Measured: hoisting all shared-memory reads ahead of the
+        // REDs, as hex8::scatter does, removes the latency stalls ncu shows here and makes the kernel SLOWER, 14.40 ->
+        // 14.86 ms on config 4 -- the REDs themselves are the limit, 3.56e9 lane-adds in runs of three doubles against
+        // 412 G/s of the run-3 microbenchmark = 8.6 ms, and issuing them in bursts only backs up the LSU queue;
+        // profiles/r02w_summary.md)
 #pragma unroll
         for (int i = 0; i < NN; ++i)
         {

@@ -40,6 +40,10 @@ for path in sys.argv[3:]:
     L.b200s_last_error.restype = C.c_char_p
     hdl = vp()
     assert L.b200s_create(0, 0, 1, C.byref(hdl)) == 0
+    L.b200s_set_option.argtypes = [vp, C.c_char_p, C.c_double]
+    for kv in os.environ.get("LIBPROBE_OPTS", "").split():  # e.g. LIBPROBE_OPTS="scatter_mode=1"
+        k, v = kv.split("=")
+        assert L.b200s_set_option(hdl, k.encode(), float(v)) == 0, kv
     assert L.b200s_set_mesh(hdl, rm.celltype, len(Xc), Xc.ctypes.data, len(cc), cc.ctypes.data) == 0
     assert L.b200s_set_material(hdl, mat, p.ctypes.data, len(p), None) == 0
     nnz = i64(0)
@@ -55,5 +59,5 @@ for path in sys.argv[3:]:
         L.b200s_evaluate_async(hdl, 1)
     L.b200s_synchronize(hdl, None)
     L.b200s_kernel_time(hdl, C.byref(s), C.byref(c), 1)
-    print(f"LIBPROBE {os.path.basename(path):16s} {cell} n={n} nnz={nnz.value} kernel {s.value / max(c.value, 1):.3f} ms over {c.value} evaluates", flush=True)
+    print(f"LIBPROBE {os.path.basename(path):16s} {os.environ.get('LIBPROBE_OPTS', ''):16s} {cell} n={n} nnz={nnz.value} kernel {s.value / max(c.value, 1):.3f} ms over {c.value} evaluates", flush=True)
     L.b200s_destroy(hdl)
