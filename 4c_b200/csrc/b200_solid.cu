@@ -1444,6 +1444,7 @@ struct b200s_ctx
   double* d_fibers = nullptr;   // unit element fibres FIBER1, 3 per column element, device element order
   double density = 0.0;         // Mat::So3Material::density()
   double visco_in[6] = {0, 0, 0, 0, 0, 0};  // MAT_VISCONEOHOOKE input-file parameters
+  double plastic_in[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // MAT_Struct_PlasticNlnLogNeoHooke input-file parameters
   double dt = 0.0;              // EvaluationContext::time_step_size
   bool dt_set = false;
   // cell tables in global memory for the post / mass kernels (post_kernels.cuh)
@@ -1950,7 +1951,9 @@ namespace
   // history doubles per Gauss point of the block's material
   inline int mat_hist_per_gp(const b200s_ctx* ctx)
   {
-    return ctx->matkind == B200S_MAT_DRUCKER_PRAGER ? DP_HIST : (ctx->matkind == B200S_MAT_VISCONEOHOOKE ? VISCO_HIST : 0);
+    return ctx->matkind == B200S_MAT_DRUCKER_PRAGER
+               ? DP_HIST
+               : (ctx->matkind == B200S_MAT_VISCONEOHOOKE ? VISCO_HIST : (ctx->matkind == B200S_MAT_PLASTIC_NLNLOG ? PLASTIC_HIST : 0));
   }
   // fresh history of a history material: what Mat::PlasticDruckerPrager::setup(numgp) does per element
   // (src/mat/4C_mat_plasticdruckerprager.cpp:109-117): zero plastic strains at every Gauss point
@@ -1961,6 +1964,13 @@ namespace
     const int64_t n = ctx->n_col_eles * ctx->ngp * mat_hist_per_gp(ctx);
     if (to_device(ctx, &ctx->d_mat_hist, (const double*)nullptr, n)) return B200S_ERR_CUDA;
     CK(cudaMemsetAsync(ctx->d_mat_hist, 0, sizeof(double) * (size_t)(n > 0 ? n : 1), ctx->stream));
+    if (ctx->matkind == B200S_MAT_PLASTIC_NLNLOG && n > 0)
+    {
+      // PlasticNlnLogNeoHooke::setup (:337-349): inverse plastic right Cauchy-Green tensors = identity
+      const int64_t np = ctx->n_col_eles * ctx->ngp;
+      k_plastic_history_init<<<nblk(np, 128), 128, 0, ctx->stream>>>(np, ctx->d_mat_hist);
+      ctx->launches += 1;
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
   }
@@ -1993,7 +2003,7 @@ namespace
   static int launch_hex8_eas(b200s_ctx* ctx, const EvalArgs& A)
   {
     if (!ctx->d_eas_hist) return fail(ctx, B200S_ERR_INVALID, "EAS history missing");
-    if (ctx->eas_mma)
+    if (ctx->eas_mma || MAT == MAT_PLASTIC)  // MAT_PLASTIC: tensor-core kernel only (one instantiation less)
     {
       auto kern = k_hex8_eas_mma_eval_assemble<MAT, STIFF, NEAS>;
       using Cfg = EasMmaCfg<NEAS>;
@@ -2007,7 +2017,8 @@ namespace
       ctx->launches += 1;
       return 0;
     }
-    auto kern = k_hex8_eas_eval_assemble<MAT, STIFF, NEAS>;
+    if constexpr (MAT == MAT_PLASTIC) return fail(ctx, B200S_ERR_UNSUPPORTED, "unreachable");
+    auto kern = k_hex8_eas_eval_assemble<MAT == MAT_PLASTIC ? MAT_VISCO : MAT, STIFF, NEAS>;
     constexpr size_t bytes = hex8_eas_smem_bytes<NEAS>();
     if (set_smem_attr(kern, bytes)) return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", bytes);
     int64_t grid = (A.n_ele + HEX8_EAS_WARPS - 1) / HEX8_EAS_WARPS;
@@ -2033,6 +2044,8 @@ namespace b200s_parts
   {
     if (ctx->matkind == B200S_MAT_VISCONEOHOOKE)
       return stiff ? launch_hex8_eas_any<MAT_VISCO, true>(ctx, A) : launch_hex8_eas_any<MAT_VISCO, false>(ctx, A);
+    if (ctx->matkind == B200S_MAT_PLASTIC_NLNLOG)
+      return stiff ? launch_hex8_eas_any<MAT_PLASTIC, true>(ctx, A) : launch_hex8_eas_any<MAT_PLASTIC, false>(ctx, A);
     B200S_DISPATCH_MATERIAL(launch_hex8_eas_any);
   }
   int set_tables_hex8_eas(b200s_ctx* ctx, const Hex8Const& h)
@@ -2070,7 +2083,7 @@ namespace
   template <int MAT, bool STIFF>
   static int launch_hex8_t(b200s_ctx* ctx, const EvalArgs& A)
   {
-    if constexpr (MAT != MAT_DP && MAT != MAT_VISCO)
+    if constexpr (MAT != MAT_DP && MAT != MAT_VISCO && MAT != MAT_PLASTIC)
     if (ctx->tech == B200S_TECH_FBAR)
     {
       auto kern = k_hex8_eval_assemble<MAT, STIFF, 1>;
@@ -2090,7 +2103,7 @@ namespace
     {
       if constexpr (MAT == MAT_DP)
         return k_hex8_eval_assemble<MAT, STIFF, 3>;
-      else if constexpr (MAT == MAT_VISCO)
+      else if constexpr (MAT == MAT_VISCO || MAT == MAT_PLASTIC)
         return k_hex8_eval_assemble<MAT, STIFF, 0>;
       else
         return ctx->prestress == B200S_PRESTRESS_MULF
@@ -2123,6 +2136,8 @@ namespace b200s_parts
       return stiff ? launch_hex8_t<MAT_DP, true>(ctx, A) : launch_hex8_t<MAT_DP, false>(ctx, A);
     if (ctx->matkind == B200S_MAT_VISCONEOHOOKE)
       return stiff ? launch_hex8_t<MAT_VISCO, true>(ctx, A) : launch_hex8_t<MAT_VISCO, false>(ctx, A);
+    if (ctx->matkind == B200S_MAT_PLASTIC_NLNLOG)
+      return stiff ? launch_hex8_t<MAT_PLASTIC, true>(ctx, A) : launch_hex8_t<MAT_PLASTIC, false>(ctx, A);
     B200S_DISPATCH_MATERIAL(launch_hex8_t);
   }
   int set_tables_hex8(b200s_ctx* ctx, const Hex8Const& h)
@@ -2298,6 +2313,8 @@ namespace
         return launch_generic_mat<MAT_DP>(ctx, Ga, grid);
       case B200S_MAT_VISCONEOHOOKE:
         return launch_generic_mat<MAT_VISCO>(ctx, Ga, grid);
+      case B200S_MAT_PLASTIC_NLNLOG:
+        return launch_generic_mat<MAT_PLASTIC>(ctx, Ga, grid);
     }
     return fail(ctx, B200S_ERR_UNSUPPORTED, "general kernel: material kind %d", ctx->matkind);
   }
@@ -2313,7 +2330,8 @@ namespace
   {
     if (ctx->matkind < 0) return fail(ctx, B200S_ERR_INVALID, "material not set");
     if (ctx->general_tangent || ctx->general_kernel || is_general_cell(ctx->celltype) ||
-        (ctx->tech == B200S_TECH_FBAR && ctx->prestress == B200S_PRESTRESS_MULF))
+        (ctx->tech == B200S_TECH_FBAR && ctx->prestress == B200S_PRESTRESS_MULF) ||
+        (ctx->matkind == B200S_MAT_PLASTIC_NLNLOG && ctx->celltype != B200S_HEX8))  // fast kernels: hex8 (+ EAS) only
       return launch_generic(ctx, A, STIFF);
     if (ctx->tech != B200S_TECH_NONE && ctx->celltype != B200S_HEX8)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "element technology %d needs hex8", ctx->tech);
@@ -2675,6 +2693,32 @@ extern "C"
       if (!(params[4] > 0.0)) return fail(ctx, B200S_ERR_INVALID, "Relaxation time tau has to be positive!");
       for (int i = 0; i < 6; ++i) ctx->visco_in[i] = params[i];
       make_visco_neohooke(ctx->visco_in, ctx->dt, mp.p);
+      const bool fresh = ctx->matkind != kind || !ctx->d_mat_hist;
+      ctx->matkind = kind, ctx->mp = mp;
+      if (params[2] > 0.0) ctx->density = params[2];
+      dfree(ctx->d_per_ele);
+      return (fresh && material_history_allocate(ctx)) ? B200S_ERR_CUDA : B200S_OK;
+    }
+    if (kind == B200S_MAT_PLASTIC_NLNLOG)
+    {
+      if (nparams < 10 || per_ele_param)
+        return fail(ctx, B200S_ERR_INVALID,
+            "MAT_Struct_PlasticNlnLogNeoHooke: 10 parameters {YOUNG NUE DENS YIELD ISOHARD SATHARDENING HARDEXPO VISC "
+            "RATE_DEPENDENCY TOL}");
+      if (params[3] == 0.0)
+        return fail(ctx, B200S_ERR_UNSUPPORTED,
+            "You have to provide either a parameter for HARDENING_FUNC or YIELD in MAT_Struct_PlasticNlnLogNeoHooke "
+            "(HARDENING_FUNC, a parsed function, stays on the CPU path)");
+      for (int i = 0; i < 10; ++i) ctx->plastic_in[i] = params[i];
+      double q[PLASTIC_NPAR];
+      // the rate term divides by the time step size: a placeholder until b200s_set_time_step_size has been called
+      if (!make_plastic_nlnlog(ctx->plastic_in, ctx->dt_set && ctx->dt > 0.0 ? ctx->dt : 1.0, q))
+        return fail(ctx, B200S_ERR_INVALID, "MAT_Struct_PlasticNlnLogNeoHooke: parameters rejected");
+      for (double& v : mp.p) v = 0.0;
+      mp.hyper = nullptr, mp.fiber = nullptr, mp.hist = nullptr;
+      if (to_device(ctx, &ctx->d_mat_ext, q, PLASTIC_NPAR)) return B200S_ERR_CUDA;
+      CK(cudaStreamSynchronize(ctx->stream));  // q is a local
+      mp.ext = ctx->d_mat_ext;
       const bool fresh = ctx->matkind != kind || !ctx->d_mat_hist;
       ctx->matkind = kind, ctx->mp = mp;
       if (params[2] > 0.0) ctx->density = params[2];
@@ -3334,13 +3378,13 @@ extern "C"
             "MAT_Struct_DruckerPrager is a small-strain material: KINEM linear without element technology / prestress");
       if (!ctx->d_mat_hist) return fail(ctx, B200S_ERR_INVALID, "material history missing (set_mesh first)");
     }
-    if (ctx->matkind == B200S_MAT_VISCONEOHOOKE)
+    if (ctx->matkind == B200S_MAT_VISCONEOHOOKE || ctx->matkind == B200S_MAT_PLASTIC_NLNLOG)
     {
       const bool eas = ctx->tech == B200S_TECH_EAS_MILD || ctx->tech == B200S_TECH_EAS_FULL;
       if (ctx->kinem != B200S_KINEM_NONLINEAR_TOTLAG || (ctx->tech != B200S_TECH_NONE && !eas) ||
           ctx->prestress != B200S_PRESTRESS_NONE)
         return fail(ctx, B200S_ERR_UNSUPPORTED,
-            "MAT_VISCONEOHOOKE on the device: KINEM nonlinear, TECH none or eas_mild / eas_full, no prestress");
+            "finite-strain history materials on the device: KINEM nonlinear, TECH none or eas_mild / eas_full, no prestress");
       if (!ctx->dt_set)
         return fail(ctx, B200S_ERR_INVALID,
             "Time step size not given in evaluation context. (b200s_set_time_step_size)");
@@ -3730,6 +3774,14 @@ extern "C"
     if (!(dt >= 0.0)) return fail(ctx, B200S_ERR_INVALID, "time step size must be >= 0");
     ctx->dt = dt, ctx->dt_set = true;
     if (ctx->matkind == B200S_MAT_VISCONEOHOOKE) make_visco_neohooke(ctx->visco_in, dt, ctx->mp.p);
+    if (ctx->matkind == B200S_MAT_PLASTIC_NLNLOG && ctx->d_mat_ext)
+    {
+      double q[PLASTIC_NPAR];
+      if (!make_plastic_nlnlog(ctx->plastic_in, dt, q)) return fail(ctx, B200S_ERR_INVALID, "time step size must be > 0 for MAT_Struct_PlasticNlnLogNeoHooke");
+      cudaSetDevice(ctx->device);
+      CK(cudaMemcpyAsync(ctx->d_mat_ext, q, sizeof q, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));  // q is a local
+    }
     return B200S_OK;
   }
 
@@ -3886,6 +3938,11 @@ extern "C"
         if (d_energy) return fail(ctx, B200S_ERR_UNSUPPORTED, "MAT_VISCONEOHOOKE has no strain energy");
         if (!ctx->dt_set) return fail(ctx, B200S_ERR_INVALID, "Time step size not given in evaluation context.");
         k_post_points<MAT_VISCO><<<grid, 128, 0, ctx->stream>>>(P);
+        break;
+      case B200S_MAT_PLASTIC_NLNLOG:
+        if (d_energy) return fail(ctx, B200S_ERR_UNSUPPORTED, "MAT_Struct_PlasticNlnLogNeoHooke has no strain energy");
+        if (!ctx->dt_set) return fail(ctx, B200S_ERR_INVALID, "Time step size not given in evaluation context.");
+        k_post_points<MAT_PLASTIC><<<grid, 128, 0, ctx->stream>>>(P);
         break;
       case B200S_MAT_DRUCKER_PRAGER:
         if (d_energy) return fail(ctx, B200S_ERR_UNSUPPORTED, "MAT_Struct_DruckerPrager has no strain energy");
@@ -4073,7 +4130,8 @@ extern "C"
       // reset: current <- last
       const int H = mat_hist_per_gp(ctx);
       k_material_history_commit<<<nblk(np * (H / 2)), 256, 0, ctx->stream>>>(np, H, H / 2,
-          restore ? 1 : (ctx->matkind == B200S_MAT_VISCONEOHOOKE ? 2 : 0), ctx->d_mat_hist);
+          restore ? 1 : (ctx->matkind == B200S_MAT_VISCONEOHOOKE ? 2 : (ctx->matkind == B200S_MAT_PLASTIC_NLNLOG ? 3 : 0)),
+          ctx->d_mat_hist);
       ctx->launches += 1;
     }
     CK(cudaStreamSynchronize(ctx->stream));

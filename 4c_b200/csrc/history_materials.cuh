@@ -241,7 +241,187 @@ namespace b200s
       }
   }
 
+
+  // ---- MAT_Struct_PlasticNlnLogNeoHooke ---------------------------------------------------------------------------
+  // Mat::PlasticNlnLogNeoHooke::evaluate (src/mat/4C_mat_plasticnlnlogneohooke.cpp:385-611): finite-strain von Mises
+  // plasticity in principal logarithmic strains with nonlinear isotropic hardening and a visco-plastic rate factor;
+  // trial state b_e^trial = F Cp_n^-1 F^T, spectral return mapping, S = sum_a tau_a N_a (x) N_a with N_a = F^-1 n_a.
+  // The response depends on F only through C (the eigenvalues of b_e^trial are those of Cp^-1 C, N_a is unchanged by a
+  // rotation of F), so the device evaluates the reference's algorithm with the upper-triangular F = L^T of the Cholesky
+  // factorisation C = L L^T -- what the kernels carry is C, for EAS blocks the enhanced one.
+  // Parameter block (device memory, MatParams::ext, PLASTIC_NPAR doubles): {G, kappa, YIELD, ISOHARD, SATHARDENING,
+  // HARDEXPO, VISC, RATE_DEPENDENCY, TOL, dt}.  History per Gauss point (PLASTIC_HIST doubles, the pack order :96-104):
+  // accplstrainlast, invplrcglast[6], accplstraincurr, invplrcgcurr[6]; a fresh point holds Cp^-1 = I (setup :337-349),
+  // update() copies current -> last and resets current to {0, I} (:359-378).  A local Newton that does not converge in 50
+  // iterations (the reference throws) poisons the stress with NaN, which the optional finite check reports.
+  constexpr int PLASTIC_HIST = 14, PLASTIC_NPAR = 10;
+
+  inline bool make_plastic_nlnlog(const double* in10, double dt, double* q)
+  {
+    // in10 = {YOUNG, NUE, DENS, YIELD, ISOHARD, SATHARDENING, HARDEXPO, VISC, RATE_DEPENDENCY, TOL}
+    const double ym = in10[0], nu = in10[1];
+    if (!(ym > 0.0) || !(nu > -1.0 && nu < 0.5) || !(dt > 0.0) || in10[3] == 0.0) return false;
+    q[0] = ym / (2.0 * (1.0 + nu)), q[1] = ym / (3.0 * (1.0 - 2.0 * nu));
+    for (int i = 0; i < 7; ++i) q[2 + i] = in10[3 + i];
+    q[9] = dt;
+    return true;
+  }
+
+  B2_HD void plastic_nlnlog_evaluate(const double* q, double* hist, const double* C, double* S, double* Cm)
+  {
+    const double G = q[0], kappa = q[1], yield = q[2], isohard = q[3], infyield = q[4], hardexp = q[5], visc = q[6],
+                 eps = q[7], tol = q[8], dt = q[9];
+    constexpr int va[6] = {0, 1, 2, 0, 1, 0}, vb[6] = {0, 1, 2, 1, 2, 2};
+    constexpr int vg[3][3] = {{0, 3, 5}, {3, 1, 4}, {5, 4, 2}};
+    // C = L L^T; F := L^T, F(a,b) = L(b,a) (upper triangular), det F = l00 l11 l22
+    const double l00 = sqrt(C[0]), l10 = C[3] / l00, l20 = C[5] / l00;
+    const double l11 = sqrt(C[1] - l10 * l10), l21 = (C[4] - l20 * l10) / l11;
+    const double l22 = sqrt(C[2] - l20 * l20 - l21 * l21);
+    const double F[3][3] = {{l00, l10, l20}, {0.0, l11, l21}, {0.0, 0.0, l22}};
+    const double logdetF = log(l00 * l11 * l22);
+    const double accpl_last = hist ? hist[0] : 0.0;
+    double iCp[6] = {1, 1, 1, 0, 0, 0};
+    if (hist)
+#pragma unroll
+      for (int v = 0; v < 6; ++v) iCp[v] = hist[1 + v];
+    // Be_trial = F Cp^-1 F^T (symmetric, Voigt)
+    double Bt[6];
+#pragma unroll
+    for (int v = 0; v < 6; ++v)
+    {
+      double acc = 0.0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) acc = fma(F[va[v]][c] * iCp[vg[c][d]], F[vb[v]][d], acc);
+      Bt[v] = acc;
+    }
+    double lam2[3], n[9];
+    sym_eig3_voigt(Bt, lam2, n);  // n_a = n[. + 3 a]
+    // N_a = F^-1 n_a: back substitution with the upper-triangular F
+    double N[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+    {
+      const double z = n[2 + 3 * a] / l22;
+      const double y = (n[1 + 3 * a] - l21 * z) / l11;
+      const double x = (n[3 * a] - l10 * y - l20 * z) / l00;
+      N[a][0] = x, N[a][1] = y, N[a][2] = z;
+    }
+    double dev_trial[3], dev[3], lam2_new[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+    {
+      dev_trial[a] = G * log(lam2[a]) - 2.0 / 3.0 * G * logdetF;
+      lam2_new[a] = lam2[a];
+    }
+    const double pressure = kappa * logdetF;
+    const double abs_trial = sqrt(dev_trial[0] * dev_trial[0] + dev_trial[1] * dev_trial[1] + dev_trial[2] * dev_trial[2]);
+    const double y_d = yield + isohard * accpl_last + (infyield - yield) * (1.0 - exp(-hardexp * accpl_last));
+    const double f_trial = sqrt(3.0 / 2.0) * abs_trial - y_d;
+    double D[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) D[a][b] = kappa + 2.0 * G * ((a == b ? 1.0 : 0.0) - 1.0 / 3.0);
+    double Dgamma = 0.0;
+    if (f_trial <= 0.0)
+    {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) dev[a] = dev_trial[a];
+    }
+    else
+    {
+      // solve_local_newton on residuum_and_jacobian (:63-92, 4C_utils_local_newton.hpp)
+      double r, jac, dy;
+      int it = 0;
+      for (;;)
+      {
+        const double acc = accpl_last + Dgamma;
+        const double ex = exp(-hardexp * acc);
+        const double yd = yield + isohard * acc + (infyield - yield) * (1.0 - ex);
+        const double pw = pow(visc * Dgamma / dt + 1.0, eps);
+        dy = (isohard + (infyield - yield) * hardexp * ex) * pw + yd * eps * pow(visc * Dgamma / dt + 1.0, eps - 1.0) * visc / dt;
+        r = sqrt(3.0 / 2.0) * abs_trial - 3.0 * G * Dgamma - yd * pw;
+        jac = -3.0 * G - dy;
+        if (!(fabs(r) > tol)) break;
+        if (it > 50)
+        {
+          Dgamma = nan("");
+          break;
+        }
+        Dgamma -= r / jac;
+        ++it;
+      }
+      double flow[3];
+      const double s23 = sqrt(2.0 / 3.0) * abs_trial;
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+      {
+        flow[a] = dev_trial[a] / s23;
+        dev[a] = (1.0 - 2.0 * G * Dgamma / s23) * dev_trial[a];
+        lam2_new[a] = lam2[a] / exp(2.0 * flow[a] * Dgamma);
+      }
+      const double f1 = -4.0 * G * G * Dgamma / s23;
+      const double f2 = 4.0 * G * G * (sqrt(2.0 / 3.0) * Dgamma / abs_trial - 1.0 / (3.0 * G + dy));
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) D[a][b] += f1 * ((a == b ? 1.0 : 0.0) - 1.0 / 3.0) + f2 * flow[a] * flow[b];
+    }
+    double tau[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) tau[a] = dev[a] + pressure;
+    // dyads N_a (x) N_b, symmetrised, in Voigt storage
+    double Dy[3][3][6];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int v = 0; v < 6; ++v) Dy[a][b][v] = 0.5 * (N[a][va[v]] * N[b][vb[v]] + N[a][vb[v]] * N[b][va[v]]);
+#pragma unroll
+    for (int v = 0; v < 6; ++v) S[v] = tau[0] * Dy[0][0][v] + tau[1] * Dy[1][1][v] + tau[2] * Dy[2][2][v];
+    // tangent in the principal directions (:520-571); major symmetric
+    double fac[3];  // pairs (0,1), (1,2), (0,2)
+    constexpr int pa[3] = {0, 1, 0}, pb[3] = {1, 2, 2};
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+    {
+      const int a = pa[k], b = pb[k];
+      fac[k] = (lam2[a] != lam2[b]) ? (tau[a] * lam2[b] - tau[b] * lam2[a]) / (lam2[a] - lam2[b])
+                                    : 0.5 * (D[b][b] - D[a][b]) - tau[b];
+    }
+#pragma unroll
+    for (int P = 0; P < 6; ++P)
+#pragma unroll
+      for (int Q = P; Q < 6; ++Q)
+      {
+        double c = 0.0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+        {
+          c = fma(-2.0 * tau[a] * Dy[a][a][P], Dy[a][a][Q], c);
+#pragma unroll
+          for (int b = 0; b < 3; ++b) c = fma(D[a][b] * Dy[a][a][P], Dy[b][b][Q], c);
+        }
+        // sum over ordered pairs a != b of fac (N_ab (x) N_ab + N_ab (x) N_ab^T) = 4 fac sym(N_ab) (x) sym(N_ab) per pair
+#pragma unroll
+        for (int k = 0; k < 3; ++k) c = fma(4.0 * fac[k] * Dy[pa[k]][pb[k]][P], Dy[pa[k]][pb[k]][Q], c);
+        Cm[c21(P, Q)] = c;
+      }
+    if (hist)
+    {
+      hist[7] = accpl_last + Dgamma;
+#pragma unroll
+      for (int v = 0; v < 6; ++v) hist[8 + v] = lam2_new[0] * Dy[0][0][v] + lam2_new[1] * Dy[1][1][v] + lam2_new[2] * Dy[2][2][v];
+    }
+  }
+
   // history doubles per Gauss point of a material kind (0: no history)
-  B2_HD constexpr int material_hist_doubles(int mat) { return mat == MAT_DP ? DP_HIST : (mat == MAT_VISCO ? VISCO_HIST : 0); }
+  B2_HD constexpr int material_hist_doubles(int mat)
+  {
+    return mat == MAT_DP ? DP_HIST : (mat == MAT_VISCO ? VISCO_HIST : (mat == MAT_PLASTIC ? PLASTIC_HIST : 0));
+  }
 
 }  // namespace b200s

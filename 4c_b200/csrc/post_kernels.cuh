@@ -538,14 +538,25 @@ namespace b200s
     if (t >= n_points * half) return;
     double* h = hist + (t / half) * stride;
     const int i = (int)(t % half);
-    // restore 0: last <- current; 1: current <- last; 2: last <- current and current <- 0
+    // restore 0: last <- current; 1: current <- last; 2: last <- current and current <- 0; 3: last <- current and
+    // current <- {0, identity} (Mat::PlasticNlnLogNeoHooke::update, 4C_mat_plasticnlnlogneohooke.cpp:359-378)
     if (restore == 1)
       h[half + i] = h[i];
     else
     {
       h[i] = h[half + i];
       if (restore == 2) h[half + i] = 0.0;
+      if (restore == 3) h[half + i] = (i >= 1 && i <= 3) ? 1.0 : 0.0;
     }
+  }
+  // fresh history of MAT_Struct_PlasticNlnLogNeoHooke: {0, I, 0, I} per Gauss point (setup, :337-349)
+  __global__ void k_plastic_history_init(int64_t n_points, double* hist)
+  {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_points) return;
+    double* h = hist + t * PLASTIC_HIST;
+#pragma unroll
+    for (int i = 0; i < PLASTIC_HIST; ++i) h[i] = ((i % 7) >= 1 && (i % 7) <= 3) ? 1.0 : 0.0;
   }
 #endif
 }  // namespace b200s

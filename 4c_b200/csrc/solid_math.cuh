@@ -86,13 +86,15 @@ namespace b200s
     MAT_SVK = 2,
     MAT_HYPER = 3, // generic MAT_ElastHyper summand list (summands.cuh)
     MAT_DP = 4,    // MAT_Struct_DruckerPrager, a history material (history_materials.cuh); KINEM linear only
-    MAT_VISCO = 5  // MAT_VISCONEOHOOKE, a finite-strain history material (history_materials.cuh)
+    MAT_VISCO = 5, // MAT_VISCONEOHOOKE, a finite-strain history material (history_materials.cuh)
+    MAT_PLASTIC = 6 // MAT_Struct_PlasticNlnLogNeoHooke, finite-strain plasticity with history (history_materials.cuh)
   };
 
   struct HyperMat;
   B2_HD void hyper_evaluate(const HyperMat& hm, const double* fiber, const double* C, double* S, double* Cm);
   B2_HD void drucker_prager_evaluate(const double* q, double* hist, const double* C, double* S, double* Cm);
   B2_HD void visco_neohooke_evaluate(const double* p, double* hist, const double* C, double* S, double* Cm);
+  B2_HD void plastic_nlnlog_evaluate(const double* q, double* hist, const double* C, double* S, double* Cm);
   B2_HD double hyper_strain_energy(const HyperMat& hm, const double* fiber, const double* C);
 
   // Material parameters preprocessed once on the host (b200s_set_material):
@@ -162,6 +164,10 @@ namespace b200s
     else if (MAT == MAT_VISCO)
     {
       visco_neohooke_evaluate(mp.p, mp.hist, C, S, Cm);
+    }
+    else if (MAT == MAT_PLASTIC)
+    {
+      plastic_nlnlog_evaluate(mp.ext, mp.hist, C, S, Cm);
     }
     else if (MAT == MAT_SVK)
     {
@@ -262,7 +268,7 @@ namespace b200s
   B2_HD double material_strain_energy(const MatParams& mp, const double* C)
   {
     if (MAT == MAT_HYPER) return hyper_strain_energy(*mp.hyper, mp.fiber, C);
-    if (MAT == MAT_DP || MAT == MAT_VISCO) return 0.0;  // no strain energy in the reference; rejected on the host
+    if (MAT == MAT_DP || MAT == MAT_VISCO || MAT == MAT_PLASTIC) return 0.0;  // no strain energy in the reference; rejected on the host
     if (MAT == MAT_SVK)
     {
       const double E[6] = {0.5 * (C[0] - 1.0), 0.5 * (C[1] - 1.0), 0.5 * (C[2] - 1.0), 0.5 * C[3],

@@ -50,6 +50,9 @@ namespace B200Solid
     }
     if (kinem != B200S_KINEM_NONLINEAR_TOTLAG) return false;
     // finite-strain history material: displacement based (all three cells) or EAS (hex8), no prestress
+    if (material_kind == B200S_MAT_PLASTIC_NLNLOG)  // every cell (general kernel beyond hex8), EAS on hex8
+      return prestress == B200S_PRESTRESS_NONE &&
+             (tech == B200S_TECH_NONE || (celltype == B200S_HEX8 && (tech == B200S_TECH_EAS_MILD || tech == B200S_TECH_EAS_FULL)));
     if (material_kind == B200S_MAT_VISCONEOHOOKE)
       return prestress == B200S_PRESTRESS_NONE &&
              (tech == B200S_TECH_NONE || (celltype == B200S_HEX8 && (tech == B200S_TECH_EAS_MILD || tech == B200S_TECH_EAS_FULL)));

@@ -73,7 +73,16 @@ extern "C"
    *                   rule over the time step given with b200s_set_time_step_size).  KINEM nonlinear blocks, TECH
    *                   none (hex8 / hex27 / tet10) or eas_mild / eas_full (hex8).  24 doubles of state per Gauss
    *                   point (last converged and current {S_dev, Q}); b200s_update_step =
-   *                   Mat::ViscoNeoHooke::update(), b200s_get/set_material_history = pack/unpack. */
+   *                   Mat::ViscoNeoHooke::update(), b200s_get/set_material_history = pack/unpack.
+   *   PLASTIC_NLNLOG: MAT_Struct_PlasticNlnLogNeoHooke (src/mat/4C_mat_plasticnlnlogneohooke.cpp), finite-strain von
+   *                   Mises plasticity in principal logarithmic strains, a HISTORY material: params = {YOUNG, NUE,
+   *                   DENS, YIELD, ISOHARD, SATHARDENING, HARDEXPO, VISC, RATE_DEPENDENCY, TOL} (HARDENING_FUNC, a
+   *                   parsed function: CPU path); the rate term uses the time step of b200s_set_time_step_size.
+   *                   KINEM nonlinear blocks, TECH none (every cell; hex8 on the fast kernel, the others on the
+   *                   general kernel) or eas_mild / eas_full (hex8).  14 doubles of state per Gauss point in the
+   *                   reference's pack order {accplstrainlast, invplrcglast[6], accplstraincurr, invplrcgcurr[6]}
+   *                   (tensor components 00,11,22,01,12,02; a fresh point holds the identity); b200s_update_step =
+   *                   update(), b200s_get/set_material_history = pack/unpack. */
   typedef enum
   {
     B200S_MAT_COUP_NEOHOOKE = 0,
@@ -81,7 +90,8 @@ extern "C"
     B200S_MAT_SVK = 2,
     B200S_MAT_ELASTHYPER = 3,
     B200S_MAT_DRUCKER_PRAGER = 4,
-    B200S_MAT_VISCONEOHOOKE = 5
+    B200S_MAT_VISCONEOHOOKE = 5,
+    B200S_MAT_PLASTIC_NLNLOG = 6
   } b200s_material;
 
   /* Mat::Elastic::Summand implementations evaluated through the principal / modified invariants

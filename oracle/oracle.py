@@ -14,6 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 HEX8, HEX27, TET10, TET4, HEX20, WEDGE6, PYRAMID5 = 0, 1, 2, 3, 4, 5, 6
 MAT_COUP_NEOHOOKE, MAT_ISO_VOL, MAT_SVK, MAT_ELASTHYPER, MAT_DRUCKER_PRAGER, MAT_VISCONEOHOOKE = 0, 1, 2, 3, 4, 5
+MAT_PLASTIC_NLNLOG = 6
+PLASTIC_HIST = 14  # {accplstrainlast, invplrcglast[6], accplstraincurr, invplrcgcurr[6]} per Gauss point
 DP_HIST = 14  # {strainpllast[6], strainbarpllast, strainplcurr[6], strainbarplcurr} per Gauss point
 VISCO_HIST = 24  # {histstresslast[6], artstresslast[6], histstresscurr[6], artstresscurr[6]} per Gauss point
 # summand ids of the generic MAT_ElastHyper (ORC_SUM_* in solid_oracle.h)
@@ -198,13 +200,26 @@ def material_hist(kind, params, E, hist=None):
 
 def material_update(kind, hist):
     """Mat::...::update(): current -> last for every Gauss point of hist (n, DP_HIST or VISCO_HIST)."""
-    per = VISCO_HIST if kind == MAT_VISCONEOHOOKE else DP_HIST
+    per = VISCO_HIST if kind == MAT_VISCONEOHOOKE else (PLASTIC_HIST if kind == MAT_PLASTIC_NLNLOG else DP_HIST)
     lib().orc_material_update(kind, C.c_int64(hist.size // per), _d(hist))
 
 
 def visco_neohooke_params(YOUNGS_SLOW, POISSON, DENS, YOUNGS_FAST, RELAX, THETA, dt, **_):
     """Parameter block of MAT_VISCONEOHOOKE from the keys of the input line + the time step size."""
     return np.array([YOUNGS_SLOW, POISSON, DENS, YOUNGS_FAST, RELAX, THETA, dt], float)
+
+
+def plastic_nlnlog_params(YOUNG, NUE, DENS, YIELD, ISOHARD, SATHARDENING, HARDEXPO, VISC, RATE_DEPENDENCY, TOL, dt, **_):
+    """Parameter block of MAT_PLASTIC_NLNLOG from the keys of MAT_Struct_PlasticNlnLogNeoHooke + the time step size."""
+    return np.array([YOUNG, NUE, DENS, YIELD, ISOHARD, SATHARDENING, HARDEXPO, VISC, RATE_DEPENDENCY, TOL, dt], float)
+
+
+def plastic_new_history(*shape):
+    """Fresh history of MAT_PLASTIC_NLNLOG (PlasticNlnLogNeoHooke::setup): (*shape, PLASTIC_HIST) with Cp^-1 = I."""
+    h = np.zeros(tuple(shape) + (PLASTIC_HIST,))
+    h[..., 1:4] = 1.0
+    h[..., 8:11] = 1.0
+    return h
 
 
 def set_material_history(mat_hist):

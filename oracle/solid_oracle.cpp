@@ -290,6 +290,11 @@ namespace
   // Voigt slot of (a,b): [00,11,22,01,12,02]
   const int VG[3][3] = {{0, 3, 5}, {3, 1, 4}, {5, 4, 2}};
   const int VA[6] = {0, 1, 2, 0, 1, 0}, VB[6] = {0, 1, 2, 1, 2, 2};
+  // doubles of Gauss-point history of the finite-strain history materials (0: none)
+  inline int finite_strain_hist(int kind)
+  {
+    return kind == ORC_MAT_VISCONEOHOOKE ? ORC_VISCO_HIST : (kind == ORC_MAT_PLASTIC_NLNLOG ? ORC_PLASTIC_HIST : 0);
+  }
 
   // ---- Jacobian mapping at one parameter point (src/solid_ele/4C_solid_ele_calc_lib.hpp:499-516)
   struct JacMap
@@ -1248,14 +1253,179 @@ namespace
       }
   }
 
+
+  // Mat::PlasticNlnLogNeoHooke::evaluate (src/mat/4C_mat_plasticnlnlogneohooke.cpp:385-611): finite-strain von Mises
+  // plasticity in principal logarithmic strains (de Souza Neto et al., ch. 14) -- trial elastic left Cauchy-Green
+  // tensor b_e^trial = F Cp_n^-1 F^T, its spectral decomposition, return mapping of the deviatoric Kirchhoff stress with
+  // the nonlinear isotropic hardening y = YIELD + ISOHARD ep + (SATHARDENING - YIELD)(1 - exp(-HARDEXPO ep)) and the
+  // visco-plastic factor (VISC Dgamma / dt + 1)^RATE_DEPENDENCY (local Newton :117-147, solve_local_newton of
+  // 4C_utils_local_newton.hpp: |r| > TOL, at most 50 iterations), S = sum_a tau_a N_a (x) N_a with N_a = F^-1 n_a and the
+  // tangent in the principal directions (:520-571).
+  // par: {YOUNG, NUE, DENS, YIELD, ISOHARD, SATHARDENING, HARDEXPO, VISC, RATE_DEPENDENCY, TOL, dt}; HARDENING_FUNC = 0.
+  // hist (ORC_PLASTIC_HIST = 14): {accplstrainlast, invplrcglast[6], accplstraincurr, invplrcgcurr[6]} (pack order
+  // :96-104; tensor components [00,11,22,01,12,02]); a fresh point holds Cp^-1 = I (setup, :337-349); null = virgin
+  // point, nothing stored.  Returns 1 if the local Newton did not converge (the reference throws).
+  int plastic_nlnlog_neohooke(const double* par, double* hist, const double* F, double* S, double* Cm)
+  {
+    const double ym = par[0], nu = par[1], yield = par[3], isohard = par[4], infyield = par[5], hardexp = par[6],
+                 visc = par[7], eps = par[8], tol = par[9], dt = par[10];
+    const double G = ym / (2.0 * (1.0 + nu)), kappa = ym / (3.0 * (1.0 - 2.0 * nu));
+    const double detF = det3(F);
+    double iF[9];
+    inv3(iF, F);
+    const double Id[6] = {1, 1, 1, 0, 0, 0};
+    const double accpl_last = hist ? hist[0] : 0.0;
+    const double* iCp = hist ? hist + 1 : Id;
+    // Be_trial = F Cp^-1 F^T
+    double Bt[9];
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b)
+      {
+        double v = 0.0;
+        for (int c = 0; c < 3; ++c)
+          for (int d = 0; d < 3; ++d) v += F[a + 3 * c] * iCp[VG[c][d]] * F[b + 3 * d];
+        Bt[a + 3 * b] = v;
+      }
+    for (int a = 0; a < 3; ++a)
+      for (int b = a + 1; b < 3; ++b) Bt[a + 3 * b] = Bt[b + 3 * a] = 0.5 * (Bt[a + 3 * b] + Bt[b + 3 * a]);
+    double lam2[3], n[9];
+    sym_eig3(Bt, lam2, n);  // n_a = n[. + 3 a]
+    double N[3][3];          // N_a = F^-1 n_a (:449-452)
+    for (int a = 0; a < 3; ++a)
+      for (int i = 0; i < 3; ++i) N[a][i] = iF[i] * n[3 * a] + iF[i + 3] * n[1 + 3 * a] + iF[i + 6] * n[2 + 3 * a];
+    double dev_trial[3], dev[3];
+    for (int a = 0; a < 3; ++a) dev_trial[a] = G * std::log(lam2[a]) - 2.0 / 3.0 * G * std::log(detF);
+    const double pressure = kappa * std::log(detF);
+    const double abs_trial = std::sqrt(dev_trial[0] * dev_trial[0] + dev_trial[1] * dev_trial[1] + dev_trial[2] * dev_trial[2]);
+    const double y_d = yield + isohard * accpl_last + (infyield - yield) * (1.0 - std::exp(-hardexp * accpl_last));
+    const double f_trial = std::sqrt(3.0 / 2.0) * abs_trial - y_d;  // (visc Dgamma / dt + 1)^eps = 1 at Dgamma = 0
+    double D[3][3];  // D_ep_principal = kappa ones + 2 G Idev
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) D[a][b] = kappa + 2.0 * G * ((a == b ? 1.0 : 0.0) - 1.0 / 3.0);
+    double Dgamma = 0.0, lam2_new[3] = {lam2[0], lam2[1], lam2[2]};
+    int fail = 0;
+    if (f_trial <= 0.0)
+      for (int a = 0; a < 3; ++a) dev[a] = dev_trial[a];
+    else
+    {
+      // residuum_and_jacobian (:63-92) inside solve_local_newton
+      auto res_jac = [&](double Dg, double& r, double& jac, double& dy)
+      {
+        const double acc = accpl_last + Dg;
+        const double yd = yield + isohard * acc + (infyield - yield) * (1.0 - std::exp(-hardexp * acc));
+        const double ydv = yd * std::pow(visc * Dg / dt + 1.0, eps);
+        dy = (isohard + (infyield - yield) * hardexp * std::exp(-hardexp * acc)) * std::pow(visc * Dg / dt + 1.0, eps) +
+             yd * eps * std::pow(visc * Dg / dt + 1.0, eps - 1.0) * visc / dt;
+        r = std::sqrt(3.0 / 2.0) * abs_trial - 3.0 * G * Dg - ydv;
+        jac = -3.0 * G - dy;
+      };
+      double r, jac, dy;
+      res_jac(Dgamma, r, jac, dy);
+      unsigned it = 0;
+      while (std::fabs(r) > tol)
+      {
+        if (it > 50)
+        {
+          fail = 1;
+          break;
+        }
+        Dgamma -= r / jac;
+        res_jac(Dgamma, r, jac, dy);
+        ++it;
+      }
+      double flow[3];
+      for (int a = 0; a < 3; ++a) flow[a] = dev_trial[a] / (std::sqrt(2.0 / 3.0) * abs_trial);
+      for (int a = 0; a < 3; ++a)
+      {
+        dev[a] = (1.0 - 2.0 * G * Dgamma / (std::sqrt(2.0 / 3.0) * abs_trial)) * dev_trial[a];
+        lam2_new[a] = lam2[a] / std::exp(2.0 * flow[a] * Dgamma);
+      }
+      const double f1 = -4.0 * G * G * Dgamma / (std::sqrt(2.0 / 3.0) * abs_trial);
+      const double f2 = 4.0 * G * G * (std::sqrt(2.0 / 3.0) * Dgamma / abs_trial - 1.0 / (3.0 * G + dy));
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) D[a][b] += f1 * ((a == b ? 1.0 : 0.0) - 1.0 / 3.0) + f2 * flow[a] * flow[b];
+    }
+    // S = sum_a (tau'_a + p) N_a (x) N_a (:513-516)
+    for (int v = 0; v < 6; ++v)
+    {
+      double sv = 0.0;
+      for (int a = 0; a < 3; ++a) sv += (dev[a] + pressure) * N[a][VA[v]] * N[a][VB[v]];
+      S[v] = sv;
+    }
+    // tangent (:520-571); cmat is a SymmetricTensor<3,3,3,3>: assume_symmetry keeps the minor-symmetric part
+    for (int I = 0; I < 6; ++I)
+      for (int J = 0; J < 6; ++J)
+      {
+        const int i = VA[I], j = VB[I], k = VA[J], l = VB[J];
+        double c = 0.0;
+        for (int a = 0; a < 3; ++a)
+        {
+          c += -2.0 * (dev[a] + pressure) * N[a][i] * N[a][j] * N[a][k] * N[a][l];
+          for (int b = 0; b < 3; ++b)
+          {
+            c += D[a][b] * N[a][i] * N[a][j] * N[b][k] * N[b][l];
+            if (a == b) continue;
+            const double fac = (lam2[a] != lam2[b])
+                                   ? ((dev[a] + pressure) * lam2[b] - (dev[b] + pressure) * lam2[a]) / (lam2[a] - lam2[b])
+                                   : 0.5 * (D[b][b] - D[a][b]) - (dev[b] + pressure);
+            // N_ab (x) N_ab + N_ab (x) N_ab^T, N_ab = N_a (x) N_b, symmetrised over (i,j) and (k,l)
+            const double t1 = 0.25 * (N[a][i] * N[b][j] + N[a][j] * N[b][i]) * (N[a][k] * N[b][l] + N[a][l] * N[b][k]);
+            const double t2 = 0.25 * (N[a][i] * N[b][j] + N[a][j] * N[b][i]) * (N[b][k] * N[a][l] + N[b][l] * N[a][k]);
+            c += fac * (t1 + t2);
+          }
+        }
+        Cm[I + 6 * J] = c;
+      }
+    if (hist)
+    {
+      // invplrcgcurr = F^-1 Be F^-T = sum_a lambda_a,n+1^2 N_a (x) N_a (:575-581)
+      hist[7] = accpl_last + Dgamma;
+      for (int v = 0; v < 6; ++v)
+      {
+        double sv = 0.0;
+        for (int a = 0; a < 3; ++a) sv += lam2_new[a] * N[a][VA[v]] * N[a][VB[v]];
+        hist[8 + v] = sv;
+      }
+    }
+    return fail;
+  }
+
   thread_local double* g_material_hist = nullptr;  // history of the point being evaluated (set by the element loop)
   // finite-strain history material in the nonlinear / EAS element loops: history block of the element being
   // evaluated (ORC_VISCO_HIST doubles per Gauss point) or null
   thread_local double* g_element_material_hist = nullptr;
   double* g_material_hist_base = nullptr;  // orc_set_material_history: [n_ele][ngp][ORC_VISCO_HIST]
-  void material(int kind, const double* par, const double* /*F*/, const double* E, double* S,
+  void material(int kind, const double* par, const double* F, const double* E, double* S,
       double* Cm)
   {
+    if (kind == ORC_MAT_PLASTIC_NLNLOG)
+    {
+      // The response depends on F only through C = 2 E + I (objectivity: N_a = F^-1 n_a and the eigenvalues of
+      // F Cp^-1 F^T are those of Cp^-1 C).  Callers whose strain is not F^T F (EAS: the reference hands in the enhanced
+      // deformation gradient R U_enh, eas_helpers.hpp:244-262) are served by ANY F with F^T F = C: the Cholesky factor.
+      double c[6], Fu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      bool same = F != nullptr;
+      for (int v = 0; v < 6; ++v)
+      {
+        c[v] = 2.0 * E[v] + (v < 3 ? 1.0 : 0.0);
+        if (F)
+        {
+          double sC = 0.0;
+          for (int q = 0; q < 3; ++q) sC += F[q + 3 * VA[v]] * F[q + 3 * VB[v]];
+          if (std::fabs(sC - c[v]) > 1e-13 * (1.0 + std::fabs(c[v]))) same = false;
+        }
+      }
+      if (!same)
+      {
+        // C = L L^T, F := L^T (upper triangular): Fu(a, b) = L(b, a)
+        const double l00 = std::sqrt(c[0]), l10 = c[3] / l00, l20 = c[5] / l00;
+        const double l11 = std::sqrt(c[1] - l10 * l10), l21 = (c[4] - l20 * l10) / l11;
+        const double l22 = std::sqrt(c[2] - l20 * l20 - l21 * l21);
+        Fu[0] = l00, Fu[0 + 3 * 1] = l10, Fu[0 + 3 * 2] = l20, Fu[1 + 3 * 1] = l11, Fu[1 + 3 * 2] = l21, Fu[2 + 3 * 2] = l22;
+      }
+      plastic_nlnlog_neohooke(par, g_material_hist, same ? F : Fu, S, Cm);
+      return;
+    }
     if (kind == ORC_MAT_SVK)
       svk(par, E, S, Cm);
     else if (kind == ORC_MAT_DRUCKER_PRAGER)
@@ -1430,8 +1600,8 @@ namespace
         C[v] = s;
         E[v] = 0.5 * (s - (v < 3 ? 1.0 : 0.0));
       }
-      g_material_hist = (g_element_material_hist && matkind == ORC_MAT_VISCONEOHOOKE)
-                            ? g_element_material_hist + ORC_VISCO_HIST * gp
+      g_material_hist = (g_element_material_hist && finite_strain_hist(matkind))
+                            ? g_element_material_hist + finite_strain_hist(matkind) * gp
                             : nullptr;
       material(matkind, par, F, E, S, Cm);
       g_material_hist = nullptr;
@@ -1954,8 +2124,8 @@ namespace
       eas_point(neas, T0invT, detJ0, jm.det, gxi + 3 * gp, alpha, F, Mt.data(), E);
       // the materials on this path use the GL strain only; the enhanced deformation gradient
       // (compute_deformation_gradient_from_gl_strains) is not needed by them
-      g_material_hist = (g_element_material_hist && matkind == ORC_MAT_VISCONEOHOOKE)
-                            ? g_element_material_hist + ORC_VISCO_HIST * gp
+      g_material_hist = (g_element_material_hist && finite_strain_hist(matkind))
+                            ? g_element_material_hist + finite_strain_hist(matkind) * gp
                             : nullptr;
       material(matkind, par, F, E, S, Cm);
       g_material_hist = nullptr;
@@ -2092,6 +2262,13 @@ extern "C"
         {
           hist[ORC_VISCO_HIST * k + i] = hist[ORC_VISCO_HIST * k + 12 + i];
           hist[ORC_VISCO_HIST * k + 12 + i] = 0.0;
+        }
+    if (kind == ORC_MAT_PLASTIC_NLNLOG)  // Mat::PlasticNlnLogNeoHooke::update (:359-378): last <- current, current <- {0, I}
+      for (int64_t k = 0; k < n_points; ++k)
+        for (int i = 0; i < 7; ++i)
+        {
+          hist[ORC_PLASTIC_HIST * k + i] = hist[ORC_PLASTIC_HIST * k + 7 + i];
+          hist[ORC_PLASTIC_HIST * k + 7 + i] = (i >= 1 && i <= 3) ? 1.0 : 0.0;
         }
     if (kind != ORC_MAT_DRUCKER_PRAGER) return;
     for (int64_t k = 0; k < n_points; ++k)
@@ -2738,7 +2915,9 @@ extern "C"
       std::vector<double> par(matparams, matparams + (matkind == ORC_MAT_ELASTHYPER ? 1 + 6 * (int)matparams[0]
                                                       : (matkind == ORC_MAT_DRUCKER_PRAGER
                                                                 ? 10
-                                                                : (matkind == ORC_MAT_VISCONEOHOOKE ? 7 : 2))));
+                                                                : (matkind == ORC_MAT_VISCONEOHOOKE
+                                                                          ? 7
+                                                                          : (matkind == ORC_MAT_PLASTIC_NLNLOG ? 11 : 2)))));
       par.resize(par.size() + 2, 0.0);
       // Discretization::evaluate loop over column elements
       // (src/core/fem/src/discretization/4C_fem_discretization_evaluate.cpp:85-117)
@@ -2769,7 +2948,7 @@ extern "C"
           par[0] = mue_per_ele[e];  // InputField MUE looked up by element id
         const bool stiff = (action == ORC_ACTION_FORCE_STIFF) && values;
         g_element_material_hist =
-            g_material_hist_base ? g_material_hist_base + (int64_t)ORC_VISCO_HIST * ngauss(ct) * e : nullptr;
+            g_material_hist_base ? g_material_hist_base + (int64_t)finite_strain_hist(matkind) * ngauss(ct) * e : nullptr;
         const int ele_err = element_tech(ct, tech, matkind, par.data(), action, Xe.data(), ue.data(),
             stiff ? Ke.data() : nullptr, fe.data(), hist ? hist + hist_per_ele * e : nullptr);
         g_element_material_hist = nullptr;

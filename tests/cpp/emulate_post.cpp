@@ -126,6 +126,22 @@ extern "C" int emu_visco_neohooke(const double* in6, double dt, double* hist, co
   return 0;
 }
 
+// MAT_Struct_PlasticNlnLogNeoHooke of the product at one point: in10 = {YOUNG NUE DENS YIELD ISOHARD SATHARDENING HARDEXPO
+// VISC RATE_DEPENDENCY TOL}, dt = time step size, hist = PLASTIC_HIST doubles (updated in place) or null
+extern "C" int emu_plastic_nlnlog(const double* in10, double dt, double* hist, const double* C, double* S, double* Cm36)
+{
+  double q[PLASTIC_NPAR];
+  if (!make_plastic_nlnlog(in10, dt, q)) return -3;
+  MatParams mp;
+  for (double& v : mp.p) v = 0.0;
+  mp.hyper = nullptr, mp.fiber = nullptr, mp.ext = q, mp.hist = hist;
+  double Cm[21];
+  material_evaluate<MAT_PLASTIC>(mp, C, S, Cm);
+  for (int I = 0; I < 6; ++I)
+    for (int J = 0; J < 6; ++J) Cm36[I + 6 * J] = Cm[c21(I, J)];
+  return 0;
+}
+
 // MAT_Struct_DruckerPrager of the product at one point: in10 = input-file parameters {YOUNG NUE ISOHARD TOL C ETA
 // XI ETABAR MAXITER TANG}, hist = DP_HIST doubles (updated in place) or null; returns -3 for parameters the device
 // rejects (non-symmetric consistent tangent)

@@ -339,6 +339,47 @@ def druckerprager_case(rel):
             "tolres": float(sd["TOLRES"]), "toldisp": float(sd["TOLDISP"]), "expected_disp": expected}
 
 
+def necking_case(rel):
+    """tests/input_files/plastic_necking_eas.4C.yaml: a quarter of a round bar of 96 EAS-mild hex8 elements,
+    MAT_Struct_PlasticNlnLogNeoHooke (finite-strain von Mises plasticity, a history material), pulled by a prescribed
+    end displacement u_z = t in 30 steps; symmetry conditions on points / lines / surfaces.  Lower-dimensional Dirichlet
+    entities override higher ones for all dofs of their nodes (Core::FE::Utils::Dbc hierarchy), so the list is stored
+    surfaces first, points last and applied in that order."""
+    with open(os.path.join(REF, rel)) as fh:
+        y = yaml.safe_load(fh)
+    ids, coords = [], []
+    for line in y["NODE COORDS"]:
+        m = re.match(r"NODE\s+(\d+)\s+COORD\s+(\S+)\s+(\S+)\s+(\S+)", line)
+        ids.append(int(m.group(1)))
+        coords.append([float(m.group(i)) for i in (2, 3, 4)])
+    index = {g: k for k, g in enumerate(ids)}
+    eles = []
+    for line in y["STRUCTURE ELEMENTS"]:
+        tok = line.split()
+        assert tok[1] == "SOLID" and tok[2] == "HEX8" and "KINEM nonlinear" in line and "TECH eas_mild" in line
+        eles.append([index[int(t)] for t in tok[3:11]])
+    dirichlet = []
+    for sec, topo, key in (("DESIGN SURF DIRICH CONDITIONS", "DSURF-NODE TOPOLOGY", "DSURFACE"),
+                           ("DESIGN LINE DIRICH CONDITIONS", "DLINE-NODE TOPOLOGY", "DLINE"),
+                           ("DESIGN POINT DIRICH CONDITIONS", "DNODE-NODE TOPOLOGY", "DNODE")):
+        for c in y[sec]:
+            nodes = [index[int(re.match(rf"NODE\s+(\d+)\s+{key}\s+(\d+)", l).group(1))] for l in y[topo]
+                     if int(re.match(rf"NODE\s+(\d+)\s+{key}\s+(\d+)", l).group(2)) == c["E"]]
+            dirichlet.append({"nodes": sorted(nodes), "ONOFF": c["ONOFF"], "VAL": c["VAL"], "FUNCT": c["FUNCT"],
+                              "level": ("DSURFACE", "DLINE", "DNODE").index(key)})
+    assert y["FUNCT1"][0]["SYMBOLIC_FUNCTION_OF_SPACE_TIME"] == "t"
+    mat = {k: float(v) for k, v in y["MATERIALS"][0]["MAT_Struct_PlasticNlnLogNeoHooke"].items()}
+    assert "HARDENING_FUNC" not in mat  # parameter hardening only
+    sd = y["STRUCTURAL DYNAMIC"]
+    expected = [{"node": index[r["STRUCTURE"]["NODE"]], "dof": "xyz".index(r["STRUCTURE"]["QUANTITY"][-1]),
+                 "value": float(r["STRUCTURE"]["VALUE"]), "tol": float(r["STRUCTURE"]["TOLERANCE"])}
+                for r in y["RESULT DESCRIPTION"] if r["STRUCTURE"]["QUANTITY"] in ("dispx", "dispy", "dispz")]
+    return {"source": rel, "celltype": "hex8", "tech": "eas_mild", "coords": coords, "elements": eles, "material": mat,
+            "dirichlet": dirichlet, "functs": {"1": {"TIMES": [0.0, 1000.0], "VALUES": [0.0, 1000.0]}},
+            "timestep": float(sd["TIMESTEP"]), "numstep": int(sd["NUMSTEP"]),
+            "tolres": float(sd["TOLRES"]), "toldisp": float(sd["TOLDISP"]), "expected_disp": expected}
+
+
 def visco_creep_case(rel):
     """tests/input_files/viscoNeoHooke_creep.4C.yaml: unit cube of 64 hex8 EAS-mild elements, MAT_VISCONEOHOOKE (finite-strain
     history material), constant surface traction, symmetry Dirichlet conditions per dof, default time integration of
@@ -546,6 +587,9 @@ if __name__ == "__main__":
     for name in ("RetToCone", "RetToCone_elastic_tang"):
         with open(os.path.join(HERE, f"integration_hex8_druckerprager_{name}.json"), "w") as fh:
             json.dump(druckerprager_case(f"tests/input_files/mat_druckerprager_{name}.4C.yaml"), fh)
+    for name in ("plastic_necking_eas",):
+        with open(os.path.join(HERE, f"integration_hex8_{name}.json"), "w") as fh:
+            json.dump(necking_case(f"tests/input_files/{name}.4C.yaml"), fh)
     with open(os.path.join(HERE, "integration_hex8_visco_creep.json"), "w") as fh:
         json.dump(visco_creep_case("tests/input_files/viscoNeoHooke_creep.4C.yaml"), fh)
     with open(os.path.join(HERE, "unit_known_answers.json"), "w") as fh:

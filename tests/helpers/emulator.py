@@ -246,6 +246,20 @@ def visco_neohooke(in6, dt, Cv, hist=None):
     return S, Cm.reshape(6, 6)
 
 
+def plastic_nlnlog(in10, dt, Cv, hist=None):
+    """Product MAT_Struct_PlasticNlnLogNeoHooke at one point: (S, Cm); hist (14,) updated in place or None."""
+    in10 = np.ascontiguousarray(in10, np.float64)
+    Cv = np.ascontiguousarray(Cv, np.float64)
+    S, Cm = np.zeros(6), np.zeros(36)
+    L = lib("post")
+    L.emu_plastic_nlnlog.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = L.emu_plastic_nlnlog(_p(in10), float(dt), _p(hist), _p(Cv), _p(S), _p(Cm))
+    if rc == -3:
+        return None
+    assert rc == 0
+    return S, Cm.reshape(6, 6)
+
+
 def hex8_visco(in6, dt, conn, X, u_col, rowptr, colind, node_row_lid, node_col_lid, n_row_nodes, mat_hist, stiff=True):
     """Emulated nonlinear hex8 kernel with MAT_VISCONEOHOOKE; mat_hist (n_ele, 8, 24) updated in place."""
     conn = np.ascontiguousarray(conn, np.int32)

@@ -76,42 +76,76 @@ def solve_case(case, evaluate, max_iter=30, update_prestress=None, recover=None,
     return u.reshape(nn, 3)
 
 
-def solve_prescribed_displacement_case(case, evaluate, max_iter=30):
-    """Statics driven by DESIGN SURF DIRICH CONDITIONS with time functions only (no external load): every
+def solve_prescribed_displacement_case(case, evaluate, max_iter=30, recover=None, update_step=None, trace=None,
+                                       predictor=None):
+    """Statics driven by DESIGN ... DIRICH CONDITIONS with time functions only (no external load): every
     step sets the prescribed dofs to VAL * FUNCT(t) (Core::FE::evaluate_dirichlet) and iterates the free
-    ones on f_int = 0.  case["dirichlet"]: [{nodes, ONOFF, VAL, FUNCT}], case["functs"][id] =
-    linearinterpolation {TIMES, VALUES}."""
+    ones on f_int = 0.  case["dirichlet"]: [{nodes, ONOFF, VAL, FUNCT[, level]}], case["functs"][id] =
+    linearinterpolation {TIMES, VALUES}.  level (0 surface, 1 line, 2 point): a lower-dimensional entity overrides the
+    higher ones for ALL dofs of its nodes, entities of one level add up (Core::FE::Utils::Dbc::read_dirichlet_condition,
+    src/core/fem/src/condition/4C_fem_condition_utils... hierarchical order).
+    recover(du_flat) / update_step(u_flat): as in solve_case (EAS recover after every Newton update with the iteration
+    increment; history materials commit at the end of a converged step).
+    predictor "constvel": PREDICT ConstVel -- the free dofs start a step from u_n + (u_n - u_(n-1)), the statics form of
+    the constant-velocity predictor (src/structure_new/src/predict/4C_structure_new_predict_constdisvelaccpress.cpp)."""
     nn = len(case["coords"])
     fixed = np.zeros(3 * nn, bool)
-    for c in case["dirichlet"]:
+    governs = -np.ones((nn, 3), int)  # index of the condition that prescribes the dof
+    level = -np.ones(nn, int)
+    for ic, c in enumerate(case["dirichlet"]):
+        lv = c.get("level", 0)
         for n in c["nodes"]:
-            for d in range(3):
-                if c["ONOFF"][d]:
-                    fixed[3 * n + d] = True
+            if lv > level[n]:
+                governs[n, :] = -1
+                level[n] = lv
+            if lv == level[n]:
+                for d in range(3):
+                    if c["ONOFF"][d]:
+                        governs[n, d] = ic
+    fixed = (governs >= 0).ravel()
     free = ~fixed
     u = np.zeros(3 * nn)
+    u_old = u.copy()
     t = 0.0
-    for _ in range(case["numstep"]):
+    for step in range(case["numstep"]):
         t += case["timestep"]
-        for c in case["dirichlet"]:
+        if predictor == "constvel":
+            u, u_old = u + (u - u_old), u.copy()
+        du_dbc = np.zeros(3 * nn)
+        for n in range(nn):
             for d in range(3):
-                if not c["ONOFF"][d]:
+                ic = governs[n, d]
+                if ic < 0:
                     continue
+                c = case["dirichlet"][ic]
                 f = case["functs"][str(c["FUNCT"][d])] if c["FUNCT"][d] else None
                 fac = 1.0 if f is None else float(np.interp(t, f["TIMES"], f["VALUES"]))
-                for n in c["nodes"]:
-                    u[3 * n + d] = c["VAL"][d] * fac
+                du_dbc[3 * n + d] = c["VAL"][d] * fac - u[3 * n + d]
+        u = u + du_dbc
         for it in range(max_iter):
             rowptr, colind, values, fint = evaluate(u)
-            K = csr_to_dense(rowptr, colind, values, 3 * nn)
             du = np.zeros(3 * nn)
-            du[free] = np.linalg.solve(K[np.ix_(free, free)], -fint[free])
+            if 3 * nn > 1500:
+                import scipy.sparse as sp
+                from scipy.sparse.linalg import spsolve
+                K = sp.csr_matrix((values, colind, rowptr), shape=(3 * nn, 3 * nn))
+                du[free] = spsolve(K[free][:, free].tocsc(), -fint[free])
+            else:
+                K = csr_to_dense(rowptr, colind, values, 3 * nn)
+                du[free] = np.linalg.solve(K[np.ix_(free, free)], -fint[free])
             u += du
+            if recover is not None:
+                recover(du)
             rowptr, colind, values, fint = evaluate(u)
-            if np.linalg.norm(fint[free]) < case["tolres"] and np.linalg.norm(du) < case["toldisp"]:
+            rn = np.linalg.norm(fint[free])
+            if trace is not None:
+                trace.append((step, it, rn, np.linalg.norm(du)))
+            if rn < case["tolres"] and np.linalg.norm(du) < case["toldisp"]:
                 break
         else:
             raise RuntimeError(f"Newton did not converge at t={t}: |r|={np.linalg.norm(fint[free])}")
+        if update_step is not None:
+            update_step(u)
     return u.reshape(nn, 3)
 
 

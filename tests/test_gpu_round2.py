@@ -831,3 +831,105 @@ def test_reference_fbar_known_answers_through_general_kernel(name):
     for e in case["expected_disp"]:
         assert abs(u[e["node"], e["dof"]] - e["value"]) < 1e-10, (e, u[e["node"], e["dof"]])
     asm.close()
+
+
+# ---- MAT_Struct_PlasticNlnLogNeoHooke: finite-strain plasticity on the device Gauss-point state store -----------------
+PLASTIC = dict(YOUNG=206.9, NUE=0.29, DENS=0.0, YIELD=0.45, ISOHARD=0.12924, SATHARDENING=0.715, HARDEXPO=16.93, VISC=1.0,
+               RATE_DEPENDENCY=0.1, TOL=1e-12)
+PLASTIC10 = [PLASTIC[k] for k in ("YOUNG", "NUE", "DENS", "YIELD", "ISOHARD", "SATHARDENING", "HARDEXPO", "VISC",
+                                  "RATE_DEPENDENCY", "TOL")]
+
+
+@pytest.mark.parametrize("cell,n,tech", [("HEX8", (6, 5, 4), "none"), ("HEX27", (3, 2, 2), "none"), ("TET10", 3, "none"),
+                                         ("HEX8", (5, 4, 3), "eas_mild"), ("HEX8", (4, 3, 3), "eas_full")])
+def test_plastic_nlnlog_matches_oracle_over_steps(cell, n, tech):
+    """Two load steps into the plastic range with a state commit in between: K, f and the stored state {accumulated
+    plastic strain, Cp^-1} of the CUDA path (evaluation from C with the Cholesky factor; hex8 on the fast kernel, the
+    other cells on the general kernel, EAS on the tensor-core kernel) against the oracle's F-based restatement, which is
+    pinned to the reference's necking known answer (tests/test_plastic_material.py)."""
+    ct = getattr(orc, cell)
+    if cell == "TET10":
+        X, conn = b200.mesh.unstructured_tet10(n)
+        rm = b200.partition.serial_mesh(b200.mesh.TET10, X, conn)
+        h = 1.0 / n
+    else:
+        rm = b200.partition.box_partition(getattr(b200.mesh, cell), n, 0, 1)
+        h = 1.0 / max(n)
+    u = 1.5 * b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, h)
+    dt = 0.175
+    par = orc.plastic_nlnlog_params(dt=dt, **PLASTIC)
+    otech = {"none": orc.TECH_NONE, "eas_mild": orc.TECH_EAS_MILD, "eas_full": orc.TECH_EAS_FULL}[tech]
+    dtech = {"none": capi.TECH_NONE, "eas_mild": capi.TECH_EAS_MILD, "eas_full": capi.TECH_EAS_FULL}[tech]
+    asm = b200.DeviceAssembler(rm, capi.MAT_PLASTIC_NLNLOG, PLASTIC10, tech=dtech)
+    rowptr, colind = asm.graph()
+    ngp = orc.num_gp(ct)
+    mh = orc.plastic_new_history(rm.n_col_eles, ngp)
+    eas = orc.eas_new_history(otech, rm.n_col_eles) if tech != "none" else None
+    asm.set_state("displacement", u.ravel())
+    rc, _ = asm.ctx.evaluate(capi.ACTION_NLNSTIFF, asm._u, None, None, check=False)
+    assert rc == capi.ERR_INVALID  # no time step size yet
+    asm.ctx.set_time_step_size(dt)
+    assert asm.ctx.L.b200s_material_history_size(asm.ctx.h) == mh.size
+    assert np.array_equal(asm.ctx.get_material_history().reshape(mh.shape), mh)  # fresh: Cp^-1 = I
+    # the tangent of a yielding point divides by differences of principal stretches: 1e-10 instead of 1e-12
+    tol = 1e-10
+    for step, fac in enumerate((1.0, 1.4)):
+        asm.set_state("displacement", (fac * u).ravel())
+        K, f, err = asm.evaluate()
+        orc.set_material_history(mh)
+        rK, rf, nbad = orc.evaluate_assemble(ct, orc.MAT_PLASTIC_NLNLOG, par, rm.conn, rm.X.ravel(), (fac * u).ravel(),
+                                             rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, rowptr, colind, tech=otech,
+                                             hist=eas)
+        orc.set_material_history(None)
+        ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, tol)
+        assert ok and nbad == 0 and err.n_neg_jacobian == 0, (step, wK, wf)
+        assert mh[..., 7].max() > 1e-3  # yielding
+        dh = asm.ctx.get_material_history().reshape(mh.shape)
+        assert np.abs(dh - mh).max() <= 1e-11
+        asm.ctx.update_step()
+        orc.material_update(orc.MAT_PLASTIC_NLNLOG, mh)
+        dh = asm.ctx.get_material_history().reshape(mh.shape)
+        assert np.abs(dh - mh).max() <= 1e-11 and np.array_equal(dh[..., 7:], orc.plastic_new_history(rm.n_col_eles, ngp)[..., 7:])
+    # restart: the state store round-trips through get / set (caller's element numbering)
+    blob = asm.ctx.get_material_history()
+    asm2 = b200.DeviceAssembler(rm, capi.MAT_PLASTIC_NLNLOG, PLASTIC10, tech=dtech)
+    asm2.ctx.set_time_step_size(dt)
+    asm2.ctx.set_material_history(blob)
+    if tech != "none":
+        asm2.ctx.set_element_history(asm.ctx.get_element_history())
+    for a in (asm, asm2):
+        a.set_state("displacement", (1.7 * u).ravel())
+    K1, f1, _ = asm.evaluate()
+    K2, f2, _ = asm2.evaluate()
+    assert np.abs(K1 - K2).max() <= 1e-12 * np.abs(K1).max() and np.abs(f1 - f2).max() <= 1e-12 * np.abs(f1).max()
+    asm.close()
+    asm2.close()
+
+
+def test_reference_plastic_necking_known_answer_through_cuda_path():
+    """tests/input_files/plastic_necking_eas.4C.yaml (96 EAS-mild hex8, MAT_Struct_PlasticNlnLogNeoHooke, 30
+    displacement-controlled steps into the necking regime, PREDICT ConstVel) with the CUDA path doing every evaluate,
+    struct_calc_recover and the state commit: RESULT DESCRIPTION displacements."""
+    import json
+    import os
+    from tests.helpers.newton import solve_prescribed_displacement_case
+    case = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "integration_hex8_plastic_necking_eas.json")))
+    X = np.array(case["coords"])
+    conn = np.array(case["elements"], np.int32)
+    rm = b200.partition.serial_mesh(b200.mesh.HEX8, X, conn)
+    m = case["material"]
+    in10 = [m[k] for k in ("YOUNG", "NUE", "DENS", "YIELD", "ISOHARD", "SATHARDENING", "HARDEXPO", "VISC", "RATE_DEPENDENCY", "TOL")]
+    asm = b200.DeviceAssembler(rm, capi.MAT_PLASTIC_NLNLOG, in10, tech=capi.TECH_EAS_MILD)
+    asm.ctx.set_time_step_size(case["timestep"])
+    rowptr, colind = asm.graph()
+
+    def evaluate(u):
+        asm.set_state("displacement", u)
+        K, f, _ = asm.evaluate()
+        return rowptr, colind, K, f
+
+    u = solve_prescribed_displacement_case(case, evaluate, recover=lambda du: asm.recover(du),
+                                           update_step=lambda u: asm.ctx.update_step(), predictor="constvel", max_iter=40)
+    for e in case["expected_disp"]:
+        assert abs(u[e["node"], e["dof"]] - e["value"]) < 1e-9, (e, u[e["node"], e["dof"]])
+    asm.close()
