@@ -8,7 +8,9 @@ Layout (only what the path needs):
   capi.py          ctypes binding of lib4c_b200_solid.so
   mesh.py          synthetic hex8 / hex27 / tet10 meshes and displacement states
   partition.py     rank-local discretization views (row/column maps, halo lists)
+  fe_export.py     row-element mode: export rows, extended graph and the export plan (FE_MATRIX assembly)
   assembler.py     host-side mirror of Discretization::evaluate + AssembleStrategy for one rank
 """
 from . import capi, mesh, partition  # noqa: F401
-from .assembler import DeviceAssembler, parity_report  # noqa: F401
+from .assembler import DeviceAssembler, RowExportAssembler, parity_report  # noqa: F401
+from . import fe_export  # noqa: F401

@@ -149,3 +149,60 @@ def parity_report(rowptr, values, ref_values, f, ref_f, rtol=1e-12):
     rf = float((np.abs(f - ref_f) / (rtol * sf)).max())
     finite = np.isfinite(values).all() and np.isfinite(f).all()
     return bool(finite and rK <= 1.0 and rf <= 1.0), rK, rf
+
+
+class RowExportAssembler:
+    """Row-element mode (FE_MATRIX: SparseMatrix::fe_assemble + complete(), 4C_linalg_sparsematrix.cpp:598-630,705-710):
+    the rank evaluates its ROW elements only, contributions to rows of ghost nodes go to export rows behind its own
+    and travel to their owners after the element kernels (b200s_set_row_export).  view / rowptr / colind / plan come
+    from fe_export.fe_plan.  evaluate() returns the rank's own rows; with a communicator the export has happened
+    inside, without one (tests) exported() / add_exported() move the rows by hand."""
+
+    def __init__(self, view, rowptr, colind, plan, matkind, matparams, device=0, options=None):
+        rm = self.rm = view.rm
+        self.view, self.plan = view, plan
+        self.ctx = capi.Context(device, rm.rank, rm.nranks)
+        opts = {"owned_rows": plan.n_rows_owned, "owned_nnz": plan.nnz_owned}
+        opts.update(options or {})
+        for k, v in opts.items():
+            self.ctx.set_option(k, v)
+        self.ctx.set_mesh(rm.celltype, rm.X, view.conn)
+        self.ctx.set_material(matkind, matparams)
+        d = np.arange(3, dtype=np.int32)
+        ext = view.node_row_lid_ext
+        row = np.where(ext[:, None] >= 0, 3 * ext[:, None] + d, -1)
+        col = 3 * rm.node_col_lid[:, None] + d
+        self.ctx.set_graph(rowptr, colind, row.astype(np.int32).ravel(), col.astype(np.int32).ravel())
+        self.ctx.set_row_export(plan)
+        self.n_rows, self.nnz = plan.n_rows_owned, plan.nnz_owned
+        self.n_rows_ext, self.nnz_ext = 3 * view.n_row_nodes_ext, int(rowptr[-1])
+        if rm.nranks > 1:
+            self.ctx.set_halo(rm.peers, rm.send_row_nodes, rm.recv_col_nodes)
+        self._u = None
+
+    def set_state(self, name, u_row):
+        v = np.ascontiguousarray(u_row, np.float64).ravel()
+        assert v.size == self.n_rows
+        self._u = v
+        self.ctx.set_state(name, v)
+
+    def evaluate(self, action="struct_calc_nlnstiff", check=True):
+        act = ACTIONS[action]
+        K = np.empty(self.nnz) if act in STIFF_ACTIONS else None
+        f = np.empty(self.n_rows)
+        rc, err = self.ctx.evaluate(act, self._u, K, f, check=check)
+        return K, f, err
+
+    def exported(self, peer_index):
+        """(values, f) slices of the export rows for peer peer_index as they stand in the device buffers."""
+        (v0, nv), (f0, nf) = self.plan.send_val[peer_index], self.plan.send_f[peer_index]
+        vals = self.ctx.get_values()[v0:v0 + nv] if nv else np.zeros(0)
+        f = self.ctx.get_f_rows(f0, f0 + nf) if nf else np.zeros(0)
+        return vals, f
+
+    def own_rows(self):
+        """(values, f) of the rank's own rows as they stand in the device buffers."""
+        return self.ctx.get_values()[:self.nnz], self.ctx.get_f_rows(0, self.n_rows)
+
+    def close(self):
+        self.ctx.close()

@@ -37,6 +37,7 @@ PRESTRESS_NONE, PRESTRESS_MULF = 0, 1
 SYMBOLS = [
     "b200s_create", "b200s_destroy", "b200s_last_error", "b200s_set_option", "b200s_set_mesh",
     "b200s_set_element_properties", "b200s_set_material", "b200s_set_graph", "b200s_set_halo", "b200s_nccl_unique_id",
+    "b200s_set_row_export", "b200s_add_exported",
     "b200s_comm_init_nccl", "b200s_evaluate", "b200s_evaluate_async", "b200s_synchronize",
     "b200s_device_values", "b200s_device_f", "b200s_device_u_row", "b200s_device_u_col",
     "b200s_stream", "b200s_nnz", "b200s_n_rows", "b200s_get_timers", "b200s_launch_count",
@@ -493,6 +494,28 @@ class Context:
         r = np.concatenate(recv_col_nodes).astype(np.int32) if n and ro[-1] else np.zeros(1, np.int32)
         self._ck(self.L.b200s_set_halo(self.h, n, _ptr(peer), _ptr(so), _ptr(np.ascontiguousarray(s)),
                                        _ptr(ro), _ptr(np.ascontiguousarray(r))))
+
+    def set_row_export(self, plan):
+        """plan: fe_export.FePlan (b200s_set_row_export)."""
+        n = len(plan.peers)
+        peer = np.ascontiguousarray(plan.peers if n else [0], np.int32)
+        sv = np.ascontiguousarray(np.asarray(plan.send_val if n else [(0, 0)], np.int64).ravel())
+        sf = np.ascontiguousarray(np.asarray(plan.send_f if n else [(0, 0)], np.int64).ravel())
+        ro = np.zeros(n + 1, np.int64)
+        fo = np.zeros(n + 1, np.int64)
+        for i in range(n):
+            ro[i + 1] = ro[i] + len(plan.recv_pos[i])
+            fo[i + 1] = fo[i] + len(plan.recv_fpos[i])
+        rp = np.ascontiguousarray(np.concatenate(plan.recv_pos) if n and ro[-1] else np.zeros(1), np.int64)
+        rf = np.ascontiguousarray(np.concatenate(plan.recv_fpos) if n and fo[-1] else np.zeros(1), np.int32)
+        self.L.b200s_set_row_export.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 7
+        self._ck(self.L.b200s_set_row_export(self.h, n, _ptr(peer), _ptr(sv), _ptr(sf), _ptr(ro), _ptr(rp), _ptr(fo), _ptr(rf)))
+
+    def add_exported(self, peer_index, values=None, f=None):
+        values = None if values is None else np.ascontiguousarray(values, np.float64)
+        f = None if f is None else np.ascontiguousarray(f, np.float64)
+        self.L.b200s_add_exported.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        self._ck(self.L.b200s_add_exported(self.h, int(peer_index), _ptr(values), _ptr(f)))
 
     def nccl_unique_id(self):
         buf = (C.c_char * 128)()

@@ -1063,7 +1063,7 @@ namespace b200s
   // key 0: the element holds a ghost node; 1 + phase of its lowest owned row otherwise.  n_spread counts the
   // elements whose owned nodes span more than two phases (a row numbering without spatial locality).
   __global__ void k_segment_keys(int nn, int64_t n_ele, const int32_t* conn, const NodeRow* node_row, int P,
-      const int64_t* phase_row, uint32_t* keys, int32_t* idx, unsigned long long* n_spread)
+      const int64_t* phase_row, uint32_t* keys, int32_t* idx, unsigned long long* n_spread, int64_t n_owned)
   {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_ele) return;
@@ -1072,7 +1072,7 @@ namespace b200s
     for (int k = 0; k < nn; ++k)
     {
       const int32_t fr = node_row[conn[e * nn + k]].frow;
-      if (fr < 0)
+      if (fr < 0 || fr >= n_owned)  // not owned (export rows of the row-element mode are ghost nodes too)
       {
         ghost = true;
         continue;
@@ -1208,13 +1208,14 @@ namespace b200s
   }
 
   // Discretization::set_state: owned part of the column vector (4C_fem_discretization.cpp:640-661)
+  // n_owned: rows >= n_owned are export rows of ghost nodes (row-element mode), their state comes through the halo
   __global__ void k_row_to_col(int64_t n_col_nodes, const NodeRow* node_row, const double* u_row,
-      double* u_col)
+      double* u_col, int64_t n_owned)
   {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 3 * n_col_nodes) return;
     const int32_t fr = node_row[t / 3].frow;
-    if (fr >= 0) u_col[t] = u_row[fr + (int)(t % 3)];
+    if (fr >= 0 && fr < n_owned) u_col[t] = u_row[fr + (int)(t % 3)];
   }
   __global__ void k_pack_halo(int64_t n, const int32_t* send_row_lid, const double* u_row, double* buf)
   {
@@ -1556,6 +1557,15 @@ struct b200s_ctx
   int eas_mma = 1;           // hex8 EAS: element matrices on the FP64 tensor cores (0: warp-per-element FMA kernel)
   int pipeline_phases = 12;  // row phases of the host-destination pipeline (1 = off)
   int overlap_halo = 1;      // ghost import on a side stream while the elements without ghost nodes are evaluated
+  // row-element mode (FE_MATRIX: 4C_linalg_sparsematrix.cpp:598-630,705-710): the graph carries export rows behind
+  // the rank's own ones; options "owned_rows" / "owned_nnz" (before set_graph) give the split, b200s_set_row_export
+  // the peers, slices and add positions
+  int64_t n_rows_owned = 0, nnz_owned = 0;  // 0: every row of the graph is the rank's own
+  std::vector<int> exp_peer;
+  std::vector<int64_t> exp_send_val, exp_send_f, exp_recv_off, exp_recv_foff;  // per peer {start, count} pairs / offsets
+  int64_t* d_exp_pos = nullptr;   // add positions in the owned values, concatenated over the peers
+  int32_t* d_exp_fpos = nullptr;  // add positions in the owned residual
+  double *d_exp_buf = nullptr, *d_exp_fbuf = nullptr;  // receive buffers
   // what the last evaluate did (bench / tests): launches of the element kernel, overlapped D2H chunks
   int last_kernel_launches = 0, last_pipeline_chunks = 0, last_halo_overlapped = 0;
 };
@@ -1934,6 +1944,9 @@ namespace
   // MulfHistoryData per element: one per Gauss point, with TECH fbar one more for the centroid (GlobalHistory of
   // MulfFBarFormulation, 4C_solid_ele_calc_mulf_fbar.hpp:112-116)
   inline int mulf_points(const b200s_ctx* ctx) { return ctx->ngp + (ctx->tech == B200S_TECH_FBAR ? 1 : 0); }
+  // what the caller sees of the matrix / vectors: the rank's own rows (row-element mode keeps export rows behind them)
+  inline int64_t io_rows(const b200s_ctx* ctx) { return ctx->n_rows_owned > 0 ? ctx->n_rows_owned : ctx->n_rows; }
+  inline int64_t io_nnz(const b200s_ctx* ctx) { return ctx->n_rows_owned > 0 ? ctx->nnz_owned : ctx->nnz; }
   // fresh EASHistoryData of every element: all zero (4C_solid_ele_calc_eas_helpers.hpp:98-112)
   int eas_allocate(b200s_ctx* ctx)
   {
@@ -2428,6 +2441,7 @@ extern "C"
     b200s_clear_neumann(ctx);
     dfree(ctx->d_face_N), dfree(ctx->d_face_d0), dfree(ctx->d_face_d1), dfree(ctx->d_face_w);
     dfree(ctx->d_N_gp), dfree(ctx->d_fext), dfree(ctx->d_nm_row), dfree(ctx->d_nm_col), dfree(ctx->d_nm_flag);
+    dfree(ctx->d_exp_pos), dfree(ctx->d_exp_fpos), dfree(ctx->d_exp_buf), dfree(ctx->d_exp_fbuf);
     dfree(ctx->d_hyper), dfree(ctx->d_dN_gp), dfree(ctx->d_w), dfree(ctx->d_dN_cen), dfree(ctx->d_N_mass), dfree(ctx->d_dN_pts);
     dfree(ctx->d_dN_mass), dfree(ctx->d_w_mass), dfree(ctx->d_ele_is_row), dfree(ctx->d_mass);
     dfree(ctx->d_f_inertia), dfree(ctx->d_acc_row), dfree(ctx->d_acc_col), dfree(ctx->d_energy);
@@ -2461,6 +2475,10 @@ extern "C"
       ctx->pipeline_phases = (int)value;
     else if (!strcmp(key, "overlap_halo"))
       ctx->overlap_halo = value != 0;
+    else if (!strcmp(key, "owned_rows"))  // row-element mode, before set_graph: dof rows the rank owns
+      ctx->n_rows_owned = (int64_t)value;
+    else if (!strcmp(key, "owned_nnz"))  // ... and the non-zeros of those rows
+      ctx->nnz_owned = (int64_t)value;
     else if (!strcmp(key, "general_kernel"))  // A/B and tests: route every block through the table-driven general kernel
       ctx->general_kernel = value != 0;
     else if (!strcmp(key, "tma_gather"))
@@ -2785,7 +2803,7 @@ extern "C"
       unsigned long long spread = 0;
       k_phase_rows<<<1, b200s_ctx::MAX_PHASES, 0, st>>>(P, ctx->n_rows, ctx->d_rowptr, d_prow, d_poff);
       CK(cudaMemsetAsync(d_spread, 0, 8, st));
-      k_segment_keys<<<nblk(n), 256, 0, st>>>(ctx->nn, n, ctx->dconn, ctx->d_node_row, P, d_prow, k0, i0, d_spread);
+      k_segment_keys<<<nblk(n), 256, 0, st>>>(ctx->nn, n, ctx->dconn, ctx->d_node_row, P, d_prow, k0, i0, d_spread, io_rows(ctx));
       ctx->launches += 2;
       CK(cudaMemcpyAsync(&spread, d_spread, 8, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
@@ -3294,7 +3312,7 @@ extern "C"
           ctx->n_col_nodes, ctx->d_node_row, ctx->d_node_colbase, d_src_row, d_dst);
     else
       k_row_to_col<<<nblk(3 * ctx->n_col_nodes), 256, 0, st>>>(
-          ctx->n_col_nodes, ctx->d_node_row, d_src_row, d_dst);
+          ctx->n_col_nodes, ctx->d_node_row, d_src_row, d_dst, io_rows(ctx));
     ctx->launches += 1;
     return B200S_OK;
   }
@@ -3340,6 +3358,51 @@ extern "C"
     first = false;
     ctx->kev_pending += 1;
     ctx->last_kernel_launches += 1;
+    return B200S_OK;
+  }
+
+
+  // ---- row-element mode: export of the off-rank rows ------------------------------------------------------------------
+  __global__ void k_add_exported(int64_t n, const int64_t* pos, const double* buf, double* vals)
+  {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) atomicAdd(vals + pos[t], buf[t]);  // two peers may add into one entry
+  }
+  __global__ void k_add_exported_f(int64_t n, const int32_t* pos, const double* buf, double* f)
+  {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) atomicAdd(f + pos[t], buf[t]);
+  }
+  // the received export rows of peer k (already in the receive buffers) are added to the rank's own rows
+  static void add_exported(b200s_ctx* ctx, int k, bool stiff)
+  {
+    cudaStream_t st = ctx->stream;
+    const int64_t v0 = ctx->exp_recv_off[(size_t)k], nv = ctx->exp_recv_off[(size_t)k + 1] - v0;
+    const int64_t f0 = ctx->exp_recv_foff[(size_t)k], nf = ctx->exp_recv_foff[(size_t)k + 1] - f0;
+    if (stiff && nv > 0) k_add_exported<<<nblk(nv), 256, 0, st>>>(nv, ctx->d_exp_pos + v0, ctx->d_exp_buf + v0, ctx->d_vals);
+    if (nf > 0) k_add_exported_f<<<nblk(nf), 256, 0, st>>>(nf, ctx->d_exp_fpos + f0, ctx->d_exp_fbuf + f0, ctx->d_f);
+    ctx->launches += (stiff && nv > 0) + (nf > 0);
+  }
+  static int export_rows(b200s_ctx* ctx, bool stiff)
+  {
+    cudaStream_t st = ctx->stream;
+    const int np = (int)ctx->exp_peer.size();
+    ctx->nccl.GroupStart();
+    for (int k = 0; k < np; ++k)
+    {
+      const int64_t sv = ctx->exp_send_val[2 * (size_t)k], nv = ctx->exp_send_val[2 * (size_t)k + 1];
+      const int64_t sf = ctx->exp_send_f[2 * (size_t)k], nf = ctx->exp_send_f[2 * (size_t)k + 1];
+      const int64_t r0 = ctx->exp_recv_off[(size_t)k], rn = ctx->exp_recv_off[(size_t)k + 1] - r0;
+      const int64_t g0 = ctx->exp_recv_foff[(size_t)k], gn = ctx->exp_recv_foff[(size_t)k + 1] - g0;
+      // the export rows of one owner are contiguous in the extended values / residual: sent in place
+      if (stiff && nv > 0) ctx->nccl.Send(ctx->d_vals + sv, (size_t)nv, /*ncclDouble*/ 8, ctx->exp_peer[(size_t)k], ctx->comm, st);
+      if (nf > 0) ctx->nccl.Send(ctx->d_f + sf, (size_t)nf, 8, ctx->exp_peer[(size_t)k], ctx->comm, st);
+      if (stiff && rn > 0) ctx->nccl.Recv(ctx->d_exp_buf + r0, (size_t)rn, 8, ctx->exp_peer[(size_t)k], ctx->comm, st);
+      if (gn > 0) ctx->nccl.Recv(ctx->d_exp_fbuf + g0, (size_t)gn, 8, ctx->exp_peer[(size_t)k], ctx->comm, st);
+    }
+    const int rc = ctx->nccl.GroupEnd();
+    if (rc) return fail(ctx, B200S_ERR_COMM, "row export: %s", ctx->nccl.GetErrorString(rc));
+    for (int k = 0; k < np; ++k) add_exported(ctx, k, stiff);
     return B200S_OK;
   }
 
@@ -3405,7 +3468,7 @@ extern "C"
     const int64_t n_ghost_eles = ctx->segmented ? ctx->seg_begin[1] : 0;
     // pipeline: host destination for K, at least two non-empty phases
     const bool pipeline = stiff && K_dst && ctx->segmented && ctx->n_phases > 1 && ctx->pipeline_phases > 1 &&
-                          !mass && !ctx->check_finite && is_host_pointer(K_dst);
+                          !mass && !ctx->check_finite && ctx->exp_peer.empty() && is_host_pointer(K_dst);
     // block-upper transfer: symmetric K_e (every device formulation but F-bar), tables usable for this graph
     bool symmetric = pipeline && ctx->symmetric_transfer && !accumulate && ctx->tech != B200S_TECH_FBAR;
     if (symmetric)
@@ -3546,6 +3609,18 @@ extern "C"
       nvtxRangePop();
       return rc;
     }
+    if (!ctx->exp_peer.empty() && ctx->comm)
+    {
+      // complete() of the FE matrix: export rows -> owners, Add mode (4C_linalg_sparsematrix.cpp:598-630)
+      nvtxRangePushA("row export");
+      const int erc = export_rows(ctx, stiff);
+      nvtxRangePop();
+      if (erc)
+      {
+        nvtxRangePop();
+        return erc;
+      }
+    }
     if (mass)
     {
       const int mrc = launch_mass(ctx, action);
@@ -3571,13 +3646,13 @@ extern "C"
       if (pipeline)
         CK(cudaStreamWaitEvent(st, ctx->ev_copy_done, 0));  // the context stream ends after the last chunk
       else
-        CK(cudaMemcpyAsync(K_dst, ctx->d_vals, sizeof(double) * (size_t)ctx->nnz, cudaMemcpyDefault, st));
+        CK(cudaMemcpyAsync(K_dst, ctx->d_vals, sizeof(double) * (size_t)io_nnz(ctx), cudaMemcpyDefault, st));
       nvtxRangePop();
     }
     if (f_dst && f_dst != ctx->d_f)
-      CK(cudaMemcpyAsync(f_dst, ctx->d_f, sizeof(double) * (size_t)ctx->n_rows, cudaMemcpyDefault, st));
+      CK(cudaMemcpyAsync(f_dst, ctx->d_f, sizeof(double) * (size_t)io_rows(ctx), cudaMemcpyDefault, st));
     CK(cudaGetLastError());
-    if (K_dst && stiff) ctx->last_d2h_bytes = 8 * (symmetric ? ctx->sym->n_packed : ctx->nnz);
+    if (K_dst && stiff) ctx->last_d2h_bytes = 8 * (symmetric ? ctx->sym->n_packed : io_nnz(ctx));
     if (symmetric)
     {
       // host side of the block-upper transfer: as the packed rows of a phase arrive, the pool writes the full
@@ -3603,6 +3678,61 @@ extern "C"
       nvtxRangePop();
     }
     nvtxRangePop();
+    return B200S_OK;
+  }
+
+
+  int b200s_set_row_export(b200s_ctx* ctx, int n_peers, const int32_t* peers, const int64_t* send_val, const int64_t* send_f,
+      const int64_t* recv_offsets, const int64_t* recv_pos, const int64_t* recv_f_offsets, const int32_t* recv_fpos)
+  {
+    if (!ctx || n_peers < 0) return B200S_ERR_INVALID;
+    if (ctx->n_rows_owned <= 0 || ctx->nnz_owned <= 0 || ctx->n_rows_owned > ctx->n_rows || ctx->nnz_owned > ctx->nnz)
+      return fail(ctx, B200S_ERR_INVALID,
+          "row export: options owned_rows / owned_nnz must be set before set_graph (rows %lld of %lld, nnz %lld of %lld)",
+          (long long)ctx->n_rows_owned, (long long)ctx->n_rows, (long long)ctx->nnz_owned, (long long)ctx->nnz);
+    cudaSetDevice(ctx->device);
+    ctx->exp_peer.assign(peers, peers + n_peers);
+    ctx->exp_send_val.assign(send_val, send_val + 2 * (size_t)n_peers);
+    ctx->exp_send_f.assign(send_f, send_f + 2 * (size_t)n_peers);
+    ctx->exp_recv_off.assign(recv_offsets, recv_offsets + n_peers + 1);
+    ctx->exp_recv_foff.assign(recv_f_offsets, recv_f_offsets + n_peers + 1);
+    for (int k = 0; k < n_peers; ++k)
+    {
+      const int64_t sv = send_val[2 * k], nv = send_val[2 * k + 1], sf = send_f[2 * k], nf = send_f[2 * k + 1];
+      if (nv < 0 || nf < 0 || (nv > 0 && (sv < ctx->nnz_owned || sv + nv > ctx->nnz)) ||
+          (nf > 0 && (sf < ctx->n_rows_owned || sf + nf > ctx->n_rows)))
+        return fail(ctx, B200S_ERR_INVALID, "row export: send slice of peer %d lies outside the export rows", peers[k]);
+    }
+    const int64_t nr = ctx->exp_recv_off[(size_t)n_peers], nfr = ctx->exp_recv_foff[(size_t)n_peers];
+    if (to_device(ctx, &ctx->d_exp_pos, recv_pos, nr) || to_device(ctx, &ctx->d_exp_fpos, recv_fpos, nfr) ||
+        to_device(ctx, &ctx->d_exp_buf, (const double*)nullptr, nr) || to_device(ctx, &ctx->d_exp_fbuf, (const double*)nullptr, nfr))
+      return B200S_ERR_CUDA;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B200S_OK;
+  }
+
+  int b200s_add_exported(b200s_ctx* ctx, int peer_index, const double* values, const double* f)
+  {
+    if (!ctx || peer_index < 0 || peer_index >= (int)ctx->exp_peer.size()) return B200S_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    const int64_t v0 = ctx->exp_recv_off[(size_t)peer_index], nv = ctx->exp_recv_off[(size_t)peer_index + 1] - v0;
+    const int64_t f0 = ctx->exp_recv_foff[(size_t)peer_index], nf = ctx->exp_recv_foff[(size_t)peer_index + 1] - f0;
+    if (values && nv > 0)
+      CK(cudaMemcpyAsync(ctx->d_exp_buf + v0, values, sizeof(double) * (size_t)nv, cudaMemcpyDefault, ctx->stream));
+    if (f && nf > 0) CK(cudaMemcpyAsync(ctx->d_exp_fbuf + f0, f, sizeof(double) * (size_t)nf, cudaMemcpyDefault, ctx->stream));
+    if (!f)
+    {
+      // values only
+      if (values && nv > 0)
+      {
+        k_add_exported<<<nblk(nv), 256, 0, ctx->stream>>>(nv, ctx->d_exp_pos + v0, ctx->d_exp_buf + v0, ctx->d_vals);
+        ctx->launches += 1;
+      }
+    }
+    else
+      add_exported(ctx, peer_index, values != nullptr);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
     return B200S_OK;
   }
 
@@ -3664,7 +3794,7 @@ extern "C"
     if (u_row && u_row != ctx->d_u_row)
     {
       nvtxRangePushA("h2d");
-      CK(cudaMemcpyAsync(ctx->d_u_row, u_row, sizeof(double) * (size_t)ctx->n_rows, cudaMemcpyDefault, st));
+      CK(cudaMemcpyAsync(ctx->d_u_row, u_row, sizeof(double) * (size_t)io_rows(ctx), cudaMemcpyDefault, st));
       nvtxRangePop();
     }
     const int rc = evaluate_impl(ctx, action, K_values, f_row);
@@ -3814,7 +3944,7 @@ extern "C"
     else
       return fail(ctx, B200S_ERR_UNSUPPORTED, "state '%s' is not used on the device path", name);
     if (v_row != dst)
-      CK(cudaMemcpyAsync(dst, v_row, sizeof(double) * (size_t)ctx->n_rows, cudaMemcpyDefault, ctx->stream));
+      CK(cudaMemcpyAsync(dst, v_row, sizeof(double) * (size_t)io_rows(ctx), cudaMemcpyDefault, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return B200S_OK;
   }

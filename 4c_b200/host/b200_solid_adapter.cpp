@@ -115,6 +115,25 @@ namespace B200Solid
     check(b200s_set_halo(ctx_, n, peer.data(), so.data(), s.data(), ro.data(), r.data()));
   }
 
+  void DeviceElementBlock::set_row_export(const RowExportView& e)
+  {
+    const int n = (int)e.peers.size();
+    std::vector<std::int32_t> peer(e.peers.begin(), e.peers.end()), fpos;
+    std::vector<std::int64_t> sv(2 * (size_t)n + 2, 0), sf(2 * (size_t)n + 2, 0), ro(n + 1, 0), fo(n + 1, 0), pos;
+    for (int i = 0; i < n; ++i)
+    {
+      sv[2 * i] = e.send_val_start[i], sv[2 * i + 1] = e.send_val_count[i];
+      sf[2 * i] = e.send_f_start[i], sf[2 * i + 1] = e.send_f_count[i];
+      pos.insert(pos.end(), e.recv_pos[i].begin(), e.recv_pos[i].end());
+      fpos.insert(fpos.end(), e.recv_fpos[i].begin(), e.recv_fpos[i].end());
+      ro[i + 1] = (std::int64_t)pos.size(), fo[i + 1] = (std::int64_t)fpos.size();
+    }
+    if (peer.empty()) peer.push_back(0);
+    if (pos.empty()) pos.push_back(0);
+    if (fpos.empty()) fpos.push_back(0);
+    check(b200s_set_row_export(ctx_, n, peer.data(), sv.data(), sf.data(), ro.data(), pos.data(), fo.data(), fpos.data()));
+  }
+
   std::string DeviceElementBlock::nccl_unique_id()
   {
     std::string id(128, '\0');

@@ -78,6 +78,18 @@ namespace B200Solid
     std::vector<std::vector<std::int32_t>> recv_col_nodes; // column-node lids filled from the peer
   };
 
+  // Export plan of an FE_MATRIX (Epetra_Export of the non-local rows, Add mode: 4C_linalg_sparsematrix.cpp:598-630):
+  // what b200s_set_row_export takes, per peer.  The block is then set up with the rank's ROW elements and the extended
+  // graph (own rows + export rows); set_option("owned_rows" / "owned_nnz") before set_graph.
+  struct RowExportView
+  {
+    std::vector<int> peers;
+    std::vector<std::int64_t> send_val_start, send_val_count;  // slice of the extended CSR values for the peer
+    std::vector<std::int64_t> send_f_start, send_f_count;      // slice of the extended residual
+    std::vector<std::vector<std::int64_t>> recv_pos;           // where the peer's export values are added (own CSR values)
+    std::vector<std::vector<std::int32_t>> recv_fpos;          // ... and its residual entries
+  };
+
   class DeviceElementBlock
   {
    public:
@@ -114,6 +126,7 @@ namespace B200Solid
     void set_row_elements(const std::uint8_t* is_row);
     void set_graph(const ElementBlockView& block, const CrsView& crs);
     void set_import(const ImportView& imp);
+    void set_row_export(const RowExportView& exp);  // row-element mode: SparseMatrix::fe_assemble + complete()
     void init_communicator(const char* nccl_id128);  // id from rank 0's nccl_unique_id(), MPI_Bcast by 4C
     std::string nccl_unique_id();
 

@@ -337,6 +337,23 @@ extern "C"
    * between a pack and an unpack kernel; the communicator comes from b200s_comm_init_nccl. */
   int b200s_set_halo(b200s_ctx* ctx, int n_nbr, const int32_t* peer, const int64_t* send_offsets,
       const int32_t* send_row_lids, const int64_t* recv_offsets, const int32_t* recv_col_lids);
+  /* Row-element mode = FE_MATRIX assembly (SparseMatrix::fe_assemble collects the rows a rank does not own, complete()
+   * exports them to their owners in Add mode: 4C_linalg_sparsematrix.cpp:598-630,705-710).  The caller hands
+   * b200s_set_mesh its ROW elements only and b200s_set_graph an EXTENDED graph: the rank's own dof rows (full pattern)
+   * followed by "export rows" for the ghost nodes its row elements touch; before b200s_set_graph the options
+   * "owned_rows" / "owned_nnz" (b200s_set_option) give the split.  u_row, K_values, f_row of b200s_evaluate keep their
+   * meaning (own rows only).  After the element kernels the export rows travel:
+   *   send_val / send_f [2 n_peers] : {start, count} of the slice of the extended values / residual for peer k (the
+   *                                   export rows of one owner are contiguous), sent in place with ncclSend
+   *   recv_pos[recv_offsets[k]..recv_offsets[k+1])  : for what peer k sends, in its order, the position in the rank's
+   *                                   own CSR values to add it to; recv_fpos / recv_f_offsets likewise for the residual
+   * = the plan of the Epetra_Export of the FE matrix ([host] arrays).  No peers: plain evaluation of the given elements.
+   * The pipelined host copy, mass actions, Neumann loads and the device linear algebra are not offered in this mode. */
+  int b200s_set_row_export(b200s_ctx* ctx, int n_peers, const int32_t* peers, const int64_t* send_val, const int64_t* send_f,
+      const int64_t* recv_offsets, const int64_t* recv_pos, const int64_t* recv_f_offsets, const int32_t* recv_fpos);
+  /* Host-mediated flavour of the same Add (tests without a communicator): adds export rows handed in by the caller --
+   * values / f [host|dev] in the order of peer peer_index, either may be NULL -- at the positions of the plan. */
+  int b200s_add_exported(b200s_ctx* ctx, int peer_index, const double* values, const double* f);
   /* NCCL bootstrap without MPI: rank 0 creates the 128-byte ncclUniqueId, the caller distributes
    * it (the harness uses torch.distributed; 4C would MPI_Bcast it), every rank initialises.
    * libnccl.so.2 is resolved at run time (dlopen), the library has no link-time NCCL dependency. */

@@ -102,11 +102,48 @@ def post_checks(rank, world, rm, asm, u, rowptr, colind):
           f"true residual {true_rel:.2e}", flush=True)
 
 
+def export_main(rank, world, local, n):
+    """Row-element mode: every rank evaluates its row elements only, the export rows travel over NCCL inside
+    b200s_evaluate (ghost displacements in, off-rank rows out) and the rank's own rows equal the owner-computes assembly
+    of the oracle over the column elements."""
+    capi = b200.capi
+    fe = b200.fe_export
+    view, rowptr, colind, plan = fe.fe_plan(lambda q: b200.partition.box_partition(b200.mesh.HEX8, n, q, world), rank, world)
+    rm = view.rm
+    asm = b200.RowExportAssembler(view, rowptr, colind, plan, capi.MAT_COUP_NEOHOOKE, [200.0, 0.25], device=local)
+    uid = [asm.ctx.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    asm.ctx.comm_init_nccl(uid[0])
+    o_rowptr, o_colind = orc.build_graph(orc.HEX8, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    assert np.array_equal(rowptr[:plan.n_rows_owned + 1], o_rowptr) and np.array_equal(colind[:plan.nnz_owned], o_colind)
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 1.0 / max(n))
+    worst = 0.0
+    for it in range(2):
+        uu = u * (1.0 + 0.25 * it)
+        asm.set_state("displacement", uu[:rm.n_row_nodes].ravel())
+        K, f, err = asm.evaluate("struct_calc_nlnstiff")
+        rK, rf, nbad = orc.evaluate_assemble(orc.HEX8, orc.MAT_COUP_NEOHOOKE, [200.0, 0.25], rm.conn, rm.X.ravel(), uu.ravel(),
+                                             rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, o_rowptr, o_colind, nthreads=4)
+        ok, wK, wf = b200.parity_report(o_rowptr, K, rK, f, rf, 1e-12)
+        assert ok and nbad == 0 and err.n_neg_jacobian == 0, (rank, it, wK, wf)
+        _, f2, _ = asm.evaluate("struct_calc_internalforce")
+        assert np.abs(f2 - rf).max() <= 1e-12 * np.abs(rf).max()
+        worst = max(worst, wK, wf)
+    sent = sum(c for _, c in plan.send_val)
+    asm.close()
+    dist.barrier()
+    print(f"MGPU_EXPORT_OK rank {rank}/{world} row elements {len(view.ele_ids)} of {rm.n_col_eles} column elements, "
+          f"export values sent {sent}, peers {plan.peers}, worst ratio {worst:.3g}", flush=True)
+    dist.destroy_process_group()
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     n = tuple(int(x) for x in sys.argv[1].split(","))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if len(sys.argv) > 2 and sys.argv[2] == "export":
+        return export_main(rank, world, local, n)
     capi = b200.capi
     rm = b200.partition.box_partition(b200.mesh.HEX8, n, rank, world)
     u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 1.0 / max(n))

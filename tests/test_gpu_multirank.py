@@ -55,3 +55,13 @@ def test_nccl_actions_around_the_path(world, n):
     r = _launch(world, [",".join(map(str, n)), "post"])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("MGPU_OK") == world and r.stdout.count("MGPU_POST") == world, r.stdout[-3000:]
+
+
+@pytest.mark.parametrize("world,n", [(2, (12, 7, 5)), (4, (10, 9, 6))])
+def test_nccl_row_export_matches_owner_computes(world, n):
+    """Row-element mode (FE_MATRIX): row elements only, export of the off-rank rows over NCCL inside b200s_evaluate."""
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    r = _launch(world, [",".join(map(str, n)), "export"])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("MGPU_EXPORT_OK") == world, r.stdout[-3000:]

@@ -933,3 +933,66 @@ def test_reference_plastic_necking_known_answer_through_cuda_path():
     for e in case["expected_disp"]:
         assert abs(u[e["node"], e["dof"]] - e["value"]) < 1e-9, (e, u[e["node"], e["dof"]])
     asm.close()
+
+
+# ---- row-element mode: export of the off-rank rows (FE_MATRIX; 4C_linalg_sparsematrix.cpp:598-630,705-710) ----------
+@pytest.mark.parametrize("case,world", [("hex8", 2), ("hex8", 4), ("tet10", 2)])
+def test_row_export_on_one_gpu_matches_owner_computes(case, world):
+    """All ranks of a partition as contexts on ONE GPU: every rank evaluates its row elements only (element kernels write
+    own + export rows), the export rows are carried by hand (b200s_add_exported = the Add of the export without a
+    communicator) and every rank's own rows equal the oracle's owner-computes assembly over its column elements.  The
+    NCCL flavour of the same exchange: tests/test_gpu_multirank.py."""
+    fe = b200.fe_export
+    if case == "hex8":
+        ct, mk, par = orc.HEX8, capi.MAT_COUP_NEOHOOKE, [200.0, 0.25]
+        mesh_of = lambda r: b200.partition.box_partition(b200.mesh.HEX8, (9, 7, 6), r, world)
+    else:
+        X, conn = b200.mesh.unstructured_tet10(4)
+        owner = (X[:, 0] > 0.5).astype(int)
+        ct, mk, par = orc.TET10, capi.MAT_ISO_VOL, [1.0, 1000.0]
+        mesh_of = lambda r: b200.partition.generic_partition(b200.mesh.TET10, X, conn, owner, r, world)
+    graphs = {}
+    asms = []
+    for r in range(world):
+        view, rowptr, colind, plan = fe.fe_plan(mesh_of, r, world, graphs)
+        asm = b200.RowExportAssembler(view, rowptr, colind, plan, mk, par)
+        rm = view.rm
+        u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 0.1)
+        # one GPU, no communicator: the ghost displacements are written into the column state by hand, i.e. the
+        # state vector handed in is the exact column state (row part) and the halo lists stay unused
+        asm.ctx.set_halo([], [], [])
+        asm.set_state("displacement", u[:rm.n_row_nodes].ravel())
+        asms.append((asm, view, plan, rowptr, colind, u))
+    # ghost part of the column state: the library imports it through the halo; without a communicator the test writes
+    # it through the device pointer of u_col
+    from cuda.bindings import runtime as cudart
+    for asm, view, plan, rowptr, colind, u in asms:
+        ptr = asm.ctx.device_ptrs()["u_col"]
+        buf = np.ascontiguousarray(u, np.float64)
+        err, = cudart.cudaMemcpy(ptr, buf.ctypes.data, buf.nbytes, cudart.cudaMemcpyKind.cudaMemcpyHostToDevice)
+        assert int(err) == 0, err
+    for asm, view, plan, rowptr, colind, u in asms:
+        asm.evaluate("struct_calc_nlnstiff")
+    n_moved = 0
+    for r, (asm, view, plan, rowptr, colind, u) in enumerate(asms):
+        for k, p in enumerate(plan.peers):
+            src, _, splan = asms[p][0], asms[p][1], asms[p][2]
+            vals, f = src.exported(splan.peers.index(r))
+            assert len(vals) == len(plan.recv_pos[k]) and len(f) == len(plan.recv_fpos[k])
+            if len(vals) or len(f):
+                asm.ctx.add_exported(k, vals, f)
+                n_moved += len(vals)
+    assert n_moved > 0
+    for r, (asm, view, plan, rowptr, colind, u) in enumerate(asms):
+        rm = view.rm
+        K, f = asm.own_rows()
+        o_rowptr, o_colind = orc.build_graph(ct, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+        assert np.array_equal(rowptr[:plan.n_rows_owned + 1], o_rowptr) and np.array_equal(colind[:plan.nnz_owned], o_colind)
+        rK, rf, nbad = orc.evaluate_assemble(ct, mk, par, rm.conn, rm.X.ravel(), u.ravel(), rm.node_row_lid, rm.node_col_lid,
+                                             rm.n_row_nodes, o_rowptr, o_colind, nthreads=4)
+        ok, wK, wf = b200.parity_report(o_rowptr, K, rK, f, rf, RTOL)
+        assert ok and nbad == 0, (r, wK, wf)
+    # fewer elements evaluated than on the owner-computes path (its ghost layer is evaluated twice)
+    assert sum(len(a[1].ele_ids) for a in asms) < sum(a[1].rm.n_col_eles for a in asms)
+    for a in asms:
+        a[0].close()
