@@ -2628,10 +2628,12 @@ extern "C"
     if (!ctx) return B200S_ERR_INVALID;
     if (kinem_type != B200S_KINEM_NONLINEAR_TOTLAG && kinem_type != B200S_KINEM_LINEAR)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "kinematic type %d has no device kernel", kinem_type);
-    // linear kinematics with F-bar / EAS / MULF (e.g. EASFormulation<..., linear>): CPU path
+    // linear kinematics: displacement based, or EAS (EASFormulation<hex8, h8_9 | h8_21, linear>,
+    // 4C_solid_ele_factory.hpp:71-74); F-bar / MULF have no linear variant in the reference
+    const bool eas_tech = element_technology == B200S_TECH_EAS_MILD || element_technology == B200S_TECH_EAS_FULL;
     if (kinem_type == B200S_KINEM_LINEAR &&
-        (element_technology != B200S_TECH_NONE || prestress_technology != B200S_PRESTRESS_NONE))
-      return fail(ctx, B200S_ERR_UNSUPPORTED, "KINEM linear with an element technology or prestress has no device kernel");
+        ((element_technology != B200S_TECH_NONE && !eas_tech) || prestress_technology != B200S_PRESTRESS_NONE))
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "KINEM linear with F-bar or prestress has no device kernel");
     if (prestress_technology != B200S_PRESTRESS_NONE && prestress_technology != B200S_PRESTRESS_MULF)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "prestress technology %d has no device kernel",
           prestress_technology);

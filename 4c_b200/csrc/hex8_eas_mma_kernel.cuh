@@ -194,6 +194,9 @@ namespace b200s
       const double scale = detJ0 / detJ;
       double C[6];
       right_cauchy_green(F, C);
+      // KINEM linear (EASFormulation<..., linear>, eas_helpers.hpp:648-666): linear strain, B-operator of F = I; the
+      // geometric term stays, as in the reference's add_stiffness_matrix (eas.hpp:142-157)
+      if (A.linear) linear_kinematics(F, C);
       {
         double v[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll

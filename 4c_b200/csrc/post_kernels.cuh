@@ -251,9 +251,10 @@ namespace b200s
     double C[6], S[6], Cm[21];
     right_cauchy_green(F, C);
     if (A.linear) linear_kinematics(F, C);
-    if (A.eas_neas)
+    if (A.eas_neas)  // (KINEM linear: the enhanced deformation gradient is the identity, eas_helpers.hpp:663-665)
       eas_enhance(A, e, g, detJ,
-          (stress6 != nullptr && A.stress_type == STRESS_CAUCHY) || (strain6 != nullptr && A.strain_type == STRAIN_EA), F, C);
+          !A.linear && ((stress6 != nullptr && A.stress_type == STRESS_CAUCHY) || (strain6 != nullptr && A.strain_type == STRAIN_EA)),
+          F, C);
     MatParams mp = A.mp;
     if (A.per_ele_param != nullptr) mp.p[0] = A.per_ele_param[e];
     if (MAT == MAT_HYPER && A.fibers != nullptr) mp.fiber = A.fibers + 3 * e;

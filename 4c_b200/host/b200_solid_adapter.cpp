@@ -44,8 +44,11 @@ namespace B200Solid
                        material_kind == B200S_MAT_SVK || material_kind == B200S_MAT_ELASTHYPER;
     if (kinem == B200S_KINEM_LINEAR)
     {
-      // displacement based, small strains: the hyperelastic kinds and the history material
-      if (tech != B200S_TECH_NONE || prestress != B200S_PRESTRESS_NONE) return false;
+      // small strains: displacement based (the hyperelastic kinds and the history material) or hex8 EAS
+      // (EASFormulation<hex8, h8_9 | h8_21, linear>)
+      if (prestress != B200S_PRESTRESS_NONE) return false;
+      if (tech == B200S_TECH_EAS_MILD || tech == B200S_TECH_EAS_FULL) return celltype == B200S_HEX8 && hyper;
+      if (tech != B200S_TECH_NONE) return false;
       return hyper || material_kind == B200S_MAT_DRUCKER_PRAGER;
     }
     if (kinem != B200S_KINEM_NONLINEAR_TOTLAG) return false;

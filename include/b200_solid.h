@@ -147,8 +147,9 @@ extern "C"
   typedef enum
   {
     B200S_KINEM_NONLINEAR_TOTLAG = 0, /* KINEM nonlinear */
-    B200S_KINEM_LINEAR = 1            /* KINEM linear, displacement based (4C_solid_ele_calc_displacement_based_
-                                         linear_kinematics.hpp); with TECH / PRESTRESS_TECH: CPU path */
+    B200S_KINEM_LINEAR = 1            /* KINEM linear: displacement based (4C_solid_ele_calc_displacement_based_
+                                         linear_kinematics.hpp) or hex8 TECH eas_mild / eas_full (EASFormulation<...,
+                                         linear>, 4C_solid_ele_calc_eas_helpers.hpp:648-666) */
   } b200s_kinem_type;
   typedef enum
   {

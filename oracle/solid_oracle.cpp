@@ -1968,7 +1968,15 @@ namespace
   // Element history (EASHistoryData / EasIterationData, in the order pack() writes it, eas.hpp:266-275),
   // orc_eas_hist_size(neas) doubles: alpha_inc[neas], alpha[neas], s[neas], invKaa[neas x neas],
   // Kda[24 x neas] (both column-major).  A fresh history is all zero.
-  int eas_num(int tech) { return tech == ORC_TECH_EAS_MILD ? 9 : 21; }
+  // EASFormulation<hex8, eastype_h8_9 | eastype_h8_21, nonlinearTotLag | linear>: the four EAS evaluators of the factory
+  // (4C_solid_ele_factory.hpp:62-76)
+  bool is_eas(int tech)
+  {
+    return tech == ORC_TECH_EAS_MILD || tech == ORC_TECH_EAS_FULL || tech == ORC_TECH_EAS_MILD_LINEAR ||
+           tech == ORC_TECH_EAS_FULL_LINEAR;
+  }
+  bool is_eas_linear(int tech) { return tech == ORC_TECH_EAS_MILD_LINEAR || tech == ORC_TECH_EAS_FULL_LINEAR; }
+  int eas_num(int tech) { return (tech == ORC_TECH_EAS_MILD || tech == ORC_TECH_EAS_MILD_LINEAR) ? 9 : 21; }
 
   // dense inverse by Gauss-Jordan with partial pivoting (the reference calls LAPACK getrf/getri through
   // FixedSizeSerialDenseSolver::invert; same operator up to round-off)
@@ -2120,8 +2128,19 @@ namespace
       const double fac = jm.det * gw[gp];
       double F[9], E[6], S[6], Cm[36];
       deformation_gradient(n, u, jm, F);
+      double Elin[6] = {0, 0, 0, 0, 0, 0};
+      if (is_eas_linear(tech))
+      {
+        // evaluate_eas_kinematics<..., KinemType::linear> (eas_helpers.hpp:648-666): b_op = linear strain gradient,
+        // enhanced strain = B_lin u + Mtilde alpha, deformation gradient = identity.  add_stiffness_matrix below keeps
+        // its geometric term, as the reference's EASFormulation does for both kinematic types (eas.hpp:142-157)
+        for (int v = 0; v < 6; ++v)
+          Elin[v] = 0.5 * ((F[VA[v] + 3 * VB[v]] - (v < 3 ? 1.0 : 0.0)) + (F[VB[v] + 3 * VA[v]] - (v < 3 ? 1.0 : 0.0)));
+        for (int i = 0; i < 9; ++i) F[i] = (i % 4 == 0) ? 1.0 : 0.0;
+      }
       strain_gradient(n, jm, F, B.data());
       eas_point(neas, T0invT, detJ0, jm.det, gxi + 3 * gp, alpha, F, Mt.data(), E);
+      for (int v = 0; v < 6; ++v) E[v] += Elin[v];
       // the materials on this path use the GL strain only; the enhanced deformation gradient
       // (compute_deformation_gradient_from_gl_strains) is not needed by them
       g_material_hist = (g_element_material_hist && finite_strain_hist(matkind))
@@ -2210,7 +2229,7 @@ namespace
   int element_tech(int ct, int tech, int matkind, const double* par, int action, const double* X,
       const double* u, double* Ke, double* fe, double* hist = nullptr)
   {
-    if (tech == ORC_TECH_EAS_MILD || tech == ORC_TECH_EAS_FULL)
+    if (is_eas(tech))
       return element_eas(ct, tech, matkind, par, action, X, u, hist, Ke, fe);
     if (tech == ORC_TECH_LINEAR) return element_linear(ct, matkind, par, action, X, u, Ke, fe, hist);
     if (tech == ORC_TECH_MULF) return element_mulf(ct, matkind, par, action, X, u, hist, Ke, fe);
@@ -2424,12 +2443,23 @@ extern "C"
     {
       const int n = nnodes(ct);
       deformation_gradient(n, u, jm, F);
-      if (tech == ORC_TECH_EAS_MILD || tech == ORC_TECH_EAS_FULL)
+      if (is_eas(tech))
       {
         // EASFormulation::evaluate (4C_solid_ele_calc_eas.hpp:72-88): enhanced GL strain and deformation gradient
         const int neas = eas_num(tech);
         double T0invT[36], detJ0, Mt[6 * 21], Fenh[9];
         eas_centroid_transformation(ct, X, T0invT, detJ0);
+        if (is_eas_linear(tech))
+        {
+          // KINEM linear (eas_helpers.hpp:648-666): linear strain + Mtilde alpha, deformation gradient = identity
+          double Elin[6];
+          for (int v = 0; v < 6; ++v)
+            Elin[v] = 0.5 * ((F[VA[v] + 3 * VB[v]] - (v < 3 ? 1.0 : 0.0)) + (F[VB[v] + 3 * VA[v]] - (v < 3 ? 1.0 : 0.0)));
+          for (int i = 0; i < 9; ++i) F[i] = (i % 4 == 0) ? 1.0 : 0.0;
+          eas_point(neas, T0invT, detJ0, jm.det, g_xi, g_eas_hist + neas, F, Mt, E);
+          for (int v = 0; v < 6; ++v) E[v] += Elin[v];
+          return;
+        }
         eas_point(neas, T0invT, detJ0, jm.det, g_xi, g_eas_hist + neas, F, Mt, E);
         enhanced_deformation_gradient(F, E, Fenh);
         for (int i = 0; i < 9; ++i) F[i] = Fenh[i];
@@ -2683,7 +2713,7 @@ extern "C"
           ue[3 * i + d] = u_col[3 * (int64_t)conn[e * n + i] + d];
         }
       if (mue_per_ele) par[0] = mue_per_ele[e];
-      if (g_output_hist && (tech == ORC_TECH_EAS_MILD || tech == ORC_TECH_EAS_FULL))
+      if (g_output_hist && is_eas(tech))
         g_eas_hist = g_output_hist + orc_eas_hist_size(tech) * e;
       orc_element_stress(ct, tech, matkind, par.data(), Xe.data(), ue.data(), stress_type, strain_type,
           stress ? stress + e * ng * 6 : nullptr, strain ? strain + e * ng * 6 : nullptr);
@@ -2708,7 +2738,7 @@ extern "C"
           ue[3 * i + d] = u_col[3 * (int64_t)conn[e * n + i] + d];
         }
       if (mue_per_ele) par[0] = mue_per_ele[e];
-      if (g_output_hist && (tech == ORC_TECH_EAS_MILD || tech == ORC_TECH_EAS_FULL))
+      if (g_output_hist && is_eas(tech))
         g_eas_hist = g_output_hist + orc_eas_hist_size(tech) * e;
       sum += orc_element_energy(ct, tech, matkind, par.data(), Xe.data(), ue.data());
     }
@@ -2891,8 +2921,7 @@ extern "C"
     (void)n_col_nodes;
     const bool mat_hist = matkind == ORC_MAT_DRUCKER_PRAGER;  // history material: small strains only
     if (mat_hist && tech != ORC_TECH_LINEAR) return -1;
-    const bool needs_hist = tech == ORC_TECH_MULF || tech == ORC_TECH_MULF_FBAR || tech == ORC_TECH_EAS_MILD ||
-                            tech == ORC_TECH_EAS_FULL || mat_hist;
+    const bool needs_hist = tech == ORC_TECH_MULF || tech == ORC_TECH_MULF_FBAR || is_eas(tech) || mat_hist;
     if (needs_hist && hist == nullptr) return -1;
     const int64_t hist_per_ele = mat_hist ? (int64_t)ORC_DP_HIST * ngauss(ct)
                                  : tech == ORC_TECH_MULF_FBAR ? (int64_t)ORC_MULF_HIST * (ngauss(ct) + 1)

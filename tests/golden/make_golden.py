@@ -428,7 +428,7 @@ def visco_creep_case(rel):
             "expected_disp": expected}
 
 
-def cooks_case(rel, tech):
+def cooks_case(rel, tech, kinem="nonlinear"):
     """Cook's membrane inputs (64 hex8, CoupNeoHooke nu=0.4999): several Dirichlet conditions with
     per-dof ONOFF, one dead surface load, known answer = dispy of node 162 (and internal energy)."""
     with open(os.path.join(REF, rel)) as fh:
@@ -441,16 +441,21 @@ def cooks_case(rel, tech):
     eles = []
     for line in y["STRUCTURE ELEMENTS"]:
         tok = line.split()
-        assert tok[1] == "SOLID" and tok[2] == "HEX8" and f"TECH {tech}" in line and "nonlinear" in line
+        assert tok[1] == "SOLID" and tok[2] == "HEX8" and f"TECH {tech}" in line and (("KINEM " + kinem) in line)
         eles.append([int(t) - 1 for t in tok[3:11]])
     surf = {}
     for line in y["DSURF-NODE TOPOLOGY"]:
         m = re.match(r"NODE\s+(\d+)\s+DSURFACE\s+(\d+)", line)
         surf.setdefault(int(m.group(2)), []).append(int(m.group(1)) - 1)
     mats = {m["MAT"]: m for m in y["MATERIALS"]}
-    eh = mats[1]["MAT_ElastHyper"]
-    assert eh["NUMMAT"] == 1
-    nh = mats[eh["MATIDS"][0]]["ELAST_CoupNeoHooke"]
+    if "MAT_ElastHyper" in mats[1]:
+        eh = mats[1]["MAT_ElastHyper"]
+        assert eh["NUMMAT"] == 1
+        nh = mats[eh["MATIDS"][0]]["ELAST_CoupNeoHooke"]
+        matkind = "ELAST_CoupNeoHooke"
+    else:
+        nh = mats[1]["MAT_Struct_StVenantKirchhoff"]
+        matkind = "MAT_Struct_StVenantKirchhoff"
     fixed = set()
     for dbc in y["DESIGN SURF DIRICH CONDITIONS"]:
         assert all(v == 0 for v in dbc["VAL"])
@@ -469,8 +474,8 @@ def cooks_case(rel, tech):
         if s["QUANTITY"] == "internal_energy":
             energy = {"value": float(s["VALUE"]), "tol": float(s["TOLERANCE"])}
     return {
-        "source": rel, "celltype": "hex8", "tech": tech, "coords": coords, "elements": eles,
-        "material": {"kind": "ELAST_CoupNeoHooke", "YOUNG": float(nh["YOUNG"]), "NUE": float(nh["NUE"])},
+        "source": rel, "celltype": "hex8", "tech": tech, "kinem": kinem, "coords": coords, "elements": eles,
+        "material": {"kind": matkind, "YOUNG": float(nh["YOUNG"]), "NUE": float(nh["NUE"])},
         "dirichlet_dofs": sorted(fixed), "dirichlet_nodes": [],
         "neumann_nodes": sorted(surf[neu["E"]]),
         "neumann": {"ONOFF": neu["ONOFF"] + [0] * 3, "VAL": neu["VAL"] + [0] * 3,
@@ -570,6 +575,9 @@ if __name__ == "__main__":
             ("cooks_fbar", "tests/input_files/sohex8fbar_cooks_nl_new_struc.4C.yaml", "fbar"),):
         with open(os.path.join(HERE, f"integration_{name}.json"), "w") as fh:
             json.dump(cooks_case(rel, tech), fh)
+    for tech, name in (("eas_mild", "sohex8_easmild_cooks_lin"), ("eas_full", "sohex8_easfull_cooks_lin")):
+        with open(os.path.join(HERE, f"integration_cooks_{tech}_linear.json"), "w") as fh:
+            json.dump(cooks_case(f"tests/input_files/{name}.4C.yaml", tech, "linear"), fh)
     for cell in ("hex8", "hex27", "tet10", "tet4", "hex20", "wedge6", "pyramid5"):
         with open(os.path.join(HERE, f"integration_{cell}_mulf.json"), "w") as fh:
             json.dump(mulf_case(cell, f"tests/input_files/solid_ele_{cell}_Standard_mulf.4C.yaml"), fh, indent=1)

@@ -996,3 +996,63 @@ def test_row_export_on_one_gpu_matches_owner_computes(case, world):
     assert sum(len(a[1].ele_ids) for a in asms) < sum(a[1].rm.n_col_eles for a in asms)
     for a in asms:
         a[0].close()
+
+
+# ---- KINEM linear with TECH eas_mild / eas_full (EASFormulation<hex8, h8_9 | h8_21, linear>) -------------------------
+@pytest.mark.parametrize("tech", ["eas_mild", "eas_full"])
+@pytest.mark.parametrize("mma", [1, 0])
+def test_linear_kinematics_eas_matches_oracle(tech, mma):
+    """Linear B-operator, enhanced strain B u + Mtilde alpha, deformation gradient = identity; K (with the geometric term
+    the reference's EAS formulation keeps), f and the element history after recover against the oracle, on the tensor-core
+    kernel and on the FMA kernel."""
+    rm = b200.partition.box_partition(b200.mesh.HEX8, (5, 4, 3), 0, 1)
+    u = 0.3 * b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 0.2)
+    otech = {"eas_mild": orc.TECH_EAS_MILD_LINEAR, "eas_full": orc.TECH_EAS_FULL_LINEAR}[tech]
+    dtech = {"eas_mild": capi.TECH_EAS_MILD, "eas_full": capi.TECH_EAS_FULL}[tech]
+    mk, par = capi.MAT_SVK, [1000.0, 0.3]
+    asm = b200.DeviceAssembler(rm, mk, par, tech=dtech, kinem=capi.KINEM_LINEAR, options={"eas_mma": mma})
+    rowptr, colind = asm.graph()
+    hist = orc.eas_new_history(otech, rm.n_col_eles)
+    maps = (rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, rowptr, colind)
+    rng = np.random.default_rng(3)
+    for it in range(2):
+        us = (1.0 + 0.5 * it) * u.ravel()
+        asm.set_state("displacement", us)
+        K, f, err = asm.evaluate()
+        rK, rf, nbad = orc.evaluate_assemble(orc.HEX8, mk, par, rm.conn, rm.X.ravel(), us, *maps, tech=otech, hist=hist)
+        ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, 1e-11)
+        assert ok and nbad == 0 and err.n_neg_jacobian == 0, (it, wK, wf)
+        du = 1e-2 * rng.standard_normal(asm.n_rows)
+        asm.recover(du)
+        orc.eas_recover(otech, rm.conn, du, hist)
+        dh = asm.ctx.get_element_history().reshape(hist.shape)
+        neas = 9 if tech == "eas_mild" else 21
+        assert np.abs(dh[:, :2 * neas] - hist[:, :2 * neas]).max() <= 1e-9 * max(np.abs(hist[:, :2 * neas]).max(), 1e-6)
+    asm.close()
+
+
+@pytest.mark.parametrize("tech", ["eas_mild", "eas_full"])
+def test_reference_linear_eas_cooks_known_answer_through_cuda_path(tech):
+    """tests/input_files/sohex8_easmild_cooks_lin.4C.yaml / sohex8_easfull_cooks_lin.4C.yaml with the CUDA path doing every
+    evaluate and struct_calc_recover: dispy of node 162."""
+    import json
+    import os
+    from tests.helpers.newton import solve_case
+    case = json.load(open(os.path.join(os.path.dirname(__file__), "golden", f"integration_cooks_{tech}_linear.json")))
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    rm = b200.partition.serial_mesh(b200.mesh.HEX8, X, conn)
+    dtech = {"eas_mild": capi.TECH_EAS_MILD, "eas_full": capi.TECH_EAS_FULL}[tech]
+    asm = b200.DeviceAssembler(rm, capi.MAT_SVK, [case["material"]["YOUNG"], case["material"]["NUE"]], tech=dtech,
+                               kinem=capi.KINEM_LINEAR)
+    rowptr, colind = asm.graph()
+
+    def ev(u):
+        asm.set_state("displacement", u)
+        K, f, _ = asm.evaluate()
+        return rowptr, colind, K, f
+
+    u = solve_case(case, ev, recover=lambda du: asm.recover(du, 1.0))
+    (e,) = case["expected_disp"]
+    assert abs(u[e["node"], e["dof"]] - e["value"]) < 1e-8, (e, u[e["node"], e["dof"]])
+    asm.close()

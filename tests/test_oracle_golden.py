@@ -258,3 +258,30 @@ def test_linear_kinematics_known_answers(cell):
     assert len(case["expected_disp"]) >= 12
     for e in case["expected_disp"]:
         assert abs(u[e["node"], e["dof"]] - e["value"]) < e["tol"], (e, u[e["node"], e["dof"]])
+
+
+@pytest.mark.parametrize("tech", ["eas_mild", "eas_full"])
+def test_cooks_membrane_linear_eas_known_answer(tech):
+    """tests/input_files/sohex8_easmild_cooks_lin.4C.yaml / sohex8_easfull_cooks_lin.4C.yaml (64 hex8, KINEM linear with
+    TECH eas_mild / eas_full = EASFormulation<hex8, h8_9 | h8_21, linear>, St.Venant-Kirchhoff nu = 0.4999, one load
+    step): dispy of node 162 -- pins the linear-kinematics EAS restatement (linear B-operator, enhanced strain
+    B u + Mtilde alpha, deformation gradient = identity)."""
+    case = json.load(open(os.path.join(G, f"integration_cooks_{tech}_linear.json")))
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    nn = len(X)
+    row, col = serial_maps(nn)
+    rowptr, colind = orc.build_graph(orc.HEX8, conn, row, col, nn)
+    par = [case["material"]["YOUNG"], case["material"]["NUE"]]
+    otech = {"eas_mild": orc.TECH_EAS_MILD_LINEAR, "eas_full": orc.TECH_EAS_FULL_LINEAR}[tech]
+    hist = orc.eas_new_history(otech, len(conn))
+
+    def evaluate(u):
+        vals, f, nbad = orc.evaluate_assemble(orc.HEX8, orc.MAT_SVK, par, conn, X.ravel(), u, row, col, nn, rowptr, colind,
+                                              tech=otech, hist=hist)
+        assert nbad == 0
+        return rowptr, colind, vals, f
+
+    u = solve_case(case, evaluate, recover=lambda du: orc.eas_recover(otech, conn, du, hist))
+    (e,) = case["expected_disp"]
+    assert abs(u[e["node"], e["dof"]] - e["value"]) < max(e["tol"], 1e-10), (e, u[e["node"], e["dof"]])
