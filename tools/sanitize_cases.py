@@ -18,7 +18,16 @@ CASES = [("hex8", "HEX8", (7, 6, 5), capi.MAT_COUP_NEOHOOKE, [200.0, 0.25], {}),
          ("hex8 eas_full", "HEX8", (5, 4, 3), capi.MAT_SVK, [1000.0, 0.3], dict(tech=capi.TECH_EAS_FULL)),
          ("hex8 mulf", "HEX8", (5, 4, 3), capi.MAT_COUP_NEOHOOKE, [200.0, 0.25], dict(prestress=capi.PRESTRESS_MULF)),
          ("hex27", "HEX27", (3, 3, 2), capi.MAT_SVK, [1000.0, 0.3], {}),
-         ("tet10", "TET10", 4, capi.MAT_ISO_VOL, [1.0, 1000.0], {})]
+         ("tet10", "TET10", 4, capi.MAT_ISO_VOL, [1.0, 1000.0], {}),
+         # round 2, later additions: general kernel with F-bar (+ MULF), plastic material on the hex8 / EAS / general kernels,
+         # linear-kinematics EAS
+         ("general fbar_mulf", "HEX8", (4, 3, 3), capi.MAT_COUP_NEOHOOKE, [200.0, 0.25],
+          dict(tech=capi.TECH_FBAR, prestress=capi.PRESTRESS_MULF)),
+         ("hex8 plastic", "HEX8", (5, 4, 3), capi.MAT_PLASTIC_NLNLOG, [206.9, 0.29, 0.0, 0.45, 0.13, 0.715, 16.93, 1.0, 0.1, 1e-12], {}),
+         ("eas_mild plastic", "HEX8", (4, 3, 3), capi.MAT_PLASTIC_NLNLOG, [206.9, 0.29, 0.0, 0.45, 0.13, 0.715, 16.93, 1.0, 0.1, 1e-12],
+          dict(tech=capi.TECH_EAS_MILD)),
+         ("hex27 plastic", "HEX27", (2, 2, 2), capi.MAT_PLASTIC_NLNLOG, [206.9, 0.29, 0.0, 0.45, 0.13, 0.715, 16.93, 1.0, 0.1, 1e-12], {}),
+         ("eas_full linear", "HEX8", (4, 3, 3), capi.MAT_SVK, [1000.0, 0.3], dict(tech=capi.TECH_EAS_FULL, kinem=capi.KINEM_LINEAR))]
 only = sys.argv[1:] or None
 for name, cell, n, mk, par, kw in CASES:
     if only and name.split()[-1] not in only and name not in only:
@@ -32,6 +41,8 @@ for name, cell, n, mk, par, kw in CASES:
         h = 1.0 / max(n)
     u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, h)
     asm = b200.DeviceAssembler(rm, mk, par, **kw)
+    if mk == capi.MAT_PLASTIC_NLNLOG:
+        asm.ctx.set_time_step_size(0.175)
     if name.endswith("tma"):
         asm.ctx.set_option("tma_gather", 1)
     asm.set_state("displacement", u.ravel())
