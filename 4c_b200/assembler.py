@@ -18,7 +18,7 @@ ACTIONS = {"struct_calc_nlnstiff": capi.ACTION_NLNSTIFF,
            "struct_calc_nlnstifflmass": capi.ACTION_NLNSTIFFLMASS,
            "struct_calc_internalinertiaforce": capi.ACTION_INTERNALINERTIAFORCE}
 STIFF_ACTIONS = (capi.ACTION_NLNSTIFF, capi.ACTION_NLNSTIFFMASS, capi.ACTION_NLNSTIFFLMASS)
-NUM_GP = {capi.HEX8: 8, capi.HEX27: 27, capi.TET10: 4, capi.TET4: 1, capi.HEX20: 27, capi.WEDGE6: 6, capi.PYRAMID5: 8}
+NUM_GP = {capi.HEX8: 8, capi.HEX27: 27, capi.TET10: 4, capi.TET4: 1, capi.HEX20: 27, capi.WEDGE6: 6, capi.PYRAMID5: 8, capi.HEX18: 18}
 
 
 class DeviceAssembler:

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("B200S_LIB") or os.path.join(_HERE, "lib4c_b200_solid.
 
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NEG_JACOBIAN, ERR_NONFINITE, ERR_COMM = -1, -2, -3, -4, -5, -6
-HEX8, HEX27, TET10, TET4, HEX20, WEDGE6, PYRAMID5 = 0, 1, 2, 3, 4, 5, 6
+HEX8, HEX27, TET10, TET4, HEX20, WEDGE6, PYRAMID5, HEX18 = 0, 1, 2, 3, 4, 5, 6, 7
 MAT_COUP_NEOHOOKE, MAT_ISO_VOL, MAT_SVK, MAT_ELASTHYPER, MAT_DRUCKER_PRAGER, MAT_VISCONEOHOOKE = 0, 1, 2, 3, 4, 5
 MAT_PLASTIC_NLNLOG = 6  # MAT_Struct_PlasticNlnLogNeoHooke
 ACTION_INTERNALFORCE, ACTION_NLNSTIFF, ACTION_NLNSTIFFMASS, ACTION_NLNSTIFFLMASS, ACTION_INTERNALINERTIAFORCE = 0, 1, 2, 3, 4

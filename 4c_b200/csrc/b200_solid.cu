@@ -2287,6 +2287,9 @@ namespace
       case 10:
         k_generic_eval_assemble<MAT, 10><<<grid, 64, 0, ctx->stream>>>(Ga);
         break;
+      case 18:
+        k_generic_eval_assemble<MAT, 18><<<grid, 64, 0, ctx->stream>>>(Ga);
+        break;
       case 20:
         k_generic_eval_assemble<MAT, 20><<<grid, 64, 0, ctx->stream>>>(Ga);
         break;
@@ -2335,7 +2338,7 @@ namespace
   // cell types that only the table-driven general kernel hosts
   static bool is_general_cell(int ct)
   {
-    return ct == B200S_TET4 || ct == B200S_HEX20 || ct == B200S_WEDGE6 || ct == B200S_PYRAMID5;
+    return ct == B200S_TET4 || ct == B200S_HEX20 || ct == B200S_WEDGE6 || ct == B200S_PYRAMID5 || ct == B200S_HEX18;
   }
 
   template <bool STIFF>
@@ -3263,6 +3266,9 @@ extern "C"
           break;
         case B200S_PYRAMID5:
           k_mass_assemble<5><<<grid, 128, 0, st>>>(M);
+          break;
+        case B200S_HEX18:
+          k_mass_assemble<18><<<grid, 128, 0, st>>>(M);
           break;
       }
       ctx->launches += 1;
@@ -4379,7 +4385,7 @@ extern "C"
     if (!ctx || n_faces < 0 || (n_faces > 0 && !face_nodes) || !onoff || !val) return B200S_ERR_INVALID;
     if (ctx->celltype < 0) return fail(ctx, B200S_ERR_INVALID, "set_mesh must precede add_surface_neumann");
     if (ctx->face_nn == 0)
-      return fail(ctx, B200S_ERR_UNSUPPORTED, "surface loads on wedge6 / pyramid5 blocks (two surface shapes) have no device kernel");
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "surface loads on wedge6 / pyramid5 / hex18 blocks (two surface shapes) have no device kernel");
     if (neumann_type < B200S_NEUMANN_LIVE || neumann_type > B200S_NEUMANN_ORTHOPRESSURE)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "Unknown type of SurfaceNeumann condition");
     if (neumann_type != B200S_NEUMANN_LIVE && (onoff[0] != 1 || onoff[1] != 0 || onoff[2] != 0))

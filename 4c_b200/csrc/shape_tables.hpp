@@ -48,6 +48,15 @@ namespace b200s
           {0, 0, 1}, {0, 0, 0}};
       return c;
     }
+    // hex18 node order (4C_fem_general_utils_local_connectivity_matrices.hpp:174-179): the quad9 of the plane (corners,
+    // mid-sides, centre) at t = -1, then at t = +1
+    inline const double (*hex18_nodes())[3]
+    {
+      static const double c[18][3] = {{-1, -1, -1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1}, {0, -1, -1}, {1, 0, -1},
+          {0, 1, -1}, {-1, 0, -1}, {0, 0, -1}, {-1, -1, 1}, {1, -1, 1}, {1, 1, 1}, {-1, 1, 1}, {0, -1, 1}, {1, 0, 1},
+          {0, 1, 1}, {-1, 0, 1}, {0, 0, 1}};
+      return c;
+    }
     inline const double (*tet_nodes())[3]
     {
       static const double c[10][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0.5, 0, 0},
@@ -86,6 +95,26 @@ namespace b200s
           dN[3 * k + 0] = L[1][b] * L[2][e] * dL[0][a];
           dN[3 * k + 1] = L[0][a] * L[2][e] * dL[1][b];
           dN[3 * k + 2] = L[0][a] * L[1][b] * dL[2][e];
+        }
+      }
+      else if (celltype == 7)
+      {
+        // hex18 (:531-600): quadratic Lagrange functions in r and s times (1 -+ t) / 2
+        const double(*c)[3] = hex18_nodes();
+        double L[2][3], dL[2][3];
+        for (int d = 0; d < 2; ++d)
+        {
+          const double x = xi[d];
+          L[d][0] = 0.5 * x * (x - 1.0), L[d][1] = 1.0 - x * x, L[d][2] = 0.5 * x * (x + 1.0);
+          dL[d][0] = x - 0.5, dL[d][1] = -2.0 * x, dL[d][2] = x + 0.5;
+        }
+        for (int k = 0; k < 18; ++k)
+        {
+          const int a = (int)c[k][0] + 1, b = (int)c[k][1] + 1;
+          const double lin = 0.5 * (1.0 + c[k][2] * t);
+          dN[3 * k + 0] = dL[0][a] * L[1][b] * lin;
+          dN[3 * k + 1] = L[0][a] * dL[1][b] * lin;
+          dN[3 * k + 2] = L[0][a] * L[1][b] * 0.5 * c[k][2];
         }
       }
       else if (celltype == 5)
@@ -187,6 +216,17 @@ namespace b200s
         for (int k = 0; k < 27; ++k)
           N[k] = L[0][(int)c[k][0] + 1] * L[1][(int)c[k][1] + 1] * L[2][(int)c[k][2] + 1];
       }
+      else if (celltype == 7)
+      {
+        const double(*c)[3] = hex18_nodes();  // hex18 (:112-145)
+        double L[2][3];
+        for (int d = 0; d < 2; ++d)
+        {
+          const double x = xi[d];
+          L[d][0] = 0.5 * x * (x - 1.0), L[d][1] = 1.0 - x * x, L[d][2] = 0.5 * x * (x + 1.0);
+        }
+        for (int k = 0; k < 18; ++k) N[k] = L[0][(int)c[k][0] + 1] * L[1][(int)c[k][1] + 1] * 0.5 * (1.0 + c[k][2] * t);
+      }
       else if (celltype == 3)
       {
         N[0] = 1.0 - r - s - t, N[1] = r, N[2] = s, N[3] = t;  // tet4 (:239-251)
@@ -240,8 +280,9 @@ namespace b200s
     // tet_4point (tet10), tet_1point (tet4) (4C_solid_ele_calc_lib_integration.hpp:43-64)
     // 5 wedge6 (wedge_6point), 6 pyramid5 (pyramid_8point): DisTypeToOptGaussRule for stiffness and mass
     // (4C_fem_general_element_integration_select.hpp:68-82)
-    T.nn = celltype == 0 ? 8 : (celltype == 1 ? 27 : (celltype == 3 ? 4 : (celltype == 4 ? 20 : (celltype == 5 ? 6 : (celltype == 6 ? 5 : 10)))));
-    T.ngp = celltype == 0 ? 8 : ((celltype == 1 || celltype == 4) ? 27 : (celltype == 3 ? 1 : (celltype == 5 ? 6 : (celltype == 6 ? 8 : 4))));
+    // 7 hex18 (hex_18point = quad_9point x line_2point, 4C_fem_general_utils_integration.cpp:112-129)
+    T.nn = celltype == 0 ? 8 : (celltype == 1 ? 27 : (celltype == 3 ? 4 : (celltype == 4 ? 20 : (celltype == 5 ? 6 : (celltype == 6 ? 5 : (celltype == 7 ? 18 : 10))))));
+    T.ngp = celltype == 0 ? 8 : ((celltype == 1 || celltype == 4) ? 27 : (celltype == 3 ? 1 : (celltype == 5 ? 6 : (celltype == 6 ? 8 : (celltype == 7 ? 18 : 4)))));
     std::vector<double> gxi(3 * T.ngp);
     T.w.resize(T.ngp);
     const double(*hc)[3] = detail::hex_nodes();
@@ -252,6 +293,18 @@ namespace b200s
       {
         for (int d = 0; d < 3; ++d) gxi[3 * q + d] = hc[q][d] * g;
         T.w[q] = 1.0;
+      }
+    }
+    else if (celltype == 7)
+    {
+      // quad_9point (:6185-6233: corners, mid-sides, centre; truncated decimals as tabulated) at the two points of
+      // line_2point (:6946-6953)
+      const double g = 0.7745966692415, w1 = 0.5555555555556, w2 = 0.8888888888889, d = 0.5773502691896;
+      const double(*c)[3] = detail::hex18_nodes();
+      for (int q = 0; q < 18; ++q)
+      {
+        gxi[3 * q] = c[q % 9][0] * g, gxi[3 * q + 1] = c[q % 9][1] * g, gxi[3 * q + 2] = q < 9 ? -d : d;
+        T.w[q] = (c[q % 9][0] == 0.0 ? w2 : w1) * (c[q % 9][1] == 0.0 ? w2 : w1);
       }
     }
     else if (celltype == 3)
@@ -310,7 +363,7 @@ namespace b200s
     static const double wedge_nodes[6][3] = {{0, 0, -1}, {1, 0, -1}, {0, 1, -1}, {0, 0, 1}, {1, 0, 1}, {0, 1, 1}};
     static const double pyramid_nodes[5][3] = {{-1, -1, 0}, {1, -1, 0}, {1, 1, 0}, {-1, 1, 0}, {0, 0, 1}};
     const double(*nc)[3] = (celltype == 2 || celltype == 3) ? detail::tet_nodes()
-                           : (celltype == 5 ? wedge_nodes : (celltype == 6 ? pyramid_nodes : hc));
+                           : (celltype == 5 ? wedge_nodes : (celltype == 6 ? pyramid_nodes : (celltype == 7 ? detail::hex18_nodes() : hc)));
     for (int k = 0; k < T.nn; ++k) detail::deriv1(celltype, nc[k], &T.dN_node[(size_t)k * T.nn * 3]);
     T.xi_gp = gxi;
     T.N_gp.resize((size_t)T.ngp * T.nn);
@@ -369,7 +422,7 @@ namespace b200s
   inline FaceTables make_face_tables(int celltype)
   {
     FaceTables T;
-    if (celltype == 5 || celltype == 6) return T;  // wedge6 / pyramid5 have two surface shapes: no single face table
+    if (celltype == 5 || celltype == 6 || celltype == 7) return T;  // wedge6 / pyramid5 / hex18 have two surface shapes: no single face table
     std::vector<double> xi;
     if (celltype == 0)
     {

@@ -36,7 +36,8 @@ namespace B200Solid
   bool DeviceElementBlock::supported(int celltype, int kinem, int tech, int prestress, int material_kind)
   {
     // general kernel: displacement based (+ MULF), pyramid5 also F-bar (+ MULF)
-    const bool general_cell = celltype == B200S_TET4 || celltype == B200S_HEX20 || celltype == B200S_WEDGE6 || celltype == B200S_PYRAMID5;
+    const bool general_cell = celltype == B200S_TET4 || celltype == B200S_HEX20 || celltype == B200S_WEDGE6 || celltype == B200S_PYRAMID5 ||
+                              celltype == B200S_HEX18;
     const bool cell = celltype == B200S_HEX8 || celltype == B200S_HEX27 || celltype == B200S_TET10 || general_cell;
     if (!cell) return false;
     if (general_cell && tech != B200S_TECH_NONE && !(celltype == B200S_PYRAMID5 && tech == B200S_TECH_FBAR)) return false;

@@ -9,8 +9,8 @@ seeded permutation (config 4).
 """
 import numpy as np
 
-HEX8, HEX27, TET10, TET4, HEX20, WEDGE6, PYRAMID5 = 0, 1, 2, 3, 4, 5, 6
-NODES = {HEX8: 8, HEX27: 27, TET10: 10, TET4: 4, HEX20: 20, WEDGE6: 6, PYRAMID5: 5}
+HEX8, HEX27, TET10, TET4, HEX20, WEDGE6, PYRAMID5, HEX18 = 0, 1, 2, 3, 4, 5, 6, 7
+NODES = {HEX8: 8, HEX27: 27, TET10: 10, TET4: 4, HEX20: 20, WEDGE6: 6, PYRAMID5: 5, HEX18: 18}
 
 # node order of hex27 in parameter space (first 8 = hex8);
 # 4C_fem_general_utils_local_connectivity_matrices.hpp:291
@@ -116,6 +116,17 @@ def structured_hex20(n, box=(1.0, 1.0, 1.0)):
     mid-edge nodes, 4C_fem_general_utils_local_connectivity_matrices.hpp), unused grid nodes removed."""
     X27, c27 = structured_hex(HEX27, n, box)
     c = c27[:, :20]
+    used = np.unique(c)
+    new = np.full(len(X27), -1, np.int64)
+    new[used] = np.arange(len(used))
+    return X27[used], new[c].astype(np.int32)
+
+
+def structured_hex18(n, box=(1.0, 1.0, 1.0)):
+    """hex18 version of the structured hex27 mesh: the bottom and top quad9 of every hex27 element (corners, mid-sides,
+    face centre; 4C_fem_general_utils_local_connectivity_matrices.hpp:174-179), unused grid nodes removed."""
+    X27, c27 = structured_hex(HEX27, n, box)
+    c = c27[:, [0, 1, 2, 3, 8, 9, 10, 11, 20, 4, 5, 6, 7, 16, 17, 18, 19, 25]]
     used = np.unique(c)
     new = np.full(len(X27), -1, np.int64)
     new[used] = np.arange(len(used))

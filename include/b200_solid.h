@@ -49,7 +49,8 @@ extern "C"
     B200S_TET4 = 3, /* tet_1point stiffness rule, tet_4point mass rule */
     B200S_HEX20 = 4, /* hex_27point */
     B200S_WEDGE6 = 5,  /* wedge_6point; general kernel, no surface loads (two surface shapes) */
-    B200S_PYRAMID5 = 6 /* pyramid_8point, the reference's rational shape functions; general kernel, no surface loads */
+    B200S_PYRAMID5 = 6, /* pyramid_8point, the reference's rational shape functions; general kernel, no surface loads */
+    B200S_HEX18 = 7     /* quad9 in the plane x linear through the thickness, hex_18point; general kernel, no surface loads */
   } b200s_celltype;
 
   /* Mat::So3Material implementations on the device path (Core::Materials::MaterialType):

@@ -12,7 +12,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-HEX8, HEX27, TET10, TET4, HEX20, WEDGE6, PYRAMID5 = 0, 1, 2, 3, 4, 5, 6
+HEX8, HEX27, TET10, TET4, HEX20, WEDGE6, PYRAMID5, HEX18 = 0, 1, 2, 3, 4, 5, 6, 7
 MAT_COUP_NEOHOOKE, MAT_ISO_VOL, MAT_SVK, MAT_ELASTHYPER, MAT_DRUCKER_PRAGER, MAT_VISCONEOHOOKE = 0, 1, 2, 3, 4, 5
 MAT_PLASTIC_NLNLOG = 6
 PLASTIC_HIST = 14  # {accplstrainlast, invplrcglast[6], accplstraincurr, invplrcgcurr[6]} per Gauss point

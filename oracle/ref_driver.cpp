@@ -335,6 +335,8 @@ extern "C"
       run.template operator()<CT::wedge6>();
     else if (ct == 6)
       run.template operator()<CT::pyramid5>();
+    else if (ct == 7)
+      run.template operator()<CT::hex18>();
     else
       run.template operator()<CT::tet10>();
   }
@@ -362,6 +364,8 @@ extern "C"
       run.template operator()<CT::wedge6>();
     else if (ct == 6)
       run.template operator()<CT::pyramid5>();
+    else if (ct == 7)
+      run.template operator()<CT::hex18>();
     else
       run.template operator()<CT::tet10>();
   }
@@ -385,6 +389,7 @@ extern "C"
     if (ct == 4) return element<CT::hex20>(matkind, par, action, X, u, gxi, gw, ngp, Ke, fe);
     if (ct == 5) return element<CT::wedge6>(matkind, par, action, X, u, gxi, gw, ngp, Ke, fe);
     if (ct == 6) return element<CT::pyramid5>(matkind, par, action, X, u, gxi, gw, ngp, Ke, fe);
+    if (ct == 7) return element<CT::hex18>(matkind, par, action, X, u, gxi, gw, ngp, Ke, fe);
     return element<CT::tet10>(matkind, par, action, X, u, gxi, gw, ngp, Ke, fe);
   }
 
@@ -503,6 +508,8 @@ extern "C"
       run.template operator()<CT::wedge6>();
     else if (ct == 6)
       run.template operator()<CT::pyramid5>();
+    else if (ct == 7)
+      run.template operator()<CT::hex18>();
     else
       run.template operator()<CT::tet10>();
   }

@@ -35,11 +35,16 @@ namespace
   // nodal Jacobian check therefore visits the corners in a permuted order, which changes nothing for the check)
   const double wedge6_ref[6][3] = {{0, 0, -1}, {1, 0, -1}, {0, 1, -1}, {0, 0, 1}, {1, 0, 1}, {0, 1, 1}};
   const double pyramid5_ref[5][3] = {{-1, -1, 0}, {1, -1, 0}, {1, 1, 0}, {-1, 1, 0}, {0, 0, 1}};
+  // hex18: quad9 in the plane (corners, mid-sides, centre) at t = -1, then the same at t = +1 (:174-179)
+  const double hex18_ref[18][3] = {{-1, -1, -1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1}, {0, -1, -1}, {1, 0, -1}, {0, 1, -1},
+      {-1, 0, -1}, {0, 0, -1}, {-1, -1, 1}, {1, -1, 1}, {1, 1, 1}, {-1, 1, 1}, {0, -1, 1}, {1, 0, 1}, {0, 1, 1}, {-1, 0, 1},
+      {0, 0, 1}};
 
   int nnodes(int ct)
   {
     if (ct == ORC_WEDGE6) return 6;
     if (ct == ORC_PYRAMID5) return 5;
+    if (ct == ORC_HEX18) return 18;
     return ct == ORC_HEX8 ? 8 : (ct == ORC_HEX27 ? 27 : (ct == ORC_TET4 ? 4 : (ct == ORC_HEX20 ? 20 : 10)));
   }
   // stiffness rule (get_gauss_rule_stiffness_matrix, 4C_solid_ele_calc_lib_integration.hpp:43-64): hex_8point,
@@ -50,13 +55,15 @@ namespace
   {
     if (ct == ORC_WEDGE6) return 6;
     if (ct == ORC_PYRAMID5) return 8;
+    if (ct == ORC_HEX18) return 18;  // hex_18point: quad_9point in the plane x line_2point (integration.cpp:112-129)
     return ct == ORC_HEX8 ? 8 : ((ct == ORC_HEX27 || ct == ORC_HEX20) ? 27 : (ct == ORC_TET4 ? 1 : 4));
   }
 
   void node_ref(int ct, int k, double* xi)
   {
     // hex8 / hex20 = first 8 / 20 of hex27, tet4 = first 4 of tet10
-    const double* p = (ct == ORC_TET10 || ct == ORC_TET4) ? tet10_ref[k]
+    const double* p = ct == ORC_HEX18 ? hex18_ref[k]
+                      : (ct == ORC_TET10 || ct == ORC_TET4) ? tet10_ref[k]
                       : (ct == ORC_WEDGE6 ? wedge6_ref[k] : (ct == ORC_PYRAMID5 ? pyramid5_ref[k] : hex27_ref[k]));
     xi[0] = p[0], xi[1] = p[1], xi[2] = p[2];
   }
@@ -97,6 +104,26 @@ namespace
         dN[0 + 3 * k] = Ls[b] * Lt[c] * dLr[a];
         dN[1 + 3 * k] = Lr[a] * Lt[c] * dLs[b];
         dN[2 + 3 * k] = Lr[a] * Ls[b] * dLt[c];
+      }
+    }
+    else if (ct == ORC_HEX18)
+    {
+      // hex18 (shapefunctions.hpp:112-145, 531-600): the quad9 functions of (r, s) times (1 -+ t) / 2
+      auto lag = [](double x, double* L, double* dL)
+      {
+        L[0] = 0.5 * x * (x - 1.0), L[1] = 1.0 - x * x, L[2] = 0.5 * x * (x + 1.0);
+        dL[0] = x - 0.5, dL[1] = -2.0 * x, dL[2] = x + 0.5;
+      };
+      double Lr[3], Ls[3], dLr[3], dLs[3];
+      lag(r, Lr, dLr), lag(s, Ls, dLs);
+      for (int k = 0; k < 18; ++k)
+      {
+        const int a = (int)hex18_ref[k][0] + 1, b = (int)hex18_ref[k][1] + 1;
+        const double sg = hex18_ref[k][2], lin = 0.5 * (1.0 + sg * t);
+        N[k] = Lr[a] * Ls[b] * lin;
+        dN[0 + 3 * k] = dLr[a] * Ls[b] * lin;
+        dN[1 + 3 * k] = Lr[a] * dLs[b] * lin;
+        dN[2 + 3 * k] = Lr[a] * Ls[b] * 0.5 * sg;
       }
     }
     else if (ct == ORC_WEDGE6)
@@ -231,6 +258,19 @@ namespace
         xi[3 * q + 1] = ((q & 2) ? a : -a);
         xi[3 * q + 2] = (q & 1) ? t2 : t1;
         w[q] = (q & 1) ? w2 : w1;
+      }
+    }
+    else if (ct == ORC_HEX18)
+    {
+      // hex_18point (4C_fem_general_utils_integration.cpp:112-129): quad_9point (:6185-6233, corners, mid-sides, centre,
+      // decimals as tabulated) for every point of line_2point (:6946-6953)
+      const double g = 0.7745966692415, w1 = 0.5555555555556, w2 = 0.8888888888889, d = 0.5773502691896;
+      for (int q = 0; q < 18; ++q)
+      {
+        const int p = q % 9;
+        xi[3 * q] = hex18_ref[p][0] * g, xi[3 * q + 1] = hex18_ref[p][1] * g, xi[3 * q + 2] = q < 9 ? -d : d;
+        const double wr = hex18_ref[p][0] == 0.0 ? w2 : w1, ws = hex18_ref[p][1] == 0.0 ? w2 : w1;
+        w[q] = 1.0 * (wr * ws);  // line_2point weights are 1
       }
     }
     else if (ct == ORC_TET4)

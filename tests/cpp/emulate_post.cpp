@@ -199,6 +199,7 @@ static int run_generic_nn(const GenericArgs& Ga)
     case 6: return run_generic<MAT, 6>(Ga);
     case 8: return run_generic<MAT, 8>(Ga);
     case 10: return run_generic<MAT, 10>(Ga);
+    case 18: return run_generic<MAT, 18>(Ga);
     case 20: return run_generic<MAT, 20>(Ga);
     default: return run_generic<MAT, 27>(Ga);
   }

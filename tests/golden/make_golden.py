@@ -52,6 +52,7 @@ CASES = {
     "hex20": "tests/input_files/solid_ele_hex20_Standard_stressout.4C.yaml",
     "wedge6": "tests/input_files/solid_ele_wedge6_Standard_stressout.4C.yaml",
     "pyramid5": "tests/input_files/solid_ele_pyramid5_Standard_stressout.4C.yaml",
+    "hex18": "tests/input_files/solid_ele_hex18_Standard_volume_neumann.4C.yaml",  # (no stressout input for hex18)
 }
 
 
@@ -117,7 +118,7 @@ def integration_case(cell, rel, linear=False):
         **extra,
         "source": rel,
         "celltype": cell,
-        "iostress": y["IO"]["STRUCT_STRESS"],
+        "iostress": y.get("IO", {}).get("STRUCT_STRESS"),
         "expected_stress": expected_stress,
         "coords": coords,
         "elements": eles,
@@ -530,7 +531,7 @@ def ref_elements():
             orc.MAT_SVK: [1000.0, 0.3]}
     # (new cells are appended so that the random stream of the earlier fixtures stays what it was)
     for ct, name in ((orc.HEX8, "hex8"), (orc.HEX27, "hex27"), (orc.TET10, "tet10"), (orc.TET4, "tet4"), (orc.HEX20, "hex20"),
-                     (orc.WEDGE6, "wedge6"), (orc.PYRAMID5, "pyramid5")):
+                     (orc.WEDGE6, "wedge6"), (orc.PYRAMID5, "pyramid5"), (orc.HEX18, "hex18")):
         n = orc.num_nodes(ct)
         X = orc.node_param_coords(ct) * np.array([1.0, 1.1, 1.2]) + 0.05 * rng.uniform(-1, 1, (n, 3))
         u = 0.04 * rng.uniform(-1, 1, (n, 3))

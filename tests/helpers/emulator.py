@@ -97,7 +97,7 @@ def mulf_history(celltype, conn, X, u_col=None, hist=None, fbar=False):
     fbar: MULF + F-bar, ngp + 1 histories per element (the centroid's last)."""
     conn = np.ascontiguousarray(conn, np.int32)
     X = np.ascontiguousarray(X, np.float64)
-    ngp = {0: 8, 1: 27, 2: 4, 3: 1, 4: 27, 5: 6, 6: 8}[celltype]
+    ngp = {0: 8, 1: 27, 2: 4, 3: 1, 4: 27, 5: 6, 6: 8, 7: 18}[celltype]
     update = hist is not None
     if hist is None:
         hist = np.zeros((len(conn), ngp + (1 if fbar else 0), 18))

@@ -20,7 +20,10 @@ HEX20_FACES = [f[:8] for f in HEX27_FACES]    # quad8: corners + mid-edge nodes 
 # (4C_fem_general_utils_local_connectivity_matrices.hpp:68-86, .cpp:697-765: first corners of the wedge18 tables)
 WEDGE6_FACES = [[0, 1, 4, 3], [1, 2, 5, 4], [2, 0, 3, 5], [2, 1, 0], [5, 3, 4]]
 PYRAMID5_FACES = [[0, 3, 2, 1], [0, 1, 4], [1, 2, 4], [2, 3, 4], [0, 4, 3]]
-FACES = {"hex8": HEX8_FACES, "hex27": HEX27_FACES, "tet10": TET10_FACES, "tet4": TET4_FACES, "hex20": HEX20_FACES,
+# hex18: two quad9 surfaces (bottom, top), then four quad6 side surfaces (:36-43)
+HEX18_FACES = [[0, 3, 2, 1, 7, 6, 5, 4, 8], [9, 10, 11, 12, 13, 14, 15, 16, 17],
+               [0, 1, 4, 9, 10, 13], [1, 2, 5, 10, 11, 14], [2, 3, 6, 11, 12, 15], [3, 0, 7, 12, 9, 16]]
+FACES = {"hex18": HEX18_FACES, "hex8": HEX8_FACES, "hex27": HEX27_FACES, "tet10": TET10_FACES, "tet4": TET4_FACES, "hex20": HEX20_FACES,
          "wedge6": WEDGE6_FACES, "pyramid5": PYRAMID5_FACES}
 
 
@@ -80,7 +83,20 @@ def _quad8(r, s):
     return N, np.stack([d0, d1])
 
 
+def _quad6(r, s):
+    """6-node quadrilateral, quadratic in r and linear in s (4C_fem_general_utils_fem_shapefunctions.hpp:2038-2047,
+    2204-2220): nodes (-1,-1), (1,-1), (0,-1), (-1,1), (1,1), (0,1)."""
+    q = np.array([0.5 * r * (r - 1), 0.5 * r * (r + 1), -(r - 1) * (r + 1)])
+    dq = np.array([r - 0.5, r + 0.5, -2 * r])
+    N = np.concatenate([q * 0.5 * (1 - s), q * 0.5 * (1 + s)])
+    dN = np.array([np.concatenate([dq * 0.5 * (1 - s), dq * 0.5 * (1 + s)]), np.concatenate([-0.5 * q, 0.5 * q])])
+    return N, dN
+
+
 def _rule(kind):
+    if kind == "quad6":  # quad_6point (4C_fem_general_utils_integration.cpp:6235-6261)
+        g, d, w1, w2 = 0.7745966692415, 0.5773502691896, 0.5555555555556, 0.8888888888889
+        return (np.array([[-g, -d], [g, -d], [0, -d], [-g, d], [g, d], [0, d]]), np.array([w1, w1, w2, w1, w1, w2]))
     if kind == "tri3":   # tri_3point (4C_fem_general_utils_integration.cpp:6341-6355)
         return np.array([[1 / 6, 1 / 6], [2 / 3, 1 / 6], [1 / 6, 2 / 3]]), np.full(3, 1 / 6)
     if kind == "quad8":  # get_optimal_gauss_rule(quad8) = quad_9point
@@ -113,7 +129,7 @@ def volume_neumann_load(case, time):
     (src/solid_ele/4C_solid_ele_neumann_evaluator.cpp:43-123)."""
     from oracle import oracle as orc
     ct = {"hex8": orc.HEX8, "hex27": orc.HEX27, "tet10": orc.TET10, "tet4": orc.TET4, "hex20": orc.HEX20,
-          "wedge6": orc.WEDGE6, "pyramid5": orc.PYRAMID5}[case["celltype"]]
+          "wedge6": orc.WEDGE6, "pyramid5": orc.PYRAMID5, "hex18": orc.HEX18}[case["celltype"]]
     X = np.asarray(case["coords"], float)
     vn = case["vol_neumann"]
     gxi, gw = orc.gauss(ct)
@@ -155,7 +171,10 @@ def _surface_neumann_load(case, time):
             if not all(i in nset for i in ids):
                 continue
             x = X[ids]
-            kind, fn = kinds[cell] if cell in kinds else (("tri3", _tri3) if len(face) == 3 else ("quad4", _quad4))
+            if cell == "hex18":
+                kind, fn = ("quad9", _quad9) if len(face) == 9 else ("quad6", _quad6)
+            else:
+                kind, fn = kinds[cell] if cell in kinds else (("tri3", _tri3) if len(face) == 3 else ("quad4", _quad4))
             gx, gw = _rule(kind)
             for (r, s), w in zip(gx, gw):
                 N, dN = fn(r, s)

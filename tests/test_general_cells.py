@@ -26,11 +26,14 @@ def _mesh(cell):
     if cell == "pyramid5":
         X, conn = b200.mesh.structured_pyramid5((2, 2, 2))
         return orc.PYRAMID5, b200.partition.serial_mesh(b200.mesh.PYRAMID5, X, conn), 0.25
+    if cell == "hex18":
+        X, conn = b200.mesh.structured_hex18((2, 2, 2))
+        return orc.HEX18, b200.partition.serial_mesh(b200.mesh.HEX18, X, conn), 0.5
     X, conn = b200.mesh.structured_hex20((2, 2, 1))
     return orc.HEX20, b200.partition.serial_mesh(b200.mesh.HEX20, X, conn), 0.5
 
 
-@pytest.mark.parametrize("cell", ["tet4", "hex20", "wedge6", "pyramid5"])
+@pytest.mark.parametrize("cell", ["tet4", "hex20", "wedge6", "pyramid5", "hex18"])
 @pytest.mark.parametrize("mk", list(MATS))
 @pytest.mark.parametrize("linear", [False, True])
 def test_emulated_general_kernel_matches_oracle(cell, mk, linear):
@@ -64,7 +67,7 @@ def test_general_kernel_equals_fast_kernels_on_their_cells():
         assert ok, (cell, wK, wf)
 
 
-@pytest.mark.parametrize("cell", ["tet4", "hex20", "wedge6", "pyramid5"])
+@pytest.mark.parametrize("cell", ["tet4", "hex20", "wedge6", "pyramid5", "hex18"])
 def test_emulated_general_kernel_mulf_matches_oracle(cell):
     """PRESTRESS_TECH mulf on the general cells (MulfFormulation is instantiated for every displacement-based cell,
     src/solid_ele/4C_solid_ele_factory.hpp:59-60; ctests solid_ele_{tet4,hex20,wedge6,pyramid5}_Standard_mulf): the general

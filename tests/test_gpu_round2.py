@@ -515,11 +515,14 @@ def _general_mesh(cell, n=None):
     if cell == "pyramid5":
         X, conn = b200.mesh.structured_pyramid5(n or (4, 3, 3))
         return orc.PYRAMID5, b200.partition.serial_mesh(b200.mesh.PYRAMID5, X, conn), 0.25
+    if cell == "hex18":
+        X, conn = b200.mesh.structured_hex18(n or (4, 3, 3))
+        return orc.HEX18, b200.partition.serial_mesh(b200.mesh.HEX18, X, conn), 0.3
     X, conn = b200.mesh.structured_hex20(n or (4, 3, 3))
     return orc.HEX20, b200.partition.serial_mesh(b200.mesh.HEX20, X, conn), 0.3
 
 
-@pytest.mark.parametrize("cell", ["tet4", "hex20", "wedge6", "pyramid5"])
+@pytest.mark.parametrize("cell", ["tet4", "hex20", "wedge6", "pyramid5", "hex18"])
 @pytest.mark.parametrize("mk", list(GEN_MATS))
 @pytest.mark.parametrize("kinem", [capi.KINEM_NONLINEAR_TOTLAG, capi.KINEM_LINEAR])
 def test_tet4_hex20_match_oracle(cell, mk, kinem):
@@ -541,7 +544,7 @@ def test_tet4_hex20_match_oracle(cell, mk, kinem):
     asm.close()
 
 
-@pytest.mark.parametrize("cell", ["tet4", "hex20", "wedge6", "pyramid5"])
+@pytest.mark.parametrize("cell", ["tet4", "hex20", "wedge6", "pyramid5", "hex18"])
 def test_tet4_hex20_mass_stress_energy(cell):
     ct, rm, h = _general_mesh(cell)
     u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, h)
@@ -572,7 +575,7 @@ def test_tet4_hex20_mass_stress_energy(cell):
     asm.close()
 
 
-@pytest.mark.parametrize("cell", ["tet4", "hex20", "wedge6", "pyramid5"])
+@pytest.mark.parametrize("cell", ["tet4", "hex20", "wedge6", "pyramid5", "hex18"])
 def test_reference_tet4_hex20_known_answers_through_cuda_path(cell):
     """RESULT DESCRIPTION displacements of tests/input_files/solid_ele_{tet4,hex20,wedge6,pyramid5}_Standard_stressout.4C.yaml."""
     import json
@@ -689,7 +692,7 @@ def test_reference_linear_kinematics_known_answers_through_cuda_path(cell):
 
 
 # ---- PRESTRESS_TECH mulf on the general cells (MulfFormulation: src/solid_ele/4C_solid_ele_factory.hpp:59-60) ----
-@pytest.mark.parametrize("cell", ["tet4", "hex20", "wedge6", "pyramid5"])
+@pytest.mark.parametrize("cell", ["tet4", "hex20", "wedge6", "pyramid5", "hex18"])
 def test_general_cells_mulf_evaluate_update_and_history_match_oracle(cell):
     ct, rm, h = _general_mesh(cell)
     u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, h)

@@ -14,7 +14,7 @@ G = os.path.join(os.path.dirname(__file__), "golden")
 KA = json.load(open(os.path.join(G, "unit_known_answers.json")))
 REFEL = np.load(os.path.join(G, "ref_elements.npz"))
 CELLS = {"hex8": orc.HEX8, "hex27": orc.HEX27, "tet10": orc.TET10, "tet4": orc.TET4, "hex20": orc.HEX20,
-         "wedge6": orc.WEDGE6, "pyramid5": orc.PYRAMID5}
+         "wedge6": orc.WEDGE6, "pyramid5": orc.PYRAMID5, "hex18": orc.HEX18}
 
 
 def _dp(a):
@@ -99,7 +99,7 @@ def test_bfree_equals_boperator_stiffness(cell):
         assert np.abs(Kf - Kr).max() < k["tol"]
 
 
-@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10", "tet4", "hex20", "wedge6", "pyramid5"])
+@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10", "tet4", "hex20", "wedge6", "pyramid5", "hex18"])
 @pytest.mark.parametrize("mk", [orc.MAT_COUP_NEOHOOKE, orc.MAT_ISO_VOL, orc.MAT_SVK])
 def test_oracle_matches_reference_header_fixtures(cell, mk):
     """oracle == oracle/_ref outputs committed in tests/golden/ref_elements.npz."""
@@ -116,7 +116,7 @@ def test_oracle_matches_reference_header_fixtures(cell, mk):
 
 
 @pytest.mark.skipif(orc.ref_lib() is None, reason="oracle/_ref not built (no /root/reference)")
-@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10", "tet4", "hex20", "wedge6", "pyramid5"])
+@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10", "tet4", "hex20", "wedge6", "pyramid5", "hex18"])
 def test_shape_functions_match_reference_headers(cell):
     import ctypes as C
     ct = CELLS[cell]
@@ -153,7 +153,7 @@ def test_element_tangent_is_derivative_of_force():
             assert np.abs(Ke - Ke.T).max() < 1e-12 * np.abs(Ke).max()
 
 
-@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10", "tet4", "hex20", "wedge6", "pyramid5"])
+@pytest.mark.parametrize("cell", ["hex8", "hex27", "tet10", "tet4", "hex20", "wedge6", "pyramid5", "hex18"])
 def test_integration_known_answers(cell):
     """RESULT DESCRIPTION displacements (1e-12) of the reference's ctest inputs, reproduced by the
     oracle's evaluate+assemble inside a Newton loop (tests/golden/integration_*.json)."""
