@@ -1428,6 +1428,7 @@ struct b200s_ctx
   int kinem = B200S_KINEM_NONLINEAR_TOTLAG;
   double* d_gp_hist = nullptr;  // MULF: n_col_eles * mulf_points * MULF_HIST doubles, device element order (mulf_points = ngp,
                                 // + 1 with TECH fbar: the element's global history at the centroid follows its Gauss points)
+  double* d_dN_ans = nullptr;   // hex8: [8][nn][3] shape derivatives at the ANS sampling points (TECH shell_ans)
   double* d_dN_pts = nullptr;   // [ngp + 1][nn][3]: d_dN_gp followed by d_dN_cen (history set-up / update of MULF + F-bar)
   double* d_eas_hist = nullptr; // EAS: n_col_eles * hex8eas::hist_size(neas) doubles, device element order
   double* d_eas_t0 = nullptr;   // EAS: T0invT[36] + detJ0 per element (stride hex8eas::T0_STRIDE)
@@ -2311,10 +2312,15 @@ namespace
     // TECH fbar (hex8, pyramid5; with PRESTRESS_TECH mulf: MulfFBarFormulation)
     Ga.dN_cen = ctx->tech == B200S_TECH_FBAR ? ctx->d_dN_cen : nullptr;
     Ga.hist_pts = mulf_points(ctx);
+    // TECH shell_ans (hex8): sampling-point tables
+    Ga.dN_ans = ctx->tech == B200S_TECH_SHELL_ANS ? ctx->d_dN_ans : nullptr;
+    Ga.xi_gp = ctx->d_xi_gp;
+    if (ctx->tech == B200S_TECH_SHELL_ANS && (ctx->celltype != B200S_HEX8 || !ctx->d_dN_ans))
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "TECH shell_ans on the device: hex8 blocks");
     const unsigned grid = nblk(A.n_ele * ctx->nn, 64);
     if (!grid) return 0;
-    if (ctx->tech != B200S_TECH_NONE && ctx->tech != B200S_TECH_FBAR)
-      return fail(ctx, B200S_ERR_UNSUPPORTED, "the general kernel evaluates displacement-based and F-bar blocks only (no EAS)");
+    if (ctx->tech != B200S_TECH_NONE && ctx->tech != B200S_TECH_FBAR && ctx->tech != B200S_TECH_SHELL_ANS)
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "the general kernel evaluates displacement-based, F-bar and shell_ans blocks only (no EAS)");
     switch (ctx->matkind)
     {
       case B200S_MAT_COUP_NEOHOOKE:
@@ -2346,7 +2352,7 @@ namespace
   {
     if (ctx->matkind < 0) return fail(ctx, B200S_ERR_INVALID, "material not set");
     if (ctx->general_tangent || ctx->general_kernel || is_general_cell(ctx->celltype) ||
-        (ctx->tech == B200S_TECH_FBAR && ctx->prestress == B200S_PRESTRESS_MULF) ||
+        (ctx->tech == B200S_TECH_FBAR && ctx->prestress == B200S_PRESTRESS_MULF) || ctx->tech == B200S_TECH_SHELL_ANS ||
         (ctx->matkind == B200S_MAT_PLASTIC_NLNLOG && ctx->celltype != B200S_HEX8))  // fast kernels: hex8 (+ EAS) only
       return launch_generic(ctx, A, STIFF);
     if (ctx->tech != B200S_TECH_NONE && ctx->celltype != B200S_HEX8)
@@ -2445,7 +2451,7 @@ extern "C"
     dfree(ctx->d_face_N), dfree(ctx->d_face_d0), dfree(ctx->d_face_d1), dfree(ctx->d_face_w);
     dfree(ctx->d_N_gp), dfree(ctx->d_fext), dfree(ctx->d_nm_row), dfree(ctx->d_nm_col), dfree(ctx->d_nm_flag);
     dfree(ctx->d_exp_pos), dfree(ctx->d_exp_fpos), dfree(ctx->d_exp_buf), dfree(ctx->d_exp_fbuf);
-    dfree(ctx->d_hyper), dfree(ctx->d_dN_gp), dfree(ctx->d_w), dfree(ctx->d_dN_cen), dfree(ctx->d_N_mass), dfree(ctx->d_dN_pts);
+    dfree(ctx->d_hyper), dfree(ctx->d_dN_gp), dfree(ctx->d_w), dfree(ctx->d_dN_cen), dfree(ctx->d_N_mass), dfree(ctx->d_dN_pts), dfree(ctx->d_dN_ans);
     dfree(ctx->d_dN_mass), dfree(ctx->d_w_mass), dfree(ctx->d_ele_is_row), dfree(ctx->d_mass);
     dfree(ctx->d_f_inertia), dfree(ctx->d_acc_row), dfree(ctx->d_acc_col), dfree(ctx->d_energy);
     dfree(ctx->d_xmat), dfree(ctx->d_la_x), dfree(ctx->d_la_y), dfree(ctx->d_toggle);
@@ -2525,6 +2531,7 @@ extern "C"
     if (to_device(ctx, &ctx->d_dN_gp, T.dN_gp.data(), (int64_t)T.dN_gp.size()) ||
         to_device(ctx, &ctx->d_w, T.w.data(), (int64_t)T.w.size()) ||
         to_device(ctx, &ctx->d_dN_cen, T.dN_cen.data(), (int64_t)T.dN_cen.size()) ||
+        (!T.dN_ans.empty() && to_device(ctx, &ctx->d_dN_ans, T.dN_ans.data(), (int64_t)T.dN_ans.size())) ||
         to_device(ctx, &ctx->d_dN_pts, (const double*)nullptr, (int64_t)(T.dN_gp.size() + T.dN_cen.size())) ||
         to_device(ctx, &ctx->d_dN_node, T.dN_node.data(), (int64_t)T.dN_node.size()) ||
         to_device(ctx, &ctx->d_xi_gp, T.xi_gp.data(), (int64_t)T.xi_gp.size()) ||
@@ -2646,14 +2653,20 @@ extern "C"
         element_technology != B200S_TECH_FBAR)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "MULF prestress with element technology %d has no device kernel",
           element_technology);
-    if (element_technology < B200S_TECH_NONE || element_technology > B200S_TECH_EAS_FULL)
+    if (element_technology < B200S_TECH_NONE || element_technology > B200S_TECH_SHELL_ANS)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "element technology %d has no device kernel",
           element_technology);
     // the reference offers F-bar and EAS for hex8 only among the device cell types
     // (4C_solid_ele_factory_lib.hpp)
     if (element_technology != B200S_TECH_NONE && ctx->celltype >= 0 && ctx->celltype != B200S_HEX8 &&
         !(element_technology == B200S_TECH_FBAR && ctx->celltype == B200S_PYRAMID5))
-      return fail(ctx, B200S_ERR_UNSUPPORTED, "F-bar is a hex8 / pyramid5 technology, EAS a hex8 technology");
+      return fail(ctx, B200S_ERR_UNSUPPORTED,
+          "F-bar is a hex8 / pyramid5 technology, EAS a hex8 technology, shell_ans on the device a hex8 technology (the "
+          "wedge6 solid shell stays on the CPU path)");
+    // ShellANSFormulation exists for KINEM nonlinear without prestress (4C_solid_ele_factory.cpp)
+    if (element_technology == B200S_TECH_SHELL_ANS &&
+        (kinem_type != B200S_KINEM_NONLINEAR_TOTLAG || prestress_technology != B200S_PRESTRESS_NONE))
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "TECH shell_ans: KINEM nonlinear, no prestress");
     const int old_points = mulf_points(ctx);
     ctx->kinem = kinem_type;
     dfree(ctx->d_hist_old);
@@ -4037,6 +4050,8 @@ extern "C"
       return fail(ctx, B200S_ERR_INVALID, "set_mesh and set_material must precede this action");
     if (material_needs_fibers(ctx) && !ctx->d_fibers)
       return fail(ctx, B200S_ERR_INVALID, "the material has a fibre summand: b200s_set_element_fibers first");
+    if (ctx->tech == B200S_TECH_SHELL_ANS)
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "stress / energy output of shell_ans blocks has no device kernel (CPU path)");
     PostArgs P;
     P.X = ctx->dX, P.u = ctx->d_u_col, P.conn = ctx->dconn, P.per_ele_param = ctx->d_per_ele;
     P.fibers = ctx->d_fibers;

@@ -23,6 +23,8 @@ namespace b200s
     const double* dN_node;  // [nn][nn][3] (Jacobian check) or nullptr
     const double* w;        // [ngp]
     const double* dN_cen;   // [nn][3] at the element centroid: TECH fbar (nullptr otherwise)
+    const double* dN_ans;   // [8][nn][3] at the ANS sampling points: TECH shell_ans on hex8 (nullptr otherwise)
+    const double* xi_gp;    // [ngp][3] Gauss point coordinates (ANS interpolation weights)
     int nn, ngp, pos_stride, stiff;
     int hist_pts;           // MULF histories per element: ngp, or ngp + 1 with TECH fbar (the centroid's follows the points')
   };
@@ -220,6 +222,221 @@ namespace b200s
     return neg;
   }
 
+
+  // ---- TECH shell_ans on hex8: ShellANSFormulation (src/solid_ele/4C_solid_ele_calc_shell_ans.hpp:52-196,
+  // 4C_solid_ele_calc_shell_ans_lib.hpp).  Strains, B-operator and geometric stiffness are formed in the parametric frame;
+  // the transverse normal row tt and the transverse shear rows st, rt are interpolated from the sampling points
+  // A..D (shears) and E..H (tt) of the mid-surface, T^-T of the Gauss point's Jacobian takes them to the global frame.
+  // T(J) is the strain-like Voigt transformation of E' = J E J^T, so T(J)^-1 = T(J^-1) -- formed directly, where the
+  // reference inverts numerically (evaluate_voigt_transformation_matrix, 4C_solid_ele_calc_lib.hpp:1451-1517).
+  B2_HD void voigt_strain_transformation(const double* M /*a + 3 b*/, double* T /*r + 6 c*/)
+  {
+    constexpr int pa[3] = {0, 1, 0}, pb[3] = {1, 2, 2};
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+    {
+      const int a = r < 3 ? r : pa[r - 3], b = r < 3 ? r : pb[r - 3];
+#pragma unroll
+      for (int c = 0; c < 6; ++c)
+      {
+        const int cc = c < 3 ? c : pa[c - 3], dd = c < 3 ? c : pb[c - 3];
+        double v;
+        if (r < 3)
+          v = M[a + 3 * cc] * M[a + 3 * dd];
+        else
+          v = c < 3 ? 2.0 * M[a + 3 * cc] * M[b + 3 * cc] : M[a + 3 * cc] * M[b + 3 * dd] + M[a + 3 * dd] * M[b + 3 * cc];
+        T[r + 6 * c] = v;
+      }
+    }
+  }
+
+  // local (parametric) B-operator columns of node k, dofs d = 0..2: Bl[r][d]; Jc = current Jacobian at the Gauss point,
+  // Jcs = current Jacobians at the eight sampling points, dNs = shape derivatives there, w = interpolation weights
+  B2_HD void ans_local_bop_node(const double* dN, const double* dNs, int nn, int k, const double* Jc, const double (*Jcs)[9],
+      const double* w_tt, const double* w_st, const double* w_rt, double (*Bl)[3])
+  {
+    const double* D = dN + 3 * k;
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+    {
+      Bl[0][d] = D[0] * Jc[0 + 3 * d];
+      Bl[1][d] = D[1] * Jc[1 + 3 * d];
+      Bl[3][d] = D[0] * Jc[1 + 3 * d] + D[1] * Jc[0 + 3 * d];
+      double tt = 0.0, st = 0.0, rt = 0.0;
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+      {
+        const double* Ds = dNs + ((size_t)(4 + m) * nn + k) * 3;  // sampling points E..H
+        tt = fma(w_tt[m], Ds[2] * Jcs[4 + m][2 + 3 * d], tt);
+      }
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+      {
+        const double* Db = dNs + ((size_t)(1 + 2 * m) * nn + k) * 3;  // B, D
+        st = fma(w_st[m], Db[1] * Jcs[1 + 2 * m][2 + 3 * d] + Db[2] * Jcs[1 + 2 * m][1 + 3 * d], st);
+        const double* Da = dNs + ((size_t)(2 * m) * nn + k) * 3;  // A, C
+        rt = fma(w_rt[m], Da[0] * Jcs[2 * m][2 + 3 * d] + Da[2] * Jcs[2 * m][0 + 3 * d], rt);
+      }
+      Bl[2][d] = tt, Bl[4][d] = st, Bl[5][d] = rt;
+    }
+  }
+
+  template <int MAT>
+  B2_HD bool generic_block_row_ans(const GenericArgs& Ga, int64_t e, int i, double (*Krow)[9], double* fi, double& detJ_min,
+      double& detF_min)
+  {
+    constexpr int NN = 8;
+    const EvalArgs& A = Ga.A;
+    double X[NN][3], x[NN][3];
+    const int32_t* ce = A.conn + e * NN;
+    for (int k = 0; k < NN; ++k)
+      for (int d = 0; d < 3; ++d)
+      {
+        X[k][d] = A.X[3 * (int64_t)ce[k] + d];
+        x[k][d] = X[k][d] + A.u[3 * (int64_t)ce[k] + d];
+      }
+    for (int j = 0; j < NN; ++j)
+      for (int q = 0; q < 9; ++q) Krow[j][q] = 0.0;
+    fi[0] = fi[1] = fi[2] = 0.0;
+    auto jac = [&](const double* dN, const double (*P)[3], double* J)
+    {
+      for (int q = 0; q < 9; ++q) J[q] = 0.0;
+      for (int k = 0; k < NN; ++k)
+        for (int a = 0; a < 3; ++a)
+          for (int d = 0; d < 3; ++d) J[a + 3 * d] = fma(dN[3 * k + a], P[k][d], J[a + 3 * d]);
+    };
+    bool neg = false;
+    if (Ga.dN_node && i == 0)
+      for (int q = 0; q < NN; ++q)
+      {
+        double J[9];
+        jac(Ga.dN_node + (size_t)q * NN * 3, X, J);
+        const double dj = det3(J);
+        detJ_min = fmin(detJ_min, dj);
+        neg = neg || !(dj > 0.0);
+      }
+    // evaluate_sampling_point_data (shell_ans_lib.hpp:515-571)
+    double Jrs[8][9], Jcs[8][9];
+    for (int q = 0; q < 8; ++q)
+    {
+      jac(Ga.dN_ans + (size_t)q * NN * 3, X, Jrs[q]);
+      jac(Ga.dN_ans + (size_t)q * NN * 3, x, Jcs[q]);
+    }
+    auto rows = [](const double* J, int a, int b) { return J[a] * J[b] + J[a + 3] * J[b + 3] + J[a + 6] * J[b + 6]; };
+    for (int g = 0; g < Ga.ngp; ++g)
+    {
+      const double* dN = Ga.dN_gp + (size_t)g * NN * 3;
+      const double* xi = Ga.xi_gp + 3 * g;
+      double J[9], Jc[9], iJ[9], T[36];
+      jac(dN, X, J), jac(dN, x, Jc);
+      const double detJ = inv3(iJ, J);
+      detJ_min = fmin(detJ_min, detJ);
+      detF_min = fmin(detF_min, det3(Jc) / detJ);
+      voigt_strain_transformation(iJ, T);
+      const double w_tt[4] = {0.25 * (1 - xi[0]) * (1 - xi[1]), 0.25 * (1 + xi[0]) * (1 - xi[1]), 0.25 * (1 + xi[0]) * (1 + xi[1]),
+          0.25 * (1 - xi[0]) * (1 + xi[1])};
+      const double w_st[2] = {0.5 * (1 + xi[0]), 0.5 * (1 - xi[0])}, w_rt[2] = {0.5 * (1 - xi[1]), 0.5 * (1 + xi[1])};
+      // evaluate_local_glstrain (:169-291), to the global frame, shear rows halved (strain-like -> tensor components)
+      double El[6], C[6];
+      El[0] = 0.5 * (rows(Jc, 0, 0) - rows(J, 0, 0));
+      El[1] = 0.5 * (rows(Jc, 1, 1) - rows(J, 1, 1));
+      El[3] = rows(Jc, 0, 1) - rows(J, 0, 1);
+      double tt = 0.0, st = 0.0, rt = 0.0;
+      for (int m = 0; m < 4; ++m) tt = fma(w_tt[m], rows(Jcs[4 + m], 2, 2) - rows(Jrs[4 + m], 2, 2), tt);
+      for (int m = 0; m < 2; ++m)
+      {
+        st = fma(w_st[m], rows(Jcs[1 + 2 * m], 1, 2) - rows(Jrs[1 + 2 * m], 1, 2), st);
+        rt = fma(w_rt[m], rows(Jcs[2 * m], 0, 2) - rows(Jrs[2 * m], 0, 2), rt);
+      }
+      El[2] = 0.5 * tt, El[4] = st, El[5] = rt;
+      for (int r = 0; r < 6; ++r)
+      {
+        double v = 0.0;
+        for (int q = 0; q < 6; ++q) v = fma(T[r + 6 * q], El[q], v);
+        C[r] = r < 3 ? 2.0 * v + 1.0 : v;  // C = 2 E + I in tensor components (shear: 2 * (v / 2))
+      }
+      double S[6], Cm[36];
+      MatParams mp = A.mp;
+      if (A.per_ele_param != nullptr) mp.p[0] = A.per_ele_param[e];
+      if (MAT == MAT_HYPER && A.fibers != nullptr) mp.fiber = A.fibers + 3 * e;
+      if (material_hist_doubles(MAT) > 0 && A.mat_hist != nullptr)
+        mp.hist = A.mat_hist + (e * Ga.ngp + g) * material_hist_doubles(MAT);
+      material_evaluate_full<MAT>(mp, C, S, Cm);
+      const double w = detJ * Ga.w[g];
+      // B_i = T^-T Bl_i (6 x 3), f_i += w B_i^T S, A_i = w B_i^T C (3 x 6)
+      double Bl[6][3], Bi[6][3], Ai[3][6];
+      ans_local_bop_node(dN, Ga.dN_ans, NN, i, Jc, Jcs, w_tt, w_st, w_rt, Bl);
+      for (int r = 0; r < 6; ++r)
+        for (int d = 0; d < 3; ++d)
+        {
+          double v = 0.0;
+          for (int q = 0; q < 6; ++q) v = fma(T[r + 6 * q], Bl[q][d], v);
+          Bi[r][d] = v;
+        }
+      for (int d = 0; d < 3; ++d)
+      {
+        double v = 0.0;
+        for (int r = 0; r < 6; ++r) v = fma(Bi[r][d], S[r], v);
+        fi[d] = fma(w, v, fi[d]);
+      }
+      if (!Ga.stiff) continue;
+      for (int b = 0; b < 3; ++b)
+        for (int W = 0; W < 6; ++W)
+        {
+          double v = 0.0;
+          for (int V = 0; V < 6; ++V) v = fma(Bi[V][b], Cm[V + 6 * W], v);
+          Ai[b][W] = w * v;
+        }
+      // Sl = T^-T^T S: the geometric term w S . (T^-T G_ij) = w Sl . G_ij (add_ans_geometric_stiffness, :383-454)
+      double Sl[6];
+      for (int q = 0; q < 6; ++q)
+      {
+        double v = 0.0;
+        for (int r = 0; r < 6; ++r) v = fma(T[r + 6 * q], S[r], v);
+        Sl[q] = w * v;
+      }
+      const double* Di = dN + 3 * i;
+      for (int j = 0; j < NN; ++j)
+      {
+        double Bj[6][3];
+        ans_local_bop_node(dN, Ga.dN_ans, NN, j, Jc, Jcs, w_tt, w_st, w_rt, Bl);
+        for (int r = 0; r < 6; ++r)
+          for (int d = 0; d < 3; ++d)
+          {
+            double v = 0.0;
+            for (int q = 0; q < 6; ++q) v = fma(T[r + 6 * q], Bl[q][d], v);
+            Bj[r][d] = v;
+          }
+        const double* Dj = dN + 3 * j;
+        double G[6];
+        G[0] = Di[0] * Dj[0], G[1] = Di[1] * Dj[1], G[3] = Di[0] * Dj[1] + Di[1] * Dj[0];
+        double gtt = 0.0, gst = 0.0, grt = 0.0;
+        for (int m = 0; m < 4; ++m)
+          gtt = fma(w_tt[m], Ga.dN_ans[((size_t)(4 + m) * NN + i) * 3 + 2] * Ga.dN_ans[((size_t)(4 + m) * NN + j) * 3 + 2], gtt);
+        for (int m = 0; m < 2; ++m)
+        {
+          const double* Bi_ = Ga.dN_ans + ((size_t)(1 + 2 * m) * NN + i) * 3;
+          const double* Bj_ = Ga.dN_ans + ((size_t)(1 + 2 * m) * NN + j) * 3;
+          gst = fma(w_st[m], Bi_[1] * Bj_[2] + Bi_[2] * Bj_[1], gst);
+          const double* Ai_ = Ga.dN_ans + ((size_t)(2 * m) * NN + i) * 3;
+          const double* Aj_ = Ga.dN_ans + ((size_t)(2 * m) * NN + j) * 3;
+          grt = fma(w_rt[m], Ai_[0] * Aj_[2] + Ai_[2] * Aj_[0], grt);
+        }
+        G[2] = gtt, G[4] = gst, G[5] = grt;
+        double Gij = 0.0;
+        for (int q = 0; q < 6; ++q) Gij = fma(Sl[q], G[q], Gij);
+        for (int b = 0; b < 3; ++b)
+          for (int c = 0; c < 3; ++c)
+          {
+            double v = (b == c) ? Gij : 0.0;
+            for (int W = 0; W < 6; ++W) v = fma(Ai[b][W], Bj[W][c], v);
+            Krow[j][b + 3 * c] += v;
+          }
+      }
+    }
+    return neg;
+  }
+
 #if defined(__CUDACC__)
   __device__ __forceinline__ void atomic_min_double_generic(double* addr, double v)
   {
@@ -242,7 +459,12 @@ namespace b200s
     const int i = (int)(t - e * Ga.nn);
     if (e >= A.n_ele) return;
     double Krow[NN][9], fi[3], dj = 1e300, df = 1e300;
-    const bool neg = generic_block_row<MAT, NN>(Ga, e, i, Krow, fi, dj, df);
+    bool neg;
+    if constexpr (NN == 8)
+      neg = Ga.dN_ans != nullptr ? generic_block_row_ans<MAT>(Ga, e, i, Krow, fi, dj, df)
+                                 : generic_block_row<MAT, NN>(Ga, e, i, Krow, fi, dj, df);
+    else
+      neg = generic_block_row<MAT, NN>(Ga, e, i, Krow, fi, dj, df);
     atomic_min_double_generic(&A.err->min_detJ, dj);
     atomic_min_double_generic(&A.err->min_detF, df);
     if (neg)

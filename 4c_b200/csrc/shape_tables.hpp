@@ -33,6 +33,7 @@ namespace b200s
     std::vector<double> w_mass;   // [ngp_mass]
     std::vector<double> N_gp;     // [ngp][nn] values at the stiffness rule's points
     std::vector<double> dN_cen;   // [nn][3] derivatives at the element centroid (F-bar, EAS)
+    std::vector<double> dN_ans;   // hex8 only: [8][nn][3] derivatives at the ANS sampling points A..H (TECH shell_ans)
     std::vector<double> xi_gp;    // [ngp][3] parameter coordinates of the stiffness rule's points (EAS)
   };
 
@@ -403,6 +404,13 @@ namespace b200s
     }
     const double cen_hex[3] = {0.0, 0.0, 0.0}, cen_tet[3] = {0.25, 0.25, 0.25}, cen_wedge[3] = {1.0 / 3.0, 1.0 / 3.0, 0.0},
                  cen_pyramid[3] = {0.0, 0.0, 0.25};
+    if (celltype == 0)
+    {
+      // SamplingPoints<hex8> (4C_solid_ele_calc_shell_ans_lib.hpp:26-33): A..D for the transverse shears, E..H for tt
+      const double sp[8][3] = {{0, -1, 0}, {1, 0, 0}, {0, 1, 0}, {-1, 0, 0}, {-1, -1, 0}, {1, -1, 0}, {1, 1, 0}, {-1, 1, 0}};
+      T.dN_ans.resize((size_t)8 * T.nn * 3);
+      for (int q = 0; q < 8; ++q) detail::deriv1(celltype, sp[q], &T.dN_ans[(size_t)q * T.nn * 3]);
+    }
     T.dN_cen.resize((size_t)T.nn * 3);
     detail::deriv1(celltype, (celltype == 2 || celltype == 3) ? cen_tet : (celltype == 5 ? cen_wedge : (celltype == 6 ? cen_pyramid : cen_hex)),
         T.dN_cen.data());

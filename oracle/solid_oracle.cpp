@@ -2086,6 +2086,227 @@ namespace
     dense_inverse(6, T);
   }
 
+
+  // evaluate_voigt_transformation_matrix (src/solid_ele/4C_solid_ele_calc_lib.hpp:1451-1517): T^-T of the Jacobian jm.J
+  // for strain-like Voigt vectors [xx,yy,zz,xy,yz,xz], column-major 6 x 6 (the matrix eas_centroid_transformation builds
+  // at the centroid)
+  void voigt_transformation(const double* Jm, double* TinvT)
+  {
+    auto J = [&](int a, int b) { return Jm[a + 3 * b]; };
+    auto at = [&](int r, int c) -> double& { return TinvT[r + 6 * c]; };
+    for (int c = 0; c < 3; ++c)
+    {
+      at(0, c) = J(0, c) * J(0, c);
+      at(1, c) = J(1, c) * J(1, c);
+      at(2, c) = J(2, c) * J(2, c);
+      at(3, c) = 2 * J(0, c) * J(1, c);
+      at(4, c) = 2 * J(1, c) * J(2, c);
+      at(5, c) = 2 * J(0, c) * J(2, c);
+    }
+    const int pa[3] = {0, 1, 0}, pb[3] = {1, 2, 2};
+    for (int q = 0; q < 3; ++q)
+    {
+      const int a = pa[q], b = pb[q], c = 3 + q;
+      at(0, c) = J(0, a) * J(0, b);
+      at(1, c) = J(1, a) * J(1, b);
+      at(2, c) = J(2, a) * J(2, b);
+      at(3, c) = J(0, a) * J(1, b) + J(1, a) * J(0, b);
+      at(4, c) = J(1, a) * J(2, b) + J(2, a) * J(1, b);
+      at(5, c) = J(0, a) * J(2, b) + J(2, a) * J(0, b);
+    }
+    dense_inverse(6, TinvT);
+  }
+
+  // ---- SolidEleCalc<hex8 | wedge6, ShellANSFormulation>  (TECH shell_ans: src/solid_ele/4C_solid_ele_calc_shell_ans.hpp:52-196,
+  //      4C_solid_ele_calc_shell_ans_lib.hpp).  The thickness direction is the t-direction of the parameter space.  In
+  //      the parametric strain components the transverse normal strain tt and the transverse shear strains st, rt are
+  //      not taken at the Gauss point but interpolated from sampling points (hex8: A..D mid-edges of the mid-surface for
+  //      the shears, E..H its corners for tt; wedge6: five points), for the strains, the B-operator and the geometric
+  //      stiffness alike; T^-T of the Jacobian at the Gauss point takes everything to the global frame.
+  int element_shell_ans(int ct, int matkind, const double* par, int action, const double* X, const double* u, double* Ke,
+      double* fe)
+  {
+    if (ct != ORC_HEX8 && ct != ORC_WEDGE6) return 2;
+    const int n = nnodes(ct), nd = 3 * n, ng = ngauss(ct);
+    const bool hex = ct == ORC_HEX8;
+    const int nsp = hex ? 8 : 5;
+    // SamplingPoints<celltype>::value (shell_ans_lib.hpp:26-40)
+    const double sp_hex[8][3] = {{0, -1, 0}, {1, 0, 0}, {0, 1, 0}, {-1, 0, 0}, {-1, -1, 0}, {1, -1, 0}, {1, 1, 0}, {-1, 1, 0}};
+    const double sp_wedge[5][3] = {{0.5, 0, 0}, {0, 0.5, 0}, {0, 0, 0}, {1, 0, 0}, {0, 1, 0}};
+    double N[MAXN], dN[3 * MAXN];
+    JacMap jm;
+    if (Ke) std::memset(Ke, 0, sizeof(double) * nd * nd);
+    std::memset(fe, 0, sizeof(double) * nd);
+    int err = 0;
+    for (int k = 0; k < n; ++k)
+    {
+      double xi[3];
+      node_ref(ct, k, xi);
+      shape(ct, xi, N, dN);
+      jacobian_mapping(n, dN, X, jm);
+      if (!(jm.det > 0)) err = 1;
+    }
+    if (err) return 1;
+    // evaluate_sampling_point_data (shell_ans_lib.hpp:515-571): J(a,d) = sum_k dN(a,k) x(k,d), reference and current
+    struct SP
+    {
+      double dN[3 * MAXN], Jr[9], Jc[9];
+      std::vector<double> bop;  // 3 x nd: rows tt, st, rt
+    };
+    std::vector<SP> sp(nsp);
+    auto jac = [&](const double* dNq, bool current, double* J)
+    {
+      for (int a = 0; a < 3; ++a)
+        for (int d = 0; d < 3; ++d)
+        {
+          double v = 0.0;
+          for (int k = 0; k < n; ++k) v += dNq[a + 3 * k] * (X[3 * k + d] + (current ? u[3 * k + d] : 0.0));
+          J[a + 3 * d] = v;
+        }
+    };
+    for (int q = 0; q < nsp; ++q)
+    {
+      shape(ct, hex ? sp_hex[q] : sp_wedge[q], N, sp[q].dN);
+      jac(sp[q].dN, false, sp[q].Jr), jac(sp[q].dN, true, sp[q].Jc);
+      sp[q].bop.assign(3 * nd, 0.0);
+      for (int k = 0; k < n; ++k)
+        for (int d = 0; d < 3; ++d)
+        {
+          const double* D = sp[q].dN + 3 * k;
+          const double* Jc = sp[q].Jc;
+          sp[q].bop[0 + 3 * (3 * k + d)] = D[2] * Jc[2 + 3 * d];
+          sp[q].bop[1 + 3 * (3 * k + d)] = D[1] * Jc[2 + 3 * d] + D[2] * Jc[1 + 3 * d];
+          sp[q].bop[2 + 3 * (3 * k + d)] = D[0] * Jc[2 + 3 * d] + D[2] * Jc[0 + 3 * d];
+        }
+    }
+    double gxi[3 * MAXN], gw[MAXN];
+    gauss(ct, gxi, gw);
+    std::vector<double> Bl(6 * nd), B(6 * nd), CB(6 * nd);
+    for (int gp = 0; gp < ng; ++gp)
+    {
+      const double* xi = gxi + 3 * gp;
+      shape(ct, xi, N, dN);
+      jacobian_mapping(n, dN, X, jm);
+      const double fac = jm.det * gw[gp];
+      double Jc[9];
+      jac(dN, true, Jc);
+      // interpolation of the sampled rows: (sampling point, weight) lists of tt, st, rt
+      int q_tt[4], q_st[2], q_rt[2], n_tt, n_st, n_rt;
+      double w_tt[4], w_st[2], w_rt[2];
+      if (hex)
+      {
+        n_tt = 4, n_st = 2, n_rt = 2;
+        q_tt[0] = 4, q_tt[1] = 5, q_tt[2] = 6, q_tt[3] = 7;
+        w_tt[0] = 0.25 * (1 - xi[0]) * (1 - xi[1]), w_tt[1] = 0.25 * (1 + xi[0]) * (1 - xi[1]);
+        w_tt[2] = 0.25 * (1 + xi[0]) * (1 + xi[1]), w_tt[3] = 0.25 * (1 - xi[0]) * (1 + xi[1]);
+        q_st[0] = 1, q_st[1] = 3, w_st[0] = 0.5 * (1 + xi[0]), w_st[1] = 0.5 * (1 - xi[0]);
+        q_rt[0] = 0, q_rt[1] = 2, w_rt[0] = 0.5 * (1 - xi[1]), w_rt[1] = 0.5 * (1 + xi[1]);
+      }
+      else
+      {
+        n_tt = 3, n_st = 1, n_rt = 1;
+        q_tt[0] = 2, q_tt[1] = 3, q_tt[2] = 4, w_tt[0] = 1 - xi[0] - xi[1], w_tt[1] = xi[0], w_tt[2] = xi[1];
+        q_st[0] = 1, w_st[0] = xi[0];
+        q_rt[0] = 0, w_rt[0] = xi[1];
+      }
+      // evaluate_local_b_operator (:60-118 / :119-167)
+      for (int k = 0; k < n; ++k)
+        for (int d = 0; d < 3; ++d)
+        {
+          const int c = 3 * k + d;
+          const double* D = dN + 3 * k;
+          Bl[0 + 6 * c] = D[0] * Jc[0 + 3 * d];
+          Bl[1 + 6 * c] = D[1] * Jc[1 + 3 * d];
+          Bl[3 + 6 * c] = D[0] * Jc[1 + 3 * d] + D[1] * Jc[0 + 3 * d];
+          double tt = 0.0, st = 0.0, rt = 0.0;
+          for (int m = 0; m < n_tt; ++m) tt += w_tt[m] * sp[q_tt[m]].bop[0 + 3 * c];
+          for (int m = 0; m < n_st; ++m) st += w_st[m] * sp[q_st[m]].bop[1 + 3 * c];
+          for (int m = 0; m < n_rt; ++m) rt += w_rt[m] * sp[q_rt[m]].bop[2 + 3 * c];
+          Bl[2 + 6 * c] = tt, Bl[4 + 6 * c] = st, Bl[5 + 6 * c] = rt;
+        }
+      double TinvT[36];
+      voigt_transformation(jm.J, TinvT);
+      for (int c = 0; c < nd; ++c)
+        for (int r = 0; r < 6; ++r)
+        {
+          double v = 0.0;
+          for (int q = 0; q < 6; ++q) v += TinvT[r + 6 * q] * Bl[q + 6 * c];
+          B[r + 6 * c] = v;
+        }
+      // evaluate_local_glstrain (:169-291 / :294-380)
+      auto row_dot = [](const double* J, int a, int b) { return J[a] * J[b] + J[a + 3] * J[b + 3] + J[a + 6] * J[b + 6]; };
+      double El[6];
+      El[0] = 0.5 * (row_dot(Jc, 0, 0) - row_dot(jm.J, 0, 0));
+      El[1] = 0.5 * (row_dot(Jc, 1, 1) - row_dot(jm.J, 1, 1));
+      El[3] = row_dot(Jc, 0, 1) - row_dot(jm.J, 0, 1);
+      double tt = 0.0, st = 0.0, rt = 0.0;
+      for (int m = 0; m < n_tt; ++m) tt += w_tt[m] * (row_dot(sp[q_tt[m]].Jc, 2, 2) - row_dot(sp[q_tt[m]].Jr, 2, 2));
+      for (int m = 0; m < n_st; ++m) st += w_st[m] * (row_dot(sp[q_st[m]].Jc, 1, 2) - row_dot(sp[q_st[m]].Jr, 1, 2));
+      for (int m = 0; m < n_rt; ++m) rt += w_rt[m] * (row_dot(sp[q_rt[m]].Jc, 0, 2) - row_dot(sp[q_rt[m]].Jr, 0, 2));
+      El[2] = 0.5 * tt, El[4] = st, El[5] = rt;
+      double E[6], S[6], Cm[36], F[9];
+      for (int r = 0; r < 6; ++r)
+      {
+        double v = 0.0;
+        for (int q = 0; q < 6; ++q) v += TinvT[r + 6 * q] * El[q];
+        E[r] = r < 3 ? v : 0.5 * v;  // Voigt::Strains::to_stress_like
+      }
+      // the materials of this path use the strain only (the reference also hands in a deformation gradient consistent
+      // with it, compute_deformation_gradient_from_gl_strains)
+      deformation_gradient(n, u, jm, F);
+      material(matkind, par, F, E, S, Cm);
+      // add_internal_force_vector(Bop, stress) (calc_lib.hpp)
+      for (int c = 0; c < nd; ++c)
+      {
+        double v = 0.0;
+        for (int r = 0; r < 6; ++r) v += B[r + 6 * c] * S[r];
+        fe[c] += fac * v;
+      }
+      if (!(action == ORC_ACTION_FORCE_STIFF && Ke)) continue;
+      for (int c = 0; c < nd; ++c)
+        for (int I = 0; I < 6; ++I)
+        {
+          double v = 0.0;
+          for (int J = 0; J < 6; ++J) v += Cm[I + 6 * J] * B[J + 6 * c];
+          CB[I + 6 * c] = v;
+        }
+      for (int r = 0; r < nd; ++r)
+        for (int c = 0; c < nd; ++c)
+        {
+          double v = 0.0;
+          for (int I = 0; I < 6; ++I) v += B[I + 6 * r] * CB[I + 6 * c];
+          Ke[r + nd * c] += fac * v;
+        }
+      // add_ans_geometric_stiffness (:383-454 / :456-512)
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j)
+        {
+          const double* Di = dN + 3 * i;
+          const double* Dj = dN + 3 * j;
+          double G[6];
+          G[0] = Di[0] * Dj[0];
+          G[1] = Di[1] * Dj[1];
+          G[3] = Di[0] * Dj[1] + Di[1] * Dj[0];
+          double gtt = 0.0, gst = 0.0, grt = 0.0;
+          for (int m = 0; m < n_tt; ++m) gtt += w_tt[m] * sp[q_tt[m]].dN[2 + 3 * i] * sp[q_tt[m]].dN[2 + 3 * j];
+          for (int m = 0; m < n_st; ++m)
+            gst += w_st[m] * (sp[q_st[m]].dN[1 + 3 * i] * sp[q_st[m]].dN[2 + 3 * j] + sp[q_st[m]].dN[2 + 3 * i] * sp[q_st[m]].dN[1 + 3 * j]);
+          for (int m = 0; m < n_rt; ++m)
+            grt += w_rt[m] * (sp[q_rt[m]].dN[0 + 3 * i] * sp[q_rt[m]].dN[2 + 3 * j] + sp[q_rt[m]].dN[2 + 3 * i] * sp[q_rt[m]].dN[0 + 3 * j]);
+          G[2] = gtt, G[4] = gst, G[5] = grt;
+          double Gij = 0.0;
+          for (int r = 0; r < 6; ++r)
+          {
+            double v = 0.0;
+            for (int q = 0; q < 6; ++q) v += TinvT[r + 6 * q] * G[q];
+            Gij += S[r] * v;
+          }
+          for (int d = 0; d < 3; ++d) Ke[(3 * i + d) + nd * (3 * j + d)] += fac * Gij;
+        }
+    }
+    return 0;
+  }
+
   // evaluate_eas_shape_functions_parameter_space (eas_helpers.hpp:205-275): M 6 x neas column-major
   void eas_shape_functions(int neas, const double* xi, double* M)
   {
@@ -2275,6 +2496,7 @@ namespace
     if (tech == ORC_TECH_MULF) return element_mulf(ct, matkind, par, action, X, u, hist, Ke, fe);
     if (tech == ORC_TECH_FBAR) return element_fbar(ct, matkind, par, action, X, u, Ke, fe);
     if (tech == ORC_TECH_MULF_FBAR) return element_fbar(ct, matkind, par, action, X, u, Ke, fe, hist);
+    if (tech == ORC_TECH_SHELL_ANS) return element_shell_ans(ct, matkind, par, action, X, u, Ke, fe);
     return element(ct, matkind, par, action, X, u, Ke, fe);
   }
 }  // namespace

@@ -177,7 +177,13 @@ static int run_generic(const GenericArgs& Ga)
     for (int i = 0; i < Ga.nn; ++i)
     {
       double Krow[NN][9], fi[3], dj = 1e300, df = 1e300;
-      if (generic_block_row<MAT, NN>(Ga, e, i, Krow, fi, dj, df)) ++bad;
+      bool neg;
+      if constexpr (NN == 8)
+        neg = Ga.dN_ans != nullptr ? generic_block_row_ans<MAT>(Ga, e, i, Krow, fi, dj, df)
+                                   : generic_block_row<MAT, NN>(Ga, e, i, Krow, fi, dj, df);
+      else
+        neg = generic_block_row<MAT, NN>(Ga, e, i, Krow, fi, dj, df);
+      if (neg) ++bad;
       const NodeRow nr = A.node_row[A.conn[e * Ga.nn + i]];
       if (nr.rowstart < 0) continue;
       for (int b = 0; b < 3; ++b) A.f[nr.frow + b] += fi[b];
@@ -209,7 +215,7 @@ static int run_generic_nn(const GenericArgs& Ga)
 extern "C" int emu_generic(int celltype, int matkind, const double* params, int linear, int stiff, int64_t n_ele,
     const int32_t* conn, const double* X, const double* u_col, const int32_t* pos, int pos_stride,
     const int64_t* node_rowstart, const int32_t* node_rowlen, const int32_t* node_frow, int64_t n_col_nodes, double* vals,
-    double* f, const double* gp_hist, int fbar)
+    double* f, const double* gp_hist, int fbar, int ans)
 {
   std::vector<NodeRow> node_row(n_col_nodes);
   for (int64_t k = 0; k < n_col_nodes; ++k)
@@ -224,6 +230,8 @@ extern "C" int emu_generic(int celltype, int matkind, const double* params, int 
   Ga.dN_gp = T.dN_gp.data(), Ga.dN_node = T.dN_node.data(), Ga.w = T.w.data();
   Ga.nn = T.nn, Ga.ngp = T.ngp, Ga.pos_stride = pos_stride, Ga.stiff = stiff;
   Ga.dN_cen = fbar ? T.dN_cen.data() : nullptr, Ga.hist_pts = T.ngp + (fbar ? 1 : 0);
+  Ga.dN_ans = (ans && !T.dN_ans.empty()) ? T.dN_ans.data() : nullptr, Ga.xi_gp = T.xi_gp.data();
+  if (ans && !Ga.dN_ans) return -4;
   if (matkind == MAT_COUP_NEOHOOKE) return run_generic_nn<MAT_COUP_NEOHOOKE>(Ga);
   if (matkind == MAT_ISO_VOL) return run_generic_nn<MAT_ISO_VOL>(Ga);
   return run_generic_nn<MAT_SVK>(Ga);
@@ -269,7 +277,7 @@ extern "C" int emu_generic_drucker_prager(int celltype, const double* in10, int 
   A.mp.hyper = nullptr, A.mp.fiber = nullptr, A.mp.ext = q, A.mp.hist = nullptr;
   Ga.dN_gp = T.dN_gp.data(), Ga.dN_node = T.dN_node.data(), Ga.w = T.w.data();
   Ga.nn = T.nn, Ga.ngp = T.ngp, Ga.pos_stride = pos_stride, Ga.stiff = stiff;
-  Ga.dN_cen = nullptr, Ga.hist_pts = T.ngp;
+  Ga.dN_cen = nullptr, Ga.hist_pts = T.ngp, Ga.dN_ans = nullptr, Ga.xi_gp = T.xi_gp.data();
   return T.nn == 8 ? run_generic_dp<8>(Ga) : (T.nn == 10 ? run_generic_dp<10>(Ga) : run_generic_dp<27>(Ga));
 }
 

@@ -295,7 +295,7 @@ def generic_drucker_prager(celltype, in10, conn, X, u_col, rowptr, colind, node_
 
 
 def generic(celltype, matkind, params, conn, X, u_col, rowptr, colind, node_row_lid, node_col_lid, n_row_nodes, linear=False,
-            stiff=True, gp_hist=None, fbar=False):
+            stiff=True, gp_hist=None, fbar=False, ans=False):
     """Emulated general kernel (generic_kernel.cuh) for the hyperelastic kinds 0..2 and any cell type of
     shape_tables.hpp (tet4 / hex20 blocks run through it on the device)."""
     conn = np.ascontiguousarray(conn, np.int32)
@@ -304,10 +304,10 @@ def generic(celltype, matkind, params, conn, X, u_col, rowptr, colind, node_row_
     vals, f = np.zeros(rowptr[-1]), np.zeros(3 * n_row_nodes)
     L = lib("post")
     L.emu_generic.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 4 + [C.c_int] + \
-        [C.c_void_p] * 3 + [C.c_int64] + [C.c_void_p] * 3 + [C.c_int]
+        [C.c_void_p] * 3 + [C.c_int64] + [C.c_void_p] * 3 + [C.c_int, C.c_int]
     rc = L.emu_generic(int(celltype), int(matkind), _p(np.ascontiguousarray(params, np.float64)), int(linear), int(stiff),
                        len(conn), _p(conn), _p(np.ascontiguousarray(X, np.float64)),
                        _p(np.ascontiguousarray(u_col, np.float64)), _p(pos), pos.shape[1], _p(rowstart), _p(rowlen),
-                       _p(frow), len(rowstart), _p(vals), _p(f), _p(gp_hist), int(fbar))
+                       _p(frow), len(rowstart), _p(vals), _p(f), _p(gp_hist), int(fbar), int(ans))
     assert rc == 0, rc
     return vals, f

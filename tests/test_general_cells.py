@@ -122,3 +122,28 @@ def test_emulated_general_kernel_fbar_matches_oracle(cell, mulf):
                 orc.update_prestress(ct, rm.conn, rm.X.ravel(), us, ohist)
                 emu.mulf_history(rm.celltype, rm.conn, rm.X.ravel(), us, phist, fbar=True)
                 assert np.abs(phist - ohist[:, :, :18]).max() <= 1e-13 * np.abs(ohist).max()
+
+
+def test_emulated_general_kernel_shell_ans_matches_oracle():
+    """TECH shell_ans on hex8 (ShellANSFormulation, src/solid_ele/4C_solid_ele_calc_shell_ans.hpp): sampling-point
+    interpolation of the transverse strain rows, T^-T formed from the inverse Jacobian, ANS geometric stiffness -- the
+    product's general-kernel arithmetic stepped on the CPU against the oracle (pinned to the reference's
+    solid_ele_hex8_Standard_shell_ans known answers, tests/test_post_actions.py)."""
+    rm = b200.partition.box_partition(b200.mesh.HEX8, (3, 2, 2), 0, 1)
+    rowptr, colind = orc.build_graph(orc.HEX8, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    maps = (rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    # a distorted mesh: jitter the interior nodes so that the Jacobians differ between the Gauss and sampling points
+    X = rm.X.copy()
+    rng = np.random.default_rng(4)
+    inner = np.all((X > 1e-9) & (X < 1 - 1e-9), axis=1)
+    X[inner] += 0.05 * rng.uniform(-1, 1, (int(inner.sum()), 3))
+    u = 2.0 * b200.mesh.displacement_field(X, rm.node_gid, 1.0, 0.4)
+    for mk, par in MATS.items():
+        rK, rf, nbad = orc.evaluate_assemble(orc.HEX8, mk, par, rm.conn, X.ravel(), u.ravel(), *maps, rowptr, colind,
+                                             tech=orc.TECH_SHELL_ANS)
+        K, f = emu.generic(rm.celltype, mk, par, rm.conn, X.ravel(), u.ravel(), rowptr, colind, *maps, ans=True)
+        ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, 1e-12)
+        assert ok and nbad == 0, (mk, wK, wf)
+        # and it is not the displacement-based element
+        K0, f0 = emu.generic(rm.celltype, mk, par, rm.conn, X.ravel(), u.ravel(), rowptr, colind, *maps)
+        assert np.abs(K - K0).max() > 1e-3 * np.abs(K0).max()

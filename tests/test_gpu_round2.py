@@ -1059,3 +1059,57 @@ def test_reference_linear_eas_cooks_known_answer_through_cuda_path(tech):
     (e,) = case["expected_disp"]
     assert abs(u[e["node"], e["dof"]] - e["value"]) < 1e-8, (e, u[e["node"], e["dof"]])
     asm.close()
+
+
+# ---- TECH shell_ans on hex8 (ShellANSFormulation, general kernel) ------------------------------------------------------
+@pytest.mark.parametrize("mk", list(GEN_MATS))
+def test_shell_ans_matches_oracle(mk):
+    rm = b200.partition.box_partition(b200.mesh.HEX8, (5, 4, 3), 0, 1)
+    rng = np.random.default_rng(4)
+    inner = np.all((rm.X > 1e-9) & (rm.X < 1 - 1e-9), axis=1)
+    rm.X[inner] += 0.03 * rng.uniform(-1, 1, (int(inner.sum()), 3))
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 0.2)
+    asm = b200.DeviceAssembler(rm, mk, GEN_MATS[mk], tech=capi.TECH_SHELL_ANS)
+    rowptr, colind = asm.graph()
+    asm.set_state("displacement", u.ravel())
+    K, f, err = asm.evaluate()
+    rK, rf, nbad = orc.evaluate_assemble(orc.HEX8, mk, GEN_MATS[mk], rm.conn, rm.X.ravel(), u.ravel(), rm.node_row_lid,
+                                         rm.node_col_lid, rm.n_row_nodes, rowptr, colind, nthreads=4, tech=orc.TECH_SHELL_ANS)
+    ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
+    assert ok and nbad == 0 and err.n_neg_jacobian == 0, (wK, wf)
+    _, f2, _ = asm.evaluate("struct_calc_internalforce")
+    assert np.abs(f2 - rf).max() <= RTOL * np.abs(rf).max()
+    asm.close()
+    # refused where the device has no kernel: wedge6 solid shell, shell_ans with KINEM linear
+    X, conn = b200.mesh.structured_wedge6((2, 2, 2))
+    ctx = capi.Context(0, 0, 1)
+    ctx.set_mesh(b200.mesh.WEDGE6, X, conn)
+    with pytest.raises(capi.B200SolidError) as ei:
+        ctx.set_element_properties(tech=capi.TECH_SHELL_ANS)
+    assert ei.value.code == capi.ERR_UNSUPPORTED
+    ctx.close()
+
+
+def test_reference_shell_ans_known_answers_through_cuda_path():
+    """RESULT DESCRIPTION displacements of tests/input_files/solid_ele_hex8_Standard_shell_ans.4C.yaml."""
+    import json
+    import os
+    from tests.helpers.newton import solve_case
+    case = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "integration_hex8_shell_ans.json")))
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    rm = b200.partition.serial_mesh(b200.mesh.HEX8, X, conn)
+    asm = b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, [case["material"]["YOUNG"], case["material"]["NUE"]],
+                               tech=capi.TECH_SHELL_ANS)
+    rowptr, colind = asm.graph()
+
+    def ev(u):
+        asm.set_state("displacement", u)
+        K, f, _ = asm.evaluate()
+        return rowptr, colind, K, f
+
+    u = solve_case(case, ev)
+    assert len(case["expected_disp"]) >= 12
+    for e in case["expected_disp"]:
+        assert abs(u[e["node"], e["dof"]] - e["value"]) < 1e-11, (e, u[e["node"], e["dof"]])
+    asm.close()
