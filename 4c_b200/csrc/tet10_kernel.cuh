@@ -308,7 +308,11 @@ namespace b200s
       facc[0] = facc[1] = facc[2] = 0.0;
       if (el >= EPW) return;
 
+#if defined(B200S_TET10_UNROLL_GP) && B200S_TET10_UNROLL_GP  // experiment: profiles/r02w_summary.md
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
       for (int g = 0; g < NGP; ++g)
       {
         const double* Gg = S.g + el * G_ESTRIDE + g * G_GSTRIDE;
