@@ -1010,8 +1010,37 @@ namespace b200s
     v = (v | (v << 2)) & 0x1249249249249249ull;
     return v;
   }
+  // Hilbert index of a point with 21-bit integer coordinates (Skilling's transpose form, then interleaved): a
+  // space-filling curve without the long jumps of the Z-order curve -- the set of partially assembled CSR rows behind the
+  // evaluation front stays smaller (option reorder = 2; A/B in profiles/r02z_summary.md)
+  __device__ __forceinline__ unsigned long long hilbert_key21(unsigned int x0, unsigned int x1, unsigned int x2)
+  {
+    unsigned int X[3] = {x0, x1, x2};
+    const unsigned int M = 1u << 20;
+    for (unsigned int Q = M; Q > 1; Q >>= 1)
+    {
+      const unsigned int P = Q - 1;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+      {
+        if (X[i] & Q)
+          X[0] ^= P;
+        else
+        {
+          const unsigned int t = (X[0] ^ X[i]) & P;
+          X[0] ^= t, X[i] ^= t;
+        }
+      }
+    }
+    X[1] ^= X[0], X[2] ^= X[1];
+    unsigned int t = 0;
+    for (unsigned int Q = M; Q > 1; Q >>= 1)
+      if (X[2] & Q) t ^= Q - 1;
+    X[0] ^= t, X[1] ^= t, X[2] ^= t;
+    return (spread21(X[0]) << 2) | (spread21(X[1]) << 1) | spread21(X[2]);
+  }
   __global__ void k_morton_keys(int nn, int64_t n_ele, const int32_t* conn, const double* X,
-      const double* box, unsigned long long* keys, int32_t* idx)
+      const double* box, unsigned long long* keys, int32_t* idx, int hilbert)
   {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_ele) return;
@@ -1020,14 +1049,16 @@ namespace b200s
     for (int k = 0; k < nc; ++k)
       for (int d = 0; d < 3; ++d) c[d] += X[3 * (int64_t)conn[e * nn + k] + d];
     unsigned long long key = 0;
+    unsigned int q[3];
     for (int d = 0; d < 3; ++d)
     {
       const double ext = box[3 + d] - box[d];
       double t = ext > 0 ? (c[d] / nc - box[d]) / ext : 0.0;
       t = fmin(fmax(t, 0.0), 1.0);
-      key |= spread21((unsigned long long)(t * 2097151.0)) << d;
+      q[d] = (unsigned int)(t * 2097151.0);
+      key |= spread21((unsigned long long)q[d]) << d;
     }
-    keys[e] = key;
+    keys[e] = hilbert ? hilbert_key21(q[2], q[1], q[0]) : key;
     idx[e] = (int32_t)e;
   }
   __global__ void k_permute_conn(int nn, int64_t n_ele, const int32_t* conn_in, const int32_t* idx,
@@ -2476,8 +2507,8 @@ extern "C"
       ctx->ctas_per_sm = (int)value;
     else if (!strcmp(key, "scatter_mode"))
       ctx->scatter_mode = (int)value;
-    else if (!strcmp(key, "reorder"))  // takes effect at the next set_mesh
-      ctx->reorder = value != 0;
+    else if (!strcmp(key, "reorder"))  // takes effect at the next set_mesh: 0 caller's order, 1 Z-order curve, 2 Hilbert curve
+      ctx->reorder = (int)value;
     else if (!strcmp(key, "double_buffer"))  // takes effect at the next set_graph / build_graph
       ctx->double_buffer = (int)value;  // 0 off, 1 memset on a side stream, 2 copy-engine zeroing on a side stream
     else if (!strcmp(key, "pipeline_phases"))  // takes effect at the next set_graph / build_graph
@@ -2607,7 +2638,7 @@ extern "C"
       CK(cudaMalloc((void**)&ctx->d_ele_id, 4 * (size_t)n_col_eles));
       CK(cudaMalloc((void**)&conn2, 4 * (size_t)n_col_eles * T.nn));
       k_bbox<<<ctx->n_sm * 4, 256, 0, st>>>(n_col_nodes, ctx->dX, d_box);
-      k_morton_keys<<<nblk(n_col_eles), 256, 0, st>>>(T.nn, n_col_eles, ctx->dconn, ctx->dX, d_box, k0, i0);
+      k_morton_keys<<<nblk(n_col_eles), 256, 0, st>>>(T.nn, n_col_eles, ctx->dconn, ctx->dX, d_box, k0, i0, ctx->reorder == 2);
       size_t tb = 0;
       cub::DeviceRadixSort::SortPairs(nullptr, tb, k0, k1, i0, ctx->d_ele_id, n_col_eles, 0, 63, st);
       CK(cudaMalloc(&tmp, tb));
