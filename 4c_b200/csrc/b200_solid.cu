@@ -1972,7 +1972,10 @@ namespace
       if (summand_needs_fiber(ctx->hm.s[k].kind)) return true;
     return false;
   }
-  inline int eas_neas(int tech) { return tech == B200S_TECH_EAS_MILD ? 9 : (tech == B200S_TECH_EAS_FULL ? 21 : 0); }
+  inline int eas_neas(int tech)
+  {
+    return tech == B200S_TECH_EAS_MILD ? 9 : (tech == B200S_TECH_EAS_FULL ? 21 : (tech == B200S_TECH_SHELL_EAS ? 7 : 0));
+  }
   // MulfHistoryData per element: one per Gauss point, with TECH fbar one more for the centroid (GlobalHistory of
   // MulfFBarFormulation, 4C_solid_ele_calc_mulf_fbar.hpp:112-116)
   inline int mulf_points(const b200s_ctx* ctx) { return ctx->ngp + (ctx->tech == B200S_TECH_FBAR ? 1 : 0); }
@@ -2048,6 +2051,7 @@ namespace
   static int launch_hex8_eas(b200s_ctx* ctx, const EvalArgs& A)
   {
     if (!ctx->d_eas_hist) return fail(ctx, B200S_ERR_INVALID, "EAS history missing");
+    if constexpr (NEAS != 7)  // eastype_sh8_7 (TECH shell_eas): FMA kernel only
     if (ctx->eas_mma || MAT == MAT_PLASTIC)  // MAT_PLASTIC: tensor-core kernel only (one instantiation less)
     {
       auto kern = k_hex8_eas_mma_eval_assemble<MAT, STIFF, NEAS>;
@@ -2062,7 +2066,7 @@ namespace
       ctx->launches += 1;
       return 0;
     }
-    if constexpr (MAT == MAT_PLASTIC) return fail(ctx, B200S_ERR_UNSUPPORTED, "unreachable");
+    if constexpr (MAT == MAT_PLASTIC) return fail(ctx, B200S_ERR_UNSUPPORTED, "MAT_Struct_PlasticNlnLogNeoHooke with TECH shell_eas has no device kernel");
     auto kern = k_hex8_eas_eval_assemble<MAT == MAT_PLASTIC ? MAT_VISCO : MAT, STIFF, NEAS>;
     constexpr size_t bytes = hex8_eas_smem_bytes<NEAS>();
     if (set_smem_attr(kern, bytes)) return fail(ctx, B200S_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed", bytes);
@@ -2079,6 +2083,7 @@ namespace
   template <int MAT, bool STIFF>
   static int launch_hex8_eas_any(b200s_ctx* ctx, const EvalArgs& A)
   {
+    if (ctx->tech == B200S_TECH_SHELL_EAS) return launch_hex8_eas<MAT, STIFF, 7>(ctx, A);
     return ctx->tech == B200S_TECH_EAS_MILD ? launch_hex8_eas<MAT, STIFF, 9>(ctx, A)
                                             : launch_hex8_eas<MAT, STIFF, 21>(ctx, A);
   }
@@ -2110,7 +2115,9 @@ namespace b200s_parts
   {
     const unsigned grid = nblk(32 * ctx->n_col_eles, 128);
     if (!grid) return 0;
-    if (neas == 9)
+    if (neas == 7)
+      k_eas_recover<7><<<grid, 128, 0, ctx->stream>>>(ctx->n_col_eles, ctx->dconn, ctx->d_du_col, step_length, ctx->d_eas_hist);
+    else if (neas == 9)
       k_eas_recover<9><<<grid, 128, 0, ctx->stream>>>(ctx->n_col_eles, ctx->dconn, ctx->d_du_col, step_length,
           ctx->d_eas_hist);
     else
@@ -2393,8 +2400,7 @@ namespace
       case B200S_HEX27:
         return b200s_parts::launch_hex27(ctx, A, STIFF);
       case B200S_HEX8:
-        if (ctx->tech == B200S_TECH_EAS_MILD || ctx->tech == B200S_TECH_EAS_FULL)
-          return b200s_parts::launch_hex8_eas(ctx, A, STIFF);
+        if (eas_neas(ctx->tech)) return b200s_parts::launch_hex8_eas(ctx, A, STIFF);
         return b200s_parts::launch_hex8(ctx, A, STIFF);
       case B200S_TET10:
         return b200s_parts::launch_tet10(ctx, A, STIFF);
@@ -2671,7 +2677,7 @@ extern "C"
       return fail(ctx, B200S_ERR_UNSUPPORTED, "kinematic type %d has no device kernel", kinem_type);
     // linear kinematics: displacement based, or EAS (EASFormulation<hex8, h8_9 | h8_21, linear>,
     // 4C_solid_ele_factory.hpp:71-74); F-bar / MULF have no linear variant in the reference
-    const bool eas_tech = element_technology == B200S_TECH_EAS_MILD || element_technology == B200S_TECH_EAS_FULL;
+    const bool eas_tech = element_technology == B200S_TECH_EAS_MILD || element_technology == B200S_TECH_EAS_FULL;  // (not shell_eas)
     if (kinem_type == B200S_KINEM_LINEAR &&
         ((element_technology != B200S_TECH_NONE && !eas_tech) || prestress_technology != B200S_PRESTRESS_NONE))
       return fail(ctx, B200S_ERR_UNSUPPORTED, "KINEM linear with F-bar or prestress has no device kernel");
@@ -2684,7 +2690,7 @@ extern "C"
         element_technology != B200S_TECH_FBAR)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "MULF prestress with element technology %d has no device kernel",
           element_technology);
-    if (element_technology < B200S_TECH_NONE || element_technology > B200S_TECH_SHELL_ANS)
+    if (element_technology < B200S_TECH_NONE || element_technology > B200S_TECH_SHELL_EAS)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "element technology %d has no device kernel",
           element_technology);
     // the reference offers F-bar and EAS for hex8 only among the device cell types
@@ -2695,9 +2701,9 @@ extern "C"
           "F-bar is a hex8 / pyramid5 technology, EAS a hex8 technology, shell_ans on the device a hex8 technology (the "
           "wedge6 solid shell stays on the CPU path)");
     // ShellANSFormulation exists for KINEM nonlinear without prestress (4C_solid_ele_factory.cpp)
-    if (element_technology == B200S_TECH_SHELL_ANS &&
+    if ((element_technology == B200S_TECH_SHELL_ANS || element_technology == B200S_TECH_SHELL_EAS) &&
         (kinem_type != B200S_KINEM_NONLINEAR_TOTLAG || prestress_technology != B200S_PRESTRESS_NONE))
-      return fail(ctx, B200S_ERR_UNSUPPORTED, "TECH shell_ans: KINEM nonlinear, no prestress");
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "TECH shell_ans / shell_eas: KINEM nonlinear, no prestress");
     const int old_points = mulf_points(ctx);
     ctx->kinem = kinem_type;
     dfree(ctx->d_hist_old);

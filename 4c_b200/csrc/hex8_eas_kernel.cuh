@@ -41,6 +41,10 @@ namespace b200s
     // (0 r, 1 s, 2 t, 3 rs, 4 rt, 5 st) of column c
     __constant__ int c_eas_row[21] = {0, 1, 2, 3, 3, 4, 4, 5, 5, 3, 3, 4, 4, 5, 5, 0, 0, 1, 1, 2, 2};
     __constant__ int c_eas_mono[21] = {0, 1, 2, 0, 1, 1, 2, 0, 2, 4, 5, 3, 4, 3, 5, 3, 4, 3, 5, 4, 5};
+    // eastype_sh8_7 (TECH shell_eas, the solid-shell interpolation with t = thickness direction, eas_helpers.hpp:330-357):
+    // r | s | t, rt, st | r, s in the rows rr | ss | tt | rs
+    __constant__ int c_eas_row7[7] = {0, 1, 2, 3, 3, 2, 2};
+    __constant__ int c_eas_mono7[7] = {0, 1, 2, 0, 1, 4, 5};
     __device__ __forceinline__ double monomial(int m, double r, double s, double t)
     {
       return m == 0 ? r : m == 1 ? s : m == 2 ? t : m == 3 ? r * s : m == 4 ? r * t : s * t;
@@ -339,7 +343,9 @@ namespace b200s
           {
             constexpr int rows[21] = {0, 1, 2, 3, 3, 4, 4, 5, 5, 3, 3, 4, 4, 5, 5, 0, 0, 1, 1, 2, 2};
             constexpr int mono[21] = {0, 1, 2, 0, 1, 1, 2, 0, 2, 4, 5, 3, 4, 3, 5, 3, 4, 3, 5, 4, 5};
-            v[rows[c]] = fma(monomial(mono[c], xr, xs, xt), alpha[c], v[rows[c]]);
+            constexpr int rows7[7] = {0, 1, 2, 3, 3, 2, 2}, mono7[7] = {0, 1, 2, 0, 1, 4, 5};  // eastype_sh8_7
+            const int rw = NEAS == 7 ? rows7[c < 7 ? c : 0] : rows[c], mn = NEAS == 7 ? mono7[c < 7 ? c : 0] : mono[c];
+            v[rw] = fma(monomial(mn, xr, xs, xt), alpha[c], v[rw]);
           }
 #pragma unroll
           for (int k = 0; k < 6; ++k)
@@ -374,7 +380,7 @@ namespace b200s
       const int r_ = lane < ND ? lane : 0;      // lanes >= 24 shadow row 0, results unused
       const int ni = r_ / 3, ei = r_ - 3 * ni;  // node and direction of the row
       const int a_ = lane < NEAS ? lane : 0;
-      const int arow = c_eas_row[a_], amono = c_eas_mono[a_];
+      const int arow = NEAS == 7 ? c_eas_row7[a_] : c_eas_row[a_], amono = NEAS == 7 ? c_eas_mono7[a_] : c_eas_mono[a_];
       double facc = 0.0;
       double mK[NEAS];
       double* aug = sm + L::AUG;

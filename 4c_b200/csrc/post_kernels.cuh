@@ -197,7 +197,15 @@ namespace b200s
     const double mono[21] = {r, s, t, r, s, s, t, r, t, r * t, s * t, r * s, r * t, r * s, s * t, r * s, r * t,
         r * s, s * t, r * t, s * t};
     double v[6] = {0, 0, 0, 0, 0, 0};
-    for (int c = 0; c < A.eas_neas; ++c) v[rows[c]] += mono[c] * alpha[c];
+    if (A.eas_neas == 7)
+    {
+      // eastype_sh8_7 (TECH shell_eas): r | s | t, rt, st | r, s in the rows rr | ss | tt | rs
+      const int rows7[7] = {0, 1, 2, 3, 3, 2, 2};
+      const double mono7[7] = {r, s, t, r, s, r * t, s * t};
+      for (int c = 0; c < 7; ++c) v[rows7[c]] += mono7[c] * alpha[c];
+    }
+    else
+      for (int c = 0; c < A.eas_neas; ++c) v[rows[c]] += mono[c] * alpha[c];
     double Cd[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) Cd[k] = C[k];

@@ -158,8 +158,10 @@ extern "C"
     B200S_TECH_FBAR = 1,     /* hex8, pyramid5: 4C_solid_ele_calc_fbar.hpp (pyramid5 and the MULF combination: general kernel) */
     B200S_TECH_EAS_MILD = 2, /* hex8, 9 enhanced strain parameters: 4C_solid_ele_calc_eas.hpp */
     B200S_TECH_EAS_FULL = 3, /* hex8, 21 parameters */
-    B200S_TECH_SHELL_ANS = 4 /* hex8 solid shell with assumed natural strains (thickness = t-direction of the element):
-                                4C_solid_ele_calc_shell_ans.hpp; general kernel.  wedge6 shell_ans, shell_eas, shell_eas_ans: CPU path */
+    B200S_TECH_SHELL_ANS = 4, /* hex8 solid shell with assumed natural strains (thickness = t-direction of the element):
+                                 4C_solid_ele_calc_shell_ans.hpp; general kernel.  wedge6 shell_ans, shell_eas_ans: CPU path */
+    B200S_TECH_SHELL_EAS = 5 /* hex8, EAS with the 7 solid-shell modes (eastype_sh8_7, t = thickness direction):
+                                EASSolidIntegrator<hex8, eastype_sh8_7, nonlinearTotLag>; the FMA EAS kernel */
   } b200s_element_technology;
   typedef enum
   {

@@ -2013,10 +2013,14 @@ namespace
   bool is_eas(int tech)
   {
     return tech == ORC_TECH_EAS_MILD || tech == ORC_TECH_EAS_FULL || tech == ORC_TECH_EAS_MILD_LINEAR ||
-           tech == ORC_TECH_EAS_FULL_LINEAR;
+           tech == ORC_TECH_EAS_FULL_LINEAR || tech == ORC_TECH_SHELL_EAS;
   }
   bool is_eas_linear(int tech) { return tech == ORC_TECH_EAS_MILD_LINEAR || tech == ORC_TECH_EAS_FULL_LINEAR; }
-  int eas_num(int tech) { return (tech == ORC_TECH_EAS_MILD || tech == ORC_TECH_EAS_MILD_LINEAR) ? 9 : 21; }
+  int eas_num(int tech)
+  {
+    if (tech == ORC_TECH_SHELL_EAS) return 7;  // eastype_sh8_7
+    return (tech == ORC_TECH_EAS_MILD || tech == ORC_TECH_EAS_MILD_LINEAR) ? 9 : 21;
+  }
 
   // dense inverse by Gauss-Jordan with partial pivoting (the reference calls LAPACK getrf/getri through
   // FixedSizeSerialDenseSolver::invert; same operator up to round-off)
@@ -2312,6 +2316,13 @@ namespace
   {
     std::fill(M, M + 6 * neas, 0.0);
     auto at = [&](int r, int c) -> double& { return M[r + 6 * c]; };
+    if (neas == 7)
+    {
+      // eastype_sh8_7 (:330-357): the solid-shell interpolation with t = thickness direction
+      at(0, 0) = xi[0], at(1, 1) = xi[1], at(2, 2) = xi[2], at(2, 5) = xi[0] * xi[2], at(2, 6) = xi[1] * xi[2];
+      at(3, 3) = xi[0], at(3, 4) = xi[1];
+      return;
+    }
     at(0, 0) = xi[0], at(1, 1) = xi[1], at(2, 2) = xi[2];
     at(3, 3) = xi[0], at(3, 4) = xi[1], at(4, 5) = xi[1], at(4, 6) = xi[2], at(5, 7) = xi[0], at(5, 8) = xi[2];
     if (neas == 21)

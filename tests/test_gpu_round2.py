@@ -1113,3 +1113,48 @@ def test_reference_shell_ans_known_answers_through_cuda_path():
     for e in case["expected_disp"]:
         assert abs(u[e["node"], e["dof"]] - e["value"]) < 1e-11, (e, u[e["node"], e["dof"]])
     asm.close()
+
+
+# ---- TECH shell_eas on hex8: EAS with the seven solid-shell modes (eastype_sh8_7), the FMA EAS kernel ------------------
+def test_shell_eas_matches_oracle_and_known_answers():
+    import json
+    import os
+    from tests.helpers.newton import solve_case
+    rm = b200.partition.box_partition(b200.mesh.HEX8, (5, 4, 3), 0, 1)
+    u = 0.5 * b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 0.2)
+    mk, par = capi.MAT_COUP_NEOHOOKE, [200.0, 0.25]
+    asm = b200.DeviceAssembler(rm, mk, par, tech=capi.TECH_SHELL_EAS)
+    rowptr, colind = asm.graph()
+    hist = orc.eas_new_history(orc.TECH_SHELL_EAS, rm.n_col_eles)
+    maps = (rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, rowptr, colind)
+    rng = np.random.default_rng(5)
+    for it in range(2):
+        us = (1.0 + 0.5 * it) * u.ravel()
+        asm.set_state("displacement", us)
+        K, f, err = asm.evaluate()
+        rK, rf, nbad = orc.evaluate_assemble(orc.HEX8, mk, par, rm.conn, rm.X.ravel(), us, *maps, tech=orc.TECH_SHELL_EAS, hist=hist)
+        ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, 1e-10)
+        assert ok and nbad == 0 and err.n_neg_jacobian == 0, (it, wK, wf)
+        du = 1e-2 * rng.standard_normal(asm.n_rows)
+        asm.recover(du)
+        orc.eas_recover(orc.TECH_SHELL_EAS, rm.conn, du, hist)
+        dh = asm.ctx.get_element_history().reshape(hist.shape)
+        assert np.abs(dh[:, :14] - hist[:, :14]).max() <= 1e-8 * max(np.abs(hist[:, :14]).max(), 1e-6)
+    asm.close()
+    # the reference's known answers (solid_ele_hex8_Standard_shell_eas.4C.yaml) through the CUDA path
+    case = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "integration_hex8_shell_eas.json")))
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    rm = b200.partition.serial_mesh(b200.mesh.HEX8, X, conn)
+    asm = b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, [case["material"]["YOUNG"], case["material"]["NUE"]], tech=capi.TECH_SHELL_EAS)
+    rowptr, colind = asm.graph()
+
+    def ev(uu):
+        asm.set_state("displacement", uu)
+        K, f, _ = asm.evaluate()
+        return rowptr, colind, K, f
+
+    uu = solve_case(case, ev, recover=lambda du: asm.recover(du, 1.0))
+    for e in case["expected_disp"]:
+        assert abs(uu[e["node"], e["dof"]] - e["value"]) < 1e-10, (e, uu[e["node"], e["dof"]])
+    asm.close()
