@@ -30,7 +30,7 @@ SUMMANDS = ["COUP_NEOHOOKE", "COUP_MOONEYRIVLIN", "COUP_LOGNEOHOOKE", "COUP_LOGM
             "ISO_OGDEN", "COUP_VARGA", "ISO_VARGA"]
 SUM = {name: i for i, name in enumerate(SUMMANDS)}
 KINEM_NONLINEAR_TOTLAG, KINEM_LINEAR = 0, 1
-TECH_NONE, TECH_FBAR, TECH_EAS_MILD, TECH_EAS_FULL, TECH_SHELL_ANS, TECH_SHELL_EAS = 0, 1, 2, 3, 4, 5
+TECH_NONE, TECH_FBAR, TECH_EAS_MILD, TECH_EAS_FULL, TECH_SHELL_ANS, TECH_SHELL_EAS, TECH_SHELL_EAS_ANS = 0, 1, 2, 3, 4, 5, 6
 PRESTRESS_NONE, PRESTRESS_MULF = 0, 1
 
 # every symbol include/b200_solid.h declares (checked by the CPU test-suite)

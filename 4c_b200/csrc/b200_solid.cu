@@ -1974,7 +1974,7 @@ namespace
   }
   inline int eas_neas(int tech)
   {
-    return tech == B200S_TECH_EAS_MILD ? 9 : (tech == B200S_TECH_EAS_FULL ? 21 : (tech == B200S_TECH_SHELL_EAS ? 7 : 0));
+    return tech == B200S_TECH_EAS_MILD ? 9 : (tech == B200S_TECH_EAS_FULL ? 21 : ((tech == B200S_TECH_SHELL_EAS || tech == B200S_TECH_SHELL_EAS_ANS) ? 7 : 0));
   }
   // MulfHistoryData per element: one per Gauss point, with TECH fbar one more for the centroid (GlobalHistory of
   // MulfFBarFormulation, 4C_solid_ele_calc_mulf_fbar.hpp:112-116)
@@ -2351,14 +2351,24 @@ namespace
     Ga.dN_cen = ctx->tech == B200S_TECH_FBAR ? ctx->d_dN_cen : nullptr;
     Ga.hist_pts = mulf_points(ctx);
     // TECH shell_ans (hex8): sampling-point tables
-    Ga.dN_ans = ctx->tech == B200S_TECH_SHELL_ANS ? ctx->d_dN_ans : nullptr;
+    const bool ans = ctx->tech == B200S_TECH_SHELL_ANS || ctx->tech == B200S_TECH_SHELL_EAS_ANS;
+    Ga.dN_ans = ans ? ctx->d_dN_ans : nullptr;
     Ga.xi_gp = ctx->d_xi_gp;
-    if (ctx->tech == B200S_TECH_SHELL_ANS && (ctx->celltype != B200S_HEX8 || !ctx->d_dN_ans))
-      return fail(ctx, B200S_ERR_UNSUPPORTED, "TECH shell_ans on the device: hex8 blocks");
+    if (ans && (ctx->celltype != B200S_HEX8 || !ctx->d_dN_ans))
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "TECH shell_ans / shell_eas_ans on the device: hex8 blocks");
+    // TECH shell_eas_ans: the seven EAS modes on top (history and centroid table of the block's elements)
+    Ga.eas_hist = nullptr, Ga.eas_t0 = nullptr;
+    if (ctx->tech == B200S_TECH_SHELL_EAS_ANS)
+    {
+      static_assert(ANS_EAS_HIST == hex8eas::hist_size(ANS_NEAS) && ANS_EAS_T0_STRIDE == hex8eas::T0_STRIDE, "EAS history layout");
+      if (!ctx->d_eas_hist || !ctx->d_eas_t0) return fail(ctx, B200S_ERR_INVALID, "EAS history missing");
+      Ga.eas_hist = ctx->d_eas_hist + A.e_begin * ANS_EAS_HIST, Ga.eas_t0 = ctx->d_eas_t0 + A.e_begin * ANS_EAS_T0_STRIDE;
+    }
     const unsigned grid = nblk(A.n_ele * ctx->nn, 64);
     if (!grid) return 0;
-    if (ctx->tech != B200S_TECH_NONE && ctx->tech != B200S_TECH_FBAR && ctx->tech != B200S_TECH_SHELL_ANS)
-      return fail(ctx, B200S_ERR_UNSUPPORTED, "the general kernel evaluates displacement-based, F-bar and shell_ans blocks only (no EAS)");
+    if (ctx->tech != B200S_TECH_NONE && ctx->tech != B200S_TECH_FBAR && !ans)
+      return fail(ctx, B200S_ERR_UNSUPPORTED,
+          "the general kernel evaluates displacement-based, F-bar, shell_ans and shell_eas_ans blocks only (no plain EAS)");
     switch (ctx->matkind)
     {
       case B200S_MAT_COUP_NEOHOOKE:
@@ -2391,7 +2401,7 @@ namespace
     if (ctx->matkind < 0) return fail(ctx, B200S_ERR_INVALID, "material not set");
     if (ctx->general_tangent || ctx->general_kernel || is_general_cell(ctx->celltype) ||
         (ctx->tech == B200S_TECH_FBAR && ctx->prestress == B200S_PRESTRESS_MULF) || ctx->tech == B200S_TECH_SHELL_ANS ||
-        (ctx->matkind == B200S_MAT_PLASTIC_NLNLOG && ctx->celltype != B200S_HEX8))  // fast kernels: hex8 (+ EAS) only
+        ctx->tech == B200S_TECH_SHELL_EAS_ANS || (ctx->matkind == B200S_MAT_PLASTIC_NLNLOG && ctx->celltype != B200S_HEX8))  // fast kernels: hex8 (+ EAS) only
       return launch_generic(ctx, A, STIFF);
     if (ctx->tech != B200S_TECH_NONE && ctx->celltype != B200S_HEX8)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "element technology %d needs hex8", ctx->tech);
@@ -2690,7 +2700,7 @@ extern "C"
         element_technology != B200S_TECH_FBAR)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "MULF prestress with element technology %d has no device kernel",
           element_technology);
-    if (element_technology < B200S_TECH_NONE || element_technology > B200S_TECH_SHELL_EAS)
+    if (element_technology < B200S_TECH_NONE || element_technology > B200S_TECH_SHELL_EAS_ANS)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "element technology %d has no device kernel",
           element_technology);
     // the reference offers F-bar and EAS for hex8 only among the device cell types
@@ -2701,9 +2711,10 @@ extern "C"
           "F-bar is a hex8 / pyramid5 technology, EAS a hex8 technology, shell_ans on the device a hex8 technology (the "
           "wedge6 solid shell stays on the CPU path)");
     // ShellANSFormulation exists for KINEM nonlinear without prestress (4C_solid_ele_factory.cpp)
-    if ((element_technology == B200S_TECH_SHELL_ANS || element_technology == B200S_TECH_SHELL_EAS) &&
+    if ((element_technology == B200S_TECH_SHELL_ANS || element_technology == B200S_TECH_SHELL_EAS ||
+            element_technology == B200S_TECH_SHELL_EAS_ANS) &&
         (kinem_type != B200S_KINEM_NONLINEAR_TOTLAG || prestress_technology != B200S_PRESTRESS_NONE))
-      return fail(ctx, B200S_ERR_UNSUPPORTED, "TECH shell_ans / shell_eas: KINEM nonlinear, no prestress");
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "TECH shell_ans / shell_eas / shell_eas_ans: KINEM nonlinear, no prestress");
     const int old_points = mulf_points(ctx);
     ctx->kinem = kinem_type;
     dfree(ctx->d_hist_old);
@@ -4087,8 +4098,9 @@ extern "C"
       return fail(ctx, B200S_ERR_INVALID, "set_mesh and set_material must precede this action");
     if (material_needs_fibers(ctx) && !ctx->d_fibers)
       return fail(ctx, B200S_ERR_INVALID, "the material has a fibre summand: b200s_set_element_fibers first");
-    if (ctx->tech == B200S_TECH_SHELL_ANS)
-      return fail(ctx, B200S_ERR_UNSUPPORTED, "stress / energy output of shell_ans blocks has no device kernel (CPU path)");
+    if (ctx->tech == B200S_TECH_SHELL_ANS || ctx->tech == B200S_TECH_SHELL_EAS_ANS)
+      return fail(ctx, B200S_ERR_UNSUPPORTED,
+          "stress / energy output of shell_ans / shell_eas_ans blocks has no device kernel (CPU path)");
     PostArgs P;
     P.X = ctx->dX, P.u = ctx->d_u_col, P.conn = ctx->dconn, P.per_ele_param = ctx->d_per_ele;
     P.fibers = ctx->d_fibers;

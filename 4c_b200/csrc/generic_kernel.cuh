@@ -27,7 +27,106 @@ namespace b200s
     const double* xi_gp;    // [ngp][3] Gauss point coordinates (ANS interpolation weights)
     int nn, ngp, pos_stride, stiff;
     int hist_pts;           // MULF histories per element: ngp, or ngp + 1 with TECH fbar (the centroid's follows the points')
+    double* eas_hist;       // TECH shell_eas_ans: EAS history of the block's elements (alpha_inc | alpha | s | invKaa | Kda,
+                            // hex8eas::hist_size(7) doubles per element), nullptr otherwise
+    const double* eas_t0;   // ... and the centroid transformation T0^-T[36], detJ0 (stride ANS_EAS_T0_STRIDE)
   };
+
+  // ---- TECH shell_eas_ans on hex8: ShellEASANSFormulation<hex8, eastype_sh8_7> (4C_solid_ele_calc_shell_eas_ans.hpp:70-343).
+  // The thread of row node i integrates K_aa, s (the same numbers in the eight threads of an element) and its three rows of
+  // K_da next to the ANS block row; the rows meet in the element's history (which the reference keeps too, for recover),
+  // then every thread condenses its block row: K_i: -= K_da,i K_aa^-1 K_da^T, f_i -= K_da,i K_aa^-1 s.
+  constexpr int ANS_NEAS = 7;
+  constexpr int ANS_EAS_HIST = 3 * ANS_NEAS + ANS_NEAS * ANS_NEAS + 24 * ANS_NEAS;
+  constexpr int ANS_EAS_T0_STRIDE = 40;
+  struct AnsEas
+  {
+    double Kaa[ANS_NEAS * ANS_NEAS], s[ANS_NEAS], Kda[3][ANS_NEAS];
+  };
+
+  // in-place inverse by Gauss-Jordan with partial pivoting (the reference: LAPACK getrf / getri through
+  // solve_for_inverse_ignoring_errors, shell_eas_ans.hpp:231)
+  template <int N>
+  B2_HD void dense_inverse_small(double* A /*r + N c*/)
+  {
+    int perm[N];
+    for (int k = 0; k < N; ++k) perm[k] = k;
+    for (int k = 0; k < N; ++k)
+    {
+      int p = k;
+      double best = fabs(A[k + N * k]);
+      for (int r = k + 1; r < N; ++r)
+        if (fabs(A[r + N * k]) > best) best = fabs(A[r + N * k]), p = r;
+      if (p != k)
+      {
+        for (int c = 0; c < N; ++c)
+        {
+          const double t = A[k + N * c];
+          A[k + N * c] = A[p + N * c], A[p + N * c] = t;
+        }
+        const int t = perm[k];
+        perm[k] = perm[p], perm[p] = t;
+      }
+      const double piv = 1.0 / A[k + N * k];
+      A[k + N * k] = 1.0;
+      for (int c = 0; c < N; ++c) A[k + N * c] *= piv;
+      for (int r = 0; r < N; ++r)
+      {
+        if (r == k) continue;
+        const double f = A[r + N * k];
+        A[r + N * k] = 0.0;
+        for (int c = 0; c < N; ++c) A[r + N * c] = fma(-f, A[k + N * c], A[r + N * c]);
+      }
+    }
+    // the row exchanges of A become column exchanges of the inverse: column perm[k] of A^-1 is column k of the result
+    double tmp[N * N];
+    for (int k = 0; k < N; ++k)
+      for (int r = 0; r < N; ++r) tmp[r + N * perm[k]] = A[r + N * k];
+    for (int q = 0; q < N * N; ++q) A[q] = tmp[q];
+  }
+
+  // thread i of the element: its K_da rows into the history; thread 0 also s and K_aa^-1 (reset_condensed_variable_integration
+  // + integrate_eas + prepare_condensed_contribution).  ea.Kaa holds the inverse afterwards.
+  B2_HD void ans_eas_store(double* h, int i, AnsEas& ea)
+  {
+    dense_inverse_small<ANS_NEAS>(ea.Kaa);
+    double* Kda = h + 3 * ANS_NEAS + ANS_NEAS * ANS_NEAS;
+    for (int d = 0; d < 3; ++d)
+      for (int c = 0; c < ANS_NEAS; ++c) Kda[(3 * i + d) + 24 * c] = ea.Kda[d][c];
+    if (i != 0) return;
+    for (int c = 0; c < ANS_NEAS; ++c) h[2 * ANS_NEAS + c] = ea.s[c];
+    for (int q = 0; q < ANS_NEAS * ANS_NEAS; ++q) h[3 * ANS_NEAS + q] = ea.Kaa[q];
+  }
+
+  // add_condensed_contribution_to_force_vector / _to_stiffness_matrix (shell_eas_ans.hpp:300-320) for block row i; every
+  // K_da row of the element is in the history by now
+  B2_HD void ans_eas_condense(const double* h, int i, const AnsEas& ea, bool stiff, double (*Krow)[9], double* fi)
+  {
+    const double* Kda = h + 3 * ANS_NEAS + ANS_NEAS * ANS_NEAS;
+    double m[3][ANS_NEAS];  // -K_da,i K_aa^-1
+    for (int b = 0; b < 3; ++b)
+      for (int c = 0; c < ANS_NEAS; ++c)
+      {
+        double v = 0.0;
+        for (int k = 0; k < ANS_NEAS; ++k) v = fma(ea.Kda[b][k], ea.Kaa[k + ANS_NEAS * c], v);
+        m[b][c] = -v;
+      }
+    for (int b = 0; b < 3; ++b)
+    {
+      double v = 0.0;
+      for (int c = 0; c < ANS_NEAS; ++c) v = fma(m[b][c], ea.s[c], v);
+      fi[b] += v;
+    }
+    if (!stiff) return;
+    for (int j = 0; j < 8; ++j)
+      for (int b = 0; b < 3; ++b)
+        for (int c = 0; c < 3; ++c)
+        {
+          double v = 0.0;
+          for (int k = 0; k < ANS_NEAS; ++k) v = fma(m[b][k], Kda[(3 * j + c) + 24 * k], v);
+          Krow[j][b + 3 * c] += v;
+        }
+  }
 
   // S[6], Cm36[I + 6 J] of the block's material at one point (C = tensor components 00,11,22,01,12,02)
   template <int MAT>
@@ -283,9 +382,16 @@ namespace b200s
 
   template <int MAT>
   B2_HD bool generic_block_row_ans(const GenericArgs& Ga, int64_t e, int i, double (*Krow)[9], double* fi, double& detJ_min,
-      double& detF_min)
+      double& detF_min, AnsEas* ea = nullptr)
   {
     constexpr int NN = 8;
+    if (ea)
+    {
+      for (double& v : ea->Kaa) v = 0.0;
+      for (double& v : ea->s) v = 0.0;
+      for (int d = 0; d < 3; ++d)
+        for (int c = 0; c < ANS_NEAS; ++c) ea->Kda[d][c] = 0.0;
+    }
     const EvalArgs& A = Ga.A;
     double X[NN][3], x[NN][3];
     const int32_t* ce = A.conn + e * NN;
@@ -349,10 +455,25 @@ namespace b200s
         rt = fma(w_rt[m], rows(Jcs[2 * m], 0, 2) - rows(Jrs[2 * m], 0, 2), rt);
       }
       El[2] = 0.5 * tt, El[4] = st, El[5] = rt;
+      // TECH shell_eas_ans: m_tilde = detJ0 / detJ T0^-T M(xi) with the seven modes r | s | t, rt, st | r, s in the rows
+      // rr | ss | tt | rs (eastype_sh8_7, eas_helpers.hpp:330-357, :438-453); strain-like rows
+      double Mt[6][ANS_NEAS];
+      if (ea)
+      {
+        const double* t0 = Ga.eas_t0 + e * ANS_EAS_T0_STRIDE;
+        constexpr int rows7[ANS_NEAS] = {0, 1, 2, 3, 3, 2, 2};
+        const double mono7[ANS_NEAS] = {xi[0], xi[1], xi[2], xi[0], xi[1], xi[0] * xi[2], xi[1] * xi[2]};
+        const double sc = t0[36] / detJ;
+        for (int c = 0; c < ANS_NEAS; ++c)
+          for (int r = 0; r < 6; ++r) Mt[r][c] = sc * t0[r + 6 * rows7[c]] * mono7[c];
+      }
+      const double* alpha = ea ? Ga.eas_hist + e * ANS_EAS_HIST + ANS_NEAS : nullptr;
       for (int r = 0; r < 6; ++r)
       {
         double v = 0.0;
         for (int q = 0; q < 6; ++q) v = fma(T[r + 6 * q], El[q], v);
+        if (ea)  // gl_strain_eas = gl_strain + Mtilde alpha (shell_eas_ans.hpp:129-131)
+          for (int c = 0; c < ANS_NEAS; ++c) v = fma(Mt[r][c], alpha[c], v);
         C[r] = r < 3 ? 2.0 * v + 1.0 : v;  // C = 2 E + I in tensor components (shear: 2 * (v / 2))
       }
       double S[6], Cm[36];
@@ -378,6 +499,37 @@ namespace b200s
         double v = 0.0;
         for (int r = 0; r < 6; ++r) v = fma(Bi[r][d], S[r], v);
         fi[d] = fma(w, v, fi[d]);
+      }
+      if (ea)
+      {
+        // integrate_eas (eas_helpers.hpp:352-371) with the ANS B-operator: K_aa += w Mt^T C Mt, K_da,i += w B_i^T C Mt,
+        // s += w Mt^T S -- for both actions, as the reference does
+        double cM[6][ANS_NEAS];
+        for (int r = 0; r < 6; ++r)
+          for (int c = 0; c < ANS_NEAS; ++c)
+          {
+            double v = 0.0;
+            for (int k = 0; k < 6; ++k) v = fma(Cm[r + 6 * k], Mt[k][c], v);
+            cM[r][c] = w * v;
+          }
+        for (int c = 0; c < ANS_NEAS; ++c)
+        {
+          for (int r = 0; r < ANS_NEAS; ++r)
+          {
+            double v = 0.0;
+            for (int k = 0; k < 6; ++k) v = fma(Mt[k][r], cM[k][c], v);
+            ea->Kaa[r + ANS_NEAS * c] += v;
+          }
+          for (int d = 0; d < 3; ++d)
+          {
+            double v = 0.0;
+            for (int k = 0; k < 6; ++k) v = fma(Bi[k][d], cM[k][c], v);
+            ea->Kda[d][c] += v;
+          }
+          double v = 0.0;
+          for (int k = 0; k < 6; ++k) v = fma(Mt[k][c], S[k], v);
+          ea->s[c] = fma(w, v, ea->s[c]);
+        }
       }
       if (!Ga.stiff) continue;
       for (int b = 0; b < 3; ++b)
@@ -461,8 +613,22 @@ namespace b200s
     double Krow[NN][9], fi[3], dj = 1e300, df = 1e300;
     bool neg;
     if constexpr (NN == 8)
-      neg = Ga.dN_ans != nullptr ? generic_block_row_ans<MAT>(Ga, e, i, Krow, fi, dj, df)
-                                 : generic_block_row<MAT, NN>(Ga, e, i, Krow, fi, dj, df);
+    {
+      if (Ga.dN_ans != nullptr && Ga.eas_hist != nullptr)
+      {
+        // TECH shell_eas_ans: the eight threads of an element are eight adjacent lanes of one warp (blockDim 64, nn 8)
+        AnsEas ea;
+        neg = generic_block_row_ans<MAT>(Ga, e, i, Krow, fi, dj, df, &ea);
+        double* h = Ga.eas_hist + e * ANS_EAS_HIST;
+        const unsigned mask = 0xFFu << (threadIdx.x & 24);
+        ans_eas_store(h, i, ea);
+        __syncwarp(mask);
+        ans_eas_condense(h, i, ea, Ga.stiff != 0, Krow, fi);
+      }
+      else
+        neg = Ga.dN_ans != nullptr ? generic_block_row_ans<MAT>(Ga, e, i, Krow, fi, dj, df)
+                                   : generic_block_row<MAT, NN>(Ga, e, i, Krow, fi, dj, df);
+    }
     else
       neg = generic_block_row<MAT, NN>(Ga, e, i, Krow, fi, dj, df);
     atomic_min_double_generic(&A.err->min_detJ, dj);

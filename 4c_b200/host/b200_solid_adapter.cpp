@@ -67,7 +67,8 @@ namespace B200Solid
     if (prestress != B200S_PRESTRESS_NONE) return false;
     if (tech == B200S_TECH_NONE) return true;
     if (tech == B200S_TECH_FBAR) return fbar_cell;
-    if (tech == B200S_TECH_SHELL_ANS || tech == B200S_TECH_SHELL_EAS) return celltype == B200S_HEX8;  // wedge6 shell_ans, shell_eas_ans: CPU loop
+    if (tech == B200S_TECH_SHELL_ANS || tech == B200S_TECH_SHELL_EAS || tech == B200S_TECH_SHELL_EAS_ANS)
+      return celltype == B200S_HEX8;  // the wedge6 solid shells: CPU loop
     // EAS is a hex8 technology (4C_solid_ele_factory_lib.hpp)
     return celltype == B200S_HEX8 && (tech == B200S_TECH_EAS_MILD || tech == B200S_TECH_EAS_FULL);
   }

@@ -160,8 +160,11 @@ extern "C"
     B200S_TECH_EAS_FULL = 3, /* hex8, 21 parameters */
     B200S_TECH_SHELL_ANS = 4, /* hex8 solid shell with assumed natural strains (thickness = t-direction of the element):
                                  4C_solid_ele_calc_shell_ans.hpp; general kernel.  wedge6 shell_ans, shell_eas_ans: CPU path */
-    B200S_TECH_SHELL_EAS = 5 /* hex8, EAS with the 7 solid-shell modes (eastype_sh8_7, t = thickness direction):
-                                EASSolidIntegrator<hex8, eastype_sh8_7, nonlinearTotLag>; the FMA EAS kernel */
+    B200S_TECH_SHELL_EAS = 5, /* hex8, EAS with the 7 solid-shell modes (eastype_sh8_7, t = thickness direction):
+                                 EASSolidIntegrator<hex8, eastype_sh8_7, nonlinearTotLag>; the FMA EAS kernel */
+    B200S_TECH_SHELL_EAS_ANS = 6 /* hex8 solid shell with ANS and the 7 EAS modes condensed with the ANS B-operator:
+                                    EasAnsSolidShellIntegrator<hex8, eastype_sh8_7> (4C_solid_ele_calc_shell_eas_ans.hpp);
+                                    general kernel.  wedge6 (eastype_sw6_1): CPU path */
   } b200s_element_technology;
   typedef enum
   {

@@ -33,6 +33,7 @@ TECH_NONE, TECH_FBAR, TECH_MULF, TECH_EAS_MILD, TECH_EAS_FULL, TECH_LINEAR, TECH
 TECH_EAS_MILD_LINEAR, TECH_EAS_FULL_LINEAR = 7, 8  # hex8 EAS with KINEM linear
 TECH_SHELL_ANS = 9  # hex8 / wedge6 solid shell with assumed natural strains
 TECH_SHELL_EAS = 10  # hex8 EAS with the 7 solid-shell modes (eastype_sh8_7)
+TECH_SHELL_EAS_ANS = 11  # hex8 solid shell: ANS + the 7 EAS modes
 MULF_HIST = 19
 
 _dp = C.POINTER(C.c_double)

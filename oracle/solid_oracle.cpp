@@ -2013,12 +2013,12 @@ namespace
   bool is_eas(int tech)
   {
     return tech == ORC_TECH_EAS_MILD || tech == ORC_TECH_EAS_FULL || tech == ORC_TECH_EAS_MILD_LINEAR ||
-           tech == ORC_TECH_EAS_FULL_LINEAR || tech == ORC_TECH_SHELL_EAS;
+           tech == ORC_TECH_EAS_FULL_LINEAR || tech == ORC_TECH_SHELL_EAS || tech == ORC_TECH_SHELL_EAS_ANS;
   }
   bool is_eas_linear(int tech) { return tech == ORC_TECH_EAS_MILD_LINEAR || tech == ORC_TECH_EAS_FULL_LINEAR; }
   int eas_num(int tech)
   {
-    if (tech == ORC_TECH_SHELL_EAS) return 7;  // eastype_sh8_7
+    if (tech == ORC_TECH_SHELL_EAS || tech == ORC_TECH_SHELL_EAS_ANS) return 7;  // eastype_sh8_7
     return (tech == ORC_TECH_EAS_MILD || tech == ORC_TECH_EAS_MILD_LINEAR) ? 9 : 21;
   }
 
@@ -2127,11 +2127,29 @@ namespace
   //      not taken at the Gauss point but interpolated from sampling points (hex8: A..D mid-edges of the mid-surface for
   //      the shears, E..H its corners for tt; wedge6: five points), for the strains, the B-operator and the geometric
   //      stiffness alike; T^-T of the Jacobian at the Gauss point takes everything to the global frame.
+  void eas_shape_functions(int neas, const double* xi, double* M);
+  // hist != nullptr: TECH shell_eas_ans = SolidEleCalc<hex8, ShellEASANSFormulation<hex8, eastype_sh8_7>>
+  // (src/solid_ele/4C_solid_ele_calc_shell_eas_ans.hpp:70-343): the ANS strains / B-operator / geometric stiffness below, the
+  // strain enhanced by Mtilde alpha (:126-131), and the EAS condensation with the ANS B-operator (integrate_eas with
+  // linearization.b_op, :217-225; prepare_condensed_contribution :227-241; the two condensed contributions :300-320).
+  // hist layout as element_eas: alpha_inc | alpha | s | invKaa | Kda.  wedge6 (eastype_sw6_1) is not restated.
   int element_shell_ans(int ct, int matkind, const double* par, int action, const double* X, const double* u, double* Ke,
-      double* fe)
+      double* fe, double* hist = nullptr)
   {
     if (ct != ORC_HEX8 && ct != ORC_WEDGE6) return 2;
+    if (hist && ct != ORC_HEX8) return 2;
+    const int neas = 7;
+    double *alpha = nullptr, *s_eas = nullptr, *invKaa = nullptr, *Kda = nullptr, T0invT[36], detJ0 = 0.0;
     const int n = nnodes(ct), nd = 3 * n, ng = ngauss(ct);
+    if (hist)
+    {
+      alpha = hist + neas, s_eas = hist + 2 * neas, invKaa = hist + 3 * neas, Kda = invKaa + neas * neas;
+      eas_centroid_transformation(ct, X, T0invT, detJ0);
+      // reset_condensed_variable_integration (:208-215)
+      std::fill(invKaa, invKaa + neas * neas, 0.0);
+      std::fill(Kda, Kda + nd * neas, 0.0);
+      std::fill(s_eas, s_eas + neas, 0.0);
+    }
     const bool hex = ct == ORC_HEX8;
     const int nsp = hex ? 8 : 5;
     // SamplingPoints<celltype>::value (shell_ans_lib.hpp:26-40)
@@ -2255,6 +2273,27 @@ namespace
         for (int q = 0; q < 6; ++q) v += TinvT[r + 6 * q] * El[q];
         E[r] = r < 3 ? v : 0.5 * v;  // Voigt::Strains::to_stress_like
       }
+      double Mt[6 * 7];
+      if (hist)
+      {
+        // m_tilde = detJ0 / detJ T0^-T M(xi) (evaluate_eas_shape_functions_material_config, eas_helpers.hpp:438-453);
+        // gl_strain_eas = gl_strain + stress-like(Mtilde alpha) (shell_eas_ans.hpp:129-131)
+        double M[6 * 21];
+        eas_shape_functions(neas, xi, M);
+        for (int c = 0; c < neas; ++c)
+          for (int r = 0; r < 6; ++r)
+          {
+            double v = 0.0;
+            for (int k = 0; k < 6; ++k) v += T0invT[r + 6 * k] * M[k + 6 * c];
+            Mt[r + 6 * c] = (detJ0 / jm.det) * v;
+          }
+        for (int r = 0; r < 6; ++r)
+        {
+          double v = 0.0;
+          for (int c = 0; c < neas; ++c) v += Mt[r + 6 * c] * alpha[c];
+          E[r] += r < 3 ? v : 0.5 * v;
+        }
+      }
       // the materials of this path use the strain only (the reference also hands in a deformation gradient consistent
       // with it, compute_deformation_gradient_from_gl_strains)
       deformation_gradient(n, u, jm, F);
@@ -2265,6 +2304,36 @@ namespace
         double v = 0.0;
         for (int r = 0; r < 6; ++r) v += B[r + 6 * c] * S[r];
         fe[c] += fac * v;
+      }
+      if (hist)
+      {
+        // integrate_eas (eas_helpers.hpp:352-371) with the ANS B-operator
+        double cmatM[6 * 7];
+        for (int c = 0; c < neas; ++c)
+          for (int r = 0; r < 6; ++r)
+          {
+            double v = 0.0;
+            for (int k = 0; k < 6; ++k) v += Cm[r + 6 * k] * Mt[k + 6 * c];
+            cmatM[r + 6 * c] = v;
+          }
+        for (int c = 0; c < neas; ++c)
+        {
+          for (int r = 0; r < neas; ++r)
+          {
+            double v = 0.0;
+            for (int k = 0; k < 6; ++k) v += Mt[k + 6 * r] * cmatM[k + 6 * c];
+            invKaa[r + neas * c] += fac * v;
+          }
+          for (int r = 0; r < nd; ++r)
+          {
+            double v = 0.0;
+            for (int k = 0; k < 6; ++k) v += B[k + 6 * r] * cmatM[k + 6 * c];
+            Kda[r + nd * c] += fac * v;
+          }
+          double v = 0.0;
+          for (int k = 0; k < 6; ++k) v += Mt[k + 6 * c] * S[k];
+          s_eas[c] += fac * v;
+        }
       }
       if (!(action == ORC_ACTION_FORCE_STIFF && Ke)) continue;
       for (int c = 0; c < nd; ++c)
@@ -2307,6 +2376,32 @@ namespace
           }
           for (int d = 0; d < 3; ++d) Ke[(3 * i + d) + nd * (3 * j + d)] += fac * Gij;
         }
+    }
+    if (hist)
+    {
+      dense_inverse(neas, invKaa);
+      std::vector<double> mKdaiKaa(nd * neas);
+      for (int r = 0; r < nd; ++r)
+        for (int c = 0; c < neas; ++c)
+        {
+          double v = 0.0;
+          for (int k = 0; k < neas; ++k) v += Kda[r + nd * k] * invKaa[k + neas * c];
+          mKdaiKaa[r + nd * c] = -v;
+        }
+      for (int r = 0; r < nd; ++r)
+      {
+        double v = 0.0;
+        for (int c = 0; c < neas; ++c) v += mKdaiKaa[r + nd * c] * s_eas[c];
+        fe[r] += v;
+      }
+      if (action == ORC_ACTION_FORCE_STIFF && Ke)
+        for (int r = 0; r < nd; ++r)
+          for (int c = 0; c < nd; ++c)
+          {
+            double v = 0.0;
+            for (int k = 0; k < neas; ++k) v += mKdaiKaa[r + nd * k] * Kda[c + nd * k];
+            Ke[r + nd * c] += v;
+          }
     }
     return 0;
   }
@@ -2501,6 +2596,7 @@ namespace
   int element_tech(int ct, int tech, int matkind, const double* par, int action, const double* X,
       const double* u, double* Ke, double* fe, double* hist = nullptr)
   {
+    if (tech == ORC_TECH_SHELL_EAS_ANS) return element_shell_ans(ct, matkind, par, action, X, u, Ke, fe, hist);
     if (is_eas(tech))
       return element_eas(ct, tech, matkind, par, action, X, u, hist, Ke, fe);
     if (tech == ORC_TECH_LINEAR) return element_linear(ct, matkind, par, action, X, u, Ke, fe, hist);

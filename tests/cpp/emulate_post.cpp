@@ -168,11 +168,58 @@ extern "C" int emu_drucker_prager(const double* in10, double* hist, const double
 // The general (non-symmetric tangent) kernel of generic_kernel.cuh stepped on the host: one call of generic_block_row
 // per (element, row node) and the kernel's scatter.  celltype 0 hex8 / 1 hex27 / 2 tet10, KINEM linear,
 // MAT_Struct_DruckerPrager with its state store (n_ele * ngp * DP_HIST, updated in place).
+// host twin of hex8eas::centroid_transformation (a warp routine): T0^-T = T(J0^-1) in strain-like Voigt notation and det J0
+static void emu_centroid_t0(const double* X, const int32_t* ce, double* t0)
+{
+  double J0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, iJ0[9];
+  // dN_k/dxi_a(0) = +-1/8: parametric sign of corner k in direction a (hex8 node order)
+  auto sgn = [](int k, int a) { return a == 0 ? (((k ^ (k >> 1)) & 1) ? 1.0 : -1.0) : (a == 1 ? ((k & 2) ? 1.0 : -1.0) : ((k & 4) ? 1.0 : -1.0)); };
+  for (int k = 0; k < 8; ++k)
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) J0[a + 3 * b] = fma(0.125 * sgn(k, a), X[3 * (int64_t)ce[k] + b], J0[a + 3 * b]);
+  t0[36] = inv3(iJ0, J0);
+  voigt_strain_transformation(iJ0, t0);
+}
+
 template <int MAT, int NN>
 static int run_generic(const GenericArgs& Ga)
 {
   const EvalArgs& A = Ga.A;
   int bad = 0;
+  auto scatter = [&](int64_t e, int i, const double (*Krow)[9], const double* fi)
+  {
+    const NodeRow nr = A.node_row[A.conn[e * Ga.nn + i]];
+    if (nr.rowstart < 0) return;
+    for (int b = 0; b < 3; ++b) A.f[nr.frow + b] += fi[b];
+    if (!Ga.stiff) return;
+    const int32_t* pos = A.pos + e * Ga.pos_stride + i * Ga.nn;
+    for (int j = 0; j < Ga.nn; ++j)
+      for (int b = 0; b < 3; ++b)
+        for (int c = 0; c < 3; ++c) A.vals[nr.rowstart + (int64_t)b * nr.rowlen + pos[j] + c] += Krow[j][b + 3 * c];
+  };
+  if constexpr (NN == 8)
+    if (Ga.dN_ans != nullptr && Ga.eas_hist != nullptr)
+    {
+      // TECH shell_eas_ans: the kernel's two steps around its __syncwarp -- every row thread of the element integrates and
+      // stores, then every row thread condenses
+      for (int64_t e = 0; e < A.n_ele; ++e)
+      {
+        double Krow[8][8][9], fi[8][3], dj = 1e300, df = 1e300;
+        AnsEas ea[8];
+        double* h = Ga.eas_hist + e * ANS_EAS_HIST;
+        for (int i = 0; i < 8; ++i)
+        {
+          if (generic_block_row_ans<MAT>(Ga, e, i, Krow[i], fi[i], dj, df, &ea[i])) ++bad;
+          ans_eas_store(h, i, ea[i]);
+        }
+        for (int i = 0; i < 8; ++i)
+        {
+          ans_eas_condense(h, i, ea[i], Ga.stiff != 0, Krow[i], fi[i]);
+          scatter(e, i, Krow[i], fi[i]);
+        }
+      }
+      return bad;
+    }
   for (int64_t e = 0; e < A.n_ele; ++e)
     for (int i = 0; i < Ga.nn; ++i)
     {
@@ -215,7 +262,7 @@ static int run_generic_nn(const GenericArgs& Ga)
 extern "C" int emu_generic(int celltype, int matkind, const double* params, int linear, int stiff, int64_t n_ele,
     const int32_t* conn, const double* X, const double* u_col, const int32_t* pos, int pos_stride,
     const int64_t* node_rowstart, const int32_t* node_rowlen, const int32_t* node_frow, int64_t n_col_nodes, double* vals,
-    double* f, const double* gp_hist, int fbar, int ans)
+    double* f, const double* gp_hist, int fbar, int ans, double* eas_hist)
 {
   std::vector<NodeRow> node_row(n_col_nodes);
   for (int64_t k = 0; k < n_col_nodes; ++k)
@@ -232,6 +279,17 @@ extern "C" int emu_generic(int celltype, int matkind, const double* params, int 
   Ga.dN_cen = fbar ? T.dN_cen.data() : nullptr, Ga.hist_pts = T.ngp + (fbar ? 1 : 0);
   Ga.dN_ans = (ans && !T.dN_ans.empty()) ? T.dN_ans.data() : nullptr, Ga.xi_gp = T.xi_gp.data();
   if (ans && !Ga.dN_ans) return -4;
+  // TECH shell_eas_ans: EAS history (n_ele x ANS_EAS_HIST, updated in place) and the centroid table of
+  // hex8eas::centroid_transformation, here through the host twin the EAS emulation uses
+  std::vector<double> t0;
+  Ga.eas_hist = nullptr, Ga.eas_t0 = nullptr;
+  if (eas_hist)
+  {
+    if (!ans || T.nn != 8) return -5;
+    t0.resize((size_t)n_ele * ANS_EAS_T0_STRIDE);
+    for (int64_t e = 0; e < n_ele; ++e) emu_centroid_t0(X, conn + 8 * e, t0.data() + e * ANS_EAS_T0_STRIDE);
+    Ga.eas_hist = eas_hist, Ga.eas_t0 = t0.data();
+  }
   if (matkind == MAT_COUP_NEOHOOKE) return run_generic_nn<MAT_COUP_NEOHOOKE>(Ga);
   if (matkind == MAT_ISO_VOL) return run_generic_nn<MAT_ISO_VOL>(Ga);
   return run_generic_nn<MAT_SVK>(Ga);

@@ -576,7 +576,7 @@ if __name__ == "__main__":
             ("cooks_fbar", "tests/input_files/sohex8fbar_cooks_nl_new_struc.4C.yaml", "fbar"),):
         with open(os.path.join(HERE, f"integration_{name}.json"), "w") as fh:
             json.dump(cooks_case(rel, tech), fh)
-    for tech in ("shell_ans", "shell_eas"):
+    for tech in ("shell_ans", "shell_eas", "shell_eas_ans"):
         with open(os.path.join(HERE, f"integration_hex8_{tech}.json"), "w") as fh:
             json.dump(integration_case("hex8", f"tests/input_files/solid_ele_hex8_Standard_{tech}.4C.yaml"), fh, indent=1)
     for tech, name in (("eas_mild", "sohex8_easmild_cooks_lin"), ("eas_full", "sohex8_easfull_cooks_lin")):

@@ -295,7 +295,7 @@ def generic_drucker_prager(celltype, in10, conn, X, u_col, rowptr, colind, node_
 
 
 def generic(celltype, matkind, params, conn, X, u_col, rowptr, colind, node_row_lid, node_col_lid, n_row_nodes, linear=False,
-            stiff=True, gp_hist=None, fbar=False, ans=False):
+            stiff=True, gp_hist=None, fbar=False, ans=False, eas_hist=None):
     """Emulated general kernel (generic_kernel.cuh) for the hyperelastic kinds 0..2 and any cell type of
     shape_tables.hpp (tet4 / hex20 blocks run through it on the device)."""
     conn = np.ascontiguousarray(conn, np.int32)
@@ -304,10 +304,12 @@ def generic(celltype, matkind, params, conn, X, u_col, rowptr, colind, node_row_
     vals, f = np.zeros(rowptr[-1]), np.zeros(3 * n_row_nodes)
     L = lib("post")
     L.emu_generic.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 4 + [C.c_int] + \
-        [C.c_void_p] * 3 + [C.c_int64] + [C.c_void_p] * 3 + [C.c_int, C.c_int]
+        [C.c_void_p] * 3 + [C.c_int64] + [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_void_p]
+    if eas_hist is not None:  # TECH shell_eas_ans: (n_ele, 238) doubles, updated in place
+        assert eas_hist.dtype == np.float64 and eas_hist.flags["C_CONTIGUOUS"]
     rc = L.emu_generic(int(celltype), int(matkind), _p(np.ascontiguousarray(params, np.float64)), int(linear), int(stiff),
                        len(conn), _p(conn), _p(np.ascontiguousarray(X, np.float64)),
                        _p(np.ascontiguousarray(u_col, np.float64)), _p(pos), pos.shape[1], _p(rowstart), _p(rowlen),
-                       _p(frow), len(rowstart), _p(vals), _p(f), _p(gp_hist), int(fbar), int(ans))
+                       _p(frow), len(rowstart), _p(vals), _p(f), _p(gp_hist), int(fbar), int(ans), _p(eas_hist))
     assert rc == 0, rc
     return vals, f

@@ -124,6 +124,49 @@ def test_emulated_general_kernel_fbar_matches_oracle(cell, mulf):
                 assert np.abs(phist - ohist[:, :, :18]).max() <= 1e-13 * np.abs(ohist).max()
 
 
+def test_emulated_general_kernel_shell_eas_ans_matches_oracle():
+    """TECH shell_eas_ans on hex8 (ShellEASANSFormulation<hex8, eastype_sh8_7>, 4C_solid_ele_calc_shell_eas_ans.hpp): the ANS block
+    row plus the seven EAS modes (strain enhancement, K_aa / K_da / s with the ANS B-operator, condensation) -- the general
+    kernel's arithmetic stepped on the CPU against the oracle (pinned to the reference's
+    solid_ele_hex8_Standard_shell_eas_ans known answers, tests/test_post_actions.py), over two states with a recover of
+    the EAS parameters in between so that alpha != 0 enters the second evaluate."""
+    rm = b200.partition.box_partition(b200.mesh.HEX8, (3, 2, 2), 0, 1)
+    rowptr, colind = orc.build_graph(orc.HEX8, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    maps = (rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    X = rm.X.copy()
+    rng = np.random.default_rng(4)
+    inner = np.all((X > 1e-9) & (X < 1 - 1e-9), axis=1)
+    X[inner] += 0.05 * rng.uniform(-1, 1, (int(inner.sum()), 3))
+    u = 0.4 * b200.mesh.displacement_field(X, rm.node_gid, 1.0, 0.4)
+    for mk, par in MATS.items():
+        ohist = orc.eas_new_history(orc.TECH_SHELL_EAS_ANS, rm.n_col_eles)
+        phist = np.zeros_like(ohist)
+        for it in range(2):
+            us = (1.0 + 0.3 * it) * u.ravel()
+            for stiff in (True, False):
+                rK, rf, nbad = orc.evaluate_assemble(orc.HEX8, mk, par, rm.conn, X.ravel(), us, *maps, rowptr, colind,
+                                                     tech=orc.TECH_SHELL_EAS_ANS, hist=ohist,
+                                                     action=orc.ACTION_FORCE_STIFF if stiff else orc.ACTION_FORCE)
+                K, f = emu.generic(rm.celltype, mk, par, rm.conn, X.ravel(), us, rowptr, colind, *maps, ans=True,
+                                   eas_hist=phist, stiff=stiff)
+                # the nearly incompressible block (kappa / mue = 1000) amplifies round-off once alpha != 0: 4.5e-11 observed,
+                # 1e-15 for the other two materials on the same element arithmetic
+                tol = 1e-9 if mk == orc.MAT_ISO_VOL else 1e-12
+                ok, wK, wf = b200.parity_report(rowptr, K, rK if stiff else 0 * K, f, rf, tol)
+                assert ok and nbad == 0, (mk, it, stiff, wK, wf)
+            # s, K_aa^-1, K_da of the element history (what recover reads)
+            assert np.abs(phist - ohist).max() <= 1e-9 * np.abs(ohist).max()
+            du = 1e-3 * rng.standard_normal(3 * rm.n_col_nodes)
+            orc.eas_recover(orc.TECH_SHELL_EAS_ANS, rm.conn, du, ohist)
+            orc.eas_recover(orc.TECH_SHELL_EAS_ANS, rm.conn, du, phist)
+            assert np.abs(ohist[:, 7:14]).max() > 0
+            assert np.abs(phist[:, :14] - ohist[:, :14]).max() <= 1e-9 * np.abs(ohist[:, :14]).max()
+            phist[:] = ohist  # the same alpha on both sides of the next comparison (the nearly incompressible block amplifies 1e-13)
+        # and it is not the plain ANS element
+        K1, f1 = emu.generic(rm.celltype, mk, par, rm.conn, X.ravel(), us, rowptr, colind, *maps, ans=True)
+        assert np.abs(K - K1).max() > 1e-4 * np.abs(K1).max() or np.abs(f - f1).max() > 1e-4 * np.abs(f1).max()
+
+
 def test_emulated_general_kernel_shell_ans_matches_oracle():
     """TECH shell_ans on hex8 (ShellANSFormulation, src/solid_ele/4C_solid_ele_calc_shell_ans.hpp): sampling-point
     interpolation of the transverse strain rows, T^-T formed from the inverse Jacobian, ANS geometric stiffness -- the

@@ -1158,3 +1158,55 @@ def test_shell_eas_matches_oracle_and_known_answers():
     for e in case["expected_disp"]:
         assert abs(uu[e["node"], e["dof"]] - e["value"]) < 1e-10, (e, uu[e["node"], e["dof"]])
     asm.close()
+
+
+# ---- TECH shell_eas_ans on hex8: ANS + the seven EAS modes, condensed with the ANS B-operator (general kernel) ---------
+def test_shell_eas_ans_matches_oracle_and_known_answers():
+    import json
+    import os
+    from tests.helpers.newton import solve_case
+    rm = b200.partition.box_partition(b200.mesh.HEX8, (5, 4, 3), 0, 1)
+    u = 0.4 * b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 0.2)
+    mk, par = capi.MAT_COUP_NEOHOOKE, [200.0, 0.25]
+    asm = b200.DeviceAssembler(rm, mk, par, tech=capi.TECH_SHELL_EAS_ANS)
+    rowptr, colind = asm.graph()
+    hist = orc.eas_new_history(orc.TECH_SHELL_EAS_ANS, rm.n_col_eles)
+    maps = (rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, rowptr, colind)
+    rng = np.random.default_rng(5)
+    for it in range(2):
+        us = (1.0 + 0.5 * it) * u.ravel()
+        asm.set_state("displacement", us)
+        for action, oaction in (("struct_calc_nlnstiff", orc.ACTION_FORCE_STIFF), ("struct_calc_internalforce", orc.ACTION_FORCE)):
+            K, f, err = asm.evaluate(action)
+            rK, rf, nbad = orc.evaluate_assemble(orc.HEX8, mk, par, rm.conn, rm.X.ravel(), us, *maps, tech=orc.TECH_SHELL_EAS_ANS,
+                                                 hist=hist, action=oaction)
+            if oaction == orc.ACTION_FORCE:
+                assert np.abs(f - rf).max() <= 1e-10 * np.abs(rf).max()
+            else:
+                ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, 1e-10)
+                assert ok and nbad == 0 and err.n_neg_jacobian == 0, (it, wK, wf)
+        du = 1e-3 * rng.standard_normal(asm.n_rows)
+        asm.recover(du)
+        orc.eas_recover(orc.TECH_SHELL_EAS_ANS, rm.conn, du, hist)
+        dh = asm.ctx.get_element_history().reshape(hist.shape)
+        assert np.abs(dh[:, :14] - hist[:, :14]).max() <= 1e-8 * max(np.abs(hist[:, :14]).max(), 1e-6)
+        assert np.abs(hist[:, 7:14]).max() > 0
+    asm.close()
+    # the reference's known answers (solid_ele_hex8_Standard_shell_eas_ans.4C.yaml) through the CUDA path
+    case = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "integration_hex8_shell_eas_ans.json")))
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    rm = b200.partition.serial_mesh(b200.mesh.HEX8, X, conn)
+    asm = b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, [case["material"]["YOUNG"], case["material"]["NUE"]],
+                               tech=capi.TECH_SHELL_EAS_ANS)
+    rowptr, colind = asm.graph()
+
+    def ev(uu):
+        asm.set_state("displacement", uu)
+        K, f, _ = asm.evaluate()
+        return rowptr, colind, K, f
+
+    uu = solve_case(case, ev, recover=lambda du: asm.recover(du, 1.0))
+    for e in case["expected_disp"]:
+        assert abs(uu[e["node"], e["dof"]] - e["value"]) < 1e-10, (e, uu[e["node"], e["dof"]])
+    asm.close()

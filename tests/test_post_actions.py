@@ -439,6 +439,32 @@ def test_shell_eas_known_answers():
         assert abs(u[e["node"], e["dof"]] - e["value"]) < 1e-12, (e, u[e["node"], e["dof"]])
 
 
+def test_shell_eas_ans_known_answers():
+    """TECH shell_eas_ans = SolidEleCalc<hex8, ShellEASANSFormulation<hex8, eastype_sh8_7>> (ANS strains and B-operator, the
+    seven solid-shell EAS modes condensed with the ANS B-operator): RESULT DESCRIPTION displacements (1e-12) of
+    tests/input_files/solid_ele_hex8_Standard_shell_eas_ans.4C.yaml."""
+    case = json.load(open(os.path.join(G, "integration_hex8_shell_eas_ans.json")))
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    nn = len(X)
+    row, col = serial_maps(nn)
+    rowptr, colind = orc.build_graph(orc.HEX8, conn, row, col, nn)
+    par = [case["material"]["YOUNG"], case["material"]["NUE"]]
+    hist = orc.eas_new_history(orc.TECH_SHELL_EAS_ANS, len(conn))
+    assert hist.shape[1] == 3 * 7 + 49 + 24 * 7
+
+    def evaluate(u):
+        vals, f, nbad = orc.evaluate_assemble(orc.HEX8, orc.MAT_COUP_NEOHOOKE, par, conn, X.ravel(), u, row, col, nn, rowptr,
+                                              colind, tech=orc.TECH_SHELL_EAS_ANS, hist=hist)
+        assert nbad == 0
+        return rowptr, colind, vals, f
+
+    u = solve_case(case, evaluate, recover=lambda du: orc.eas_recover(orc.TECH_SHELL_EAS_ANS, conn, du, hist))
+    assert len(case["expected_disp"]) >= 12
+    for e in case["expected_disp"]:
+        assert abs(u[e["node"], e["dof"]] - e["value"]) < 1e-12, (e, u[e["node"], e["dof"]])
+
+
 def test_mulf_update_keeps_the_stress_state():
     """After struct_update_prestress and the displacement reset the element sees the same deformation
     gradient (F_delta = I, F = F_hist), hence the same internal force."""
