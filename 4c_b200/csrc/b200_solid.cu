@@ -4098,10 +4098,11 @@ extern "C"
       return fail(ctx, B200S_ERR_INVALID, "set_mesh and set_material must precede this action");
     if (material_needs_fibers(ctx) && !ctx->d_fibers)
       return fail(ctx, B200S_ERR_INVALID, "the material has a fibre summand: b200s_set_element_fibers first");
-    if (ctx->tech == B200S_TECH_SHELL_ANS || ctx->tech == B200S_TECH_SHELL_EAS_ANS)
-      return fail(ctx, B200S_ERR_UNSUPPORTED,
-          "stress / energy output of shell_ans / shell_eas_ans blocks has no device kernel (CPU path)");
+    const bool ans = ctx->tech == B200S_TECH_SHELL_ANS || ctx->tech == B200S_TECH_SHELL_EAS_ANS;
+    if (ans && (ctx->celltype != B200S_HEX8 || !ctx->d_dN_ans))
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "TECH shell_ans / shell_eas_ans on the device: hex8 blocks");
     PostArgs P;
+    P.dN_ans = ans ? ctx->d_dN_ans : nullptr;
     P.X = ctx->dX, P.u = ctx->d_u_col, P.conn = ctx->dconn, P.per_ele_param = ctx->d_per_ele;
     P.fibers = ctx->d_fibers;
     P.ele_id = ctx->d_ele_id, P.ele_is_row = ctx->d_ele_is_row;

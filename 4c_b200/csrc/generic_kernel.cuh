@@ -328,26 +328,7 @@ namespace b200s
   // A..D (shears) and E..H (tt) of the mid-surface, T^-T of the Gauss point's Jacobian takes them to the global frame.
   // T(J) is the strain-like Voigt transformation of E' = J E J^T, so T(J)^-1 = T(J^-1) -- formed directly, where the
   // reference inverts numerically (evaluate_voigt_transformation_matrix, 4C_solid_ele_calc_lib.hpp:1451-1517).
-  B2_HD void voigt_strain_transformation(const double* M /*a + 3 b*/, double* T /*r + 6 c*/)
-  {
-    constexpr int pa[3] = {0, 1, 0}, pb[3] = {1, 2, 2};
-#pragma unroll
-    for (int r = 0; r < 6; ++r)
-    {
-      const int a = r < 3 ? r : pa[r - 3], b = r < 3 ? r : pb[r - 3];
-#pragma unroll
-      for (int c = 0; c < 6; ++c)
-      {
-        const int cc = c < 3 ? c : pa[c - 3], dd = c < 3 ? c : pb[c - 3];
-        double v;
-        if (r < 3)
-          v = M[a + 3 * cc] * M[a + 3 * dd];
-        else
-          v = c < 3 ? 2.0 * M[a + 3 * cc] * M[b + 3 * cc] : M[a + 3 * cc] * M[b + 3 * dd] + M[a + 3 * dd] * M[b + 3 * cc];
-        T[r + 6 * c] = v;
-      }
-    }
-  }
+  // (voigt_strain_transformation: solid_math.cuh)
 
   // local (parametric) B-operator columns of node k, dofs d = 0..2: Bl[r][d]; Jc = current Jacobian at the Gauss point,
   // Jcs = current Jacobians at the eight sampling points, dNs = shape derivatives there, w = interpolation weights

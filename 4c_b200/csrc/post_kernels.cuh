@@ -51,6 +51,7 @@ namespace b200s
     const double* eas_hist;
     const double* eas_t0;
     const double* xi_gp;          // [ngp][3]
+    const double* dN_ans;         // TECH shell_ans / shell_eas_ans (hex8): [8][nn][3] at the ANS sampling points, else nullptr
     MatParams mp;
     int64_t n_ele;
     int nn, ngp;
@@ -187,7 +188,10 @@ namespace b200s
   // EAS kinematics at one Gauss point of a hex8 (evaluate_eas_kinematics, 4C_solid_ele_calc_eas_helpers.hpp:
   // 405-448): C <- C_enh = C + 2 stress-like(Mtilde alpha); with want_F also F <- F_enh = R U_enh,
   // R = F U^-1 (compute_deformation_gradient_from_gl_strains)
-  B2_HD void eas_enhance(const PostArgs& A, int64_t e, int g, double detJ, bool want_F, double* F, double* C)
+  B2_HD void consistent_deformation_gradient(const double* Cd, const double* C, double* F);
+  // Cd (may be null): right Cauchy-Green tensor of the incoming F where it is not the incoming C (ANS blocks)
+  B2_HD void eas_enhance(const PostArgs& A, int64_t e, int g, double detJ, bool want_F, double* F, double* C,
+      const double* Cd_in = nullptr)
   {
     const double* t0 = A.eas_t0 + e * A.eas_t0_stride;
     const double* alpha = A.eas_hist + e * A.eas_hist_size + A.eas_neas;
@@ -208,7 +212,7 @@ namespace b200s
       for (int c = 0; c < A.eas_neas; ++c) v[rows[c]] += mono[c] * alpha[c];
     double Cd[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) Cd[k] = C[k];
+    for (int k = 0; k < 6; ++k) Cd[k] = Cd_in ? Cd_in[k] : C[k];
 #pragma unroll
     for (int k = 0; k < 6; ++k)
     {
@@ -218,6 +222,13 @@ namespace b200s
       C[k] += (k < 3 ? 2.0 : 1.0) * scale * q;
     }
     if (!want_F) return;
+    consistent_deformation_gradient(Cd, C, F);
+  }
+
+  // compute_deformation_gradient_from_gl_strains (4C_solid_ele_calc_lib.hpp:1566-1595): F <- R U(C), R = F U(Cd)^-1 with Cd the
+  // right Cauchy-Green tensor of the incoming F
+  B2_HD void consistent_deformation_gradient(const double* Cd, const double* C, double* F)
+  {
     double U[9], iU[9], Ue[9], iUe[9], R[9];
     sqrt_sym3(Cd, U, iU);
     sqrt_sym3(C, Ue, iUe);
@@ -229,6 +240,54 @@ namespace b200s
     for (int a = 0; a < 3; ++a)
 #pragma unroll
       for (int b = 0; b < 3; ++b) F[a + 3 * b] = R[a] * Ue[3 * b] + R[a + 3] * Ue[1 + 3 * b] + R[a + 6] * Ue[2 + 3 * b];
+  }
+
+  // TECH shell_ans / shell_eas_ans on hex8: right Cauchy-Green tensor C = 2 E_ans + I of the ANS strain at Gauss point g
+  // (evaluate_local_glstrain, 4C_solid_ele_calc_shell_ans_lib.hpp:169-291; T^-T as in generic_block_row_ans)
+  B2_HD void ans_right_cauchy_green(const PostArgs& A, const int32_t* ce, int g, double* C)
+  {
+    constexpr int NN = 8;
+    double X[NN][3], x[NN][3];
+    for (int k = 0; k < NN; ++k)
+      for (int d = 0; d < 3; ++d)
+      {
+        X[k][d] = A.X[3 * (int64_t)ce[k] + d];
+        x[k][d] = X[k][d] + A.u[3 * (int64_t)ce[k] + d];
+      }
+    auto jac = [&](const double* dN, const double (*P)[3], double* J)
+    {
+      for (int q = 0; q < 9; ++q) J[q] = 0.0;
+      for (int k = 0; k < NN; ++k)
+        for (int a = 0; a < 3; ++a)
+          for (int d = 0; d < 3; ++d) J[a + 3 * d] = fma(dN[3 * k + a], P[k][d], J[a + 3 * d]);
+    };
+    auto rows = [](const double* J, int a, int b) { return J[a] * J[b] + J[a + 3] * J[b + 3] + J[a + 6] * J[b + 6]; };
+    // metric difference (a, b) between the current and the reference configuration at sampling point q
+    auto sampled = [&](int q, int a, int b)
+    {
+      double Jr[9], Jc[9];
+      jac(A.dN_ans + (size_t)q * NN * 3, X, Jr), jac(A.dN_ans + (size_t)q * NN * 3, x, Jc);
+      return rows(Jc, a, b) - rows(Jr, a, b);
+    };
+    const double* dN = A.dN_gp + (size_t)g * NN * 3;
+    const double* xi = A.xi_gp + 3 * g;
+    double J[9], Jc[9], iJ[9], T[36], El[6];
+    jac(dN, X, J), jac(dN, x, Jc);
+    inv3(iJ, J);
+    voigt_strain_transformation(iJ, T);
+    El[0] = 0.5 * (rows(Jc, 0, 0) - rows(J, 0, 0));
+    El[1] = 0.5 * (rows(Jc, 1, 1) - rows(J, 1, 1));
+    El[3] = rows(Jc, 0, 1) - rows(J, 0, 1);
+    El[2] = 0.5 * (0.25 * (1 - xi[0]) * (1 - xi[1]) * sampled(4, 2, 2) + 0.25 * (1 + xi[0]) * (1 - xi[1]) * sampled(5, 2, 2) +
+                      0.25 * (1 + xi[0]) * (1 + xi[1]) * sampled(6, 2, 2) + 0.25 * (1 - xi[0]) * (1 + xi[1]) * sampled(7, 2, 2));
+    El[4] = 0.5 * (1 + xi[0]) * sampled(1, 1, 2) + 0.5 * (1 - xi[0]) * sampled(3, 1, 2);
+    El[5] = 0.5 * (1 - xi[1]) * sampled(0, 0, 2) + 0.5 * (1 + xi[1]) * sampled(2, 0, 2);
+    for (int r = 0; r < 6; ++r)
+    {
+      double v = 0.0;
+      for (int q = 0; q < 6; ++q) v = fma(T[r + 6 * q], El[q], v);
+      C[r] = r < 3 ? 2.0 * v + 1.0 : v;
+    }
   }
 
   // One Gauss point of calculate_stress / calculate_internal_energy.  Returns psi * integration
@@ -259,10 +318,19 @@ namespace b200s
     double C[6], S[6], Cm[21];
     right_cauchy_green(F, C);
     if (A.linear) linear_kinematics(F, C);
+    const bool want_F =
+        !A.linear && ((stress6 != nullptr && A.stress_type == STRESS_CAUCHY) || (strain6 != nullptr && A.strain_type == STRAIN_EA));
+    double Cd[6];
+    if (A.dN_ans != nullptr)
+    {
+      // ShellANSFormulation::evaluate (shell_ans.hpp:96-117): the ANS strain and the deformation gradient consistent with it
+#pragma unroll
+      for (int v = 0; v < 6; ++v) Cd[v] = C[v];
+      ans_right_cauchy_green(A, ce, g, C);
+      if (!A.eas_neas && want_F) consistent_deformation_gradient(Cd, C, F);
+    }
     if (A.eas_neas)  // (KINEM linear: the enhanced deformation gradient is the identity, eas_helpers.hpp:663-665)
-      eas_enhance(A, e, g, detJ,
-          !A.linear && ((stress6 != nullptr && A.stress_type == STRESS_CAUCHY) || (strain6 != nullptr && A.strain_type == STRAIN_EA)),
-          F, C);
+      eas_enhance(A, e, g, detJ, want_F, F, C, A.dN_ans != nullptr ? Cd : nullptr);
     MatParams mp = A.mp;
     if (A.per_ele_param != nullptr) mp.p[0] = A.per_ele_param[e];
     if (MAT == MAT_HYPER && A.fibers != nullptr) mp.fiber = A.fibers + 3 * e;

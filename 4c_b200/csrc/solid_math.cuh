@@ -415,6 +415,30 @@ namespace b200s
           }
     }
   }
+  // Strain-like Voigt transformation of E' = M E M^T (rows / columns xx,yy,zz,xy,yz,xz, T[r + 6 c]); with M = J^-1 this is
+  // T^-T of evaluate_voigt_transformation_matrix (4C_solid_ele_calc_lib.hpp:1451-1517), which the reference obtains by
+  // inverting T(J) numerically
+  B2_HD void voigt_strain_transformation(const double* M /*a + 3 b*/, double* T /*r + 6 c*/)
+  {
+    constexpr int pa[3] = {0, 1, 0}, pb[3] = {1, 2, 2};
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+    {
+      const int a = r < 3 ? r : pa[r - 3], b = r < 3 ? r : pb[r - 3];
+#pragma unroll
+      for (int c = 0; c < 6; ++c)
+      {
+        const int cc = c < 3 ? c : pa[c - 3], dd = c < 3 ? c : pb[c - 3];
+        double v;
+        if (r < 3)
+          v = M[a + 3 * cc] * M[a + 3 * dd];
+        else
+          v = c < 3 ? 2.0 * M[a + 3 * cc] * M[b + 3 * cc] : M[a + 3 * cc] * M[b + 3 * dd] + M[a + 3 * dd] * M[b + 3 * cc];
+        T[r + 6 * c] = v;
+      }
+    }
+  }
+
 }  // namespace b200s
 
 #include "summands.cuh"

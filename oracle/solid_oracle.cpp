@@ -2127,6 +2127,66 @@ namespace
   //      not taken at the Gauss point but interpolated from sampling points (hex8: A..D mid-edges of the mid-surface for
   //      the shears, E..H its corners for tt; wedge6: five points), for the strains, the B-operator and the geometric
   //      stiffness alike; T^-T of the Jacobian at the Gauss point takes everything to the global frame.
+  // ANS Green-Lagrange strain at xi in the global frame, stress-like Voigt (evaluate_local_glstrain,
+  // shell_ans_lib.hpp:169-291 hex8 / :294-380 wedge6, then T^-T and Voigt::Strains::to_stress_like as in
+  // ShellANSFormulation::evaluate, shell_ans.hpp:96-110): rr, ss, rs at the point itself, tt / st / rt interpolated from
+  // the sampling points of the mid-surface.  Used by the element routine below and by the output actions.
+  void ans_gl_strain(int ct, const double* X, const double* u, const double* xi, const JacMap& jm, double* E)
+  {
+    const int n = nnodes(ct);
+    const bool hex = ct == ORC_HEX8;
+    const double sp_hex[8][3] = {{0, -1, 0}, {1, 0, 0}, {0, 1, 0}, {-1, 0, 0}, {-1, -1, 0}, {1, -1, 0}, {1, 1, 0}, {-1, 1, 0}};
+    const double sp_wedge[5][3] = {{0.5, 0, 0}, {0, 0.5, 0}, {0, 0, 0}, {1, 0, 0}, {0, 1, 0}};
+    double N[MAXN], dN[3 * MAXN];
+    auto jac = [&](const double* dNq, bool current, double* J)
+    {
+      for (int a = 0; a < 3; ++a)
+        for (int d = 0; d < 3; ++d)
+        {
+          double v = 0.0;
+          for (int k = 0; k < n; ++k) v += dNq[a + 3 * k] * (X[3 * k + d] + (current ? u[3 * k + d] : 0.0));
+          J[a + 3 * d] = v;
+        }
+    };
+    auto row_dot = [](const double* J, int a, int b) { return J[a] * J[b] + J[a + 3] * J[b + 3] + J[a + 6] * J[b + 6]; };
+    // difference of the metric components (a, b) between the current and the reference configuration at sampling point q
+    auto sampled = [&](int q, int a, int b)
+    {
+      double Jr[9], Jc[9];
+      shape(ct, hex ? sp_hex[q] : sp_wedge[q], N, dN);
+      jac(dN, false, Jr), jac(dN, true, Jc);
+      return row_dot(Jc, a, b) - row_dot(Jr, a, b);
+    };
+    double tt, st, rt;
+    if (hex)
+    {
+      tt = 0.25 * (1 - xi[0]) * (1 - xi[1]) * sampled(4, 2, 2) + 0.25 * (1 + xi[0]) * (1 - xi[1]) * sampled(5, 2, 2) +
+           0.25 * (1 + xi[0]) * (1 + xi[1]) * sampled(6, 2, 2) + 0.25 * (1 - xi[0]) * (1 + xi[1]) * sampled(7, 2, 2);
+      st = 0.5 * (1 + xi[0]) * sampled(1, 1, 2) + 0.5 * (1 - xi[0]) * sampled(3, 1, 2);
+      rt = 0.5 * (1 - xi[1]) * sampled(0, 0, 2) + 0.5 * (1 + xi[1]) * sampled(2, 0, 2);
+    }
+    else
+    {
+      tt = (1 - xi[0] - xi[1]) * sampled(2, 2, 2) + xi[0] * sampled(3, 2, 2) + xi[1] * sampled(4, 2, 2);
+      st = xi[0] * sampled(1, 1, 2);
+      rt = xi[1] * sampled(0, 0, 2);
+    }
+    double Jc[9], El[6], TinvT[36];
+    shape(ct, xi, N, dN);
+    jac(dN, true, Jc);
+    El[0] = 0.5 * (row_dot(Jc, 0, 0) - row_dot(jm.J, 0, 0));
+    El[1] = 0.5 * (row_dot(Jc, 1, 1) - row_dot(jm.J, 1, 1));
+    El[3] = row_dot(Jc, 0, 1) - row_dot(jm.J, 0, 1);
+    El[2] = 0.5 * tt, El[4] = st, El[5] = rt;
+    voigt_transformation(jm.J, TinvT);
+    for (int r = 0; r < 6; ++r)
+    {
+      double v = 0.0;
+      for (int q = 0; q < 6; ++q) v += TinvT[r + 6 * q] * El[q];
+      E[r] = r < 3 ? v : 0.5 * v;  // Voigt::Strains::to_stress_like
+    }
+  }
+
   void eas_shape_functions(int neas, const double* xi, double* M);
   // hist != nullptr: TECH shell_eas_ans = SolidEleCalc<hex8, ShellEASANSFormulation<hex8, eastype_sh8_7>>
   // (src/solid_ele/4C_solid_ele_calc_shell_eas_ans.hpp:70-343): the ANS strains / B-operator / geometric stiffness below, the
@@ -2255,24 +2315,9 @@ namespace
           for (int q = 0; q < 6; ++q) v += TinvT[r + 6 * q] * Bl[q + 6 * c];
           B[r + 6 * c] = v;
         }
-      // evaluate_local_glstrain (:169-291 / :294-380)
-      auto row_dot = [](const double* J, int a, int b) { return J[a] * J[b] + J[a + 3] * J[b + 3] + J[a + 6] * J[b + 6]; };
-      double El[6];
-      El[0] = 0.5 * (row_dot(Jc, 0, 0) - row_dot(jm.J, 0, 0));
-      El[1] = 0.5 * (row_dot(Jc, 1, 1) - row_dot(jm.J, 1, 1));
-      El[3] = row_dot(Jc, 0, 1) - row_dot(jm.J, 0, 1);
-      double tt = 0.0, st = 0.0, rt = 0.0;
-      for (int m = 0; m < n_tt; ++m) tt += w_tt[m] * (row_dot(sp[q_tt[m]].Jc, 2, 2) - row_dot(sp[q_tt[m]].Jr, 2, 2));
-      for (int m = 0; m < n_st; ++m) st += w_st[m] * (row_dot(sp[q_st[m]].Jc, 1, 2) - row_dot(sp[q_st[m]].Jr, 1, 2));
-      for (int m = 0; m < n_rt; ++m) rt += w_rt[m] * (row_dot(sp[q_rt[m]].Jc, 0, 2) - row_dot(sp[q_rt[m]].Jr, 0, 2));
-      El[2] = 0.5 * tt, El[4] = st, El[5] = rt;
+      // evaluate_local_glstrain (:169-291 / :294-380), to the global frame, stress-like: ans_gl_strain above
       double E[6], S[6], Cm[36], F[9];
-      for (int r = 0; r < 6; ++r)
-      {
-        double v = 0.0;
-        for (int q = 0; q < 6; ++q) v += TinvT[r + 6 * q] * El[q];
-        E[r] = r < 3 ? v : 0.5 * v;  // Voigt::Strains::to_stress_like
-      }
+      ans_gl_strain(ct, X, u, xi, jm, E);
       double Mt[6 * 7];
       if (hist)
       {
@@ -2812,6 +2857,31 @@ extern "C"
     {
       const int n = nnodes(ct);
       deformation_gradient(n, u, jm, F);
+      if (tech == ORC_TECH_SHELL_ANS || tech == ORC_TECH_SHELL_EAS_ANS)
+      {
+        // ShellANSFormulation::evaluate (shell_ans.hpp:96-117) / ShellEASANSFormulation::evaluate (shell_eas_ans.hpp:
+        // 116-139): the ANS strain, with EAS enhanced by Mtilde alpha; deformation gradient consistent with it
+        double Fc[9];
+        ans_gl_strain(ct, X, u, g_xi, jm, E);
+        if (tech == ORC_TECH_SHELL_EAS_ANS)
+        {
+          const int neas = eas_num(tech);
+          double T0invT[36], detJ0, M[6 * 21];
+          eas_centroid_transformation(ct, X, T0invT, detJ0);
+          eas_shape_functions(neas, g_xi, M);
+          const double* alpha = g_eas_hist + neas;
+          for (int r = 0; r < 6; ++r)
+          {
+            double v = 0.0;
+            for (int c = 0; c < neas; ++c)
+              for (int k = 0; k < 6; ++k) v += (detJ0 / jm.det) * T0invT[r + 6 * k] * M[k + 6 * c] * alpha[c];
+            E[r] += r < 3 ? v : 0.5 * v;
+          }
+        }
+        enhanced_deformation_gradient(F, E, Fc);
+        for (int i = 0; i < 9; ++i) F[i] = Fc[i];
+        return;
+      }
       if (is_eas(tech))
       {
         // EASFormulation::evaluate (4C_solid_ele_calc_eas.hpp:72-88): enhanced GL strain and deformation gradient

@@ -355,6 +355,12 @@ extern "C" int emu_post(int celltype, int fbar, int matkind, const double* param
   A.mat_hist = nullptr;
   A.eas_neas = 0, A.eas_hist_size = 0, A.eas_t0_stride = 0, A.eas_hist = nullptr, A.eas_t0 = nullptr;
   A.xi_gp = T.xi_gp.data();
+  A.dN_ans = nullptr;
+  if (fbar == 3)  // TECH shell_ans (hex8)
+  {
+    if (T.dN_ans.empty()) return -4;
+    A.dN_ans = T.dN_ans.data();
+  }
   A.stress_type = stress_type, A.strain_type = strain_type;
   A.stress = stress, A.strain = strain, A.energy = nullptr;
   switch (matkind)

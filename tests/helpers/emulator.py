@@ -123,7 +123,7 @@ def post(celltype, matkind, params, conn, X, u_col, stress_type=1, strain_type=1
         ele_is_row = np.ascontiguousarray(ele_is_row, np.uint8)
     if per_ele is not None:
         per_ele = np.ascontiguousarray(per_ele, np.float64)
-    # fbar: False / True, or 2 = KINEM linear
+    # fbar: False / True, or 2 = KINEM linear, 3 = TECH shell_ans (hex8)
     rc = lib("post").emu_post(C.c_int(celltype), C.c_int(int(fbar)), C.c_int(matkind), _p(params), _p(per_ele),
                               C.c_int64(len(conn)), _p(conn), _p(X), _p(u_col), _p(ele_is_row),
                               C.c_int(stress_type), C.c_int(strain_type), _p(st), _p(en),

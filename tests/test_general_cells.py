@@ -167,6 +167,29 @@ def test_emulated_general_kernel_shell_eas_ans_matches_oracle():
         assert np.abs(K - K1).max() > 1e-4 * np.abs(K1).max() or np.abs(f - f1).max() > 1e-4 * np.abs(f1).max()
 
 
+def test_emulated_stress_output_shell_ans_matches_oracle():
+    """struct_calc_stress / internal energy of a TECH shell_ans block: the product's post arithmetic (ANS strain at the
+    Gauss point, deformation gradient consistent with it) stepped on the CPU against the oracle (pinned to the reference's
+    nodal stresses of solid_ele_hex8_Standard_shell_ans.4C.yaml, tests/test_post_actions.py)."""
+    rm = b200.partition.box_partition(b200.mesh.HEX8, (3, 2, 2), 0, 1)
+    X = rm.X.copy()
+    rng = np.random.default_rng(4)
+    inner = np.all((X > 1e-9) & (X < 1 - 1e-9), axis=1)
+    X[inner] += 0.05 * rng.uniform(-1, 1, (int(inner.sum()), 3))
+    u = 1.0 * b200.mesh.displacement_field(X, rm.node_gid, 1.0, 0.4)
+    for mk, par in MATS.items():
+        for stype, etype in ((orc.STRESS_2PK, orc.STRAIN_GL), (orc.STRESS_CAUCHY, orc.STRAIN_EA)):
+            ost, oen = orc.calc_stress(orc.HEX8, mk, par, rm.conn, X.ravel(), u.ravel(), stype, etype, tech=orc.TECH_SHELL_ANS)
+            st, en, energy = emu.post(rm.celltype, mk, par, rm.conn, X.ravel(), u.ravel(), stype, etype, fbar=3)
+            assert np.abs(st - ost).max() <= 1e-11 * np.abs(ost).max(), (mk, stype)
+            assert np.abs(en - oen).max() <= 1e-11 * np.abs(oen).max(), (mk, etype)
+        oe = orc.calc_energy(orc.HEX8, mk, par, rm.conn, X.ravel(), u.ravel(), tech=orc.TECH_SHELL_ANS)
+        assert abs(energy - oe) <= 1e-11 * abs(oe)
+        # and it is not the displacement-based element's output
+        st0, _, _ = emu.post(rm.celltype, mk, par, rm.conn, X.ravel(), u.ravel(), stype, etype)
+        assert np.abs(st - st0).max() > 1e-4 * np.abs(st0).max()
+
+
 def test_emulated_general_kernel_shell_ans_matches_oracle():
     """TECH shell_ans on hex8 (ShellANSFormulation, src/solid_ele/4C_solid_ele_calc_shell_ans.hpp): sampling-point
     interpolation of the transverse strain rows, T^-T formed from the inverse Jacobian, ANS geometric stiffness -- the

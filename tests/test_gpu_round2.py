@@ -1210,3 +1210,44 @@ def test_shell_eas_ans_matches_oracle_and_known_answers():
     for e in case["expected_disp"]:
         assert abs(uu[e["node"], e["dof"]] - e["value"]) < 1e-10, (e, uu[e["node"], e["dof"]])
     asm.close()
+
+
+# ---- struct_calc_stress of the three hex8 solid shells: the reference's nodal Cauchy stresses through the CUDA path -------
+@pytest.mark.parametrize("tech", ["shell_ans", "shell_eas", "shell_eas_ans"])
+def test_solid_shell_stress_output_known_answers_through_cuda_path(tech):
+    import json
+    import os
+    from tests.helpers.newton import solve_case
+    from tests.helpers.postprocess import nodal_stresses
+    dtech, otech = {"shell_ans": (capi.TECH_SHELL_ANS, orc.TECH_SHELL_ANS), "shell_eas": (capi.TECH_SHELL_EAS, orc.TECH_SHELL_EAS),
+                    "shell_eas_ans": (capi.TECH_SHELL_EAS_ANS, orc.TECH_SHELL_EAS_ANS)}[tech]
+    case = json.load(open(os.path.join(os.path.dirname(__file__), "golden", f"integration_hex8_{tech}.json")))
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    rm = b200.partition.serial_mesh(b200.mesh.HEX8, X, conn)
+    par = [case["material"]["YOUNG"], case["material"]["NUE"]]
+    asm = b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, par, tech=dtech)
+    rowptr, colind = asm.graph()
+
+    def ev(uu):
+        asm.set_state("displacement", uu)
+        K, f, _ = asm.evaluate()
+        return rowptr, colind, K, f
+
+    u = solve_case(case, ev, recover=None if tech == "shell_ans" else (lambda du: asm.recover(du, 1.0)))
+    asm.set_state("displacement", u.ravel())
+    st, en = asm.calc_stress("cauchy", "gl")
+    ns = nodal_stresses(orc.HEX8, conn, st, len(X))
+    assert len(case["expected_stress"]) >= 24
+    for e in case["expected_stress"]:
+        assert abs(ns[e["node"], e["comp"]] - e["value"]) < 1e-8, (e, ns[e["node"], e["comp"]])
+    # and against the oracle at the same state, Gauss point by Gauss point (2PK / GL and Cauchy / Euler-Almansi), energy
+    hist = None if tech == "shell_ans" else asm.ctx.get_element_history().reshape(len(conn), -1).copy()
+    for names, types in ((("2pk", "gl"), (orc.STRESS_2PK, orc.STRAIN_GL)), (("cauchy", "ea"), (orc.STRESS_CAUCHY, orc.STRAIN_EA))):
+        st, en = asm.calc_stress(*names)
+        ost, oen = orc.calc_stress(orc.HEX8, orc.MAT_COUP_NEOHOOKE, par, conn, X.ravel(), u.ravel(), *types, tech=otech, hist=hist)
+        assert np.abs(st - ost).max() <= 1e-10 * np.abs(ost).max(), (tech, names)
+        assert np.abs(en - oen).max() <= 1e-10 * np.abs(oen).max(), (tech, names)
+    oe = orc.calc_energy(orc.HEX8, orc.MAT_COUP_NEOHOOKE, par, conn, X.ravel(), u.ravel(), tech=otech, hist=hist)
+    assert abs(asm.calc_energy() - oe) <= 1e-10 * abs(oe)
+    asm.close()

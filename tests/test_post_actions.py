@@ -465,6 +465,36 @@ def test_shell_eas_ans_known_answers():
         assert abs(u[e["node"], e["dof"]] - e["value"]) < 1e-12, (e, u[e["node"], e["dof"]])
 
 
+@pytest.mark.parametrize("tech", ["shell_ans", "shell_eas", "shell_eas_ans"])
+def test_solid_shell_nodal_cauchy_stress_known_answers(tech):
+    """RESULT DESCRIPTION stress_xx..stress_yz (1e-12 in the reference) of tests/input_files/solid_ele_hex8_Standard_<tech>.4C.yaml:
+    struct_calc_stress of the three hex8 solid shells -- the strain of the formulation (ANS, EAS-enhanced, both) and the
+    deformation gradient consistent with it (compute_deformation_gradient_from_gl_strains) behind pk2_to_cauchy."""
+    case = json.load(open(os.path.join(G, f"integration_hex8_{tech}.json")))
+    assert case["iostress"] == "Cauchy" and len(case["expected_stress"]) >= 24
+    otech = {"shell_ans": orc.TECH_SHELL_ANS, "shell_eas": orc.TECH_SHELL_EAS, "shell_eas_ans": orc.TECH_SHELL_EAS_ANS}[tech]
+    X = np.asarray(case["coords"], float)
+    conn = np.asarray(case["elements"], np.int32)
+    nn = len(X)
+    row, col = serial_maps(nn)
+    rowptr, colind = orc.build_graph(orc.HEX8, conn, row, col, nn)
+    par = [case["material"]["YOUNG"], case["material"]["NUE"]]
+    hist = orc.eas_new_history(otech, len(conn)) if otech != orc.TECH_SHELL_ANS else None
+
+    def evaluate(u):
+        vals, f, nbad = orc.evaluate_assemble(orc.HEX8, orc.MAT_COUP_NEOHOOKE, par, conn, X.ravel(), u, row, col, nn, rowptr,
+                                              colind, tech=otech, hist=hist)
+        assert nbad == 0
+        return rowptr, colind, vals, f
+
+    u = solve_case(case, evaluate, recover=None if hist is None else (lambda du: orc.eas_recover(otech, conn, du, hist)))
+    st, _ = orc.calc_stress(orc.HEX8, orc.MAT_COUP_NEOHOOKE, par, conn, X.ravel(), u.ravel(), orc.STRESS_CAUCHY, orc.STRAIN_GL,
+                            tech=otech, hist=hist)
+    nodal = nodal_stresses(orc.HEX8, conn, st, nn)
+    for e in case["expected_stress"]:
+        assert abs(nodal[e["node"], e["comp"]] - e["value"]) < 2e-10, (e, nodal[e["node"], e["comp"]])
+
+
 def test_mulf_update_keeps_the_stress_state():
     """After struct_update_prestress and the displacement reset the element sees the same deformation
     gradient (F_delta = I, F = F_hist), hence the same internal force."""
