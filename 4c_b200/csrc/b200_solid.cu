@@ -1640,7 +1640,9 @@ namespace
     if (p) cudaFree(p);
     p = nullptr;
   }
-  inline unsigned nblk(int64_t n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
+  // blocks for n work items; at least one, so that a processor without elements / row nodes (ordinary in the reference's
+  // column-element loop) launches a block that finds nothing to do instead of an invalid empty grid
+  inline unsigned nblk(int64_t n, int bs = 256) { return n > 0 ? (unsigned)((n + bs - 1) / bs) : 1u; }
 
   template <class K>
   int set_smem_attr(K kernel, size_t bytes)
@@ -2561,7 +2563,9 @@ extern "C"
   int b200s_set_mesh(b200s_ctx* ctx, int celltype, int64_t n_col_nodes, const double* X,
       int64_t n_col_eles, const int32_t* conn)
   {
-    if (!ctx || !X || !conn || n_col_nodes <= 0 || n_col_eles < 0) return B200S_ERR_INVALID;
+    // a processor may hold no element (empty column-element loop) or nothing at all
+    if (!ctx || n_col_nodes < 0 || n_col_eles < 0 || (n_col_nodes > 0 && !X) || (n_col_eles > 0 && (!conn || n_col_nodes == 0)))
+      return B200S_ERR_INVALID;
     cudaSetDevice(ctx->device);
     if (ctx->primary) detach_shared(ctx);  // a new mesh: attach again afterwards
     if (celltype != B200S_HEX8 && celltype != B200S_TET10 && celltype != B200S_HEX27 && !is_general_cell(celltype))
@@ -3046,9 +3050,11 @@ extern "C"
   int b200s_set_graph(b200s_ctx* ctx, int64_t n_rows, const int64_t* rowptr, const int32_t* colind,
       const int32_t* dof_row_lid, const int32_t* dof_col_lid)
   {
-    if (!ctx || !rowptr || !colind || !dof_row_lid || !dof_col_lid || n_rows <= 0)
-      return B200S_ERR_INVALID;
+    if (!ctx || !rowptr || n_rows < 0) return B200S_ERR_INVALID;
     if (ctx->celltype < 0) return fail(ctx, B200S_ERR_INVALID, "set_mesh must precede set_graph");
+    // empty graphs (no row dofs / no entries) are valid; colind and the dof maps may then be absent
+    if ((ctx->n_col_nodes > 0 && (!dof_row_lid || !dof_col_lid)) || (n_rows > 0 && !colind))
+      return fail(ctx, B200S_ERR_INVALID, "set_graph: colind / dof_row_lid / dof_col_lid missing");
     if (ctx->primary) return fail(ctx, B200S_ERR_INVALID, "an attached element block uses its primary's graph");
     cudaSetDevice(ctx->device);
     // stage the caller's (host or device) arrays on the device; they are only needed to build the map
@@ -3069,8 +3075,11 @@ extern "C"
   int b200s_build_graph(b200s_ctx* ctx, int64_t n_row_nodes, const int32_t* node_row_lid,
       const int32_t* node_col_lid, int64_t* rowptr_out, int32_t* colind_out, int64_t* nnz_out)
   {
-    if (!ctx || !node_row_lid || !node_col_lid || n_row_nodes <= 0) return B200S_ERR_INVALID;
+    if (!ctx || n_row_nodes < 0) return B200S_ERR_INVALID;
     if (ctx->celltype < 0) return fail(ctx, B200S_ERR_INVALID, "set_mesh must precede build_graph");
+    // a processor without row nodes (ghost elements only) or without any node is valid: empty graph
+    if (ctx->n_col_nodes > 0 && (!node_row_lid || !node_col_lid))
+      return fail(ctx, B200S_ERR_INVALID, "build_graph: node_row_lid / node_col_lid missing");
     if (ctx->primary) return fail(ctx, B200S_ERR_INVALID, "an attached element block uses its primary's graph");
     cudaSetDevice(ctx->device);
     cudaStream_t st = ctx->stream;
@@ -3999,7 +4008,7 @@ extern "C"
   int b200s_set_state(b200s_ctx* ctx, const char* name, const double* v_row)
   {
     if (!ctx || !name || !v_row) return B200S_ERR_INVALID;
-    if (ctx->n_rows <= 0) return fail(ctx, B200S_ERR_INVALID, "set_graph must precede set_state");
+    if (!ctx->d_rowptr) return fail(ctx, B200S_ERR_INVALID, "set_graph must precede set_state");
     cudaSetDevice(ctx->device);
     double* dst = nullptr;
     if (!strcmp(name, "displacement"))
@@ -4167,7 +4176,7 @@ extern "C"
         strain_type < B200S_STRAIN_NONE || strain_type > B200S_STRAIN_EA)
       return fail(ctx, B200S_ERR_UNSUPPORTED, "stress/strain output type %d/%d has no device kernel",
           stress_type, strain_type);
-    if (ctx->n_rows <= 0) return fail(ctx, B200S_ERR_INVALID, "set_graph must precede calc_stress");
+    if (!ctx->d_rowptr) return fail(ctx, B200S_ERR_INVALID, "set_graph must precede calc_stress");
     cudaSetDevice(ctx->device);
     const size_t n = (size_t)ctx->n_col_eles * ctx->ngp * 6;
     double *d_s = nullptr, *d_e = nullptr;
@@ -4190,7 +4199,7 @@ extern "C"
   int b200s_calc_energy(b200s_ctx* ctx, double* energy_out)
   {
     if (!ctx || !energy_out) return B200S_ERR_INVALID;
-    if (ctx->n_rows <= 0) return fail(ctx, B200S_ERR_INVALID, "set_graph must precede calc_energy");
+    if (!ctx->d_rowptr) return fail(ctx, B200S_ERR_INVALID, "set_graph must precede calc_energy");
     if (ctx->nranks > 1 && !ctx->d_ele_is_row)
       return fail(ctx, B200S_ERR_INVALID,
           "calc_energy on a partitioned mesh needs b200s_set_row_elements (row elements only)");
@@ -4218,7 +4227,7 @@ extern "C"
       return fail(ctx, B200S_ERR_UNSUPPORTED,
           "Your element evaluation does not allow to update prestress. You may need to add MULF to your "
           "element line definitions.");
-    if (ctx->n_rows <= 0) return fail(ctx, B200S_ERR_INVALID, "set_graph must precede update_prestress");
+    if (!ctx->d_rowptr) return fail(ctx, B200S_ERR_INVALID, "set_graph must precede update_prestress");
     cudaSetDevice(ctx->device);
     const int rc = import_row_to_col(ctx, ctx->d_u_row, ctx->d_u_col, false);
     if (rc) return rc;
@@ -4245,7 +4254,7 @@ extern "C"
   int b200s_recover(b200s_ctx* ctx, const double* du_row, double step_length)
   {
     if (!ctx || !du_row) return B200S_ERR_INVALID;
-    if (ctx->n_rows <= 0) return fail(ctx, B200S_ERR_INVALID, "set_graph must precede recover");
+    if (!ctx->d_rowptr) return fail(ctx, B200S_ERR_INVALID, "set_graph must precede recover");
     const int neas = eas_neas(ctx->tech);
     if (!neas) return B200S_OK;  // formulations without condensed variables: nothing to recover
     if (!ctx->d_eas_hist) return fail(ctx, B200S_ERR_INVALID, "EAS history missing");
@@ -4574,7 +4583,7 @@ extern "C"
   int b200s_neumann_gp_coords(b200s_ctx* ctx, int cond, int flags, double* xyz_out)
   {
     if (!ctx || !xyz_out || cond < 0 || cond >= (int)ctx->neumann.size()) return B200S_ERR_INVALID;
-    if (ctx->n_rows <= 0) return fail(ctx, B200S_ERR_INVALID, "set_graph must precede neumann_gp_coords");
+    if (!ctx->d_rowptr) return fail(ctx, B200S_ERR_INVALID, "set_graph must precede neumann_gp_coords");
     cudaSetDevice(ctx->device);
     const auto& c = ctx->neumann[cond];
     const int64_t n = b200s_neumann_gp_count(ctx, cond);
@@ -4606,7 +4615,7 @@ extern "C"
   int b200s_evaluate_neumann(b200s_ctx* ctx, const double* u_row, int flags, double* fext_row)
   {
     if (!ctx) return B200S_ERR_INVALID;
-    if (ctx->n_rows <= 0 || !ctx->d_node_row)
+    if (!ctx->d_rowptr || !ctx->d_node_row)
       return fail(ctx, B200S_ERR_INVALID, "set_mesh and set_graph must precede evaluate_neumann");
     cudaSetDevice(ctx->device);
     cudaStream_t st = ctx->stream;
@@ -4694,7 +4703,7 @@ extern "C"
       const double* dbcval_row, const double* dbctoggle_row)
   {
     if (!ctx || !dbcval_row || !dbctoggle_row || (!x_row && !b_row)) return B200S_ERR_INVALID;
-    if (ctx->n_rows <= 0) return fail(ctx, B200S_ERR_INVALID, "set_graph first");
+    if (!ctx->d_rowptr) return fail(ctx, B200S_ERR_INVALID, "set_graph first");
     cudaSetDevice(ctx->device);
     cudaStream_t st = ctx->stream;
     const size_t bytes = sizeof(double) * (size_t)ctx->n_rows;
@@ -4739,7 +4748,7 @@ extern "C"
   int b200s_multiply(b200s_ctx* ctx, int which, const double* x_row, double* y_row)
   {
     if (!ctx || !x_row || !y_row) return B200S_ERR_INVALID;
-    if (ctx->n_rows <= 0) return fail(ctx, B200S_ERR_INVALID, "set_graph first");
+    if (!ctx->d_rowptr) return fail(ctx, B200S_ERR_INVALID, "set_graph first");
     cudaSetDevice(ctx->device);
     cudaStream_t st = ctx->stream;
     if (stage_row_vector(ctx, &ctx->d_la_x, x_row)) return B200S_ERR_CUDA;
@@ -4762,7 +4771,7 @@ extern "C"
       int* iters_out, double* relres_out)
   {
     if (!ctx || !b_row || !x_row || maxit < 1) return B200S_ERR_INVALID;
-    if (ctx->n_rows <= 0 || !ctx->d_vals) return fail(ctx, B200S_ERR_INVALID, "no assembled matrix");
+    if (!ctx->d_rowptr || !ctx->d_vals) return fail(ctx, B200S_ERR_INVALID, "no assembled matrix");
     cudaSetDevice(ctx->device);
     cudaStream_t st = ctx->stream;
     const int64_t n = ctx->n_rows, nrn = n / 3;

@@ -266,7 +266,10 @@ extern "C"
    *   X    [host|dev] 3*n_col_nodes, node-major xyz       (Node::x(), calc_lib.hpp:161-190)
    *   conn [host|dev] n_col_eles*nodes_per_ele, column-node local ids in element node order
    * All elements of one context share cell type, formulation (displacement based, nonlinear TL)
-   * and material; other element blocks use further contexts or stay on the CPU path. */
+   * and material; other element blocks use further contexts or stay on the CPU path.
+   * n_col_eles == 0 (a processor without elements) and n_col_nodes == 0 (a processor that holds nothing) are valid, as are
+   * n_row_nodes == 0 in b200s_build_graph / n_rows == 0 in b200s_set_graph (ghost elements only): the evaluate of such a
+   * context has nothing to add, as the reference's column-element loop has nothing to do. */
   int b200s_set_mesh(b200s_ctx* ctx, int celltype, int64_t n_col_nodes, const double* X,
       int64_t n_col_eles, const int32_t* conn);
 
