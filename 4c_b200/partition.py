@@ -89,6 +89,10 @@ def _axis_sets(celltype, nd, rng_d, s):
 def box_partition(celltype, n, rank, nranks, box=(1.0, 1.0, 1.0)):
     """Rank-local structured hex8/hex27 mesh for the grid generator's box partition."""
     sub, ranges = box_subdivisions(n, nranks)
+    if any(ranges[d][k + 1] <= ranges[d][k] for d in range(3) for k in range(sub[d])):
+        # a section without elements has no interface plane of its own: the ownership rule below ("lower interface plane
+        # belongs to the lower rank") is not defined for it
+        raise ValueError(f"box_partition: {n} elements cannot be cut into {sub} non-empty sections ({nranks} ranks)")
     sec = _section(rank, sub)
     (gx, gy, gz), step = _mesh.hex_grid_dims(celltype, n)
     own, col, cel = zip(*[_axis_sets(celltype, n[d], ranges[d], sec[d]) for d in range(3)])

@@ -72,7 +72,7 @@ def _worker(rank, world, port, n, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n", [(2, (6, 4, 3)), (4, (6, 5, 3))])
+@pytest.mark.parametrize("world,n", [(2, (6, 4, 3)), (4, (6, 5, 3)), (2, (2, 1, 1))])
 def test_owner_computes_rows_over_gloo_equal_serial(world, n, tmp_path):
     mp.spawn(_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
     b200 = importlib.import_module("4c_b200")
@@ -103,3 +103,13 @@ def test_owner_computes_rows_over_gloo_equal_serial(world, n, tmp_path):
     assert len(seen_rows) == ndof and n_entries == len(K)
     assert np.abs(f_all - f).max() <= 1e-12 * np.abs(f).max()
     assert row_eles == n[0] * n[1] * n[2]
+
+
+def test_box_partition_refuses_empty_sections():
+    """More ranks than elements along the cut axis: refused loudly (the halo lists of an empty section are undefined)."""
+    b200 = importlib.import_module("4c_b200")
+    for n, world in (((1, 1, 1), 2), ((2, 1, 1), 4)):
+        with pytest.raises(ValueError):
+            b200.partition.box_partition(b200.mesh.HEX8, n, 0, world)
+    rm = b200.partition.box_partition(b200.mesh.HEX8, (2, 1, 1), 1, 2)
+    assert rm.n_row_eles == 1 and rm.n_col_eles == 1
