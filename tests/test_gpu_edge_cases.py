@@ -117,3 +117,60 @@ def test_empty_block_through_every_action(tech, prestress):
     asm.ctx.update_step()
     asm.ctx.reset_step()
     asm.close()
+
+
+def _with_extra_blocks(rowptr, colind, n_row_nodes, extra_cols_of_node):
+    """CSR graph with more node blocks per row node (all three dof rows of a node get the same columns, sorted)."""
+    rp, ci = [0], []
+    for k in range(n_row_nodes):
+        base = set((colind[rowptr[3 * k]:rowptr[3 * k + 1]] // 3).tolist()) | set(extra_cols_of_node(k))
+        cols = np.array(sorted(base), np.int64)
+        dof = (3 * cols[:, None] + np.arange(3)).ravel()
+        for _ in range(3):
+            ci.append(dof)
+            rp.append(rp[-1] + len(dof))
+    return np.asarray(rp, np.int64), np.concatenate(ci).astype(np.int32)
+
+
+def test_caller_graph_with_more_entries_than_the_block_needs():
+    """The matrix of the reference carries the graph of everything that assembles into it (other element blocks, coupling
+    conditions): a caller graph that is a superset of the block's own pattern.  The extra entries stay zero, the others are
+    what the oracle adds into the same graph (assemble looks positions up per row, 4C_linalg_sparsematrix.cpp:386-447)."""
+    rm = b200.partition.box_partition(b200.mesh.HEX8, (4, 3, 2), 0, 1)
+    u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 0.2)
+    rowptr0, colind0 = orc.build_graph(orc.HEX8, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    nn = rm.n_row_nodes
+    rowptr, colind = _with_extra_blocks(rowptr0, colind0, nn, lambda k: (0, nn - 1, (7 * k + 3) % nn))
+    assert rowptr[-1] > rowptr0[-1]
+    asm = b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, PAR, graph=(rowptr, colind))
+    asm.set_state("displacement", u.ravel())
+    K, f, err = asm.evaluate()
+    rK, rf, nbad = orc.evaluate_assemble(orc.HEX8, orc.MAT_COUP_NEOHOOKE, PAR, rm.conn, rm.X.ravel(), u.ravel(), rm.node_row_lid,
+                                         rm.node_col_lid, rm.n_row_nodes, rowptr, colind)
+    ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, 1e-12)
+    assert ok and nbad == 0, (wK, wf)
+    # the entries outside the block's own pattern are exactly zero
+    own = set()
+    for r in range(3 * nn):
+        own |= {(r, c) for c in colind0[rowptr0[r]:rowptr0[r + 1]].tolist()}
+    rows = np.repeat(np.arange(3 * nn), np.diff(rowptr))
+    extra = np.array([(r, c) not in own for r, c in zip(rows.tolist(), colind.tolist())])
+    assert extra.any() and not K[extra].any() and np.abs(K[~extra]).max() > 0
+    asm.close()
+
+
+def test_caller_graph_missing_an_entry_is_refused():
+    """A caller graph that lacks a block the elements add into: the reference throws in assemble (a filled matrix cannot take
+    new entries); here set_graph refuses the graph."""
+    rm = b200.partition.box_partition(b200.mesh.HEX8, (3, 2, 2), 0, 1)
+    rowptr0, colind0 = orc.build_graph(orc.HEX8, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    # drop the last node block of row node 0
+    keep = np.ones(len(colind0), bool)
+    for r in range(3):
+        keep[rowptr0[r + 1] - 3:rowptr0[r + 1]] = False
+    colind = colind0[keep]
+    rowptr = rowptr0.copy()
+    for r in range(3):
+        rowptr[r + 1:] -= 3
+    with pytest.raises(capi.B200SolidError):
+        b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, PAR, graph=(rowptr, colind))
