@@ -822,10 +822,17 @@ namespace b200s
         cp_async8(xu + NDOF + d, gu + d);
       }
     }
+    template <bool PAD>
     __device__ __forceinline__ void issue_rowpos(
         const EvalArgs& A, const PairSmem& S, int pt, int node, int64_t e)
     {
-      if (node >= 0) cp_async16(S.nrow + pt, A.node_row + node);
+      if (node >= 0)
+      {
+        if (PAD && pt >= A.nn_real)  // padding node of a hex20 block: owns no row
+          S.nrow[pt] = NodeRow{-1, 0, -1};
+        else
+          cp_async16(S.nrow + pt, A.node_row + node);
+      }
       if (e >= A.n_ele) return;
 #pragma unroll
       for (int h = 0; h < 3; ++h)
@@ -837,8 +844,9 @@ namespace b200s
   }  // namespace hex27
 
 #if B200S_HAS(B200S_PART_HEX27)
-  // FORM 0: displacement based, 1: MULF prestress, 2: KINEM linear
-  template <int MAT, bool STIFF, int FORM>
+  // FORM 0: displacement based, 1: MULF prestress, 2: KINEM linear.  PAD: a hex20 block (tables from EvalArgs::tab_override,
+  // element nodes >= EvalArgs::nn_real are padding)
+  template <int MAT, bool STIFF, int FORM, bool PAD = false>
   __global__ void __launch_bounds__(HEX27_PAIRS * 64, 1) k_hex27_eval_assemble(const EvalArgs A)
   {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -846,12 +854,14 @@ namespace b200s
     double* wgt = tab_gp + hex27::TAB_SIZE + 1;
     hex27::IntTables* itab = reinterpret_cast<hex27::IntTables*>(wgt + 28);
     int* flags = reinterpret_cast<int*>(itab->abc + 28);  // 4 spare ints of the table = per-pair flags
-    for (int t = threadIdx.x; t < hex27::TAB_SIZE; t += blockDim.x) tab_gp[t] = c_hex27.dN_gp[t];
-    if (threadIdx.x < 28) wgt[threadIdx.x] = c_hex27.w[threadIdx.x];
+    // hex27 tables, or the padded tables of a hex20 block (EvalArgs::tab_override)
+    const Hex27Const& tabs = PAD ? *static_cast<const Hex27Const*>(A.tab_override) : c_hex27;
+    for (int t = threadIdx.x; t < hex27::TAB_SIZE; t += blockDim.x) tab_gp[t] = tabs.dN_gp[t];
+    if (threadIdx.x < 28) wgt[threadIdx.x] = tabs.w[threadIdx.x];
     if (threadIdx.x < 32)
     {
-      itab->abc[threadIdx.x] = threadIdx.x < 28 ? c_hex27.it.abc[threadIdx.x] : 0;
-      itab->node_of[threadIdx.x] = c_hex27.it.node_of[threadIdx.x];
+      itab->abc[threadIdx.x] = threadIdx.x < 28 ? tabs.it.abc[threadIdx.x] : 0;
+      itab->node_of[threadIdx.x] = tabs.it.node_of[threadIdx.x];
     }
     __syncthreads();
 
@@ -876,7 +886,7 @@ namespace b200s
     int node_next = hex27::load_node(A, pt, e);
     hex27::issue_xu(A, S, pt, node_next);
     cp_async_commit();
-    hex27::issue_rowpos(A, S, pt, node_next, e);
+    hex27::issue_rowpos<PAD>(A, S, pt, node_next, e);
     cp_async_commit();
     node_next = hex27::load_node(A, pt, e + stride);
 
@@ -894,7 +904,7 @@ namespace b200s
         detJ_min = fmin(detJ_min, dJ);
         detF_min = fmin(detF_min, dF);
       }
-      else if (my_chk >= 0)
+      else if (!PAD && my_chk >= 0)  // (hex20 blocks: k_nodal_jacobian_check ahead of this kernel)
       {
         const double dJn = hex27::node_jacobian_det(S, *itab, my_chk);
         detJ_min = fmin(detJ_min, dJn);
@@ -925,14 +935,14 @@ namespace b200s
           {
             if (lane < hex27::NN) hex27::stage_blocks(stage, lane, s, Kacc);
             __syncwarp();
-            hex27::scatter_blocks(A, S, stage, w, s, lane);
+            hex27::scatter_blocks<PAD>(A, S, stage, w, s, lane);
             __syncwarp();
           }
         }
         if (w == 0 && lane < hex27::NN) hex27::scatter_force(A, S, lane, facc);
       }
       hex27::pair_barrier(pair);  // everything of this element consumed
-      hex27::issue_rowpos(A, S, pt, node_next, e + stride);
+      hex27::issue_rowpos<PAD>(A, S, pt, node_next, e + stride);
       cp_async_commit();
       node_next = node_next2;
     }
@@ -1194,11 +1204,55 @@ namespace b200s
     node_row[k] = nr;
   }
 
+  // connectivity of a block padded from nn to nn_pad nodes per element (padding = node 0 of the element)
+  __global__ void k_pad_conn(int64_t n_ele, int nn, int nn_pad, const int32_t* conn, int32_t* out)
+  {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_ele * nn_pad) return;
+    const int64_t e = t / nn_pad;
+    const int q = (int)(t - e * nn_pad);
+    out[t] = conn[e * nn + (q < nn ? q : 0)];
+  }
+
+  // ensure_positive_jacobian_determinant_at_element_nodes (4C_solid_ele_calc_lib.hpp:543-562) from the tabulated shape
+  // derivatives at the nodes, one thread per element; offending elements are counted once (hex20 blocks ahead of the hex27
+  // kernel, whose own check uses the Lagrange structure of hex27)
+  __global__ void k_nodal_jacobian_check(int nn, int64_t n_ele, const int32_t* conn, const double* X, const double* dN_node,
+      const int32_t* ele_id, ErrWord* err)
+  {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_ele) return;
+    const int32_t* ce = conn + e * nn;
+    bool neg = false;
+    double dmin = 1e300;
+    for (int q = 0; q < nn; ++q)
+    {
+      double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      const double* dN = dN_node + (size_t)q * nn * 3;
+      for (int k = 0; k < nn; ++k)
+      {
+        const double* x = X + 3 * (int64_t)ce[k];
+        for (int a = 0; a < 3; ++a)
+          for (int b = 0; b < 3; ++b) J[a + 3 * b] = fma(dN[3 * k + a], x[b], J[a + 3 * b]);
+      }
+      const double dj = det3(J);
+      dmin = fmin(dmin, dj);
+      neg = neg || !(dj > 0.0);
+    }
+    atomic_min_double(&err->min_detJ, dmin);
+    if (neg)
+    {
+      atomicMin(&err->first_bad, ele_id ? (long long)ele_id[e] : (long long)e);
+      atomicAdd(&err->n_neg_jac, 1ull);
+    }
+  }
+
   // element -> CSR slot map: pos[e][i][j] = offset of the 3 columns of node j inside each row of
   // node i (same lower_bound + stride-3 contiguity rule as SparseMatrix::assemble :404-441)
+  // nn_real < nn: the element nodes >= nn_real are padding (hex20 blocks through the hex27 kernel): entries -1
   __global__ void k_build_scatter_map(int nn, int pos_stride, int64_t n_ele, const int32_t* conn,
       const int32_t* colind, const NodeRow* node_row, const int32_t* node_colbase, int32_t* pos,
-      int* flag)
+      int* flag, int nn_real)
   {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_ele * nn) return;
@@ -1210,7 +1264,7 @@ namespace b200s
     int32_t* out = pos + e * pos_stride + i * nn;
     if (i == 0)
       for (int t = nn * nn; t < pos_stride; ++t) pos[e * pos_stride + t] = 0;  // 16-byte padding
-    if (rs < 0)
+    if (rs < 0 || i >= nn_real)
     {
       for (int j = 0; j < nn; ++j) out[j] = -1;
       return;
@@ -1219,6 +1273,11 @@ namespace b200s
     const int32_t* idx = colind + rs;
     for (int j = 0; j < nn; ++j)
     {
+      if (j >= nn_real)
+      {
+        out[j] = -1;
+        continue;
+      }
       const int32_t col = node_colbase[ce[j]];
       int lo = 0, hi = len;  // lower_bound
       while (lo < hi)
@@ -1450,6 +1509,9 @@ struct b200s_ctx
   std::string err;
   // mesh
   int celltype = -1, nn = 0, pos_stride = 0;
+  // hex20 blocks through the hex27 kernel: padded connectivity, its scatter map, padded shape tables (Hex27Const)
+  int32_t *d_conn27 = nullptr, *d_pos27 = nullptr;
+  void* d_tab20 = nullptr;
   int64_t n_col_nodes = 0, n_col_eles = 0;
   double* dX = nullptr;
   int32_t* dconn = nullptr;
@@ -2260,12 +2322,17 @@ namespace
   template <int MAT, bool STIFF>
   static int launch_hex27_t(b200s_ctx* ctx, const EvalArgs& A)
   {
+    if (A.nn_real > 0 && (MAT == MAT_DP || MAT == MAT_VISCO || ctx->prestress == B200S_PRESTRESS_MULF || !A.tab_override))
+      return fail(ctx, B200S_ERR_UNSUPPORTED, "hex20 through the hex27 kernel: displacement-based blocks of the hyperelastic kinds");
     auto kern = [&]
     {
       if constexpr (MAT == MAT_DP)
         return k_hex27_eval_assemble<MAT, STIFF, 2>;
       else if constexpr (MAT == MAT_VISCO)
         return k_hex27_eval_assemble<MAT, STIFF, 0>;
+      else if (A.nn_real > 0)  // hex20 block
+        return ctx->kinem == B200S_KINEM_LINEAR ? k_hex27_eval_assemble<MAT, STIFF, 2, true>
+                                                : k_hex27_eval_assemble<MAT, STIFF, 0, true>;
       else
         return ctx->prestress == B200S_PRESTRESS_MULF
                    ? k_hex27_eval_assemble<MAT, STIFF, 1>
@@ -2397,10 +2464,32 @@ namespace
     return ct == B200S_TET4 || ct == B200S_HEX20 || ct == B200S_WEDGE6 || ct == B200S_PYRAMID5 || ct == B200S_HEX18;
   }
 
+  // hex20 displacement-based blocks with a major-symmetric tangent run through the hex27 kernel (same 27-point rule, shape
+  // tables padded to 27 nodes, padding rows / columns masked in the scatter map): 7 x the rate of the general kernel, whose
+  // row threads repeat the Gauss-point work 20 times.  Option general_kernel = 1 keeps the general kernel (A/B, tests).
+  static bool hex20_as_hex27(const b200s_ctx* ctx)
+  {
+    const bool hyper = ctx->matkind == B200S_MAT_COUP_NEOHOOKE || ctx->matkind == B200S_MAT_ISO_VOL ||
+                       ctx->matkind == B200S_MAT_SVK || ctx->matkind == B200S_MAT_ELASTHYPER;
+    return ctx->celltype == B200S_HEX20 && !ctx->general_tangent && !ctx->general_kernel && ctx->tech == B200S_TECH_NONE &&
+           ctx->prestress == B200S_PRESTRESS_NONE && hyper && ctx->d_conn27 && ctx->d_pos27 && ctx->d_tab20 && ctx->d_dN_node;
+  }
+
   template <bool STIFF>
   static int launch_eval(b200s_ctx* ctx, const EvalArgs& A)
   {
     if (ctx->matkind < 0) return fail(ctx, B200S_ERR_INVALID, "material not set");
+    if (hex20_as_hex27(ctx))
+    {
+      EvalArgs B = A;
+      B.conn = ctx->d_conn27 + A.e_begin * 27;
+      B.pos = ctx->d_pos27 + A.e_begin * hex27::POS_STRIDE;
+      B.tab_override = ctx->d_tab20, B.nn_real = 20;
+      k_nodal_jacobian_check<<<nblk(A.n_ele, 128), 128, 0, ctx->stream>>>(20, A.n_ele, A.conn, A.X, ctx->d_dN_node, A.ele_id,
+          A.err);
+      ctx->launches += 1;
+      return b200s_parts::launch_hex27(ctx, B, STIFF);
+    }
     if (ctx->general_tangent || ctx->general_kernel || is_general_cell(ctx->celltype) ||
         (ctx->tech == B200S_TECH_FBAR && ctx->prestress == B200S_PRESTRESS_MULF) || ctx->tech == B200S_TECH_SHELL_ANS ||
         ctx->tech == B200S_TECH_SHELL_EAS_ANS || (ctx->matkind == B200S_MAT_PLASTIC_NLNLOG && ctx->celltype != B200S_HEX8))  // fast kernels: hex8 (+ EAS) only
@@ -2501,6 +2590,9 @@ extern "C"
     dfree(ctx->d_N_gp), dfree(ctx->d_fext), dfree(ctx->d_nm_row), dfree(ctx->d_nm_col), dfree(ctx->d_nm_flag);
     dfree(ctx->d_exp_pos), dfree(ctx->d_exp_fpos), dfree(ctx->d_exp_buf), dfree(ctx->d_exp_fbuf);
     dfree(ctx->d_hyper), dfree(ctx->d_dN_gp), dfree(ctx->d_w), dfree(ctx->d_dN_cen), dfree(ctx->d_N_mass), dfree(ctx->d_dN_pts), dfree(ctx->d_dN_ans);
+    dfree(ctx->d_conn27), dfree(ctx->d_pos27);
+    if (ctx->d_tab20) cudaFree(ctx->d_tab20);
+    ctx->d_tab20 = nullptr;
     dfree(ctx->d_dN_mass), dfree(ctx->d_w_mass), dfree(ctx->d_ele_is_row), dfree(ctx->d_mass);
     dfree(ctx->d_f_inertia), dfree(ctx->d_acc_row), dfree(ctx->d_acc_col), dfree(ctx->d_energy);
     dfree(ctx->d_xmat), dfree(ctx->d_la_x), dfree(ctx->d_la_y), dfree(ctx->d_toggle);
@@ -2632,6 +2724,31 @@ extern "C"
       }
       if (b200s_parts::set_tables_hex27(ctx, h)) return B200S_ERR_CUDA;
     }
+    else if (celltype == B200S_HEX20)
+    {
+      // hex20 blocks through the hex27 kernel: serendipity shape derivatives at the 27 Gauss points (the same hex_27point
+      // rule) in the hex27 table layout, zero for the seven padding nodes; the integer tables are hex27's (reference
+      // coordinates of the padding elements at the end of the grid)
+      std::vector<Hex27Const> hbuf(1);
+      Hex27Const& h = hbuf[0];
+      memset(&h, 0, sizeof h);
+      for (int g = 0; g < 27; ++g)
+        for (int k = 0; k < 20; ++k)
+          for (int a = 0; a < 3; ++a) h.dN_gp[g * 81 + 3 * k + a] = T.dN_gp[((size_t)g * 20 + k) * 3 + a];
+      memcpy(h.w, T.w.data(), 27 * sizeof(double));
+      const double(*hc)[3] = detail::hex_nodes();
+      for (int k = 0; k < 27; ++k)
+      {
+        const int a = (int)hc[k][0] + 1, b = (int)hc[k][1] + 1, c = (int)hc[k][2] + 1;
+        h.it.abc[k] = a | (b << 2) | (c << 4);
+        h.it.node_of[a + 3 * b + 9 * c] = k;
+      }
+      Hex27Const* d = nullptr;
+      if (to_device(ctx, &d, &h, 1)) return B200S_ERR_CUDA;
+      CK(cudaStreamSynchronize(ctx->stream));  // h leaves scope
+      if (ctx->d_tab20) cudaFree(ctx->d_tab20);
+      ctx->d_tab20 = d;
+    }
     else if (celltype == B200S_TET10)
     {
       Tet10Const h;
@@ -2678,7 +2795,7 @@ extern "C"
     if (eas_neas(ctx->tech) && eas_allocate(ctx)) return B200S_ERR_CUDA;
     if (material_history_allocate(ctx)) return B200S_ERR_CUDA;
     // graph-dependent data is stale now (build_graph / set_graph must follow)
-    dfree(ctx->d_pos), dfree(ctx->d_rowptr), dfree(ctx->d_colind);
+    dfree(ctx->d_pos), dfree(ctx->d_rowptr), dfree(ctx->d_colind), dfree(ctx->d_conn27), dfree(ctx->d_pos27);
     ctx->nnz = 0, ctx->n_rows = 0;
     return B200S_OK;
   }
@@ -2941,7 +3058,19 @@ extern "C"
     CK(cudaMemsetAsync(ctx->d_nm_flag, 0, sizeof(int), ctx->stream));
     k_build_scatter_map<<<nblk(ctx->n_col_eles * ctx->nn), 256, 0, ctx->stream>>>(ctx->nn,
         ctx->pos_stride, ctx->n_col_eles, ctx->dconn, ctx->d_colind, ctx->d_node_row, ctx->d_node_colbase, ctx->d_pos,
-        ctx->d_nm_flag);
+        ctx->d_nm_flag, ctx->nn);
+    if (ctx->celltype == B200S_HEX20)
+    {
+      // hex20 blocks run through the hex27 kernel: connectivity padded to 27 nodes (padding = the element's node 0, whose
+      // coordinates meet zero shape derivatives) and the 27 x 27 scatter map with -1 for the padding rows / columns
+      if (to_device(ctx, &ctx->d_conn27, (const int32_t*)nullptr, ctx->n_col_eles * 27) ||
+          to_device(ctx, &ctx->d_pos27, (const int32_t*)nullptr, ctx->n_col_eles * hex27::POS_STRIDE))
+        return B200S_ERR_CUDA;
+      k_pad_conn<<<nblk(ctx->n_col_eles * 27), 256, 0, ctx->stream>>>(ctx->n_col_eles, 20, 27, ctx->dconn, ctx->d_conn27);
+      k_build_scatter_map<<<nblk(ctx->n_col_eles * 27), 256, 0, ctx->stream>>>(27, hex27::POS_STRIDE, ctx->n_col_eles,
+          ctx->d_conn27, ctx->d_colind, ctx->d_node_row, ctx->d_node_colbase, ctx->d_pos27, ctx->d_nm_flag, 20);
+      ctx->launches += 2;
+    }
     ctx->launches += 1;
     int flag = 0;
     CK(cudaMemcpyAsync(&flag, ctx->d_nm_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

@@ -300,6 +300,9 @@ namespace b200s
     // direct:      K_{i, i+k}(b,c)   = stage[i][t][b+3c]      -> row (i,b), columns of node i+k
     // transposed:  K_{i, i-k}(b,c)   = stage[i-k][t][c+3b]    -> row (i,b), columns of node i-k  (k > 0)
     // lanes 0..11 direct, lanes 16..27 transposed: one RED instruction = one CSR row, 24 entries.
+    // PAD: hex20 blocks through this kernel (element nodes >= 20 are padding, map entries -1); a compile-time flag, because
+    // the run-time test of the map entry alone costs the hex27 kernel 1.8 % (profiles/r02h_hex27_ab.log)
+    template <bool PAD = false>
     B2_HD void scatter_blocks(const EvalArgs& A, const PairSmem& S, const double* stage, int w, int s,
         int lane)
     {
@@ -324,8 +327,9 @@ namespace b200s
           const NodeRow r = S.nrow[i];
           int j = tr ? i - k : i + k;
           j = j < 0 ? j + NN : (j >= NN ? j - NN : j);
-          const bool act = on && r.rowstart >= 0;  // the row-ownership part is warp uniform
-          off[q] = act ? r.rowstart + S.pos[i * NN + (on ? j : 0)] + c : -1;
+          const int32_t pj = S.pos[i * NN + (on ? j : 0)];  // < 0: padding column (hex20 blocks through this kernel)
+          const bool act = on && r.rowstart >= 0 && (!PAD || pj >= 0);  // the row-ownership part is warp uniform
+          off[q] = act ? r.rowstart + pj + c : -1;
           len[q] = r.rowlen;
           const double* src = tr ? stage + j * STAGE_LSTRIDE + 9 * t + c : stage + i * STAGE_LSTRIDE + 9 * t + 3 * c;
           const int sb = tr ? 3 : 1;  // stride over the row dof b inside the staged block

@@ -75,6 +75,11 @@ namespace b200s
     int64_t e_begin = 0;  // first device element of this launch's segment: every per-element pointer above is
                           // already offset by it (the kernels index from 0); launch wrappers with further
                           // per-element arrays (EAS history) use it
+    // hex20 blocks through the hex27 kernel (b200_solid.cu, launch_hex20_as_hex27): shape tables of the serendipity cell
+    // padded to 27 nodes (device pointer to a Hex27Const, nullptr = the hex27 tables) and the number of real nodes --
+    // element nodes >= nn_real are padding: no rows, no columns, no nodal Jacobian check inside the kernel
+    const void* tab_override = nullptr;
+    int nn_real = 0;  // 0: every node is real
   };
 
   namespace hex8

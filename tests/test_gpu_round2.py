@@ -1251,3 +1251,63 @@ def test_solid_shell_stress_output_known_answers_through_cuda_path(tech):
     oe = orc.calc_energy(orc.HEX8, orc.MAT_COUP_NEOHOOKE, par, conn, X.ravel(), u.ravel(), tech=otech, hist=hist)
     assert abs(asm.calc_energy() - oe) <= 1e-10 * abs(oe)
     asm.close()
+
+
+# ---- hex20 blocks through the hex27 kernel (shape tables padded to 27 nodes, padding masked in the scatter map) -----------------
+def test_hex20_fast_path_equals_general_kernel_and_oracle_on_partitioned_rows():
+    """Rank views of a 3-way node partition (ghost rows next to the padding rows), per-element material parameter, both
+    actions: the hex27-kernel route of a hex20 block against the oracle and against the general kernel (option
+    general_kernel = 1) on the same context set-up."""
+    import ctypes
+    import torch
+    cudart = ctypes.CDLL("libcudart.so")
+    X, conn = b200.mesh.structured_hex20((5, 3, 3))
+    rng = np.random.default_rng(11)
+    owner = (X[:, 0] * 2.999).astype(int).clip(0, 2)
+    flip = rng.random(len(X)) < 0.05
+    owner[flip] = rng.integers(0, 3, flip.sum())
+    mk, par = capi.MAT_ISO_VOL, [1.0, 1000.0]
+    for rank in range(3):
+        rm = b200.partition.generic_partition(b200.mesh.HEX20, X, conn, owner, rank, 3)
+        u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 0.25)
+        mue = 1.0 + 0.5 * rng.random(rm.n_col_eles)
+        rm1 = b200.partition.RankMesh(**{**rm.__dict__, "nranks": 1, "rank": 0})
+        res = {}
+        for general in (0, 1):
+            asm = b200.DeviceAssembler(rm1, mk, par, per_ele_param=mue, options={"general_kernel": general})
+            rowptr, colind = asm.graph()
+            ucol = torch.from_numpy(u.ravel().copy()).cuda()
+            cudart.cudaMemcpy(ctypes.c_void_p(asm.ctx.device_ptrs()["u_col"]), ctypes.c_void_p(ucol.data_ptr()),
+                              ctypes.c_size_t(ucol.numel() * 8), 3)
+            asm.set_state("displacement", u[:rm.n_row_nodes].ravel())
+            K, f, err = asm.evaluate()
+            _, f2, _ = asm.evaluate("struct_calc_internalforce")
+            res[general] = (K, f, f2, err.min_detJ)
+            asm.close()
+        rK, rf, nbad = orc.evaluate_assemble(orc.HEX20, mk, par, rm.conn, rm.X.ravel(), u.ravel(), rm.node_row_lid, rm.node_col_lid,
+                                             rm.n_row_nodes, rowptr, colind, nthreads=4, mue_per_ele=mue)
+        for general in (0, 1):
+            K, f, f2, _ = res[general]
+            ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, RTOL)
+            assert ok and nbad == 0, (rank, general, wK, wf)
+            assert np.abs(f2 - rf).max() <= RTOL * np.abs(rf).max()
+        assert abs(res[0][3] - res[1][3]) <= 1e-12 * abs(res[1][3])  # the same minimal Jacobian determinant from both routes
+
+
+def test_hex20_fast_path_reports_negative_nodal_jacobians_like_the_general_kernel():
+    """An element folded at one corner: det J <= 0 at a node (not at the Gauss points of its neighbours): both routes count
+    the same elements and name the same first offender in the caller's numbering."""
+    X, conn = b200.mesh.structured_hex20((3, 2, 2))
+    X = X.copy()
+    bad_ele = 7
+    X[conn[bad_ele, 6]] = X[conn[bad_ele, 0]] - 0.05   # corner 6 pulled through corner 0
+    rm = b200.partition.serial_mesh(b200.mesh.HEX20, X, conn)
+    out = {}
+    for general in (0, 1):
+        asm = b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, [200.0, 0.25], options={"general_kernel": general})
+        asm.set_state("displacement", np.zeros(asm.n_rows))
+        rc, err = asm.ctx.evaluate(capi.ACTION_NLNSTIFF, asm._u, None, None, check=False)
+        out[general] = (rc, err.n_neg_jacobian, err.first_bad_element)
+        asm.close()
+    assert out[0][0] == capi.ERR_NEG_JACOBIAN and out[0] == out[1], out
+    assert out[0][1] >= 1

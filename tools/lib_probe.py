@@ -15,6 +15,12 @@ if cell == "tet10":
     X, conn = b200.mesh.unstructured_tet10(n)
     rm = b200.partition.serial_mesh(b200.mesh.TET10, X, conn)
     mat, par, h = 1, [1.0, 1000.0], 1.0 / n
+elif cell in ("tet4", "hex20", "wedge6", "pyramid5", "hex18"):  # cells of the table-driven general kernel
+    gen = {"tet4": b200.mesh.unstructured_tet4, "hex20": b200.mesh.structured_hex20, "wedge6": b200.mesh.structured_wedge6,
+           "pyramid5": b200.mesh.structured_pyramid5, "hex18": b200.mesh.structured_hex18}[cell]
+    X, conn = gen(n) if cell == "tet4" else gen((n,) * 3)
+    rm = b200.partition.serial_mesh(getattr(b200.mesh, cell.upper()), X, conn)
+    mat, par, h = 0, [200.0, 0.25], 1.0 / n
 else:
     rm = b200.partition.box_partition(getattr(b200.mesh, cell.upper()), (n,) * 3, 0, 1)
     mat, par, h = 0, [200.0, 0.25], 0.01
@@ -59,5 +65,5 @@ for path in sys.argv[3:]:
         L.b200s_evaluate_async(hdl, 1)
     L.b200s_synchronize(hdl, None)
     L.b200s_kernel_time(hdl, C.byref(s), C.byref(c), 1)
-    print(f"LIBPROBE {os.path.basename(path):16s} {os.environ.get('LIBPROBE_OPTS', ''):16s} {cell} n={n} nnz={nnz.value} kernel {s.value / max(c.value, 1):.3f} ms over {c.value} evaluates", flush=True)
+    print(f"LIBPROBE {os.path.basename(path):16s} {os.environ.get('LIBPROBE_OPTS', ''):16s} {cell} n={n} nnz={nnz.value} kernel {s.value / max(c.value, 1):.3f} ms over {c.value} evaluates, {len(cc)} elements, {len(cc) / (s.value / max(c.value, 1)) / 1e3:.2f} M elements/s", flush=True)
     L.b200s_destroy(hdl)
