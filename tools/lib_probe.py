@@ -50,11 +50,14 @@ for path in sys.argv[3:]:
     for kv in os.environ.get("LIBPROBE_OPTS", "").split():  # e.g. LIBPROBE_OPTS="scatter_mode=1"
         k, v = kv.split("=")
         assert L.b200s_set_option(hdl, k.encode(), float(v)) == 0, kv
+    import time
+    t_setup = time.perf_counter()
     assert L.b200s_set_mesh(hdl, rm.celltype, len(Xc), Xc.ctypes.data, len(cc), cc.ctypes.data) == 0
     assert L.b200s_set_material(hdl, mat, p.ctypes.data, len(p), None) == 0
     nnz = i64(0)
     rc = L.b200s_build_graph(hdl, rm.n_row_nodes, rl.ctypes.data, cl.ctypes.data, None, None, C.byref(nnz))
     assert rc == 0, L.b200s_last_error(hdl)
+    t_setup = time.perf_counter() - t_setup  # set_mesh (H2D, locality order) + set_material + build_graph (graph, row phases, scatter map); synchronous calls
     assert L.b200s_evaluate(hdl, 1, u.ctypes.data, None, None, None) == 0
     for _ in range(3):
         L.b200s_evaluate_async(hdl, 1)
@@ -65,5 +68,5 @@ for path in sys.argv[3:]:
         L.b200s_evaluate_async(hdl, 1)
     L.b200s_synchronize(hdl, None)
     L.b200s_kernel_time(hdl, C.byref(s), C.byref(c), 1)
-    print(f"LIBPROBE {os.path.basename(path):16s} {os.environ.get('LIBPROBE_OPTS', ''):16s} {cell} n={n} nnz={nnz.value} kernel {s.value / max(c.value, 1):.3f} ms over {c.value} evaluates, {len(cc)} elements, {len(cc) / (s.value / max(c.value, 1)) / 1e3:.2f} M elements/s", flush=True)
+    print(f"LIBPROBE {os.path.basename(path):16s} {os.environ.get('LIBPROBE_OPTS', ''):16s} {cell} n={n} nnz={nnz.value} kernel {s.value / max(c.value, 1):.3f} ms over {c.value} evaluates, {len(cc)} elements, {len(cc) / (s.value / max(c.value, 1)) / 1e3:.2f} M elements/s, set-up {t_setup * 1e3:.0f} ms", flush=True)
     L.b200s_destroy(hdl)
