@@ -76,6 +76,13 @@ WORKLOADS = {
                   matname="IsoNeoHooke mu=1 + VolSussmanBathe kappa=1000", flops=43.3e3, bytes=3300.0,
                   kernel="k_tet10_eval_assemble<ISO_VOL,STIFF>", default_n=87,
                   metric="tet10 iso/vol Neo-Hooke element evaluate+assemble (force + tangent stiffness into CSR), FP64"),
+    # hex20 (20-node serendipity hexahedron) through the hex27 kernel with padded shape tables; model per Gauss
+    # point 62 n^2 + 228 n + 1183 + M with n = 20 nodes, M = 1000, 27 points; bytes: 60 doubles of X, u,
+    # 3600 + 60 K_e / f_e entries, 400 map entries
+    "hex20": dict(config="3 mesh family, 20-node serendipity cell (not a BASELINE config)", cell="HEX20", mat="MAT_COUP_NEOHOOKE",
+                  par=[200.0, 0.25], matname="CoupNeoHooke (E=200, nu=0.25)", flops=27 * (62 * 400 + 228 * 20 + 1183 + 1000),
+                  bytes=8.0 * (120 + 3660) + 4 * 400, kernel="k_hex27_eval_assemble<COUP_NEOHOOKE,STIFF,0,PAD> (hex20 tables padded to 27 nodes)",
+                  default_n=64, metric="hex20 Neo-Hooke element evaluate+assemble (force + tangent stiffness into CSR), FP64"),
     "hex27": dict(config="3", cell="HEX27", mat="MAT_SVK", par=[1000.0, 0.3], matname="St.Venant-Kirchhoff (E=1000, nu=0.3)",
                   flops=1.419e6, bytes=40e3, kernel="k_hex27_eval_assemble<SVK,STIFF>", default_n=80,
                   metric="hex27 St.Venant-Kirchhoff element evaluate+assemble (force + tangent stiffness into CSR), FP64"),
@@ -202,6 +209,13 @@ def build_rank(wl, per_gpu_n, rank, nranks, strong=False):
         rm = b200.partition.serial_mesh(cell, X, conn)
         u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 1.0 / per_gpu_n)
         return rm, u, f"unstructured tet10 ({per_gpu_n}^3 hex cells x 6, jittered, randomly renumbered)"
+    if wl["cell"] == "HEX20":
+        if nranks != 1:
+            raise SystemExit("the hex20 workload is a single-GPU configuration")
+        X, conn = b200.mesh.structured_hex20((per_gpu_n,) * 3, box=(per_gpu_n / 100.0,) * 3)
+        rm = b200.partition.serial_mesh(cell, X, conn)
+        u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 0.01)
+        return rm, u, f"structured hex20 cube {per_gpu_n}^3"
     n, box = global_box(per_gpu_n, nranks, strong)
     rm = b200.partition.box_partition(cell, n, rank, nranks, box=box)
     u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 0.01)
@@ -220,13 +234,18 @@ class CpuArm:
         self.impl = "ref" if self.kind == "reference" else "oracle"
         self.ct, self.mk = getattr(orc, wl["cell"]), getattr(orc, wl["mat"])
         self.tech = getattr(orc, wl.get("tech", "TECH_NONE"))
-        if self.tech != orc.TECH_NONE:  # oracle/_ref covers the displacement-based formulation only
+        if self.tech != orc.TECH_NONE or wl["cell"] == "HEX20":
+            # oracle/_ref's assembled path covers the displacement-based formulation of hex8 / hex27 / tet10 only
             self.kind, self.impl = "port", "oracle"
         self.hist = None
         if wl["cell"] == "TET10":
             X, conn = b200.mesh.unstructured_tet10(n_sample)
             self.rm = b200.partition.serial_mesh(b200.mesh.TET10, X, conn)
             self.u = b200.mesh.displacement_field(self.rm.X, self.rm.node_gid, 1.0, 1.0 / n_sample)
+        elif wl["cell"] == "HEX20":
+            X, conn = b200.mesh.structured_hex20((n_sample,) * 3, box=(n_sample / 100.0,) * 3)
+            self.rm = b200.partition.serial_mesh(b200.mesh.HEX20, X, conn)
+            self.u = b200.mesh.displacement_field(self.rm.X, self.rm.node_gid, 1.0, 0.01)
         else:
             n = (n_sample,) * 3
             self.rm = b200.partition.box_partition(getattr(b200.mesh, wl["cell"]), n, 0, 1,
@@ -245,10 +264,13 @@ class CpuArm:
             threads = 1  # the oracle's history-carrying formulations are evaluated by one thread
         rm, orc = self.rm, self.orc
         t = time.perf_counter()
-        orc.evaluate_assemble(self.ct, self.mk, self.wl["par"], rm.conn, rm.X.ravel(), self.u.ravel(),
-                              rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, self.graph[0], self.graph[1],
-                              nthreads=threads, impl=self.impl, tech=self.tech, hist=self.hist)
-        return time.perf_counter() - t
+        _, _, nbad = orc.evaluate_assemble(self.ct, self.mk, self.wl["par"], rm.conn, rm.X.ravel(), self.u.ravel(),
+                                           rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes, self.graph[0], self.graph[1],
+                                           nthreads=threads, impl=self.impl, tech=self.tech, hist=self.hist)
+        dt = time.perf_counter() - t
+        if nbad:  # a CPU arm that bailed out of its elements is not a baseline
+            raise SystemExit(f"CPU arm ({self.impl}): {nbad} elements with a non-positive Jacobian determinant")
+        return dt
 
     def describe(self):
         return (f"{self.rm.n_col_eles} {self.wl['cell'].lower()} {self.wl['matname']} elements of the same mesh "
@@ -265,7 +287,7 @@ def cpu_sample_size(wl, threads, target_s):
     """Mesh edge parameter so that one CPU step takes about target_s (hex8: 33k elements/s/thread with
     oracle/_ref measured; scaled by the flop model for the other cells)."""
     threads = cpu_threads(wl, threads)
-    rate = {"HEX8": 30e3, "TET10": 7e3, "HEX27": 1.3e3}[wl["cell"]]  # elements/s/thread, measured
+    rate = {"HEX8": 30e3, "TET10": 7e3, "HEX27": 1.3e3, "HEX20": 2.2e3}[wl["cell"]]  # elements/s/thread, measured
     rate *= 63.8e3 / wl["flops"] if wl["cell"] == "HEX8" else 1.0
     ne = rate * max(threads, 1) * 0.7 * target_s
     if wl["cell"] == "TET10":
@@ -305,7 +327,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
-PARITY_WORKLOADS = ("hex8", "hex8_fbar", "tet10", "hex27")
+PARITY_WORKLOADS = ("hex8", "hex8_fbar", "tet10", "hex27", "hex20")
 
 
 def parity_record(args, wl, ctx, rm, u, world, dist, torch, n_random=150, n_interface=50):
