@@ -2464,14 +2464,14 @@ namespace
     return ct == B200S_TET4 || ct == B200S_HEX20 || ct == B200S_WEDGE6 || ct == B200S_PYRAMID5 || ct == B200S_HEX18;
   }
 
-  // hex20 displacement-based blocks with a major-symmetric tangent run through the hex27 kernel (same 27-point rule, shape
-  // tables padded to 27 nodes, padding rows / columns masked in the scatter map): 7 x the rate of the general kernel, whose
-  // row threads repeat the Gauss-point work 20 times.  Option general_kernel = 1 keeps the general kernel (A/B, tests).
+  // hex20 / hex18 displacement-based blocks with a major-symmetric tangent run through the hex27 kernel (shape tables padded
+  // to 27 nodes -- hex18 also to 27 Gauss points, the padding points with weight zero --, padding rows / columns masked in
+  // the scatter map): 7 x / 4 x the rate of the general kernel, whose row threads repeat the Gauss-point work nn times.  Option general_kernel = 1 keeps the general kernel (A/B, tests).
   static bool hex20_as_hex27(const b200s_ctx* ctx)
   {
     const bool hyper = ctx->matkind == B200S_MAT_COUP_NEOHOOKE || ctx->matkind == B200S_MAT_ISO_VOL ||
                        ctx->matkind == B200S_MAT_SVK || ctx->matkind == B200S_MAT_ELASTHYPER;
-    return ctx->celltype == B200S_HEX20 && !ctx->general_tangent && !ctx->general_kernel && ctx->tech == B200S_TECH_NONE &&
+    return (ctx->celltype == B200S_HEX20 || ctx->celltype == B200S_HEX18) && !ctx->general_tangent && !ctx->general_kernel && ctx->tech == B200S_TECH_NONE &&
            ctx->prestress == B200S_PRESTRESS_NONE && hyper && ctx->d_conn27 && ctx->d_pos27 && ctx->d_tab20 && ctx->d_dN_node;
   }
 
@@ -2484,8 +2484,8 @@ namespace
       EvalArgs B = A;
       B.conn = ctx->d_conn27 + A.e_begin * 27;
       B.pos = ctx->d_pos27 + A.e_begin * hex27::POS_STRIDE;
-      B.tab_override = ctx->d_tab20, B.nn_real = 20;
-      k_nodal_jacobian_check<<<nblk(A.n_ele, 128), 128, 0, ctx->stream>>>(20, A.n_ele, A.conn, A.X, ctx->d_dN_node, A.ele_id,
+      B.tab_override = ctx->d_tab20, B.nn_real = ctx->nn;
+      k_nodal_jacobian_check<<<nblk(A.n_ele, 128), 128, 0, ctx->stream>>>(ctx->nn, A.n_ele, A.conn, A.X, ctx->d_dN_node, A.ele_id,
           A.err);
       ctx->launches += 1;
       return b200s_parts::launch_hex27(ctx, B, STIFF);
@@ -2724,18 +2724,23 @@ extern "C"
       }
       if (b200s_parts::set_tables_hex27(ctx, h)) return B200S_ERR_CUDA;
     }
-    else if (celltype == B200S_HEX20)
+    else if (celltype == B200S_HEX20 || celltype == B200S_HEX18)
     {
-      // hex20 blocks through the hex27 kernel: serendipity shape derivatives at the 27 Gauss points (the same hex_27point
-      // rule) in the hex27 table layout, zero for the seven padding nodes; the integer tables are hex27's (reference
-      // coordinates of the padding elements at the end of the grid)
+      // hex20 / hex18 blocks through the hex27 kernel: the cell's shape derivatives at its Gauss points in the hex27 table
+      // layout, zero for the padding nodes (hex20: the same hex_27point rule, 7 padding nodes; hex18: hex_18point, 9
+      // padding nodes and 9 padding points = copies of point 0 with weight zero, which contribute exactly nothing); the
+      // integer tables are hex27's (only the native hex27 launches use them)
       std::vector<Hex27Const> hbuf(1);
       Hex27Const& h = hbuf[0];
       memset(&h, 0, sizeof h);
+      const int nn_c = T.nn, ngp_c = T.ngp;
       for (int g = 0; g < 27; ++g)
-        for (int k = 0; k < 20; ++k)
-          for (int a = 0; a < 3; ++a) h.dN_gp[g * 81 + 3 * k + a] = T.dN_gp[((size_t)g * 20 + k) * 3 + a];
-      memcpy(h.w, T.w.data(), 27 * sizeof(double));
+      {
+        const int gs = g < ngp_c ? g : 0;
+        for (int k = 0; k < nn_c; ++k)
+          for (int a = 0; a < 3; ++a) h.dN_gp[g * 81 + 3 * k + a] = T.dN_gp[((size_t)gs * nn_c + k) * 3 + a];
+        h.w[g] = g < ngp_c ? T.w[g] : 0.0;
+      }
       const double(*hc)[3] = detail::hex_nodes();
       for (int k = 0; k < 27; ++k)
       {
@@ -3059,16 +3064,16 @@ extern "C"
     k_build_scatter_map<<<nblk(ctx->n_col_eles * ctx->nn), 256, 0, ctx->stream>>>(ctx->nn,
         ctx->pos_stride, ctx->n_col_eles, ctx->dconn, ctx->d_colind, ctx->d_node_row, ctx->d_node_colbase, ctx->d_pos,
         ctx->d_nm_flag, ctx->nn);
-    if (ctx->celltype == B200S_HEX20)
+    if (ctx->celltype == B200S_HEX20 || ctx->celltype == B200S_HEX18)
     {
-      // hex20 blocks run through the hex27 kernel: connectivity padded to 27 nodes (padding = the element's node 0, whose
-      // coordinates meet zero shape derivatives) and the 27 x 27 scatter map with -1 for the padding rows / columns
+      // hex20 / hex18 blocks run through the hex27 kernel: connectivity padded to 27 nodes (padding = the element's node 0,
+      // whose coordinates meet zero shape derivatives) and the 27 x 27 scatter map with -1 for the padding rows / columns
       if (to_device(ctx, &ctx->d_conn27, (const int32_t*)nullptr, ctx->n_col_eles * 27) ||
           to_device(ctx, &ctx->d_pos27, (const int32_t*)nullptr, ctx->n_col_eles * hex27::POS_STRIDE))
         return B200S_ERR_CUDA;
-      k_pad_conn<<<nblk(ctx->n_col_eles * 27), 256, 0, ctx->stream>>>(ctx->n_col_eles, 20, 27, ctx->dconn, ctx->d_conn27);
+      k_pad_conn<<<nblk(ctx->n_col_eles * 27), 256, 0, ctx->stream>>>(ctx->n_col_eles, ctx->nn, 27, ctx->dconn, ctx->d_conn27);
       k_build_scatter_map<<<nblk(ctx->n_col_eles * 27), 256, 0, ctx->stream>>>(27, hex27::POS_STRIDE, ctx->n_col_eles,
-          ctx->d_conn27, ctx->d_colind, ctx->d_node_row, ctx->d_node_colbase, ctx->d_pos27, ctx->d_nm_flag, 20);
+          ctx->d_conn27, ctx->d_colind, ctx->d_node_row, ctx->d_node_colbase, ctx->d_pos27, ctx->d_nm_flag, ctx->nn);
       ctx->launches += 2;
     }
     ctx->launches += 1;

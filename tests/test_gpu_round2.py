@@ -1254,21 +1254,23 @@ def test_solid_shell_stress_output_known_answers_through_cuda_path(tech):
 
 
 # ---- hex20 blocks through the hex27 kernel (shape tables padded to 27 nodes, padding masked in the scatter map) -----------------
-def test_hex20_fast_path_equals_general_kernel_and_oracle_on_partitioned_rows():
+@pytest.mark.parametrize("cell", ["hex20", "hex18"])
+def test_hex20_fast_path_equals_general_kernel_and_oracle_on_partitioned_rows(cell):
     """Rank views of a 3-way node partition (ghost rows next to the padding rows), per-element material parameter, both
     actions: the hex27-kernel route of a hex20 block against the oracle and against the general kernel (option
     general_kernel = 1) on the same context set-up."""
     import ctypes
     import torch
     cudart = ctypes.CDLL("libcudart.so")
-    X, conn = b200.mesh.structured_hex20((5, 3, 3))
+    X, conn = (b200.mesh.structured_hex20 if cell == "hex20" else b200.mesh.structured_hex18)((5, 3, 3))
+    dcell, ocell = (b200.mesh.HEX20, orc.HEX20) if cell == "hex20" else (b200.mesh.HEX18, orc.HEX18)
     rng = np.random.default_rng(11)
     owner = (X[:, 0] * 2.999).astype(int).clip(0, 2)
     flip = rng.random(len(X)) < 0.05
     owner[flip] = rng.integers(0, 3, flip.sum())
     mk, par = capi.MAT_ISO_VOL, [1.0, 1000.0]
     for rank in range(3):
-        rm = b200.partition.generic_partition(b200.mesh.HEX20, X, conn, owner, rank, 3)
+        rm = b200.partition.generic_partition(dcell, X, conn, owner, rank, 3)
         u = b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, 0.25)
         mue = 1.0 + 0.5 * rng.random(rm.n_col_eles)
         rm1 = b200.partition.RankMesh(**{**rm.__dict__, "nranks": 1, "rank": 0})
@@ -1284,7 +1286,7 @@ def test_hex20_fast_path_equals_general_kernel_and_oracle_on_partitioned_rows():
             _, f2, _ = asm.evaluate("struct_calc_internalforce")
             res[general] = (K, f, f2, err.min_detJ)
             asm.close()
-        rK, rf, nbad = orc.evaluate_assemble(orc.HEX20, mk, par, rm.conn, rm.X.ravel(), u.ravel(), rm.node_row_lid, rm.node_col_lid,
+        rK, rf, nbad = orc.evaluate_assemble(ocell, mk, par, rm.conn, rm.X.ravel(), u.ravel(), rm.node_row_lid, rm.node_col_lid,
                                              rm.n_row_nodes, rowptr, colind, nthreads=4, mue_per_ele=mue)
         for general in (0, 1):
             K, f, f2, _ = res[general]
@@ -1294,14 +1296,16 @@ def test_hex20_fast_path_equals_general_kernel_and_oracle_on_partitioned_rows():
         assert abs(res[0][3] - res[1][3]) <= 1e-12 * abs(res[1][3])  # the same minimal Jacobian determinant from both routes
 
 
-def test_hex20_fast_path_reports_negative_nodal_jacobians_like_the_general_kernel():
+@pytest.mark.parametrize("cell", ["hex20", "hex18"])
+def test_hex20_fast_path_reports_negative_nodal_jacobians_like_the_general_kernel(cell):
     """An element folded at one corner: det J <= 0 at a node (not at the Gauss points of its neighbours): both routes count
     the same elements and name the same first offender in the caller's numbering."""
-    X, conn = b200.mesh.structured_hex20((3, 2, 2))
+    X, conn = (b200.mesh.structured_hex20 if cell == "hex20" else b200.mesh.structured_hex18)((3, 2, 2))
     X = X.copy()
     bad_ele = 7
-    X[conn[bad_ele, 6]] = X[conn[bad_ele, 0]] - 0.05   # corner 6 pulled through corner 0
-    rm = b200.partition.serial_mesh(b200.mesh.HEX20, X, conn)
+    far = 6 if cell == "hex20" else 11   # the corner opposite to node 0 (hex18 numbers the top corners 9..12)
+    X[conn[bad_ele, far]] = X[conn[bad_ele, 0]] - 0.05   # pulled through corner 0
+    rm = b200.partition.serial_mesh(b200.mesh.HEX20 if cell == "hex20" else b200.mesh.HEX18, X, conn)
     out = {}
     for general in (0, 1):
         asm = b200.DeviceAssembler(rm, capi.MAT_COUP_NEOHOOKE, [200.0, 0.25], options={"general_kernel": general})
