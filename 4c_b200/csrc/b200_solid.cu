@@ -2322,7 +2322,7 @@ namespace
   template <int MAT, bool STIFF>
   static int launch_hex27_t(b200s_ctx* ctx, const EvalArgs& A)
   {
-    if (A.nn_real > 0 && (MAT == MAT_DP || MAT == MAT_VISCO || ctx->prestress == B200S_PRESTRESS_MULF || !A.tab_override))
+    if (A.nn_real > 0 && (MAT == MAT_DP || MAT == MAT_VISCO || !A.tab_override))
       return fail(ctx, B200S_ERR_UNSUPPORTED, "hex20 through the hex27 kernel: displacement-based blocks of the hyperelastic kinds");
     auto kern = [&]
     {
@@ -2330,9 +2330,11 @@ namespace
         return k_hex27_eval_assemble<MAT, STIFF, 2>;
       else if constexpr (MAT == MAT_VISCO)
         return k_hex27_eval_assemble<MAT, STIFF, 0>;
-      else if (A.nn_real > 0)  // hex20 block
-        return ctx->kinem == B200S_KINEM_LINEAR ? k_hex27_eval_assemble<MAT, STIFF, 2, true>
-                                                : k_hex27_eval_assemble<MAT, STIFF, 0, true>;
+      else if (A.nn_real > 0)  // hex20 / hex18 block (MULF: hex20 only, its 27 Gauss points are the kernel's)
+        return ctx->prestress == B200S_PRESTRESS_MULF
+                   ? k_hex27_eval_assemble<MAT, STIFF, 1, true>
+                   : (ctx->kinem == B200S_KINEM_LINEAR ? k_hex27_eval_assemble<MAT, STIFF, 2, true>
+                                                       : k_hex27_eval_assemble<MAT, STIFF, 0, true>);
       else
         return ctx->prestress == B200S_PRESTRESS_MULF
                    ? k_hex27_eval_assemble<MAT, STIFF, 1>
@@ -2471,8 +2473,11 @@ namespace
   {
     const bool hyper = ctx->matkind == B200S_MAT_COUP_NEOHOOKE || ctx->matkind == B200S_MAT_ISO_VOL ||
                        ctx->matkind == B200S_MAT_SVK || ctx->matkind == B200S_MAT_ELASTHYPER;
+    // MULF histories are indexed by the cell's own Gauss points: hex20 has the kernel's 27, hex18 does not
+    const bool prestress_ok = ctx->prestress == B200S_PRESTRESS_NONE ||
+                              (ctx->prestress == B200S_PRESTRESS_MULF && ctx->celltype == B200S_HEX20 && ctx->d_gp_hist);
     return (ctx->celltype == B200S_HEX20 || ctx->celltype == B200S_HEX18) && !ctx->general_tangent && !ctx->general_kernel && ctx->tech == B200S_TECH_NONE &&
-           ctx->prestress == B200S_PRESTRESS_NONE && hyper && ctx->d_conn27 && ctx->d_pos27 && ctx->d_tab20 && ctx->d_dN_node;
+           prestress_ok && hyper && ctx->d_conn27 && ctx->d_pos27 && ctx->d_tab20 && ctx->d_dN_node;
   }
 
   template <bool STIFF>
