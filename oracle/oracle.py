@@ -317,6 +317,9 @@ def evaluate_assemble(ct, matkind, params, conn, X, u_col, node_row_lid, node_co
     f = np.zeros(3 * n_row_nodes)
     if impl == "ref":
         assert tech == TECH_NONE, "oracle/_ref covers the displacement-based formulation only"
+        # ref_evaluate_assemble sizes its element arrays for these three cells (ref_driver.cpp); the other cells have
+        # element-level entries only (ref_element)
+        assert ct in (HEX8, HEX27, TET10), "oracle/_ref assembles hex8 / hex27 / tet10 blocks only"
         gxi, gw = gauss(ct)
         gxi = np.ascontiguousarray(gxi)
         nbad = ref_lib().ref_evaluate_assemble(ct, matkind, _d(params), _d(mue_per_ele), action,
