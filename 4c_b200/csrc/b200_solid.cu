@@ -2738,14 +2738,7 @@ extern "C"
       std::vector<Hex27Const> hbuf(1);
       Hex27Const& h = hbuf[0];
       memset(&h, 0, sizeof h);
-      const int nn_c = T.nn, ngp_c = T.ngp;
-      for (int g = 0; g < 27; ++g)
-      {
-        const int gs = g < ngp_c ? g : 0;
-        for (int k = 0; k < nn_c; ++k)
-          for (int a = 0; a < 3; ++a) h.dN_gp[g * 81 + 3 * k + a] = T.dN_gp[((size_t)gs * nn_c + k) * 3 + a];
-        h.w[g] = g < ngp_c ? T.w[g] : 0.0;
-      }
+      pad_tables_to_hex27(T, h.dN_gp, h.w);
       const double(*hc)[3] = detail::hex_nodes();
       for (int k = 0; k < 27; ++k)
       {

@@ -274,6 +274,20 @@ namespace b200s
     }
   }  // namespace detail
 
+  // Shape-derivative tables of a hexahedral cell with <= 27 nodes and <= 27 Gauss points in the layout of the hex27 kernel
+  // (dN[g * 81 + 3 k + a], w[g]): zero derivatives for the padding nodes, and padding Gauss points that repeat point 0 with
+  // weight zero -- they contribute exactly nothing (hex20: 7 padding nodes; hex18: 9 padding nodes, 9 padding points)
+  inline void pad_tables_to_hex27(const CellTables& T, double* dN /*27 * 81*/, double* w /*27*/)
+  {
+    for (int g = 0; g < 27; ++g)
+    {
+      const int gs = g < T.ngp ? g : 0;
+      for (int k = 0; k < 27; ++k)
+        for (int a = 0; a < 3; ++a) dN[g * 81 + 3 * k + a] = k < T.nn ? T.dN_gp[((size_t)gs * T.nn + k) * 3 + a] : 0.0;
+      w[g] = g < T.ngp ? T.w[g] : 0.0;
+    }
+  }
+
   inline CellTables make_cell_tables(int celltype)
   {
     CellTables T;

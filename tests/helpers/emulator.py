@@ -313,3 +313,27 @@ def generic(celltype, matkind, params, conn, X, u_col, rowptr, colind, node_row_
                        _p(frow), len(rowstart), _p(vals), _p(f), _p(gp_hist), int(fbar), int(ans), _p(eas_hist))
     assert rc == 0, rc
     return vals, f
+
+
+def hex27_padded(celltype, matkind, params, conn, X, u_col, rowptr, colind, node_row_lid, node_col_lid, n_row_nodes, stiff=True):
+    """hex20 (celltype 4) / hex18 (7) block through the emulated hex27 kernel in its PAD instantiation: connectivity padded to 27
+    nodes with the element's node 0 (k_pad_conn), 27 x 27 scatter map with -1 for padding rows / columns
+    (k_build_scatter_map(nn_real)), padded shape tables from the product's pad_tables_to_hex27."""
+    conn = np.ascontiguousarray(conn, np.int32)
+    n_ele, nn = conn.shape
+    conn27 = np.concatenate([conn, np.repeat(conn[:, :1], 27 - nn, axis=1)], axis=1).astype(np.int32)
+    pos, rowstart, rowlen, frow = scatter_map(conn27, rowptr, colind, node_row_lid, node_col_lid)
+    pos = np.ascontiguousarray(pos.reshape(n_ele, 27, 27))
+    pos[:, nn:, :] = -1
+    pos[:, :, nn:] = -1
+    pos = np.ascontiguousarray(pos.reshape(n_ele, 729))
+    conn27 = np.ascontiguousarray(conn27)
+    vals, f = np.zeros(rowptr[-1]), np.zeros(3 * n_row_nodes)
+    dJ, dF = C.c_double(0), C.c_double(0)
+    L = lib("hex27")
+    L.emu_hex27_padded.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int64] + [C.c_void_p] * 7 + [C.c_int64] + [C.c_void_p] * 4
+    rc = L.emu_hex27_padded(int(celltype), int(matkind), _p(np.ascontiguousarray(params, np.float64)), int(stiff), n_ele, _p(conn27),
+                            _p(np.ascontiguousarray(X, np.float64)), _p(np.ascontiguousarray(u_col, np.float64)), _p(pos),
+                            _p(rowstart), _p(rowlen), _p(frow), len(rowstart), _p(vals), _p(f), C.byref(dJ), C.byref(dF))
+    assert rc == 0, rc
+    return vals, f, dict(min_detJ=dJ.value, min_detF=dF.value)

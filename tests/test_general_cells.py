@@ -213,3 +213,25 @@ def test_emulated_general_kernel_shell_ans_matches_oracle():
         # and it is not the displacement-based element
         K0, f0 = emu.generic(rm.celltype, mk, par, rm.conn, X.ravel(), u.ravel(), rowptr, colind, *maps)
         assert np.abs(K - K0).max() > 1e-3 * np.abs(K0).max()
+
+
+@pytest.mark.parametrize("cell", ["hex20", "hex18"])
+def test_emulated_padded_hex27_route_matches_oracle(cell):
+    """hex20 / hex18 blocks through the hex27 kernel (PAD instantiation): the kernel's steps on the CPU with the product's padded
+    shape tables (pad_tables_to_hex27: zero derivatives for the padding nodes, zero-weight copies of Gauss point 0 for the
+    padding points), the padded connectivity and the masked scatter map, on a rank view with ghost rows, against the oracle."""
+    ct, rm0, h = _mesh(cell)
+    X, conn = rm0.X, rm0.conn
+    owner = (X[:, 0] > 0.45).astype(int)
+    rm = b200.partition.generic_partition(rm0.celltype, X, conn, owner, 0, 2)
+    assert 0 < rm.n_row_nodes < rm.n_col_nodes
+    u = 2.0 * b200.mesh.displacement_field(rm.X, rm.node_gid, 1.0, h)
+    rowptr, colind = orc.build_graph(ct, rm.conn, rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    maps = (rm.node_row_lid, rm.node_col_lid, rm.n_row_nodes)
+    for mk, par in MATS.items():
+        rK, rf, nbad = orc.evaluate_assemble(ct, mk, par, rm.conn, rm.X.ravel(), u.ravel(), *maps, rowptr, colind)
+        K, f, info = emu.hex27_padded(rm.celltype, mk, par, rm.conn, rm.X.ravel(), u.ravel(), rowptr, colind, *maps)
+        ok, wK, wf = b200.parity_report(rowptr, K, rK, f, rf, 1e-12)
+        assert ok and nbad == 0 and info["min_detJ"] > 0, (cell, mk, wK, wf)
+        _, f2, _ = emu.hex27_padded(rm.celltype, mk, par, rm.conn, rm.X.ravel(), u.ravel(), rowptr, colind, *maps, stiff=False)
+        assert np.abs(f2 - rf).max() <= 1e-12 * np.abs(rf).max()
