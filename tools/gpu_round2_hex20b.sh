@@ -1,4 +1,5 @@
-# A/B of the hex27 kernel: build without any hex20 padding code (tools/_libs/nopad.so) vs the product (padding as a template flag),
+# A/B of the hex27 kernel: build without any hex20 padding code (tools/_libs/nopad.so: the library of commit 48090ef or earlier, built with
+# tools/build_variant.py there and copied here; not kept in the tree) vs the product (padding as a template flag),
 # same box, alternating; hex20 rate; then the whole GPU suite on the tree
 mkdir -p gpurun_out; L=gpurun_out/r02h_hex27_ab2.log; : > $L
 for i in 1 2; do
